@@ -1,0 +1,296 @@
+"""ctypes binding of include/gdbgpu.h (the C-ABI drop-in boundary).  Plumbing only: no computation happens here.
+
+The library is built in-tree by __graft_entry__.build() (genomicsdb_b200/lib/libgdbgpu.so).  Loading fails loudly when
+it is missing; every computing entry point fails with GDBGPU_ERR_CUDA when there is no CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libgdbgpu.so")
+
+OK, ERR_ARG, ERR_IO, ERR_CUDA, ERR_OVERLAP, ERR_LIMIT = 0, -1, -2, -3, -4, -5
+LEN_R, LEN_A, LEN_G = 0, 1, 2
+ELEM_INT32, ELEM_FLOAT32 = 0, 1
+SCAN_FULL, SCAN_NO_DELETIONS, SCAN_MIN_PL_GT, SCAN_WANT_LUT, SCAN_DEVICE_OUTPUT = 1, 2, 4, 8, 16
+SITE_NONREF, SITE_REMAPPED, SITE_G_SUPPRESSED = 1, 2, 4
+CALL_REDUCED = 0x40000000
+KIND = {"R": LEN_R, "A": LEN_A, "G": LEN_G}
+
+EXPORTS = ["gdbgpu_version", "gdbgpu_ctx_create", "gdbgpu_ctx_destroy", "gdbgpu_last_error", "gdbgpu_ctx_stream",
+           "gdbgpu_ctx_launch_count", "gdbgpu_array_open", "gdbgpu_array_from_columns", "gdbgpu_array_get_info",
+           "gdbgpu_array_copy_cells", "gdbgpu_array_close", "gdbgpu_scan_begin", "gdbgpu_scan_get_info",
+           "gdbgpu_scan_next_batch", "gdbgpu_scan_seek", "gdbgpu_scan_end"]
+
+
+class FieldDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("length_kind", C.c_int32), ("elem_type", C.c_int32)]
+
+
+class VarColumn(C.Structure):
+    _fields_ = [("offsets", C.c_void_p), ("values", C.c_void_p), ("values_bytes", C.c_uint64)]
+
+
+class Columns(C.Structure):
+    _fields_ = [("n_cells", C.c_uint64), ("coords", C.c_void_p), ("end", C.c_void_p),
+                ("ref", VarColumn), ("alt", VarColumn), ("gt", VarColumn), ("gt_phased", C.c_int32),
+                ("n_fields", C.c_int32), ("field_descs", C.POINTER(FieldDesc)), ("fields", C.POINTER(VarColumn)),
+                ("lb_row_idx", C.c_int64), ("num_rows", C.c_int64)]
+
+
+class ArrayInfo(C.Structure):
+    _fields_ = [("n_cells", C.c_uint64), ("n_begin_cells", C.c_uint64), ("n_fragments", C.c_uint32),
+                ("lb_row_idx", C.c_int64), ("num_rows", C.c_int64), ("min_col", C.c_int64), ("max_col", C.c_int64),
+                ("max_end", C.c_int64), ("staged_bytes", C.c_uint64), ("hbm_bytes", C.c_uint64),
+                ("n_fields", C.c_int32), ("has_gt", C.c_int32), ("gt_phased", C.c_int32)]
+
+
+class ScanParams(C.Structure):
+    _fields_ = [("col_lo", C.c_int64), ("col_hi", C.c_int64), ("query_rows", C.c_void_p), ("n_query_rows", C.c_uint64),
+                ("flags", C.c_uint32), ("max_diploid_alt_alleles", C.c_uint32)]
+
+
+class ScanInfo(C.Structure):
+    _fields_ = [("n_sites", C.c_uint64), ("n_breakpoints", C.c_uint64), ("n_query_rows", C.c_uint64),
+                ("n_forward_cells", C.c_uint64)]
+
+
+class FieldOut(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("base", C.c_void_p), ("stride", C.c_void_p), ("len", C.c_void_p)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("first_site", C.c_uint64), ("n_sites", C.c_uint32), ("n_query_rows", C.c_uint64),
+                ("site_begin", C.c_void_p), ("site_end", C.c_void_p), ("site_flags", C.c_void_p),
+                ("n_alleles", C.c_void_p), ("n_live", C.c_void_p),
+                ("allele_first", C.c_void_p), ("allele_pos", C.c_void_p), ("allele_bytes", C.c_void_p),
+                ("live", C.c_void_p), ("n_fields", C.c_int32), ("fields", FieldOut * 16),
+                ("lut_first", C.c_void_p), ("lut_len", C.c_void_p), ("lut_in2m", C.c_void_p), ("out_bytes", C.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libgdbgpu.so; raises (never falls back) when the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libgdbgpu.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                               "There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.gdbgpu_version.restype = C.c_char_p
+        L.gdbgpu_last_error.restype = C.c_char_p
+        L.gdbgpu_last_error.argtypes = [C.c_void_p]
+        L.gdbgpu_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.gdbgpu_ctx_destroy.argtypes = [C.c_void_p]
+        L.gdbgpu_ctx_stream.restype = C.c_void_p
+        L.gdbgpu_ctx_stream.argtypes = [C.c_void_p]
+        L.gdbgpu_ctx_launch_count.restype = C.c_uint64
+        L.gdbgpu_ctx_launch_count.argtypes = [C.c_void_p]
+        L.gdbgpu_array_open.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(FieldDesc), C.c_int32, C.c_int32,
+                                        C.POINTER(C.c_void_p)]
+        L.gdbgpu_array_from_columns.argtypes = [C.c_void_p, C.POINTER(Columns), C.POINTER(C.c_void_p)]
+        L.gdbgpu_array_get_info.argtypes = [C.c_void_p, C.POINTER(ArrayInfo)]
+        L.gdbgpu_array_copy_cells.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.gdbgpu_array_close.argtypes = [C.c_void_p]
+        L.gdbgpu_scan_begin.argtypes = [C.c_void_p, C.POINTER(ScanParams), C.POINTER(C.c_void_p)]
+        L.gdbgpu_scan_get_info.argtypes = [C.c_void_p, C.POINTER(ScanInfo)]
+        L.gdbgpu_scan_next_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(Batch)]
+        L.gdbgpu_scan_seek.argtypes = [C.c_void_p, C.c_uint64]
+        L.gdbgpu_scan_end.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class GdbGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("gdbgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _view(ptr, dtype, count):
+    if not ptr or count == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (int(count) * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=int(count))
+
+
+class Context:
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        rc = lib().gdbgpu_ctx_create(device, C.byref(self.h))
+        if rc != OK:
+            raise GdbGpuError(rc, "cannot create a context on CUDA device %d (no GPU? there is no CPU fallback)" % device)
+
+    def check(self, rc):
+        if rc != OK:
+            raise GdbGpuError(rc, lib().gdbgpu_last_error(self.h).decode())
+
+    @property
+    def stream(self):
+        return lib().gdbgpu_ctx_stream(self.h)
+
+    @property
+    def launches(self):
+        return lib().gdbgpu_ctx_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().gdbgpu_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def _field_descs(fields):
+    arr = (FieldDesc * max(1, len(fields)))()
+    for i, (name, kind, elem) in enumerate(fields):
+        arr[i] = FieldDesc(name.encode(), KIND[kind] if isinstance(kind, str) else kind,
+                           ELEM_FLOAT32 if elem in ("float", ELEM_FLOAT32) else ELEM_INT32)
+    return arr
+
+
+class Array:
+    """fields: list of (attribute name, 'R'|'A'|'G', 'int'|'float')"""
+
+    def __init__(self, ctx, handle, keep=None):
+        self.ctx, self.h, self._keep = ctx, handle, keep
+
+    @classmethod
+    def open(cls, ctx, workspace, array_name, fields, gt_phased=False):
+        h = C.c_void_p()
+        fd = _field_descs(fields)
+        ctx.check(lib().gdbgpu_array_open(ctx.h, workspace.encode(), array_name.encode(), fd, len(fields), int(gt_phased), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_columns(cls, ctx, coords, end, ref, alt, gt, fields, lb_row, num_rows, gt_phased=False):
+        """ref/alt/gt/fields[i]['col'] = (byte_offsets uint64[n], values ndarray); fields = list of dict(name, kind, elem, col)"""
+        keep = []
+
+        def vc(col):
+            if col is None:
+                return VarColumn(None, None, 0)
+            off = np.ascontiguousarray(col[0], dtype=np.uint64)
+            val = np.ascontiguousarray(col[1])
+            keep.extend([off, val])
+            return VarColumn(off.ctypes.data, val.ctypes.data if val.size else None, val.nbytes)
+
+        coords = np.ascontiguousarray(coords, dtype=np.int64)
+        end = np.ascontiguousarray(end, dtype=np.int64)
+        keep += [coords, end]
+        c = Columns()
+        c.n_cells = len(end)
+        c.coords, c.end = coords.ctypes.data, end.ctypes.data
+        c.ref, c.alt, c.gt = vc(ref), vc(alt), vc(gt)
+        c.gt_phased = int(gt_phased)
+        c.n_fields = len(fields)
+        fd = _field_descs([(f["name"], f["kind"], f["elem"]) for f in fields])
+        fv = (VarColumn * max(1, len(fields)))()
+        for i, f in enumerate(fields):
+            fv[i] = vc(f["col"])
+        keep += [fd, fv]
+        c.field_descs, c.fields = fd, fv
+        c.lb_row_idx, c.num_rows = lb_row, num_rows
+        h = C.c_void_p()
+        ctx.check(lib().gdbgpu_array_from_columns(ctx.h, C.byref(c), C.byref(h)))
+        return cls(ctx, h, keep=None)
+
+    def info(self):
+        i = ArrayInfo()
+        self.ctx.check(lib().gdbgpu_array_get_info(self.h, C.byref(i)))
+        return i
+
+    def cells(self):
+        n = self.info().n_cells
+        coords = np.zeros((n, 2), dtype=np.int64)
+        end = np.zeros(n, dtype=np.int64)
+        if n:
+            self.ctx.check(lib().gdbgpu_array_copy_cells(self.h, 0, n, coords.ctypes.data, end.ctypes.data))
+        return coords, end
+
+    def close(self):
+        if self.h:
+            lib().gdbgpu_array_close(self.h)
+            self.h = C.c_void_p()
+
+
+class BatchView:
+    """numpy views over one gdbgpu_batch (host output mode); valid until the next next_batch() call."""
+
+    def __init__(self, b, n_out):
+        ns, nq = b.n_sites, b.n_query_rows
+        self.first_site, self.n_sites, self.nq, self.out_bytes = b.first_site, ns, nq, b.out_bytes
+        self.site_begin = _view(b.site_begin, np.int64, ns)
+        self.site_end = _view(b.site_end, np.int64, ns)
+        self.site_flags = _view(b.site_flags, np.uint8, ns)
+        self.n_alleles = _view(b.n_alleles, np.uint32, ns)
+        self.n_live = _view(b.n_live, np.uint32, ns)
+        self.allele_first = _view(b.allele_first, np.uint32, ns)
+        tot = int((self.allele_first + self.n_alleles).max()) if ns else 0
+        self.allele_pos = _view(b.allele_pos, np.uint32, 2 * tot).reshape(-1, 2)
+        nbytes = int((self.allele_pos[:, 0] + self.allele_pos[:, 1]).max()) if tot else 0
+        self.allele_bytes = _view(b.allele_bytes, np.uint8, nbytes)
+        self.live = _view(b.live, np.int32, ns * nq).reshape(ns, nq)
+        self.fields = []
+        for o in range(n_out):
+            f = b.fields[o]
+            base = _view(f.base, np.uint64, ns + 1)
+            stride = _view(f.stride, np.uint32, ns)
+            ln = _view(f.len, np.uint16, ns * nq).reshape(ns, nq)
+            data = _view(f.data, np.uint32, int(base[ns]) if ns else 0)
+            self.fields.append(dict(base=base, stride=stride, len=ln, data=data))
+        self.lut_first = _view(b.lut_first, np.uint32, ns * nq).reshape(ns, nq) if b.lut_first else None
+        self.lut_len = _view(b.lut_len, np.uint16, ns * nq).reshape(ns, nq) if b.lut_len else None
+        self._lut_ptr = b.lut_in2m
+
+    def alleles(self, s):
+        out = []
+        for m in range(int(self.n_alleles[s])):
+            off, ln = self.allele_pos[int(self.allele_first[s]) + m]
+            out.append(bytes(self.allele_bytes[off:off + ln]))
+        return out
+
+    def lut(self, s, q):
+        first = int(self.lut_first[s, q])
+        return _view(self._lut_ptr + 2 * first, np.int16, int(self.lut_len[s, q]))
+
+
+class Scan:
+    def __init__(self, arr, col_lo=None, col_hi=None, query_rows=None, flags=0, max_alt=0):
+        self.arr, self.ctx = arr, arr.ctx
+        p = ScanParams()
+        if col_lo is None:
+            flags |= SCAN_FULL
+        else:
+            p.col_lo, p.col_hi = int(col_lo), int(col_hi)
+        self._rows = None
+        if query_rows is not None:
+            self._rows = np.ascontiguousarray(query_rows, dtype=np.int64)
+            p.query_rows, p.n_query_rows = self._rows.ctypes.data, len(self._rows)
+        p.flags, p.max_diploid_alt_alleles = flags, max_alt
+        self.h = C.c_void_p()
+        self.ctx.check(lib().gdbgpu_scan_begin(arr.h, C.byref(p), C.byref(self.h)))
+        i = arr.info()
+        self.n_out = (1 if i.has_gt else 0) + i.n_fields
+
+    def info(self):
+        i = ScanInfo()
+        self.ctx.check(lib().gdbgpu_scan_get_info(self.h, C.byref(i)))
+        return i
+
+    def next_batch(self, max_sites=0, max_bytes=0, raw=False):
+        b = Batch()
+        self.ctx.check(lib().gdbgpu_scan_next_batch(self.h, max_sites, max_bytes, C.byref(b)))
+        if raw:
+            return b
+        return BatchView(b, self.n_out) if b.n_sites else None
+
+    def seek(self, site):
+        self.ctx.check(lib().gdbgpu_scan_seek(self.h, site))
+
+    def close(self):
+        if self.h:
+            lib().gdbgpu_scan_end(self.h)
+            self.h = C.c_void_p()

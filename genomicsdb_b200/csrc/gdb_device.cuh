@@ -1,0 +1,145 @@
+// Device-side data model and small device functions shared by the kernels of the variant-combine path.
+// Semantics restated from the reference (paths relative to src/main/cpp in GenomicsDB v0.10.2):
+//   allele classes        include/utils/gt_common.h:33-47, include/vcf/known_field_info.h:209-237, src/utils/known_field_info.cc:310-319
+//   field lengths         src/utils/known_field_info.cc:130-162 ; nCr include/query_operations/variant_operations.h:317-343
+//   genotype index        src/genomicsdb/variant_field_handler.cc:299-321
+//   sentinels             include/vcf/vcf.h:61-218 ; TileDB tiledb_constants.h:105-109
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gdb {
+
+constexpr uint32_t BCF_INT_MISSING = 0x80000000u, BCF_INT_VEND = 0x80000001u;
+constexpr uint32_t BCF_FLT_MISSING = 0x7F800001u, BCF_FLT_VEND = 0x7F800002u;
+constexpr uint32_t TDB_NULL_INT = 0x7FFFFFFFu, TDB_NULL_FLT = 0x7F7FFFFFu;
+constexpr int64_t I64_MIN = INT64_MIN;
+
+enum : uint8_t { F_ENDCOPY = 1, F_REFBLOCK = 2, F_DELETION = 4, F_GTVALID = 8, F_ROWOUT = 16, F_BADEVICT = 32, F_TRIVIAL = 64 };
+enum { KIND_R = 0, KIND_A = 1, KIND_G = 2 };
+constexpr int MAX_FIELDS = 15;          // remapped fields besides GT
+constexpr int MAX_PLOIDY = 8;           // general-ploidy enumeration keeps the genotype in registers
+constexpr int MAX_CALL_ALLELES = 1024;  // alleles (REF+ALT) of one input call / of a merged site
+constexpr int LIVE_REDUCED = 0x40000000;
+
+// 16 bytes per cell, written once when the array is staged (K2 classify)
+struct CellDesc {
+  uint8_t flags;     // F_*
+  uint8_t ploidy;    // from GT length (0 when GT invalid)
+  uint16_t n_alt;    // '|'-separated non-empty ALT tokens
+  uint16_t nr_idx;   // input allele index of <NON_REF> ('&'), 0 = none
+  uint16_t pad;
+  uint32_t ref_len;
+  uint32_t gt_len;   // words
+};
+
+struct VarCol {
+  const uint64_t* off;   // n_cells + 1 absolute byte offsets
+  const uint8_t* val;
+};
+
+struct FieldMeta { int32_t kind, elem, is_pl; };
+
+// the staged array as kernels see it
+struct ArrayDev {
+  uint64_t n;
+  const int64_t* coords;   // (row, col) pairs
+  const int64_t* end;
+  VarCol ref, alt, gt;
+  int32_t has_gt, gt_phased, n_fields;
+  VarCol f[MAX_FIELDS];
+  FieldMeta fm[MAX_FIELDS];
+  int64_t lb_row, num_rows;
+  const CellDesc* desc;
+  const int64_t* effend;   // cell order; I64_MIN for END copies / rows outside the array
+  // row-major index (per-sample cell lists, column ascending)
+  uint64_t n_rs;
+  const uint32_t* rs_cell;
+  const int64_t* rs_col;
+  const int64_t* rs_effend;
+  const uint64_t* row_start;   // num_rows + 1
+};
+
+// spanning-deletion ("reduced") form of a deletion cell: REF N, ALT * [,<NON_REF>] (broad_combined_gvcf.cc:912-1078)
+struct DelRec {
+  uint32_t cell;
+  uint8_t has_nr, n_alt, pad0, pad1;
+  uint32_t gt_off, gt_len;
+  uint32_t f_off[MAX_FIELDS];
+  uint32_t f_len[MAX_FIELDS];   // 0xFFFFFFFF : field invalid
+};
+
+__host__ __device__ inline bool is_non_ref(const uint8_t* s, int n) { return n > 0 && s[0] == '&'; }
+__host__ __device__ inline bool is_symbolic(const uint8_t* s, int n) {
+  if (n <= 0) return false;
+  if (s[0] == '&') return true;
+  if (n == 1 && s[0] == '*') return true;
+  if (s[0] == '<' && s[n - 1] == '>') return true;
+  for (int i = 0; i < n; ++i) if (s[i] == '[' || s[i] == ']') return true;
+  return false;
+}
+// strtok_r(.., "|") over strndup'ed bytes: NUL ends the string, empty tokens vanish (variant_field_data.h:511-537)
+__host__ __device__ inline int alt_effective_len(const uint8_t* s, int n) {
+  for (int i = 0; i < n; ++i) if (s[i] == 0) return i;
+  return n;
+}
+__host__ __device__ inline bool next_token(const uint8_t* s, int n, int& pos, int& ts, int& tl) {
+  while (pos < n && s[pos] == '|') ++pos;
+  if (pos >= n) return false;
+  ts = pos;
+  while (pos < n && s[pos] != '|') ++pos;
+  tl = pos - ts;
+  return true;
+}
+
+__host__ __device__ inline uint64_t nCr_u64(int64_t n, int64_t r) {
+  if (n < 0 || r < 0 || n < r) return 0;
+  uint64_t begin_idx, end_idx;
+  if (r > n - r) { begin_idx = (uint64_t)r + 1u; end_idx = (uint64_t)(n - r); }
+  else { begin_idx = (uint64_t)(n - r) + 1u; end_idx = (uint64_t)r; }
+  uint64_t num = 1, den = 1;
+  for (uint64_t i = begin_idx; i <= (uint64_t)n; ++i) num *= i;
+  for (uint64_t i = 1; i <= end_idx; ++i) den *= i;
+  return num / den;
+}
+__host__ __device__ inline int64_t alleles2gt(int64_t a, int64_t b) { return a > b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+__host__ __device__ inline uint32_t num_genotypes(uint32_t n_alt, uint32_t ploidy) {
+  if (ploidy == 1) return n_alt + 1u;
+  if (ploidy == 2) return ((n_alt + 1u) * (n_alt + 2u)) >> 1;
+  return (uint32_t)nCr_u64((int64_t)ploidy + n_alt, n_alt);
+}
+__host__ __device__ inline uint32_t num_elements(int kind, uint32_t n_alt, uint32_t ploidy) {
+  if (kind == KIND_A) return n_alt;
+  if (kind == KIND_R) return n_alt + 1u;
+  return num_genotypes(n_alt, ploidy);
+}
+__host__ __device__ inline uint32_t ploidy_of(int phased, uint32_t gt_len) { return phased ? ((gt_len + 1u) >> 1) : gt_len; }
+// sorted (ascending) allele tuple -> genotype index, ploidy > 2
+__host__ __device__ inline uint64_t genotype_index_sorted(const int* a, int ploidy) {
+  uint64_t g = 0;
+  for (int i = 0; i < ploidy; ++i) g += nCr_u64((int64_t)i + a[i], (int64_t)a[i] - 1);
+  return g;
+}
+__host__ __device__ inline void sort_small(int* v, int n) {
+  for (int i = 1; i < n; ++i) { int x = v[i], j = i - 1; while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; } v[j + 1] = x; }
+}
+// next genotype in VCF order (highest ploidy slot is the slowest digit, slots non-decreasing); false when exhausted
+__host__ __device__ inline bool next_genotype(int* vec, int ploidy, int n_alleles) {
+  for (int i = 0; i < ploidy; ++i) {
+    int lim = (i + 1 < ploidy) ? vec[i + 1] : n_alleles - 1;
+    if (vec[i] < lim) { ++vec[i]; for (int k = 0; k < i; ++k) vec[k] = 0; return true; }
+  }
+  return false;
+}
+
+__host__ __device__ inline uint64_t fnv1a(uint64_t h, const uint8_t* s, int n) {
+  for (int i = 0; i < n; ++i) { h ^= s[i]; h *= 1099511628211ull; }
+  return h;
+}
+__host__ __device__ inline uint64_t hash_finish(uint64_t h) {
+  h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+  return h | 1ull;   // never 0 (0 marks an empty slot)
+}
+constexpr uint64_t FNV_BASIS = 1469598103934665603ull;
+
+}  // namespace gdb

@@ -1,0 +1,714 @@
+// Host orchestration of the B200 variant-combine path + the extern "C" ABI of include/gdbgpu.h.
+// Everything that computes runs in the kernels of gdb_kernels*.cuh; this file stages fragment bytes into HBM, sizes
+// buffers, launches, and hands batches back.  No CPU fallback: without a CUDA device every entry point fails.
+#include "../../include/gdbgpu.h"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "gdb_kernels2.cuh"
+#include "gdb_tiledb.h"
+
+using namespace gdb;
+
+// ------------------------------------------------------------------------------------------------ plumbing
+struct gdbgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+};
+
+namespace {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct LimitError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct OverlapError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct ArgError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__)); } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  void alloc(size_t count) { if (p) { cudaFree(p); p = nullptr; } n = count; if (count) CK(cudaMalloc((void**)&p, count * sizeof(T))); }
+  void ensure(size_t count) { if (count > n) alloc(count + count / 4 + 16); }
+  size_t bytes() const { return n * sizeof(T); }
+};
+template <class T>
+struct PinBuf {
+  T* p = nullptr; size_t n = 0;
+  PinBuf() = default;
+  PinBuf(const PinBuf&) = delete; PinBuf& operator=(const PinBuf&) = delete;
+  ~PinBuf() { if (p) cudaFreeHost(p); }
+  void ensure(size_t count) { if (count > n) { if (p) cudaFreeHost(p); p = nullptr; n = count + count / 4 + 16; CK(cudaMallocHost((void**)&p, n * sizeof(T))); } }
+};
+
+inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)std::max<uint64_t>(1, (n + per - 1) / per); }
+
+#define LAUNCH(ctx, kernel, grid, block, ...) do { kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__); ++(ctx)->launches; CK(cudaGetLastError()); } while (0)
+
+// exclusive scan; `total` (device) receives the sum.  in/out may alias when TI == TO.
+template <class TI, class TO>
+void exclusive_scan(gdbgpu_ctx* ctx, const TI* in, TO* out, uint64_t n, TO* total_dev, DevBuf<TO>& tile_sums) {
+  uint64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (tiles == 0) { CK(cudaMemsetAsync(total_dev, 0, sizeof(TO), ctx->stream)); return; }
+  tile_sums.ensure(tiles);
+  LAUNCH(ctx, (k_scan_tiles<TI, TO>), (unsigned)tiles, SCAN_THREADS, in, out, tile_sums.p, n);
+  LAUNCH(ctx, (k_scan_sums<TO>), 1, 1024, tile_sums.p, tiles, total_dev);
+  if (tiles > 1) LAUNCH(ctx, (k_scan_add<TO>), (unsigned)tiles, SCAN_THREADS, out, tile_sums.p, n);
+}
+
+template <class K, class V>
+void radix_sort_pairs(gdbgpu_ctx* ctx, const K* kin, K* kout, const V* vin, V* vout, uint64_t n, int end_bit, DevBuf<uint8_t>& tmp) {
+  size_t bytes = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int64_t)n, 0, end_bit, ctx->stream));
+  tmp.ensure(bytes);
+  CK(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int64_t)n, 0, end_bit, ctx->stream));
+  ctx->launches += 4;
+}
+
+__global__ void k_iota(uint32_t* p, uint64_t n) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = (uint32_t)i; }
+__global__ void k_gather_u64(const uint64_t* in, const uint32_t* perm, uint64_t n, uint64_t* out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = in[perm[i]]; }
+__global__ void k_gather_u32(const uint32_t* in, const uint32_t* perm, uint64_t n, uint32_t* out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = in[perm[i]]; }
+__global__ void k_flag_del(ArrayDev A, uint32_t* flag) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < A.n) flag[i] = (A.desc[i].flags & F_DELETION) && !(A.desc[i].flags & F_ROWOUT) ? 1u : 0u; }
+__global__ void k_compact_idx(const uint32_t* flag, const uint32_t* pos, uint64_t n, uint32_t* out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n && flag[i]) out[pos[i]] = (uint32_t)i; }
+__global__ void k_bounds(const int64_t* coords, uint64_t n, int64_t q_lo, int64_t q_hi, uint64_t* out) {
+  // out[0] = first cell with col >= q_lo, out[1] = first with col > q_lo, out[2] = first with col > q_hi
+  int t = threadIdx.x;
+  if (t > 2) return;
+  int64_t key = (t == 0) ? q_lo : (t == 1 ? q_lo : q_hi);
+  bool strict = (t != 0);
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) { uint64_t mid = (lo + hi) >> 1; int64_t c = coords[2 * mid + 1]; if (strict ? (c <= key) : (c < key)) lo = mid + 1; else hi = mid; }
+  out[t] = lo;
+}
+__global__ void k_add_i32(const int32_t* a, const int32_t* b, int32_t* out, uint64_t n) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = a[i] + b[i]; }
+
+struct HostVar { const uint64_t* off = nullptr; const void* val = nullptr; uint64_t bytes = 0; };
+struct HostCols {
+  uint64_t n = 0;
+  const int64_t* coords = nullptr; const int64_t* end = nullptr;
+  HostVar ref, alt, gt; bool has_gt = false;
+  std::vector<HostVar> fields;
+};
+
+struct DevVar { DevBuf<uint64_t> off; DevBuf<uint8_t> val; uint64_t bytes = 0; };
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ array
+struct gdbgpu_array {
+  gdbgpu_ctx* ctx = nullptr;
+  uint64_t n = 0; uint32_t n_fragments = 1;
+  int64_t lb_row = 0, num_rows = 0, min_col = 0, max_col = 0, max_end = 0;
+  uint64_t n_begin = 0, n_bad = 0, n_del_cells = 0, staged_bytes = 0;
+  bool has_gt = false; int gt_phased = 0;
+  std::vector<FieldMeta> fm; std::vector<std::string> field_names;
+  DevBuf<int64_t> coords, end;
+  DevVar ref, alt, gt; std::vector<std::unique_ptr<DevVar>> fields;
+  DevBuf<CellDesc> desc; DevBuf<int64_t> effend;
+  DevBuf<uint32_t> rs_cell, rs_keys; DevBuf<int64_t> rs_col, rs_effend; DevBuf<uint64_t> row_start; uint64_t n_rs = 0;
+  DevBuf<uint32_t> bad_cell; DevBuf<int64_t> bad_pred_col;
+  ArrayDev dev{};
+  uint64_t hbm_bytes() const {
+    uint64_t b = coords.bytes() + end.bytes() + ref.off.bytes() + ref.val.bytes() + alt.off.bytes() + alt.val.bytes() + gt.off.bytes() + gt.val.bytes() +
+                 desc.bytes() + effend.bytes() + rs_cell.bytes() + rs_keys.bytes() + rs_col.bytes() + rs_effend.bytes() + row_start.bytes();
+    for (auto& f : fields) b += f->off.bytes() + f->val.bytes();
+    return b;
+  }
+};
+
+namespace {
+
+constexpr uint32_t BAD_CAP = 4096;
+
+void upload_var(gdbgpu_ctx* ctx, const HostVar& h, uint64_t n, DevVar& d, uint64_t& staged) {
+  d.off.alloc(n + 1);
+  d.val.alloc(std::max<uint64_t>(h.bytes, 1));
+  d.bytes = h.bytes;
+  if (n) CK(cudaMemcpyAsync(d.off.p, h.off, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d.off.p + n, &h.bytes, 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (h.bytes) CK(cudaMemcpyAsync(d.val.p, h.val, h.bytes, cudaMemcpyHostToDevice, ctx->stream));
+  staged += n * 8 + h.bytes;
+}
+
+void fill_dev_view(gdbgpu_array* a) {
+  ArrayDev& D = a->dev;
+  D.n = a->n; D.coords = a->coords.p; D.end = a->end.p;
+  D.ref = VarCol{a->ref.off.p, a->ref.val.p}; D.alt = VarCol{a->alt.off.p, a->alt.val.p};
+  D.gt = VarCol{a->gt.off.p, a->gt.val.p};
+  D.has_gt = a->has_gt; D.gt_phased = a->gt_phased; D.n_fields = (int)a->fields.size();
+  for (size_t f = 0; f < a->fields.size(); ++f) { D.f[f] = VarCol{a->fields[f]->off.p, a->fields[f]->val.p}; D.fm[f] = a->fm[f]; }
+  D.lb_row = a->lb_row; D.num_rows = a->num_rows;
+  D.desc = a->desc.p; D.effend = a->effend.p;
+  D.n_rs = a->n_rs; D.rs_cell = a->rs_cell.p; D.rs_col = a->rs_col.p; D.rs_effend = a->rs_effend.p; D.row_start = a->row_start.p;
+}
+
+// K1: merge the concatenated cells of several fragments into global (col,row) order, newest fragment wins.
+// Returns src[] (device) = for each surviving merged cell, its index in the concatenation.
+void fragment_merge(gdbgpu_ctx* ctx, const int64_t* d_coords, uint64_t n_all, const std::vector<uint64_t>& frag_cells, DevBuf<uint32_t>& src, uint64_t& n_out) {
+  std::vector<uint32_t> frag_of(n_all);
+  { uint64_t p = 0; for (uint32_t f = 0; f < frag_cells.size(); ++f) for (uint64_t k = 0; k < frag_cells[f]; ++k) frag_of[p++] = f; }
+  DevBuf<uint32_t> d_frag, kfrag, perm_a, perm_b, k32; DevBuf<uint64_t> kcol, krow, k64a, k64b; DevBuf<uint8_t> tmp;
+  d_frag.alloc(n_all); kfrag.alloc(n_all); perm_a.alloc(n_all); perm_b.alloc(n_all); k32.alloc(n_all);
+  kcol.alloc(n_all); krow.alloc(n_all); k64a.alloc(n_all); k64b.alloc(n_all);
+  CK(cudaMemcpyAsync(d_frag.p, frag_of.data(), n_all * 4, cudaMemcpyHostToDevice, ctx->stream));
+  unsigned g = blocks_for(n_all, 256);
+  LAUNCH(ctx, k_merge_keys, g, 256, d_coords, d_frag.p, (uint32_t)frag_cells.size(), n_all, kcol.p, krow.p, kfrag.p);
+  LAUNCH(ctx, k_iota, g, 256, perm_a.p, n_all);
+  // LSD: fragment (newest first), then row, then column -- each pass stable
+  radix_sort_pairs(ctx, kfrag.p, k32.p, perm_a.p, perm_b.p, n_all, 32, tmp);
+  LAUNCH(ctx, k_gather_u64, g, 256, krow.p, perm_b.p, n_all, k64a.p);
+  radix_sort_pairs(ctx, k64a.p, k64b.p, perm_b.p, perm_a.p, n_all, 64, tmp);
+  LAUNCH(ctx, k_gather_u64, g, 256, kcol.p, perm_a.p, n_all, k64a.p);
+  radix_sort_pairs(ctx, k64a.p, k64b.p, perm_a.p, perm_b.p, n_all, 64, tmp);
+  // perm_b = merged order incl. shadowed duplicates
+  DevBuf<uint32_t> keep, pos, total; DevBuf<uint32_t> sums;
+  keep.alloc(n_all); pos.alloc(n_all); total.alloc(1);
+  LAUNCH(ctx, k_merge_keep, g, 256, d_coords, perm_b.p, n_all, keep.p);
+  exclusive_scan<uint32_t, uint32_t>(ctx, keep.p, pos.p, n_all, total.p, sums);
+  uint32_t h_total = 0;
+  CK(cudaMemcpyAsync(&h_total, total.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  n_out = h_total;
+  src.alloc(std::max<uint64_t>(n_out, 1));
+  LAUNCH(ctx, k_merge_compact, g, 256, perm_b.p, keep.p, pos.p, n_all, src.p);
+  CK(cudaStreamSynchronize(ctx->stream));
+}
+
+void gather_var(gdbgpu_ctx* ctx, const DevVar& in, const uint32_t* src, uint64_t n_out, DevVar& out) {
+  DevBuf<uint64_t> len, sums, total;
+  len.alloc(n_out + 1); total.alloc(1);
+  out.off.alloc(n_out + 1);
+  LAUNCH(ctx, k_gather_len, blocks_for(n_out, 256), 256, in.off.p, src, n_out, len.p);
+  exclusive_scan<uint64_t, uint64_t>(ctx, len.p, out.off.p, n_out, total.p, sums);
+  uint64_t h_total = 0;
+  CK(cudaMemcpyAsync(&h_total, total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpyAsync(out.off.p + n_out, &h_total, 8, cudaMemcpyHostToDevice, ctx->stream));
+  out.val.alloc(std::max<uint64_t>(h_total, 1)); out.bytes = h_total;
+  LAUNCH(ctx, k_gather_var, blocks_for(n_out * 32, 256), 256, in.off.p, in.val.p, src, out.off.p, n_out, out.val.p);
+  CK(cudaStreamSynchronize(ctx->stream));
+}
+
+// stage host columns (already concatenated over fragments) and build the per-array indexes
+gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<uint64_t>& frag_cells, int64_t lb_row, int64_t num_rows, int gt_phased,
+                          const std::vector<FieldMeta>& fm, const std::vector<std::string>& names) {
+  if (h.n >= (1ull << 30)) throw LimitError("more than 2^30 cells in one staged array: shard the column range across GPUs");
+  if (h.fields.size() > (size_t)MAX_FIELDS) throw LimitError("more than 15 allele-dependent fields queried");
+  if (num_rows < 0 || num_rows >= (1ll << 31)) throw LimitError("row count out of range");
+  std::unique_ptr<gdbgpu_array> a(new gdbgpu_array());
+  a->ctx = ctx; a->n = h.n; a->lb_row = lb_row; a->num_rows = num_rows; a->gt_phased = gt_phased; a->has_gt = h.has_gt; a->fm = fm; a->field_names = names;
+  a->n_fragments = (uint32_t)std::max<size_t>(1, frag_cells.size());
+  uint64_t n = h.n;
+  a->coords.alloc(std::max<uint64_t>(2 * n, 2)); a->end.alloc(std::max<uint64_t>(n, 1));
+  if (n) { CK(cudaMemcpyAsync(a->coords.p, h.coords, n * 16, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaMemcpyAsync(a->end.p, h.end, n * 8, cudaMemcpyHostToDevice, ctx->stream)); }
+  a->staged_bytes = n * 24;
+  upload_var(ctx, h.ref, n, a->ref, a->staged_bytes);
+  upload_var(ctx, h.alt, n, a->alt, a->staged_bytes);
+  if (h.has_gt) upload_var(ctx, h.gt, n, a->gt, a->staged_bytes);
+  for (auto& f : h.fields) { a->fields.emplace_back(new DevVar()); upload_var(ctx, f, n, *a->fields.back(), a->staged_bytes); }
+  CK(cudaStreamSynchronize(ctx->stream));
+
+  if (frag_cells.size() > 1 && n) {   // K1
+    DevBuf<uint32_t> src; uint64_t n_out = 0;
+    fragment_merge(ctx, a->coords.p, n, frag_cells, src, n_out);
+    DevBuf<int64_t> c2, e2; c2.alloc(std::max<uint64_t>(2 * n_out, 2)); e2.alloc(std::max<uint64_t>(n_out, 1));
+    LAUNCH(ctx, k_gather_fixed, blocks_for(n_out * 2, 256), 256, (const uint8_t*)a->coords.p, src.p, n_out, 16u, (uint8_t*)c2.p);
+    LAUNCH(ctx, k_gather_fixed, blocks_for(n_out, 256), 256, (const uint8_t*)a->end.p, src.p, n_out, 8u, (uint8_t*)e2.p);
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::swap(a->coords.p, c2.p); std::swap(a->coords.n, c2.n); std::swap(a->end.p, e2.p); std::swap(a->end.n, e2.n);
+    auto regather = [&](DevVar& v) { DevVar o; gather_var(ctx, v, src.p, n_out, o); std::swap(v.off.p, o.off.p); std::swap(v.off.n, o.off.n); std::swap(v.val.p, o.val.p); std::swap(v.val.n, o.val.n); v.bytes = o.bytes; };
+    regather(a->ref); regather(a->alt); if (h.has_gt) regather(a->gt);
+    for (auto& f : a->fields) regather(*f);
+    a->n = n = n_out;
+  }
+  // K2: classify + row-major index
+  a->desc.alloc(std::max<uint64_t>(n, 1)); a->effend.alloc(std::max<uint64_t>(n, 1));
+  a->rs_cell.alloc(std::max<uint64_t>(n, 1)); a->rs_keys.alloc(std::max<uint64_t>(n, 1)); a->rs_col.alloc(std::max<uint64_t>(n, 1)); a->rs_effend.alloc(std::max<uint64_t>(n, 1));
+  a->row_start.alloc((uint64_t)num_rows + 2);
+  a->bad_cell.alloc(BAD_CAP); a->bad_pred_col.alloc(BAD_CAP);
+  fill_dev_view(a.get());
+  if (n) {
+    unsigned g = blocks_for(n, 256);
+    LAUNCH(ctx, k_classify, g, 256, a->dev, a->desc.p);
+    DevBuf<uint32_t> keys, vals; DevBuf<uint8_t> tmp;
+    keys.alloc(n); vals.alloc(n);
+    LAUNCH(ctx, k_row_keys, g, 256, a->dev, a->desc.p, keys.p, vals.p);
+    int bits = 1; while ((1ll << bits) <= num_rows) ++bits;
+    radix_sort_pairs(ctx, keys.p, a->rs_keys.p, vals.p, a->rs_cell.p, n, bits, tmp);
+    LAUNCH(ctx, k_row_bounds, blocks_for((uint64_t)num_rows + 1, 256), 256, a->rs_keys.p, n, num_rows, a->row_start.p);
+    uint64_t n_rs = 0;
+    CK(cudaMemcpyAsync(&n_rs, a->row_start.p + num_rows, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    a->n_rs = n_rs;
+    DevBuf<unsigned long long> stats; stats.alloc(4);
+    long long init[4] = {0, 0, INT64_MIN, 0};
+    CK(cudaMemcpyAsync(stats.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_effend_rowout, g, 256, a->dev, a->desc.p, a->effend.p);
+    if (n_rs) {
+      LAUNCH(ctx, k_rs_cols, blocks_for(n_rs, 256), 256, a->dev, a->rs_cell.p, n_rs, a->rs_col.p);
+      LAUNCH(ctx, k_effend, blocks_for(n_rs, 256), 256, a->dev, a->desc.p, a->rs_cell.p, a->rs_col.p, a->rs_keys.p, n_rs, a->rs_effend.p, a->effend.p, stats.p,
+             a->bad_cell.p, a->bad_pred_col.p, BAD_CAP);
+    }
+    long long hs[4];
+    CK(cudaMemcpyAsync(hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    int64_t first_last[2];
+    CK(cudaMemcpyAsync(&first_last[0], a->coords.p + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&first_last[1], a->coords.p + 2 * (n - 1) + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    a->n_begin = (uint64_t)hs[0]; a->n_bad = (uint64_t)hs[1]; a->max_end = hs[2] == INT64_MIN ? first_last[1] : hs[2]; a->n_del_cells = (uint64_t)hs[3];
+    a->min_col = first_last[0]; a->max_col = first_last[1];
+    if (a->max_end < a->max_col) a->max_end = a->max_col;
+  }
+  fill_dev_view(a.get());
+  return a.release();
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ scan
+struct gdbgpu_scan {
+  gdbgpu_array* arr = nullptr; gdbgpu_ctx* ctx = nullptr;
+  gdbgpu_scan_params params{}; bool device_output = false;
+  ScanDev S{};
+  uint64_t cursor = 0;
+  std::vector<int64_t> h_rows;
+  DevBuf<int32_t> qrow_of_row, init_cell, dlive, ddel, live_excl, del_excl; DevBuf<int64_t> row_of_qrow, init_effend, bp, site_begin, site_end;
+  DevBuf<unsigned long long> bitmap; DevBuf<uint32_t> word_rank, bp_cell0, err, del_cells, del_words; DevBuf<uint64_t> site_start; DevBuf<DelRec> del_recs;
+  // per batch (device)
+  DevBuf<int32_t> live; DevBuf<SiteRec> sites; DevBuf<uint32_t> cursors, allele_pos, lut_first; DevBuf<uint16_t> lut_len; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes; DevBuf<int16_t> lut_in2m;
+  DevBuf<uint32_t> out_data[MAX_FIELDS + 1], out_stride[MAX_FIELDS + 1]; DevBuf<uint64_t> out_base[MAX_FIELDS + 1]; DevBuf<uint16_t> out_len[MAX_FIELDS + 1];
+  DevBuf<uint8_t> d_site_flags; DevBuf<uint32_t> d_n_alleles, d_n_live, d_allele_first;
+  // per batch (host mirrors)
+  std::vector<SiteRec> h_sites;
+  std::vector<uint8_t> h_site_flags; std::vector<uint32_t> h_n_alleles, h_n_live, h_allele_first;
+  std::vector<uint64_t> h_base[MAX_FIELDS + 1]; std::vector<uint32_t> h_stride[MAX_FIELDS + 1];
+  PinBuf<int64_t> p_site_begin, p_site_end; PinBuf<int32_t> p_live; PinBuf<uint32_t> p_allele_pos, p_lut_first, p_out_data[MAX_FIELDS + 1]; PinBuf<uint8_t> p_allele_bytes;
+  PinBuf<uint16_t> p_out_len[MAX_FIELDS + 1], p_lut_len; PinBuf<int16_t> p_lut_in2m;
+  uint32_t cap_allele_recs = 0, cap_allele_bytes = 0, cap_lut = 0;
+  uint64_t avg_site_bytes = 0;
+  int n_out = 0;
+};
+
+namespace {
+
+void check_scan_errors(gdbgpu_scan* s, bool& pool_overflow) {
+  uint32_t e[4];
+  CK(cudaMemcpyAsync(e, s->err.p, sizeof(e), cudaMemcpyDeviceToHost, s->ctx->stream));
+  CK(cudaStreamSynchronize(s->ctx->stream));
+  if (e[0]) throw OverlapError("Unhandled overlapping variants (a call that is neither a deletion nor a reference block is overlapped by a later call of the same sample)");
+  if (e[1] == 1) throw LimitError("a call has more than 1023 ALT alleles");
+  if (e[1] == 2) throw LimitError("more than 512 distinct ALT alleles at one site");
+  if (e[1] == 3) throw LimitError("ploidy above 8 needs the general-ploidy genotype enumeration, which keeps at most 8 slots");
+  if (e[1] == 4) throw LimitError("merged REF assembled from more than 32 pieces");
+  pool_overflow = e[2] != 0;
+  if (pool_overflow) CK(cudaMemsetAsync(s->err.p + 2, 0, 4, s->ctx->stream));
+}
+
+void scan_prepare(gdbgpu_scan* s) {
+  gdbgpu_array* a = s->arr; gdbgpu_ctx* ctx = s->ctx; ScanDev& S = s->S;
+  const gdbgpu_scan_params& p = s->params;
+  S.scan_full = (p.flags & GDBGPU_SCAN_FULL) ? 1 : 0;
+  S.handle_del = (p.flags & GDBGPU_SCAN_NO_DELETIONS) ? 0 : 1;
+  S.min_pl_gt = (p.flags & GDBGPU_SCAN_MIN_PL_GT) ? 1 : 0;
+  S.want_lut = (p.flags & GDBGPU_SCAN_WANT_LUT) ? 1 : 0;
+  S.max_alt = p.max_diploid_alt_alleles ? p.max_diploid_alt_alleles : 50u;
+  s->device_output = (p.flags & GDBGPU_SCAN_DEVICE_OUTPUT) != 0;
+  // queried rows: sorted, unique, inside the array (variant_query_config.cc:60-117)
+  if (p.query_rows) {
+    s->h_rows.assign(p.query_rows, p.query_rows + p.n_query_rows);
+    std::sort(s->h_rows.begin(), s->h_rows.end());
+    s->h_rows.erase(std::unique(s->h_rows.begin(), s->h_rows.end()), s->h_rows.end());
+    s->h_rows.erase(std::remove_if(s->h_rows.begin(), s->h_rows.end(), [&](int64_t r) { return r < a->lb_row || r >= a->lb_row + a->num_rows; }), s->h_rows.end());
+  } else { s->h_rows.resize((size_t)a->num_rows); for (int64_t r = 0; r < a->num_rows; ++r) s->h_rows[(size_t)r] = a->lb_row + r; }
+  S.nq = s->h_rows.size();
+  s->err.alloc(4); CK(cudaMemsetAsync(s->err.p, 0, 16, ctx->stream));
+  S.err = s->err.p;
+  s->row_of_qrow.alloc(std::max<uint64_t>(S.nq, 1));
+  if (S.nq) CK(cudaMemcpyAsync(s->row_of_qrow.p, s->h_rows.data(), S.nq * 8, cudaMemcpyHostToDevice, ctx->stream));
+  S.row_of_qrow = s->row_of_qrow.p;
+  S.qrow_of_row = nullptr;
+  if (p.query_rows) {
+    std::vector<int32_t> m((size_t)a->num_rows, -1);
+    for (size_t q = 0; q < s->h_rows.size(); ++q) m[(size_t)(s->h_rows[q] - a->lb_row)] = (int32_t)q;
+    s->qrow_of_row.alloc(std::max<size_t>(m.size(), 1));
+    if (!m.empty()) CK(cudaMemcpyAsync(s->qrow_of_row.p, m.data(), m.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    S.qrow_of_row = s->qrow_of_row.p;
+  }
+  s->init_cell.alloc(std::max<uint64_t>(S.nq, 1)); s->init_effend.alloc(std::max<uint64_t>(S.nq, 1));
+  S.init_cell = s->init_cell.p; S.init_effend = s->init_effend.p;
+  S.n_sites = 0; S.m = 0;
+  s->n_out = (a->has_gt ? 1 : 0) + (int)a->fields.size();
+  if (a->n == 0 || S.nq == 0) return;
+  // clamp the interval to where data can be
+  int64_t hi_data = std::max(a->max_end, a->max_col);
+  if (S.scan_full) { S.q_lo = a->min_col; S.q_hi = hi_data; }
+  else { S.q_lo = p.col_lo; S.q_hi = std::min(p.col_hi, hi_data); if (p.col_lo > p.col_hi) throw ArgError("col_lo > col_hi"); }
+  if (S.q_lo > S.q_hi) return;
+  S.base = S.q_lo;
+  S.span_bits = (uint64_t)(S.q_hi - S.base) + 2ull;
+  if (S.span_bits > (1ull << 37)) throw LimitError("query column span above 2^37 positions: split the interval");
+  S.n_words = (S.span_bits + 63) / 64;
+  // forward range
+  DevBuf<uint64_t> d_bounds; d_bounds.alloc(3);
+  uint64_t hb[3] = {0, 0, a->n};
+  if (!S.scan_full) {
+    LAUNCH(ctx, k_bounds, 1, 32, a->coords.p, a->n, S.q_lo, S.q_hi, d_bounds.p);
+    CK(cudaMemcpyAsync(hb, d_bounds.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  S.iL = hb[0]; S.i0 = hb[1]; S.i1 = hb[2];
+  if (a->n_bad) {
+    if (a->n_bad > BAD_CAP) throw OverlapError("Unhandled overlapping variants (too many to enumerate)");
+    LAUNCH(ctx, k_check_evictions, blocks_for(a->n_bad, 128), 128, a->dev, S, a->bad_cell.p, a->bad_pred_col.p, (uint32_t)a->n_bad);
+  }
+  // K2b deletion pre-pass
+  S.n_del = 0;
+  if (S.handle_del && a->n_del_cells) {
+    DevBuf<uint32_t> flag, pos, total, sums, words;
+    flag.alloc(a->n); pos.alloc(a->n); total.alloc(1);
+    LAUNCH(ctx, k_flag_del, blocks_for(a->n, 256), 256, a->dev, flag.p);
+    exclusive_scan<uint32_t, uint32_t>(ctx, flag.p, pos.p, a->n, total.p, sums);
+    uint32_t nd = 0;
+    CK(cudaMemcpyAsync(&nd, total.p, 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+    if (nd) {
+      s->del_cells.alloc(nd); s->del_recs.alloc(nd); words.alloc(nd);
+      LAUNCH(ctx, k_compact_idx, blocks_for(a->n, 256), 256, flag.p, pos.p, a->n, s->del_cells.p);
+      LAUNCH(ctx, k_del_size, blocks_for(nd, 128), 128, a->dev, s->del_cells.p, (uint64_t)nd, words.p);
+      exclusive_scan<uint32_t, uint32_t>(ctx, words.p, words.p, nd, total.p, sums);
+      uint32_t nw = 0;
+      CK(cudaMemcpyAsync(&nw, total.p, 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+      s->del_words.alloc(std::max<uint32_t>(nw, 1));
+      LAUNCH(ctx, k_del_fill, blocks_for(nd, 128), 128, a->dev, S.min_pl_gt, s->del_cells.p, (uint64_t)nd, words.p, s->del_recs.p, s->del_words.p, s->err.p);
+      CK(cudaStreamSynchronize(ctx->stream));
+      S.n_del = nd; S.del_cells = s->del_cells.p; S.del_recs = s->del_recs.p; S.del_words = s->del_words.p;
+    }
+  }
+  // K3: breakpoints
+  s->bitmap.alloc(S.n_words); s->word_rank.alloc(S.n_words + 1);
+  CK(cudaMemsetAsync(s->bitmap.p, 0, S.n_words * 8, ctx->stream));
+  S.bitmap = s->bitmap.p; S.word_rank = s->word_rank.p;
+  LAUNCH(ctx, k_left_sweep, blocks_for(S.nq, 256), 256, a->dev, S);
+  if (S.i1 > S.i0) LAUNCH(ctx, k_mark_events, blocks_for(S.i1 - S.i0, 256), 256, a->dev, S);
+  DevBuf<uint32_t> cnt, total32, sums32;
+  cnt.alloc(S.n_words); total32.alloc(1);
+  LAUNCH(ctx, k_popc, blocks_for(S.n_words, 256), 256, S.bitmap, S.n_words, cnt.p);
+  exclusive_scan<uint32_t, uint32_t>(ctx, cnt.p, s->word_rank.p, S.n_words, total32.p, sums32);
+  uint32_t m = 0;
+  CK(cudaMemcpyAsync(&m, total32.p, 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+  S.m = m;
+  if (m < 2) { S.m = m; return; }
+  s->bp.alloc(m); s->bp_cell0.alloc(m); s->dlive.alloc(m); s->ddel.alloc(m); s->live_excl.alloc(m); s->del_excl.alloc(m); s->site_start.alloc((uint64_t)m + 1);
+  S.bp = s->bp.p; S.bp_cell0 = s->bp_cell0.p; S.dlive = s->dlive.p; S.ddel = s->ddel.p; S.site_start = s->site_start.p;
+  CK(cudaMemsetAsync(s->dlive.p, 0, (size_t)m * 4, ctx->stream)); CK(cudaMemsetAsync(s->ddel.p, 0, (size_t)m * 4, ctx->stream));
+  LAUNCH(ctx, k_extract_bp, blocks_for(S.n_words, 256), 256, S);
+  LAUNCH(ctx, k_deltas, blocks_for((S.i1 - S.iL) + S.nq, 256), 256, a->dev, S);
+  DevBuf<int32_t> total_i, sums_i; total_i.alloc(1);
+  exclusive_scan<int32_t, int32_t>(ctx, s->dlive.p, s->live_excl.p, m, total_i.p, sums_i);
+  exclusive_scan<int32_t, int32_t>(ctx, s->ddel.p, s->del_excl.p, m, total_i.p, sums_i);
+  DevBuf<uint64_t> cnt64, total64, sums64; cnt64.alloc(m); total64.alloc(1);
+  LAUNCH(ctx, k_site_counts, blocks_for(m, 256), 256, S, s->live_excl.p, s->del_excl.p, cnt64.p);
+  exclusive_scan<uint64_t, uint64_t>(ctx, cnt64.p, s->site_start.p, m, total64.p, sums64);
+  uint64_t T = 0;
+  CK(cudaMemcpyAsync(&T, total64.p, 8, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpyAsync(s->site_start.p + m, &T, 8, cudaMemcpyHostToDevice, ctx->stream));
+  S.n_sites = T;
+  if (T) {
+    s->site_begin.alloc(T); s->site_end.alloc(T);
+    S.site_begin = s->site_begin.p; S.site_end = s->site_end.p;
+    LAUNCH(ctx, k_fill_sites, blocks_for(T, 256), 256, S, s->del_excl.p);
+  }
+  bool ovf = false;
+  check_scan_errors(s, ovf);
+}
+
+uint32_t stride_of(const gdbgpu_array* a, const SiteRec& r, int o) {
+  if (a->has_gt && o == 0) return r.max_gt_len;
+  int f = o - (a->has_gt ? 1 : 0);
+  if (r.max_in_len[f] == 0) return 0;
+  if (!(r.flags & 2u)) return r.max_in_len[f];
+  int kind = a->fm[f].kind;
+  if (kind == KIND_G && (r.flags & 4u)) return 0;
+  return num_elements(kind, r.n_alleles - 1u, r.max_ploidy[f]);
+}
+
+int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_batch* out) {
+  gdbgpu_array* a = s->arr; gdbgpu_ctx* ctx = s->ctx; ScanDev& S = s->S;
+  memset(out, 0, sizeof(*out));
+  out->first_site = s->cursor; out->n_query_rows = S.nq; out->n_fields = s->n_out;
+  if (s->cursor >= S.n_sites) return GDBGPU_OK;
+  if (max_bytes == 0) max_bytes = 1ull << 30;
+  uint64_t remaining = S.n_sites - s->cursor;
+  // sites whose live matrix fits a fixed budget, and (by the running average) whose output fits max_bytes
+  uint64_t by_live = std::max<uint64_t>(1, (256ull << 20) / std::max<uint64_t>(1, S.nq * 4));
+  uint64_t guess = s->avg_site_bytes ? std::max<uint64_t>(1, max_bytes / s->avg_site_bytes) : 64;
+  uint32_t nb = (uint32_t)std::min<uint64_t>({remaining, max_sites ? max_sites : 0xFFFFFFFFull, by_live, guess + guess / 2 + 1, 1u << 20});
+  const int n_out = s->n_out;
+  for (;;) {
+    s->live.ensure((uint64_t)nb * S.nq); s->sites.ensure(nb); s->cursors.ensure(4);
+    if (!s->cap_allele_recs) { s->cap_allele_recs = 1u << 16; s->cap_allele_bytes = 1u << 20; }
+    s->allele_pos.ensure(2ull * s->cap_allele_recs); s->allele_hash.ensure(s->cap_allele_recs); s->allele_bytes.ensure(s->cap_allele_bytes);
+    CK(cudaMemsetAsync(s->cursors.p, 0, 16, ctx->stream));
+    BatchDev B{};
+    B.first_site = s->cursor; B.n_sites = nb; B.live = s->live.p; B.sites = s->sites.p; B.cursors = s->cursors.p;
+    B.allele_pos = s->allele_pos.p; B.allele_hash = s->allele_hash.p; B.cap_allele_recs = s->cap_allele_recs; B.allele_bytes = s->allele_bytes.p; B.cap_allele_bytes = s->cap_allele_bytes;
+    LAUNCH(ctx, k_live_walk, blocks_for(S.nq, 256), 256, a->dev, S, s->cursor, nb, s->live.p);
+    LAUNCH(ctx, k_union, nb, UNION_THREADS, a->dev, S, B);
+    s->h_sites.resize(nb);
+    CK(cudaMemcpyAsync(s->h_sites.data(), s->sites.p, (size_t)nb * sizeof(SiteRec), cudaMemcpyDeviceToHost, ctx->stream));
+    bool ovf = false;
+    check_scan_errors(s, ovf);
+    if (ovf) { s->cap_allele_recs *= 4; s->cap_allele_bytes *= 4; continue; }
+    // strides / bases; keep the prefix of sites that fits
+    for (int o = 0; o < n_out; ++o) { s->h_base[o].assign(nb + 1, 0); s->h_stride[o].assign(nb, 0); }
+    uint64_t bytes = 0; uint32_t keep = 0; uint64_t lut_words = 0;
+    for (uint32_t i = 0; i < nb; ++i) {
+      uint64_t site_bytes = 0;
+      for (int o = 0; o < n_out; ++o) { uint32_t st = stride_of(a, s->h_sites[i], o); s->h_stride[o][i] = st; site_bytes += (uint64_t)st * S.nq * 4 + S.nq * 2; }
+      if (i > 0 && bytes + site_bytes > max_bytes) break;
+      for (int o = 0; o < n_out; ++o) s->h_base[o][i + 1] = s->h_base[o][i] + (uint64_t)s->h_stride[o][i] * S.nq;
+      bytes += site_bytes; lut_words += (uint64_t)s->h_sites[i].max_ain * S.nq; keep = i + 1;
+    }
+    s->avg_site_bytes = std::max<uint64_t>(1, bytes / keep);
+    RemapOut O{};
+    O.n_out = n_out;
+    for (int o = 0; o < n_out; ++o) {
+      s->out_data[o].ensure(std::max<uint64_t>(s->h_base[o][keep], 1)); s->out_base[o].ensure(keep + 1); s->out_stride[o].ensure(keep); s->out_len[o].ensure((uint64_t)keep * S.nq);
+      CK(cudaMemcpyAsync(s->out_base[o].p, s->h_base[o].data(), (size_t)(keep + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(s->out_stride[o].p, s->h_stride[o].data(), (size_t)keep * 4, cudaMemcpyHostToDevice, ctx->stream));
+      O.f[o] = FieldOutDev{s->out_data[o].p, s->out_base[o].p, s->out_stride[o].p, s->out_len[o].p};
+    }
+    if (S.want_lut) {
+      if (lut_words >= (1ull << 32)) throw LimitError("LUT output of one batch above 2^32 entries: lower max_sites");
+      s->cap_lut = (uint32_t)std::max<uint64_t>(lut_words, 1);
+      s->lut_first.ensure((uint64_t)keep * S.nq); s->lut_len.ensure((uint64_t)keep * S.nq); s->lut_in2m.ensure(s->cap_lut);
+      O.lut_first = s->lut_first.p; O.lut_len = s->lut_len.p; O.lut_in2m = s->lut_in2m.p; O.cap_lut = s->cap_lut;
+    }
+    B.n_sites = keep;
+    uint32_t tiles = (uint32_t)((S.nq + REMAP_ROWS - 1) / REMAP_ROWS);
+    LAUNCH(ctx, k_remap, keep * tiles, REMAP_THREADS, a->dev, S, B, O);
+    check_scan_errors(s, ovf);
+    if (ovf) throw CudaError("internal: LUT pool overflow");
+    // ---- publish
+    s->h_site_flags.resize(keep); s->h_n_alleles.resize(keep); s->h_n_live.resize(keep); s->h_allele_first.resize(keep);
+    for (uint32_t i = 0; i < keep; ++i) { const SiteRec& r = s->h_sites[i]; s->h_site_flags[i] = (uint8_t)r.flags; s->h_n_alleles[i] = r.n_alleles; s->h_n_live[i] = r.n_live; s->h_allele_first[i] = r.allele_first; }
+    uint32_t hc[4];
+    CK(cudaMemcpyAsync(hc, s->cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+    out->n_sites = keep; out->out_bytes = bytes;
+    if (s->device_output) {
+      s->d_site_flags.ensure(keep); s->d_n_alleles.ensure(keep); s->d_n_live.ensure(keep); s->d_allele_first.ensure(keep);
+      CK(cudaMemcpyAsync(s->d_site_flags.p, s->h_site_flags.data(), keep, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(s->d_n_alleles.p, s->h_n_alleles.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(s->d_n_live.p, s->h_n_live.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(s->d_allele_first.p, s->h_allele_first.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
+      out->site_begin = s->site_begin.p + s->cursor; out->site_end = s->site_end.p + s->cursor;
+      out->site_flags = s->d_site_flags.p; out->n_alleles = s->d_n_alleles.p; out->n_live = s->d_n_live.p; out->allele_first = s->d_allele_first.p;
+      out->allele_pos = s->allele_pos.p; out->allele_bytes = s->allele_bytes.p; out->live = s->live.p;
+      for (int o = 0; o < n_out; ++o) out->fields[o] = gdbgpu_field_out{s->out_data[o].p, s->out_base[o].p, s->out_stride[o].p, s->out_len[o].p};
+      if (S.want_lut) { out->lut_first = s->lut_first.p; out->lut_len = s->lut_len.p; out->lut_in2m = s->lut_in2m.p; }
+      CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+      s->p_site_begin.ensure(keep); s->p_site_end.ensure(keep); s->p_live.ensure((uint64_t)keep * S.nq);
+      s->p_allele_pos.ensure(2ull * std::max<uint32_t>(hc[0], 1)); s->p_allele_bytes.ensure(std::max<uint32_t>(hc[1], 1));
+      CK(cudaMemcpyAsync(s->p_site_begin.p, s->site_begin.p + s->cursor, (size_t)keep * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(s->p_site_end.p, s->site_end.p + s->cursor, (size_t)keep * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(s->p_live.p, s->live.p, (size_t)keep * S.nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(s->p_allele_pos.p, s->allele_pos.p, (size_t)hc[0] * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(s->p_allele_bytes.p, s->allele_bytes.p, hc[1], cudaMemcpyDeviceToHost, ctx->stream));
+      for (int o = 0; o < n_out; ++o) {
+        s->p_out_data[o].ensure(std::max<uint64_t>(s->h_base[o][keep], 1)); s->p_out_len[o].ensure((uint64_t)keep * S.nq);
+        if (s->h_base[o][keep]) CK(cudaMemcpyAsync(s->p_out_data[o].p, s->out_data[o].p, s->h_base[o][keep] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(s->p_out_len[o].p, s->out_len[o].p, (size_t)keep * S.nq * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        out->fields[o] = gdbgpu_field_out{s->p_out_data[o].p, s->h_base[o].data(), s->h_stride[o].data(), s->p_out_len[o].p};
+      }
+      if (S.want_lut) {
+        s->p_lut_first.ensure((uint64_t)keep * S.nq); s->p_lut_len.ensure((uint64_t)keep * S.nq); s->p_lut_in2m.ensure(std::max<uint32_t>(hc[2], 1));
+        CK(cudaMemcpyAsync(s->p_lut_first.p, s->lut_first.p, (size_t)keep * S.nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(s->p_lut_len.p, s->lut_len.p, (size_t)keep * S.nq * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(s->p_lut_in2m.p, s->lut_in2m.p, (size_t)hc[2] * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        out->lut_first = s->p_lut_first.p; out->lut_len = s->p_lut_len.p; out->lut_in2m = s->p_lut_in2m.p;
+      }
+      CK(cudaStreamSynchronize(ctx->stream));
+      out->site_begin = s->p_site_begin.p; out->site_end = s->p_site_end.p;
+      out->site_flags = s->h_site_flags.data(); out->n_alleles = s->h_n_alleles.data(); out->n_live = s->h_n_live.data(); out->allele_first = s->h_allele_first.data();
+      out->allele_pos = s->p_allele_pos.p; out->allele_bytes = s->p_allele_bytes.p; out->live = s->p_live.p;
+    }
+    s->cursor += keep;
+    return GDBGPU_OK;
+  }
+}
+
+template <class F>
+int guarded(gdbgpu_ctx* ctx, F&& f) {
+  try { f(); return GDBGPU_OK; }
+  catch (const CudaError& e) { if (ctx) ctx->err = e.what(); return GDBGPU_ERR_CUDA; }
+  catch (const LimitError& e) { if (ctx) ctx->err = e.what(); return GDBGPU_ERR_LIMIT; }
+  catch (const OverlapError& e) { if (ctx) ctx->err = e.what(); return GDBGPU_ERR_OVERLAP; }
+  catch (const ArgError& e) { if (ctx) ctx->err = e.what(); return GDBGPU_ERR_ARG; }
+  catch (const std::bad_alloc&) { if (ctx) ctx->err = "host out of memory"; return GDBGPU_ERR_CUDA; }
+  catch (const std::exception& e) { if (ctx) ctx->err = e.what(); return GDBGPU_ERR_IO; }
+}
+
+}  // namespace
+
+// ================================================================================================ extern "C"
+extern "C" {
+
+const char* gdbgpu_version(void) { return "gdbgpu 0.1 (sm_100a)"; }
+
+int gdbgpu_ctx_create(int device, gdbgpu_ctx** out) {
+  if (!out) return GDBGPU_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return GDBGPU_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return GDBGPU_ERR_CUDA;
+  gdbgpu_ctx* c = new gdbgpu_ctx();
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GDBGPU_ERR_CUDA; }
+  *out = c;
+  return GDBGPU_OK;
+}
+void gdbgpu_ctx_destroy(gdbgpu_ctx* ctx) { if (!ctx) return; if (ctx->stream) cudaStreamDestroy(ctx->stream); delete ctx; }
+const char* gdbgpu_last_error(const gdbgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
+void* gdbgpu_ctx_stream(gdbgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t gdbgpu_ctx_launch_count(const gdbgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gdbgpu_array_from_columns(gdbgpu_ctx* ctx, const gdbgpu_columns* c, gdbgpu_array** out) {
+  if (!ctx || !c || !out) return GDBGPU_ERR_ARG;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CK(cudaSetDevice(ctx->device));
+    if (c->n_fields < 0 || c->n_fields > MAX_FIELDS) throw LimitError("more than 15 allele-dependent fields");
+    HostCols h; h.n = c->n_cells; h.coords = c->coords; h.end = c->end;
+    h.ref = HostVar{c->ref.offsets, c->ref.values, c->ref.values_bytes};
+    h.alt = HostVar{c->alt.offsets, c->alt.values, c->alt.values_bytes};
+    h.has_gt = c->gt.offsets != nullptr;
+    if (h.has_gt) h.gt = HostVar{c->gt.offsets, c->gt.values, c->gt.values_bytes};
+    std::vector<FieldMeta> fm; std::vector<std::string> names;
+    for (int f = 0; f < c->n_fields; ++f) {
+      h.fields.push_back(HostVar{c->fields[f].offsets, c->fields[f].values, c->fields[f].values_bytes});
+      std::string nm = c->field_descs[f].name ? c->field_descs[f].name : "";
+      fm.push_back(FieldMeta{c->field_descs[f].length_kind, c->field_descs[f].elem_type, nm == "PL" ? 1 : 0});
+      names.push_back(nm);
+    }
+    *out = build_array(ctx, h, {h.n}, c->lb_row_idx, c->num_rows, c->gt_phased, fm, names);
+  });
+}
+
+int gdbgpu_array_open(gdbgpu_ctx* ctx, const char* workspace, const char* array_name, const gdbgpu_field_desc* fields, int32_t n_fields, int32_t gt_phased,
+                      gdbgpu_array** out) {
+  if (!ctx || !workspace || !array_name || !out || n_fields < 0) return GDBGPU_ERR_ARG;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CK(cudaSetDevice(ctx->device));
+    TdbArray ta(workspace, array_name);
+    const TdbSchema& sc = ta.schema();
+    const int nattr = (int)sc.attributes.size();
+    auto need = [&](const char* nm) { int id = sc.attr_id(nm); if (id < 0) throw std::runtime_error(std::string("array has no attribute ") + nm); return id; };
+    int id_end = need("END"), id_ref = need("REF"), id_alt = need("ALT"), id_gt = sc.attr_id("GT");
+    std::vector<int> ids = {nattr, id_end, id_ref, id_alt};
+    if (id_gt >= 0) ids.push_back(id_gt);
+    std::vector<FieldMeta> fm; std::vector<std::string> names;
+    for (int f = 0; f < n_fields; ++f) {
+      int id = need(fields[f].name);
+      if (!sc.is_var(id) || sc.type_size(id) != 4) throw std::runtime_error(std::string("field is not a variable-length 4-byte attribute: ") + fields[f].name);
+      ids.push_back(id);
+      fm.push_back(FieldMeta{fields[f].length_kind, fields[f].elem_type, std::string(fields[f].name) == "PL" ? 1 : 0});
+      names.push_back(fields[f].name);
+    }
+    // read every needed column of every fragment, concatenating (var offsets rebased onto the concatenated stream)
+    size_t nfrag = ta.num_fragments();
+    std::vector<uint64_t> frag_cells;
+    std::vector<std::vector<uint8_t>> fixed(ids.size()), var(ids.size());
+    uint64_t n_total = 0;
+    for (size_t fi = 0; fi < nfrag; ++fi) {
+      uint64_t nc = (uint64_t)ta.fragment(fi).bk.cell_num;
+      frag_cells.push_back(nc);
+      for (size_t k = 0; k < ids.size(); ++k) {
+        TdbColumn col;
+        ta.read_column(fi, ids[k], col);
+        bool is_var = ids[k] < nattr && sc.is_var(ids[k]);
+        if (nfrag == 1) { fixed[k].swap(col.fixed); var[k].swap(col.var); continue; }
+        if (is_var) {
+          uint64_t base = var[k].size();
+          uint64_t* o = reinterpret_cast<uint64_t*>(col.fixed.data());
+          for (uint64_t i = 0; i < nc; ++i) o[i] += base;
+          var[k].insert(var[k].end(), col.var.begin(), col.var.end());
+        }
+        fixed[k].insert(fixed[k].end(), col.fixed.begin(), col.fixed.end());
+      }
+      n_total += nc;
+    }
+    HostCols h; h.n = n_total;
+    h.coords = reinterpret_cast<const int64_t*>(fixed[0].data()); h.end = reinterpret_cast<const int64_t*>(fixed[1].data());
+    auto hv = [&](size_t k) { return HostVar{reinterpret_cast<const uint64_t*>(fixed[k].data()), var[k].data(), var[k].size()}; };
+    h.ref = hv(2); h.alt = hv(3);
+    size_t k = 4;
+    h.has_gt = id_gt >= 0;
+    if (h.has_gt) h.gt = hv(k++);
+    for (int f = 0; f < n_fields; ++f) h.fields.push_back(hv(k++));
+    int64_t lb = 0, ub = 0;
+    if (!ta.row_bounds(lb, ub)) {   // no GenomicsDB metadata: bound by the data
+      ub = -1;
+      for (uint64_t i = 0; i < n_total; ++i) ub = std::max(ub, h.coords[2 * i]);
+    }
+    *out = build_array(ctx, h, frag_cells, lb, ub - lb + 1, gt_phased, fm, names);
+  });
+}
+
+int gdbgpu_array_get_info(const gdbgpu_array* a, gdbgpu_array_info* info) {
+  if (!a || !info) return GDBGPU_ERR_ARG;
+  info->n_cells = a->n; info->n_begin_cells = a->n_begin; info->n_fragments = a->n_fragments; info->lb_row_idx = a->lb_row; info->num_rows = a->num_rows;
+  info->min_col = a->min_col; info->max_col = a->max_col; info->max_end = a->max_end; info->staged_bytes = a->staged_bytes; info->hbm_bytes = a->hbm_bytes();
+  info->n_fields = (int)a->fields.size(); info->has_gt = a->has_gt; info->gt_phased = a->gt_phased;
+  return GDBGPU_OK;
+}
+int gdbgpu_array_copy_cells(const gdbgpu_array* a, uint64_t first, uint64_t count, int64_t* coords, int64_t* end) {
+  if (!a || first + count > a->n) return GDBGPU_ERR_ARG;
+  return guarded(a->ctx, [&] {
+    CK(cudaSetDevice(a->ctx->device));
+    if (coords && count) CK(cudaMemcpy(coords, a->coords.p + 2 * first, count * 16, cudaMemcpyDeviceToHost));
+    if (end && count) CK(cudaMemcpy(end, a->end.p + first, count * 8, cudaMemcpyDeviceToHost));
+  });
+}
+void gdbgpu_array_close(gdbgpu_array* a) { if (a) { cudaSetDevice(a->ctx->device); delete a; } }
+
+int gdbgpu_scan_begin(gdbgpu_array* arr, const gdbgpu_scan_params* params, gdbgpu_scan** out) {
+  if (!arr || !params || !out) return GDBGPU_ERR_ARG;
+  *out = nullptr;
+  std::unique_ptr<gdbgpu_scan> s(new gdbgpu_scan());
+  s->arr = arr; s->ctx = arr->ctx; s->params = *params;
+  int rc = guarded(arr->ctx, [&] { CK(cudaSetDevice(arr->ctx->device)); scan_prepare(s.get()); });
+  if (rc == GDBGPU_OK) *out = s.release();
+  return rc;
+}
+int gdbgpu_scan_get_info(const gdbgpu_scan* s, gdbgpu_scan_info* info) {
+  if (!s || !info) return GDBGPU_ERR_ARG;
+  info->n_sites = s->S.n_sites; info->n_breakpoints = s->S.m; info->n_query_rows = s->S.nq; info->n_forward_cells = s->S.i1 - s->S.i0;
+  return GDBGPU_OK;
+}
+int gdbgpu_scan_next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_batch* batch) {
+  if (!s || !batch) return GDBGPU_ERR_ARG;
+  return guarded(s->ctx, [&] { CK(cudaSetDevice(s->ctx->device)); next_batch(s, max_sites, max_bytes, batch); });
+}
+int gdbgpu_scan_seek(gdbgpu_scan* s, uint64_t site_idx) {
+  if (!s || site_idx > s->S.n_sites) return GDBGPU_ERR_ARG;
+  s->cursor = site_idx;
+  return GDBGPU_OK;
+}
+void gdbgpu_scan_end(gdbgpu_scan* s) { if (s) { cudaSetDevice(s->ctx->device); delete s; } }
+
+}  // extern "C"

@@ -1,0 +1,402 @@
+// CUDA kernels of the variant-combine hot path (sm_100a).  One kernel (family) per stage of SURVEY.md section 2:
+//   K1 fragment merge      k_merge_*            (array_read_state.cc:1836-2132, newest fragment wins)
+//   K2 classify / filter   k_classify, k_effend (genomicsdb_iterators.cc:535-636, query_variants.cc:422-428,1014-1117)
+//   K2b deletion pre-pass  k_del_*              (broad_combined_gvcf.cc:912-1118)
+//   K3 interval sweep      k_left_sweep, k_mark_events, k_extract_bp, k_deltas, k_site_counts, k_fill_sites, k_live_walk
+//                                               (query_variants.cc:296-332,334-555,845-941)
+//   K4 allele union        k_union              (variant_operations.cc:73-228,362-378)
+//   K5 remap               k_remap              (variant_operations.cc:233-263,572-695; variant_field_handler.cc:41-398)
+// All of it is integer indexing and byte moves; the roofline that bounds it is HBM bandwidth.
+#pragma once
+#include "gdb_device.cuh"
+
+namespace gdb {
+
+// ------------------------------------------------------------------------------------------------ scan primitive
+// Three-launch exclusive scan (block scan, scan of block sums, add-back).  T is uint32_t / int32_t / uint64_t.
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <class T>
+__device__ inline T warp_incl_scan(T v) {
+  for (int d = 1; d < 32; d <<= 1) { T o = __shfl_up_sync(0xffffffffu, v, d); if ((threadIdx.x & 31) >= d) v += o; }
+  return v;
+}
+template <class TI, class TO>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const TI* __restrict__ in, TO* __restrict__ out, TO* __restrict__ tile_sums, uint64_t n) {
+  __shared__ TO warp_tot[SCAN_THREADS / 32];
+  uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  TO v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = (base + i < n) ? (TO)in[base + i] : (TO)0; sum += v[i]; }
+  TO incl = warp_incl_scan(sum);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 31) warp_tot[w] = incl;
+  __syncthreads();
+  if (w == 0) { TO t = (lane < SCAN_THREADS / 32) ? warp_tot[lane] : (TO)0; TO ti = warp_incl_scan(t); if (lane < SCAN_THREADS / 32) warp_tot[lane] = ti - t; }
+  __syncthreads();
+  TO run = warp_tot[w] + incl - sum;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) out[base + i] = run; run += v[i]; }
+  if (threadIdx.x == SCAN_THREADS - 1) tile_sums[blockIdx.x] = run;
+}
+template <class TO>
+__global__ void __launch_bounds__(1024) k_scan_sums(TO* __restrict__ tile_sums, uint64_t n_tiles, TO* __restrict__ total) {
+  __shared__ TO warp_tot[32];
+  __shared__ TO carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint64_t base = 0; base < n_tiles; base += 1024) {
+    uint64_t i = base + threadIdx.x;
+    TO v = (i < n_tiles) ? tile_sums[i] : (TO)0;
+    TO incl = warp_incl_scan(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) { TO t = warp_tot[lane]; TO ti = warp_incl_scan(t); warp_tot[lane] = ti - t; }
+    __syncthreads();
+    TO excl = carry + warp_tot[w] + incl - v;
+    if (i < n_tiles) tile_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+template <class TO>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(TO* __restrict__ out, const TO* __restrict__ tile_sums, uint64_t n) {
+  uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  TO add = tile_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) if (base + i < n) out[base + i] += add;
+}
+
+// ------------------------------------------------------------------------------------------------ K2 classify
+// One thread per cell: what gt_fill_row derives from a cell (query_variants.cc:1014-1117) plus END-copy detection
+// (query_variants.cc:422-428), computed once per staged array.
+__global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restrict__ desc) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  int64_t row = A.coords[2 * i], col = A.coords[2 * i + 1], END = A.end[i];
+  CellDesc d;
+  d.flags = 0; d.pad = 0;
+  if (col > END) d.flags |= F_ENDCOPY;
+  if (row < A.lb_row || row >= A.lb_row + A.num_rows) d.flags |= F_ROWOUT;
+  uint64_t r0 = A.ref.off[i], r1 = A.ref.off[i + 1];
+  d.ref_len = (uint32_t)(r1 - r0);
+  const uint8_t* alt = A.alt.val + A.alt.off[i];
+  int an = alt_effective_len(alt, (int)(A.alt.off[i + 1] - A.alt.off[i]));
+  int pos = 0, ts, tl, n_alt = 0, nr = 0;
+  bool deletion = false, first_is_nr = false;
+  while (next_token(alt, an, pos, ts, tl)) {
+    ++n_alt;
+    if (is_non_ref(alt + ts, tl)) { nr = n_alt; if (n_alt == 1) first_is_nr = true; }
+    else if (d.ref_len > 1 && !is_symbolic(alt + ts, tl) && (uint32_t)tl < d.ref_len) deletion = true;
+  }
+  d.n_alt = (uint16_t)(n_alt > 0xFFFF ? 0xFFFF : n_alt);
+  d.nr_idx = (uint16_t)nr;
+  if (deletion) d.flags |= F_DELETION;
+  if (d.ref_len == 1 && n_alt == 1 && first_is_nr) d.flags |= F_REFBLOCK;
+  if (n_alt == 0 || (n_alt == 1 && first_is_nr)) d.flags |= F_TRIVIAL;   // allele LUT is implied: REF->REF, NON_REF->last
+  d.gt_len = 0; d.ploidy = 0;
+  if (A.has_gt) {
+    uint64_t g0 = A.gt.off[i], g1 = A.gt.off[i + 1];
+    uint32_t n = (uint32_t)((g1 - g0) >> 2);
+    const uint32_t* g = reinterpret_cast<const uint32_t*>(A.gt.val + g0);
+    bool all_null = true;
+    for (uint32_t k = 0; k < n; ++k) if (g[k] != TDB_NULL_INT) { all_null = false; break; }
+    if (!all_null) { d.flags |= F_GTVALID; d.gt_len = n; uint32_t p = ploidy_of(A.gt_phased, n); d.ploidy = (uint8_t)(p > 255 ? 255 : p); }
+  }
+  desc[i] = d;
+}
+
+__global__ void __launch_bounds__(256) k_row_keys(ArrayDev A, const CellDesc* __restrict__ desc, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  keys[i] = (desc[i].flags & F_ROWOUT) ? (uint32_t)A.num_rows : (uint32_t)(A.coords[2 * i] - A.lb_row);
+  vals[i] = (uint32_t)i;
+}
+// row_start[r] = first position in the row-sorted list whose key >= r
+__global__ void __launch_bounds__(256) k_row_bounds(const uint32_t* __restrict__ sorted_keys, uint64_t n, int64_t num_rows, uint64_t* __restrict__ row_start) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > num_rows) return;
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (sorted_keys[mid] < (uint32_t)r) lo = mid + 1; else hi = mid; }
+  row_start[r] = lo;
+}
+__global__ void __launch_bounds__(256) k_rs_cols(ArrayDev A, const uint32_t* __restrict__ rs_cell, uint64_t n_rs, int64_t* __restrict__ rs_col) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_rs) rs_col[k] = A.coords[2 * (uint64_t)rs_cell[k] + 1];
+}
+// Effective end of every begin cell: a later cell of the same sample that begins while the call is still live evicts it
+// (query_variants.cc:519-543).  stats: [0] #begin cells, [1] #bad evictions, [2] max END (as int64), [3] #deletion cells
+__global__ void __launch_bounds__(256) k_effend(ArrayDev A, CellDesc* __restrict__ desc, const uint32_t* __restrict__ rs_cell, const int64_t* __restrict__ rs_col,
+                                                 const uint32_t* __restrict__ sorted_keys, uint64_t n_rs, int64_t* __restrict__ rs_effend,
+                                                 int64_t* __restrict__ effend, unsigned long long* __restrict__ stats,
+                                                 uint32_t* __restrict__ bad_cell, int64_t* __restrict__ bad_pred_col, uint32_t bad_cap) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_rs) return;
+  uint32_t c = rs_cell[k];
+  uint8_t fl = desc[c].flags;
+  if (fl & F_ENDCOPY) { rs_effend[k] = I64_MIN; effend[c] = I64_MIN; atomicMax((long long*)&stats[2], (long long)rs_col[k]); return; }
+  int64_t END = A.end[c];
+  int64_t eff = END;
+  uint32_t key = sorted_keys[k];
+  for (uint64_t k2 = k + 1; k2 < n_rs && sorted_keys[k2] == key; ++k2) {
+    uint32_t c2 = rs_cell[k2];
+    if (desc[c2].flags & F_ENDCOPY) continue;
+    int64_t nb = rs_col[k2];
+    if (nb <= END) {
+      eff = nb - 1;
+      if (!(fl & (F_DELETION | F_REFBLOCK))) {
+        unsigned long long slot = atomicAdd(&stats[1], 1ull);
+        if (slot < bad_cap) { bad_cell[slot] = c2; bad_pred_col[slot] = rs_col[k]; }
+      }
+    }
+    break;
+  }
+  rs_effend[k] = eff; effend[c] = eff;
+  atomicAdd(&stats[0], 1ull);
+  atomicMax((long long*)&stats[2], (long long)END);
+  if (fl & F_DELETION) atomicAdd(&stats[3], 1ull);
+}
+__global__ void __launch_bounds__(256) k_effend_rowout(ArrayDev A, const CellDesc* __restrict__ desc, int64_t* __restrict__ effend) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < A.n && (desc[i].flags & F_ROWOUT)) effend[i] = I64_MIN;
+}
+
+// ------------------------------------------------------------------------------------------------ K1 fragment merge
+// Cells of all fragments concatenated; key = (col, row, newest fragment first).  The sort itself is a radix sort on
+// three 64-bit passes (host side, gdb_engine.cu); these kernels build keys, drop shadowed duplicates and gather.
+__global__ void __launch_bounds__(256) k_merge_keys(const int64_t* __restrict__ coords, const uint32_t* __restrict__ frag_of, uint32_t n_frag, uint64_t n,
+                                                     uint64_t* __restrict__ kcol, uint64_t* __restrict__ krow, uint32_t* __restrict__ kfrag) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  kcol[i] = (uint64_t)coords[2 * i + 1] ^ 0x8000000000000000ull;   // order-preserving for signed values
+  krow[i] = (uint64_t)coords[2 * i] ^ 0x8000000000000000ull;
+  kfrag[i] = n_frag - 1 - frag_of[i];
+}
+__global__ void __launch_bounds__(256) k_merge_keep(const int64_t* __restrict__ coords, const uint32_t* __restrict__ perm, uint64_t n, uint32_t* __restrict__ keep) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k = 1;
+  if (i > 0) {
+    uint64_t a = perm[i], b = perm[i - 1];
+    if (coords[2 * a] == coords[2 * b] && coords[2 * a + 1] == coords[2 * b + 1]) k = 0;   // older fragment, same coordinates
+  }
+  keep[i] = k;
+}
+__global__ void __launch_bounds__(256) k_merge_compact(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, uint64_t n,
+                                                        uint32_t* __restrict__ src) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && keep[i]) src[pos[i]] = perm[i];
+}
+__global__ void __launch_bounds__(256) k_gather_fixed(const uint8_t* __restrict__ in, const uint32_t* __restrict__ src, uint64_t n_out, uint32_t cell_bytes, uint8_t* __restrict__ out) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t words = cell_bytes / 8;   // coords (16) and END (8) only
+  if (t >= n_out * words) return;
+  uint64_t i = t / words, w = t % words;
+  reinterpret_cast<uint64_t*>(out)[t] = reinterpret_cast<const uint64_t*>(in)[(uint64_t)src[i] * words + w];
+}
+__global__ void __launch_bounds__(256) k_gather_len(const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ src, uint64_t n_out, uint64_t* __restrict__ len) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_out) { uint64_t s = src[i]; len[i] = in_off[s + 1] - in_off[s]; }
+}
+__global__ void __launch_bounds__(256) k_gather_var(const uint64_t* __restrict__ in_off, const uint8_t* __restrict__ in_val, const uint32_t* __restrict__ src,
+                                                     const uint64_t* __restrict__ out_off, uint64_t n_out, uint8_t* __restrict__ out_val) {
+  // one warp per cell
+  uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n_out) return;
+  uint64_t s = src[i], so = in_off[s], n = in_off[s + 1] - so, d = out_off[i];
+  for (uint64_t k = threadIdx.x & 31; k < n; k += 32) out_val[d + k] = in_val[so + k];
+}
+
+// ------------------------------------------------------------------------------------------------ per-query state
+struct ScanDev {
+  int32_t scan_full, handle_del, min_pl_gt, want_lut;
+  int64_t q_lo, q_hi;            // query interval (clamped hi)
+  uint64_t nq;                   // queried rows
+  const int32_t* qrow_of_row;    // num_rows entries, -1 = not queried (nullptr: identity)
+  const int64_t* row_of_qrow;    // nq
+  uint32_t max_alt;              // G-length fields dropped above this many ALT alleles
+  // left sweep result
+  int32_t* init_cell;            // nq : cell of the call live at q_lo (-1 none)
+  int64_t* init_effend;
+  // forward cell range in merged order: [iL, i1) has col >= q_lo, [i0, i1) has col > q_lo
+  uint64_t iL, i0, i1;
+  // breakpoints
+  int64_t base; uint64_t span_bits, n_words;
+  unsigned long long* bitmap; uint32_t* word_rank;
+  uint64_t m;                    // number of breakpoints
+  int64_t* bp; uint32_t* bp_cell0;
+  int32_t* dlive; int32_t* ddel;
+  uint64_t* site_start;          // m + 1
+  uint64_t n_sites;
+  int64_t* site_begin; int64_t* site_end;
+  // deletion pre-pass
+  uint64_t n_del; const uint32_t* del_cells; const DelRec* del_recs; const uint32_t* del_words;
+  // error flags: [0] bad eviction hit, [1] limit exceeded (code), [2] pool overflow
+  uint32_t* err;
+};
+
+__device__ inline int32_t qrow_of(const ArrayDev& A, const ScanDev& S, int64_t row) {
+  int64_t r = row - A.lb_row;
+  if (r < 0 || r >= A.num_rows) return -1;
+  return S.qrow_of_row ? S.qrow_of_row[r] : (int32_t)r;
+}
+__device__ inline uint64_t bp_rank(const ScanDev& S, int64_t pos) {
+  uint64_t bit = (uint64_t)(pos - S.base);
+  uint64_t w = bit >> 6;
+  unsigned long long word = S.bitmap[w];
+  unsigned long long below = word & ((1ull << (bit & 63)) - 1ull);
+  return (uint64_t)S.word_rank[w] + (uint64_t)__popcll(below);
+}
+__device__ inline void set_bit(const ScanDev& S, int64_t pos) {
+  uint64_t bit = (uint64_t)(pos - S.base);
+  atomicOr(&S.bitmap[bit >> 6], 1ull << (bit & 63));
+}
+__device__ inline int64_t clip_end(const ScanDev& S, int64_t e) { return (!S.scan_full && e > S.q_hi) ? S.q_hi : e; }
+
+// gt_get_column (query_variants.cc:845-941): per queried sample, the first cell at or after q_lo decides.
+__global__ void __launch_bounds__(256) k_left_sweep(ArrayDev A, ScanDev S) {
+  uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= S.nq) return;
+  int32_t cell = -1; int64_t eff = 0;
+  if (!S.scan_full) {
+    int64_t r = S.row_of_qrow[q] - A.lb_row;
+    uint64_t lo = A.row_start[r], hi = A.row_start[r + 1], e = hi;
+    while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (A.rs_col[mid] < S.q_lo) lo = mid + 1; else hi = mid; }
+    if (lo < e) {
+      int64_t c = A.rs_col[lo], ef = A.rs_effend[lo];
+      if (ef == I64_MIN) { cell = (int32_t)A.rs_cell[lo]; eff = c; }          // END copy: call [END field, col]
+      else if (c == S.q_lo) { cell = (int32_t)A.rs_cell[lo]; eff = ef; }     // begin cell exactly at q_lo
+    }
+  }
+  S.init_cell[q] = cell; S.init_effend[q] = eff;
+  if (cell >= 0) { set_bit(S, S.q_lo); set_bit(S, clip_end(S, eff) + 1); }
+}
+
+// breakpoints = begin columns of every cell the forward scan visits + (effective end + 1) of every queried call
+__global__ void __launch_bounds__(256) k_mark_events(ArrayDev A, ScanDev S) {
+  uint64_t i = S.i0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S.i1) return;
+  uint8_t fl = A.desc[i].flags;
+  if (fl & (F_ENDCOPY | F_ROWOUT)) return;
+  int64_t col = A.coords[2 * i + 1];
+  set_bit(S, col);
+  if (qrow_of(A, S, A.coords[2 * i]) >= 0) set_bit(S, clip_end(S, A.effend[i]) + 1);
+}
+// "Unhandled overlapping variants" (query_variants.cc:519-535): an eviction of a call that is neither a deletion nor a
+// reference block throws, but only when the evicted call is live, i.e. it began inside this query.
+__global__ void k_check_evictions(ArrayDev A, ScanDev S, const uint32_t* __restrict__ bad_cell, const int64_t* __restrict__ bad_pred_col, uint32_t n_bad) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_bad) return;
+  uint64_t c = bad_cell[t];
+  int64_t col = A.coords[2 * c + 1];
+  if (qrow_of(A, S, A.coords[2 * c]) < 0) return;
+  if (S.scan_full || (col > S.q_lo && col <= S.q_hi && bad_pred_col[t] >= S.q_lo)) atomicOr(&S.err[0], 1u);
+}
+__global__ void __launch_bounds__(256) k_popc(const unsigned long long* __restrict__ bitmap, uint64_t n_words, uint32_t* __restrict__ cnt) {
+  uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < n_words) cnt[w] = (uint32_t)__popcll(bitmap[w]);
+}
+__global__ void __launch_bounds__(256) k_extract_bp(ScanDev S) {
+  uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= S.n_words) return;
+  unsigned long long word = S.bitmap[w];
+  uint64_t r = S.word_rank[w];
+  while (word) { int b = __ffsll((long long)word) - 1; S.bp[r] = S.base + (int64_t)(w * 64 + b); S.bp_cell0[r] = 0xFFFFFFFFu; ++r; word &= word - 1; }
+}
+// +1/-1 live-call deltas per breakpoint (and the same for calls containing a deletion); first cell of each column
+__global__ void __launch_bounds__(256) k_deltas(ArrayDev A, ScanDev S) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t n_cells = S.i1 - S.iL;
+  if (t < n_cells) {
+    uint64_t i = S.iL + t;
+    uint8_t fl = A.desc[i].flags;
+    int64_t col = A.coords[2 * i + 1];
+    bool first_of_col = (i == 0) || (A.coords[2 * (i - 1) + 1] != col);
+    bool forward = i >= S.i0;
+    if (first_of_col) {
+      // record where column `col` starts if `col` is a breakpoint (it is whenever a call begins there)
+      uint64_t bit = (uint64_t)(col - S.base);
+      if (col >= S.base && bit < S.span_bits && ((S.bitmap[bit >> 6] >> (bit & 63)) & 1ull)) S.bp_cell0[bp_rank(S, col)] = (uint32_t)i;
+    }
+    if (fl & F_ROWOUT) return;
+    if (!forward || (fl & F_ENDCOPY)) return;
+    if (qrow_of(A, S, A.coords[2 * i]) < 0) return;
+    uint64_t rs = bp_rank(S, col), re = bp_rank(S, clip_end(S, A.effend[i]) + 1);
+    // warp-aggregate the +1 (cells of one column are adjacent)
+    unsigned mask = __match_any_sync(__activemask(), rs);
+    if ((int)(threadIdx.x & 31) == __ffs(mask) - 1) atomicAdd(&S.dlive[rs], __popc(mask));
+    atomicSub(&S.dlive[re], 1);
+    if (S.handle_del && (fl & F_DELETION)) { atomicAdd(&S.ddel[rs], 1); atomicSub(&S.ddel[re], 1); }
+  } else {
+    uint64_t q = t - n_cells;
+    if (q >= S.nq) return;
+    int32_t c = S.init_cell[q];
+    if (c < 0) return;
+    uint64_t rs = bp_rank(S, S.q_lo), re = bp_rank(S, clip_end(S, S.init_effend[q]) + 1);
+    atomicAdd(&S.dlive[rs], 1); atomicSub(&S.dlive[re], 1);
+    if (S.handle_del && (A.desc[c].flags & F_DELETION)) { atomicAdd(&S.ddel[rs], 1); atomicSub(&S.ddel[re], 1); }
+  }
+}
+// after the inclusive scans: number of operate() calls per breakpoint interval (1 bp stepping while a deletion is live,
+// query_variants.cc:310)
+__global__ void __launch_bounds__(256) k_site_counts(ScanDev S, const int32_t* __restrict__ live_excl, const int32_t* __restrict__ del_excl, uint64_t* __restrict__ cnt) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S.m) return;
+  int32_t live = live_excl[i] + S.dlive[i], del = del_excl[i] + S.ddel[i];
+  uint64_t c = 0;
+  if (live > 0 && i + 1 < S.m) c = (del > 0) ? (uint64_t)(S.bp[i + 1] - S.bp[i]) : 1ull;
+  cnt[i] = c;
+}
+__global__ void __launch_bounds__(256) k_fill_sites(ScanDev S, const int32_t* __restrict__ del_excl) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= S.n_sites) return;
+  uint64_t lo = 0, hi = S.m;   // last i with site_start[i] <= j
+  while (lo + 1 < hi) { uint64_t mid = (lo + hi) >> 1; if (S.site_start[mid] <= j) lo = mid; else hi = mid; }
+  uint64_t i = lo, k = j - S.site_start[i];
+  bool stepping = (del_excl[i] + S.ddel[i]) > 0;
+  int64_t b = S.bp[i] + (stepping ? (int64_t)k : 0);
+  S.site_begin[j] = b;
+  S.site_end[j] = stepping ? b : S.bp[i + 1] - 1;
+}
+
+// ------------------------------------------------------------------------------------------------ K3 live matrix
+// One thread per queried sample walks that sample's cell list against the batch's sites ("k-way merge" of the sample
+// lists with the site list); adjacent threads write adjacent entries of each site's row -> coalesced.
+__global__ void __launch_bounds__(256) k_live_walk(ArrayDev A, ScanDev S, uint64_t first_site, uint32_t n_sites, int32_t* __restrict__ live) {
+  uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= S.nq) return;
+  int64_t r = S.row_of_qrow[q] - A.lb_row;
+  uint64_t lo = A.row_start[r], e = A.row_start[r + 1];
+  int64_t b0 = S.site_begin[first_site];
+  // first entry with col > b0
+  uint64_t k = lo, hi = e;
+  while (k < hi) { uint64_t mid = (k + hi) >> 1; if (A.rs_col[mid] <= b0) k = mid + 1; else hi = mid; }
+  // current call: last begin cell with q_lo < col <= b0 (or any col for a full scan), else the left-sweep call
+  int32_t cur = S.init_cell[q]; int64_t cur_eff = S.init_effend[q]; int64_t cur_begin = 0; bool cur_del = false;
+  if (cur >= 0) { uint8_t fl = A.desc[cur].flags; cur_del = fl & F_DELETION; cur_begin = (fl & F_ENDCOPY) ? A.end[cur] : A.coords[2 * (uint64_t)cur + 1]; }
+  for (uint64_t kk = k; kk > lo;) {
+    --kk;
+    int64_t c = A.rs_col[kk];
+    if (!S.scan_full && c <= S.q_lo) break;
+    int64_t ef = A.rs_effend[kk];
+    if (ef != I64_MIN) { cur = (int32_t)A.rs_cell[kk]; cur_eff = ef; cur_begin = c; cur_del = A.desc[cur].flags & F_DELETION; break; }
+  }
+  for (uint32_t s = 0; s < n_sites; ++s) {
+    int64_t b = S.site_begin[first_site + s];
+    while (k < e) {
+      int64_t c = A.rs_col[k];
+      if (c > b) break;
+      int64_t ef = A.rs_effend[k];
+      if (ef != I64_MIN) { cur = (int32_t)A.rs_cell[k]; cur_eff = ef; cur_begin = c; cur_del = A.desc[cur].flags & F_DELETION; }
+      ++k;
+    }
+    int32_t v = -1;
+    if (cur >= 0 && cur_eff >= b) { v = cur; if (S.handle_del && cur_del && b > cur_begin) v |= LIVE_REDUCED; }
+    live[(uint64_t)s * S.nq + q] = v;
+  }
+}
+
+}  // namespace gdb

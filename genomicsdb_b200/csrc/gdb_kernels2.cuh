@@ -1,0 +1,644 @@
+// K2b (spanning-deletion pre-pass), K4 (allele union) and K5 (remap) kernels.  See gdb_kernels.cuh for the map.
+#pragma once
+#include "gdb_kernels.cuh"
+
+namespace gdb {
+
+__device__ __constant__ uint8_t c_str_N[1] = {'N'};
+__device__ __constant__ uint8_t c_str_star[1] = {'*'};
+__device__ __constant__ uint8_t c_str_amp[1] = {'&'};
+__device__ __constant__ uint8_t c_str_nonref[9] = {'<', 'N', 'O', 'N', '_', 'R', 'E', 'F', '>'};
+
+__device__ inline uint32_t missing_word(int elem) { return elem ? BCF_FLT_MISSING : BCF_INT_MISSING; }
+__device__ inline uint32_t vend_word(int elem) { return elem ? BCF_FLT_VEND : BCF_INT_VEND; }
+__device__ inline uint32_t null_word(int elem) { return elem ? TDB_NULL_FLT : TDB_NULL_INT; }
+
+// ------------------------------------------------------------------------------------------------ sequential remap math
+// One call, one thread.  m2in(j) answers "input allele index of merged allele j" (-1 = none); in_nr is the call's own
+// NON_REF index (or -1).  Restates variant_field_handler.cc:41-398 (R/A, G haploid / diploid / general).
+template <class M2IN>
+__device__ inline void remap_field_seq(int kind, const uint32_t* in, uint32_t n_in, M2IN m2in, uint32_t A, int in_nr, uint32_t ploidy,
+                                       uint32_t* out, uint32_t missing) {
+  if (kind != KIND_G || ploidy == 1) {
+    bool alt_only = (kind == KIND_A);
+    uint32_t length = (kind == KIND_G) ? A : (alt_only ? A - 1u : A);
+    for (uint32_t j = 0; j < length; ++j) {
+      int ij = m2in(alt_only ? j + 1u : j);
+      if (ij < 0) ij = in_nr;
+      if (ij < 0) { out[j] = missing; continue; }
+      int64_t ix = alt_only ? (int64_t)ij - 1 : ij;
+      out[j] = (ix < 0 || ix >= (int64_t)n_in) ? missing : in[ix];
+    }
+  } else if (ploidy == 2) {
+    for (uint32_t k = 0; k < A; ++k) {
+      int ik = m2in(k); if (ik < 0) ik = in_nr;
+      for (uint32_t j = 0; j <= k; ++j) {
+        int ij = m2in(j); if (ij < 0) ij = in_nr;
+        uint32_t g = k * (k + 1) / 2 + j;
+        if (ij < 0 || ik < 0) { out[g] = missing; continue; }
+        int64_t ig = alleles2gt(ij, ik);
+        out[g] = (ig >= (int64_t)n_in) ? missing : in[ig];
+      }
+    }
+  } else if (ploidy > 2 && ploidy <= MAX_PLOIDY) {
+    int vec[MAX_PLOIDY], iv[MAX_PLOIDY];
+    for (uint32_t i = 0; i < ploidy; ++i) vec[i] = 0;
+    uint32_t g = 0;
+    do {
+      bool miss = false;
+      for (uint32_t i = 0; i < ploidy; ++i) { int ia = m2in((uint32_t)vec[i]); if (ia < 0) ia = in_nr; if (ia < 0) miss = true; iv[i] = ia; }
+      if (miss) out[g] = missing;
+      else { sort_small(iv, (int)ploidy); uint64_t ig = genotype_index_sorted(iv, (int)ploidy); out[g] = (ig >= n_in) ? missing : in[ig]; }
+      ++g;
+    } while (next_genotype(vec, (int)ploidy, (int)A));
+  }
+  // ploidy 0: the general routine returns at once; the caller pre-filled out[] with the copied input (variant_operations.cc:640-652)
+}
+template <class IN2M>
+__device__ inline uint32_t remap_gt_word(uint32_t w, IN2M in2m, uint32_t A, bool nonref) {
+  if (w == TDB_NULL_INT || w == 0xFFFFFFFFu || w == BCF_INT_MISSING) return w;
+  int m = in2m((int32_t)w);
+  return (m < 0) ? (nonref ? A - 1u : 0xFFFFFFFFu) : (uint32_t)m;
+}
+__device__ inline bool words_all_null(const uint32_t* v, uint32_t n, uint32_t nullw) {
+  for (uint32_t i = 0; i < n; ++i) if (v[i] != nullw) return false;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ K2b deletion pre-pass
+// For every cell whose call contains a deletion: the form handle_deletions gives it at positions past its begin
+// (REF "N", ALT "*"[, <NON_REF>], PL/AD/GT reduced through a 3-allele LUT; broad_combined_gvcf.cc:912-1078).
+// Pure function of the cell, so it is computed once per scan instead of once per site.
+struct DelLut { int lowest; int nr; __device__ int operator()(uint32_t m) const { return m == 0 ? 0 : (m == 1 ? lowest : (m == 2 ? nr : -1)); } };
+
+__device__ inline void del_analyse(const ArrayDev& A, uint64_t c, int& lowest, int& nr_idx, uint32_t& ploidy) {
+  const CellDesc d = A.desc[c];
+  ploidy = (d.flags & F_GTVALID) ? ploidy_of(A.gt_phased, d.gt_len) : 0u;
+  const uint8_t* alt = A.alt.val + A.alt.off[c];
+  int an = alt_effective_len(alt, (int)(A.alt.off[c + 1] - A.alt.off[c]));
+  const uint32_t* pl = nullptr; uint32_t pl_n = 0;
+  for (int f = 0; f < A.n_fields; ++f) if (A.fm[f].is_pl) {
+    uint64_t o0 = A.f[f].off[c], o1 = A.f[f].off[c + 1];
+    uint32_t n = (uint32_t)((o1 - o0) >> 2);
+    const uint32_t* v = reinterpret_cast<const uint32_t*>(A.f[f].val + o0);
+    if (n > 0 && !words_all_null(v, n, TDB_NULL_INT)) { pl = v; pl_n = n; }
+  }
+  lowest = -1; nr_idx = -1;
+  int32_t lowest_pl = INT32_MAX;
+  int pos = 0, ts, tl, idx = 0;
+  while (next_token(alt, an, pos, ts, tl)) {
+    ++idx;
+    const uint8_t* t = alt + ts;
+    bool del = d.ref_len > 1 && ((tl == 1 && t[0] == '*') || (!is_symbolic(t, tl) && (uint32_t)tl < d.ref_len));
+    if (del) {
+      if (lowest < 0) lowest = idx;
+      if (pl) {
+        uint64_t gi;
+        if (ploidy == 0) gi = 0; else if (ploidy == 1) gi = (uint64_t)idx; else if (ploidy == 2) gi = (uint64_t)alleles2gt(idx, idx);
+        else { gi = 0; for (uint32_t i = 0; i < ploidy; ++i) gi += nCr_u64((int64_t)i + idx, (int64_t)idx - 1); }
+        if (gi < pl_n && (int32_t)pl[gi] < lowest_pl) { lowest_pl = (int32_t)pl[gi]; lowest = idx; }
+      }
+    } else if (is_non_ref(t, tl)) nr_idx = idx;
+  }
+}
+// pass 1: words needed per deletion cell
+__global__ void __launch_bounds__(128) k_del_size(ArrayDev A, const uint32_t* __restrict__ del_cells, uint64_t n_del, uint32_t* __restrict__ words) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_del) return;
+  uint64_t c = del_cells[t];
+  const CellDesc d = A.desc[c];
+  uint32_t ploidy = (d.flags & F_GTVALID) ? ploidy_of(A.gt_phased, d.gt_len) : 0u;
+  uint32_t n_red_alt = d.nr_idx ? 2u : 1u;
+  uint32_t w = d.gt_len;
+  for (int f = 0; f < A.n_fields; ++f) w += num_elements(A.fm[f].kind, n_red_alt, ploidy);
+  words[t] = w;
+}
+// pass 2: fill
+__global__ void __launch_bounds__(128) k_del_fill(ArrayDev A, int min_pl_gt, const uint32_t* __restrict__ del_cells, uint64_t n_del, const uint32_t* __restrict__ word_off,
+                                                   DelRec* __restrict__ recs, uint32_t* __restrict__ pool, uint32_t* __restrict__ err) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_del) return;
+  uint64_t c = del_cells[t];
+  const CellDesc d = A.desc[c];
+  int lowest, nr_idx; uint32_t ploidy;
+  del_analyse(A, c, lowest, nr_idx, ploidy);
+  if (ploidy > MAX_PLOIDY) { atomicMax(&err[1], 3u); ploidy = 0; }
+  DelRec r;
+  r.cell = (uint32_t)c; r.has_nr = nr_idx > 0; r.n_alt = r.has_nr ? 2 : 1; r.pad0 = r.pad1 = 0;
+  uint32_t A_red = (uint32_t)r.n_alt + 1u;
+  DelLut lut{lowest, nr_idx > 0 ? nr_idx : -1};
+  int in_nr = nr_idx > 0 ? nr_idx : -1;
+  uint32_t o = word_off[t];
+  const uint32_t* pl_red = nullptr; uint32_t pl_red_n = 0;
+  for (int f = 0; f < A.n_fields; ++f) {
+    uint64_t o0 = A.f[f].off[c], o1 = A.f[f].off[c + 1];
+    uint32_t n_in = (uint32_t)((o1 - o0) >> 2);
+    const uint32_t* in = reinterpret_cast<const uint32_t*>(A.f[f].val + o0);
+    uint32_t n_out = num_elements(A.fm[f].kind, A_red - 1u, ploidy);
+    r.f_off[f] = o;
+    if (n_in == 0 || words_all_null(in, n_in, null_word(A.fm[f].elem))) { r.f_len[f] = 0xFFFFFFFFu; o += n_out; continue; }
+    for (uint32_t i = 0; i < n_out; ++i) pool[o + i] = (i < n_in) ? in[i] : 0u;
+    remap_field_seq(A.fm[f].kind, in, n_in, lut, A_red, in_nr, ploidy, pool + o, missing_word(A.fm[f].elem));
+    r.f_len[f] = n_out;
+    if (A.fm[f].is_pl) { pl_red = pool + o; pl_red_n = n_out; }
+    o += n_out;
+  }
+  for (int f = A.n_fields; f < MAX_FIELDS; ++f) { r.f_off[f] = 0; r.f_len[f] = 0xFFFFFFFFu; }
+  r.gt_off = o; r.gt_len = d.gt_len;
+  if (d.flags & F_GTVALID) {
+    const uint32_t* g = reinterpret_cast<const uint32_t*>(A.gt.val + A.gt.off[c]);
+    int step = A.gt_phased ? 2 : 1;
+    bool from_input = true;
+    if (min_pl_gt && pl_red) {
+      // update_GT_to_correspond_to_min_PL_value (broad_combined_gvcf.cc:1080-1118) over the ALREADY reduced PL
+      int best[MAX_PLOIDY]; int32_t cur_min = INT32_MAX; bool found = false;
+      int vec[MAX_PLOIDY];
+      auto track = [&](const int* v, uint64_t gi) {
+        if (gi < pl_red_n) { uint32_t w = pl_red[gi]; if (w != BCF_INT_MISSING && w != BCF_INT_VEND && (int32_t)w < cur_min) { cur_min = (int32_t)w; found = true; for (uint32_t i = 0; i < ploidy; ++i) best[i] = v[i]; } }
+      };
+      if (ploidy == 1) {
+        uint32_t lim = num_genotypes(A_red - 1u, 1); if (pl_red_n < lim) lim = pl_red_n;
+        for (uint32_t i = 0; i < lim; ++i) { vec[0] = (int)i; track(vec, i); }
+      } else if (ploidy == 2) {
+        for (uint32_t i = 0; i < A_red; ++i) for (uint32_t j = i; j < A_red; ++j) { vec[0] = (int)i; vec[1] = (int)j; track(vec, (uint64_t)alleles2gt(i, j)); }
+      } else if (ploidy > 2) {
+        for (uint32_t i = 0; i < ploidy; ++i) vec[i] = 0;
+        do { track(vec, genotype_index_sorted(vec, (int)ploidy)); } while (next_genotype(vec, (int)ploidy, (int)A_red));
+      }
+      if (found) {
+        from_input = false;
+        for (uint32_t i = 0; i < d.gt_len; ++i) pool[o + i] = g[i];
+        for (uint32_t i = 0, j = 0; i < d.gt_len; i += step, ++j) pool[o + i] = (uint32_t)best[j];
+      }
+    }
+    if (from_input) {
+      auto in2m = [&](int32_t a) { return a == 0 ? 0 : (a == lowest ? 1 : ((nr_idx > 0 && a == nr_idx) ? 2 : -1)); };
+      for (uint32_t i = 0; i < d.gt_len; ++i) pool[o + i] = ((i % step) == 0) ? remap_gt_word(g[i], in2m, A_red, r.has_nr) : g[i];
+    }
+  }
+  recs[t] = r;
+}
+
+// ------------------------------------------------------------------------------------------------ a call as the operator sees it
+struct CallView {
+  uint32_t cell; bool reduced; uint8_t flags;
+  uint32_t ref_len; const uint8_t* ref;
+  int n_alt, nr_idx;
+  const uint8_t* alt; int alt_n;       // original ALT bytes; unused for the reduced form
+  uint32_t ploidy, gt_len; const uint32_t* gt;
+  const DelRec* dr;
+  int64_t begin, end;
+};
+__device__ inline const DelRec* find_delrec(const ScanDev& S, uint32_t cell) {
+  uint64_t lo = 0, hi = S.n_del;
+  while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (S.del_cells[mid] < cell) lo = mid + 1; else hi = mid; }
+  return &S.del_recs[lo];
+}
+__device__ inline CallView make_view(const ArrayDev& A, const ScanDev& S, int32_t live_entry) {
+  CallView v;
+  v.cell = (uint32_t)(live_entry & (LIVE_REDUCED - 1));
+  v.reduced = (live_entry & LIVE_REDUCED) != 0;
+  const CellDesc d = A.desc[v.cell];
+  v.flags = d.flags;
+  int64_t col = A.coords[2 * (uint64_t)v.cell + 1], END = A.end[v.cell];
+  if (d.flags & F_ENDCOPY) { v.begin = END; v.end = col; } else { v.begin = col; v.end = END; }
+  v.ploidy = (d.flags & F_GTVALID) ? ploidy_of(A.gt_phased, d.gt_len) : 0u;
+  v.gt_len = (d.flags & F_GTVALID) ? d.gt_len : 0u;
+  if (!v.reduced) {
+    v.dr = nullptr;
+    v.ref_len = d.ref_len; v.ref = A.ref.val + A.ref.off[v.cell];
+    v.n_alt = d.n_alt; v.nr_idx = d.nr_idx;
+    v.alt = A.alt.val + A.alt.off[v.cell];
+    v.alt_n = alt_effective_len(v.alt, (int)(A.alt.off[v.cell + 1] - A.alt.off[v.cell]));
+    v.gt = A.has_gt ? reinterpret_cast<const uint32_t*>(A.gt.val + A.gt.off[v.cell]) : nullptr;
+  } else {
+    v.dr = find_delrec(S, v.cell);
+    v.ref_len = 1; v.ref = c_str_N;
+    v.n_alt = v.dr->n_alt; v.nr_idx = v.dr->has_nr ? 2 : 0;
+    v.alt = nullptr; v.alt_n = 0;
+    v.gt = S.del_words + v.dr->gt_off;
+  }
+  return v;
+}
+// field f of a call: pointer, length in words, validity (variant_field_data.h:365-384)
+__device__ inline bool field_of(const ArrayDev& A, const ScanDev& S, const CallView& v, int f, const uint32_t*& p, uint32_t& n) {
+  if (v.reduced) {
+    if (v.dr->f_len[f] == 0xFFFFFFFFu) { p = nullptr; n = 0; return false; }
+    p = S.del_words + v.dr->f_off[f]; n = v.dr->f_len[f]; return true;
+  }
+  uint64_t o0 = A.f[f].off[v.cell], o1 = A.f[f].off[v.cell + 1];
+  n = (uint32_t)((o1 - o0) >> 2);
+  p = reinterpret_cast<const uint32_t*>(A.f[f].val + o0);
+  return n > 0;   // caller still has to rule out "every element is TileDB NULL"
+}
+// hash of an ALT allele as it enters the merged list: the allele, plus the tail of the merged REF when the call's own
+// REF is shorter and the allele is not symbolic (variant_operations.cc:163-190)
+__device__ inline uint64_t allele_hash(const uint8_t* t, int tl, const uint8_t* mref, uint32_t mref_len, uint32_t call_ref_len, int& suffix) {
+  suffix = 0;
+  if (call_ref_len < mref_len && !is_symbolic(t, tl)) suffix = (int)(mref_len - call_ref_len);
+  uint64_t h = fnv1a(FNV_BASIS, t, tl);
+  if (suffix) h = fnv1a(h, mref + call_ref_len, suffix);
+  return hash_finish(h ^ ((uint64_t)(tl + suffix) << 40));
+}
+
+// ------------------------------------------------------------------------------------------------ K4 allele union
+constexpr int UNION_THREADS = 256;
+constexpr int UNION_SLOTS = 1024;        // open-addressing table in shared memory
+constexpr int UNION_MAX_DISTINCT = 512;  // documented engine limit on distinct ALT alleles per site (excluding NON_REF)
+constexpr int REF_MAX_PIECES = 32;
+
+// what K4 leaves behind for a site; K5 reads it
+struct SiteRec {
+  uint32_t n_alleles;      // A_m = 1 + merged ALT count
+  uint32_t n_live;
+  uint32_t flags;          // GDBGPU_SITE_*
+  uint32_t allele_first;   // index into allele_pos pairs / allele_hash
+  uint32_t ref_off, ref_len;            // merged REF bytes in the allele pool
+  uint32_t max_gt_len, max_ain;         // max GT words / max (n_alt+1) over live calls
+  uint32_t max_ploidy[MAX_FIELDS];      // over calls whose field is present
+  uint32_t max_in_len[MAX_FIELDS];
+};
+struct BatchDev {
+  uint64_t first_site; uint32_t n_sites;
+  const int32_t* live;        // n_sites x nq
+  SiteRec* sites;
+  // pools (atomic bump allocation; overflow -> err[2])
+  uint32_t* cursors;          // [0] allele records, [1] allele bytes, [2] lut words
+  uint32_t* allele_pos; uint64_t* allele_hash; uint32_t cap_allele_recs;
+  uint8_t* allele_bytes; uint32_t cap_allele_bytes;
+};
+
+__global__ void __launch_bounds__(UNION_THREADS) k_union(ArrayDev A, ScanDev S, BatchDev B) {
+  __shared__ unsigned long long s_hash[UNION_SLOTS];
+  __shared__ unsigned long long s_order[UNION_SLOTS];
+  __shared__ uint16_t s_list[UNION_MAX_DISTINCT];
+  __shared__ uint16_t s_rank[UNION_MAX_DISTINCT];
+  __shared__ uint32_t s_piece_cell[REF_MAX_PIECES], s_piece_from[REF_MAX_PIECES], s_piece_to[REF_MAX_PIECES];
+  __shared__ unsigned int s_k, s_next, s_maxN, s_ndist, s_nonref, s_nlive, s_maxgt, s_maxain, s_npieces, s_reflen, s_refoff, s_afirst, s_overflow;
+  __shared__ unsigned int s_maxpl[MAX_FIELDS], s_maxin[MAX_FIELDS];
+
+  const uint32_t js = blockIdx.x;
+  const uint64_t j = B.first_site + js;
+  const int64_t b = S.site_begin[j];
+  const int32_t* live = B.live + (uint64_t)js * S.nq;
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < UNION_SLOTS; i += UNION_THREADS) { s_hash[i] = 0ull; s_order[i] = ~0ull; }
+  if (tid == 0) { s_k = 0xFFFFFFFFu; s_next = 0xFFFFFFFFu; s_maxN = 0; s_ndist = 0; s_nonref = 0; s_nlive = 0; s_maxgt = 0; s_maxain = 0; s_npieces = 0; s_overflow = 0; }
+  if (tid < MAX_FIELDS) { s_maxpl[tid] = 0; s_maxin[tid] = 0; }
+  __syncthreads();
+
+  // ---- merged REF (variant_operations.cc:73-122): fold over the calls that BEGIN at this site, in row order.
+  // Those are exactly the begin cells of column b (contiguous in the merged cell order).
+  uint64_t c0 = 0, c1 = 0;
+  {
+    // breakpoint index of b -> first cell of that column
+    uint64_t lo = 0, hi = S.m;
+    while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (S.bp[mid] < b) lo = mid + 1; else hi = mid; }
+    if (lo < S.m && S.bp[lo] == b && S.bp_cell0[lo] != 0xFFFFFFFFu) {
+      c0 = S.bp_cell0[lo];
+      // column extent: gallop then bisect on the col coordinate
+      uint64_t step = 1, e = c0 + 1;
+      while (e < A.n && A.coords[2 * e + 1] == b) { e += step; step <<= 1; }
+      uint64_t l2 = (e - (step >> 1) > c0) ? e - (step >> 1) : c0 + 1, h2 = e < A.n ? e : A.n;
+      while (l2 < h2) { uint64_t mid = (l2 + h2) >> 1; if (A.coords[2 * mid + 1] == b) l2 = mid + 1; else h2 = mid; }
+      c1 = l2;
+    }
+  }
+  auto candidate = [&](uint64_t c, uint32_t& rl, uint8_t& first) -> bool {
+    const CellDesc d = A.desc[c];
+    if (d.flags & (F_ENDCOPY | F_ROWOUT)) return false;
+    int32_t q = qrow_of(A, S, A.coords[2 * c]);
+    if (q < 0 || (live[q] & ~LIVE_REDUCED) != (int32_t)c || (live[q] & LIVE_REDUCED) || live[q] < 0) return false;
+    rl = d.ref_len; first = rl ? A.ref.val[A.ref.off[c]] : 0;
+    return true;
+  };
+  for (uint64_t c = c0 + tid; c < c1; c += UNION_THREADS) {
+    uint32_t rl; uint8_t first;
+    if (!candidate(c, rl, first)) continue;
+    if (first != 'N') atomicMin(&s_k, (unsigned int)(c - c0));
+    else atomicMax(&s_maxN, rl);
+  }
+  __syncthreads();
+  if (s_k == 0xFFFFFFFFu) {
+    if (s_maxN > 1) {   // only N-leading REFs: the first one of maximal length replaces the default "N"
+      for (uint64_t c = c0 + tid; c < c1; c += UNION_THREADS) {
+        uint32_t rl; uint8_t first;
+        if (candidate(c, rl, first) && first == 'N' && rl == s_maxN) atomicMin(&s_next, (unsigned int)(c - c0));
+      }
+      __syncthreads();
+      if (tid == 0) { s_piece_cell[0] = (uint32_t)(c0 + s_next); s_piece_from[0] = 0; s_piece_to[0] = s_maxN; s_npieces = 1; s_reflen = s_maxN; }
+    } else if (tid == 0) { s_npieces = 0; s_reflen = 1; }
+    __syncthreads();
+  } else {
+    uint32_t last = s_k, cur_len = A.desc[c0 + s_k].ref_len;
+    if (tid == 0) { s_piece_cell[0] = (uint32_t)(c0 + last); s_piece_from[0] = 0; s_piece_to[0] = cur_len; s_npieces = 1; }
+    for (;;) {   // later, longer REFs append their tail ("record breakers")
+      __syncthreads();
+      if (tid == 0) s_next = 0xFFFFFFFFu;
+      __syncthreads();
+      for (uint64_t c = c0 + last + 1 + tid; c < c1; c += UNION_THREADS) {
+        uint32_t rl; uint8_t first;
+        if (candidate(c, rl, first) && rl > cur_len) atomicMin(&s_next, (unsigned int)(c - c0));
+      }
+      __syncthreads();
+      uint32_t nx = s_next;
+      if (nx == 0xFFFFFFFFu) break;
+      uint32_t nl = A.desc[c0 + nx].ref_len;
+      if (tid == 0) {
+        if (s_npieces < REF_MAX_PIECES) { s_piece_cell[s_npieces] = (uint32_t)(c0 + nx); s_piece_from[s_npieces] = cur_len; s_piece_to[s_npieces] = nl; ++s_npieces; }
+        else atomicMax(&S.err[1], 4u);
+      }
+      last = nx; cur_len = nl;
+    }
+    if (tid == 0) s_reflen = cur_len;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    uint32_t off = atomicAdd(&B.cursors[1], s_reflen);
+    if (off + s_reflen > B.cap_allele_bytes) { s_overflow = 1; off = 0; }
+    s_refoff = off;
+  }
+  __syncthreads();
+  const uint32_t mref_len = s_reflen;
+  uint8_t* mref = B.allele_bytes + s_refoff;
+  if (!s_overflow) {
+    if (s_npieces == 0) { if (tid == 0) mref[0] = 'N'; }
+    else for (uint32_t p = 0; p < s_npieces; ++p) {
+      const uint8_t* src = A.ref.val + A.ref.off[s_piece_cell[p]];
+      for (uint32_t i = s_piece_from[p] + tid; i < s_piece_to[p]; i += UNION_THREADS) mref[i] = src[i];
+    }
+  }
+  __syncthreads();   // mref is read below by other threads of this block (global memory, same block: needs the barrier only)
+
+  // ---- merged ALT list (variant_operations.cc:134-228): first-seen order over live calls in row order
+  uint32_t my_live = 0;
+  if (!s_overflow) for (uint64_t q = tid; q < S.nq; q += UNION_THREADS) {
+    int32_t e = live[q];
+    if (e < 0) continue;
+    ++my_live;
+    CallView v = make_view(A, S, e);
+    atomicMax(&s_maxgt, v.gt_len);
+    atomicMax(&s_maxain, (unsigned int)v.n_alt + 1u);
+    for (int f = 0; f < A.n_fields; ++f) {
+      const uint32_t* p; uint32_t n;
+      if (field_of(A, S, v, f, p, n)) { atomicMax(&s_maxpl[f], v.ploidy); atomicMax(&s_maxin[f], n); }
+    }
+    if (v.nr_idx) s_nonref = 1;
+    if (v.n_alt > MAX_CALL_ALLELES - 1) { atomicMax(&S.err[1], 1u); continue; }
+    auto insert = [&](uint64_t h, uint32_t idx) {
+      unsigned long long order = ((unsigned long long)q << 12) | idx;
+      uint32_t slot = (uint32_t)(h % UNION_SLOTS);
+      for (int probe = 0; probe < UNION_SLOTS; ++probe) {
+        unsigned long long old = atomicCAS(&s_hash[slot], 0ull, (unsigned long long)h);
+        if (old == 0ull) { if (atomicAdd(&s_ndist, 1u) >= UNION_MAX_DISTINCT) atomicMax(&S.err[1], 2u); }
+        if (old == 0ull || old == h) { atomicMin(&s_order[slot], order); return; }
+        slot = (slot + 1) % UNION_SLOTS;
+      }
+      atomicMax(&S.err[1], 2u);
+    };
+    if (v.reduced) { int sfx; insert(allele_hash(c_str_star, 1, mref, mref_len, 1, sfx), 1); continue; }
+    if (v.flags & F_TRIVIAL) continue;
+    int pos = 0, ts, tl; uint32_t idx = 0;
+    while (next_token(v.alt, v.alt_n, pos, ts, tl)) {
+      ++idx;
+      if (is_non_ref(v.alt + ts, tl)) continue;
+      int sfx;
+      insert(allele_hash(v.alt + ts, tl, mref, mref_len, v.ref_len, sfx), idx);
+    }
+  }
+  if (my_live) atomicAdd(&s_nlive, my_live);
+  __syncthreads();
+  const uint32_t ndist = s_ndist < UNION_MAX_DISTINCT ? s_ndist : UNION_MAX_DISTINCT;
+  // compact occupied slots, rank them by first occurrence
+  if (tid == 0) s_next = 0;
+  __syncthreads();
+  for (int i = tid; i < UNION_SLOTS; i += UNION_THREADS) if (s_hash[i] != 0ull) { uint32_t p = atomicAdd(&s_next, 1u); if (p < UNION_MAX_DISTINCT) s_list[p] = (uint16_t)i; }
+  __syncthreads();
+  for (uint32_t i = tid; i < ndist; i += UNION_THREADS) {
+    unsigned long long o = s_order[s_list[i]]; uint32_t r = 0;
+    for (uint32_t k = 0; k < ndist; ++k) r += s_order[s_list[k]] < o;
+    s_rank[i] = (uint16_t)r;
+  }
+  const uint32_t A_m = 1u + ndist + (s_nonref ? 1u : 0u);
+  if (tid == 0) {
+    uint32_t first = atomicAdd(&B.cursors[0], A_m);
+    if (first + A_m > B.cap_allele_recs) { s_overflow = 1; first = 0; }
+    s_afirst = first;
+  }
+  __syncthreads();
+  if (!s_overflow) {
+    uint32_t first = s_afirst;
+    if (tid == 0) {
+      B.allele_pos[2 * first] = s_refoff; B.allele_pos[2 * first + 1] = mref_len; B.allele_hash[first] = 0;
+      if (s_nonref) {
+        uint32_t off = atomicAdd(&B.cursors[1], 9u);
+        if (off + 9u > B.cap_allele_bytes) s_overflow = 1;
+        else { for (int i = 0; i < 9; ++i) B.allele_bytes[off + i] = c_str_nonref[i]; B.allele_pos[2 * (first + A_m - 1)] = off; B.allele_pos[2 * (first + A_m - 1) + 1] = 9; B.allele_hash[first + A_m - 1] = 0; }
+      }
+    }
+    // one thread per distinct allele writes its string (representative = first occurrence)
+    for (uint32_t i = tid; i < ndist; i += UNION_THREADS) {
+      uint32_t slot = s_list[i], m = 1u + s_rank[i];
+      unsigned long long o = s_order[slot];
+      uint64_t q = o >> 12; uint32_t idx = (uint32_t)(o & 0xFFFu);
+      CallView v = make_view(A, S, live[q]);
+      const uint8_t* t = c_str_star; int tl = 1; uint32_t crl = 1;
+      if (!v.reduced) {
+        int pos = 0, ts = 0, l = 0; uint32_t k = 0;
+        while (next_token(v.alt, v.alt_n, pos, ts, l)) { if (++k == idx) break; }
+        t = v.alt + ts; tl = l; crl = v.ref_len;
+      }
+      int sfx = (crl < mref_len && !is_symbolic(t, tl)) ? (int)(mref_len - crl) : 0;
+      uint32_t len = (uint32_t)(tl + sfx);
+      uint32_t off = atomicAdd(&B.cursors[1], len);
+      if (off + len > B.cap_allele_bytes) { s_overflow = 1; continue; }
+      for (int k2 = 0; k2 < tl; ++k2) B.allele_bytes[off + k2] = t[k2];
+      for (int k2 = 0; k2 < sfx; ++k2) B.allele_bytes[off + tl + k2] = mref[crl + k2];
+      B.allele_pos[2 * (first + m)] = off; B.allele_pos[2 * (first + m) + 1] = len;
+      B.allele_hash[first + m] = s_hash[slot];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (s_overflow) atomicOr(&S.err[2], 1u);
+    SiteRec r;
+    r.n_alleles = A_m; r.n_live = s_nlive; r.allele_first = s_afirst; r.ref_off = s_refoff; r.ref_len = mref_len;
+    bool ref_block_only = (mref_len == 1 && ndist == 0 && s_nonref);
+    r.flags = (s_nonref ? 1u : 0u) | (ref_block_only ? 0u : 2u);
+    if (!ref_block_only && A_m - 1u > S.max_alt) r.flags |= 4u;
+    r.max_gt_len = s_maxgt; r.max_ain = s_maxain;
+    for (int f = 0; f < MAX_FIELDS; ++f) { r.max_ploidy[f] = s_maxpl[f]; r.max_in_len[f] = s_maxin[f]; }
+    B.sites[js] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K5 remap
+constexpr int REMAP_THREADS = 256;
+constexpr int REMAP_WARPS = REMAP_THREADS / 32;
+constexpr int REMAP_ROWS = 64;            // rows of one site handled by one block
+
+struct FieldOutDev { uint32_t* data; const uint64_t* base; const uint32_t* stride; uint16_t* len; };
+struct RemapOut {
+  int32_t n_out;                 // GT (if present) + remapped fields
+  FieldOutDev f[MAX_FIELDS + 1];
+  uint32_t* lut_first; uint16_t* lut_len; int16_t* lut_in2m; uint32_t cap_lut;   // optional
+};
+
+// One warp per call.  The allele LUT of the call is rebuilt in shared memory from the site's merged-allele hashes
+// (K4), then every output word is an indexed read of the call's input vector.
+__global__ void __launch_bounds__(REMAP_THREADS) k_remap(ArrayDev A, ScanDev S, BatchDev B, RemapOut O) {
+  __shared__ unsigned long long s_ahash[UNION_MAX_DISTINCT + 2];
+  __shared__ int16_t s_m2in[REMAP_WARPS][MAX_CALL_ALLELES];
+  __shared__ int16_t s_in2m[REMAP_WARPS][MAX_CALL_ALLELES];
+  const uint32_t tiles_per_site = (uint32_t)((S.nq + REMAP_ROWS - 1) / REMAP_ROWS);
+  const uint32_t js = blockIdx.x / tiles_per_site, tile = blockIdx.x % tiles_per_site;
+  const SiteRec site = B.sites[js];
+  const int32_t* live = B.live + (uint64_t)js * S.nq;
+  const uint32_t A_m = site.n_alleles;
+  const bool nonref = site.flags & 1u, remap = site.flags & 2u, g_suppressed = site.flags & 4u;
+  const uint8_t* mref = B.allele_bytes + site.ref_off;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < A_m && i < UNION_MAX_DISTINCT + 2; i += REMAP_THREADS) s_ahash[i] = B.allele_hash[site.allele_first + i];
+  __syncthreads();
+  int16_t* m2in = s_m2in[w]; int16_t* in2m = s_in2m[w];
+  const uint64_t q_end = min((uint64_t)(tile + 1) * REMAP_ROWS, S.nq);
+  for (uint64_t q = (uint64_t)tile * REMAP_ROWS + w; q < q_end; q += REMAP_WARPS) {
+    const int32_t e = live[q];
+    const uint64_t sq = (uint64_t)js * S.nq + q;
+    if (e < 0) {
+      for (int o = 0; o < O.n_out; ++o) {
+        const FieldOutDev fo = O.f[o];
+        uint32_t stride = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + q * stride;
+        int fi = o - (A.has_gt ? 1 : 0);
+        uint32_t pad = (fi >= 0) ? vend_word(A.fm[fi].elem) : BCF_INT_VEND;
+        for (uint32_t i = lane; i < stride; i += 32) dst[i] = pad;
+        if (lane == 0) fo.len[sq] = 0;
+      }
+      if (O.lut_first && lane == 0) { O.lut_first[sq] = 0xFFFFFFFFu; O.lut_len[sq] = 0; }
+      continue;
+    }
+    const CallView v = make_view(A, S, e);
+    const uint32_t A_in = (uint32_t)v.n_alt + 1u;
+    const bool trivial = !v.reduced && (v.flags & F_TRIVIAL);
+    int in_nr = (nonref && v.nr_idx) ? v.nr_idx : -1;
+    // ---- allele LUT (merge_alt_alleles' add_input_merged_idx_pair calls for this call, variant_operations.cc:160-227)
+    if (remap && !trivial) {
+      for (uint32_t i = lane; i < A_m; i += 32) m2in[i] = -1;
+      for (uint32_t i = lane; i < A_in; i += 32) in2m[i] = -1;
+      __syncwarp();
+      if (lane == 0) {
+        m2in[0] = 0; in2m[0] = 0;
+        if (v.reduced) {
+          int sfx; uint64_t h = allele_hash(c_str_star, 1, mref, site.ref_len, 1, sfx);
+          for (uint32_t m = 1; m < A_m; ++m) if (s_ahash[m] == h) { in2m[1] = (int16_t)m; m2in[m] = 1; break; }
+        } else {
+          int pos = 0, ts, tl; uint32_t idx = 0;
+          while (next_token(v.alt, v.alt_n, pos, ts, tl)) {
+            ++idx;
+            if (is_non_ref(v.alt + ts, tl)) continue;
+            int sfx; uint64_t h = allele_hash(v.alt + ts, tl, mref, site.ref_len, v.ref_len, sfx);
+            for (uint32_t m = 1; m < A_m; ++m) if (s_ahash[m] == h) { in2m[idx] = (int16_t)m; m2in[m] = (int16_t)idx; break; }
+          }
+        }
+        if (v.nr_idx) { in2m[v.nr_idx] = (int16_t)(A_m - 1); m2in[A_m - 1] = (int16_t)v.nr_idx; }
+      }
+      __syncwarp();
+    }
+    auto M2IN = [&](uint32_t m) -> int {
+      if (trivial) return m == 0 ? 0 : ((v.nr_idx && m == A_m - 1) ? v.nr_idx : -1);
+      return m < A_m ? (int)m2in[m] : -1;
+    };
+    auto IN2M = [&](int32_t a) -> int {
+      if (a < 0 || (uint32_t)a >= A_in) return -1;
+      if (trivial) return a == 0 ? 0 : ((v.nr_idx && a == v.nr_idx) ? (int)A_m - 1 : -1);
+      return (int)in2m[a];
+    };
+    if (O.lut_first) {
+      uint32_t first = 0;
+      if (lane == 0) { first = atomicAdd(&B.cursors[2], A_in); if (first + A_in > O.cap_lut) { atomicOr(&S.err[2], 2u); first = 0xFFFFFFFFu; } O.lut_first[sq] = first; O.lut_len[sq] = (uint16_t)A_in; }
+      first = __shfl_sync(0xffffffffu, first, 0);
+      if (first != 0xFFFFFFFFu) for (uint32_t i = lane; i < A_in; i += 32) O.lut_in2m[first + i] = remap ? (int16_t)IN2M((int32_t)i) : (int16_t)(i == 0 ? 0 : ((v.nr_idx && (int)i == v.nr_idx) ? (int)A_m - 1 : -1));
+    }
+    int o = 0;
+    // ---- GT (variant_operations.cc:233-263)
+    if (A.has_gt) {
+      const FieldOutDev fo = O.f[o++];
+      uint32_t stride = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + q * stride;
+      int step = A.gt_phased ? 2 : 1;
+      for (uint32_t i = lane; i < stride; i += 32) {
+        uint32_t val = BCF_INT_VEND;
+        if (i < v.gt_len) { uint32_t g = v.gt[i]; val = (remap && (i % step) == 0) ? remap_gt_word(g, IN2M, A_m, nonref) : g; }
+        dst[i] = val;
+      }
+      if (lane == 0) fo.len[sq] = (uint16_t)v.gt_len;
+    }
+    // ---- allele-dependent fields
+    for (int f = 0; f < A.n_fields; ++f) {
+      const FieldOutDev fo = O.f[o++];
+      const uint32_t stride = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + q * stride;
+      const int kind = A.fm[f].kind, elem = A.fm[f].elem;
+      const uint32_t pad = vend_word(elem), miss = missing_word(elem);
+      const uint32_t* in; uint32_t n_in;
+      bool valid = field_of(A, S, v, f, in, n_in);
+      if (valid && !v.reduced) {   // every element TileDB-NULL -> invalid
+        bool any = false;
+        for (uint32_t i = lane; i < n_in; i += 32) any |= (in[i] != null_word(elem));
+        valid = __any_sync(0xffffffffu, any);
+      }
+      if (!valid || (kind == KIND_G && g_suppressed)) {
+        for (uint32_t i = lane; i < stride; i += 32) dst[i] = pad;
+        if (lane == 0) fo.len[sq] = 0;
+        continue;
+      }
+      if (!remap) {
+        for (uint32_t i = lane; i < stride; i += 32) dst[i] = (i < n_in) ? in[i] : pad;
+        if (lane == 0) fo.len[sq] = (uint16_t)n_in;
+        continue;
+      }
+      const uint32_t n_out = num_elements(kind, A_m - 1u, v.ploidy);
+      if (kind != KIND_G || v.ploidy == 1) {
+        const bool alt_only = (kind == KIND_A);
+        for (uint32_t j = lane; j < stride; j += 32) {
+          uint32_t val = pad;
+          if (j < n_out) {
+            int ij = M2IN(alt_only ? j + 1u : j);
+            if (ij < 0) ij = in_nr;
+            if (ij < 0) val = miss;
+            else { int64_t ix = alt_only ? (int64_t)ij - 1 : ij; val = (ix < 0 || ix >= (int64_t)n_in) ? miss : in[ix]; }
+          }
+          dst[j] = val;
+        }
+      } else if (v.ploidy == 2) {
+        for (uint32_t g = lane; g < stride; g += 32) {
+          uint32_t val = pad;
+          if (g < n_out) {
+            // g = k(k+1)/2 + j, j <= k
+            uint32_t k = (uint32_t)((sqrtf(8.0f * (float)g + 1.0f) - 1.0f) * 0.5f);
+            while (k * (k + 1) / 2 > g) --k;
+            while ((k + 1) * (k + 2) / 2 <= g) ++k;
+            uint32_t jj = g - k * (k + 1) / 2;
+            int ij = M2IN(jj), ik = M2IN(k);
+            if (ij < 0) ij = in_nr;
+            if (ik < 0) ik = in_nr;
+            if (ij < 0 || ik < 0) val = miss;
+            else { int64_t ig = alleles2gt(ij, ik); val = (ig >= (int64_t)n_in) ? miss : in[ig]; }
+          }
+          dst[g] = val;
+        }
+      } else {
+        // ploidy 0 (copy of the first element) or general ploidy: sequential on one lane (rare)
+        if (v.ploidy > MAX_PLOIDY) { if (lane == 0) atomicMax(&S.err[1], 3u); }
+        else if (lane == 0) {
+          for (uint32_t i = 0; i < n_out && i < stride; ++i) dst[i] = (i < n_in) ? in[i] : 0u;
+          if (n_out <= stride) remap_field_seq(kind, in, n_in, M2IN, A_m, in_nr, v.ploidy, dst, miss);
+        }
+        __syncwarp();
+        for (uint32_t i = n_out + lane; i < stride; i += 32) dst[i] = pad;
+      }
+      if (lane == 0) fo.len[sq] = (uint16_t)n_out;
+    }
+  }
+}
+
+}  // namespace gdb

@@ -1,0 +1,70 @@
+// Host-side reader for the on-disk format GenomicsDB arrays use (TileDB 0.5.x sparse, column-major, read mode).
+// Written from the format, not from the reference's classes: one pass per attribute file, whole columns out.
+//   schema layout        dependencies/TileDB/core/src/array/array_schema.cc:569-594
+//   book-keeping layout  dependencies/TileDB/core/src/fragment/book_keeping.cc:217-243
+//   tile location/inflate dependencies/TileDB/core/src/fragment/read_state.cc:2442-2889, misc/utils.cc:466-512
+//   fragment ordering    dependencies/TileDB/core/src/storage_manager/storage_manager.cc:2169-2207
+//   array row bounds     src/main/cpp/src/genomicsdb/variant_storage_manager.cc:313-377
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace gdb {
+
+struct TdbSchema {
+  std::string array_name;
+  bool dense = false;
+  int tile_order = 0, cell_order = 0;
+  int64_t capacity = 0;
+  std::vector<std::string> attributes;   // without __coords
+  std::vector<int> types;                // attribute_num + 1 (coords last)
+  std::vector<int> cell_val_num;         // attribute_num
+  std::vector<int> compression;          // attribute_num + 1
+  int attr_id(const std::string& name) const;
+  bool is_var(int id) const { return cell_val_num[id] == 0x7FFFFFFF; }
+  size_t type_size(int id) const;
+};
+
+struct TdbBookKeeping {
+  int64_t tile_num = 0;
+  int64_t last_tile_cell_num = 0;
+  int64_t cell_num = 0;
+  std::vector<int64_t> bounding_coords;               // tile_num x 4 (first row, first col, last row, last col)
+  std::vector<std::vector<int64_t>> tile_offsets;      // attribute_num + 1
+  std::vector<std::vector<int64_t>> tile_var_offsets;  // attribute_num
+  std::vector<std::vector<uint64_t>> tile_var_sizes;   // attribute_num
+};
+
+// A whole attribute column of one fragment, decoded (tiles inflated) but otherwise byte-identical to the file.
+struct TdbColumn {
+  std::vector<uint8_t> fixed;   // fixed attr: values; var attr: n_cells uint64 absolute byte offsets
+  std::vector<uint8_t> var;     // var attr: value stream
+};
+
+struct TdbFragment {
+  std::string dir;
+  TdbBookKeeping bk;
+};
+
+class TdbArray {
+ public:
+  // throws std::runtime_error on malformed input
+  TdbArray(const std::string& workspace, const std::string& array_name);
+  const TdbSchema& schema() const { return schema_; }
+  size_t num_fragments() const { return fragments_.size(); }
+  const TdbFragment& fragment(size_t i) const { return fragments_[i]; }
+  // lb_row_idx / max_valid_row_idx_in_array merged over genomicsdb_meta_dir (false if no metadata present)
+  bool row_bounds(int64_t& lb, int64_t& max_valid) const;
+  // attr_id == schema().attributes.size() reads __coords
+  void read_column(size_t fragment_idx, int attr_id, TdbColumn& out) const;
+
+ private:
+  std::string dir_;
+  TdbSchema schema_;
+  std::vector<TdbFragment> fragments_;
+  bool has_lb_ = false, has_ub_ = false;
+  int64_t lb_ = 0, ub_ = 0;
+};
+
+}  // namespace gdb

@@ -1,0 +1,185 @@
+/*
+ * libgdbgpu -- C ABI of the B200-native GenomicsDB variant-combine hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handles, int status returns (0 = ok, <0 = error, message via
+ * gdbgpu_last_error), no C++ or torch types.  Every entry point names the reference interface it stands in for
+ * (paths relative to the GenomicsDB v0.10.2 source tree).  The host-side C++ mirror of the reference's plugin surface
+ * (genomicsdb_b200/csrc/gdb_host_api.h: VariantQueryProcessor::scan_and_operate, SingleVariantOperatorBase::operate)
+ * is written on top of exactly these calls; INTEGRATION.md shows the binding a GenomicsDB maintainer would add.
+ *
+ * There is NO CPU fallback behind this ABI: every call that computes needs a CUDA device (sm_100a) and fails with
+ * GDBGPU_ERR_CUDA otherwise.
+ */
+#ifndef GDBGPU_H
+#define GDBGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDBGPU_OK              0
+#define GDBGPU_ERR_ARG        -1
+#define GDBGPU_ERR_IO         -2   /* fragment files missing / malformed */
+#define GDBGPU_ERR_CUDA       -3   /* no device, launch failure, out of memory */
+#define GDBGPU_ERR_OVERLAP    -4   /* "Unhandled overlapping variants" (query_variants.cc:533-535) */
+#define GDBGPU_ERR_LIMIT      -5   /* a documented engine limit was exceeded (message says which) */
+
+typedef struct gdbgpu_ctx gdbgpu_ctx;
+typedef struct gdbgpu_array gdbgpu_array;
+typedef struct gdbgpu_scan gdbgpu_scan;
+
+/* Length descriptor of an allele-dependent field (known_field_info.h:95-101: BCF_VL_R / BCF_VL_A / BCF_VL_G). */
+enum { GDBGPU_LEN_R = 0, GDBGPU_LEN_A = 1, GDBGPU_LEN_G = 2 };
+/* Element type of a 4-byte field; decides the BCF missing / vector-end words written (vcf.h:61-134). */
+enum { GDBGPU_ELEM_INT32 = 0, GDBGPU_ELEM_FLOAT32 = 1 };
+
+/* One remapped field = one TileDB attribute whose length depends on the allele list (PL, AD, MLEAC, ...);
+ * stands in for GA4GHOperator::m_remapped_fields_query_idxs (variant_operations.cc:410-425). */
+typedef struct gdbgpu_field_desc {
+  const char* name;      /* TileDB attribute name, e.g. "PL" */
+  int32_t length_kind;   /* GDBGPU_LEN_* */
+  int32_t elem_type;     /* GDBGPU_ELEM_* */
+} gdbgpu_field_desc;
+
+/* Host-resident columns in TileDB's own in-file layout (global cell order = column-major (col,row)); what
+ * ArrayReadState::read_sparse hands to GenomicsDB one segment at a time (array_read_state.cc:1529-1598), here whole.
+ * Variable attributes: byte offsets (n_cells entries, absolute into the value stream, as in <ATTR>.tdb) + stream. */
+typedef struct gdbgpu_var_column {
+  const uint64_t* offsets;   /* n_cells absolute byte offsets */
+  const void* values;        /* value stream */
+  uint64_t values_bytes;
+} gdbgpu_var_column;
+
+typedef struct gdbgpu_columns {
+  uint64_t n_cells;
+  const int64_t* coords;     /* n_cells x (row, col)  == __coords.tdb */
+  const int64_t* end;        /* END.tdb */
+  gdbgpu_var_column ref;     /* REF.tdb / REF_var.tdb (char) */
+  gdbgpu_var_column alt;     /* ALT (char, '|' separated, NON_REF stored as '&') */
+  gdbgpu_var_column gt;      /* GT (int32); offsets==NULL when the array has no GT */
+  int32_t gt_phased;         /* vid length "PP": [a0, phase, a1, ...] (known_field_info.h:142-156) */
+  int32_t n_fields;
+  const gdbgpu_field_desc* field_descs;
+  const gdbgpu_var_column* fields;   /* n_fields columns of 4-byte elements */
+  int64_t lb_row_idx;        /* genomicsdb_meta lb_row_idx */
+  int64_t num_rows;          /* max_valid_row_idx_in_array - lb_row_idx + 1 */
+} gdbgpu_columns;
+
+typedef struct gdbgpu_array_info {
+  uint64_t n_cells;          /* after the fragment merge */
+  uint64_t n_begin_cells;    /* cells with col <= END */
+  uint32_t n_fragments;
+  int64_t lb_row_idx, num_rows;
+  int64_t min_col, max_col, max_end;
+  uint64_t staged_bytes;     /* fragment bytes copied host -> HBM */
+  uint64_t hbm_bytes;        /* total device footprint incl. indexes */
+  int32_t n_fields, has_gt, gt_phased;
+} gdbgpu_array_info;
+
+/* ---- context: one per host thread / CUDA device (VariantStorageManager's role, variant_storage_manager.h:160-235) */
+int gdbgpu_ctx_create(int device, gdbgpu_ctx** out);
+void gdbgpu_ctx_destroy(gdbgpu_ctx* ctx);
+const char* gdbgpu_last_error(const gdbgpu_ctx* ctx);
+/* the CUDA stream all work of this context is enqueued on (cudaStream_t as void*), for event timing by the caller */
+void* gdbgpu_ctx_stream(gdbgpu_ctx* ctx);
+/* number of kernel launches issued by this context so far */
+uint64_t gdbgpu_ctx_launch_count(const gdbgpu_ctx* ctx);
+
+/* ---- array: fragment bytes staged to HBM.
+ * gdbgpu_array_open replaces VariantStorageManager::open_array + TileDB array/fragment/book-keeping load
+ * (variant_storage_manager.cc:434-520; storage_manager.cc array_open; book_keeping.cc:368-422; read_state.cc:2442-2889):
+ * it reads <workspace>/<array>/__array_schema.tdb and, per fragment dir, __book_keeping.tdb.gz, <ATTR>.tdb, <ATTR>_var.tdb,
+ * inflates GZIP tiles on the host, copies the columns to the device and runs the fragment merge there. */
+int gdbgpu_array_open(gdbgpu_ctx* ctx, const char* workspace, const char* array_name,
+                      const gdbgpu_field_desc* fields, int32_t n_fields, int32_t gt_phased, gdbgpu_array** out);
+/* Same, from columns already decoded in host memory (loader hand-off, JNI buffers, synthetic generators). */
+int gdbgpu_array_from_columns(gdbgpu_ctx* ctx, const gdbgpu_columns* cols, gdbgpu_array** out);
+int gdbgpu_array_get_info(const gdbgpu_array* arr, gdbgpu_array_info* info);
+/* Host copies of the merged coordinate / END columns (for consumers that materialise VariantCall objects). */
+int gdbgpu_array_copy_cells(const gdbgpu_array* arr, uint64_t first, uint64_t count, int64_t* coords, int64_t* end);
+void gdbgpu_array_close(gdbgpu_array* arr);
+
+/* ---- scan: one query column interval == one VariantQueryProcessor::scan_and_operate call chain
+ * (query_variants.h:241-243, query_variants.cc:334-476) with handle_spanning_deletions as the Broad operator asks. */
+#define GDBGPU_SCAN_FULL               1u   /* query_config.get_num_column_intervals()==0 (scan_full) */
+#define GDBGPU_SCAN_NO_DELETIONS       2u   /* handle_spanning_deletions=false and no handle_deletions pre-pass (GA4GHOperator only) */
+#define GDBGPU_SCAN_MIN_PL_GT          4u   /* produce_GT_with_min_PL_value_for_spanning_deletions */
+#define GDBGPU_SCAN_WANT_LUT           8u   /* also return the per-call input->merged allele LUT (CombineAllelesLUT) */
+#define GDBGPU_SCAN_DEVICE_OUTPUT     16u   /* batch pointers are DEVICE pointers (consumer is another kernel) */
+
+typedef struct gdbgpu_scan_params {
+  int64_t col_lo, col_hi;            /* inclusive TileDB column interval; ignored with GDBGPU_SCAN_FULL */
+  const int64_t* query_rows;         /* array row idxs, any order, NULL = all rows (query_row_ranges) */
+  uint64_t n_query_rows;
+  uint32_t flags;
+  uint32_t max_diploid_alt_alleles;  /* 0 -> 50 (gt_common.h:48) */
+} gdbgpu_scan_params;
+
+typedef struct gdbgpu_scan_info {
+  uint64_t n_sites;                  /* operate() invocations this interval will produce */
+  uint64_t n_breakpoints;
+  uint64_t n_query_rows;
+  uint64_t n_forward_cells;          /* cells visited by the forward scan */
+} gdbgpu_scan_info;
+
+/* One remapped field of a batch: dense, sample-major.  Site s occupies words
+ * [base[s], base[s] + n_query_rows*stride[s]) ; query row q's vector starts at base[s] + q*stride[s], holds len[s*nq+q]
+ * valid words followed by BCF vector-end padding.  len==0: field invalid for that call / row not live / suppressed. */
+typedef struct gdbgpu_field_out {
+  const uint32_t* data;
+  const uint64_t* base;      /* n_sites + 1 */
+  const uint32_t* stride;    /* n_sites */
+  const uint16_t* len;       /* n_sites x n_query_rows */
+} gdbgpu_field_out;
+
+#define GDBGPU_SITE_NONREF      1u   /* m_NON_REF_exists */
+#define GDBGPU_SITE_REMAPPED    2u   /* m_remapping_needed */
+#define GDBGPU_SITE_G_SUPPRESSED 4u  /* too many ALT alleles: G-length fields dropped (variant_operations.cc:613-629) */
+
+#define GDBGPU_CALL_REDUCED  0x40000000   /* live[] flag (bit 30): call is in its spanning-deletion form (REF N, ALT *[,NON_REF]) */
+
+typedef struct gdbgpu_batch {
+  uint64_t first_site;       /* index of the first site of this batch within the interval */
+  uint32_t n_sites;
+  uint64_t n_query_rows;
+  const int64_t* site_begin; /* variant.get_column_begin() */
+  const int64_t* site_end;   /* variant.get_column_end() */
+  const uint8_t* site_flags; /* GDBGPU_SITE_* */
+  const uint32_t* n_alleles; /* 1 + merged ALT count */
+  const uint32_t* n_live;    /* valid calls at the site */
+  /* merged allele strings: allele m of site s is allele_bytes[allele_pos[2*(allele_first[s]+m)] .. +allele_pos[..+1]) */
+  const uint32_t* allele_first;  /* n_sites */
+  const uint32_t* allele_pos;    /* (offset,len) pairs */
+  const uint8_t* allele_bytes;
+  /* live[s*nq+q] = merged-order cell index of query row q's call at site s (bit 30: GDBGPU_CALL_REDUCED), or -1 */
+  const int32_t* live;
+  /* fields[0] is GT when the array has GT, then the remapped fields in array order */
+  int32_t n_fields;
+  gdbgpu_field_out fields[16];
+  /* optional (GDBGPU_SCAN_WANT_LUT): in2m[lut_first[s*nq+q] + i] = merged idx of input allele i < lut_len[s*nq+q] (-1 missing) */
+  const uint32_t* lut_first;
+  const uint16_t* lut_len;   /* number of input alleles (1 + ALT count) of the call as the operator saw it */
+  const int16_t* lut_in2m;
+  uint64_t out_bytes;        /* bytes of remapped output written for this batch */
+} gdbgpu_batch;
+
+int gdbgpu_scan_begin(gdbgpu_array* arr, const gdbgpu_scan_params* params, gdbgpu_scan** out);
+int gdbgpu_scan_get_info(const gdbgpu_scan* scan, gdbgpu_scan_info* info);
+/* Produces the next <= max_sites sites whose remapped output fits max_bytes (0 = engine default); n_sites==0 at the end.
+ * The batch stays valid until the next call on the same scan.  Re-entrant like the reference's overflow/resume
+ * protocol (query_variants.cc:305,415,460-475): the caller drains a batch, then asks for the next. */
+int gdbgpu_scan_next_batch(gdbgpu_scan* scan, uint32_t max_sites, uint64_t max_bytes, gdbgpu_batch* batch);
+/* Rewind to site idx (resume after a consumer-side overflow in the middle of a batch). */
+int gdbgpu_scan_seek(gdbgpu_scan* scan, uint64_t site_idx);
+void gdbgpu_scan_end(gdbgpu_scan* scan);
+
+/* library identity (for the test that checks every declared symbol is exported) */
+const char* gdbgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
