@@ -1,0 +1,336 @@
+#!/usr/bin/env python3
+"""bench.py -- combined variant sites/s of the B200 variant-combine hot path (contract: see the task statement).
+
+A "step" is one pass of the hot path (interval sweep -> allele union -> GT/AD/PL remap) over this rank's column shard of
+the GDBSYN-1 cohort named in BASELINE.json (config #4: 100 k samples x 10 M positions, 10 k candidate sites, max 8 ALT
+alleles per site).  One rank holds 1/8 of the columns (1 250 candidate sites = 1.25 M positions); 8 ranks = config #4.
+  value : sites/s with the shard already resident in HBM and the output left in HBM (CUDA events on the engine's stream)
+  e2e   : the same metric through the C ABI with HOST buffers: gdbgpu_array_from_columns (H2D of the fragment columns,
+          pinned) -> scan -> every batch copied back to pinned host memory (D2H) -> close
+  roofline : the remap kernel (k_remap), algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref/bin/gdb_ref_dump --mode hot: scan_and_operate + handle_deletions
+          + GA4GHOperator::operate, no VCF serialisation) on all host cores, on a bounded sample of the same cohort.
+--impl reference prints the reference arm's line (same metric/config, CPU only).
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+COHORT = dict(n_samples=100000, n_sites=10000, spacing=1000, p_var=0.1, a_pool=8)
+SITES_PER_GPU = 1250
+METRIC = "combined_variant_sites_per_sec"
+REF_BIN = os.path.join(REPO, "oracle", "_ref", "bin", "gdb_ref_dump")
+
+
+def workload_config(args, n_gpus):
+    c = dict(COHORT)
+    c["n_samples"] = args.samples
+    return dict(workload="GDBSYN-1 config#4 column shard: %d samples x %d candidate sites (%d positions) per GPU, a_pool=%d, p_var=%.2f; %d shard(s)"
+                % (c["n_samples"], args.sites_per_gpu, args.sites_per_gpu * c["spacing"], c["a_pool"], c["p_var"], n_gpus),
+                samples=c["n_samples"], sites_per_gpu=args.sites_per_gpu, shards=n_gpus,
+                l2="inputs (GBs of fragment columns) and outputs (tens of GB per step) are far larger than the 126 MB L2; no explicit flush",
+                sharding="contig-interval (column) shards, one per GPU, no data-path collective")
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                    reasons=reasons, samples=len(self.rows))
+
+
+# ------------------------------------------------------------------------------------------------ reference (CPU) arm
+def reference_sample(args, n_sites_sample, n_procs, tmp):
+    """Times the unmodified reference on `n_procs` host cores, each combining its own `n_sites_sample`-site slice of the
+    same cohort (all samples).  Returns (sites_per_sec over all processes, detail)."""
+    from tools import gdbsyn, tiledb_writer
+    c = dict(COHORT)
+    c["n_samples"] = args.samples
+    jobs = []
+    for k in range(n_procs):
+        lo = (k * n_sites_sample) % max(1, c["n_sites"] - n_sites_sample)
+        d = gdbsyn.generate(**c, site_lo=lo, site_hi=lo + n_sites_sample, with_fixed=True)
+        ws = os.path.join(tmp, "ws%d" % k)
+        info = tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+        q = tiledb_writer.write_query_json(os.path.join(ws, "q.json"), info, d["col_range"][0], d["col_range"][1])
+        jobs.append(q)
+        del d
+    t0 = time.time()
+    procs = [subprocess.Popen([REF_BIN, "-j", q, "--mode", "hot"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for q in jobs]
+    outs = [p.communicate()[0] for p in procs]
+    wall = time.time() - t0
+    sites, secs = 0, 0.0
+    for o in outs:
+        j = json.loads(o.strip().splitlines()[-1])
+        sites += j["sites"]
+        secs = max(secs, j["seconds"])
+    return sites / secs, dict(sites=sites, max_seconds=secs, wall=wall, procs=n_procs)
+
+
+def port_sample(args, n_sites_sample):
+    """Fallback when oracle/_ref is not present: the plain-C oracle port, single thread."""
+    from oracle import oracle
+    from tools import gdbsyn
+    c = dict(COHORT)
+    c["n_samples"] = args.samples
+    d = gdbsyn.generate(**c, site_lo=0, site_hi=n_sites_sample)
+    cols = gdbsyn.to_oracle_columns(d)
+    t0 = time.time()
+    _, n = oracle.combine(cols, d["col_range"][0], d["col_range"][1])
+    dt = time.time() - t0
+    return n / dt, dict(sites=n, max_seconds=dt, procs=1)
+
+
+def cpu_baseline(args, budget_s=12.0):
+    cores = os.cpu_count() or 1
+    tmp = tempfile.mkdtemp(prefix="gdbbench")
+    try:
+        if os.path.exists(REF_BIN):
+            # ~0.9 us per sample*site per core (measured); size the per-core slice for `budget_s` seconds
+            per_core = max(2, int(budget_s / (0.9e-6 * args.samples * 2)))
+            per_core = min(per_core, 64)
+            v, det = reference_sample(args, per_core, cores, tmp)
+            return dict(value=v, unit="sites/s", cores=cores, kind="reference",
+                        sample="%d processes x %d candidate sites x %d samples of the same cohort through oracle/_ref/bin/gdb_ref_dump --mode hot "
+                               "(unmodified scan_and_operate + handle_deletions + GA4GHOperator::operate, no VCF output); %d sites in %.1f s (max over processes)"
+                               % (cores, per_core, args.samples, det["sites"], det["max_seconds"]))
+        per = max(2, int(budget_s / (1.0e-6 * args.samples * 2)))
+        v, det = port_sample(args, min(per, 64))
+        return dict(value=v, unit="sites/s", cores=1, kind="port",
+                    sample="oracle/combine_oracle.c single thread, %d sites x %d samples in %.1f s" % (det["sites"], args.samples, det["max_seconds"]))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    base = None
+    for _ in range(args.warmup):
+        pass    # nothing to warm: every sample is a fresh process over fresh files
+    for _ in range(max(1, args.steps)):
+        base = cpu_baseline(args, budget_s=max(2.0, 60.0 / max(1, args.steps)))
+        vals.append(base["value"])
+    v = float(np.median(vals))
+    n = args.gpus
+    line = dict(metric=METRIC, value=v, unit="sites/s", n_gpus=n, steps=args.steps, warmup=args.warmup,
+                ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32", data="synthetic",
+                config=workload_config(args, n), impl="reference",
+                cpu_baseline=dict(base, value=v),
+                e2e=dict(value=v, unit="sites/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--samples", type=int, default=COHORT["n_samples"])
+    ap.add_argument("--sites-per-gpu", type=int, default=SITES_PER_GPU)
+    ap.add_argument("--batch-bytes", type=int, default=8 << 30)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from genomicsdb_b200 import capi
+    from tools import gdbsyn
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        sys.exit("bench.py needs a CUDA device: the combine path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    cohort = dict(COHORT)
+    cohort["n_samples"] = args.samples
+    lo = (rank * args.sites_per_gpu) % cohort["n_sites"]
+    d = gdbsyn.generate(**cohort, site_lo=lo, site_hi=min(cohort["n_sites"], lo + args.sites_per_gpu))
+    q_lo, q_hi = d["col_range"]
+    manifest = gdbsyn.algorithmic_bytes(d)
+
+    ctx = capi.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    def one_pass(arr, flags):
+        sc = capi.Scan(arr, q_lo, q_hi, flags=flags)
+        sites = out_bytes = live_words = 0
+        while True:
+            b = sc.next_batch(0, args.batch_bytes, raw=True)
+            if b.n_sites == 0:
+                break
+            sites += b.n_sites
+            out_bytes += b.out_bytes
+            live_words += b.n_sites * b.n_query_rows
+        sc.close()
+        return sites, out_bytes, live_words
+
+    # ---------------- HBM-resident metric
+    arr = gdbsyn.to_gpu_array(ctx, d)
+    info = arr.info()
+    for _ in range(max(3, args.warmup)):
+        one_pass(arr, capi.SCAN_DEVICE_OUTPUT)
+    ctx.set_profiling(True)
+    ctx.reset_kernel_stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launches
+    ev0.record(stream)
+    sites = out_bytes = 0
+    for _ in range(args.steps):
+        s, ob, _ = one_pass(arr, capi.SCAN_DEVICE_OUTPUT)
+        sites += s
+        out_bytes += ob
+    ev1.record(stream)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    sampler.stop_flag = True
+    launches = ctx.launches - launches0
+    remap_ms, remap_n = ctx.kernel_stats("k_remap")
+    union_ms, _ = ctx.kernel_stats("k_union")
+    walk_ms, _ = ctx.kernel_stats("k_live_walk")
+    ctx.set_profiling(False)
+    sites_per_step = sites // args.steps
+    total_sites = sum_over_ranks(float(sites))
+    value = total_sites / (ms * 1e-3)
+    arr.close()
+
+    # ---------------- roofline of the dominant kernel (remap): algorithmic bytes per launch / its event-timed duration
+    peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    b_in_step = manifest["b_in"]
+    b_out_step = out_bytes / args.steps
+    achieved = ((b_in_step + b_out_step) * args.steps / 1e9) / (remap_ms * 1e-3) if remap_ms > 0 else 0.0
+    roofline = dict(bound="hbm", kernel="gdb::k_remap", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                    peak_source=peak_src, algorithmic_bytes_per_step=dict(b_in=b_in_step, b_out=b_out_step),
+                    launches=int(remap_n), avg_launch_ms=remap_ms / max(1, remap_n),
+                    kernel_ms_per_step=dict(k_remap=remap_ms / args.steps, k_union=union_ms / args.steps, k_live_walk=walk_ms / args.steps),
+                    step_gbs=((b_in_step + b_out_step) * args.steps / 1e9) / (ms * 1e-3))
+
+    # ---------------- end to end through the C ABI with host buffers
+    e2e = None
+    if not args.no_e2e:
+        pinned = {}
+
+        def pin(a):
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            pinned[id(t)] = t
+            return t.numpy()
+
+        dp = dict(d)
+        dp["coords"], dp["end"] = pin(d["coords"]), pin(d["end"])
+        for k in ("ref", "alt", "gt", "pl", "ad"):
+            dp[k] = (pin(d[k][0]), pin(d[k][1]))
+
+        def e2e_step():
+            a = gdbsyn.to_gpu_array(ctx, dp)
+            i = a.info()
+            s, ob, lw = one_pass(a, 0)
+            a.close()
+            return s, i.staged_bytes, ob + lw * 4 + s * 24
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        es = h2d = d2h = 0
+        for _ in range(args.e2e_steps):
+            s, hb, db = e2e_step()
+            es += s
+            h2d += hb
+            d2h += db
+        ctx.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = dict(value=sum_over_ranks(float(es)) / dt, unit="sites/s", h2d_bytes_per_step=int(h2d // args.e2e_steps),
+                   d2h_bytes_per_step=int(d2h // args.e2e_steps), steps=args.e2e_steps, ms_per_step=dt * 1e3 / args.e2e_steps,
+                   path="gdbgpu_array_from_columns(pinned host columns) -> gdbgpu_scan_next_batch(host output) -> close")
+    ctx.close()
+
+    base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        base = cpu_baseline(args)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit="sites/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
+                    data="synthetic", config=workload_config(args, world), clocks=sampler.summary(), e2e=e2e,
+                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=base,
+                    sites_per_step_per_gpu=int(sites_per_step), cells_per_gpu=int(info.n_cells),
+                    staged_bytes_per_gpu=int(info.staged_bytes), hbm_bytes_per_gpu=int(info.hbm_bytes))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

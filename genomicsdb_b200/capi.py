@@ -20,7 +20,8 @@ CALL_REDUCED = 0x40000000
 KIND = {"R": LEN_R, "A": LEN_A, "G": LEN_G}
 
 EXPORTS = ["gdbgpu_version", "gdbgpu_ctx_create", "gdbgpu_ctx_destroy", "gdbgpu_last_error", "gdbgpu_ctx_stream",
-           "gdbgpu_ctx_launch_count", "gdbgpu_array_open", "gdbgpu_array_from_columns", "gdbgpu_array_get_info",
+           "gdbgpu_ctx_launch_count", "gdbgpu_ctx_synchronize", "gdbgpu_ctx_set_profiling",
+           "gdbgpu_ctx_reset_kernel_stats", "gdbgpu_ctx_kernel_stats", "gdbgpu_array_open", "gdbgpu_array_from_columns", "gdbgpu_array_get_info",
            "gdbgpu_array_copy_cells", "gdbgpu_array_close", "gdbgpu_scan_begin", "gdbgpu_scan_get_info",
            "gdbgpu_scan_next_batch", "gdbgpu_scan_seek", "gdbgpu_scan_end"]
 
@@ -90,6 +91,10 @@ def lib():
         L.gdbgpu_ctx_stream.argtypes = [C.c_void_p]
         L.gdbgpu_ctx_launch_count.restype = C.c_uint64
         L.gdbgpu_ctx_launch_count.argtypes = [C.c_void_p]
+        L.gdbgpu_ctx_synchronize.argtypes = [C.c_void_p]
+        L.gdbgpu_ctx_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.gdbgpu_ctx_reset_kernel_stats.argtypes = [C.c_void_p]
+        L.gdbgpu_ctx_kernel_stats.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.gdbgpu_array_open.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(FieldDesc), C.c_int32, C.c_int32,
                                         C.POINTER(C.c_void_p)]
         L.gdbgpu_array_from_columns.argtypes = [C.c_void_p, C.POINTER(Columns), C.POINTER(C.c_void_p)]
@@ -136,6 +141,20 @@ class Context:
     @property
     def launches(self):
         return lib().gdbgpu_ctx_launch_count(self.h)
+
+    def synchronize(self):
+        self.check(lib().gdbgpu_ctx_synchronize(self.h))
+
+    def set_profiling(self, on):
+        lib().gdbgpu_ctx_set_profiling(self.h, int(on))
+
+    def reset_kernel_stats(self):
+        lib().gdbgpu_ctx_reset_kernel_stats(self.h)
+
+    def kernel_stats(self, name):
+        ms, n = C.c_double(), C.c_uint64()
+        self.check(lib().gdbgpu_ctx_kernel_stats(self.h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def close(self):
         if self.h:

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -19,11 +20,29 @@
 using namespace gdb;
 
 // ------------------------------------------------------------------------------------------------ plumbing
+struct ProfRec { const char* name; cudaEvent_t a, b; };
 struct gdbgpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
+  // optional per-kernel device timing (CUDA events on the launching stream), see gdbgpu_ctx_set_profiling
+  bool profiling = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  std::map<std::string, std::pair<double, uint64_t>> stats;
+  cudaEvent_t get_event() { if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
+  void resolve() {
+    if (recs.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (auto& r : recs) { float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b); auto& st = stats[r.name]; st.first += ms; st.second += 1; pool.push_back(r.a); pool.push_back(r.b); }
+    recs.clear();
+  }
+};
+struct ProfScope {
+  gdbgpu_ctx* c; ProfRec r;
+  ProfScope(gdbgpu_ctx* ctx, const char* name) : c(ctx) { if (c->profiling) { r.name = name; r.a = c->get_event(); r.b = c->get_event(); cudaEventRecord(r.a, c->stream); } }
+  ~ProfScope() { if (c->profiling) { cudaEventRecord(r.b, c->stream); c->recs.push_back(r); } }
 };
 
 namespace {
@@ -56,7 +75,7 @@ struct PinBuf {
 
 inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)std::max<uint64_t>(1, (n + per - 1) / per); }
 
-#define LAUNCH(ctx, kernel, grid, block, ...) do { kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__); ++(ctx)->launches; CK(cudaGetLastError()); } while (0)
+#define LAUNCH(ctx, kernel, grid, block, ...) do { { ProfScope ps__(ctx, #kernel); kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__); } ++(ctx)->launches; CK(cudaGetLastError()); } while (0)
 
 // exclusive scan; `total` (device) receives the sum.  in/out may alias when TI == TO.
 template <class TI, class TO>
@@ -465,7 +484,7 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
     BatchDev B{};
     B.first_site = s->cursor; B.n_sites = nb; B.live = s->live.p; B.sites = s->sites.p; B.cursors = s->cursors.p;
     B.allele_pos = s->allele_pos.p; B.allele_hash = s->allele_hash.p; B.cap_allele_recs = s->cap_allele_recs; B.allele_bytes = s->allele_bytes.p; B.cap_allele_bytes = s->cap_allele_bytes;
-    LAUNCH(ctx, k_live_walk, blocks_for(S.nq, 256), 256, a->dev, S, s->cursor, nb, s->live.p);
+    LAUNCH(ctx, k_live_walk, dim3(blocks_for(S.nq, 256), (nb + WALK_CHUNK - 1) / WALK_CHUNK), 256, a->dev, S, s->cursor, nb, s->live.p);
     LAUNCH(ctx, k_union, nb, UNION_THREADS, a->dev, S, B);
     s->h_sites.resize(nb);
     CK(cudaMemcpyAsync(s->h_sites.data(), s->sites.p, (size_t)nb * sizeof(SiteRec), cudaMemcpyDeviceToHost, ctx->stream));
@@ -581,7 +600,25 @@ int gdbgpu_ctx_create(int device, gdbgpu_ctx** out) {
   *out = c;
   return GDBGPU_OK;
 }
-void gdbgpu_ctx_destroy(gdbgpu_ctx* ctx) { if (!ctx) return; if (ctx->stream) cudaStreamDestroy(ctx->stream); delete ctx; }
+void gdbgpu_ctx_destroy(gdbgpu_ctx* ctx) {
+  if (!ctx) return;
+  ctx->resolve();
+  for (auto e : ctx->pool) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+void gdbgpu_ctx_set_profiling(gdbgpu_ctx* ctx, int enable) { if (ctx) { ctx->resolve(); ctx->profiling = enable != 0; } }
+void gdbgpu_ctx_reset_kernel_stats(gdbgpu_ctx* ctx) { if (ctx) { ctx->resolve(); ctx->stats.clear(); } }
+int gdbgpu_ctx_kernel_stats(gdbgpu_ctx* ctx, const char* kernel_name, double* total_ms, uint64_t* launches) {
+  if (!ctx || !kernel_name) return GDBGPU_ERR_ARG;
+  ctx->resolve();
+  double ms = 0; uint64_t n = 0;
+  for (auto& kv : ctx->stats) if (kv.first.find(kernel_name) != std::string::npos) { ms += kv.second.first; n += kv.second.second; }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = n;
+  return GDBGPU_OK;
+}
+int gdbgpu_ctx_synchronize(gdbgpu_ctx* ctx) { if (!ctx) return GDBGPU_ERR_ARG; return cudaStreamSynchronize(ctx->stream) == cudaSuccess ? GDBGPU_OK : GDBGPU_ERR_CUDA; }
 const char* gdbgpu_last_error(const gdbgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
 void* gdbgpu_ctx_stream(gdbgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t gdbgpu_ctx_launch_count(const gdbgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }

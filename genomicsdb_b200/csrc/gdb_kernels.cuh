@@ -133,31 +133,44 @@ __global__ void __launch_bounds__(256) k_effend(ArrayDev A, CellDesc* __restrict
                                                  const uint32_t* __restrict__ sorted_keys, uint64_t n_rs, int64_t* __restrict__ rs_effend,
                                                  int64_t* __restrict__ effend, unsigned long long* __restrict__ stats,
                                                  uint32_t* __restrict__ bad_cell, int64_t* __restrict__ bad_pred_col, uint32_t bad_cap) {
+  __shared__ unsigned int s_begin, s_del;
+  __shared__ long long s_max;
+  if (threadIdx.x == 0) { s_begin = 0; s_del = 0; s_max = INT64_MIN; }
+  __syncthreads();
   uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_rs) return;
-  uint32_t c = rs_cell[k];
-  uint8_t fl = desc[c].flags;
-  if (fl & F_ENDCOPY) { rs_effend[k] = I64_MIN; effend[c] = I64_MIN; atomicMax((long long*)&stats[2], (long long)rs_col[k]); return; }
-  int64_t END = A.end[c];
-  int64_t eff = END;
-  uint32_t key = sorted_keys[k];
-  for (uint64_t k2 = k + 1; k2 < n_rs && sorted_keys[k2] == key; ++k2) {
-    uint32_t c2 = rs_cell[k2];
-    if (desc[c2].flags & F_ENDCOPY) continue;
-    int64_t nb = rs_col[k2];
-    if (nb <= END) {
-      eff = nb - 1;
-      if (!(fl & (F_DELETION | F_REFBLOCK))) {
-        unsigned long long slot = atomicAdd(&stats[1], 1ull);
-        if (slot < bad_cap) { bad_cell[slot] = c2; bad_pred_col[slot] = rs_col[k]; }
+  if (k < n_rs) {
+    uint32_t c = rs_cell[k];
+    uint8_t fl = desc[c].flags;
+    if (fl & F_ENDCOPY) { rs_effend[k] = I64_MIN; effend[c] = I64_MIN; atomicMax(&s_max, (long long)rs_col[k]); }
+    else {
+      int64_t END = A.end[c];
+      int64_t eff = END;
+      uint32_t key = sorted_keys[k];
+      for (uint64_t k2 = k + 1; k2 < n_rs && sorted_keys[k2] == key; ++k2) {
+        uint32_t c2 = rs_cell[k2];
+        if (desc[c2].flags & F_ENDCOPY) continue;
+        int64_t nb = rs_col[k2];
+        if (nb <= END) {
+          eff = nb - 1;
+          if (!(fl & (F_DELETION | F_REFBLOCK))) {
+            unsigned long long slot = atomicAdd(&stats[1], 1ull);
+            if (slot < bad_cap) { bad_cell[slot] = c2; bad_pred_col[slot] = rs_col[k]; }
+          }
+        }
+        break;
       }
+      rs_effend[k] = eff; effend[c] = eff;
+      atomicAdd(&s_begin, 1u);
+      atomicMax(&s_max, (long long)END);
+      if (fl & F_DELETION) atomicAdd(&s_del, 1u);
     }
-    break;
   }
-  rs_effend[k] = eff; effend[c] = eff;
-  atomicAdd(&stats[0], 1ull);
-  atomicMax((long long*)&stats[2], (long long)END);
-  if (fl & F_DELETION) atomicAdd(&stats[3], 1ull);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_begin) atomicAdd(&stats[0], (unsigned long long)s_begin);
+    if (s_del) atomicAdd(&stats[3], (unsigned long long)s_del);
+    if (s_max != INT64_MIN) atomicMax((long long*)&stats[2], s_max);
+  }
 }
 __global__ void __launch_bounds__(256) k_effend_rowout(ArrayDev A, const CellDesc* __restrict__ desc, int64_t* __restrict__ effend) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -252,7 +265,8 @@ __device__ inline uint64_t bp_rank(const ScanDev& S, int64_t pos) {
 }
 __device__ inline void set_bit(const ScanDev& S, int64_t pos) {
   uint64_t bit = (uint64_t)(pos - S.base);
-  atomicOr(&S.bitmap[bit >> 6], 1ull << (bit & 63));
+  unsigned long long m = 1ull << (bit & 63);
+  if (!(S.bitmap[bit >> 6] & m)) atomicOr(&S.bitmap[bit >> 6], m);   // thousands of cells share a column: test first
 }
 __device__ inline int64_t clip_end(const ScanDev& S, int64_t e) { return (!S.scan_full && e > S.q_hi) ? S.q_hi : e; }
 
@@ -326,9 +340,11 @@ __global__ void __launch_bounds__(256) k_deltas(ArrayDev A, ScanDev S) {
     if (qrow_of(A, S, A.coords[2 * i]) < 0) return;
     uint64_t rs = bp_rank(S, col), re = bp_rank(S, clip_end(S, A.effend[i]) + 1);
     // warp-aggregate the +1 (cells of one column are adjacent)
-    unsigned mask = __match_any_sync(__activemask(), rs);
+    unsigned act = __activemask();
+    unsigned mask = __match_any_sync(act, rs);
     if ((int)(threadIdx.x & 31) == __ffs(mask) - 1) atomicAdd(&S.dlive[rs], __popc(mask));
-    atomicSub(&S.dlive[re], 1);
+    unsigned mask_e = __match_any_sync(act, re);
+    if ((int)(threadIdx.x & 31) == __ffs(mask_e) - 1) atomicSub(&S.dlive[re], __popc(mask_e));
     if (S.handle_del && (fl & F_DELETION)) { atomicAdd(&S.ddel[rs], 1); atomicSub(&S.ddel[re], 1); }
   } else {
     uint64_t q = t - n_cells;
@@ -365,12 +381,14 @@ __global__ void __launch_bounds__(256) k_fill_sites(ScanDev S, const int32_t* __
 // ------------------------------------------------------------------------------------------------ K3 live matrix
 // One thread per queried sample walks that sample's cell list against the batch's sites ("k-way merge" of the sample
 // lists with the site list); adjacent threads write adjacent entries of each site's row -> coalesced.
+constexpr uint32_t WALK_CHUNK = 32;   // sites walked by one thread after one binary search
 __global__ void __launch_bounds__(256) k_live_walk(ArrayDev A, ScanDev S, uint64_t first_site, uint32_t n_sites, int32_t* __restrict__ live) {
   uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= S.nq) return;
+  const uint32_t s0 = blockIdx.y * WALK_CHUNK, s1 = min(n_sites, s0 + WALK_CHUNK);
   int64_t r = S.row_of_qrow[q] - A.lb_row;
   uint64_t lo = A.row_start[r], e = A.row_start[r + 1];
-  int64_t b0 = S.site_begin[first_site];
+  int64_t b0 = S.site_begin[first_site + s0];
   // first entry with col > b0
   uint64_t k = lo, hi = e;
   while (k < hi) { uint64_t mid = (k + hi) >> 1; if (A.rs_col[mid] <= b0) k = mid + 1; else hi = mid; }
@@ -384,7 +402,7 @@ __global__ void __launch_bounds__(256) k_live_walk(ArrayDev A, ScanDev S, uint64
     int64_t ef = A.rs_effend[kk];
     if (ef != I64_MIN) { cur = (int32_t)A.rs_cell[kk]; cur_eff = ef; cur_begin = c; cur_del = A.desc[cur].flags & F_DELETION; break; }
   }
-  for (uint32_t s = 0; s < n_sites; ++s) {
+  for (uint32_t s = s0; s < s1; ++s) {
     int64_t b = S.site_begin[first_site + s];
     while (k < e) {
       int64_t c = A.rs_col[k];

@@ -87,6 +87,13 @@ const char* gdbgpu_last_error(const gdbgpu_ctx* ctx);
 void* gdbgpu_ctx_stream(gdbgpu_ctx* ctx);
 /* number of kernel launches issued by this context so far */
 uint64_t gdbgpu_ctx_launch_count(const gdbgpu_ctx* ctx);
+int gdbgpu_ctx_synchronize(gdbgpu_ctx* ctx);
+/* Per-kernel device time, measured with CUDA events on the launching stream (the reference's DO_PROFILING timers,
+ * query_variants.h:67-124, have this role).  Off by default; stats are summed over kernels whose name contains
+ * `kernel_name` (e.g. "k_remap"). */
+void gdbgpu_ctx_set_profiling(gdbgpu_ctx* ctx, int enable);
+void gdbgpu_ctx_reset_kernel_stats(gdbgpu_ctx* ctx);
+int gdbgpu_ctx_kernel_stats(gdbgpu_ctx* ctx, const char* kernel_name, double* total_ms, uint64_t* launches);
 
 /* ---- array: fragment bytes staged to HBM.
  * gdbgpu_array_open replaces VariantStorageManager::open_array + TileDB array/fragment/book-keeping load

@@ -81,8 +81,9 @@ def generate(n_samples, n_sites, spacing, p_var, a_pool, site_lo=0, site_hi=None
     d["params"] = dict(n_samples=n_samples, n_sites=n_sites, spacing=spacing, p_var=p_var, a_pool=a_pool,
                        site_lo=site_lo, site_hi=site_hi, seed=seed, first_col=first_col)
     # column interval a query over exactly this shard uses (what the rank's column partition covers)
-    lo = first_col - 2 if site_lo == 0 else first_col + site_lo * spacing - 1
-    hi = first_col + (n_sites - 1) * spacing + 2 if site_hi == n_sites else first_col + (site_hi - 1) * spacing + 1
+    # shards tile the genome: boundaries sit half a spacing before the first site of the next shard
+    lo = first_col - 2 if site_lo == 0 else first_col + site_lo * spacing - spacing // 2
+    hi = first_col + (n_sites - 1) * spacing + 2 if site_hi == n_sites else first_col + site_hi * spacing - spacing // 2 - 1
     d["col_range"] = (lo, hi)
     return d
 
