@@ -33,6 +33,23 @@ struct CellDesc {
   uint32_t gt_len;   // words
 };
 
+// 32 bytes per cell: everything the union / remap kernels need from a *small* cell in one sector.  A reference block
+// (GT 0/0, PL of 3, no AD) fits entirely, so 90 % of the calls live at a site cost one 32-byte gather.
+constexpr int HOT_WORDS = 5;
+constexpr int HOT_FIELDS = 4;
+struct __align__(16) HotRec {
+  uint8_t flags;              // F_*
+  uint8_t ploidy;
+  uint8_t n_alt;              // saturates at 255 (then `inl` is 0 and kernels read CellDesc)
+  uint8_t nr_idx;
+  uint8_t gt_len;             // words; 0 when GT is invalid
+  uint8_t inl;                // 1: w[] holds GT then the valid fields' words, flen[] their lengths
+  uint8_t flen[HOT_FIELDS];   // input length (words) of field f, 0 = absent / every element NULL
+  uint8_t pad[2];
+  uint32_t w[HOT_WORDS];
+};
+static_assert(sizeof(HotRec) == 32, "HotRec must be one 32-byte sector");
+
 struct VarCol {
   const uint64_t* off;   // n_cells + 1 absolute byte offsets
   const uint8_t* val;
@@ -51,6 +68,7 @@ struct ArrayDev {
   FieldMeta fm[MAX_FIELDS];
   int64_t lb_row, num_rows;
   const CellDesc* desc;
+  const HotRec* hot;
   const int64_t* effend;   // cell order; I64_MIN for END copies / rows outside the array
   // row-major index (per-sample cell lists, column ascending)
   uint64_t n_rs;

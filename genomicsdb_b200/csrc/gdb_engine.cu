@@ -20,6 +20,7 @@
 using namespace gdb;
 
 // ------------------------------------------------------------------------------------------------ plumbing
+struct BatchBuffers;
 struct ProfRec { const char* name; cudaEvent_t a, b; };
 struct gdbgpu_ctx {
   int device = 0;
@@ -31,6 +32,7 @@ struct gdbgpu_ctx {
   std::vector<ProfRec> recs;
   std::vector<cudaEvent_t> pool;
   std::map<std::string, std::pair<double, uint64_t>> stats;
+  std::vector<BatchBuffers*> bb_pool;
   cudaEvent_t get_event() { if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
   void resolve() {
     if (recs.empty()) return;
@@ -136,13 +138,13 @@ struct gdbgpu_array {
   std::vector<FieldMeta> fm; std::vector<std::string> field_names;
   DevBuf<int64_t> coords, end;
   DevVar ref, alt, gt; std::vector<std::unique_ptr<DevVar>> fields;
-  DevBuf<CellDesc> desc; DevBuf<int64_t> effend;
+  DevBuf<CellDesc> desc; DevBuf<HotRec> hot; DevBuf<int64_t> effend;
   DevBuf<uint32_t> rs_cell, rs_keys; DevBuf<int64_t> rs_col, rs_effend; DevBuf<uint64_t> row_start; uint64_t n_rs = 0;
   DevBuf<uint32_t> bad_cell; DevBuf<int64_t> bad_pred_col;
   ArrayDev dev{};
   uint64_t hbm_bytes() const {
     uint64_t b = coords.bytes() + end.bytes() + ref.off.bytes() + ref.val.bytes() + alt.off.bytes() + alt.val.bytes() + gt.off.bytes() + gt.val.bytes() +
-                 desc.bytes() + effend.bytes() + rs_cell.bytes() + rs_keys.bytes() + rs_col.bytes() + rs_effend.bytes() + row_start.bytes();
+                 desc.bytes() + hot.bytes() + effend.bytes() + rs_cell.bytes() + rs_keys.bytes() + rs_col.bytes() + rs_effend.bytes() + row_start.bytes();
     for (auto& f : fields) b += f->off.bytes() + f->val.bytes();
     return b;
   }
@@ -170,7 +172,7 @@ void fill_dev_view(gdbgpu_array* a) {
   D.has_gt = a->has_gt; D.gt_phased = a->gt_phased; D.n_fields = (int)a->fields.size();
   for (size_t f = 0; f < a->fields.size(); ++f) { D.f[f] = VarCol{a->fields[f]->off.p, a->fields[f]->val.p}; D.fm[f] = a->fm[f]; }
   D.lb_row = a->lb_row; D.num_rows = a->num_rows;
-  D.desc = a->desc.p; D.effend = a->effend.p;
+  D.desc = a->desc.p; D.hot = a->hot.p; D.effend = a->effend.p;
   D.n_rs = a->n_rs; D.rs_cell = a->rs_cell.p; D.rs_col = a->rs_col.p; D.rs_effend = a->rs_effend.p; D.row_start = a->row_start.p;
 }
 
@@ -254,14 +256,14 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
     a->n = n = n_out;
   }
   // K2: classify + row-major index
-  a->desc.alloc(std::max<uint64_t>(n, 1)); a->effend.alloc(std::max<uint64_t>(n, 1));
+  a->desc.alloc(std::max<uint64_t>(n, 1)); a->hot.alloc(std::max<uint64_t>(n, 1)); a->effend.alloc(std::max<uint64_t>(n, 1));
   a->rs_cell.alloc(std::max<uint64_t>(n, 1)); a->rs_keys.alloc(std::max<uint64_t>(n, 1)); a->rs_col.alloc(std::max<uint64_t>(n, 1)); a->rs_effend.alloc(std::max<uint64_t>(n, 1));
   a->row_start.alloc((uint64_t)num_rows + 2);
   a->bad_cell.alloc(BAD_CAP); a->bad_pred_col.alloc(BAD_CAP);
   fill_dev_view(a.get());
   if (n) {
     unsigned g = blocks_for(n, 256);
-    LAUNCH(ctx, k_classify, g, 256, a->dev, a->desc.p);
+    LAUNCH(ctx, k_classify, g, 256, a->dev, a->desc.p, a->hot.p);
     DevBuf<uint32_t> keys, vals; DevBuf<uint8_t> tmp;
     keys.alloc(n); vals.alloc(n);
     LAUNCH(ctx, k_row_keys, g, 256, a->dev, a->desc.p, keys.p, vals.p);
@@ -297,15 +299,9 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
 
 }  // namespace
 
-// ------------------------------------------------------------------------------------------------ scan
-struct gdbgpu_scan {
-  gdbgpu_array* arr = nullptr; gdbgpu_ctx* ctx = nullptr;
-  gdbgpu_scan_params params{}; bool device_output = false;
-  ScanDev S{};
-  uint64_t cursor = 0;
-  std::vector<int64_t> h_rows;
-  DevBuf<int32_t> qrow_of_row, init_cell, dlive, ddel, live_excl, del_excl; DevBuf<int64_t> row_of_qrow, init_effend, bp, site_begin, site_end;
-  DevBuf<unsigned long long> bitmap; DevBuf<uint32_t> word_rank, bp_cell0, err, del_cells, del_words; DevBuf<uint64_t> site_start; DevBuf<DelRec> del_recs;
+// Per-batch device / pinned-host buffers.  They are large (GBs) and expensive to create (cudaMalloc, cudaMallocHost), so a
+// context keeps finished scans' buffers and hands them to the next scan.
+struct BatchBuffers {
   // per batch (device)
   DevBuf<int32_t> live; DevBuf<SiteRec> sites; DevBuf<uint32_t> cursors, allele_pos, lut_first; DevBuf<uint16_t> lut_len; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes; DevBuf<int16_t> lut_in2m;
   DevBuf<uint32_t> out_data[MAX_FIELDS + 1], out_stride[MAX_FIELDS + 1]; DevBuf<uint64_t> out_base[MAX_FIELDS + 1]; DevBuf<uint16_t> out_len[MAX_FIELDS + 1];
@@ -316,6 +312,19 @@ struct gdbgpu_scan {
   std::vector<uint64_t> h_base[MAX_FIELDS + 1]; std::vector<uint32_t> h_stride[MAX_FIELDS + 1];
   PinBuf<int64_t> p_site_begin, p_site_end; PinBuf<int32_t> p_live; PinBuf<uint32_t> p_allele_pos, p_lut_first, p_out_data[MAX_FIELDS + 1]; PinBuf<uint8_t> p_allele_bytes;
   PinBuf<uint16_t> p_out_len[MAX_FIELDS + 1], p_lut_len; PinBuf<int16_t> p_lut_in2m;
+  DevBuf<uint32_t> fast_sites, slow_sites;
+};
+
+// ------------------------------------------------------------------------------------------------ scan
+struct gdbgpu_scan {
+  gdbgpu_array* arr = nullptr; gdbgpu_ctx* ctx = nullptr;
+  gdbgpu_scan_params params{}; bool device_output = false;
+  ScanDev S{};
+  uint64_t cursor = 0;
+  std::vector<int64_t> h_rows;
+  DevBuf<int32_t> qrow_of_row, init_cell, dlive, ddel, live_excl, del_excl; DevBuf<int64_t> row_of_qrow, init_effend, bp, site_begin, site_end;
+  DevBuf<unsigned long long> bitmap; DevBuf<uint32_t> word_rank, bp_cell0, err, del_cells, del_words; DevBuf<uint64_t> site_start; DevBuf<DelRec> del_recs;
+  std::unique_ptr<BatchBuffers> bb;   // borrowed from the context's pool for the lifetime of the scan
   uint32_t cap_allele_recs = 0, cap_allele_bytes = 0, cap_lut = 0;
   uint64_t avg_site_bytes = 0;
   int n_out = 0;
@@ -466,6 +475,7 @@ uint32_t stride_of(const gdbgpu_array* a, const SiteRec& r, int o) {
 
 int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_batch* out) {
   gdbgpu_array* a = s->arr; gdbgpu_ctx* ctx = s->ctx; ScanDev& S = s->S;
+  BatchBuffers& bb = *s->bb;
   memset(out, 0, sizeof(*out));
   out->first_site = s->cursor; out->n_query_rows = S.nq; out->n_fields = s->n_out;
   if (s->cursor >= S.n_sites) return GDBGPU_OK;
@@ -477,93 +487,122 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
   uint32_t nb = (uint32_t)std::min<uint64_t>({remaining, max_sites ? max_sites : 0xFFFFFFFFull, by_live, guess + guess / 2 + 1, 1u << 20});
   const int n_out = s->n_out;
   for (;;) {
-    s->live.ensure((uint64_t)nb * S.nq); s->sites.ensure(nb); s->cursors.ensure(4);
+    bb.live.ensure((uint64_t)nb * S.nq); bb.sites.ensure(nb); bb.cursors.ensure(4);
     if (!s->cap_allele_recs) { s->cap_allele_recs = 1u << 16; s->cap_allele_bytes = 1u << 20; }
-    s->allele_pos.ensure(2ull * s->cap_allele_recs); s->allele_hash.ensure(s->cap_allele_recs); s->allele_bytes.ensure(s->cap_allele_bytes);
-    CK(cudaMemsetAsync(s->cursors.p, 0, 16, ctx->stream));
+    bb.allele_pos.ensure(2ull * s->cap_allele_recs); bb.allele_hash.ensure(s->cap_allele_recs); bb.allele_bytes.ensure(s->cap_allele_bytes);
+    CK(cudaMemsetAsync(bb.cursors.p, 0, 16, ctx->stream));
     BatchDev B{};
-    B.first_site = s->cursor; B.n_sites = nb; B.live = s->live.p; B.sites = s->sites.p; B.cursors = s->cursors.p;
-    B.allele_pos = s->allele_pos.p; B.allele_hash = s->allele_hash.p; B.cap_allele_recs = s->cap_allele_recs; B.allele_bytes = s->allele_bytes.p; B.cap_allele_bytes = s->cap_allele_bytes;
-    LAUNCH(ctx, k_live_walk, dim3(blocks_for(S.nq, 256), (nb + WALK_CHUNK - 1) / WALK_CHUNK), 256, a->dev, S, s->cursor, nb, s->live.p);
+    B.first_site = s->cursor; B.n_sites = nb; B.live = bb.live.p; B.sites = bb.sites.p; B.cursors = bb.cursors.p;
+    B.allele_pos = bb.allele_pos.p; B.allele_hash = bb.allele_hash.p; B.cap_allele_recs = s->cap_allele_recs; B.allele_bytes = bb.allele_bytes.p; B.cap_allele_bytes = s->cap_allele_bytes;
+    LAUNCH(ctx, k_live_walk, dim3(blocks_for(S.nq, 256), (nb + WALK_CHUNK - 1) / WALK_CHUNK), 256, a->dev, S, s->cursor, nb, bb.live.p);
     LAUNCH(ctx, k_union, nb, UNION_THREADS, a->dev, S, B);
-    s->h_sites.resize(nb);
-    CK(cudaMemcpyAsync(s->h_sites.data(), s->sites.p, (size_t)nb * sizeof(SiteRec), cudaMemcpyDeviceToHost, ctx->stream));
+    bb.h_sites.resize(nb);
+    CK(cudaMemcpyAsync(bb.h_sites.data(), bb.sites.p, (size_t)nb * sizeof(SiteRec), cudaMemcpyDeviceToHost, ctx->stream));
     bool ovf = false;
     check_scan_errors(s, ovf);
     if (ovf) { s->cap_allele_recs *= 4; s->cap_allele_bytes *= 4; continue; }
     // strides / bases; keep the prefix of sites that fits
-    for (int o = 0; o < n_out; ++o) { s->h_base[o].assign(nb + 1, 0); s->h_stride[o].assign(nb, 0); }
+    for (int o = 0; o < n_out; ++o) { bb.h_base[o].assign(nb + 1, 0); bb.h_stride[o].assign(nb, 0); }
     uint64_t bytes = 0; uint32_t keep = 0; uint64_t lut_words = 0;
     for (uint32_t i = 0; i < nb; ++i) {
       uint64_t site_bytes = 0;
-      for (int o = 0; o < n_out; ++o) { uint32_t st = stride_of(a, s->h_sites[i], o); s->h_stride[o][i] = st; site_bytes += (uint64_t)st * S.nq * 4 + S.nq * 2; }
+      for (int o = 0; o < n_out; ++o) { uint32_t st = stride_of(a, bb.h_sites[i], o); bb.h_stride[o][i] = st; site_bytes += (uint64_t)st * S.nq * 4 + S.nq * 2; }
       if (i > 0 && bytes + site_bytes > max_bytes) break;
-      for (int o = 0; o < n_out; ++o) s->h_base[o][i + 1] = s->h_base[o][i] + (uint64_t)s->h_stride[o][i] * S.nq;
-      bytes += site_bytes; lut_words += (uint64_t)s->h_sites[i].max_ain * S.nq; keep = i + 1;
+      for (int o = 0; o < n_out; ++o) bb.h_base[o][i + 1] = bb.h_base[o][i] + (uint64_t)bb.h_stride[o][i] * S.nq;
+      bytes += site_bytes; lut_words += (uint64_t)bb.h_sites[i].max_ain * S.nq; keep = i + 1;
     }
     s->avg_site_bytes = std::max<uint64_t>(1, bytes / keep);
     RemapOut O{};
     O.n_out = n_out;
     for (int o = 0; o < n_out; ++o) {
-      s->out_data[o].ensure(std::max<uint64_t>(s->h_base[o][keep], 1)); s->out_base[o].ensure(keep + 1); s->out_stride[o].ensure(keep); s->out_len[o].ensure((uint64_t)keep * S.nq);
-      CK(cudaMemcpyAsync(s->out_base[o].p, s->h_base[o].data(), (size_t)(keep + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(s->out_stride[o].p, s->h_stride[o].data(), (size_t)keep * 4, cudaMemcpyHostToDevice, ctx->stream));
-      O.f[o] = FieldOutDev{s->out_data[o].p, s->out_base[o].p, s->out_stride[o].p, s->out_len[o].p};
+      bb.out_data[o].ensure(std::max<uint64_t>(bb.h_base[o][keep], 1)); bb.out_base[o].ensure(keep + 1); bb.out_stride[o].ensure(keep); bb.out_len[o].ensure((uint64_t)keep * S.nq);
+      CK(cudaMemcpyAsync(bb.out_base[o].p, bb.h_base[o].data(), (size_t)(keep + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(bb.out_stride[o].p, bb.h_stride[o].data(), (size_t)keep * 4, cudaMemcpyHostToDevice, ctx->stream));
+      O.f[o] = FieldOutDev{bb.out_data[o].p, bb.out_base[o].p, bb.out_stride[o].p, bb.out_len[o].p};
     }
     if (S.want_lut) {
       if (lut_words >= (1ull << 32)) throw LimitError("LUT output of one batch above 2^32 entries: lower max_sites");
       s->cap_lut = (uint32_t)std::max<uint64_t>(lut_words, 1);
-      s->lut_first.ensure((uint64_t)keep * S.nq); s->lut_len.ensure((uint64_t)keep * S.nq); s->lut_in2m.ensure(s->cap_lut);
-      O.lut_first = s->lut_first.p; O.lut_len = s->lut_len.p; O.lut_in2m = s->lut_in2m.p; O.cap_lut = s->cap_lut;
+      bb.lut_first.ensure((uint64_t)keep * S.nq); bb.lut_len.ensure((uint64_t)keep * S.nq); bb.lut_in2m.ensure(s->cap_lut);
+      O.lut_first = bb.lut_first.p; O.lut_len = bb.lut_len.p; O.lut_in2m = bb.lut_in2m.p; O.cap_lut = s->cap_lut;
     }
     B.n_sites = keep;
-    uint32_t tiles = (uint32_t)((S.nq + REMAP_ROWS - 1) / REMAP_ROWS);
-    LAUNCH(ctx, k_remap, keep * tiles, REMAP_THREADS, a->dev, S, B, O);
+    // split the batch: the tile kernel takes every ordinary site, the generic kernel the pathological ones
+    std::vector<uint32_t> fast, slow;
+    TileShape shape{4, 3, 1};
+    for (uint32_t i = 0; i < keep; ++i) {
+      const SiteRec& r = bb.h_sites[i];
+      uint32_t inw = 0;
+      for (size_t f = 0; f < a->fields.size(); ++f) inw += std::max<uint32_t>(3u, r.max_in_len[f]);
+      bool ok = r.n_alleles <= (uint32_t)TILE_MAX_A && r.max_ain <= (uint32_t)TILE_MAX_A && r.max_gt_len <= (uint32_t)TILE_MAX_GT && r.max_ploidy_all <= 2u && inw <= (uint32_t)TILE_MAX_INW;
+      if (ok) {
+        fast.push_back(i);
+        shape.lw = std::max(shape.lw, (r.n_alleles + 3u) / 4u * 4u);
+        shape.inw = std::max(shape.inw, inw | 1u);   // odd stride: no shared-memory bank conflicts between rows
+        shape.g = std::max(shape.g, r.n_alleles * (r.n_alleles + 1u) / 2u);
+      } else slow.push_back(i);
+    }
+    if (!fast.empty()) {
+      bb.fast_sites.ensure(fast.size());
+      CK(cudaMemcpyAsync(bb.fast_sites.p, fast.data(), fast.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      size_t smem = tile_smem_bytes(shape, (int)a->fields.size());
+      static size_t smem_set = 0;
+      if (smem > smem_set) { CK(cudaFuncSetAttribute(k_remap_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 100 * 1024))); smem_set = std::max<size_t>(smem, 100 * 1024); }
+      uint32_t tiles = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
+      { ProfScope ps__(ctx, "k_remap_tile"); k_remap_tile<<<(unsigned)(fast.size() * tiles), TILE_ROWS, smem, ctx->stream>>>(a->dev, S, B, O, bb.fast_sites.p, shape); }
+      ++ctx->launches; CK(cudaGetLastError());
+    }
+    if (!slow.empty()) {
+      bb.slow_sites.ensure(slow.size());
+      CK(cudaMemcpyAsync(bb.slow_sites.p, slow.data(), slow.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      uint32_t tiles = (uint32_t)((S.nq + REMAP_ROWS - 1) / REMAP_ROWS);
+      LAUNCH(ctx, k_remap_generic, (unsigned)(slow.size() * tiles), REMAP_THREADS, a->dev, S, B, O, bb.slow_sites.p);
+    }
     check_scan_errors(s, ovf);
     if (ovf) throw CudaError("internal: LUT pool overflow");
     // ---- publish
-    s->h_site_flags.resize(keep); s->h_n_alleles.resize(keep); s->h_n_live.resize(keep); s->h_allele_first.resize(keep);
-    for (uint32_t i = 0; i < keep; ++i) { const SiteRec& r = s->h_sites[i]; s->h_site_flags[i] = (uint8_t)r.flags; s->h_n_alleles[i] = r.n_alleles; s->h_n_live[i] = r.n_live; s->h_allele_first[i] = r.allele_first; }
+    bb.h_site_flags.resize(keep); bb.h_n_alleles.resize(keep); bb.h_n_live.resize(keep); bb.h_allele_first.resize(keep);
+    for (uint32_t i = 0; i < keep; ++i) { const SiteRec& r = bb.h_sites[i]; bb.h_site_flags[i] = (uint8_t)r.flags; bb.h_n_alleles[i] = r.n_alleles; bb.h_n_live[i] = r.n_live; bb.h_allele_first[i] = r.allele_first; }
     uint32_t hc[4];
-    CK(cudaMemcpyAsync(hc, s->cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(hc, bb.cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
     out->n_sites = keep; out->out_bytes = bytes;
     if (s->device_output) {
-      s->d_site_flags.ensure(keep); s->d_n_alleles.ensure(keep); s->d_n_live.ensure(keep); s->d_allele_first.ensure(keep);
-      CK(cudaMemcpyAsync(s->d_site_flags.p, s->h_site_flags.data(), keep, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(s->d_n_alleles.p, s->h_n_alleles.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(s->d_n_live.p, s->h_n_live.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(s->d_allele_first.p, s->h_allele_first.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
+      bb.d_site_flags.ensure(keep); bb.d_n_alleles.ensure(keep); bb.d_n_live.ensure(keep); bb.d_allele_first.ensure(keep);
+      CK(cudaMemcpyAsync(bb.d_site_flags.p, bb.h_site_flags.data(), keep, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(bb.d_n_alleles.p, bb.h_n_alleles.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(bb.d_n_live.p, bb.h_n_live.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(bb.d_allele_first.p, bb.h_allele_first.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
       out->site_begin = s->site_begin.p + s->cursor; out->site_end = s->site_end.p + s->cursor;
-      out->site_flags = s->d_site_flags.p; out->n_alleles = s->d_n_alleles.p; out->n_live = s->d_n_live.p; out->allele_first = s->d_allele_first.p;
-      out->allele_pos = s->allele_pos.p; out->allele_bytes = s->allele_bytes.p; out->live = s->live.p;
-      for (int o = 0; o < n_out; ++o) out->fields[o] = gdbgpu_field_out{s->out_data[o].p, s->out_base[o].p, s->out_stride[o].p, s->out_len[o].p};
-      if (S.want_lut) { out->lut_first = s->lut_first.p; out->lut_len = s->lut_len.p; out->lut_in2m = s->lut_in2m.p; }
+      out->site_flags = bb.d_site_flags.p; out->n_alleles = bb.d_n_alleles.p; out->n_live = bb.d_n_live.p; out->allele_first = bb.d_allele_first.p;
+      out->allele_pos = bb.allele_pos.p; out->allele_bytes = bb.allele_bytes.p; out->live = bb.live.p;
+      for (int o = 0; o < n_out; ++o) out->fields[o] = gdbgpu_field_out{bb.out_data[o].p, bb.out_base[o].p, bb.out_stride[o].p, bb.out_len[o].p};
+      if (S.want_lut) { out->lut_first = bb.lut_first.p; out->lut_len = bb.lut_len.p; out->lut_in2m = bb.lut_in2m.p; }
       CK(cudaStreamSynchronize(ctx->stream));
     } else {
-      s->p_site_begin.ensure(keep); s->p_site_end.ensure(keep); s->p_live.ensure((uint64_t)keep * S.nq);
-      s->p_allele_pos.ensure(2ull * std::max<uint32_t>(hc[0], 1)); s->p_allele_bytes.ensure(std::max<uint32_t>(hc[1], 1));
-      CK(cudaMemcpyAsync(s->p_site_begin.p, s->site_begin.p + s->cursor, (size_t)keep * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaMemcpyAsync(s->p_site_end.p, s->site_end.p + s->cursor, (size_t)keep * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaMemcpyAsync(s->p_live.p, s->live.p, (size_t)keep * S.nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaMemcpyAsync(s->p_allele_pos.p, s->allele_pos.p, (size_t)hc[0] * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaMemcpyAsync(s->p_allele_bytes.p, s->allele_bytes.p, hc[1], cudaMemcpyDeviceToHost, ctx->stream));
+      bb.p_site_begin.ensure(keep); bb.p_site_end.ensure(keep); bb.p_live.ensure((uint64_t)keep * S.nq);
+      bb.p_allele_pos.ensure(2ull * std::max<uint32_t>(hc[0], 1)); bb.p_allele_bytes.ensure(std::max<uint32_t>(hc[1], 1));
+      CK(cudaMemcpyAsync(bb.p_site_begin.p, s->site_begin.p + s->cursor, (size_t)keep * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(bb.p_site_end.p, s->site_end.p + s->cursor, (size_t)keep * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(bb.p_live.p, bb.live.p, (size_t)keep * S.nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(bb.p_allele_pos.p, bb.allele_pos.p, (size_t)hc[0] * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(bb.p_allele_bytes.p, bb.allele_bytes.p, hc[1], cudaMemcpyDeviceToHost, ctx->stream));
       for (int o = 0; o < n_out; ++o) {
-        s->p_out_data[o].ensure(std::max<uint64_t>(s->h_base[o][keep], 1)); s->p_out_len[o].ensure((uint64_t)keep * S.nq);
-        if (s->h_base[o][keep]) CK(cudaMemcpyAsync(s->p_out_data[o].p, s->out_data[o].p, s->h_base[o][keep] * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(s->p_out_len[o].p, s->out_len[o].p, (size_t)keep * S.nq * 2, cudaMemcpyDeviceToHost, ctx->stream));
-        out->fields[o] = gdbgpu_field_out{s->p_out_data[o].p, s->h_base[o].data(), s->h_stride[o].data(), s->p_out_len[o].p};
+        bb.p_out_data[o].ensure(std::max<uint64_t>(bb.h_base[o][keep], 1)); bb.p_out_len[o].ensure((uint64_t)keep * S.nq);
+        if (bb.h_base[o][keep]) CK(cudaMemcpyAsync(bb.p_out_data[o].p, bb.out_data[o].p, bb.h_base[o][keep] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(bb.p_out_len[o].p, bb.out_len[o].p, (size_t)keep * S.nq * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        out->fields[o] = gdbgpu_field_out{bb.p_out_data[o].p, bb.h_base[o].data(), bb.h_stride[o].data(), bb.p_out_len[o].p};
       }
       if (S.want_lut) {
-        s->p_lut_first.ensure((uint64_t)keep * S.nq); s->p_lut_len.ensure((uint64_t)keep * S.nq); s->p_lut_in2m.ensure(std::max<uint32_t>(hc[2], 1));
-        CK(cudaMemcpyAsync(s->p_lut_first.p, s->lut_first.p, (size_t)keep * S.nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(s->p_lut_len.p, s->lut_len.p, (size_t)keep * S.nq * 2, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(s->p_lut_in2m.p, s->lut_in2m.p, (size_t)hc[2] * 2, cudaMemcpyDeviceToHost, ctx->stream));
-        out->lut_first = s->p_lut_first.p; out->lut_len = s->p_lut_len.p; out->lut_in2m = s->p_lut_in2m.p;
+        bb.p_lut_first.ensure((uint64_t)keep * S.nq); bb.p_lut_len.ensure((uint64_t)keep * S.nq); bb.p_lut_in2m.ensure(std::max<uint32_t>(hc[2], 1));
+        CK(cudaMemcpyAsync(bb.p_lut_first.p, bb.lut_first.p, (size_t)keep * S.nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(bb.p_lut_len.p, bb.lut_len.p, (size_t)keep * S.nq * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(bb.p_lut_in2m.p, bb.lut_in2m.p, (size_t)hc[2] * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        out->lut_first = bb.p_lut_first.p; out->lut_len = bb.p_lut_len.p; out->lut_in2m = bb.p_lut_in2m.p;
       }
       CK(cudaStreamSynchronize(ctx->stream));
-      out->site_begin = s->p_site_begin.p; out->site_end = s->p_site_end.p;
-      out->site_flags = s->h_site_flags.data(); out->n_alleles = s->h_n_alleles.data(); out->n_live = s->h_n_live.data(); out->allele_first = s->h_allele_first.data();
-      out->allele_pos = s->p_allele_pos.p; out->allele_bytes = s->p_allele_bytes.p; out->live = s->p_live.p;
+      out->site_begin = bb.p_site_begin.p; out->site_end = bb.p_site_end.p;
+      out->site_flags = bb.h_site_flags.data(); out->n_alleles = bb.h_n_alleles.data(); out->n_live = bb.h_n_live.data(); out->allele_first = bb.h_allele_first.data();
+      out->allele_pos = bb.p_allele_pos.p; out->allele_bytes = bb.p_allele_bytes.p; out->live = bb.p_live.p;
     }
     s->cursor += keep;
     return GDBGPU_OK;
@@ -604,6 +643,7 @@ void gdbgpu_ctx_destroy(gdbgpu_ctx* ctx) {
   if (!ctx) return;
   ctx->resolve();
   for (auto e : ctx->pool) cudaEventDestroy(e);
+  for (auto* b : ctx->bb_pool) delete b;
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -728,6 +768,7 @@ int gdbgpu_scan_begin(gdbgpu_array* arr, const gdbgpu_scan_params* params, gdbgp
   *out = nullptr;
   std::unique_ptr<gdbgpu_scan> s(new gdbgpu_scan());
   s->arr = arr; s->ctx = arr->ctx; s->params = *params;
+  if (!arr->ctx->bb_pool.empty()) { s->bb.reset(arr->ctx->bb_pool.back()); arr->ctx->bb_pool.pop_back(); } else s->bb.reset(new BatchBuffers());
   int rc = guarded(arr->ctx, [&] { CK(cudaSetDevice(arr->ctx->device)); scan_prepare(s.get()); });
   if (rc == GDBGPU_OK) *out = s.release();
   return rc;
@@ -746,6 +787,12 @@ int gdbgpu_scan_seek(gdbgpu_scan* s, uint64_t site_idx) {
   s->cursor = site_idx;
   return GDBGPU_OK;
 }
-void gdbgpu_scan_end(gdbgpu_scan* s) { if (s) { cudaSetDevice(s->ctx->device); delete s; } }
+void gdbgpu_scan_end(gdbgpu_scan* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  if (s->bb) s->ctx->bb_pool.push_back(s->bb.release());
+  delete s;
+}
 
 }  // extern "C"

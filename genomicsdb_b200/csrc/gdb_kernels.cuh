@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(TO* __restrict__ out,
 // ------------------------------------------------------------------------------------------------ K2 classify
 // One thread per cell: what gt_fill_row derives from a cell (query_variants.cc:1014-1117) plus END-copy detection
 // (query_variants.cc:422-428), computed once per staged array.
-__global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restrict__ desc) {
+__global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restrict__ desc, HotRec* __restrict__ hot) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
   int64_t row = A.coords[2 * i], col = A.coords[2 * i + 1], END = A.end[i];
@@ -107,6 +107,36 @@ __global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restri
     if (!all_null) { d.flags |= F_GTVALID; d.gt_len = n; uint32_t p = ploidy_of(A.gt_phased, n); d.ploidy = (uint8_t)(p > 255 ? 255 : p); }
   }
   desc[i] = d;
+  // hot record
+  HotRec h;
+  h.flags = d.flags; h.ploidy = d.ploidy; h.n_alt = (uint8_t)(n_alt > 255 ? 255 : n_alt); h.nr_idx = (uint8_t)(nr > 255 ? 255 : nr);
+  h.gt_len = (uint8_t)(d.gt_len > 255 ? 255 : d.gt_len); h.inl = 0; h.pad[0] = h.pad[1] = 0;
+  for (int f = 0; f < HOT_FIELDS; ++f) h.flen[f] = 0;
+  for (int k = 0; k < HOT_WORDS; ++k) h.w[k] = 0;
+  bool fits = (n_alt < 255) && (d.gt_len <= 255) && (A.n_fields <= HOT_FIELDS);
+  uint32_t used = d.gt_len;
+  uint32_t flen[HOT_FIELDS] = {0, 0, 0, 0};
+  if (fits) for (int f = 0; f < A.n_fields; ++f) {
+    uint64_t o0 = A.f[f].off[i], o1 = A.f[f].off[i + 1];
+    uint32_t n = (uint32_t)((o1 - o0) >> 2);
+    const uint32_t* v = reinterpret_cast<const uint32_t*>(A.f[f].val + o0);
+    uint32_t nullw = A.fm[f].elem ? TDB_NULL_FLT : TDB_NULL_INT;
+    bool all_null = true;
+    for (uint32_t k = 0; k < n; ++k) if (v[k] != nullw) { all_null = false; break; }
+    if (all_null) n = 0;     // invalid field (variant_field_data.h:365-384)
+    flen[f] = n; used += n;
+  }
+  if (fits && used <= HOT_WORDS) {
+    h.inl = 1;
+    uint32_t k = 0;
+    if (d.gt_len) { const uint32_t* g = reinterpret_cast<const uint32_t*>(A.gt.val + A.gt.off[i]); for (uint32_t x = 0; x < d.gt_len; ++x) h.w[k++] = g[x]; }
+    for (int f = 0; f < A.n_fields; ++f) {
+      h.flen[f] = (uint8_t)flen[f];
+      const uint32_t* v = reinterpret_cast<const uint32_t*>(A.f[f].val + A.f[f].off[i]);
+      for (uint32_t x = 0; x < flen[f]; ++x) h.w[k++] = v[x];
+    }
+  }
+  hot[i] = h;
 }
 
 __global__ void __launch_bounds__(256) k_row_keys(ArrayDev A, const CellDesc* __restrict__ desc, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {

@@ -255,6 +255,7 @@ struct SiteRec {
   uint32_t allele_first;   // index into allele_pos pairs / allele_hash
   uint32_t ref_off, ref_len;            // merged REF bytes in the allele pool
   uint32_t max_gt_len, max_ain;         // max GT words / max (n_alt+1) over live calls
+  uint32_t max_ploidy_all;              // max ploidy over live calls
   uint32_t max_ploidy[MAX_FIELDS];      // over calls whose field is present
   uint32_t max_in_len[MAX_FIELDS];
 };
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(ArrayDev A, ScanDev S, 
   __shared__ uint16_t s_list[UNION_MAX_DISTINCT];
   __shared__ uint16_t s_rank[UNION_MAX_DISTINCT];
   __shared__ uint32_t s_piece_cell[REF_MAX_PIECES], s_piece_from[REF_MAX_PIECES], s_piece_to[REF_MAX_PIECES];
-  __shared__ unsigned int s_k, s_next, s_maxN, s_ndist, s_nonref, s_nlive, s_maxgt, s_maxain, s_npieces, s_reflen, s_refoff, s_afirst, s_overflow;
+  __shared__ unsigned int s_k, s_next, s_maxN, s_ndist, s_nonref, s_nlive, s_maxgt, s_maxain, s_maxploidy, s_npieces, s_reflen, s_refoff, s_afirst, s_overflow;
   __shared__ unsigned int s_maxpl[MAX_FIELDS], s_maxin[MAX_FIELDS];
 
   const uint32_t js = blockIdx.x;
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(ArrayDev A, ScanDev S, 
   const int tid = threadIdx.x;
 
   for (int i = tid; i < UNION_SLOTS; i += UNION_THREADS) { s_hash[i] = 0ull; s_order[i] = ~0ull; }
-  if (tid == 0) { s_k = 0xFFFFFFFFu; s_next = 0xFFFFFFFFu; s_maxN = 0; s_ndist = 0; s_nonref = 0; s_nlive = 0; s_maxgt = 0; s_maxain = 0; s_npieces = 0; s_overflow = 0; }
+  if (tid == 0) { s_k = 0xFFFFFFFFu; s_next = 0xFFFFFFFFu; s_maxN = 0; s_ndist = 0; s_nonref = 0; s_nlive = 0; s_maxgt = 0; s_maxain = 0; s_maxploidy = 0; s_npieces = 0; s_overflow = 0; }
   if (tid < MAX_FIELDS) { s_maxpl[tid] = 0; s_maxin[tid] = 0; }
   __syncthreads();
 
@@ -372,40 +373,66 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(ArrayDev A, ScanDev S, 
   __syncthreads();   // mref is read below by other threads of this block (global memory, same block: needs the barrier only)
 
   // ---- merged ALT list (variant_operations.cc:134-228): first-seen order over live calls in row order
-  uint32_t my_live = 0;
+  uint32_t my_live = 0, loc_maxgt = 0, loc_maxain = 0, loc_maxploidy = 0;
+  uint32_t loc_maxpl[MAX_FIELDS], loc_maxin[MAX_FIELDS];
+#pragma unroll
+  for (int f = 0; f < MAX_FIELDS; ++f) { loc_maxpl[f] = 0; loc_maxin[f] = 0; }
+  bool loc_nonref = false;
+  auto insert = [&](uint64_t h, uint64_t q, uint32_t idx) {
+    unsigned long long order = ((unsigned long long)q << 12) | idx;
+    uint32_t slot = (uint32_t)(h % UNION_SLOTS);
+    for (int probe = 0; probe < UNION_SLOTS; ++probe) {
+      unsigned long long old = atomicCAS(&s_hash[slot], 0ull, (unsigned long long)h);
+      if (old == 0ull) { if (atomicAdd(&s_ndist, 1u) >= UNION_MAX_DISTINCT) atomicMax(&S.err[1], 2u); }
+      if (old == 0ull || old == h) { atomicMin(&s_order[slot], order); return; }
+      slot = (slot + 1) % UNION_SLOTS;
+    }
+    atomicMax(&S.err[1], 2u);
+  };
   if (!s_overflow) for (uint64_t q = tid; q < S.nq; q += UNION_THREADS) {
     int32_t e = live[q];
     if (e < 0) continue;
     ++my_live;
-    CallView v = make_view(A, S, e);
-    atomicMax(&s_maxgt, v.gt_len);
-    atomicMax(&s_maxain, (unsigned int)v.n_alt + 1u);
-    for (int f = 0; f < A.n_fields; ++f) {
-      const uint32_t* p; uint32_t n;
-      if (field_of(A, S, v, f, p, n)) { atomicMax(&s_maxpl[f], v.ploidy); atomicMax(&s_maxin[f], n); }
-    }
-    if (v.nr_idx) s_nonref = 1;
-    if (v.n_alt > MAX_CALL_ALLELES - 1) { atomicMax(&S.err[1], 1u); continue; }
-    auto insert = [&](uint64_t h, uint32_t idx) {
-      unsigned long long order = ((unsigned long long)q << 12) | idx;
-      uint32_t slot = (uint32_t)(h % UNION_SLOTS);
-      for (int probe = 0; probe < UNION_SLOTS; ++probe) {
-        unsigned long long old = atomicCAS(&s_hash[slot], 0ull, (unsigned long long)h);
-        if (old == 0ull) { if (atomicAdd(&s_ndist, 1u) >= UNION_MAX_DISTINCT) atomicMax(&S.err[1], 2u); }
-        if (old == 0ull || old == h) { atomicMin(&s_order[slot], order); return; }
-        slot = (slot + 1) % UNION_SLOTS;
+    if (!(e & LIVE_REDUCED)) {
+      // fast path: a trivial call (reference block, or ALT == <NON_REF> only) adds no allele; its lengths come from
+      // the 32-byte hot record
+      const uint4 h0 = *reinterpret_cast<const uint4*>(&A.hot[e]);
+      const uint32_t b0 = h0.x, b1 = h0.y, b2 = h0.z;
+      const uint32_t hflags = b0 & 0xFF, hploidy = (b0 >> 8) & 0xFF, hnalt = (b0 >> 16) & 0xFF, hnr = b0 >> 24;
+      const uint32_t hgt = b1 & 0xFF, hinl = (b1 >> 8) & 0xFF;
+      if ((hflags & F_TRIVIAL) && hinl) {
+        loc_maxgt = max(loc_maxgt, hgt); loc_maxain = max(loc_maxain, hnalt + 1u); loc_maxploidy = max(loc_maxploidy, hploidy);
+        if (hnr) loc_nonref = true;
+        const uint32_t fl4 = (b1 >> 16) | (b2 << 16);   // flen[0..3]
+#pragma unroll
+        for (int f = 0; f < HOT_FIELDS; ++f) { uint32_t n = (fl4 >> (8 * f)) & 0xFF; if (f < A.n_fields && n) { loc_maxpl[f] = max(loc_maxpl[f], hploidy); loc_maxin[f] = max(loc_maxin[f], n); } }
+        continue;
       }
-      atomicMax(&S.err[1], 2u);
-    };
-    if (v.reduced) { int sfx; insert(allele_hash(c_str_star, 1, mref, mref_len, 1, sfx), 1); continue; }
+    }
+    CallView v = make_view(A, S, e);
+    loc_maxgt = max(loc_maxgt, v.gt_len); loc_maxain = max(loc_maxain, (uint32_t)v.n_alt + 1u); loc_maxploidy = max(loc_maxploidy, v.ploidy);
+#pragma unroll
+    for (int f = 0; f < MAX_FIELDS; ++f) if (f < A.n_fields) {
+      const uint32_t* p; uint32_t n;
+      if (field_of(A, S, v, f, p, n)) { loc_maxpl[f] = max(loc_maxpl[f], v.ploidy); loc_maxin[f] = max(loc_maxin[f], n); }
+    }
+    if (v.nr_idx) loc_nonref = true;
+    if (v.n_alt > MAX_CALL_ALLELES - 1) { atomicMax(&S.err[1], 1u); continue; }
+    if (v.reduced) { int sfx; insert(allele_hash(c_str_star, 1, mref, mref_len, 1, sfx), q, 1); continue; }
     if (v.flags & F_TRIVIAL) continue;
     int pos = 0, ts, tl; uint32_t idx = 0;
     while (next_token(v.alt, v.alt_n, pos, ts, tl)) {
       ++idx;
       if (is_non_ref(v.alt + ts, tl)) continue;
       int sfx;
-      insert(allele_hash(v.alt + ts, tl, mref, mref_len, v.ref_len, sfx), idx);
+      insert(allele_hash(v.alt + ts, tl, mref, mref_len, v.ref_len, sfx), q, idx);
     }
+  }
+  if (my_live) {
+    atomicMax(&s_maxgt, loc_maxgt); atomicMax(&s_maxain, loc_maxain); atomicMax(&s_maxploidy, loc_maxploidy);
+    if (loc_nonref) s_nonref = 1;
+#pragma unroll
+    for (int f = 0; f < MAX_FIELDS; ++f) if (f < A.n_fields) { if (loc_maxin[f]) { atomicMax(&s_maxpl[f], loc_maxpl[f]); atomicMax(&s_maxin[f], loc_maxin[f]); } }
   }
   if (my_live) atomicAdd(&s_nlive, my_live);
   __syncthreads();
@@ -467,7 +494,7 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(ArrayDev A, ScanDev S, 
     bool ref_block_only = (mref_len == 1 && ndist == 0 && s_nonref);
     r.flags = (s_nonref ? 1u : 0u) | (ref_block_only ? 0u : 2u);
     if (!ref_block_only && A_m - 1u > S.max_alt) r.flags |= 4u;
-    r.max_gt_len = s_maxgt; r.max_ain = s_maxain;
+    r.max_gt_len = s_maxgt; r.max_ain = s_maxain; r.max_ploidy_all = s_maxploidy;
     for (int f = 0; f < MAX_FIELDS; ++f) { r.max_ploidy[f] = s_maxpl[f]; r.max_in_len[f] = s_maxin[f]; }
     B.sites[js] = r;
   }
@@ -487,12 +514,12 @@ struct RemapOut {
 
 // One warp per call.  The allele LUT of the call is rebuilt in shared memory from the site's merged-allele hashes
 // (K4), then every output word is an indexed read of the call's input vector.
-__global__ void __launch_bounds__(REMAP_THREADS) k_remap(ArrayDev A, ScanDev S, BatchDev B, RemapOut O) {
+__global__ void __launch_bounds__(REMAP_THREADS) k_remap_generic(ArrayDev A, ScanDev S, BatchDev B, RemapOut O, const uint32_t* __restrict__ site_list) {
   __shared__ unsigned long long s_ahash[UNION_MAX_DISTINCT + 2];
   __shared__ int16_t s_m2in[REMAP_WARPS][MAX_CALL_ALLELES];
   __shared__ int16_t s_in2m[REMAP_WARPS][MAX_CALL_ALLELES];
   const uint32_t tiles_per_site = (uint32_t)((S.nq + REMAP_ROWS - 1) / REMAP_ROWS);
-  const uint32_t js = blockIdx.x / tiles_per_site, tile = blockIdx.x % tiles_per_site;
+  const uint32_t js = site_list[blockIdx.x / tiles_per_site], tile = blockIdx.x % tiles_per_site;
   const SiteRec site = B.sites[js];
   const int32_t* live = B.live + (uint64_t)js * S.nq;
   const uint32_t A_m = site.n_alleles;
@@ -637,6 +664,280 @@ __global__ void __launch_bounds__(REMAP_THREADS) k_remap(ArrayDev A, ScanDev S, 
         for (uint32_t i = n_out + lane; i < stride; i += 32) dst[i] = pad;
       }
       if (lane == 0) fo.len[sq] = (uint16_t)n_out;
+    }
+  }
+}
+
+}  // namespace gdb
+
+// ================================================================================================ K5 tile kernel
+// The fast path of the remap (sites with <= 64 merged alleles, ploidy <= 2, short input vectors -- everything but
+// pathological sites, which k_remap_generic keeps handling).
+//   phase A  one thread per sample (256 samples of one site per block): ONE 32-byte hot-record gather gives a trivial
+//            call's GT and PL/AD; the thread remaps GT, writes the lengths, and leaves in shared memory either the
+//            2-3 distinct output values of a trivial call (reference block / <NON_REF>-only: 90 % of live calls) or the
+//            call's allele LUT + raw input vector.
+//   phase B  warps stream the dense sample-major output: lane <-> genotype index, one (sample, 32-genotype chunk) per
+//            warp iteration, fully coalesced stores; a trivial sample costs a 3-way select per word.
+// Output bytes dominate (26.8 MB per site at 100 k samples x 10 alleles), so the kernel is bound by HBM write bandwidth.
+namespace gdb {
+
+constexpr int TILE_ROWS = 256;
+constexpr int TILE_MAX_A = 64;
+constexpr int TILE_MAX_INW = 48;
+constexpr int TILE_MAX_GT = 8;
+
+struct TileShape { uint32_t lw, inw, g; };   // per-launch shared-memory strides: LUT bytes/row, input words/row, jk entries
+
+__host__ __device__ inline size_t tile_smem_bytes(TileShape t, int n_fields) {
+  size_t b = 8 * (size_t)TILE_MAX_A;                 // allele hashes
+  b += ((size_t)t.g * 2 + 15) / 16 * 16;             // (j,k) table
+  b += (size_t)TILE_ROWS * t.lw;                     // LUT rows (int8)
+  b += (size_t)TILE_ROWS * t.inw * 4;                // staged inputs
+  b += (size_t)TILE_ROWS * (4 + n_fields);           // kind, ploidy, pad, pad, n_in[f]
+  return (b + 15) / 16 * 16;
+}
+
+__global__ void __launch_bounds__(TILE_ROWS) k_remap_tile(ArrayDev A, ScanDev S, BatchDev B, RemapOut O, const uint32_t* __restrict__ site_list, TileShape T) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t tiles_per_site = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
+  const uint32_t js = site_list[blockIdx.x / tiles_per_site], tile = blockIdx.x % tiles_per_site;
+  const SiteRec site = B.sites[js];
+  const uint32_t A_m = site.n_alleles;
+  const bool nonref = site.flags & 1u, remap = site.flags & 2u, g_suppressed = site.flags & 4u;
+  const int nf = A.n_fields;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  unsigned long long* s_ahash = reinterpret_cast<unsigned long long*>(smem);
+  uint16_t* s_jk = reinterpret_cast<uint16_t*>(smem + 8 * TILE_MAX_A);
+  int8_t* s_lut = reinterpret_cast<int8_t*>(smem + 8 * TILE_MAX_A + ((size_t)T.g * 2 + 15) / 16 * 16);
+  uint32_t* s_in = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_lut) + (size_t)TILE_ROWS * T.lw);
+  uint8_t* s_meta = reinterpret_cast<uint8_t*>(s_in + (size_t)TILE_ROWS * T.inw);
+  const int meta_w = 4 + nf;   // [0] kind (0 dead, 1 trivial, 2 general) [1] ploidy [4+f] n_in of field f
+
+  // per-field slot offsets inside a staged row: a trivial call needs up to 3 words
+  uint32_t foff[MAX_FIELDS];
+  {
+    uint32_t o = 0;
+#pragma unroll
+    for (int f = 0; f < MAX_FIELDS; ++f) if (f < nf) { foff[f] = o; uint32_t w = site.max_in_len[f]; o += (w < 3u ? 3u : w); }
+  }
+  for (uint32_t i = tid; i < A_m; i += TILE_ROWS) s_ahash[i] = B.allele_hash[site.allele_first + i];
+  const uint32_t G = A_m * (A_m + 1) / 2;
+  if (remap) for (uint32_t g = tid; g < G; g += TILE_ROWS) {
+    uint32_t k = (uint32_t)((sqrtf(8.0f * (float)g + 1.0f) - 1.0f) * 0.5f);
+    while (k * (k + 1) / 2 > g) --k;
+    while ((k + 1) * (k + 2) / 2 <= g) ++k;
+    s_jk[g] = (uint16_t)((k << 8) | (g - k * (k + 1) / 2));
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase A: one thread per sample
+  const uint64_t q = (uint64_t)tile * TILE_ROWS + tid;
+  const int o_gt = 0, o_f0 = A.has_gt ? 1 : 0;
+  if (q < S.nq) {
+    const uint64_t sq = (uint64_t)js * S.nq + q;
+    const int32_t e = B.live[sq];
+    uint8_t* meta = s_meta + (size_t)tid * meta_w;
+    uint32_t* in_row = s_in + (size_t)tid * T.inw;
+    uint32_t gt_stride = 0; uint32_t* gt_dst = nullptr;
+    if (A.has_gt) { gt_stride = O.f[o_gt].stride[js]; gt_dst = O.f[o_gt].data + O.f[o_gt].base[js] + q * gt_stride; }
+    if (e < 0) {
+      meta[0] = 0; meta[1] = 0;
+      for (int f = 0; f < nf; ++f) { meta[4 + f] = 0; O.f[o_f0 + f].len[sq] = 0; }
+      if (A.has_gt) { for (uint32_t i = 0; i < gt_stride; ++i) gt_dst[i] = BCF_INT_VEND; O.f[o_gt].len[sq] = 0; }
+      if (O.lut_first) { O.lut_first[sq] = 0xFFFFFFFFu; O.lut_len[sq] = 0; }
+    } else {
+      const uint32_t cell = (uint32_t)(e & (LIVE_REDUCED - 1));
+      const bool reduced = (e & LIVE_REDUCED) != 0;
+      const uint4 h0 = reinterpret_cast<const uint4*>(&A.hot[cell])[0];
+      const uint4 h1 = reinterpret_cast<const uint4*>(&A.hot[cell])[1];
+      const uint32_t hw[HOT_WORDS] = {h0.w, h1.x, h1.y, h1.z, h1.w};
+      const uint32_t hflags = h0.x & 0xFF;
+      uint32_t ploidy = (h0.x >> 8) & 0xFF, n_alt = (h0.x >> 16) & 0xFF, nr = h0.x >> 24, gt_len = h0.y & 0xFF;
+      const bool inl = ((h0.y >> 8) & 0xFF) != 0;
+      const bool trivial = !reduced && (hflags & F_TRIVIAL) && inl;
+      uint32_t gtw[TILE_MAX_GT];
+      const uint32_t* fptr[MAX_FIELDS]; uint32_t flen[MAX_FIELDS];
+      const DelRec* dr = nullptr;
+      uint32_t ref_len = 1;
+      if (reduced) {
+        dr = find_delrec(S, cell);
+        n_alt = dr->n_alt; nr = dr->has_nr ? 2u : 0u;
+        const uint32_t* g = S.del_words + dr->gt_off;
+        for (uint32_t i = 0; i < gt_len && i < TILE_MAX_GT; ++i) gtw[i] = g[i];
+        for (int f = 0; f < nf; ++f) { if (dr->f_len[f] == 0xFFFFFFFFu) { flen[f] = 0; fptr[f] = nullptr; } else { flen[f] = dr->f_len[f]; fptr[f] = S.del_words + dr->f_off[f]; } }
+      } else if (inl) {
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < gt_len; ++i) { gtw[i] = hw[k < HOT_WORDS ? k : 0]; ++k; }
+        const uint32_t fl4 = (h0.y >> 16) | (h0.z << 16);
+        for (int f = 0; f < nf; ++f) { flen[f] = (f < HOT_FIELDS) ? ((fl4 >> (8 * f)) & 0xFF) : 0u; fptr[f] = nullptr; }
+        // copy the inline words to the staged row right away (offset k onwards, field by field)
+        for (int f = 0; f < nf; ++f) for (uint32_t x = 0; x < flen[f]; ++x) { in_row[foff[f] + x] = hw[k < HOT_WORDS ? k : 0]; ++k; }
+      } else {
+        const CellDesc d = A.desc[cell];
+        n_alt = d.n_alt; nr = d.nr_idx; gt_len = (d.flags & F_GTVALID) ? d.gt_len : 0u; ref_len = d.ref_len;
+        if (A.has_gt) { const uint32_t* g = reinterpret_cast<const uint32_t*>(A.gt.val + A.gt.off[cell]); for (uint32_t i = 0; i < gt_len && i < TILE_MAX_GT; ++i) gtw[i] = g[i]; }
+        for (int f = 0; f < nf; ++f) {
+          uint64_t o0 = A.f[f].off[cell], o1 = A.f[f].off[cell + 1];
+          uint32_t n = (uint32_t)((o1 - o0) >> 2);
+          const uint32_t* v = reinterpret_cast<const uint32_t*>(A.f[f].val + o0);
+          const uint32_t nullw = null_word(A.fm[f].elem);
+          bool any = false;
+          for (uint32_t x = 0; x < n; ++x) { uint32_t wv = v[x]; any |= (wv != nullw); }
+          flen[f] = any ? n : 0u; fptr[f] = v;
+        }
+      }
+      if (!reduced && inl && !(hflags & F_TRIVIAL)) ref_len = A.desc[cell].ref_len;   // exact REF length decides the ALT suffix
+      if (!inl || reduced) for (int f = 0; f < nf; ++f) { uint32_t* r = in_row + foff[f]; for (uint32_t x = 0; x < flen[f]; ++x) r[x] = fptr[f][x]; }
+      const uint32_t A_in = n_alt + 1u;
+      const int in_nr = (nonref && nr) ? (int)nr : -1;
+      const int step = A.gt_phased ? 2 : 1;
+      uint32_t gto[TILE_MAX_GT];
+      uint32_t lut_first = 0xFFFFFFFFu;
+      if (O.lut_first) { lut_first = atomicAdd(&B.cursors[2], A_in); if (lut_first + A_in > O.cap_lut) { atomicOr(&S.err[2], 2u); lut_first = 0xFFFFFFFFu; } O.lut_first[sq] = lut_first; O.lut_len[sq] = (uint16_t)A_in; }
+      meta[1] = (uint8_t)ploidy;
+      const bool is_triv = trivial || !remap;
+      if (is_triv) {
+        meta[0] = 1;
+        for (uint32_t i = 0; i < gt_len; ++i) {
+          uint32_t g = gtw[i];
+          if (remap && (i % step) == 0 && !(g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING))
+            g = (g == 0) ? 0u : ((nr && g == nr) ? A_m - 1u : (nonref ? A_m - 1u : 0xFFFFFFFFu));
+          gto[i] = g;
+        }
+        if (lut_first != 0xFFFFFFFFu) for (uint32_t i = 0; i < A_in; ++i) O.lut_in2m[lut_first + i] = (int16_t)(i == 0 ? 0 : ((nr && i == nr) ? (int)A_m - 1 : -1));
+        if (remap) {
+          // the 2-3 distinct values a trivial call can contribute (m2in: REF->0, every ALT -> its own NON_REF or nothing)
+          for (int f = 0; f < nf; ++f) {
+            const uint32_t n = flen[f]; if (!n) continue;
+            const uint32_t miss = missing_word(A.fm[f].elem);
+            uint32_t* r = in_row + foff[f];
+            // values currently staged at r[0..n) (inline) ; trivial implies inline
+            uint32_t v0 = r[0], v1 = miss, v2 = miss;
+            const int kind = A.fm[f].kind;
+            if (in_nr >= 0) {
+              if (kind == KIND_A) { v1 = ((uint32_t)in_nr - 1u < n) ? r[in_nr - 1] : miss; }
+              else if (kind == KIND_R || ploidy != 2) { v1 = ((uint32_t)in_nr < n) ? r[in_nr] : miss; }
+              else { uint32_t g1 = (uint32_t)alleles2gt(0, in_nr), g2 = (uint32_t)alleles2gt(in_nr, in_nr); v1 = g1 < n ? r[g1] : miss; v2 = g2 < n ? r[g2] : miss; }
+            }
+            r[0] = v0; r[1] = v1; r[2] = v2;
+          }
+        }
+      } else {
+        meta[0] = 2;
+        int8_t* lut = s_lut + (size_t)tid * T.lw;
+        for (uint32_t m = 0; m < A_m; ++m) lut[m] = -1;
+        lut[0] = 0;
+        uint32_t mapped = 0;   // GT slots already assigned
+        for (uint32_t i = 0; i < gt_len; ++i) { uint32_t g = gtw[i]; gto[i] = g; if ((i % step) || g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING) mapped |= 1u << i; else if (g == 0) mapped |= 1u << i; }
+        if (lut_first != 0xFFFFFFFFu) { O.lut_in2m[lut_first] = 0; for (uint32_t i = 1; i < A_in; ++i) O.lut_in2m[lut_first + i] = -1; }
+        const uint8_t* mref = B.allele_bytes + site.ref_off;
+        auto assign = [&](uint32_t idx, uint32_t m) {
+          lut[m] = (int8_t)idx;
+          for (uint32_t i = 0; i < gt_len; ++i) if (!(i % step) && gtw[i] == idx && !(gtw[i] == TDB_NULL_INT || gtw[i] == 0xFFFFFFFFu || gtw[i] == BCF_INT_MISSING)) { gto[i] = m; mapped |= 1u << i; }
+          if (lut_first != 0xFFFFFFFFu) O.lut_in2m[lut_first + idx] = (int16_t)m;
+        };
+        if (reduced) {
+          int sfx; uint64_t h = allele_hash(c_str_star, 1, mref, site.ref_len, 1, sfx);
+          for (uint32_t m = 1; m < A_m; ++m) if (s_ahash[m] == h) { assign(1, m); break; }
+        } else {
+          const uint8_t* alt = A.alt.val + A.alt.off[cell];
+          const int an = alt_effective_len(alt, (int)(A.alt.off[cell + 1] - A.alt.off[cell]));
+          int pos = 0, ts, tl; uint32_t idx = 0;
+          while (next_token(alt, an, pos, ts, tl)) {
+            ++idx;
+            if (is_non_ref(alt + ts, tl)) continue;
+            int sfx; uint64_t h = allele_hash(alt + ts, tl, mref, site.ref_len, ref_len, sfx);
+            for (uint32_t m = 1; m < A_m; ++m) if (s_ahash[m] == h) { assign(idx, m); break; }
+          }
+        }
+        if (nr) assign(nr, A_m - 1u);
+        for (uint32_t i = 0; i < gt_len; ++i) if (!(mapped & (1u << i))) gto[i] = nonref ? A_m - 1u : 0xFFFFFFFFu;
+        for (uint32_t m = 0; m < A_m; ++m) if (lut[m] < 0) lut[m] = (int8_t)in_nr;   // NON_REF fallback folded in
+      }
+      // GT + lengths straight to global (adjacent threads -> adjacent samples -> contiguous)
+      if (A.has_gt) {
+        for (uint32_t i = 0; i < gt_stride; ++i) gt_dst[i] = (i < gt_len) ? gto[i] : BCF_INT_VEND;
+        O.f[o_gt].len[sq] = (uint16_t)gt_len;
+      }
+      for (int f = 0; f < nf; ++f) {
+        const int kind = A.fm[f].kind;
+        uint32_t n_out = 0;
+        if (flen[f] && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, ploidy) : flen[f];
+        meta[4 + f] = (uint8_t)((flen[f] && n_out) ? flen[f] : 0u);
+        O.f[o_f0 + f].len[sq] = (uint16_t)n_out;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase B: stream the dense output
+  const uint32_t rows = (uint32_t)min((uint64_t)TILE_ROWS, S.nq - (uint64_t)tile * TILE_ROWS);
+  for (int f = 0; f < nf; ++f) {
+    const FieldOutDev fo = O.f[o_f0 + f];
+    const uint32_t stride = fo.stride[js];
+    if (stride == 0) continue;
+    uint32_t* dst = fo.data + fo.base[js] + (uint64_t)tile * TILE_ROWS * stride;
+    const int kind = A.fm[f].kind, elem = A.fm[f].elem;
+    const uint32_t pad = vend_word(elem), miss = missing_word(elem);
+    const uint32_t fo_in = foff[f];
+    if (remap && kind == KIND_G) {
+      const uint32_t n_chunks = (stride + 31) / 32, items = n_chunks * rows;
+      for (uint32_t item = warp; item < items; item += TILE_ROWS / 32) {
+        const uint32_t row = item / n_chunks, g = (item % n_chunks) * 32 + lane;
+        const uint8_t* meta = s_meta + (size_t)row * meta_w;
+        const uint32_t kindr = meta[0], ploidy = meta[1], n_in = meta[4 + f];
+        if (g >= stride) continue;
+        uint32_t val = pad;
+        if (n_in) {
+          const uint32_t* in = s_in + (size_t)row * T.inw + fo_in;
+          const uint32_t n_out = (ploidy == 2) ? G : (ploidy == 1 ? A_m : 1u);
+          if (g < n_out) {
+            if (ploidy == 2) {
+              const uint32_t jk = s_jk[g], j = jk & 0xFF, k = jk >> 8;
+              if (kindr == 1) val = in[(k == 0) ? 0 : (j == 0 ? 1 : 2)];
+              else {
+                const int8_t* lut = s_lut + (size_t)row * T.lw;
+                const int ij = lut[j], ik = lut[k];
+                if (ij < 0 || ik < 0) val = miss;
+                else { const uint32_t ig = (uint32_t)alleles2gt(ij, ik); val = ig < n_in ? in[ig] : miss; }
+              }
+            } else if (ploidy == 1) {
+              if (kindr == 1) val = in[g == 0 ? 0 : 1];
+              else { const int ij = (s_lut + (size_t)row * T.lw)[g]; val = (ij < 0 || (uint32_t)ij >= n_in) ? miss : in[ij]; }
+            } else val = in[0];
+          }
+        }
+        dst[(uint64_t)row * stride + g] = val;
+      }
+    } else {
+      const uint32_t total = rows * stride;
+      const float inv = 1.0f / (float)stride;
+      for (uint32_t w = tid; w < total; w += TILE_ROWS) {
+        uint32_t row = (uint32_t)(((float)w + 0.5f) * inv);
+        if (row * stride > w) --row; else if ((row + 1) * stride <= w) ++row;
+        const uint32_t j = w - row * stride;
+        const uint8_t* meta = s_meta + (size_t)row * meta_w;
+        const uint32_t kindr = meta[0], n_in = meta[4 + f];
+        uint32_t val = pad;
+        if (n_in) {
+          const uint32_t* in = s_in + (size_t)row * T.inw + fo_in;
+          if (!remap) val = j < n_in ? in[j] : pad;
+          else {
+            const uint32_t n_out = (kind == KIND_A) ? A_m - 1u : A_m;
+            if (j < n_out) {
+              if (kindr == 1) val = (kind == KIND_A) ? in[1] : in[j == 0 ? 0 : 1];
+              else {
+                const int ij = (s_lut + (size_t)row * T.lw)[kind == KIND_A ? j + 1 : j];
+                if (ij < 0) val = miss;
+                else { const int ix = (kind == KIND_A) ? ij - 1 : ij; val = (ix < 0 || (uint32_t)ix >= n_in) ? miss : in[ix]; }
+              }
+            }
+          }
+        }
+        dst[w] = val;
+      }
     }
   }
 }
