@@ -533,8 +533,9 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
     for (uint32_t i = 0; i < keep; ++i) {
       const SiteRec& r = bb.h_sites[i];
       uint32_t inw = 0;
-      for (size_t f = 0; f < a->fields.size(); ++f) inw += std::max<uint32_t>(3u, r.max_in_len[f]);
-      bool ok = r.n_alleles <= (uint32_t)TILE_MAX_A && r.max_ain <= (uint32_t)TILE_MAX_A && r.max_gt_len <= (uint32_t)TILE_MAX_GT && r.max_ploidy_all <= 2u && inw <= (uint32_t)TILE_MAX_INW;
+      for (size_t f = 0; f < a->fields.size(); ++f) inw += r.max_in_len[f];
+      bool ok = a->fields.size() >= 1 && a->fields.size() <= (size_t)TILE_MAX_FIELDS && r.n_alleles <= (uint32_t)TILE_MAX_A && r.max_ain <= (uint32_t)TILE_MAX_A &&
+                r.max_gt_len <= (uint32_t)TILE_MAX_GT && r.max_ploidy_all <= 2u && inw <= (uint32_t)TILE_MAX_INW;
       if (ok) {
         fast.push_back(i);
         shape.lw = std::max(shape.lw, (r.n_alleles + 3u) / 4u * 4u);
@@ -545,11 +546,21 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
     if (!fast.empty()) {
       bb.fast_sites.ensure(fast.size());
       CK(cudaMemcpyAsync(bb.fast_sites.p, fast.data(), fast.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-      size_t smem = tile_smem_bytes(shape, (int)a->fields.size());
-      static size_t smem_set = 0;
-      if (smem > smem_set) { CK(cudaFuncSetAttribute(k_remap_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 100 * 1024))); smem_set = std::max<size_t>(smem, 100 * 1024); }
+      const int nf = (int)a->fields.size();
+      size_t smem = tile_smem_bytes(shape, nf);
       uint32_t tiles = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
-      { ProfScope ps__(ctx, "k_remap_tile"); k_remap_tile<<<(unsigned)(fast.size() * tiles), TILE_ROWS, smem, ctx->stream>>>(a->dev, S, B, O, bb.fast_sites.p, shape); }
+      unsigned grid = (unsigned)(fast.size() * tiles);
+      auto launch_tile = [&](auto kern) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        ProfScope ps__(ctx, "k_remap_tile");
+        kern<<<grid, TILE_ROWS, smem, ctx->stream>>>(a->dev, S, B, O, bb.fast_sites.p, shape);
+      };
+      switch (nf) {
+        case 1: launch_tile(k_remap_tile<1>); break;
+        case 2: launch_tile(k_remap_tile<2>); break;
+        case 3: launch_tile(k_remap_tile<3>); break;
+        default: launch_tile(k_remap_tile<4>); break;
+      }
       ++ctx->launches; CK(cudaGetLastError());
     }
     if (!slow.empty()) {

@@ -1,0 +1,237 @@
+// Host-side C++ mirror of the reference's plugin surface for the variant-combine path, written on top of the C ABI
+// (include/gdbgpu.h) only.  Same class names, method names, argument meaning and error behaviour (C++ exceptions) as
+// GenomicsDB v0.10.2, so that tools/src/gt_mpi_gather.cc:322-366 (scan_and_produce_Broad_GVCF) and
+// src/main/cpp/src/vcf/genomicsdb_bcf_generator.cc:83,135 read the same against either implementation:
+//
+//   reference                                                         here
+//   VariantStorageManager(workspace, segment_size)                    VariantStorageManager(workspace, segment_size, device)
+//     variant_storage_manager.h:160-235
+//   VariantQueryConfig::read_from_file(json)                          same keys (json_config.cc:207-656), see .cc
+//   VariantQueryProcessor(&sm, array_name, vid_mapper)                same
+//   qp.do_query_bookkeeping(schema, config, vid_mapper, alleles)      same role: opens + stages the array on the GPU
+//     query_variants.cc:578-685
+//   qp.scan_and_operate(ad, config, op, interval_idx,                 same signature (query_variants.h:241-243); batches
+//       handle_spanning_deletions, &scan_state)                       come from gdbgpu_scan_next_batch, overflow()/resume
+//                                                                     protocol identical (query_variants.cc:305,415,460-475)
+//   SingleVariantOperatorBase::operate(Variant&, config)              same virtual; the merged REF/ALT, NON_REF flag and
+//     variant_operations.h:349-388                                    remapping flag are already computed by the kernels
+//   GA4GHOperator::operate / get_remapped_variant()                   same; the remapped GT / allele-dependent fields are
+//     variant_operations.h:648-686                                    views into the batch (no per-element virtual calls)
+//
+// Difference that matters to an operator author: the Variant handed to operate() carries the REMAPPED fields of every
+// valid call (what GA4GHOperator::m_remapped_variant holds in the reference); the un-remapped inputs stay in HBM.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/gdbgpu.h"
+
+namespace genomicsdb_b200 {
+
+class GenomicsDBGPUException : public std::runtime_error {
+ public:
+  GenomicsDBGPUException(int code, const std::string& m) : std::runtime_error(m), code_(code) {}
+  int code() const { return code_; }
+ private:
+  int code_;
+};
+// query_variants.cc:533-535
+class VariantQueryProcessorException : public GenomicsDBGPUException { using GenomicsDBGPUException::GenomicsDBGPUException; };
+
+// ---- field / contig / callset mapping (src/main/cpp/src/utils/vid_mapper.cc, file-based mapper)
+struct FieldInfo {
+  std::string name;
+  std::string type;        // "int", "float", "char", ...
+  std::string length;      // "1", "R", "A", "G", "P", "PP", "VAR", "<n>"; 2-D descriptors are kept as "2D"
+  bool is_format = false, is_info = false;
+  bool is_allele_dependent() const { return length == "R" || length == "A" || length == "G"; }
+};
+class VidMapper {
+ public:
+  VidMapper() = default;
+  explicit VidMapper(const std::string& vid_json_file);
+  bool is_initialized() const { return !fields_.empty(); }
+  const FieldInfo* get_field_info(const std::string& name) const;
+  const std::vector<FieldInfo>& fields() const { return fields_; }
+ private:
+  std::vector<FieldInfo> fields_;
+};
+
+// ---- query configuration (include/config/variant_query_config.h)
+class VariantQueryConfig {
+ public:
+  void read_from_file(const std::string& filename, int rank = 0);
+  // programmatic setters, same names as the reference
+  void set_workspace(const std::string& w) { workspace_ = w; }
+  void set_array_name(const std::string& a) { array_name_ = a; }
+  void set_attributes_to_query(const std::vector<std::string>& a) { attributes_ = a; }
+  void add_column_interval_to_query(int64_t b, int64_t e);
+  void set_column_interval_to_query(int64_t b, int64_t e) { intervals_.assign(1, {b, e}); }
+  void set_rows_to_query(const std::vector<int64_t>& rows);
+  void set_vid_mapper(const VidMapper& v) { vid_ = v; }
+  void set_max_diploid_alt_alleles_that_can_be_genotyped(unsigned v) { max_alt_ = v; }
+  void set_produce_GT_with_min_PL_value_for_spanning_deletions(bool v) { min_pl_gt_ = v; }
+
+  const std::string& get_workspace(int = 0) const { return workspace_; }
+  const std::string& get_array_name(int = 0) const { return array_name_; }
+  unsigned get_num_column_intervals() const { return (unsigned)intervals_.size(); }
+  int64_t get_column_begin(unsigned i) const { return intervals_[i].first; }
+  int64_t get_column_end(unsigned i) const { return intervals_[i].second; }
+  bool query_all_rows() const { return rows_.empty(); }
+  const std::vector<int64_t>& get_rows_to_query() const { return rows_; }
+  const std::vector<std::string>& get_query_attributes() const { return attributes_; }
+  const VidMapper& get_vid_mapper() const { return vid_; }
+  unsigned get_max_diploid_alt_alleles_that_can_be_genotyped() const { return max_alt_; }
+  bool produce_GT_with_min_PL_value_for_spanning_deletions() const { return min_pl_gt_; }
+  bool is_bookkeeping_done() const { return bookkeeping_done_; }
+  // after do_query_bookkeeping: the fields the operator sees (GT first when present), in query order
+  unsigned get_num_remapped_fields() const { return (unsigned)remapped_names_.size(); }
+  const std::string& get_remapped_field_name(unsigned i) const { return remapped_names_[i]; }
+
+ private:
+  friend class VariantQueryProcessor;
+  std::string workspace_, array_name_;
+  std::vector<std::pair<int64_t, int64_t>> intervals_;
+  std::vector<int64_t> rows_;
+  std::vector<std::string> attributes_;
+  VidMapper vid_;
+  unsigned max_alt_ = 50;
+  bool min_pl_gt_ = false;
+  bool bookkeeping_done_ = false;
+  std::vector<std::string> remapped_names_;
+};
+
+// ---- data model (include/genomicsdb/variant.h).  Views into the current batch: valid until the next operate() call.
+class Variant;
+class VariantCall {
+ public:
+  bool is_valid() const { return valid_; }
+  uint64_t get_row_idx() const { return row_; }
+  uint64_t get_column_begin() const { return (uint64_t)begin_; }
+  uint64_t get_column_end() const { return (uint64_t)end_; }
+  bool is_spanning_deletion_form() const { return reduced_; }   // handle_deletions already applied (REF N, ALT *[,NON_REF])
+  // remapped field i (0 = GT when the array has GT): words and length; length 0 == field invalid for this call
+  const uint32_t* get_field_words(unsigned i) const { return fields_[i].first; }
+  unsigned get_field_length(unsigned i) const { return fields_[i].second; }
+  template <class T> const T* get_field(unsigned i) const { return reinterpret_cast<const T*>(fields_[i].first); }
+  // input->merged allele index LUT of this call (only when the scan asked for it)
+  const int16_t* get_alleles_LUT() const { return lut_; }
+  unsigned get_num_input_alleles() const { return lut_len_; }
+ private:
+  friend class VariantQueryProcessor;
+  bool valid_ = false, reduced_ = false;
+  uint64_t row_ = 0; int64_t begin_ = 0, end_ = 0;
+  std::vector<std::pair<const uint32_t*, unsigned>> fields_;
+  const int16_t* lut_ = nullptr; unsigned lut_len_ = 0;
+};
+
+class Variant {
+ public:
+  uint64_t get_column_begin() const { return (uint64_t)begin_; }
+  uint64_t get_column_end() const { return (uint64_t)end_; }
+  uint64_t get_num_calls() const { return calls_.size(); }
+  VariantCall& get_call(uint64_t i) { return calls_[i]; }
+  const VariantCall& get_call(uint64_t i) const { return calls_[i]; }
+  // iteration over valid calls in query-row order (variant.h:290-320)
+  class valid_calls_iterator {
+   public:
+    valid_calls_iterator(const std::vector<VariantCall>* c, uint64_t i) : c_(c), i_(i) { skip(); }
+    bool operator!=(const valid_calls_iterator& o) const { return i_ != o.i_; }
+    const VariantCall& operator*() const { return (*c_)[i_]; }
+    valid_calls_iterator& operator++() { ++i_; skip(); return *this; }
+    uint64_t get_call_idx_in_variant() const { return i_; }
+   private:
+    void skip() { while (i_ < c_->size() && !(*c_)[i_].is_valid()) ++i_; }
+    const std::vector<VariantCall>* c_; uint64_t i_;
+  };
+  valid_calls_iterator begin() const { return valid_calls_iterator(&calls_, 0); }
+  valid_calls_iterator end() const { return valid_calls_iterator(&calls_, calls_.size()); }
+ private:
+  friend class VariantQueryProcessor;
+  friend class SingleVariantOperatorBase;
+  int64_t begin_ = 0, end_ = 0;
+  std::vector<VariantCall> calls_;
+  // merged-site results of the kernels, picked up by SingleVariantOperatorBase::operate
+  std::string merged_ref_;
+  std::vector<std::string> merged_alts_;
+  bool nonref_ = false, remapped_ = false, g_suppressed_ = false;
+};
+
+// ---- operators (include/query_operations/variant_operations.h:349-388, 648-686)
+class SingleVariantOperatorBase {
+ public:
+  virtual ~SingleVariantOperatorBase() = default;
+  virtual void operate(Variant& variant, const VariantQueryConfig& query_config);
+  virtual bool overflow() const { return false; }
+ protected:
+  bool m_NON_REF_exists = false, m_remapping_needed = false, m_is_reference_block_only = false;
+  std::string m_merged_reference_allele;
+  std::vector<std::string> m_merged_alt_alleles;
+};
+class GA4GHOperator : public SingleVariantOperatorBase {
+ public:
+  void operate(Variant& variant, const VariantQueryConfig& query_config) override;
+  const Variant& get_remapped_variant() const { return *m_remapped_variant; }
+  bool too_many_alt_alleles_for_genotype_length_fields(unsigned num_alt_alleles) const { return num_alt_alleles > m_max_diploid_alt_alleles_that_can_be_genotyped; }
+ protected:
+  const Variant* m_remapped_variant = nullptr;
+  unsigned m_max_diploid_alt_alleles_that_can_be_genotyped = 50;
+};
+
+// ---- storage + engine
+class VariantStorageManager {
+ public:
+  VariantStorageManager(const std::string& workspace, unsigned segment_size = 10u * 1024u * 1024u, int cuda_device = 0);
+  ~VariantStorageManager();
+  VariantStorageManager(const VariantStorageManager&) = delete;
+  VariantStorageManager& operator=(const VariantStorageManager&) = delete;
+  const std::string& get_workspace() const { return workspace_; }
+  gdbgpu_ctx* ctx() const { return ctx_; }
+ private:
+  std::string workspace_;
+  gdbgpu_ctx* ctx_ = nullptr;
+};
+
+// query_variants.h:126-191
+class VariantQueryProcessorScanState {
+ public:
+  ~VariantQueryProcessorScanState() { reset(); }
+  bool end() const { return m_done; }
+  void reset();
+  uint64_t get_num_sites_done() const { return sites_done_; }
+ private:
+  friend class VariantQueryProcessor;
+  bool m_done = false;
+  gdbgpu_scan* scan_ = nullptr;
+  gdbgpu_batch batch_{};
+  bool have_batch_ = false;
+  uint32_t pos_in_batch_ = 0;
+  uint64_t sites_done_ = 0;
+};
+
+class VariantQueryProcessor {
+ public:
+  VariantQueryProcessor(VariantStorageManager* storage_manager, const std::string& array_name, const VidMapper& vid_mapper);
+  ~VariantQueryProcessor();
+  // Adds END/REF/ALT/GT, resolves the allele-dependent fields among the queried attributes, stages the array in HBM.
+  void do_query_bookkeeping(VariantQueryConfig& query_config, bool alleles_required = true);
+  int get_array_descriptor() const { return 0; }
+  void scan_and_operate(const int ad, const VariantQueryConfig& query_config, SingleVariantOperatorBase& variant_operator,
+                        unsigned column_interval_idx = 0, bool handle_spanning_deletions = false,
+                        VariantQueryProcessorScanState* scan_state = nullptr, bool want_alleles_LUT = false) const;
+  gdbgpu_array* array() const { return arr_; }
+ private:
+  void check(int rc) const;
+  void fill_variant(const gdbgpu_batch& b, uint32_t s, Variant& v) const;
+  VariantStorageManager* sm_;
+  std::string array_name_;
+  VidMapper vid_;
+  gdbgpu_array* arr_ = nullptr;
+  std::vector<int64_t> coords_, end_;   // merged cell coordinates (row, col) and END, host copy
+  int n_out_ = 0;
+};
+
+}  // namespace genomicsdb_b200

@@ -671,272 +671,337 @@ __global__ void __launch_bounds__(REMAP_THREADS) k_remap_generic(ArrayDev A, Sca
 }  // namespace gdb
 
 // ================================================================================================ K5 tile kernel
-// The fast path of the remap (sites with <= 64 merged alleles, ploidy <= 2, short input vectors -- everything but
-// pathological sites, which k_remap_generic keeps handling).
-//   phase A  one thread per sample (256 samples of one site per block): ONE 32-byte hot-record gather gives a trivial
-//            call's GT and PL/AD; the thread remaps GT, writes the lengths, and leaves in shared memory either the
-//            2-3 distinct output values of a trivial call (reference block / <NON_REF>-only: 90 % of live calls) or the
-//            call's allele LUT + raw input vector.
-//   phase B  warps stream the dense sample-major output: lane <-> genotype index, one (sample, 32-genotype chunk) per
-//            warp iteration, fully coalesced stores; a trivial sample costs a 3-way select per word.
-// Output bytes dominate (26.8 MB per site at 100 k samples x 10 alleles), so the kernel is bound by HBM write bandwidth.
+// The fast path of the remap (sites with <= 64 merged alleles, ploidy <= 2, short input vectors, <= 4 remapped fields --
+// everything but pathological sites, which k_remap_generic keeps handling).
+//   phase A  one thread per sample (256 samples of one site per block).  ONE 32-byte hot-record gather gives a trivial
+//            call's GT and PL/AD (reference block or <NON_REF>-only call: ~90 % of the calls live at a site); the thread
+//            remaps GT, writes the lengths, and leaves in shared memory, per field, the 2-3 distinct values such a call
+//            can contribute to the output.  Non-trivial calls build their allele LUT and stage their raw input vector.
+//   phase B  warps stream the dense sample-major output: one sample per warp iteration, lane <-> genotype index, fully
+//            coalesced stores; a trivial sample costs one LDS.128 and a 3-way select per word.
+// Output bytes dominate (26.8 MB per site at 100 k samples x 10 alleles): the kernel is bound by HBM write bandwidth.
 namespace gdb {
 
 constexpr int TILE_ROWS = 256;
 constexpr int TILE_MAX_A = 64;
 constexpr int TILE_MAX_INW = 48;
 constexpr int TILE_MAX_GT = 8;
+constexpr int TILE_MAX_FIELDS = 4;
 
 struct TileShape { uint32_t lw, inw, g; };   // per-launch shared-memory strides: LUT bytes/row, input words/row, jk entries
 
 __host__ __device__ inline size_t tile_smem_bytes(TileShape t, int n_fields) {
-  size_t b = 8 * (size_t)TILE_MAX_A;                 // allele hashes
-  b += ((size_t)t.g * 2 + 15) / 16 * 16;             // (j,k) table
-  b += (size_t)TILE_ROWS * t.lw;                     // LUT rows (int8)
-  b += (size_t)TILE_ROWS * t.inw * 4;                // staged inputs
-  b += (size_t)TILE_ROWS * (4 + n_fields);           // kind, ploidy, pad, pad, n_in[f]
+  size_t b = 8 * (size_t)TILE_MAX_A;                       // allele hashes
+  b += ((size_t)t.g * 2 + 15) / 16 * 16;                   // (j,k) table
+  b += (size_t)TILE_ROWS * n_fields * 16;                  // per (sample, field): v0, v1, v2, info
+  b += (size_t)TILE_ROWS * t.lw;                           // LUT rows (int8), non-trivial calls only
+  b += (size_t)TILE_ROWS * t.inw * 4;                      // staged inputs, non-trivial calls only
   return (b + 15) / 16 * 16;
 }
+// info word of a (sample, field) slot
+__device__ inline uint32_t tri_info(uint32_t n_out, uint32_t kind, uint32_t ploidy, uint32_t n_in) { return (n_out & 0xFFFF) | (kind << 16) | (ploidy << 18) | (n_in << 24); }
+__device__ inline uint32_t sel5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t i) { return i == 0 ? a : (i == 1 ? b : (i == 2 ? c : (i == 3 ? d : e))); }
 
-__global__ void __launch_bounds__(TILE_ROWS) k_remap_tile(ArrayDev A, ScanDev S, BatchDev B, RemapOut O, const uint32_t* __restrict__ site_list, TileShape T) {
+struct TileCtx {
+  unsigned long long* s_ahash; uint16_t* s_jk; uint4* s_tri; int8_t* s_lut; uint32_t* s_in;
+  uint32_t lw, inw;
+};
+
+// non-trivial / non-inline / reduced calls: rare, kept out of line so the common path stays small
+template <int NF>
+__device__ __noinline__ void tile_general_row(const ArrayDev& A, const ScanDev& S, const BatchDev& B, const RemapOut& O, const SiteRec* __restrict__ site_g, const TileCtx T,
+                                              uint32_t js, uint64_t q, int tid, int32_t e, const uint4 foff4) {
+  // `tid` is the sample's row inside the tile (not necessarily the calling thread)
+  const uint64_t sq = (uint64_t)js * S.nq + q;
+  const uint32_t foff[4] = {foff4.x, foff4.y, foff4.z, foff4.w};
+  struct { uint32_t n_alleles, flags, ref_off, ref_len; } site = {site_g->n_alleles, site_g->flags, site_g->ref_off, site_g->ref_len};
+  const uint32_t A_m = site.n_alleles;
+  const bool nonref = site.flags & 1u, remap = site.flags & 2u, g_suppressed = site.flags & 4u;
+  const int o_f0 = A.has_gt ? 1 : 0;
+  const CallView v = make_view(A, S, e);
+  const uint32_t A_in = (uint32_t)v.n_alt + 1u;
+  const int in_nr = (nonref && v.nr_idx) ? v.nr_idx : -1;
+  const int step = A.gt_phased ? 2 : 1;
+  int8_t* lut = T.s_lut + (size_t)tid * T.lw;
+  uint32_t* in_row = T.s_in + (size_t)tid * T.inw;
+  uint32_t lut_first = 0xFFFFFFFFu;
+  if (O.lut_first) { lut_first = atomicAdd(&B.cursors[2], A_in); if (lut_first + A_in > O.cap_lut) { atomicOr(&S.err[2], 2u); lut_first = 0xFFFFFFFFu; } O.lut_first[sq] = lut_first; O.lut_len[sq] = (uint16_t)A_in; }
+  uint32_t gto[TILE_MAX_GT]; uint32_t mapped = 0;
+  for (uint32_t i = 0; i < v.gt_len && i < TILE_MAX_GT; ++i) {
+    uint32_t g = v.gt[i]; gto[i] = g;
+    if (!remap || (i % step) || g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING || g == 0) mapped |= 1u << i;
+  }
+  if (remap) {
+    for (uint32_t m = 0; m < A_m; ++m) lut[m] = -1;
+    lut[0] = 0;
+    if (lut_first != 0xFFFFFFFFu) { O.lut_in2m[lut_first] = 0; for (uint32_t i = 1; i < A_in; ++i) O.lut_in2m[lut_first + i] = -1; }
+    const uint8_t* mref = B.allele_bytes + site.ref_off;
+    auto assign = [&](uint32_t idx, uint32_t m) {
+      lut[m] = (int8_t)idx;
+      for (uint32_t i = 0; i < v.gt_len && i < TILE_MAX_GT; ++i) if (!(mapped & (1u << i)) && v.gt[i] == idx) { gto[i] = m; mapped |= 1u << i; }
+      if (lut_first != 0xFFFFFFFFu) O.lut_in2m[lut_first + idx] = (int16_t)m;
+    };
+    if (v.reduced) {
+      int sfx; uint64_t h = allele_hash(c_str_star, 1, mref, site.ref_len, 1, sfx);
+      for (uint32_t m = 1; m < A_m; ++m) if (T.s_ahash[m] == h) { assign(1, m); break; }
+    } else {
+      int pos = 0, ts, tl; uint32_t idx = 0;
+      while (next_token(v.alt, v.alt_n, pos, ts, tl)) {
+        ++idx;
+        if (is_non_ref(v.alt + ts, tl)) continue;
+        int sfx; uint64_t h = allele_hash(v.alt + ts, tl, mref, site.ref_len, v.ref_len, sfx);
+        for (uint32_t m = 1; m < A_m; ++m) if (T.s_ahash[m] == h) { assign(idx, m); break; }
+      }
+    }
+    if (v.nr_idx) assign((uint32_t)v.nr_idx, A_m - 1u);
+    for (uint32_t i = 0; i < v.gt_len && i < TILE_MAX_GT; ++i) if (!(mapped & (1u << i))) gto[i] = nonref ? A_m - 1u : 0xFFFFFFFFu;
+    for (uint32_t m = 0; m < A_m; ++m) if (lut[m] < 0) lut[m] = (int8_t)in_nr;   // NON_REF fallback folded in
+  } else if (lut_first != 0xFFFFFFFFu) {
+    for (uint32_t i = 0; i < A_in; ++i) O.lut_in2m[lut_first + i] = (int16_t)(i == 0 ? 0 : ((v.nr_idx && (int)i == v.nr_idx) ? (int)A_m - 1 : -1));
+  }
+  if (A.has_gt) {
+    const uint32_t gt_stride = O.f[0].stride[js]; uint32_t* gt_dst = O.f[0].data + O.f[0].base[js] + q * gt_stride;
+    for (uint32_t i = 0; i < gt_stride; ++i) gt_dst[i] = (i < v.gt_len) ? gto[i] : BCF_INT_VEND;
+    O.f[0].len[sq] = (uint16_t)v.gt_len;
+  }
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    const uint32_t* p; uint32_t n;
+    bool valid = field_of(A, S, v, f, p, n);
+    if (valid && !v.reduced) { bool any = false; const uint32_t nullw = null_word(A.fm[f].elem); for (uint32_t x = 0; x < n; ++x) any |= (p[x] != nullw); valid = any; }
+    const int kind = A.fm[f].kind;
+    uint32_t n_out = 0;
+    if (valid && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, v.ploidy) : n;
+    if (!n_out) n = 0;
+    for (uint32_t x = 0; x < n; ++x) in_row[foff[f] + x] = p[x];
+    T.s_tri[tid * NF + f] = make_uint4(0, 0, 0, tri_info(n_out, 2, v.ploidy, n));
+    O.f[o_f0 + f].len[sq] = (uint16_t)n_out;
+  }
+}
+
+// one output row the fast loops do not cover: dead / invalid (all padding), trivial with an unusual length, or a
+// non-trivial call (allele LUT + staged input vector).  Whole warp, lane <-> word.
+__device__ __noinline__ void tile_slow_row(const TileCtx T, const uint4 t, uint32_t row, const uint4 foff4, int f, int kind, int elem, bool remap,
+                                           uint32_t A_m, uint32_t G, uint32_t stride, uint32_t* __restrict__ drow, int lane) {
+  const uint32_t n_out = t.w & 0xFFFF, kindr = (t.w >> 16) & 3, ploidy = (t.w >> 18) & 63, n_in = t.w >> 24;
+  const uint32_t pad = vend_word(elem), miss = missing_word(elem);
+  const uint32_t foff = f == 0 ? foff4.x : (f == 1 ? foff4.y : (f == 2 ? foff4.z : foff4.w));
+  const uint32_t* in = T.s_in + (size_t)row * T.inw + foff;
+  const int8_t* lut = T.s_lut + (size_t)row * T.lw;
+  const bool is_g = remap && kind == KIND_G;
+  for (uint32_t g = lane; g < stride; g += 32) {
+    uint32_t val = pad;
+    if (g < n_out) {
+      if (kindr != 2) {
+        if (!remap) val = g == 0 ? t.x : (g == 1 ? t.y : t.z);
+        else if (is_g && ploidy == 2) { const uint32_t jk = T.s_jk[g]; val = (jk >> 8) == 0 ? t.x : ((jk & 0xFF) == 0 ? t.y : t.z); }
+        else if (kind == KIND_A) val = t.y;
+        else val = g == 0 ? t.x : t.y;
+      } else if (!remap) val = in[g];
+      else if (is_g && ploidy == 2) {
+        const uint32_t jk = T.s_jk[g];
+        const int ij = lut[jk & 0xFF], ik = lut[jk >> 8];
+        if (ij < 0 || ik < 0) val = miss;
+        else { const uint32_t ig = (uint32_t)alleles2gt(ij, ik); val = ig < n_in ? in[ig] : miss; }
+      } else if (is_g && ploidy == 0) val = in[0];
+      else {
+        const int ij = lut[kind == KIND_A ? g + 1 : g];
+        if (ij < 0) val = miss;
+        else { const int ix = (kind == KIND_A) ? ij - 1 : ij; val = (ix < 0 || (uint32_t)ix >= n_in) ? miss : in[ix]; }
+      }
+    }
+    drow[g] = val;
+  }
+}
+
+template <int NF>
+__global__ void __launch_bounds__(TILE_ROWS, 4) k_remap_tile(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
+                                                         const __grid_constant__ RemapOut O, const uint32_t* __restrict__ site_list, const TileShape TS) {
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t tiles_per_site = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
   const uint32_t js = site_list[blockIdx.x / tiles_per_site], tile = blockIdx.x % tiles_per_site;
-  const SiteRec site = B.sites[js];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t q = (uint64_t)tile * TILE_ROWS + tid;
+  const uint64_t sq = (uint64_t)js * S.nq + q;
+  // issue the two dependent gathers of this thread's sample first; everything below overlaps their latency
+  int32_t e = -1;
+  uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
+  if (q < S.nq) {
+    e = B.live[sq];
+    if (e >= 0) { const uint4* hp = reinterpret_cast<const uint4*>(&A.hot[e & (LIVE_REDUCED - 1)]); h0 = hp[0]; h1 = hp[1]; }
+  }
+  const SiteRec* __restrict__ site_g = &B.sites[js];
+  struct { uint32_t n_alleles, flags, allele_first; } site = {site_g->n_alleles, site_g->flags, site_g->allele_first};
   const uint32_t A_m = site.n_alleles;
   const bool nonref = site.flags & 1u, remap = site.flags & 2u, g_suppressed = site.flags & 4u;
-  const int nf = A.n_fields;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t G = A_m * (A_m + 1) / 2;
 
-  unsigned long long* s_ahash = reinterpret_cast<unsigned long long*>(smem);
-  uint16_t* s_jk = reinterpret_cast<uint16_t*>(smem + 8 * TILE_MAX_A);
-  int8_t* s_lut = reinterpret_cast<int8_t*>(smem + 8 * TILE_MAX_A + ((size_t)T.g * 2 + 15) / 16 * 16);
-  uint32_t* s_in = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_lut) + (size_t)TILE_ROWS * T.lw);
-  uint8_t* s_meta = reinterpret_cast<uint8_t*>(s_in + (size_t)TILE_ROWS * T.inw);
-  const int meta_w = 4 + nf;   // [0] kind (0 dead, 1 trivial, 2 general) [1] ploidy [4+f] n_in of field f
+  TileCtx T;
+  T.s_ahash = reinterpret_cast<unsigned long long*>(smem);
+  T.s_jk = reinterpret_cast<uint16_t*>(smem + 8 * TILE_MAX_A);
+  T.s_tri = reinterpret_cast<uint4*>(smem + 8 * TILE_MAX_A + ((size_t)TS.g * 2 + 15) / 16 * 16);
+  T.s_lut = reinterpret_cast<int8_t*>(T.s_tri + (size_t)TILE_ROWS * NF);
+  T.s_in = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(T.s_lut) + (size_t)TILE_ROWS * TS.lw);
+  T.lw = TS.lw; T.inw = TS.inw;
+  __shared__ uint32_t s_nlist, s_direct_only;
+  __shared__ uint16_t s_list[TILE_ROWS];
+  if (tid == 0) { s_nlist = 0; s_direct_only = 1; }
 
-  // per-field slot offsets inside a staged row: a trivial call needs up to 3 words
-  uint32_t foff[MAX_FIELDS];
+  uint32_t foff[NF];
   {
     uint32_t o = 0;
 #pragma unroll
-    for (int f = 0; f < MAX_FIELDS; ++f) if (f < nf) { foff[f] = o; uint32_t w = site.max_in_len[f]; o += (w < 3u ? 3u : w); }
+    for (int f = 0; f < NF; ++f) { foff[f] = o; o += site_g->max_in_len[f]; }
   }
-  for (uint32_t i = tid; i < A_m; i += TILE_ROWS) s_ahash[i] = B.allele_hash[site.allele_first + i];
-  const uint32_t G = A_m * (A_m + 1) / 2;
+  const uint4 foff4 = make_uint4(foff[0], NF > 1 ? foff[NF > 1 ? 1 : 0] : 0, NF > 2 ? foff[NF > 2 ? 2 : 0] : 0, NF > 3 ? foff[NF > 3 ? 3 : 0] : 0);
+  for (uint32_t i = tid; i < A_m; i += TILE_ROWS) T.s_ahash[i] = B.allele_hash[site.allele_first + i];
   if (remap) for (uint32_t g = tid; g < G; g += TILE_ROWS) {
     uint32_t k = (uint32_t)((sqrtf(8.0f * (float)g + 1.0f) - 1.0f) * 0.5f);
     while (k * (k + 1) / 2 > g) --k;
     while ((k + 1) * (k + 2) / 2 <= g) ++k;
-    s_jk[g] = (uint16_t)((k << 8) | (g - k * (k + 1) / 2));
+    T.s_jk[g] = (uint16_t)((k << 8) | (g - k * (k + 1) / 2));
   }
   __syncthreads();
 
   // ---------------------------------------------------------------- phase A: one thread per sample
-  const uint64_t q = (uint64_t)tile * TILE_ROWS + tid;
-  const int o_gt = 0, o_f0 = A.has_gt ? 1 : 0;
+  const int o_f0 = A.has_gt ? 1 : 0;
   if (q < S.nq) {
-    const uint64_t sq = (uint64_t)js * S.nq + q;
-    const int32_t e = B.live[sq];
-    uint8_t* meta = s_meta + (size_t)tid * meta_w;
-    uint32_t* in_row = s_in + (size_t)tid * T.inw;
-    uint32_t gt_stride = 0; uint32_t* gt_dst = nullptr;
-    if (A.has_gt) { gt_stride = O.f[o_gt].stride[js]; gt_dst = O.f[o_gt].data + O.f[o_gt].base[js] + q * gt_stride; }
     if (e < 0) {
-      meta[0] = 0; meta[1] = 0;
-      for (int f = 0; f < nf; ++f) { meta[4 + f] = 0; O.f[o_f0 + f].len[sq] = 0; }
-      if (A.has_gt) { for (uint32_t i = 0; i < gt_stride; ++i) gt_dst[i] = BCF_INT_VEND; O.f[o_gt].len[sq] = 0; }
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        T.s_tri[tid * NF + f] = make_uint4(0, 0, 0, tri_info(0, remap ? 0u : 3u, 0, 0));
+        O.f[o_f0 + f].len[sq] = 0;
+        if (!remap) { const FieldOutDev fo = O.f[o_f0 + f]; const uint32_t fs = fo.stride[js]; uint32_t* d = fo.data + fo.base[js] + q * fs; const uint32_t padw = vend_word(A.fm[f].elem); for (uint32_t x = 0; x < fs; ++x) d[x] = padw; }
+      }
+      if (A.has_gt) { const uint32_t gs = O.f[0].stride[js]; uint32_t* d = O.f[0].data + O.f[0].base[js] + q * gs; for (uint32_t i = 0; i < gs; ++i) d[i] = BCF_INT_VEND; O.f[0].len[sq] = 0; }
       if (O.lut_first) { O.lut_first[sq] = 0xFFFFFFFFu; O.lut_len[sq] = 0; }
     } else {
-      const uint32_t cell = (uint32_t)(e & (LIVE_REDUCED - 1));
-      const bool reduced = (e & LIVE_REDUCED) != 0;
-      const uint4 h0 = reinterpret_cast<const uint4*>(&A.hot[cell])[0];
-      const uint4 h1 = reinterpret_cast<const uint4*>(&A.hot[cell])[1];
-      const uint32_t hw[HOT_WORDS] = {h0.w, h1.x, h1.y, h1.z, h1.w};
-      const uint32_t hflags = h0.x & 0xFF;
-      uint32_t ploidy = (h0.x >> 8) & 0xFF, n_alt = (h0.x >> 16) & 0xFF, nr = h0.x >> 24, gt_len = h0.y & 0xFF;
+      const uint32_t hflags = h0.x & 0xFF, ploidy = (h0.x >> 8) & 0xFF, n_alt = (h0.x >> 16) & 0xFF, nr = h0.x >> 24, gt_len = h0.y & 0xFF;
       const bool inl = ((h0.y >> 8) & 0xFF) != 0;
-      const bool trivial = !reduced && (hflags & F_TRIVIAL) && inl;
-      uint32_t gtw[TILE_MAX_GT];
-      const uint32_t* fptr[MAX_FIELDS]; uint32_t flen[MAX_FIELDS];
-      const DelRec* dr = nullptr;
-      uint32_t ref_len = 1;
-      if (reduced) {
-        dr = find_delrec(S, cell);
-        n_alt = dr->n_alt; nr = dr->has_nr ? 2u : 0u;
-        const uint32_t* g = S.del_words + dr->gt_off;
-        for (uint32_t i = 0; i < gt_len && i < TILE_MAX_GT; ++i) gtw[i] = g[i];
-        for (int f = 0; f < nf; ++f) { if (dr->f_len[f] == 0xFFFFFFFFu) { flen[f] = 0; fptr[f] = nullptr; } else { flen[f] = dr->f_len[f]; fptr[f] = S.del_words + dr->f_off[f]; } }
-      } else if (inl) {
-        uint32_t k = 0;
-        for (uint32_t i = 0; i < gt_len; ++i) { gtw[i] = hw[k < HOT_WORDS ? k : 0]; ++k; }
+      if ((e & LIVE_REDUCED) || !inl || !(hflags & F_TRIVIAL)) {
+        // rare: queue the sample; the queue is drained by consecutive threads below so that few warps diverge
+        s_list[atomicAdd(&s_nlist, 1u)] = (uint16_t)tid;
+        if (!remap) s_direct_only = 0;
+      } else {
+        // ---- trivial call, fully described by its hot record
         const uint32_t fl4 = (h0.y >> 16) | (h0.z << 16);
-        for (int f = 0; f < nf; ++f) { flen[f] = (f < HOT_FIELDS) ? ((fl4 >> (8 * f)) & 0xFF) : 0u; fptr[f] = nullptr; }
-        // copy the inline words to the staged row right away (offset k onwards, field by field)
-        for (int f = 0; f < nf; ++f) for (uint32_t x = 0; x < flen[f]; ++x) { in_row[foff[f] + x] = hw[k < HOT_WORDS ? k : 0]; ++k; }
-      } else {
-        const CellDesc d = A.desc[cell];
-        n_alt = d.n_alt; nr = d.nr_idx; gt_len = (d.flags & F_GTVALID) ? d.gt_len : 0u; ref_len = d.ref_len;
-        if (A.has_gt) { const uint32_t* g = reinterpret_cast<const uint32_t*>(A.gt.val + A.gt.off[cell]); for (uint32_t i = 0; i < gt_len && i < TILE_MAX_GT; ++i) gtw[i] = g[i]; }
-        for (int f = 0; f < nf; ++f) {
-          uint64_t o0 = A.f[f].off[cell], o1 = A.f[f].off[cell + 1];
-          uint32_t n = (uint32_t)((o1 - o0) >> 2);
-          const uint32_t* v = reinterpret_cast<const uint32_t*>(A.f[f].val + o0);
-          const uint32_t nullw = null_word(A.fm[f].elem);
-          bool any = false;
-          for (uint32_t x = 0; x < n; ++x) { uint32_t wv = v[x]; any |= (wv != nullw); }
-          flen[f] = any ? n : 0u; fptr[f] = v;
-        }
-      }
-      if (!reduced && inl && !(hflags & F_TRIVIAL)) ref_len = A.desc[cell].ref_len;   // exact REF length decides the ALT suffix
-      if (!inl || reduced) for (int f = 0; f < nf; ++f) { uint32_t* r = in_row + foff[f]; for (uint32_t x = 0; x < flen[f]; ++x) r[x] = fptr[f][x]; }
-      const uint32_t A_in = n_alt + 1u;
-      const int in_nr = (nonref && nr) ? (int)nr : -1;
-      const int step = A.gt_phased ? 2 : 1;
-      uint32_t gto[TILE_MAX_GT];
-      uint32_t lut_first = 0xFFFFFFFFu;
-      if (O.lut_first) { lut_first = atomicAdd(&B.cursors[2], A_in); if (lut_first + A_in > O.cap_lut) { atomicOr(&S.err[2], 2u); lut_first = 0xFFFFFFFFu; } O.lut_first[sq] = lut_first; O.lut_len[sq] = (uint16_t)A_in; }
-      meta[1] = (uint8_t)ploidy;
-      const bool is_triv = trivial || !remap;
-      if (is_triv) {
-        meta[0] = 1;
-        for (uint32_t i = 0; i < gt_len; ++i) {
-          uint32_t g = gtw[i];
-          if (remap && (i % step) == 0 && !(g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING))
-            g = (g == 0) ? 0u : ((nr && g == nr) ? A_m - 1u : (nonref ? A_m - 1u : 0xFFFFFFFFu));
-          gto[i] = g;
-        }
-        if (lut_first != 0xFFFFFFFFu) for (uint32_t i = 0; i < A_in; ++i) O.lut_in2m[lut_first + i] = (int16_t)(i == 0 ? 0 : ((nr && i == nr) ? (int)A_m - 1 : -1));
-        if (remap) {
-          // the 2-3 distinct values a trivial call can contribute (m2in: REF->0, every ALT -> its own NON_REF or nothing)
-          for (int f = 0; f < nf; ++f) {
-            const uint32_t n = flen[f]; if (!n) continue;
-            const uint32_t miss = missing_word(A.fm[f].elem);
-            uint32_t* r = in_row + foff[f];
-            // values currently staged at r[0..n) (inline) ; trivial implies inline
-            uint32_t v0 = r[0], v1 = miss, v2 = miss;
-            const int kind = A.fm[f].kind;
-            if (in_nr >= 0) {
-              if (kind == KIND_A) { v1 = ((uint32_t)in_nr - 1u < n) ? r[in_nr - 1] : miss; }
-              else if (kind == KIND_R || ploidy != 2) { v1 = ((uint32_t)in_nr < n) ? r[in_nr] : miss; }
-              else { uint32_t g1 = (uint32_t)alleles2gt(0, in_nr), g2 = (uint32_t)alleles2gt(in_nr, in_nr); v1 = g1 < n ? r[g1] : miss; v2 = g2 < n ? r[g2] : miss; }
+        const int in_nr = (nonref && nr) ? (int)nr : -1;
+        if (A.has_gt) {
+          const uint32_t gs = O.f[0].stride[js]; uint32_t* d = O.f[0].data + O.f[0].base[js] + q * gs;
+          const int step = A.gt_phased ? 2 : 1;
+          for (uint32_t i = 0; i < gs; ++i) {
+            uint32_t g = BCF_INT_VEND;
+            if (i < gt_len) {
+              g = sel5(h0.w, h1.x, h1.y, h1.z, h1.w, i);
+              if (remap && (i % step) == 0 && !(g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING))
+                g = (g == 0) ? 0u : ((nr && g == nr) ? A_m - 1u : (nonref ? A_m - 1u : 0xFFFFFFFFu));
             }
-            r[0] = v0; r[1] = v1; r[2] = v2;
+            d[i] = g;
           }
+          O.f[0].len[sq] = (uint16_t)gt_len;
         }
-      } else {
-        meta[0] = 2;
-        int8_t* lut = s_lut + (size_t)tid * T.lw;
-        for (uint32_t m = 0; m < A_m; ++m) lut[m] = -1;
-        lut[0] = 0;
-        uint32_t mapped = 0;   // GT slots already assigned
-        for (uint32_t i = 0; i < gt_len; ++i) { uint32_t g = gtw[i]; gto[i] = g; if ((i % step) || g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING) mapped |= 1u << i; else if (g == 0) mapped |= 1u << i; }
-        if (lut_first != 0xFFFFFFFFu) { O.lut_in2m[lut_first] = 0; for (uint32_t i = 1; i < A_in; ++i) O.lut_in2m[lut_first + i] = -1; }
-        const uint8_t* mref = B.allele_bytes + site.ref_off;
-        auto assign = [&](uint32_t idx, uint32_t m) {
-          lut[m] = (int8_t)idx;
-          for (uint32_t i = 0; i < gt_len; ++i) if (!(i % step) && gtw[i] == idx && !(gtw[i] == TDB_NULL_INT || gtw[i] == 0xFFFFFFFFu || gtw[i] == BCF_INT_MISSING)) { gto[i] = m; mapped |= 1u << i; }
-          if (lut_first != 0xFFFFFFFFu) O.lut_in2m[lut_first + idx] = (int16_t)m;
-        };
-        if (reduced) {
-          int sfx; uint64_t h = allele_hash(c_str_star, 1, mref, site.ref_len, 1, sfx);
-          for (uint32_t m = 1; m < A_m; ++m) if (s_ahash[m] == h) { assign(1, m); break; }
-        } else {
-          const uint8_t* alt = A.alt.val + A.alt.off[cell];
-          const int an = alt_effective_len(alt, (int)(A.alt.off[cell + 1] - A.alt.off[cell]));
-          int pos = 0, ts, tl; uint32_t idx = 0;
-          while (next_token(alt, an, pos, ts, tl)) {
-            ++idx;
-            if (is_non_ref(alt + ts, tl)) continue;
-            int sfx; uint64_t h = allele_hash(alt + ts, tl, mref, site.ref_len, ref_len, sfx);
-            for (uint32_t m = 1; m < A_m; ++m) if (s_ahash[m] == h) { assign(idx, m); break; }
+        if (O.lut_first) {
+          const uint32_t A_in = n_alt + 1u;
+          uint32_t first = atomicAdd(&B.cursors[2], A_in);
+          if (first + A_in > O.cap_lut) { atomicOr(&S.err[2], 2u); first = 0xFFFFFFFFu; }
+          O.lut_first[sq] = first; O.lut_len[sq] = (uint16_t)A_in;
+          if (first != 0xFFFFFFFFu) for (uint32_t i = 0; i < A_in; ++i) O.lut_in2m[first + i] = (int16_t)(i == 0 ? 0 : ((nr && i == nr) ? (int)A_m - 1 : -1));
+        }
+        uint32_t k = gt_len;   // fields follow GT in the record
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          const uint32_t n = (fl4 >> (8 * f)) & 0xFF;
+          const int kind = A.fm[f].kind;
+          const uint32_t miss = missing_word(A.fm[f].elem);
+          uint32_t n_out = 0;
+          if (n && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, ploidy) : n;
+          uint32_t v0 = 0, v1 = miss, v2 = miss;
+          if (n_out) {
+            if (!remap) { v0 = sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k); v1 = n > 1 ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + 1) : 0; v2 = n > 2 ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + 2) : 0; }
+            else {
+              v0 = sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k);
+              if (in_nr >= 0) {
+                if (kind == KIND_A) { const uint32_t i1 = (uint32_t)in_nr - 1u; v1 = i1 < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + i1) : miss; }
+                else if (kind == KIND_R || ploidy != 2) { v1 = (uint32_t)in_nr < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + in_nr) : miss; }
+                else {
+                  const uint32_t g1 = (uint32_t)in_nr * ((uint32_t)in_nr + 1u) / 2u, g2 = g1 + (uint32_t)in_nr;
+                  v1 = g1 < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + g1) : miss;
+                  v2 = g2 < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + g2) : miss;
+                }
+              }
+            }
           }
+          if (!remap) {
+            // a site that needs no remapping copies the (inline, <= 5 words) input through, straight from this thread
+            const FieldOutDev fo = O.f[o_f0 + f];
+            const uint32_t fs = fo.stride[js]; uint32_t* d = fo.data + fo.base[js] + q * fs;
+            const uint32_t padw = vend_word(A.fm[f].elem);
+            for (uint32_t x = 0; x < fs; ++x) d[x] = x < n_out ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + x) : padw;
+          }
+          T.s_tri[tid * NF + f] = make_uint4(v0, v1, v2, tri_info(n_out, remap ? 1u : 3u, ploidy, n));   // kind 3: already written
+          O.f[o_f0 + f].len[sq] = (uint16_t)n_out;
+          k += n;
         }
-        if (nr) assign(nr, A_m - 1u);
-        for (uint32_t i = 0; i < gt_len; ++i) if (!(mapped & (1u << i))) gto[i] = nonref ? A_m - 1u : 0xFFFFFFFFu;
-        for (uint32_t m = 0; m < A_m; ++m) if (lut[m] < 0) lut[m] = (int8_t)in_nr;   // NON_REF fallback folded in
-      }
-      // GT + lengths straight to global (adjacent threads -> adjacent samples -> contiguous)
-      if (A.has_gt) {
-        for (uint32_t i = 0; i < gt_stride; ++i) gt_dst[i] = (i < gt_len) ? gto[i] : BCF_INT_VEND;
-        O.f[o_gt].len[sq] = (uint16_t)gt_len;
-      }
-      for (int f = 0; f < nf; ++f) {
-        const int kind = A.fm[f].kind;
-        uint32_t n_out = 0;
-        if (flen[f] && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, ploidy) : flen[f];
-        meta[4 + f] = (uint8_t)((flen[f] && n_out) ? flen[f] : 0u);
-        O.f[o_f0 + f].len[sq] = (uint16_t)n_out;
       }
     }
   }
   __syncthreads();
+  for (uint32_t i = tid; i < s_nlist; i += TILE_ROWS) {
+    const uint32_t row = s_list[i];
+    const uint64_t qr = (uint64_t)tile * TILE_ROWS + row;
+    tile_general_row<NF>(A, S, B, O, site_g, T, js, qr, (int)row, B.live[(uint64_t)js * S.nq + qr], foff4);
+  }
+  __syncthreads();
 
-  // ---------------------------------------------------------------- phase B: stream the dense output
+  // ---------------------------------------------------------------- phase B: stream the dense output, one sample per warp iteration
   const uint32_t rows = (uint32_t)min((uint64_t)TILE_ROWS, S.nq - (uint64_t)tile * TILE_ROWS);
-  for (int f = 0; f < nf; ++f) {
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
     const FieldOutDev fo = O.f[o_f0 + f];
     const uint32_t stride = fo.stride[js];
     if (stride == 0) continue;
-    uint32_t* dst = fo.data + fo.base[js] + (uint64_t)tile * TILE_ROWS * stride;
+    uint32_t* __restrict__ dst = fo.data + fo.base[js] + (uint64_t)tile * TILE_ROWS * stride + lane;
     const int kind = A.fm[f].kind, elem = A.fm[f].elem;
-    const uint32_t pad = vend_word(elem), miss = missing_word(elem);
-    const uint32_t fo_in = foff[f];
+    const uint32_t pad = vend_word(elem);
+    const bool act0 = (uint32_t)lane < stride, act1 = (uint32_t)lane + 32u < stride;
     if (remap && kind == KIND_G) {
-      const uint32_t n_chunks = (stride + 31) / 32, items = n_chunks * rows;
-      for (uint32_t item = warp; item < items; item += TILE_ROWS / 32) {
-        const uint32_t row = item / n_chunks, g = (item % n_chunks) * 32 + lane;
-        const uint8_t* meta = s_meta + (size_t)row * meta_w;
-        const uint32_t kindr = meta[0], ploidy = meta[1], n_in = meta[4 + f];
-        if (g >= stride) continue;
-        uint32_t val = pad;
-        if (n_in) {
-          const uint32_t* in = s_in + (size_t)row * T.inw + fo_in;
-          const uint32_t n_out = (ploidy == 2) ? G : (ploidy == 1 ? A_m : 1u);
-          if (g < n_out) {
-            if (ploidy == 2) {
-              const uint32_t jk = s_jk[g], j = jk & 0xFF, k = jk >> 8;
-              if (kindr == 1) val = in[(k == 0) ? 0 : (j == 0 ? 1 : 2)];
-              else {
-                const int8_t* lut = s_lut + (size_t)row * T.lw;
-                const int ij = lut[j], ik = lut[k];
-                if (ij < 0 || ik < 0) val = miss;
-                else { const uint32_t ig = (uint32_t)alleles2gt(ij, ik); val = ig < n_in ? in[ig] : miss; }
-              }
-            } else if (ploidy == 1) {
-              if (kindr == 1) val = in[g == 0 ? 0 : 1];
-              else { const int ij = (s_lut + (size_t)row * T.lw)[g]; val = (ij < 0 || (uint32_t)ij >= n_in) ? miss : in[ij]; }
-            } else val = in[0];
-          }
-        }
-        dst[(uint64_t)row * stride + g] = val;
+      // diploid trivial sample: word g is v0 for genotype (0,0), v1 for (0,k), v2 for (j>0,k)
+      const uint32_t expect = (G & 0xFFFF) | (1u << 16) | (2u << 18);
+      bool a0 = false, b0 = false, a1 = false, b1 = false;   // a: class 0, b: class 2
+      if ((uint32_t)lane < G) { const uint32_t jk = T.s_jk[lane]; a0 = (jk >> 8) == 0; b0 = (jk & 0xFF) != 0; }
+      if ((uint32_t)lane + 32u < G) { const uint32_t jk = T.s_jk[lane + 32]; a1 = (jk >> 8) == 0; b1 = (jk & 0xFF) != 0; }
+      for (uint32_t row = warp; row < rows; row += TILE_ROWS / 32) {
+        const uint4 t = T.s_tri[row * NF + f];
+        uint32_t* __restrict__ pr = dst + row * stride;
+        if ((t.w & 0xFFFFFFu) == expect && stride == G) {
+          if (act0) pr[0] = a0 ? t.x : (b0 ? t.z : t.y);
+          if (act1) pr[32] = a1 ? t.x : (b1 ? t.z : t.y);
+          for (uint32_t g = lane + 64; g < stride; g += 32) { const uint32_t jk = T.s_jk[g]; pr[g - lane] = (jk >> 8) == 0 ? t.x : ((jk & 0xFF) == 0 ? t.y : t.z); }
+        } else if ((t.w & 0xFFFFu) == 0) {   // sample not live / field absent: padding only
+          if (act0) pr[0] = pad;
+          if (act1) pr[32] = pad;
+          for (uint32_t g = lane + 64; g < stride; g += 32) pr[g - lane] = pad;
+        } else tile_slow_row(T, t, row, foff4, f, kind, elem, true, A_m, G, stride, pr - lane, lane);
       }
-    } else {
-      const uint32_t total = rows * stride;
-      const float inv = 1.0f / (float)stride;
-      for (uint32_t w = tid; w < total; w += TILE_ROWS) {
-        uint32_t row = (uint32_t)(((float)w + 0.5f) * inv);
-        if (row * stride > w) --row; else if ((row + 1) * stride <= w) ++row;
-        const uint32_t j = w - row * stride;
-        const uint8_t* meta = s_meta + (size_t)row * meta_w;
-        const uint32_t kindr = meta[0], n_in = meta[4 + f];
-        uint32_t val = pad;
-        if (n_in) {
-          const uint32_t* in = s_in + (size_t)row * T.inw + fo_in;
-          if (!remap) val = j < n_in ? in[j] : pad;
-          else {
-            const uint32_t n_out = (kind == KIND_A) ? A_m - 1u : A_m;
-            if (j < n_out) {
-              if (kindr == 1) val = (kind == KIND_A) ? in[1] : in[j == 0 ? 0 : 1];
-              else {
-                const int ij = (s_lut + (size_t)row * T.lw)[kind == KIND_A ? j + 1 : j];
-                if (ij < 0) val = miss;
-                else { const int ix = (kind == KIND_A) ? ij - 1 : ij; val = (ix < 0 || (uint32_t)ix >= n_in) ? miss : in[ix]; }
-              }
-            }
-          }
-        }
-        dst[w] = val;
+    } else if (remap) {
+      const uint32_t n_full = (kind == KIND_A) ? A_m - 1u : A_m;
+      const uint32_t expect = (n_full & 0xFFFF) | (1u << 16);
+      const bool first = (kind != KIND_A) && lane == 0;
+      for (uint32_t row = warp; row < rows; row += TILE_ROWS / 32) {
+        const uint4 t = T.s_tri[row * NF + f];
+        uint32_t* __restrict__ pr = dst + row * stride;
+        if ((t.w & 0x3FFFFu) == expect && stride == n_full) {
+          if (act0) pr[0] = first ? t.x : t.y;
+          for (uint32_t g = lane + 32; g < stride; g += 32) pr[g - lane] = t.y;
+        } else if ((t.w & 0xFFFFu) == 0) {
+          if (act0) pr[0] = pad;
+          for (uint32_t g = lane + 32; g < stride; g += 32) pr[g - lane] = pad;
+        } else tile_slow_row(T, t, row, foff4, f, kind, elem, true, A_m, G, stride, pr - lane, lane);
+      }
+    } else if (!s_direct_only) {
+      for (uint32_t row = warp; row < rows; row += TILE_ROWS / 32) {
+        const uint4 t = T.s_tri[row * NF + f];
+        if (((t.w >> 16) & 3u) == 2u) tile_slow_row(T, t, row, foff4, f, kind, elem, false, A_m, G, stride, dst - lane + row * stride, lane);
       }
     }
   }

@@ -1,0 +1,53 @@
+"""GPU: the host-side C++ mirror of the reference's plugin surface (VariantQueryProcessor::scan_and_operate +
+SingleVariantOperatorBase::operate, genomicsdb_b200/csrc/gdb_host_api.h) driven by tools/gt_gpu_gather.cc -- the
+counterpart of oracle/ref_harness/gdb_ref_dump.cc -- against the reference's dumps."""
+import json
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, golden_cases
+
+pytestmark = pytest.mark.gpu
+CASES = [c for c in golden_cases() if c["id"] in (
+    "t0_1_2_at_0", "t0_1_2_multiple_positions", "t0_1_2_at_12150", "t6_7_8_at_8029500", "haploid_triploid_deletion_min_PL",
+    "min_PL_spanning_deletion_no_min_PL", "t0_1_2_two_fragments_at_0", "test_new_fields_at_0", "t0_overlapping_at_0")]
+
+
+@pytest.fixture(scope="module")
+def exe():
+    import __graft_entry__ as g
+    g.build_gpu_lib()
+    return g.build_tools()
+
+
+def run_case(exe, case, tmp_path, page):
+    q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
+         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": case["attributes"],
+         "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_column_ranges"]]}],
+         "query_row_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_row_ranges"]]}],
+         "produce_GT_with_min_PL_value_for_spanning_deletions": case["produce_GT_with_min_PL_value_for_spanning_deletions"]}
+    qf = tmp_path / "query.json"
+    qf.write_text(json.dumps(q))
+    out = tmp_path / "dump.bin"
+    cmd = [exe, "-j", str(qf), "-o", str(out)] + (["-p", str(page)] if page else [])
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    return out.read_bytes(), json.loads(p.stdout.strip().splitlines()[-1])["sites"]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_scan_and_operate_mirror_matches_reference(exe, case, tmp_path):
+    gold = open(os.path.join(GOLDEN, case["dump"]), "rb").read()
+    got, n = run_case(exe, case, tmp_path, 0)
+    assert n == case["sites"]
+    assert got == gold
+
+
+@pytest.mark.parametrize("case", CASES[:3], ids=[c["id"] for c in CASES[:3]])
+def test_overflow_resume_protocol(exe, case, tmp_path):
+    """an operator that reports overflow() after every site forces scan_and_operate to return and be re-entered"""
+    gold = open(os.path.join(GOLDEN, case["dump"]), "rb").read()
+    got, n = run_case(exe, case, tmp_path, 1)
+    assert got == gold

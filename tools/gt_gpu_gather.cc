@@ -1,0 +1,101 @@
+// gt_gpu_gather -- the reference's query driver for the combine path (tools/src/gt_mpi_gather.cc:322-366,413-614),
+// restated over the host mirror (genomicsdb_b200/csrc/gdb_host_api.h).  Same JSON query file, same rank convention
+// (-r, no MPI needed: the combine path has no collectives), same scan_state / overflow loop.  Output: the canonical
+// hot-path dump (layout in oracle/ref_harness/gdb_ref_dump.cc) written by an operator plugged into
+// SingleVariantOperatorBase::operate -- the same seam the reference harness uses, so the two programs read alike.
+#include <getopt.h>
+
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <string>
+
+#include "../genomicsdb_b200/csrc/gdb_host_api.h"
+
+using namespace genomicsdb_b200;
+
+class HotPathDumpOperator : public GA4GHOperator {
+ public:
+  HotPathDumpOperator(const VariantQueryConfig& qc, FILE* out, size_t overflow_every) : m_out(out), m_overflow_every(overflow_every) {
+    put<uint32_t>(0x31444247u);
+    put<uint32_t>(qc.get_num_remapped_fields());
+    for (unsigned i = 0; i < qc.get_num_remapped_fields(); ++i) put_string(qc.get_remapped_field_name(i));
+    m_num_fields = qc.get_num_remapped_fields();
+  }
+  void operate(Variant& variant, const VariantQueryConfig& query_config) override {
+    GA4GHOperator::operate(variant, query_config);
+    ++m_num_sites; ++m_since_drain;
+    put<int64_t>(variant.get_column_begin());
+    put<int64_t>(variant.get_column_end());
+    put<uint8_t>(m_NON_REF_exists ? 1 : 0);
+    put<uint8_t>(m_remapping_needed ? 1 : 0);
+    put<uint16_t>(m_merged_alt_alleles.size());
+    put_string(m_merged_reference_allele);
+    for (const auto& alt : m_merged_alt_alleles) put_string(alt);
+    const Variant& src = get_remapped_variant();
+    uint32_t L = 0;
+    for (auto it = src.begin(); it != src.end(); ++it) ++L;
+    put<uint32_t>(L);
+    for (auto it = src.begin(); it != src.end(); ++it) {
+      const VariantCall& call = *it;
+      put<int64_t>(call.get_row_idx());
+      put<int64_t>(call.get_column_begin());
+      put<int64_t>(call.get_column_end());
+      put<uint16_t>(call.get_num_input_alleles());
+      for (unsigned i = 0; i < call.get_num_input_alleles(); ++i) put<int32_t>(call.get_alleles_LUT()[i]);
+      for (unsigned f = 0; f < m_num_fields; ++f) {
+        put<uint32_t>(call.get_field_length(f));
+        if (call.get_field_length(f)) fwrite(call.get_field_words(f), 4u, call.get_field_length(f), m_out);
+      }
+    }
+  }
+  // emulates a consumer with a bounded buffer (VCFSerializedBufferAdapter::overflow, vcf_adapter.h:190-195)
+  bool overflow() const override { return m_overflow_every && m_since_drain >= m_overflow_every; }
+  void drain() { m_since_drain = 0; }
+  uint64_t num_sites() const { return m_num_sites; }
+ private:
+  template <class T> void put(T v) { fwrite(&v, sizeof(T), 1u, m_out); }
+  void put_string(const std::string& s) { put<uint32_t>(s.length()); if (s.length()) fwrite(s.data(), 1u, s.length(), m_out); }
+  FILE* m_out; unsigned m_num_fields = 0; uint64_t m_num_sites = 0; size_t m_overflow_every, m_since_drain = 0;
+};
+
+int main(int argc, char** argv) {
+  std::string query_json, out_file; int rank = 0, device = 0; size_t page = 0;
+  static struct option long_options[] = {{"query", 1, 0, 'j'}, {"rank", 1, 0, 'r'}, {"output", 1, 0, 'o'}, {"device", 1, 0, 'd'}, {"page-size", 1, 0, 'p'}, {0, 0, 0, 0}};
+  int c;
+  while ((c = getopt_long(argc, argv, "j:r:o:d:p:", long_options, NULL)) >= 0) {
+    switch (c) {
+      case 'j': query_json = optarg; break;
+      case 'r': rank = atoi(optarg); break;
+      case 'o': out_file = optarg; break;
+      case 'd': device = atoi(optarg); break;
+      case 'p': page = strtoull(optarg, 0, 10); break;   // operate() calls between two "drains" (exercises overflow/resume)
+      default: return -1;
+    }
+  }
+  if (query_json.empty() || out_file.empty()) { std::cerr << "usage: gt_gpu_gather -j query.json -o dump.bin [-r rank] [-d cuda_device] [-p sites_per_page]\n"; return -1; }
+  try {
+    VariantQueryConfig query_config;
+    query_config.read_from_file(query_json, rank);
+    VariantStorageManager sm(query_config.get_workspace(rank), 10u * 1024u * 1024u, device);
+    VariantQueryProcessor qp(&sm, query_config.get_array_name(rank), query_config.get_vid_mapper());
+    qp.do_query_bookkeeping(query_config, true);
+    FILE* out = fopen(out_file.c_str(), "wb");
+    if (!out) { std::cerr << "cannot open " << out_file << "\n"; return -1; }
+    HotPathDumpOperator op(query_config, out, page);
+    VariantQueryProcessorScanState scan_state;
+    for (auto i = 0u; i < std::max(1u, query_config.get_num_column_intervals()); ++i) {
+      while (!scan_state.end()) {
+        qp.scan_and_operate(qp.get_array_descriptor(), query_config, op, i, true, &scan_state, true);
+        op.drain();
+      }
+      scan_state.reset();
+    }
+    fclose(out);
+    printf("{\"sites\": %llu}\n", (unsigned long long)op.num_sites());
+  } catch (const std::exception& e) {
+    std::cerr << "gt_gpu_gather: " << e.what() << "\n";
+    return 1;
+  }
+  return 0;
+}
