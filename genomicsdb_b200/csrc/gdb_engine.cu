@@ -463,7 +463,8 @@ void scan_prepare(gdbgpu_scan* s) {
   check_scan_errors(s, ovf);
 }
 
-uint32_t stride_of(const gdbgpu_array* a, const SiteRec& r, int o) {
+// words a sample's vector needs at this site (the algorithmic figure) ...
+uint32_t stride_needed(const gdbgpu_array* a, const SiteRec& r, int o) {
   if (a->has_gt && o == 0) return r.max_gt_len;
   int f = o - (a->has_gt ? 1 : 0);
   if (r.max_in_len[f] == 0) return 0;
@@ -471,6 +472,14 @@ uint32_t stride_of(const gdbgpu_array* a, const SiteRec& r, int o) {
   int kind = a->fm[f].kind;
   if (kind == KIND_G && (r.flags & 4u)) return 0;
   return num_elements(kind, r.n_alleles - 1u, r.max_ploidy[f]);
+}
+// ... and the stride actually used: remapped fields are padded to a multiple of 4 words so that every sample's vector
+// is 16-byte aligned (the tile kernel stores 128 bits per lane); the padding holds BCF vector-end words
+uint32_t stride_of(const gdbgpu_array* a, const SiteRec& r, int o) {
+  uint32_t st = stride_needed(a, r, o);
+  if (a->has_gt && o == 0) return st;
+  if (r.flags & 2u) st = (st + 3u) & ~3u;
+  return st;
 }
 
 int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_batch* out) {
@@ -503,13 +512,17 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
     if (ovf) { s->cap_allele_recs *= 4; s->cap_allele_bytes *= 4; continue; }
     // strides / bases; keep the prefix of sites that fits
     for (int o = 0; o < n_out; ++o) { bb.h_base[o].assign(nb + 1, 0); bb.h_stride[o].assign(nb, 0); }
-    uint64_t bytes = 0; uint32_t keep = 0; uint64_t lut_words = 0;
+    uint64_t bytes = 0, alg_bytes = 0; uint32_t keep = 0; uint64_t lut_words = 0;
     for (uint32_t i = 0; i < nb; ++i) {
-      uint64_t site_bytes = 0;
-      for (int o = 0; o < n_out; ++o) { uint32_t st = stride_of(a, bb.h_sites[i], o); bb.h_stride[o][i] = st; site_bytes += (uint64_t)st * S.nq * 4 + S.nq * 2; }
+      uint64_t site_bytes = 0, site_alg = 0;
+      for (int o = 0; o < n_out; ++o) {
+        uint32_t st = stride_of(a, bb.h_sites[i], o); bb.h_stride[o][i] = st;
+        site_bytes += (((uint64_t)st * S.nq + 3) & ~3ull) * 4 + S.nq * 2;
+        site_alg += (uint64_t)stride_needed(a, bb.h_sites[i], o) * S.nq * 4;
+      }
       if (i > 0 && bytes + site_bytes > max_bytes) break;
-      for (int o = 0; o < n_out; ++o) bb.h_base[o][i + 1] = bb.h_base[o][i] + (uint64_t)bb.h_stride[o][i] * S.nq;
-      bytes += site_bytes; lut_words += (uint64_t)bb.h_sites[i].max_ain * S.nq; keep = i + 1;
+      for (int o = 0; o < n_out; ++o) bb.h_base[o][i + 1] = (bb.h_base[o][i] + (uint64_t)bb.h_stride[o][i] * S.nq + 3) & ~3ull;   // 16-byte aligned sites
+      bytes += site_bytes; alg_bytes += site_alg; lut_words += (uint64_t)bb.h_sites[i].max_ain * S.nq; keep = i + 1;
     }
     s->avg_site_bytes = std::max<uint64_t>(1, bytes / keep);
     RemapOut O{};
@@ -576,7 +589,7 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
     for (uint32_t i = 0; i < keep; ++i) { const SiteRec& r = bb.h_sites[i]; bb.h_site_flags[i] = (uint8_t)r.flags; bb.h_n_alleles[i] = r.n_alleles; bb.h_n_live[i] = r.n_live; bb.h_allele_first[i] = r.allele_first; }
     uint32_t hc[4];
     CK(cudaMemcpyAsync(hc, bb.cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
-    out->n_sites = keep; out->out_bytes = bytes;
+    out->n_sites = keep; out->out_bytes = alg_bytes;
     if (s->device_output) {
       bb.d_site_flags.ensure(keep); bb.d_n_alleles.ensure(keep); bb.d_n_live.ensure(keep); bb.d_allele_first.ensure(keep);
       CK(cudaMemcpyAsync(bb.d_site_flags.p, bb.h_site_flags.data(), keep, cudaMemcpyHostToDevice, ctx->stream));

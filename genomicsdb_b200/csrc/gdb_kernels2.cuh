@@ -672,14 +672,19 @@ __global__ void __launch_bounds__(REMAP_THREADS) k_remap_generic(ArrayDev A, Sca
 
 // ================================================================================================ K5 tile kernel
 // The fast path of the remap (sites with <= 64 merged alleles, ploidy <= 2, short input vectors, <= 4 remapped fields --
-// everything but pathological sites, which k_remap_generic keeps handling).
-//   phase A  one thread per sample (256 samples of one site per block).  ONE 32-byte hot-record gather gives a trivial
-//            call's GT and PL/AD (reference block or <NON_REF>-only call: ~90 % of the calls live at a site); the thread
-//            remaps GT, writes the lengths, and leaves in shared memory, per field, the 2-3 distinct values such a call
-//            can contribute to the output.  Non-trivial calls build their allele LUT and stage their raw input vector.
-//   phase B  warps stream the dense sample-major output: one sample per warp iteration, lane <-> genotype index, fully
-//            coalesced stores; a trivial sample costs one LDS.128 and a 3-way select per word.
-// Output bytes dominate (26.8 MB per site at 100 k samples x 10 alleles): the kernel is bound by HBM write bandwidth.
+// everything but pathological sites, which k_remap_generic keeps handling).  One block = 256 samples of one site.
+//   phase A  one thread per sample.  ONE 32-byte hot-record gather describes a trivial call completely (reference block
+//            or <NON_REF>-only call: ~90 % of the calls live at a site): the thread remaps GT, writes the lengths and
+//            leaves, per field, the (at most) three distinct values such a call contributes: genotype (0,0), (0,k),
+//            (j>0,k) -- plus the padding word.  Every other call is queued.
+//   queue    consecutive threads drain the queue (one warp diverges, not eight): tokenise ALT, hash, look the tokens up
+//            in the site's allele hashes, build the merged->input LUT (NON_REF fallback folded in), stage the raw vector.
+//   phase B  per field, (1) a vectorised pass: each lane owns one 16-byte quad of the dense sample-major output, a
+//            per-site class table says which of the four words (v0,v1,v2,pad) every output word takes -> 6 LDS + one
+//            coalesced STG.128 per 4 words; (2) a pass over the queued samples only, lane-parallel over their quads.
+// Field strides of remapped sites are multiples of 4 words so that every sample's vector is 16-byte aligned.
+// Output bytes dominate (26.8 MB per site at 100 k samples x 10 alleles): the kernel is a store stream bound by HBM
+// write bandwidth; no tensor cores, no TMA (inputs are 256 scattered 32-byte sectors per block, not a tile).
 namespace gdb {
 
 constexpr int TILE_ROWS = 256;
@@ -687,31 +692,60 @@ constexpr int TILE_MAX_A = 64;
 constexpr int TILE_MAX_INW = 48;
 constexpr int TILE_MAX_GT = 8;
 constexpr int TILE_MAX_FIELDS = 4;
+constexpr uint32_t INFO_FAST = 1u << 30;
 
-struct TileShape { uint32_t lw, inw, g; };   // per-launch shared-memory strides: LUT bytes/row, input words/row, jk entries
+struct TileShape { uint32_t lw, inw, g; };   // per-launch shared-memory strides: LUT bytes/row, input words/row, max #genotypes
 
+__host__ __device__ inline uint32_t tile_cls_bytes(TileShape t) { return ((t.g + 3) / 4 + 15) / 16 * 16; }   // class table of one field
 __host__ __device__ inline size_t tile_smem_bytes(TileShape t, int n_fields) {
   size_t b = 8 * (size_t)TILE_MAX_A;                       // allele hashes
   b += ((size_t)t.g * 2 + 15) / 16 * 16;                   // (j,k) table
-  b += (size_t)TILE_ROWS * n_fields * 16;                  // per (sample, field): v0, v1, v2, info
-  b += (size_t)TILE_ROWS * t.lw;                           // LUT rows (int8), non-trivial calls only
-  b += (size_t)TILE_ROWS * t.inw * 4;                      // staged inputs, non-trivial calls only
+  b += (size_t)n_fields * tile_cls_bytes(t);               // class tables
+  b += (size_t)TILE_ROWS * n_fields * 16;                  // per (sample, field): v0, v1, v2, pad
+  b += (size_t)TILE_ROWS * n_fields * 4;                   // per (sample, field): info word
+  b += (size_t)TILE_ROWS * t.lw;                           // LUT rows (int8), queued samples only
+  b += (size_t)TILE_ROWS * t.inw * 4;                      // staged inputs, queued samples only
   return (b + 15) / 16 * 16;
 }
-// info word of a (sample, field) slot
-__device__ inline uint32_t tri_info(uint32_t n_out, uint32_t kind, uint32_t ploidy, uint32_t n_in) { return (n_out & 0xFFFF) | (kind << 16) | (ploidy << 18) | (n_in << 24); }
+// info word of a (sample, field) slot: n_out | kind (0 dead, 1 trivial, 2 general) | ploidy | n_in | FAST
+__device__ inline uint32_t tri_info(uint32_t n_out, uint32_t kind, uint32_t ploidy, uint32_t n_in) { return (n_out & 0xFFFF) | (kind << 16) | ((ploidy & 15u) << 18) | ((n_in & 0xFF) << 22); }
 __device__ inline uint32_t sel5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t i) { return i == 0 ? a : (i == 1 ? b : (i == 2 ? c : (i == 3 ? d : e))); }
 
 struct TileCtx {
-  unsigned long long* s_ahash; uint16_t* s_jk; uint4* s_tri; int8_t* s_lut; uint32_t* s_in;
-  uint32_t lw, inw;
+  unsigned long long* s_ahash; uint16_t* s_jk; uint8_t* s_cls; uint4* s_tri; uint32_t* s_info; int8_t* s_lut; uint32_t* s_in;
+  uint32_t lw, inw, cls_bytes;
 };
 
-// non-trivial / non-inline / reduced calls: rare, kept out of line so the common path stays small
+// one word of a queued sample's output (generic in kind / ploidy): variant_field_handler.cc:41-191
+__device__ inline uint32_t tile_slow_word(const TileCtx& T, uint32_t info, const uint4 t, uint32_t row, uint32_t foff, int kind, bool is_g, uint32_t g,
+                                          uint32_t pad, uint32_t miss) {
+  const uint32_t n_out = info & 0xFFFF, kindr = (info >> 16) & 3, ploidy = (info >> 18) & 15, n_in = (info >> 22) & 0xFF;
+  if (g >= n_out) return pad;
+  if (kindr != 2) {   // trivial call with an unusual length (haploid, ploidy 0, ...)
+    if (is_g && ploidy == 2) { const uint32_t jk = T.s_jk[g]; return (jk >> 8) == 0 ? t.x : ((jk & 0xFF) == 0 ? t.y : t.z); }
+    if (kind == KIND_A) return t.y;
+    return g == 0 ? t.x : t.y;
+  }
+  const uint32_t* in = T.s_in + (size_t)row * T.inw + foff;
+  const int8_t* lut = T.s_lut + (size_t)row * T.lw;
+  if (is_g && ploidy == 2) {
+    const uint32_t jk = T.s_jk[g];
+    const int ij = lut[jk & 0xFF], ik = lut[jk >> 8];
+    if (ij < 0 || ik < 0) return miss;
+    const uint32_t ig = (uint32_t)alleles2gt(ij, ik);
+    return ig < n_in ? in[ig] : miss;
+  }
+  if (is_g && ploidy == 0) return in[0];
+  const int ij = lut[kind == KIND_A ? g + 1 : g];
+  if (ij < 0) return miss;
+  const int ix = (kind == KIND_A) ? ij - 1 : ij;
+  return (ix < 0 || (uint32_t)ix >= n_in) ? miss : in[ix];
+}
+
+// queued samples: non-trivial / non-inline / spanning-deletion calls.  Out of line so that the common path stays small.
 template <int NF>
 __device__ __noinline__ void tile_general_row(const ArrayDev& A, const ScanDev& S, const BatchDev& B, const RemapOut& O, const SiteRec* __restrict__ site_g, const TileCtx T,
-                                              uint32_t js, uint64_t q, int tid, int32_t e, const uint4 foff4) {
-  // `tid` is the sample's row inside the tile (not necessarily the calling thread)
+                                              uint32_t js, uint64_t q, int row, int32_t e, const uint4 foff4) {
   const uint64_t sq = (uint64_t)js * S.nq + q;
   const uint32_t foff[4] = {foff4.x, foff4.y, foff4.z, foff4.w};
   struct { uint32_t n_alleles, flags, ref_off, ref_len; } site = {site_g->n_alleles, site_g->flags, site_g->ref_off, site_g->ref_len};
@@ -722,8 +756,8 @@ __device__ __noinline__ void tile_general_row(const ArrayDev& A, const ScanDev& 
   const uint32_t A_in = (uint32_t)v.n_alt + 1u;
   const int in_nr = (nonref && v.nr_idx) ? v.nr_idx : -1;
   const int step = A.gt_phased ? 2 : 1;
-  int8_t* lut = T.s_lut + (size_t)tid * T.lw;
-  uint32_t* in_row = T.s_in + (size_t)tid * T.inw;
+  int8_t* lut = T.s_lut + (size_t)row * T.lw;
+  uint32_t* in_row = T.s_in + (size_t)row * T.inw;
   uint32_t lut_first = 0xFFFFFFFFu;
   if (O.lut_first) { lut_first = atomicAdd(&B.cursors[2], A_in); if (lut_first + A_in > O.cap_lut) { atomicOr(&S.err[2], 2u); lut_first = 0xFFFFFFFFu; } O.lut_first[sq] = lut_first; O.lut_len[sq] = (uint16_t)A_in; }
   uint32_t gto[TILE_MAX_GT]; uint32_t mapped = 0;
@@ -770,54 +804,28 @@ __device__ __noinline__ void tile_general_row(const ArrayDev& A, const ScanDev& 
     bool valid = field_of(A, S, v, f, p, n);
     if (valid && !v.reduced) { bool any = false; const uint32_t nullw = null_word(A.fm[f].elem); for (uint32_t x = 0; x < n; ++x) any |= (p[x] != nullw); valid = any; }
     const int kind = A.fm[f].kind;
+    const uint32_t padw = vend_word(A.fm[f].elem);
     uint32_t n_out = 0;
     if (valid && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, v.ploidy) : n;
     if (!n_out) n = 0;
     for (uint32_t x = 0; x < n; ++x) in_row[foff[f] + x] = p[x];
-    T.s_tri[tid * NF + f] = make_uint4(0, 0, 0, tri_info(n_out, 2, v.ploidy, n));
+    T.s_tri[row * NF + f] = make_uint4(padw, padw, padw, padw);
+    T.s_info[row * NF + f] = n_out ? tri_info(n_out, 2, v.ploidy, n) : (remap ? INFO_FAST : 0u);   // nothing to write: all padding
     O.f[o_f0 + f].len[sq] = (uint16_t)n_out;
-  }
-}
-
-// one output row the fast loops do not cover: dead / invalid (all padding), trivial with an unusual length, or a
-// non-trivial call (allele LUT + staged input vector).  Whole warp, lane <-> word.
-__device__ __noinline__ void tile_slow_row(const TileCtx T, const uint4 t, uint32_t row, const uint4 foff4, int f, int kind, int elem, bool remap,
-                                           uint32_t A_m, uint32_t G, uint32_t stride, uint32_t* __restrict__ drow, int lane) {
-  const uint32_t n_out = t.w & 0xFFFF, kindr = (t.w >> 16) & 3, ploidy = (t.w >> 18) & 63, n_in = t.w >> 24;
-  const uint32_t pad = vend_word(elem), miss = missing_word(elem);
-  const uint32_t foff = f == 0 ? foff4.x : (f == 1 ? foff4.y : (f == 2 ? foff4.z : foff4.w));
-  const uint32_t* in = T.s_in + (size_t)row * T.inw + foff;
-  const int8_t* lut = T.s_lut + (size_t)row * T.lw;
-  const bool is_g = remap && kind == KIND_G;
-  for (uint32_t g = lane; g < stride; g += 32) {
-    uint32_t val = pad;
-    if (g < n_out) {
-      if (kindr != 2) {
-        if (!remap) val = g == 0 ? t.x : (g == 1 ? t.y : t.z);
-        else if (is_g && ploidy == 2) { const uint32_t jk = T.s_jk[g]; val = (jk >> 8) == 0 ? t.x : ((jk & 0xFF) == 0 ? t.y : t.z); }
-        else if (kind == KIND_A) val = t.y;
-        else val = g == 0 ? t.x : t.y;
-      } else if (!remap) val = in[g];
-      else if (is_g && ploidy == 2) {
-        const uint32_t jk = T.s_jk[g];
-        const int ij = lut[jk & 0xFF], ik = lut[jk >> 8];
-        if (ij < 0 || ik < 0) val = miss;
-        else { const uint32_t ig = (uint32_t)alleles2gt(ij, ik); val = ig < n_in ? in[ig] : miss; }
-      } else if (is_g && ploidy == 0) val = in[0];
-      else {
-        const int ij = lut[kind == KIND_A ? g + 1 : g];
-        if (ij < 0) val = miss;
-        else { const int ix = (kind == KIND_A) ? ij - 1 : ij; val = (ix < 0 || (uint32_t)ix >= n_in) ? miss : in[ix]; }
-      }
+    if (!remap) {   // no remapping at this site: copy through
+      const FieldOutDev fo = O.f[o_f0 + f];
+      const uint32_t fs = fo.stride[js]; uint32_t* d = fo.data + fo.base[js] + q * fs;
+      for (uint32_t x = 0; x < fs; ++x) d[x] = x < n_out ? p[x] : padw;
     }
-    drow[g] = val;
   }
 }
 
 template <int NF>
-__global__ void __launch_bounds__(TILE_ROWS, 4) k_remap_tile(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
-                                                         const __grid_constant__ RemapOut O, const uint32_t* __restrict__ site_list, const TileShape TS) {
+__global__ void __launch_bounds__(TILE_ROWS, 3) k_remap_tile(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
+                                                            const __grid_constant__ RemapOut O, const uint32_t* __restrict__ site_list, const TileShape TS) {
   extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ uint32_t s_nlist;
+  __shared__ uint16_t s_list[TILE_ROWS];
   const uint32_t tiles_per_site = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
   const uint32_t js = site_list[blockIdx.x / tiles_per_site], tile = blockIdx.x % tiles_per_site;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -835,54 +843,76 @@ __global__ void __launch_bounds__(TILE_ROWS, 4) k_remap_tile(const __grid_consta
   const uint32_t A_m = site.n_alleles;
   const bool nonref = site.flags & 1u, remap = site.flags & 2u, g_suppressed = site.flags & 4u;
   const uint32_t G = A_m * (A_m + 1) / 2;
+  const int o_f0 = A.has_gt ? 1 : 0;
 
   TileCtx T;
+  T.cls_bytes = tile_cls_bytes(TS);
   T.s_ahash = reinterpret_cast<unsigned long long*>(smem);
   T.s_jk = reinterpret_cast<uint16_t*>(smem + 8 * TILE_MAX_A);
-  T.s_tri = reinterpret_cast<uint4*>(smem + 8 * TILE_MAX_A + ((size_t)TS.g * 2 + 15) / 16 * 16);
-  T.s_lut = reinterpret_cast<int8_t*>(T.s_tri + (size_t)TILE_ROWS * NF);
+  T.s_cls = smem + 8 * TILE_MAX_A + ((size_t)TS.g * 2 + 15) / 16 * 16;
+  T.s_tri = reinterpret_cast<uint4*>(T.s_cls + (size_t)NF * T.cls_bytes);
+  T.s_info = reinterpret_cast<uint32_t*>(T.s_tri + (size_t)TILE_ROWS * NF);
+  T.s_lut = reinterpret_cast<int8_t*>(T.s_info + (size_t)TILE_ROWS * NF);
   T.s_in = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(T.s_lut) + (size_t)TILE_ROWS * TS.lw);
   T.lw = TS.lw; T.inw = TS.inw;
-  __shared__ uint32_t s_nlist, s_direct_only;
-  __shared__ uint16_t s_list[TILE_ROWS];
-  if (tid == 0) { s_nlist = 0; s_direct_only = 1; }
 
-  uint32_t foff[NF];
+  uint32_t foff[NF], fstride[NF];
   {
     uint32_t o = 0;
 #pragma unroll
-    for (int f = 0; f < NF; ++f) { foff[f] = o; o += site_g->max_in_len[f]; }
+    for (int f = 0; f < NF; ++f) { foff[f] = o; o += site_g->max_in_len[f]; fstride[f] = O.f[o_f0 + f].stride[js]; }
   }
   const uint4 foff4 = make_uint4(foff[0], NF > 1 ? foff[NF > 1 ? 1 : 0] : 0, NF > 2 ? foff[NF > 2 ? 2 : 0] : 0, NF > 3 ? foff[NF > 3 ? 3 : 0] : 0);
-  for (uint32_t i = tid; i < A_m; i += TILE_ROWS) T.s_ahash[i] = B.allele_hash[site.allele_first + i];
-  if (remap) for (uint32_t g = tid; g < G; g += TILE_ROWS) {
-    uint32_t k = (uint32_t)((sqrtf(8.0f * (float)g + 1.0f) - 1.0f) * 0.5f);
-    while (k * (k + 1) / 2 > g) --k;
-    while ((k + 1) * (k + 2) / 2 <= g) ++k;
-    T.s_jk[g] = (uint16_t)((k << 8) | (g - k * (k + 1) / 2));
+  if (tid == 0) s_nlist = 0;
+  if (remap) {
+    for (uint32_t i = tid; i < A_m; i += TILE_ROWS) T.s_ahash[i] = B.allele_hash[site.allele_first + i];
+    for (uint32_t g = tid; g < G; g += TILE_ROWS) {
+      uint32_t k = (uint32_t)((sqrtf(8.0f * (float)g + 1.0f) - 1.0f) * 0.5f);
+      while (k * (k + 1) / 2 > g) --k;
+      while ((k + 1) * (k + 2) / 2 <= g) ++k;
+      T.s_jk[g] = (uint16_t)((k << 8) | (g - k * (k + 1) / 2));
+    }
+    // class tables: for each quad of a full-length vector, which of (v0, v1, v2, pad) each of its 4 words takes
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const int kind = A.fm[f].kind;
+      const uint32_t n_full = kind == KIND_G ? G : (kind == KIND_A ? A_m - 1u : A_m);
+      for (uint32_t qd = tid; qd < fstride[f] / 4; qd += TILE_ROWS) {
+        uint32_t c = 0;
+        for (uint32_t x = 0; x < 4; ++x) {
+          const uint32_t g = 4 * qd + x;
+          uint32_t code = 3;
+          if (g < n_full) {
+            if (kind == KIND_G) { uint32_t k = (uint32_t)((sqrtf(8.0f * (float)g + 1.0f) - 1.0f) * 0.5f); while (k * (k + 1) / 2 > g) --k; while ((k + 1) * (k + 2) / 2 <= g) ++k; const uint32_t j = g - k * (k + 1) / 2; code = k == 0 ? 0 : (j == 0 ? 1 : 2); }
+            else if (kind == KIND_A) code = 1;
+            else code = g == 0 ? 0 : 1;
+          }
+          c |= code << (2 * x);
+        }
+        T.s_cls[f * T.cls_bytes + qd] = (uint8_t)c;
+      }
+    }
   }
   __syncthreads();
 
   // ---------------------------------------------------------------- phase A: one thread per sample
-  const int o_f0 = A.has_gt ? 1 : 0;
   if (q < S.nq) {
     if (e < 0) {
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
-        T.s_tri[tid * NF + f] = make_uint4(0, 0, 0, tri_info(0, remap ? 0u : 3u, 0, 0));
+        const uint32_t padw = vend_word(A.fm[f].elem);
+        T.s_tri[tid * NF + f] = make_uint4(padw, padw, padw, padw);
+        T.s_info[tid * NF + f] = INFO_FAST;
         O.f[o_f0 + f].len[sq] = 0;
-        if (!remap) { const FieldOutDev fo = O.f[o_f0 + f]; const uint32_t fs = fo.stride[js]; uint32_t* d = fo.data + fo.base[js] + q * fs; const uint32_t padw = vend_word(A.fm[f].elem); for (uint32_t x = 0; x < fs; ++x) d[x] = padw; }
+        if (!remap) { const FieldOutDev fo = O.f[o_f0 + f]; uint32_t* d = fo.data + fo.base[js] + q * fstride[f]; for (uint32_t x = 0; x < fstride[f]; ++x) d[x] = padw; }
       }
       if (A.has_gt) { const uint32_t gs = O.f[0].stride[js]; uint32_t* d = O.f[0].data + O.f[0].base[js] + q * gs; for (uint32_t i = 0; i < gs; ++i) d[i] = BCF_INT_VEND; O.f[0].len[sq] = 0; }
       if (O.lut_first) { O.lut_first[sq] = 0xFFFFFFFFu; O.lut_len[sq] = 0; }
     } else {
       const uint32_t hflags = h0.x & 0xFF, ploidy = (h0.x >> 8) & 0xFF, n_alt = (h0.x >> 16) & 0xFF, nr = h0.x >> 24, gt_len = h0.y & 0xFF;
       const bool inl = ((h0.y >> 8) & 0xFF) != 0;
-      if ((e & LIVE_REDUCED) || !inl || !(hflags & F_TRIVIAL)) {
-        // rare: queue the sample; the queue is drained by consecutive threads below so that few warps diverge
-        s_list[atomicAdd(&s_nlist, 1u)] = (uint16_t)tid;
-        if (!remap) s_direct_only = 0;
-      } else {
+      if ((e & LIVE_REDUCED) || !inl || !(hflags & F_TRIVIAL)) s_list[atomicAdd(&s_nlist, 1u)] = (uint16_t)tid;   // rare: queue
+      else {
         // ---- trivial call, fully described by its hot record
         const uint32_t fl4 = (h0.y >> 16) | (h0.z << 16);
         const int in_nr = (nonref && nr) ? (int)nr : -1;
@@ -908,100 +938,104 @@ __global__ void __launch_bounds__(TILE_ROWS, 4) k_remap_tile(const __grid_consta
           if (first != 0xFFFFFFFFu) for (uint32_t i = 0; i < A_in; ++i) O.lut_in2m[first + i] = (int16_t)(i == 0 ? 0 : ((nr && i == nr) ? (int)A_m - 1 : -1));
         }
         uint32_t k = gt_len;   // fields follow GT in the record
+        bool queued = false;
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
           const uint32_t n = (fl4 >> (8 * f)) & 0xFF;
           const int kind = A.fm[f].kind;
-          const uint32_t miss = missing_word(A.fm[f].elem);
+          const uint32_t miss = missing_word(A.fm[f].elem), padw = vend_word(A.fm[f].elem);
           uint32_t n_out = 0;
           if (n && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, ploidy) : n;
-          uint32_t v0 = 0, v1 = miss, v2 = miss;
-          if (n_out) {
-            if (!remap) { v0 = sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k); v1 = n > 1 ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + 1) : 0; v2 = n > 2 ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + 2) : 0; }
-            else {
-              v0 = sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k);
-              if (in_nr >= 0) {
-                if (kind == KIND_A) { const uint32_t i1 = (uint32_t)in_nr - 1u; v1 = i1 < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + i1) : miss; }
-                else if (kind == KIND_R || ploidy != 2) { v1 = (uint32_t)in_nr < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + in_nr) : miss; }
-                else {
-                  const uint32_t g1 = (uint32_t)in_nr * ((uint32_t)in_nr + 1u) / 2u, g2 = g1 + (uint32_t)in_nr;
-                  v1 = g1 < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + g1) : miss;
-                  v2 = g2 < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + g2) : miss;
-                }
+          O.f[o_f0 + f].len[sq] = (uint16_t)n_out;
+          if (!remap) {
+            // no remapping at this site: the (inline, <= 5 words) input goes straight through, from this thread
+            uint32_t* d = O.f[o_f0 + f].data + O.f[o_f0 + f].base[js] + q * fstride[f];
+            for (uint32_t x = 0; x < fstride[f]; ++x) d[x] = x < n_out ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + x) : padw;
+          } else if (!n_out) {
+            T.s_tri[tid * NF + f] = make_uint4(padw, padw, padw, padw);
+            T.s_info[tid * NF + f] = INFO_FAST;
+          } else {
+            uint32_t v0 = sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k), v1 = miss, v2 = miss;
+            if (in_nr >= 0) {
+              if (kind == KIND_A) { const uint32_t i1 = (uint32_t)in_nr - 1u; v1 = i1 < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + i1) : miss; }
+              else if (kind == KIND_R || ploidy != 2) { v1 = (uint32_t)in_nr < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + in_nr) : miss; }
+              else {
+                const uint32_t g1 = (uint32_t)in_nr * ((uint32_t)in_nr + 1u) / 2u, g2 = g1 + (uint32_t)in_nr;
+                v1 = g1 < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + g1) : miss;
+                v2 = g2 < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + g2) : miss;
               }
             }
+            const uint32_t n_full = kind == KIND_G ? G : (kind == KIND_A ? A_m - 1u : A_m);
+            const bool fast = (n_out == n_full) && (kind != KIND_G || ploidy == 2);
+            T.s_tri[tid * NF + f] = make_uint4(v0, v1, v2, padw);
+            T.s_info[tid * NF + f] = tri_info(n_out, 1, ploidy, n) | (fast ? INFO_FAST : 0u);
+            if (!fast) queued = true;
           }
-          if (!remap) {
-            // a site that needs no remapping copies the (inline, <= 5 words) input through, straight from this thread
-            const FieldOutDev fo = O.f[o_f0 + f];
-            const uint32_t fs = fo.stride[js]; uint32_t* d = fo.data + fo.base[js] + q * fs;
-            const uint32_t padw = vend_word(A.fm[f].elem);
-            for (uint32_t x = 0; x < fs; ++x) d[x] = x < n_out ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + x) : padw;
-          }
-          T.s_tri[tid * NF + f] = make_uint4(v0, v1, v2, tri_info(n_out, remap ? 1u : 3u, ploidy, n));   // kind 3: already written
-          O.f[o_f0 + f].len[sq] = (uint16_t)n_out;
           k += n;
         }
+        if (queued) s_list[atomicAdd(&s_nlist, 1u)] = (uint16_t)(tid | 0x8000);   // trivial, but some vector has an unusual length
       }
     }
   }
   __syncthreads();
-  for (uint32_t i = tid; i < s_nlist; i += TILE_ROWS) {
-    const uint32_t row = s_list[i];
-    const uint64_t qr = (uint64_t)tile * TILE_ROWS + row;
-    tile_general_row<NF>(A, S, B, O, site_g, T, js, qr, (int)row, B.live[(uint64_t)js * S.nq + qr], foff4);
+  const uint32_t n_list = s_nlist;
+  for (uint32_t i = tid; i < n_list; i += TILE_ROWS) {
+    const uint32_t ent = s_list[i];
+    if (ent & 0x8000) continue;
+    const uint64_t qr = (uint64_t)tile * TILE_ROWS + ent;
+    tile_general_row<NF>(A, S, B, O, site_g, T, js, qr, (int)ent, B.live[(uint64_t)js * S.nq + qr], foff4);
   }
+  if (!remap) return;   // copy-through sites are complete (uniform per block)
   __syncthreads();
 
-  // ---------------------------------------------------------------- phase B: stream the dense output, one sample per warp iteration
+  // ---------------------------------------------------------------- phase B
   const uint32_t rows = (uint32_t)min((uint64_t)TILE_ROWS, S.nq - (uint64_t)tile * TILE_ROWS);
+  const uint32_t r0 = warp * 32;
 #pragma unroll
   for (int f = 0; f < NF; ++f) {
-    const FieldOutDev fo = O.f[o_f0 + f];
-    const uint32_t stride = fo.stride[js];
+    const uint32_t stride = fstride[f];
     if (stride == 0) continue;
-    uint32_t* __restrict__ dst = fo.data + fo.base[js] + (uint64_t)tile * TILE_ROWS * stride + lane;
+    const FieldOutDev fo = O.f[o_f0 + f];
     const int kind = A.fm[f].kind, elem = A.fm[f].elem;
-    const uint32_t pad = vend_word(elem);
-    const bool act0 = (uint32_t)lane < stride, act1 = (uint32_t)lane + 32u < stride;
-    if (remap && kind == KIND_G) {
-      // diploid trivial sample: word g is v0 for genotype (0,0), v1 for (0,k), v2 for (j>0,k)
-      const uint32_t expect = (G & 0xFFFF) | (1u << 16) | (2u << 18);
-      bool a0 = false, b0 = false, a1 = false, b1 = false;   // a: class 0, b: class 2
-      if ((uint32_t)lane < G) { const uint32_t jk = T.s_jk[lane]; a0 = (jk >> 8) == 0; b0 = (jk & 0xFF) != 0; }
-      if ((uint32_t)lane + 32u < G) { const uint32_t jk = T.s_jk[lane + 32]; a1 = (jk >> 8) == 0; b1 = (jk & 0xFF) != 0; }
-      for (uint32_t row = warp; row < rows; row += TILE_ROWS / 32) {
-        const uint4 t = T.s_tri[row * NF + f];
-        uint32_t* __restrict__ pr = dst + row * stride;
-        if ((t.w & 0xFFFFFFu) == expect && stride == G) {
-          if (act0) pr[0] = a0 ? t.x : (b0 ? t.z : t.y);
-          if (act1) pr[32] = a1 ? t.x : (b1 ? t.z : t.y);
-          for (uint32_t g = lane + 64; g < stride; g += 32) { const uint32_t jk = T.s_jk[g]; pr[g - lane] = (jk >> 8) == 0 ? t.x : ((jk & 0xFF) == 0 ? t.y : t.z); }
-        } else if ((t.w & 0xFFFFu) == 0) {   // sample not live / field absent: padding only
-          if (act0) pr[0] = pad;
-          if (act1) pr[32] = pad;
-          for (uint32_t g = lane + 64; g < stride; g += 32) pr[g - lane] = pad;
-        } else tile_slow_row(T, t, row, foff4, f, kind, elem, true, A_m, G, stride, pr - lane, lane);
+    const uint32_t lpr = stride >> 2;   // quads per sample (stride is a multiple of 4 at remapped sites)
+    uint32_t* tile_dst = fo.data + fo.base[js] + (uint64_t)tile * TILE_ROWS * stride;
+    // (1) vectorised pass over this warp's 32 samples: flat quad index i <-> (sample, quad)
+    if (r0 < rows) {
+      const uint32_t nr = min(32u, rows - r0), total = nr * lpr;
+      uint4* out4 = reinterpret_cast<uint4*>(tile_dst + (uint64_t)r0 * stride);
+      const uint8_t* cls = T.s_cls + f * T.cls_bytes;
+      uint32_t row_l = (uint32_t)lane / lpr, qd = (uint32_t)lane % lpr;
+      const uint32_t dr = 32u / lpr, dq = 32u % lpr;
+      for (uint32_t i = lane; i < total; i += 32) {
+        const uint32_t slot = (r0 + row_l) * NF + f;
+        if (T.s_info[slot] & INFO_FAST) {
+          const uint32_t* tw = reinterpret_cast<const uint32_t*>(&T.s_tri[slot]);
+          const uint32_t c = cls[qd];
+          uint4 v;
+          v.x = tw[c & 3]; v.y = tw[(c >> 2) & 3]; v.z = tw[(c >> 4) & 3]; v.w = tw[(c >> 6) & 3];
+          out4[i] = v;
+        }
+        row_l += dr; qd += dq;
+        if (qd >= lpr) { qd -= lpr; ++row_l; }
       }
-    } else if (remap) {
-      const uint32_t n_full = (kind == KIND_A) ? A_m - 1u : A_m;
-      const uint32_t expect = (n_full & 0xFFFF) | (1u << 16);
-      const bool first = (kind != KIND_A) && lane == 0;
-      for (uint32_t row = warp; row < rows; row += TILE_ROWS / 32) {
+    }
+    // (2) the queued samples, lane-parallel over their quads
+    if (n_list) {
+      const bool is_g = kind == KIND_G;
+      const uint32_t pad = vend_word(elem), miss = missing_word(elem);
+      const uint32_t total = n_list * lpr;
+      for (uint32_t i = tid; i < total; i += TILE_ROWS) {
+        const uint32_t li = i / lpr, qd = i - li * lpr;
+        const uint32_t row = s_list[li] & 0x7FFF;
+        const uint32_t info = T.s_info[row * NF + f];
+        if (info & INFO_FAST) continue;
         const uint4 t = T.s_tri[row * NF + f];
-        uint32_t* __restrict__ pr = dst + row * stride;
-        if ((t.w & 0x3FFFFu) == expect && stride == n_full) {
-          if (act0) pr[0] = first ? t.x : t.y;
-          for (uint32_t g = lane + 32; g < stride; g += 32) pr[g - lane] = t.y;
-        } else if ((t.w & 0xFFFFu) == 0) {
-          if (act0) pr[0] = pad;
-          for (uint32_t g = lane + 32; g < stride; g += 32) pr[g - lane] = pad;
-        } else tile_slow_row(T, t, row, foff4, f, kind, elem, true, A_m, G, stride, pr - lane, lane);
-      }
-    } else if (!s_direct_only) {
-      for (uint32_t row = warp; row < rows; row += TILE_ROWS / 32) {
-        const uint4 t = T.s_tri[row * NF + f];
-        if (((t.w >> 16) & 3u) == 2u) tile_slow_row(T, t, row, foff4, f, kind, elem, false, A_m, G, stride, dst - lane + row * stride, lane);
+        uint4 v;
+        v.x = tile_slow_word(T, info, t, row, foff[f], kind, is_g, 4 * qd, pad, miss);
+        v.y = tile_slow_word(T, info, t, row, foff[f], kind, is_g, 4 * qd + 1, pad, miss);
+        v.z = tile_slow_word(T, info, t, row, foff[f], kind, is_g, 4 * qd + 2, pad, miss);
+        v.w = tile_slow_word(T, info, t, row, foff[f], kind, is_g, 4 * qd + 3, pad, miss);
+        reinterpret_cast<uint4*>(tile_dst + (uint64_t)row * stride)[qd] = v;
       }
     }
   }

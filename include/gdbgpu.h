@@ -170,7 +170,8 @@ typedef struct gdbgpu_batch {
   const uint32_t* lut_first;
   const uint16_t* lut_len;   /* number of input alleles (1 + ALT count) of the call as the operator saw it */
   const int16_t* lut_in2m;
-  uint64_t out_bytes;        /* bytes of remapped output written for this batch */
+  uint64_t out_bytes;        /* algorithmic bytes of remapped output of this batch: 4 x n_query_rows x sum of the strides
+                              * each field needs (alignment padding and the length arrays not counted) */
 } gdbgpu_batch;
 
 int gdbgpu_scan_begin(gdbgpu_array* arr, const gdbgpu_scan_params* params, gdbgpu_scan** out);
