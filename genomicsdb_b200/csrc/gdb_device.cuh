@@ -50,6 +50,18 @@ struct __align__(16) HotRec {
 };
 static_assert(sizeof(HotRec) == 32, "HotRec must be one 32-byte sector");
 
+// Warm blob: every cell that is NOT (trivial and inline) gets one contiguous, 16-byte aligned record in a pool built
+// when the array is staged, so that a non-trivial call costs one more gather (hot record -> blob) instead of a chain of
+// offset/value loads over five columns plus a byte-wise re-hash of its ALT string.  HotRec.w[0] = blob offset in 16-byte
+// units, HotRec.w[1] = blob length in words.  Words:
+//   [0] n_alt  [1] nr_idx  [2] ref_len  [3] gt_len (0: GT invalid)   [4 .. 4+NF) valid input length of field f
+//   (pad to an even index) then n_alt x u64 : FNV-1a state over the token's bytes (not finished, so a REF-tail suffix can
+//   still be appended at a site whose merged REF is longer; 0 for the <NON_REF> token)
+//   then n_alt x u32 : token length | symbolic << 31 | non_ref << 30
+//   then GT words (gt_len), then the valid words of every field in field order
+constexpr uint32_t WARM_TOK_SYMBOLIC = 0x80000000u, WARM_TOK_NONREF = 0x40000000u;
+__host__ __device__ inline uint32_t warm_hash_word(uint32_t n_fields) { return (4u + n_fields + 1u) & ~1u; }
+
 struct VarCol {
   const uint64_t* off;   // n_cells + 1 absolute byte offsets
   const uint8_t* val;
@@ -69,6 +81,7 @@ struct ArrayDev {
   int64_t lb_row, num_rows;
   const CellDesc* desc;
   const HotRec* hot;
+  const uint32_t* warm;    // warm blob pool (see above)
   const int64_t* effend;   // cell order; I64_MIN for END copies / rows outside the array
   // row-major index (per-sample cell lists, column ascending)
   uint64_t n_rs;

@@ -99,6 +99,7 @@ void radix_sort_pairs(gdbgpu_ctx* ctx, const K* kin, K* kout, const V* vin, V* v
   ctx->launches += 4;
 }
 
+__global__ void k_narrow_u64(const uint64_t* in, uint64_t n, uint32_t* out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = (uint32_t)in[i]; }
 __global__ void k_iota(uint32_t* p, uint64_t n) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = (uint32_t)i; }
 __global__ void k_gather_u64(const uint64_t* in, const uint32_t* perm, uint64_t n, uint64_t* out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = in[perm[i]]; }
 __global__ void k_gather_u32(const uint32_t* in, const uint32_t* perm, uint64_t n, uint32_t* out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = in[perm[i]]; }
@@ -138,13 +139,13 @@ struct gdbgpu_array {
   std::vector<FieldMeta> fm; std::vector<std::string> field_names;
   DevBuf<int64_t> coords, end;
   DevVar ref, alt, gt; std::vector<std::unique_ptr<DevVar>> fields;
-  DevBuf<CellDesc> desc; DevBuf<HotRec> hot; DevBuf<int64_t> effend;
+  DevBuf<CellDesc> desc; DevBuf<HotRec> hot; DevBuf<uint32_t> warm; DevBuf<int64_t> effend;
   DevBuf<uint32_t> rs_cell, rs_keys; DevBuf<int64_t> rs_col, rs_effend; DevBuf<uint64_t> row_start; uint64_t n_rs = 0;
   DevBuf<uint32_t> bad_cell; DevBuf<int64_t> bad_pred_col;
   ArrayDev dev{};
   uint64_t hbm_bytes() const {
     uint64_t b = coords.bytes() + end.bytes() + ref.off.bytes() + ref.val.bytes() + alt.off.bytes() + alt.val.bytes() + gt.off.bytes() + gt.val.bytes() +
-                 desc.bytes() + hot.bytes() + effend.bytes() + rs_cell.bytes() + rs_keys.bytes() + rs_col.bytes() + rs_effend.bytes() + row_start.bytes();
+                 desc.bytes() + hot.bytes() + warm.bytes() + effend.bytes() + rs_cell.bytes() + rs_keys.bytes() + rs_col.bytes() + rs_effend.bytes() + row_start.bytes();
     for (auto& f : fields) b += f->off.bytes() + f->val.bytes();
     return b;
   }
@@ -172,7 +173,7 @@ void fill_dev_view(gdbgpu_array* a) {
   D.has_gt = a->has_gt; D.gt_phased = a->gt_phased; D.n_fields = (int)a->fields.size();
   for (size_t f = 0; f < a->fields.size(); ++f) { D.f[f] = VarCol{a->fields[f]->off.p, a->fields[f]->val.p}; D.fm[f] = a->fm[f]; }
   D.lb_row = a->lb_row; D.num_rows = a->num_rows;
-  D.desc = a->desc.p; D.hot = a->hot.p; D.effend = a->effend.p;
+  D.desc = a->desc.p; D.hot = a->hot.p; D.warm = a->warm.p; D.effend = a->effend.p;
   D.n_rs = a->n_rs; D.rs_cell = a->rs_cell.p; D.rs_col = a->rs_col.p; D.rs_effend = a->rs_effend.p; D.row_start = a->row_start.p;
 }
 
@@ -263,7 +264,21 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
   fill_dev_view(a.get());
   if (n) {
     unsigned g = blocks_for(n, 256);
-    LAUNCH(ctx, k_classify, g, 256, a->dev, a->desc.p, a->hot.p);
+    {   // hot records + warm blobs
+      DevBuf<uint32_t> units, offs; DevBuf<uint64_t> total, sums;
+      units.alloc(n); offs.alloc(n); total.alloc(1);
+      LAUNCH(ctx, k_classify, g, 256, a->dev, a->desc.p, a->hot.p, units.p);
+      DevBuf<uint64_t> offs64; offs64.alloc(n);
+      exclusive_scan<uint32_t, uint64_t>(ctx, units.p, offs64.p, n, total.p, sums);
+      uint64_t h_units = 0;
+      CK(cudaMemcpyAsync(&h_units, total.p, 8, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+      if (h_units >= (1ull << 32)) throw LimitError("warm-blob pool above 64 GB: shard the column range across GPUs");
+      a->warm.alloc(std::max<uint64_t>(h_units * 4, 4));
+      a->dev.warm = a->warm.p;
+      LAUNCH(ctx, k_narrow_u64, g, 256, offs64.p, n, offs.p);
+      LAUNCH(ctx, k_warm_fill, g, 256, a->dev, a->desc.p, a->hot.p, units.p, offs.p, a->warm.p);
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
     DevBuf<uint32_t> keys, vals; DevBuf<uint8_t> tmp;
     keys.alloc(n); vals.alloc(n);
     LAUNCH(ctx, k_row_keys, g, 256, a->dev, a->desc.p, keys.p, vals.p);
@@ -303,7 +318,7 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
 // context keeps finished scans' buffers and hands them to the next scan.
 struct BatchBuffers {
   // per batch (device)
-  DevBuf<int32_t> live; DevBuf<SiteRec> sites; DevBuf<uint32_t> cursors, allele_pos, lut_first; DevBuf<uint16_t> lut_len; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes; DevBuf<int16_t> lut_in2m;
+  DevBuf<int32_t> live; DevBuf<SiteRec> sites; DevBuf<uint32_t> agg, nt_q, nt_prefix; DevBuf<uint32_t> cursors, allele_pos, lut_first; DevBuf<uint16_t> lut_len; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes; DevBuf<int16_t> lut_in2m;
   DevBuf<uint32_t> out_data[MAX_FIELDS + 1], out_stride[MAX_FIELDS + 1]; DevBuf<uint64_t> out_base[MAX_FIELDS + 1]; DevBuf<uint16_t> out_len[MAX_FIELDS + 1];
   DevBuf<uint8_t> d_site_flags; DevBuf<uint32_t> d_n_alleles, d_n_live, d_allele_first;
   // per batch (host mirrors)
@@ -497,13 +512,16 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
   const int n_out = s->n_out;
   for (;;) {
     bb.live.ensure((uint64_t)nb * S.nq); bb.sites.ensure(nb); bb.cursors.ensure(4);
+    bb.agg.ensure((uint64_t)nb * AGG_WORDS); bb.nt_q.ensure((uint64_t)nb * S.nq);
+    CK(cudaMemsetAsync(bb.agg.p, 0, (size_t)nb * AGG_WORDS * 4, ctx->stream));
     if (!s->cap_allele_recs) { s->cap_allele_recs = 1u << 16; s->cap_allele_bytes = 1u << 20; }
     bb.allele_pos.ensure(2ull * s->cap_allele_recs); bb.allele_hash.ensure(s->cap_allele_recs); bb.allele_bytes.ensure(s->cap_allele_bytes);
     CK(cudaMemsetAsync(bb.cursors.p, 0, 16, ctx->stream));
     BatchDev B{};
-    B.first_site = s->cursor; B.n_sites = nb; B.live = bb.live.p; B.sites = bb.sites.p; B.cursors = bb.cursors.p;
+    B.first_site = s->cursor; B.n_sites = nb; B.live = bb.live.p; B.sites = bb.sites.p; B.agg = bb.agg.p; B.nt_q = bb.nt_q.p; B.cursors = bb.cursors.p;
     B.allele_pos = bb.allele_pos.p; B.allele_hash = bb.allele_hash.p; B.cap_allele_recs = s->cap_allele_recs; B.allele_bytes = bb.allele_bytes.p; B.cap_allele_bytes = s->cap_allele_bytes;
     LAUNCH(ctx, k_live_walk, dim3(blocks_for(S.nq, 256), (nb + WALK_CHUNK - 1) / WALK_CHUNK), 256, a->dev, S, s->cursor, nb, bb.live.p);
+    LAUNCH(ctx, k_site_scan, dim3(nb, blocks_for(S.nq, SSCAN_ROWS)), SSCAN_THREADS, a->dev, S, B);
     LAUNCH(ctx, k_union, nb, UNION_THREADS, a->dev, S, B);
     bb.h_sites.resize(nb);
     CK(cudaMemcpyAsync(bb.h_sites.data(), bb.sites.p, (size_t)nb * sizeof(SiteRec), cudaMemcpyDeviceToHost, ctx->stream));
@@ -540,25 +558,24 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
       O.lut_first = bb.lut_first.p; O.lut_len = bb.lut_len.p; O.lut_in2m = bb.lut_in2m.p; O.cap_lut = s->cap_lut;
     }
     B.n_sites = keep;
-    // split the batch: the tile kernel takes every ordinary site, the generic kernel the pathological ones
-    std::vector<uint32_t> fast, slow;
-    TileShape shape{4, 3, 1};
+    // split the batch: the tile kernels take every ordinary site, the generic kernel the pathological ones
+    std::vector<uint32_t> fast, slow, nt_prefix;
+    TileShape shape{4};
     for (uint32_t i = 0; i < keep; ++i) {
       const SiteRec& r = bb.h_sites[i];
-      uint32_t inw = 0;
-      for (size_t f = 0; f < a->fields.size(); ++f) inw += r.max_in_len[f];
       bool ok = a->fields.size() >= 1 && a->fields.size() <= (size_t)TILE_MAX_FIELDS && r.n_alleles <= (uint32_t)TILE_MAX_A && r.max_ain <= (uint32_t)TILE_MAX_A &&
-                r.max_gt_len <= (uint32_t)TILE_MAX_GT && r.max_ploidy_all <= 2u && inw <= (uint32_t)TILE_MAX_INW;
+                r.max_gt_len <= (uint32_t)TILE_MAX_GT && r.max_ploidy_all <= 2u;
       if (ok) {
+        nt_prefix.push_back(fast.empty() ? 0u : nt_prefix.back() + bb.h_sites[fast.back()].n_nt);
         fast.push_back(i);
-        shape.lw = std::max(shape.lw, (r.n_alleles + 3u) / 4u * 4u);
-        shape.inw = std::max(shape.inw, inw | 1u);   // odd stride: no shared-memory bank conflicts between rows
         shape.g = std::max(shape.g, r.n_alleles * (r.n_alleles + 1u) / 2u);
       } else slow.push_back(i);
     }
     if (!fast.empty()) {
-      bb.fast_sites.ensure(fast.size());
+      nt_prefix.push_back(nt_prefix.back() + bb.h_sites[fast.back()].n_nt);
+      bb.fast_sites.ensure(fast.size()); bb.nt_prefix.ensure(nt_prefix.size());
       CK(cudaMemcpyAsync(bb.fast_sites.p, fast.data(), fast.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(bb.nt_prefix.p, nt_prefix.data(), nt_prefix.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
       const int nf = (int)a->fields.size();
       size_t smem = tile_smem_bytes(shape, nf);
       uint32_t tiles = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
@@ -575,6 +592,21 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
         default: launch_tile(k_remap_tile<4>); break;
       }
       ++ctx->launches; CK(cudaGetLastError());
+      const uint32_t n_nt = nt_prefix.back();
+      if (n_nt) {
+        unsigned grid_nt = (n_nt + NT_WARPS - 1) / NT_WARPS;
+        auto launch_nt = [&](auto kern) {
+          ProfScope ps__(ctx, "k_remap_nt");
+          kern<<<grid_nt, NT_WARPS * 32, 0, ctx->stream>>>(a->dev, S, B, O, bb.fast_sites.p, bb.nt_prefix.p, (uint32_t)fast.size(), shape.g);
+        };
+        switch (nf) {
+          case 1: launch_nt(k_remap_nt<1>); break;
+          case 2: launch_nt(k_remap_nt<2>); break;
+          case 3: launch_nt(k_remap_nt<3>); break;
+          default: launch_nt(k_remap_nt<4>); break;
+        }
+        ++ctx->launches; CK(cudaGetLastError());
+      }
     }
     if (!slow.empty()) {
       bb.slow_sites.ensure(slow.size());

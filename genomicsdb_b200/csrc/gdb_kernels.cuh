@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(TO* __restrict__ out,
 // ------------------------------------------------------------------------------------------------ K2 classify
 // One thread per cell: what gt_fill_row derives from a cell (query_variants.cc:1014-1117) plus END-copy detection
 // (query_variants.cc:422-428), computed once per staged array.
-__global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restrict__ desc, HotRec* __restrict__ hot) {
+__global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restrict__ desc, HotRec* __restrict__ hot, uint32_t* __restrict__ warm_units) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
   int64_t row = A.coords[2 * i], col = A.coords[2 * i + 1], END = A.end[i];
@@ -114,9 +114,9 @@ __global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restri
   for (int f = 0; f < HOT_FIELDS; ++f) h.flen[f] = 0;
   for (int k = 0; k < HOT_WORDS; ++k) h.w[k] = 0;
   bool fits = (n_alt < 255) && (d.gt_len <= 255) && (A.n_fields <= HOT_FIELDS);
-  uint32_t used = d.gt_len;
+  uint32_t used = d.gt_len, field_words = 0;
   uint32_t flen[HOT_FIELDS] = {0, 0, 0, 0};
-  if (fits) for (int f = 0; f < A.n_fields; ++f) {
+  for (int f = 0; f < A.n_fields; ++f) {
     uint64_t o0 = A.f[f].off[i], o1 = A.f[f].off[i + 1];
     uint32_t n = (uint32_t)((o1 - o0) >> 2);
     const uint32_t* v = reinterpret_cast<const uint32_t*>(A.f[f].val + o0);
@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restri
     bool all_null = true;
     for (uint32_t k = 0; k < n; ++k) if (v[k] != nullw) { all_null = false; break; }
     if (all_null) n = 0;     // invalid field (variant_field_data.h:365-384)
-    flen[f] = n; used += n;
+    if (f < HOT_FIELDS) flen[f] = n;
+    used += n; field_words += n;
   }
   if (fits && used <= HOT_WORDS) {
     h.inl = 1;
@@ -136,7 +137,59 @@ __global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restri
       for (uint32_t x = 0; x < flen[f]; ++x) h.w[k++] = v[x];
     }
   }
+  // every other cell gets a warm blob (filled by k_warm_fill once the pool offsets are known); 16-byte units
+  uint32_t units = 0;
+  if (!(h.inl && (d.flags & F_TRIVIAL))) {
+    uint64_t words = (uint64_t)warm_hash_word((uint32_t)A.n_fields) + 3ull * (uint64_t)n_alt + d.gt_len + field_words;
+    units = (uint32_t)((words + 3) >> 2);
+    h.w[1] = (uint32_t)words;
+  }
+  warm_units[i] = units;
   hot[i] = h;
+}
+
+// fills the warm blobs (layout: gdb_device.cuh); warm_off = exclusive scan of warm_units
+__global__ void __launch_bounds__(256) k_warm_fill(ArrayDev A, const CellDesc* __restrict__ desc, HotRec* __restrict__ hot, const uint32_t* __restrict__ warm_units,
+                                                    const uint32_t* __restrict__ warm_off, uint32_t* __restrict__ pool) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n || warm_units[i] == 0) return;
+  const CellDesc d = desc[i];
+  uint32_t* b = pool + (uint64_t)warm_off[i] * 4u;
+  hot[i].w[0] = warm_off[i];
+  const uint8_t* alt = A.alt.val + A.alt.off[i];
+  int an = alt_effective_len(alt, (int)(A.alt.off[i + 1] - A.alt.off[i]));
+  uint32_t n_alt = 0;
+  { int pos = 0, ts, tl; while (next_token(alt, an, pos, ts, tl)) ++n_alt; }
+  b[0] = n_alt; b[1] = d.nr_idx; b[2] = d.ref_len;
+  b[3] = d.gt_len;
+  const uint32_t H0 = warm_hash_word((uint32_t)A.n_fields);
+  if ((4u + (uint32_t)A.n_fields) < H0) b[H0 - 1] = 0;
+  uint32_t* tok = b + H0 + 2u * n_alt;
+  {
+    int pos = 0, ts, tl; uint32_t t = 0;
+    while (next_token(alt, an, pos, ts, tl)) {
+      const bool nrt = is_non_ref(alt + ts, tl);
+      uint64_t hs = nrt ? 0ull : fnv1a(FNV_BASIS, alt + ts, tl);
+      b[H0 + 2u * t] = (uint32_t)hs; b[H0 + 2u * t + 1] = (uint32_t)(hs >> 32);
+      tok[t] = (uint32_t)tl | (is_symbolic(alt + ts, tl) ? WARM_TOK_SYMBOLIC : 0u) | (nrt ? WARM_TOK_NONREF : 0u);
+      ++t;
+    }
+  }
+  uint32_t* w = tok + n_alt;
+  if (d.gt_len) { const uint32_t* g = reinterpret_cast<const uint32_t*>(A.gt.val + A.gt.off[i]); for (uint32_t x = 0; x < d.gt_len; ++x) *w++ = g[x]; }
+  for (int f = 0; f < A.n_fields; ++f) {
+    uint64_t o0 = A.f[f].off[i], o1 = A.f[f].off[i + 1];
+    uint32_t n = (uint32_t)((o1 - o0) >> 2);
+    const uint32_t* v = reinterpret_cast<const uint32_t*>(A.f[f].val + o0);
+    uint32_t nullw = A.fm[f].elem ? TDB_NULL_FLT : TDB_NULL_INT;
+    bool all_null = true;
+    for (uint32_t k = 0; k < n; ++k) if (v[k] != nullw) { all_null = false; break; }
+    if (all_null) n = 0;
+    b[4 + f] = n;
+    for (uint32_t x = 0; x < n; ++x) *w++ = v[x];
+  }
+  const uint32_t words = hot[i].w[1];
+  for (uint32_t* e = b + (((uint64_t)words + 3) & ~3ull); w < e; ++w) *w = 0;
 }
 
 __global__ void __launch_bounds__(256) k_row_keys(ArrayDev A, const CellDesc* __restrict__ desc, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {

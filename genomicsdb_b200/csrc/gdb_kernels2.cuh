@@ -242,7 +242,7 @@ __device__ inline uint64_t allele_hash(const uint8_t* t, int tl, const uint8_t* 
 }
 
 // ------------------------------------------------------------------------------------------------ K4 allele union
-constexpr int UNION_THREADS = 256;
+constexpr int UNION_THREADS = 512;
 constexpr int UNION_SLOTS = 1024;        // open-addressing table in shared memory
 constexpr int UNION_MAX_DISTINCT = 512;  // documented engine limit on distinct ALT alleles per site (excluding NON_REF)
 constexpr int REF_MAX_PIECES = 32;
@@ -256,37 +256,141 @@ struct SiteRec {
   uint32_t ref_off, ref_len;            // merged REF bytes in the allele pool
   uint32_t max_gt_len, max_ain;         // max GT words / max (n_alt+1) over live calls
   uint32_t max_ploidy_all;              // max ploidy over live calls
+  uint32_t n_nt;                        // live calls that are not (trivial and inline): entries of the site's nt list
   uint32_t max_ploidy[MAX_FIELDS];      // over calls whose field is present
   uint32_t max_in_len[MAX_FIELDS];
 };
+// per-site accumulators of k_site_scan (zeroed per batch), as words
+enum { AGG_NLIVE = 0, AGG_NONREF, AGG_MAXGT, AGG_MAXAIN, AGG_MAXPLOIDY, AGG_NNT, AGG_MAXPL = 6, AGG_MAXIN = 6 + HOT_FIELDS, AGG_WORDS = 6 + 2 * HOT_FIELDS };
 struct BatchDev {
   uint64_t first_site; uint32_t n_sites;
   const int32_t* live;        // n_sites x nq
   SiteRec* sites;
+  uint32_t* agg;              // n_sites x AGG_WORDS
+  uint32_t* nt_q;             // n_sites x nq : per site, the query rows of its non-trivial live calls (first agg[AGG_NNT]), any order
   // pools (atomic bump allocation; overflow -> err[2])
   uint32_t* cursors;          // [0] allele records, [1] allele bytes, [2] lut words
   uint32_t* allele_pos; uint64_t* allele_hash; uint32_t cap_allele_recs;
   uint8_t* allele_bytes; uint32_t cap_allele_bytes;
 };
 
-__global__ void __launch_bounds__(UNION_THREADS) k_union(ArrayDev A, ScanDev S, BatchDev B) {
+// a non-reduced, non-(trivial and inline) call through its warm blob
+struct WarmView { const uint32_t* b; uint32_t n_alt, nr_idx, ref_len, gt_len, ploidy; };
+__device__ inline WarmView warm_view(const ArrayDev& A, uint32_t cell) {
+  WarmView v;
+  v.b = A.warm + (uint64_t)A.hot[cell].w[0] * 4u;
+  const uint4 hd = *reinterpret_cast<const uint4*>(v.b);
+  v.n_alt = hd.x; v.nr_idx = hd.y; v.ref_len = hd.z; v.gt_len = hd.w;
+  v.ploidy = hd.w ? ploidy_of(A.gt_phased, hd.w) : 0u;
+  return v;
+}
+// hash of ALT token t (0-based) as it enters the merged list at a site with merged REF `mref`; 0 for <NON_REF>
+__device__ inline uint64_t warm_token_hash(const WarmView& v, uint32_t H0, uint32_t t, const uint8_t* mref, uint32_t mref_len) {
+  const uint32_t tokw = v.b[H0 + 2u * v.n_alt + t];
+  if (tokw & WARM_TOK_NONREF) return 0ull;
+  uint64_t hs = (uint64_t)v.b[H0 + 2u * t] | ((uint64_t)v.b[H0 + 2u * t + 1] << 32);
+  uint32_t tl = tokw & 0x3FFFFFFFu;
+  if (v.ref_len < mref_len && !(tokw & WARM_TOK_SYMBOLIC)) { hs = fnv1a(hs, mref + v.ref_len, (int)(mref_len - v.ref_len)); tl += mref_len - v.ref_len; }
+  return hash_finish(hs ^ ((uint64_t)tl << 40));
+}
+__device__ inline uint64_t star_hash() { const uint8_t s = '*'; return hash_finish(fnv1a(FNV_BASIS, &s, 1) ^ (1ull << 40)); }
+
+// K4a: one pass over the live matrix.  Per site: number of live calls, the maxima the output layout needs (from the
+// 16-byte header of the hot record of every trivial inline call) and the list of all other live calls.  Grid = (sites,
+// row chunks), so the whole GPU works on a batch whatever its number of sites.
+constexpr int SSCAN_THREADS = 256, SSCAN_PER_THREAD = 8, SSCAN_ROWS = SSCAN_THREADS * SSCAN_PER_THREAD;
+__global__ void __launch_bounds__(SSCAN_THREADS) k_site_scan(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B) {
+  __shared__ uint32_t s_list[SSCAN_ROWS];
+  __shared__ uint32_t s_red[AGG_WORDS];
+  __shared__ uint32_t s_cnt, s_base;
+  const uint32_t js = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint64_t q0 = (uint64_t)blockIdx.y * SSCAN_ROWS;
+  const int32_t* live = B.live + (uint64_t)js * S.nq;
+  if (tid == 0) s_cnt = 0;
+  if (tid < AGG_WORDS) s_red[tid] = 0;
+  __syncthreads();
+  int32_t e[SSCAN_PER_THREAD];
+#pragma unroll
+  for (int i = 0; i < SSCAN_PER_THREAD; ++i) { const uint64_t q = q0 + (uint64_t)i * SSCAN_THREADS + tid; e[i] = q < S.nq ? live[q] : -1; }
+  uint4 h[SSCAN_PER_THREAD];
+#pragma unroll
+  for (int i = 0; i < SSCAN_PER_THREAD; ++i) {
+    h[i] = make_uint4(0, 0, 0, 0);
+    if (e[i] >= 0 && !(e[i] & LIVE_REDUCED)) h[i] = *reinterpret_cast<const uint4*>(&A.hot[e[i]]);
+  }
+  uint32_t n_live = 0, nonref = 0, mgt = 0, main_ = 0, mpl = 0;
+  uint32_t fpl[HOT_FIELDS] = {0, 0, 0, 0}, fin[HOT_FIELDS] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < SSCAN_PER_THREAD; ++i) {
+    bool general = false;
+    if (e[i] >= 0) {
+      ++n_live;
+      const uint32_t hflags = h[i].x & 0xFF, ploidy = (h[i].x >> 8) & 0xFF, n_alt = (h[i].x >> 16) & 0xFF, nr = h[i].x >> 24;
+      const uint32_t gt_len = h[i].y & 0xFF, inl = (h[i].y >> 8) & 0xFF;
+      general = (e[i] & LIVE_REDUCED) || !inl || !(hflags & F_TRIVIAL);
+      if (!general) {
+        mgt = max(mgt, gt_len); main_ = max(main_, n_alt + 1u); mpl = max(mpl, ploidy);
+        if (nr) nonref = 1;
+        const uint32_t fl4 = (h[i].y >> 16) | (h[i].z << 16);
+#pragma unroll
+        for (int f = 0; f < HOT_FIELDS; ++f) { const uint32_t n = (fl4 >> (8 * f)) & 0xFF; if (n) { fpl[f] = max(fpl[f], ploidy); fin[f] = max(fin[f], n); } }
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, general);
+    if (m) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&s_cnt, (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (general) s_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(q0 + (uint64_t)i * SSCAN_THREADS + tid);
+    }
+  }
+  uint32_t r;
+  r = __reduce_add_sync(0xffffffffu, n_live); if (lane == 0 && r) atomicAdd(&s_red[AGG_NLIVE], r);
+  r = __reduce_max_sync(0xffffffffu, nonref); if (lane == 0 && r) atomicMax(&s_red[AGG_NONREF], r);
+  r = __reduce_max_sync(0xffffffffu, mgt); if (lane == 0 && r) atomicMax(&s_red[AGG_MAXGT], r);
+  r = __reduce_max_sync(0xffffffffu, main_); if (lane == 0 && r) atomicMax(&s_red[AGG_MAXAIN], r);
+  r = __reduce_max_sync(0xffffffffu, mpl); if (lane == 0 && r) atomicMax(&s_red[AGG_MAXPLOIDY], r);
+#pragma unroll
+  for (int f = 0; f < HOT_FIELDS; ++f) {
+    r = __reduce_max_sync(0xffffffffu, fin[f]);
+    if (r) {   // warp-uniform
+      if (lane == 0) atomicMax(&s_red[AGG_MAXIN + f], r);
+      r = __reduce_max_sync(0xffffffffu, fpl[f]); if (lane == 0 && r) atomicMax(&s_red[AGG_MAXPL + f], r);
+    }
+  }
+  __syncthreads();
+  uint32_t* agg = B.agg + (uint64_t)js * AGG_WORDS;
+  if (tid == 0) { s_base = s_cnt ? atomicAdd(&agg[AGG_NNT], s_cnt) : 0u; if (s_red[AGG_NLIVE]) atomicAdd(&agg[AGG_NLIVE], s_red[AGG_NLIVE]); }
+  else if (tid < AGG_WORDS && tid != AGG_NNT && s_red[tid]) atomicMax(&agg[tid], s_red[tid]);
+  __syncthreads();
+  uint32_t* dst = B.nt_q + (uint64_t)js * S.nq + s_base;
+  for (uint32_t i = tid; i < s_cnt; i += SSCAN_THREADS) dst[i] = s_list[i];
+}
+
+// K4b: one block per site.  Merged REF from the begin cells of the site's column, merged ALT list from the site's nt list.
+__global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B) {
   __shared__ unsigned long long s_hash[UNION_SLOTS];
   __shared__ unsigned long long s_order[UNION_SLOTS];
   __shared__ uint16_t s_list[UNION_MAX_DISTINCT];
   __shared__ uint16_t s_rank[UNION_MAX_DISTINCT];
   __shared__ uint32_t s_piece_cell[REF_MAX_PIECES], s_piece_from[REF_MAX_PIECES], s_piece_to[REF_MAX_PIECES];
-  __shared__ unsigned int s_k, s_next, s_maxN, s_ndist, s_nonref, s_nlive, s_maxgt, s_maxain, s_maxploidy, s_npieces, s_reflen, s_refoff, s_afirst, s_overflow;
+  __shared__ unsigned int s_k, s_next, s_maxN, s_ndist, s_nonref, s_maxgt, s_maxain, s_maxploidy, s_npieces, s_reflen, s_refoff, s_afirst, s_overflow;
   __shared__ unsigned int s_maxpl[MAX_FIELDS], s_maxin[MAX_FIELDS];
 
   const uint32_t js = blockIdx.x;
   const uint64_t j = B.first_site + js;
   const int64_t b = S.site_begin[j];
   const int32_t* live = B.live + (uint64_t)js * S.nq;
+  const uint32_t* agg = B.agg + (uint64_t)js * AGG_WORDS;
   const int tid = threadIdx.x;
 
   for (int i = tid; i < UNION_SLOTS; i += UNION_THREADS) { s_hash[i] = 0ull; s_order[i] = ~0ull; }
-  if (tid == 0) { s_k = 0xFFFFFFFFu; s_next = 0xFFFFFFFFu; s_maxN = 0; s_ndist = 0; s_nonref = 0; s_nlive = 0; s_maxgt = 0; s_maxain = 0; s_maxploidy = 0; s_npieces = 0; s_overflow = 0; }
-  if (tid < MAX_FIELDS) { s_maxpl[tid] = 0; s_maxin[tid] = 0; }
+  if (tid == 0) {
+    s_k = 0xFFFFFFFFu; s_next = 0xFFFFFFFFu; s_maxN = 0; s_ndist = 0; s_npieces = 0; s_overflow = 0;
+    s_nonref = agg[AGG_NONREF]; s_maxgt = agg[AGG_MAXGT]; s_maxain = agg[AGG_MAXAIN]; s_maxploidy = agg[AGG_MAXPLOIDY];
+  }
+  if (tid < MAX_FIELDS) { s_maxpl[tid] = tid < HOT_FIELDS ? agg[AGG_MAXPL + tid] : 0u; s_maxin[tid] = tid < HOT_FIELDS ? agg[AGG_MAXIN + tid] : 0u; }
   __syncthreads();
 
   // ---- merged REF (variant_operations.cc:73-122): fold over the calls that BEGIN at this site, in row order.
@@ -372,12 +476,14 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(ArrayDev A, ScanDev S, 
   }
   __syncthreads();   // mref is read below by other threads of this block (global memory, same block: needs the barrier only)
 
-  // ---- merged ALT list (variant_operations.cc:134-228): first-seen order over live calls in row order
-  uint32_t my_live = 0, loc_maxgt = 0, loc_maxain = 0, loc_maxploidy = 0;
+  // ---- merged ALT list (variant_operations.cc:134-228): first-seen order over live calls in row order.  Trivial calls
+  // add no allele, so only the site's nt list is visited; the order key (row, token index) makes the result independent
+  // of the order of that list.
+  uint32_t loc_maxgt = 0, loc_maxain = 0, loc_maxploidy = 0;
   uint32_t loc_maxpl[MAX_FIELDS], loc_maxin[MAX_FIELDS];
 #pragma unroll
   for (int f = 0; f < MAX_FIELDS; ++f) { loc_maxpl[f] = 0; loc_maxin[f] = 0; }
-  bool loc_nonref = false;
+  bool loc_nonref = false, any = false;
   auto insert = [&](uint64_t h, uint64_t q, uint32_t idx) {
     unsigned long long order = ((unsigned long long)q << 12) | idx;
     uint32_t slot = (uint32_t)(h % UNION_SLOTS);
@@ -389,52 +495,42 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(ArrayDev A, ScanDev S, 
     }
     atomicMax(&S.err[1], 2u);
   };
-  if (!s_overflow) for (uint64_t q = tid; q < S.nq; q += UNION_THREADS) {
-    int32_t e = live[q];
-    if (e < 0) continue;
-    ++my_live;
-    if (!(e & LIVE_REDUCED)) {
-      // fast path: a trivial call (reference block, or ALT == <NON_REF> only) adds no allele; its lengths come from
-      // the 32-byte hot record
-      const uint4 h0 = *reinterpret_cast<const uint4*>(&A.hot[e]);
-      const uint32_t b0 = h0.x, b1 = h0.y, b2 = h0.z;
-      const uint32_t hflags = b0 & 0xFF, hploidy = (b0 >> 8) & 0xFF, hnalt = (b0 >> 16) & 0xFF, hnr = b0 >> 24;
-      const uint32_t hgt = b1 & 0xFF, hinl = (b1 >> 8) & 0xFF;
-      if ((hflags & F_TRIVIAL) && hinl) {
-        loc_maxgt = max(loc_maxgt, hgt); loc_maxain = max(loc_maxain, hnalt + 1u); loc_maxploidy = max(loc_maxploidy, hploidy);
-        if (hnr) loc_nonref = true;
-        const uint32_t fl4 = (b1 >> 16) | (b2 << 16);   // flen[0..3]
+  const uint32_t n_nt = agg[AGG_NNT];
+  const uint32_t* nt = B.nt_q + (uint64_t)js * S.nq;
+  const uint32_t H0 = warm_hash_word((uint32_t)A.n_fields);
+  if (!s_overflow) for (uint32_t i = tid; i < n_nt; i += UNION_THREADS) {
+    const uint32_t q = nt[i];
+    const int32_t e = live[q];
+    any = true;
+    if (e & LIVE_REDUCED) {
+      CallView v = make_view(A, S, e);
+      loc_maxgt = max(loc_maxgt, v.gt_len); loc_maxain = max(loc_maxain, (uint32_t)v.n_alt + 1u); loc_maxploidy = max(loc_maxploidy, v.ploidy);
 #pragma unroll
-        for (int f = 0; f < HOT_FIELDS; ++f) { uint32_t n = (fl4 >> (8 * f)) & 0xFF; if (f < A.n_fields && n) { loc_maxpl[f] = max(loc_maxpl[f], hploidy); loc_maxin[f] = max(loc_maxin[f], n); } }
-        continue;
+      for (int f = 0; f < MAX_FIELDS; ++f) if (f < A.n_fields) {
+        const uint32_t* p; uint32_t n;
+        if (field_of(A, S, v, f, p, n)) { loc_maxpl[f] = max(loc_maxpl[f], v.ploidy); loc_maxin[f] = max(loc_maxin[f], n); }
       }
+      if (v.nr_idx) loc_nonref = true;
+      insert(star_hash(), q, 1);
+      continue;
     }
-    CallView v = make_view(A, S, e);
-    loc_maxgt = max(loc_maxgt, v.gt_len); loc_maxain = max(loc_maxain, (uint32_t)v.n_alt + 1u); loc_maxploidy = max(loc_maxploidy, v.ploidy);
+    const WarmView v = warm_view(A, (uint32_t)e);
+    loc_maxgt = max(loc_maxgt, v.gt_len); loc_maxain = max(loc_maxain, v.n_alt + 1u); loc_maxploidy = max(loc_maxploidy, v.ploidy);
 #pragma unroll
-    for (int f = 0; f < MAX_FIELDS; ++f) if (f < A.n_fields) {
-      const uint32_t* p; uint32_t n;
-      if (field_of(A, S, v, f, p, n)) { loc_maxpl[f] = max(loc_maxpl[f], v.ploidy); loc_maxin[f] = max(loc_maxin[f], n); }
-    }
+    for (int f = 0; f < MAX_FIELDS; ++f) if (f < A.n_fields) { const uint32_t n = v.b[4 + f]; if (n) { loc_maxpl[f] = max(loc_maxpl[f], v.ploidy); loc_maxin[f] = max(loc_maxin[f], n); } }
     if (v.nr_idx) loc_nonref = true;
-    if (v.n_alt > MAX_CALL_ALLELES - 1) { atomicMax(&S.err[1], 1u); continue; }
-    if (v.reduced) { int sfx; insert(allele_hash(c_str_star, 1, mref, mref_len, 1, sfx), q, 1); continue; }
-    if (v.flags & F_TRIVIAL) continue;
-    int pos = 0, ts, tl; uint32_t idx = 0;
-    while (next_token(v.alt, v.alt_n, pos, ts, tl)) {
-      ++idx;
-      if (is_non_ref(v.alt + ts, tl)) continue;
-      int sfx;
-      insert(allele_hash(v.alt + ts, tl, mref, mref_len, v.ref_len, sfx), q, idx);
+    if (v.n_alt > (uint32_t)MAX_CALL_ALLELES - 1u) { atomicMax(&S.err[1], 1u); continue; }
+    for (uint32_t t = 0; t < v.n_alt; ++t) {
+      const uint64_t h = warm_token_hash(v, H0, t, mref, mref_len);
+      if (h) insert(h, q, t + 1u);
     }
   }
-  if (my_live) {
+  if (any) {
     atomicMax(&s_maxgt, loc_maxgt); atomicMax(&s_maxain, loc_maxain); atomicMax(&s_maxploidy, loc_maxploidy);
     if (loc_nonref) s_nonref = 1;
 #pragma unroll
     for (int f = 0; f < MAX_FIELDS; ++f) if (f < A.n_fields) { if (loc_maxin[f]) { atomicMax(&s_maxpl[f], loc_maxpl[f]); atomicMax(&s_maxin[f], loc_maxin[f]); } }
   }
-  if (my_live) atomicAdd(&s_nlive, my_live);
   __syncthreads();
   const uint32_t ndist = s_ndist < UNION_MAX_DISTINCT ? s_ndist : UNION_MAX_DISTINCT;
   // compact occupied slots, rank them by first occurrence
@@ -490,7 +586,7 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(ArrayDev A, ScanDev S, 
   if (tid == 0) {
     if (s_overflow) atomicOr(&S.err[2], 1u);
     SiteRec r;
-    r.n_alleles = A_m; r.n_live = s_nlive; r.allele_first = s_afirst; r.ref_off = s_refoff; r.ref_len = mref_len;
+    r.n_alleles = A_m; r.n_live = agg[AGG_NLIVE]; r.allele_first = s_afirst; r.ref_off = s_refoff; r.ref_len = mref_len; r.n_nt = n_nt;
     bool ref_block_only = (mref_len == 1 && ndist == 0 && s_nonref);
     r.flags = (s_nonref ? 1u : 0u) | (ref_block_only ? 0u : 2u);
     if (!ref_block_only && A_m - 1u > S.max_alt) r.flags |= 4u;
@@ -670,162 +766,61 @@ __global__ void __launch_bounds__(REMAP_THREADS) k_remap_generic(ArrayDev A, Sca
 
 }  // namespace gdb
 
-// ================================================================================================ K5 tile kernel
-// The fast path of the remap (sites with <= 64 merged alleles, ploidy <= 2, short input vectors, <= 4 remapped fields --
-// everything but pathological sites, which k_remap_generic keeps handling).  One block = 256 samples of one site.
-//   phase A  one thread per sample.  ONE 32-byte hot-record gather describes a trivial call completely (reference block
-//            or <NON_REF>-only call: ~90 % of the calls live at a site): the thread remaps GT, writes the lengths and
-//            leaves, per field, the (at most) three distinct values such a call contributes: genotype (0,0), (0,k),
-//            (j>0,k) -- plus the padding word.  Every other call is queued.
-//   queue    consecutive threads drain the queue (one warp diverges, not eight): tokenise ALT, hash, look the tokens up
-//            in the site's allele hashes, build the merged->input LUT (NON_REF fallback folded in), stage the raw vector.
-//   phase B  per field, (1) a vectorised pass: each lane owns one 16-byte quad of the dense sample-major output, a
-//            per-site class table says which of the four words (v0,v1,v2,pad) every output word takes -> 6 LDS + one
-//            coalesced STG.128 per 4 words; (2) a pass over the queued samples only, lane-parallel over their quads.
+// ================================================================================================ K5 tile kernels
+// The fast path of the remap (sites with <= 64 merged alleles, ploidy <= 2, short GT, <= 4 remapped fields -- everything
+// but pathological sites, which k_remap_generic keeps handling) is two kernels:
+//   k_remap_tile  one block = 256 samples of one site; handles the dead rows and the trivial inline calls (reference
+//                 block or <NON_REF>-only call whose GT/PL/AD fit the 32-byte hot record: ~90 % of the calls live at a
+//                 site) and is a pure store stream:
+//       phase A   one thread per sample: ONE 32-byte gather describes the call; the thread remaps GT, writes the lengths
+//                 and leaves, per field, the (at most) three distinct values such a call contributes: genotype (0,0),
+//                 (0,k), (j>0,k) -- plus the padding word.
+//       phase B   per field, each lane owns one 16-byte quad of the dense sample-major output; a per-site class table
+//                 says which of the four words (v0,v1,v2,pad) every output word takes -> coalesced STG.128.
+//   k_remap_nt    one warp per entry of the sites' nt lists (every other live call): one more gather (hot record -> warm
+//                 blob) brings the pre-hashed ALT tokens and the GT/field words; lanes look the tokens up in the site's
+//                 allele hashes (merged<->input LUT in shared memory, NON_REF fallback folded in) and write the row's
+//                 vectors lane-parallel.
 // Field strides of remapped sites are multiples of 4 words so that every sample's vector is 16-byte aligned.
-// Output bytes dominate (26.8 MB per site at 100 k samples x 10 alleles): the kernel is a store stream bound by HBM
-// write bandwidth; no tensor cores, no TMA (inputs are 256 scattered 32-byte sectors per block, not a tile).
+// Output bytes dominate (26.8 MB per site at 100 k samples x 10 alleles): the bound is HBM write bandwidth; no tensor
+// cores, no TMA (inputs are 256 scattered 32-byte sectors per block, not a tile).
 namespace gdb {
 
 constexpr int TILE_ROWS = 256;
 constexpr int TILE_MAX_A = 64;
-constexpr int TILE_MAX_INW = 48;
 constexpr int TILE_MAX_GT = 8;
 constexpr int TILE_MAX_FIELDS = 4;
-constexpr uint32_t INFO_FAST = 1u << 30;
+constexpr int TILE_MAX_G = TILE_MAX_A * (TILE_MAX_A + 1) / 2;
+constexpr uint32_t INFO_FAST = 1u;
 
-struct TileShape { uint32_t lw, inw, g; };   // per-launch shared-memory strides: LUT bytes/row, input words/row, max #genotypes
+struct TileShape { uint32_t g; };   // per launch: max #elements of a field vector over the launch's sites
 
 __host__ __device__ inline uint32_t tile_cls_bytes(TileShape t) { return ((t.g + 3) / 4 + 15) / 16 * 16; }   // class table of one field
 __host__ __device__ inline size_t tile_smem_bytes(TileShape t, int n_fields) {
-  size_t b = 8 * (size_t)TILE_MAX_A;                       // allele hashes
-  b += ((size_t)t.g * 2 + 15) / 16 * 16;                   // (j,k) table
-  b += (size_t)n_fields * tile_cls_bytes(t);               // class tables
+  size_t b = (size_t)n_fields * tile_cls_bytes(t);         // class tables
   b += (size_t)TILE_ROWS * n_fields * 16;                  // per (sample, field): v0, v1, v2, pad
   b += (size_t)TILE_ROWS * n_fields * 4;                   // per (sample, field): info word
-  b += (size_t)TILE_ROWS * t.lw;                           // LUT rows (int8), queued samples only
-  b += (size_t)TILE_ROWS * t.inw * 4;                      // staged inputs, queued samples only
   return (b + 15) / 16 * 16;
 }
-// info word of a (sample, field) slot: n_out | kind (0 dead, 1 trivial, 2 general) | ploidy | n_in | FAST
-__device__ inline uint32_t tri_info(uint32_t n_out, uint32_t kind, uint32_t ploidy, uint32_t n_in) { return (n_out & 0xFFFF) | (kind << 16) | ((ploidy & 15u) << 18) | ((n_in & 0xFF) << 22); }
 __device__ inline uint32_t sel5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t i) { return i == 0 ? a : (i == 1 ? b : (i == 2 ? c : (i == 3 ? d : e))); }
-
-struct TileCtx {
-  unsigned long long* s_ahash; uint16_t* s_jk; uint8_t* s_cls; uint4* s_tri; uint32_t* s_info; int8_t* s_lut; uint32_t* s_in;
-  uint32_t lw, inw, cls_bytes;
-};
-
-// one word of a queued sample's output (generic in kind / ploidy): variant_field_handler.cc:41-191
-__device__ inline uint32_t tile_slow_word(const TileCtx& T, uint32_t info, const uint4 t, uint32_t row, uint32_t foff, int kind, bool is_g, uint32_t g,
-                                          uint32_t pad, uint32_t miss) {
-  const uint32_t n_out = info & 0xFFFF, kindr = (info >> 16) & 3, ploidy = (info >> 18) & 15, n_in = (info >> 22) & 0xFF;
-  if (g >= n_out) return pad;
-  if (kindr != 2) {   // trivial call with an unusual length (haploid, ploidy 0, ...)
-    if (is_g && ploidy == 2) { const uint32_t jk = T.s_jk[g]; return (jk >> 8) == 0 ? t.x : ((jk & 0xFF) == 0 ? t.y : t.z); }
-    if (kind == KIND_A) return t.y;
-    return g == 0 ? t.x : t.y;
-  }
-  const uint32_t* in = T.s_in + (size_t)row * T.inw + foff;
-  const int8_t* lut = T.s_lut + (size_t)row * T.lw;
-  if (is_g && ploidy == 2) {
-    const uint32_t jk = T.s_jk[g];
-    const int ij = lut[jk & 0xFF], ik = lut[jk >> 8];
-    if (ij < 0 || ik < 0) return miss;
-    const uint32_t ig = (uint32_t)alleles2gt(ij, ik);
-    return ig < n_in ? in[ig] : miss;
-  }
-  if (is_g && ploidy == 0) return in[0];
-  const int ij = lut[kind == KIND_A ? g + 1 : g];
-  if (ij < 0) return miss;
-  const int ix = (kind == KIND_A) ? ij - 1 : ij;
-  return (ix < 0 || (uint32_t)ix >= n_in) ? miss : in[ix];
+// g = k(k+1)/2 + j, j <= k
+__device__ inline void tri_unrank(uint32_t g, uint32_t& j, uint32_t& k) {
+  k = (uint32_t)((sqrtf(8.0f * (float)g + 1.0f) - 1.0f) * 0.5f);
+  while (k * (k + 1) / 2 > g) --k;
+  while ((k + 1) * (k + 2) / 2 <= g) ++k;
+  j = g - k * (k + 1) / 2;
 }
-
-// queued samples: non-trivial / non-inline / spanning-deletion calls.  Out of line so that the common path stays small.
-template <int NF>
-__device__ __noinline__ void tile_general_row(const ArrayDev& A, const ScanDev& S, const BatchDev& B, const RemapOut& O, const SiteRec* __restrict__ site_g, const TileCtx T,
-                                              uint32_t js, uint64_t q, int row, int32_t e, const uint4 foff4) {
-  const uint64_t sq = (uint64_t)js * S.nq + q;
-  const uint32_t foff[4] = {foff4.x, foff4.y, foff4.z, foff4.w};
-  struct { uint32_t n_alleles, flags, ref_off, ref_len; } site = {site_g->n_alleles, site_g->flags, site_g->ref_off, site_g->ref_len};
-  const uint32_t A_m = site.n_alleles;
-  const bool nonref = site.flags & 1u, remap = site.flags & 2u, g_suppressed = site.flags & 4u;
-  const int o_f0 = A.has_gt ? 1 : 0;
-  const CallView v = make_view(A, S, e);
-  const uint32_t A_in = (uint32_t)v.n_alt + 1u;
-  const int in_nr = (nonref && v.nr_idx) ? v.nr_idx : -1;
-  const int step = A.gt_phased ? 2 : 1;
-  int8_t* lut = T.s_lut + (size_t)row * T.lw;
-  uint32_t* in_row = T.s_in + (size_t)row * T.inw;
-  uint32_t lut_first = 0xFFFFFFFFu;
-  if (O.lut_first) { lut_first = atomicAdd(&B.cursors[2], A_in); if (lut_first + A_in > O.cap_lut) { atomicOr(&S.err[2], 2u); lut_first = 0xFFFFFFFFu; } O.lut_first[sq] = lut_first; O.lut_len[sq] = (uint16_t)A_in; }
-  uint32_t gto[TILE_MAX_GT]; uint32_t mapped = 0;
-  for (uint32_t i = 0; i < v.gt_len && i < TILE_MAX_GT; ++i) {
-    uint32_t g = v.gt[i]; gto[i] = g;
-    if (!remap || (i % step) || g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING || g == 0) mapped |= 1u << i;
-  }
-  if (remap) {
-    for (uint32_t m = 0; m < A_m; ++m) lut[m] = -1;
-    lut[0] = 0;
-    if (lut_first != 0xFFFFFFFFu) { O.lut_in2m[lut_first] = 0; for (uint32_t i = 1; i < A_in; ++i) O.lut_in2m[lut_first + i] = -1; }
-    const uint8_t* mref = B.allele_bytes + site.ref_off;
-    auto assign = [&](uint32_t idx, uint32_t m) {
-      lut[m] = (int8_t)idx;
-      for (uint32_t i = 0; i < v.gt_len && i < TILE_MAX_GT; ++i) if (!(mapped & (1u << i)) && v.gt[i] == idx) { gto[i] = m; mapped |= 1u << i; }
-      if (lut_first != 0xFFFFFFFFu) O.lut_in2m[lut_first + idx] = (int16_t)m;
-    };
-    if (v.reduced) {
-      int sfx; uint64_t h = allele_hash(c_str_star, 1, mref, site.ref_len, 1, sfx);
-      for (uint32_t m = 1; m < A_m; ++m) if (T.s_ahash[m] == h) { assign(1, m); break; }
-    } else {
-      int pos = 0, ts, tl; uint32_t idx = 0;
-      while (next_token(v.alt, v.alt_n, pos, ts, tl)) {
-        ++idx;
-        if (is_non_ref(v.alt + ts, tl)) continue;
-        int sfx; uint64_t h = allele_hash(v.alt + ts, tl, mref, site.ref_len, v.ref_len, sfx);
-        for (uint32_t m = 1; m < A_m; ++m) if (T.s_ahash[m] == h) { assign(idx, m); break; }
-      }
-    }
-    if (v.nr_idx) assign((uint32_t)v.nr_idx, A_m - 1u);
-    for (uint32_t i = 0; i < v.gt_len && i < TILE_MAX_GT; ++i) if (!(mapped & (1u << i))) gto[i] = nonref ? A_m - 1u : 0xFFFFFFFFu;
-    for (uint32_t m = 0; m < A_m; ++m) if (lut[m] < 0) lut[m] = (int8_t)in_nr;   // NON_REF fallback folded in
-  } else if (lut_first != 0xFFFFFFFFu) {
-    for (uint32_t i = 0; i < A_in; ++i) O.lut_in2m[lut_first + i] = (int16_t)(i == 0 ? 0 : ((v.nr_idx && (int)i == v.nr_idx) ? (int)A_m - 1 : -1));
-  }
-  if (A.has_gt) {
-    const uint32_t gt_stride = O.f[0].stride[js]; uint32_t* gt_dst = O.f[0].data + O.f[0].base[js] + q * gt_stride;
-    for (uint32_t i = 0; i < gt_stride; ++i) gt_dst[i] = (i < v.gt_len) ? gto[i] : BCF_INT_VEND;
-    O.f[0].len[sq] = (uint16_t)v.gt_len;
-  }
-#pragma unroll
-  for (int f = 0; f < NF; ++f) {
-    const uint32_t* p; uint32_t n;
-    bool valid = field_of(A, S, v, f, p, n);
-    if (valid && !v.reduced) { bool any = false; const uint32_t nullw = null_word(A.fm[f].elem); for (uint32_t x = 0; x < n; ++x) any |= (p[x] != nullw); valid = any; }
-    const int kind = A.fm[f].kind;
-    const uint32_t padw = vend_word(A.fm[f].elem);
-    uint32_t n_out = 0;
-    if (valid && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, v.ploidy) : n;
-    if (!n_out) n = 0;
-    for (uint32_t x = 0; x < n; ++x) in_row[foff[f] + x] = p[x];
-    T.s_tri[row * NF + f] = make_uint4(padw, padw, padw, padw);
-    T.s_info[row * NF + f] = n_out ? tri_info(n_out, 2, v.ploidy, n) : (remap ? INFO_FAST : 0u);   // nothing to write: all padding
-    O.f[o_f0 + f].len[sq] = (uint16_t)n_out;
-    if (!remap) {   // no remapping at this site: copy through
-      const FieldOutDev fo = O.f[o_f0 + f];
-      const uint32_t fs = fo.stride[js]; uint32_t* d = fo.data + fo.base[js] + q * fs;
-      for (uint32_t x = 0; x < fs; ++x) d[x] = x < n_out ? p[x] : padw;
-    }
-  }
+// class of output word g of a trivial call's vector: 0 -> v0, 1 -> v1, 2 -> v2 (see phase A)
+__device__ inline uint32_t trivial_class(int kind, uint32_t ploidy, uint32_t g) {
+  if (kind == KIND_A) return 1;
+  if (kind == KIND_G && ploidy == 2) { uint32_t j, k; tri_unrank(g, j, k); return k == 0 ? 0 : (j == 0 ? 1 : 2); }
+  return g == 0 ? 0 : 1;   // R fields, haploid G fields; ploidy 0 G fields have one element
 }
 
 template <int NF>
-__global__ void __launch_bounds__(TILE_ROWS, 3) k_remap_tile(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
+__global__ void __launch_bounds__(TILE_ROWS, 4) k_remap_tile(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
                                                             const __grid_constant__ RemapOut O, const uint32_t* __restrict__ site_list, const TileShape TS) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ uint32_t s_nlist;
-  __shared__ uint16_t s_list[TILE_ROWS];
   const uint32_t tiles_per_site = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
   const uint32_t js = site_list[blockIdx.x / tiles_per_site], tile = blockIdx.x % tiles_per_site;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -836,64 +831,37 @@ __global__ void __launch_bounds__(TILE_ROWS, 3) k_remap_tile(const __grid_consta
   uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
   if (q < S.nq) {
     e = B.live[sq];
-    if (e >= 0) { const uint4* hp = reinterpret_cast<const uint4*>(&A.hot[e & (LIVE_REDUCED - 1)]); h0 = hp[0]; h1 = hp[1]; }
+    if (e >= 0 && !(e & LIVE_REDUCED)) { const uint4* hp = reinterpret_cast<const uint4*>(&A.hot[e]); h0 = hp[0]; h1 = hp[1]; }
   }
   const SiteRec* __restrict__ site_g = &B.sites[js];
-  struct { uint32_t n_alleles, flags, allele_first; } site = {site_g->n_alleles, site_g->flags, site_g->allele_first};
-  const uint32_t A_m = site.n_alleles;
-  const bool nonref = site.flags & 1u, remap = site.flags & 2u, g_suppressed = site.flags & 4u;
-  const uint32_t G = A_m * (A_m + 1) / 2;
+  const uint32_t A_m = site_g->n_alleles, sflags = site_g->flags;
+  const bool nonref = sflags & 1u, remap = sflags & 2u, g_suppressed = sflags & 4u;
   const int o_f0 = A.has_gt ? 1 : 0;
 
-  TileCtx T;
-  T.cls_bytes = tile_cls_bytes(TS);
-  T.s_ahash = reinterpret_cast<unsigned long long*>(smem);
-  T.s_jk = reinterpret_cast<uint16_t*>(smem + 8 * TILE_MAX_A);
-  T.s_cls = smem + 8 * TILE_MAX_A + ((size_t)TS.g * 2 + 15) / 16 * 16;
-  T.s_tri = reinterpret_cast<uint4*>(T.s_cls + (size_t)NF * T.cls_bytes);
-  T.s_info = reinterpret_cast<uint32_t*>(T.s_tri + (size_t)TILE_ROWS * NF);
-  T.s_lut = reinterpret_cast<int8_t*>(T.s_info + (size_t)TILE_ROWS * NF);
-  T.s_in = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(T.s_lut) + (size_t)TILE_ROWS * TS.lw);
-  T.lw = TS.lw; T.inw = TS.inw;
+  const uint32_t cls_bytes = tile_cls_bytes(TS);
+  uint8_t* s_cls = smem;
+  uint4* s_tri = reinterpret_cast<uint4*>(s_cls + (size_t)NF * cls_bytes);
+  uint32_t* s_info = reinterpret_cast<uint32_t*>(s_tri + (size_t)TILE_ROWS * NF);
 
-  uint32_t foff[NF], fstride[NF];
-  {
-    uint32_t o = 0;
+  uint32_t fstride[NF], fploidy[NF], nfull[NF];
 #pragma unroll
-    for (int f = 0; f < NF; ++f) { foff[f] = o; o += site_g->max_in_len[f]; fstride[f] = O.f[o_f0 + f].stride[js]; }
+  for (int f = 0; f < NF; ++f) {
+    fstride[f] = O.f[o_f0 + f].stride[js];
+    fploidy[f] = site_g->max_ploidy[f];
+    nfull[f] = num_elements(A.fm[f].kind, A_m - 1u, fploidy[f]);   // length of a full vector of this field at this site
   }
-  const uint4 foff4 = make_uint4(foff[0], NF > 1 ? foff[NF > 1 ? 1 : 0] : 0, NF > 2 ? foff[NF > 2 ? 2 : 0] : 0, NF > 3 ? foff[NF > 3 ? 3 : 0] : 0);
-  if (tid == 0) s_nlist = 0;
   if (remap) {
-    for (uint32_t i = tid; i < A_m; i += TILE_ROWS) T.s_ahash[i] = B.allele_hash[site.allele_first + i];
-    for (uint32_t g = tid; g < G; g += TILE_ROWS) {
-      uint32_t k = (uint32_t)((sqrtf(8.0f * (float)g + 1.0f) - 1.0f) * 0.5f);
-      while (k * (k + 1) / 2 > g) --k;
-      while ((k + 1) * (k + 2) / 2 <= g) ++k;
-      T.s_jk[g] = (uint16_t)((k << 8) | (g - k * (k + 1) / 2));
-    }
     // class tables: for each quad of a full-length vector, which of (v0, v1, v2, pad) each of its 4 words takes
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
       const int kind = A.fm[f].kind;
-      const uint32_t n_full = kind == KIND_G ? G : (kind == KIND_A ? A_m - 1u : A_m);
       for (uint32_t qd = tid; qd < fstride[f] / 4; qd += TILE_ROWS) {
         uint32_t c = 0;
-        for (uint32_t x = 0; x < 4; ++x) {
-          const uint32_t g = 4 * qd + x;
-          uint32_t code = 3;
-          if (g < n_full) {
-            if (kind == KIND_G) { uint32_t k = (uint32_t)((sqrtf(8.0f * (float)g + 1.0f) - 1.0f) * 0.5f); while (k * (k + 1) / 2 > g) --k; while ((k + 1) * (k + 2) / 2 <= g) ++k; const uint32_t j = g - k * (k + 1) / 2; code = k == 0 ? 0 : (j == 0 ? 1 : 2); }
-            else if (kind == KIND_A) code = 1;
-            else code = g == 0 ? 0 : 1;
-          }
-          c |= code << (2 * x);
-        }
-        T.s_cls[f * T.cls_bytes + qd] = (uint8_t)c;
+        for (uint32_t x = 0; x < 4; ++x) { const uint32_t g = 4 * qd + x; c |= (g < nfull[f] ? trivial_class(kind, fploidy[f], g) : 3u) << (2 * x); }
+        s_cls[f * cls_bytes + qd] = (uint8_t)c;
       }
     }
   }
-  __syncthreads();
 
   // ---------------------------------------------------------------- phase A: one thread per sample
   if (q < S.nq) {
@@ -901,8 +869,8 @@ __global__ void __launch_bounds__(TILE_ROWS, 3) k_remap_tile(const __grid_consta
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
         const uint32_t padw = vend_word(A.fm[f].elem);
-        T.s_tri[tid * NF + f] = make_uint4(padw, padw, padw, padw);
-        T.s_info[tid * NF + f] = INFO_FAST;
+        s_tri[tid * NF + f] = make_uint4(padw, padw, padw, padw);
+        s_info[tid * NF + f] = INFO_FAST;
         O.f[o_f0 + f].len[sq] = 0;
         if (!remap) { const FieldOutDev fo = O.f[o_f0 + f]; uint32_t* d = fo.data + fo.base[js] + q * fstride[f]; for (uint32_t x = 0; x < fstride[f]; ++x) d[x] = padw; }
       }
@@ -911,8 +879,11 @@ __global__ void __launch_bounds__(TILE_ROWS, 3) k_remap_tile(const __grid_consta
     } else {
       const uint32_t hflags = h0.x & 0xFF, ploidy = (h0.x >> 8) & 0xFF, n_alt = (h0.x >> 16) & 0xFF, nr = h0.x >> 24, gt_len = h0.y & 0xFF;
       const bool inl = ((h0.y >> 8) & 0xFF) != 0;
-      if ((e & LIVE_REDUCED) || !inl || !(hflags & F_TRIVIAL)) s_list[atomicAdd(&s_nlist, 1u)] = (uint16_t)tid;   // rare: queue
-      else {
+      if ((e & LIVE_REDUCED) || !inl || !(hflags & F_TRIVIAL)) {
+        // on the site's nt list: k_remap_nt writes this row
+#pragma unroll
+        for (int f = 0; f < NF; ++f) s_info[tid * NF + f] = 0;
+      } else {
         // ---- trivial call, fully described by its hot record
         const uint32_t fl4 = (h0.y >> 16) | (h0.z << 16);
         const int in_nr = (nonref && nr) ? (int)nr : -1;
@@ -938,7 +909,6 @@ __global__ void __launch_bounds__(TILE_ROWS, 3) k_remap_tile(const __grid_consta
           if (first != 0xFFFFFFFFu) for (uint32_t i = 0; i < A_in; ++i) O.lut_in2m[first + i] = (int16_t)(i == 0 ? 0 : ((nr && i == nr) ? (int)A_m - 1 : -1));
         }
         uint32_t k = gt_len;   // fields follow GT in the record
-        bool queued = false;
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
           const uint32_t n = (fl4 >> (8 * f)) & 0xFF;
@@ -952,8 +922,8 @@ __global__ void __launch_bounds__(TILE_ROWS, 3) k_remap_tile(const __grid_consta
             uint32_t* d = O.f[o_f0 + f].data + O.f[o_f0 + f].base[js] + q * fstride[f];
             for (uint32_t x = 0; x < fstride[f]; ++x) d[x] = x < n_out ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + x) : padw;
           } else if (!n_out) {
-            T.s_tri[tid * NF + f] = make_uint4(padw, padw, padw, padw);
-            T.s_info[tid * NF + f] = INFO_FAST;
+            s_tri[tid * NF + f] = make_uint4(padw, padw, padw, padw);
+            s_info[tid * NF + f] = INFO_FAST;
           } else {
             uint32_t v0 = sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k), v1 = miss, v2 = miss;
             if (in_nr >= 0) {
@@ -965,25 +935,24 @@ __global__ void __launch_bounds__(TILE_ROWS, 3) k_remap_tile(const __grid_consta
                 v2 = g2 < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + g2) : miss;
               }
             }
-            const uint32_t n_full = kind == KIND_G ? G : (kind == KIND_A ? A_m - 1u : A_m);
-            const bool fast = (n_out == n_full) && (kind != KIND_G || ploidy == 2);
-            T.s_tri[tid * NF + f] = make_uint4(v0, v1, v2, padw);
-            T.s_info[tid * NF + f] = tri_info(n_out, 1, ploidy, n) | (fast ? INFO_FAST : 0u);
-            if (!fast) queued = true;
+            // the class table is the one of the site's ploidy for this field; a sample of another ploidy (a haploid
+            // call among diploid ones ...) writes its own, shorter vector from this thread
+            const bool fast = (kind != KIND_G) || (ploidy == fploidy[f]);
+            s_tri[tid * NF + f] = make_uint4(v0, v1, v2, padw);
+            s_info[tid * NF + f] = fast ? INFO_FAST : 0u;
+            if (!fast) {
+              uint32_t* d = O.f[o_f0 + f].data + O.f[o_f0 + f].base[js] + q * fstride[f];
+              for (uint32_t x = 0; x < fstride[f]; ++x) {
+                uint32_t w = padw;
+                if (x < n_out) { const uint32_t c = trivial_class(kind, ploidy, x); w = c == 0 ? v0 : (c == 1 ? v1 : v2); }
+                d[x] = w;
+              }
+            }
           }
           k += n;
         }
-        if (queued) s_list[atomicAdd(&s_nlist, 1u)] = (uint16_t)(tid | 0x8000);   // trivial, but some vector has an unusual length
       }
     }
-  }
-  __syncthreads();
-  const uint32_t n_list = s_nlist;
-  for (uint32_t i = tid; i < n_list; i += TILE_ROWS) {
-    const uint32_t ent = s_list[i];
-    if (ent & 0x8000) continue;
-    const uint64_t qr = (uint64_t)tile * TILE_ROWS + ent;
-    tile_general_row<NF>(A, S, B, O, site_g, T, js, qr, (int)ent, B.live[(uint64_t)js * S.nq + qr], foff4);
   }
   if (!remap) return;   // copy-through sites are complete (uniform per block)
   __syncthreads();
@@ -991,52 +960,161 @@ __global__ void __launch_bounds__(TILE_ROWS, 3) k_remap_tile(const __grid_consta
   // ---------------------------------------------------------------- phase B
   const uint32_t rows = (uint32_t)min((uint64_t)TILE_ROWS, S.nq - (uint64_t)tile * TILE_ROWS);
   const uint32_t r0 = warp * 32;
+  if (r0 >= rows) return;
 #pragma unroll
   for (int f = 0; f < NF; ++f) {
     const uint32_t stride = fstride[f];
     if (stride == 0) continue;
     const FieldOutDev fo = O.f[o_f0 + f];
-    const int kind = A.fm[f].kind, elem = A.fm[f].elem;
     const uint32_t lpr = stride >> 2;   // quads per sample (stride is a multiple of 4 at remapped sites)
     uint32_t* tile_dst = fo.data + fo.base[js] + (uint64_t)tile * TILE_ROWS * stride;
-    // (1) vectorised pass over this warp's 32 samples: flat quad index i <-> (sample, quad)
-    if (r0 < rows) {
-      const uint32_t nr = min(32u, rows - r0), total = nr * lpr;
-      uint4* out4 = reinterpret_cast<uint4*>(tile_dst + (uint64_t)r0 * stride);
-      const uint8_t* cls = T.s_cls + f * T.cls_bytes;
-      uint32_t row_l = (uint32_t)lane / lpr, qd = (uint32_t)lane % lpr;
-      const uint32_t dr = 32u / lpr, dq = 32u % lpr;
-      for (uint32_t i = lane; i < total; i += 32) {
-        const uint32_t slot = (r0 + row_l) * NF + f;
-        if (T.s_info[slot] & INFO_FAST) {
-          const uint32_t* tw = reinterpret_cast<const uint32_t*>(&T.s_tri[slot]);
-          const uint32_t c = cls[qd];
-          uint4 v;
-          v.x = tw[c & 3]; v.y = tw[(c >> 2) & 3]; v.z = tw[(c >> 4) & 3]; v.w = tw[(c >> 6) & 3];
-          out4[i] = v;
-        }
-        row_l += dr; qd += dq;
-        if (qd >= lpr) { qd -= lpr; ++row_l; }
-      }
-    }
-    // (2) the queued samples, lane-parallel over their quads
-    if (n_list) {
-      const bool is_g = kind == KIND_G;
-      const uint32_t pad = vend_word(elem), miss = missing_word(elem);
-      const uint32_t total = n_list * lpr;
-      for (uint32_t i = tid; i < total; i += TILE_ROWS) {
-        const uint32_t li = i / lpr, qd = i - li * lpr;
-        const uint32_t row = s_list[li] & 0x7FFF;
-        const uint32_t info = T.s_info[row * NF + f];
-        if (info & INFO_FAST) continue;
-        const uint4 t = T.s_tri[row * NF + f];
+    // this warp's 32 samples: flat quad index i <-> (sample, quad)
+    const uint32_t nr = min(32u, rows - r0), total = nr * lpr;
+    uint4* out4 = reinterpret_cast<uint4*>(tile_dst + (uint64_t)r0 * stride);
+    const uint8_t* cls = s_cls + f * cls_bytes;
+    uint32_t row_l = (uint32_t)lane / lpr, qd = (uint32_t)lane % lpr;
+    const uint32_t dr = 32u / lpr, dq = 32u % lpr;
+    for (uint32_t i = lane; i < total; i += 32) {
+      const uint32_t slot = (r0 + row_l) * NF + f;
+      if (s_info[slot] & INFO_FAST) {
+        const uint32_t* tw = reinterpret_cast<const uint32_t*>(&s_tri[slot]);
+        const uint32_t c = cls[qd];
         uint4 v;
-        v.x = tile_slow_word(T, info, t, row, foff[f], kind, is_g, 4 * qd, pad, miss);
-        v.y = tile_slow_word(T, info, t, row, foff[f], kind, is_g, 4 * qd + 1, pad, miss);
-        v.z = tile_slow_word(T, info, t, row, foff[f], kind, is_g, 4 * qd + 2, pad, miss);
-        v.w = tile_slow_word(T, info, t, row, foff[f], kind, is_g, 4 * qd + 3, pad, miss);
-        reinterpret_cast<uint4*>(tile_dst + (uint64_t)row * stride)[qd] = v;
+        v.x = tw[c & 3]; v.y = tw[(c >> 2) & 3]; v.z = tw[(c >> 4) & 3]; v.w = tw[(c >> 6) & 3];
+        out4[i] = v;
       }
+      row_l += dr; qd += dq;
+      if (qd >= lpr) { qd -= lpr; ++row_l; }
+    }
+  }
+}
+
+// One warp per nt-list entry (non-trivial, non-inline or spanning-deletion call) of the launch's sites.
+constexpr int NT_WARPS = 8;
+template <int NF>
+__global__ void __launch_bounds__(NT_WARPS * 32) k_remap_nt(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
+                                                           const __grid_constant__ RemapOut O, const uint32_t* __restrict__ site_list,
+                                                           const uint32_t* __restrict__ nt_prefix, const uint32_t n_list_sites, const uint32_t jk_n) {
+  __shared__ uint16_t s_jk[TILE_MAX_G];                      // g -> (k << 8 | j), the same for every site
+  __shared__ unsigned long long s_ah[NT_WARPS][TILE_MAX_A];  // the site's merged-allele hashes
+  __shared__ int s_m2in[NT_WARPS][TILE_MAX_A];
+  __shared__ int16_t s_in2m[NT_WARPS][TILE_MAX_A];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (uint32_t g = threadIdx.x; g < jk_n && g < (uint32_t)TILE_MAX_G; g += NT_WARPS * 32) { uint32_t j, k; tri_unrank(g, j, k); s_jk[g] = (uint16_t)((k << 8) | j); }
+  __syncthreads();
+  const uint32_t wid = blockIdx.x * NT_WARPS + w;
+  if (wid >= nt_prefix[n_list_sites]) return;
+  uint32_t lo = 0, hi = n_list_sites;   // last si with nt_prefix[si] <= wid
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (nt_prefix[mid] <= wid) lo = mid; else hi = mid; }
+  const uint32_t js = site_list[lo];
+  const uint32_t q = B.nt_q[(uint64_t)js * S.nq + (wid - nt_prefix[lo])];
+  const uint64_t sq = (uint64_t)js * S.nq + q;
+  const int32_t e = B.live[sq];
+  const SiteRec* __restrict__ site_g = &B.sites[js];
+  const uint32_t A_m = site_g->n_alleles, sflags = site_g->flags, allele_first = site_g->allele_first, mref_len = site_g->ref_len;
+  const uint8_t* mref = B.allele_bytes + site_g->ref_off;
+  const bool nonref = sflags & 1u, remap = sflags & 2u, g_suppressed = sflags & 4u;
+  const int o_f0 = A.has_gt ? 1 : 0;
+  for (uint32_t m = lane; m < A_m; m += 32) { s_ah[w][m] = B.allele_hash[allele_first + m]; s_m2in[w][m] = m == 0 ? 0 : -1; }
+
+  // ---- the call
+  const bool reduced = (e & LIVE_REDUCED) != 0;
+  uint32_t n_alt, nr_idx, gt_len, ploidy;
+  const uint32_t* gt; const uint32_t* fin[NF]; uint32_t fn[NF];
+  WarmView wv{};
+  const uint32_t H0 = warm_hash_word((uint32_t)A.n_fields);
+  if (reduced) {
+    const uint32_t cell = (uint32_t)(e & (LIVE_REDUCED - 1));
+    const DelRec* dr = find_delrec(S, cell);
+    const CellDesc d = A.desc[cell];
+    n_alt = dr->n_alt; nr_idx = dr->has_nr ? 2u : 0u;
+    gt_len = (d.flags & F_GTVALID) ? d.gt_len : 0u; ploidy = gt_len ? ploidy_of(A.gt_phased, gt_len) : 0u;
+    gt = S.del_words + dr->gt_off;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) { const uint32_t n = dr->f_len[f]; fn[f] = n == 0xFFFFFFFFu ? 0u : n; fin[f] = S.del_words + dr->f_off[f]; }
+  } else {
+    wv = warm_view(A, (uint32_t)e);
+    n_alt = wv.n_alt; nr_idx = wv.nr_idx; gt_len = wv.gt_len; ploidy = wv.ploidy;
+    gt = wv.b + H0 + 3u * n_alt;
+    const uint32_t* p = gt + gt_len;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) { fn[f] = wv.b[4 + f]; fin[f] = p; p += fn[f]; }
+  }
+  const uint32_t A_in = n_alt + 1u;
+  __syncwarp();
+  // ---- allele LUT (merge_alt_alleles' add_input_merged_idx_pair calls for this call, variant_operations.cc:160-227)
+  if (lane == 0) s_in2m[w][0] = 0;
+  for (uint32_t t = lane; t < n_alt && t + 1u < (uint32_t)TILE_MAX_A; t += 32) {
+    const uint32_t idx = t + 1u;
+    int m = -1;
+    if (remap) {
+      uint64_t h = 0;
+      if (reduced) { if (idx == 1) h = star_hash(); }
+      else h = warm_token_hash(wv, H0, t, mref, mref_len);
+      if (h) for (uint32_t mm = 1; mm < A_m; ++mm) if (s_ah[w][mm] == h) { m = (int)mm; break; }
+    }
+    if (nr_idx && idx == nr_idx) m = (int)A_m - 1;
+    s_in2m[w][idx] = (int16_t)m;
+    if (remap && m >= 0) atomicMax(&s_m2in[w][m], (int)idx);   // a merged allele named twice by one call: the last one wins
+  }
+  __syncwarp();
+  if (remap) {
+    const int in_nr = (nonref && nr_idx) ? (int)nr_idx : -1;   // NON_REF fallback folded in
+    for (uint32_t m = lane; m < A_m; m += 32) if (s_m2in[w][m] < 0) s_m2in[w][m] = in_nr;
+    __syncwarp();
+  }
+  if (O.lut_first) {
+    uint32_t first = 0;
+    if (lane == 0) { first = atomicAdd(&B.cursors[2], A_in); if (first + A_in > O.cap_lut) { atomicOr(&S.err[2], 2u); first = 0xFFFFFFFFu; } O.lut_first[sq] = first; O.lut_len[sq] = (uint16_t)A_in; }
+    first = __shfl_sync(0xffffffffu, first, 0);
+    if (first != 0xFFFFFFFFu) for (uint32_t i = lane; i < A_in; i += 32) O.lut_in2m[first + i] = s_in2m[w][i];
+  }
+  // ---- GT (variant_operations.cc:233-263)
+  if (A.has_gt) {
+    const FieldOutDev fo = O.f[0];
+    const uint32_t gs = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + (uint64_t)q * gs;
+    const uint32_t step = A.gt_phased ? 2u : 1u;
+    for (uint32_t i = lane; i < gs; i += 32) {
+      uint32_t val = BCF_INT_VEND;
+      if (i < gt_len) {
+        const uint32_t g = gt[i]; val = g;
+        if (remap && (i % step) == 0 && !(g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING)) {
+          const int m = g < A_in ? (int)s_in2m[w][g] : -1;
+          val = m < 0 ? (nonref ? A_m - 1u : 0xFFFFFFFFu) : (uint32_t)m;
+        }
+      }
+      dst[i] = val;
+    }
+    if (lane == 0) fo.len[sq] = (uint16_t)gt_len;
+  }
+  // ---- allele-dependent fields (variant_field_handler.cc:41-191)
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    const FieldOutDev fo = O.f[o_f0 + f];
+    const int kind = A.fm[f].kind, elem = A.fm[f].elem;
+    const uint32_t pad = vend_word(elem), miss = missing_word(elem);
+    const uint32_t n = fn[f]; const uint32_t* in = fin[f];
+    uint32_t n_out = 0;
+    if (n && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, ploidy) : n;
+    const uint32_t stride = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + (uint64_t)q * stride;
+    if (lane == 0) fo.len[sq] = (uint16_t)n_out;
+    for (uint32_t g = lane; g < stride; g += 32) {
+      uint32_t val = pad;
+      if (g < n_out) {
+        if (!remap) val = in[g];
+        else if (kind == KIND_G && ploidy == 2) {
+          const uint32_t jk = s_jk[g];
+          const int ij = s_m2in[w][jk & 0xFF], ik = s_m2in[w][jk >> 8];
+          if (ij < 0 || ik < 0) val = miss;
+          else { const uint32_t ig = (uint32_t)alleles2gt(ij, ik); val = ig < n ? in[ig] : miss; }
+        } else if (kind == KIND_G && ploidy == 0) val = in[0];
+        else {
+          const int ij = s_m2in[w][kind == KIND_A ? g + 1u : g];
+          const int ix = kind == KIND_A ? ij - 1 : ij;
+          val = (ij < 0 || ix < 0 || (uint32_t)ix >= n) ? miss : in[ix];
+        }
+      }
+      dst[g] = val;
     }
   }
 }
