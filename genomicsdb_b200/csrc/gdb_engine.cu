@@ -272,7 +272,7 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
       exclusive_scan<uint32_t, uint64_t>(ctx, units.p, offs64.p, n, total.p, sums);
       uint64_t h_units = 0;
       CK(cudaMemcpyAsync(&h_units, total.p, 8, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
-      if (h_units >= (1ull << 32)) throw LimitError("warm-blob pool above 64 GB: shard the column range across GPUs");
+      if (h_units >= (1ull << 31)) throw LimitError("warm-blob pool above 32 GB: shard the column range across GPUs");
       a->warm.alloc(std::max<uint64_t>(h_units * 4, 4));
       a->dev.warm = a->warm.p;
       LAUNCH(ctx, k_narrow_u64, g, 256, offs64.p, n, offs.p);
@@ -318,7 +318,7 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
 // context keeps finished scans' buffers and hands them to the next scan.
 struct BatchBuffers {
   // per batch (device)
-  DevBuf<int32_t> live; DevBuf<SiteRec> sites; DevBuf<uint32_t> agg, nt_q, nt_prefix; DevBuf<uint32_t> cursors, allele_pos, lut_first; DevBuf<uint16_t> lut_len; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes; DevBuf<int16_t> lut_in2m;
+  DevBuf<int32_t> live; DevBuf<SiteRec> sites; DevBuf<uint32_t> agg, nt_prefix; DevBuf<uint2> nt, blk_map; DevBuf<uint32_t> cursors, allele_pos, lut_first; DevBuf<uint16_t> lut_len; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes; DevBuf<int16_t> lut_in2m;
   DevBuf<uint32_t> out_data[MAX_FIELDS + 1], out_stride[MAX_FIELDS + 1]; DevBuf<uint64_t> out_base[MAX_FIELDS + 1]; DevBuf<uint16_t> out_len[MAX_FIELDS + 1];
   DevBuf<uint8_t> d_site_flags; DevBuf<uint32_t> d_n_alleles, d_n_live, d_allele_first;
   // per batch (host mirrors)
@@ -512,13 +512,13 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
   const int n_out = s->n_out;
   for (;;) {
     bb.live.ensure((uint64_t)nb * S.nq); bb.sites.ensure(nb); bb.cursors.ensure(4);
-    bb.agg.ensure((uint64_t)nb * AGG_WORDS); bb.nt_q.ensure((uint64_t)nb * S.nq);
+    bb.agg.ensure((uint64_t)nb * AGG_WORDS); bb.nt.ensure((uint64_t)nb * S.nq);
     CK(cudaMemsetAsync(bb.agg.p, 0, (size_t)nb * AGG_WORDS * 4, ctx->stream));
     if (!s->cap_allele_recs) { s->cap_allele_recs = 1u << 16; s->cap_allele_bytes = 1u << 20; }
     bb.allele_pos.ensure(2ull * s->cap_allele_recs); bb.allele_hash.ensure(s->cap_allele_recs); bb.allele_bytes.ensure(s->cap_allele_bytes);
     CK(cudaMemsetAsync(bb.cursors.p, 0, 16, ctx->stream));
     BatchDev B{};
-    B.first_site = s->cursor; B.n_sites = nb; B.live = bb.live.p; B.sites = bb.sites.p; B.agg = bb.agg.p; B.nt_q = bb.nt_q.p; B.cursors = bb.cursors.p;
+    B.first_site = s->cursor; B.n_sites = nb; B.live = bb.live.p; B.sites = bb.sites.p; B.agg = bb.agg.p; B.nt = bb.nt.p; B.cursors = bb.cursors.p;
     B.allele_pos = bb.allele_pos.p; B.allele_hash = bb.allele_hash.p; B.cap_allele_recs = s->cap_allele_recs; B.allele_bytes = bb.allele_bytes.p; B.cap_allele_bytes = s->cap_allele_bytes;
     LAUNCH(ctx, k_live_walk, dim3(blocks_for(S.nq, 256), (nb + WALK_CHUNK - 1) / WALK_CHUNK), 256, a->dev, S, s->cursor, nb, bb.live.p);
     LAUNCH(ctx, k_site_scan, dim3(nb, blocks_for(S.nq, SSCAN_ROWS)), SSCAN_THREADS, a->dev, S, B);
@@ -566,13 +566,13 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
       bool ok = a->fields.size() >= 1 && a->fields.size() <= (size_t)TILE_MAX_FIELDS && r.n_alleles <= (uint32_t)TILE_MAX_A && r.max_ain <= (uint32_t)TILE_MAX_A &&
                 r.max_gt_len <= (uint32_t)TILE_MAX_GT && r.max_ploidy_all <= 2u;
       if (ok) {
-        nt_prefix.push_back(fast.empty() ? 0u : nt_prefix.back() + bb.h_sites[fast.back()].n_nt);
+        nt_prefix.push_back(fast.empty() ? 0u : nt_prefix.back() + (bb.h_sites[fast.back()].n_nt + NT_GROUPS - 1) / NT_GROUPS);
         fast.push_back(i);
         shape.g = std::max(shape.g, r.n_alleles * (r.n_alleles + 1u) / 2u);
       } else slow.push_back(i);
     }
     if (!fast.empty()) {
-      nt_prefix.push_back(nt_prefix.back() + bb.h_sites[fast.back()].n_nt);
+      nt_prefix.push_back(nt_prefix.back() + (bb.h_sites[fast.back()].n_nt + NT_GROUPS - 1) / NT_GROUPS);   // blocks of k_remap_nt, per site
       bb.fast_sites.ensure(fast.size()); bb.nt_prefix.ensure(nt_prefix.size());
       CK(cudaMemcpyAsync(bb.fast_sites.p, fast.data(), fast.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaMemcpyAsync(bb.nt_prefix.p, nt_prefix.data(), nt_prefix.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -592,12 +592,13 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
         default: launch_tile(k_remap_tile<4>); break;
       }
       ++ctx->launches; CK(cudaGetLastError());
-      const uint32_t n_nt = nt_prefix.back();
-      if (n_nt) {
-        unsigned grid_nt = (n_nt + NT_WARPS - 1) / NT_WARPS;
+      const uint32_t n_blk = nt_prefix.back();
+      if (n_blk) {
+        bb.blk_map.ensure(n_blk);
+        LAUNCH(ctx, k_nt_blocks, (unsigned)fast.size(), 256, B, bb.fast_sites.p, bb.nt_prefix.p, bb.blk_map.p);
         auto launch_nt = [&](auto kern) {
           ProfScope ps__(ctx, "k_remap_nt");
-          kern<<<grid_nt, NT_WARPS * 32, 0, ctx->stream>>>(a->dev, S, B, O, bb.fast_sites.p, bb.nt_prefix.p, (uint32_t)fast.size(), shape.g);
+          kern<<<n_blk, NT_THREADS, 0, ctx->stream>>>(a->dev, S, B, O, bb.blk_map.p, shape.g);
         };
         switch (nf) {
           case 1: launch_nt(k_remap_nt<1>); break;

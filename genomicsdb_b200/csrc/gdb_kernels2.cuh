@@ -267,18 +267,20 @@ struct BatchDev {
   const int32_t* live;        // n_sites x nq
   SiteRec* sites;
   uint32_t* agg;              // n_sites x AGG_WORDS
-  uint32_t* nt_q;             // n_sites x nq : per site, the query rows of its non-trivial live calls (first agg[AGG_NNT]), any order
+  uint2* nt;                  // n_sites x nq : per site, its non-trivial live calls (first agg[AGG_NNT] entries, any order):
+                              //   .x = query row, .y = warm-blob offset (16-byte units), or NT_REDUCED | cell for a spanning deletion
   // pools (atomic bump allocation; overflow -> err[2])
   uint32_t* cursors;          // [0] allele records, [1] allele bytes, [2] lut words
   uint32_t* allele_pos; uint64_t* allele_hash; uint32_t cap_allele_recs;
   uint8_t* allele_bytes; uint32_t cap_allele_bytes;
 };
 
+constexpr uint32_t NT_REDUCED = 0x80000000u;
 // a non-reduced, non-(trivial and inline) call through its warm blob
 struct WarmView { const uint32_t* b; uint32_t n_alt, nr_idx, ref_len, gt_len, ploidy; };
-__device__ inline WarmView warm_view(const ArrayDev& A, uint32_t cell) {
+__device__ inline WarmView warm_view(const ArrayDev& A, uint32_t blob_off) {
   WarmView v;
-  v.b = A.warm + (uint64_t)A.hot[cell].w[0] * 4u;
+  v.b = A.warm + (uint64_t)blob_off * 4u;
   const uint4 hd = *reinterpret_cast<const uint4*>(v.b);
   v.n_alt = hd.x; v.nr_idx = hd.y; v.ref_len = hd.z; v.gt_len = hd.w;
   v.ploidy = hd.w ? ploidy_of(A.gt_phased, hd.w) : 0u;
@@ -300,7 +302,7 @@ __device__ inline uint64_t star_hash() { const uint8_t s = '*'; return hash_fini
 // row chunks), so the whole GPU works on a batch whatever its number of sites.
 constexpr int SSCAN_THREADS = 256, SSCAN_PER_THREAD = 8, SSCAN_ROWS = SSCAN_THREADS * SSCAN_PER_THREAD;
 __global__ void __launch_bounds__(SSCAN_THREADS) k_site_scan(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B) {
-  __shared__ uint32_t s_list[SSCAN_ROWS];
+  __shared__ uint2 s_list[SSCAN_ROWS];
   __shared__ uint32_t s_red[AGG_WORDS];
   __shared__ uint32_t s_cnt, s_base;
   const uint32_t js = blockIdx.x;
@@ -342,7 +344,8 @@ __global__ void __launch_bounds__(SSCAN_THREADS) k_site_scan(const __grid_consta
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(&s_cnt, (uint32_t)__popc(m));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (general) s_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(q0 + (uint64_t)i * SSCAN_THREADS + tid);
+      if (general) s_list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)(q0 + (uint64_t)i * SSCAN_THREADS + tid),
+                                                                              (e[i] & LIVE_REDUCED) ? (NT_REDUCED | (uint32_t)(e[i] & (LIVE_REDUCED - 1))) : h[i].w);
     }
   }
   uint32_t r;
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(SSCAN_THREADS) k_site_scan(const __grid_consta
   if (tid == 0) { s_base = s_cnt ? atomicAdd(&agg[AGG_NNT], s_cnt) : 0u; if (s_red[AGG_NLIVE]) atomicAdd(&agg[AGG_NLIVE], s_red[AGG_NLIVE]); }
   else if (tid < AGG_WORDS && tid != AGG_NNT && s_red[tid]) atomicMax(&agg[tid], s_red[tid]);
   __syncthreads();
-  uint32_t* dst = B.nt_q + (uint64_t)js * S.nq + s_base;
+  uint2* dst = B.nt + (uint64_t)js * S.nq + s_base;
   for (uint32_t i = tid; i < s_cnt; i += SSCAN_THREADS) dst[i] = s_list[i];
 }
 
@@ -496,14 +499,14 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__
     atomicMax(&S.err[1], 2u);
   };
   const uint32_t n_nt = agg[AGG_NNT];
-  const uint32_t* nt = B.nt_q + (uint64_t)js * S.nq;
+  const uint2* nt = B.nt + (uint64_t)js * S.nq;
   const uint32_t H0 = warm_hash_word((uint32_t)A.n_fields);
   if (!s_overflow) for (uint32_t i = tid; i < n_nt; i += UNION_THREADS) {
-    const uint32_t q = nt[i];
-    const int32_t e = live[q];
+    const uint2 ent = nt[i];
+    const uint32_t q = ent.x;
     any = true;
-    if (e & LIVE_REDUCED) {
-      CallView v = make_view(A, S, e);
+    if (ent.y & NT_REDUCED) {
+      CallView v = make_view(A, S, (int32_t)((ent.y & ~NT_REDUCED) | (uint32_t)LIVE_REDUCED));
       loc_maxgt = max(loc_maxgt, v.gt_len); loc_maxain = max(loc_maxain, (uint32_t)v.n_alt + 1u); loc_maxploidy = max(loc_maxploidy, v.ploidy);
 #pragma unroll
       for (int f = 0; f < MAX_FIELDS; ++f) if (f < A.n_fields) {
@@ -514,7 +517,7 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__
       insert(star_hash(), q, 1);
       continue;
     }
-    const WarmView v = warm_view(A, (uint32_t)e);
+    const WarmView v = warm_view(A, ent.y);
     loc_maxgt = max(loc_maxgt, v.gt_len); loc_maxain = max(loc_maxain, v.n_alt + 1u); loc_maxploidy = max(loc_maxploidy, v.ploidy);
 #pragma unroll
     for (int f = 0; f < MAX_FIELDS; ++f) if (f < A.n_fields) { const uint32_t n = v.b[4 + f]; if (n) { loc_maxpl[f] = max(loc_maxpl[f], v.ploidy); loc_maxin[f] = max(loc_maxin[f], n); } }
@@ -989,103 +992,116 @@ __global__ void __launch_bounds__(TILE_ROWS, 4) k_remap_tile(const __grid_consta
   }
 }
 
-// One warp per nt-list entry (non-trivial, non-inline or spanning-deletion call) of the launch's sites.
-constexpr int NT_WARPS = 8;
+// k_remap_nt: NT_GL lanes per nt-list entry (non-trivial, non-inline or spanning-deletion call), NT_GROUPS entries of ONE
+// site per block (block -> (site, first entry) comes from a map built by k_nt_blocks), so a warp keeps four independent
+// gather chains in flight: entry -> blob header -> tokens / GT / field words.
+constexpr int NT_THREADS = 256, NT_GL = 8, NT_GROUPS = NT_THREADS / NT_GL;
+__global__ void __launch_bounds__(256) k_nt_blocks(const __grid_constant__ BatchDev B, const uint32_t* __restrict__ site_list, const uint32_t* __restrict__ blk_prefix, uint2* __restrict__ blk_map) {
+  const uint32_t si = blockIdx.x, js = site_list[si], b0 = blk_prefix[si], nb = blk_prefix[si + 1] - b0;
+  for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) blk_map[b0 + b] = make_uint2(js, b * NT_GROUPS);
+}
 template <int NF>
-__global__ void __launch_bounds__(NT_WARPS * 32) k_remap_nt(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
-                                                           const __grid_constant__ RemapOut O, const uint32_t* __restrict__ site_list,
-                                                           const uint32_t* __restrict__ nt_prefix, const uint32_t n_list_sites, const uint32_t jk_n) {
+__global__ void __launch_bounds__(NT_THREADS) k_remap_nt(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
+                                                        const __grid_constant__ RemapOut O, const uint2* __restrict__ blk_map, const uint32_t jk_n) {
   __shared__ uint16_t s_jk[TILE_MAX_G];                      // g -> (k << 8 | j), the same for every site
-  __shared__ unsigned long long s_ah[NT_WARPS][TILE_MAX_A];  // the site's merged-allele hashes
-  __shared__ int s_m2in[NT_WARPS][TILE_MAX_A];
-  __shared__ int16_t s_in2m[NT_WARPS][TILE_MAX_A];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (uint32_t g = threadIdx.x; g < jk_n && g < (uint32_t)TILE_MAX_G; g += NT_WARPS * 32) { uint32_t j, k; tri_unrank(g, j, k); s_jk[g] = (uint16_t)((k << 8) | j); }
-  __syncthreads();
-  const uint32_t wid = blockIdx.x * NT_WARPS + w;
-  if (wid >= nt_prefix[n_list_sites]) return;
-  uint32_t lo = 0, hi = n_list_sites;   // last si with nt_prefix[si] <= wid
-  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (nt_prefix[mid] <= wid) lo = mid; else hi = mid; }
-  const uint32_t js = site_list[lo];
-  const uint32_t q = B.nt_q[(uint64_t)js * S.nq + (wid - nt_prefix[lo])];
-  const uint64_t sq = (uint64_t)js * S.nq + q;
-  const int32_t e = B.live[sq];
+  __shared__ unsigned long long s_ah[TILE_MAX_A];            // the site's merged-allele hashes
+  __shared__ int s_m2in[NT_GROUPS][TILE_MAX_A];
+  __shared__ int8_t s_in2m[NT_GROUPS][TILE_MAX_A];
+  const int tid = threadIdx.x, grp = tid / NT_GL, gl = tid % NT_GL;
+  const uint2 bm = blk_map[blockIdx.x];
+  const uint32_t js = bm.x;
   const SiteRec* __restrict__ site_g = &B.sites[js];
-  const uint32_t A_m = site_g->n_alleles, sflags = site_g->flags, allele_first = site_g->allele_first, mref_len = site_g->ref_len;
+  const uint32_t A_m = site_g->n_alleles, sflags = site_g->flags, allele_first = site_g->allele_first, mref_len = site_g->ref_len, n_nt = site_g->n_nt;
+  const uint32_t ei = bm.y + grp;
+  const bool active = ei < n_nt;
+  uint2 ent = make_uint2(0, 0);
+  if (active) ent = B.nt[(uint64_t)js * S.nq + ei];
   const uint8_t* mref = B.allele_bytes + site_g->ref_off;
   const bool nonref = sflags & 1u, remap = sflags & 2u, g_suppressed = sflags & 4u;
   const int o_f0 = A.has_gt ? 1 : 0;
-  for (uint32_t m = lane; m < A_m; m += 32) { s_ah[w][m] = B.allele_hash[allele_first + m]; s_m2in[w][m] = m == 0 ? 0 : -1; }
+  if ((uint32_t)tid < A_m) s_ah[tid] = B.allele_hash[allele_first + tid];
+  for (uint32_t g = tid; g < jk_n && g < (uint32_t)TILE_MAX_G; g += NT_THREADS) { uint32_t j, k; tri_unrank(g, j, k); s_jk[g] = (uint16_t)((k << 8) | j); }
+  for (uint32_t m = gl; m < A_m; m += NT_GL) s_m2in[grp][m] = m == 0 ? 0 : -1;
 
   // ---- the call
-  const bool reduced = (e & LIVE_REDUCED) != 0;
-  uint32_t n_alt, nr_idx, gt_len, ploidy;
-  const uint32_t* gt; const uint32_t* fin[NF]; uint32_t fn[NF];
+  const uint32_t q = ent.x;
+  const uint64_t sq = (uint64_t)js * S.nq + q;
+  const bool reduced = (ent.y & NT_REDUCED) != 0;
+  uint32_t n_alt = 0, nr_idx = 0, gt_len = 0, ploidy = 0;
+  const uint32_t* gt = nullptr; const uint32_t* fin[NF]; uint32_t fn[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) { fin[f] = nullptr; fn[f] = 0; }
   WarmView wv{};
   const uint32_t H0 = warm_hash_word((uint32_t)A.n_fields);
-  if (reduced) {
-    const uint32_t cell = (uint32_t)(e & (LIVE_REDUCED - 1));
-    const DelRec* dr = find_delrec(S, cell);
-    const CellDesc d = A.desc[cell];
-    n_alt = dr->n_alt; nr_idx = dr->has_nr ? 2u : 0u;
-    gt_len = (d.flags & F_GTVALID) ? d.gt_len : 0u; ploidy = gt_len ? ploidy_of(A.gt_phased, gt_len) : 0u;
-    gt = S.del_words + dr->gt_off;
+  if (active) {
+    if (reduced) {
+      const uint32_t cell = ent.y & ~NT_REDUCED;
+      const DelRec* dr = find_delrec(S, cell);
+      const CellDesc d = A.desc[cell];
+      n_alt = dr->n_alt; nr_idx = dr->has_nr ? 2u : 0u;
+      gt_len = (d.flags & F_GTVALID) ? d.gt_len : 0u; ploidy = gt_len ? ploidy_of(A.gt_phased, gt_len) : 0u;
+      gt = S.del_words + dr->gt_off;
 #pragma unroll
-    for (int f = 0; f < NF; ++f) { const uint32_t n = dr->f_len[f]; fn[f] = n == 0xFFFFFFFFu ? 0u : n; fin[f] = S.del_words + dr->f_off[f]; }
-  } else {
-    wv = warm_view(A, (uint32_t)e);
-    n_alt = wv.n_alt; nr_idx = wv.nr_idx; gt_len = wv.gt_len; ploidy = wv.ploidy;
-    gt = wv.b + H0 + 3u * n_alt;
-    const uint32_t* p = gt + gt_len;
+      for (int f = 0; f < NF; ++f) { const uint32_t n = dr->f_len[f]; fn[f] = n == 0xFFFFFFFFu ? 0u : n; fin[f] = S.del_words + dr->f_off[f]; }
+    } else {
+      wv = warm_view(A, ent.y);
+      n_alt = wv.n_alt; nr_idx = wv.nr_idx; gt_len = wv.gt_len; ploidy = wv.ploidy;
+      gt = wv.b + H0 + 3u * n_alt;
+      const uint32_t* p = gt + gt_len;
 #pragma unroll
-    for (int f = 0; f < NF; ++f) { fn[f] = wv.b[4 + f]; fin[f] = p; p += fn[f]; }
+      for (int f = 0; f < NF; ++f) { fn[f] = wv.b[4 + f]; fin[f] = p; p += fn[f]; }
+    }
   }
   const uint32_t A_in = n_alt + 1u;
-  __syncwarp();
+  __syncthreads();
   // ---- allele LUT (merge_alt_alleles' add_input_merged_idx_pair calls for this call, variant_operations.cc:160-227)
-  if (lane == 0) s_in2m[w][0] = 0;
-  for (uint32_t t = lane; t < n_alt && t + 1u < (uint32_t)TILE_MAX_A; t += 32) {
-    const uint32_t idx = t + 1u;
-    int m = -1;
-    if (remap) {
-      uint64_t h = 0;
-      if (reduced) { if (idx == 1) h = star_hash(); }
-      else h = warm_token_hash(wv, H0, t, mref, mref_len);
-      if (h) for (uint32_t mm = 1; mm < A_m; ++mm) if (s_ah[w][mm] == h) { m = (int)mm; break; }
+  if (active) {
+    if (gl == 0) s_in2m[grp][0] = 0;
+    for (uint32_t t = gl; t < n_alt && t + 1u < (uint32_t)TILE_MAX_A; t += NT_GL) {
+      const uint32_t idx = t + 1u;
+      int m = -1;
+      if (remap) {
+        uint64_t h = 0;
+        if (reduced) { if (idx == 1) h = star_hash(); }
+        else h = warm_token_hash(wv, H0, t, mref, mref_len);
+        if (h) for (uint32_t mm = 1; mm < A_m; ++mm) if (s_ah[mm] == h) { m = (int)mm; break; }
+      }
+      if (nr_idx && idx == nr_idx) m = (int)A_m - 1;
+      s_in2m[grp][idx] = (int8_t)m;
+      if (remap && m >= 0) atomicMax(&s_m2in[grp][m], (int)idx);   // a merged allele named twice by one call: the last one wins
     }
-    if (nr_idx && idx == nr_idx) m = (int)A_m - 1;
-    s_in2m[w][idx] = (int16_t)m;
-    if (remap && m >= 0) atomicMax(&s_m2in[w][m], (int)idx);   // a merged allele named twice by one call: the last one wins
   }
   __syncwarp();
-  if (remap) {
+  if (active && remap) {
     const int in_nr = (nonref && nr_idx) ? (int)nr_idx : -1;   // NON_REF fallback folded in
-    for (uint32_t m = lane; m < A_m; m += 32) if (s_m2in[w][m] < 0) s_m2in[w][m] = in_nr;
-    __syncwarp();
+    for (uint32_t m = gl; m < A_m; m += NT_GL) if (s_m2in[grp][m] < 0) s_m2in[grp][m] = in_nr;
   }
+  __syncwarp();
+  if (!active) return;
+  const int* m2in = s_m2in[grp];
   if (O.lut_first) {
     uint32_t first = 0;
-    if (lane == 0) { first = atomicAdd(&B.cursors[2], A_in); if (first + A_in > O.cap_lut) { atomicOr(&S.err[2], 2u); first = 0xFFFFFFFFu; } O.lut_first[sq] = first; O.lut_len[sq] = (uint16_t)A_in; }
-    first = __shfl_sync(0xffffffffu, first, 0);
-    if (first != 0xFFFFFFFFu) for (uint32_t i = lane; i < A_in; i += 32) O.lut_in2m[first + i] = s_in2m[w][i];
+    if (gl == 0) { first = atomicAdd(&B.cursors[2], A_in); if (first + A_in > O.cap_lut) { atomicOr(&S.err[2], 2u); first = 0xFFFFFFFFu; } O.lut_first[sq] = first; O.lut_len[sq] = (uint16_t)A_in; }
+    first = __shfl_sync(__activemask(), first, 0, NT_GL);
+    if (first != 0xFFFFFFFFu) for (uint32_t i = gl; i < A_in; i += NT_GL) O.lut_in2m[first + i] = (int16_t)s_in2m[grp][i];
   }
   // ---- GT (variant_operations.cc:233-263)
   if (A.has_gt) {
     const FieldOutDev fo = O.f[0];
     const uint32_t gs = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + (uint64_t)q * gs;
     const uint32_t step = A.gt_phased ? 2u : 1u;
-    for (uint32_t i = lane; i < gs; i += 32) {
+    for (uint32_t i = gl; i < gs; i += NT_GL) {
       uint32_t val = BCF_INT_VEND;
       if (i < gt_len) {
         const uint32_t g = gt[i]; val = g;
         if (remap && (i % step) == 0 && !(g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING)) {
-          const int m = g < A_in ? (int)s_in2m[w][g] : -1;
+          const int m = g < A_in ? (int)s_in2m[grp][g] : -1;
           val = m < 0 ? (nonref ? A_m - 1u : 0xFFFFFFFFu) : (uint32_t)m;
         }
       }
       dst[i] = val;
     }
-    if (lane == 0) fo.len[sq] = (uint16_t)gt_len;
+    if (gl == 0) fo.len[sq] = (uint16_t)gt_len;
   }
   // ---- allele-dependent fields (variant_field_handler.cc:41-191)
 #pragma unroll
@@ -1097,24 +1113,28 @@ __global__ void __launch_bounds__(NT_WARPS * 32) k_remap_nt(const __grid_constan
     uint32_t n_out = 0;
     if (n && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, ploidy) : n;
     const uint32_t stride = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + (uint64_t)q * stride;
-    if (lane == 0) fo.len[sq] = (uint16_t)n_out;
-    for (uint32_t g = lane; g < stride; g += 32) {
-      uint32_t val = pad;
-      if (g < n_out) {
-        if (!remap) val = in[g];
-        else if (kind == KIND_G && ploidy == 2) {
-          const uint32_t jk = s_jk[g];
-          const int ij = s_m2in[w][jk & 0xFF], ik = s_m2in[w][jk >> 8];
-          if (ij < 0 || ik < 0) val = miss;
-          else { const uint32_t ig = (uint32_t)alleles2gt(ij, ik); val = ig < n ? in[ig] : miss; }
-        } else if (kind == KIND_G && ploidy == 0) val = in[0];
-        else {
-          const int ij = s_m2in[w][kind == KIND_A ? g + 1u : g];
-          const int ix = kind == KIND_A ? ij - 1 : ij;
-          val = (ij < 0 || ix < 0 || (uint32_t)ix >= n) ? miss : in[ix];
-        }
+    if (gl == 0) fo.len[sq] = (uint16_t)n_out;
+    const int mode = !remap ? 0 : ((kind == KIND_G && ploidy == 2) ? 1 : ((kind == KIND_G && ploidy == 0) ? 2 : (kind == KIND_A ? 3 : 4)));
+    auto word = [&](uint32_t g) -> uint32_t {
+      if (g >= n_out) return pad;
+      if (mode == 0) return in[g];
+      if (mode == 1) {
+        const uint32_t jk = s_jk[g];
+        const int ij = m2in[jk & 0xFF], ik = m2in[jk >> 8];
+        if (ij < 0 || ik < 0) return miss;
+        const uint32_t ig = (uint32_t)alleles2gt(ij, ik);
+        return ig < n ? in[ig] : miss;
       }
-      dst[g] = val;
+      if (mode == 2) return in[0];
+      const int ij = m2in[mode == 3 ? g + 1u : g];
+      const int ix = mode == 3 ? ij - 1 : ij;
+      return (ij < 0 || ix < 0 || (uint32_t)ix >= n) ? miss : in[ix];
+    };
+    if (remap && (stride & 3u) == 0) {   // 16-byte aligned vector: one quad per lane
+      uint4* dst4 = reinterpret_cast<uint4*>(dst);
+      for (uint32_t qd = gl; qd < (stride >> 2); qd += NT_GL) dst4[qd] = make_uint4(word(4 * qd), word(4 * qd + 1), word(4 * qd + 2), word(4 * qd + 3));
+    } else {
+      for (uint32_t g = gl; g < stride; g += NT_GL) dst[g] = word(g);
     }
   }
 }
