@@ -260,6 +260,7 @@ def main():
     sscan_ms, _ = ctx.kernel_stats("k_site_scan")
     tile_ms, _ = ctx.kernel_stats("k_remap_tile")
     nt_ms, _ = ctx.kernel_stats("k_remap_nt")
+    all_ms, _ = ctx.kernel_stats("k_")
     ctx.set_profiling(False)
     sites_per_step = sites // args.steps
     total_sites = sum_over_ranks(float(sites))
@@ -279,7 +280,8 @@ def main():
                     peak_source=peak_src, algorithmic_bytes_per_step=dict(b_in=b_in_step, b_out=b_out_step),
                     launches=int(remap_n), avg_launch_ms=remap_ms / max(1, remap_n),
                     kernel_ms_per_step=dict(k_remap=remap_ms / args.steps, k_remap_tile=tile_ms / args.steps, k_remap_nt=nt_ms / args.steps,
-                                            k_site_scan=sscan_ms / args.steps, k_union=union_ms / args.steps, k_live_walk=walk_ms / args.steps),
+                                            k_site_scan=sscan_ms / args.steps, k_union=union_ms / args.steps, k_live_walk=walk_ms / args.steps,
+                                            all_kernels=all_ms / args.steps),
                     step_gbs=((b_in_step + b_out_step) * args.steps / 1e9) / (ms * 1e-3))
 
     # ---------------- end to end through the C ABI with host buffers

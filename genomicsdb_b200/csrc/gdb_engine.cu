@@ -560,7 +560,7 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
     B.n_sites = keep;
     // split the batch: the tile kernels take every ordinary site, the generic kernel the pathological ones
     std::vector<uint32_t> fast, slow, nt_prefix;
-    TileShape shape{4};
+    uint32_t jk_n = 4;
     for (uint32_t i = 0; i < keep; ++i) {
       const SiteRec& r = bb.h_sites[i];
       bool ok = a->fields.size() >= 1 && a->fields.size() <= (size_t)TILE_MAX_FIELDS && r.n_alleles <= (uint32_t)TILE_MAX_A && r.max_ain <= (uint32_t)TILE_MAX_A &&
@@ -568,7 +568,7 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
       if (ok) {
         nt_prefix.push_back(fast.empty() ? 0u : nt_prefix.back() + (bb.h_sites[fast.back()].n_nt + NT_GROUPS - 1) / NT_GROUPS);
         fast.push_back(i);
-        shape.g = std::max(shape.g, r.n_alleles * (r.n_alleles + 1u) / 2u);
+        jk_n = std::max(jk_n, r.n_alleles * (r.n_alleles + 1u) / 2u);
       } else slow.push_back(i);
     }
     if (!fast.empty()) {
@@ -577,13 +577,11 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
       CK(cudaMemcpyAsync(bb.fast_sites.p, fast.data(), fast.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaMemcpyAsync(bb.nt_prefix.p, nt_prefix.data(), nt_prefix.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
       const int nf = (int)a->fields.size();
-      size_t smem = tile_smem_bytes(shape, nf);
       uint32_t tiles = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
       unsigned grid = (unsigned)(fast.size() * tiles);
       auto launch_tile = [&](auto kern) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         ProfScope ps__(ctx, "k_remap_tile");
-        kern<<<grid, TILE_ROWS, smem, ctx->stream>>>(a->dev, S, B, O, bb.fast_sites.p, shape);
+        kern<<<grid, TILE_ROWS, 0, ctx->stream>>>(a->dev, S, B, O, bb.fast_sites.p, tiles);
       };
       switch (nf) {
         case 1: launch_tile(k_remap_tile<1>); break;
@@ -598,7 +596,7 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
         LAUNCH(ctx, k_nt_blocks, (unsigned)fast.size(), 256, B, bb.fast_sites.p, bb.nt_prefix.p, bb.blk_map.p);
         auto launch_nt = [&](auto kern) {
           ProfScope ps__(ctx, "k_remap_nt");
-          kern<<<n_blk, NT_THREADS, 0, ctx->stream>>>(a->dev, S, B, O, bb.blk_map.p, shape.g);
+          kern<<<n_blk, NT_THREADS, 0, ctx->stream>>>(a->dev, S, B, O, bb.blk_map.p, jk_n);
         };
         switch (nf) {
           case 1: launch_nt(k_remap_nt<1>); break;

@@ -790,22 +790,12 @@ __global__ void __launch_bounds__(REMAP_THREADS) k_remap_generic(ArrayDev A, Sca
 namespace gdb {
 
 constexpr int TILE_ROWS = 256;
-constexpr int TILE_MAX_A = 64;
+constexpr int TILE_MAX_A = 44;            // merged alleles (incl. REF) of a tile-path site: G(44) = 990 genotypes <= 256 quads
 constexpr int TILE_MAX_GT = 8;
 constexpr int TILE_MAX_FIELDS = 4;
 constexpr int TILE_MAX_G = TILE_MAX_A * (TILE_MAX_A + 1) / 2;
 constexpr uint32_t INFO_FAST = 1u;
 
-struct TileShape { uint32_t g; };   // per launch: max #elements of a field vector over the launch's sites
-
-__host__ __device__ inline uint32_t tile_cls_bytes(TileShape t) { return ((t.g + 3) / 4 + 15) / 16 * 16; }   // class table of one field
-__host__ __device__ inline size_t tile_smem_bytes(TileShape t, int n_fields) {
-  size_t b = (size_t)n_fields * tile_cls_bytes(t);         // class tables
-  b += (size_t)TILE_ROWS * n_fields * 16;                  // per (sample, field): v0, v1, v2, pad
-  b += (size_t)TILE_ROWS * n_fields * 4;                   // per (sample, field): info word
-  return (b + 15) / 16 * 16;
-}
-__device__ inline uint32_t sel5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t i) { return i == 0 ? a : (i == 1 ? b : (i == 2 ? c : (i == 3 ? d : e))); }
 // g = k(k+1)/2 + j, j <= k
 __device__ inline void tri_unrank(uint32_t g, uint32_t& j, uint32_t& k) {
   k = (uint32_t)((sqrtf(8.0f * (float)g + 1.0f) - 1.0f) * 0.5f);
@@ -819,20 +809,30 @@ __device__ inline uint32_t trivial_class(int kind, uint32_t ploidy, uint32_t g) 
   if (kind == KIND_G && ploidy == 2) { uint32_t j, k; tri_unrank(g, j, k); return k == 0 ? 0 : (j == 0 ? 1 : 2); }
   return g == 0 ? 0 : 1;   // R fields, haploid G fields; ploidy 0 G fields have one element
 }
+// num_elements for ploidy <= 2 (the only ploidies a tile-path site holds)
+__device__ inline uint32_t num_elements_le2(int kind, uint32_t n_alt, uint32_t ploidy) {
+  if (kind == KIND_A) return n_alt;
+  if (kind == KIND_R || ploidy == 1) return n_alt + 1u;
+  return ploidy == 2 ? ((n_alt + 1u) * (n_alt + 2u)) >> 1 : 1u;
+}
 
 template <int NF>
-__global__ void __launch_bounds__(TILE_ROWS, 4) k_remap_tile(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
-                                                            const __grid_constant__ RemapOut O, const uint32_t* __restrict__ site_list, const TileShape TS) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const uint32_t tiles_per_site = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
-  const uint32_t js = site_list[blockIdx.x / tiles_per_site], tile = blockIdx.x % tiles_per_site;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t q = (uint64_t)tile * TILE_ROWS + tid;
-  const uint64_t sq = (uint64_t)js * S.nq + q;
+__global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
+                                                            const __grid_constant__ RemapOut O, const uint32_t* __restrict__ site_list, const uint32_t tiles_per_site) {
+  __shared__ __align__(16) uint4 s_tri[TILE_ROWS * NF];     // per (sample, field): v0, v1, v2, pad
+  __shared__ uint32_t s_info[TILE_ROWS * NF];               // per (sample, field): INFO_FAST or 0
+  __shared__ uint32_t s_hw[HOT_WORDS * TILE_ROWS];          // the samples' hot words, word i of thread t at [i * TILE_ROWS + t]:
+                                                            // an indexable register file (each thread reads only its own column)
+  const uint32_t si = blockIdx.x / tiles_per_site, tile = blockIdx.x - si * tiles_per_site;
+  const uint32_t js = site_list[si];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nq = (uint32_t)S.nq;
+  const uint32_t q = tile * TILE_ROWS + tid;
+  const uint64_t sq = (uint64_t)js * nq + q;
   // issue the two dependent gathers of this thread's sample first; everything below overlaps their latency
   int32_t e = -1;
   uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
-  if (q < S.nq) {
+  if (q < nq) {
     e = B.live[sq];
     if (e >= 0 && !(e & LIVE_REDUCED)) { const uint4* hp = reinterpret_cast<const uint4*>(&A.hot[e]); h0 = hp[0]; h1 = hp[1]; }
   }
@@ -840,34 +840,15 @@ __global__ void __launch_bounds__(TILE_ROWS, 4) k_remap_tile(const __grid_consta
   const uint32_t A_m = site_g->n_alleles, sflags = site_g->flags;
   const bool nonref = sflags & 1u, remap = sflags & 2u, g_suppressed = sflags & 4u;
   const int o_f0 = A.has_gt ? 1 : 0;
-
-  const uint32_t cls_bytes = tile_cls_bytes(TS);
-  uint8_t* s_cls = smem;
-  uint4* s_tri = reinterpret_cast<uint4*>(s_cls + (size_t)NF * cls_bytes);
-  uint32_t* s_info = reinterpret_cast<uint32_t*>(s_tri + (size_t)TILE_ROWS * NF);
-
-  uint32_t fstride[NF], fploidy[NF], nfull[NF];
+  uint32_t fstride[NF];
+  uint32_t* fdst[NF];   // this site's block of field f
 #pragma unroll
-  for (int f = 0; f < NF; ++f) {
-    fstride[f] = O.f[o_f0 + f].stride[js];
-    fploidy[f] = site_g->max_ploidy[f];
-    nfull[f] = num_elements(A.fm[f].kind, A_m - 1u, fploidy[f]);   // length of a full vector of this field at this site
-  }
-  if (remap) {
-    // class tables: for each quad of a full-length vector, which of (v0, v1, v2, pad) each of its 4 words takes
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const int kind = A.fm[f].kind;
-      for (uint32_t qd = tid; qd < fstride[f] / 4; qd += TILE_ROWS) {
-        uint32_t c = 0;
-        for (uint32_t x = 0; x < 4; ++x) { const uint32_t g = 4 * qd + x; c |= (g < nfull[f] ? trivial_class(kind, fploidy[f], g) : 3u) << (2 * x); }
-        s_cls[f * cls_bytes + qd] = (uint8_t)c;
-      }
-    }
-  }
+  for (int f = 0; f < NF; ++f) { fstride[f] = O.f[o_f0 + f].stride[js]; fdst[f] = O.f[o_f0 + f].data + O.f[o_f0 + f].base[js]; }
+  uint32_t* const hw = s_hw + tid;
+  hw[0] = h0.w; hw[TILE_ROWS] = h1.x; hw[2 * TILE_ROWS] = h1.y; hw[3 * TILE_ROWS] = h1.z; hw[4 * TILE_ROWS] = h1.w;
 
   // ---------------------------------------------------------------- phase A: one thread per sample
-  if (q < S.nq) {
+  if (q < nq) {
     if (e < 0) {
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
@@ -875,9 +856,9 @@ __global__ void __launch_bounds__(TILE_ROWS, 4) k_remap_tile(const __grid_consta
         s_tri[tid * NF + f] = make_uint4(padw, padw, padw, padw);
         s_info[tid * NF + f] = INFO_FAST;
         O.f[o_f0 + f].len[sq] = 0;
-        if (!remap) { const FieldOutDev fo = O.f[o_f0 + f]; uint32_t* d = fo.data + fo.base[js] + q * fstride[f]; for (uint32_t x = 0; x < fstride[f]; ++x) d[x] = padw; }
+        if (!remap) { uint32_t* d = fdst[f] + (uint64_t)q * fstride[f]; for (uint32_t x = 0; x < fstride[f]; ++x) d[x] = padw; }
       }
-      if (A.has_gt) { const uint32_t gs = O.f[0].stride[js]; uint32_t* d = O.f[0].data + O.f[0].base[js] + q * gs; for (uint32_t i = 0; i < gs; ++i) d[i] = BCF_INT_VEND; O.f[0].len[sq] = 0; }
+      if (A.has_gt) { const uint32_t gs = O.f[0].stride[js]; uint32_t* d = O.f[0].data + O.f[0].base[js] + (uint64_t)q * gs; for (uint32_t i = 0; i < gs; ++i) d[i] = BCF_INT_VEND; O.f[0].len[sq] = 0; }
       if (O.lut_first) { O.lut_first[sq] = 0xFFFFFFFFu; O.lut_len[sq] = 0; }
     } else {
       const uint32_t hflags = h0.x & 0xFF, ploidy = (h0.x >> 8) & 0xFF, n_alt = (h0.x >> 16) & 0xFF, nr = h0.x >> 24, gt_len = h0.y & 0xFF;
@@ -891,17 +872,17 @@ __global__ void __launch_bounds__(TILE_ROWS, 4) k_remap_tile(const __grid_consta
         const uint32_t fl4 = (h0.y >> 16) | (h0.z << 16);
         const int in_nr = (nonref && nr) ? (int)nr : -1;
         if (A.has_gt) {
-          const uint32_t gs = O.f[0].stride[js]; uint32_t* d = O.f[0].data + O.f[0].base[js] + q * gs;
-          const int step = A.gt_phased ? 2 : 1;
-          for (uint32_t i = 0; i < gs; ++i) {
-            uint32_t g = BCF_INT_VEND;
-            if (i < gt_len) {
-              g = sel5(h0.w, h1.x, h1.y, h1.z, h1.w, i);
-              if (remap && (i % step) == 0 && !(g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING))
-                g = (g == 0) ? 0u : ((nr && g == nr) ? A_m - 1u : (nonref ? A_m - 1u : 0xFFFFFFFFu));
-            }
-            d[i] = g;
-          }
+          const uint32_t gs = O.f[0].stride[js]; uint32_t* d = O.f[0].data + O.f[0].base[js] + (uint64_t)q * gs;
+          const uint32_t step = A.gt_phased ? 2u : 1u;
+          auto gt_word = [&](uint32_t i) -> uint32_t {
+            if (i >= gt_len) return BCF_INT_VEND;
+            uint32_t g = hw[i * TILE_ROWS];
+            if (remap && (i % step) == 0 && !(g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING))
+              g = (g == 0) ? 0u : ((nr && g == nr) ? A_m - 1u : (nonref ? A_m - 1u : 0xFFFFFFFFu));
+            return g;
+          };
+          if (gs == 2) *reinterpret_cast<uint2*>(d) = make_uint2(gt_word(0), gt_word(1));   // site blocks are 16-byte aligned
+          else for (uint32_t i = 0; i < gs; ++i) d[i] = gt_word(i);
           O.f[0].len[sq] = (uint16_t)gt_len;
         }
         if (O.lut_first) {
@@ -918,33 +899,35 @@ __global__ void __launch_bounds__(TILE_ROWS, 4) k_remap_tile(const __grid_consta
           const int kind = A.fm[f].kind;
           const uint32_t miss = missing_word(A.fm[f].elem), padw = vend_word(A.fm[f].elem);
           uint32_t n_out = 0;
-          if (n && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, ploidy) : n;
+          if (n && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements_le2(kind, A_m - 1u, ploidy) : n;
           O.f[o_f0 + f].len[sq] = (uint16_t)n_out;
+          const uint32_t* fw = hw + k * TILE_ROWS;   // this field's inline words
           if (!remap) {
             // no remapping at this site: the (inline, <= 5 words) input goes straight through, from this thread
-            uint32_t* d = O.f[o_f0 + f].data + O.f[o_f0 + f].base[js] + q * fstride[f];
-            for (uint32_t x = 0; x < fstride[f]; ++x) d[x] = x < n_out ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + x) : padw;
+            uint32_t* d = fdst[f] + (uint64_t)q * fstride[f];
+            for (uint32_t x = 0; x < fstride[f]; ++x) d[x] = x < n_out ? fw[x * TILE_ROWS] : padw;
           } else if (!n_out) {
             s_tri[tid * NF + f] = make_uint4(padw, padw, padw, padw);
             s_info[tid * NF + f] = INFO_FAST;
           } else {
-            uint32_t v0 = sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k), v1 = miss, v2 = miss;
+            uint32_t v0 = fw[0], v1 = miss, v2 = miss;
             if (in_nr >= 0) {
-              if (kind == KIND_A) { const uint32_t i1 = (uint32_t)in_nr - 1u; v1 = i1 < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + i1) : miss; }
-              else if (kind == KIND_R || ploidy != 2) { v1 = (uint32_t)in_nr < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + in_nr) : miss; }
+              if (kind == KIND_A) { const uint32_t i1 = (uint32_t)in_nr - 1u; if (i1 < n) v1 = fw[i1 * TILE_ROWS]; }
+              else if (kind == KIND_R || ploidy != 2) { if ((uint32_t)in_nr < n) v1 = fw[in_nr * TILE_ROWS]; }
               else {
                 const uint32_t g1 = (uint32_t)in_nr * ((uint32_t)in_nr + 1u) / 2u, g2 = g1 + (uint32_t)in_nr;
-                v1 = g1 < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + g1) : miss;
-                v2 = g2 < n ? sel5(h0.w, h1.x, h1.y, h1.z, h1.w, k + g2) : miss;
+                if (g1 < n) v1 = fw[g1 * TILE_ROWS];
+                if (g2 < n) v2 = fw[g2 * TILE_ROWS];
               }
             }
-            // the class table is the one of the site's ploidy for this field; a sample of another ploidy (a haploid
-            // call among diploid ones ...) writes its own, shorter vector from this thread
-            const bool fast = (kind != KIND_G) || (ploidy == fploidy[f]);
+            // the class pattern of phase B is the one of the site's ploidy for this field; a sample of another ploidy
+            // (a haploid call among diploid ones ...) writes its own, shorter vector from this thread
+            const uint32_t fploidy = site_g->max_ploidy[f];
+            const bool fast = (kind != KIND_G) || (ploidy == fploidy);
             s_tri[tid * NF + f] = make_uint4(v0, v1, v2, padw);
             s_info[tid * NF + f] = fast ? INFO_FAST : 0u;
             if (!fast) {
-              uint32_t* d = O.f[o_f0 + f].data + O.f[o_f0 + f].base[js] + q * fstride[f];
+              uint32_t* d = fdst[f] + (uint64_t)q * fstride[f];
               for (uint32_t x = 0; x < fstride[f]; ++x) {
                 uint32_t w = padw;
                 if (x < n_out) { const uint32_t c = trivial_class(kind, ploidy, x); w = c == 0 ? v0 : (c == 1 ? v1 : v2); }
@@ -960,34 +943,33 @@ __global__ void __launch_bounds__(TILE_ROWS, 4) k_remap_tile(const __grid_consta
   if (!remap) return;   // copy-through sites are complete (uniform per block)
   __syncthreads();
 
-  // ---------------------------------------------------------------- phase B
-  const uint32_t rows = (uint32_t)min((uint64_t)TILE_ROWS, S.nq - (uint64_t)tile * TILE_ROWS);
-  const uint32_t r0 = warp * 32;
-  if (r0 >= rows) return;
+  // ---------------------------------------------------------------- phase B: the block streams the tile out
+  // Field f of the tile is rows x lpr quads, contiguous.  Thread t keeps ONE quad column (t % lpr) and walks the rows
+  // (t / lpr, + 256 / lpr per step), so which of (v0, v1, v2, pad) each of its four words takes is loop-invariant, and
+  // a warp's stores cover 512 contiguous bytes.
+  const uint32_t rows = min((uint32_t)TILE_ROWS, nq - tile * TILE_ROWS);
 #pragma unroll
   for (int f = 0; f < NF; ++f) {
     const uint32_t stride = fstride[f];
     if (stride == 0) continue;
-    const FieldOutDev fo = O.f[o_f0 + f];
-    const uint32_t lpr = stride >> 2;   // quads per sample (stride is a multiple of 4 at remapped sites)
-    uint32_t* tile_dst = fo.data + fo.base[js] + (uint64_t)tile * TILE_ROWS * stride;
-    // this warp's 32 samples: flat quad index i <-> (sample, quad)
-    const uint32_t nr = min(32u, rows - r0), total = nr * lpr;
-    uint4* out4 = reinterpret_cast<uint4*>(tile_dst + (uint64_t)r0 * stride);
-    const uint8_t* cls = s_cls + f * cls_bytes;
-    uint32_t row_l = (uint32_t)lane / lpr, qd = (uint32_t)lane % lpr;
-    const uint32_t dr = 32u / lpr, dq = 32u % lpr;
-    for (uint32_t i = lane; i < total; i += 32) {
-      const uint32_t slot = (r0 + row_l) * NF + f;
+    const uint32_t lpr = stride >> 2;   // quads per sample (stride is a multiple of 4 at remapped sites), <= 256
+    const uint32_t rpi = (uint32_t)TILE_ROWS / lpr;   // rows per step
+    const uint32_t r_off = tid / lpr, col = tid - r_off * lpr;
+    if (r_off >= rpi) continue;
+    const int kind = A.fm[f].kind;
+    const uint32_t fploidy = site_g->max_ploidy[f];
+    const uint32_t nfull = num_elements_le2(kind, A_m - 1u, fploidy);   // length of a full vector of this field at this site
+    uint32_t c[4];
+#pragma unroll
+    for (uint32_t x = 0; x < 4; ++x) { const uint32_t g = 4 * col + x; c[x] = g < nfull ? trivial_class(kind, fploidy, g) : 3u; }
+    uint4* out4 = reinterpret_cast<uint4*>(fdst[f] + (uint64_t)tile * TILE_ROWS * stride) + col;
+    const uint32_t* tri = reinterpret_cast<const uint32_t*>(s_tri);
+    for (uint32_t r = r_off; r < rows; r += rpi) {
+      const uint32_t slot = r * NF + f;
       if (s_info[slot] & INFO_FAST) {
-        const uint32_t* tw = reinterpret_cast<const uint32_t*>(&s_tri[slot]);
-        const uint32_t c = cls[qd];
-        uint4 v;
-        v.x = tw[c & 3]; v.y = tw[(c >> 2) & 3]; v.z = tw[(c >> 4) & 3]; v.w = tw[(c >> 6) & 3];
-        out4[i] = v;
+        const uint32_t* tw = tri + 4 * slot;
+        out4[(uint64_t)r * lpr] = make_uint4(tw[c[0]], tw[c[1]], tw[c[2]], tw[c[3]]);
       }
-      row_l += dr; qd += dq;
-      if (qd >= lpr) { qd -= lpr; ++row_l; }
     }
   }
 }
