@@ -255,11 +255,14 @@ def main():
     sampler.stop_flag = True
     launches = ctx.launches - launches0
     remap_ms, remap_n = ctx.kernel_stats("k_remap")
+    copy0_ms, _ = ctx.kernel_stats("k_copy_tile")
+    remap_ms += copy0_ms   # K5 = k_remap_tile + k_copy_tile + k_remap_nt; remap_n stays the number of tile+nt launches
     union_ms, _ = ctx.kernel_stats("k_union")
     walk_ms, _ = ctx.kernel_stats("k_live_walk")
     sscan_ms, _ = ctx.kernel_stats("k_site_scan")
     tile_ms, _ = ctx.kernel_stats("k_remap_tile")
     nt_ms, _ = ctx.kernel_stats("k_remap_nt")
+    copy_ms, _ = ctx.kernel_stats("k_copy_tile")
     all_ms, _ = ctx.kernel_stats("k_")
     ctx.set_profiling(False)
     sites_per_step = sites // args.steps
@@ -276,10 +279,10 @@ def main():
     b_in_step = manifest["b_in"]
     b_out_step = out_bytes / args.steps
     achieved = ((b_in_step + b_out_step) * args.steps / 1e9) / (remap_ms * 1e-3) if remap_ms > 0 else 0.0
-    roofline = dict(bound="hbm", kernel="gdb::k_remap_tile + gdb::k_remap_nt (K5 remap)", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+    roofline = dict(bound="hbm", kernel="gdb::k_remap_tile + gdb::k_copy_tile + gdb::k_remap_nt (K5 remap)", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
                     peak_source=peak_src, algorithmic_bytes_per_step=dict(b_in=b_in_step, b_out=b_out_step),
                     launches=int(remap_n), avg_launch_ms=remap_ms / max(1, remap_n),
-                    kernel_ms_per_step=dict(k_remap=remap_ms / args.steps, k_remap_tile=tile_ms / args.steps, k_remap_nt=nt_ms / args.steps,
+                    kernel_ms_per_step=dict(k_remap=remap_ms / args.steps, k_remap_tile=tile_ms / args.steps, k_remap_nt=nt_ms / args.steps, k_copy_tile=copy_ms / args.steps,
                                             k_site_scan=sscan_ms / args.steps, k_union=union_ms / args.steps, k_live_walk=walk_ms / args.steps,
                                             all_kernels=all_ms / args.steps),
                     step_gbs=((b_in_step + b_out_step) * args.steps / 1e9) / (ms * 1e-3))

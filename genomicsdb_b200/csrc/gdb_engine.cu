@@ -33,6 +33,7 @@ struct gdbgpu_ctx {
   std::vector<cudaEvent_t> pool;
   std::map<std::string, std::pair<double, uint64_t>> stats;
   std::vector<BatchBuffers*> bb_pool;
+  uint32_t* d_cls_tab = nullptr; uint16_t* d_jk_tab = nullptr; int n_sms = 148;   // universal genotype tables (gdb_kernels2.cuh: TileTabs)
   cudaEvent_t get_event() { if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
   void resolve() {
     if (recs.empty()) return;
@@ -327,7 +328,7 @@ struct BatchBuffers {
   std::vector<uint64_t> h_base[MAX_FIELDS + 1]; std::vector<uint32_t> h_stride[MAX_FIELDS + 1];
   PinBuf<int64_t> p_site_begin, p_site_end; PinBuf<int32_t> p_live; PinBuf<uint32_t> p_allele_pos, p_lut_first, p_out_data[MAX_FIELDS + 1]; PinBuf<uint8_t> p_allele_bytes;
   PinBuf<uint16_t> p_out_len[MAX_FIELDS + 1], p_lut_len; PinBuf<int16_t> p_lut_in2m;
-  DevBuf<uint32_t> fast_sites, slow_sites;
+  DevBuf<uint32_t> fast_sites, slow_sites, tile_sites;
 };
 
 // ------------------------------------------------------------------------------------------------ scan
@@ -577,32 +578,70 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
       CK(cudaMemcpyAsync(bb.fast_sites.p, fast.data(), fast.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaMemcpyAsync(bb.nt_prefix.p, nt_prefix.data(), nt_prefix.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
       const int nf = (int)a->fields.size();
-      uint32_t tiles = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
-      unsigned grid = (unsigned)(fast.size() * tiles);
-      auto launch_tile = [&](auto kern) {
-        ProfScope ps__(ctx, "k_remap_tile");
-        kern<<<grid, TILE_ROWS, 0, ctx->stream>>>(a->dev, S, B, O, bb.fast_sites.p, tiles);
-      };
-      switch (nf) {
-        case 1: launch_tile(k_remap_tile<1>); break;
-        case 2: launch_tile(k_remap_tile<2>); break;
-        case 3: launch_tile(k_remap_tile<3>); break;
-        default: launch_tile(k_remap_tile<4>); break;
+      const TileTabs tabs{ctx->d_cls_tab, ctx->d_jk_tab};
+      const uint32_t tiles = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
+      if (tiles > 65535u) throw LimitError("more than 16.7 M query rows");
+      // remapped sites -> k_remap_tile, copy-through sites -> k_copy_tile; both lists live in fast_sites (remapped ones first)
+      std::vector<uint32_t> order; order.reserve(fast.size());
+      for (uint32_t i : fast) if (bb.h_sites[i].flags & 2u) order.push_back(i);
+      const size_t n_remap = order.size();
+      for (uint32_t i : fast) if (!(bb.h_sites[i].flags & 2u)) order.push_back(i);
+      bb.tile_sites.ensure(order.size());
+      CK(cudaMemcpyAsync(bb.tile_sites.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      const int key = nf * 2 + (a->has_gt ? 1 : 0);
+      for (size_t first = 0; first < n_remap; first += 65535) {
+        const unsigned ny = (unsigned)std::min<size_t>(65535, n_remap - first);
+        auto launch_tile = [&](auto kern) {
+          ProfScope ps__(ctx, "k_remap_tile");
+          kern<<<dim3(tiles, ny), TILE_ROWS, 0, ctx->stream>>>(a->dev, S, B, O, bb.tile_sites.p + first, tabs);
+        };
+        switch (key) {
+          case 2: launch_tile(k_remap_tile<1, false>); break;
+          case 3: launch_tile(k_remap_tile<1, true>); break;
+          case 4: launch_tile(k_remap_tile<2, false>); break;
+          case 5: launch_tile(k_remap_tile<2, true>); break;
+          case 6: launch_tile(k_remap_tile<3, false>); break;
+          case 7: launch_tile(k_remap_tile<3, true>); break;
+          case 8: launch_tile(k_remap_tile<4, false>); break;
+          default: launch_tile(k_remap_tile<4, true>); break;
+        }
+        ++ctx->launches; CK(cudaGetLastError());
       }
-      ++ctx->launches; CK(cudaGetLastError());
+      for (size_t first = n_remap; first < order.size(); first += 65535) {
+        const unsigned ny = (unsigned)std::min<size_t>(65535, order.size() - first);
+        auto launch_copy = [&](auto kern) {
+          ProfScope ps__(ctx, "k_copy_tile");
+          kern<<<dim3(tiles, ny), TILE_ROWS, 0, ctx->stream>>>(a->dev, S, B, O, bb.tile_sites.p + first);
+        };
+        switch (key) {
+          case 2: launch_copy(k_copy_tile<1, false>); break;
+          case 3: launch_copy(k_copy_tile<1, true>); break;
+          case 4: launch_copy(k_copy_tile<2, false>); break;
+          case 5: launch_copy(k_copy_tile<2, true>); break;
+          case 6: launch_copy(k_copy_tile<3, false>); break;
+          case 7: launch_copy(k_copy_tile<3, true>); break;
+          case 8: launch_copy(k_copy_tile<4, false>); break;
+          default: launch_copy(k_copy_tile<4, true>); break;
+        }
+        ++ctx->launches; CK(cudaGetLastError());
+      }
       const uint32_t n_blk = nt_prefix.back();
       if (n_blk) {
         bb.blk_map.ensure(n_blk);
         LAUNCH(ctx, k_nt_blocks, (unsigned)fast.size(), 256, B, bb.fast_sites.p, bb.nt_prefix.p, bb.blk_map.p);
         auto launch_nt = [&](auto kern) {
           ProfScope ps__(ctx, "k_remap_nt");
-          kern<<<n_blk, NT_THREADS, 0, ctx->stream>>>(a->dev, S, B, O, bb.blk_map.p, jk_n);
+          kern<<<n_blk, NT_THREADS, 0, ctx->stream>>>(a->dev, S, B, O, bb.blk_map.p, jk_n, tabs);
         };
-        switch (nf) {
-          case 1: launch_nt(k_remap_nt<1>); break;
-          case 2: launch_nt(k_remap_nt<2>); break;
-          case 3: launch_nt(k_remap_nt<3>); break;
-          default: launch_nt(k_remap_nt<4>); break;
+        switch (key) {
+          case 2: launch_nt(k_remap_nt<1, false>); break;
+          case 3: launch_nt(k_remap_nt<1, true>); break;
+          case 4: launch_nt(k_remap_nt<2, false>); break;
+          case 5: launch_nt(k_remap_nt<2, true>); break;
+          case 6: launch_nt(k_remap_nt<3, false>); break;
+          case 7: launch_nt(k_remap_nt<3, true>); break;
+          case 8: launch_nt(k_remap_nt<4, false>); break;
+          default: launch_nt(k_remap_nt<4, true>); break;
         }
         ++ctx->launches; CK(cudaGetLastError());
       }
@@ -691,6 +730,19 @@ int gdbgpu_ctx_create(int device, gdbgpu_ctx** out) {
   gdbgpu_ctx* c = new gdbgpu_ctx();
   c->device = device;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GDBGPU_ERR_CUDA; }
+  {   // diploid genotype tables: g -> class of a trivial call's word, g -> (j, k)
+    std::vector<uint32_t> cls(256, 0); std::vector<uint16_t> jk(1024, 0);
+    uint32_t g = 0;
+    for (uint32_t k = 0; g < 1024; ++k) for (uint32_t j = 0; j <= k && g < 1024; ++j, ++g) {
+      jk[g] = (uint16_t)((k << 8) | j);
+      cls[g >> 2] |= (k == 0 ? 0u : (j == 0 ? 1u : 2u)) << (8 * (g & 3));
+    }
+    cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaMalloc((void**)&c->d_cls_tab, 1024) != cudaSuccess || cudaMalloc((void**)&c->d_jk_tab, 2048) != cudaSuccess ||
+        cudaMemcpy(c->d_cls_tab, cls.data(), 1024, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(c->d_jk_tab, jk.data(), 2048, cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaStreamDestroy(c->stream); delete c; return GDBGPU_ERR_CUDA;
+    }
+  }
   *out = c;
   return GDBGPU_OK;
 }
@@ -699,6 +751,8 @@ void gdbgpu_ctx_destroy(gdbgpu_ctx* ctx) {
   ctx->resolve();
   for (auto e : ctx->pool) cudaEventDestroy(e);
   for (auto* b : ctx->bb_pool) delete b;
+  if (ctx->d_cls_tab) cudaFree(ctx->d_cls_tab);
+  if (ctx->d_jk_tab) cudaFree(ctx->d_jk_tab);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -816,15 +816,80 @@ __device__ inline uint32_t num_elements_le2(int kind, uint32_t n_alt, uint32_t p
   return ploidy == 2 ? ((n_alt + 1u) * (n_alt + 2u)) >> 1 : 1u;
 }
 
-template <int NF>
+// n / d for n, d <= 65535 without the integer-division sequence
+__device__ inline uint32_t small_div(uint32_t n, uint32_t d) {
+  uint32_t qt = (uint32_t)(__uint2float_rz(n) * __frcp_rn(__uint2float_rz(d)));
+  if (qt * d > n) --qt;
+  if ((qt + 1u) * d <= n) ++qt;
+  return qt;
+}
+// Universal tables (built once per context, gdb_engine.cu): for genotype index g < 1024 of a diploid vector,
+//   cls_tab[g / 4] byte g % 4 = class of word g (0: (0,0)  1: (0,k)  2: (j>0,k)),  jk_tab[g] = k << 8 | j.
+struct TileTabs { const uint32_t* cls; const uint16_t* jk; };
+
+// Sites that need no remapping (merged REF of length 1 and <NON_REF> the only ALT: the reference-block intervals between
+// variant sites): every call's vectors go through unchanged.  One thread per sample; grid = (tiles, sites).
+template <int NF, bool GT>
+__global__ void __launch_bounds__(TILE_ROWS) k_copy_tile(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
+                                                        const __grid_constant__ RemapOut O, const uint32_t* __restrict__ site_list) {
+  __shared__ uint32_t s_hw[HOT_WORDS * TILE_ROWS];   // hot words as an indexable register file, word i of thread t at [i * TILE_ROWS + t]
+  constexpr int o_f0 = GT ? 1 : 0;
+  const uint32_t js = site_list[blockIdx.y], tid = threadIdx.x, nq = (uint32_t)S.nq;
+  const uint32_t q = blockIdx.x * TILE_ROWS + tid;
+  if (q >= nq) return;
+  const uint64_t sq = (uint64_t)js * nq + q;
+  const int32_t e = B.live[sq];
+  uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
+  if (e >= 0 && !(e & LIVE_REDUCED)) { const uint4* hp = reinterpret_cast<const uint4*>(&A.hot[e]); h0 = hp[0]; h1 = hp[1]; }
+  const uint32_t A_m = B.sites[js].n_alleles;
+  uint32_t* const hw = s_hw + tid;
+  hw[0] = h0.w; hw[TILE_ROWS] = h1.x; hw[2 * TILE_ROWS] = h1.y; hw[3 * TILE_ROWS] = h1.z; hw[4 * TILE_ROWS] = h1.w;
+  const uint32_t hflags = h0.x & 0xFF, n_alt = (h0.x >> 16) & 0xFF, nr = h0.x >> 24, gt_len = h0.y & 0xFF;
+  const bool inl = ((h0.y >> 8) & 0xFF) != 0;
+  if (e >= 0 && ((e & LIVE_REDUCED) || !inl || !(hflags & F_TRIVIAL))) return;   // on the site's nt list: k_remap_nt writes this row
+  const bool dead = e < 0;
+  if (GT) {
+    const uint32_t gs = O.f[0].stride[js]; uint32_t* d = O.f[0].data + O.f[0].base[js] + (uint64_t)q * gs;
+    if (gs == 2) *reinterpret_cast<uint2*>(d) = make_uint2(gt_len > 0 ? hw[0] : BCF_INT_VEND, gt_len > 1 ? hw[TILE_ROWS] : BCF_INT_VEND);
+    else for (uint32_t i = 0; i < gs; ++i) d[i] = i < gt_len ? hw[i * TILE_ROWS] : BCF_INT_VEND;
+    O.f[0].len[sq] = (uint16_t)gt_len;
+  }
+  if (O.lut_first) {
+    if (dead) { O.lut_first[sq] = 0xFFFFFFFFu; O.lut_len[sq] = 0; }
+    else {
+      const uint32_t A_in = n_alt + 1u;
+      uint32_t first = atomicAdd(&B.cursors[2], A_in);
+      if (first + A_in > O.cap_lut) { atomicOr(&S.err[2], 2u); first = 0xFFFFFFFFu; }
+      O.lut_first[sq] = first; O.lut_len[sq] = (uint16_t)A_in;
+      if (first != 0xFFFFFFFFu) for (uint32_t i = 0; i < A_in; ++i) O.lut_in2m[first + i] = (int16_t)(i == 0 ? 0 : ((nr && i == nr) ? (int)A_m - 1 : -1));
+    }
+  }
+  const uint32_t fl4 = (h0.y >> 16) | (h0.z << 16);
+  uint32_t k = gt_len;   // fields follow GT in the record
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    const uint32_t n = (fl4 >> (8 * f)) & 0xFF;   // 0 for a dead row
+    const uint32_t padw = vend_word(A.fm[f].elem);
+    const FieldOutDev fo = O.f[o_f0 + f];
+    const uint32_t stride = fo.stride[js];
+    fo.len[sq] = (uint16_t)n;
+    const uint32_t* fw = hw + k * TILE_ROWS;
+    uint32_t* d = fo.data + fo.base[js] + (uint64_t)q * stride;
+    for (uint32_t x = 0; x < stride; ++x) d[x] = x < n ? fw[x * TILE_ROWS] : padw;
+    k += n;
+  }
+}
+
+// Remapped sites.  One block = 256 samples of one site; grid = (tiles, sites).
+template <int NF, bool GT>
 __global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
-                                                            const __grid_constant__ RemapOut O, const uint32_t* __restrict__ site_list, const uint32_t tiles_per_site) {
+                                                            const __grid_constant__ RemapOut O, const uint32_t* __restrict__ site_list, const TileTabs tabs) {
   __shared__ __align__(16) uint4 s_tri[TILE_ROWS * NF];     // per (sample, field): v0, v1, v2, pad
   __shared__ uint32_t s_info[TILE_ROWS * NF];               // per (sample, field): INFO_FAST or 0
   __shared__ uint32_t s_hw[HOT_WORDS * TILE_ROWS];          // the samples' hot words, word i of thread t at [i * TILE_ROWS + t]:
                                                             // an indexable register file (each thread reads only its own column)
-  const uint32_t si = blockIdx.x / tiles_per_site, tile = blockIdx.x - si * tiles_per_site;
-  const uint32_t js = site_list[si];
+  constexpr int o_f0 = GT ? 1 : 0;
+  const uint32_t js = site_list[blockIdx.y], tile = blockIdx.x;
   const uint32_t tid = threadIdx.x;
   const uint32_t nq = (uint32_t)S.nq;
   const uint32_t q = tile * TILE_ROWS + tid;
@@ -838,8 +903,7 @@ __global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_consta
   }
   const SiteRec* __restrict__ site_g = &B.sites[js];
   const uint32_t A_m = site_g->n_alleles, sflags = site_g->flags;
-  const bool nonref = sflags & 1u, remap = sflags & 2u, g_suppressed = sflags & 4u;
-  const int o_f0 = A.has_gt ? 1 : 0;
+  const bool nonref = sflags & 1u, g_suppressed = sflags & 4u;
   uint32_t fstride[NF];
   uint32_t* fdst[NF];   // this site's block of field f
 #pragma unroll
@@ -856,9 +920,8 @@ __global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_consta
         s_tri[tid * NF + f] = make_uint4(padw, padw, padw, padw);
         s_info[tid * NF + f] = INFO_FAST;
         O.f[o_f0 + f].len[sq] = 0;
-        if (!remap) { uint32_t* d = fdst[f] + (uint64_t)q * fstride[f]; for (uint32_t x = 0; x < fstride[f]; ++x) d[x] = padw; }
       }
-      if (A.has_gt) { const uint32_t gs = O.f[0].stride[js]; uint32_t* d = O.f[0].data + O.f[0].base[js] + (uint64_t)q * gs; for (uint32_t i = 0; i < gs; ++i) d[i] = BCF_INT_VEND; O.f[0].len[sq] = 0; }
+      if (GT) { const uint32_t gs = O.f[0].stride[js]; uint32_t* d = O.f[0].data + O.f[0].base[js] + (uint64_t)q * gs; for (uint32_t i = 0; i < gs; ++i) d[i] = BCF_INT_VEND; O.f[0].len[sq] = 0; }
       if (O.lut_first) { O.lut_first[sq] = 0xFFFFFFFFu; O.lut_len[sq] = 0; }
     } else {
       const uint32_t hflags = h0.x & 0xFF, ploidy = (h0.x >> 8) & 0xFF, n_alt = (h0.x >> 16) & 0xFF, nr = h0.x >> 24, gt_len = h0.y & 0xFF;
@@ -871,13 +934,13 @@ __global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_consta
         // ---- trivial call, fully described by its hot record
         const uint32_t fl4 = (h0.y >> 16) | (h0.z << 16);
         const int in_nr = (nonref && nr) ? (int)nr : -1;
-        if (A.has_gt) {
+        if (GT) {
           const uint32_t gs = O.f[0].stride[js]; uint32_t* d = O.f[0].data + O.f[0].base[js] + (uint64_t)q * gs;
           const uint32_t step = A.gt_phased ? 2u : 1u;
           auto gt_word = [&](uint32_t i) -> uint32_t {
             if (i >= gt_len) return BCF_INT_VEND;
             uint32_t g = hw[i * TILE_ROWS];
-            if (remap && (i % step) == 0 && !(g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING))
+            if ((i % step) == 0 && !(g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING))
               g = (g == 0) ? 0u : ((nr && g == nr) ? A_m - 1u : (nonref ? A_m - 1u : 0xFFFFFFFFu));
             return g;
           };
@@ -899,14 +962,10 @@ __global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_consta
           const int kind = A.fm[f].kind;
           const uint32_t miss = missing_word(A.fm[f].elem), padw = vend_word(A.fm[f].elem);
           uint32_t n_out = 0;
-          if (n && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements_le2(kind, A_m - 1u, ploidy) : n;
+          if (n && !(kind == KIND_G && g_suppressed)) n_out = num_elements_le2(kind, A_m - 1u, ploidy);
           O.f[o_f0 + f].len[sq] = (uint16_t)n_out;
           const uint32_t* fw = hw + k * TILE_ROWS;   // this field's inline words
-          if (!remap) {
-            // no remapping at this site: the (inline, <= 5 words) input goes straight through, from this thread
-            uint32_t* d = fdst[f] + (uint64_t)q * fstride[f];
-            for (uint32_t x = 0; x < fstride[f]; ++x) d[x] = x < n_out ? fw[x * TILE_ROWS] : padw;
-          } else if (!n_out) {
+          if (!n_out) {
             s_tri[tid * NF + f] = make_uint4(padw, padw, padw, padw);
             s_info[tid * NF + f] = INFO_FAST;
           } else {
@@ -940,36 +999,39 @@ __global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_consta
       }
     }
   }
-  if (!remap) return;   // copy-through sites are complete (uniform per block)
   __syncthreads();
 
   // ---------------------------------------------------------------- phase B: the block streams the tile out
   // Field f of the tile is rows x lpr quads, contiguous.  Thread t keeps ONE quad column (t % lpr) and walks the rows
   // (t / lpr, + 256 / lpr per step), so which of (v0, v1, v2, pad) each of its four words takes is loop-invariant, and
-  // a warp's stores cover 512 contiguous bytes.
+  // a warp's stores cover 512 contiguous bytes.  Two rows per trip, loads first, stores predicated.
   const uint32_t rows = min((uint32_t)TILE_ROWS, nq - tile * TILE_ROWS);
 #pragma unroll
   for (int f = 0; f < NF; ++f) {
     const uint32_t stride = fstride[f];
     if (stride == 0) continue;
     const uint32_t lpr = stride >> 2;   // quads per sample (stride is a multiple of 4 at remapped sites), <= 256
-    const uint32_t rpi = (uint32_t)TILE_ROWS / lpr;   // rows per step
-    const uint32_t r_off = tid / lpr, col = tid - r_off * lpr;
+    const uint32_t rpi = small_div((uint32_t)TILE_ROWS, lpr);   // rows per step
+    const uint32_t r_off = small_div(tid, lpr), col = tid - r_off * lpr;
     if (r_off >= rpi) continue;
     const int kind = A.fm[f].kind;
     const uint32_t fploidy = site_g->max_ploidy[f];
     const uint32_t nfull = num_elements_le2(kind, A_m - 1u, fploidy);   // length of a full vector of this field at this site
+    const uint32_t cw = (kind == KIND_A) ? 0x01010101u : ((kind == KIND_G && fploidy == 2) ? tabs.cls[col] : (col == 0 ? 0x01010100u : 0x01010101u));
     uint32_t c[4];
 #pragma unroll
-    for (uint32_t x = 0; x < 4; ++x) { const uint32_t g = 4 * col + x; c[x] = g < nfull ? trivial_class(kind, fploidy, g) : 3u; }
+    for (uint32_t x = 0; x < 4; ++x) c[x] = (4 * col + x < nfull) ? ((cw >> (8 * x)) & 0xFFu) : 3u;
     uint4* out4 = reinterpret_cast<uint4*>(fdst[f] + (uint64_t)tile * TILE_ROWS * stride) + col;
     const uint32_t* tri = reinterpret_cast<const uint32_t*>(s_tri);
-    for (uint32_t r = r_off; r < rows; r += rpi) {
-      const uint32_t slot = r * NF + f;
-      if (s_info[slot] & INFO_FAST) {
-        const uint32_t* tw = tri + 4 * slot;
-        out4[(uint64_t)r * lpr] = make_uint4(tw[c[0]], tw[c[1]], tw[c[2]], tw[c[3]]);
-      }
+    for (uint32_t r = r_off; r < rows; r += 2 * rpi) {
+      const uint32_t rb = min(r + rpi, (uint32_t)TILE_ROWS - 1u);
+      const uint32_t sa = r * NF + f, sb = rb * NF + f;
+      const uint32_t ia = s_info[sa], ib = s_info[sb];
+      const uint32_t* ta = tri + 4 * sa; const uint32_t* tb = tri + 4 * sb;
+      const uint4 va = make_uint4(ta[c[0]], ta[c[1]], ta[c[2]], ta[c[3]]);
+      const uint4 vb = make_uint4(tb[c[0]], tb[c[1]], tb[c[2]], tb[c[3]]);
+      if (ia & INFO_FAST) out4[(uint64_t)r * lpr] = va;
+      if ((ib & INFO_FAST) && r + rpi < rows) out4[(uint64_t)(r + rpi) * lpr] = vb;
     }
   }
 }
@@ -982,9 +1044,9 @@ __global__ void __launch_bounds__(256) k_nt_blocks(const __grid_constant__ Batch
   const uint32_t si = blockIdx.x, js = site_list[si], b0 = blk_prefix[si], nb = blk_prefix[si + 1] - b0;
   for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) blk_map[b0 + b] = make_uint2(js, b * NT_GROUPS);
 }
-template <int NF>
+template <int NF, bool GT>
 __global__ void __launch_bounds__(NT_THREADS) k_remap_nt(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
-                                                        const __grid_constant__ RemapOut O, const uint2* __restrict__ blk_map, const uint32_t jk_n) {
+                                                        const __grid_constant__ RemapOut O, const uint2* __restrict__ blk_map, const uint32_t jk_n, const TileTabs tabs) {
   __shared__ uint16_t s_jk[TILE_MAX_G];                      // g -> (k << 8 | j), the same for every site
   __shared__ unsigned long long s_ah[TILE_MAX_A];            // the site's merged-allele hashes
   __shared__ int s_m2in[NT_GROUPS][TILE_MAX_A];
@@ -1000,9 +1062,9 @@ __global__ void __launch_bounds__(NT_THREADS) k_remap_nt(const __grid_constant__
   if (active) ent = B.nt[(uint64_t)js * S.nq + ei];
   const uint8_t* mref = B.allele_bytes + site_g->ref_off;
   const bool nonref = sflags & 1u, remap = sflags & 2u, g_suppressed = sflags & 4u;
-  const int o_f0 = A.has_gt ? 1 : 0;
+  constexpr int o_f0 = GT ? 1 : 0;
   if ((uint32_t)tid < A_m) s_ah[tid] = B.allele_hash[allele_first + tid];
-  for (uint32_t g = tid; g < jk_n && g < (uint32_t)TILE_MAX_G; g += NT_THREADS) { uint32_t j, k; tri_unrank(g, j, k); s_jk[g] = (uint16_t)((k << 8) | j); }
+  for (uint32_t g = tid; g < jk_n && g < (uint32_t)TILE_MAX_G; g += NT_THREADS) s_jk[g] = tabs.jk[g];
   for (uint32_t m = gl; m < A_m; m += NT_GL) s_m2in[grp][m] = m == 0 ? 0 : -1;
 
   // ---- the call
@@ -1068,7 +1130,7 @@ __global__ void __launch_bounds__(NT_THREADS) k_remap_nt(const __grid_constant__
     if (first != 0xFFFFFFFFu) for (uint32_t i = gl; i < A_in; i += NT_GL) O.lut_in2m[first + i] = (int16_t)s_in2m[grp][i];
   }
   // ---- GT (variant_operations.cc:233-263)
-  if (A.has_gt) {
+  if (GT) {
     const FieldOutDev fo = O.f[0];
     const uint32_t gs = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + (uint64_t)q * gs;
     const uint32_t step = A.gt_phased ? 2u : 1u;
