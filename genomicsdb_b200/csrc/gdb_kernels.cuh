@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restri
   // hot record
   HotRec h;
   h.flags = d.flags; h.ploidy = d.ploidy; h.n_alt = (uint8_t)(n_alt > 255 ? 255 : n_alt); h.nr_idx = (uint8_t)(nr > 255 ? 255 : nr);
-  h.gt_len = (uint8_t)(d.gt_len > 255 ? 255 : d.gt_len); h.inl = 0; h.pad[0] = h.pad[1] = 0;
+  h.gt_len = (uint8_t)(d.gt_len > 255 ? 255 : d.gt_len); h.inl = 0;
+  h.ref_len8 = (uint8_t)(d.ref_len > 255 ? 255 : d.ref_len); h.ref0 = d.ref_len ? A.ref.val[r0] : (uint8_t)0;
   for (int f = 0; f < HOT_FIELDS; ++f) h.flen[f] = 0;
   for (int k = 0; k < HOT_WORDS; ++k) h.w[k] = 0;
   bool fits = (n_alt < 255) && (d.gt_len <= 255) && (A.n_fields <= HOT_FIELDS);
@@ -372,15 +373,29 @@ __global__ void __launch_bounds__(256) k_left_sweep(ArrayDev A, ScanDev S) {
   if (cell >= 0) { set_bit(S, S.q_lo); set_bit(S, clip_end(S, eff) + 1); }
 }
 
-// breakpoints = begin columns of every cell the forward scan visits + (effective end + 1) of every queried call
+// breakpoints = begin columns of every cell the forward scan visits + (effective end + 1) of every queried call.
+// Thousands of cells share a column (and most calls end where another sample's call begins), so lanes holding the same
+// position elect one leader per warp before touching the bitmap.
+__device__ inline void set_bit_warp(const ScanDev& S, bool want, int64_t pos) {
+  const unsigned act = __ballot_sync(0xffffffffu, want);
+  if (!want) return;
+  const unsigned same = __match_any_sync(act, pos);
+  if ((int)(threadIdx.x & 31) == __ffs(same) - 1) set_bit(S, pos);
+}
 __global__ void __launch_bounds__(256) k_mark_events(ArrayDev A, ScanDev S) {
   uint64_t i = S.i0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S.i1) return;
-  uint8_t fl = A.desc[i].flags;
-  if (fl & (F_ENDCOPY | F_ROWOUT)) return;
-  int64_t col = A.coords[2 * i + 1];
-  set_bit(S, col);
-  if (qrow_of(A, S, A.coords[2 * i]) >= 0) set_bit(S, clip_end(S, A.effend[i]) + 1);
+  bool begin = false, queried = false;
+  int64_t col = 0, end1 = 0;
+  if (i < S.i1) {
+    uint8_t fl = A.desc[i].flags;
+    if (!(fl & (F_ENDCOPY | F_ROWOUT))) {
+      begin = true;
+      col = A.coords[2 * i + 1];
+      if (qrow_of(A, S, A.coords[2 * i]) >= 0) { queried = true; end1 = clip_end(S, A.effend[i]) + 1; }
+    }
+  }
+  set_bit_warp(S, begin, col);
+  set_bit_warp(S, queried, end1);
 }
 // "Unhandled overlapping variants" (query_variants.cc:519-535): an eviction of a call that is neither a deletion nor a
 // reference block throws, but only when the evicted call is live, i.e. it began inside this query.
@@ -403,10 +418,28 @@ __global__ void __launch_bounds__(256) k_extract_bp(ScanDev S) {
   uint64_t r = S.word_rank[w];
   while (word) { int b = __ffsll((long long)word) - 1; S.bp[r] = S.base + (int64_t)(w * 64 + b); S.bp_cell0[r] = 0xFFFFFFFFu; ++r; word &= word - 1; }
 }
-// +1/-1 live-call deltas per breakpoint (and the same for calls containing a deletion); first cell of each column
+// +1/-1 live-call deltas per breakpoint (and the same for calls containing a deletion); first cell of each column.
+// Cells are sorted by column, so the breakpoint ranks a block touches start at the rank of its first cell's column and
+// mostly fall within the next few thousand: they are accumulated in shared-memory bins and flushed once per block.
+constexpr int DELTA_BINS = 2048;
 __global__ void __launch_bounds__(256) k_deltas(ArrayDev A, ScanDev S) {
-  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t n_cells = S.i1 - S.iL;
+  __shared__ int s_live[DELTA_BINS];
+  __shared__ int s_del[DELTA_BINS];
+  __shared__ unsigned long long s_r0;
+  const uint64_t t0 = (uint64_t)blockIdx.x * blockDim.x, t = t0 + threadIdx.x;
+  const uint64_t n_cells = S.i1 - S.iL;
+  for (int i = threadIdx.x; i < DELTA_BINS; i += 256) { s_live[i] = 0; s_del[i] = 0; }
+  if (threadIdx.x == 0) {
+    // lowest rank this block can touch: its first cell's column, or q_lo for the left-sweep calls
+    int64_t c = (t0 < n_cells) ? A.coords[2 * (S.iL + t0) + 1] : S.q_lo;
+    if (c < S.q_lo) c = S.q_lo;
+    s_r0 = bp_rank(S, c);
+  }
+  __syncthreads();
+  const uint64_t r0 = s_r0;
+  auto add = [&](int* bins, int32_t* glob, uint64_t r, int v) {
+    if (r >= r0 && r - r0 < (uint64_t)DELTA_BINS) atomicAdd(&bins[r - r0], v); else atomicAdd(&glob[r], v);
+  };
   if (t < n_cells) {
     uint64_t i = S.iL + t;
     uint8_t fl = A.desc[i].flags;
@@ -418,25 +451,27 @@ __global__ void __launch_bounds__(256) k_deltas(ArrayDev A, ScanDev S) {
       uint64_t bit = (uint64_t)(col - S.base);
       if (col >= S.base && bit < S.span_bits && ((S.bitmap[bit >> 6] >> (bit & 63)) & 1ull)) S.bp_cell0[bp_rank(S, col)] = (uint32_t)i;
     }
-    if (fl & F_ROWOUT) return;
-    if (!forward || (fl & F_ENDCOPY)) return;
-    if (qrow_of(A, S, A.coords[2 * i]) < 0) return;
-    uint64_t rs = bp_rank(S, col), re = bp_rank(S, clip_end(S, A.effend[i]) + 1);
-    // warp-aggregate the +1 (cells of one column are adjacent)
-    unsigned act = __activemask();
-    unsigned mask = __match_any_sync(act, rs);
-    if ((int)(threadIdx.x & 31) == __ffs(mask) - 1) atomicAdd(&S.dlive[rs], __popc(mask));
-    unsigned mask_e = __match_any_sync(act, re);
-    if ((int)(threadIdx.x & 31) == __ffs(mask_e) - 1) atomicSub(&S.dlive[re], __popc(mask_e));
-    if (S.handle_del && (fl & F_DELETION)) { atomicAdd(&S.ddel[rs], 1); atomicSub(&S.ddel[re], 1); }
+    if (!(fl & (F_ROWOUT | F_ENDCOPY)) && forward && qrow_of(A, S, A.coords[2 * i]) >= 0) {
+      uint64_t rs = bp_rank(S, col), re = bp_rank(S, clip_end(S, A.effend[i]) + 1);
+      add(s_live, S.dlive, rs, 1); add(s_live, S.dlive, re, -1);
+      if (S.handle_del && (fl & F_DELETION)) { add(s_del, S.ddel, rs, 1); add(s_del, S.ddel, re, -1); }
+    }
   } else {
     uint64_t q = t - n_cells;
-    if (q >= S.nq) return;
-    int32_t c = S.init_cell[q];
-    if (c < 0) return;
-    uint64_t rs = bp_rank(S, S.q_lo), re = bp_rank(S, clip_end(S, S.init_effend[q]) + 1);
-    atomicAdd(&S.dlive[rs], 1); atomicSub(&S.dlive[re], 1);
-    if (S.handle_del && (A.desc[c].flags & F_DELETION)) { atomicAdd(&S.ddel[rs], 1); atomicSub(&S.ddel[re], 1); }
+    if (q < S.nq) {
+      int32_t c = S.init_cell[q];
+      if (c >= 0) {
+        uint64_t rs = bp_rank(S, S.q_lo), re = bp_rank(S, clip_end(S, S.init_effend[q]) + 1);
+        add(s_live, S.dlive, rs, 1); add(s_live, S.dlive, re, -1);
+        if (S.handle_del && (A.desc[c].flags & F_DELETION)) { add(s_del, S.ddel, rs, 1); add(s_del, S.ddel, re, -1); }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < DELTA_BINS; i += 256) {
+    const int v = s_live[i], d = s_del[i];
+    if (v) atomicAdd(&S.dlive[r0 + i], v);
+    if (d) atomicAdd(&S.ddel[r0 + i], d);
   }
 }
 // after the inclusive scans: number of operate() calls per breakpoint interval (1 bp stepping while a deletion is live,

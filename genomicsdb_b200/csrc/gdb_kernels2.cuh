@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__
   __shared__ uint16_t s_list[UNION_MAX_DISTINCT];
   __shared__ uint16_t s_rank[UNION_MAX_DISTINCT];
   __shared__ uint32_t s_piece_cell[REF_MAX_PIECES], s_piece_from[REF_MAX_PIECES], s_piece_to[REF_MAX_PIECES];
-  __shared__ unsigned int s_k, s_next, s_maxN, s_ndist, s_nonref, s_maxgt, s_maxain, s_maxploidy, s_npieces, s_reflen, s_refoff, s_afirst, s_overflow;
+  __shared__ unsigned int s_k, s_next, s_maxN, s_maxlen, s_ndist, s_nonref, s_maxgt, s_maxain, s_maxploidy, s_npieces, s_reflen, s_refoff, s_afirst, s_overflow;
   __shared__ unsigned int s_maxpl[MAX_FIELDS], s_maxin[MAX_FIELDS];
 
   const uint32_t js = blockIdx.x;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__
 
   for (int i = tid; i < UNION_SLOTS; i += UNION_THREADS) { s_hash[i] = 0ull; s_order[i] = ~0ull; }
   if (tid == 0) {
-    s_k = 0xFFFFFFFFu; s_next = 0xFFFFFFFFu; s_maxN = 0; s_ndist = 0; s_npieces = 0; s_overflow = 0;
+    s_k = 0xFFFFFFFFu; s_next = 0xFFFFFFFFu; s_maxN = 0; s_maxlen = 0; s_ndist = 0; s_npieces = 0; s_overflow = 0;
     s_nonref = agg[AGG_NONREF]; s_maxgt = agg[AGG_MAXGT]; s_maxain = agg[AGG_MAXAIN]; s_maxploidy = agg[AGG_MAXPLOIDY];
   }
   if (tid < MAX_FIELDS) { s_maxpl[tid] = tid < HOT_FIELDS ? agg[AGG_MAXPL + tid] : 0u; s_maxin[tid] = tid < HOT_FIELDS ? agg[AGG_MAXIN + tid] : 0u; }
@@ -413,17 +413,20 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__
       c1 = l2;
     }
   }
+  // a begin cell of column b whose row is queried IS the live call of that row at this site (k_live_walk), so the 16-byte
+  // header of its hot record answers everything the fold asks: flags, REF length, first REF byte
   auto candidate = [&](uint64_t c, uint32_t& rl, uint8_t& first) -> bool {
-    const CellDesc d = A.desc[c];
-    if (d.flags & (F_ENDCOPY | F_ROWOUT)) return false;
-    int32_t q = qrow_of(A, S, A.coords[2 * c]);
-    if (q < 0 || (live[q] & ~LIVE_REDUCED) != (int32_t)c || (live[q] & LIVE_REDUCED) || live[q] < 0) return false;
-    rl = d.ref_len; first = rl ? A.ref.val[A.ref.off[c]] : 0;
+    const uint4 hh = *reinterpret_cast<const uint4*>(&A.hot[c]);
+    if (hh.x & (uint32_t)(F_ENDCOPY | F_ROWOUT)) return false;
+    if (S.qrow_of_row && qrow_of(A, S, A.coords[2 * c]) < 0) return false;
+    rl = (hh.z >> 16) & 0xFFu; first = (uint8_t)(hh.z >> 24);
+    if (rl == 255u) rl = A.desc[c].ref_len;
     return true;
   };
   for (uint64_t c = c0 + tid; c < c1; c += UNION_THREADS) {
     uint32_t rl; uint8_t first;
     if (!candidate(c, rl, first)) continue;
+    atomicMax(&s_maxlen, rl);
     if (first != 'N') atomicMin(&s_k, (unsigned int)(c - c0));
     else atomicMax(&s_maxN, rl);
   }
@@ -441,7 +444,7 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__
   } else {
     uint32_t last = s_k, cur_len = A.desc[c0 + s_k].ref_len;
     if (tid == 0) { s_piece_cell[0] = (uint32_t)(c0 + last); s_piece_from[0] = 0; s_piece_to[0] = cur_len; s_npieces = 1; }
-    for (;;) {   // later, longer REFs append their tail ("record breakers")
+    while (s_maxlen > cur_len) {   // later, longer REFs append their tail ("record breakers"); none when nothing is longer
       __syncthreads();
       if (tid == 0) s_next = 0xFFFFFFFFu;
       __syncthreads();
@@ -459,6 +462,7 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__
       }
       last = nx; cur_len = nl;
     }
+    __syncthreads();
     if (tid == 0) s_reflen = cur_len;
     __syncthreads();
   }
