@@ -1051,7 +1051,7 @@ __global__ void __launch_bounds__(256) k_nt_blocks(const __grid_constant__ Batch
 template <int NF, bool GT>
 __global__ void __launch_bounds__(NT_THREADS) k_remap_nt(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
                                                         const __grid_constant__ RemapOut O, const uint2* __restrict__ blk_map, const uint32_t jk_n, const TileTabs tabs) {
-  __shared__ uint16_t s_jk[TILE_MAX_G];                      // g -> (k << 8 | j), the same for every site
+  __shared__ __align__(8) uint16_t s_jk[TILE_MAX_G + 6];     // g -> (k << 8 | j), the same for every site
   __shared__ unsigned long long s_ah[TILE_MAX_A];            // the site's merged-allele hashes
   __shared__ int s_m2in[NT_GROUPS][TILE_MAX_A];
   __shared__ int8_t s_in2m[NT_GROUPS][TILE_MAX_A];
@@ -1068,7 +1068,7 @@ __global__ void __launch_bounds__(NT_THREADS) k_remap_nt(const __grid_constant__
   const bool nonref = sflags & 1u, remap = sflags & 2u, g_suppressed = sflags & 4u;
   constexpr int o_f0 = GT ? 1 : 0;
   if ((uint32_t)tid < A_m) s_ah[tid] = B.allele_hash[allele_first + tid];
-  for (uint32_t g = tid; g < jk_n && g < (uint32_t)TILE_MAX_G; g += NT_THREADS) s_jk[g] = tabs.jk[g];
+  for (uint32_t g = tid; g < ((jk_n + 3u) & ~3u) && g < (uint32_t)TILE_MAX_G + 6u; g += NT_THREADS) s_jk[g] = tabs.jk[g];   // whole quads: the tail is read, then discarded
   for (uint32_t m = gl; m < A_m; m += NT_GL) s_m2in[grp][m] = m == 0 ? 0 : -1;
 
   // ---- the call
@@ -1122,7 +1122,11 @@ __global__ void __launch_bounds__(NT_THREADS) k_remap_nt(const __grid_constant__
   __syncwarp();
   if (active && remap) {
     const int in_nr = (nonref && nr_idx) ? (int)nr_idx : -1;   // NON_REF fallback folded in
-    for (uint32_t m = gl; m < A_m; m += NT_GL) if (s_m2in[grp][m] < 0) s_m2in[grp][m] = in_nr;
+    for (uint32_t m = gl; m < A_m; m += NT_GL) {
+      int a = s_m2in[grp][m];
+      if (a < 0) a = in_nr;
+      s_m2in[grp][m] = a < 0 ? -1 : (a | ((a * (a + 1) / 2) << 8));
+    }
   }
   __syncwarp();
   if (!active) return;
@@ -1162,27 +1166,50 @@ __global__ void __launch_bounds__(NT_THREADS) k_remap_nt(const __grid_constant__
     if (n && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, ploidy) : n;
     const uint32_t stride = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + (uint64_t)q * stride;
     if (gl == 0) fo.len[sq] = (uint16_t)n_out;
-    const int mode = !remap ? 0 : ((kind == KIND_G && ploidy == 2) ? 1 : ((kind == KIND_G && ploidy == 0) ? 2 : (kind == KIND_A ? 3 : 4)));
-    auto word = [&](uint32_t g) -> uint32_t {
-      if (g >= n_out) return pad;
-      if (mode == 0) return in[g];
-      if (mode == 1) {
-        const uint32_t jk = s_jk[g];
-        const int ij = m2in[jk & 0xFF], ik = m2in[jk >> 8];
-        if (ij < 0 || ik < 0) return miss;
-        const uint32_t ig = (uint32_t)alleles2gt(ij, ik);
-        return ig < n ? in[ig] : miss;
-      }
-      if (mode == 2) return in[0];
-      const int ij = m2in[mode == 3 ? g + 1u : g];
-      const int ix = mode == 3 ? ij - 1 : ij;
-      return (ij < 0 || ix < 0 || (uint32_t)ix >= n) ? miss : in[ix];
-    };
-    if (remap && (stride & 3u) == 0) {   // 16-byte aligned vector: one quad per lane
+    // s_m2in[m] = input allele of merged allele m (NON_REF fallback folded in), or -1; the diploid loop wants it packed
+    // with its triangular number: a | a(a+1)/2 << 8 (still negative when there is no input allele)
+    if (remap && (stride & 3u) == 0 && kind == KIND_G && ploidy == 2) {
       uint4* dst4 = reinterpret_cast<uint4*>(dst);
-      for (uint32_t qd = gl; qd < (stride >> 2); qd += NT_GL) dst4[qd] = make_uint4(word(4 * qd), word(4 * qd + 1), word(4 * qd + 2), word(4 * qd + 3));
+      for (uint32_t qd = gl; qd < (stride >> 2); qd += NT_GL) {
+        const uint2 jk4 = *reinterpret_cast<const uint2*>(&s_jk[4 * qd]);   // (k << 8 | j) of words 4qd .. 4qd+3
+        uint32_t w[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const uint32_t jk = ((x < 2 ? jk4.x : jk4.y) >> (16 * (x & 1))) & 0xFFFFu;
+          const int pj = m2in[jk & 0xFF], pk = m2in[jk >> 8];
+          const uint32_t aj = (uint32_t)pj & 0xFFu, ak = (uint32_t)pk & 0xFFu;
+          const uint32_t ig = aj > ak ? ((uint32_t)pj >> 8) + ak : ((uint32_t)pk >> 8) + aj;
+          uint32_t v = miss;
+          if ((pj | pk) >= 0 && ig < n) v = in[ig];
+          w[x] = (4 * qd + x < n_out) ? v : pad;
+        }
+        dst4[qd] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
     } else {
-      for (uint32_t g = gl; g < stride; g += NT_GL) dst[g] = word(g);
+      const int mode = !remap ? 0 : ((kind == KIND_G && ploidy == 2) ? 1 : ((kind == KIND_G && ploidy == 0) ? 2 : (kind == KIND_A ? 3 : 4)));
+      auto word = [&](uint32_t g) -> uint32_t {
+        if (g >= n_out) return pad;
+        if (mode == 0) return in[g];
+        if (mode == 1) {
+          const uint32_t jk = s_jk[g];
+          const int pj = m2in[jk & 0xFF], pk = m2in[jk >> 8];
+          if ((pj | pk) < 0) return miss;
+          const uint32_t aj = (uint32_t)pj & 0xFFu, ak = (uint32_t)pk & 0xFFu;
+          const uint32_t ig = aj > ak ? ((uint32_t)pj >> 8) + ak : ((uint32_t)pk >> 8) + aj;
+          return ig < n ? in[ig] : miss;
+        }
+        if (mode == 2) return in[0];
+        const int pj = m2in[mode == 3 ? g + 1u : g];
+        const int ij = pj < 0 ? -1 : (pj & 0xFF);
+        const int ix = mode == 3 ? ij - 1 : ij;
+        return (ij < 0 || ix < 0 || (uint32_t)ix >= n) ? miss : in[ix];
+      };
+      if (remap && (stride & 3u) == 0) {   // 16-byte aligned vector: one quad per lane
+        uint4* dst4 = reinterpret_cast<uint4*>(dst);
+        for (uint32_t qd = gl; qd < (stride >> 2); qd += NT_GL) dst4[qd] = make_uint4(word(4 * qd), word(4 * qd + 1), word(4 * qd + 2), word(4 * qd + 3));
+      } else {
+        for (uint32_t g = gl; g < stride; g += NT_GL) dst[g] = word(g);
+      }
     }
   }
 }
