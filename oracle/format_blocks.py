@@ -1,0 +1,119 @@
+"""TEST INFRASTRUCTURE ONLY: CPU restatement of the FORMAT collation + BCF typed encoding of the Broad combine operator.
+
+Input: the canonical hot-path dump (remapped GT / allele-dependent fields per valid call); output: for every site and
+field the block htslib would put into bcf1_t.indiv.  Restates, for the fields of the hot path:
+  VariantFieldHandler<T>::collect_and_extend_fields   src/main/cpp/src/genomicsdb/variant_field_handler.cc:804-871
+      nps = max length over valid calls with a valid field (no such call: the field is not emitted); every query row
+      gets nps values: its vector, or [missing] ([vector_end] for GT) when the row has no valid field, then vector_end
+  encode_GT_vector<phase?, produce_GT?>                src/main/cpp/src/query_operations/broad_combined_gvcf.cc:53-138,646-658
+      allele a -> (a + 1) << 1 | phased; phase slots dropped; !produce_GT_field: every valid allele -> no-call
+  G-length fields dropped above max_diploid_alt_alleles  broad_combined_gvcf.cc:620-623
+  bcf_enc_vint / bcf_enc_int1 / bcf_enc_size           dependencies/htslib/vcf.c:1885-1972
+      int8 when max <= 127 and min > -127, int16 when max <= 32767 and min > -32767 (missing / vector_end excluded), else int32
+Pure-python loops: small cases only.  Pinned against the reference's own BCF output (tests/golden/bcf, tests/test_format_oracle.py).
+"""
+import struct
+
+import numpy as np
+
+I32_MISSING, I32_VEND = -2147483648, -2147483647
+F32_MISSING, F32_VEND = 0x7F800001, 0x7F800002
+BT_INT8, BT_INT16, BT_INT32, BT_FLOAT = 1, 2, 3, 5
+
+
+def enc_int1(x):
+    """bcf_enc_int1 (vcf.h): one typed integer"""
+    if x == I32_VEND:
+        return bytes([1 << 4 | BT_INT8, 0x81])
+    if x == I32_MISSING:
+        return bytes([1 << 4 | BT_INT8, 0x80])
+    if -120 <= x <= 127:
+        return bytes([1 << 4 | BT_INT8]) + struct.pack("<b", x)
+    if -32760 <= x <= 32767:
+        return bytes([1 << 4 | BT_INT16]) + struct.pack("<h", x)
+    return bytes([1 << 4 | BT_INT32]) + struct.pack("<i", x)
+
+
+def enc_size(n, bt):
+    """bcf_enc_size (vcf.h)"""
+    if n >= 15:
+        return bytes([15 << 4 | bt]) + enc_int1(n)
+    return bytes([n << 4 | bt])
+
+
+def enc_vint(a, nps):
+    """bcf_enc_vint (vcf.c:1926-1972) over int32 values `a`, nps per sample -> (type, descriptor bytes, data bytes)"""
+    a = np.asarray(a, dtype=np.int64)
+    n = len(a)
+    if n == 1:
+        b = enc_int1(int(a[0]))
+        return b[0] & 0xF, b[:1], b[1:]
+    valid = a[(a != I32_MISSING) & (a != I32_VEND)]
+    mx = int(valid.max()) if len(valid) else I32_VEND
+    mn = int(valid.min()) if len(valid) else 2147483647
+    if mx <= 127 and mn > -127:
+        out = np.where(a == I32_VEND, -127, np.where(a == I32_MISSING, -128, a)).astype("<i1")
+        return BT_INT8, enc_size(nps, BT_INT8), out.tobytes()
+    if mx <= 32767 and mn > -32767:
+        out = np.where(a == I32_VEND, -32767, np.where(a == I32_MISSING, -32768, a)).astype("<i2")
+        return BT_INT16, enc_size(nps, BT_INT16), out.tobytes()
+    return BT_INT32, enc_size(nps, BT_INT32), a.astype("<i4").tobytes()
+
+
+def encode_gt(vec, phased_layout, produce_gt):
+    """encode_GT_vector over one sample's padded vector (int32 values) -> BCF genotype ints"""
+    def valid(v):
+        return v != I32_MISSING and v != I32_VEND
+
+    def enc(v, ph):
+        if not valid(v):
+            return v
+        if not produce_gt:
+            return 1 if ph else 0
+        return ((((v + 1) << 1) | (1 if ph else 0)) + 2 ** 31) % 2 ** 32 - 2 ** 31
+    if not len(vec):
+        return []
+    out = [enc(vec[0], False)]
+    if phased_layout:
+        for k in range(2, len(vec), 2):
+            out.append(enc(vec[k], vec[k - 1] > 0))
+    else:
+        for k in range(1, len(vec)):
+            out.append(enc(vec[k], False))
+    return out
+
+
+def site_blocks(site, names, query_rows, field_elem, gt_phased, produce_gt, g_fields=(), max_alt=50):
+    """-> {field name: (type, nps, data bytes, descriptor bytes)} for one parsed dump site (oracle.parse_dump)"""
+    by_row = {c["row"]: c for c in site["calls"]}
+    n_alt = len(site["alleles"]) - 1
+    out = {}
+    for nm in names:
+        if nm in g_fields and site["remap"] and n_alt > max_alt:
+            continue
+        is_gt = nm == "GT"
+        is_float = field_elem.get(nm) == "float"
+        lens = [len(c["fields"][nm]) for c in site["calls"]]
+        nps = max(lens) if lens else 0
+        if nps == 0:
+            continue
+        miss, vend = (F32_MISSING, F32_VEND) if is_float else (I32_MISSING, I32_VEND)
+        rows = []
+        for r in query_rows:
+            c = by_row.get(r)
+            v = [] if c is None else list(c["fields"][nm].view(np.uint32 if is_float else np.int32))
+            v = [int(x) for x in v]
+            if not v:
+                v = [vend if is_gt else miss]
+            v += [vend] * (nps - len(v))
+            rows.append(v)
+        if is_gt:
+            rows = [encode_gt(v, gt_phased, produce_gt) for v in rows]
+            nps = len(rows[0])
+        flat = [x for v in rows for x in v]
+        if is_float:
+            out[nm] = (BT_FLOAT, nps, np.asarray(flat, dtype="<u4").tobytes(), enc_size(nps, BT_FLOAT))
+        else:
+            bt, desc, data = enc_vint(flat, nps)
+            out[nm] = (bt, nps, data, desc)
+    return out

@@ -1,0 +1,62 @@
+#!/usr/bin/env python3
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/bcf/<case>.bcf from the UNMODIFIED reference (oracle/_ref).
+
+For every case of tests/golden/manifest.json it runs the reference's own
+    gt_mpi_gather --produce-Broad-GVCF -O bu          (BroadCombinedGVCFOperator -> htslib, uncompressed BCF2)
+over the committed golden array and keeps the BCF bytes.  The FORMAT blocks of those records (GT and the allele-dependent
+fields: typed width, values per sample, bytes) pin the FORMAT collation + BCF typed encoding row of SURVEY 8f-1
+(variant_field_handler.cc:804-871, broad_combined_gvcf.cc:53-138,603-727, htslib vcf.c:1926-1972).
+
+Runs in THIS container only (needs /root/reference/tests for the VCF header template and the reference genome).
+Usage: python oracle/make_golden_bcf.py          (after bash oracle/build_ref.sh and oracle/make_golden.py)
+"""
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF_TESTS = os.environ.get("GDB_REFERENCE", "/root/reference") + "/tests"
+BIN = os.path.join(HERE, "_ref", "bin")
+GOLD = os.path.join(REPO, "tests", "golden")
+
+
+def main():
+    if not os.path.isdir(REF_TESTS):
+        sys.exit("reference tests not present; BCF fixtures can only be regenerated where /root/reference exists")
+    cases = json.load(open(os.path.join(GOLD, "manifest.json")))["cases"]
+    out_dir = os.path.join(GOLD, "bcf")
+    shutil.rmtree(out_dir, ignore_errors=True)
+    os.makedirs(out_dir)
+    tmp = tempfile.mkdtemp(prefix="gdbbcf")
+    for c in cases:
+        ws = os.path.join(tmp, "ws_" + c["id"])
+        shutil.copytree(os.path.join(GOLD, c["workspace"]), ws)
+        open(os.path.join(ws, c["array"], ".__consolidation_lock"), "wb").close()
+        q = {
+            "workspace": ws, "array_name": c["array"],
+            "vcf_header_filename": ["inputs/template_vcf_header.vcf"],
+            "query_row_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in c["query_row_ranges"]]}],
+            "reference_genome": "inputs/chr1_10MB.fasta.gz",
+            "attributes": c["attributes"], "segment_size": 10000,
+            "vid_mapping_file": os.path.join(GOLD, c["vid_mapping_file"]),
+            "callset_mapping_file": os.path.join(GOLD, c["callset_mapping_file"]),
+            "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in c["query_column_ranges"]]}],
+            "produce_GT_field": c["produce_GT_field"],
+            "produce_GT_with_min_PL_value_for_spanning_deletions": c["produce_GT_with_min_PL_value_for_spanning_deletions"],
+        }
+        qf = os.path.join(tmp, c["id"] + ".json")
+        json.dump(q, open(qf, "w"))
+        p = subprocess.run([BIN + "/gt_mpi_gather", "-j", qf, "--produce-Broad-GVCF", "-O", "bu"], capture_output=True, cwd=REF_TESTS)
+        if p.returncode != 0:
+            sys.exit("reference failed on %s: %s" % (c["id"], p.stderr.decode()[-1500:]))
+        open(os.path.join(out_dir, c["id"] + ".bcf"), "wb").write(p.stdout)
+        print("%-50s %6d bytes" % (c["id"], len(p.stdout)))
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,59 @@
+"""CPU: pins the FORMAT collation + BCF typed-encoding restatement (oracle/format_blocks.py) against the reference.
+
+tests/golden/bcf/<case>.bcf is the UNMODIFIED reference's own `gt_mpi_gather --produce-Broad-GVCF -O bu` output on the
+golden arrays (oracle/make_golden_bcf.py).  For every record the blocks of GT and of every allele-dependent FORMAT field
+(descriptor bytes and data bytes as htslib laid them into bcf1_t.indiv) must equal what the restatement derives from the
+reference's hot-path dump of the same query.
+"""
+import os
+
+import pytest
+
+from conftest import GOLDEN, golden_cases
+from oracle import bcf_reader, format_blocks, oracle
+from util import case_fields, case_query_rows, format_field_names
+
+CASES = golden_cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_format_blocks_match_reference_bcf(case):
+    _, samples, recs = bcf_reader.read_bcf(os.path.join(GOLDEN, "bcf", case["id"] + ".bcf"))
+    names, sites = oracle.parse_dump(open(os.path.join(GOLDEN, case["dump"]), "rb").read())
+    assert len(recs) == len(sites) == case["sites"]
+    fields, phased = case_fields(case)
+    elem = {f[0]: f[2] for f in fields}
+    fmt_names = format_field_names(case, names)
+    rows = [r for r in case_query_rows(case) if r < len(samples)]
+    assert len(rows) == len(samples)
+    n_blocks = 0
+    for rec, site in zip(recs, sites):
+        want = {k: v for k, v in rec["fmt"].items() if k in fmt_names}
+        got = format_blocks.site_blocks(site, fmt_names, rows, elem, phased, case["produce_GT_field"])
+        assert sorted(got) == sorted(want), (site["begin"], sorted(got), sorted(want))
+        for k, (bt, nps, data, hdr) in want.items():
+            g = got[k]
+            assert (g[0], g[1]) == (bt, nps), (site["begin"], k)
+            assert g[2] == data, (site["begin"], k, g[2].hex(), data.hex())
+            assert hdr.endswith(g[3]), (site["begin"], k)     # hdr = typed key + descriptor
+            n_blocks += 1
+    assert n_blocks > 0
+
+
+def test_enc_int1_and_size_known_answers():
+    # htslib vcf.h bcf_enc_int1 / bcf_enc_size thresholds
+    assert format_blocks.enc_int1(127) == bytes([0x11, 0x7F])
+    assert format_blocks.enc_int1(-120) == bytes([0x11, 0x88])
+    assert format_blocks.enc_int1(-121) == bytes([0x12, 0x87, 0xFF])
+    assert format_blocks.enc_int1(128) == bytes([0x12, 0x80, 0x00])
+    assert format_blocks.enc_int1(40000) == bytes([0x13, 0x40, 0x9C, 0x00, 0x00])
+    assert format_blocks.enc_size(3, 1) == bytes([0x31])
+    assert format_blocks.enc_size(55, 2) == bytes([0xF2, 0x11, 55])
+    bt, desc, data = format_blocks.enc_vint([0, 127, -126, format_blocks.I32_MISSING, format_blocks.I32_VEND, 5], 3)
+    assert (bt, desc, data) == (1, bytes([0x31]), bytes([0, 127, 0x82, 0x80, 0x81, 5]))
+    bt, desc, data = format_blocks.enc_vint([0, 128, 1, 2], 2)
+    assert bt == 2 and data == bytes([0, 0, 128, 0, 1, 0, 2, 0])
+    bt, desc, data = format_blocks.enc_vint([0, -127, 1, 2], 2)
+    assert bt == 2
+    bt, desc, data = format_blocks.enc_vint([0, 32768, 1, 2], 2)
+    assert bt == 3

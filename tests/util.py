@@ -29,3 +29,9 @@ def oracle_dump(case):
                                os.path.join(GOLDEN, case["vid_mapping_file"]), case["attributes"])
     return oracle.combine_query(cols, case["query_column_ranges"], query_rows=case_query_rows(case),
                                 produce_GT_with_min_PL=case["produce_GT_with_min_PL_value_for_spanning_deletions"])
+
+
+def format_field_names(case, dump_names):
+    """GT + the allele-dependent fields of the dump that are FORMAT fields of the VCF (vid vcf_field_class)."""
+    vid = oracle.load_vid_fields(os.path.join(GOLDEN, case["vid_mapping_file"]))
+    return [n for n in dump_names if n == "GT" or "FORMAT" in (vid.get(n, {}).get("classes") or [])]
