@@ -6,7 +6,9 @@ the GDBSYN-1 cohort named in BASELINE.json (config #4: 100 k samples x 10 M posi
 alleles per site).  One rank holds 1/8 of the columns (1 250 candidate sites = 1.25 M positions); 8 ranks = config #4.
   value : sites/s with the shard already resident in HBM and the output left in HBM (CUDA events on the engine's stream)
   e2e   : the same metric through the C ABI with HOST buffers: gdbgpu_array_from_columns (H2D of the fragment columns,
-          pinned) -> scan -> every batch copied back to pinned host memory (D2H) -> close
+          pinned) -> scan -> every batch copied back to pinned host memory (D2H) -> close.  The headline e2e asks for the
+          output a Broad-GVCF consumer takes (GDBGPU_SCAN_BCF_FORMAT: remap + FORMAT collation + BCF typed encoding on
+          the device, the typed blocks copied back); e2e_int32 is the same with the raw 32-bit remapped vectors copied back
   roofline : the remap kernel (k_remap), algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline : the UNMODIFIED reference (oracle/_ref/bin/gdb_ref_dump --mode hot: scan_and_operate + handle_deletions
           + GA4GHOperator::operate, no VCF serialisation) on all host cores, on a bounded sample of the same cohort.
@@ -166,7 +168,8 @@ def main():
     ap.add_argument("--samples", type=int, default=COHORT["n_samples"])
     ap.add_argument("--sites-per-gpu", type=int, default=SITES_PER_GPU)
     ap.add_argument("--batch-bytes", type=int, default=8 << 30)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-batch-bytes", type=int, default=2 << 30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -215,18 +218,19 @@ def main():
     ctx = capi.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
 
-    def one_pass(arr, flags):
+    def one_pass(arr, flags, batch_bytes=None):
         sc = capi.Scan(arr, q_lo, q_hi, flags=flags)
-        sites = out_bytes = live_words = 0
+        sites = out_bytes = live_words = fmt_bytes = 0
         while True:
-            b = sc.next_batch(0, args.batch_bytes, raw=True)
+            b = sc.next_batch(0, batch_bytes or args.batch_bytes, raw=True)
             if b.n_sites == 0:
                 break
             sites += b.n_sites
             out_bytes += b.out_bytes
+            fmt_bytes += b.fmt_total_bytes
             live_words += b.n_sites * b.n_query_rows
         sc.close()
-        return sites, out_bytes, live_words
+        return sites, out_bytes, live_words, fmt_bytes
 
     # ---------------- HBM-resident metric
     arr = gdbsyn.to_gpu_array(ctx, d)
@@ -244,7 +248,7 @@ def main():
     ev0.record(stream)
     sites = out_bytes = 0
     for _ in range(args.steps):
-        s, ob, _ = one_pass(arr, capi.SCAN_DEVICE_OUTPUT)
+        s, ob, _, _ = one_pass(arr, capi.SCAN_DEVICE_OUTPUT)
         sites += s
         out_bytes += ob
     ev1.record(stream)
@@ -288,7 +292,7 @@ def main():
                     step_gbs=((b_in_step + b_out_step) * args.steps / 1e9) / (ms * 1e-3))
 
     # ---------------- end to end through the C ABI with host buffers
-    e2e = None
+    e2e = e2e_int32 = None
     if not args.no_e2e:
         pinned = {}
 
@@ -302,27 +306,37 @@ def main():
         for k in ("ref", "alt", "gt", "pl", "ad"):
             dp[k] = (pin(d[k][0]), pin(d[k][1]))
 
-        def e2e_step():
+        def e2e_step(flags):
             a = gdbsyn.to_gpu_array(ctx, dp)
             i = a.info()
-            s, ob, lw = one_pass(a, 0)
+            s, ob, lw, fb = one_pass(a, flags, args.e2e_batch_bytes)
             a.close()
-            return s, i.staged_bytes, ob + lw * 4 + s * 24
+            # host output: BCF mode copies the typed blocks + the site table; int32 mode the vectors, their lengths and the live matrix
+            d2h_bytes = fb + s * 24 if flags & capi.SCAN_BCF_FORMAT else ob + lw * 4 + lw * 2 * 3 + s * 24
+            return s, i.staged_bytes, d2h_bytes
 
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        es = h2d = d2h = 0
-        for _ in range(args.e2e_steps):
-            s, hb, db = e2e_step()
-            es += s
-            h2d += hb
-            d2h += db
-        ctx.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = dict(value=sum_over_ranks(float(es)) / dt, unit="sites/s", h2d_bytes_per_step=int(h2d // args.e2e_steps),
-                   d2h_bytes_per_step=int(d2h // args.e2e_steps), steps=args.e2e_steps, ms_per_step=dt * 1e3 / args.e2e_steps,
-                   path="gdbgpu_array_from_columns(pinned host columns) -> gdbgpu_scan_next_batch(host output) -> close")
+        def e2e_run(flags, path):
+            for _ in range(2):
+                e2e_step(flags)
+            barrier()
+            t0 = time.perf_counter()
+            es = h2d = d2h = 0
+            for _ in range(args.e2e_steps):
+                s, hb, db = e2e_step(flags)
+                es += s
+                h2d += hb
+                d2h += db
+            ctx.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            return dict(value=sum_over_ranks(float(es)) / dt, unit="sites/s", h2d_bytes_per_step=int(h2d // args.e2e_steps),
+                        d2h_bytes_per_step=int(d2h // args.e2e_steps), steps=args.e2e_steps, ms_per_step=dt * 1e3 / args.e2e_steps,
+                        batch_bytes=args.e2e_batch_bytes, path=path)
+
+        e2e = e2e_run(capi.SCAN_BCF_FORMAT | capi.SCAN_PRODUCE_GT,
+                      "gdbgpu_array_from_columns(pinned host columns) -> gdbgpu_scan_next_batch(GDBGPU_SCAN_BCF_FORMAT, host output: "
+                      "remapped GT/AD/PL collated and BCF-typed on the device, blocks copied to pinned host memory) -> close")
+        e2e_int32 = e2e_run(0, "gdbgpu_array_from_columns(pinned host columns) -> gdbgpu_scan_next_batch(host output: 32-bit remapped "
+                               "vectors + lengths + live matrix copied to pinned host memory) -> close")
     ctx.close()
 
     base = None
@@ -332,7 +346,7 @@ def main():
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="sites/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
-                    data="synthetic", config=workload_config(args, world), clocks=sampler.summary(), e2e=e2e,
+                    data="synthetic", config=workload_config(args, world), clocks=sampler.summary(), e2e=e2e, e2e_int32=e2e_int32,
                     gpu_launches=int(launches), roofline=roofline, cpu_baseline=base,
                     sites_per_step_per_gpu=int(sites_per_step), cells_per_gpu=int(info.n_cells),
                     staged_bytes_per_gpu=int(info.staged_bytes), hbm_bytes_per_gpu=int(info.hbm_bytes))

@@ -15,6 +15,8 @@ OK, ERR_ARG, ERR_IO, ERR_CUDA, ERR_OVERLAP, ERR_LIMIT = 0, -1, -2, -3, -4, -5
 LEN_R, LEN_A, LEN_G = 0, 1, 2
 ELEM_INT32, ELEM_FLOAT32 = 0, 1
 SCAN_FULL, SCAN_NO_DELETIONS, SCAN_MIN_PL_GT, SCAN_WANT_LUT, SCAN_DEVICE_OUTPUT = 1, 2, 4, 8, 16
+SCAN_BCF_FORMAT, SCAN_PRODUCE_GT, SCAN_NO_PREFETCH = 32, 64, 128
+BT_SIZE = {1: 1, 2: 2, 3: 4, 5: 4}
 SITE_NONREF, SITE_REMAPPED, SITE_G_SUPPRESSED = 1, 2, 4
 CALL_REDUCED = 0x40000000
 KIND = {"R": LEN_R, "A": LEN_A, "G": LEN_G}
@@ -68,7 +70,9 @@ class Batch(C.Structure):
                 ("n_alleles", C.c_void_p), ("n_live", C.c_void_p),
                 ("allele_first", C.c_void_p), ("allele_pos", C.c_void_p), ("allele_bytes", C.c_void_p),
                 ("live", C.c_void_p), ("n_fields", C.c_int32), ("fields", FieldOut * 16),
-                ("lut_first", C.c_void_p), ("lut_len", C.c_void_p), ("lut_in2m", C.c_void_p), ("out_bytes", C.c_uint64)]
+                ("lut_first", C.c_void_p), ("lut_len", C.c_void_p), ("lut_in2m", C.c_void_p), ("out_bytes", C.c_uint64),
+                ("fmt_type", C.c_void_p), ("fmt_nps", C.c_void_p), ("fmt_offset", C.c_void_p), ("fmt_bytes", C.c_void_p),
+                ("fmt_total_bytes", C.c_uint64)]
 
 
 _lib = None
@@ -251,15 +255,23 @@ class BatchView:
         self.allele_pos = _view(b.allele_pos, np.uint32, 2 * tot).reshape(-1, 2)
         nbytes = int((self.allele_pos[:, 0] + self.allele_pos[:, 1]).max()) if tot else 0
         self.allele_bytes = _view(b.allele_bytes, np.uint8, nbytes)
-        self.live = _view(b.live, np.int32, ns * nq).reshape(ns, nq)
+        self.live = _view(b.live, np.int32, ns * nq).reshape(ns, nq) if b.live else None
         self.fields = []
         for o in range(n_out):
             f = b.fields[o]
             base = _view(f.base, np.uint64, ns + 1)
             stride = _view(f.stride, np.uint32, ns)
-            ln = _view(f.len, np.uint16, ns * nq).reshape(ns, nq)
-            data = _view(f.data, np.uint32, int(base[ns]) if ns else 0)
+            ln = _view(f.len, np.uint16, ns * nq).reshape(ns, nq) if f.len else None
+            data = _view(f.data, np.uint32, int(base[ns]) if ns else 0) if f.data else None
             self.fields.append(dict(base=base, stride=stride, len=ln, data=data))
+        self.fmt_total_bytes = b.fmt_total_bytes
+        if b.fmt_type:
+            self.fmt_type = _view(b.fmt_type, np.uint8, n_out * ns).reshape(n_out, ns)
+            self.fmt_nps = _view(b.fmt_nps, np.uint32, n_out * ns).reshape(n_out, ns)
+            self.fmt_offset = _view(b.fmt_offset, np.uint64, n_out * ns).reshape(n_out, ns)
+            self.fmt_bytes = _view(b.fmt_bytes, np.uint8, b.fmt_total_bytes)
+        else:
+            self.fmt_type = None
         self.lut_first = _view(b.lut_first, np.uint32, ns * nq).reshape(ns, nq) if b.lut_first else None
         self.lut_len = _view(b.lut_len, np.uint16, ns * nq).reshape(ns, nq) if b.lut_len else None
         self._lut_ptr = b.lut_in2m
@@ -270,6 +282,14 @@ class BatchView:
             off, ln = self.allele_pos[int(self.allele_first[s]) + m]
             out.append(bytes(self.allele_bytes[off:off + ln]))
         return out
+
+    def fmt_block(self, o, s):
+        """(BCF type, values per sample, block bytes) of output field o at site s, or None when it is not emitted"""
+        t = int(self.fmt_type[o, s])
+        if t == 0:
+            return None
+        nps, off = int(self.fmt_nps[o, s]), int(self.fmt_offset[o, s])
+        return t, nps, bytes(self.fmt_bytes[off:off + self.nq * nps * BT_SIZE[t]])
 
     def lut(self, s, q):
         first = int(self.lut_first[s, q])

@@ -14,7 +14,7 @@
 #include <string>
 #include <vector>
 
-#include "gdb_kernels2.cuh"
+#include "gdb_kernels3.cuh"
 #include "gdb_tiledb.h"
 
 using namespace gdb;
@@ -24,7 +24,8 @@ struct BatchBuffers;
 struct ProfRec { const char* name; cudaEvent_t a, b; };
 struct gdbgpu_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;        // kernels and the small control copies
+  cudaStream_t copy_stream = nullptr;   // device -> host copies of finished batches (overlap the next batch's kernels)
   std::string err;
   uint64_t launches = 0;
   // optional per-kernel device timing (CUDA events on the launching stream), see gdbgpu_ctx_set_profiling
@@ -329,6 +330,16 @@ struct BatchBuffers {
   PinBuf<int64_t> p_site_begin, p_site_end; PinBuf<int32_t> p_live; PinBuf<uint32_t> p_allele_pos, p_lut_first, p_out_data[MAX_FIELDS + 1]; PinBuf<uint8_t> p_allele_bytes;
   PinBuf<uint16_t> p_out_len[MAX_FIELDS + 1], p_lut_len; PinBuf<int16_t> p_lut_in2m;
   DevBuf<uint32_t> fast_sites, slow_sites, tile_sites;
+  // K6 (GDBGPU_SCAN_BCF_FORMAT): per (field, site) plan + the packed FORMAT blocks
+  DevBuf<int32_t> fmt_mm; DevBuf<uint8_t> fmt_type, fmt_bytes; DevBuf<uint32_t> fmt_nps; DevBuf<uint64_t> fmt_off;
+  std::vector<int32_t> h_fmt_mm; std::vector<uint8_t> h_fmt_type; std::vector<uint32_t> h_fmt_nps; std::vector<uint64_t> h_fmt_off;
+  PinBuf<uint8_t> p_fmt_bytes;
+  // state of the batch these buffers hold
+  bool valid = false; uint64_t first = 0; uint32_t keep = 0, arg_sites = 0; uint64_t arg_bytes = 0, alg_bytes = 0, fmt_total = 0;
+  uint32_t hc[4] = {0, 0, 0, 0};
+  PinBuf<uint32_t> p_tail;            // err[4] + cursors[4] as they stood when the batch's last kernel had run
+  cudaEvent_t ev_compute = nullptr, ev_done = nullptr;
+  ~BatchBuffers() { if (ev_compute) cudaEventDestroy(ev_compute); if (ev_done) cudaEventDestroy(ev_done); }
 };
 
 // ------------------------------------------------------------------------------------------------ scan
@@ -340,7 +351,8 @@ struct gdbgpu_scan {
   std::vector<int64_t> h_rows;
   DevBuf<int32_t> qrow_of_row, init_cell, dlive, ddel, live_excl, del_excl; DevBuf<int64_t> row_of_qrow, init_effend, bp, site_begin, site_end;
   DevBuf<unsigned long long> bitmap; DevBuf<uint32_t> word_rank, bp_cell0, err, del_cells, del_words; DevBuf<uint64_t> site_start; DevBuf<DelRec> del_recs;
-  std::unique_ptr<BatchBuffers> bb;   // borrowed from the context's pool for the lifetime of the scan
+  std::unique_ptr<BatchBuffers> slot[2];   // borrowed from the context's pool for the lifetime of the scan; [cur] = batch being handed out, the other = prefetched
+  int cur = 0; bool bcf_format = false, prefetch = true; int produce_gt = 0;
   uint32_t cap_allele_recs = 0, cap_allele_bytes = 0, cap_lut = 0;
   uint64_t avg_site_bytes = 0;
   int n_out = 0;
@@ -370,6 +382,9 @@ void scan_prepare(gdbgpu_scan* s) {
   S.want_lut = (p.flags & GDBGPU_SCAN_WANT_LUT) ? 1 : 0;
   S.max_alt = p.max_diploid_alt_alleles ? p.max_diploid_alt_alleles : 50u;
   s->device_output = (p.flags & GDBGPU_SCAN_DEVICE_OUTPUT) != 0;
+  s->bcf_format = (p.flags & GDBGPU_SCAN_BCF_FORMAT) != 0;
+  s->produce_gt = (p.flags & GDBGPU_SCAN_PRODUCE_GT) ? 1 : 0;
+  s->prefetch = !(p.flags & GDBGPU_SCAN_NO_PREFETCH);
   // queried rows: sorted, unique, inside the array (variant_query_config.cc:60-117)
   if (p.query_rows) {
     s->h_rows.assign(p.query_rows, p.query_rows + p.n_query_rows);
@@ -498,14 +513,14 @@ uint32_t stride_of(const gdbgpu_array* a, const SiteRec& r, int o) {
   return st;
 }
 
-int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_batch* out) {
+// Runs every kernel of the batch starting at site `first` into `bb` and queues the device -> host copies of its results
+// on the copy stream.  Nothing here waits for those copies: publish_batch does.
+void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32_t max_sites, uint64_t max_bytes) {
   gdbgpu_array* a = s->arr; gdbgpu_ctx* ctx = s->ctx; ScanDev& S = s->S;
-  BatchBuffers& bb = *s->bb;
-  memset(out, 0, sizeof(*out));
-  out->first_site = s->cursor; out->n_query_rows = S.nq; out->n_fields = s->n_out;
-  if (s->cursor >= S.n_sites) return GDBGPU_OK;
+  bb.valid = false; bb.first = first_site; bb.arg_sites = max_sites; bb.arg_bytes = max_bytes; bb.keep = 0; bb.fmt_total = 0;
+  if (!bb.ev_compute) { CK(cudaEventCreateWithFlags(&bb.ev_compute, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&bb.ev_done, cudaEventDisableTiming)); }
   if (max_bytes == 0) max_bytes = 1ull << 30;
-  uint64_t remaining = S.n_sites - s->cursor;
+  uint64_t remaining = S.n_sites - first_site;
   // sites whose live matrix fits a fixed budget, and (by the running average) whose output fits max_bytes
   uint64_t by_live = std::max<uint64_t>(1, (256ull << 20) / std::max<uint64_t>(1, S.nq * 4));
   uint64_t guess = s->avg_site_bytes ? std::max<uint64_t>(1, max_bytes / s->avg_site_bytes) : 64;
@@ -519,13 +534,14 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
     bb.allele_pos.ensure(2ull * s->cap_allele_recs); bb.allele_hash.ensure(s->cap_allele_recs); bb.allele_bytes.ensure(s->cap_allele_bytes);
     CK(cudaMemsetAsync(bb.cursors.p, 0, 16, ctx->stream));
     BatchDev B{};
-    B.first_site = s->cursor; B.n_sites = nb; B.live = bb.live.p; B.sites = bb.sites.p; B.agg = bb.agg.p; B.nt = bb.nt.p; B.cursors = bb.cursors.p;
+    B.first_site = first_site; B.n_sites = nb; B.live = bb.live.p; B.sites = bb.sites.p; B.agg = bb.agg.p; B.nt = bb.nt.p; B.cursors = bb.cursors.p;
     B.allele_pos = bb.allele_pos.p; B.allele_hash = bb.allele_hash.p; B.cap_allele_recs = s->cap_allele_recs; B.allele_bytes = bb.allele_bytes.p; B.cap_allele_bytes = s->cap_allele_bytes;
-    LAUNCH(ctx, k_live_walk, dim3(blocks_for(S.nq, 256), (nb + WALK_CHUNK - 1) / WALK_CHUNK), 256, a->dev, S, s->cursor, nb, bb.live.p);
+    LAUNCH(ctx, k_live_walk, dim3(blocks_for(S.nq, 256), (nb + WALK_CHUNK - 1) / WALK_CHUNK), 256, a->dev, S, first_site, nb, bb.live.p);
     LAUNCH(ctx, k_site_scan, dim3(nb, blocks_for(S.nq, SSCAN_ROWS)), SSCAN_THREADS, a->dev, S, B);
     LAUNCH(ctx, k_union, nb, UNION_THREADS, a->dev, S, B);
     bb.h_sites.resize(nb);
     CK(cudaMemcpyAsync(bb.h_sites.data(), bb.sites.p, (size_t)nb * sizeof(SiteRec), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(bb.hc, bb.cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream));   // allele pools are final after k_union
     bool ovf = false;
     check_scan_errors(s, ovf);
     if (ovf) { s->cap_allele_recs *= 4; s->cap_allele_bytes *= 4; continue; }
@@ -652,55 +668,160 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
       uint32_t tiles = (uint32_t)((S.nq + REMAP_ROWS - 1) / REMAP_ROWS);
       LAUNCH(ctx, k_remap_generic, (unsigned)(slow.size() * tiles), REMAP_THREADS, a->dev, S, B, O, bb.slow_sites.p);
     }
-    check_scan_errors(s, ovf);
-    if (ovf) throw CudaError("internal: LUT pool overflow");
-    // ---- publish
+    // ---- K6: FORMAT collation + BCF typed encoding
+    if (s->bcf_format) {
+      const uint64_t n_plan = (uint64_t)n_out * keep;
+      bb.fmt_mm.ensure(2 * n_plan); bb.fmt_type.ensure(n_plan); bb.fmt_nps.ensure(n_plan); bb.fmt_off.ensure(n_plan);
+      bb.h_fmt_mm.resize(2 * n_plan); bb.h_fmt_type.assign(n_plan, 0); bb.h_fmt_nps.assign(n_plan, 0); bb.h_fmt_off.assign(n_plan, 0);
+      for (uint64_t i = 0; i < n_plan; ++i) { bb.h_fmt_mm[2 * i] = INT32_MAX; bb.h_fmt_mm[2 * i + 1] = INT32_MIN + 1; }
+      CK(cudaMemcpyAsync(bb.fmt_mm.p, bb.h_fmt_mm.data(), 2 * n_plan * 4, cudaMemcpyHostToDevice, ctx->stream));
+      uint64_t max_words = 1;
+      for (int o = 0; o < n_out; ++o) for (uint32_t i = 0; i < keep; ++i) max_words = std::max<uint64_t>(max_words, (uint64_t)bb.h_stride[o][i] * S.nq);
+      const unsigned chunks = (unsigned)std::min<uint64_t>(64, std::max<uint64_t>(1, max_words / (FMT_THREADS * 16)));
+      LAUNCH(ctx, k_fmt_range, dim3(chunks, keep), FMT_THREADS, a->dev, O, keep, (uint32_t)S.nq, s->produce_gt, bb.fmt_mm.p);
+      CK(cudaMemcpyAsync(bb.h_fmt_mm.data(), bb.fmt_mm.p, 2 * n_plan * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      uint64_t off = 0;
+      for (uint32_t i = 0; i < keep; ++i) for (int o = 0; o < n_out; ++o) {   // the blocks of one site are neighbours
+        const uint64_t pi = (uint64_t)o * keep + i;
+        const bool is_gt = a->has_gt && o == 0;
+        const uint32_t need = stride_needed(a, bb.h_sites[i], o);
+        if (need == 0) continue;
+        const uint32_t nps = (is_gt && a->gt_phased) ? (need + 1u) / 2u : need;
+        const int64_t lo = bb.h_fmt_mm[2 * pi], hi = bb.h_fmt_mm[2 * pi + 1];
+        uint8_t type;
+        if (!is_gt && a->fm[o - (a->has_gt ? 1 : 0)].elem) type = BT_FLOAT;
+        else if ((uint64_t)nps * S.nq == 1) {   // bcf_enc_vint hands a single value to bcf_enc_int1 (vcf.c:1931, vcf.h bcf_enc_int1)
+          if (lo > hi) type = BT_INT8;          // the value is missing / vector_end
+          else type = (lo >= -120 && hi <= 127) ? BT_INT8 : ((lo >= -32760 && hi <= 32767) ? BT_INT16 : BT_INT32);
+        } else type = (hi <= 127 && lo > -127) ? BT_INT8 : ((hi <= 32767 && lo > -32767) ? BT_INT16 : BT_INT32);
+        const uint64_t size = (uint64_t)nps * S.nq * (type == BT_INT8 ? 1u : (type == BT_INT16 ? 2u : 4u));
+        bb.h_fmt_type[pi] = type; bb.h_fmt_nps[pi] = nps; bb.h_fmt_off[pi] = off;
+        off += (size + 15u) & ~15ull;
+      }
+      bb.fmt_total = off;
+      bb.fmt_bytes.ensure(std::max<uint64_t>(off, 16));
+      CK(cudaMemcpyAsync(bb.fmt_type.p, bb.h_fmt_type.data(), n_plan, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(bb.fmt_nps.p, bb.h_fmt_nps.data(), n_plan * 4, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(bb.fmt_off.p, bb.h_fmt_off.data(), n_plan * 8, cudaMemcpyHostToDevice, ctx->stream));
+      const FmtPlanDev P{bb.fmt_type.p, bb.fmt_nps.p, bb.fmt_off.p, bb.fmt_bytes.p};
+      LAUNCH(ctx, k_fmt_pack, dim3(chunks, keep), FMT_THREADS, a->dev, O, P, keep, (uint32_t)S.nq, s->produce_gt);
+    }
+    // ---- results: site metadata (host mirrors), then the copies of everything the caller asked for
     bb.h_site_flags.resize(keep); bb.h_n_alleles.resize(keep); bb.h_n_live.resize(keep); bb.h_allele_first.resize(keep);
     for (uint32_t i = 0; i < keep; ++i) { const SiteRec& r = bb.h_sites[i]; bb.h_site_flags[i] = (uint8_t)r.flags; bb.h_n_alleles[i] = r.n_alleles; bb.h_n_live[i] = r.n_live; bb.h_allele_first[i] = r.allele_first; }
-    uint32_t hc[4];
-    CK(cudaMemcpyAsync(hc, bb.cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
-    out->n_sites = keep; out->out_bytes = alg_bytes;
+    bb.keep = keep; bb.alg_bytes = alg_bytes;
+    bb.p_tail.ensure(8);
+    if (S.want_lut) {   // the LUT copy is sized by a cursor only the remap kernels advance
+      CK(cudaMemcpyAsync(bb.hc, bb.cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+    }
     if (s->device_output) {
       bb.d_site_flags.ensure(keep); bb.d_n_alleles.ensure(keep); bb.d_n_live.ensure(keep); bb.d_allele_first.ensure(keep);
       CK(cudaMemcpyAsync(bb.d_site_flags.p, bb.h_site_flags.data(), keep, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaMemcpyAsync(bb.d_n_alleles.p, bb.h_n_alleles.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaMemcpyAsync(bb.d_n_live.p, bb.h_n_live.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaMemcpyAsync(bb.d_allele_first.p, bb.h_allele_first.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
-      out->site_begin = s->site_begin.p + s->cursor; out->site_end = s->site_end.p + s->cursor;
-      out->site_flags = bb.d_site_flags.p; out->n_alleles = bb.d_n_alleles.p; out->n_live = bb.d_n_live.p; out->allele_first = bb.d_allele_first.p;
-      out->allele_pos = bb.allele_pos.p; out->allele_bytes = bb.allele_bytes.p; out->live = bb.live.p;
-      for (int o = 0; o < n_out; ++o) out->fields[o] = gdbgpu_field_out{bb.out_data[o].p, bb.out_base[o].p, bb.out_stride[o].p, bb.out_len[o].p};
-      if (S.want_lut) { out->lut_first = bb.lut_first.p; out->lut_len = bb.lut_len.p; out->lut_in2m = bb.lut_in2m.p; }
-      CK(cudaStreamSynchronize(ctx->stream));
-    } else {
-      bb.p_site_begin.ensure(keep); bb.p_site_end.ensure(keep); bb.p_live.ensure((uint64_t)keep * S.nq);
-      bb.p_allele_pos.ensure(2ull * std::max<uint32_t>(hc[0], 1)); bb.p_allele_bytes.ensure(std::max<uint32_t>(hc[1], 1));
-      CK(cudaMemcpyAsync(bb.p_site_begin.p, s->site_begin.p + s->cursor, (size_t)keep * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaMemcpyAsync(bb.p_site_end.p, s->site_end.p + s->cursor, (size_t)keep * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaMemcpyAsync(bb.p_live.p, bb.live.p, (size_t)keep * S.nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaMemcpyAsync(bb.p_allele_pos.p, bb.allele_pos.p, (size_t)hc[0] * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaMemcpyAsync(bb.p_allele_bytes.p, bb.allele_bytes.p, hc[1], cudaMemcpyDeviceToHost, ctx->stream));
-      for (int o = 0; o < n_out; ++o) {
-        bb.p_out_data[o].ensure(std::max<uint64_t>(bb.h_base[o][keep], 1)); bb.p_out_len[o].ensure((uint64_t)keep * S.nq);
-        if (bb.h_base[o][keep]) CK(cudaMemcpyAsync(bb.p_out_data[o].p, bb.out_data[o].p, bb.h_base[o][keep] * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(bb.p_out_len[o].p, bb.out_len[o].p, (size_t)keep * S.nq * 2, cudaMemcpyDeviceToHost, ctx->stream));
-        out->fields[o] = gdbgpu_field_out{bb.p_out_data[o].p, bb.h_base[o].data(), bb.h_stride[o].data(), bb.p_out_len[o].p};
-      }
-      if (S.want_lut) {
-        bb.p_lut_first.ensure((uint64_t)keep * S.nq); bb.p_lut_len.ensure((uint64_t)keep * S.nq); bb.p_lut_in2m.ensure(std::max<uint32_t>(hc[2], 1));
-        CK(cudaMemcpyAsync(bb.p_lut_first.p, bb.lut_first.p, (size_t)keep * S.nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(bb.p_lut_len.p, bb.lut_len.p, (size_t)keep * S.nq * 2, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(bb.p_lut_in2m.p, bb.lut_in2m.p, (size_t)hc[2] * 2, cudaMemcpyDeviceToHost, ctx->stream));
-        out->lut_first = bb.p_lut_first.p; out->lut_len = bb.p_lut_len.p; out->lut_in2m = bb.p_lut_in2m.p;
-      }
-      CK(cudaStreamSynchronize(ctx->stream));
-      out->site_begin = bb.p_site_begin.p; out->site_end = bb.p_site_end.p;
-      out->site_flags = bb.h_site_flags.data(); out->n_alleles = bb.h_n_alleles.data(); out->n_live = bb.h_n_live.data(); out->allele_first = bb.h_allele_first.data();
-      out->allele_pos = bb.p_allele_pos.p; out->allele_bytes = bb.p_allele_bytes.p; out->live = bb.p_live.p;
     }
-    s->cursor += keep;
-    return GDBGPU_OK;
+    CK(cudaMemcpyAsync(bb.p_tail.p, s->err.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(bb.p_tail.p + 4, bb.cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(bb.ev_compute, ctx->stream));
+    if (!s->device_output) {
+      cudaStream_t cs = ctx->copy_stream;
+      CK(cudaStreamWaitEvent(cs, bb.ev_compute, 0));
+      bb.p_site_begin.ensure(keep); bb.p_site_end.ensure(keep);
+      bb.p_allele_pos.ensure(2ull * std::max<uint32_t>(bb.hc[0], 1)); bb.p_allele_bytes.ensure(std::max<uint32_t>(bb.hc[1], 1));
+      CK(cudaMemcpyAsync(bb.p_site_begin.p, s->site_begin.p + first_site, (size_t)keep * 8, cudaMemcpyDeviceToHost, cs));
+      CK(cudaMemcpyAsync(bb.p_site_end.p, s->site_end.p + first_site, (size_t)keep * 8, cudaMemcpyDeviceToHost, cs));
+      CK(cudaMemcpyAsync(bb.p_allele_pos.p, bb.allele_pos.p, (size_t)bb.hc[0] * 8, cudaMemcpyDeviceToHost, cs));
+      CK(cudaMemcpyAsync(bb.p_allele_bytes.p, bb.allele_bytes.p, bb.hc[1], cudaMemcpyDeviceToHost, cs));
+      if (s->bcf_format) {
+        bb.p_fmt_bytes.ensure(std::max<uint64_t>(bb.fmt_total, 16));
+        if (bb.fmt_total) CK(cudaMemcpyAsync(bb.p_fmt_bytes.p, bb.fmt_bytes.p, bb.fmt_total, cudaMemcpyDeviceToHost, cs));
+      } else {
+        bb.p_live.ensure((uint64_t)keep * S.nq);
+        CK(cudaMemcpyAsync(bb.p_live.p, bb.live.p, (size_t)keep * S.nq * 4, cudaMemcpyDeviceToHost, cs));
+        for (int o = 0; o < n_out; ++o) {
+          bb.p_out_data[o].ensure(std::max<uint64_t>(bb.h_base[o][keep], 1)); bb.p_out_len[o].ensure((uint64_t)keep * S.nq);
+          if (bb.h_base[o][keep]) CK(cudaMemcpyAsync(bb.p_out_data[o].p, bb.out_data[o].p, bb.h_base[o][keep] * 4, cudaMemcpyDeviceToHost, cs));
+          CK(cudaMemcpyAsync(bb.p_out_len[o].p, bb.out_len[o].p, (size_t)keep * S.nq * 2, cudaMemcpyDeviceToHost, cs));
+        }
+        if (S.want_lut) {
+          bb.p_lut_first.ensure((uint64_t)keep * S.nq); bb.p_lut_len.ensure((uint64_t)keep * S.nq); bb.p_lut_in2m.ensure(std::max<uint32_t>(bb.hc[2], 1));
+          CK(cudaMemcpyAsync(bb.p_lut_first.p, bb.lut_first.p, (size_t)keep * S.nq * 4, cudaMemcpyDeviceToHost, cs));
+          CK(cudaMemcpyAsync(bb.p_lut_len.p, bb.lut_len.p, (size_t)keep * S.nq * 2, cudaMemcpyDeviceToHost, cs));
+          CK(cudaMemcpyAsync(bb.p_lut_in2m.p, bb.lut_in2m.p, (size_t)bb.hc[2] * 2, cudaMemcpyDeviceToHost, cs));
+        }
+      }
+      CK(cudaEventRecord(bb.ev_done, cs));
+    } else CK(cudaEventRecord(bb.ev_done, ctx->stream));
+    bb.valid = true;
+    return;
   }
+}
+
+// Waits for the batch in `bb` and fills the caller's view of it.
+void publish_batch(gdbgpu_scan* s, BatchBuffers& bb, gdbgpu_batch* out) {
+  gdbgpu_array* a = s->arr; ScanDev& S = s->S;
+  CK(cudaEventSynchronize(bb.ev_done));
+  const uint32_t* e = bb.p_tail.p;
+  if (e[0]) throw OverlapError("Unhandled overlapping variants (a call that is neither a deletion nor a reference block is overlapped by a later call of the same sample)");
+  if (e[1] == 3) throw LimitError("ploidy above 8 needs the general-ploidy genotype enumeration, which keeps at most 8 slots");
+  if (e[1]) throw LimitError("engine limit exceeded in the remap kernels");
+  if (e[2]) throw CudaError("internal: LUT pool overflow");
+  const uint32_t keep = bb.keep; const int n_out = s->n_out;
+  out->n_sites = keep; out->out_bytes = bb.alg_bytes;
+  out->site_flags = bb.h_site_flags.data(); out->n_alleles = bb.h_n_alleles.data(); out->n_live = bb.h_n_live.data(); out->allele_first = bb.h_allele_first.data();
+  if (s->device_output) {
+    out->site_begin = s->site_begin.p + bb.first; out->site_end = s->site_end.p + bb.first;
+    out->site_flags = bb.d_site_flags.p; out->n_alleles = bb.d_n_alleles.p; out->n_live = bb.d_n_live.p; out->allele_first = bb.d_allele_first.p;
+    out->allele_pos = bb.allele_pos.p; out->allele_bytes = bb.allele_bytes.p; out->live = bb.live.p;
+    for (int o = 0; o < n_out; ++o) out->fields[o] = gdbgpu_field_out{bb.out_data[o].p, bb.out_base[o].p, bb.out_stride[o].p, bb.out_len[o].p};
+    if (S.want_lut) { out->lut_first = bb.lut_first.p; out->lut_len = bb.lut_len.p; out->lut_in2m = bb.lut_in2m.p; }
+    if (s->bcf_format) { out->fmt_bytes = bb.fmt_bytes.p; out->fmt_type = bb.fmt_type.p; out->fmt_nps = bb.fmt_nps.p; out->fmt_offset = bb.fmt_off.p; }
+  } else {
+    out->site_begin = bb.p_site_begin.p; out->site_end = bb.p_site_end.p;
+    out->allele_pos = bb.p_allele_pos.p; out->allele_bytes = bb.p_allele_bytes.p;
+    if (s->bcf_format) {
+      out->fmt_bytes = bb.p_fmt_bytes.p; out->fmt_type = bb.h_fmt_type.data(); out->fmt_nps = bb.h_fmt_nps.data(); out->fmt_offset = bb.h_fmt_off.data();
+      for (int o = 0; o < n_out; ++o) out->fields[o] = gdbgpu_field_out{nullptr, bb.h_base[o].data(), bb.h_stride[o].data(), nullptr};
+    } else {
+      out->live = bb.p_live.p;
+      for (int o = 0; o < n_out; ++o) out->fields[o] = gdbgpu_field_out{bb.p_out_data[o].p, bb.h_base[o].data(), bb.h_stride[o].data(), bb.p_out_len[o].p};
+      if (S.want_lut) { out->lut_first = bb.p_lut_first.p; out->lut_len = bb.p_lut_len.p; out->lut_in2m = bb.p_lut_in2m.p; }
+    }
+  }
+  out->fmt_total_bytes = bb.fmt_total;
+  (void)a;
+}
+
+BatchBuffers& scan_slot(gdbgpu_scan* s, int i) {
+  if (!s->slot[i]) {
+    gdbgpu_ctx* ctx = s->ctx;
+    if (!ctx->bb_pool.empty()) { s->slot[i].reset(ctx->bb_pool.back()); ctx->bb_pool.pop_back(); } else s->slot[i].reset(new BatchBuffers());
+    s->slot[i]->valid = false;
+  }
+  return *s->slot[i];
+}
+
+// Hands out the batch at the cursor and, unless told otherwise, starts the next one before waiting for this one's copies:
+// the device -> host transfer of batch n runs while the kernels of batch n+1 do.
+int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_batch* out) {
+  ScanDev& S = s->S;
+  memset(out, 0, sizeof(*out));
+  out->first_site = s->cursor; out->n_query_rows = S.nq; out->n_fields = s->n_out;
+  if (s->cursor >= S.n_sites) return GDBGPU_OK;
+  auto holds = [&](const BatchBuffers& b, uint64_t first) { return b.valid && b.first == first && b.arg_sites == max_sites && b.arg_bytes == max_bytes; };
+  BatchBuffers& c = scan_slot(s, s->cur);
+  if (!holds(c, s->cursor)) compute_batch(s, c, s->cursor, max_sites, max_bytes);
+  const uint64_t next_first = c.first + c.keep;
+  if (s->prefetch && next_first < S.n_sites) {
+    BatchBuffers& n = scan_slot(s, s->cur ^ 1);
+    if (!holds(n, next_first)) compute_batch(s, n, next_first, max_sites, max_bytes);
+  }
+  publish_batch(s, c, out);
+  c.valid = false;
+  s->cursor = next_first; s->cur ^= 1;
+  return GDBGPU_OK;
 }
 
 template <class F>
@@ -730,6 +851,7 @@ int gdbgpu_ctx_create(int device, gdbgpu_ctx** out) {
   gdbgpu_ctx* c = new gdbgpu_ctx();
   c->device = device;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GDBGPU_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return GDBGPU_ERR_CUDA; }
   {   // diploid genotype tables: g -> class of a trivial call's word, g -> (j, k)
     std::vector<uint32_t> cls(256, 0); std::vector<uint16_t> jk(1024, 0);
     uint32_t g = 0;
@@ -753,6 +875,7 @@ void gdbgpu_ctx_destroy(gdbgpu_ctx* ctx) {
   for (auto* b : ctx->bb_pool) delete b;
   if (ctx->d_cls_tab) cudaFree(ctx->d_cls_tab);
   if (ctx->d_jk_tab) cudaFree(ctx->d_jk_tab);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -767,7 +890,10 @@ int gdbgpu_ctx_kernel_stats(gdbgpu_ctx* ctx, const char* kernel_name, double* to
   if (launches) *launches = n;
   return GDBGPU_OK;
 }
-int gdbgpu_ctx_synchronize(gdbgpu_ctx* ctx) { if (!ctx) return GDBGPU_ERR_ARG; return cudaStreamSynchronize(ctx->stream) == cudaSuccess ? GDBGPU_OK : GDBGPU_ERR_CUDA; }
+int gdbgpu_ctx_synchronize(gdbgpu_ctx* ctx) {
+  if (!ctx) return GDBGPU_ERR_ARG;
+  return (cudaStreamSynchronize(ctx->stream) == cudaSuccess && cudaStreamSynchronize(ctx->copy_stream) == cudaSuccess) ? GDBGPU_OK : GDBGPU_ERR_CUDA;
+}
 const char* gdbgpu_last_error(const gdbgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
 void* gdbgpu_ctx_stream(gdbgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t gdbgpu_ctx_launch_count(const gdbgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -877,7 +1003,6 @@ int gdbgpu_scan_begin(gdbgpu_array* arr, const gdbgpu_scan_params* params, gdbgp
   *out = nullptr;
   std::unique_ptr<gdbgpu_scan> s(new gdbgpu_scan());
   s->arr = arr; s->ctx = arr->ctx; s->params = *params;
-  if (!arr->ctx->bb_pool.empty()) { s->bb.reset(arr->ctx->bb_pool.back()); arr->ctx->bb_pool.pop_back(); } else s->bb.reset(new BatchBuffers());
   int rc = guarded(arr->ctx, [&] { CK(cudaSetDevice(arr->ctx->device)); scan_prepare(s.get()); });
   if (rc == GDBGPU_OK) *out = s.release();
   return rc;
@@ -900,7 +1025,8 @@ void gdbgpu_scan_end(gdbgpu_scan* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
-  if (s->bb) s->ctx->bb_pool.push_back(s->bb.release());
+  cudaStreamSynchronize(s->ctx->copy_stream);
+  for (auto& b : s->slot) if (b) { b->valid = false; s->ctx->bb_pool.push_back(b.release()); }
   delete s;
 }
 

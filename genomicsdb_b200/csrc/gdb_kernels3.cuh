@@ -1,0 +1,150 @@
+// K6: FORMAT collation + BCF typed encoding of the remapped fields (first slice).
+//
+// What the reference does per site after the remap (paths relative to GenomicsDB v0.10.2):
+//   VariantFieldHandler<T>::collect_and_extend_fields   src/main/cpp/src/genomicsdb/variant_field_handler.cc:804-871
+//       every query row gets `nps` values (nps = longest valid vector at the site): its vector, or [missing]
+//       ([vector_end] for GT) when the row has no valid field, padded with vector_end
+//   encode_GT_vector                                    src/main/cpp/src/query_operations/broad_combined_gvcf.cc:53-138,646-658
+//   bcf_update_format -> bcf_enc_vint                   dependencies/htslib/vcf.c:3607-3700,1926-1972
+//       one scan for min / max (missing and vector_end excluded) picks int8 / int16 / int32 for the whole block
+// K5's output already is the collated layout (dense, sample-major, vector_end padded) in 32-bit words, so K6 is
+//   k_fmt_range   min / max per (site, field) over the words the block will hold          (HBM read, 4 B / word)
+//   (host)        type + values-per-sample + 16-byte aligned byte offset of every block
+//   k_fmt_pack    narrows the words into the block bytes htslib would have produced        (HBM read 4 B, write 1-4 B / word)
+// The blocks are what bcf1_t.indiv holds after the field's typed key and size descriptor; the host emits those few
+// header bytes (gdb_host_api).  Integer / byte work, bound by HBM bandwidth.
+#pragma once
+#include "gdb_kernels2.cuh"
+
+namespace gdb {
+
+enum : uint8_t { BT_NONE = 0, BT_INT8 = 1, BT_INT16 = 2, BT_INT32 = 3, BT_FLOAT = 5 };
+constexpr int FMT_THREADS = 256;
+
+struct FmtPlanDev {          // [o * n_sites + site]
+  const uint8_t* type;       // BT_*; BT_NONE: the field is not emitted at this site
+  const uint32_t* nps;       // values per sample
+  const uint64_t* off;       // byte offset of the block in `bytes`, multiple of 16
+  uint8_t* bytes;
+};
+
+// allele value -> BCF genotype int (encode_GT_element); missing / vector_end pass through
+__device__ inline uint32_t gt_encode(uint32_t v, uint32_t phased, int produce_gt) {
+  if (v == BCF_INT_MISSING || v == BCF_INT_VEND) return v;
+  return produce_gt ? (((v + 1u) << 1) | phased) : phased;
+}
+// element i (< nps) of query row q's GT vector as the FORMAT block holds it
+__device__ inline uint32_t gt_element(const uint32_t* __restrict__ row, uint32_t i, int layout_phased, int produce_gt) {
+  if (!layout_phased || i == 0) return gt_encode(row[i], 0u, produce_gt);
+  return gt_encode(row[2 * i], (int32_t)row[2 * i - 1] > 0 ? 1u : 0u, produce_gt);
+}
+
+// min / max of the values of every (site, field) block; mm[(o * n_sites + site) * 2 + {0: min, 1: max}] starts at
+// {INT32_MAX, INT32_MIN + 1} like bcf_enc_vint's accumulators.  grid = (chunks, sites)
+__global__ void __launch_bounds__(FMT_THREADS) k_fmt_range(const __grid_constant__ ArrayDev A, const __grid_constant__ RemapOut O, const uint32_t n_sites, const uint32_t nq,
+                                                           const int produce_gt, int32_t* __restrict__ mm) {
+  __shared__ int32_t s_min[FMT_THREADS / 32], s_max[FMT_THREADS / 32];
+  const uint32_t js = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int o = 0; o < O.n_out; ++o) {
+    const FieldOutDev fo = O.f[o];
+    const uint32_t stride = fo.stride[js];
+    if (stride == 0) continue;
+    const bool is_gt = A.has_gt && o == 0;
+    const int fi = o - (A.has_gt ? 1 : 0);
+    if (!is_gt && A.fm[fi].elem) continue;   // float blocks are never narrowed
+    const uint32_t* __restrict__ src = fo.data + fo.base[js];
+    int32_t lo = INT32_MAX, hi = INT32_MIN + 1;
+    if (is_gt) {
+      const uint32_t nps = A.gt_phased ? (stride + 1u) >> 1 : stride;
+      for (uint32_t q = blockIdx.x * FMT_THREADS + tid; q < nq; q += gridDim.x * FMT_THREADS) {
+        const uint32_t* row = src + (uint64_t)q * stride;
+        for (uint32_t i = 0; i < nps; ++i) {
+          const uint32_t v = gt_element(row, i, A.gt_phased, produce_gt);
+          if (v != BCF_INT_MISSING && v != BCF_INT_VEND) { lo = min(lo, (int32_t)v); hi = max(hi, (int32_t)v); }
+        }
+      }
+    } else {
+      const uint64_t n_words = (uint64_t)nq * stride, n_quads = n_words >> 2;
+      const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(src);   // site blocks start on 16-byte boundaries
+      for (uint64_t g = (uint64_t)blockIdx.x * FMT_THREADS + tid; g < n_quads; g += (uint64_t)gridDim.x * FMT_THREADS) {
+        const uint4 v = src4[g];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int x = 0; x < 4; ++x) if (w[x] != BCF_INT_MISSING && w[x] != BCF_INT_VEND) { lo = min(lo, (int32_t)w[x]); hi = max(hi, (int32_t)w[x]); }
+      }
+      if (blockIdx.x == 0 && tid < (uint32_t)(n_words & 3u)) {
+        const uint32_t w = src[(n_quads << 2) + tid];
+        if (w != BCF_INT_MISSING && w != BCF_INT_VEND) { lo = min(lo, (int32_t)w); hi = max(hi, (int32_t)w); }
+      }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) { s_min[wid] = lo; s_max[wid] = hi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 1; k < FMT_THREADS / 32; ++k) { lo = min(lo, s_min[k]); hi = max(hi, s_max[k]); }
+      int32_t* p = mm + ((uint64_t)o * n_sites + js) * 2;
+      if (lo != INT32_MAX) atomicMin(p, lo);
+      if (hi != INT32_MIN + 1) atomicMax(p + 1, hi);
+    }
+    __syncthreads();
+  }
+}
+
+// narrows the words of every emitted (site, field) into its block.  grid = (chunks, sites); a thread makes 4 consecutive
+// values of the block per trip (one 4 / 8 / 16-byte store).
+__global__ void __launch_bounds__(FMT_THREADS) k_fmt_pack(const __grid_constant__ ArrayDev A, const __grid_constant__ RemapOut O, const __grid_constant__ FmtPlanDev P,
+                                                          const uint32_t n_sites, const uint32_t nq, const int produce_gt) {
+  const uint32_t js = blockIdx.y, tid = threadIdx.x;
+  for (int o = 0; o < O.n_out; ++o) {
+    const uint64_t pi = (uint64_t)o * n_sites + js;
+    const uint32_t type = P.type[pi];
+    if (type == BT_NONE) continue;
+    const FieldOutDev fo = O.f[o];
+    const uint32_t stride = fo.stride[js], nps = P.nps[pi];
+    const bool is_gt = A.has_gt && o == 0;
+    const int fi = o - (A.has_gt ? 1 : 0);
+    const uint32_t miss = is_gt ? BCF_INT_VEND : missing_word(A.fm[fi].elem);   // first value of a row without the field
+    const uint32_t* __restrict__ src = fo.data + fo.base[js];
+    const uint16_t* __restrict__ len = fo.len + (uint64_t)js * nq;
+    uint8_t* __restrict__ dst = P.bytes + P.off[pi];
+    const uint64_t n_el = (uint64_t)nq * nps, n_grp = (n_el + 3) >> 2;
+    const bool flat = !is_gt && stride == nps;
+    for (uint64_t g = (uint64_t)blockIdx.x * FMT_THREADS + tid; g < n_grp; g += (uint64_t)gridDim.x * FMT_THREADS) {
+      const uint64_t e = g << 2;
+      uint32_t q = (uint32_t)(e / nps), i = (uint32_t)(e - (uint64_t)q * nps);
+      uint32_t w[4];
+      const uint32_t cnt = (uint32_t)min((uint64_t)4, n_el - e);
+      if (flat && cnt == 4) { const uint4 v = *reinterpret_cast<const uint4*>(src + e); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+#pragma unroll
+      for (uint32_t x = 0; x < 4; ++x) {
+        if (x < cnt) {
+          const uint32_t* row = src + (uint64_t)q * stride;
+          if (is_gt) w[x] = gt_element(row, i, A.gt_phased, produce_gt);
+          else {
+            if (!(flat && cnt == 4)) w[x] = row[i];
+            if (i == 0 && len[q] == 0) w[x] = miss;
+          }
+          if (++i == nps) { i = 0; ++q; }
+        } else w[x] = 0;
+      }
+      if (type == BT_INT8) {
+        uint32_t pk = 0;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) pk |= (w[x] == BCF_INT_VEND ? 0x81u : (w[x] == BCF_INT_MISSING ? 0x80u : (w[x] & 0xFFu))) << (8 * x);
+        if (cnt == 4) *reinterpret_cast<uint32_t*>(dst + e) = pk;
+        else for (uint32_t x = 0; x < cnt; ++x) dst[e + x] = (uint8_t)(pk >> (8 * x));
+      } else if (type == BT_INT16) {
+        uint32_t h[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) h[x] = w[x] == BCF_INT_VEND ? 0x8001u : (w[x] == BCF_INT_MISSING ? 0x8000u : (w[x] & 0xFFFFu));
+        if (cnt == 4) *reinterpret_cast<uint2*>(dst + 2 * e) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+        else for (uint32_t x = 0; x < cnt; ++x) *reinterpret_cast<uint16_t*>(dst + 2 * (e + x)) = (uint16_t)h[x];
+      } else {   // int32 / float: the words as they are
+        if (cnt == 4) *reinterpret_cast<uint4*>(dst + 4 * e) = make_uint4(w[0], w[1], w[2], w[3]);
+        else for (uint32_t x = 0; x < cnt; ++x) *reinterpret_cast<uint32_t*>(dst + 4 * (e + x)) = w[x];
+      }
+    }
+  }
+}
+
+}  // namespace gdb

@@ -116,6 +116,12 @@ void gdbgpu_array_close(gdbgpu_array* arr);
 #define GDBGPU_SCAN_MIN_PL_GT          4u   /* produce_GT_with_min_PL_value_for_spanning_deletions */
 #define GDBGPU_SCAN_WANT_LUT           8u   /* also return the per-call input->merged allele LUT (CombineAllelesLUT) */
 #define GDBGPU_SCAN_DEVICE_OUTPUT     16u   /* batch pointers are DEVICE pointers (consumer is another kernel) */
+#define GDBGPU_SCAN_BCF_FORMAT        32u   /* also collate GT + the remapped fields over all query rows and encode them as BCF typed
+                                             * FORMAT blocks (collect_and_extend_fields, variant_field_handler.cc:804-871; encode_GT_vector,
+                                             * broad_combined_gvcf.cc:53-138; bcf_enc_vint, htslib vcf.c:1926-1972).  With host output only the
+                                             * blocks, the site table and the alleles are copied back (fields[].data / .len and live are NULL) */
+#define GDBGPU_SCAN_PRODUCE_GT        64u   /* query JSON "produce_GT_field": GT blocks carry the alleles, else no-calls (broad_combined_gvcf.cc:60-76) */
+#define GDBGPU_SCAN_NO_PREFETCH      128u   /* do not start batch n+1 while batch n is being handed out */
 
 typedef struct gdbgpu_scan_params {
   int64_t col_lo, col_hi;            /* inclusive TileDB column interval; ignored with GDBGPU_SCAN_FULL */
@@ -172,12 +178,23 @@ typedef struct gdbgpu_batch {
   const int16_t* lut_in2m;
   uint64_t out_bytes;        /* algorithmic bytes of remapped output of this batch: 4 x n_query_rows x sum of the strides
                               * each field needs (alignment padding and the length arrays not counted) */
+  /* GDBGPU_SCAN_BCF_FORMAT: the FORMAT block of field o (same order as fields[]) at site s is described by entry
+   * o*n_sites + s: fmt_type = 0 when the field is not emitted at the site (no valid call has it / G field suppressed),
+   * else the BCF type (1 int8, 2 int16, 3 int32, 5 float); fmt_nps values per sample; the n_query_rows*fmt_nps values
+   * start at fmt_bytes + fmt_offset (16-byte aligned), sample-major, little-endian: exactly the bytes htslib puts into
+   * bcf1_t.indiv after the field's typed key and (fmt_nps, fmt_type) size descriptor. */
+  const uint8_t* fmt_type;
+  const uint32_t* fmt_nps;
+  const uint64_t* fmt_offset;
+  const uint8_t* fmt_bytes;
+  uint64_t fmt_total_bytes;
 } gdbgpu_batch;
 
 int gdbgpu_scan_begin(gdbgpu_array* arr, const gdbgpu_scan_params* params, gdbgpu_scan** out);
 int gdbgpu_scan_get_info(const gdbgpu_scan* scan, gdbgpu_scan_info* info);
 /* Produces the next <= max_sites sites whose remapped output fits max_bytes (0 = engine default); n_sites==0 at the end.
- * The batch stays valid until the next call on the same scan.  Re-entrant like the reference's overflow/resume
+ * The batch stays valid until the next call on the same scan.  Unless GDBGPU_SCAN_NO_PREFETCH is set the engine starts
+ * computing the following batch (same limits) before it returns, so its kernels overlap this batch's copy to the host.  Re-entrant like the reference's overflow/resume
  * protocol (query_variants.cc:305,415,460-475): the caller drains a batch, then asks for the next. */
 int gdbgpu_scan_next_batch(gdbgpu_scan* scan, uint32_t max_sites, uint64_t max_bytes, gdbgpu_batch* batch);
 /* Rewind to site idx (resume after a consumer-side overflow in the middle of a batch). */

@@ -1,0 +1,156 @@
+"""GPU: FORMAT collation + BCF typed encoding on the device (GDBGPU_SCAN_BCF_FORMAT, kernels k_fmt_range / k_fmt_pack)
+against (1) the UNMODIFIED reference's own BCF output on the golden arrays, (2) the oracle restatement on GDBSYN-1
+cohorts, (3) the int32 output of the ordinary scan (decode round trip at a size the python oracle cannot reach)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases
+from oracle import bcf_reader, format_blocks, oracle
+from tools import gdbsyn
+from util import case_fields, case_query_rows, format_field_names
+
+pytestmark = pytest.mark.gpu
+CASES = golden_cases()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from genomicsdb_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def gpu_blocks(arr, ranges, names, query_rows=None, flags=0, max_sites=0, max_bytes=0):
+    """-> [ {field name: (type, nps, bytes)} per site ] through the C ABI"""
+    from genomicsdb_b200 import capi
+    out = []
+    for r in (sorted(tuple(r) for r in ranges) if ranges else [None]):
+        sc = capi.Scan(arr, None if r is None else r[0], None if r is None else r[1], query_rows=query_rows,
+                       flags=flags | capi.SCAN_BCF_FORMAT)
+        try:
+            while True:
+                bv = sc.next_batch(max_sites, max_bytes)
+                if bv is None:
+                    break
+                assert bv.live is None and bv.fields[0]["data"] is None     # only the blocks travel
+                for s in range(bv.n_sites):
+                    d = {}
+                    for o, nm in enumerate(names):
+                        blk = bv.fmt_block(o, s)
+                        if blk is not None:
+                            d[nm] = blk
+                    out.append(d)
+        finally:
+            sc.close()
+    return out
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_blocks_match_reference_bcf(ctx, case):
+    from genomicsdb_b200 import capi
+    _, samples, recs = bcf_reader.read_bcf(os.path.join(GOLDEN, "bcf", case["id"] + ".bcf"))
+    fields, phased = case_fields(case)
+    names = ["GT"] + [f[0] for f in fields]
+    fmt_names = format_field_names(case, names)
+    flags = (capi.SCAN_MIN_PL_GT if case["produce_GT_with_min_PL_value_for_spanning_deletions"] else 0) | \
+            (capi.SCAN_PRODUCE_GT if case["produce_GT_field"] else 0)
+    arr = capi.Array.open(ctx, os.path.join(GOLDEN, case["workspace"]), case["array"], fields, gt_phased=phased)
+    try:
+        for kw in (dict(), dict(max_sites=1)):
+            got = gpu_blocks(arr, case["query_column_ranges"], names, query_rows=case_query_rows(case), flags=flags, **kw)
+            assert len(got) == len(recs) == case["sites"]
+            for rec, g in zip(recs, got):
+                want = {k: v[:3] for k, v in rec["fmt"].items() if k in fmt_names}
+                g = {k: v for k, v in g.items() if k in fmt_names}
+                assert sorted(g) == sorted(want), (rec["pos"], sorted(g), sorted(want))
+                for k in want:
+                    assert g[k] == want[k], (rec["pos"], k, g[k][:2], want[k][:2], g[k][2].hex(), want[k][2].hex())
+    finally:
+        arr.close()
+
+
+def oracle_blocks(d, ranges, rows, produce_gt):
+    cols = gdbsyn.to_oracle_columns(d)
+    dump, n = oracle.combine_query(cols, ranges, query_rows=rows)
+    names, sites = oracle.parse_dump(dump)
+    q = sorted(set(r for r in (rows if rows is not None else range(d["num_rows"])) if r < d["num_rows"]))
+    return [format_blocks.site_blocks(s, names, q, {"AD": "int", "PL": "int"}, False, produce_gt) for s in sites]
+
+
+@pytest.mark.parametrize("shape,produce_gt", [(dict(n_samples=50, n_sites=120, spacing=100, p_var=0.1, a_pool=8), True),
+                                              (dict(n_samples=300, n_sites=60, spacing=100, p_var=0.1, a_pool=3), False),
+                                              (dict(n_samples=7, n_sites=300, spacing=3, p_var=0.4, a_pool=5), True),
+                                              (dict(n_samples=1, n_sites=50, spacing=10, p_var=0.3, a_pool=4), True)],
+                         ids=["50x120", "300x60", "7x300dense", "1sample"])
+def test_blocks_match_oracle_on_synthetic(ctx, shape, produce_gt):
+    from genomicsdb_b200 import capi
+    d = gdbsyn.generate(**shape)
+    arr = gdbsyn.to_gpu_array(ctx, d)
+    try:
+        flags = capi.SCAN_PRODUCE_GT if produce_gt else 0
+        for ranges, rows, kw in (([], None, {}), ([list(d["col_range"])], None, dict(max_bytes=100000)),
+                                 ([[1500, 4000]], [0, 2, 3, 5, 40, 41, 290], dict(max_sites=2))):
+            want = oracle_blocks(d, ranges, rows, produce_gt)
+            got = gpu_blocks(arr, ranges, ["GT", "AD", "PL"], query_rows=rows, flags=flags, **kw)
+            assert len(got) == len(want)
+            for i, (g, w) in enumerate(zip(got, want)):
+                assert sorted(g) == sorted(w), (i, sorted(g), sorted(w))
+                for k in w:
+                    assert g[k] == w[k][:3], (i, k, g[k][:2], w[k][:2])
+    finally:
+        arr.close()
+
+
+def test_blocks_decode_to_the_int32_output(ctx):
+    """10 k samples: every block, widened again, equals the collated int32 vectors of the ordinary scan"""
+    from genomicsdb_b200 import capi
+    d = gdbsyn.generate(n_samples=10000, n_sites=24, spacing=1000, p_var=0.1, a_pool=8)
+    arr = gdbsyn.to_gpu_array(ctx, d)
+    widths = set()
+    try:
+        a, b = capi.Scan(arr), capi.Scan(arr, flags=capi.SCAN_BCF_FORMAT | capi.SCAN_PRODUCE_GT)
+        n = 0
+        while True:
+            x = a.next_batch(5, 0)
+            y = b.next_batch(5, 0)
+            if x is None:
+                assert y is None
+                break
+            assert x.n_sites == y.n_sites
+            nq = x.nq
+            for s in range(x.n_sites):
+                for o in range(3):
+                    f = x.fields[o]
+                    stride, ln = int(f["stride"][s]), f["len"][s].astype(np.int64)
+                    blk = y.fmt_block(o, s)
+                    if ln.max() == 0:
+                        assert blk is None
+                        continue
+                    t, nps, raw = blk
+                    widths.add((o, t))
+                    base = int(f["base"][s])
+                    v = f["data"][base:base + nq * stride].view(np.int32).reshape(nq, stride)[:, :nps].astype(np.int64).copy()
+                    if o == 0:
+                        valid = (v != format_blocks.I32_MISSING) & (v != format_blocks.I32_VEND)
+                        v = np.where(valid, (v + 1) << 1, v)
+                    else:
+                        v[ln == 0, 0] = format_blocks.I32_MISSING
+                    dt = {1: "<i1", 2: "<i2", 3: "<i4"}[t]
+                    w = np.frombuffer(raw, dtype=dt).reshape(nq, nps).astype(np.int64)
+                    lo = {1: -128, 2: -32768, 3: format_blocks.I32_MISSING}[t]
+                    w = np.where(w == lo, format_blocks.I32_MISSING, np.where(w == lo + 1, format_blocks.I32_VEND, w))
+                    assert np.array_equal(v, w), (n + s, o)
+                    valid = v[(v != format_blocks.I32_MISSING) & (v != format_blocks.I32_VEND)]
+                    if t == 1:
+                        assert valid.max() <= 127 and valid.min() > -127
+                    elif t == 2:
+                        assert valid.max() <= 32767 and not (valid.max() <= 127 and valid.min() > -127)
+            n += x.n_sites
+        a.close()
+        b.close()
+    finally:
+        arr.close()
+    assert (0, 1) in widths and (2, 2) in widths     # GT int8, PL int16
