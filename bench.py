@@ -283,7 +283,15 @@ def main():
     b_in_step = manifest["b_in"]
     b_out_step = out_bytes / args.steps
     achieved = ((b_in_step + b_out_step) * args.steps / 1e9) / (remap_ms * 1e-3) if remap_ms > 0 else 0.0
-    roofline = dict(bound="hbm", kernel="gdb::k_remap_tile + gdb::k_copy_tile + gdb::k_remap_nt (K5 remap)", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+    # DRAM traffic of the same kernels from the committed ncu capture (dram__bytes_read.sum + dram__bytes_write.sum), per launch
+    traffic, traffic_src = None, None
+    tpath = os.path.join(REPO, "profiles", "r01_k5_traffic.json")
+    if os.path.exists(tpath) and args.samples == COHORT["n_samples"] and remap_n:
+        tj = json.load(open(tpath))
+        traffic = tj["k5_dram_bytes_per_site"] * sites / remap_n
+        traffic_src = "profiles/r01_k5_traffic.json (ncu, bytes per site of the same shard) x sites per launch"
+    roofline = dict(bound="hbm", kernel="gdb::k_remap_tile + gdb::k_copy_tile + gdb::k_remap_nt (K5 remap)", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                    traffic_source=traffic_src, algorithmic_bytes_per_launch=(b_in_step + b_out_step) * args.steps / max(1, remap_n),
                     peak_source=peak_src, algorithmic_bytes_per_step=dict(b_in=b_in_step, b_out=b_out_step),
                     launches=int(remap_n), avg_launch_ms=remap_ms / max(1, remap_n),
                     kernel_ms_per_step=dict(k_remap=remap_ms / args.steps, k_remap_tile=tile_ms / args.steps, k_remap_nt=nt_ms / args.steps, k_copy_tile=copy_ms / args.steps,
