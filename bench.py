@@ -314,11 +314,20 @@ def main():
         for k in ("ref", "alt", "gt", "pl", "ad"):
             dp[k] = (pin(d[k][0]), pin(d[k][1]))
 
+        phase_s = dict(stage=0.0, scan=0.0, close=0.0)
+
         def e2e_step(flags):
+            t0 = time.perf_counter()
             a = gdbsyn.to_gpu_array(ctx, dp)
             i = a.info()
+            t1 = time.perf_counter()
             s, ob, lw, fb = one_pass(a, flags, args.e2e_batch_bytes)
+            t2 = time.perf_counter()
             a.close()
+            t3 = time.perf_counter()
+            phase_s["stage"] += t1 - t0
+            phase_s["scan"] += t2 - t1
+            phase_s["close"] += t3 - t2
             # host output: BCF mode copies the typed blocks + the site table; int32 mode the vectors, their lengths and the live matrix
             d2h_bytes = fb + s * 24 if flags & capi.SCAN_BCF_FORMAT else ob + lw * 4 + lw * 2 * 3 + s * 24
             return s, i.staged_bytes, d2h_bytes
@@ -327,6 +336,8 @@ def main():
             for _ in range(2):
                 e2e_step(flags)
             barrier()
+            for k in phase_s:
+                phase_s[k] = 0.0
             t0 = time.perf_counter()
             es = h2d = d2h = 0
             for _ in range(args.e2e_steps):
@@ -338,7 +349,8 @@ def main():
             dt = max_over_ranks(time.perf_counter() - t0)
             return dict(value=sum_over_ranks(float(es)) / dt, unit="sites/s", h2d_bytes_per_step=int(h2d // args.e2e_steps),
                         d2h_bytes_per_step=int(d2h // args.e2e_steps), steps=args.e2e_steps, ms_per_step=dt * 1e3 / args.e2e_steps,
-                        batch_bytes=args.e2e_batch_bytes, path=path)
+                        batch_bytes=args.e2e_batch_bytes, path=path,
+                        phase_ms_per_step={k: v * 1e3 / args.e2e_steps for k, v in phase_s.items()})
 
         e2e = e2e_run(capi.SCAN_BCF_FORMAT | capi.SCAN_PRODUCE_GT,
                       "gdbgpu_array_from_columns(pinned host columns) -> gdbgpu_scan_next_batch(GDBGPU_SCAN_BCF_FORMAT, host output: "

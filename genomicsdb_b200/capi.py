@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libgdbgpu.so")
+LIB_PATH = os.environ.get("GDBGPU_LIB") or os.path.join(HERE, "lib", "libgdbgpu.so")   # GDBGPU_LIB: a differently tuned build of the same library
 
 OK, ERR_ARG, ERR_IO, ERR_CUDA, ERR_OVERLAP, ERR_LIMIT = 0, -1, -2, -3, -4, -5
 LEN_R, LEN_A, LEN_G = 0, 1, 2

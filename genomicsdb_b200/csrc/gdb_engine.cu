@@ -299,6 +299,7 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
       LAUNCH(ctx, k_rs_cols, blocks_for(n_rs, 256), 256, a->dev, a->rs_cell.p, n_rs, a->rs_col.p);
       LAUNCH(ctx, k_effend, blocks_for(n_rs, 256), 256, a->dev, a->desc.p, a->rs_cell.p, a->rs_col.p, a->rs_keys.p, n_rs, a->rs_effend.p, a->effend.p, stats.p,
              a->bad_cell.p, a->bad_pred_col.p, BAD_CAP);
+      LAUNCH(ctx, k_rs_flag_del, blocks_for(n_rs, 256), 256, a->desc.p, a->rs_cell.p, n_rs);
     }
     long long hs[4];
     CK(cudaMemcpyAsync(hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));

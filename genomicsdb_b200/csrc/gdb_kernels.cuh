@@ -207,6 +207,12 @@ __global__ void __launch_bounds__(256) k_row_bounds(const uint32_t* __restrict__
   while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (sorted_keys[mid] < (uint32_t)r) lo = mid + 1; else hi = mid; }
   row_start[r] = lo;
 }
+// rs_cell entries carry the cell's "contains a deletion" flag in bit 31 (cells < 2^30), so the walk needs no CellDesc gather
+constexpr uint32_t RS_CELL_MASK = 0x7FFFFFFFu;
+__global__ void __launch_bounds__(256) k_rs_flag_del(const CellDesc* __restrict__ desc, uint32_t* __restrict__ rs_cell, uint64_t n_rs) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_rs && (desc[rs_cell[k]].flags & F_DELETION)) rs_cell[k] |= 0x80000000u;
+}
 __global__ void __launch_bounds__(256) k_rs_cols(ArrayDev A, const uint32_t* __restrict__ rs_cell, uint64_t n_rs, int64_t* __restrict__ rs_col) {
   uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n_rs) rs_col[k] = A.coords[2 * (uint64_t)rs_cell[k] + 1];
@@ -365,8 +371,8 @@ __global__ void __launch_bounds__(256) k_left_sweep(ArrayDev A, ScanDev S) {
     while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (A.rs_col[mid] < S.q_lo) lo = mid + 1; else hi = mid; }
     if (lo < e) {
       int64_t c = A.rs_col[lo], ef = A.rs_effend[lo];
-      if (ef == I64_MIN) { cell = (int32_t)A.rs_cell[lo]; eff = c; }          // END copy: call [END field, col]
-      else if (c == S.q_lo) { cell = (int32_t)A.rs_cell[lo]; eff = ef; }     // begin cell exactly at q_lo
+      if (ef == I64_MIN) { cell = (int32_t)(A.rs_cell[lo] & RS_CELL_MASK); eff = c; }          // END copy: call [END field, col]
+      else if (c == S.q_lo) { cell = (int32_t)(A.rs_cell[lo] & RS_CELL_MASK); eff = ef; }     // begin cell exactly at q_lo
     }
   }
   S.init_cell[q] = cell; S.init_effend[q] = eff;
@@ -499,7 +505,10 @@ __global__ void __launch_bounds__(256) k_fill_sites(ScanDev S, const int32_t* __
 // ------------------------------------------------------------------------------------------------ K3 live matrix
 // One thread per queried sample walks that sample's cell list against the batch's sites ("k-way merge" of the sample
 // lists with the site list); adjacent threads write adjacent entries of each site's row -> coalesced.
-constexpr uint32_t WALK_CHUNK = 32;   // sites walked by one thread after one binary search
+#ifndef GDB_WALK_CHUNK
+#define GDB_WALK_CHUNK 32
+#endif
+constexpr uint32_t WALK_CHUNK = GDB_WALK_CHUNK;   // sites walked by one thread after one binary search
 __global__ void __launch_bounds__(256) k_live_walk(ArrayDev A, ScanDev S, uint64_t first_site, uint32_t n_sites, int32_t* __restrict__ live) {
   uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= S.nq) return;
@@ -518,16 +527,17 @@ __global__ void __launch_bounds__(256) k_live_walk(ArrayDev A, ScanDev S, uint64
     int64_t c = A.rs_col[kk];
     if (!S.scan_full && c <= S.q_lo) break;
     int64_t ef = A.rs_effend[kk];
-    if (ef != I64_MIN) { cur = (int32_t)A.rs_cell[kk]; cur_eff = ef; cur_begin = c; cur_del = A.desc[cur].flags & F_DELETION; break; }
+    if (ef != I64_MIN) { const uint32_t rc = A.rs_cell[kk]; cur = (int32_t)(rc & RS_CELL_MASK); cur_eff = ef; cur_begin = c; cur_del = rc >> 31; break; }
   }
+  // the column of the sample's next cell stays in a register: most sites of the chunk do not advance the list
+  int64_t next_col = k < e ? A.rs_col[k] : INT64_MAX;
   for (uint32_t s = s0; s < s1; ++s) {
-    int64_t b = S.site_begin[first_site + s];
-    while (k < e) {
-      int64_t c = A.rs_col[k];
-      if (c > b) break;
-      int64_t ef = A.rs_effend[k];
-      if (ef != I64_MIN) { cur = (int32_t)A.rs_cell[k]; cur_eff = ef; cur_begin = c; cur_del = A.desc[cur].flags & F_DELETION; }
+    const int64_t b = S.site_begin[first_site + s];
+    while (next_col <= b) {
+      const int64_t ef = A.rs_effend[k];
+      if (ef != I64_MIN) { const uint32_t rc = A.rs_cell[k]; cur = (int32_t)(rc & RS_CELL_MASK); cur_eff = ef; cur_begin = next_col; cur_del = rc >> 31; }
       ++k;
+      next_col = k < e ? A.rs_col[k] : INT64_MAX;
     }
     int32_t v = -1;
     if (cur >= 0 && cur_eff >= b) { v = cur; if (S.handle_del && cur_del && b > cur_begin) v |= LIVE_REDUCED; }

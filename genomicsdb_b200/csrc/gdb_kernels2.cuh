@@ -1040,10 +1040,15 @@ __global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_consta
   }
 }
 
+// k_remap_nt: NT_GL lanes per nt-list entry (4: a diploid 10-allele PL row is 14 quads = 4 trips at 87 % lane use, AD / tokens / GT
+// one trip; measured 3.9 -> 2.7 ms per step against 8 lanes)
 // k_remap_nt: NT_GL lanes per nt-list entry (non-trivial, non-inline or spanning-deletion call), NT_GROUPS entries of ONE
 // site per block (block -> (site, first entry) comes from a map built by k_nt_blocks), so a warp keeps four independent
 // gather chains in flight: entry -> blob header -> tokens / GT / field words.
-constexpr int NT_THREADS = 256, NT_GL = 8, NT_GROUPS = NT_THREADS / NT_GL;
+#ifndef GDB_NT_GL
+#define GDB_NT_GL 4
+#endif
+constexpr int NT_THREADS = 256, NT_GL = GDB_NT_GL, NT_GROUPS = NT_THREADS / NT_GL;
 __global__ void __launch_bounds__(256) k_nt_blocks(const __grid_constant__ BatchDev B, const uint32_t* __restrict__ site_list, const uint32_t* __restrict__ blk_prefix, uint2* __restrict__ blk_map) {
   const uint32_t si = blockIdx.x, js = site_list[si], b0 = blk_prefix[si], nb = blk_prefix[si + 1] - b0;
   for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) blk_map[b0 + b] = make_uint2(js, b * NT_GROUPS);
