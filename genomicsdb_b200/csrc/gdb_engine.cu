@@ -6,6 +6,8 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -34,6 +36,7 @@ struct gdbgpu_ctx {
   std::vector<cudaEvent_t> pool;
   std::map<std::string, std::pair<double, uint64_t>> stats;
   std::vector<BatchBuffers*> bb_pool;
+  std::multimap<size_t, void*> free_blocks; size_t cached_bytes = 0;   // device blocks waiting for reuse (see dev_alloc)
   uint32_t* d_cls_tab = nullptr; uint16_t* d_jk_tab = nullptr; int n_sms = 148;   // universal genotype tables (gdb_kernels2.cuh: TileTabs)
   cudaEvent_t get_event() { if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
   void resolve() {
@@ -58,13 +61,49 @@ struct ArgError : std::runtime_error { using std::runtime_error::runtime_error; 
 
 #define CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__)); } while (0)
 
+// Device memory goes through a per-context caching allocator: a block given back by an array / scan / batch is kept and
+// handed to the next request of (nearly) the same size, so staging an array or growing a batch buffer in steady state
+// never reaches cudaMalloc / cudaFree (multi-GB calls cost 100+ ms and synchronise the device).  All work of a context is
+// ordered on its compute stream (the copy stream only reads batch buffers that are not recycled before their copies are
+// waited for), so immediate reuse is safe.
+thread_local gdbgpu_ctx* tl_ctx = nullptr;
+inline void* dev_alloc(gdbgpu_ctx* c, size_t bytes, size_t& cap) {
+  bytes = (bytes + 511) & ~(size_t)511;
+  if (c) {
+    auto it = c->free_blocks.lower_bound(bytes);
+    if (it != c->free_blocks.end() && it->first <= bytes + bytes / 4 + (1u << 20)) {
+      void* p = it->second; cap = it->first; c->cached_bytes -= cap; c->free_blocks.erase(it); return p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess && c && !c->free_blocks.empty()) {   // give the cache back to the driver and retry
+    cudaGetLastError();
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->free_blocks) cudaFree(kv.second);
+    c->free_blocks.clear(); c->cached_bytes = 0;
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  cap = bytes;
+  return p;
+}
+inline void dev_free(gdbgpu_ctx* c, void* p, size_t cap) {
+  if (!p) return;
+  if (c) { c->free_blocks.emplace(cap, p); c->cached_bytes += cap; }
+  else cudaFree(p);
+}
 template <class T>
 struct DevBuf {
-  T* p = nullptr; size_t n = 0;
+  T* p = nullptr; size_t n = 0, cap = 0; gdbgpu_ctx* owner = nullptr;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
-  ~DevBuf() { if (p) cudaFree(p); }
-  void alloc(size_t count) { if (p) { cudaFree(p); p = nullptr; } n = count; if (count) CK(cudaMalloc((void**)&p, count * sizeof(T))); }
+  ~DevBuf() { release(); }
+  void release() { if (p) { dev_free(owner, p, cap); p = nullptr; } }
+  void alloc(size_t count) {
+    release(); n = count; owner = tl_ctx;
+    if (count) p = static_cast<T*>(dev_alloc(owner, count * sizeof(T), cap));
+  }
   void ensure(size_t count) { if (count > n) alloc(count + count / 4 + 16); }
   size_t bytes() const { return n * sizeof(T); }
 };
@@ -229,6 +268,15 @@ void gather_var(gdbgpu_ctx* ctx, const DevVar& in, const uint32_t* src, uint64_t
 // stage host columns (already concatenated over fragments) and build the per-array indexes
 gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<uint64_t>& frag_cells, int64_t lb_row, int64_t num_rows, int gt_phased,
                           const std::vector<FieldMeta>& fm, const std::vector<std::string>& names) {
+  static const bool trace = getenv("GDBGPU_TRACE") != nullptr;   // phase times of the staging on stderr
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(ctx->stream);
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gdbgpu] build_array %-10s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+    t_prev = t;
+  };
   if (h.n >= (1ull << 30)) throw LimitError("more than 2^30 cells in one staged array: shard the column range across GPUs");
   if (h.fields.size() > (size_t)MAX_FIELDS) throw LimitError("more than 15 allele-dependent fields queried");
   if (num_rows < 0 || num_rows >= (1ll << 31)) throw LimitError("row count out of range");
@@ -244,6 +292,7 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
   if (h.has_gt) upload_var(ctx, h.gt, n, a->gt, a->staged_bytes);
   for (auto& f : h.fields) { a->fields.emplace_back(new DevVar()); upload_var(ctx, f, n, *a->fields.back(), a->staged_bytes); }
   CK(cudaStreamSynchronize(ctx->stream));
+  lap("upload");
 
   if (frag_cells.size() > 1 && n) {   // K1
     DevBuf<uint32_t> src; uint64_t n_out = 0;
@@ -281,6 +330,7 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
       LAUNCH(ctx, k_warm_fill, g, 256, a->dev, a->desc.p, a->hot.p, units.p, offs.p, a->warm.p);
       CK(cudaStreamSynchronize(ctx->stream));
     }
+    lap("classify");
     DevBuf<uint32_t> keys, vals; DevBuf<uint8_t> tmp;
     keys.alloc(n); vals.alloc(n);
     LAUNCH(ctx, k_row_keys, g, 256, a->dev, a->desc.p, keys.p, vals.p);
@@ -310,6 +360,7 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
     a->n_begin = (uint64_t)hs[0]; a->n_bad = (uint64_t)hs[1]; a->max_end = hs[2] == INT64_MIN ? first_last[1] : hs[2]; a->n_del_cells = (uint64_t)hs[3];
     a->min_col = first_last[0]; a->max_col = first_last[1];
     if (a->max_end < a->max_col) a->max_end = a->max_col;
+    lap("row index");
   }
   fill_dev_view(a.get());
   return a.release();
@@ -317,22 +368,44 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
 
 }  // namespace
 
+// Small host -> device control tables of one batch (strides, bases, site lists, plans) travel in ONE pinned block and one
+// copy instead of a dozen pageable cudaMemcpyAsync calls: the device idles while the host prepares a batch's remap launch.
+struct CtlArena {
+  PinBuf<uint8_t> h; DevBuf<uint8_t> d; size_t used = 0, flushed = 0;
+  void begin(size_t cap) { h.ensure(cap); d.ensure(cap); used = flushed = 0; }
+  template <class T> T* push(const T* src, size_t n) {
+    const size_t off = (used + 15) & ~(size_t)15, bytes = n * sizeof(T);
+    if (off + bytes > h.n || off + bytes > d.n) throw CudaError("internal: control arena overflow");
+    if (bytes) memcpy(h.p + off, src, bytes);
+    used = off + bytes;
+    return reinterpret_cast<T*>(d.p + off);
+  }
+  void flush(cudaStream_t st) {   // copies what was pushed since the last flush
+    const size_t from = flushed & ~(size_t)15;
+    if (used > from) CK(cudaMemcpyAsync(d.p + from, h.p + from, used - from, cudaMemcpyHostToDevice, st));
+    flushed = used;
+  }
+};
+
 // Per-batch device / pinned-host buffers.  They are large (GBs) and expensive to create (cudaMalloc, cudaMallocHost), so a
 // context keeps finished scans' buffers and hands them to the next scan.
 struct BatchBuffers {
   // per batch (device)
-  DevBuf<int32_t> live; DevBuf<SiteRec> sites; DevBuf<uint32_t> agg, nt_prefix; DevBuf<uint2> nt, blk_map; DevBuf<uint32_t> cursors, allele_pos, lut_first; DevBuf<uint16_t> lut_len; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes; DevBuf<int16_t> lut_in2m;
-  DevBuf<uint32_t> out_data[MAX_FIELDS + 1], out_stride[MAX_FIELDS + 1]; DevBuf<uint64_t> out_base[MAX_FIELDS + 1]; DevBuf<uint16_t> out_len[MAX_FIELDS + 1];
-  DevBuf<uint8_t> d_site_flags; DevBuf<uint32_t> d_n_alleles, d_n_live, d_allele_first;
+  DevBuf<int32_t> live; DevBuf<SiteRec> sites; DevBuf<uint32_t> agg; DevBuf<uint2> nt, blk_map; DevBuf<uint32_t> cursors, allele_pos, lut_first; DevBuf<uint16_t> lut_len; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes; DevBuf<int16_t> lut_in2m;
+  DevBuf<uint32_t> out_data[MAX_FIELDS + 1]; DevBuf<uint16_t> out_len[MAX_FIELDS + 1];
+  CtlArena ctl;   // everything below points into ctl.d
+  uint32_t* out_stride[MAX_FIELDS + 1] = {}; uint64_t* out_base[MAX_FIELDS + 1] = {};
+  uint8_t* d_site_flags = nullptr; uint32_t *d_n_alleles = nullptr, *d_n_live = nullptr, *d_allele_first = nullptr;
+  uint32_t *fast_sites = nullptr, *slow_sites = nullptr, *tile_sites = nullptr, *nt_prefix_d = nullptr;
+  uint8_t* fmt_type_d = nullptr; uint32_t* fmt_nps_d = nullptr; uint64_t* fmt_off_d = nullptr;
   // per batch (host mirrors)
   std::vector<SiteRec> h_sites;
   std::vector<uint8_t> h_site_flags; std::vector<uint32_t> h_n_alleles, h_n_live, h_allele_first;
   std::vector<uint64_t> h_base[MAX_FIELDS + 1]; std::vector<uint32_t> h_stride[MAX_FIELDS + 1];
   PinBuf<int64_t> p_site_begin, p_site_end; PinBuf<int32_t> p_live; PinBuf<uint32_t> p_allele_pos, p_lut_first, p_out_data[MAX_FIELDS + 1]; PinBuf<uint8_t> p_allele_bytes;
   PinBuf<uint16_t> p_out_len[MAX_FIELDS + 1], p_lut_len; PinBuf<int16_t> p_lut_in2m;
-  DevBuf<uint32_t> fast_sites, slow_sites, tile_sites;
   // K6 (GDBGPU_SCAN_BCF_FORMAT): per (field, site) plan + the packed FORMAT blocks
-  DevBuf<int32_t> fmt_mm; DevBuf<uint8_t> fmt_type, fmt_bytes; DevBuf<uint32_t> fmt_nps; DevBuf<uint64_t> fmt_off;
+  DevBuf<int32_t> fmt_mm; DevBuf<uint8_t> fmt_bytes;
   std::vector<int32_t> h_fmt_mm; std::vector<uint8_t> h_fmt_type; std::vector<uint32_t> h_fmt_nps; std::vector<uint64_t> h_fmt_off;
   PinBuf<uint8_t> p_fmt_bytes;
   // state of the batch these buffers hold
@@ -561,23 +634,8 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       bytes += site_bytes; alg_bytes += site_alg; lut_words += (uint64_t)bb.h_sites[i].max_ain * S.nq; keep = i + 1;
     }
     s->avg_site_bytes = std::max<uint64_t>(1, bytes / keep);
-    RemapOut O{};
-    O.n_out = n_out;
-    for (int o = 0; o < n_out; ++o) {
-      bb.out_data[o].ensure(std::max<uint64_t>(bb.h_base[o][keep], 1)); bb.out_base[o].ensure(keep + 1); bb.out_stride[o].ensure(keep); bb.out_len[o].ensure((uint64_t)keep * S.nq);
-      CK(cudaMemcpyAsync(bb.out_base[o].p, bb.h_base[o].data(), (size_t)(keep + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(bb.out_stride[o].p, bb.h_stride[o].data(), (size_t)keep * 4, cudaMemcpyHostToDevice, ctx->stream));
-      O.f[o] = FieldOutDev{bb.out_data[o].p, bb.out_base[o].p, bb.out_stride[o].p, bb.out_len[o].p};
-    }
-    if (S.want_lut) {
-      if (lut_words >= (1ull << 32)) throw LimitError("LUT output of one batch above 2^32 entries: lower max_sites");
-      s->cap_lut = (uint32_t)std::max<uint64_t>(lut_words, 1);
-      bb.lut_first.ensure((uint64_t)keep * S.nq); bb.lut_len.ensure((uint64_t)keep * S.nq); bb.lut_in2m.ensure(s->cap_lut);
-      O.lut_first = bb.lut_first.p; O.lut_len = bb.lut_len.p; O.lut_in2m = bb.lut_in2m.p; O.cap_lut = s->cap_lut;
-    }
-    B.n_sites = keep;
     // split the batch: the tile kernels take every ordinary site, the generic kernel the pathological ones
-    std::vector<uint32_t> fast, slow, nt_prefix;
+    std::vector<uint32_t> fast, slow, nt_prefix, order;
     uint32_t jk_n = 4;
     for (uint32_t i = 0; i < keep; ++i) {
       const SiteRec& r = bb.h_sites[i];
@@ -589,28 +647,52 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
         jk_n = std::max(jk_n, r.n_alleles * (r.n_alleles + 1u) / 2u);
       } else slow.push_back(i);
     }
+    size_t n_remap = 0;
     if (!fast.empty()) {
       nt_prefix.push_back(nt_prefix.back() + (bb.h_sites[fast.back()].n_nt + NT_GROUPS - 1) / NT_GROUPS);   // blocks of k_remap_nt, per site
-      bb.fast_sites.ensure(fast.size()); bb.nt_prefix.ensure(nt_prefix.size());
-      CK(cudaMemcpyAsync(bb.fast_sites.p, fast.data(), fast.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(bb.nt_prefix.p, nt_prefix.data(), nt_prefix.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      // remapped sites -> k_remap_tile, copy-through sites -> k_copy_tile; both lists live in tile_sites (remapped ones first)
+      order.reserve(fast.size());
+      for (uint32_t i : fast) if (bb.h_sites[i].flags & 2u) order.push_back(i);
+      n_remap = order.size();
+      for (uint32_t i : fast) if (!(bb.h_sites[i].flags & 2u)) order.push_back(i);
+    }
+    bb.h_site_flags.resize(keep); bb.h_n_alleles.resize(keep); bb.h_n_live.resize(keep); bb.h_allele_first.resize(keep);
+    for (uint32_t i = 0; i < keep; ++i) { const SiteRec& r = bb.h_sites[i]; bb.h_site_flags[i] = (uint8_t)r.flags; bb.h_n_alleles[i] = r.n_alleles; bb.h_n_live[i] = r.n_live; bb.h_allele_first[i] = r.allele_first; }
+    // one pinned block, one copy: bases, strides, site lists, site table (+ the FORMAT plan later)
+    bb.ctl.begin((size_t)n_out * ((size_t)keep * 12 + 64) + (size_t)keep * 48 + (size_t)n_out * keep * 13 + 4096);
+    RemapOut O{};
+    O.n_out = n_out;
+    for (int o = 0; o < n_out; ++o) {
+      bb.out_data[o].ensure(std::max<uint64_t>(bb.h_base[o][keep], 1)); bb.out_len[o].ensure((uint64_t)keep * S.nq);
+      bb.out_base[o] = bb.ctl.push(bb.h_base[o].data(), (size_t)keep + 1);
+      bb.out_stride[o] = bb.ctl.push(bb.h_stride[o].data(), keep);
+      O.f[o] = FieldOutDev{bb.out_data[o].p, bb.out_base[o], bb.out_stride[o], bb.out_len[o].p};
+    }
+    bb.fast_sites = bb.ctl.push(fast.data(), fast.size()); bb.nt_prefix_d = bb.ctl.push(nt_prefix.data(), nt_prefix.size());
+    bb.tile_sites = bb.ctl.push(order.data(), order.size()); bb.slow_sites = bb.ctl.push(slow.data(), slow.size());
+    if (s->device_output) {
+      bb.d_site_flags = bb.ctl.push(bb.h_site_flags.data(), keep); bb.d_n_alleles = bb.ctl.push(bb.h_n_alleles.data(), keep);
+      bb.d_n_live = bb.ctl.push(bb.h_n_live.data(), keep); bb.d_allele_first = bb.ctl.push(bb.h_allele_first.data(), keep);
+    }
+    bb.ctl.flush(ctx->stream);
+    if (S.want_lut) {
+      if (lut_words >= (1ull << 32)) throw LimitError("LUT output of one batch above 2^32 entries: lower max_sites");
+      s->cap_lut = (uint32_t)std::max<uint64_t>(lut_words, 1);
+      bb.lut_first.ensure((uint64_t)keep * S.nq); bb.lut_len.ensure((uint64_t)keep * S.nq); bb.lut_in2m.ensure(s->cap_lut);
+      O.lut_first = bb.lut_first.p; O.lut_len = bb.lut_len.p; O.lut_in2m = bb.lut_in2m.p; O.cap_lut = s->cap_lut;
+    }
+    B.n_sites = keep;
+    if (!fast.empty()) {
       const int nf = (int)a->fields.size();
       const TileTabs tabs{ctx->d_cls_tab, ctx->d_jk_tab};
       const uint32_t tiles = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
       if (tiles > 65535u) throw LimitError("more than 16.7 M query rows");
-      // remapped sites -> k_remap_tile, copy-through sites -> k_copy_tile; both lists live in fast_sites (remapped ones first)
-      std::vector<uint32_t> order; order.reserve(fast.size());
-      for (uint32_t i : fast) if (bb.h_sites[i].flags & 2u) order.push_back(i);
-      const size_t n_remap = order.size();
-      for (uint32_t i : fast) if (!(bb.h_sites[i].flags & 2u)) order.push_back(i);
-      bb.tile_sites.ensure(order.size());
-      CK(cudaMemcpyAsync(bb.tile_sites.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
       const int key = nf * 2 + (a->has_gt ? 1 : 0);
       for (size_t first = 0; first < n_remap; first += 65535) {
         const unsigned ny = (unsigned)std::min<size_t>(65535, n_remap - first);
         auto launch_tile = [&](auto kern) {
           ProfScope ps__(ctx, "k_remap_tile");
-          kern<<<dim3(tiles, ny), TILE_ROWS, 0, ctx->stream>>>(a->dev, S, B, O, bb.tile_sites.p + first, tabs);
+          kern<<<dim3(tiles, ny), TILE_ROWS, 0, ctx->stream>>>(a->dev, S, B, O, bb.tile_sites + first, tabs);
         };
         switch (key) {
           case 2: launch_tile(k_remap_tile<1, false>); break;
@@ -628,7 +710,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
         const unsigned ny = (unsigned)std::min<size_t>(65535, order.size() - first);
         auto launch_copy = [&](auto kern) {
           ProfScope ps__(ctx, "k_copy_tile");
-          kern<<<dim3(tiles, ny), TILE_ROWS, 0, ctx->stream>>>(a->dev, S, B, O, bb.tile_sites.p + first);
+          kern<<<dim3(tiles, ny), TILE_ROWS, 0, ctx->stream>>>(a->dev, S, B, O, bb.tile_sites + first);
         };
         switch (key) {
           case 2: launch_copy(k_copy_tile<1, false>); break;
@@ -645,7 +727,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       const uint32_t n_blk = nt_prefix.back();
       if (n_blk) {
         bb.blk_map.ensure(n_blk);
-        LAUNCH(ctx, k_nt_blocks, (unsigned)fast.size(), 256, B, bb.fast_sites.p, bb.nt_prefix.p, bb.blk_map.p);
+        LAUNCH(ctx, k_nt_blocks, (unsigned)fast.size(), 256, B, bb.fast_sites, bb.nt_prefix_d, bb.blk_map.p);
         auto launch_nt = [&](auto kern) {
           ProfScope ps__(ctx, "k_remap_nt");
           kern<<<n_blk, NT_THREADS, 0, ctx->stream>>>(a->dev, S, B, O, bb.blk_map.p, jk_n, tabs);
@@ -664,15 +746,13 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       }
     }
     if (!slow.empty()) {
-      bb.slow_sites.ensure(slow.size());
-      CK(cudaMemcpyAsync(bb.slow_sites.p, slow.data(), slow.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
       uint32_t tiles = (uint32_t)((S.nq + REMAP_ROWS - 1) / REMAP_ROWS);
-      LAUNCH(ctx, k_remap_generic, (unsigned)(slow.size() * tiles), REMAP_THREADS, a->dev, S, B, O, bb.slow_sites.p);
+      LAUNCH(ctx, k_remap_generic, (unsigned)(slow.size() * tiles), REMAP_THREADS, a->dev, S, B, O, bb.slow_sites);
     }
     // ---- K6: FORMAT collation + BCF typed encoding
     if (s->bcf_format) {
       const uint64_t n_plan = (uint64_t)n_out * keep;
-      bb.fmt_mm.ensure(2 * n_plan); bb.fmt_type.ensure(n_plan); bb.fmt_nps.ensure(n_plan); bb.fmt_off.ensure(n_plan);
+      bb.fmt_mm.ensure(2 * n_plan);
       bb.h_fmt_mm.resize(2 * n_plan); bb.h_fmt_type.assign(n_plan, 0); bb.h_fmt_nps.assign(n_plan, 0); bb.h_fmt_off.assign(n_plan, 0);
       for (uint64_t i = 0; i < n_plan; ++i) { bb.h_fmt_mm[2 * i] = INT32_MAX; bb.h_fmt_mm[2 * i + 1] = INT32_MIN + 1; }
       CK(cudaMemcpyAsync(bb.fmt_mm.p, bb.h_fmt_mm.data(), 2 * n_plan * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -702,26 +782,16 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       }
       bb.fmt_total = off;
       bb.fmt_bytes.ensure(std::max<uint64_t>(off, 16));
-      CK(cudaMemcpyAsync(bb.fmt_type.p, bb.h_fmt_type.data(), n_plan, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(bb.fmt_nps.p, bb.h_fmt_nps.data(), n_plan * 4, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(bb.fmt_off.p, bb.h_fmt_off.data(), n_plan * 8, cudaMemcpyHostToDevice, ctx->stream));
-      const FmtPlanDev P{bb.fmt_type.p, bb.fmt_nps.p, bb.fmt_off.p, bb.fmt_bytes.p};
+      bb.fmt_type_d = bb.ctl.push(bb.h_fmt_type.data(), n_plan); bb.fmt_nps_d = bb.ctl.push(bb.h_fmt_nps.data(), n_plan); bb.fmt_off_d = bb.ctl.push(bb.h_fmt_off.data(), n_plan);
+      bb.ctl.flush(ctx->stream);
+      const FmtPlanDev P{bb.fmt_type_d, bb.fmt_nps_d, bb.fmt_off_d, bb.fmt_bytes.p};
       LAUNCH(ctx, k_fmt_pack, dim3(chunks, keep), FMT_THREADS, a->dev, O, P, keep, (uint32_t)S.nq, s->produce_gt);
     }
     // ---- results: site metadata (host mirrors), then the copies of everything the caller asked for
-    bb.h_site_flags.resize(keep); bb.h_n_alleles.resize(keep); bb.h_n_live.resize(keep); bb.h_allele_first.resize(keep);
-    for (uint32_t i = 0; i < keep; ++i) { const SiteRec& r = bb.h_sites[i]; bb.h_site_flags[i] = (uint8_t)r.flags; bb.h_n_alleles[i] = r.n_alleles; bb.h_n_live[i] = r.n_live; bb.h_allele_first[i] = r.allele_first; }
     bb.keep = keep; bb.alg_bytes = alg_bytes;
     bb.p_tail.ensure(8);
     if (S.want_lut) {   // the LUT copy is sized by a cursor only the remap kernels advance
       CK(cudaMemcpyAsync(bb.hc, bb.cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
-    }
-    if (s->device_output) {
-      bb.d_site_flags.ensure(keep); bb.d_n_alleles.ensure(keep); bb.d_n_live.ensure(keep); bb.d_allele_first.ensure(keep);
-      CK(cudaMemcpyAsync(bb.d_site_flags.p, bb.h_site_flags.data(), keep, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(bb.d_n_alleles.p, bb.h_n_alleles.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(bb.d_n_live.p, bb.h_n_live.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(bb.d_allele_first.p, bb.h_allele_first.data(), keep * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     CK(cudaMemcpyAsync(bb.p_tail.p, s->err.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(bb.p_tail.p + 4, bb.cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -774,11 +844,11 @@ void publish_batch(gdbgpu_scan* s, BatchBuffers& bb, gdbgpu_batch* out) {
   out->site_flags = bb.h_site_flags.data(); out->n_alleles = bb.h_n_alleles.data(); out->n_live = bb.h_n_live.data(); out->allele_first = bb.h_allele_first.data();
   if (s->device_output) {
     out->site_begin = s->site_begin.p + bb.first; out->site_end = s->site_end.p + bb.first;
-    out->site_flags = bb.d_site_flags.p; out->n_alleles = bb.d_n_alleles.p; out->n_live = bb.d_n_live.p; out->allele_first = bb.d_allele_first.p;
+    out->site_flags = bb.d_site_flags; out->n_alleles = bb.d_n_alleles; out->n_live = bb.d_n_live; out->allele_first = bb.d_allele_first;
     out->allele_pos = bb.allele_pos.p; out->allele_bytes = bb.allele_bytes.p; out->live = bb.live.p;
-    for (int o = 0; o < n_out; ++o) out->fields[o] = gdbgpu_field_out{bb.out_data[o].p, bb.out_base[o].p, bb.out_stride[o].p, bb.out_len[o].p};
+    for (int o = 0; o < n_out; ++o) out->fields[o] = gdbgpu_field_out{bb.out_data[o].p, bb.out_base[o], bb.out_stride[o], bb.out_len[o].p};
     if (S.want_lut) { out->lut_first = bb.lut_first.p; out->lut_len = bb.lut_len.p; out->lut_in2m = bb.lut_in2m.p; }
-    if (s->bcf_format) { out->fmt_bytes = bb.fmt_bytes.p; out->fmt_type = bb.fmt_type.p; out->fmt_nps = bb.fmt_nps.p; out->fmt_offset = bb.fmt_off.p; }
+    if (s->bcf_format) { out->fmt_bytes = bb.fmt_bytes.p; out->fmt_type = bb.fmt_type_d; out->fmt_nps = bb.fmt_nps_d; out->fmt_offset = bb.fmt_off_d; }
   } else {
     out->site_begin = bb.p_site_begin.p; out->site_end = bb.p_site_end.p;
     out->allele_pos = bb.p_allele_pos.p; out->allele_bytes = bb.p_allele_bytes.p;
@@ -827,6 +897,7 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
 
 template <class F>
 int guarded(gdbgpu_ctx* ctx, F&& f) {
+  tl_ctx = ctx;
   try { f(); return GDBGPU_OK; }
   catch (const CudaError& e) { if (ctx) ctx->err = e.what(); return GDBGPU_ERR_CUDA; }
   catch (const LimitError& e) { if (ctx) ctx->err = e.what(); return GDBGPU_ERR_LIMIT; }
@@ -871,9 +942,15 @@ int gdbgpu_ctx_create(int device, gdbgpu_ctx** out) {
 }
 void gdbgpu_ctx_destroy(gdbgpu_ctx* ctx) {
   if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  tl_ctx = ctx;
   ctx->resolve();
   for (auto e : ctx->pool) cudaEventDestroy(e);
   for (auto* b : ctx->bb_pool) delete b;
+  cudaStreamSynchronize(ctx->stream);
+  tl_ctx = nullptr;
+  for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+  ctx->free_blocks.clear();
   if (ctx->d_cls_tab) cudaFree(ctx->d_cls_tab);
   if (ctx->d_jk_tab) cudaFree(ctx->d_jk_tab);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -997,7 +1074,7 @@ int gdbgpu_array_copy_cells(const gdbgpu_array* a, uint64_t first, uint64_t coun
     if (end && count) CK(cudaMemcpy(end, a->end.p + first, count * 8, cudaMemcpyDeviceToHost));
   });
 }
-void gdbgpu_array_close(gdbgpu_array* a) { if (a) { cudaSetDevice(a->ctx->device); delete a; } }
+void gdbgpu_array_close(gdbgpu_array* a) { if (a) { cudaSetDevice(a->ctx->device); tl_ctx = a->ctx; delete a; } }
 
 int gdbgpu_scan_begin(gdbgpu_array* arr, const gdbgpu_scan_params* params, gdbgpu_scan** out) {
   if (!arr || !params || !out) return GDBGPU_ERR_ARG;
@@ -1025,6 +1102,7 @@ int gdbgpu_scan_seek(gdbgpu_scan* s, uint64_t site_idx) {
 void gdbgpu_scan_end(gdbgpu_scan* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
+  tl_ctx = s->ctx;
   cudaStreamSynchronize(s->ctx->stream);
   cudaStreamSynchronize(s->ctx->copy_stream);
   for (auto& b : s->slot) if (b) { b->valid = false; s->ctx->bb_pool.push_back(b.release()); }
