@@ -13,23 +13,27 @@ LIB_PATH = os.environ.get("GDBGPU_LIB") or os.path.join(HERE, "lib", "libgdbgpu.
 
 OK, ERR_ARG, ERR_IO, ERR_CUDA, ERR_OVERLAP, ERR_LIMIT = 0, -1, -2, -3, -4, -5
 LEN_R, LEN_A, LEN_G = 0, 1, 2
-ELEM_INT32, ELEM_FLOAT32 = 0, 1
+ELEM_INT32, ELEM_FLOAT32, ELEM_CHAR = 0, 1, 2
 SCAN_FULL, SCAN_NO_DELETIONS, SCAN_MIN_PL_GT, SCAN_WANT_LUT, SCAN_DEVICE_OUTPUT = 1, 2, 4, 8, 16
 SCAN_BCF_FORMAT, SCAN_PRODUCE_GT, SCAN_NO_PREFETCH = 32, 64, 128
-BT_SIZE = {1: 1, 2: 2, 3: 4, 5: 4}
+BT_SIZE = {1: 1, 2: 2, 3: 4, 5: 4, 7: 1}
 SITE_NONREF, SITE_REMAPPED, SITE_G_SUPPRESSED = 1, 2, 4
 CALL_REDUCED = 0x40000000
 KIND = {"R": LEN_R, "A": LEN_A, "G": LEN_G}
 
 EXPORTS = ["gdbgpu_version", "gdbgpu_ctx_create", "gdbgpu_ctx_destroy", "gdbgpu_last_error", "gdbgpu_ctx_stream",
            "gdbgpu_ctx_launch_count", "gdbgpu_ctx_synchronize", "gdbgpu_ctx_set_profiling",
-           "gdbgpu_ctx_reset_kernel_stats", "gdbgpu_ctx_kernel_stats", "gdbgpu_array_open", "gdbgpu_array_from_columns", "gdbgpu_array_get_info",
+           "gdbgpu_ctx_reset_kernel_stats", "gdbgpu_ctx_kernel_stats", "gdbgpu_array_open", "gdbgpu_array_open_ex", "gdbgpu_array_from_columns", "gdbgpu_array_get_info",
            "gdbgpu_array_copy_cells", "gdbgpu_array_close", "gdbgpu_scan_begin", "gdbgpu_scan_get_info",
            "gdbgpu_scan_next_batch", "gdbgpu_scan_seek", "gdbgpu_scan_end"]
 
 
 class FieldDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("length_kind", C.c_int32), ("elem_type", C.c_int32)]
+
+
+class PlainFieldDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("elem_type", C.c_int32), ("fixed_len", C.c_int32)]
 
 
 class VarColumn(C.Structure):
@@ -40,14 +44,15 @@ class Columns(C.Structure):
     _fields_ = [("n_cells", C.c_uint64), ("coords", C.c_void_p), ("end", C.c_void_p),
                 ("ref", VarColumn), ("alt", VarColumn), ("gt", VarColumn), ("gt_phased", C.c_int32),
                 ("n_fields", C.c_int32), ("field_descs", C.POINTER(FieldDesc)), ("fields", C.POINTER(VarColumn)),
-                ("lb_row_idx", C.c_int64), ("num_rows", C.c_int64)]
+                ("lb_row_idx", C.c_int64), ("num_rows", C.c_int64),
+                ("n_plain_fields", C.c_int32), ("plain_descs", C.POINTER(PlainFieldDesc)), ("plain_fields", C.POINTER(VarColumn))]
 
 
 class ArrayInfo(C.Structure):
     _fields_ = [("n_cells", C.c_uint64), ("n_begin_cells", C.c_uint64), ("n_fragments", C.c_uint32),
                 ("lb_row_idx", C.c_int64), ("num_rows", C.c_int64), ("min_col", C.c_int64), ("max_col", C.c_int64),
                 ("max_end", C.c_int64), ("staged_bytes", C.c_uint64), ("hbm_bytes", C.c_uint64),
-                ("n_fields", C.c_int32), ("has_gt", C.c_int32), ("gt_phased", C.c_int32)]
+                ("n_fields", C.c_int32), ("has_gt", C.c_int32), ("gt_phased", C.c_int32), ("n_plain_fields", C.c_int32)]
 
 
 class ScanParams(C.Structure):
@@ -71,7 +76,7 @@ class Batch(C.Structure):
                 ("allele_first", C.c_void_p), ("allele_pos", C.c_void_p), ("allele_bytes", C.c_void_p),
                 ("live", C.c_void_p), ("n_fields", C.c_int32), ("fields", FieldOut * 16),
                 ("lut_first", C.c_void_p), ("lut_len", C.c_void_p), ("lut_in2m", C.c_void_p), ("out_bytes", C.c_uint64),
-                ("fmt_type", C.c_void_p), ("fmt_nps", C.c_void_p), ("fmt_offset", C.c_void_p), ("fmt_bytes", C.c_void_p),
+                ("n_fmt_fields", C.c_int32), ("fmt_type", C.c_void_p), ("fmt_nps", C.c_void_p), ("fmt_offset", C.c_void_p), ("fmt_bytes", C.c_void_p),
                 ("fmt_total_bytes", C.c_uint64)]
 
 
@@ -101,6 +106,8 @@ def lib():
         L.gdbgpu_ctx_kernel_stats.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.gdbgpu_array_open.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(FieldDesc), C.c_int32, C.c_int32,
                                         C.POINTER(C.c_void_p)]
+        L.gdbgpu_array_open_ex.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(FieldDesc), C.c_int32,
+                                           C.POINTER(PlainFieldDesc), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
         L.gdbgpu_array_from_columns.argtypes = [C.c_void_p, C.POINTER(Columns), C.POINTER(C.c_void_p)]
         L.gdbgpu_array_get_info.argtypes = [C.c_void_p, C.POINTER(ArrayInfo)]
         L.gdbgpu_array_copy_cells.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -174,6 +181,15 @@ def _field_descs(fields):
     return arr
 
 
+def _plain_descs(plain):
+    """plain: list of (attribute name, 'int'|'float'|'char', fixed length or 0 for variable)"""
+    arr = (PlainFieldDesc * max(1, len(plain)))()
+    code = {"int": ELEM_INT32, "float": ELEM_FLOAT32, "char": ELEM_CHAR}
+    for i, (name, elem, fixed) in enumerate(plain):
+        arr[i] = PlainFieldDesc(name.encode(), code.get(elem, elem), int(fixed))
+    return arr
+
+
 class Array:
     """fields: list of (attribute name, 'R'|'A'|'G', 'int'|'float')"""
 
@@ -181,15 +197,18 @@ class Array:
         self.ctx, self.h, self._keep = ctx, handle, keep
 
     @classmethod
-    def open(cls, ctx, workspace, array_name, fields, gt_phased=False):
+    def open(cls, ctx, workspace, array_name, fields, gt_phased=False, plain=()):
         h = C.c_void_p()
         fd = _field_descs(fields)
-        ctx.check(lib().gdbgpu_array_open(ctx.h, workspace.encode(), array_name.encode(), fd, len(fields), int(gt_phased), C.byref(h)))
+        pd = _plain_descs(list(plain))
+        ctx.check(lib().gdbgpu_array_open_ex(ctx.h, workspace.encode(), array_name.encode(), fd, len(fields), pd, len(plain),
+                                             int(gt_phased), C.byref(h)))
         return cls(ctx, h)
 
     @classmethod
-    def from_columns(cls, ctx, coords, end, ref, alt, gt, fields, lb_row, num_rows, gt_phased=False):
-        """ref/alt/gt/fields[i]['col'] = (byte_offsets uint64[n], values ndarray); fields = list of dict(name, kind, elem, col)"""
+    def from_columns(cls, ctx, coords, end, ref, alt, gt, fields, lb_row, num_rows, gt_phased=False, plain=()):
+        """ref/alt/gt/fields[i]['col'] = (byte_offsets uint64[n], values ndarray); fields = list of dict(name, kind, elem, col);
+        plain = list of dict(name, elem, fixed_len, col) with col = (None, values) for a fixed-length field"""
         keep = []
 
         def vc(col):
@@ -216,6 +235,18 @@ class Array:
         keep += [fd, fv]
         c.field_descs, c.fields = fd, fv
         c.lb_row_idx, c.num_rows = lb_row, num_rows
+        plain = list(plain)
+        pd = _plain_descs([(f["name"], f["elem"], f["fixed_len"]) for f in plain])
+        pv = (VarColumn * max(1, len(plain)))()
+        for i, f in enumerate(plain):
+            if f["fixed_len"]:
+                val = np.ascontiguousarray(f["col"][1])
+                keep.append(val)
+                pv[i] = VarColumn(None, val.ctypes.data if val.size else None, val.nbytes)
+            else:
+                pv[i] = vc(f["col"])
+        keep += [pd, pv]
+        c.n_plain_fields, c.plain_descs, c.plain_fields = len(plain), pd, pv
         h = C.c_void_p()
         ctx.check(lib().gdbgpu_array_from_columns(ctx.h, C.byref(c), C.byref(h)))
         return cls(ctx, h, keep=None)
@@ -265,10 +296,12 @@ class BatchView:
             data = _view(f.data, np.uint32, int(base[ns]) if ns else 0) if f.data else None
             self.fields.append(dict(base=base, stride=stride, len=ln, data=data))
         self.fmt_total_bytes = b.fmt_total_bytes
+        self.n_fmt_fields = b.n_fmt_fields
         if b.fmt_type:
-            self.fmt_type = _view(b.fmt_type, np.uint8, n_out * ns).reshape(n_out, ns)
-            self.fmt_nps = _view(b.fmt_nps, np.uint32, n_out * ns).reshape(n_out, ns)
-            self.fmt_offset = _view(b.fmt_offset, np.uint64, n_out * ns).reshape(n_out, ns)
+            nf = b.n_fmt_fields
+            self.fmt_type = _view(b.fmt_type, np.uint8, nf * ns).reshape(nf, ns)
+            self.fmt_nps = _view(b.fmt_nps, np.uint32, nf * ns).reshape(nf, ns)
+            self.fmt_offset = _view(b.fmt_offset, np.uint64, nf * ns).reshape(nf, ns)
             self.fmt_bytes = _view(b.fmt_bytes, np.uint8, b.fmt_total_bytes)
         else:
             self.fmt_type = None

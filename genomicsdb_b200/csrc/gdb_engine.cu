@@ -100,6 +100,7 @@ struct DevBuf {
   DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() { if (p) { dev_free(owner, p, cap); p = nullptr; } }
+  void swap(DevBuf& o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); std::swap(owner, o.owner); }
   void alloc(size_t count) {
     release(); n = count; owner = tl_ctx;
     if (count) p = static_cast<T*>(dev_alloc(owner, count * sizeof(T), cap));
@@ -156,6 +157,10 @@ __global__ void k_bounds(const int64_t* coords, uint64_t n, int64_t q_lo, int64_
   while (lo < hi) { uint64_t mid = (lo + hi) >> 1; int64_t c = coords[2 * mid + 1]; if (strict ? (c <= key) : (c < key)) lo = mid + 1; else hi = mid; }
   out[t] = lo;
 }
+__global__ void k_gather_bytes(const uint8_t* in, const uint32_t* perm, uint64_t n, uint32_t cell_bytes, uint8_t* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) for (uint32_t b = 0; b < cell_bytes; ++b) out[i * cell_bytes + b] = in[(uint64_t)perm[i] * cell_bytes + b];
+}
 __global__ void k_add_i32(const int32_t* a, const int32_t* b, int32_t* out, uint64_t n) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = a[i] + b[i]; }
 
 struct HostVar { const uint64_t* off = nullptr; const void* val = nullptr; uint64_t bytes = 0; };
@@ -164,7 +169,9 @@ struct HostCols {
   const int64_t* coords = nullptr; const int64_t* end = nullptr;
   HostVar ref, alt, gt; bool has_gt = false;
   std::vector<HostVar> fields;
+  std::vector<HostVar> plain;   // fixed-length plain field: off == nullptr
 };
+struct PlainMeta { std::string name; int32_t elem, fixed_len; };
 
 struct DevVar { DevBuf<uint64_t> off; DevBuf<uint8_t> val; uint64_t bytes = 0; };
 
@@ -180,6 +187,7 @@ struct gdbgpu_array {
   std::vector<FieldMeta> fm; std::vector<std::string> field_names;
   DevBuf<int64_t> coords, end;
   DevVar ref, alt, gt; std::vector<std::unique_ptr<DevVar>> fields;
+  std::vector<std::unique_ptr<DevVar>> plain; std::vector<PlainMeta> pm; PlainSet plain_dev{};   // plain FORMAT fields (K6)
   DevBuf<CellDesc> desc; DevBuf<HotRec> hot; DevBuf<uint32_t> warm; DevBuf<int64_t> effend;
   DevBuf<uint32_t> rs_cell, rs_keys; DevBuf<int64_t> rs_col, rs_effend; DevBuf<uint64_t> row_start; uint64_t n_rs = 0;
   DevBuf<uint32_t> bad_cell; DevBuf<int64_t> bad_pred_col;
@@ -188,6 +196,7 @@ struct gdbgpu_array {
     uint64_t b = coords.bytes() + end.bytes() + ref.off.bytes() + ref.val.bytes() + alt.off.bytes() + alt.val.bytes() + gt.off.bytes() + gt.val.bytes() +
                  desc.bytes() + hot.bytes() + warm.bytes() + effend.bytes() + rs_cell.bytes() + rs_keys.bytes() + rs_col.bytes() + rs_effend.bytes() + row_start.bytes();
     for (auto& f : fields) b += f->off.bytes() + f->val.bytes();
+    for (auto& f : plain) b += f->off.bytes() + f->val.bytes();
     return b;
   }
 };
@@ -215,6 +224,8 @@ void fill_dev_view(gdbgpu_array* a) {
   for (size_t f = 0; f < a->fields.size(); ++f) { D.f[f] = VarCol{a->fields[f]->off.p, a->fields[f]->val.p}; D.fm[f] = a->fm[f]; }
   D.lb_row = a->lb_row; D.num_rows = a->num_rows;
   D.desc = a->desc.p; D.hot = a->hot.p; D.warm = a->warm.p; D.effend = a->effend.p;
+  a->plain_dev.n = (int32_t)a->plain.size();
+  for (size_t f = 0; f < a->plain.size(); ++f) a->plain_dev.f[f] = PlainDev{a->pm[f].fixed_len ? nullptr : a->plain[f]->off.p, a->plain[f]->val.p, a->pm[f].elem, a->pm[f].fixed_len};
   D.n_rs = a->n_rs; D.rs_cell = a->rs_cell.p; D.rs_col = a->rs_col.p; D.rs_effend = a->rs_effend.p; D.row_start = a->row_start.p;
 }
 
@@ -267,7 +278,7 @@ void gather_var(gdbgpu_ctx* ctx, const DevVar& in, const uint32_t* src, uint64_t
 
 // stage host columns (already concatenated over fragments) and build the per-array indexes
 gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<uint64_t>& frag_cells, int64_t lb_row, int64_t num_rows, int gt_phased,
-                          const std::vector<FieldMeta>& fm, const std::vector<std::string>& names) {
+                          const std::vector<FieldMeta>& fm, const std::vector<std::string>& names, const std::vector<PlainMeta>& pm = {}) {
   static const bool trace = getenv("GDBGPU_TRACE") != nullptr;   // phase times of the staging on stderr
   auto t_prev = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -280,7 +291,9 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
   if (h.n >= (1ull << 30)) throw LimitError("more than 2^30 cells in one staged array: shard the column range across GPUs");
   if (h.fields.size() > (size_t)MAX_FIELDS) throw LimitError("more than 15 allele-dependent fields queried");
   if (num_rows < 0 || num_rows >= (1ll << 31)) throw LimitError("row count out of range");
+  if (pm.size() > (size_t)MAX_PLAIN || pm.size() != h.plain.size()) throw LimitError("more than 16 plain FORMAT fields");
   std::unique_ptr<gdbgpu_array> a(new gdbgpu_array());
+  a->pm = pm;
   a->ctx = ctx; a->n = h.n; a->lb_row = lb_row; a->num_rows = num_rows; a->gt_phased = gt_phased; a->has_gt = h.has_gt; a->fm = fm; a->field_names = names;
   a->n_fragments = (uint32_t)std::max<size_t>(1, frag_cells.size());
   uint64_t n = h.n;
@@ -291,6 +304,16 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
   upload_var(ctx, h.alt, n, a->alt, a->staged_bytes);
   if (h.has_gt) upload_var(ctx, h.gt, n, a->gt, a->staged_bytes);
   for (auto& f : h.fields) { a->fields.emplace_back(new DevVar()); upload_var(ctx, f, n, *a->fields.back(), a->staged_bytes); }
+  for (size_t f = 0; f < h.plain.size(); ++f) {
+    a->plain.emplace_back(new DevVar());
+    if (!pm[f].fixed_len) { upload_var(ctx, h.plain[f], n, *a->plain.back(), a->staged_bytes); continue; }
+    DevVar& d = *a->plain.back();
+    d.bytes = h.plain[f].bytes;
+    if (d.bytes != n * (uint64_t)pm[f].fixed_len * (pm[f].elem == ELEM_CHAR ? 1u : 4u)) throw ArgError("plain field " + pm[f].name + ": value bytes do not match n_cells x fixed_len");
+    d.val.alloc(std::max<uint64_t>(d.bytes, 1));
+    if (d.bytes) CK(cudaMemcpyAsync(d.val.p, h.plain[f].val, d.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    a->staged_bytes += d.bytes;
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   lap("upload");
 
@@ -301,10 +324,19 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
     LAUNCH(ctx, k_gather_fixed, blocks_for(n_out * 2, 256), 256, (const uint8_t*)a->coords.p, src.p, n_out, 16u, (uint8_t*)c2.p);
     LAUNCH(ctx, k_gather_fixed, blocks_for(n_out, 256), 256, (const uint8_t*)a->end.p, src.p, n_out, 8u, (uint8_t*)e2.p);
     CK(cudaStreamSynchronize(ctx->stream));
-    std::swap(a->coords.p, c2.p); std::swap(a->coords.n, c2.n); std::swap(a->end.p, e2.p); std::swap(a->end.n, e2.n);
-    auto regather = [&](DevVar& v) { DevVar o; gather_var(ctx, v, src.p, n_out, o); std::swap(v.off.p, o.off.p); std::swap(v.off.n, o.off.n); std::swap(v.val.p, o.val.p); std::swap(v.val.n, o.val.n); v.bytes = o.bytes; };
+    a->coords.swap(c2); a->end.swap(e2);
+    auto regather = [&](DevVar& v) { DevVar o; gather_var(ctx, v, src.p, n_out, o); v.off.swap(o.off); v.val.swap(o.val); v.bytes = o.bytes; };
     regather(a->ref); regather(a->alt); if (h.has_gt) regather(a->gt);
     for (auto& f : a->fields) regather(*f);
+    for (size_t f = 0; f < a->plain.size(); ++f) {
+      if (!pm[f].fixed_len) { regather(*a->plain[f]); continue; }
+      const uint32_t cb = (uint32_t)pm[f].fixed_len * (pm[f].elem == ELEM_CHAR ? 1u : 4u);
+      DevBuf<uint8_t> v2; v2.alloc(std::max<uint64_t>(n_out * cb, 1));
+      LAUNCH(ctx, k_gather_bytes, blocks_for(n_out, 256), 256, a->plain[f]->val.p, src.p, n_out, cb, v2.p);
+      CK(cudaStreamSynchronize(ctx->stream));
+      a->plain[f]->val.swap(v2);
+      a->plain[f]->bytes = n_out * cb;
+    }
     a->n = n = n_out;
   }
   // K2: classify + row-major index
@@ -659,7 +691,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
     bb.h_site_flags.resize(keep); bb.h_n_alleles.resize(keep); bb.h_n_live.resize(keep); bb.h_allele_first.resize(keep);
     for (uint32_t i = 0; i < keep; ++i) { const SiteRec& r = bb.h_sites[i]; bb.h_site_flags[i] = (uint8_t)r.flags; bb.h_n_alleles[i] = r.n_alleles; bb.h_n_live[i] = r.n_live; bb.h_allele_first[i] = r.allele_first; }
     // one pinned block, one copy: bases, strides, site lists, site table (+ the FORMAT plan later)
-    bb.ctl.begin((size_t)n_out * ((size_t)keep * 12 + 64) + (size_t)keep * 48 + (size_t)n_out * keep * 13 + 4096);
+    bb.ctl.begin((size_t)n_out * ((size_t)keep * 12 + 64) + (size_t)keep * 48 + (size_t)(n_out + MAX_PLAIN) * keep * 13 + 4096);
     RemapOut O{};
     O.n_out = n_out;
     for (int o = 0; o < n_out; ++o) {
@@ -749,34 +781,52 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       uint32_t tiles = (uint32_t)((S.nq + REMAP_ROWS - 1) / REMAP_ROWS);
       LAUNCH(ctx, k_remap_generic, (unsigned)(slow.size() * tiles), REMAP_THREADS, a->dev, S, B, O, bb.slow_sites);
     }
-    // ---- K6: FORMAT collation + BCF typed encoding
+    // ---- K6: FORMAT collation + BCF typed encoding (remapped fields from K5's output, plain fields through the live matrix)
     if (s->bcf_format) {
-      const uint64_t n_plan = (uint64_t)n_out * keep;
-      bb.fmt_mm.ensure(2 * n_plan);
-      bb.h_fmt_mm.resize(2 * n_plan); bb.h_fmt_type.assign(n_plan, 0); bb.h_fmt_nps.assign(n_plan, 0); bb.h_fmt_off.assign(n_plan, 0);
-      for (uint64_t i = 0; i < n_plan; ++i) { bb.h_fmt_mm[2 * i] = INT32_MAX; bb.h_fmt_mm[2 * i + 1] = INT32_MIN + 1; }
-      CK(cudaMemcpyAsync(bb.fmt_mm.p, bb.h_fmt_mm.data(), 2 * n_plan * 4, cudaMemcpyHostToDevice, ctx->stream));
+      const int n_plain = (int)a->plain.size(), n_fmt = n_out + n_plain;
+      const uint64_t n_plan = (uint64_t)n_fmt * keep, n_rp = (uint64_t)n_out * keep, n_pp = (uint64_t)n_plain * keep;
+      bb.fmt_mm.ensure(2 * n_rp + PS_WORDS * n_pp + 4);
+      bb.h_fmt_mm.resize(2 * n_rp + PS_WORDS * n_pp); bb.h_fmt_type.assign(n_plan, 0); bb.h_fmt_nps.assign(n_plan, 0); bb.h_fmt_off.assign(n_plan, 0);
+      for (uint64_t i = 0; i < n_rp; ++i) { bb.h_fmt_mm[2 * i] = INT32_MAX; bb.h_fmt_mm[2 * i + 1] = INT32_MIN + 1; }
+      int32_t* h_ps = bb.h_fmt_mm.data() + 2 * n_rp;
+      for (uint64_t i = 0; i < n_pp; ++i) { h_ps[PS_WORDS * i + PS_MIN] = INT32_MAX; h_ps[PS_WORDS * i + PS_MAX] = INT32_MIN + 1; h_ps[PS_WORDS * i + PS_MAXLEN] = 0; h_ps[PS_WORDS * i + PS_ANY] = 0; }
+      CK(cudaMemcpyAsync(bb.fmt_mm.p, bb.h_fmt_mm.data(), bb.h_fmt_mm.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
       uint64_t max_words = 1;
       for (int o = 0; o < n_out; ++o) for (uint32_t i = 0; i < keep; ++i) max_words = std::max<uint64_t>(max_words, (uint64_t)bb.h_stride[o][i] * S.nq);
       const unsigned chunks = (unsigned)std::min<uint64_t>(64, std::max<uint64_t>(1, max_words / (FMT_THREADS * 16)));
+      const unsigned row_blocks = blocks_for(S.nq, FMT_THREADS);
       LAUNCH(ctx, k_fmt_range, dim3(chunks, keep), FMT_THREADS, a->dev, O, keep, (uint32_t)S.nq, s->produce_gt, bb.fmt_mm.p);
-      CK(cudaMemcpyAsync(bb.h_fmt_mm.data(), bb.fmt_mm.p, 2 * n_plan * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      if (n_plain) LAUNCH(ctx, k_plain_scan, dim3(row_blocks, keep), FMT_THREADS, a->plain_dev, bb.live.p, keep, (uint32_t)S.nq, bb.fmt_mm.p + 2 * n_rp);
+      CK(cudaMemcpyAsync(bb.h_fmt_mm.data(), bb.fmt_mm.p, bb.h_fmt_mm.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
+      // bcf_enc_vint's width rule (vcf.c:1926-1972); a block of ONE value goes through bcf_enc_int1 instead (vcf.c:1931)
+      auto int_type = [&](int64_t lo, int64_t hi, uint64_t n_values) -> uint8_t {
+        if (n_values == 1) {
+          if (lo > hi) return BT_INT8;          // the value is missing / vector_end
+          return (lo >= -120 && hi <= 127) ? BT_INT8 : ((lo >= -32760 && hi <= 32767) ? BT_INT16 : BT_INT32);
+        }
+        return (hi <= 127 && lo > -127) ? BT_INT8 : ((hi <= 32767 && lo > -32767) ? BT_INT16 : BT_INT32);
+      };
       uint64_t off = 0;
-      for (uint32_t i = 0; i < keep; ++i) for (int o = 0; o < n_out; ++o) {   // the blocks of one site are neighbours
+      for (uint32_t i = 0; i < keep; ++i) for (int o = 0; o < n_fmt; ++o) {   // the blocks of one site are neighbours
         const uint64_t pi = (uint64_t)o * keep + i;
-        const bool is_gt = a->has_gt && o == 0;
-        const uint32_t need = stride_needed(a, bb.h_sites[i], o);
-        if (need == 0) continue;
-        const uint32_t nps = (is_gt && a->gt_phased) ? (need + 1u) / 2u : need;
-        const int64_t lo = bb.h_fmt_mm[2 * pi], hi = bb.h_fmt_mm[2 * pi + 1];
-        uint8_t type;
-        if (!is_gt && a->fm[o - (a->has_gt ? 1 : 0)].elem) type = BT_FLOAT;
-        else if ((uint64_t)nps * S.nq == 1) {   // bcf_enc_vint hands a single value to bcf_enc_int1 (vcf.c:1931, vcf.h bcf_enc_int1)
-          if (lo > hi) type = BT_INT8;          // the value is missing / vector_end
-          else type = (lo >= -120 && hi <= 127) ? BT_INT8 : ((lo >= -32760 && hi <= 32767) ? BT_INT16 : BT_INT32);
-        } else type = (hi <= 127 && lo > -127) ? BT_INT8 : ((hi <= 32767 && lo > -32767) ? BT_INT16 : BT_INT32);
-        const uint64_t size = (uint64_t)nps * S.nq * (type == BT_INT8 ? 1u : (type == BT_INT16 ? 2u : 4u));
+        uint32_t nps; uint8_t type;
+        if (o < n_out) {
+          const bool is_gt = a->has_gt && o == 0;
+          const uint32_t need = stride_needed(a, bb.h_sites[i], o);
+          if (need == 0) continue;
+          nps = (is_gt && a->gt_phased) ? (need + 1u) / 2u : need;
+          if (!is_gt && a->fm[o - (a->has_gt ? 1 : 0)].elem) type = BT_FLOAT;
+          else type = int_type(bb.h_fmt_mm[2 * pi], bb.h_fmt_mm[2 * pi + 1], (uint64_t)nps * S.nq);
+        } else {
+          const int f = o - n_out;
+          const int32_t* st = h_ps + ((uint64_t)f * keep + i) * PS_WORDS;
+          if (!st[PS_ANY]) continue;
+          nps = (uint32_t)st[PS_MAXLEN];
+          if (nps == 0) continue;
+          type = a->pm[f].elem == ELEM_CHAR ? BT_CHAR : (a->pm[f].elem == ELEM_FLOAT32 ? BT_FLOAT : int_type(st[PS_MIN], st[PS_MAX], (uint64_t)nps * S.nq));
+        }
+        const uint64_t size = (uint64_t)nps * S.nq * ((type == BT_INT8 || type == BT_CHAR) ? 1u : (type == BT_INT16 ? 2u : 4u));
         bb.h_fmt_type[pi] = type; bb.h_fmt_nps[pi] = nps; bb.h_fmt_off[pi] = off;
         off += (size + 15u) & ~15ull;
       }
@@ -786,6 +836,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       bb.ctl.flush(ctx->stream);
       const FmtPlanDev P{bb.fmt_type_d, bb.fmt_nps_d, bb.fmt_off_d, bb.fmt_bytes.p};
       LAUNCH(ctx, k_fmt_pack, dim3(chunks, keep), FMT_THREADS, a->dev, O, P, keep, (uint32_t)S.nq, s->produce_gt);
+      if (n_plain) LAUNCH(ctx, k_plain_pack, dim3(row_blocks, keep), FMT_THREADS, a->plain_dev, P, n_out, bb.live.p, keep, (uint32_t)S.nq);
     }
     // ---- results: site metadata (host mirrors), then the copies of everything the caller asked for
     bb.keep = keep; bb.alg_bytes = alg_bytes;
@@ -862,6 +913,7 @@ void publish_batch(gdbgpu_scan* s, BatchBuffers& bb, gdbgpu_batch* out) {
     }
   }
   out->fmt_total_bytes = bb.fmt_total;
+  out->n_fmt_fields = s->bcf_format ? n_out + (int)a->plain.size() : 0;
   (void)a;
 }
 
@@ -994,13 +1046,26 @@ int gdbgpu_array_from_columns(gdbgpu_ctx* ctx, const gdbgpu_columns* c, gdbgpu_a
       fm.push_back(FieldMeta{c->field_descs[f].length_kind, c->field_descs[f].elem_type, nm == "PL" ? 1 : 0});
       names.push_back(nm);
     }
-    *out = build_array(ctx, h, {h.n}, c->lb_row_idx, c->num_rows, c->gt_phased, fm, names);
+    std::vector<PlainMeta> pm;
+    if (c->n_plain_fields < 0 || c->n_plain_fields > MAX_PLAIN) throw LimitError("more than 16 plain FORMAT fields");
+    for (int f = 0; f < c->n_plain_fields; ++f) {
+      const gdbgpu_plain_field_desc& d = c->plain_descs[f];
+      if (d.elem_type < 0 || d.elem_type > GDBGPU_ELEM_CHAR || d.fixed_len < 0) throw ArgError("bad plain field descriptor");
+      if (!d.fixed_len && !c->plain_fields[f].offsets) throw ArgError("variable-length plain field without offsets");
+      h.plain.push_back(HostVar{d.fixed_len ? nullptr : c->plain_fields[f].offsets, c->plain_fields[f].values, c->plain_fields[f].values_bytes});
+      pm.push_back(PlainMeta{d.name ? d.name : "", d.elem_type, d.fixed_len});
+    }
+    *out = build_array(ctx, h, {h.n}, c->lb_row_idx, c->num_rows, c->gt_phased, fm, names, pm);
   });
 }
 
 int gdbgpu_array_open(gdbgpu_ctx* ctx, const char* workspace, const char* array_name, const gdbgpu_field_desc* fields, int32_t n_fields, int32_t gt_phased,
                       gdbgpu_array** out) {
-  if (!ctx || !workspace || !array_name || !out || n_fields < 0) return GDBGPU_ERR_ARG;
+  return gdbgpu_array_open_ex(ctx, workspace, array_name, fields, n_fields, nullptr, 0, gt_phased, out);
+}
+int gdbgpu_array_open_ex(gdbgpu_ctx* ctx, const char* workspace, const char* array_name, const gdbgpu_field_desc* fields, int32_t n_fields,
+                         const gdbgpu_plain_field_desc* plain, int32_t n_plain, int32_t gt_phased, gdbgpu_array** out) {
+  if (!ctx || !workspace || !array_name || !out || n_fields < 0 || n_plain < 0 || n_plain > MAX_PLAIN || (n_plain && !plain)) return GDBGPU_ERR_ARG;
   *out = nullptr;
   return guarded(ctx, [&] {
     CK(cudaSetDevice(ctx->device));
@@ -1018,6 +1083,16 @@ int gdbgpu_array_open(gdbgpu_ctx* ctx, const char* workspace, const char* array_
       ids.push_back(id);
       fm.push_back(FieldMeta{fields[f].length_kind, fields[f].elem_type, std::string(fields[f].name) == "PL" ? 1 : 0});
       names.push_back(fields[f].name);
+    }
+    std::vector<PlainMeta> pm;
+    for (int f = 0; f < n_plain; ++f) {   // the schema decides fixed / variable and the element size; the descriptor must agree
+      int id = need(plain[f].name);
+      const size_t es = plain[f].elem_type == GDBGPU_ELEM_CHAR ? 1 : 4;
+      if (sc.type_size(id) != es) throw std::runtime_error(std::string("plain field element size does not match the array schema: ") + plain[f].name);
+      const int fixed = sc.is_var(id) ? 0 : sc.cell_val_num[id];
+      if (plain[f].fixed_len != fixed) throw std::runtime_error(std::string("plain field length does not match the array schema: ") + plain[f].name);
+      ids.push_back(id);
+      pm.push_back(PlainMeta{plain[f].name, plain[f].elem_type, fixed});
     }
     // read every needed column of every fragment, concatenating (var offsets rebased onto the concatenated stream)
     size_t nfrag = ta.num_fragments();
@@ -1050,12 +1125,13 @@ int gdbgpu_array_open(gdbgpu_ctx* ctx, const char* workspace, const char* array_
     h.has_gt = id_gt >= 0;
     if (h.has_gt) h.gt = hv(k++);
     for (int f = 0; f < n_fields; ++f) h.fields.push_back(hv(k++));
+    for (int f = 0; f < n_plain; ++f, ++k) h.plain.push_back(pm[f].fixed_len ? HostVar{nullptr, fixed[k].data(), fixed[k].size()} : hv(k));
     int64_t lb = 0, ub = 0;
     if (!ta.row_bounds(lb, ub)) {   // no GenomicsDB metadata: bound by the data
       ub = -1;
       for (uint64_t i = 0; i < n_total; ++i) ub = std::max(ub, h.coords[2 * i]);
     }
-    *out = build_array(ctx, h, frag_cells, lb, ub - lb + 1, gt_phased, fm, names);
+    *out = build_array(ctx, h, frag_cells, lb, ub - lb + 1, gt_phased, fm, names, pm);
   });
 }
 
@@ -1063,7 +1139,7 @@ int gdbgpu_array_get_info(const gdbgpu_array* a, gdbgpu_array_info* info) {
   if (!a || !info) return GDBGPU_ERR_ARG;
   info->n_cells = a->n; info->n_begin_cells = a->n_begin; info->n_fragments = a->n_fragments; info->lb_row_idx = a->lb_row; info->num_rows = a->num_rows;
   info->min_col = a->min_col; info->max_col = a->max_col; info->max_end = a->max_end; info->staged_bytes = a->staged_bytes; info->hbm_bytes = a->hbm_bytes();
-  info->n_fields = (int)a->fields.size(); info->has_gt = a->has_gt; info->gt_phased = a->gt_phased;
+  info->n_fields = (int)a->fields.size(); info->has_gt = a->has_gt; info->gt_phased = a->gt_phased; info->n_plain_fields = (int)a->plain.size();
   return GDBGPU_OK;
 }
 int gdbgpu_array_copy_cells(const gdbgpu_array* a, uint64_t first, uint64_t count, int64_t* coords, int64_t* end) {

@@ -18,7 +18,7 @@
 
 namespace gdb {
 
-enum : uint8_t { BT_NONE = 0, BT_INT8 = 1, BT_INT16 = 2, BT_INT32 = 3, BT_FLOAT = 5 };
+enum : uint8_t { BT_NONE = 0, BT_INT8 = 1, BT_INT16 = 2, BT_INT32 = 3, BT_FLOAT = 5, BT_CHAR = 7 };
 constexpr int FMT_THREADS = 256;
 
 struct FmtPlanDev {          // [o * n_sites + site]
@@ -143,6 +143,99 @@ __global__ void __launch_bounds__(FMT_THREADS) k_fmt_pack(const __grid_constant_
         if (cnt == 4) *reinterpret_cast<uint4*>(dst + 4 * e) = make_uint4(w[0], w[1], w[2], w[3]);
         else for (uint32_t x = 0; x < cnt; ++x) *reinterpret_cast<uint32_t*>(dst + 4 * (e + x)) = w[x];
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ plain FORMAT fields
+// FORMAT fields whose length does not depend on the alleles (GQ, MIN_DP, DP_FORMAT, SB, PGT, PID ...) are not remapped:
+// their collation is a gather through the live matrix (the call of query row q at site s -> its cell -> the cell's
+// values), with the same row rules as above (collect_and_extend_fields, variant_field_handler.cc:804-871) and, for
+// strings, bcf_str_missing / bcf_str_vector_end (htslib vcf.h) and BCF_BT_CHAR blocks (vcf.c:3653-3657).  A field of a
+// call is valid unless every element is the TileDB null of its type (variant_field_data.h:236-251,365-384).
+constexpr int MAX_PLAIN = 16;
+enum { ELEM_INT32 = 0, ELEM_FLOAT32 = 1, ELEM_CHAR = 2 };
+constexpr uint8_t TDB_NULL_CHAR = 127, BCF_STR_MISSING = 0x07, BCF_STR_VEND = 0x00;
+struct PlainDev { const uint64_t* off; const uint8_t* val; int32_t elem, fixed_len; };
+struct PlainSet { int32_t n; PlainDev f[MAX_PLAIN]; };
+enum { PS_MIN = 0, PS_MAX, PS_MAXLEN, PS_ANY, PS_WORDS };   // per (plain field, site) statistics, int32 each
+
+// values of plain field F in `cell`: pointer, number of elements, validity
+__device__ inline bool plain_fetch(const PlainDev& F, uint32_t cell, const uint8_t*& p, uint32_t& n) {
+  const uint32_t es = F.elem == ELEM_CHAR ? 1u : 4u;
+  if (F.fixed_len) { n = (uint32_t)F.fixed_len; p = F.val + (uint64_t)cell * n * es; }
+  else { const uint64_t o0 = F.off[cell], o1 = F.off[cell + 1]; p = F.val + o0; n = (uint32_t)((o1 - o0) / es); }
+  if (F.elem == ELEM_CHAR) { for (uint32_t i = 0; i < n; ++i) if (p[i] != TDB_NULL_CHAR) return true; return false; }
+  const uint32_t nullw = F.elem == ELEM_FLOAT32 ? TDB_NULL_FLT : TDB_NULL_INT;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+  for (uint32_t i = 0; i < n; ++i) if (w[i] != nullw) return true;
+  return false;
+}
+
+// pass 1: per (field, site): is any row's field valid, the longest valid vector, min / max of the integer values.
+// grid = (row chunks, sites), one thread per query row.
+__global__ void __launch_bounds__(FMT_THREADS) k_plain_scan(const __grid_constant__ PlainSet P, const int32_t* __restrict__ live, const uint32_t n_sites, const uint32_t nq,
+                                                            int32_t* __restrict__ stat) {
+  __shared__ int32_t s_st[MAX_PLAIN][PS_WORDS];
+  const uint32_t js = blockIdx.y, tid = threadIdx.x, q = blockIdx.x * FMT_THREADS + tid;
+  if (tid < (uint32_t)P.n * PS_WORDS) { const int w = tid % PS_WORDS; s_st[tid / PS_WORDS][w] = w == PS_MIN ? INT32_MAX : (w == PS_MAX ? INT32_MIN + 1 : 0); }
+  __syncthreads();
+  const int32_t e = q < nq ? live[(uint64_t)js * nq + q] : -1;
+  if (e >= 0) {
+    const uint32_t cell = (uint32_t)(e & (LIVE_REDUCED - 1));
+    for (int f = 0; f < P.n; ++f) {
+      const uint8_t* p; uint32_t n;
+      if (!plain_fetch(P.f[f], cell, p, n)) continue;
+      atomicMax(&s_st[f][PS_MAXLEN], (int32_t)n);
+      s_st[f][PS_ANY] = 1;
+      if (P.f[f].elem == ELEM_INT32) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+        int32_t lo = INT32_MAX, hi = INT32_MIN + 1;
+        for (uint32_t i = 0; i < n; ++i) if (w[i] != BCF_INT_MISSING && w[i] != BCF_INT_VEND) { lo = min(lo, (int32_t)w[i]); hi = max(hi, (int32_t)w[i]); }
+        if (lo != INT32_MAX) { atomicMin(&s_st[f][PS_MIN], lo); atomicMax(&s_st[f][PS_MAX], hi); }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < (uint32_t)P.n * PS_WORDS) {
+    const int f = tid / PS_WORDS, w = tid % PS_WORDS;
+    int32_t* g = stat + ((uint64_t)f * n_sites + js) * PS_WORDS + w;
+    const int32_t v = s_st[f][w];
+    if (w == PS_MIN) { if (v < *g) atomicMin(g, v); }
+    else if (v > *g) atomicMax(g, v);
+  }
+}
+
+// pass 2: writes every emitted (field, site) block; the plan entries of the plain fields follow those of the remapped
+// fields (index (n_out + f) * n_sites + site).  One thread per (site, query row).
+__global__ void __launch_bounds__(FMT_THREADS) k_plain_pack(const __grid_constant__ PlainSet P, const __grid_constant__ FmtPlanDev plan, const int n_out,
+                                                            const int32_t* __restrict__ live, const uint32_t n_sites, const uint32_t nq) {
+  const uint32_t js = blockIdx.y, q = blockIdx.x * FMT_THREADS + threadIdx.x;
+  if (q >= nq) return;
+  const int32_t e = live[(uint64_t)js * nq + q];
+  const uint32_t cell = e >= 0 ? (uint32_t)(e & (LIVE_REDUCED - 1)) : 0u;
+  for (int f = 0; f < P.n; ++f) {
+    const uint64_t pi = (uint64_t)(n_out + f) * n_sites + js;
+    const uint32_t type = plan.type[pi];
+    if (type == BT_NONE) continue;
+    const uint32_t nps = plan.nps[pi];
+    const uint8_t* p = nullptr; uint32_t n = 0;
+    const bool valid = e >= 0 && plain_fetch(P.f[f], cell, p, n);
+    if (!valid) n = 0;
+    uint8_t* dst = plan.bytes + plan.off[pi];
+    if (type == BT_CHAR) {
+      uint8_t* d = dst + (uint64_t)q * nps;
+      for (uint32_t i = 0; i < nps; ++i) d[i] = i < n ? p[i] : ((i == 0 && n == 0) ? BCF_STR_MISSING : BCF_STR_VEND);
+      continue;
+    }
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+    const uint32_t miss = missing_word(P.f[f].elem == ELEM_FLOAT32), vend = vend_word(P.f[f].elem == ELEM_FLOAT32);
+    for (uint32_t i = 0; i < nps; ++i) {
+      const uint32_t v = i < n ? w[i] : ((i == 0 && n == 0) ? miss : vend);
+      const uint64_t k = (uint64_t)q * nps + i;
+      if (type == BT_INT8) dst[k] = v == BCF_INT_VEND ? 0x81u : (v == BCF_INT_MISSING ? 0x80u : (uint8_t)v);
+      else if (type == BT_INT16) reinterpret_cast<uint16_t*>(dst)[k] = v == BCF_INT_VEND ? 0x8001u : (v == BCF_INT_MISSING ? 0x8000u : (uint16_t)v);
+      else reinterpret_cast<uint32_t*>(dst)[k] = v;
     }
   }
 }

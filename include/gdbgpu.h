@@ -34,7 +34,7 @@ typedef struct gdbgpu_scan gdbgpu_scan;
 /* Length descriptor of an allele-dependent field (known_field_info.h:95-101: BCF_VL_R / BCF_VL_A / BCF_VL_G). */
 enum { GDBGPU_LEN_R = 0, GDBGPU_LEN_A = 1, GDBGPU_LEN_G = 2 };
 /* Element type of a 4-byte field; decides the BCF missing / vector-end words written (vcf.h:61-134). */
-enum { GDBGPU_ELEM_INT32 = 0, GDBGPU_ELEM_FLOAT32 = 1 };
+enum { GDBGPU_ELEM_INT32 = 0, GDBGPU_ELEM_FLOAT32 = 1, GDBGPU_ELEM_CHAR = 2 /* plain fields only */ };
 
 /* One remapped field = one TileDB attribute whose length depends on the allele list (PL, AD, MLEAC, ...);
  * stands in for GA4GHOperator::m_remapped_fields_query_idxs (variant_operations.cc:410-425). */
@@ -43,6 +43,16 @@ typedef struct gdbgpu_field_desc {
   int32_t length_kind;   /* GDBGPU_LEN_* */
   int32_t elem_type;     /* GDBGPU_ELEM_* */
 } gdbgpu_field_desc;
+
+/* A FORMAT field whose length does not depend on the allele list (GQ, MIN_DP, DP_FORMAT, SB, PGT, PID, ...): never
+ * remapped, only collated over the query rows and BCF-encoded (GDBGPU_SCAN_BCF_FORMAT); the other entries of
+ * BroadCombinedGVCFOperator::m_FORMAT_fields_vec (broad_combined_gvcf.cc:168-232,603-727). */
+typedef struct gdbgpu_plain_field_desc {
+  const char* name;      /* TileDB attribute name, e.g. "MIN_DP" */
+  int32_t elem_type;     /* GDBGPU_ELEM_* (CHAR: a string per cell) */
+  int32_t fixed_len;     /* values per cell; 0 = variable length */
+} gdbgpu_plain_field_desc;
+#define GDBGPU_MAX_PLAIN_FIELDS 16
 
 /* Host-resident columns in TileDB's own in-file layout (global cell order = column-major (col,row)); what
  * ArrayReadState::read_sparse hands to GenomicsDB one segment at a time (array_read_state.cc:1529-1598), here whole.
@@ -66,6 +76,9 @@ typedef struct gdbgpu_columns {
   const gdbgpu_var_column* fields;   /* n_fields columns of 4-byte elements */
   int64_t lb_row_idx;        /* genomicsdb_meta lb_row_idx */
   int64_t num_rows;          /* max_valid_row_idx_in_array - lb_row_idx + 1 */
+  int32_t n_plain_fields;    /* optional: plain FORMAT fields (see gdbgpu_plain_field_desc) */
+  const gdbgpu_plain_field_desc* plain_descs;
+  const gdbgpu_var_column* plain_fields;   /* fixed-length field: offsets == NULL, values = n_cells x fixed_len elements */
 } gdbgpu_columns;
 
 typedef struct gdbgpu_array_info {
@@ -77,6 +90,7 @@ typedef struct gdbgpu_array_info {
   uint64_t staged_bytes;     /* fragment bytes copied host -> HBM */
   uint64_t hbm_bytes;        /* total device footprint incl. indexes */
   int32_t n_fields, has_gt, gt_phased;
+  int32_t n_plain_fields;
 } gdbgpu_array_info;
 
 /* ---- context: one per host thread / CUDA device (VariantStorageManager's role, variant_storage_manager.h:160-235) */
@@ -102,6 +116,11 @@ int gdbgpu_ctx_kernel_stats(gdbgpu_ctx* ctx, const char* kernel_name, double* to
  * inflates GZIP tiles on the host, copies the columns to the device and runs the fragment merge there. */
 int gdbgpu_array_open(gdbgpu_ctx* ctx, const char* workspace, const char* array_name,
                       const gdbgpu_field_desc* fields, int32_t n_fields, int32_t gt_phased, gdbgpu_array** out);
+/* Same, also staging plain FORMAT fields for the FORMAT collation of GDBGPU_SCAN_BCF_FORMAT. */
+int gdbgpu_array_open_ex(gdbgpu_ctx* ctx, const char* workspace, const char* array_name,
+                         const gdbgpu_field_desc* fields, int32_t n_fields,
+                         const gdbgpu_plain_field_desc* plain_fields, int32_t n_plain_fields,
+                         int32_t gt_phased, gdbgpu_array** out);
 /* Same, from columns already decoded in host memory (loader hand-off, JNI buffers, synthetic generators). */
 int gdbgpu_array_from_columns(gdbgpu_ctx* ctx, const gdbgpu_columns* cols, gdbgpu_array** out);
 int gdbgpu_array_get_info(const gdbgpu_array* arr, gdbgpu_array_info* info);
@@ -178,11 +197,13 @@ typedef struct gdbgpu_batch {
   const int16_t* lut_in2m;
   uint64_t out_bytes;        /* algorithmic bytes of remapped output of this batch: 4 x n_query_rows x sum of the strides
                               * each field needs (alignment padding and the length arrays not counted) */
-  /* GDBGPU_SCAN_BCF_FORMAT: the FORMAT block of field o (same order as fields[]) at site s is described by entry
+  /* GDBGPU_SCAN_BCF_FORMAT: n_fmt_fields = n_fields + the array's plain FORMAT fields (in the order they were given to
+   * gdbgpu_array_open_ex).  The FORMAT block of field o (fields[] order, then the plain fields) at site s is described by entry
    * o*n_sites + s: fmt_type = 0 when the field is not emitted at the site (no valid call has it / G field suppressed),
-   * else the BCF type (1 int8, 2 int16, 3 int32, 5 float); fmt_nps values per sample; the n_query_rows*fmt_nps values
+   * else the BCF type (1 int8, 2 int16, 3 int32, 5 float, 7 char); fmt_nps values per sample; the n_query_rows*fmt_nps values
    * start at fmt_bytes + fmt_offset (16-byte aligned), sample-major, little-endian: exactly the bytes htslib puts into
    * bcf1_t.indiv after the field's typed key and (fmt_nps, fmt_type) size descriptor. */
+  int32_t n_fmt_fields;
   const uint8_t* fmt_type;
   const uint32_t* fmt_nps;
   const uint64_t* fmt_offset;

@@ -60,7 +60,8 @@ def header_dict(text):
 
 
 def read_bcf(path):
-    """-> (header text, sample names, [record dict(pos, n_allele, n_sample, alleles, fmt={name: (type, nps, bytes, key_and_descriptor_bytes)})])"""
+    """-> (header text, sample names, [record dict(pos, n_allele, n_sample, alleles, indiv=raw bytes, fmt_order,
+    fmt={name: (type, nps, bytes, key_and_descriptor_bytes)})])"""
     b = open(path, "rb").read()
     assert b[:5] == b"BCF\x02\x02", "not an uncompressed BCF2 file"
     l_text = struct.unpack_from("<I", b, 5)[0]
@@ -100,5 +101,6 @@ def read_bcf(path):
             fmt[names[key]] = (bt, nps, ind[o:o + nbytes], ind[o0:o])
             o += nbytes
         assert o == len(ind)
-        recs.append(dict(chrom=chrom, pos=pos, rlen=rlen, n_allele=n_allele, n_sample=n_sample, alleles=alleles, fmt=fmt))
+        recs.append(dict(chrom=chrom, pos=pos, rlen=rlen, n_allele=n_allele, n_sample=n_sample, alleles=alleles, fmt=fmt,
+                         fmt_order=list(fmt), indiv=bytes(ind)))
     return text, samples, recs

@@ -18,7 +18,9 @@ import numpy as np
 
 I32_MISSING, I32_VEND = -2147483648, -2147483647
 F32_MISSING, F32_VEND = 0x7F800001, 0x7F800002
-BT_INT8, BT_INT16, BT_INT32, BT_FLOAT = 1, 2, 3, 5
+BT_INT8, BT_INT16, BT_INT32, BT_FLOAT, BT_CHAR = 1, 2, 3, 5, 7
+TDB_NULL_INT, TDB_NULL_FLT, TDB_NULL_CHAR = 0x7FFFFFFF, 0x7F7FFFFF, 127
+STR_MISSING, STR_VEND = 0x07, 0x00
 
 
 def enc_int1(x):
@@ -117,3 +119,79 @@ def site_blocks(site, names, query_rows, field_elem, gt_phased, produce_gt, g_fi
             bt, desc, data = enc_vint(flat, nps)
             out[nm] = (bt, nps, data, desc)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- plain FORMAT fields
+class PlainColumns:
+    """Values of the FORMAT attributes that are not allele-dependent, per cell of an array in global cell order
+    (oracle.tiledb_fragment.Array), and the (row, begin column) -> begin cell map the dump's calls are looked up with."""
+
+    def __init__(self, arr, end, fields):
+        """fields: list of (attribute name, 'int'|'float'|'char', fixed length or 0)"""
+        self.fields = fields
+        self.cols = {}
+        for name, elem, fixed in fields:
+            if fixed:
+                v = np.ascontiguousarray(arr.fixed(name))
+                self.cols[name] = (None, v.view(np.uint32) if elem != "char" else v.view(np.uint8))
+            else:
+                off, val = arr.var(name)
+                val = np.ascontiguousarray(val)
+                self.cols[name] = (off, val.view(np.uint8) if elem == "char" else val.view(np.uint32))
+        begin = arr.col <= end
+        self.cell_of = {(int(r), int(c)): int(i) for i, (r, c, b) in enumerate(zip(arr.row, arr.col, begin)) if b}
+
+    def values(self, name, elem, cell):
+        """-> list of the field's elements in `cell`, [] when the field is invalid (every element TileDB-null)"""
+        off, val = self.cols[name]
+        v = val[cell] if off is None else val[off[cell]:off[cell + 1]]
+        v = [int(x) for x in np.atleast_1d(v)]
+        null = {"int": TDB_NULL_INT, "float": TDB_NULL_FLT, "char": TDB_NULL_CHAR}[elem]
+        return v if any(x != null for x in v) else []
+
+
+def plain_site_blocks(site, query_rows, plain):
+    """collect_and_extend_fields + bcf_update_format for the plain FORMAT fields of one parsed dump site
+    -> {attribute name: (type, nps, data bytes, descriptor bytes)}"""
+    by_row = {c["row"]: c for c in site["calls"]}
+    out = {}
+    for name, elem, _ in plain.fields:
+        vecs = {}
+        for r, c in by_row.items():
+            vecs[r] = plain.values(name, elem, plain.cell_of[(r, c["begin"])])
+        nps = max([len(v) for v in vecs.values()] or [0])
+        if nps == 0:
+            continue
+        if elem == "char":
+            miss, vend = STR_MISSING, STR_VEND
+        elif elem == "float":
+            miss, vend = F32_MISSING, F32_VEND
+        else:
+            miss, vend = I32_MISSING, I32_VEND
+        flat = []
+        for r in query_rows:
+            v = list(vecs.get(r, []))
+            if elem == "int":
+                v = [x - (1 << 32) if x >= (1 << 31) else x for x in v]
+            if not v:
+                v = [miss]
+            flat += v + [vend] * (nps - len(v))
+        if elem == "char":
+            out[name] = (BT_CHAR, nps, bytes(flat), enc_size(nps, BT_CHAR))
+        elif elem == "float":
+            out[name] = (BT_FLOAT, nps, np.asarray(flat, dtype="<u4").tobytes(), enc_size(nps, BT_FLOAT))
+        else:
+            bt, desc, data = enc_vint(flat, nps)
+            out[name] = (bt, nps, data, desc)
+    return out
+
+
+def assemble_indiv(order, blocks, key_ids):
+    """bcf1_t.indiv as htslib serialises it: per emitted field typed key, size descriptor, data; `order` = VCF names in
+    m_FORMAT_fields_vec order with GT first and DP last (broad_combined_gvcf.cc:168-240, vcf.c:3670-3676)"""
+    b = b""
+    for vcf_name in order:
+        if vcf_name in blocks:
+            bt, nps, data = blocks[vcf_name][:3]
+            b += enc_int1(key_ids[vcf_name]) + enc_size(nps, bt) + data
+    return b

@@ -67,7 +67,8 @@ def load_vid_fields(path):
     out = {}
     for name, v in items:
         classes = v.get("vcf_field_class", [])
-        ent = dict(type=v.get("type", "int"), length=v.get("length", 1), classes=classes)
+        ent = dict(type=v.get("type", "int"), length=v.get("length", 1), classes=classes,
+                   combine=v.get("VCF_field_combine_operation"))
         out[name] = ent
         if "FORMAT" in classes and "INFO" in classes:   # vid_mapper.cc: FORMAT twin gets the _FORMAT suffix
             out[name + "_FORMAT"] = ent

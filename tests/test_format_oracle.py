@@ -11,7 +11,8 @@ import pytest
 
 from conftest import GOLDEN, golden_cases
 from oracle import bcf_reader, format_blocks, oracle
-from util import case_fields, case_query_rows, format_field_names
+from oracle import tiledb_fragment as tf
+from util import case_fields, case_query_rows, format_field_names, format_order, plain_format_fields, vcf_format_name
 
 CASES = golden_cases()
 
@@ -38,6 +39,29 @@ def test_format_blocks_match_reference_bcf(case):
             assert hdr.endswith(g[3]), (site["begin"], k)     # hdr = typed key + descriptor
             n_blocks += 1
     assert n_blocks > 0
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_whole_indiv_matches_reference_bcf(case):
+    """remapped + plain FORMAT fields, assembled in the reference's field order, equal bcf1_t.indiv byte for byte"""
+    text, samples, recs = bcf_reader.read_bcf(os.path.join(GOLDEN, "bcf", case["id"] + ".bcf"))
+    key_ids = bcf_reader.header_dict(text)
+    names, sites = oracle.parse_dump(open(os.path.join(GOLDEN, case["dump"]), "rb").read())
+    fields, phased = case_fields(case)
+    elem = {f[0]: f[2] for f in fields}
+    fmt_names = format_field_names(case, names)
+    plain_fields = plain_format_fields(case)
+    arr = tf.Array(os.path.join(GOLDEN, case["workspace"]), case["array"])
+    plain = format_blocks.PlainColumns(arr, arr.fixed("END")[:, 0], plain_fields)
+    rows = [r for r in case_query_rows(case) if r < len(samples)]
+    order = format_order(case, fmt_names, plain_fields)
+    for rec, site in zip(recs, sites):
+        blocks = format_blocks.site_blocks(site, fmt_names, rows, elem, phased, case["produce_GT_field"])
+        for attr, b in format_blocks.plain_site_blocks(site, rows, plain).items():
+            blocks[vcf_format_name(attr)] = b
+        assert sorted(blocks) == sorted(rec["fmt"]), (site["begin"], sorted(blocks), sorted(rec["fmt"]))
+        assert [n for n in order if n in blocks] == rec["fmt_order"], (site["begin"], order, rec["fmt_order"])
+        assert format_blocks.assemble_indiv(order, blocks, key_ids) == rec["indiv"], site["begin"]
 
 
 def test_enc_int1_and_size_known_answers():

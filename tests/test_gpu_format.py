@@ -9,7 +9,7 @@ import pytest
 from conftest import GOLDEN, golden_cases
 from oracle import bcf_reader, format_blocks, oracle
 from tools import gdbsyn
-from util import case_fields, case_query_rows, format_field_names
+from util import case_fields, case_query_rows, format_field_names, format_order, plain_format_fields, vcf_format_name
 
 pytestmark = pytest.mark.gpu
 CASES = golden_cases()
@@ -68,6 +68,36 @@ def test_blocks_match_reference_bcf(ctx, case):
                 assert sorted(g) == sorted(want), (rec["pos"], sorted(g), sorted(want))
                 for k in want:
                     assert g[k] == want[k], (rec["pos"], k, g[k][:2], want[k][:2], g[k][2].hex(), want[k][2].hex())
+    finally:
+        arr.close()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_whole_indiv_matches_reference_bcf(ctx, case):
+    """remapped + plain FORMAT fields (GQ, SB, PGT, PID, MIN_DP, DP_FORMAT -> DP) collated and encoded on the device; the
+    blocks, laid out in the reference's field order behind their typed keys and size descriptors, equal the reference's
+    bcf1_t.indiv byte for byte"""
+    from genomicsdb_b200 import capi
+    text, samples, recs = bcf_reader.read_bcf(os.path.join(GOLDEN, "bcf", case["id"] + ".bcf"))
+    key_ids = bcf_reader.header_dict(text)
+    fields, phased = case_fields(case)
+    names = ["GT"] + [f[0] for f in fields]
+    fmt_names = format_field_names(case, names)
+    plain = plain_format_fields(case)
+    order = format_order(case, fmt_names, plain)
+    all_names = names + [p[0] for p in plain]
+    flags = (capi.SCAN_MIN_PL_GT if case["produce_GT_with_min_PL_value_for_spanning_deletions"] else 0) | \
+            (capi.SCAN_PRODUCE_GT if case["produce_GT_field"] else 0)
+    arr = capi.Array.open(ctx, os.path.join(GOLDEN, case["workspace"]), case["array"], fields, gt_phased=phased, plain=plain)
+    try:
+        assert arr.info().n_plain_fields == len(plain)
+        for kw in (dict(), dict(max_sites=2)):
+            got = gpu_blocks(arr, case["query_column_ranges"], all_names, query_rows=case_query_rows(case), flags=flags, **kw)
+            assert len(got) == len(recs)
+            for rec, g in zip(recs, got):
+                blocks = {vcf_format_name(k): v for k, v in g.items() if k in fmt_names or k in [p[0] for p in plain]}
+                assert sorted(blocks) == sorted(rec["fmt"]), (rec["pos"], sorted(blocks), sorted(rec["fmt"]))
+                assert format_blocks.assemble_indiv(order, blocks, key_ids) == rec["indiv"], rec["pos"]
     finally:
         arr.close()
 

@@ -34,4 +34,44 @@ def oracle_dump(case):
 def format_field_names(case, dump_names):
     """GT + the allele-dependent fields of the dump that are FORMAT fields of the VCF (vid vcf_field_class)."""
     vid = oracle.load_vid_fields(os.path.join(GOLDEN, case["vid_mapping_file"]))
-    return [n for n in dump_names if n == "GT" or "FORMAT" in (vid.get(n, {}).get("classes") or [])]
+    # an INFO field whose combine operation is move_to_FORMAT is emitted as a FORMAT field (broad_combined_gvcf.cc:183-189)
+    return [n for n in dump_names if n == "GT" or "FORMAT" in (vid.get(n, {}).get("classes") or [])
+            or vid.get(n, {}).get("combine") == "move_to_FORMAT"]
+
+
+def plain_format_fields(case):
+    """(attribute, 'int'|'float'|'char', fixed length | 0) of the queried FORMAT attributes that are not allele-dependent
+    and not GT (GQ, SB, PGT, PID, MIN_DP, DP_FORMAT ...), in query order."""
+    vid = oracle.load_vid_fields(os.path.join(GOLDEN, case["vid_mapping_file"]))
+    out = []
+    for name in case["attributes"]:
+        ent = vid.get(name)
+        if ent is None or name == "GT":
+            continue
+        base = name[:-7] if name.endswith("_FORMAT") else name
+        classes = ent.get("classes") or []
+        is_format = "FORMAT" in classes and (name.endswith("_FORMAT") or "INFO" not in classes)
+        if not is_format or (isinstance(ent["length"], str) and ent["length"] in oracle.KIND):
+            continue
+        ln = ent["length"]
+        fixed = 0 if (isinstance(ln, str) and not ln.isdigit()) else int(ln)
+        elem = "char" if ent["type"] == "char" else ("float" if ent["type"] == "float" else "int")
+        out.append((name, elem, fixed))
+    return out
+
+
+def vcf_format_name(attr):
+    """DP_FORMAT is the FORMAT twin of the INFO field DP (vid_mapper.cc): it is written as FORMAT/DP"""
+    return attr[:-7] if attr.endswith("_FORMAT") else attr
+
+
+def format_order(case, remapped_names, plain):
+    """VCF names in the order the reference emits FORMAT fields: GT first (vcf.c:3670-3676), then query order, DP last
+    (broad_combined_gvcf.cc:168-240,688-720)"""
+    names = []
+    for a in case["attributes"]:
+        if a in remapped_names and a != "GT":
+            names.append(a)
+        elif any(a == p[0] for p in plain) and a != "DP_FORMAT":
+            names.append(a)
+    return ["GT"] + names + (["DP"] if any(p[0] == "DP_FORMAT" for p in plain) else [])
