@@ -63,6 +63,18 @@ static_assert(sizeof(HotRec) == 32, "HotRec must be one 32-byte sector");
 constexpr uint32_t WARM_TOK_SYMBOLIC = 0x80000000u, WARM_TOK_NONREF = 0x40000000u;
 __host__ __device__ inline uint32_t warm_hash_word(uint32_t n_fields) { return (4u + n_fields + 1u) & ~1u; }
 
+// Class word of a cell (4 bytes, built when the array is staged): the per-site scan (k_site_scan) gathers this word -- from
+// an array small enough to live in L2 -- instead of the 32-byte hot record of every live call:
+//   00 | packed  trivial inline call: nr(1) n_alt(1) gt_len(3) ploidy(3) flen[4](3 each) -- everything the site layout needs
+//   01 | blob    any other call: warm-blob offset in 16-byte units (< 2^30)
+//   10 | cell    (formed in k_site_scan from the live entry) the call is in its spanning-deletion form
+//   0xFFFFFFFF   (formed in k_site_scan) sample not live at the site
+constexpr uint32_t CLS_GENERAL = 0x40000000u, CLS_REDUCED = 0x80000000u, CLS_DEAD = 0xFFFFFFFFu, CLS_LOW = 0x3FFFFFFFu;
+__host__ __device__ inline uint32_t cls_pack(uint32_t nr, uint32_t n_alt, uint32_t gt_len, uint32_t ploidy, const uint8_t* flen) {
+  return (nr ? 1u : 0u) | ((n_alt & 1u) << 1) | ((gt_len & 7u) << 2) | ((ploidy & 7u) << 5) |
+         ((uint32_t)(flen[0] & 7u) << 8) | ((uint32_t)(flen[1] & 7u) << 11) | ((uint32_t)(flen[2] & 7u) << 14) | ((uint32_t)(flen[3] & 7u) << 17);
+}
+
 struct VarCol {
   const uint64_t* off;   // n_cells + 1 absolute byte offsets
   const uint8_t* val;
@@ -83,6 +95,7 @@ struct ArrayDev {
   const CellDesc* desc;
   const HotRec* hot;
   const uint32_t* warm;    // warm blob pool (see above)
+  const uint32_t* cls;     // class word per cell (see above)
   const int64_t* effend;   // cell order; I64_MIN for END copies / rows outside the array
   // row-major index (per-sample cell lists, column ascending)
   uint64_t n_rs;

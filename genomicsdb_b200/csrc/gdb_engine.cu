@@ -188,13 +188,13 @@ struct gdbgpu_array {
   DevBuf<int64_t> coords, end;
   DevVar ref, alt, gt; std::vector<std::unique_ptr<DevVar>> fields;
   std::vector<std::unique_ptr<DevVar>> plain; std::vector<PlainMeta> pm; PlainSet plain_dev{};   // plain FORMAT fields (K6)
-  DevBuf<CellDesc> desc; DevBuf<HotRec> hot; DevBuf<uint32_t> warm; DevBuf<int64_t> effend;
+  DevBuf<CellDesc> desc; DevBuf<HotRec> hot; DevBuf<uint32_t> warm, cls; DevBuf<int64_t> effend;
   DevBuf<uint32_t> rs_cell, rs_keys; DevBuf<int64_t> rs_col, rs_effend; DevBuf<uint64_t> row_start; uint64_t n_rs = 0;
   DevBuf<uint32_t> bad_cell; DevBuf<int64_t> bad_pred_col;
   ArrayDev dev{};
   uint64_t hbm_bytes() const {
     uint64_t b = coords.bytes() + end.bytes() + ref.off.bytes() + ref.val.bytes() + alt.off.bytes() + alt.val.bytes() + gt.off.bytes() + gt.val.bytes() +
-                 desc.bytes() + hot.bytes() + warm.bytes() + effend.bytes() + rs_cell.bytes() + rs_keys.bytes() + rs_col.bytes() + rs_effend.bytes() + row_start.bytes();
+                 desc.bytes() + hot.bytes() + warm.bytes() + cls.bytes() + effend.bytes() + rs_cell.bytes() + rs_keys.bytes() + rs_col.bytes() + rs_effend.bytes() + row_start.bytes();
     for (auto& f : fields) b += f->off.bytes() + f->val.bytes();
     for (auto& f : plain) b += f->off.bytes() + f->val.bytes();
     return b;
@@ -223,7 +223,7 @@ void fill_dev_view(gdbgpu_array* a) {
   D.has_gt = a->has_gt; D.gt_phased = a->gt_phased; D.n_fields = (int)a->fields.size();
   for (size_t f = 0; f < a->fields.size(); ++f) { D.f[f] = VarCol{a->fields[f]->off.p, a->fields[f]->val.p}; D.fm[f] = a->fm[f]; }
   D.lb_row = a->lb_row; D.num_rows = a->num_rows;
-  D.desc = a->desc.p; D.hot = a->hot.p; D.warm = a->warm.p; D.effend = a->effend.p;
+  D.desc = a->desc.p; D.hot = a->hot.p; D.warm = a->warm.p; D.cls = a->cls.p; D.effend = a->effend.p;
   a->plain_dev.n = (int32_t)a->plain.size();
   for (size_t f = 0; f < a->plain.size(); ++f) a->plain_dev.f[f] = PlainDev{a->pm[f].fixed_len ? nullptr : a->plain[f]->off.p, a->plain[f]->val.p, a->pm[f].elem, a->pm[f].fixed_len};
   D.n_rs = a->n_rs; D.rs_cell = a->rs_cell.p; D.rs_col = a->rs_col.p; D.rs_effend = a->rs_effend.p; D.row_start = a->row_start.p;
@@ -355,11 +355,13 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
       exclusive_scan<uint32_t, uint64_t>(ctx, units.p, offs64.p, n, total.p, sums);
       uint64_t h_units = 0;
       CK(cudaMemcpyAsync(&h_units, total.p, 8, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
-      if (h_units >= (1ull << 31)) throw LimitError("warm-blob pool above 32 GB: shard the column range across GPUs");
+      if (h_units >= (1ull << 30)) throw LimitError("warm-blob pool above 16 GB: shard the column range across GPUs");
       a->warm.alloc(std::max<uint64_t>(h_units * 4, 4));
       a->dev.warm = a->warm.p;
       LAUNCH(ctx, k_narrow_u64, g, 256, offs64.p, n, offs.p);
       LAUNCH(ctx, k_warm_fill, g, 256, a->dev, a->desc.p, a->hot.p, units.p, offs.p, a->warm.p);
+      a->cls.alloc(n);
+      LAUNCH(ctx, k_cls_fill, g, 256, a->hot.p, n, a->cls.p);
       CK(cudaStreamSynchronize(ctx->stream));
     }
     lap("classify");

@@ -193,6 +193,14 @@ __global__ void __launch_bounds__(256) k_warm_fill(ArrayDev A, const CellDesc* _
   for (uint32_t* e = b + (((uint64_t)words + 3) & ~3ull); w < e; ++w) *w = 0;
 }
 
+// class word per cell (layout: gdb_device.cuh), once the hot records are final
+__global__ void __launch_bounds__(256) k_cls_fill(const HotRec* __restrict__ hot, uint64_t n, uint32_t* __restrict__ cls) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const HotRec h = hot[i];
+  cls[i] = (h.inl && (h.flags & F_TRIVIAL)) ? cls_pack(h.nr_idx, h.n_alt, h.gt_len, h.ploidy, h.flen) : (CLS_GENERAL | (h.w[0] & CLS_LOW));
+}
+
 __global__ void __launch_bounds__(256) k_row_keys(ArrayDev A, const CellDesc* __restrict__ desc, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;

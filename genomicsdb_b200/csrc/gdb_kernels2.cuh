@@ -297,10 +297,11 @@ __device__ inline uint64_t warm_token_hash(const WarmView& v, uint32_t H0, uint3
 }
 __device__ inline uint64_t star_hash() { const uint8_t s = '*'; return hash_finish(fnv1a(FNV_BASIS, &s, 1) ^ (1ull << 40)); }
 
-// K4a: one pass over the live matrix.  Per site: number of live calls, the maxima the output layout needs (from the
-// 16-byte header of the hot record of every trivial inline call) and the list of all other live calls.  Grid = (sites,
-// row chunks), so the whole GPU works on a batch whatever its number of sites.
-constexpr int SSCAN_THREADS = 256, SSCAN_PER_THREAD = 8, SSCAN_ROWS = SSCAN_THREADS * SSCAN_PER_THREAD;
+// K4a: one pass over the live matrix; every live call contributes its 4-byte class word (layout: gdb_device.cuh).  Per
+// site: number of live calls, the maxima the output layout needs (packed into the class word of every trivial inline call)
+// and the list of all other live calls.  Grid = (sites, row chunks), so the whole GPU works on a batch whatever its number
+// of sites.
+constexpr int SSCAN_THREADS = 256, SSCAN_PER_THREAD = 16, SSCAN_ROWS = SSCAN_THREADS * SSCAN_PER_THREAD;
 __global__ void __launch_bounds__(SSCAN_THREADS) k_site_scan(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B) {
   __shared__ uint2 s_list[SSCAN_ROWS];
   __shared__ uint32_t s_red[AGG_WORDS];
@@ -312,31 +313,28 @@ __global__ void __launch_bounds__(SSCAN_THREADS) k_site_scan(const __grid_consta
   if (tid == 0) s_cnt = 0;
   if (tid < AGG_WORDS) s_red[tid] = 0;
   __syncthreads();
-  int32_t e[SSCAN_PER_THREAD];
+  uint32_t c[SSCAN_PER_THREAD];
 #pragma unroll
-  for (int i = 0; i < SSCAN_PER_THREAD; ++i) { const uint64_t q = q0 + (uint64_t)i * SSCAN_THREADS + tid; e[i] = q < S.nq ? live[q] : -1; }
-  uint4 h[SSCAN_PER_THREAD];
+  for (int i = 0; i < SSCAN_PER_THREAD; ++i) { const uint64_t q = q0 + (uint64_t)i * SSCAN_THREADS + tid; c[i] = q < S.nq ? (uint32_t)live[q] : CLS_DEAD; }
 #pragma unroll
-  for (int i = 0; i < SSCAN_PER_THREAD; ++i) {
-    h[i] = make_uint4(0, 0, 0, 0);
-    if (e[i] >= 0 && !(e[i] & LIVE_REDUCED)) h[i] = *reinterpret_cast<const uint4*>(&A.hot[e[i]]);
+  for (int i = 0; i < SSCAN_PER_THREAD; ++i) {   // live entry -> class word (all gathers of the thread in flight together)
+    const int32_t e = (int32_t)c[i];
+    c[i] = e < 0 ? CLS_DEAD : ((e & LIVE_REDUCED) ? (CLS_REDUCED | (uint32_t)(e & (LIVE_REDUCED - 1))) : A.cls[e]);
   }
   uint32_t n_live = 0, nonref = 0, mgt = 0, main_ = 0, mpl = 0;
   uint32_t fpl[HOT_FIELDS] = {0, 0, 0, 0}, fin[HOT_FIELDS] = {0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < SSCAN_PER_THREAD; ++i) {
-    bool general = false;
-    if (e[i] >= 0) {
+    const bool live = c[i] != CLS_DEAD;
+    const bool general = live && (c[i] & (CLS_GENERAL | CLS_REDUCED));
+    if (live) {
       ++n_live;
-      const uint32_t hflags = h[i].x & 0xFF, ploidy = (h[i].x >> 8) & 0xFF, n_alt = (h[i].x >> 16) & 0xFF, nr = h[i].x >> 24;
-      const uint32_t gt_len = h[i].y & 0xFF, inl = (h[i].y >> 8) & 0xFF;
-      general = (e[i] & LIVE_REDUCED) || !inl || !(hflags & F_TRIVIAL);
       if (!general) {
+        const uint32_t nr = c[i] & 1u, n_alt = (c[i] >> 1) & 1u, gt_len = (c[i] >> 2) & 7u, ploidy = (c[i] >> 5) & 7u;
         mgt = max(mgt, gt_len); main_ = max(main_, n_alt + 1u); mpl = max(mpl, ploidy);
         if (nr) nonref = 1;
-        const uint32_t fl4 = (h[i].y >> 16) | (h[i].z << 16);
 #pragma unroll
-        for (int f = 0; f < HOT_FIELDS; ++f) { const uint32_t n = (fl4 >> (8 * f)) & 0xFF; if (n) { fpl[f] = max(fpl[f], ploidy); fin[f] = max(fin[f], n); } }
+        for (int f = 0; f < HOT_FIELDS; ++f) { const uint32_t n = (c[i] >> (8 + 3 * f)) & 7u; if (n) { fpl[f] = max(fpl[f], ploidy); fin[f] = max(fin[f], n); } }
       }
     }
     const unsigned m = __ballot_sync(0xffffffffu, general);
@@ -345,7 +343,7 @@ __global__ void __launch_bounds__(SSCAN_THREADS) k_site_scan(const __grid_consta
       if (lane == 0) base = atomicAdd(&s_cnt, (uint32_t)__popc(m));
       base = __shfl_sync(0xffffffffu, base, 0);
       if (general) s_list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)(q0 + (uint64_t)i * SSCAN_THREADS + tid),
-                                                                              (e[i] & LIVE_REDUCED) ? (NT_REDUCED | (uint32_t)(e[i] & (LIVE_REDUCED - 1))) : h[i].w);
+                                                                              (c[i] & CLS_REDUCED) ? (NT_REDUCED | (c[i] & CLS_LOW)) : (c[i] & CLS_LOW));
     }
   }
   uint32_t r;
