@@ -33,7 +33,8 @@ class FieldDesc(C.Structure):
 
 
 class PlainFieldDesc(C.Structure):
-    _fields_ = [("name", C.c_char_p), ("elem_type", C.c_int32), ("fixed_len", C.c_int32)]
+    _fields_ = [("name", C.c_char_p), ("elem_type", C.c_int32), ("fixed_len", C.c_int32), ("no_format", C.c_int32),
+                ("info_op", C.c_int32)]
 
 
 class VarColumn(C.Structure):
@@ -57,7 +58,8 @@ class ArrayInfo(C.Structure):
 
 class ScanParams(C.Structure):
     _fields_ = [("col_lo", C.c_int64), ("col_hi", C.c_int64), ("query_rows", C.c_void_p), ("n_query_rows", C.c_uint64),
-                ("flags", C.c_uint32), ("max_diploid_alt_alleles", C.c_uint32)]
+                ("flags", C.c_uint32), ("max_diploid_alt_alleles", C.c_uint32),
+                ("dp_info_field", C.c_uint32), ("dp_min_dp_field", C.c_uint32), ("dp_format_field", C.c_uint32)]
 
 
 class ScanInfo(C.Structure):
@@ -77,7 +79,8 @@ class Batch(C.Structure):
                 ("live", C.c_void_p), ("n_fields", C.c_int32), ("fields", FieldOut * 16),
                 ("lut_first", C.c_void_p), ("lut_len", C.c_void_p), ("lut_in2m", C.c_void_p), ("out_bytes", C.c_uint64),
                 ("n_fmt_fields", C.c_int32), ("fmt_type", C.c_void_p), ("fmt_nps", C.c_void_p), ("fmt_offset", C.c_void_p), ("fmt_bytes", C.c_void_p),
-                ("fmt_total_bytes", C.c_uint64)]
+                ("fmt_total_bytes", C.c_uint64), ("info_valid", C.c_void_p), ("info_value", C.c_void_p),
+                ("info_dp_sum", C.c_void_p)]
 
 
 _lib = None
@@ -182,11 +185,15 @@ def _field_descs(fields):
 
 
 def _plain_descs(plain):
-    """plain: list of (attribute name, 'int'|'float'|'char', fixed length or 0 for variable)"""
+    """plain: list of (attribute name, 'int'|'float'|'char', fixed length or 0 for variable[, no_format[, info_op]])
+    info_op: None | 'median' | 'sum' | 'mean'"""
     arr = (PlainFieldDesc * max(1, len(plain)))()
     code = {"int": ELEM_INT32, "float": ELEM_FLOAT32, "char": ELEM_CHAR}
-    for i, (name, elem, fixed) in enumerate(plain):
-        arr[i] = PlainFieldDesc(name.encode(), code.get(elem, elem), int(fixed))
+    ops = {None: 0, "median": 1, "sum": 2, "mean": 3}
+    for i, p in enumerate(plain):
+        name, elem, fixed = p[:3]
+        arr[i] = PlainFieldDesc(name.encode(), code.get(elem, elem), int(fixed), int(bool(p[3])) if len(p) > 3 else 0,
+                                ops.get(p[4], p[4]) if len(p) > 4 else 0)
     return arr
 
 
@@ -236,7 +243,7 @@ class Array:
         c.field_descs, c.fields = fd, fv
         c.lb_row_idx, c.num_rows = lb_row, num_rows
         plain = list(plain)
-        pd = _plain_descs([(f["name"], f["elem"], f["fixed_len"]) for f in plain])
+        pd = _plain_descs([(f["name"], f["elem"], f["fixed_len"], f.get("no_format", 0), f.get("info_op")) for f in plain])
         pv = (VarColumn * max(1, len(plain)))()
         for i, f in enumerate(plain):
             if f["fixed_len"]:
@@ -303,6 +310,10 @@ class BatchView:
             self.fmt_nps = _view(b.fmt_nps, np.uint32, nf * ns).reshape(nf, ns)
             self.fmt_offset = _view(b.fmt_offset, np.uint64, nf * ns).reshape(nf, ns)
             self.fmt_bytes = _view(b.fmt_bytes, np.uint8, b.fmt_total_bytes)
+            npl = nf - n_out
+            self.info_valid = _view(b.info_valid, np.uint8, npl * ns).reshape(npl, ns)
+            self.info_value = _view(b.info_value, np.uint32, npl * ns).reshape(npl, ns)
+            self.info_dp_sum = _view(b.info_dp_sum, np.int32, ns)
         else:
             self.fmt_type = None
         self.lut_first = _view(b.lut_first, np.uint32, ns * nq).reshape(ns, nq) if b.lut_first else None
@@ -330,7 +341,8 @@ class BatchView:
 
 
 class Scan:
-    def __init__(self, arr, col_lo=None, col_hi=None, query_rows=None, flags=0, max_alt=0):
+    def __init__(self, arr, col_lo=None, col_hi=None, query_rows=None, flags=0, max_alt=0, dp_fields=(0, 0, 0)):
+        """dp_fields: 1-based plain-field indices of (INFO DP, MIN_DP, DP_FORMAT) for the DP rule, 0 = absent"""
         self.arr, self.ctx = arr, arr.ctx
         p = ScanParams()
         if col_lo is None:
@@ -342,6 +354,7 @@ class Scan:
             self._rows = np.ascontiguousarray(query_rows, dtype=np.int64)
             p.query_rows, p.n_query_rows = self._rows.ctypes.data, len(self._rows)
         p.flags, p.max_diploid_alt_alleles = flags, max_alt
+        p.dp_info_field, p.dp_min_dp_field, p.dp_format_field = dp_fields
         self.h = C.c_void_p()
         self.ctx.check(lib().gdbgpu_scan_begin(arr.h, C.byref(p), C.byref(self.h)))
         i = arr.info()

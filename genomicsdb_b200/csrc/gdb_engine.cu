@@ -171,7 +171,7 @@ struct HostCols {
   std::vector<HostVar> fields;
   std::vector<HostVar> plain;   // fixed-length plain field: off == nullptr
 };
-struct PlainMeta { std::string name; int32_t elem, fixed_len; };
+struct PlainMeta { std::string name; int32_t elem, fixed_len; int32_t no_format = 0, info_op = 0; };
 
 struct DevVar { DevBuf<uint64_t> off; DevBuf<uint8_t> val; uint64_t bytes = 0; };
 
@@ -440,6 +440,8 @@ struct BatchBuffers {
   PinBuf<uint16_t> p_out_len[MAX_FIELDS + 1], p_lut_len; PinBuf<int16_t> p_lut_in2m;
   // K6 (GDBGPU_SCAN_BCF_FORMAT): per (field, site) plan + the packed FORMAT blocks
   DevBuf<int32_t> fmt_mm; DevBuf<uint8_t> fmt_bytes;
+  DevBuf<uint32_t> info_vals, info_cnt, info_value_d; DevBuf<uint8_t> info_valid_d; DevBuf<int32_t> dp_sum_d;
+  std::vector<uint32_t> h_info_value; std::vector<uint8_t> h_info_valid; std::vector<int32_t> h_dp_sum;
   std::vector<int32_t> h_fmt_mm; std::vector<uint8_t> h_fmt_type; std::vector<uint32_t> h_fmt_nps; std::vector<uint64_t> h_fmt_off;
   PinBuf<uint8_t> p_fmt_bytes;
   // state of the batch these buffers hold
@@ -461,6 +463,7 @@ struct gdbgpu_scan {
   DevBuf<unsigned long long> bitmap; DevBuf<uint32_t> word_rank, bp_cell0, err, del_cells, del_words; DevBuf<uint64_t> site_start; DevBuf<DelRec> del_recs;
   std::unique_ptr<BatchBuffers> slot[2];   // borrowed from the context's pool for the lifetime of the scan; [cur] = batch being handed out, the other = prefetched
   int cur = 0; bool bcf_format = false, prefetch = true; int produce_gt = 0;
+  InfoSet info{};   // INFO scalars to combine + the DP rule's fields (GDBGPU_SCAN_BCF_FORMAT)
   uint32_t cap_allele_recs = 0, cap_allele_bytes = 0, cap_lut = 0;
   uint64_t avg_site_bytes = 0;
   int n_out = 0;
@@ -493,6 +496,14 @@ void scan_prepare(gdbgpu_scan* s) {
   s->bcf_format = (p.flags & GDBGPU_SCAN_BCF_FORMAT) != 0;
   s->produce_gt = (p.flags & GDBGPU_SCAN_PRODUCE_GT) ? 1 : 0;
   s->prefetch = !(p.flags & GDBGPU_SCAN_NO_PREFETCH);
+  s->info.n = 0;
+  for (size_t f = 0; f < a->pm.size(); ++f) if (a->pm[f].info_op) { s->info.field[s->info.n] = (int32_t)f; s->info.op[s->info.n] = a->pm[f].info_op; ++s->info.n; }
+  auto dp_index = [&](uint32_t one_based) -> int32_t {
+    if (!one_based) return -1;
+    if (one_based > a->pm.size() || a->pm[one_based - 1].fixed_len < 1 || a->pm[one_based - 1].elem != ELEM_INT32) throw ArgError("DP rule: not a fixed-length int32 plain field");
+    return (int32_t)one_based - 1;
+  };
+  s->info.dp_info = dp_index(p.dp_info_field); s->info.dp_min_dp = dp_index(p.dp_min_dp_field); s->info.dp_format = dp_index(p.dp_format_field);
   // queried rows: sorted, unique, inside the array (variant_query_config.cc:60-117)
   if (p.query_rows) {
     s->h_rows.assign(p.query_rows, p.query_rows + p.n_query_rows);
@@ -799,6 +810,22 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       const unsigned row_blocks = blocks_for(S.nq, FMT_THREADS);
       LAUNCH(ctx, k_fmt_range, dim3(chunks, keep), FMT_THREADS, a->dev, O, keep, (uint32_t)S.nq, s->produce_gt, bb.fmt_mm.p);
       if (n_plain) LAUNCH(ctx, k_plain_scan, dim3(row_blocks, keep), FMT_THREADS, a->plain_dev, bb.live.p, keep, (uint32_t)S.nq, bb.fmt_mm.p + 2 * n_rp);
+      const bool dp_rule = s->info.dp_info >= 0 || s->info.dp_format >= 0;
+      bb.h_info_value.assign((size_t)n_plain * keep, 0); bb.h_info_valid.assign((size_t)n_plain * keep, 0); bb.h_dp_sum.assign(keep, 0);
+      const int n_info = s->info.n;
+      if (n_info || dp_rule) {   // INFO scalars: ordered compaction of the valid values, then median / sum / mean; DP sum
+        bb.info_vals.ensure(std::max<uint64_t>((uint64_t)n_info * keep * S.nq, 1)); bb.info_cnt.ensure(std::max<uint64_t>((uint64_t)n_info * keep, 1));
+        bb.info_value_d.ensure(std::max<uint64_t>((uint64_t)n_info * keep, 1)); bb.info_valid_d.ensure(std::max<uint64_t>((uint64_t)n_info * keep, 1)); bb.dp_sum_d.ensure(keep);
+        LAUNCH(ctx, k_info_collect, keep, FMT_THREADS, a->plain_dev, s->info, bb.live.p, keep, (uint32_t)S.nq, bb.info_vals.p, bb.info_cnt.p, bb.dp_sum_d.p);
+        if (n_info) LAUNCH(ctx, k_info_reduce, dim3(keep, n_info), FMT_THREADS, a->plain_dev, s->info, keep, (uint32_t)S.nq, bb.info_vals.p, bb.info_cnt.p, bb.info_value_d.p, bb.info_valid_d.p);
+        // results land at the plain-field index of every INFO field
+        for (int k = 0; k < n_info; ++k) {
+          const size_t dst = (size_t)s->info.field[k] * keep;
+          CK(cudaMemcpyAsync(bb.h_info_value.data() + dst, bb.info_value_d.p + (size_t)k * keep, (size_t)keep * 4, cudaMemcpyDeviceToHost, ctx->stream));
+          CK(cudaMemcpyAsync(bb.h_info_valid.data() + dst, bb.info_valid_d.p + (size_t)k * keep, keep, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CK(cudaMemcpyAsync(bb.h_dp_sum.data(), bb.dp_sum_d.p, (size_t)keep * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      }
       CK(cudaMemcpyAsync(bb.h_fmt_mm.data(), bb.fmt_mm.p, bb.h_fmt_mm.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
       // bcf_enc_vint's width rule (vcf.c:1926-1972); a block of ONE value goes through bcf_enc_int1 instead (vcf.c:1931)
@@ -823,7 +850,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
         } else {
           const int f = o - n_out;
           const int32_t* st = h_ps + ((uint64_t)f * keep + i) * PS_WORDS;
-          if (!st[PS_ANY]) continue;
+          if (!st[PS_ANY] || a->pm[f].no_format) continue;
           nps = (uint32_t)st[PS_MAXLEN];
           if (nps == 0) continue;
           type = a->pm[f].elem == ELEM_CHAR ? BT_CHAR : (a->pm[f].elem == ELEM_FLOAT32 ? BT_FLOAT : int_type(st[PS_MIN], st[PS_MAX], (uint64_t)nps * S.nq));
@@ -916,6 +943,7 @@ void publish_batch(gdbgpu_scan* s, BatchBuffers& bb, gdbgpu_batch* out) {
   }
   out->fmt_total_bytes = bb.fmt_total;
   out->n_fmt_fields = s->bcf_format ? n_out + (int)a->plain.size() : 0;
+  if (s->bcf_format) { out->info_valid = bb.h_info_valid.data(); out->info_value = bb.h_info_value.data(); out->info_dp_sum = bb.h_dp_sum.data(); }
   (void)a;
 }
 
@@ -1055,7 +1083,8 @@ int gdbgpu_array_from_columns(gdbgpu_ctx* ctx, const gdbgpu_columns* c, gdbgpu_a
       if (d.elem_type < 0 || d.elem_type > GDBGPU_ELEM_CHAR || d.fixed_len < 0) throw ArgError("bad plain field descriptor");
       if (!d.fixed_len && !c->plain_fields[f].offsets) throw ArgError("variable-length plain field without offsets");
       h.plain.push_back(HostVar{d.fixed_len ? nullptr : c->plain_fields[f].offsets, c->plain_fields[f].values, c->plain_fields[f].values_bytes});
-      pm.push_back(PlainMeta{d.name ? d.name : "", d.elem_type, d.fixed_len});
+      if (d.info_op && (d.fixed_len < 1 || d.elem_type == GDBGPU_ELEM_CHAR)) throw ArgError("an INFO combine operation needs a fixed-length 4-byte field");
+      pm.push_back(PlainMeta{d.name ? d.name : "", d.elem_type, d.fixed_len, d.no_format, d.info_op});
     }
     *out = build_array(ctx, h, {h.n}, c->lb_row_idx, c->num_rows, c->gt_phased, fm, names, pm);
   });
@@ -1094,7 +1123,8 @@ int gdbgpu_array_open_ex(gdbgpu_ctx* ctx, const char* workspace, const char* arr
       const int fixed = sc.is_var(id) ? 0 : sc.cell_val_num[id];
       if (plain[f].fixed_len != fixed) throw std::runtime_error(std::string("plain field length does not match the array schema: ") + plain[f].name);
       ids.push_back(id);
-      pm.push_back(PlainMeta{plain[f].name, plain[f].elem_type, fixed});
+      if (plain[f].info_op && (fixed < 1 || plain[f].elem_type == GDBGPU_ELEM_CHAR)) throw std::runtime_error(std::string("an INFO combine operation needs a fixed-length 4-byte field: ") + plain[f].name);
+      pm.push_back(PlainMeta{plain[f].name, plain[f].elem_type, fixed, plain[f].no_format, plain[f].info_op});
     }
     // read every needed column of every fragment, concatenating (var offsets rebased onto the concatenated stream)
     size_t nfrag = ta.num_fragments();

@@ -240,4 +240,121 @@ __global__ void __launch_bounds__(FMT_THREADS) k_plain_pack(const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------ INFO scalars
+// BroadCombinedGVCFOperator::handle_INFO_fields (broad_combined_gvcf.cc:524-545) combines every scalar INFO field over the
+// valid calls of the site: median = element n/2 of the sorted valid values (std::nth_element, variant_field_handler.cc:
+// 529-560), sum = left-to-right sum in row order (:562-593; float addition is not associative, so the order is kept), mean
+// = sum / n (:596-607).  A value counts when the call is live, is not in its spanning-deletion form (handle_deletions
+// invalidates the INFO fields of such calls, broad_combined_gvcf.cc:1067-1075), the field is not the TileDB null and the
+// value is neither BCF missing nor vector_end.  INFO/DP follows the GATK rule of broad_combined_gvcf.cc:688-727.
+struct InfoSet { int32_t n; int32_t field[MAX_PLAIN]; int32_t op[MAX_PLAIN]; int32_t dp_info, dp_min_dp, dp_format; };   // field: index into PlainSet; dp_*: index or -1
+enum { INFO_MEDIAN = 1, INFO_SUM = 2, INFO_MEAN = 3 };
+
+__device__ inline bool info_value_ok(const PlainDev& F, uint32_t cell, uint32_t& v) {
+  v = reinterpret_cast<const uint32_t*>(F.val)[(uint64_t)cell * (uint32_t)F.fixed_len];
+  if (F.elem == ELEM_FLOAT32) return v != TDB_NULL_FLT && v != BCF_FLT_MISSING && v != BCF_FLT_VEND;
+  return v != TDB_NULL_INT && v != BCF_INT_MISSING && v != BCF_INT_VEND;
+}
+// first element of plain field F of a call, or BCF missing when the field is invalid there (collect_and_extend_fields)
+__device__ inline uint32_t scalar_or_missing(const PlainDev& F, bool call_valid, uint32_t cell) {
+  if (!call_valid) return BCF_INT_MISSING;
+  const uint32_t v = reinterpret_cast<const uint32_t*>(F.val)[(uint64_t)cell * (uint32_t)F.fixed_len];
+  return v == TDB_NULL_INT ? BCF_INT_MISSING : v;
+}
+
+// one block per site: the valid values of every INFO field, compacted in row order, + the DP sum
+__global__ void __launch_bounds__(FMT_THREADS) k_info_collect(const __grid_constant__ PlainSet P, const __grid_constant__ InfoSet I, const int32_t* __restrict__ live,
+                                                              const uint32_t n_sites, const uint32_t nq, uint32_t* __restrict__ vals, uint32_t* __restrict__ cnt,
+                                                              int32_t* __restrict__ dp_sum) {
+  __shared__ uint32_t s_warp[FMT_THREADS / 32];
+  __shared__ uint32_t s_base[MAX_PLAIN];
+  __shared__ int32_t s_dp;
+  const uint32_t js = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid < MAX_PLAIN) s_base[tid] = 0;
+  if (tid == 0) s_dp = 0;
+  __syncthreads();
+  int32_t dp = 0;
+  for (uint32_t q0 = 0; q0 < nq; q0 += FMT_THREADS) {
+    const uint32_t q = q0 + tid;
+    const int32_t e = q < nq ? live[(uint64_t)js * nq + q] : -1;
+    const bool call = e >= 0, plain_call = call && !(e & LIVE_REDUCED);
+    const uint32_t cell = call ? (uint32_t)(e & (LIVE_REDUCED - 1)) : 0u;
+    for (int k = 0; k < I.n; ++k) {
+      uint32_t v = 0;
+      const bool ok = plain_call && info_value_ok(P.f[I.field[k]], cell, v);
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) s_warp[wid] = __popc(m);
+      __syncthreads();
+      uint32_t before = s_base[k], total = 0;
+      for (uint32_t w = 0; w < FMT_THREADS / 32; ++w) { if (w < wid) before += s_warp[w]; total += s_warp[w]; }
+      if (ok) vals[((uint64_t)k * n_sites + js) * nq + before + __popc(m & ((1u << lane) - 1u))] = v;
+      __syncthreads();
+      if (tid == 0) s_base[k] += total;
+    }
+    if (call && (I.dp_info >= 0 || I.dp_format >= 0)) {
+      auto ok32 = [](uint32_t v) { return v != BCF_INT_MISSING && v != BCF_INT_VEND; };
+      uint32_t a = I.dp_info >= 0 ? scalar_or_missing(P.f[I.dp_info], true, cell) : BCF_INT_MISSING;
+      if (!ok32(a)) {
+        const uint32_t mdp = I.dp_min_dp >= 0 ? scalar_or_missing(P.f[I.dp_min_dp], true, cell) : BCF_INT_MISSING;
+        a = ok32(mdp) ? mdp : (I.dp_format >= 0 ? scalar_or_missing(P.f[I.dp_format], true, cell) : BCF_INT_MISSING);
+      }
+      if (ok32(a)) dp += (int32_t)a;
+    }
+  }
+  dp = __reduce_add_sync(0xffffffffu, dp);
+  if (lane == 0 && dp) atomicAdd(&s_dp, dp);
+  __syncthreads();
+  if (tid < (uint32_t)I.n) cnt[(uint64_t)tid * n_sites + js] = s_base[tid];
+  if (tid == 0) dp_sum[js] = s_dp;
+}
+
+// order-preserving key of a 4-byte value: floats by value, ints by value
+__device__ inline uint32_t info_key(uint32_t v, bool is_float) { return is_float ? ((v & 0x80000000u) ? ~v : (v | 0x80000000u)) : (v ^ 0x80000000u); }
+
+// one block per (site, INFO field): median by radix select, sum / mean by one thread in row order
+__global__ void __launch_bounds__(FMT_THREADS) k_info_reduce(const __grid_constant__ PlainSet P, const __grid_constant__ InfoSet I, const uint32_t n_sites, const uint32_t nq,
+                                                             const uint32_t* __restrict__ vals, const uint32_t* __restrict__ cnt, uint32_t* __restrict__ out_value,
+                                                             uint8_t* __restrict__ out_valid) {
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_prefix, s_rank;
+  const uint32_t js = blockIdx.x, k = blockIdx.y, tid = threadIdx.x;
+  const uint64_t slot = (uint64_t)k * n_sites + js;
+  const uint32_t n = cnt[slot];
+  const uint32_t* v = vals + slot * nq;
+  const bool is_float = P.f[I.field[k]].elem == ELEM_FLOAT32;
+  if (n == 0) { if (tid == 0) { out_valid[slot] = 0; out_value[slot] = 0; } return; }
+  if (I.op[k] != INFO_MEDIAN) {
+    if (tid == 0) {
+      uint32_t r;
+      if (is_float) { float s = 0.0f; for (uint32_t i = 0; i < n; ++i) s = __fadd_rn(s, __uint_as_float(v[i])); if (I.op[k] == INFO_MEAN) s = __fdiv_rn(s, (float)n); r = __float_as_uint(s); }
+      else { int32_t s = 0; for (uint32_t i = 0; i < n; ++i) s += (int32_t)v[i]; if (I.op[k] == INFO_MEAN) s = (int32_t)((uint32_t)s / n); r = (uint32_t)s; }
+      out_value[slot] = r; out_valid[slot] = 1;
+    }
+    return;
+  }
+  // the key of rank n/2 (ascending), one byte per pass from the top
+  if (tid == 0) { s_prefix = 0; s_rank = n / 2u; }
+  for (int pass = 3; pass >= 0; --pass) {
+    s_hist[tid] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix, hi_mask = pass == 3 ? 0u : (0xFFFFFFFFu << (8 * (pass + 1)));
+    for (uint32_t i = tid; i < n; i += FMT_THREADS) {
+      const uint32_t key = info_key(v[i], is_float);
+      if ((key & hi_mask) == prefix) atomicAdd(&s_hist[(key >> (8 * pass)) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t r = s_rank, b = 0;
+      for (; b < 256; ++b) { if (r < s_hist[b]) break; r -= s_hist[b]; }
+      s_rank = r; s_prefix = prefix | (b << (8 * pass));
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const uint32_t key = s_prefix;
+    out_value[slot] = is_float ? ((key & 0x80000000u) ? (key & 0x7FFFFFFFu) : ~key) : (key ^ 0x80000000u);
+    out_valid[slot] = 1;
+  }
+}
+
 }  // namespace gdb

@@ -47,10 +47,16 @@ typedef struct gdbgpu_field_desc {
 /* A FORMAT field whose length does not depend on the allele list (GQ, MIN_DP, DP_FORMAT, SB, PGT, PID, ...): never
  * remapped, only collated over the query rows and BCF-encoded (GDBGPU_SCAN_BCF_FORMAT); the other entries of
  * BroadCombinedGVCFOperator::m_FORMAT_fields_vec (broad_combined_gvcf.cc:168-232,603-727). */
+/* The same descriptor stages the scalar INFO fields the Broad operator combines over the valid calls of a site
+ * (BroadCombinedGVCFOperator::handle_INFO_fields, broad_combined_gvcf.cc:374-420,524-545; median / sum / mean of the first
+ * element: VariantFieldHandler::get_valid_median / get_valid_sum / get_valid_mean, variant_field_handler.cc:529-612). */
+enum { GDBGPU_INFO_NONE = 0, GDBGPU_INFO_MEDIAN = 1, GDBGPU_INFO_SUM = 2, GDBGPU_INFO_MEAN = 3 };
 typedef struct gdbgpu_plain_field_desc {
   const char* name;      /* TileDB attribute name, e.g. "MIN_DP" */
   int32_t elem_type;     /* GDBGPU_ELEM_* (CHAR: a string per cell) */
   int32_t fixed_len;     /* values per cell; 0 = variable length */
+  int32_t no_format;     /* 1: the field is not a FORMAT field (no block is produced for it) */
+  int32_t info_op;       /* GDBGPU_INFO_*: combine the field over the valid calls of every site (4-byte fixed-length fields) */
 } gdbgpu_plain_field_desc;
 #define GDBGPU_MAX_PLAIN_FIELDS 16
 
@@ -148,6 +154,10 @@ typedef struct gdbgpu_scan_params {
   uint64_t n_query_rows;
   uint32_t flags;
   uint32_t max_diploid_alt_alleles;  /* 0 -> 50 (gt_common.h:48) */
+  /* GATK-style DP (VCF_FIELD_COMBINE_OPERATION_DP, broad_combined_gvcf.cc:688-727): 1-based indices into the array's plain
+   * fields of the INFO DP attribute, MIN_DP and DP_FORMAT (0 = not queried); INFO/DP of a site = sum over its rows of
+   * DP, else MIN_DP, else DP_FORMAT.  Used with GDBGPU_SCAN_BCF_FORMAT. */
+  uint32_t dp_info_field, dp_min_dp_field, dp_format_field;
 } gdbgpu_scan_params;
 
 typedef struct gdbgpu_scan_info {
@@ -209,6 +219,11 @@ typedef struct gdbgpu_batch {
   const uint64_t* fmt_offset;
   const uint8_t* fmt_bytes;
   uint64_t fmt_total_bytes;
+  /* combined INFO scalars (host arrays): entry p*n_sites + s for plain field p (info_op != 0): info_valid = some valid call
+   * of the site has the field, info_value = the 4-byte result (int32 or float bits); info_dp_sum[s] = the DP rule's sum */
+  const uint8_t* info_valid;
+  const uint32_t* info_value;
+  const int32_t* info_dp_sum;
 } gdbgpu_batch;
 
 int gdbgpu_scan_begin(gdbgpu_array* arr, const gdbgpu_scan_params* params, gdbgpu_scan** out);

@@ -85,12 +85,24 @@ def read_bcf(path):
         n_fmt, n_sample = nf_ns >> 24, nf_ns & 0xFFFFFF
         o = 24
         n, bt, o = _descriptor(sh, o)      # ID
+        rec_id = sh[o:o + n].decode()
         o += n
         alleles = []
         for _ in range(n_allele):
             n, bt, o = _descriptor(sh, o)
             alleles.append(sh[o:o + n].decode())
             o += n
+        n, bt, o = _descriptor(sh, o)      # FILTER: typed vector of dictionary indices
+        flt = [int.from_bytes(sh[o + k * BT_SIZE[bt]:o + (k + 1) * BT_SIZE[bt]], "little", signed=True) for k in range(n)] if n else []
+        o += n * (BT_SIZE[bt] if n else 0)
+        info = {}
+        for _ in range(n_info):
+            key, o = _typed_int(sh, o)
+            n, bt, o = _descriptor(sh, o)
+            nb = n * (BT_SIZE[bt] if n else 0)
+            info[names[key]] = (bt, n, sh[o:o + nb])
+            o += nb
+        assert o == len(sh)
         fmt = {}
         o = 0
         for _ in range(n_fmt):
@@ -101,6 +113,7 @@ def read_bcf(path):
             fmt[names[key]] = (bt, nps, ind[o:o + nbytes], ind[o0:o])
             o += nbytes
         assert o == len(ind)
-        recs.append(dict(chrom=chrom, pos=pos, rlen=rlen, n_allele=n_allele, n_sample=n_sample, alleles=alleles, fmt=fmt,
-                         fmt_order=list(fmt), indiv=bytes(ind)))
+        recs.append(dict(chrom=chrom, pos=pos, rlen=rlen, qual_bits=struct.unpack_from("<I", sh, 12)[0], n_allele=n_allele, n_sample=n_sample,
+                         id=rec_id, alleles=alleles, filter=flt, info=info, info_order=list(info), fmt=fmt, fmt_order=list(fmt),
+                         shared=bytes(sh), indiv=bytes(ind)))
     return text, samples, recs

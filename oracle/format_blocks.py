@@ -140,6 +140,24 @@ class PlainColumns:
                 self.cols[name] = (off, val.view(np.uint8) if elem == "char" else val.view(np.uint32))
         begin = arr.col <= end
         self.cell_of = {(int(r), int(c)): int(i) for i, (r, c, b) in enumerate(zip(arr.row, arr.col, begin)) if b}
+        self._ref = arr.var("REF")
+        self._alt = arr.var("ALT")
+
+    def contains_deletion(self, cell):
+        """VariantUtils::contains_deletion (src/main/cpp/src/utils/known_field_info.cc:310-319) over the cell's REF / ALT"""
+        ro, rv = self._ref
+        ao, av = self._alt
+        ref_len = int(ro[cell + 1] - ro[cell])
+        if ref_len <= 1:
+            return False
+        alt = bytes(np.asarray(av[ao[cell]:ao[cell + 1]], dtype=np.uint8)).split(b"\0")[0]
+        for t in alt.split(b"|"):
+            if not t:
+                continue
+            symbolic = t[:1] == b"&" or t == b"*" or (t[:1] == b"<" and t[-1:] == b">") or b"[" in t or b"]" in t
+            if not symbolic and len(t) < ref_len:
+                return True
+        return False
 
     def values(self, name, elem, cell):
         """-> list of the field's elements in `cell`, [] when the field is invalid (every element TileDB-null)"""
@@ -195,3 +213,65 @@ def assemble_indiv(order, blocks, key_ids):
             bt, nps, data = blocks[vcf_name][:3]
             b += enc_int1(key_ids[vcf_name]) + enc_size(nps, bt) + data
     return b
+
+
+# ---------------------------------------------------------------------------------------------- INFO scalars
+def info_site_values(site, plain, info_fields, dp_fields=(None, None, None)):
+    """BroadCombinedGVCFOperator::handle_INFO_fields for scalar fields (broad_combined_gvcf.cc:524-545) + the DP rule
+    (:688-727) at one parsed dump site.  info_fields: [(attribute, 'int'|'float', 'median'|'sum'|'mean')];
+    dp_fields: attribute names of (INFO DP, MIN_DP, DP_FORMAT) or None.
+    -> ({attribute: 4-byte result as uint32 bits}, dp_sum)"""
+    calls = sorted(site["calls"], key=lambda c: c["row"])
+    cells = [plain.cell_of[(c["row"], c["begin"])] for c in calls]
+    # a call seen past its begin that contains a deletion had its INFO fields invalidated (broad_combined_gvcf.cc:1067-1075)
+    reduced = [site["begin"] > c["begin"] and plain.contains_deletion(cell) for c, cell in zip(calls, cells)]
+    out = {}
+    for name, elem, op in info_fields:
+        bad = (F32_MISSING, F32_VEND) if elem == "float" else (I32_MISSING & 0xFFFFFFFF, I32_VEND & 0xFFFFFFFF)
+        vals = []
+        for cell, red in zip(cells, reduced):
+            v = plain.values(name, elem, cell)
+            if red or not v or v[0] in bad:
+                continue
+            vals.append(v[0])
+        if not vals:
+            continue
+        a = np.asarray(vals, dtype=np.uint32).view(np.float32 if elem == "float" else np.int32)
+        if op == "median":                      # std::nth_element at n/2 (variant_field_handler.cc:529-560)
+            r = np.sort(a)[len(a) // 2]
+        else:                                   # left-to-right sum in the field's own type (:562-607)
+            r = a.dtype.type(0)
+            with np.errstate(over="ignore"):
+                for x in a:
+                    r = a.dtype.type(r + x)
+                if op == "mean":
+                    r = a.dtype.type(r / a.dtype.type(len(a))) if elem == "float" else np.int32(np.uint32(r) // np.uint32(len(a)))
+        out[name] = int(np.asarray(r).view(np.uint32))
+    dp_sum = 0
+    dp, min_dp, dp_format = dp_fields
+
+    def scalar(name, cell):
+        if name is None:
+            return None
+        v = plain.values(name, "int", cell)
+        if not v:
+            return None
+        x = v[0] - (1 << 32) if v[0] >= (1 << 31) else v[0]
+        return None if x in (I32_MISSING, I32_VEND) else x
+    if dp is not None or dp_format is not None:
+        for cell in cells:
+            a = scalar(dp, cell)
+            if a is None:
+                a = scalar(min_dp, cell)
+                if a is None:
+                    a = scalar(dp_format, cell)
+            dp_sum += a or 0
+    dp_sum = (dp_sum + 2 ** 31) % 2 ** 32 - 2 ** 31
+    return out, dp_sum
+
+
+def enc_info_value(bits, elem):
+    """typed value of a one-element INFO field as bcf_update_info writes it: ints through bcf_enc_int1, floats as float32"""
+    if elem == "float":
+        return bytes([1 << 4 | BT_FLOAT]) + struct.pack("<I", bits)
+    return enc_int1(bits - (1 << 32) if bits >= (1 << 31) else bits)

@@ -12,7 +12,8 @@ import pytest
 from conftest import GOLDEN, golden_cases
 from oracle import bcf_reader, format_blocks, oracle
 from oracle import tiledb_fragment as tf
-from util import case_fields, case_query_rows, format_field_names, format_order, plain_format_fields, vcf_format_name
+from util import (case_fields, case_query_rows, format_field_names, format_order, info_scalar_fields, plain_format_fields,
+                  vcf_format_name)
 
 CASES = golden_cases()
 
@@ -62,6 +63,36 @@ def test_whole_indiv_matches_reference_bcf(case):
         assert sorted(blocks) == sorted(rec["fmt"]), (site["begin"], sorted(blocks), sorted(rec["fmt"]))
         assert [n for n in order if n in blocks] == rec["fmt_order"], (site["begin"], order, rec["fmt_order"])
         assert format_blocks.assemble_indiv(order, blocks, key_ids) == rec["indiv"], site["begin"]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_info_scalars_match_reference_bcf(case):
+    """END, the median / sum combined INFO scalars and the GATK-style INFO/DP of every record"""
+    _, samples, recs = bcf_reader.read_bcf(os.path.join(GOLDEN, "bcf", case["id"] + ".bcf"))
+    names, sites = oracle.parse_dump(open(os.path.join(GOLDEN, case["dump"]), "rb").read())
+    info_fields = info_scalar_fields(case)
+    arr = tf.Array(os.path.join(GOLDEN, case["workspace"]), case["array"])
+    extra = [(n, e, 1) for n, e, _ in info_fields] + [("DP", "int", 1), ("MIN_DP", "int", 1), ("DP_FORMAT", "int", 1)]
+    plain = format_blocks.PlainColumns(arr, arr.fixed("END")[:, 0], extra)
+    n_checked = 0
+    for rec, site in zip(recs, sites):
+        vals, dp_sum = format_blocks.info_site_values(site, plain, info_fields, ("DP", "MIN_DP", "DP_FORMAT"))
+        want = {k: v for k, v in rec["info"].items() if k in [f[0] for f in info_fields]}
+        assert sorted(vals) == sorted(want), (site["begin"], sorted(vals), sorted(want))
+        for name, elem, _ in info_fields:
+            if name in want:
+                bt, n, raw = want[name]
+                assert bytes([n << 4 | bt]) + raw == format_blocks.enc_info_value(vals[name], elem), (site["begin"], name)
+                n_checked += 1
+        assert ("END" in rec["info"]) == (site["end"] > site["begin"])
+        if "END" in rec["info"]:
+            bt, n, raw = rec["info"]["END"]
+            assert bytes([n << 4 | bt]) + raw == format_blocks.enc_int1(site["end"] + 1)
+        assert ("DP" in rec["info"]) == (dp_sum > 0 and bool(site["remap"])), (site["begin"], dp_sum)
+        if "DP" in rec["info"]:
+            bt, n, raw = rec["info"]["DP"]
+            assert bytes([n << 4 | bt]) + raw == format_blocks.enc_int1(dp_sum), (site["begin"], dp_sum)
+    assert n_checked or not any(r["info"].keys() - {"END", "DP"} for r in recs)
 
 
 def test_enc_int1_and_size_known_answers():

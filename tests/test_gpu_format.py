@@ -9,7 +9,8 @@ import pytest
 from conftest import GOLDEN, golden_cases
 from oracle import bcf_reader, format_blocks, oracle
 from tools import gdbsyn
-from util import case_fields, case_query_rows, format_field_names, format_order, plain_format_fields, vcf_format_name
+from util import (case_fields, case_query_rows, format_field_names, format_order, info_scalar_fields, plain_format_fields,
+                  vcf_format_name)
 
 pytestmark = pytest.mark.gpu
 CASES = golden_cases()
@@ -98,6 +99,50 @@ def test_whole_indiv_matches_reference_bcf(ctx, case):
                 blocks = {vcf_format_name(k): v for k, v in g.items() if k in fmt_names or k in [p[0] for p in plain]}
                 assert sorted(blocks) == sorted(rec["fmt"]), (rec["pos"], sorted(blocks), sorted(rec["fmt"]))
                 assert format_blocks.assemble_indiv(order, blocks, key_ids) == rec["indiv"], rec["pos"]
+    finally:
+        arr.close()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_info_scalars_match_reference_bcf(ctx, case):
+    """median / sum combined INFO scalars (k_info_collect + k_info_reduce) and the GATK-style INFO/DP sum of every record,
+    as typed BCF values, against the reference's BCF output"""
+    from genomicsdb_b200 import capi
+    _, samples, recs = bcf_reader.read_bcf(os.path.join(GOLDEN, "bcf", case["id"] + ".bcf"))
+    fields, phased = case_fields(case)
+    info_fields = info_scalar_fields(case)
+    plain = [(n, e, 1, 1, op) for n, e, op in info_fields]                         # INFO scalars: staged, combined, no FORMAT block
+    plain += [("DP", "int", 1, 1), ("MIN_DP", "int", 1, 1), ("DP_FORMAT", "int", 1, 1)]   # the DP rule's inputs
+    n_info = len(info_fields)
+    arr = capi.Array.open(ctx, os.path.join(GOLDEN, case["workspace"]), case["array"], fields, gt_phased=phased, plain=plain)
+    try:
+        for kw in (dict(), dict(max_sites=1)):
+            got = []
+            for r in sorted(tuple(r) for r in case["query_column_ranges"]):
+                sc = capi.Scan(arr, r[0], r[1], query_rows=case_query_rows(case), flags=capi.SCAN_BCF_FORMAT,
+                               dp_fields=(n_info + 1, n_info + 2, n_info + 3))
+                while True:
+                    bv = sc.next_batch(**kw)
+                    if bv is None:
+                        break
+                    for s in range(bv.n_sites):
+                        got.append(dict(begin=int(bv.site_begin[s]), end=int(bv.site_end[s]), remap=bool(bv.site_flags[s] & capi.SITE_REMAPPED),
+                                        dp=int(bv.info_dp_sum[s]),
+                                        vals={info_fields[k][0]: int(bv.info_value[k, s]) for k in range(n_info) if bv.info_valid[k, s]}))
+                sc.close()
+            assert len(got) == len(recs)
+            for rec, g in zip(recs, got):
+                want = {k: v for k, v in rec["info"].items() if k in [f[0] for f in info_fields]}
+                assert sorted(g["vals"]) == sorted(want), (g["begin"], sorted(g["vals"]), sorted(want))
+                for name, elem, _ in info_fields:
+                    if name in want:
+                        bt, n, raw = want[name]
+                        assert bytes([n << 4 | bt]) + raw == format_blocks.enc_info_value(g["vals"][name], elem), (g["begin"], name)
+                assert ("END" in rec["info"]) == (g["end"] > g["begin"])
+                assert ("DP" in rec["info"]) == (g["dp"] > 0 and g["remap"]), (g["begin"], g["dp"])
+                if "DP" in rec["info"]:
+                    bt, n, raw = rec["info"]["DP"]
+                    assert bytes([n << 4 | bt]) + raw == format_blocks.enc_int1(g["dp"])
     finally:
         arr.close()
 

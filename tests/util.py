@@ -75,3 +75,23 @@ def format_order(case, remapped_names, plain):
         elif any(a == p[0] for p in plain) and a != "DP_FORMAT":
             names.append(a)
     return ["GT"] + names + (["DP"] if any(p[0] == "DP_FORMAT" for p in plain) else [])
+
+
+KNOWN_INFO_OPS = {"BaseQRankSum": "median", "ClippingRankSum": "median", "MQRankSum": "median", "ReadPosRankSum": "median",
+                  "MQ": "median", "MQ0": "median", "ExcessHet": "median", "RAW_MQ": "sum"}   # known_field_info.cc:284-308
+
+
+def info_scalar_fields(case):
+    """(attribute, 'int'|'float', op) of the queried scalar INFO attributes the Broad operator combines with median / sum /
+    mean, in query order (m_INFO_fields_vec, broad_combined_gvcf.cc:168-215); DP and END are handled separately."""
+    vid = oracle.load_vid_fields(os.path.join(GOLDEN, case["vid_mapping_file"]))
+    out = []
+    for name in case["attributes"]:
+        ent = vid.get(name)
+        if ent is None or name in ("END", "DP") or "INFO" not in (ent.get("classes") or []):
+            continue
+        op = ent.get("combine") or KNOWN_INFO_OPS.get(name)
+        if op not in ("median", "sum", "mean") or ent["length"] not in (1, "1", None) or ent["type"] not in ("int", "float"):
+            continue
+        out.append((name, ent["type"], op))
+    return out
