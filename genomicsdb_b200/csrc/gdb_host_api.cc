@@ -24,11 +24,34 @@ VidMapper::VidMapper(const std::string& file) {
       else if (l->type == JsonValue::ARR) f.length = "2D";
     }
     if (const JsonValue* c = v.find("vcf_field_class")) for (auto& x : c->arr) { if (x.str == "FORMAT") f.is_format = true; if (x.str == "INFO") f.is_info = true; }
+    if (const JsonValue* c = v.find("VCF_field_combine_operation")) f.combine_op = c->str;
+    else {   // defaults of the known fields (known_field_info.cc:284-308)
+      static const char* medians[] = {"BaseQRankSum", "ClippingRankSum", "MQRankSum", "ReadPosRankSum", "MQ", "MQ0", "ExcessHet"};
+      for (const char* m : medians) if (name == m) f.combine_op = "median";
+      if (name == "RAW_MQ") f.combine_op = "sum";
+      if (name == "DP") f.combine_op = "DP";
+    }
     fields_.push_back(f);
     if (f.is_format && f.is_info) { FieldInfo g = f; g.name = name + "_FORMAT"; fields_.push_back(g); }   // vid_mapper.cc: FORMAT twin
   };
   if (fl.type == JsonValue::OBJ) for (auto& kv : fl.obj) add(kv.first, kv.second);
   else for (auto& v : fl.arr) add(v.at("name").str, v);
+  if (const JsonValue* cl = d.find("contigs")) {
+    auto addc = [&](const std::string& name, const JsonValue& v) {
+      ContigInfo c; c.name = name;
+      if (const JsonValue* o = v.find("tiledb_column_offset")) c.tiledb_column_offset = o->as_int();
+      if (const JsonValue* l = v.find("length")) c.length = l->as_int();
+      contigs_.push_back(c);
+    };
+    if (cl->type == JsonValue::OBJ) for (auto& kv : cl->obj) addc(kv.first, kv.second);
+    else for (auto& v : cl->arr) addc(v.at("name").str, v);
+    std::sort(contigs_.begin(), contigs_.end(), [](const ContigInfo& a, const ContigInfo& b) { return a.tiledb_column_offset < b.tiledb_column_offset; });
+  }
+}
+const ContigInfo* VidMapper::get_contig_location(int64_t column) const {
+  const ContigInfo* best = nullptr;
+  for (auto& c : contigs_) { if (c.tiledb_column_offset <= column) best = &c; else break; }
+  return (best && column < best->tiledb_column_offset + best->length) ? best : nullptr;
 }
 const FieldInfo* VidMapper::get_field_info(const std::string& name) const {
   for (auto& f : fields_) if (f.name == name) return &f;
@@ -82,6 +105,7 @@ void VariantQueryConfig::read_from_file(const std::string& filename, int rank) {
   if (const JsonValue* v = d.find("vid_mapping_file")) vid_ = VidMapper(v->str);
   if (const JsonValue* v = d.find("max_diploid_alt_alleles_that_can_be_genotyped")) max_alt_ = (unsigned)v->as_int();
   if (const JsonValue* v = d.find("produce_GT_with_min_PL_value_for_spanning_deletions")) min_pl_gt_ = v->as_bool();
+  if (const JsonValue* v = d.find("produce_GT_field")) produce_gt_ = v->as_bool();
 }
 
 // ------------------------------------------------------------------------------------------------ operators
@@ -98,6 +122,169 @@ void GA4GHOperator::operate(Variant& variant, const VariantQueryConfig& query_co
   SingleVariantOperatorBase::operate(variant, query_config);
   m_max_diploid_alt_alleles_that_can_be_genotyped = query_config.get_max_diploid_alt_alleles_that_can_be_genotyped();
   m_remapped_variant = &variant;
+}
+
+// ------------------------------------------------------------------------------------------------ VCFAdapter
+// BCF dictionary of strings: FILTER / INFO / FORMAT IDs share one index space (IDX= when htslib wrote it, else order of first
+// appearance, PASS = 0); contigs have their own (htslib vcf.c bcf_hdr_sync)
+void VCFAdapter::set_vcf_header_text(const std::string& header) {
+  header_ = header; ids_.clear(); contigs_.clear();
+  int next_id = 0, next_ctg = 0;
+  size_t pos = 0;
+  while (pos < header.size()) {
+    size_t eol = header.find('\n', pos);
+    if (eol == std::string::npos) eol = header.size();
+    const std::string line = header.substr(pos, eol - pos);
+    pos = eol + 1;
+    auto attr = [&](const char* key) -> std::string {
+      size_t k = line.find(key);
+      if (k == std::string::npos) return "";
+      k += strlen(key);
+      size_t e = line.find_first_of(",>", k);
+      return line.substr(k, e == std::string::npos ? std::string::npos : e - k);
+    };
+    const bool dict = line.compare(0, 10, "##FILTER=<") == 0 || line.compare(0, 8, "##INFO=<") == 0 || line.compare(0, 10, "##FORMAT=<") == 0;
+    if (dict) {
+      const std::string id = attr("ID=");
+      bool known = false;
+      for (auto& kv : ids_) if (kv.first == id) known = true;
+      if (known) continue;
+      const std::string idx = attr("IDX=");
+      const int v = idx.empty() ? next_id : std::stoi(idx);
+      ids_.push_back({id, v});
+      next_id = std::max(next_id, v + 1);
+    } else if (line.compare(0, 10, "##contig=<") == 0) {
+      const std::string idx = attr("IDX=");
+      const int v = idx.empty() ? next_ctg : std::stoi(idx);
+      contigs_.push_back({attr("ID="), v});
+      next_ctg = std::max(next_ctg, v + 1);
+    }
+  }
+}
+int VCFAdapter::get_dictionary_id(const std::string& name) const { for (auto& kv : ids_) if (kv.first == name) return kv.second; return -1; }
+int VCFAdapter::get_contig_id(const std::string& name) const { for (auto& kv : contigs_) if (kv.first == name) return kv.second; return -1; }
+char VCFAdapter::get_reference_base_at_position(const std::string& contig, int64_t pos) const {
+  auto it = ref_bases_.find(contig + ":" + std::to_string(pos));
+  return it == ref_bases_.end() ? 'N' : it->second;
+}
+
+// ------------------------------------------------------------------------------------------------ BroadCombinedGVCFOperator
+namespace {
+// htslib typed values (vcf.h bcf_enc_int1 / bcf_enc_size, vcf.c bcf_enc_vchar / bcf_enc_vfloat)
+enum { BT_INT8 = 1, BT_INT16 = 2, BT_INT32 = 3, BT_FLOAT = 5, BT_CHAR = 7 };
+void put_bytes(std::vector<uint8_t>& b, const void* p, size_t n) { const uint8_t* s = static_cast<const uint8_t*>(p); b.insert(b.end(), s, s + n); }
+template <class T> void put(std::vector<uint8_t>& b, T v) { put_bytes(b, &v, sizeof(T)); }
+void enc_int1(std::vector<uint8_t>& b, int32_t x) {
+  if (x == INT32_MIN + 1) { b.push_back(1 << 4 | BT_INT8); b.push_back(0x81); }
+  else if (x == INT32_MIN) { b.push_back(1 << 4 | BT_INT8); b.push_back(0x80); }
+  else if (x <= 127 && x >= -120) { b.push_back(1 << 4 | BT_INT8); b.push_back((uint8_t)(int8_t)x); }
+  else if (x <= 32767 && x >= -32760) { b.push_back(1 << 4 | BT_INT16); put<int16_t>(b, (int16_t)x); }
+  else { b.push_back(1 << 4 | BT_INT32); put<int32_t>(b, x); }
+}
+void enc_size(std::vector<uint8_t>& b, int size, int type) {
+  if (size >= 15) { b.push_back((uint8_t)(15 << 4 | type)); enc_int1(b, size); }
+  else b.push_back((uint8_t)(size << 4 | type));
+}
+void enc_vchar(std::vector<uint8_t>& b, const std::string& s) { enc_size(b, (int)s.size(), BT_CHAR); put_bytes(b, s.data(), s.size()); }
+}  // namespace
+
+BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, const VidMapper& id_mapper, const VariantQueryConfig& qc)
+    : m_vcf_adapter(&vcf_adapter), m_vid_mapper(&id_mapper) {
+  if (!qc.is_bookkeeping_done()) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "BroadCombinedGVCFOperator: do_query_bookkeeping(config, true, true) must be called first");
+  auto key_of = [&](const std::string& vcf_name) {
+    int k = vcf_adapter.get_dictionary_id(vcf_name);
+    if (k < 0) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "field " + vcf_name + " is not in the VCF header");
+    return k;
+  };
+  const unsigned n_remapped = qc.get_num_remapped_fields();
+  const auto& plain = qc.get_plain_fields();
+  auto remapped_index = [&](const std::string& name) -> int { for (unsigned i = 0; i < n_remapped; ++i) if (qc.get_remapped_field_name(i) == name) return (int)i; return -1; };
+  // FORMAT fields: GT first (htslib moves it to the front, vcf.c:3670-3676), then query order, DP (from DP_FORMAT) last
+  if (remapped_index("GT") >= 0) m_FORMAT_fields_vec.push_back({"GT", key_of("GT"), remapped_index("GT")});
+  int dp_format_plain = -1;
+  for (auto& name : qc.get_query_attributes()) {
+    if (name == "GT") continue;
+    const FieldInfo* fi = id_mapper.get_field_info(name);
+    if (!fi) continue;
+    const int ri = remapped_index(name);
+    if (ri >= 0) {
+      const bool twin = name.size() > 7 && name.compare(name.size() - 7, 7, "_FORMAT") == 0;
+      if ((fi->is_format && (twin || !fi->is_info)) || fi->combine_op == "move_to_FORMAT") m_FORMAT_fields_vec.push_back({name, key_of(name), ri});
+      continue;
+    }
+    for (size_t p = 0; p < plain.size(); ++p) if (plain[p].attribute == name) {
+      if (plain[p].format) {
+        if (name == "DP_FORMAT") dp_format_plain = (int)p;
+        else m_FORMAT_fields_vec.push_back({plain[p].vcf_name, key_of(plain[p].vcf_name), (int)(n_remapped + p)});
+      } else if (plain[p].info_op)
+        m_INFO_fields_vec.push_back({plain[p].vcf_name, key_of(plain[p].vcf_name), (int)p, plain[p].elem == GDBGPU_ELEM_FLOAT32});
+    }
+  }
+  if (dp_format_plain >= 0) m_FORMAT_fields_vec.push_back({"DP", key_of("DP"), (int)(n_remapped + dp_format_plain)});
+  m_dp_rule = qc.get_dp_rule_fields()[0] != 0 || qc.get_dp_rule_fields()[2] != 0;
+  if (m_dp_rule) m_DP_key = key_of("DP");
+  m_END_key = key_of("END");
+}
+
+// BroadCombinedGVCFOperator::operate (broad_combined_gvcf.cc:765-901) + bcf_write (htslib vcf.c) for one site
+void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint32_t s, const VariantQueryConfig&) {
+  const uint64_t nq = b.n_query_rows, ns = b.n_sites;
+  const int64_t begin = b.site_begin[s], end = b.site_end[s];
+  const ContigInfo* contig = m_vid_mapper->get_contig_location(begin);
+  if (!contig) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Unknown contig for position " + std::to_string(begin));
+  const int rid = m_vcf_adapter->get_contig_id(contig->name);
+  const int32_t pos = (int32_t)(begin - contig->tiledb_column_offset);
+  const uint32_t first = b.allele_first[s], n_allele = b.n_alleles[s];
+  auto allele = [&](uint32_t m) { return std::string((const char*)b.allele_bytes + b.allele_pos[2 * (first + m)], b.allele_pos[2 * (first + m) + 1]); };
+  std::string ref = allele(0);
+  if (ref.size() == 1 && ref[0] == 'N') {   // broad_combined_gvcf.cc:811-816
+    char base = m_vcf_adapter->get_reference_base_at_position(contig->name, pos);
+    ref[0] = (base == 'A' || base == 'C' || base == 'G' || base == 'T') ? base : 'N';
+  }
+  std::vector<uint8_t> shared, indiv;
+  enc_vchar(shared, "");   // ID
+  enc_vchar(shared, ref);
+  for (uint32_t m = 1; m < n_allele; ++m) enc_vchar(shared, allele(m));
+  shared.push_back(0x00);   // FILTER: empty typed vector
+  uint32_t n_info = 0;
+  int32_t rlen = (int32_t)ref.size();
+  if (end > begin) {   // handle_INFO_fields: interval -> END (1-based); bcf_update_info sets rlen from END
+    const int32_t vcf_end = (int32_t)(end - contig->tiledb_column_offset + 1);
+    enc_int1(shared, m_END_key); enc_int1(shared, vcf_end); ++n_info;
+    rlen = vcf_end - pos;
+  }
+  for (auto& f : m_INFO_fields_vec) {
+    const uint64_t slot = (uint64_t)f.plain_index * ns + s;
+    if (!b.info_valid[slot]) continue;
+    enc_int1(shared, f.key);
+    if (f.is_float) { enc_size(shared, 1, BT_FLOAT); put<uint32_t>(shared, b.info_value[slot]); }
+    else enc_int1(shared, (int32_t)b.info_value[slot]);
+    ++n_info;
+  }
+  const bool remapped = b.site_flags[s] & GDBGPU_SITE_REMAPPED;
+  if (m_dp_rule && b.info_dp_sum[s] > 0 && remapped) { enc_int1(shared, m_DP_key); enc_int1(shared, b.info_dp_sum[s]); ++n_info; }   // :721-725
+  uint32_t n_fmt = 0;
+  for (auto& f : m_FORMAT_fields_vec) {
+    const uint64_t slot = (uint64_t)f.fmt_index * ns + s;
+    const uint8_t type = b.fmt_type[slot];
+    if (!type) continue;
+    const uint32_t nps = b.fmt_nps[slot];
+    enc_int1(indiv, f.key);
+    enc_size(indiv, (int)nps, type);
+    const size_t w = (type == BT_INT8 || type == BT_CHAR) ? 1 : (type == BT_INT16 ? 2 : 4);
+    put_bytes(indiv, b.fmt_bytes + b.fmt_offset[slot], (size_t)nq * nps * w);
+    ++n_fmt;
+  }
+  std::vector<uint8_t>& out = m_vcf_adapter->get_buffer();
+  put<uint32_t>(out, (uint32_t)(24 + shared.size()));
+  put<uint32_t>(out, (uint32_t)indiv.size());
+  put<int32_t>(out, rid); put<int32_t>(out, pos); put<int32_t>(out, rlen);
+  put<uint32_t>(out, 0x7F800001u);   // QUAL missing (GATK CombineGVCFs does not carry QUAL, broad_combined_gvcf.cc:796-808)
+  put<uint32_t>(out, n_allele << 16 | n_info);
+  put<uint32_t>(out, n_fmt << 24 | (uint32_t)nq);
+  put_bytes(out, shared.data(), shared.size());
+  put_bytes(out, indiv.data(), indiv.size());
+  ++m_num_records;
 }
 
 // ------------------------------------------------------------------------------------------------ storage manager
@@ -124,7 +311,7 @@ void VariantQueryProcessor::check(int rc) const {
   throw GenomicsDBGPUException(rc, m);
 }
 
-void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool) {
+void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool, bool stage_broad_gvcf_fields) {
   const VidMapper& vid = qc.get_vid_mapper().is_initialized() ? qc.get_vid_mapper() : vid_;
   std::vector<gdbgpu_field_desc> fd;
   qc.remapped_names_.clear();
@@ -141,8 +328,42 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool) {
   }
   const FieldInfo* gt = vid.get_field_info("GT");
   int phased = gt && gt->length == "PP";
+  // what BroadCombinedGVCFOperator's constructor sorts the queried attributes into (broad_combined_gvcf.cc:160-240)
+  qc.plain_.clear(); qc.dp_fields_[0] = qc.dp_fields_[1] = qc.dp_fields_[2] = 0;
+  std::vector<gdbgpu_plain_field_desc> pd;
+  if (stage_broad_gvcf_fields) {
+    static const char* skip[] = {"END", "REF", "ALT", "GT", "QUAL", "FILTER", "ID"};
+    for (auto& name : qc.get_query_attributes()) {
+      const FieldInfo* fi = vid.get_field_info(name);
+      if (!fi || fi->is_allele_dependent()) continue;
+      bool skipped = false;
+      for (const char* k : skip) if (name == k) skipped = true;
+      if (skipped) continue;
+      if (fi->length == "2D") throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "BroadCombinedGVCFOperator on the GPU: multi-dimensional field " + name + " is not supported");
+      const bool twin = name.size() > 7 && name.compare(name.size() - 7, 7, "_FORMAT") == 0;
+      VariantQueryConfig::PlainField pf;
+      pf.attribute = name; pf.vcf_name = twin ? name.substr(0, name.size() - 7) : name;
+      pf.elem = fi->type == "char" ? GDBGPU_ELEM_CHAR : (fi->type == "float" ? GDBGPU_ELEM_FLOAT32 : GDBGPU_ELEM_INT32);
+      bool numeric_len = !fi->length.empty() && fi->length.find_first_not_of("0123456789") == std::string::npos;
+      pf.fixed_len = numeric_len ? std::stoi(fi->length) : 0;
+      const bool as_format = (fi->is_format && (twin || !fi->is_info)) || (fi->is_info && fi->combine_op == "move_to_FORMAT");
+      if (as_format) pf.format = true;
+      else if (fi->is_info && name == "DP" && fi->combine_op == "DP") { /* DP rule input only */ }
+      else if (fi->is_info && (fi->combine_op == "median" || fi->combine_op == "sum" || fi->combine_op == "mean")) {
+        if (pf.fixed_len != 1 || pf.elem == GDBGPU_ELEM_CHAR) throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "INFO combine operation on a non-scalar field: " + name);
+        pf.info_op = fi->combine_op == "median" ? GDBGPU_INFO_MEDIAN : (fi->combine_op == "sum" ? GDBGPU_INFO_SUM : GDBGPU_INFO_MEAN);
+      } else if (fi->is_info && !fi->combine_op.empty())
+        throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "INFO combine operation " + fi->combine_op + " of field " + name + " is not supported on the GPU");
+      else continue;   // INFO field without a combine operation: the reference drops it with a warning (broad_combined_gvcf.cc:175-178)
+      qc.plain_.push_back(pf);
+      if (name == "DP" && !as_format) qc.dp_fields_[0] = (unsigned)qc.plain_.size();
+      if (name == "MIN_DP") qc.dp_fields_[1] = (unsigned)qc.plain_.size();
+      if (name == "DP_FORMAT") qc.dp_fields_[2] = (unsigned)qc.plain_.size();
+    }
+    for (auto& pf : qc.plain_) pd.push_back(gdbgpu_plain_field_desc{pf.attribute.c_str(), pf.elem, pf.fixed_len, pf.format ? 0 : 1, pf.info_op});
+  }
   if (arr_) { gdbgpu_array_close(arr_); arr_ = nullptr; }
-  check(gdbgpu_array_open(sm_->ctx(), sm_->get_workspace().c_str(), array_name_.c_str(), fd.data(), (int32_t)fd.size(), phased, &arr_));
+  check(gdbgpu_array_open_ex(sm_->ctx(), sm_->get_workspace().c_str(), array_name_.c_str(), fd.data(), (int32_t)fd.size(), pd.data(), (int32_t)pd.size(), phased, &arr_));
   gdbgpu_array_info info;
   check(gdbgpu_array_get_info(arr_, &info));
   if (!info.has_gt) qc.remapped_names_.erase(qc.remapped_names_.begin());
@@ -196,6 +417,11 @@ void VariantQueryProcessor::scan_and_operate(const int, const VariantQueryConfig
     if (!handle_spanning_deletions) p.flags |= GDBGPU_SCAN_NO_DELETIONS;
     if (qc.produce_GT_with_min_PL_value_for_spanning_deletions()) p.flags |= GDBGPU_SCAN_MIN_PL_GT;
     if (want_lut) p.flags |= GDBGPU_SCAN_WANT_LUT;
+    if (op.wants_bcf_blocks()) {
+      p.flags |= GDBGPU_SCAN_BCF_FORMAT;
+      if (qc.produce_GT_field()) p.flags |= GDBGPU_SCAN_PRODUCE_GT;
+      p.dp_info_field = qc.dp_fields_[0]; p.dp_min_dp_field = qc.dp_fields_[1]; p.dp_format_field = qc.dp_fields_[2];
+    }
     if (!qc.query_all_rows()) { p.query_rows = qc.get_rows_to_query().data(); p.n_query_rows = qc.get_rows_to_query().size(); }
     p.max_diploid_alt_alleles = qc.get_max_diploid_alt_alleles_that_can_be_genotyped();
     check(gdbgpu_scan_begin(arr_, &p, &st.scan_));
@@ -210,8 +436,8 @@ void VariantQueryProcessor::scan_and_operate(const int, const VariantQueryConfig
     }
     while (st.pos_in_batch_ < st.batch_.n_sites) {
       if (op.overflow()) { if (!scan_state) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "operator overflow without a scan state"); return; }   // caller drains, then re-enters
-      fill_variant(st.batch_, st.pos_in_batch_, variant);
-      op.operate(variant, qc);
+      if (op.wants_bcf_blocks()) op.operate_on_bcf_site(st.batch_, st.pos_in_batch_, qc);
+      else { fill_variant(st.batch_, st.pos_in_batch_, variant); op.operate(variant, qc); }
       ++st.pos_in_batch_; ++st.sites_done_;
     }
   }

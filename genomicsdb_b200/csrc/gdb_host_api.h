@@ -22,6 +22,7 @@
 // valid call (what GA4GHOperator::m_remapped_variant holds in the reference); the un-remapped inputs stay in HBM.
 #pragma once
 #include <cstdint>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -47,8 +48,10 @@ struct FieldInfo {
   std::string type;        // "int", "float", "char", ...
   std::string length;      // "1", "R", "A", "G", "P", "PP", "VAR", "<n>"; 2-D descriptors are kept as "2D"
   bool is_format = false, is_info = false;
+  std::string combine_op;  // "VCF_field_combine_operation" of the vid mapping, else the known field's default (known_field_info.cc:284-308)
   bool is_allele_dependent() const { return length == "R" || length == "A" || length == "G"; }
 };
+struct ContigInfo { std::string name; int64_t tiledb_column_offset = 0, length = 0; };
 class VidMapper {
  public:
   VidMapper() = default;
@@ -56,8 +59,11 @@ class VidMapper {
   bool is_initialized() const { return !fields_.empty(); }
   const FieldInfo* get_field_info(const std::string& name) const;
   const std::vector<FieldInfo>& fields() const { return fields_; }
+  // vid_mapper.cc get_contig_location: the contig a TileDB column falls into (nullptr: unknown position)
+  const ContigInfo* get_contig_location(int64_t column) const;
  private:
   std::vector<FieldInfo> fields_;
+  std::vector<ContigInfo> contigs_;   // sorted by tiledb_column_offset
 };
 
 // ---- query configuration (include/config/variant_query_config.h)
@@ -74,6 +80,8 @@ class VariantQueryConfig {
   void set_vid_mapper(const VidMapper& v) { vid_ = v; }
   void set_max_diploid_alt_alleles_that_can_be_genotyped(unsigned v) { max_alt_ = v; }
   void set_produce_GT_with_min_PL_value_for_spanning_deletions(bool v) { min_pl_gt_ = v; }
+  void set_produce_GT_field(bool v) { produce_gt_ = v; }
+  bool produce_GT_field() const { return produce_gt_; }
 
   const std::string& get_workspace(int = 0) const { return workspace_; }
   const std::string& get_array_name(int = 0) const { return array_name_; }
@@ -99,9 +107,17 @@ class VariantQueryConfig {
   std::vector<std::string> attributes_;
   VidMapper vid_;
   unsigned max_alt_ = 50;
-  bool min_pl_gt_ = false;
+  bool min_pl_gt_ = false, produce_gt_ = false;
   bool bookkeeping_done_ = false;
   std::vector<std::string> remapped_names_;
+  // plain fields staged for the Broad operator (do_query_bookkeeping): FORMAT fields that are not allele-dependent, scalar
+  // INFO fields with a median / sum / mean combine operation, the inputs of the DP rule
+  struct PlainField { std::string attribute, vcf_name; int elem = 0, fixed_len = 0; bool format = false; int info_op = 0; };
+  std::vector<PlainField> plain_;
+  unsigned dp_fields_[3] = {0, 0, 0};   // 1-based plain indices of INFO DP, MIN_DP, DP_FORMAT
+ public:
+  const std::vector<PlainField>& get_plain_fields() const { return plain_; }
+  const unsigned* get_dp_rule_fields() const { return dp_fields_; }
 };
 
 // ---- data model (include/genomicsdb/variant.h).  Views into the current batch: valid until the next operate() call.
@@ -166,6 +182,10 @@ class SingleVariantOperatorBase {
   virtual ~SingleVariantOperatorBase() = default;
   virtual void operate(Variant& variant, const VariantQueryConfig& query_config);
   virtual bool overflow() const { return false; }
+  // Opt-in fast path: an operator that consumes the kernels' BCF-typed FORMAT blocks and combined INFO scalars
+  // per site instead of a materialised Variant; scan_and_operate then scans with GDBGPU_SCAN_BCF_FORMAT.
+  virtual bool wants_bcf_blocks() const { return false; }
+  virtual void operate_on_bcf_site(const gdbgpu_batch&, uint32_t /*site*/, const VariantQueryConfig&) {}
  protected:
   bool m_NON_REF_exists = false, m_remapping_needed = false, m_is_reference_block_only = false;
   std::string m_merged_reference_allele;
@@ -179,6 +199,53 @@ class GA4GHOperator : public SingleVariantOperatorBase {
  protected:
   const Variant* m_remapped_variant = nullptr;
   unsigned m_max_diploid_alt_alleles_that_can_be_genotyped = 50;
+};
+
+// ---- what BroadCombinedGVCFOperator takes from the reference's VCFAdapter (include/vcf/vcf_adapter.h:84-190): the BCF header's
+// dictionary (bcf_hdr_id2int), the reference genome (get_reference_base_at_position) and the output buffer whose fill level
+// drives overflow() (VCFSerializedBufferAdapter, vcf_adapter.h:190-260).  The header itself is produced by the unchanged
+// host code (htslib); here it is read back from its serialised form.
+class VCFAdapter {
+ public:
+  // `header` = the BCF header text (bcf_hdr_t as htslib writes it: ##FILTER / ##INFO / ##FORMAT / ##contig lines, #CHROM line)
+  void set_vcf_header_text(const std::string& header);
+  const std::string& get_vcf_header_text() const { return header_; }
+  int get_dictionary_id(const std::string& name) const;   // -1: not in the header
+  int get_contig_id(const std::string& name) const;
+  void set_reference_base(const std::string& contig, int64_t pos, char base) { ref_bases_[contig + ":" + std::to_string(pos)] = base; }
+  char get_reference_base_at_position(const std::string& contig, int64_t pos) const;   // 'N' when unknown
+  void set_buffer_capacity(size_t bytes) { capacity_ = bytes; }
+  std::vector<uint8_t>& get_buffer() { return buffer_; }
+  bool overflow() const { return capacity_ && buffer_.size() >= capacity_; }
+ private:
+  std::string header_;
+  std::vector<std::pair<std::string, int>> ids_, contigs_;
+  std::map<std::string, char> ref_bases_;
+  std::vector<uint8_t> buffer_;
+  size_t capacity_ = 0;
+};
+
+// broad_combined_gvcf.h: one BCF2 record per operate() call, appended to the adapter's buffer in serialised form
+// (u32 l_shared, u32 l_indiv, shared, indiv -- what bcf_write emits for an uncompressed BCF).  FORMAT blocks, INFO scalars
+// and the DP sum come from the kernels (GDBGPU_SCAN_BCF_FORMAT); this class adds the typed keys / size descriptors and the
+// fixed part of the record.  Not supported (throws): ID merge, FILTER, QUAL combine, 2-D / histogram / element-wise INFO.
+class BroadCombinedGVCFOperator : public GA4GHOperator {
+ public:
+  BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, const VidMapper& id_mapper, const VariantQueryConfig& query_config);
+  bool wants_bcf_blocks() const override { return true; }
+  void operate_on_bcf_site(const gdbgpu_batch& batch, uint32_t site, const VariantQueryConfig& query_config) override;
+  bool overflow() const override { return m_vcf_adapter->overflow(); }
+  uint64_t get_num_records() const { return m_num_records; }
+ private:
+  VCFAdapter* m_vcf_adapter;
+  const VidMapper* m_vid_mapper;
+  struct FormatField { std::string vcf_name; int key = -1; int fmt_index = -1; };   // fmt_index: index into the batch's fmt_* tables
+  std::vector<FormatField> m_FORMAT_fields_vec;   // emission order: GT first, query order, DP last (broad_combined_gvcf.cc:168-240)
+  struct InfoField { std::string vcf_name; int key = -1; int plain_index = -1; bool is_float = false; };
+  std::vector<InfoField> m_INFO_fields_vec;
+  int m_END_key = -1, m_DP_key = -1;
+  bool m_dp_rule = false;
+  uint64_t m_num_records = 0;
 };
 
 // ---- storage + engine
@@ -217,7 +284,9 @@ class VariantQueryProcessor {
   VariantQueryProcessor(VariantStorageManager* storage_manager, const std::string& array_name, const VidMapper& vid_mapper);
   ~VariantQueryProcessor();
   // Adds END/REF/ALT/GT, resolves the allele-dependent fields among the queried attributes, stages the array in HBM.
-  void do_query_bookkeeping(VariantQueryConfig& query_config, bool alleles_required = true);
+  // stage_broad_gvcf_fields: also stage what BroadCombinedGVCFOperator combines besides the remapped fields (plain FORMAT
+  // fields, scalar INFO fields, the DP rule's inputs)
+  void do_query_bookkeeping(VariantQueryConfig& query_config, bool alleles_required = true, bool stage_broad_gvcf_fields = false);
   int get_array_descriptor() const { return 0; }
   void scan_and_operate(const int ad, const VariantQueryConfig& query_config, SingleVariantOperatorBase& variant_operator,
                         unsigned column_interval_idx = 0, bool handle_spanning_deletions = false,

@@ -56,6 +56,37 @@ def main():
         open(os.path.join(out_dir, c["id"] + ".bcf"), "wb").write(p.stdout)
         print("%-50s %6d bytes" % (c["id"], len(p.stdout)))
     shutil.rmtree(tmp, ignore_errors=True)
+    write_reference_bases(out_dir)
+
+
+def write_reference_bases(bcf_dir):
+    """tests/golden/inputs/ref_bases.tsv: the reference-genome base at every record position of the BCF fixtures (what
+    VCFAdapter::get_reference_base_at_position returns when a merged REF is 'N', broad_combined_gvcf.cc:811-816) -- the
+    few bytes of tests/inputs/chr1_10MB.fasta.gz the record assembly needs, so the 2.8 MB FASTA does not have to travel."""
+    import gzip
+    sys.path.insert(0, REPO)
+    from oracle import bcf_reader
+    seq = {}
+    name = None
+    with gzip.open(os.path.join(REF_TESTS, "inputs", "chr1_10MB.fasta.gz"), "rt") as f:
+        for line in f:
+            if line.startswith(">"):
+                name = line[1:].split()[0]
+                seq[name] = []
+            else:
+                seq[name].append(line.strip())
+    seq = {k: "".join(v) for k, v in seq.items()}
+    need = set()
+    for fn in sorted(os.listdir(bcf_dir)):
+        text, _, recs = bcf_reader.read_bcf(os.path.join(bcf_dir, fn))
+        contigs = [l.split("ID=")[1].split(",")[0].split(">")[0] for l in text.split("\n") if l.startswith("##contig=<")]
+        for r in recs:
+            need.add((contigs[r["chrom"]], r["pos"]))
+    with open(os.path.join(GOLD, "inputs", "ref_bases.tsv"), "w") as f:
+        for contig, pos in sorted(need):
+            if contig in seq and pos < len(seq[contig]):
+                f.write("%s\t%d\t%s\n" % (contig, pos, seq[contig][pos].upper()))
+    print("reference bases: %d positions" % len(need))
 
 
 if __name__ == "__main__":

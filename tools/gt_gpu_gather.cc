@@ -3,11 +3,17 @@
 // (-r, no MPI needed: the combine path has no collectives), same scan_state / overflow loop.  Output: the canonical
 // hot-path dump (layout in oracle/ref_harness/gdb_ref_dump.cc) written by an operator plugged into
 // SingleVariantOperatorBase::operate -- the same seam the reference harness uses, so the two programs read alike.
+// With --produce-Broad-GVCF the operator is BroadCombinedGVCFOperator (as in scan_and_produce_Broad_GVCF) and the output is
+// an uncompressed BCF2 file: the header is taken verbatim from --bcf-header (a BCF written by the reference for the same
+// query: producing the header is htslib's job on the unchanged host side), the records come from the kernels' FORMAT
+// blocks / INFO scalars through the host mirror.
 #include <getopt.h>
 
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <iostream>
+#include <sstream>
 #include <string>
 
 #include "../genomicsdb_b200/csrc/gdb_host_api.h"
@@ -59,22 +65,81 @@ class HotPathDumpOperator : public GA4GHOperator {
   FILE* m_out; unsigned m_num_fields = 0; uint64_t m_num_sites = 0; size_t m_overflow_every, m_since_drain = 0;
 };
 
+// header text of a BCF2 file ("BCF\2\2", u32 l_text, text) or of a plain VCF header file
+static std::string read_header_text(const std::string& path, std::string& raw_prefix) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw std::runtime_error("cannot open " + path);
+  std::stringstream ss; ss << f.rdbuf();
+  const std::string all = ss.str();
+  if (all.size() >= 9 && all.compare(0, 5, "BCF\2\2") == 0) {
+    uint32_t l_text; memcpy(&l_text, all.data() + 5, 4);
+    raw_prefix = all.substr(0, 9 + (size_t)l_text);
+    return std::string(all.data() + 9, strnlen(all.data() + 9, l_text));
+  }
+  uint32_t l_text = (uint32_t)all.size() + 1;
+  raw_prefix = std::string("BCF\2\2", 5) + std::string((const char*)&l_text, 4) + all + std::string(1, '\0');
+  return all;
+}
+
+static int produce_broad_gvcf(const std::string& query_json, int rank, int device, const std::string& header_file, const std::string& ref_bases_file,
+                              const std::string& out_file, size_t buffer_capacity) {
+  VariantQueryConfig query_config;
+  query_config.read_from_file(query_json, rank);
+  VariantStorageManager sm(query_config.get_workspace(rank), 10u * 1024u * 1024u, device);
+  VariantQueryProcessor qp(&sm, query_config.get_array_name(rank), query_config.get_vid_mapper());
+  qp.do_query_bookkeeping(query_config, true, /*stage_broad_gvcf_fields=*/true);
+  VCFAdapter vcf_adapter;
+  std::string raw_prefix;
+  vcf_adapter.set_vcf_header_text(read_header_text(header_file, raw_prefix));
+  vcf_adapter.set_buffer_capacity(buffer_capacity);
+  if (!ref_bases_file.empty()) {
+    std::ifstream rb(ref_bases_file);
+    std::string contig, base; long long pos;
+    while (rb >> contig >> pos >> base) vcf_adapter.set_reference_base(contig, pos, base[0]);
+  }
+  FILE* out = fopen(out_file.c_str(), "wb");
+  if (!out) { std::cerr << "cannot open " << out_file << "\n"; return -1; }
+  fwrite(raw_prefix.data(), 1, raw_prefix.size(), out);
+  BroadCombinedGVCFOperator op(vcf_adapter, query_config.get_vid_mapper(), query_config);
+  auto drain = [&] { auto& b = vcf_adapter.get_buffer(); if (!b.empty()) fwrite(b.data(), 1, b.size(), out); b.clear(); };
+  // tools/src/gt_mpi_gather.cc:350-362
+  VariantQueryProcessorScanState scan_state;
+  for (auto i = 0u; i < std::max(1u, query_config.get_num_column_intervals()); ++i) {
+    while (!scan_state.end()) {
+      qp.scan_and_operate(qp.get_array_descriptor(), query_config, op, i, true, &scan_state);
+      drain();
+    }
+    scan_state.reset();
+  }
+  fclose(out);
+  printf("{\"records\": %llu}\n", (unsigned long long)op.get_num_records());
+  return 0;
+}
+
 int main(int argc, char** argv) {
-  std::string query_json, out_file; int rank = 0, device = 0; size_t page = 0;
-  static struct option long_options[] = {{"query", 1, 0, 'j'}, {"rank", 1, 0, 'r'}, {"output", 1, 0, 'o'}, {"device", 1, 0, 'd'}, {"page-size", 1, 0, 'p'}, {0, 0, 0, 0}};
+  std::string query_json, out_file, header_file, ref_bases_file; int rank = 0, device = 0; size_t page = 0; bool broad = false;
+  static struct option long_options[] = {{"query", 1, 0, 'j'}, {"rank", 1, 0, 'r'}, {"output", 1, 0, 'o'}, {"device", 1, 0, 'd'}, {"page-size", 1, 0, 'p'},
+                                         {"produce-Broad-GVCF", 0, 0, 'B'}, {"bcf-header", 1, 0, 'H'}, {"reference-bases", 1, 0, 'R'}, {0, 0, 0, 0}};
   int c;
-  while ((c = getopt_long(argc, argv, "j:r:o:d:p:", long_options, NULL)) >= 0) {
+  while ((c = getopt_long(argc, argv, "j:r:o:d:p:BH:R:", long_options, NULL)) >= 0) {
     switch (c) {
       case 'j': query_json = optarg; break;
       case 'r': rank = atoi(optarg); break;
       case 'o': out_file = optarg; break;
       case 'd': device = atoi(optarg); break;
-      case 'p': page = strtoull(optarg, 0, 10); break;   // operate() calls between two "drains" (exercises overflow/resume)
+      case 'p': page = strtoull(optarg, 0, 10); break;   // operate() calls (dump) / buffered bytes (Broad GVCF) between two "drains" (exercises overflow/resume)
+      case 'B': broad = true; break;
+      case 'H': header_file = optarg; break;
+      case 'R': ref_bases_file = optarg; break;
       default: return -1;
     }
   }
   if (query_json.empty() || out_file.empty()) { std::cerr << "usage: gt_gpu_gather -j query.json -o dump.bin [-r rank] [-d cuda_device] [-p sites_per_page]\n"; return -1; }
   try {
+    if (broad) {
+      if (header_file.empty()) { std::cerr << "--produce-Broad-GVCF needs --bcf-header\n"; return -1; }
+      return produce_broad_gvcf(query_json, rank, device, header_file, ref_bases_file, out_file, page);
+    }
     VariantQueryConfig query_config;
     query_config.read_from_file(query_json, rank);
     VariantStorageManager sm(query_config.get_workspace(rank), 10u * 1024u * 1024u, device);
