@@ -179,6 +179,46 @@ def test_blocks_match_oracle_on_synthetic(ctx, shape, produce_gt):
         arr.close()
 
 
+def test_plain_fields_and_dp_rule_match_oracle_on_synthetic(ctx):
+    """GQ / MIN_DP blocks and the INFO/DP sum on a GDBSYN-1 cohort (MIN_DP exists on reference blocks only, DP everywhere)"""
+    from genomicsdb_b200 import capi
+    d = gdbsyn.generate(n_samples=200, n_sites=80, spacing=100, p_var=0.15, a_pool=8, with_fixed=True)
+    arr = gdbsyn.to_gpu_array(ctx, d, plain=True)
+    try:
+        view = gdbsyn.OracleArrayView(d)
+        plain = format_blocks.PlainColumns(view, d["end"], [("DP", "int", 1), ("GQ", "int", 1), ("MIN_DP", "int", 1)])
+        fmt_plain = format_blocks.PlainColumns(view, d["end"], [("GQ", "int", 1), ("MIN_DP", "int", 1)])
+        for ranges, rows, kw in (([], None, {}), ([[2500, 6000]], list(range(0, 200, 3)), dict(max_sites=3))):
+            cols = gdbsyn.to_oracle_columns(d)
+            dump, n = oracle.combine_query(cols, ranges, query_rows=rows)
+            names, sites = oracle.parse_dump(dump)
+            q = sorted(rows) if rows is not None else list(range(200))
+            got_blocks, got_dp = [], []
+            for r in (ranges or [None]):
+                sc = capi.Scan(arr, None if r is None else r[0], None if r is None else r[1], query_rows=rows, flags=capi.SCAN_BCF_FORMAT,
+                               dp_fields=gdbsyn.PLAIN_DP_RULE)
+                while True:
+                    bv = sc.next_batch(**kw)
+                    if bv is None:
+                        break
+                    for s in range(bv.n_sites):
+                        got_blocks.append({nm: bv.fmt_block(3 + k, s) for k, nm in enumerate(["DP", "GQ", "MIN_DP"])})
+                        got_dp.append(int(bv.info_dp_sum[s]))
+                sc.close()
+            assert len(got_blocks) == len(sites)
+            for i, site in enumerate(sites):
+                want = format_blocks.plain_site_blocks(site, q, fmt_plain)
+                assert got_blocks[i]["DP"] is None                      # no_format: staged for the DP rule only
+                for nm in ("GQ", "MIN_DP"):
+                    assert (got_blocks[i][nm] is None) == (nm not in want), (i, nm)
+                    if nm in want:
+                        assert got_blocks[i][nm] == want[nm][:3], (i, nm)
+                _, dp_sum = format_blocks.info_site_values(site, plain, [], ("DP", "MIN_DP", None))
+                assert got_dp[i] == dp_sum, (i, got_dp[i], dp_sum)
+    finally:
+        arr.close()
+
+
 def test_blocks_decode_to_the_int32_output(ctx):
     """10 k samples: every block, widened again, equals the collated int32 vectors of the ordinary scan"""
     from genomicsdb_b200 import capi

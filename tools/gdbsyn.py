@@ -106,10 +106,33 @@ def algorithmic_bytes(d):
     return dict(n_cells=n, n_begin_cells=n - n_copy, n_end_copies=n_copy, b_in=int(b_in))
 
 
-def to_gpu_array(ctx, d):
+PLAIN_FIELDS = [("DP", "int", 1, 1), ("GQ", "int", 1, 0), ("MIN_DP", "int", 1, 0)]   # (attribute, elem, fixed_len, no_format) of generate(with_fixed=True)
+PLAIN_DP_RULE = (1, 3, 0)    # 1-based plain indices of (INFO DP, MIN_DP, DP_FORMAT) for capi.Scan(dp_fields=...)
+
+
+def to_gpu_array(ctx, d, plain=False):
+    """plain=True (needs generate(with_fixed=True)): also stage DP (INFO, input of the DP rule), GQ and MIN_DP as plain fields"""
     from genomicsdb_b200 import capi
     fields = [dict(name="AD", kind="R", elem="int", col=d["ad"]), dict(name="PL", kind="G", elem="int", col=d["pl"])]
-    return capi.Array.from_columns(ctx, d["coords"], d["end"], d["ref"], d["alt"], d["gt"], fields, 0, d["num_rows"])
+    pl = []
+    if plain:
+        pl = [dict(name=n, elem=e, fixed_len=k, no_format=nf, col=(None, d[n.lower()])) for n, e, k, nf in PLAIN_FIELDS]
+    return capi.Array.from_columns(ctx, d["coords"], d["end"], d["ref"], d["alt"], d["gt"], fields, 0, d["num_rows"], plain=pl)
+
+
+class OracleArrayView:
+    """the accessors oracle.format_blocks.PlainColumns takes from a TileDB array, over a generated cohort"""
+
+    def __init__(self, d):
+        self.d, self.row, self.col = d, d["coords"][:, 0], d["coords"][:, 1]
+
+    def fixed(self, name):
+        return self.d[name.lower()].reshape(-1, 1)
+
+    def var(self, name):
+        off, val = self.d[name.lower()]
+        item = val.dtype.itemsize
+        return np.concatenate([off.astype(np.int64), [val.nbytes]]) // item, val
 
 
 def to_oracle_columns(d):

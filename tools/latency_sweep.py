@@ -25,14 +25,18 @@ def main():
     ap.add_argument("--sites", type=int, default=1250)
     ap.add_argument("--batch-bytes", type=int, default=8 << 30)
     ap.add_argument("--bcf", action="store_true", help="GDBGPU_SCAN_BCF_FORMAT: also collate + BCF-encode on the device")
+    ap.add_argument("--records", action="store_true", help="--bcf plus the plain FORMAT fields (GQ, MIN_DP) and the INFO/DP rule: "
+                                                          "everything BroadCombinedGVCFOperator needs for a record of this cohort")
     args = ap.parse_args()
     from genomicsdb_b200 import capi
     from tools import gdbsyn
     cfg = dict(gdbsyn.CONFIGS["config4"], n_samples=args.samples)
-    d = gdbsyn.generate(**cfg, site_lo=0, site_hi=args.sites)
+    if args.records:
+        args.bcf = True
+    d = gdbsyn.generate(**cfg, site_lo=0, site_hi=args.sites, with_fixed=args.records)
     lo, hi = d["col_range"]
     ctx = capi.Context(0)
-    arr = gdbsyn.to_gpu_array(ctx, d)
+    arr = gdbsyn.to_gpu_array(ctx, d, plain=args.records)
     rng = np.random.RandomState(4321)
     span = max(1, hi - lo + 1 - args.length)
     starts = lo + rng.randint(0, span, size=args.intervals)
@@ -41,7 +45,7 @@ def main():
 
     def one(a, b):
         t0 = time.perf_counter()
-        sc = capi.Scan(arr, int(a), int(b), flags=flags)
+        sc = capi.Scan(arr, int(a), int(b), flags=flags, dp_fields=gdbsyn.PLAIN_DP_RULE if args.records else (0, 0, 0))
         n = 0
         while True:
             bt = sc.next_batch(0, args.batch_bytes, raw=True)
@@ -62,7 +66,7 @@ def main():
     t_all = time.perf_counter() - t_all
     lat_ms = np.array(lat) * 1e3
     out = dict(config="BASELINE config #5: %d random %d-position intervals over a %d-sample x %d-candidate-site shard, one B200, output left in HBM%s"
-               % (args.intervals, args.length, args.samples, args.sites, ", BCF-typed FORMAT blocks" if args.bcf else ""),
+               % (args.intervals, args.length, args.samples, args.sites, (", BCF records (FORMAT blocks of GT/AD/PL/GQ/MIN_DP + INFO/DP)" if args.records else ", BCF-typed FORMAT blocks") if args.bcf else ""),
                intervals=args.intervals, sites_per_interval_mean=float(np.mean(sites)),
                latency_ms=dict(p50=float(np.percentile(lat_ms, 50)), p95=float(np.percentile(lat_ms, 95)), p99=float(np.percentile(lat_ms, 99)),
                                max=float(lat_ms.max()), mean=float(lat_ms.mean()), min=float(lat_ms.min())),
