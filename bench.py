@@ -75,7 +75,7 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ reference (CPU) arm
-def reference_sample(args, n_sites_sample, n_procs, tmp):
+def reference_sample(args, n_sites_sample, n_procs, tmp, mode="hot"):
     """Times the unmodified reference on `n_procs` host cores, each combining its own `n_sites_sample`-site slice of the
     same cohort (all samples).  Returns (sites_per_sec over all processes, detail)."""
     from tools import gdbsyn, tiledb_writer
@@ -91,7 +91,7 @@ def reference_sample(args, n_sites_sample, n_procs, tmp):
         jobs.append(q)
         del d
     t0 = time.time()
-    procs = [subprocess.Popen([REF_BIN, "-j", q, "--mode", "hot"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for q in jobs]
+    procs = [subprocess.Popen([REF_BIN, "-j", q, "--mode", mode], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for q in jobs]
     outs = [p.communicate()[0] for p in procs]
     wall = time.time() - t0
     sites, secs = 0, 0.0
@@ -116,7 +116,7 @@ def port_sample(args, n_sites_sample):
     return n / dt, dict(sites=n, max_seconds=dt, procs=1)
 
 
-def cpu_baseline(args, budget_s=12.0):
+def cpu_baseline(args, budget_s=12.0, mode="hot"):
     cores = os.cpu_count() or 1
     tmp = tempfile.mkdtemp(prefix="gdbbench")
     try:
@@ -124,11 +124,15 @@ def cpu_baseline(args, budget_s=12.0):
             # ~0.9 us per sample*site per core (measured); size the per-core slice for `budget_s` seconds
             per_core = max(2, int(budget_s / (0.9e-6 * args.samples * 2)))
             per_core = min(per_core, 64)
-            v, det = reference_sample(args, per_core, cores, tmp)
+            if mode == "null":
+                per_core = max(2, per_core // 2)
+            v, det = reference_sample(args, per_core, cores, tmp, mode)
+            what = ("(unmodified scan_and_operate + handle_deletions + GA4GHOperator::operate, no VCF output)" if mode == "hot" else
+                    "(unmodified scan_and_operate + the whole BroadCombinedGVCFOperator::operate incl. htslib bcf_update_*; the finished bcf1_t is dropped)")
             return dict(value=v, unit="sites/s", cores=cores, kind="reference",
-                        sample="%d processes x %d candidate sites x %d samples of the same cohort through oracle/_ref/bin/gdb_ref_dump --mode hot "
-                               "(unmodified scan_and_operate + handle_deletions + GA4GHOperator::operate, no VCF output); %d sites in %.1f s (max over processes)"
-                               % (cores, per_core, args.samples, det["sites"], det["max_seconds"]))
+                        sample="%d processes x %d candidate sites x %d samples of the same cohort through oracle/_ref/bin/gdb_ref_dump --mode %s "
+                               "%s; %d sites in %.1f s (max over processes)"
+                               % (cores, per_core, args.samples, mode, what, det["sites"], det["max_seconds"]))
         per = max(2, int(budget_s / (1.0e-6 * args.samples * 2)))
         v, det = port_sample(args, min(per, 64))
         return dict(value=v, unit="sites/s", cores=1, kind="port",
@@ -359,15 +363,17 @@ def main():
                                "vectors + lengths + live matrix copied to pinned host memory) -> close")
     ctx.close()
 
-    base = None
+    base = base_bcf = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base = cpu_baseline(args)
+        if os.path.exists(REF_BIN):   # like-for-like for `e2e` (which also collates + BCF-encodes): the reference's whole Broad operator
+            base_bcf = cpu_baseline(args, budget_s=8.0, mode="null")
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="sites/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
                     data="synthetic", config=workload_config(args, world), clocks=sampler.summary(), e2e=e2e, e2e_int32=e2e_int32,
-                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=base,
+                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=base, cpu_baseline_broad_gvcf_operator=base_bcf,
                     sites_per_step_per_gpu=int(sites_per_step), cells_per_gpu=int(info.n_cells),
                     staged_bytes_per_gpu=int(info.staged_bytes), hbm_bytes_per_gpu=int(info.hbm_bytes))
         print(json.dumps(line))
