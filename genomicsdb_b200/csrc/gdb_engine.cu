@@ -144,7 +144,6 @@ void radix_sort_pairs(gdbgpu_ctx* ctx, const K* kin, K* kout, const V* vin, V* v
 __global__ void k_narrow_u64(const uint64_t* in, uint64_t n, uint32_t* out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = (uint32_t)in[i]; }
 __global__ void k_iota(uint32_t* p, uint64_t n) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = (uint32_t)i; }
 __global__ void k_gather_u64(const uint64_t* in, const uint32_t* perm, uint64_t n, uint64_t* out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = in[perm[i]]; }
-__global__ void k_gather_u32(const uint32_t* in, const uint32_t* perm, uint64_t n, uint32_t* out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = in[perm[i]]; }
 __global__ void k_flag_del(ArrayDev A, uint32_t* flag) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < A.n) flag[i] = (A.desc[i].flags & F_DELETION) && !(A.desc[i].flags & F_ROWOUT) ? 1u : 0u; }
 __global__ void k_compact_idx(const uint32_t* flag, const uint32_t* pos, uint64_t n, uint32_t* out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n && flag[i]) out[pos[i]] = (uint32_t)i; }
 __global__ void k_bounds(const int64_t* coords, uint64_t n, int64_t q_lo, int64_t q_hi, uint64_t* out) {
@@ -161,7 +160,6 @@ __global__ void k_gather_bytes(const uint8_t* in, const uint32_t* perm, uint64_t
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) for (uint32_t b = 0; b < cell_bytes; ++b) out[i * cell_bytes + b] = in[(uint64_t)perm[i] * cell_bytes + b];
 }
-__global__ void k_add_i32(const int32_t* a, const int32_t* b, int32_t* out, uint64_t n) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = a[i] + b[i]; }
 
 struct HostVar { const uint64_t* off = nullptr; const void* val = nullptr; uint64_t bytes = 0; };
 struct HostCols {
@@ -865,6 +863,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       bb.ctl.flush(ctx->stream);
       const FmtPlanDev P{bb.fmt_type_d, bb.fmt_nps_d, bb.fmt_off_d, bb.fmt_bytes.p};
       LAUNCH(ctx, k_fmt_pack, dim3(chunks, keep), FMT_THREADS, a->dev, O, P, keep, (uint32_t)S.nq, s->produce_gt);
+      LAUNCH(ctx, k_fmt_pack_tile, dim3(blocks_for(S.nq, PACK_ROWS), keep), FMT_THREADS, a->dev, O, P, keep, (uint32_t)S.nq);
       if (n_plain) LAUNCH(ctx, k_plain_pack, dim3(row_blocks, keep), FMT_THREADS, a->plain_dev, P, n_out, bb.live.p, keep, (uint32_t)S.nq);
     }
     // ---- results: site metadata (host mirrors), then the copies of everything the caller asked for

@@ -90,6 +90,104 @@ __global__ void __launch_bounds__(FMT_THREADS) k_fmt_range(const __grid_constant
   }
 }
 
+// Which kernel narrows a block: k_fmt_pack_tile stages PACK_ROWS rows of the block in shared memory (coalesced 16-byte loads
+// of K5's padded rows in, 16-byte stores of the dense block out), which needs PACK_ROWS * nps * width bytes; GT (encoded
+// on the fly) and very long vectors stay with k_fmt_pack.
+constexpr uint32_t PACK_ROWS = 256, PACK_SMEM = 40 * 1024;   // rows of a site per block; bytes of the staging buffer
+__host__ __device__ inline uint32_t bt_width(uint32_t type) { return (type == BT_INT8 || type == BT_CHAR) ? 1u : (type == BT_INT16 ? 2u : 4u); }
+// rows staged at a time: a multiple of 16 (so every slice of a block starts on a 16-byte boundary whatever nps and the width are)
+__host__ __device__ inline uint32_t pack_tile_rows(uint32_t nps, uint32_t type) { const uint32_t r = (PACK_SMEM / (nps * bt_width(type))) & ~15u; return r > PACK_ROWS ? PACK_ROWS : r; }
+__host__ __device__ inline bool pack_tile_takes(uint32_t nps, uint32_t type) { return pack_tile_rows(nps, type) >= 16u; }
+
+// one value into the staging buffer, narrowed to the block's type (the type is a compile-time constant of the loop)
+template <uint32_t TYPE>
+__device__ inline void pack_put(uint8_t* buf, uint32_t k, uint32_t v) {
+  if (TYPE == BT_INT8) buf[k] = v == BCF_INT_VEND ? 0x81u : (v == BCF_INT_MISSING ? 0x80u : (uint8_t)v);
+  else if (TYPE == BT_INT16) reinterpret_cast<uint16_t*>(buf)[k] = v == BCF_INT_VEND ? 0x8001u : (v == BCF_INT_MISSING ? 0x8000u : (uint16_t)v);
+  else reinterpret_cast<uint32_t*>(buf)[k] = v;
+}
+// `rows` rows of whole quads (stride = 4 * qpr words) -> the dense slice in `buf`.  Thread t takes quads t, t + 256, ...;
+// (row, quad-in-row) advance without a division; ILP independent 16-byte loads are in flight per thread.
+template <uint32_t TYPE>
+__device__ inline void pack_quads(uint8_t* buf, const uint4* __restrict__ src4, const uint16_t* __restrict__ len, uint32_t rows, uint32_t qpr, uint32_t nps,
+                                  uint32_t miss, uint32_t vend, uint32_t tid) {
+  constexpr int ILP = 4;
+  const uint32_t n_quads = rows * qpr, dr = FMT_THREADS / qpr, dj = FMT_THREADS - dr * qpr;
+  uint32_t r = tid / qpr, j = tid - r * qpr;
+  for (uint32_t g0 = tid; g0 < n_quads; g0 += ILP * FMT_THREADS) {
+    uint4 v[ILP];
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) { const uint32_t g = g0 + u * FMT_THREADS; v[u] = g < n_quads ? src4[g] : make_uint4(0, 0, 0, 0); }
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+      if (g0 + u * FMT_THREADS < n_quads) {
+        uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        // a row without the field is all vector_end (K5); its first value becomes missing.  Only such rows look at len[].
+        if (j == 0 && x[0] == vend && len[r] == 0) x[0] = miss;
+        const uint32_t k = r * nps + 4 * j;
+#pragma unroll
+        for (uint32_t t = 0; t < 4; ++t) if (4 * j + t < nps) pack_put<TYPE>(buf, k + t, x[t]);
+      }
+      r += dr; j += dj;
+      if (j >= qpr) { j -= qpr; ++r; }
+    }
+  }
+}
+
+// grid = (row groups of PACK_ROWS, sites); a block walks its rows in slices that fit the staging buffer.
+__global__ void __launch_bounds__(FMT_THREADS) k_fmt_pack_tile(const __grid_constant__ ArrayDev A, const __grid_constant__ RemapOut O, const __grid_constant__ FmtPlanDev P,
+                                                               const uint32_t n_sites, const uint32_t nq) {
+  __shared__ __align__(16) uint8_t s_buf[PACK_SMEM];
+  const uint32_t js = blockIdx.y, tid = threadIdx.x;
+  const uint32_t qb = blockIdx.x * PACK_ROWS, qe = min(qb + PACK_ROWS, nq);
+  const int o0 = A.has_gt ? 1 : 0;
+  for (int o = o0; o < O.n_out; ++o) {
+    const uint64_t pi = (uint64_t)o * n_sites + js;
+    const uint32_t type = P.type[pi];
+    if (type == BT_NONE) continue;
+    const uint32_t nps = P.nps[pi];
+    if (!pack_tile_takes(nps, type)) continue;
+    const uint32_t slice = pack_tile_rows(nps, type);
+    const FieldOutDev fo = O.f[o];
+    const uint32_t stride = fo.stride[js], w = bt_width(type);
+    const uint32_t miss = missing_word(A.fm[o - o0].elem);
+    auto put = [&](uint32_t r, uint32_t i, uint32_t v) {   // value i of local row r -> its place in the dense block slice
+      const uint32_t k = r * nps + i;
+      if (type == BT_INT8) s_buf[k] = v == BCF_INT_VEND ? 0x81u : (v == BCF_INT_MISSING ? 0x80u : (uint8_t)v);
+      else if (type == BT_INT16) reinterpret_cast<uint16_t*>(s_buf)[k] = v == BCF_INT_VEND ? 0x8001u : (v == BCF_INT_MISSING ? 0x8000u : (uint16_t)v);
+      else reinterpret_cast<uint32_t*>(s_buf)[k] = v;
+    };
+    for (uint32_t q0 = qb; q0 < qe; q0 += slice) {
+      const uint32_t rows = min(slice, qe - q0);
+      const uint32_t* __restrict__ src = fo.data + fo.base[js] + (uint64_t)q0 * stride;
+      const uint16_t* __restrict__ len = fo.len + (uint64_t)js * nq + q0;
+      if ((stride & 3u) == 0) {   // rows are whole quads (every remapped site)
+        const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(src);
+        const uint32_t vend = vend_word(A.fm[o - o0].elem);
+        if (type == BT_INT8) pack_quads<BT_INT8>(s_buf, src4, len, rows, stride >> 2, nps, miss, vend, tid);
+        else if (type == BT_INT16) pack_quads<BT_INT16>(s_buf, src4, len, rows, stride >> 2, nps, miss, vend, tid);
+        else pack_quads<BT_INT32>(s_buf, src4, len, rows, stride >> 2, nps, miss, vend, tid);
+      } else {
+        const uint32_t n_words = rows * stride;
+        for (uint32_t g = tid; g < n_words; g += FMT_THREADS) {
+          const uint32_t r = g / stride, i = g - r * stride;
+          if (i >= nps) continue;
+          uint32_t v = src[g];
+          if (i == 0 && len[r] == 0) v = miss;
+          put(r, i, v);
+        }
+      }
+      __syncthreads();
+      const uint32_t bytes = rows * nps * w;
+      uint8_t* __restrict__ dst = P.bytes + P.off[pi] + (uint64_t)q0 * nps * w;
+      const uint32_t n16 = bytes >> 4;
+      for (uint32_t g = tid; g < n16; g += FMT_THREADS) reinterpret_cast<uint4*>(dst)[g] = reinterpret_cast<const uint4*>(s_buf)[g];
+      for (uint32_t b = (n16 << 4) + tid; b < bytes; b += FMT_THREADS) dst[b] = s_buf[b];
+      __syncthreads();
+    }
+  }
+}
+
 // narrows the words of every emitted (site, field) into its block.  grid = (chunks, sites); a thread makes 4 consecutive
 // values of the block per trip (one 4 / 8 / 16-byte store).
 __global__ void __launch_bounds__(FMT_THREADS) k_fmt_pack(const __grid_constant__ ArrayDev A, const __grid_constant__ RemapOut O, const __grid_constant__ FmtPlanDev P,
@@ -102,6 +200,7 @@ __global__ void __launch_bounds__(FMT_THREADS) k_fmt_pack(const __grid_constant_
     const FieldOutDev fo = O.f[o];
     const uint32_t stride = fo.stride[js], nps = P.nps[pi];
     const bool is_gt = A.has_gt && o == 0;
+    if (!is_gt && pack_tile_takes(nps, type)) continue;   // k_fmt_pack_tile writes this block
     const int fi = o - (A.has_gt ? 1 : 0);
     const uint32_t miss = is_gt ? BCF_INT_VEND : missing_word(A.fm[fi].elem);   // first value of a row without the field
     const uint32_t* __restrict__ src = fo.data + fo.base[js];
@@ -181,19 +280,23 @@ __global__ void __launch_bounds__(FMT_THREADS) k_plain_scan(const __grid_constan
   if (tid < (uint32_t)P.n * PS_WORDS) { const int w = tid % PS_WORDS; s_st[tid / PS_WORDS][w] = w == PS_MIN ? INT32_MAX : (w == PS_MAX ? INT32_MIN + 1 : 0); }
   __syncthreads();
   const int32_t e = q < nq ? live[(uint64_t)js * nq + q] : -1;
-  if (e >= 0) {
-    const uint32_t cell = (uint32_t)(e & (LIVE_REDUCED - 1));
-    for (int f = 0; f < P.n; ++f) {
-      const uint8_t* p; uint32_t n;
-      if (!plain_fetch(P.f[f], cell, p, n)) continue;
-      atomicMax(&s_st[f][PS_MAXLEN], (int32_t)n);
+  const uint32_t cell = e >= 0 ? (uint32_t)(e & (LIVE_REDUCED - 1)) : 0u;
+  const uint32_t lane = tid & 31;
+  for (int f = 0; f < P.n; ++f) {   // every lane takes part: the statistics are reduced over the warp before they touch shared memory
+    const uint8_t* p = nullptr; uint32_t n = 0;
+    const bool valid = e >= 0 && plain_fetch(P.f[f], cell, p, n);
+    int32_t lo = INT32_MAX, hi = INT32_MIN + 1;
+    if (valid && P.f[f].elem == ELEM_INT32) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+      for (uint32_t i = 0; i < n; ++i) if (w[i] != BCF_INT_MISSING && w[i] != BCF_INT_VEND) { lo = min(lo, (int32_t)w[i]); hi = max(hi, (int32_t)w[i]); }
+    }
+    const uint32_t maxlen = __reduce_max_sync(0xffffffffu, valid ? n : 0u);
+    if (!__any_sync(0xffffffffu, valid)) continue;
+    lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) {
+      atomicMax(&s_st[f][PS_MAXLEN], (int32_t)maxlen);
       s_st[f][PS_ANY] = 1;
-      if (P.f[f].elem == ELEM_INT32) {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
-        int32_t lo = INT32_MAX, hi = INT32_MIN + 1;
-        for (uint32_t i = 0; i < n; ++i) if (w[i] != BCF_INT_MISSING && w[i] != BCF_INT_VEND) { lo = min(lo, (int32_t)w[i]); hi = max(hi, (int32_t)w[i]); }
-        if (lo != INT32_MAX) { atomicMin(&s_st[f][PS_MIN], lo); atomicMax(&s_st[f][PS_MAX], hi); }
-      }
+      if (lo != INT32_MAX) { atomicMin(&s_st[f][PS_MIN], lo); atomicMax(&s_st[f][PS_MAX], hi); }
     }
   }
   __syncthreads();

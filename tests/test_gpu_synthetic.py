@@ -73,3 +73,58 @@ def test_column_shard_equals_partition(ctx):
     assert np.array_equal(full["coords"][sel], part["coords"])
     assert np.array_equal(full["end"][sel], part["end"])
     both(ctx, part, [[lo, hi]])
+
+
+def test_empty_inputs(ctx):
+    """empty array, interval past the data, interval before the data, no queried row inside the array: zero sites, no error --
+    in the plain and in the BCF-typed mode"""
+    from genomicsdb_b200 import capi
+    d = gdbsyn.generate(n_samples=20, n_sites=30, spacing=100, p_var=0.2, a_pool=4)
+    arr = gdbsyn.to_gpu_array(ctx, d)
+    lo, hi = d["col_range"]
+    try:
+        for flags in (0, capi.SCAN_BCF_FORMAT, capi.SCAN_DEVICE_OUTPUT):
+            for a, b, rows in ((hi + 1000, hi + 2000, None), (0, 3, None), (lo, hi, [100, 200, 4000])):
+                sc = capi.Scan(arr, a, b, query_rows=rows, flags=flags)
+                assert sc.info().n_sites == 0
+                assert sc.next_batch() is None
+                assert sc.next_batch() is None          # asking again after the end is fine
+                sc.close()
+    finally:
+        arr.close()
+    e = dict(coords=np.zeros((0, 2), dtype=np.int64), end=np.zeros(0, dtype=np.int64), num_rows=5)
+    for k, dt in (("ref", np.uint8), ("alt", np.uint8), ("gt", np.int32), ("pl", np.int32), ("ad", np.int32)):
+        e[k] = (np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=dt))
+    arr = gdbsyn.to_gpu_array(ctx, e)
+    try:
+        assert arr.info().n_cells == 0
+        for flags in (0, capi.SCAN_BCF_FORMAT):
+            sc = capi.Scan(arr, flags=flags)
+            assert sc.next_batch() is None
+            sc.close()
+    finally:
+        arr.close()
+
+
+def test_seek_and_rescan_give_the_same_batches(ctx):
+    """gdbgpu_scan_seek (resume after a consumer-side overflow) with the prefetch in flight: the re-read sites are identical"""
+    from genomicsdb_b200 import capi
+    d = gdbsyn.generate(n_samples=64, n_sites=60, spacing=100, p_var=0.15, a_pool=8)
+    arr = gdbsyn.to_gpu_array(ctx, d)
+    try:
+        sc = capi.Scan(arr)
+        first = sc.next_batch(7, 0)
+        snap = [first.fields[2]["data"].copy(), first.site_begin.copy()]
+        second = sc.next_batch(7, 0)
+        s2 = [second.fields[2]["data"].copy(), second.site_begin.copy()]
+        sc.seek(0)
+        again = sc.next_batch(7, 0)
+        assert np.array_equal(again.site_begin, snap[1]) and np.array_equal(again.fields[2]["data"], snap[0])
+        sc.seek(3)                                   # into the middle of a batch
+        mid = sc.next_batch(4, 0)
+        assert np.array_equal(mid.site_begin, snap[1][3:7])
+        nxt = sc.next_batch(7, 0)
+        assert np.array_equal(nxt.site_begin, s2[1]) and np.array_equal(nxt.fields[2]["data"], s2[0])
+        sc.close()
+    finally:
+        arr.close()
