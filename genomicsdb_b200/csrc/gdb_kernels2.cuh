@@ -1188,6 +1188,20 @@ __global__ void __launch_bounds__(NT_THREADS) k_remap_nt(const __grid_constant__
         }
         dst4[qd] = make_uint4(w[0], w[1], w[2], w[3]);
       }
+    } else if (remap && (stride & 3u) == 0 && kind == KIND_R) {
+      // R field (AD): out[j] = in[input allele of merged allele j]
+      uint4* dst4 = reinterpret_cast<uint4*>(dst);
+      for (uint32_t qd = gl; qd < (stride >> 2); qd += NT_GL) {
+        uint32_t w[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const uint32_t j = 4 * qd + x;
+          uint32_t v = pad;
+          if (j < n_out) { const int pj = m2in[j]; const uint32_t a = (uint32_t)pj & 0xFFu; v = (pj >= 0 && a < n) ? in[a] : miss; }
+          w[x] = v;
+        }
+        dst4[qd] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
     } else {
       const int mode = !remap ? 0 : ((kind == KIND_G && ploidy == 2) ? 1 : ((kind == KIND_G && ploidy == 0) ? 2 : (kind == KIND_A ? 3 : 4)));
       auto word = [&](uint32_t g) -> uint32_t {
