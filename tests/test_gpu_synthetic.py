@@ -128,3 +128,53 @@ def test_seek_and_rescan_give_the_same_batches(ctx):
         sc.close()
     finally:
         arr.close()
+
+
+def test_full_width_100k_samples(ctx):
+    """BASELINE config #4's width (100 k samples, up to 8 ALT alleles): (1) a 300-row query over the 100 k-row array equals the
+    oracle byte for byte (sites are cut by all samples, the union runs over the queried ones); (2) over all rows the remapped
+    output does not depend on how the scan is batched, every row's PL vector has the length its ploidy and the merged allele
+    count dictate, and every remapped value is one of the call's input values or missing."""
+    from genomicsdb_b200 import capi
+    d = gdbsyn.generate(n_samples=100000, n_sites=10000, spacing=1000, p_var=0.1, a_pool=8, site_lo=100, site_hi=124)
+    lo, hi = d["col_range"]
+    rng = np.random.RandomState(7)
+    rows = sorted(set(int(r) for r in rng.randint(0, 100000, size=300)))
+    both(ctx, d, [[lo, hi]], rows=rows)
+    arr = gdbsyn.to_gpu_array(ctx, d)
+    try:
+        def collect(max_bytes):
+            sc = capi.Scan(arr, lo, hi)
+            out = []
+            while True:
+                bv = sc.next_batch(0, max_bytes)
+                if bv is None:
+                    break
+                for s in range(bv.n_sites):
+                    rec = [int(bv.site_begin[s]), int(bv.site_end[s]), int(bv.n_alleles[s]), int(bv.site_flags[s])]
+                    for f in bv.fields:
+                        st, base = int(f["stride"][s]), int(f["base"][s])
+                        need = int(f["len"][s].max())
+                        rec.append(f["data"][base:base + bv.nq * st].reshape(bv.nq, st)[:, :need].copy())
+                        rec.append(f["len"][s].copy())
+                    out.append(rec)
+            sc.close()
+            return out
+        a, b = collect(1 << 30), collect(64 << 20)
+        assert len(a) == len(b) == 49
+        n_remapped = 0
+        for x, y in zip(a, b):
+            assert x[:4] == y[:4]
+            for u, v in zip(x[4:], y[4:]):
+                assert np.array_equal(u, v)
+            n_alleles, flags = x[2], x[3]
+            pl, pl_len = x[8], x[9]
+            if flags & capi.SITE_REMAPPED:
+                n_remapped += 1
+                assert set(np.unique(pl_len)) <= {0, n_alleles * (n_alleles + 1) // 2}
+                assert (x[7] == n_alleles).all() or set(np.unique(x[7])) <= {0, n_alleles}        # AD: one value per merged allele
+                vals = pl.view(np.int32)
+                assert ((vals >= 0) & (vals <= 3000) | (vals == -2147483648) | (vals == -2147483647)).all()
+        assert n_remapped == 24
+    finally:
+        arr.close()
