@@ -537,15 +537,16 @@ __global__ void __launch_bounds__(256) k_live_walk(ArrayDev A, ScanDev S, uint64
     int64_t ef = A.rs_effend[kk];
     if (ef != I64_MIN) { const uint32_t rc = A.rs_cell[kk]; cur = (int32_t)(rc & RS_CELL_MASK); cur_eff = ef; cur_begin = c; cur_del = rc >> 31; break; }
   }
-  // the column of the sample's next cell stays in a register: most sites of the chunk do not advance the list
-  int64_t next_col = k < e ? A.rs_col[k] : INT64_MAX;
+  // the sample's next cell (column, effective end, cell) stays in registers: most sites of the chunk do not advance the
+  // list, and an advance issues the three loads of the following cell together instead of one after the other
+  int64_t next_col = INT64_MAX, next_ef = I64_MIN; uint32_t next_rc = 0;
+  if (k < e) { next_col = A.rs_col[k]; next_ef = A.rs_effend[k]; next_rc = A.rs_cell[k]; }
   for (uint32_t s = s0; s < s1; ++s) {
     const int64_t b = S.site_begin[first_site + s];
     while (next_col <= b) {
-      const int64_t ef = A.rs_effend[k];
-      if (ef != I64_MIN) { const uint32_t rc = A.rs_cell[k]; cur = (int32_t)(rc & RS_CELL_MASK); cur_eff = ef; cur_begin = next_col; cur_del = rc >> 31; }
+      if (next_ef != I64_MIN) { cur = (int32_t)(next_rc & RS_CELL_MASK); cur_eff = next_ef; cur_begin = next_col; cur_del = next_rc >> 31; }
       ++k;
-      next_col = k < e ? A.rs_col[k] : INT64_MAX;
+      if (k < e) { next_col = A.rs_col[k]; next_ef = A.rs_effend[k]; next_rc = A.rs_cell[k]; } else next_col = INT64_MAX;
     }
     int32_t v = -1;
     if (cur >= 0 && cur_eff >= b) { v = cur; if (S.handle_del && cur_del && b > cur_begin) v |= LIVE_REDUCED; }
