@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include "gdb_inflate.cuh"
 #include "gdb_kernels3.cuh"
 #include "gdb_tiledb.h"
 
@@ -156,6 +157,7 @@ __global__ void k_bounds(const int64_t* coords, uint64_t n, int64_t q_lo, int64_
   while (lo < hi) { uint64_t mid = (lo + hi) >> 1; int64_t c = coords[2 * mid + 1]; if (strict ? (c <= key) : (c < key)) lo = mid + 1; else hi = mid; }
   out[t] = lo;
 }
+__global__ void k_add_u64(uint64_t* p, uint64_t n, uint64_t add) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] += add; }
 __global__ void k_gather_bytes(const uint8_t* in, const uint32_t* perm, uint64_t n, uint32_t cell_bytes, uint8_t* out) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) for (uint32_t b = 0; b < cell_bytes; ++b) out[i * cell_bytes + b] = in[(uint64_t)perm[i] * cell_bytes + b];
@@ -207,9 +209,9 @@ void upload_var(gdbgpu_ctx* ctx, const HostVar& h, uint64_t n, DevVar& d, uint64
   d.off.alloc(n + 1);
   d.val.alloc(std::max<uint64_t>(h.bytes, 1));
   d.bytes = h.bytes;
-  if (n) CK(cudaMemcpyAsync(d.off.p, h.off, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d.off.p + n, &h.bytes, 8, cudaMemcpyHostToDevice, ctx->stream));
-  if (h.bytes) CK(cudaMemcpyAsync(d.val.p, h.val, h.bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (n) CK(cudaMemcpyAsync(d.off.p, h.off, n * 8, cudaMemcpyDefault, ctx->stream));
+  CK(cudaMemcpyAsync(d.off.p + n, &h.bytes, 8, cudaMemcpyDefault, ctx->stream));
+  if (h.bytes) CK(cudaMemcpyAsync(d.val.p, h.val, h.bytes, cudaMemcpyDefault, ctx->stream));
   staged += n * 8 + h.bytes;
 }
 
@@ -274,7 +276,8 @@ void gather_var(gdbgpu_ctx* ctx, const DevVar& in, const uint32_t* src, uint64_t
   CK(cudaStreamSynchronize(ctx->stream));
 }
 
-// stage host columns (already concatenated over fragments) and build the per-array indexes
+// stage columns (already concatenated over fragments; host memory, or HBM when the tiles were inflated on the device) and
+// build the per-array indexes
 gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<uint64_t>& frag_cells, int64_t lb_row, int64_t num_rows, int gt_phased,
                           const std::vector<FieldMeta>& fm, const std::vector<std::string>& names, const std::vector<PlainMeta>& pm = {}) {
   static const bool trace = getenv("GDBGPU_TRACE") != nullptr;   // phase times of the staging on stderr
@@ -296,7 +299,7 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
   a->n_fragments = (uint32_t)std::max<size_t>(1, frag_cells.size());
   uint64_t n = h.n;
   a->coords.alloc(std::max<uint64_t>(2 * n, 2)); a->end.alloc(std::max<uint64_t>(n, 1));
-  if (n) { CK(cudaMemcpyAsync(a->coords.p, h.coords, n * 16, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaMemcpyAsync(a->end.p, h.end, n * 8, cudaMemcpyHostToDevice, ctx->stream)); }
+  if (n) { CK(cudaMemcpyAsync(a->coords.p, h.coords, n * 16, cudaMemcpyDefault, ctx->stream)); CK(cudaMemcpyAsync(a->end.p, h.end, n * 8, cudaMemcpyDefault, ctx->stream)); }
   a->staged_bytes = n * 24;
   upload_var(ctx, h.ref, n, a->ref, a->staged_bytes);
   upload_var(ctx, h.alt, n, a->alt, a->staged_bytes);
@@ -309,7 +312,7 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
     d.bytes = h.plain[f].bytes;
     if (d.bytes != n * (uint64_t)pm[f].fixed_len * (pm[f].elem == ELEM_CHAR ? 1u : 4u)) throw ArgError("plain field " + pm[f].name + ": value bytes do not match n_cells x fixed_len");
     d.val.alloc(std::max<uint64_t>(d.bytes, 1));
-    if (d.bytes) CK(cudaMemcpyAsync(d.val.p, h.plain[f].val, d.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (d.bytes) CK(cudaMemcpyAsync(d.val.p, h.plain[f].val, d.bytes, cudaMemcpyDefault, ctx->stream));
     a->staged_bytes += d.bytes;
   }
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1125,44 +1128,72 @@ int gdbgpu_array_open_ex(gdbgpu_ctx* ctx, const char* workspace, const char* arr
       if (plain[f].info_op && (fixed < 1 || plain[f].elem_type == GDBGPU_ELEM_CHAR)) throw std::runtime_error(std::string("an INFO combine operation needs a fixed-length 4-byte field: ") + plain[f].name);
       pm.push_back(PlainMeta{plain[f].name, plain[f].elem_type, fixed, plain[f].no_format, plain[f].info_op});
     }
-    // read every needed column of every fragment, concatenating (var offsets rebased onto the concatenated stream)
-    size_t nfrag = ta.num_fragments();
+    // Every needed column of every fragment goes to HBM as it lies on disk; compressed tiles are inflated there (k_inflate,
+    // one thread per zlib stream), straight into the column's place in the concatenation over fragments.  Var offsets of
+    // later fragments are rebased onto the concatenated value stream.
+    const size_t nfrag = ta.num_fragments();
     std::vector<uint64_t> frag_cells;
-    std::vector<std::vector<uint8_t>> fixed(ids.size()), var(ids.size());
     uint64_t n_total = 0;
-    for (size_t fi = 0; fi < nfrag; ++fi) {
-      uint64_t nc = (uint64_t)ta.fragment(fi).bk.cell_num;
-      frag_cells.push_back(nc);
-      for (size_t k = 0; k < ids.size(); ++k) {
-        TdbColumn col;
-        ta.read_column(fi, ids[k], col);
-        bool is_var = ids[k] < nattr && sc.is_var(ids[k]);
-        if (nfrag == 1) { fixed[k].swap(col.fixed); var[k].swap(col.var); continue; }
-        if (is_var) {
-          uint64_t base = var[k].size();
-          uint64_t* o = reinterpret_cast<uint64_t*>(col.fixed.data());
-          for (uint64_t i = 0; i < nc; ++i) o[i] += base;
-          var[k].insert(var[k].end(), col.var.begin(), col.var.end());
+    for (size_t fi = 0; fi < nfrag; ++fi) { frag_cells.push_back((uint64_t)ta.fragment(fi).bk.cell_num); n_total += frag_cells.back(); }
+    uint64_t file_bytes_staged = 0;   // bytes that crossed PCIe: the files as they lie on disk
+    struct DevColumn { DevBuf<uint8_t> fixed, var; uint64_t var_bytes = 0; };
+    std::vector<DevColumn> cols(ids.size());
+    DevBuf<uint32_t> inf_err; inf_err.alloc(2);
+    CK(cudaMemsetAsync(inf_err.p, 0, 8, ctx->stream));
+    for (size_t k = 0; k < ids.size(); ++k) {
+      std::vector<TdbRawColumn> raw(nfrag);
+      uint64_t fixed_total = 0, var_total = 0;
+      for (size_t fi = 0; fi < nfrag; ++fi) { ta.read_column_raw(fi, ids[k], raw[fi]); fixed_total += raw[fi].fixed_bytes; var_total += raw[fi].var_bytes; }
+      DevColumn& dc = cols[k];
+      dc.fixed.alloc(std::max<uint64_t>(fixed_total, 1)); dc.var.alloc(std::max<uint64_t>(var_total, 1)); dc.var_bytes = var_total;
+      uint64_t fixed_at = 0, var_at = 0, cells_at = 0;
+      for (size_t fi = 0; fi < nfrag; ++fi) {
+        const TdbRawColumn& r = raw[fi];
+        auto place = [&](const std::vector<uint8_t>& file, const std::vector<TdbTileSpan>& tiles, uint64_t bytes, uint8_t* dst) {
+          if (!bytes) return;
+          if (!r.compressed) { CK(cudaMemcpyAsync(dst, file.data(), bytes, cudaMemcpyHostToDevice, ctx->stream)); file_bytes_staged += bytes; return; }
+          DevBuf<uint8_t> in; DevBuf<InflateJob> jobs;
+          in.alloc(std::max<size_t>(file.size(), 1)); jobs.alloc(std::max<size_t>(tiles.size(), 1));
+          static_assert(sizeof(InflateJob) == sizeof(TdbTileSpan), "tile span layout");
+          CK(cudaMemcpyAsync(in.p, file.data(), file.size(), cudaMemcpyHostToDevice, ctx->stream));
+          CK(cudaMemcpyAsync(jobs.p, tiles.data(), tiles.size() * sizeof(InflateJob), cudaMemcpyHostToDevice, ctx->stream));
+          LAUNCH(ctx, k_inflate, blocks_for(tiles.size(), 64), 64, in.p, jobs.p, (uint64_t)tiles.size(), dst, inf_err.p);
+          CK(cudaStreamSynchronize(ctx->stream));   // `file` / `tiles` (pageable) and the temporaries go out of scope
+          file_bytes_staged += file.size();
+        };
+        place(r.fixed_file, r.fixed_tiles, r.fixed_bytes, dc.fixed.p + fixed_at);
+        if (r.is_var) {
+          place(r.var_file, r.var_tiles, r.var_bytes, dc.var.p + var_at);
+          if (var_at) LAUNCH(ctx, k_add_u64, blocks_for(frag_cells[fi], 256), 256, reinterpret_cast<uint64_t*>(dc.fixed.p) + cells_at, frag_cells[fi], var_at);
         }
-        fixed[k].insert(fixed[k].end(), col.fixed.begin(), col.fixed.end());
+        fixed_at += r.fixed_bytes; var_at += r.var_bytes; cells_at += frag_cells[fi];
       }
-      n_total += nc;
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    {
+      uint32_t e[2] = {0, 0};
+      CK(cudaMemcpy(e, inf_err.p, 8, cudaMemcpyDeviceToHost));
+      if (e[0]) throw std::runtime_error("zlib stream of tile " + std::to_string(e[1]) + " does not inflate (" +
+                                         (e[0] == INF_ERR_HEADER ? "bad header" : e[0] == INF_ERR_SIZE ? "size mismatch" : e[0] == INF_ERR_ADLER ? "Adler-32 mismatch" : "corrupt data") + ")");
     }
     HostCols h; h.n = n_total;
-    h.coords = reinterpret_cast<const int64_t*>(fixed[0].data()); h.end = reinterpret_cast<const int64_t*>(fixed[1].data());
-    auto hv = [&](size_t k) { return HostVar{reinterpret_cast<const uint64_t*>(fixed[k].data()), var[k].data(), var[k].size()}; };
+    h.coords = reinterpret_cast<const int64_t*>(cols[0].fixed.p); h.end = reinterpret_cast<const int64_t*>(cols[1].fixed.p);
+    auto hv = [&](size_t k) { return HostVar{reinterpret_cast<const uint64_t*>(cols[k].fixed.p), cols[k].var.p, cols[k].var_bytes}; };
     h.ref = hv(2); h.alt = hv(3);
     size_t k = 4;
     h.has_gt = id_gt >= 0;
     if (h.has_gt) h.gt = hv(k++);
     for (int f = 0; f < n_fields; ++f) h.fields.push_back(hv(k++));
-    for (int f = 0; f < n_plain; ++f, ++k) h.plain.push_back(pm[f].fixed_len ? HostVar{nullptr, fixed[k].data(), fixed[k].size()} : hv(k));
+    for (int f = 0; f < n_plain; ++f, ++k) h.plain.push_back(pm[f].fixed_len ? HostVar{nullptr, cols[k].fixed.p, (uint64_t)n_total * pm[f].fixed_len * (pm[f].elem == ELEM_CHAR ? 1u : 4u)} : hv(k));
     int64_t lb = 0, ub = 0;
     if (!ta.row_bounds(lb, ub)) {   // no GenomicsDB metadata: bound by the data
+      std::vector<int64_t> hc(2 * n_total);
+      if (n_total) CK(cudaMemcpy(hc.data(), h.coords, n_total * 16, cudaMemcpyDeviceToHost));
       ub = -1;
-      for (uint64_t i = 0; i < n_total; ++i) ub = std::max(ub, h.coords[2 * i]);
+      for (uint64_t i = 0; i < n_total; ++i) ub = std::max(ub, hc[2 * i]);
     }
     *out = build_array(ctx, h, frag_cells, lb, ub - lb + 1, gt_phased, fm, names, pm);
+    (*out)->staged_bytes = file_bytes_staged;
   });
 }
 

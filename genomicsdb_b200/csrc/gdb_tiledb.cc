@@ -218,4 +218,49 @@ void TdbArray::read_column(size_t fi, int attr_id, TdbColumn& out) const {
   }
 }
 
+void TdbArray::read_column_raw(size_t fi, int attr_id, TdbRawColumn& out) const {
+  const TdbFragment& fr = fragments_[fi];
+  const int nattr = (int)schema_.attributes.size();
+  const std::string name = (attr_id == nattr) ? "__coords" : schema_.attributes[attr_id];
+  out = TdbRawColumn();
+  out.compressed = schema_.compression[attr_id] != CMP_NONE;
+  if (out.compressed && schema_.compression[attr_id] != CMP_GZIP) fail("unsupported TileDB compression for " + name);
+  out.is_var = attr_id < nattr && schema_.is_var(attr_id);
+  out.fixed_file = read_file(fr.dir + "/" + name + ".tdb");
+  const uint64_t cell = out.is_var ? 8 : ((attr_id == nattr) ? 16 : schema_.type_size(attr_id) * (uint64_t)schema_.cell_val_num[attr_id]);
+  out.fixed_bytes = (uint64_t)fr.bk.cell_num * cell;
+  if (out.is_var) out.var_file = read_file(fr.dir + "/" + name + "_var.tdb");
+  if (!out.compressed) {
+    if (out.fixed_file.size() != out.fixed_bytes) fail("column size mismatch for " + name);
+    out.var_bytes = out.var_file.size();
+    return;
+  }
+  // tile i of the fixed file holds capacity cells (the last one last_tile_cell_num), read_state.cc:2581-2620
+  const std::vector<int64_t>& offs = fr.bk.tile_offsets[attr_id];
+  if ((int64_t)offs.size() != fr.bk.tile_num) fail("tile offset count mismatch for " + name);
+  uint64_t o = 0;
+  for (size_t i = 0; i < offs.size(); ++i) {
+    const uint64_t lo = (uint64_t)offs[i], hi = (i + 1 < offs.size()) ? (uint64_t)offs[i + 1] : out.fixed_file.size();
+    if (hi < lo || hi > out.fixed_file.size()) fail("tile offsets out of range for " + name);
+    const uint64_t cells = (i + 1 < offs.size()) ? (uint64_t)schema_.capacity : (uint64_t)fr.bk.last_tile_cell_num;
+    out.fixed_tiles.push_back(TdbTileSpan{lo, hi - lo, o, cells * cell});
+    o += cells * cell;
+  }
+  if (o != out.fixed_bytes) fail("tile sizes do not add up for " + name);
+  if (out.is_var) {
+    const std::vector<int64_t>& voffs = fr.bk.tile_var_offsets[attr_id];
+    const std::vector<uint64_t>& vsz = fr.bk.tile_var_sizes[attr_id];
+    if (voffs.size() != vsz.size()) fail("var tile table mismatch for " + name);
+    uint64_t vo = 0;
+    for (size_t i = 0; i < voffs.size(); ++i) {
+      const uint64_t lo = (uint64_t)voffs[i], hi = (i + 1 < voffs.size()) ? (uint64_t)voffs[i + 1] : out.var_file.size();
+      if (hi < lo || hi > out.var_file.size()) fail("var tile offsets out of range for " + name);
+      if (vsz[i] == 0) { out.var_tiles.push_back(TdbTileSpan{lo, 0, vo, 0}); continue; }   // empty var tile: nothing was written
+      out.var_tiles.push_back(TdbTileSpan{lo, hi - lo, vo, vsz[i]});
+      vo += vsz[i];
+    }
+    out.var_bytes = vo;
+  }
+}
+
 }  // namespace gdb

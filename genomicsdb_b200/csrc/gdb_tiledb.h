@@ -42,6 +42,17 @@ struct TdbColumn {
   std::vector<uint8_t> var;     // var attr: value stream
 };
 
+// An attribute file as it lies on disk, plus where its tiles are: what the device-side inflate needs.  For an uncompressed
+// attribute the file bytes ARE the column.
+struct TdbTileSpan { uint64_t in_off, in_len, out_off, out_len; };
+struct TdbRawColumn {
+  bool compressed = false;
+  std::vector<uint8_t> fixed_file, var_file;     // <ATTR>.tdb, <ATTR>_var.tdb as read
+  std::vector<TdbTileSpan> fixed_tiles, var_tiles;   // compressed only: one zlib stream per tile
+  uint64_t fixed_bytes = 0, var_bytes = 0;       // decompressed sizes
+  bool is_var = false;
+};
+
 struct TdbFragment {
   std::string dir;
   TdbBookKeeping bk;
@@ -58,6 +69,8 @@ class TdbArray {
   bool row_bounds(int64_t& lb, int64_t& max_valid) const;
   // attr_id == schema().attributes.size() reads __coords
   void read_column(size_t fragment_idx, int attr_id, TdbColumn& out) const;
+  // the same column without inflating it (tile tables from the book-keeping: read_state.cc:2442-2889)
+  void read_column_raw(size_t fragment_idx, int attr_id, TdbRawColumn& out) const;
 
  private:
   std::string dir_;

@@ -1,4 +1,6 @@
 """GPU: CUDA path vs the oracle on GDBSYN-1 cohorts (same seeded inputs), sizes the oracle finishes in seconds."""
+import os
+
 import numpy as np
 import pytest
 
@@ -178,3 +180,45 @@ def test_full_width_100k_samples(ctx):
         assert n_remapped == 24
     finally:
         arr.close()
+
+
+@pytest.mark.parametrize("capacity", [1000, 37])
+def test_compressed_fragment_is_inflated_on_the_device(ctx, tmp_path, capacity):
+    """a GZIP-compressed fragment (one zlib stream per tile, dynamic Huffman blocks at 1000 cells per tile) written in the
+    reference's on-disk format: gdbgpu_array_open inflates the tiles on the device (k_inflate); the combine over it equals
+    the oracle over the generated columns, and equals the open of the uncompressed twin"""
+    from genomicsdb_b200 import capi, dump
+    from tools import tiledb_writer
+    d = gdbsyn.generate(n_samples=300, n_sites=200, spacing=100, p_var=0.1, a_pool=8, with_fixed=True)
+    want, n = oracle.combine_query(gdbsyn.to_oracle_columns(d), [])
+    got = {}
+    for comp in (True, False):
+        ws = str(tmp_path / ("ws%d" % comp))
+        tiledb_writer.write_array(ws, "syn", d, capacity=capacity, compress=comp)
+        arr = capi.Array.open(ctx, ws, "syn", [("AD", "R", "int"), ("PL", "G", "int")], plain=[("GQ", "int", 1), ("MIN_DP", "int", 1)])
+        try:
+            info = arr.info()
+            assert info.n_cells == len(d["end"])
+            got[comp] = (dump.combine_dump(arr, [], ["GT", "AD", "PL"]), info.staged_bytes)
+        finally:
+            arr.close()
+    assert got[True][0][1] == n
+    assert got[True][0][0] == want
+    assert got[False][0][0] == want
+    assert got[True][1] < got[False][1]          # fewer bytes crossed PCIe
+
+
+def test_corrupt_compressed_tile_is_reported(ctx, tmp_path):
+    from genomicsdb_b200 import capi
+    from tools import tiledb_writer
+    d = gdbsyn.generate(n_samples=50, n_sites=100, spacing=100, p_var=0.1, a_pool=4, with_fixed=True)
+    ws = str(tmp_path / "ws")
+    tiledb_writer.write_array(ws, "syn", d, capacity=500, compress=True)
+    frag = [p for p in os.listdir(os.path.join(ws, "syn")) if p.startswith("__") and os.path.isdir(os.path.join(ws, "syn", p))][0]
+    path = os.path.join(ws, "syn", frag, "PL_var.tdb")
+    b = bytearray(open(path, "rb").read())
+    b[len(b) // 2] ^= 0x5A
+    open(path, "wb").write(bytes(b))
+    with pytest.raises(capi.GdbGpuError) as e:
+        capi.Array.open(ctx, ws, "syn", [("AD", "R", "int"), ("PL", "G", "int")])
+    assert e.value.code == capi.ERR_IO and "inflate" in str(e.value)

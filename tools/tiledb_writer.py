@@ -12,6 +12,7 @@ import gzip
 import json
 import os
 import struct
+import zlib
 
 import numpy as np
 
@@ -52,7 +53,7 @@ VCF_HEADER = """##fileformat=VCFv4.2
 """
 
 
-def _schema_bytes(array_path, capacity):
+def _schema_bytes(array_path, capacity, compress=False):
     b = struct.pack("<I", 0xFFFFFFFF) + struct.pack("<i", 0)            # version tag, empty workspace
     name = array_path.encode()
     b += struct.pack("<i", len(name)) + name
@@ -68,11 +69,12 @@ def _schema_bytes(array_path, capacity):
     b += bytes([t for _, t, _ in ATTRS] + [T_INT64])
     for _, _, c in ATTRS:
         b += struct.pack("<i", c)
-    b += bytes([0] * (len(ATTRS) + 1))                                    # no compression
+    b += bytes([1 if compress else 0] * (len(ATTRS) + 1))                 # compression per attribute (+ coords): 1 = GZIP
     return b
 
 
-def _book_keeping_bytes(coords, capacity):
+def _book_keeping_bytes(coords, capacity, tables=None):
+    """tables (compressed fragments): dict(tile_offsets=[per attr + coords], var_offsets=[per attr], var_sizes=[per attr])"""
     n = len(coords)
     tiles = (n + capacity - 1) // capacity
     b = struct.pack("<Q", 32) + struct.pack("<qqqq", 0, I64_MAX - 1, 0, I64_MAX - 1)
@@ -85,15 +87,35 @@ def _book_keeping_bytes(coords, capacity):
     bc = np.concatenate([first, last], axis=1).astype("<i8")
     b += struct.pack("<q", tiles) + mbr.tobytes()
     b += struct.pack("<q", tiles) + bc.tobytes()
-    b += struct.pack("<q", 0) * (len(ATTRS) + 1)      # tile offsets: empty when uncompressed
-    b += struct.pack("<q", 0) * len(ATTRS)            # var tile offsets
-    b += struct.pack("<q", 0) * len(ATTRS)            # var tile sizes
+    if tables is None:
+        b += struct.pack("<q", 0) * (len(ATTRS) + 1)      # tile offsets: empty when uncompressed
+        b += struct.pack("<q", 0) * len(ATTRS)            # var tile offsets
+        b += struct.pack("<q", 0) * len(ATTRS)            # var tile sizes
+    else:                                                 # book_keeping.cc:217-243
+        for t in tables["tile_offsets"]:
+            b += struct.pack("<q", len(t)) + np.asarray(t, dtype="<i8").tobytes()
+        for t in tables["var_offsets"]:
+            b += struct.pack("<q", len(t)) + np.asarray(t, dtype="<i8").tobytes()
+        for t in tables["var_sizes"]:
+            b += struct.pack("<q", len(t)) + np.asarray(t, dtype="<u8").tobytes()
     last_n = n - (tiles - 1) * capacity
     b += struct.pack("<q", last_n)
     return b
 
 
-def write_array(workspace, array_name, d, capacity=1000):
+def _write_tiles(path, data, tile_bytes, level=6):
+    """one zlib stream per tile (ReadState::decompress_tile_gzip); returns the tile offsets in the file"""
+    offs, pos = [], 0
+    with open(path, "wb") as f:
+        for lo in range(0, len(data), tile_bytes) if len(data) else []:
+            z = zlib.compress(data[lo:lo + tile_bytes], level)
+            offs.append(pos)
+            f.write(z)
+            pos += len(z)
+    return offs
+
+
+def write_array(workspace, array_name, d, capacity=1000, compress=False):
     """d: tools.gdbsyn.generate(..., with_fixed=True).  Returns dict(workspace, array, vid, callsets, vcf_header, fasta)."""
     os.makedirs(workspace, exist_ok=True)
     open(os.path.join(workspace, "__tiledb_workspace.tdb"), "wb").close()
@@ -102,24 +124,53 @@ def write_array(workspace, array_name, d, capacity=1000):
     os.makedirs(fdir, exist_ok=True)
     os.makedirs(os.path.join(adir, "genomicsdb_meta_dir"), exist_ok=True)
     open(os.path.join(adir, ".__consolidation_lock"), "wb").close()
-    open(os.path.join(adir, "__array_schema.tdb"), "wb").write(_schema_bytes(os.path.abspath(adir), capacity))
+    open(os.path.join(adir, "__array_schema.tdb"), "wb").write(_schema_bytes(os.path.abspath(adir), capacity, compress))
     json.dump({"lb_row_idx": 0, "max_valid_row_idx_in_array": int(d["num_rows"]) - 1},
               open(os.path.join(adir, "genomicsdb_meta_dir", "genomicsdb_meta_00000000-0000-4000-8000-000000000000.json"), "w"))
     open(os.path.join(fdir, "__tiledb_fragment.tdb"), "wb").close()
     n = len(d["end"])
-    d["coords"].astype("<i8").tofile(os.path.join(fdir, "__coords.tdb"))
-    d["end"].astype("<i8").tofile(os.path.join(fdir, "END.tdb"))
-    for name, key in (("REF", "ref"), ("ALT", "alt"), ("GT", "gt"), ("AD", "ad"), ("PL", "pl")):
-        d[key][0].astype("<u8").tofile(os.path.join(fdir, name + ".tdb"))
-        d[key][1].tofile(os.path.join(fdir, name + "_var.tdb"))
-    np.full(n, np.float32(3.4028234663852886e38), dtype="<f4").tofile(os.path.join(fdir, "QUAL.tdb"))   # TileDB NULL
-    np.zeros(n, dtype="<u8").tofile(os.path.join(fdir, "FILTER.tdb"))
-    open(os.path.join(fdir, "FILTER_var.tdb"), "wb").close()
+    qual = np.full(n, np.float32(3.4028234663852886e38), dtype="<f4")    # TileDB NULL
+    fixed = {"END": d["end"].astype("<i8"), "QUAL": qual}
     for name, key in (("DP", "dp"), ("GQ", "gq"), ("MIN_DP", "min_dp")):
-        v = d[key] if d.get(key) is not None else np.full(n, 0x7FFFFFFF, dtype=np.int32)
-        v.astype("<i4").tofile(os.path.join(fdir, name + ".tdb"))
+        fixed[name] = (d[key] if d.get(key) is not None else np.full(n, 0x7FFFFFFF, dtype=np.int32)).astype("<i4")
+    var = {name: (d[key][0].astype("<u8"), d[key][1]) for name, key in (("REF", "ref"), ("ALT", "alt"), ("GT", "gt"), ("AD", "ad"), ("PL", "pl"))}
+    var["FILTER"] = (np.zeros(n, dtype="<u8"), np.zeros(0, dtype=np.uint8))
+    if not compress:
+        d["coords"].astype("<i8").tofile(os.path.join(fdir, "__coords.tdb"))
+        for name, v in fixed.items():
+            v.tofile(os.path.join(fdir, name + ".tdb"))
+        for name, (off, val) in var.items():
+            off.tofile(os.path.join(fdir, name + ".tdb"))
+            val.tofile(os.path.join(fdir, name + "_var.tdb"))
+        tables = None
+    else:
+        tables = dict(tile_offsets=[], var_offsets=[], var_sizes=[])
+        for name, _, cvn in ATTRS:
+            if cvn != VAR:
+                b = fixed[name].tobytes()
+                tables["tile_offsets"].append(_write_tiles(os.path.join(fdir, name + ".tdb"), b, capacity * fixed[name].itemsize))
+                tables["var_offsets"].append([])
+                tables["var_sizes"].append([])
+                continue
+            off, val = var[name]
+            vb = val.tobytes()
+            tables["tile_offsets"].append(_write_tiles(os.path.join(fdir, name + ".tdb"), off.tobytes(), capacity * 8))
+            # the value bytes of the cells of every tile form one stream; sizes are the decompressed ones
+            bounds = [int(off[i]) for i in range(0, n, capacity)] + [len(vb)]
+            voffs, vsizes, pos = [], [], 0
+            with open(os.path.join(fdir, name + "_var.tdb"), "wb") as f:
+                for lo, hi in zip(bounds[:-1], bounds[1:]):
+                    voffs.append(pos)
+                    vsizes.append(hi - lo)
+                    if hi > lo:
+                        z = zlib.compress(vb[lo:hi], 6)
+                        f.write(z)
+                        pos += len(z)
+            tables["var_offsets"].append(voffs)
+            tables["var_sizes"].append(vsizes)
+        tables["tile_offsets"].append(_write_tiles(os.path.join(fdir, "__coords.tdb"), d["coords"].astype("<i8").tobytes(), capacity * 16))
     with gzip.open(os.path.join(fdir, "__book_keeping.tdb.gz"), "wb", compresslevel=1) as f:
-        f.write(_book_keeping_bytes(d["coords"], capacity))
+        f.write(_book_keeping_bytes(d["coords"], capacity, tables))
     # mapping files + template header + a reference FASTA long enough for the columns used
     vid_path = os.path.join(workspace, "vid.json")
     json.dump(VID, open(vid_path, "w"))
