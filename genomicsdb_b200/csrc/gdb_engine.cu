@@ -1138,44 +1138,66 @@ int gdbgpu_array_open_ex(gdbgpu_ctx* ctx, const char* workspace, const char* arr
     uint64_t file_bytes_staged = 0;   // bytes that crossed PCIe: the files as they lie on disk
     struct DevColumn { DevBuf<uint8_t> fixed, var; uint64_t var_bytes = 0; };
     std::vector<DevColumn> cols(ids.size());
-    DevBuf<uint32_t> inf_err; inf_err.alloc(2);
-    CK(cudaMemsetAsync(inf_err.p, 0, 8, ctx->stream));
+    // compressed files of all attributes are collected first: ONE copy of their bytes, ONE k_inflate launch over every tile
+    struct Pending { size_t arena_off; const std::vector<TdbTileSpan>* tiles; uint8_t* dst; };
+    std::vector<std::vector<TdbRawColumn>> raw(ids.size(), std::vector<TdbRawColumn>(nfrag));
+    std::vector<Pending> pending;
+    size_t arena_bytes = 0, n_jobs = 0;
+    struct Rebase { uint64_t* p; uint64_t n, add; };
+    std::vector<Rebase> rebases;
     for (size_t k = 0; k < ids.size(); ++k) {
-      std::vector<TdbRawColumn> raw(nfrag);
       uint64_t fixed_total = 0, var_total = 0;
-      for (size_t fi = 0; fi < nfrag; ++fi) { ta.read_column_raw(fi, ids[k], raw[fi]); fixed_total += raw[fi].fixed_bytes; var_total += raw[fi].var_bytes; }
+      for (size_t fi = 0; fi < nfrag; ++fi) { ta.read_column_raw(fi, ids[k], raw[k][fi]); fixed_total += raw[k][fi].fixed_bytes; var_total += raw[k][fi].var_bytes; }
       DevColumn& dc = cols[k];
       dc.fixed.alloc(std::max<uint64_t>(fixed_total, 1)); dc.var.alloc(std::max<uint64_t>(var_total, 1)); dc.var_bytes = var_total;
       uint64_t fixed_at = 0, var_at = 0, cells_at = 0;
       for (size_t fi = 0; fi < nfrag; ++fi) {
-        const TdbRawColumn& r = raw[fi];
+        const TdbRawColumn& r = raw[k][fi];
         auto place = [&](const std::vector<uint8_t>& file, const std::vector<TdbTileSpan>& tiles, uint64_t bytes, uint8_t* dst) {
           if (!bytes) return;
-          if (!r.compressed) { CK(cudaMemcpyAsync(dst, file.data(), bytes, cudaMemcpyHostToDevice, ctx->stream)); file_bytes_staged += bytes; return; }
-          DevBuf<uint8_t> in; DevBuf<InflateJob> jobs;
-          in.alloc(std::max<size_t>(file.size(), 1)); jobs.alloc(std::max<size_t>(tiles.size(), 1));
-          static_assert(sizeof(InflateJob) == sizeof(TdbTileSpan), "tile span layout");
-          CK(cudaMemcpyAsync(in.p, file.data(), file.size(), cudaMemcpyHostToDevice, ctx->stream));
-          CK(cudaMemcpyAsync(jobs.p, tiles.data(), tiles.size() * sizeof(InflateJob), cudaMemcpyHostToDevice, ctx->stream));
-          LAUNCH(ctx, k_inflate, blocks_for(tiles.size(), 64), 64, in.p, jobs.p, (uint64_t)tiles.size(), dst, inf_err.p);
-          CK(cudaStreamSynchronize(ctx->stream));   // `file` / `tiles` (pageable) and the temporaries go out of scope
-          file_bytes_staged += file.size();
+          file_bytes_staged += r.compressed ? file.size() : bytes;
+          if (!r.compressed) { CK(cudaMemcpyAsync(dst, file.data(), bytes, cudaMemcpyHostToDevice, ctx->stream)); return; }
+          pending.push_back(Pending{arena_bytes, &tiles, dst});
+          arena_bytes += (file.size() + 15) & ~(size_t)15; n_jobs += tiles.size();
+          (void)file;
         };
         place(r.fixed_file, r.fixed_tiles, r.fixed_bytes, dc.fixed.p + fixed_at);
         if (r.is_var) {
           place(r.var_file, r.var_tiles, r.var_bytes, dc.var.p + var_at);
-          if (var_at) LAUNCH(ctx, k_add_u64, blocks_for(frag_cells[fi], 256), 256, reinterpret_cast<uint64_t*>(dc.fixed.p) + cells_at, frag_cells[fi], var_at);
+          if (var_at) rebases.push_back(Rebase{reinterpret_cast<uint64_t*>(dc.fixed.p) + cells_at, frag_cells[fi], var_at});
         }
         fixed_at += r.fixed_bytes; var_at += r.var_bytes; cells_at += frag_cells[fi];
       }
-      CK(cudaStreamSynchronize(ctx->stream));
     }
-    {
+    if (n_jobs) {
+      DevBuf<uint8_t> arena; DevBuf<InflateJob> d_jobs; DevBuf<uint32_t> inf_err;
+      arena.alloc(arena_bytes); d_jobs.alloc(n_jobs); inf_err.alloc(2);
+      CK(cudaMemsetAsync(inf_err.p, 0, 8, ctx->stream));
+      std::vector<InflateJob> jobs; jobs.reserve(n_jobs);
+      size_t pi = 0;
+      for (size_t k = 0; k < ids.size(); ++k) for (size_t fi = 0; fi < nfrag; ++fi) {
+        const TdbRawColumn& r = raw[k][fi];
+        if (!r.compressed) continue;
+        for (int part = 0; part < 2; ++part) {
+          const std::vector<uint8_t>& file = part ? r.var_file : r.fixed_file;
+          const uint64_t bytes = part ? r.var_bytes : r.fixed_bytes;
+          if ((part && !r.is_var) || !bytes) continue;
+          const Pending& pd = pending[pi++];
+          CK(cudaMemcpyAsync(arena.p + pd.arena_off, file.data(), file.size(), cudaMemcpyHostToDevice, ctx->stream));
+          for (const TdbTileSpan& t : *pd.tiles) jobs.push_back(InflateJob{arena.p + pd.arena_off + t.in_off, t.in_len, pd.dst + t.out_off, t.out_len});
+        }
+      }
+      CK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(InflateJob), cudaMemcpyHostToDevice, ctx->stream));
+      LAUNCH(ctx, k_inflate, blocks_for(jobs.size(), 64), 64, d_jobs.p, (uint64_t)jobs.size(), inf_err.p);
       uint32_t e[2] = {0, 0};
-      CK(cudaMemcpy(e, inf_err.p, 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpyAsync(e, inf_err.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
       if (e[0]) throw std::runtime_error("zlib stream of tile " + std::to_string(e[1]) + " does not inflate (" +
                                          (e[0] == INF_ERR_HEADER ? "bad header" : e[0] == INF_ERR_SIZE ? "size mismatch" : e[0] == INF_ERR_ADLER ? "Adler-32 mismatch" : "corrupt data") + ")");
     }
+    for (const Rebase& rb : rebases) LAUNCH(ctx, k_add_u64, blocks_for(rb.n, 256), 256, rb.p, rb.n, rb.add);
+    CK(cudaStreamSynchronize(ctx->stream));   // the host file buffers (pageable) may go once every copy has run
+    raw.clear();
     HostCols h; h.n = n_total;
     h.coords = reinterpret_cast<const int64_t*>(cols[0].fixed.p); h.end = reinterpret_cast<const int64_t*>(cols[1].fixed.p);
     auto hv = [&](size_t k) { return HostVar{reinterpret_cast<const uint64_t*>(cols[k].fixed.p), cols[k].var.p, cols[k].var_bytes}; };

@@ -11,7 +11,7 @@
 
 namespace gdb {
 
-struct InflateJob { uint64_t in_off, in_len, out_off, out_len; };   // one zlib stream -> one tile
+struct InflateJob { const uint8_t* in; uint64_t in_len; uint8_t* out; uint64_t out_len; };   // one zlib stream -> one tile (device pointers)
 enum : uint32_t { INF_OK = 0, INF_ERR_HEADER = 1, INF_ERR_DATA = 2, INF_ERR_SIZE = 3, INF_ERR_ADLER = 4 };
 
 namespace inflate_detail {
@@ -163,11 +163,11 @@ __device__ inline uint32_t inflate_stream(const uint8_t* in, uint64_t in_len, ui
 }  // namespace inflate_detail
 
 // one thread per tile; err[0] = first INF_ERR_* seen, err[1] = the job it was seen in
-__global__ void __launch_bounds__(64) k_inflate(const uint8_t* __restrict__ in, const InflateJob* __restrict__ jobs, uint64_t n_jobs, uint8_t* __restrict__ out, uint32_t* __restrict__ err) {
+__global__ void __launch_bounds__(64) k_inflate(const InflateJob* __restrict__ jobs, uint64_t n_jobs, uint32_t* __restrict__ err) {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_jobs) return;
   const InflateJob job = jobs[j];
-  const uint32_t rc = job.out_len == 0 && job.in_len == 0 ? (uint32_t)INF_OK : inflate_detail::inflate_stream(in + job.in_off, job.in_len, out + job.out_off, job.out_len);
+  const uint32_t rc = job.out_len == 0 && job.in_len == 0 ? (uint32_t)INF_OK : inflate_detail::inflate_stream(job.in, job.in_len, job.out, job.out_len);
   if (rc != INF_OK && atomicCAS(&err[0], 0u, rc) == 0u) err[1] = (uint32_t)j;
 }
 

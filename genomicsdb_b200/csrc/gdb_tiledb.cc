@@ -120,19 +120,6 @@ void parse_book_keeping(const std::string& path, const TdbSchema& s, TdbBookKeep
   bk.cell_num = mbr_num ? (mbr_num - 1) * s.capacity + bk.last_tile_cell_num : 0;
 }
 
-void inflate_tiles(const std::vector<uint8_t>& raw, const std::vector<int64_t>& offs, const std::vector<uint64_t>* sizes,
-                   std::vector<uint8_t>& out) {
-  out.clear();
-  for (size_t i = 0; i < offs.size(); ++i) {
-    size_t lo = (size_t)offs[i], hi = (i + 1 < offs.size()) ? (size_t)offs[i + 1] : raw.size();
-    if (sizes && (*sizes)[i] == 0) continue;          // empty var tile: nothing was written (read_state.cc:2719-2723)
-    if (hi < lo || hi > raw.size()) fail("tile offsets out of range");
-    size_t before = out.size();
-    inflate_into(raw.data() + lo, hi - lo, 15, out);
-    if (sizes && out.size() - before != (*sizes)[i]) fail("var tile size mismatch");
-  }
-}
-
 }  // namespace
 
 int TdbSchema::attr_id(const std::string& name) const {
@@ -195,27 +182,6 @@ bool TdbArray::row_bounds(int64_t& lb, int64_t& max_valid) const {
   lb = has_lb_ ? lb_ : 0;
   max_valid = ub_;
   return has_ub_;
-}
-
-void TdbArray::read_column(size_t fi, int attr_id, TdbColumn& out) const {
-  const TdbFragment& fr = fragments_[fi];
-  const int nattr = (int)schema_.attributes.size();
-  const std::string name = (attr_id == nattr) ? "__coords" : schema_.attributes[attr_id];
-  const bool compressed = schema_.compression[attr_id] != CMP_NONE;
-  if (compressed && schema_.compression[attr_id] != CMP_GZIP) fail("unsupported TileDB compression for " + name);
-  std::vector<uint8_t> raw = read_file(fr.dir + "/" + name + ".tdb");
-  if (compressed) inflate_tiles(raw, fr.bk.tile_offsets[attr_id], nullptr, out.fixed);
-  else out.fixed.swap(raw);
-  out.var.clear();
-  if (attr_id < nattr && schema_.is_var(attr_id)) {
-    std::vector<uint8_t> vraw = read_file(fr.dir + "/" + name + "_var.tdb");
-    if (compressed) inflate_tiles(vraw, fr.bk.tile_var_offsets[attr_id], &fr.bk.tile_var_sizes[attr_id], out.var);
-    else out.var.swap(vraw);
-    if (out.fixed.size() != (size_t)fr.bk.cell_num * 8) fail("offset column size mismatch for " + name);
-  } else {
-    size_t cell = (attr_id == nattr) ? 16 : schema_.type_size(attr_id) * (size_t)schema_.cell_val_num[attr_id];
-    if (out.fixed.size() != (size_t)fr.bk.cell_num * cell) fail("column size mismatch for " + name);
-  }
 }
 
 void TdbArray::read_column_raw(size_t fi, int attr_id, TdbRawColumn& out) const {

@@ -1,5 +1,5 @@
 // Host-side reader for the on-disk format GenomicsDB arrays use (TileDB 0.5.x sparse, column-major, read mode).
-// Written from the format, not from the reference's classes: one pass per attribute file, whole columns out.
+// Written from the format, not from the reference's classes: metadata parsed here, attribute files handed out whole and raw.
 //   schema layout        dependencies/TileDB/core/src/array/array_schema.cc:569-594
 //   book-keeping layout  dependencies/TileDB/core/src/fragment/book_keeping.cc:217-243
 //   tile location/inflate dependencies/TileDB/core/src/fragment/read_state.cc:2442-2889, misc/utils.cc:466-512
@@ -36,12 +36,6 @@ struct TdbBookKeeping {
   std::vector<std::vector<uint64_t>> tile_var_sizes;   // attribute_num
 };
 
-// A whole attribute column of one fragment, decoded (tiles inflated) but otherwise byte-identical to the file.
-struct TdbColumn {
-  std::vector<uint8_t> fixed;   // fixed attr: values; var attr: n_cells uint64 absolute byte offsets
-  std::vector<uint8_t> var;     // var attr: value stream
-};
-
 // An attribute file as it lies on disk, plus where its tiles are: what the device-side inflate needs.  For an uncompressed
 // attribute the file bytes ARE the column.
 struct TdbTileSpan { uint64_t in_off, in_len, out_off, out_len; };
@@ -67,9 +61,9 @@ class TdbArray {
   const TdbFragment& fragment(size_t i) const { return fragments_[i]; }
   // lb_row_idx / max_valid_row_idx_in_array merged over genomicsdb_meta_dir (false if no metadata present)
   bool row_bounds(int64_t& lb, int64_t& max_valid) const;
-  // attr_id == schema().attributes.size() reads __coords
-  void read_column(size_t fragment_idx, int attr_id, TdbColumn& out) const;
-  // the same column without inflating it (tile tables from the book-keeping: read_state.cc:2442-2889)
+  // One attribute column of one fragment exactly as it lies on disk + its tile table from the book-keeping
+  // (read_state.cc:2442-2889); attr_id == schema().attributes.size() reads __coords.  Compressed tiles are inflated on
+  // the device (gdb_inflate.cuh), never here; zlib is only used for the small gzip'ed book-keeping file.
   void read_column_raw(size_t fragment_idx, int attr_id, TdbRawColumn& out) const;
 
  private:

@@ -190,7 +190,8 @@ def write_array(workspace, array_name, d, capacity=1000, compress=False):
             f.write(b">1\n")
             f.write((b"ACGT" * 15 + b"\n") * nlines)
         open(fasta + ".fai", "w").write("1\t%d\t3\t%d\t%d\n" % (nlines * line, line, line + 1))
-    return dict(workspace=workspace, array=array_name, vid=vid_path, callsets=cs_path, vcf_header=hdr_path, fasta=fasta)
+    return dict(workspace=workspace, array=array_name, vid=vid_path, callsets=cs_path, vcf_header=hdr_path, fasta=fasta,
+                fragment_dir=fdir, tile_tables=tables)
 
 
 def write_query_json(path, info, col_lo=None, col_hi=None, attributes=("REF", "ALT", "GT", "AD", "PL"), segment_size=10485760):
