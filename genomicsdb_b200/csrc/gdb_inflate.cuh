@@ -48,14 +48,41 @@ __device__ int construct(Huff<NSYM>& h, const int16_t* length, int n) {
   for (int s = 0; s < n; ++s) if (length[s] != 0) h.symbol[offs[length[s]]++] = (int16_t)s;
   return left;
 }
+// Primary table of the literal/length code: the next LUT_BITS input bits -> symbol << 4 | code length, 0 when the code is
+// longer than LUT_BITS bits (decode() then walks the lengths).  Most symbols of a tile are literals with short codes, so
+// the common case is one lookup instead of a bit-by-bit walk.
+constexpr int LUT_BITS = 10;
+struct FastLit { uint16_t lut[1 << LUT_BITS]; };
+__device__ inline void build_fast(FastLit& f, const int16_t* length, int n) {
+  uint16_t next_code[MAXBITS + 2];
+  int16_t bl_count[MAXBITS + 1];
+  for (int l = 0; l <= MAXBITS; ++l) bl_count[l] = 0;
+  for (int s = 0; s < n; ++s) bl_count[length[s]]++;
+  bl_count[0] = 0;
+  uint32_t code = 0;
+  for (int l = 1; l <= MAXBITS; ++l) { code = (code + (uint32_t)bl_count[l - 1]) << 1; next_code[l] = (uint16_t)code; }
+  for (int i = 0; i < (1 << LUT_BITS); ++i) f.lut[i] = 0;
+  for (int s = 0; s < n; ++s) {
+    const int l = length[s];
+    if (l == 0) continue;
+    const uint32_t c = next_code[l]++;
+    if (l > LUT_BITS) continue;
+    const uint32_t rev = __brev(c) >> (32 - l);   // the stream carries Huffman codes most significant bit first
+    for (uint32_t k = rev; k < (1u << LUT_BITS); k += 1u << l) f.lut[k] = (uint16_t)((s << 4) | l);
+  }
+}
+
 template <int NSYM>
 __device__ int decode(BitIn& s, const Huff<NSYM>& h) {
-  int code = 0, first = 0, index = 0;
+  // top the bit buffer up to a whole code (<= 15 bits) once, then walk the code lengths on a register copy
+  while (s.cnt < MAXBITS && s.pos < s.len) { s.buf |= (uint32_t)s.in[s.pos++] << s.cnt; s.cnt += 8; }
+  uint32_t bitbuf = s.buf;
+  int left = s.cnt, code = 0, first = 0, index = 0;
   for (int l = 1; l <= MAXBITS; ++l) {
-    code |= (int)s.bits(1);
-    if (s.bad) return -1;
+    if (left == 0) { s.bad = true; return -1; }
+    code |= (int)(bitbuf & 1u); bitbuf >>= 1; --left;
     const int count = h.count[l];
-    if (code - count < first) return h.symbol[index + (code - first)];
+    if (code - count < first) { s.buf = bitbuf; s.cnt = left; return h.symbol[index + (code - first)]; }
     index += count; first += count; first <<= 1; code <<= 1;
   }
   return -1;
@@ -68,9 +95,13 @@ __device__ __constant__ uint8_t c_dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4
 __device__ __constant__ uint8_t c_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 template <int NL, int ND>
-__device__ bool codes(BitIn& s, uint8_t* out, uint64_t& pos, uint64_t cap, const Huff<NL>& lencode, const Huff<ND>& distcode) {
+__device__ bool codes(BitIn& s, uint8_t* out, uint64_t& pos, uint64_t cap, const Huff<NL>& lencode, const Huff<ND>& distcode, const FastLit& fast) {
   for (;;) {
-    int sym = decode(s, lencode);
+    while (s.cnt < MAXBITS && s.pos < s.len) { s.buf |= (uint32_t)s.in[s.pos++] << s.cnt; s.cnt += 8; }
+    int sym;
+    const uint32_t e = fast.lut[s.buf & ((1u << LUT_BITS) - 1u)];
+    if (e != 0 && (int)(e & 15u) <= s.cnt) { s.buf >>= (e & 15u); s.cnt -= (int)(e & 15u); sym = (int)(e >> 4); }
+    else sym = decode(s, lencode);
     if (sym < 0) return false;
     if (sym < 256) { if (pos >= cap) return false; out[pos++] = (uint8_t)sym; continue; }
     if (sym == 256) return true;
@@ -91,14 +122,15 @@ __device__ inline uint32_t inflate_stream(const uint8_t* in, uint64_t in_len, ui
   const uint32_t cmf = in[0], flg = in[1];
   if ((cmf & 0x0F) != 8 || ((cmf << 8) | flg) % 31 != 0 || (flg & 0x20)) return INF_ERR_HEADER;
   BitIn s{in, in_len - 4, 2, 0, 0, false};
+  FastLit fast;
   uint64_t pos = 0;
   int last;
   do {
     last = (int)s.bits(1);
     const uint32_t type = s.bits(2);
     if (s.bad) return INF_ERR_DATA;
-    if (type == 0) {   // stored
-      s.buf = 0; s.cnt = 0;
+    if (type == 0) {   // stored: back to the byte boundary (decode() may have buffered whole bytes ahead)
+      s.pos -= (uint64_t)(s.cnt >> 3); s.buf = 0; s.cnt = 0;
       if (s.pos + 4 > s.len) return INF_ERR_DATA;
       const uint32_t n = in[s.pos] | (in[s.pos + 1] << 8), nn = in[s.pos + 2] | (in[s.pos + 3] << 8);
       s.pos += 4;
@@ -115,7 +147,9 @@ __device__ inline uint32_t inflate_stream(const uint8_t* in, uint64_t in_len, ui
       construct(lencode, lengths, FIXLCODES);
       for (sym = 0; sym < MAXDCODES; ++sym) lengths[sym] = 5;
       construct(distcode, lengths, MAXDCODES);
-      if (!codes(s, out, pos, out_len, lencode, distcode)) return INF_ERR_DATA;
+      for (sym = 0; sym < 144; ++sym) lengths[sym] = 8;   // `lengths` was reused for the distance code
+      build_fast(fast, lengths, FIXLCODES);
+      if (!codes(s, out, pos, out_len, lencode, distcode, fast)) return INF_ERR_DATA;
     } else if (type == 2) {   // dynamic codes
       const int nlen = (int)s.bits(5) + 257, ndist = (int)s.bits(5) + 1, ncode = (int)s.bits(4) + 4;
       if (s.bad || nlen > MAXLCODES || ndist > MAXDCODES) return INF_ERR_DATA;
@@ -144,7 +178,8 @@ __device__ inline uint32_t inflate_stream(const uint8_t* in, uint64_t in_len, ui
       if (err < 0 || (err > 0 && nlen != lencode.count[0] + lencode.count[1])) return INF_ERR_DATA;   // incomplete only when one 1-bit code
       err = construct(distcode, lengths + nlen, ndist);
       if (err < 0 || (err > 0 && ndist != distcode.count[0] + distcode.count[1])) return INF_ERR_DATA;
-      if (!codes(s, out, pos, out_len, lencode, distcode)) return INF_ERR_DATA;
+      build_fast(fast, lengths, nlen);
+      if (!codes(s, out, pos, out_len, lencode, distcode, fast)) return INF_ERR_DATA;
     } else return INF_ERR_DATA;
     if (s.bad) return INF_ERR_DATA;
   } while (!last);
