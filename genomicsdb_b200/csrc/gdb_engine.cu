@@ -680,7 +680,9 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       bytes += site_bytes; alg_bytes += site_alg; lut_words += (uint64_t)bb.h_sites[i].max_ain * S.nq; keep = i + 1;
     }
     s->avg_site_bytes = std::max<uint64_t>(1, bytes / keep);
-    // split the batch: the tile kernels take every ordinary site, the generic kernel the pathological ones
+    // split the batch: the tile kernels take every ordinary site, the generic kernel the pathological ones.  k_remap_tile
+    // remaps the non-trivial calls of its sites itself (phase C); k_remap_nt only serves the copy-through sites
+    auto nt_blocks = [](const SiteRec& r) -> uint32_t { return (r.flags & 2u) ? 0u : (r.n_nt + NT_GROUPS - 1) / NT_GROUPS; };
     std::vector<uint32_t> fast, slow, nt_prefix, order;
     uint32_t jk_n = 4;
     for (uint32_t i = 0; i < keep; ++i) {
@@ -688,14 +690,14 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       bool ok = a->fields.size() >= 1 && a->fields.size() <= (size_t)TILE_MAX_FIELDS && r.n_alleles <= (uint32_t)TILE_MAX_A && r.max_ain <= (uint32_t)TILE_MAX_A &&
                 r.max_gt_len <= (uint32_t)TILE_MAX_GT && r.max_ploidy_all <= 2u;
       if (ok) {
-        nt_prefix.push_back(fast.empty() ? 0u : nt_prefix.back() + (bb.h_sites[fast.back()].n_nt + NT_GROUPS - 1) / NT_GROUPS);
+        nt_prefix.push_back(fast.empty() ? 0u : nt_prefix.back() + nt_blocks(bb.h_sites[fast.back()]));
         fast.push_back(i);
         jk_n = std::max(jk_n, r.n_alleles * (r.n_alleles + 1u) / 2u);
       } else slow.push_back(i);
     }
     size_t n_remap = 0;
     if (!fast.empty()) {
-      nt_prefix.push_back(nt_prefix.back() + (bb.h_sites[fast.back()].n_nt + NT_GROUPS - 1) / NT_GROUPS);   // blocks of k_remap_nt, per site
+      nt_prefix.push_back(nt_prefix.back() + nt_blocks(bb.h_sites[fast.back()]));   // blocks of k_remap_nt, per site
       // remapped sites -> k_remap_tile, copy-through sites -> k_copy_tile; both lists live in tile_sites (remapped ones first)
       order.reserve(fast.size());
       for (uint32_t i : fast) if (bb.h_sites[i].flags & 2u) order.push_back(i);

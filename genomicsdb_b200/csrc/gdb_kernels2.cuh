@@ -829,6 +829,194 @@ __device__ inline uint32_t small_div(uint32_t n, uint32_t d) {
 //   cls_tab[g / 4] byte g % 4 = class of word g (0: (0,0)  1: (0,k)  2: (j>0,k)),  jk_tab[g] = k << 8 | j.
 struct TileTabs { const uint32_t* cls; const uint16_t* jk; };
 
+// k_remap_nt: NT_GL lanes per nt-list entry (4: a diploid 10-allele PL row is 14 quads = 4 trips at 87 % lane use, AD / tokens / GT
+// one trip; measured 3.9 -> 2.7 ms per step against 8 lanes)
+// k_remap_nt: NT_GL lanes per nt-list entry (non-trivial, non-inline or spanning-deletion call), NT_GROUPS entries of ONE
+// site per block (block -> (site, first entry) comes from a map built by k_nt_blocks), so a warp keeps four independent
+// gather chains in flight: entry -> blob header -> tokens / GT / field words.
+#ifndef GDB_NT_GL
+#define GDB_NT_GL 4
+#endif
+constexpr int NT_THREADS = 256, NT_GL = GDB_NT_GL, NT_GROUPS = NT_THREADS / NT_GL;
+__global__ void __launch_bounds__(256) k_nt_blocks(const __grid_constant__ BatchDev B, const uint32_t* __restrict__ site_list, const uint32_t* __restrict__ blk_prefix, uint2* __restrict__ blk_map) {
+  const uint32_t si = blockIdx.x, js = site_list[si], b0 = blk_prefix[si], nb = blk_prefix[si + 1] - b0;
+  for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) blk_map[b0 + b] = make_uint2(js, b * NT_GROUPS);
+}
+// everything an nt-list entry needs to know about its site
+struct NtSite { uint32_t js, A_m, sflags, mref_len; const uint8_t* mref; };
+
+// One nt-list entry (non-trivial, non-inline or spanning-deletion call) handled by NT_GL consecutive lanes of a warp: gather of
+// the warm blob (pre-hashed ALT tokens, GT / field words), allele LUT against the site's hashes, GT / field vectors written
+// as 16-byte quads.  s_jk / s_ah: the site's genotype (j,k) table and merged-allele hashes in shared memory; m2in_row /
+// in2m_row: this lane group's scratch rows.  Called with all lanes of the warp (inactive groups only take part in the
+// warp barriers).
+template <int NF, bool GT>
+__device__ __forceinline__ void nt_entry(const ArrayDev& A, const ScanDev& S, const BatchDev& B, const RemapOut& O, const NtSite& st,
+                                         const uint16_t* __restrict__ s_jk, const unsigned long long* __restrict__ s_ah, int* m2in_row, int8_t* in2m_row,
+                                         const bool active, const uint2 ent, const int gl) {
+  const uint32_t js = st.js, A_m = st.A_m, mref_len = st.mref_len;
+  const uint8_t* mref = st.mref;
+  const bool nonref = st.sflags & 1u, remap = st.sflags & 2u, g_suppressed = st.sflags & 4u;
+  constexpr int o_f0 = GT ? 1 : 0;
+  for (uint32_t m = gl; m < A_m; m += NT_GL) m2in_row[m] = m == 0 ? 0 : -1;
+
+  // ---- the call
+  const uint32_t q = ent.x;
+  const uint64_t sq = (uint64_t)js * S.nq + q;
+  const bool reduced = (ent.y & NT_REDUCED) != 0;
+  uint32_t n_alt = 0, nr_idx = 0, gt_len = 0, ploidy = 0;
+  const uint32_t* gt = nullptr; const uint32_t* fin[NF]; uint32_t fn[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) { fin[f] = nullptr; fn[f] = 0; }
+  WarmView wv{};
+  const uint32_t H0 = warm_hash_word((uint32_t)A.n_fields);
+  if (active) {
+    if (reduced) {
+      const uint32_t cell = ent.y & ~NT_REDUCED;
+      const DelRec* dr = find_delrec(S, cell);
+      const CellDesc d = A.desc[cell];
+      n_alt = dr->n_alt; nr_idx = dr->has_nr ? 2u : 0u;
+      gt_len = (d.flags & F_GTVALID) ? d.gt_len : 0u; ploidy = gt_len ? ploidy_of(A.gt_phased, gt_len) : 0u;
+      gt = S.del_words + dr->gt_off;
+#pragma unroll
+      for (int f = 0; f < NF; ++f) { const uint32_t n = dr->f_len[f]; fn[f] = n == 0xFFFFFFFFu ? 0u : n; fin[f] = S.del_words + dr->f_off[f]; }
+    } else {
+      wv = warm_view(A, ent.y);
+      n_alt = wv.n_alt; nr_idx = wv.nr_idx; gt_len = wv.gt_len; ploidy = wv.ploidy;
+      gt = wv.b + H0 + 3u * n_alt;
+      const uint32_t* p = gt + gt_len;
+#pragma unroll
+      for (int f = 0; f < NF; ++f) { fn[f] = wv.b[4 + f]; fin[f] = p; p += fn[f]; }
+    }
+  }
+  const uint32_t A_in = n_alt + 1u;
+  __syncwarp();   // m2in_row is initialised; the caller made the site's tables (s_ah, s_jk) visible to the block
+  // ---- allele LUT (merge_alt_alleles' add_input_merged_idx_pair calls for this call, variant_operations.cc:160-227)
+  if (active) {
+    if (gl == 0) in2m_row[0] = 0;
+    for (uint32_t t = gl; t < n_alt && t + 1u < (uint32_t)TILE_MAX_A; t += NT_GL) {
+      const uint32_t idx = t + 1u;
+      int m = -1;
+      if (remap) {
+        uint64_t h = 0;
+        if (reduced) { if (idx == 1) h = star_hash(); }
+        else h = warm_token_hash(wv, H0, t, mref, mref_len);
+        if (h) for (uint32_t mm = 1; mm < A_m; ++mm) if (s_ah[mm] == h) { m = (int)mm; break; }
+      }
+      if (nr_idx && idx == nr_idx) m = (int)A_m - 1;
+      in2m_row[idx] = (int8_t)m;
+      if (remap && m >= 0) atomicMax(&m2in_row[m], (int)idx);   // a merged allele named twice by one call: the last one wins
+    }
+  }
+  __syncwarp();
+  if (active && remap) {
+    const int in_nr = (nonref && nr_idx) ? (int)nr_idx : -1;   // NON_REF fallback folded in
+    for (uint32_t m = gl; m < A_m; m += NT_GL) {
+      int a = m2in_row[m];
+      if (a < 0) a = in_nr;
+      m2in_row[m] = a < 0 ? -1 : (a | ((a * (a + 1) / 2) << 8));
+    }
+  }
+  __syncwarp();
+  if (!active) return;
+  const int* m2in = m2in_row;
+  if (O.lut_first) {
+    uint32_t first = 0;
+    if (gl == 0) { first = atomicAdd(&B.cursors[2], A_in); if (first + A_in > O.cap_lut) { atomicOr(&S.err[2], 2u); first = 0xFFFFFFFFu; } O.lut_first[sq] = first; O.lut_len[sq] = (uint16_t)A_in; }
+    first = __shfl_sync(__activemask(), first, 0, NT_GL);
+    if (first != 0xFFFFFFFFu) for (uint32_t i = gl; i < A_in; i += NT_GL) O.lut_in2m[first + i] = (int16_t)in2m_row[i];
+  }
+  // ---- GT (variant_operations.cc:233-263)
+  if (GT) {
+    const FieldOutDev fo = O.f[0];
+    const uint32_t gs = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + (uint64_t)q * gs;
+    const uint32_t step = A.gt_phased ? 2u : 1u;
+    for (uint32_t i = gl; i < gs; i += NT_GL) {
+      uint32_t val = BCF_INT_VEND;
+      if (i < gt_len) {
+        const uint32_t g = gt[i]; val = g;
+        if (remap && (i % step) == 0 && !(g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING)) {
+          const int m = g < A_in ? (int)in2m_row[g] : -1;
+          val = m < 0 ? (nonref ? A_m - 1u : 0xFFFFFFFFu) : (uint32_t)m;
+        }
+      }
+      dst[i] = val;
+    }
+    if (gl == 0) fo.len[sq] = (uint16_t)gt_len;
+  }
+  // ---- allele-dependent fields (variant_field_handler.cc:41-191)
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    const FieldOutDev fo = O.f[o_f0 + f];
+    const int kind = A.fm[f].kind, elem = A.fm[f].elem;
+    const uint32_t pad = vend_word(elem), miss = missing_word(elem);
+    const uint32_t n = fn[f]; const uint32_t* in = fin[f];
+    uint32_t n_out = 0;
+    if (n && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, ploidy) : n;
+    const uint32_t stride = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + (uint64_t)q * stride;
+    if (gl == 0) fo.len[sq] = (uint16_t)n_out;
+    // s_m2in[m] = input allele of merged allele m (NON_REF fallback folded in), or -1; the diploid loop wants it packed
+    // with its triangular number: a | a(a+1)/2 << 8 (still negative when there is no input allele)
+    if (remap && (stride & 3u) == 0 && kind == KIND_G && ploidy == 2) {
+      uint4* dst4 = reinterpret_cast<uint4*>(dst);
+      for (uint32_t qd = gl; qd < (stride >> 2); qd += NT_GL) {
+        const uint2 jk4 = *reinterpret_cast<const uint2*>(&s_jk[4 * qd]);   // (k << 8 | j) of words 4qd .. 4qd+3
+        uint32_t w[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const uint32_t jk = ((x < 2 ? jk4.x : jk4.y) >> (16 * (x & 1))) & 0xFFFFu;
+          const int pj = m2in[jk & 0xFF], pk = m2in[jk >> 8];
+          const uint32_t aj = (uint32_t)pj & 0xFFu, ak = (uint32_t)pk & 0xFFu;
+          const uint32_t ig = aj > ak ? ((uint32_t)pj >> 8) + ak : ((uint32_t)pk >> 8) + aj;
+          uint32_t v = miss;
+          if ((pj | pk) >= 0 && ig < n) v = in[ig];
+          w[x] = (4 * qd + x < n_out) ? v : pad;
+        }
+        dst4[qd] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else if (remap && (stride & 3u) == 0 && kind == KIND_R) {
+      // R field (AD): out[j] = in[input allele of merged allele j]
+      uint4* dst4 = reinterpret_cast<uint4*>(dst);
+      for (uint32_t qd = gl; qd < (stride >> 2); qd += NT_GL) {
+        uint32_t w[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const uint32_t j = 4 * qd + x;
+          uint32_t v = pad;
+          if (j < n_out) { const int pj = m2in[j]; const uint32_t a = (uint32_t)pj & 0xFFu; v = (pj >= 0 && a < n) ? in[a] : miss; }
+          w[x] = v;
+        }
+        dst4[qd] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else {
+      const int mode = !remap ? 0 : ((kind == KIND_G && ploidy == 2) ? 1 : ((kind == KIND_G && ploidy == 0) ? 2 : (kind == KIND_A ? 3 : 4)));
+      auto word = [&](uint32_t g) -> uint32_t {
+        if (g >= n_out) return pad;
+        if (mode == 0) return in[g];
+        if (mode == 1) {
+          const uint32_t jk = s_jk[g];
+          const int pj = m2in[jk & 0xFF], pk = m2in[jk >> 8];
+          if ((pj | pk) < 0) return miss;
+          const uint32_t aj = (uint32_t)pj & 0xFFu, ak = (uint32_t)pk & 0xFFu;
+          const uint32_t ig = aj > ak ? ((uint32_t)pj >> 8) + ak : ((uint32_t)pk >> 8) + aj;
+          return ig < n ? in[ig] : miss;
+        }
+        if (mode == 2) return in[0];
+        const int pj = m2in[mode == 3 ? g + 1u : g];
+        const int ij = pj < 0 ? -1 : (pj & 0xFF);
+        const int ix = mode == 3 ? ij - 1 : ij;
+        return (ij < 0 || ix < 0 || (uint32_t)ix >= n) ? miss : in[ix];
+      };
+      if (remap && (stride & 3u) == 0) {   // 16-byte aligned vector: one quad per lane
+        uint4* dst4 = reinterpret_cast<uint4*>(dst);
+        for (uint32_t qd = gl; qd < (stride >> 2); qd += NT_GL) dst4[qd] = make_uint4(word(4 * qd), word(4 * qd + 1), word(4 * qd + 2), word(4 * qd + 3));
+      } else {
+        for (uint32_t g = gl; g < stride; g += NT_GL) dst[g] = word(g);
+      }
+    }
+  }
+}
+
 // Sites that need no remapping (merged REF of length 1 and <NON_REF> the only ALT: the reference-block intervals between
 // variant sites): every call's vectors go through unchanged.  One thread per sample; grid = (tiles, sites).
 template <int NF, bool GT>
@@ -890,12 +1078,21 @@ __global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_consta
   __shared__ uint32_t s_info[TILE_ROWS * NF];               // per (sample, field): INFO_FAST or 0
   __shared__ uint32_t s_hw[HOT_WORDS * TILE_ROWS];          // the samples' hot words, word i of thread t at [i * TILE_ROWS + t]:
                                                             // an indexable register file (each thread reads only its own column)
+  // phase C (the tile's non-trivial calls, see nt_entry): their list and the per-group scratch
+  __shared__ uint2 s_ntl[TILE_ROWS];
+  __shared__ uint32_t s_nnt;
+  __shared__ __align__(8) uint16_t s_jk[TILE_MAX_G + 6];
+  __shared__ unsigned long long s_ah[TILE_MAX_A];
+  __shared__ int s_m2in[NT_GROUPS][TILE_MAX_A];
+  __shared__ int8_t s_in2m[NT_GROUPS][TILE_MAX_A];
   constexpr int o_f0 = GT ? 1 : 0;
   const uint32_t js = site_list[blockIdx.y], tile = blockIdx.x;
   const uint32_t tid = threadIdx.x;
   const uint32_t nq = (uint32_t)S.nq;
   const uint32_t q = tile * TILE_ROWS + tid;
   const uint64_t sq = (uint64_t)js * nq + q;
+  if (tid == 0) s_nnt = 0;
+  __syncthreads();
   // issue the two dependent gathers of this thread's sample first; everything below overlaps their latency
   int32_t e = -1;
   uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
@@ -929,9 +1126,10 @@ __global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_consta
       const uint32_t hflags = h0.x & 0xFF, ploidy = (h0.x >> 8) & 0xFF, n_alt = (h0.x >> 16) & 0xFF, nr = h0.x >> 24, gt_len = h0.y & 0xFF;
       const bool inl = ((h0.y >> 8) & 0xFF) != 0;
       if ((e & LIVE_REDUCED) || !inl || !(hflags & F_TRIVIAL)) {
-        // on the site's nt list: k_remap_nt writes this row
+        // a non-trivial call: phase C of this block writes the row
 #pragma unroll
         for (int f = 0; f < NF; ++f) s_info[tid * NF + f] = 0;
+        s_ntl[atomicAdd(&s_nnt, 1u)] = make_uint2(q, (e & LIVE_REDUCED) ? (NT_REDUCED | (uint32_t)(e & (LIVE_REDUCED - 1))) : h0.w);
       } else {
         // ---- trivial call, fully described by its hot record
         const uint32_t fl4 = (h0.y >> 16) | (h0.z << 16);
@@ -1036,21 +1234,28 @@ __global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_consta
       if ((ib & INFO_FAST) && r + rpi < rows) out4[(uint64_t)(r + rpi) * lpr] = vb;
     }
   }
+
+  // ---------------------------------------------------------------- phase C: the tile's non-trivial calls
+  // ~10 % of the rows: instruction-heavy (LUT construction, genotype index arithmetic) where phases A/B are a store stream.
+  // Doing them inside the same block lets their instructions fill the issue slots the store stream leaves idle on this
+  // SM (other resident blocks are in their phase B) instead of running as a separate, issue-bound kernel afterwards.
+  const uint32_t n_ntl = s_nnt;   // final since the barrier after phase A
+  if (n_ntl) {
+    if (tid < A_m) s_ah[tid] = B.allele_hash[site_g->allele_first + tid];
+    const uint32_t jk_n = (A_m * (A_m + 1u)) >> 1;
+    for (uint32_t g = tid; g < ((jk_n + 3u) & ~3u) && g < (uint32_t)TILE_MAX_G + 6u; g += TILE_ROWS) s_jk[g] = tabs.jk[g];
+    __syncthreads();
+    const NtSite st{js, A_m, sflags, site_g->ref_len, B.allele_bytes + site_g->ref_off};
+    const int grp = (int)tid / NT_GL, gl = (int)tid % NT_GL;
+    for (uint32_t base = 0; base < n_ntl; base += NT_GROUPS) {
+      const bool active = base + grp < n_ntl;
+      const uint2 ent = active ? s_ntl[base + grp] : make_uint2(0u, 0u);
+      nt_entry<NF, GT>(A, S, B, O, st, s_jk, s_ah, s_m2in[grp], s_in2m[grp], active, ent, gl);
+      __syncwarp();
+    }
+  }
 }
 
-// k_remap_nt: NT_GL lanes per nt-list entry (4: a diploid 10-allele PL row is 14 quads = 4 trips at 87 % lane use, AD / tokens / GT
-// one trip; measured 3.9 -> 2.7 ms per step against 8 lanes)
-// k_remap_nt: NT_GL lanes per nt-list entry (non-trivial, non-inline or spanning-deletion call), NT_GROUPS entries of ONE
-// site per block (block -> (site, first entry) comes from a map built by k_nt_blocks), so a warp keeps four independent
-// gather chains in flight: entry -> blob header -> tokens / GT / field words.
-#ifndef GDB_NT_GL
-#define GDB_NT_GL 4
-#endif
-constexpr int NT_THREADS = 256, NT_GL = GDB_NT_GL, NT_GROUPS = NT_THREADS / NT_GL;
-__global__ void __launch_bounds__(256) k_nt_blocks(const __grid_constant__ BatchDev B, const uint32_t* __restrict__ site_list, const uint32_t* __restrict__ blk_prefix, uint2* __restrict__ blk_map) {
-  const uint32_t si = blockIdx.x, js = site_list[si], b0 = blk_prefix[si], nb = blk_prefix[si + 1] - b0;
-  for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) blk_map[b0 + b] = make_uint2(js, b * NT_GROUPS);
-}
 template <int NF, bool GT>
 __global__ void __launch_bounds__(NT_THREADS) k_remap_nt(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
                                                         const __grid_constant__ RemapOut O, const uint2* __restrict__ blk_map, const uint32_t jk_n, const TileTabs tabs) {
@@ -1060,175 +1265,16 @@ __global__ void __launch_bounds__(NT_THREADS) k_remap_nt(const __grid_constant__
   __shared__ int8_t s_in2m[NT_GROUPS][TILE_MAX_A];
   const int tid = threadIdx.x, grp = tid / NT_GL, gl = tid % NT_GL;
   const uint2 bm = blk_map[blockIdx.x];
-  const uint32_t js = bm.x;
-  const SiteRec* __restrict__ site_g = &B.sites[js];
-  const uint32_t A_m = site_g->n_alleles, sflags = site_g->flags, allele_first = site_g->allele_first, mref_len = site_g->ref_len, n_nt = site_g->n_nt;
+  const SiteRec* __restrict__ site_g = &B.sites[bm.x];
+  const NtSite st{bm.x, site_g->n_alleles, site_g->flags, site_g->ref_len, B.allele_bytes + site_g->ref_off};
   const uint32_t ei = bm.y + grp;
-  const bool active = ei < n_nt;
+  const bool active = ei < site_g->n_nt;
   uint2 ent = make_uint2(0, 0);
-  if (active) ent = B.nt[(uint64_t)js * S.nq + ei];
-  const uint8_t* mref = B.allele_bytes + site_g->ref_off;
-  const bool nonref = sflags & 1u, remap = sflags & 2u, g_suppressed = sflags & 4u;
-  constexpr int o_f0 = GT ? 1 : 0;
-  if ((uint32_t)tid < A_m) s_ah[tid] = B.allele_hash[allele_first + tid];
+  if (active) ent = B.nt[(uint64_t)st.js * S.nq + ei];
+  if ((uint32_t)tid < st.A_m) s_ah[tid] = B.allele_hash[site_g->allele_first + tid];
   for (uint32_t g = tid; g < ((jk_n + 3u) & ~3u) && g < (uint32_t)TILE_MAX_G + 6u; g += NT_THREADS) s_jk[g] = tabs.jk[g];   // whole quads: the tail is read, then discarded
-  for (uint32_t m = gl; m < A_m; m += NT_GL) s_m2in[grp][m] = m == 0 ? 0 : -1;
-
-  // ---- the call
-  const uint32_t q = ent.x;
-  const uint64_t sq = (uint64_t)js * S.nq + q;
-  const bool reduced = (ent.y & NT_REDUCED) != 0;
-  uint32_t n_alt = 0, nr_idx = 0, gt_len = 0, ploidy = 0;
-  const uint32_t* gt = nullptr; const uint32_t* fin[NF]; uint32_t fn[NF];
-#pragma unroll
-  for (int f = 0; f < NF; ++f) { fin[f] = nullptr; fn[f] = 0; }
-  WarmView wv{};
-  const uint32_t H0 = warm_hash_word((uint32_t)A.n_fields);
-  if (active) {
-    if (reduced) {
-      const uint32_t cell = ent.y & ~NT_REDUCED;
-      const DelRec* dr = find_delrec(S, cell);
-      const CellDesc d = A.desc[cell];
-      n_alt = dr->n_alt; nr_idx = dr->has_nr ? 2u : 0u;
-      gt_len = (d.flags & F_GTVALID) ? d.gt_len : 0u; ploidy = gt_len ? ploidy_of(A.gt_phased, gt_len) : 0u;
-      gt = S.del_words + dr->gt_off;
-#pragma unroll
-      for (int f = 0; f < NF; ++f) { const uint32_t n = dr->f_len[f]; fn[f] = n == 0xFFFFFFFFu ? 0u : n; fin[f] = S.del_words + dr->f_off[f]; }
-    } else {
-      wv = warm_view(A, ent.y);
-      n_alt = wv.n_alt; nr_idx = wv.nr_idx; gt_len = wv.gt_len; ploidy = wv.ploidy;
-      gt = wv.b + H0 + 3u * n_alt;
-      const uint32_t* p = gt + gt_len;
-#pragma unroll
-      for (int f = 0; f < NF; ++f) { fn[f] = wv.b[4 + f]; fin[f] = p; p += fn[f]; }
-    }
-  }
-  const uint32_t A_in = n_alt + 1u;
   __syncthreads();
-  // ---- allele LUT (merge_alt_alleles' add_input_merged_idx_pair calls for this call, variant_operations.cc:160-227)
-  if (active) {
-    if (gl == 0) s_in2m[grp][0] = 0;
-    for (uint32_t t = gl; t < n_alt && t + 1u < (uint32_t)TILE_MAX_A; t += NT_GL) {
-      const uint32_t idx = t + 1u;
-      int m = -1;
-      if (remap) {
-        uint64_t h = 0;
-        if (reduced) { if (idx == 1) h = star_hash(); }
-        else h = warm_token_hash(wv, H0, t, mref, mref_len);
-        if (h) for (uint32_t mm = 1; mm < A_m; ++mm) if (s_ah[mm] == h) { m = (int)mm; break; }
-      }
-      if (nr_idx && idx == nr_idx) m = (int)A_m - 1;
-      s_in2m[grp][idx] = (int8_t)m;
-      if (remap && m >= 0) atomicMax(&s_m2in[grp][m], (int)idx);   // a merged allele named twice by one call: the last one wins
-    }
-  }
-  __syncwarp();
-  if (active && remap) {
-    const int in_nr = (nonref && nr_idx) ? (int)nr_idx : -1;   // NON_REF fallback folded in
-    for (uint32_t m = gl; m < A_m; m += NT_GL) {
-      int a = s_m2in[grp][m];
-      if (a < 0) a = in_nr;
-      s_m2in[grp][m] = a < 0 ? -1 : (a | ((a * (a + 1) / 2) << 8));
-    }
-  }
-  __syncwarp();
-  if (!active) return;
-  const int* m2in = s_m2in[grp];
-  if (O.lut_first) {
-    uint32_t first = 0;
-    if (gl == 0) { first = atomicAdd(&B.cursors[2], A_in); if (first + A_in > O.cap_lut) { atomicOr(&S.err[2], 2u); first = 0xFFFFFFFFu; } O.lut_first[sq] = first; O.lut_len[sq] = (uint16_t)A_in; }
-    first = __shfl_sync(__activemask(), first, 0, NT_GL);
-    if (first != 0xFFFFFFFFu) for (uint32_t i = gl; i < A_in; i += NT_GL) O.lut_in2m[first + i] = (int16_t)s_in2m[grp][i];
-  }
-  // ---- GT (variant_operations.cc:233-263)
-  if (GT) {
-    const FieldOutDev fo = O.f[0];
-    const uint32_t gs = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + (uint64_t)q * gs;
-    const uint32_t step = A.gt_phased ? 2u : 1u;
-    for (uint32_t i = gl; i < gs; i += NT_GL) {
-      uint32_t val = BCF_INT_VEND;
-      if (i < gt_len) {
-        const uint32_t g = gt[i]; val = g;
-        if (remap && (i % step) == 0 && !(g == TDB_NULL_INT || g == 0xFFFFFFFFu || g == BCF_INT_MISSING)) {
-          const int m = g < A_in ? (int)s_in2m[grp][g] : -1;
-          val = m < 0 ? (nonref ? A_m - 1u : 0xFFFFFFFFu) : (uint32_t)m;
-        }
-      }
-      dst[i] = val;
-    }
-    if (gl == 0) fo.len[sq] = (uint16_t)gt_len;
-  }
-  // ---- allele-dependent fields (variant_field_handler.cc:41-191)
-#pragma unroll
-  for (int f = 0; f < NF; ++f) {
-    const FieldOutDev fo = O.f[o_f0 + f];
-    const int kind = A.fm[f].kind, elem = A.fm[f].elem;
-    const uint32_t pad = vend_word(elem), miss = missing_word(elem);
-    const uint32_t n = fn[f]; const uint32_t* in = fin[f];
-    uint32_t n_out = 0;
-    if (n && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, ploidy) : n;
-    const uint32_t stride = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + (uint64_t)q * stride;
-    if (gl == 0) fo.len[sq] = (uint16_t)n_out;
-    // s_m2in[m] = input allele of merged allele m (NON_REF fallback folded in), or -1; the diploid loop wants it packed
-    // with its triangular number: a | a(a+1)/2 << 8 (still negative when there is no input allele)
-    if (remap && (stride & 3u) == 0 && kind == KIND_G && ploidy == 2) {
-      uint4* dst4 = reinterpret_cast<uint4*>(dst);
-      for (uint32_t qd = gl; qd < (stride >> 2); qd += NT_GL) {
-        const uint2 jk4 = *reinterpret_cast<const uint2*>(&s_jk[4 * qd]);   // (k << 8 | j) of words 4qd .. 4qd+3
-        uint32_t w[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const uint32_t jk = ((x < 2 ? jk4.x : jk4.y) >> (16 * (x & 1))) & 0xFFFFu;
-          const int pj = m2in[jk & 0xFF], pk = m2in[jk >> 8];
-          const uint32_t aj = (uint32_t)pj & 0xFFu, ak = (uint32_t)pk & 0xFFu;
-          const uint32_t ig = aj > ak ? ((uint32_t)pj >> 8) + ak : ((uint32_t)pk >> 8) + aj;
-          uint32_t v = miss;
-          if ((pj | pk) >= 0 && ig < n) v = in[ig];
-          w[x] = (4 * qd + x < n_out) ? v : pad;
-        }
-        dst4[qd] = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    } else if (remap && (stride & 3u) == 0 && kind == KIND_R) {
-      // R field (AD): out[j] = in[input allele of merged allele j]
-      uint4* dst4 = reinterpret_cast<uint4*>(dst);
-      for (uint32_t qd = gl; qd < (stride >> 2); qd += NT_GL) {
-        uint32_t w[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const uint32_t j = 4 * qd + x;
-          uint32_t v = pad;
-          if (j < n_out) { const int pj = m2in[j]; const uint32_t a = (uint32_t)pj & 0xFFu; v = (pj >= 0 && a < n) ? in[a] : miss; }
-          w[x] = v;
-        }
-        dst4[qd] = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    } else {
-      const int mode = !remap ? 0 : ((kind == KIND_G && ploidy == 2) ? 1 : ((kind == KIND_G && ploidy == 0) ? 2 : (kind == KIND_A ? 3 : 4)));
-      auto word = [&](uint32_t g) -> uint32_t {
-        if (g >= n_out) return pad;
-        if (mode == 0) return in[g];
-        if (mode == 1) {
-          const uint32_t jk = s_jk[g];
-          const int pj = m2in[jk & 0xFF], pk = m2in[jk >> 8];
-          if ((pj | pk) < 0) return miss;
-          const uint32_t aj = (uint32_t)pj & 0xFFu, ak = (uint32_t)pk & 0xFFu;
-          const uint32_t ig = aj > ak ? ((uint32_t)pj >> 8) + ak : ((uint32_t)pk >> 8) + aj;
-          return ig < n ? in[ig] : miss;
-        }
-        if (mode == 2) return in[0];
-        const int pj = m2in[mode == 3 ? g + 1u : g];
-        const int ij = pj < 0 ? -1 : (pj & 0xFF);
-        const int ix = mode == 3 ? ij - 1 : ij;
-        return (ij < 0 || ix < 0 || (uint32_t)ix >= n) ? miss : in[ix];
-      };
-      if (remap && (stride & 3u) == 0) {   // 16-byte aligned vector: one quad per lane
-        uint4* dst4 = reinterpret_cast<uint4*>(dst);
-        for (uint32_t qd = gl; qd < (stride >> 2); qd += NT_GL) dst4[qd] = make_uint4(word(4 * qd), word(4 * qd + 1), word(4 * qd + 2), word(4 * qd + 3));
-      } else {
-        for (uint32_t g = gl; g < stride; g += NT_GL) dst[g] = word(g);
-      }
-    }
-  }
+  nt_entry<NF, GT>(A, S, B, O, st, s_jk, s_ah, s_m2in[grp], s_in2m[grp], active, ent, gl);
 }
 
 }  // namespace gdb
