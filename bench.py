@@ -294,7 +294,7 @@ def main():
         tj = json.load(open(tpath))
         traffic = tj["k5_dram_bytes_per_site"] * sites / remap_n
         traffic_src = "profiles/r01_k5_traffic.json (ncu, bytes per site of the same shard) x sites per launch"
-    roofline = dict(bound="hbm", kernel="gdb::k_remap_tile + gdb::k_copy_tile + gdb::k_remap_nt (K5 remap)", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+    roofline = dict(bound="hbm", kernel="gdb::k_remap_tile (+ gdb::k_copy_tile for sites that need no remap, gdb::k_remap_nt for their rare non-trivial calls): K5 remap", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                     traffic_source=traffic_src, algorithmic_bytes_per_launch=(b_in_step + b_out_step) * args.steps / max(1, remap_n),
                     peak_source=peak_src, algorithmic_bytes_per_step=dict(b_in=b_in_step, b_out=b_out_step),
                     launches=int(remap_n), avg_launch_ms=remap_ms / max(1, remap_n),
