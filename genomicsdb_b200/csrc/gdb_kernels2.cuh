@@ -1130,6 +1130,10 @@ __global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_consta
 #pragma unroll
         for (int f = 0; f < NF; ++f) s_info[tid * NF + f] = 0;
         s_ntl[atomicAdd(&s_nnt, 1u)] = make_uint2(q, (e & LIVE_REDUCED) ? (NT_REDUCED | (uint32_t)(e & (LIVE_REDUCED - 1))) : h0.w);
+        if (!(e & LIVE_REDUCED)) {   // pull the call's warm blob (h1.x words at 16-byte unit h0.w) into L2 while phase B streams
+          const char* blob = reinterpret_cast<const char*>(A.warm) + (uint64_t)h0.w * 16u;
+          for (uint32_t off = 0; off < h1.x * 4u; off += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(blob + off));
+        }
       } else {
         // ---- trivial call, fully described by its hot record
         const uint32_t fl4 = (h0.y >> 16) | (h0.z << 16);
