@@ -22,7 +22,7 @@ CALL_REDUCED = 0x40000000
 KIND = {"R": LEN_R, "A": LEN_A, "G": LEN_G}
 
 EXPORTS = ["gdbgpu_version", "gdbgpu_ctx_create", "gdbgpu_ctx_destroy", "gdbgpu_last_error", "gdbgpu_ctx_stream",
-           "gdbgpu_ctx_launch_count", "gdbgpu_ctx_synchronize", "gdbgpu_ctx_set_profiling",
+           "gdbgpu_ctx_launch_count", "gdbgpu_ctx_synchronize", "gdbgpu_ctx_release_cached_memory", "gdbgpu_ctx_set_profiling",
            "gdbgpu_ctx_reset_kernel_stats", "gdbgpu_ctx_kernel_stats", "gdbgpu_array_open", "gdbgpu_array_open_ex", "gdbgpu_array_from_columns", "gdbgpu_array_get_info",
            "gdbgpu_array_copy_cells", "gdbgpu_array_close", "gdbgpu_scan_begin", "gdbgpu_scan_get_info",
            "gdbgpu_scan_next_batch", "gdbgpu_scan_seek", "gdbgpu_scan_end"]
@@ -104,6 +104,7 @@ def lib():
         L.gdbgpu_ctx_launch_count.restype = C.c_uint64
         L.gdbgpu_ctx_launch_count.argtypes = [C.c_void_p]
         L.gdbgpu_ctx_synchronize.argtypes = [C.c_void_p]
+        L.gdbgpu_ctx_release_cached_memory.argtypes = [C.c_void_p]
         L.gdbgpu_ctx_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.gdbgpu_ctx_reset_kernel_stats.argtypes = [C.c_void_p]
         L.gdbgpu_ctx_kernel_stats.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
@@ -158,6 +159,9 @@ class Context:
 
     def synchronize(self):
         self.check(lib().gdbgpu_ctx_synchronize(self.h))
+
+    def release_cached_memory(self):
+        self.check(lib().gdbgpu_ctx_release_cached_memory(self.h))
 
     def set_profiling(self, on):
         lib().gdbgpu_ctx_set_profiling(self.h, int(on))

@@ -1058,6 +1058,16 @@ int gdbgpu_ctx_synchronize(gdbgpu_ctx* ctx) {
   if (!ctx) return GDBGPU_ERR_ARG;
   return (cudaStreamSynchronize(ctx->stream) == cudaSuccess && cudaStreamSynchronize(ctx->copy_stream) == cudaSuccess) ? GDBGPU_OK : GDBGPU_ERR_CUDA;
 }
+int gdbgpu_ctx_release_cached_memory(gdbgpu_ctx* ctx) {
+  if (!ctx) return GDBGPU_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess) return GDBGPU_ERR_CUDA;
+  for (auto* b : ctx->bb_pool) { tl_ctx = ctx; delete b; }
+  ctx->bb_pool.clear();
+  for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+  ctx->free_blocks.clear(); ctx->cached_bytes = 0;
+  return GDBGPU_OK;
+}
 const char* gdbgpu_last_error(const gdbgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
 void* gdbgpu_ctx_stream(gdbgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t gdbgpu_ctx_launch_count(const gdbgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }

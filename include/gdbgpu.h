@@ -108,6 +108,9 @@ void* gdbgpu_ctx_stream(gdbgpu_ctx* ctx);
 /* number of kernel launches issued by this context so far */
 uint64_t gdbgpu_ctx_launch_count(const gdbgpu_ctx* ctx);
 int gdbgpu_ctx_synchronize(gdbgpu_ctx* ctx);
+/* Device memory given back by closed arrays / ended scans is kept by the context and reused by later opens and scans (no
+ * cudaMalloc / cudaFree in steady state).  This call returns what is currently cached to the driver. */
+int gdbgpu_ctx_release_cached_memory(gdbgpu_ctx* ctx);
 /* Per-kernel device time, measured with CUDA events on the launching stream (the reference's DO_PROFILING timers,
  * query_variants.h:67-124, have this role).  Off by default; stats are summed over kernels whose name contains
  * `kernel_name` (e.g. "k_remap"). */

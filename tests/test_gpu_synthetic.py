@@ -222,3 +222,31 @@ def test_corrupt_compressed_tile_is_reported(ctx, tmp_path):
     with pytest.raises(capi.GdbGpuError) as e:
         capi.Array.open(ctx, ws, "syn", [("AD", "R", "int"), ("PL", "G", "int")])
     assert e.value.code == capi.ERR_IO and "inflate" in str(e.value)
+
+
+def test_cached_device_memory_is_reused_and_can_be_released(ctx):
+    """array open / close cycles reuse the context's cached device blocks; gdbgpu_ctx_release_cached_memory gives them back"""
+    import torch
+    from genomicsdb_b200 import capi
+    d = gdbsyn.generate(n_samples=2000, n_sites=400, spacing=100, p_var=0.1, a_pool=8)
+    want = None
+    for it in range(4):
+        arr = gdbsyn.to_gpu_array(ctx, d)
+        sc = capi.Scan(arr)
+        chunks = []
+        while True:
+            bv = sc.next_batch()
+            if bv is None:
+                break
+            chunks.append(bv.fields[2]["data"].copy())
+        sc.close()
+        arr.close()
+        got = np.concatenate(chunks)
+        if want is None:
+            want = got
+        assert np.array_equal(got, want)
+        if it == 1:
+            free0 = torch.cuda.mem_get_info()[0]
+    assert torch.cuda.mem_get_info()[0] == free0          # steady state: nothing new from the driver
+    ctx.release_cached_memory()
+    assert torch.cuda.mem_get_info()[0] > free0
