@@ -260,13 +260,14 @@ def main():
     torch.cuda.synchronize()
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = ctx.launches - launches0
+    ctx.set_profiling(False)      # kernel statistics stay readable; nothing below adds to them
     # a short timed region may end before nvidia-smi has answered twice: keep the same load running (untimed) until the
     # sampler holds a few readings taken under it
     t_extra = time.time()
     while len(sampler.rows) < 4 and time.time() - t_extra < 3.0:
         one_pass(arr, capi.SCAN_DEVICE_OUTPUT)
     sampler.stop_flag = True
-    launches = ctx.launches - launches0
     remap_ms, remap_n = ctx.kernel_stats("k_remap")
     copy0_ms, _ = ctx.kernel_stats("k_copy_tile")
     remap_ms += copy0_ms   # K5 = k_remap_tile + k_copy_tile + k_remap_nt; remap_n stays the number of tile+nt launches
