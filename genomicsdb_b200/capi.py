@@ -59,7 +59,8 @@ class ArrayInfo(C.Structure):
 class ScanParams(C.Structure):
     _fields_ = [("col_lo", C.c_int64), ("col_hi", C.c_int64), ("query_rows", C.c_void_p), ("n_query_rows", C.c_uint64),
                 ("flags", C.c_uint32), ("max_diploid_alt_alleles", C.c_uint32),
-                ("dp_info_field", C.c_uint32), ("dp_min_dp_field", C.c_uint32), ("dp_format_field", C.c_uint32)]
+                ("dp_info_field", C.c_uint32), ("dp_min_dp_field", C.c_uint32), ("dp_format_field", C.c_uint32),
+                ("esum_remapped_mask", C.c_uint32)]
 
 
 class ScanInfo(C.Structure):
@@ -80,7 +81,7 @@ class Batch(C.Structure):
                 ("lut_first", C.c_void_p), ("lut_len", C.c_void_p), ("lut_in2m", C.c_void_p), ("out_bytes", C.c_uint64),
                 ("n_fmt_fields", C.c_int32), ("fmt_type", C.c_void_p), ("fmt_nps", C.c_void_p), ("fmt_offset", C.c_void_p), ("fmt_bytes", C.c_void_p),
                 ("fmt_total_bytes", C.c_uint64), ("info_valid", C.c_void_p), ("info_value", C.c_void_p),
-                ("info_dp_sum", C.c_void_p)]
+                ("info_dp_sum", C.c_void_p), ("vec_len", C.c_void_p), ("vec_offset", C.c_void_p), ("vec_values", C.c_void_p)]
 
 
 _lib = None
@@ -193,7 +194,7 @@ def _plain_descs(plain):
     info_op: None | 'median' | 'sum' | 'mean'"""
     arr = (PlainFieldDesc * max(1, len(plain)))()
     code = {"int": ELEM_INT32, "float": ELEM_FLOAT32, "char": ELEM_CHAR}
-    ops = {None: 0, "median": 1, "sum": 2, "mean": 3}
+    ops = {None: 0, "median": 1, "sum": 2, "mean": 3, "element_wise_sum": 4}
     for i, p in enumerate(plain):
         name, elem, fixed = p[:3]
         arr[i] = PlainFieldDesc(name.encode(), code.get(elem, elem), int(fixed), int(bool(p[3])) if len(p) > 3 else 0,
@@ -318,6 +319,7 @@ class BatchView:
             self.info_valid = _view(b.info_valid, np.uint8, npl * ns).reshape(npl, ns)
             self.info_value = _view(b.info_value, np.uint32, npl * ns).reshape(npl, ns)
             self.info_dp_sum = _view(b.info_dp_sum, np.int32, ns)
+            self._vec = (b.vec_len, b.vec_offset, b.vec_values)
         else:
             self.fmt_type = None
         self.lut_first = _view(b.lut_first, np.uint32, ns * nq).reshape(ns, nq) if b.lut_first else None
@@ -339,14 +341,22 @@ class BatchView:
         nps, off = int(self.fmt_nps[o, s]), int(self.fmt_offset[o, s])
         return t, nps, bytes(self.fmt_bytes[off:off + self.nq * nps * BT_SIZE[t]])
 
+    def info_vector(self, slot, s, n_slots):
+        """element-wise sum of vector slot `slot` (remapped field f, or n_remapped + plain index) at site s as uint32 words"""
+        ln = _view(self._vec[0], np.uint32, n_slots * self.n_sites).reshape(n_slots, self.n_sites)
+        off = _view(self._vec[1], np.uint64, n_slots * self.n_sites).reshape(n_slots, self.n_sites)
+        n = int(ln[slot, s])
+        return _view(self._vec[2] + 4 * int(off[slot, s]), np.uint32, n).copy() if n else np.zeros(0, dtype=np.uint32)
+
     def lut(self, s, q):
         first = int(self.lut_first[s, q])
         return _view(self._lut_ptr + 2 * first, np.int16, int(self.lut_len[s, q]))
 
 
 class Scan:
-    def __init__(self, arr, col_lo=None, col_hi=None, query_rows=None, flags=0, max_alt=0, dp_fields=(0, 0, 0)):
-        """dp_fields: 1-based plain-field indices of (INFO DP, MIN_DP, DP_FORMAT) for the DP rule, 0 = absent"""
+    def __init__(self, arr, col_lo=None, col_hi=None, query_rows=None, flags=0, max_alt=0, dp_fields=(0, 0, 0), esum_remapped_mask=0):
+        """dp_fields: 1-based plain-field indices of (INFO DP, MIN_DP, DP_FORMAT) for the DP rule, 0 = absent;
+        esum_remapped_mask: bit f = element-wise sum of remapped field f over the valid calls"""
         self.arr, self.ctx = arr, arr.ctx
         p = ScanParams()
         if col_lo is None:
@@ -359,6 +369,7 @@ class Scan:
             p.query_rows, p.n_query_rows = self._rows.ctypes.data, len(self._rows)
         p.flags, p.max_diploid_alt_alleles = flags, max_alt
         p.dp_info_field, p.dp_min_dp_field, p.dp_format_field = dp_fields
+        p.esum_remapped_mask = esum_remapped_mask
         self.h = C.c_void_p()
         self.ctx.check(lib().gdbgpu_scan_begin(arr.h, C.byref(p), C.byref(self.h)))
         i = arr.info()

@@ -443,6 +443,7 @@ struct BatchBuffers {
   DevBuf<int32_t> fmt_mm; DevBuf<uint8_t> fmt_bytes;
   DevBuf<uint32_t> info_vals, info_cnt, info_value_d; DevBuf<uint8_t> info_valid_d; DevBuf<int32_t> dp_sum_d;
   std::vector<uint32_t> h_info_value; std::vector<uint8_t> h_info_valid; std::vector<int32_t> h_dp_sum;
+  DevBuf<uint32_t> esum_values, esum_lens; std::vector<uint32_t> h_vec_len, h_vec_values, h_esum_raw; std::vector<uint64_t> h_vec_off;
   std::vector<int32_t> h_fmt_mm; std::vector<uint8_t> h_fmt_type; std::vector<uint32_t> h_fmt_nps; std::vector<uint64_t> h_fmt_off;
   PinBuf<uint8_t> p_fmt_bytes;
   // state of the batch these buffers hold
@@ -465,6 +466,7 @@ struct gdbgpu_scan {
   std::unique_ptr<BatchBuffers> slot[2];   // borrowed from the context's pool for the lifetime of the scan; [cur] = batch being handed out, the other = prefetched
   int cur = 0; bool bcf_format = false, prefetch = true; int produce_gt = 0;
   InfoSet info{};   // INFO scalars to combine + the DP rule's fields (GDBGPU_SCAN_BCF_FORMAT)
+  EsumSet esum{};   // vector fields combined with an element-wise sum
   uint32_t cap_allele_recs = 0, cap_allele_bytes = 0, cap_lut = 0;
   uint64_t avg_site_bytes = 0;
   int n_out = 0;
@@ -498,7 +500,12 @@ void scan_prepare(gdbgpu_scan* s) {
   s->produce_gt = (p.flags & GDBGPU_SCAN_PRODUCE_GT) ? 1 : 0;
   s->prefetch = !(p.flags & GDBGPU_SCAN_NO_PREFETCH);
   s->info.n = 0;
-  for (size_t f = 0; f < a->pm.size(); ++f) if (a->pm[f].info_op) { s->info.field[s->info.n] = (int32_t)f; s->info.op[s->info.n] = a->pm[f].info_op; ++s->info.n; }
+  s->esum.n = 0;
+  for (size_t f = 0; f < a->fields.size(); ++f) if (p.esum_remapped_mask & (1u << f)) { s->esum.remapped[s->esum.n] = 1; s->esum.index[s->esum.n] = (int32_t)f; ++s->esum.n; }
+  for (size_t f = 0; f < a->pm.size(); ++f) {
+    if (a->pm[f].info_op == GDBGPU_INFO_ELEMENT_WISE_SUM) { s->esum.remapped[s->esum.n] = 0; s->esum.index[s->esum.n] = (int32_t)f; ++s->esum.n; }
+    else if (a->pm[f].info_op) { s->info.field[s->info.n] = (int32_t)f; s->info.op[s->info.n] = a->pm[f].info_op; ++s->info.n; }
+  }
   auto dp_index = [&](uint32_t one_based) -> int32_t {
     if (!one_based) return -1;
     if (one_based > a->pm.size() || a->pm[one_based - 1].fixed_len < 1 || a->pm[one_based - 1].elem != ELEM_INT32) throw ArgError("DP rule: not a fixed-length int32 plain field");
@@ -829,8 +836,28 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
         }
         CK(cudaMemcpyAsync(bb.h_dp_sum.data(), bb.dp_sum_d.p, (size_t)keep * 4, cudaMemcpyDeviceToHost, ctx->stream));
       }
+      const int n_vec_slots = (int)a->fields.size() + n_plain, n_esum = s->esum.n;
+      bb.h_vec_len.assign((size_t)n_vec_slots * keep, 0); bb.h_vec_off.assign((size_t)n_vec_slots * keep, 0); bb.h_vec_values.clear();
+      std::vector<uint32_t> h_esum_len;
+      if (n_esum) {   // element-wise sums: fixed-capacity slots on the device, compacted on the host below
+        bb.esum_values.ensure((uint64_t)n_esum * keep * ESUM_CAP); bb.esum_lens.ensure((uint64_t)n_esum * keep);
+        LAUNCH(ctx, k_info_esum, dim3(keep, n_esum), ESUM_THREADS, a->dev, a->plain_dev, O, s->esum, bb.live.p, reinterpret_cast<const int32_t*>(bb.fmt_mm.p + 2 * n_rp), keep,
+               (uint32_t)S.nq, bb.esum_values.p, bb.esum_lens.p, s->err.p);
+        h_esum_len.resize((size_t)n_esum * keep); bb.h_esum_raw.resize((size_t)n_esum * keep * ESUM_CAP);
+        CK(cudaMemcpyAsync(h_esum_len.data(), bb.esum_lens.p, h_esum_len.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(bb.h_esum_raw.data(), bb.esum_values.p, bb.h_esum_raw.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      }
       CK(cudaMemcpyAsync(bb.h_fmt_mm.data(), bb.fmt_mm.p, bb.h_fmt_mm.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
+      for (int v = 0; v < n_esum; ++v) {
+        const int slot = s->esum.remapped[v] ? s->esum.index[v] : (int)a->fields.size() + s->esum.index[v];
+        for (uint32_t i = 0; i < keep; ++i) {
+          const uint32_t n = h_esum_len[(size_t)v * keep + i];
+          bb.h_vec_len[(size_t)slot * keep + i] = n; bb.h_vec_off[(size_t)slot * keep + i] = bb.h_vec_values.size();
+          const uint32_t* src = bb.h_esum_raw.data() + ((size_t)v * keep + i) * ESUM_CAP;
+          bb.h_vec_values.insert(bb.h_vec_values.end(), src, src + n);
+        }
+      }
       // bcf_enc_vint's width rule (vcf.c:1926-1972); a block of ONE value goes through bcf_enc_int1 instead (vcf.c:1931)
       auto int_type = [&](int64_t lo, int64_t hi, uint64_t n_values) -> uint8_t {
         if (n_values == 1) {
@@ -921,6 +948,7 @@ void publish_batch(gdbgpu_scan* s, BatchBuffers& bb, gdbgpu_batch* out) {
   const uint32_t* e = bb.p_tail.p;
   if (e[0]) throw OverlapError("Unhandled overlapping variants (a call that is neither a deletion nor a reference block is overlapped by a later call of the same sample)");
   if (e[1] == 3) throw LimitError("ploidy above 8 needs the general-ploidy genotype enumeration, which keeps at most 8 slots");
+  if (e[1] == 5) throw LimitError("element-wise INFO sum over a vector longer than 1024 values");
   if (e[1]) throw LimitError("engine limit exceeded in the remap kernels");
   if (e[2]) throw CudaError("internal: LUT pool overflow");
   const uint32_t keep = bb.keep; const int n_out = s->n_out;
@@ -947,7 +975,10 @@ void publish_batch(gdbgpu_scan* s, BatchBuffers& bb, gdbgpu_batch* out) {
   }
   out->fmt_total_bytes = bb.fmt_total;
   out->n_fmt_fields = s->bcf_format ? n_out + (int)a->plain.size() : 0;
-  if (s->bcf_format) { out->info_valid = bb.h_info_valid.data(); out->info_value = bb.h_info_value.data(); out->info_dp_sum = bb.h_dp_sum.data(); }
+  if (s->bcf_format) {
+    out->info_valid = bb.h_info_valid.data(); out->info_value = bb.h_info_value.data(); out->info_dp_sum = bb.h_dp_sum.data();
+    out->vec_len = bb.h_vec_len.data(); out->vec_offset = bb.h_vec_off.data(); out->vec_values = bb.h_vec_values.data();
+  }
   (void)a;
 }
 
@@ -1097,7 +1128,8 @@ int gdbgpu_array_from_columns(gdbgpu_ctx* ctx, const gdbgpu_columns* c, gdbgpu_a
       if (d.elem_type < 0 || d.elem_type > GDBGPU_ELEM_CHAR || d.fixed_len < 0) throw ArgError("bad plain field descriptor");
       if (!d.fixed_len && !c->plain_fields[f].offsets) throw ArgError("variable-length plain field without offsets");
       h.plain.push_back(HostVar{d.fixed_len ? nullptr : c->plain_fields[f].offsets, c->plain_fields[f].values, c->plain_fields[f].values_bytes});
-      if (d.info_op && (d.fixed_len < 1 || d.elem_type == GDBGPU_ELEM_CHAR)) throw ArgError("an INFO combine operation needs a fixed-length 4-byte field");
+      if (d.info_op && d.info_op != GDBGPU_INFO_ELEMENT_WISE_SUM && (d.fixed_len < 1 || d.elem_type == GDBGPU_ELEM_CHAR)) throw ArgError("an INFO combine operation needs a fixed-length 4-byte field");
+      if (d.info_op == GDBGPU_INFO_ELEMENT_WISE_SUM && d.elem_type == GDBGPU_ELEM_CHAR) throw ArgError("element-wise sum of a string field");
       pm.push_back(PlainMeta{d.name ? d.name : "", d.elem_type, d.fixed_len, d.no_format, d.info_op});
     }
     *out = build_array(ctx, h, {h.n}, c->lb_row_idx, c->num_rows, c->gt_phased, fm, names, pm);
@@ -1137,7 +1169,7 @@ int gdbgpu_array_open_ex(gdbgpu_ctx* ctx, const char* workspace, const char* arr
       const int fixed = sc.is_var(id) ? 0 : sc.cell_val_num[id];
       if (plain[f].fixed_len != fixed) throw std::runtime_error(std::string("plain field length does not match the array schema: ") + plain[f].name);
       ids.push_back(id);
-      if (plain[f].info_op && (fixed < 1 || plain[f].elem_type == GDBGPU_ELEM_CHAR)) throw std::runtime_error(std::string("an INFO combine operation needs a fixed-length 4-byte field: ") + plain[f].name);
+      if (plain[f].info_op && ((plain[f].info_op != GDBGPU_INFO_ELEMENT_WISE_SUM && fixed < 1) || plain[f].elem_type == GDBGPU_ELEM_CHAR)) throw std::runtime_error(std::string("an INFO combine operation needs a 4-byte field (fixed-length unless element-wise): ") + plain[f].name);
       pm.push_back(PlainMeta{plain[f].name, plain[f].elem_type, fixed, plain[f].no_format, plain[f].info_op});
     }
     // Every needed column of every fragment goes to HBM as it lies on disk; compressed tiles are inflated there (k_inflate,

@@ -186,6 +186,19 @@ void enc_size(std::vector<uint8_t>& b, int size, int type) {
   else b.push_back((uint8_t)(size << 4 | type));
 }
 void enc_vchar(std::vector<uint8_t>& b, const std::string& s) { enc_size(b, (int)s.size(), BT_CHAR); put_bytes(b, s.data(), s.size()); }
+// bcf_enc_vint (vcf.c:1926-1972) with wsize = -1: one vector of n values
+void enc_vint(std::vector<uint8_t>& b, const int32_t* a, uint32_t n) {
+  if (n == 1) { enc_int1(b, a[0]); return; }
+  int32_t mx = INT32_MIN + 1, mn = INT32_MAX;
+  for (uint32_t i = 0; i < n; ++i) { if (a[i] == INT32_MIN || a[i] == INT32_MIN + 1) continue; mx = std::max(mx, a[i]); mn = std::min(mn, a[i]); }
+  if (mx <= 127 && mn > -127) {
+    enc_size(b, (int)n, BT_INT8);
+    for (uint32_t i = 0; i < n; ++i) b.push_back(a[i] == INT32_MIN + 1 ? 0x81 : (a[i] == INT32_MIN ? 0x80 : (uint8_t)(int8_t)a[i]));
+  } else if (mx <= 32767 && mn > -32767) {
+    enc_size(b, (int)n, BT_INT16);
+    for (uint32_t i = 0; i < n; ++i) put<int16_t>(b, a[i] == INT32_MIN + 1 ? (int16_t)-32767 : (a[i] == INT32_MIN ? (int16_t)-32768 : (int16_t)a[i]));
+  } else { enc_size(b, (int)n, BT_INT32); put_bytes(b, a, (size_t)n * 4); }
+}
 }  // namespace
 
 BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, const VidMapper& id_mapper, const VariantQueryConfig& qc)
@@ -207,23 +220,29 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
     const FieldInfo* fi = id_mapper.get_field_info(name);
     if (!fi) continue;
     const int ri = remapped_index(name);
+    const int gt_shift = remapped_index("GT") >= 0 ? 1 : 0;
     if (ri >= 0) {
       const bool twin = name.size() > 7 && name.compare(name.size() - 7, 7, "_FORMAT") == 0;
       if ((fi->is_format && (twin || !fi->is_info)) || fi->combine_op == "move_to_FORMAT") m_FORMAT_fields_vec.push_back({name, key_of(name), ri});
+      else if (qc.get_element_wise_sum_mask() & (1u << (ri - gt_shift))) m_INFO_fields_vec.push_back({name, key_of(name), -1, fi->type == "float", ri - gt_shift});
       continue;
     }
     for (size_t p = 0; p < plain.size(); ++p) if (plain[p].attribute == name) {
-      if (plain[p].format) {
+      if (plain[p].is_qual) m_QUAL_plain = (int)p;
+      else if (plain[p].format) {
         if (name == "DP_FORMAT") dp_format_plain = (int)p;
         else m_FORMAT_fields_vec.push_back({plain[p].vcf_name, key_of(plain[p].vcf_name), (int)(n_remapped + p)});
-      } else if (plain[p].info_op)
-        m_INFO_fields_vec.push_back({plain[p].vcf_name, key_of(plain[p].vcf_name), (int)p, plain[p].elem == GDBGPU_ELEM_FLOAT32});
+      } else if (plain[p].info_op == GDBGPU_INFO_ELEMENT_WISE_SUM)
+        m_INFO_fields_vec.push_back({plain[p].vcf_name, key_of(plain[p].vcf_name), -1, plain[p].elem == GDBGPU_ELEM_FLOAT32, (int)(n_remapped - gt_shift + p)});
+      else if (plain[p].info_op)
+        m_INFO_fields_vec.push_back({plain[p].vcf_name, key_of(plain[p].vcf_name), (int)p, plain[p].elem == GDBGPU_ELEM_FLOAT32, -1});
     }
   }
   if (dp_format_plain >= 0) m_FORMAT_fields_vec.push_back({"DP", key_of("DP"), (int)(n_remapped + dp_format_plain)});
   m_dp_rule = qc.get_dp_rule_fields()[0] != 0 || qc.get_dp_rule_fields()[2] != 0;
   if (m_dp_rule) m_DP_key = key_of("DP");
   m_END_key = key_of("END");
+  m_num_vector_slots = n_remapped - (remapped_index("GT") >= 0 ? 1u : 0u) + (unsigned)plain.size();
 }
 
 // BroadCombinedGVCFOperator::operate (broad_combined_gvcf.cc:765-901) + bcf_write (htslib vcf.c) for one site
@@ -254,6 +273,17 @@ void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint3
     rlen = vcf_end - pos;
   }
   for (auto& f : m_INFO_fields_vec) {
+    if (f.vector_slot >= 0) {   // element-wise sum: typed vector (bcf_update_info -> bcf_enc_vint / bcf_enc_vfloat)
+      const uint64_t vs = (uint64_t)f.vector_slot * ns + s;
+      const uint32_t n = b.vec_len[vs];
+      if (!n) continue;
+      const uint32_t* v = b.vec_values + b.vec_offset[vs];
+      enc_int1(shared, f.key);
+      if (f.is_float) { enc_size(shared, (int)n, BT_FLOAT); put_bytes(shared, v, (size_t)n * 4); }
+      else enc_vint(shared, reinterpret_cast<const int32_t*>(v), n);
+      ++n_info;
+      continue;
+    }
     const uint64_t slot = (uint64_t)f.plain_index * ns + s;
     if (!b.info_valid[slot]) continue;
     enc_int1(shared, f.key);
@@ -279,7 +309,9 @@ void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint3
   put<uint32_t>(out, (uint32_t)(24 + shared.size()));
   put<uint32_t>(out, (uint32_t)indiv.size());
   put<int32_t>(out, rid); put<int32_t>(out, pos); put<int32_t>(out, rlen);
-  put<uint32_t>(out, 0x7F800001u);   // QUAL missing (GATK CombineGVCFs does not carry QUAL, broad_combined_gvcf.cc:796-808)
+  // QUAL: missing unless the vid mapping gives QUAL a combine operation (broad_combined_gvcf.cc:796-808)
+  const bool has_qual = m_QUAL_plain >= 0 && b.info_valid[(uint64_t)m_QUAL_plain * ns + s];
+  put<uint32_t>(out, has_qual ? b.info_value[(uint64_t)m_QUAL_plain * ns + s] : 0x7F800001u);
   put<uint32_t>(out, n_allele << 16 | n_info);
   put<uint32_t>(out, n_fmt << 24 | (uint32_t)nq);
   put_bytes(out, shared.data(), shared.size());
@@ -314,6 +346,7 @@ void VariantQueryProcessor::check(int rc) const {
 void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool, bool stage_broad_gvcf_fields) {
   const VidMapper& vid = qc.get_vid_mapper().is_initialized() ? qc.get_vid_mapper() : vid_;
   std::vector<gdbgpu_field_desc> fd;
+  unsigned esum_mask = 0;
   qc.remapped_names_.clear();
   qc.remapped_names_.push_back("GT");
   for (auto& name : qc.get_query_attributes()) {
@@ -323,16 +356,21 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool, b
     d.name = fi->name.c_str();
     d.length_kind = fi->length == "R" ? GDBGPU_LEN_R : (fi->length == "A" ? GDBGPU_LEN_A : GDBGPU_LEN_G);
     d.elem_type = fi->type == "float" ? GDBGPU_ELEM_FLOAT32 : GDBGPU_ELEM_INT32;
+    if (stage_broad_gvcf_fields && fi->is_info && !fi->is_format && fi->combine_op != "move_to_FORMAT") {
+      if (fi->combine_op == "element_wise_sum") esum_mask |= 1u << fd.size();
+      else if (!fi->combine_op.empty()) throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "INFO combine operation " + fi->combine_op + " of allele-dependent field " + name + " is not supported on the GPU");
+    }
     fd.push_back(d);
     qc.remapped_names_.push_back(fi->name);
   }
+  qc.esum_remapped_mask_ = esum_mask;
   const FieldInfo* gt = vid.get_field_info("GT");
   int phased = gt && gt->length == "PP";
   // what BroadCombinedGVCFOperator's constructor sorts the queried attributes into (broad_combined_gvcf.cc:160-240)
   qc.plain_.clear(); qc.dp_fields_[0] = qc.dp_fields_[1] = qc.dp_fields_[2] = 0;
   std::vector<gdbgpu_plain_field_desc> pd;
   if (stage_broad_gvcf_fields) {
-    static const char* skip[] = {"END", "REF", "ALT", "GT", "QUAL", "FILTER", "ID"};
+    static const char* skip[] = {"END", "REF", "ALT", "GT", "FILTER", "ID"};
     for (auto& name : qc.get_query_attributes()) {
       const FieldInfo* fi = vid.get_field_info(name);
       if (!fi || fi->is_allele_dependent()) continue;
@@ -347,9 +385,21 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool, b
       bool numeric_len = !fi->length.empty() && fi->length.find_first_not_of("0123456789") == std::string::npos;
       pf.fixed_len = numeric_len ? std::stoi(fi->length) : 0;
       const bool as_format = (fi->is_format && (twin || !fi->is_info)) || (fi->is_info && fi->combine_op == "move_to_FORMAT");
+      const bool scalar_op = fi->combine_op == "median" || fi->combine_op == "sum" || fi->combine_op == "mean";
+      if (name == "QUAL") {   // bcf1_t.qual through the field's combine operation, else missing (broad_combined_gvcf.cc:796-808)
+        if (!scalar_op) continue;
+        pf.is_qual = true; pf.fixed_len = 1; pf.elem = GDBGPU_ELEM_FLOAT32;
+        pf.info_op = fi->combine_op == "median" ? GDBGPU_INFO_MEDIAN : (fi->combine_op == "sum" ? GDBGPU_INFO_SUM : GDBGPU_INFO_MEAN);
+        qc.plain_.push_back(pf);
+        continue;
+      }
       if (as_format) pf.format = true;
+      else if (fi->is_info && fi->combine_op == "element_wise_sum") {
+        if (pf.elem == GDBGPU_ELEM_CHAR) throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "element-wise sum of a string field: " + name);
+        pf.info_op = GDBGPU_INFO_ELEMENT_WISE_SUM;
+      }
       else if (fi->is_info && name == "DP" && fi->combine_op == "DP") { /* DP rule input only */ }
-      else if (fi->is_info && (fi->combine_op == "median" || fi->combine_op == "sum" || fi->combine_op == "mean")) {
+      else if (fi->is_info && scalar_op) {
         if (pf.fixed_len != 1 || pf.elem == GDBGPU_ELEM_CHAR) throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "INFO combine operation on a non-scalar field: " + name);
         pf.info_op = fi->combine_op == "median" ? GDBGPU_INFO_MEDIAN : (fi->combine_op == "sum" ? GDBGPU_INFO_SUM : GDBGPU_INFO_MEAN);
       } else if (fi->is_info && !fi->combine_op.empty())
@@ -421,6 +471,7 @@ void VariantQueryProcessor::scan_and_operate(const int, const VariantQueryConfig
       p.flags |= GDBGPU_SCAN_BCF_FORMAT;
       if (qc.produce_GT_field()) p.flags |= GDBGPU_SCAN_PRODUCE_GT;
       p.dp_info_field = qc.dp_fields_[0]; p.dp_min_dp_field = qc.dp_fields_[1]; p.dp_format_field = qc.dp_fields_[2];
+      p.esum_remapped_mask = qc.esum_remapped_mask_;
     }
     if (!qc.query_all_rows()) { p.query_rows = qc.get_rows_to_query().data(); p.n_query_rows = qc.get_rows_to_query().size(); }
     p.max_diploid_alt_alleles = qc.get_max_diploid_alt_alleles_that_can_be_genotyped();

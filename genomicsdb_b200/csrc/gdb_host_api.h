@@ -112,12 +112,14 @@ class VariantQueryConfig {
   std::vector<std::string> remapped_names_;
   // plain fields staged for the Broad operator (do_query_bookkeeping): FORMAT fields that are not allele-dependent, scalar
   // INFO fields with a median / sum / mean combine operation, the inputs of the DP rule
-  struct PlainField { std::string attribute, vcf_name; int elem = 0, fixed_len = 0; bool format = false; int info_op = 0; };
+  struct PlainField { std::string attribute, vcf_name; int elem = 0, fixed_len = 0; bool format = false; int info_op = 0; bool is_qual = false; };
   std::vector<PlainField> plain_;
   unsigned dp_fields_[3] = {0, 0, 0};   // 1-based plain indices of INFO DP, MIN_DP, DP_FORMAT
+  unsigned esum_remapped_mask_ = 0;     // remapped fields (GT not counted) combined with an element-wise sum
  public:
   const std::vector<PlainField>& get_plain_fields() const { return plain_; }
   const unsigned* get_dp_rule_fields() const { return dp_fields_; }
+  unsigned get_element_wise_sum_mask() const { return esum_remapped_mask_; }
 };
 
 // ---- data model (include/genomicsdb/variant.h).  Views into the current batch: valid until the next operate() call.
@@ -228,7 +230,7 @@ class VCFAdapter {
 // broad_combined_gvcf.h: one BCF2 record per operate() call, appended to the adapter's buffer in serialised form
 // (u32 l_shared, u32 l_indiv, shared, indiv -- what bcf_write emits for an uncompressed BCF).  FORMAT blocks, INFO scalars
 // and the DP sum come from the kernels (GDBGPU_SCAN_BCF_FORMAT); this class adds the typed keys / size descriptors and the
-// fixed part of the record.  Not supported (throws): ID merge, FILTER, QUAL combine, 2-D / histogram / element-wise INFO.
+// fixed part of the record.  Not supported: 2-D / histogram / concatenate INFO operations (throws); ID merge and FILTER union are not produced.
 class BroadCombinedGVCFOperator : public GA4GHOperator {
  public:
   BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, const VidMapper& id_mapper, const VariantQueryConfig& query_config);
@@ -241,9 +243,10 @@ class BroadCombinedGVCFOperator : public GA4GHOperator {
   const VidMapper* m_vid_mapper;
   struct FormatField { std::string vcf_name; int key = -1; int fmt_index = -1; };   // fmt_index: index into the batch's fmt_* tables
   std::vector<FormatField> m_FORMAT_fields_vec;   // emission order: GT first, query order, DP last (broad_combined_gvcf.cc:168-240)
-  struct InfoField { std::string vcf_name; int key = -1; int plain_index = -1; bool is_float = false; };
+  struct InfoField { std::string vcf_name; int key = -1; int plain_index = -1; bool is_float = false; int vector_slot = -1; };   // vector_slot >= 0: element-wise sum
   std::vector<InfoField> m_INFO_fields_vec;
-  int m_END_key = -1, m_DP_key = -1;
+  int m_END_key = -1, m_DP_key = -1, m_QUAL_plain = -1;
+  unsigned m_num_vector_slots = 0;
   bool m_dp_rule = false;
   uint64_t m_num_records = 0;
 };

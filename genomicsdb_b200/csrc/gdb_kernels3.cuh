@@ -460,4 +460,53 @@ __global__ void __launch_bounds__(FMT_THREADS) k_info_reduce(const __grid_consta
   }
 }
 
+// Element-wise sum of a vector field over the valid calls of a site (compute_valid_element_wise_sum, variant_field_handler.cc:
+// 618-660): result[i] = sum, in row order, of the valid i-th values; missing where no call has one; as long as the last
+// index any call has a valid value at.  Calls in spanning-deletion form do not count (their INFO fields were invalidated).
+// One block per (site, slot); thread t owns elements t, t + 64, ... and walks the rows, so a float sum adds in row order.
+constexpr int ESUM_THREADS = 64, ESUM_CAP = 1024;
+struct EsumSet { int32_t n; int32_t remapped[MAX_FIELDS + MAX_PLAIN]; int32_t index[MAX_FIELDS + MAX_PLAIN]; };   // remapped ? field f : plain field p
+__global__ void __launch_bounds__(ESUM_THREADS) k_info_esum(const __grid_constant__ ArrayDev A, const __grid_constant__ PlainSet P, const __grid_constant__ RemapOut O,
+                                                            const __grid_constant__ EsumSet E, const int32_t* __restrict__ live, const int32_t* __restrict__ plain_stat,
+                                                            const uint32_t n_sites, const uint32_t nq, uint32_t* __restrict__ values, uint32_t* __restrict__ lens,
+                                                            uint32_t* __restrict__ err) {
+  __shared__ uint32_t s_nvalid;
+  const uint32_t js = blockIdx.x, v = blockIdx.y, tid = threadIdx.x;
+  if (tid == 0) s_nvalid = 0;
+  __syncthreads();
+  const bool remapped = E.remapped[v] != 0;
+  const int idx = E.index[v];
+  const bool is_float = remapped ? A.fm[idx].elem != 0 : P.f[idx].elem == ELEM_FLOAT32;
+  const uint32_t miss = is_float ? BCF_FLT_MISSING : BCF_INT_MISSING, vend = is_float ? BCF_FLT_VEND : BCF_INT_VEND;
+  const int o = idx + (A.has_gt ? 1 : 0);
+  const uint32_t stride = remapped ? O.f[o].stride[js] : 0u;
+  const uint32_t* __restrict__ data = remapped ? O.f[o].data + O.f[o].base[js] : nullptr;
+  const uint16_t* __restrict__ len = remapped ? O.f[o].len + (uint64_t)js * nq : nullptr;
+  uint32_t* out = values + ((uint64_t)v * n_sites + js) * ESUM_CAP;
+  // longest vector at the site: the field's stride (remapped) / the maximum k_plain_scan found (plain)
+  uint32_t n_el = remapped ? stride : (uint32_t)plain_stat[((uint64_t)idx * n_sites + js) * PS_WORDS + PS_MAXLEN];
+  if (n_el > (uint32_t)ESUM_CAP) { if (tid == 0) atomicMax(&err[1], 5u); n_el = ESUM_CAP; }
+  for (uint32_t i = tid; i < n_el; i += ESUM_THREADS) {
+    bool any = false; uint32_t acc = 0;
+    for (uint32_t q = 0; q < nq; ++q) {
+      const int32_t e = live[(uint64_t)js * nq + q];
+      if (e < 0 || (e & LIVE_REDUCED)) continue;
+      uint32_t x;
+      if (remapped) { if (i >= len[q]) continue; x = data[(uint64_t)q * stride + i]; }
+      else {
+        const uint8_t* p; uint32_t n;
+        if (!plain_fetch(P.f[idx], (uint32_t)e, p, n) || i >= n) continue;
+        x = reinterpret_cast<const uint32_t*>(p)[i];
+      }
+      if (x == miss || x == vend) continue;
+      if (!any) { acc = x; any = true; }
+      else acc = is_float ? __float_as_uint(__fadd_rn(__uint_as_float(acc), __uint_as_float(x))) : acc + x;
+    }
+    out[i] = any ? acc : miss;
+    if (any) atomicMax(&s_nvalid, i + 1u);
+  }
+  __syncthreads();
+  if (tid == 0) lens[(uint64_t)v * n_sites + js] = s_nvalid;
+}
+
 }  // namespace gdb

@@ -50,7 +50,9 @@ typedef struct gdbgpu_field_desc {
 /* The same descriptor stages the scalar INFO fields the Broad operator combines over the valid calls of a site
  * (BroadCombinedGVCFOperator::handle_INFO_fields, broad_combined_gvcf.cc:374-420,524-545; median / sum / mean of the first
  * element: VariantFieldHandler::get_valid_median / get_valid_sum / get_valid_mean, variant_field_handler.cc:529-612). */
-enum { GDBGPU_INFO_NONE = 0, GDBGPU_INFO_MEDIAN = 1, GDBGPU_INFO_SUM = 2, GDBGPU_INFO_MEAN = 3 };
+enum { GDBGPU_INFO_NONE = 0, GDBGPU_INFO_MEDIAN = 1, GDBGPU_INFO_SUM = 2, GDBGPU_INFO_MEAN = 3,
+       GDBGPU_INFO_ELEMENT_WISE_SUM = 4 /* vector result: VariantFieldHandler::compute_valid_element_wise_sum, variant_field_handler.cc:618-660 */ };
+#define GDBGPU_INFO_VECTOR_CAP 1024   /* longest element-wise result */
 typedef struct gdbgpu_plain_field_desc {
   const char* name;      /* TileDB attribute name, e.g. "MIN_DP" */
   int32_t elem_type;     /* GDBGPU_ELEM_* (CHAR: a string per cell) */
@@ -161,6 +163,10 @@ typedef struct gdbgpu_scan_params {
    * fields of the INFO DP attribute, MIN_DP and DP_FORMAT (0 = not queried); INFO/DP of a site = sum over its rows of
    * DP, else MIN_DP, else DP_FORMAT.  Used with GDBGPU_SCAN_BCF_FORMAT. */
   uint32_t dp_info_field, dp_min_dp_field, dp_format_field;
+  /* bit f set: also combine remapped field f (index into the array's allele-dependent fields, GT not counted) over the valid
+   * calls of every site with an element-wise sum -- INFO fields like MLEAC / MLEAF with VCF_field_combine_operation
+   * element_wise_sum.  Used with GDBGPU_SCAN_BCF_FORMAT. */
+  uint32_t esum_remapped_mask;
 } gdbgpu_scan_params;
 
 typedef struct gdbgpu_scan_info {
@@ -227,6 +233,12 @@ typedef struct gdbgpu_batch {
   const uint8_t* info_valid;
   const uint32_t* info_value;
   const int32_t* info_dp_sum;
+  /* element-wise sums (host arrays): slot v = remapped field f (v = f) or plain field p with GDBGPU_INFO_ELEMENT_WISE_SUM
+   * (v = n_remapped_fields + p); entry v*n_sites + s: vec_len values (0: no valid value) starting at vec_values + vec_offset;
+   * elements no call had a valid value for are BCF missing */
+  const uint32_t* vec_len;
+  const uint64_t* vec_offset;
+  const uint32_t* vec_values;
 } gdbgpu_batch;
 
 int gdbgpu_scan_begin(gdbgpu_array* arr, const gdbgpu_scan_params* params, gdbgpu_scan** out);

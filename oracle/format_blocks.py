@@ -270,6 +270,46 @@ def info_site_values(site, plain, info_fields, dp_fields=(None, None, None)):
     return out, dp_sum
 
 
+def info_vector_sums(site, plain, remapped_fields=(), plain_fields=()):
+    """compute_valid_element_wise_sum (variant_field_handler.cc:618-660) at one parsed dump site: remapped_fields = [(dump
+    field name, 'int'|'float')] take each valid call's remapped vector, plain_fields = [(attribute, elem)] the cell's own.
+    -> {name: list of uint32 words} (fields without any valid value are absent)"""
+    calls = sorted(site["calls"], key=lambda c: c["row"])
+    cells = [plain.cell_of[(c["row"], c["begin"])] for c in calls]
+    reduced = [site["begin"] > c["begin"] and plain.contains_deletion(cell) for c, cell in zip(calls, cells)]
+    out = {}
+    for name, elem, is_remapped in [(n, e, True) for n, e in remapped_fields] + [(n, e, False) for n, e in plain_fields]:
+        bad = (F32_MISSING, F32_VEND) if elem == "float" else (I32_MISSING & 0xFFFFFFFF, I32_VEND & 0xFFFFFFFF)
+        dt = np.float32 if elem == "float" else np.int32
+        res, n_valid = [], 0
+        for c, cell, red in zip(calls, cells, reduced):
+            if red:
+                continue
+            vec = [int(x) for x in c["fields"][name]] if is_remapped else plain.values(name, elem, cell)
+            for i, x in enumerate(vec):
+                if x in bad:
+                    continue
+                while len(res) <= i:
+                    res.append(None)
+                v = np.asarray([x], dtype=np.uint32).view(dt)[0]
+                with np.errstate(over="ignore"):
+                    res[i] = v if res[i] is None else dt(res[i] + v)
+                n_valid = max(n_valid, i + 1)
+        if n_valid:
+            miss = F32_MISSING if elem == "float" else I32_MISSING & 0xFFFFFFFF
+            out[name] = [miss if r is None else int(np.asarray([r], dtype=dt).view(np.uint32)[0]) for r in res[:n_valid]]
+    return out
+
+
+def enc_info_vector(words, elem):
+    """typed vector of an INFO field as bcf_update_info writes it (bcf_enc_vint with wsize = -1 / bcf_enc_vfloat)"""
+    if elem == "float":
+        return enc_size(len(words), BT_FLOAT) + np.asarray(words, dtype="<u4").tobytes()
+    vals = [w - (1 << 32) if w >= (1 << 31) else w for w in words]
+    bt, desc, data = enc_vint(vals, len(vals))
+    return desc + data
+
+
 def enc_info_value(bits, elem):
     """typed value of a one-element INFO field as bcf_update_info writes it: ints through bcf_enc_int1, floats as float32"""
     if elem == "float":

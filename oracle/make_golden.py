@@ -100,6 +100,13 @@ SCENARIOS = [
     dict(name="t6_7_8_three_fragments_gz", callsets="t6_7_8.json", compress=True, batches=[(1, 1), (0, 0), (2, 2)], queries=[
         dict(id="t6_7_8_three_fragments_at_0", ranges=FULL, vcf="t6_7_8_vcf_at_0"),
     ]),
+    # INFO combine operations (tests/run.py:598-601, vid_info_ops0.json): QUAL median, mean, element-wise sums of A-length and
+    # variable-length fields
+    dict(name="info_ops0", callsets="info_ops.json", vid="vid_info_ops0.json", queries=[
+        dict(id="info_ops0_at_0", ranges=FULL, vcf=None,
+             attributes=["REF", "ALT", "QUAL", "BaseQRankSum", "ClippingRankSum", "GT", "MLEAC", "MLEAF", "var_field"],
+             extra={"vid_mapping_file": "inputs/vid_info_ops0.json"}),
+    ]),
 ]
 
 
@@ -159,14 +166,22 @@ def query_json(ws, sc, q):
 def main():
     if not os.path.isdir(REF_TESTS):
         sys.exit("reference tests not present; golden fixtures can only be regenerated where /root/reference exists")
-    for sub in ("arrays", "dumps", "vcf", "inputs/callsets"):
-        shutil.rmtree(os.path.join(GOLD, sub), ignore_errors=True)
-        os.makedirs(os.path.join(GOLD, sub))
-    tmp = tempfile.mkdtemp(prefix="gdbgold")
+    only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None   # add scenarios, keep the others
     manifest = []
+    if only is None:
+        for sub in ("arrays", "dumps", "vcf", "inputs/callsets"):
+            shutil.rmtree(os.path.join(GOLD, sub), ignore_errors=True)
+            os.makedirs(os.path.join(GOLD, sub))
+    else:
+        manifest = [c for c in json.load(open(os.path.join(GOLD, "manifest.json")))["cases"] if c["scenario"] not in only]
+        for name in only:
+            shutil.rmtree(os.path.join(GOLD, "arrays", name), ignore_errors=True)
+    tmp = tempfile.mkdtemp(prefix="gdbgold")
     used_inputs = set()
     n_vcf_ok = n_vcf = 0
     for sc in SCENARIOS:
+        if only is not None and sc["name"] not in only:
+            continue
         ws = os.path.join(tmp, "ws_" + sc["name"])
         batches = sc.get("batches", [None])
         for bi, b in enumerate(batches):

@@ -12,8 +12,8 @@ import pytest
 from conftest import GOLDEN, golden_cases
 from oracle import bcf_reader, format_blocks, oracle
 from oracle import tiledb_fragment as tf
-from util import (case_fields, case_query_rows, format_field_names, format_order, info_scalar_fields, plain_format_fields,
-                  vcf_format_name)
+from util import (case_fields, case_query_rows, format_field_names, format_order, info_scalar_fields, info_vector_fields,
+                  plain_format_fields, qual_field, vcf_format_name)
 
 CASES = golden_cases()
 
@@ -71,12 +71,30 @@ def test_info_scalars_match_reference_bcf(case):
     _, samples, recs = bcf_reader.read_bcf(os.path.join(GOLDEN, "bcf", case["id"] + ".bcf"))
     names, sites = oracle.parse_dump(open(os.path.join(GOLDEN, case["dump"]), "rb").read())
     info_fields = info_scalar_fields(case)
+    vec_remapped, vec_plain = info_vector_fields(case, names)
+    qual = qual_field(case)
     arr = tf.Array(os.path.join(GOLDEN, case["workspace"]), case["array"])
-    extra = [(n, e, 1) for n, e, _ in info_fields] + [("DP", "int", 1), ("MIN_DP", "int", 1), ("DP_FORMAT", "int", 1)]
+    dp_names = tuple(n if n in arr.schema.attributes else None for n in ("DP", "MIN_DP", "DP_FORMAT"))
+    extra = [(n, e, 1) for n, e, _ in info_fields] + [(n, "int", 1) for n in dp_names if n] + list(vec_plain) + ([("QUAL", "float", 1)] if qual else [])
     plain = format_blocks.PlainColumns(arr, arr.fixed("END")[:, 0], extra)
     n_checked = 0
     for rec, site in zip(recs, sites):
-        vals, dp_sum = format_blocks.info_site_values(site, plain, info_fields, ("DP", "MIN_DP", "DP_FORMAT"))
+        vals, dp_sum = format_blocks.info_site_values(site, plain, info_fields + ([qual] if qual else []), dp_names)
+        if qual:
+            assert rec["qual_bits"] == vals.pop("QUAL", format_blocks.F32_MISSING), site["begin"]
+        else:
+            assert rec["qual_bits"] == format_blocks.F32_MISSING
+        vecs = format_blocks.info_vector_sums(site, plain, vec_remapped, [(n, e) for n, e, _ in vec_plain])
+        for (name, elem) in vec_remapped + [(n, e) for n, e, _ in vec_plain]:
+            assert (name in rec["info"]) == (name in vecs), (site["begin"], name)
+            if name in vecs:
+                bt, n, raw = rec["info"][name]
+                want = (format_blocks.enc_size(n, bt) + raw)
+                got = format_blocks.enc_info_vector(vecs[name], elem)
+                if n == 1:
+                    got = got if elem == "float" else format_blocks.enc_int1(vecs[name][0] - (1 << 32) if vecs[name][0] >= (1 << 31) else vecs[name][0])
+                assert got == want, (site["begin"], name, got.hex(), want.hex())
+                n_checked += 1
         want = {k: v for k, v in rec["info"].items() if k in [f[0] for f in info_fields]}
         assert sorted(vals) == sorted(want), (site["begin"], sorted(vals), sorted(want))
         for name, elem, _ in info_fields:

@@ -8,9 +8,10 @@ import pytest
 
 from conftest import GOLDEN, golden_cases
 from oracle import bcf_reader, format_blocks, oracle
+from oracle import tiledb_fragment as tf
 from tools import gdbsyn
-from util import (case_fields, case_query_rows, format_field_names, format_order, info_scalar_fields, plain_format_fields,
-                  vcf_format_name)
+from util import (case_fields, case_query_rows, format_field_names, format_order, info_scalar_fields, info_vector_fields,
+                  plain_format_fields, qual_field, vcf_format_name)
 
 pytestmark = pytest.mark.gpu
 CASES = golden_cases()
@@ -111,33 +112,55 @@ def test_info_scalars_match_reference_bcf(ctx, case):
     _, samples, recs = bcf_reader.read_bcf(os.path.join(GOLDEN, "bcf", case["id"] + ".bcf"))
     fields, phased = case_fields(case)
     info_fields = info_scalar_fields(case)
-    plain = [(n, e, 1, 1, op) for n, e, op in info_fields]                         # INFO scalars: staged, combined, no FORMAT block
-    plain += [("DP", "int", 1, 1), ("MIN_DP", "int", 1, 1), ("DP_FORMAT", "int", 1, 1)]   # the DP rule's inputs
-    n_info = len(info_fields)
+    names = ["GT"] + [f[0] for f in fields]
+    vec_remapped, vec_plain = info_vector_fields(case, names)
+    qual = qual_field(case)
+    have = set(tf.Array(os.path.join(GOLDEN, case["workspace"]), case["array"]).schema.attributes)
+    scalars = info_fields + ([qual] if qual else [])
+    plain = [(n, e, 1, 1, op) for n, e, op in scalars]                           # INFO scalars (+ QUAL): staged, combined, no FORMAT block
+    dp_names = [n for n in ("DP", "MIN_DP", "DP_FORMAT") if n in have]
+    dp_at = {n: len(plain) + k + 1 for k, n in enumerate(dp_names)}
+    plain += [(n, "int", 1, 1) for n in dp_names]                                  # the DP rule's inputs
+    vec_at = {n: len(plain) + k for k, (n, e, fx) in enumerate(vec_plain)}
+    plain += [(n, e, fx, 1, "element_wise_sum") for n, e, fx in vec_plain]
+    n_remapped = len(fields)
+    mask = sum(1 << [f[0] for f in fields].index(n) for n, _ in vec_remapped)
+    n_slots = n_remapped + len(plain)
     arr = capi.Array.open(ctx, os.path.join(GOLDEN, case["workspace"]), case["array"], fields, gt_phased=phased, plain=plain)
     try:
         for kw in (dict(), dict(max_sites=1)):
             got = []
             for r in sorted(tuple(r) for r in case["query_column_ranges"]):
                 sc = capi.Scan(arr, r[0], r[1], query_rows=case_query_rows(case), flags=capi.SCAN_BCF_FORMAT,
-                               dp_fields=(n_info + 1, n_info + 2, n_info + 3))
+                               dp_fields=(dp_at.get("DP", 0), dp_at.get("MIN_DP", 0), dp_at.get("DP_FORMAT", 0)), esum_remapped_mask=mask)
                 while True:
                     bv = sc.next_batch(**kw)
                     if bv is None:
                         break
                     for s in range(bv.n_sites):
+                        vecs = {n: bv.info_vector([f[0] for f in fields].index(n), s, n_slots) for n, _ in vec_remapped}
+                        vecs.update({n: bv.info_vector(n_remapped + vec_at[n], s, n_slots) for n, _, _ in vec_plain})
                         got.append(dict(begin=int(bv.site_begin[s]), end=int(bv.site_end[s]), remap=bool(bv.site_flags[s] & capi.SITE_REMAPPED),
-                                        dp=int(bv.info_dp_sum[s]),
-                                        vals={info_fields[k][0]: int(bv.info_value[k, s]) for k in range(n_info) if bv.info_valid[k, s]}))
+                                        dp=int(bv.info_dp_sum[s]), vecs={k: v for k, v in vecs.items() if len(v)},
+                                        vals={scalars[k][0]: int(bv.info_value[k, s]) for k in range(len(scalars)) if bv.info_valid[k, s]}))
                 sc.close()
             assert len(got) == len(recs)
             for rec, g in zip(recs, got):
+                assert rec["qual_bits"] == g["vals"].pop("QUAL", format_blocks.F32_MISSING), g["begin"]
                 want = {k: v for k, v in rec["info"].items() if k in [f[0] for f in info_fields]}
                 assert sorted(g["vals"]) == sorted(want), (g["begin"], sorted(g["vals"]), sorted(want))
                 for name, elem, _ in info_fields:
                     if name in want:
                         bt, n, raw = want[name]
                         assert bytes([n << 4 | bt]) + raw == format_blocks.enc_info_value(g["vals"][name], elem), (g["begin"], name)
+                for name, elem in vec_remapped + [(n, e) for n, e, _ in vec_plain]:
+                    assert (name in rec["info"]) == (name in g["vecs"]), (g["begin"], name)
+                    if name in g["vecs"]:
+                        bt, n, raw = rec["info"][name]
+                        words = [int(x) for x in g["vecs"][name]]
+                        enc = format_blocks.enc_info_vector(words, elem) if (n > 1 or elem == "float") else \
+                            format_blocks.enc_int1(words[0] - (1 << 32) if words[0] >= (1 << 31) else words[0])
+                        assert enc == format_blocks.enc_size(n, bt) + raw, (g["begin"], name)
                 assert ("END" in rec["info"]) == (g["end"] > g["begin"])
                 assert ("DP" in rec["info"]) == (g["dp"] > 0 and g["remap"]), (g["begin"], g["dp"])
                 if "DP" in rec["info"]:

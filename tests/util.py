@@ -95,3 +95,29 @@ def info_scalar_fields(case):
             continue
         out.append((name, ent["type"], op))
     return out
+
+
+def info_vector_fields(case, dump_names):
+    """(remapped [(name, elem)], plain [(attribute, elem, fixed_len)]) of the queried INFO fields combined with an element-wise sum"""
+    vid = oracle.load_vid_fields(os.path.join(GOLDEN, case["vid_mapping_file"]))
+    remapped, plain = [], []
+    for name in case["attributes"]:
+        ent = vid.get(name)
+        if ent is None or ent.get("combine") != "element_wise_sum" or "INFO" not in (ent.get("classes") or []) or isinstance(ent["length"], list):
+            continue   # (2-D fields such as the allele-specific annotations are not covered)
+        elem = "float" if ent["type"] == "float" else "int"
+        if name in dump_names:
+            remapped.append((name, elem))
+        else:
+            ln = ent["length"]
+            plain.append((name, elem, 0 if (isinstance(ln, str) and not ln.isdigit()) else int(ln)))
+    return remapped, plain
+
+
+def qual_field(case):
+    """('QUAL', 'float', op) when the vid mapping gives QUAL a scalar combine operation and QUAL is queried"""
+    vid = oracle.load_vid_fields(os.path.join(GOLDEN, case["vid_mapping_file"]))
+    ent = vid.get("QUAL")
+    if ent and "QUAL" in case["attributes"] and ent.get("combine") in ("median", "sum", "mean"):
+        return ("QUAL", "float", ent["combine"])
+    return None
