@@ -15,7 +15,7 @@ OK, ERR_ARG, ERR_IO, ERR_CUDA, ERR_OVERLAP, ERR_LIMIT = 0, -1, -2, -3, -4, -5
 LEN_R, LEN_A, LEN_G = 0, 1, 2
 ELEM_INT32, ELEM_FLOAT32, ELEM_CHAR = 0, 1, 2
 SCAN_FULL, SCAN_NO_DELETIONS, SCAN_MIN_PL_GT, SCAN_WANT_LUT, SCAN_DEVICE_OUTPUT = 1, 2, 4, 8, 16
-SCAN_BCF_FORMAT, SCAN_PRODUCE_GT, SCAN_NO_PREFETCH = 32, 64, 128
+SCAN_BCF_FORMAT, SCAN_PRODUCE_GT, SCAN_NO_PREFETCH, SCAN_HTSJDK_CONVENTIONS = 32, 64, 128, 256
 BT_SIZE = {1: 1, 2: 2, 3: 4, 5: 4, 7: 1}
 SITE_NONREF, SITE_REMAPPED, SITE_G_SUPPRESSED = 1, 2, 4
 CALL_REDUCED = 0x40000000

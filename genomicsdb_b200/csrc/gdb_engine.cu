@@ -464,7 +464,7 @@ struct gdbgpu_scan {
   DevBuf<int32_t> qrow_of_row, init_cell, dlive, ddel, live_excl, del_excl; DevBuf<int64_t> row_of_qrow, init_effend, bp, site_begin, site_end;
   DevBuf<unsigned long long> bitmap; DevBuf<uint32_t> word_rank, bp_cell0, err, del_cells, del_words; DevBuf<uint64_t> site_start; DevBuf<DelRec> del_recs;
   std::unique_ptr<BatchBuffers> slot[2];   // borrowed from the context's pool for the lifetime of the scan; [cur] = batch being handed out, the other = prefetched
-  int cur = 0; bool bcf_format = false, prefetch = true; int produce_gt = 0;
+  int cur = 0; bool bcf_format = false, prefetch = true; int produce_gt = 0, java = 0;
   InfoSet info{};   // INFO scalars to combine + the DP rule's fields (GDBGPU_SCAN_BCF_FORMAT)
   EsumSet esum{};   // vector fields combined with an element-wise sum
   uint32_t cap_allele_recs = 0, cap_allele_bytes = 0, cap_lut = 0;
@@ -498,6 +498,7 @@ void scan_prepare(gdbgpu_scan* s) {
   s->device_output = (p.flags & GDBGPU_SCAN_DEVICE_OUTPUT) != 0;
   s->bcf_format = (p.flags & GDBGPU_SCAN_BCF_FORMAT) != 0;
   s->produce_gt = (p.flags & GDBGPU_SCAN_PRODUCE_GT) ? 1 : 0;
+  s->java = (p.flags & GDBGPU_SCAN_HTSJDK_CONVENTIONS) ? 1 : 0;
   s->prefetch = !(p.flags & GDBGPU_SCAN_NO_PREFETCH);
   s->info.n = 0;
   s->esum.n = 0;
@@ -818,7 +819,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       for (int o = 0; o < n_out; ++o) for (uint32_t i = 0; i < keep; ++i) max_words = std::max<uint64_t>(max_words, (uint64_t)bb.h_stride[o][i] * S.nq);
       const unsigned chunks = (unsigned)std::min<uint64_t>(64, std::max<uint64_t>(1, max_words / (FMT_THREADS * 16)));
       const unsigned row_blocks = blocks_for(S.nq, FMT_THREADS);
-      LAUNCH(ctx, k_fmt_range, dim3(chunks, keep), FMT_THREADS, a->dev, O, keep, (uint32_t)S.nq, s->produce_gt, bb.fmt_mm.p);
+      LAUNCH(ctx, k_fmt_range, dim3(chunks, keep), FMT_THREADS, a->dev, O, keep, (uint32_t)S.nq, s->produce_gt, s->java, bb.fmt_mm.p);
       if (n_plain) LAUNCH(ctx, k_plain_scan, dim3(row_blocks, keep), FMT_THREADS, a->plain_dev, bb.live.p, keep, (uint32_t)S.nq, bb.fmt_mm.p + 2 * n_rp);
       const bool dp_rule = s->info.dp_info >= 0 || s->info.dp_format >= 0;
       bb.h_info_value.assign((size_t)n_plain * keep, 0); bb.h_info_valid.assign((size_t)n_plain * keep, 0); bb.h_dp_sum.assign(keep, 0);
@@ -894,9 +895,9 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       bb.fmt_type_d = bb.ctl.push(bb.h_fmt_type.data(), n_plan); bb.fmt_nps_d = bb.ctl.push(bb.h_fmt_nps.data(), n_plan); bb.fmt_off_d = bb.ctl.push(bb.h_fmt_off.data(), n_plan);
       bb.ctl.flush(ctx->stream);
       const FmtPlanDev P{bb.fmt_type_d, bb.fmt_nps_d, bb.fmt_off_d, bb.fmt_bytes.p};
-      LAUNCH(ctx, k_fmt_pack, dim3(chunks, keep), FMT_THREADS, a->dev, O, P, keep, (uint32_t)S.nq, s->produce_gt);
-      LAUNCH(ctx, k_fmt_pack_tile, dim3(blocks_for(S.nq, PACK_ROWS), keep), FMT_THREADS, a->dev, O, P, keep, (uint32_t)S.nq);
-      if (n_plain) LAUNCH(ctx, k_plain_pack, dim3(row_blocks, keep), FMT_THREADS, a->plain_dev, P, n_out, bb.live.p, keep, (uint32_t)S.nq);
+      LAUNCH(ctx, k_fmt_pack, dim3(chunks, keep), FMT_THREADS, a->dev, O, P, keep, (uint32_t)S.nq, s->produce_gt, s->java);
+      LAUNCH(ctx, k_fmt_pack_tile, dim3(blocks_for(S.nq, PACK_ROWS), keep), FMT_THREADS, a->dev, O, P, keep, (uint32_t)S.nq, s->java);
+      if (n_plain) LAUNCH(ctx, k_plain_pack, dim3(row_blocks, keep), FMT_THREADS, a->plain_dev, P, n_out, bb.live.p, keep, (uint32_t)S.nq, s->java);
     }
     // ---- results: site metadata (host mirrors), then the copies of everything the caller asked for
     bb.keep = keep; bb.alg_bytes = alg_bytes;

@@ -201,8 +201,9 @@ void enc_vint(std::vector<uint8_t>& b, const int32_t* a, uint32_t n) {
 }
 }  // namespace
 
-BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, const VidMapper& id_mapper, const VariantQueryConfig& qc)
-    : m_vcf_adapter(&vcf_adapter), m_vid_mapper(&id_mapper) {
+BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, const VidMapper& id_mapper, const VariantQueryConfig& qc,
+                                                     bool use_missing_values_only_not_vector_end)
+    : m_vcf_adapter(&vcf_adapter), m_vid_mapper(&id_mapper), m_use_missing_values_not_vector_end(use_missing_values_only_not_vector_end) {
   if (!qc.is_bookkeeping_done()) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "BroadCombinedGVCFOperator: do_query_bookkeeping(config, true, true) must be called first");
   auto key_of = [&](const std::string& vcf_name) {
     int k = vcf_adapter.get_dictionary_id(vcf_name);
@@ -470,6 +471,7 @@ void VariantQueryProcessor::scan_and_operate(const int, const VariantQueryConfig
     if (op.wants_bcf_blocks()) {
       p.flags |= GDBGPU_SCAN_BCF_FORMAT;
       if (qc.produce_GT_field()) p.flags |= GDBGPU_SCAN_PRODUCE_GT;
+      if (op.wants_htsjdk_conventions()) p.flags |= GDBGPU_SCAN_HTSJDK_CONVENTIONS;
       p.dp_info_field = qc.dp_fields_[0]; p.dp_min_dp_field = qc.dp_fields_[1]; p.dp_format_field = qc.dp_fields_[2];
       p.esum_remapped_mask = qc.esum_remapped_mask_;
     }

@@ -187,6 +187,7 @@ class SingleVariantOperatorBase {
   // Opt-in fast path: an operator that consumes the kernels' BCF-typed FORMAT blocks and combined INFO scalars
   // per site instead of a materialised Variant; scan_and_operate then scans with GDBGPU_SCAN_BCF_FORMAT.
   virtual bool wants_bcf_blocks() const { return false; }
+  virtual bool wants_htsjdk_conventions() const { return false; }   // FORMAT blocks as htsjdk's BCF2 codec needs them (JNI path)
   virtual void operate_on_bcf_site(const gdbgpu_batch&, uint32_t /*site*/, const VariantQueryConfig&) {}
  protected:
   bool m_NON_REF_exists = false, m_remapping_needed = false, m_is_reference_block_only = false;
@@ -233,8 +234,11 @@ class VCFAdapter {
 // fixed part of the record.  Not supported: 2-D / histogram / concatenate INFO operations (throws); ID merge and FILTER union are not produced.
 class BroadCombinedGVCFOperator : public GA4GHOperator {
  public:
-  BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, const VidMapper& id_mapper, const VariantQueryConfig& query_config);
+  // use_missing_values_only_not_vector_end: what GenomicsDBBCFGenerator passes for the Java reader (genomicsdb_bcf_generator.cc:60-83)
+  BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, const VidMapper& id_mapper, const VariantQueryConfig& query_config,
+                            bool use_missing_values_only_not_vector_end = false);
   bool wants_bcf_blocks() const override { return true; }
+  bool wants_htsjdk_conventions() const override { return m_use_missing_values_not_vector_end; }
   void operate_on_bcf_site(const gdbgpu_batch& batch, uint32_t site, const VariantQueryConfig& query_config) override;
   bool overflow() const override { return m_vcf_adapter->overflow(); }
   uint64_t get_num_records() const { return m_num_records; }
@@ -247,7 +251,7 @@ class BroadCombinedGVCFOperator : public GA4GHOperator {
   std::vector<InfoField> m_INFO_fields_vec;
   int m_END_key = -1, m_DP_key = -1, m_QUAL_plain = -1;
   unsigned m_num_vector_slots = 0;
-  bool m_dp_rule = false;
+  bool m_dp_rule = false, m_use_missing_values_not_vector_end = false;
   uint64_t m_num_records = 0;
 };
 

@@ -42,7 +42,7 @@ __device__ inline uint32_t gt_element(const uint32_t* __restrict__ row, uint32_t
 // min / max of the values of every (site, field) block; mm[(o * n_sites + site) * 2 + {0: min, 1: max}] starts at
 // {INT32_MAX, INT32_MIN + 1} like bcf_enc_vint's accumulators.  grid = (chunks, sites)
 __global__ void __launch_bounds__(FMT_THREADS) k_fmt_range(const __grid_constant__ ArrayDev A, const __grid_constant__ RemapOut O, const uint32_t n_sites, const uint32_t nq,
-                                                           const int produce_gt, int32_t* __restrict__ mm) {
+                                                           const int produce_gt, const int java, int32_t* __restrict__ mm) {
   __shared__ int32_t s_min[FMT_THREADS / 32], s_max[FMT_THREADS / 32];
   const uint32_t js = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int o = 0; o < O.n_out; ++o) {
@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(FMT_THREADS) k_fmt_range(const __grid_constant
       const uint32_t nps = A.gt_phased ? (stride + 1u) >> 1 : stride;
       for (uint32_t q = blockIdx.x * FMT_THREADS + tid; q < nq; q += gridDim.x * FMT_THREADS) {
         const uint32_t* row = src + (uint64_t)q * stride;
+        if (java && fo.len[(uint64_t)js * nq + q] == 0) { lo = min(lo, 0); hi = max(hi, 0); continue; }   // JNI conventions: a row without GT is a no-call
         for (uint32_t i = 0; i < nps; ++i) {
           const uint32_t v = gt_element(row, i, A.gt_phased, produce_gt);
           if (v != BCF_INT_MISSING && v != BCF_INT_VEND) { lo = min(lo, (int32_t)v); hi = max(hi, (int32_t)v); }
@@ -110,7 +111,7 @@ __device__ inline void pack_put(uint8_t* buf, uint32_t k, uint32_t v) {
 // (row, quad-in-row) advance without a division; ILP independent 16-byte loads are in flight per thread.
 template <uint32_t TYPE>
 __device__ inline void pack_quads(uint8_t* buf, const uint4* __restrict__ src4, const uint16_t* __restrict__ len, uint32_t rows, uint32_t qpr, uint32_t nps,
-                                  uint32_t miss, uint32_t vend, uint32_t tid) {
+                                  uint32_t miss, uint32_t vend, uint32_t tid, const bool java) {
   constexpr int ILP = 4;
   const uint32_t n_quads = rows * qpr, dr = FMT_THREADS / qpr, dj = FMT_THREADS - dr * qpr;
   uint32_t r = tid / qpr, j = tid - r * qpr;
@@ -124,6 +125,10 @@ __device__ inline void pack_quads(uint8_t* buf, const uint4* __restrict__ src4, 
         uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
         // a row without the field is all vector_end (K5); its first value becomes missing.  Only such rows look at len[].
         if (j == 0 && x[0] == vend && len[r] == 0) x[0] = miss;
+        if (java) {   // JNI conventions: rows are padded with missing, not vector_end
+#pragma unroll
+          for (int t = 0; t < 4; ++t) if (x[t] == vend) x[t] = miss;
+        }
         const uint32_t k = r * nps + 4 * j;
 #pragma unroll
         for (uint32_t t = 0; t < 4; ++t) if (4 * j + t < nps) pack_put<TYPE>(buf, k + t, x[t]);
@@ -136,7 +141,7 @@ __device__ inline void pack_quads(uint8_t* buf, const uint4* __restrict__ src4, 
 
 // grid = (row groups of PACK_ROWS, sites); a block walks its rows in slices that fit the staging buffer.
 __global__ void __launch_bounds__(FMT_THREADS) k_fmt_pack_tile(const __grid_constant__ ArrayDev A, const __grid_constant__ RemapOut O, const __grid_constant__ FmtPlanDev P,
-                                                               const uint32_t n_sites, const uint32_t nq) {
+                                                               const uint32_t n_sites, const uint32_t nq, const int java) {
   __shared__ __align__(16) uint8_t s_buf[PACK_SMEM];
   const uint32_t js = blockIdx.y, tid = threadIdx.x;
   const uint32_t qb = blockIdx.x * PACK_ROWS, qe = min(qb + PACK_ROWS, nq);
@@ -164,9 +169,9 @@ __global__ void __launch_bounds__(FMT_THREADS) k_fmt_pack_tile(const __grid_cons
       if ((stride & 3u) == 0) {   // rows are whole quads (every remapped site)
         const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(src);
         const uint32_t vend = vend_word(A.fm[o - o0].elem);
-        if (type == BT_INT8) pack_quads<BT_INT8>(s_buf, src4, len, rows, stride >> 2, nps, miss, vend, tid);
-        else if (type == BT_INT16) pack_quads<BT_INT16>(s_buf, src4, len, rows, stride >> 2, nps, miss, vend, tid);
-        else pack_quads<BT_INT32>(s_buf, src4, len, rows, stride >> 2, nps, miss, vend, tid);
+        if (type == BT_INT8) pack_quads<BT_INT8>(s_buf, src4, len, rows, stride >> 2, nps, miss, vend, tid, java != 0);
+        else if (type == BT_INT16) pack_quads<BT_INT16>(s_buf, src4, len, rows, stride >> 2, nps, miss, vend, tid, java != 0);
+        else pack_quads<BT_INT32>(s_buf, src4, len, rows, stride >> 2, nps, miss, vend, tid, java != 0);
       } else {
         const uint32_t n_words = rows * stride;
         for (uint32_t g = tid; g < n_words; g += FMT_THREADS) {
@@ -174,6 +179,7 @@ __global__ void __launch_bounds__(FMT_THREADS) k_fmt_pack_tile(const __grid_cons
           if (i >= nps) continue;
           uint32_t v = src[g];
           if (i == 0 && len[r] == 0) v = miss;
+          if (java && v == vend_word(A.fm[o - o0].elem)) v = miss;
           put(r, i, v);
         }
       }
@@ -191,7 +197,7 @@ __global__ void __launch_bounds__(FMT_THREADS) k_fmt_pack_tile(const __grid_cons
 // narrows the words of every emitted (site, field) into its block.  grid = (chunks, sites); a thread makes 4 consecutive
 // values of the block per trip (one 4 / 8 / 16-byte store).
 __global__ void __launch_bounds__(FMT_THREADS) k_fmt_pack(const __grid_constant__ ArrayDev A, const __grid_constant__ RemapOut O, const __grid_constant__ FmtPlanDev P,
-                                                          const uint32_t n_sites, const uint32_t nq, const int produce_gt) {
+                                                          const uint32_t n_sites, const uint32_t nq, const int produce_gt, const int java) {
   const uint32_t js = blockIdx.y, tid = threadIdx.x;
   for (int o = 0; o < O.n_out; ++o) {
     const uint64_t pi = (uint64_t)o * n_sites + js;
@@ -218,10 +224,13 @@ __global__ void __launch_bounds__(FMT_THREADS) k_fmt_pack(const __grid_constant_
       for (uint32_t x = 0; x < 4; ++x) {
         if (x < cnt) {
           const uint32_t* row = src + (uint64_t)q * stride;
-          if (is_gt) w[x] = gt_element(row, i, A.gt_phased, produce_gt);
-          else {
+          if (is_gt) {
+            w[x] = gt_element(row, i, A.gt_phased, produce_gt);
+            if (java) w[x] = len[q] == 0 ? (i == 0 ? 0u : BCF_INT_MISSING) : (w[x] == BCF_INT_VEND ? BCF_INT_MISSING : w[x]);   // no-call, missing padding
+          } else {
             if (!(flat && cnt == 4)) w[x] = row[i];
             if (i == 0 && len[q] == 0) w[x] = miss;
+            if (java && w[x] == vend_word(A.fm[fi].elem)) w[x] = missing_word(A.fm[fi].elem);
           }
           if (++i == nps) { i = 0; ++q; }
         } else w[x] = 0;
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(FMT_THREADS) k_plain_scan(const __grid_constan
 // pass 2: writes every emitted (field, site) block; the plan entries of the plain fields follow those of the remapped
 // fields (index (n_out + f) * n_sites + site).  One thread per (site, query row).
 __global__ void __launch_bounds__(FMT_THREADS) k_plain_pack(const __grid_constant__ PlainSet P, const __grid_constant__ FmtPlanDev plan, const int n_out,
-                                                            const int32_t* __restrict__ live, const uint32_t n_sites, const uint32_t nq) {
+                                                            const int32_t* __restrict__ live, const uint32_t n_sites, const uint32_t nq, const int java) {
   const uint32_t js = blockIdx.y, q = blockIdx.x * FMT_THREADS + threadIdx.x;
   if (q >= nq) return;
   const int32_t e = live[(uint64_t)js * nq + q];
@@ -328,13 +337,13 @@ __global__ void __launch_bounds__(FMT_THREADS) k_plain_pack(const __grid_constan
     uint8_t* dst = plan.bytes + plan.off[pi];
     if (type == BT_CHAR) {
       uint8_t* d = dst + (uint64_t)q * nps;
-      for (uint32_t i = 0; i < nps; ++i) d[i] = i < n ? p[i] : ((i == 0 && n == 0) ? BCF_STR_MISSING : BCF_STR_VEND);
+      for (uint32_t i = 0; i < nps; ++i) d[i] = i < n ? p[i] : ((i == 0 && n == 0 && !java) ? BCF_STR_MISSING : BCF_STR_VEND);   // JNI: vector_end only
       continue;
     }
     const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
     const uint32_t miss = missing_word(P.f[f].elem == ELEM_FLOAT32), vend = vend_word(P.f[f].elem == ELEM_FLOAT32);
     for (uint32_t i = 0; i < nps; ++i) {
-      const uint32_t v = i < n ? w[i] : ((i == 0 && n == 0) ? miss : vend);
+      const uint32_t v = i < n ? w[i] : (((i == 0 && n == 0) || java) ? miss : vend);
       const uint64_t k = (uint64_t)q * nps + i;
       if (type == BT_INT8) dst[k] = v == BCF_INT_VEND ? 0x81u : (v == BCF_INT_MISSING ? 0x80u : (uint8_t)v);
       else if (type == BT_INT16) reinterpret_cast<uint16_t*>(dst)[k] = v == BCF_INT_VEND ? 0x8001u : (v == BCF_INT_MISSING ? 0x8000u : (uint16_t)v);

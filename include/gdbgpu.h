@@ -152,6 +152,10 @@ void gdbgpu_array_close(gdbgpu_array* arr);
                                              * blocks, the site table and the alleles are copied back (fields[].data / .len and live are NULL) */
 #define GDBGPU_SCAN_PRODUCE_GT        64u   /* query JSON "produce_GT_field": GT blocks carry the alleles, else no-calls (broad_combined_gvcf.cc:60-76) */
 #define GDBGPU_SCAN_NO_PREFETCH      128u   /* do not start batch n+1 while batch n is being handed out */
+#define GDBGPU_SCAN_HTSJDK_CONVENTIONS 256u /* FORMAT blocks as the JNI path needs them for htsjdk's BCF2 codec (BroadCombinedGVCFOperator's
+                                             * use_missing_values_only_not_vector_end, genomicsdb_bcf_generator.cc:60-83; variant_field_handler.cc:
+                                             * 845-866): rows padded with missing instead of vector_end, a row without GT is a no-call, strings
+                                             * vector_end only */
 
 typedef struct gdbgpu_scan_params {
   int64_t col_lo, col_hi;            /* inclusive TileDB column interval; ignored with GDBGPU_SCAN_FULL */

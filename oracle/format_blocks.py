@@ -85,8 +85,10 @@ def encode_gt(vec, phased_layout, produce_gt):
     return out
 
 
-def site_blocks(site, names, query_rows, field_elem, gt_phased, produce_gt, g_fields=(), max_alt=50):
-    """-> {field name: (type, nps, data bytes, descriptor bytes)} for one parsed dump site (oracle.parse_dump)"""
+def site_blocks(site, names, query_rows, field_elem, gt_phased, produce_gt, g_fields=(), max_alt=50, java=False):
+    """-> {field name: (type, nps, data bytes, descriptor bytes)} for one parsed dump site (oracle.parse_dump).
+    java: the conventions of the JNI path (use_missing_values_only_not_vector_end, variant_field_handler.cc:845-866): rows are
+    padded with missing instead of vector_end, a row without GT gets the no-call allele"""
     by_row = {c["row"]: c for c in site["calls"]}
     n_alt = len(site["alleles"]) - 1
     out = {}
@@ -106,8 +108,8 @@ def site_blocks(site, names, query_rows, field_elem, gt_phased, produce_gt, g_fi
             v = [] if c is None else list(c["fields"][nm].view(np.uint32 if is_float else np.int32))
             v = [int(x) for x in v]
             if not v:
-                v = [vend if is_gt else miss]
-            v += [vend] * (nps - len(v))
+                v = [(-1 if java else vend) if is_gt else miss]
+            v += [miss if java else vend] * (nps - len(v))
             rows.append(v)
         if is_gt:
             rows = [encode_gt(v, gt_phased, produce_gt) for v in rows]
@@ -168,7 +170,7 @@ class PlainColumns:
         return v if any(x != null for x in v) else []
 
 
-def plain_site_blocks(site, query_rows, plain):
+def plain_site_blocks(site, query_rows, plain, java=False):
     """collect_and_extend_fields + bcf_update_format for the plain FORMAT fields of one parsed dump site
     -> {attribute name: (type, nps, data bytes, descriptor bytes)}"""
     by_row = {c["row"]: c for c in site["calls"]}
@@ -192,8 +194,8 @@ def plain_site_blocks(site, query_rows, plain):
             if elem == "int":
                 v = [x - (1 << 32) if x >= (1 << 31) else x for x in v]
             if not v:
-                v = [miss]
-            flat += v + [vend] * (nps - len(v))
+                v = [vend if (java and elem == "char") else miss]          # strings: use_vector_end_only in the JNI path
+            flat += v + [miss if (java and elem != "char") else vend] * (nps - len(v))
         if elem == "char":
             out[name] = (BT_CHAR, nps, bytes(flat), enc_size(nps, BT_CHAR))
         elif elem == "float":

@@ -28,9 +28,10 @@ def main():
     if not os.path.isdir(REF_TESTS):
         sys.exit("reference tests not present; BCF fixtures can only be regenerated where /root/reference exists")
     cases = json.load(open(os.path.join(GOLD, "manifest.json")))["cases"]
-    out_dir = os.path.join(GOLD, "bcf")
-    shutil.rmtree(out_dir, ignore_errors=True)
-    os.makedirs(out_dir)
+    out_dir, java_dir = os.path.join(GOLD, "bcf"), os.path.join(GOLD, "bcf_java")
+    for d in (out_dir, java_dir):
+        shutil.rmtree(d, ignore_errors=True)
+        os.makedirs(d)
     tmp = tempfile.mkdtemp(prefix="gdbbcf")
     for c in cases:
         ws = os.path.join(tmp, "ws_" + c["id"])
@@ -54,7 +55,12 @@ def main():
         if p.returncode != 0:
             sys.exit("reference failed on %s: %s" % (c["id"], p.stderr.decode()[-1500:]))
         open(os.path.join(out_dir, c["id"] + ".bcf"), "wb").write(p.stdout)
-        print("%-50s %6d bytes" % (c["id"], len(p.stdout)))
+        # the same query with the conventions of the JNI path (htsjdk's BCF2 codec: missing instead of vector_end, no-call GT)
+        pj = subprocess.run([BIN + "/gdb_ref_dump", "-j", qf, "--mode", "bcf-java"], capture_output=True, cwd=REF_TESTS)
+        if pj.returncode != 0:
+            sys.exit("reference (java conventions) failed on %s: %s" % (c["id"], pj.stderr.decode()[-1500:]))
+        open(os.path.join(java_dir, c["id"] + ".bcf"), "wb").write(pj.stdout)
+        print("%-50s %6d bytes, java conventions %6d bytes" % (c["id"], len(p.stdout), len(pj.stdout)))
     shutil.rmtree(tmp, ignore_errors=True)
     write_reference_bases(out_dir)
 

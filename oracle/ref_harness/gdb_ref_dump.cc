@@ -9,6 +9,9 @@
  *   --mode hot   : same work without the dump (CPU timing of the hot path alone)
  *   --mode null  : the full BroadCombinedGVCFOperator::operate with a VCFAdapter whose hand-off is a no-op
  *                  (INFO/FORMAT collation + bcf1_t build, no serialisation)
+ *   --mode bcf-java : the reference's own BroadCombinedGVCFOperator + VCFAdapter writing uncompressed BCF to stdout, constructed
+ *                  as the JNI path constructs it (genomicsdb_bcf_generator.cc:60-83: use_missing_values_only_not_vector_end =
+ *                  true, the conventions htsjdk's BCF2 codec needs); gt_mpi_gather has no switch for it
  * All modes print one JSON line on stdout: {"mode":..,"sites":N,"calls":M,"seconds":T}.
  *
  * Driver structure mirrors tools/src/gt_mpi_gather.cc:322-366,535-606 (scan_and_produce_Broad_GVCF / main).
@@ -160,6 +163,31 @@ int main(int argc, char** argv)
       case 's': segment_size = strtoull(optarg, 0, 10); break;
       default: std::cerr << "unknown option\n"; return -1;
     }
+  }
+  if(mode_str == "bcf-java")
+  {
+    VariantQueryConfig query_config;
+    VCFAdapter vcf_adapter;
+    query_config.read_from_file(query_json, rank);
+    query_config.set_vcf_output_format("bu");
+    vcf_adapter.initialize(query_config);
+    VariantStorageManager sm(query_config.get_workspace(rank), segment_size ? segment_size : query_config.get_segment_size());
+    VariantQueryProcessor qp(&sm, query_config.get_array_name(rank), query_config.get_vid_mapper());
+    qp.do_query_bookkeeping(qp.get_array_schema(), query_config, query_config.get_vid_mapper(), true);
+    {
+      BroadCombinedGVCFOperator op(vcf_adapter, query_config.get_vid_mapper(), query_config,
+          query_config.get_max_diploid_alt_alleles_that_can_be_genotyped(), true);
+      VariantQueryProcessorScanState scan_state;
+      for(auto i=0u;i<std::max(1u, query_config.get_num_column_intervals());++i)
+      {
+        while(!scan_state.end())
+          qp.scan_and_operate(qp.get_array_descriptor(), query_config, op, i, true, &scan_state);
+        scan_state.reset();
+      }
+    }
+    sm.close_array(qp.get_array_descriptor());
+    GenomicsDBProtoBufInitAndCleanup::shutdown_protobuf_library();
+    return 0;
   }
   HarnessMode mode = (mode_str == "hot") ? MODE_HOT : (mode_str == "null") ? MODE_NULL : MODE_DUMP;
   if(query_json.empty() || (mode == MODE_DUMP && out_file.empty()))

@@ -57,7 +57,7 @@ def test_overflow_resume_protocol(exe, case, tmp_path):
 ALL = golden_cases()
 
 
-def run_broad(exe, case, tmp_path, page=0):
+def run_broad(exe, case, tmp_path, page=0, java=False):
     q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
          "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": case["attributes"],
          "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_column_ranges"]]}],
@@ -67,18 +67,22 @@ def run_broad(exe, case, tmp_path, page=0):
     qf = tmp_path / "query.json"
     qf.write_text(json.dumps(q))
     out = tmp_path / "out.bcf"
-    cmd = [exe, "-j", str(qf), "-o", str(out), "--produce-Broad-GVCF", "--bcf-header", os.path.join(GOLDEN, "bcf", case["id"] + ".bcf"),
-           "--reference-bases", os.path.join(GOLDEN, "inputs", "ref_bases.tsv")] + (["-p", str(page)] if page else [])
+    cmd = [exe, "-j", str(qf), "-o", str(out), "--produce-Broad-GVCF", "--bcf-header",
+           os.path.join(GOLDEN, "bcf_java" if java else "bcf", case["id"] + ".bcf"),
+           "--reference-bases", os.path.join(GOLDEN, "inputs", "ref_bases.tsv")] + (["-p", str(page)] if page else []) + \
+          (["--htsjdk-conventions"] if java else [])
     return subprocess.run(cmd, capture_output=True, text=True), out
 
 
+@pytest.mark.parametrize("java", [False, True], ids=["htslib", "java"])
 @pytest.mark.parametrize("case", ALL, ids=[c["id"] for c in ALL])
-def test_broad_gvcf_bcf_file_equals_the_reference(exe, case, tmp_path):
+def test_broad_gvcf_bcf_file_equals_the_reference(exe, case, tmp_path, java):
     """gt_gpu_gather --produce-Broad-GVCF (BroadCombinedGVCFOperator of the host mirror over the kernels' FORMAT blocks, INFO
     scalars and DP sums) writes, behind the reference's header, the very bytes the unmodified reference's
-    `gt_mpi_gather --produce-Broad-GVCF -O bu` wrote for the same query"""
-    gold = open(os.path.join(GOLDEN, "bcf", case["id"] + ".bcf"), "rb").read()
-    p, out = run_broad(exe, case, tmp_path)
+    `gt_mpi_gather --produce-Broad-GVCF -O bu` wrote for the same query; with --htsjdk-conventions the bytes the reference's
+    operator writes when constructed the way the JNI path (Java GenomicsDBFeatureReader) constructs it"""
+    gold = open(os.path.join(GOLDEN, "bcf_java" if java else "bcf", case["id"] + ".bcf"), "rb").read()
+    p, out = run_broad(exe, case, tmp_path, java=java)
     if case["id"] == "t0_1_2_all_asa_at_0":       # allele-specific annotations are 2-D fields: a documented limit, reported, not guessed
         assert p.returncode != 0 and "not supported" in p.stderr
         return

@@ -82,7 +82,7 @@ static std::string read_header_text(const std::string& path, std::string& raw_pr
 }
 
 static int produce_broad_gvcf(const std::string& query_json, int rank, int device, const std::string& header_file, const std::string& ref_bases_file,
-                              const std::string& out_file, size_t buffer_capacity) {
+                              const std::string& out_file, size_t buffer_capacity, bool htsjdk_conventions) {
   VariantQueryConfig query_config;
   query_config.read_from_file(query_json, rank);
   VariantStorageManager sm(query_config.get_workspace(rank), 10u * 1024u * 1024u, device);
@@ -100,7 +100,7 @@ static int produce_broad_gvcf(const std::string& query_json, int rank, int devic
   FILE* out = fopen(out_file.c_str(), "wb");
   if (!out) { std::cerr << "cannot open " << out_file << "\n"; return -1; }
   fwrite(raw_prefix.data(), 1, raw_prefix.size(), out);
-  BroadCombinedGVCFOperator op(vcf_adapter, query_config.get_vid_mapper(), query_config);
+  BroadCombinedGVCFOperator op(vcf_adapter, query_config.get_vid_mapper(), query_config, htsjdk_conventions);
   auto drain = [&] { auto& b = vcf_adapter.get_buffer(); if (!b.empty()) fwrite(b.data(), 1, b.size(), out); b.clear(); };
   // tools/src/gt_mpi_gather.cc:350-362
   VariantQueryProcessorScanState scan_state;
@@ -117,11 +117,11 @@ static int produce_broad_gvcf(const std::string& query_json, int rank, int devic
 }
 
 int main(int argc, char** argv) {
-  std::string query_json, out_file, header_file, ref_bases_file; int rank = 0, device = 0; size_t page = 0; bool broad = false;
+  std::string query_json, out_file, header_file, ref_bases_file; int rank = 0, device = 0; size_t page = 0; bool broad = false, htsjdk = false;
   static struct option long_options[] = {{"query", 1, 0, 'j'}, {"rank", 1, 0, 'r'}, {"output", 1, 0, 'o'}, {"device", 1, 0, 'd'}, {"page-size", 1, 0, 'p'},
-                                         {"produce-Broad-GVCF", 0, 0, 'B'}, {"bcf-header", 1, 0, 'H'}, {"reference-bases", 1, 0, 'R'}, {0, 0, 0, 0}};
+                                         {"produce-Broad-GVCF", 0, 0, 'B'}, {"bcf-header", 1, 0, 'H'}, {"reference-bases", 1, 0, 'R'}, {"htsjdk-conventions", 0, 0, 'J'}, {0, 0, 0, 0}};
   int c;
-  while ((c = getopt_long(argc, argv, "j:r:o:d:p:BH:R:", long_options, NULL)) >= 0) {
+  while ((c = getopt_long(argc, argv, "j:r:o:d:p:BH:R:J", long_options, NULL)) >= 0) {
     switch (c) {
       case 'j': query_json = optarg; break;
       case 'r': rank = atoi(optarg); break;
@@ -131,6 +131,7 @@ int main(int argc, char** argv) {
       case 'B': broad = true; break;
       case 'H': header_file = optarg; break;
       case 'R': ref_bases_file = optarg; break;
+      case 'J': htsjdk = true; break;   // records as GenomicsDBBCFGenerator (JNI) makes them for the Java reader
       default: return -1;
     }
   }
@@ -138,7 +139,7 @@ int main(int argc, char** argv) {
   try {
     if (broad) {
       if (header_file.empty()) { std::cerr << "--produce-Broad-GVCF needs --bcf-header\n"; return -1; }
-      return produce_broad_gvcf(query_json, rank, device, header_file, ref_bases_file, out_file, page);
+      return produce_broad_gvcf(query_json, rank, device, header_file, ref_bases_file, out_file, page, htsjdk);
     }
     VariantQueryConfig query_config;
     query_config.read_from_file(query_json, rank);
