@@ -106,6 +106,7 @@ void VariantQueryConfig::read_from_file(const std::string& filename, int rank) {
   if (const JsonValue* v = d.find("max_diploid_alt_alleles_that_can_be_genotyped")) max_alt_ = (unsigned)v->as_int();
   if (const JsonValue* v = d.find("produce_GT_with_min_PL_value_for_spanning_deletions")) min_pl_gt_ = v->as_bool();
   if (const JsonValue* v = d.find("produce_GT_field")) produce_gt_ = v->as_bool();
+  if (const JsonValue* v = d.find("sites_only_query")) sites_only_ = v->as_bool();
 }
 
 // ------------------------------------------------------------------------------------------------ operators
@@ -247,8 +248,9 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
 }
 
 // BroadCombinedGVCFOperator::operate (broad_combined_gvcf.cc:765-901) + bcf_write (htslib vcf.c) for one site
-void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint32_t s, const VariantQueryConfig&) {
+void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint32_t s, const VariantQueryConfig& qc) {
   const uint64_t nq = b.n_query_rows, ns = b.n_sites;
+  const bool sites_only = qc.sites_only_query();   // no samples in the header, no FORMAT fields (broad_combined_gvcf.cc:178-182,302-318)
   const int64_t begin = b.site_begin[s], end = b.site_end[s];
   const ContigInfo* contig = m_vid_mapper->get_contig_location(begin);
   if (!contig) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Unknown contig for position " + std::to_string(begin));
@@ -296,6 +298,7 @@ void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint3
   if (m_dp_rule && b.info_dp_sum[s] > 0 && remapped) { enc_int1(shared, m_DP_key); enc_int1(shared, b.info_dp_sum[s]); ++n_info; }   // :721-725
   uint32_t n_fmt = 0;
   for (auto& f : m_FORMAT_fields_vec) {
+    if (sites_only) break;
     const uint64_t slot = (uint64_t)f.fmt_index * ns + s;
     const uint8_t type = b.fmt_type[slot];
     if (!type) continue;
@@ -314,7 +317,7 @@ void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint3
   const bool has_qual = m_QUAL_plain >= 0 && b.info_valid[(uint64_t)m_QUAL_plain * ns + s];
   put<uint32_t>(out, has_qual ? b.info_value[(uint64_t)m_QUAL_plain * ns + s] : 0x7F800001u);
   put<uint32_t>(out, n_allele << 16 | n_info);
-  put<uint32_t>(out, n_fmt << 24 | (uint32_t)nq);
+  put<uint32_t>(out, n_fmt << 24 | (sites_only ? 0u : (uint32_t)nq));
   put_bytes(out, shared.data(), shared.size());
   put_bytes(out, indiv.data(), indiv.size());
   ++m_num_records;

@@ -82,6 +82,8 @@ class VariantQueryConfig {
   void set_produce_GT_with_min_PL_value_for_spanning_deletions(bool v) { min_pl_gt_ = v; }
   void set_produce_GT_field(bool v) { produce_gt_ = v; }
   bool produce_GT_field() const { return produce_gt_; }
+  void set_sites_only_query(bool v) { sites_only_ = v; }
+  bool sites_only_query() const { return sites_only_; }
 
   const std::string& get_workspace(int = 0) const { return workspace_; }
   const std::string& get_array_name(int = 0) const { return array_name_; }
@@ -107,7 +109,7 @@ class VariantQueryConfig {
   std::vector<std::string> attributes_;
   VidMapper vid_;
   unsigned max_alt_ = 50;
-  bool min_pl_gt_ = false, produce_gt_ = false;
+  bool min_pl_gt_ = false, produce_gt_ = false, sites_only_ = false;
   bool bookkeeping_done_ = false;
   std::vector<std::string> remapped_names_;
   // plain fields staged for the Broad operator (do_query_bookkeeping): FORMAT fields that are not allele-dependent, scalar

@@ -28,8 +28,8 @@ def main():
     if not os.path.isdir(REF_TESTS):
         sys.exit("reference tests not present; BCF fixtures can only be regenerated where /root/reference exists")
     cases = json.load(open(os.path.join(GOLD, "manifest.json")))["cases"]
-    out_dir, java_dir = os.path.join(GOLD, "bcf"), os.path.join(GOLD, "bcf_java")
-    for d in (out_dir, java_dir):
+    out_dir, java_dir, sites_dir = os.path.join(GOLD, "bcf"), os.path.join(GOLD, "bcf_java"), os.path.join(GOLD, "bcf_sites_only")
+    for d in (out_dir, java_dir, sites_dir):
         shutil.rmtree(d, ignore_errors=True)
         os.makedirs(d)
     tmp = tempfile.mkdtemp(prefix="gdbbcf")
@@ -60,7 +60,14 @@ def main():
         if pj.returncode != 0:
             sys.exit("reference (java conventions) failed on %s: %s" % (c["id"], pj.stderr.decode()[-1500:]))
         open(os.path.join(java_dir, c["id"] + ".bcf"), "wb").write(pj.stdout)
-        print("%-50s %6d bytes, java conventions %6d bytes" % (c["id"], len(p.stdout), len(pj.stdout)))
+        # and as a sites-only query (no samples, no FORMAT fields; broad_combined_gvcf.cc:178-182,302-318)
+        qs = os.path.join(tmp, c["id"] + "_sites_only.json")
+        json.dump(dict(q, sites_only_query=True), open(qs, "w"))
+        ps = subprocess.run([BIN + "/gt_mpi_gather", "-j", qs, "--produce-Broad-GVCF", "-O", "bu"], capture_output=True, cwd=REF_TESTS)
+        if ps.returncode != 0:
+            sys.exit("reference (sites only) failed on %s: %s" % (c["id"], ps.stderr.decode()[-1500:]))
+        open(os.path.join(sites_dir, c["id"] + ".bcf"), "wb").write(ps.stdout)
+        print("%-50s %6d bytes, java conventions %6d bytes, sites only %6d bytes" % (c["id"], len(p.stdout), len(pj.stdout), len(ps.stdout)))
     shutil.rmtree(tmp, ignore_errors=True)
     write_reference_bases(out_dir)
 

@@ -57,18 +57,18 @@ def test_overflow_resume_protocol(exe, case, tmp_path):
 ALL = golden_cases()
 
 
-def run_broad(exe, case, tmp_path, page=0, java=False):
+def run_broad(exe, case, tmp_path, page=0, java=False, sites_only=False):
     q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
          "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": case["attributes"],
          "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_column_ranges"]]}],
          "query_row_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_row_ranges"]]}],
-         "produce_GT_field": case["produce_GT_field"],
+         "produce_GT_field": case["produce_GT_field"], "sites_only_query": sites_only,
          "produce_GT_with_min_PL_value_for_spanning_deletions": case["produce_GT_with_min_PL_value_for_spanning_deletions"]}
     qf = tmp_path / "query.json"
     qf.write_text(json.dumps(q))
     out = tmp_path / "out.bcf"
     cmd = [exe, "-j", str(qf), "-o", str(out), "--produce-Broad-GVCF", "--bcf-header",
-           os.path.join(GOLDEN, "bcf_java" if java else "bcf", case["id"] + ".bcf"),
+           os.path.join(GOLDEN, "bcf_sites_only" if sites_only else ("bcf_java" if java else "bcf"), case["id"] + ".bcf"),
            "--reference-bases", os.path.join(GOLDEN, "inputs", "ref_bases.tsv")] + (["-p", str(page)] if page else []) + \
           (["--htsjdk-conventions"] if java else [])
     return subprocess.run(cmd, capture_output=True, text=True), out
@@ -99,5 +99,15 @@ def test_broad_gvcf_overflow_resume(exe, case, tmp_path):
     """a 1-byte output buffer: overflow() after every record, scan_and_operate re-entered with the scan state"""
     gold = open(os.path.join(GOLDEN, "bcf", case["id"] + ".bcf"), "rb").read()
     p, out = run_broad(exe, case, tmp_path, page=1)
+    assert p.returncode == 0, p.stderr
+    assert out.read_bytes() == gold
+
+
+@pytest.mark.parametrize("case", [c for c in ALL if c["id"] in ("t0_1_2_at_0", "t6_7_8_at_0", "haploid_triploid_deletion", "info_ops0_at_0",
+                                                                 "min_PL_spanning_deletion_min_PL", "t0_overlapping_at_0")], ids=lambda c: c["id"])
+def test_broad_gvcf_sites_only(exe, case, tmp_path):
+    """"sites_only_query": true -- records without samples and FORMAT fields, INFO (incl. the DP rule over DP_FORMAT / MIN_DP) as before"""
+    gold = open(os.path.join(GOLDEN, "bcf_sites_only", case["id"] + ".bcf"), "rb").read()
+    p, out = run_broad(exe, case, tmp_path, sites_only=True)
     assert p.returncode == 0, p.stderr
     assert out.read_bytes() == gold
