@@ -1,6 +1,10 @@
 #include "gdb_host_api.h"
 
+#include <sys/uio.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <cerrno>
 #include <cstring>
 
 #include "gdb_json.h"
@@ -164,6 +168,37 @@ void VCFAdapter::set_vcf_header_text(const std::string& header) {
 }
 int VCFAdapter::get_dictionary_id(const std::string& name) const { for (auto& kv : ids_) if (kv.first == name) return kv.second; return -1; }
 int VCFAdapter::get_contig_id(const std::string& name) const { for (auto& kv : contigs_) if (kv.first == name) return kv.second; return -1; }
+void VCFAdapter::append(const void* p, size_t n, bool borrowed) {
+  if (!n) return;
+  if (fd_ < 0) { const uint8_t* b = static_cast<const uint8_t*>(p); buffer_.insert(buffer_.end(), b, b + n); return; }
+  if (!borrowed) {   // owned bytes go into chunks that never move
+    if (chunk_used_ + n > chunk_cap_) { chunk_cap_ = std::max<size_t>(n, 1u << 20); chunks_.emplace_back(new uint8_t[chunk_cap_]); chunk_used_ = 0; }
+    uint8_t* dst = chunks_.back().get() + chunk_used_;
+    memcpy(dst, p, n);
+    chunk_used_ += n;
+    p = dst;
+  }
+  if (!pending_.empty() && pending_.back().p + pending_.back().n == p) pending_.back().n += n;
+  else pending_.push_back(Range{static_cast<const uint8_t*>(p), n});
+  pending_bytes_ += n;
+}
+void VCFAdapter::flush() {
+  if (fd_ < 0 || pending_.empty()) return;
+  size_t i = 0;
+  std::vector<struct iovec> iov;
+  while (i < pending_.size()) {
+    iov.clear();
+    for (size_t k = i; k < pending_.size() && iov.size() < 512; ++k) iov.push_back({const_cast<uint8_t*>(pending_[k].p), pending_[k].n});
+    ssize_t w = writev(fd_, iov.data(), (int)iov.size());
+    if (w < 0) { if (errno == EINTR) continue; throw GenomicsDBGPUException(GDBGPU_ERR_IO, std::string("writev: ") + strerror(errno)); }
+    bytes_written_ += (uint64_t)w;
+    size_t left = (size_t)w;   // a short write ends inside some range
+    while (i < pending_.size() && left >= pending_[i].n) { left -= pending_[i].n; ++i; }
+    if (i < pending_.size() && left) { pending_[i].p += left; pending_[i].n -= left; }
+  }
+  pending_.clear(); pending_bytes_ = 0;
+  chunks_.clear(); chunk_used_ = chunk_cap_ = 0;
+}
 char VCFAdapter::get_reference_base_at_position(const std::string& contig, int64_t pos) const {
   auto it = ref_bases_.find(contig + ":" + std::to_string(pos));
   return it == ref_bases_.end() ? 'N' : it->second;
@@ -263,7 +298,10 @@ void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint3
     char base = m_vcf_adapter->get_reference_base_at_position(contig->name, pos);
     ref[0] = (base == 'A' || base == 'C' || base == 'G' || base == 'T') ? base : 'N';
   }
-  std::vector<uint8_t> shared, indiv;
+  std::vector<uint8_t> shared;
+  struct FormatPiece { std::vector<uint8_t> head; const uint8_t* block = nullptr; size_t block_bytes = 0; };
+  std::vector<FormatPiece> pieces;
+  size_t indiv_bytes = 0;
   enc_vchar(shared, "");   // ID
   enc_vchar(shared, ref);
   for (uint32_t m = 1; m < n_allele; ++m) enc_vchar(shared, allele(m));
@@ -303,15 +341,17 @@ void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint3
     const uint8_t type = b.fmt_type[slot];
     if (!type) continue;
     const uint32_t nps = b.fmt_nps[slot];
-    enc_int1(indiv, f.key);
-    enc_size(indiv, (int)nps, type);
     const size_t w = (type == BT_INT8 || type == BT_CHAR) ? 1 : (type == BT_INT16 ? 2 : 4);
-    put_bytes(indiv, b.fmt_bytes + b.fmt_offset[slot], (size_t)nq * nps * w);
+    FormatPiece pc; pc.block = b.fmt_bytes + b.fmt_offset[slot]; pc.block_bytes = (size_t)nq * nps * w;
+    enc_int1(pc.head, f.key);
+    enc_size(pc.head, (int)nps, type);
+    indiv_bytes += pc.head.size() + pc.block_bytes;
+    pieces.push_back(std::move(pc));
     ++n_fmt;
   }
-  std::vector<uint8_t>& out = m_vcf_adapter->get_buffer();
+  std::vector<uint8_t> out;   // the fixed part of the record
   put<uint32_t>(out, (uint32_t)(24 + shared.size()));
-  put<uint32_t>(out, (uint32_t)indiv.size());
+  put<uint32_t>(out, (uint32_t)indiv_bytes);
   put<int32_t>(out, rid); put<int32_t>(out, pos); put<int32_t>(out, rlen);
   // QUAL: missing unless the vid mapping gives QUAL a combine operation (broad_combined_gvcf.cc:796-808)
   const bool has_qual = m_QUAL_plain >= 0 && b.info_valid[(uint64_t)m_QUAL_plain * ns + s];
@@ -319,7 +359,11 @@ void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint3
   put<uint32_t>(out, n_allele << 16 | n_info);
   put<uint32_t>(out, n_fmt << 24 | (sites_only ? 0u : (uint32_t)nq));
   put_bytes(out, shared.data(), shared.size());
-  put_bytes(out, indiv.data(), indiv.size());
+  m_vcf_adapter->append(out.data(), out.size(), false);
+  for (auto& pc : pieces) {   // typed key + size descriptor (owned), then the block where the batch holds it (borrowed)
+    m_vcf_adapter->append(pc.head.data(), pc.head.size(), false);
+    m_vcf_adapter->append(pc.block, pc.block_bytes, true);
+  }
   ++m_num_records;
 }
 
@@ -486,6 +530,7 @@ void VariantQueryProcessor::scan_and_operate(const int, const VariantQueryConfig
   Variant variant;
   for (;;) {
     if (!st.have_batch_ || st.pos_in_batch_ >= st.batch_.n_sites) {
+      op.release_batch();   // nothing may point into the batch that is about to be replaced
       check(gdbgpu_scan_next_batch(st.scan_, 0, 0, &st.batch_));
       st.have_batch_ = true; st.pos_in_batch_ = 0;
       if (st.batch_.n_sites == 0) { st.m_done = true; gdbgpu_scan_end(st.scan_); st.scan_ = nullptr; st.have_batch_ = false; return; }

@@ -23,6 +23,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -191,6 +192,8 @@ class SingleVariantOperatorBase {
   virtual bool wants_bcf_blocks() const { return false; }
   virtual bool wants_htsjdk_conventions() const { return false; }   // FORMAT blocks as htsjdk's BCF2 codec needs them (JNI path)
   virtual void operate_on_bcf_site(const gdbgpu_batch&, uint32_t /*site*/, const VariantQueryConfig&) {}
+  // called before the memory of the current batch is reused: anything that still points into it must be consumed now
+  virtual void release_batch() {}
  protected:
   bool m_NON_REF_exists = false, m_remapping_needed = false, m_is_reference_block_only = false;
   std::string m_merged_reference_allele;
@@ -221,8 +224,22 @@ class VCFAdapter {
   char get_reference_base_at_position(const std::string& contig, int64_t pos) const;   // 'N' when unknown
   void set_buffer_capacity(size_t bytes) { capacity_ = bytes; }
   std::vector<uint8_t>& get_buffer() { return buffer_; }
-  bool overflow() const { return capacity_ && buffer_.size() >= capacity_; }
+  bool overflow() const { return capacity_ && buffer_.size() + pending_bytes_ >= capacity_; }
+  // Zero-copy output: with a file descriptor set, records are kept as a list of byte ranges -- the few header bytes of
+  // every record and field in small owned chunks, the FORMAT blocks as ranges of the batch's own (pinned) memory -- and
+  // written with writev(); nothing of the 12 MB-per-site blocks is copied on the host.  Borrowed ranges live as long as the
+  // batch: scan_and_operate flushes them before it asks for the next one.  Without a descriptor everything is appended to
+  // get_buffer() (a copy), as VCFSerializedBufferAdapter does.
+  void set_output_fd(int fd) { fd_ = fd; }
+  bool zero_copy() const { return fd_ >= 0; }
+  void append(const void* p, size_t n, bool borrowed);
+  void flush();            // write the pending ranges (zero-copy mode); no-op otherwise
+  uint64_t bytes_written() const { return bytes_written_; }
  private:
+  struct Range { const uint8_t* p; size_t n; };
+  std::vector<Range> pending_;
+  std::vector<std::unique_ptr<uint8_t[]>> chunks_; size_t chunk_used_ = 0, chunk_cap_ = 0;
+  size_t pending_bytes_ = 0; uint64_t bytes_written_ = 0; int fd_ = -1;
   std::string header_;
   std::vector<std::pair<std::string, int>> ids_, contigs_;
   std::map<std::string, char> ref_bases_;
@@ -243,6 +260,7 @@ class BroadCombinedGVCFOperator : public GA4GHOperator {
   bool wants_htsjdk_conventions() const override { return m_use_missing_values_not_vector_end; }
   void operate_on_bcf_site(const gdbgpu_batch& batch, uint32_t site, const VariantQueryConfig& query_config) override;
   bool overflow() const override { return m_vcf_adapter->overflow(); }
+  void release_batch() override { m_vcf_adapter->flush(); }
   uint64_t get_num_records() const { return m_num_records; }
  private:
   VCFAdapter* m_vcf_adapter;

@@ -7,7 +7,9 @@
 // an uncompressed BCF2 file: the header is taken verbatim from --bcf-header (a BCF written by the reference for the same
 // query: producing the header is htslib's job on the unchanged host side), the records come from the kernels' FORMAT
 // blocks / INFO scalars through the host mirror.
+#include <fcntl.h>
 #include <getopt.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstring>
@@ -97,11 +99,13 @@ static int produce_broad_gvcf(const std::string& query_json, int rank, int devic
     std::string contig, base; long long pos;
     while (rb >> contig >> pos >> base) vcf_adapter.set_reference_base(contig, pos, base[0]);
   }
-  FILE* out = fopen(out_file.c_str(), "wb");
-  if (!out) { std::cerr << "cannot open " << out_file << "\n"; return -1; }
-  fwrite(raw_prefix.data(), 1, raw_prefix.size(), out);
+  // records leave through writev(): header bytes from small owned chunks, FORMAT blocks straight from the batch's pinned memory
+  const int fd = out_file == "-" ? 1 : open(out_file.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  if (fd < 0) { std::cerr << "cannot open " << out_file << "\n"; return -1; }
+  vcf_adapter.set_output_fd(fd);
+  vcf_adapter.append(raw_prefix.data(), raw_prefix.size(), false);
   BroadCombinedGVCFOperator op(vcf_adapter, query_config.get_vid_mapper(), query_config, htsjdk_conventions);
-  auto drain = [&] { auto& b = vcf_adapter.get_buffer(); if (!b.empty()) fwrite(b.data(), 1, b.size(), out); b.clear(); };
+  auto drain = [&] { vcf_adapter.flush(); };
   // tools/src/gt_mpi_gather.cc:350-362
   VariantQueryProcessorScanState scan_state;
   for (auto i = 0u; i < std::max(1u, query_config.get_num_column_intervals()); ++i) {
@@ -111,8 +115,9 @@ static int produce_broad_gvcf(const std::string& query_json, int rank, int devic
     }
     scan_state.reset();
   }
-  fclose(out);
-  printf("{\"records\": %llu}\n", (unsigned long long)op.get_num_records());
+  drain();
+  if (fd != 1) close(fd);
+  fprintf(fd == 1 ? stderr : stdout, "{\"records\": %llu, \"bytes\": %llu}\n", (unsigned long long)op.get_num_records(), (unsigned long long)vcf_adapter.bytes_written());
   return 0;
 }
 
