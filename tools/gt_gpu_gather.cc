@@ -11,6 +11,7 @@
 #include <getopt.h>
 #include <unistd.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -71,13 +72,19 @@ class HotPathDumpOperator : public GA4GHOperator {
 static std::string read_header_text(const std::string& path, std::string& raw_prefix) {
   std::ifstream f(path, std::ios::binary);
   if (!f) throw std::runtime_error("cannot open " + path);
+  char magic[9] = {0};
+  f.read(magic, 9);
+  if (f.gcount() == 9 && memcmp(magic, "BCF\2\2", 5) == 0) {   // only the header is read: the file may hold gigabytes of records
+    uint32_t l_text; memcpy(&l_text, magic + 5, 4);
+    raw_prefix.assign(magic, 9);
+    raw_prefix.resize(9 + (size_t)l_text);
+    f.read(&raw_prefix[9], l_text);
+    if ((size_t)f.gcount() != l_text) throw std::runtime_error("truncated BCF header in " + path);
+    return std::string(raw_prefix.data() + 9, strnlen(raw_prefix.data() + 9, l_text));
+  }
+  f.clear(); f.seekg(0);
   std::stringstream ss; ss << f.rdbuf();
   const std::string all = ss.str();
-  if (all.size() >= 9 && all.compare(0, 5, "BCF\2\2") == 0) {
-    uint32_t l_text; memcpy(&l_text, all.data() + 5, 4);
-    raw_prefix = all.substr(0, 9 + (size_t)l_text);
-    return std::string(all.data() + 9, strnlen(all.data() + 9, l_text));
-  }
   uint32_t l_text = (uint32_t)all.size() + 1;
   raw_prefix = std::string("BCF\2\2", 5) + std::string((const char*)&l_text, 4) + all + std::string(1, '\0');
   return all;
@@ -85,11 +92,16 @@ static std::string read_header_text(const std::string& path, std::string& raw_pr
 
 static int produce_broad_gvcf(const std::string& query_json, int rank, int device, const std::string& header_file, const std::string& ref_bases_file,
                               const std::string& out_file, size_t buffer_capacity, bool htsjdk_conventions) {
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  const auto t0 = now();
   VariantQueryConfig query_config;
   query_config.read_from_file(query_json, rank);
   VariantStorageManager sm(query_config.get_workspace(rank), 10u * 1024u * 1024u, device);
+  const auto t1 = now();   // CUDA context is up
   VariantQueryProcessor qp(&sm, query_config.get_array_name(rank), query_config.get_vid_mapper());
   qp.do_query_bookkeeping(query_config, true, /*stage_broad_gvcf_fields=*/true);
+  const auto t2 = now();   // fragment files are staged in HBM
   VCFAdapter vcf_adapter;
   std::string raw_prefix;
   vcf_adapter.set_vcf_header_text(read_header_text(header_file, raw_prefix));
@@ -117,7 +129,9 @@ static int produce_broad_gvcf(const std::string& query_json, int rank, int devic
   }
   drain();
   if (fd != 1) close(fd);
-  fprintf(fd == 1 ? stderr : stdout, "{\"records\": %llu, \"bytes\": %llu}\n", (unsigned long long)op.get_num_records(), (unsigned long long)vcf_adapter.bytes_written());
+  const auto t3 = now();
+  fprintf(fd == 1 ? stderr : stdout, "{\"records\": %llu, \"bytes\": %llu, \"seconds\": {\"context\": %.3f, \"open_array\": %.3f, \"scan_and_write\": %.3f}}\n",
+          (unsigned long long)op.get_num_records(), (unsigned long long)vcf_adapter.bytes_written(), secs(t0, t1), secs(t1, t2), secs(t2, t3));
   return 0;
 }
 
