@@ -16,6 +16,8 @@ LEN_R, LEN_A, LEN_G = 0, 1, 2
 ELEM_INT32, ELEM_FLOAT32, ELEM_CHAR = 0, 1, 2
 SCAN_FULL, SCAN_NO_DELETIONS, SCAN_MIN_PL_GT, SCAN_WANT_LUT, SCAN_DEVICE_OUTPUT = 1, 2, 4, 8, 16
 SCAN_BCF_FORMAT, SCAN_PRODUCE_GT, SCAN_NO_PREFETCH, SCAN_HTSJDK_CONVENTIONS = 32, 64, 128, 256
+SCAN_CELLS_ONLY = 512
+CELL_FIELD_REF, CELL_FIELD_ALT, CELL_FIELD_GT, CELL_FIELD_REMAPPED, CELL_FIELD_PLAIN = 0, 1, 2, 3, 4
 BT_SIZE = {1: 1, 2: 2, 3: 4, 5: 4, 7: 1}
 SITE_NONREF, SITE_REMAPPED, SITE_G_SUPPRESSED = 1, 2, 4
 CALL_REDUCED = 0x40000000
@@ -72,6 +74,14 @@ class FieldOut(C.Structure):
     _fields_ = [("data", C.c_void_p), ("base", C.c_void_p), ("stride", C.c_void_p), ("len", C.c_void_p)]
 
 
+class CellList(C.Structure):
+    _fields_ = [("n_cells", C.c_uint64), ("n_left", C.c_uint64), ("cell", C.c_void_p), ("row", C.c_void_p), ("begin", C.c_void_p), ("end", C.c_void_p)]
+
+
+class AlleleCounts(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("column", C.c_void_p), ("count", C.c_void_p), ("ref_pos", C.c_void_p), ("alt_pos", C.c_void_p), ("bytes", C.c_void_p)]
+
+
 class Batch(C.Structure):
     _fields_ = [("first_site", C.c_uint64), ("n_sites", C.c_uint32), ("n_query_rows", C.c_uint64),
                 ("site_begin", C.c_void_p), ("site_end", C.c_void_p), ("site_flags", C.c_void_p),
@@ -121,6 +131,10 @@ def lib():
         L.gdbgpu_scan_get_info.argtypes = [C.c_void_p, C.POINTER(ScanInfo)]
         L.gdbgpu_scan_next_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(Batch)]
         L.gdbgpu_scan_seek.argtypes = [C.c_void_p, C.c_uint64]
+        L.gdbgpu_scan_cells.argtypes = [C.c_void_p, C.POINTER(CellList)]
+        L.gdbgpu_scan_cells_histogram.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.gdbgpu_scan_cells_allele_counts.argtypes = [C.c_void_p, C.POINTER(AlleleCounts)]
+        L.gdbgpu_scan_cells_fetch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.gdbgpu_scan_end.argtypes = [C.c_void_p]
         _lib = L
     return _lib
@@ -389,6 +403,40 @@ class Scan:
 
     def seek(self, site):
         self.ctx.check(lib().gdbgpu_scan_seek(self.h, site))
+
+    # ---- the columnar iterator (gdbgpu_scan_cells*) ----
+    def cells(self):
+        """-> dict(n_left, cell, row, begin, end): the cells the reference's columnar iterator visits, in its order"""
+        cl = CellList()
+        self.ctx.check(lib().gdbgpu_scan_cells(self.h, C.byref(cl)))
+        n = cl.n_cells
+        return dict(n_left=int(cl.n_left), cell=_view(cl.cell, np.uint64, n).copy(), row=_view(cl.row, np.int64, n).copy(),
+                    begin=_view(cl.begin, np.int64, n).copy(), end=_view(cl.end, np.int64, n).copy())
+
+    def cells_histogram(self, begin, end, bin_size):
+        n_bins = (end - begin) // bin_size + 1
+        counts = np.zeros(n_bins, dtype=np.uint64)
+        self.ctx.check(lib().gdbgpu_scan_cells_histogram(self.h, begin, end, bin_size, counts.ctypes.data, n_bins))
+        return counts
+
+    def cells_allele_counts(self):
+        """-> [(column, REF, ALT, count)] in the order AlleleCountOperator::print_allele_counts prints"""
+        ac = AlleleCounts()
+        self.ctx.check(lib().gdbgpu_scan_cells_allele_counts(self.h, C.byref(ac)))
+        n = ac.n
+        col, cnt = _view(ac.column, np.int64, n), _view(ac.count, np.uint64, n)
+        rp, ap = _view(ac.ref_pos, np.uint32, 2 * n), _view(ac.alt_pos, np.uint32, 2 * n)
+        nb = int(ap[2 * n - 2] + ap[2 * n - 1]) if n else 0
+        by = bytes(_view(ac.bytes, np.uint8, nb)) if nb else b""
+        return [(int(col[k]), by[rp[2 * k]:rp[2 * k] + rp[2 * k + 1]].decode(), by[ap[2 * k]:ap[2 * k] + ap[2 * k + 1]].decode(), int(cnt[k])) for k in range(n)]
+
+    def cells_fetch(self, kind, index=0):
+        """-> (offsets[n_cells + 1], bytes) of one column over the listed cells"""
+        n = self.cells()["row"].size
+        off, by = C.c_void_p(), C.c_void_p()
+        self.ctx.check(lib().gdbgpu_scan_cells_fetch(self.h, kind, index, C.byref(off), C.byref(by)))
+        o = _view(off, np.uint64, n + 1).copy()
+        return o, (bytes(_view(by, np.uint8, int(o[-1]))) if n and o[-1] else b"")
 
     def close(self):
         if self.h:

@@ -17,7 +17,7 @@
 #include <vector>
 
 #include "gdb_inflate.cuh"
-#include "gdb_kernels3.cuh"
+#include "gdb_kernels4.cuh"
 #include "gdb_tiledb.h"
 
 using namespace gdb;
@@ -470,6 +470,12 @@ struct gdbgpu_scan {
   uint32_t cap_allele_recs = 0, cap_allele_bytes = 0, cap_lut = 0;
   uint64_t avg_site_bytes = 0;
   int n_out = 0;
+  // columnar-iterator view of the query (gdbgpu_scan_cells*): the device list and what was copied out for the caller
+  bool cells_only = false, cells_built = false; uint64_t n_cells = 0, n_left = 0;
+  DevBuf<uint32_t> cell_list;
+  std::vector<uint64_t> h_cell; std::vector<int64_t> h_row, h_begin, h_end;
+  std::map<std::pair<int, int>, std::pair<std::vector<uint64_t>, std::vector<uint8_t>>> fetched;
+  std::vector<int64_t> ac_column; std::vector<uint64_t> ac_count; std::vector<uint32_t> ac_ref_pos, ac_alt_pos; std::vector<uint8_t> ac_bytes;
 };
 
 namespace {
@@ -558,6 +564,15 @@ void scan_prepare(gdbgpu_scan* s) {
     CK(cudaStreamSynchronize(ctx->stream));
   }
   S.iL = hb[0]; S.i0 = hb[1]; S.i1 = hb[2];
+  s->cells_only = (p.flags & GDBGPU_SCAN_CELLS_ONLY) != 0;
+  if (s->cells_only) {   // the columnar iterator neither merges calls nor minds overlaps: the left sweep is all it needs
+    s->bitmap.alloc(S.n_words);
+    CK(cudaMemsetAsync(s->bitmap.p, 0, S.n_words * 8, ctx->stream));
+    S.bitmap = s->bitmap.p;
+    S.i0 = S.scan_full ? 0 : hb[0];
+    LAUNCH(ctx, k_left_sweep, blocks_for(S.nq, 256), 256, a->dev, S);
+    return;
+  }
   if (a->n_bad) {
     if (a->n_bad > BAD_CAP) throw OverlapError("Unhandled overlapping variants (too many to enumerate)");
     LAUNCH(ctx, k_check_evictions, blocks_for(a->n_bad, 128), 128, a->dev, S, a->bad_cell.p, a->bad_pred_col.p, (uint32_t)a->n_bad);
@@ -1013,6 +1028,197 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
   return GDBGPU_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ K7: columnar iterator
+// genomicsdb_iterators.cc:181-300,425-510 as a list: [0, n_left) the calls reaching into the interval from the left,
+// ordered by (begin, row); then the interval's begin cells of the queried rows in storage order.
+void cells_build(gdbgpu_scan* s) {
+  if (s->cells_built) return;
+  gdbgpu_array* a = s->arr; gdbgpu_ctx* ctx = s->ctx; ScanDev S = s->S;
+  s->n_cells = s->n_left = 0; s->cells_built = true;
+  if (a->n == 0 || S.nq == 0 || S.q_lo > S.q_hi) return;
+  S.i0 = S.iL;   // the traversal starts at the first cell with column >= q_lo
+  DevBuf<uint32_t> flag, pos, total, sums, left_cell, left_sorted; DevBuf<uint64_t> key, left_key, left_key_sorted; DevBuf<uint8_t> tmp;
+  total.alloc(1);
+  uint32_t n_left = 0, n_fwd = 0;
+  if (!S.scan_full) {
+    flag.alloc(S.nq); pos.alloc(S.nq); key.alloc(S.nq);
+    LAUNCH(ctx, k_cells_left_flag, blocks_for(S.nq, 256), 256, a->dev, S, flag.p, key.p);
+    exclusive_scan<uint32_t, uint32_t>(ctx, flag.p, pos.p, S.nq, total.p, sums);
+    CK(cudaMemcpyAsync(&n_left, total.p, 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+    if (n_left) {
+      left_cell.alloc(n_left); left_sorted.alloc(n_left); left_key.alloc(n_left); left_key_sorted.alloc(n_left);
+      LAUNCH(ctx, k_cells_left_compact, blocks_for(S.nq, 256), 256, S, flag.p, pos.p, key.p, left_cell.p, left_key.p);
+      radix_sort_pairs(ctx, left_key.p, left_key_sorted.p, left_cell.p, left_sorted.p, n_left, 64, tmp);   // stable: rows stay ascending within a column
+    }
+  }
+  const uint64_t span = S.i1 - S.i0;
+  if (span) {
+    flag.alloc(span); pos.alloc(span);
+    LAUNCH(ctx, k_cells_fwd_flag, blocks_for(span, 256), 256, a->dev, S, flag.p);
+    exclusive_scan<uint32_t, uint32_t>(ctx, flag.p, pos.p, span, total.p, sums);
+    CK(cudaMemcpyAsync(&n_fwd, total.p, 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+  }
+  s->n_left = n_left; s->n_cells = (uint64_t)n_left + n_fwd;
+  s->cell_list.alloc(std::max<uint64_t>(s->n_cells, 1));
+  if (n_left) CK(cudaMemcpyAsync(s->cell_list.p, left_sorted.p, (size_t)n_left * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (n_fwd) LAUNCH(ctx, k_cells_fwd_compact, blocks_for(span, 256), 256, S, flag.p, pos.p, s->cell_list.p + n_left);
+  CK(cudaStreamSynchronize(ctx->stream));
+}
+
+void cells_to_host(gdbgpu_scan* s, gdbgpu_cell_list* out) {
+  cells_build(s);
+  gdbgpu_ctx* ctx = s->ctx; const uint64_t n = s->n_cells;
+  if (s->h_cell.size() != n || !n) {
+    s->h_cell.resize(n); s->h_row.resize(n); s->h_begin.resize(n); s->h_end.resize(n);
+    if (n) {
+      DevBuf<uint64_t> cell; DevBuf<int64_t> row, begin, end;
+      cell.alloc(n); row.alloc(n); begin.alloc(n); end.alloc(n);
+      LAUNCH(ctx, k_cells_fill, blocks_for(n, 256), 256, s->arr->dev, s->cell_list.p, n, cell.p, row.p, begin.p, end.p);
+      CK(cudaMemcpyAsync(s->h_cell.data(), cell.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(s->h_row.data(), row.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(s->h_begin.data(), begin.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(s->h_end.data(), end.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  out->n_cells = n; out->n_left = s->n_left;
+  out->cell = s->h_cell.data(); out->row = s->h_row.data(); out->begin = s->h_begin.data(); out->end = s->h_end.data();
+}
+
+void cells_histogram(gdbgpu_scan* s, uint64_t h_begin, uint64_t h_end, uint64_t bin_size, uint64_t* counts, uint64_t n_bins) {
+  if (!bin_size || h_end < h_begin || n_bins != (h_end - h_begin) / bin_size + 1) throw ArgError("histogram: n_bins must be (end - begin) / bin_size + 1");
+  cells_build(s);
+  gdbgpu_ctx* ctx = s->ctx;
+  DevBuf<unsigned long long> d; d.alloc(n_bins);
+  CK(cudaMemsetAsync(d.p, 0, n_bins * 8, ctx->stream));
+  if (s->n_cells) LAUNCH(ctx, k_cells_hist, blocks_for(s->n_cells, 256), 256, s->arr->dev, s->cell_list.p, s->n_cells, h_begin, h_end, bin_size, n_bins, d.p);
+  CK(cudaMemcpyAsync(counts, d.p, n_bins * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+}
+
+// bytes of one column for a device list of cells -> host (offsets[n + 1] + values)
+void fetch_column(gdbgpu_scan* s, const DevVar& col, int32_t fixed_bytes, const uint32_t* list, uint64_t n, std::vector<uint64_t>& off, std::vector<uint8_t>& val) {
+  gdbgpu_ctx* ctx = s->ctx;
+  off.assign(n + 1, 0); val.clear();
+  if (!n) return;
+  if (fixed_bytes) {
+    DevBuf<uint8_t> g; g.alloc(n * (uint64_t)fixed_bytes);
+    LAUNCH(ctx, k_gather_bytes, blocks_for(n, 256), 256, col.val.p, list, n, (uint32_t)fixed_bytes, g.p);
+    val.resize(n * (uint64_t)fixed_bytes);
+    CK(cudaMemcpyAsync(val.data(), g.p, val.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t i = 0; i <= n; ++i) off[i] = i * (uint64_t)fixed_bytes;
+    return;
+  }
+  DevVar g;
+  gather_var(ctx, col, list, n, g);
+  val.resize(g.bytes);
+  CK(cudaMemcpyAsync(off.data(), g.off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (g.bytes) CK(cudaMemcpyAsync(val.data(), g.val.p, g.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+}
+
+void cells_fetch(gdbgpu_scan* s, int32_t kind, int32_t index, const uint64_t** offsets, const uint8_t** bytes) {
+  cells_build(s);
+  gdbgpu_array* a = s->arr;
+  const DevVar* col = nullptr; int32_t fixed_bytes = 0;
+  switch (kind) {
+    case GDBGPU_CELL_FIELD_REF: col = &a->ref; break;
+    case GDBGPU_CELL_FIELD_ALT: col = &a->alt; break;
+    case GDBGPU_CELL_FIELD_GT: if (!a->has_gt) throw ArgError("the array has no GT column"); col = &a->gt; break;
+    case GDBGPU_CELL_FIELD_REMAPPED: if (index < 0 || (size_t)index >= a->fields.size()) throw ArgError("no such allele-dependent field"); col = a->fields[index].get(); break;
+    case GDBGPU_CELL_FIELD_PLAIN:
+      if (index < 0 || (size_t)index >= a->plain.size()) throw ArgError("no such plain field");
+      col = a->plain[index].get();
+      fixed_bytes = a->pm[index].fixed_len * (a->pm[index].elem == GDBGPU_ELEM_CHAR ? 1 : 4);
+      break;
+    default: throw ArgError("unknown cell field kind");
+  }
+  auto& slot = s->fetched[std::make_pair((int)kind, (int)index)];
+  if (slot.first.size() != s->n_cells + 1) fetch_column(s, *col, fixed_bytes, s->cell_list.p, s->n_cells, slot.first, slot.second);
+  *offsets = slot.first.data(); *bytes = slot.second.data();
+}
+
+// AlleleCountOperator (variant_operations.cc:900-1089): counted on the device per (column, normalised REF, normalised ALT)
+// hash; only one representative cell per distinct key crosses to the host, where its strings are cut and the records sorted
+// the way the reference's nested std::map prints them.
+void cells_allele_counts(gdbgpu_scan* s, gdbgpu_allele_counts* out) {
+  cells_build(s);
+  gdbgpu_array* a = s->arr; gdbgpu_ctx* ctx = s->ctx; const uint64_t n = s->n_cells;
+  s->ac_column.clear(); s->ac_count.clear(); s->ac_ref_pos.clear(); s->ac_alt_pos.clear(); s->ac_bytes.clear();
+  uint32_t n_ent = 0, n_keys = 0;
+  DevBuf<uint32_t> cnt, pos, total, sums, ent_cell, ent_alt, iota, ent_sorted, flag, head_ent, head_start, rep_cell, rep_alt, rep_list;
+  DevBuf<uint64_t> key, key_sorted; DevBuf<uint8_t> tmp;
+  const uint32_t gt_step = a->gt_phased ? 2u : 1u;
+  if (n && a->has_gt) {
+    cnt.alloc(n); pos.alloc(n); total.alloc(1);
+    LAUNCH(ctx, k_ac_count, blocks_for(n, 256), 256, a->dev, s->cell_list.p, n, gt_step, cnt.p);
+    exclusive_scan<uint32_t, uint32_t>(ctx, cnt.p, pos.p, n, total.p, sums);
+    CK(cudaMemcpyAsync(&n_ent, total.p, 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+  }
+  std::vector<uint32_t> h_start, h_cell, h_alt; std::vector<int64_t> h_column; std::vector<uint64_t> r_off, a_off; std::vector<uint8_t> r_val, a_val;
+  if (n_ent) {
+    key.alloc(n_ent); key_sorted.alloc(n_ent); ent_cell.alloc(n_ent); ent_alt.alloc(n_ent); iota.alloc(n_ent); ent_sorted.alloc(n_ent); flag.alloc(n_ent);
+    LAUNCH(ctx, k_ac_fill, blocks_for(n, 256), 256, a->dev, s->cell_list.p, n, gt_step, pos.p, key.p, ent_cell.p, ent_alt.p);
+    LAUNCH(ctx, k_iota, blocks_for(n_ent, 256), 256, iota.p, (uint64_t)n_ent);
+    radix_sort_pairs(ctx, key.p, key_sorted.p, iota.p, ent_sorted.p, n_ent, 64, tmp);
+    LAUNCH(ctx, k_ac_heads, blocks_for(n_ent, 256), 256, key_sorted.p, (uint64_t)n_ent, flag.p);
+    pos.alloc(n_ent);
+    exclusive_scan<uint32_t, uint32_t>(ctx, flag.p, pos.p, n_ent, total.p, sums);
+    CK(cudaMemcpyAsync(&n_keys, total.p, 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+    head_ent.alloc(n_keys); head_start.alloc(n_keys); rep_cell.alloc(n_keys); rep_alt.alloc(n_keys); rep_list.alloc(n_keys);
+    LAUNCH(ctx, k_ac_compact, blocks_for(n_ent, 256), 256, flag.p, pos.p, ent_sorted.p, (uint64_t)n_ent, head_ent.p, head_start.p);
+    LAUNCH(ctx, k_gather_u32, blocks_for(n_keys, 256), 256, ent_cell.p, head_ent.p, (uint64_t)n_keys, rep_cell.p);   // list index of the representative
+    LAUNCH(ctx, k_gather_u32, blocks_for(n_keys, 256), 256, ent_alt.p, head_ent.p, (uint64_t)n_keys, rep_alt.p);
+    LAUNCH(ctx, k_gather_u32, blocks_for(n_keys, 256), 256, s->cell_list.p, rep_cell.p, (uint64_t)n_keys, rep_list.p);  // its cell
+    h_start.resize(n_keys); h_cell.resize(n_keys); h_alt.resize(n_keys);
+    CK(cudaMemcpyAsync(h_start.data(), head_start.p, (size_t)n_keys * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_cell.data(), rep_list.p, (size_t)n_keys * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_alt.data(), rep_alt.p, (size_t)n_keys * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    fetch_column(s, a->ref, 0, rep_list.p, n_keys, r_off, r_val);
+    fetch_column(s, a->alt, 0, rep_list.p, n_keys, a_off, a_val);
+    DevBuf<uint64_t> c64; DevBuf<int64_t> row, begin, end;
+    c64.alloc(n_keys); row.alloc(n_keys); begin.alloc(n_keys); end.alloc(n_keys);
+    LAUNCH(ctx, k_cells_fill, blocks_for(n_keys, 256), 256, a->dev, rep_list.p, (uint64_t)n_keys, c64.p, row.p, begin.p, end.p);
+    h_column.resize(n_keys);
+    CK(cudaMemcpyAsync(h_column.data(), begin.p, (size_t)n_keys * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  // host: cut the representative strings (normalize_REF_ALT_pair), order as map<column, map<pair<REF, ALT>, count>>
+  struct Rec { int64_t column; std::string ref, alt; uint64_t count; };
+  std::vector<Rec> recs(n_keys);
+  for (uint32_t k = 0; k < n_keys; ++k) {
+    Rec& r = recs[k];
+    r.count = (k + 1 < n_keys ? h_start[k + 1] : n_ent) - h_start[k];
+    r.column = h_column[k];
+    std::string ref((const char*)r_val.data() + r_off[k], r_off[k + 1] - r_off[k]);
+    const char* ab = (const char*)a_val.data() + a_off[k]; size_t al = a_off[k + 1] - a_off[k];
+    size_t t0 = 0, tok = 0;
+    while (tok < h_alt[k] && t0 < al) { if (ab[t0] == '|') ++tok; ++t0; }
+    size_t t1 = t0; while (t1 < al && ab[t1] != '|') ++t1;
+    std::string alt(ab + t0, t1 - t0);
+    if (ref.size() > 1 && !alt.empty()) {
+      const bool symbolic = (alt.size() == 1 && (alt[0] == '&' || alt[0] == '*')) || (alt.front() == '<' && alt.back() == '>') || alt.find_first_of("[]") != std::string::npos;
+      if (symbolic) ref.resize(1);
+      else {
+        size_t suffix = 0;
+        if (alt.size() >= ref.size()) suffix = ref.size() - 1; else if (alt.size() > 1) suffix = alt.size() - 1;
+        ref.resize(ref.size() - suffix); alt.resize(alt.size() - suffix);
+      }
+    }
+    r.ref = ref; r.alt = alt;
+  }
+  std::sort(recs.begin(), recs.end(), [](const Rec& x, const Rec& y) { return x.column != y.column ? x.column < y.column : (x.ref != y.ref ? x.ref < y.ref : x.alt < y.alt); });
+  for (auto& r : recs) {
+    s->ac_column.push_back(r.column); s->ac_count.push_back(r.count);
+    s->ac_ref_pos.push_back((uint32_t)s->ac_bytes.size()); s->ac_ref_pos.push_back((uint32_t)r.ref.size()); s->ac_bytes.insert(s->ac_bytes.end(), r.ref.begin(), r.ref.end());
+    s->ac_alt_pos.push_back((uint32_t)s->ac_bytes.size()); s->ac_alt_pos.push_back((uint32_t)r.alt.size()); s->ac_bytes.insert(s->ac_bytes.end(), r.alt.begin(), r.alt.end());
+  }
+  out->n = recs.size(); out->column = s->ac_column.data(); out->count = s->ac_count.data();
+  out->ref_pos = s->ac_ref_pos.data(); out->alt_pos = s->ac_alt_pos.data(); out->bytes = s->ac_bytes.data();
+}
+
 template <class F>
 int guarded(gdbgpu_ctx* ctx, F&& f) {
   tl_ctx = ctx;
@@ -1297,7 +1503,26 @@ int gdbgpu_scan_get_info(const gdbgpu_scan* s, gdbgpu_scan_info* info) {
 }
 int gdbgpu_scan_next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_batch* batch) {
   if (!s || !batch) return GDBGPU_ERR_ARG;
-  return guarded(s->ctx, [&] { CK(cudaSetDevice(s->ctx->device)); next_batch(s, max_sites, max_bytes, batch); });
+  return guarded(s->ctx, [&] {
+    if (s->cells_only) throw ArgError("GDBGPU_SCAN_CELLS_ONLY: the scan serves gdbgpu_scan_cells* only");
+    CK(cudaSetDevice(s->ctx->device)); next_batch(s, max_sites, max_bytes, batch);
+  });
+}
+int gdbgpu_scan_cells(gdbgpu_scan* s, gdbgpu_cell_list* out) {
+  if (!s || !out) return GDBGPU_ERR_ARG;
+  return guarded(s->ctx, [&] { CK(cudaSetDevice(s->ctx->device)); cells_to_host(s, out); });
+}
+int gdbgpu_scan_cells_histogram(gdbgpu_scan* s, uint64_t begin, uint64_t end, uint64_t bin_size, uint64_t* counts, uint64_t n_bins) {
+  if (!s || !counts) return GDBGPU_ERR_ARG;
+  return guarded(s->ctx, [&] { CK(cudaSetDevice(s->ctx->device)); cells_histogram(s, begin, end, bin_size, counts, n_bins); });
+}
+int gdbgpu_scan_cells_allele_counts(gdbgpu_scan* s, gdbgpu_allele_counts* out) {
+  if (!s || !out) return GDBGPU_ERR_ARG;
+  return guarded(s->ctx, [&] { CK(cudaSetDevice(s->ctx->device)); cells_allele_counts(s, out); });
+}
+int gdbgpu_scan_cells_fetch(gdbgpu_scan* s, int32_t kind, int32_t index, const uint64_t** offsets, const uint8_t** bytes) {
+  if (!s || !offsets || !bytes) return GDBGPU_ERR_ARG;
+  return guarded(s->ctx, [&] { CK(cudaSetDevice(s->ctx->device)); cells_fetch(s, kind, index, offsets, bytes); });
 }
 int gdbgpu_scan_seek(gdbgpu_scan* s, uint64_t site_idx) {
   if (!s || site_idx > s->S.n_sites) return GDBGPU_ERR_ARG;

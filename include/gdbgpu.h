@@ -156,6 +156,8 @@ void gdbgpu_array_close(gdbgpu_array* arr);
                                              * use_missing_values_only_not_vector_end, genomicsdb_bcf_generator.cc:60-83; variant_field_handler.cc:
                                              * 845-866): rows padded with missing instead of vector_end, a row without GT is a no-call, strings
                                              * vector_end only */
+#define GDBGPU_SCAN_CELLS_ONLY       512u   /* the scan serves gdbgpu_scan_cells* only (the columnar iterator neither merges calls nor minds
+                                             * overlapping ones): no sweep state is built, gdbgpu_scan_next_batch is refused */
 
 typedef struct gdbgpu_scan_params {
   int64_t col_lo, col_hi;            /* inclusive TileDB column interval; ignored with GDBGPU_SCAN_FULL */
@@ -255,6 +257,46 @@ int gdbgpu_scan_next_batch(gdbgpu_scan* scan, uint32_t max_sites, uint64_t max_b
 /* Rewind to site idx (resume after a consumer-side overflow in the middle of a batch). */
 int gdbgpu_scan_seek(gdbgpu_scan* scan, uint64_t site_idx);
 void gdbgpu_scan_end(gdbgpu_scan* scan);
+
+/* ---- the columnar iterator ------------------------------------------------------------------------------
+ * Replaces SingleCellTileDBIterator + VariantQueryProcessor::iterate_over_cells (genomicsdb_iterators.cc:181-300,425-510;
+ * query_variants.cc:557-576) for one query interval: the cells the reference's iterator hands to a
+ * SingleCellOperatorBase, in its order -- first the calls that began before col_lo and reach into the interval (found
+ * through their END copies, ordered by begin column then row), then the interval's begin cells of the queried rows in
+ * storage order.  The list is built on the device; everything below works on any scan, GDBGPU_SCAN_CELLS_ONLY makes
+ * gdbgpu_scan_begin skip what only the combine needs.  Host pointers stay valid until gdbgpu_scan_end. */
+typedef struct gdbgpu_cell_list {
+  uint64_t n_cells, n_left;   /* the first n_left entries are the calls reaching in from the left */
+  const uint64_t* cell;       /* index in the array's merged cell order (gdbgpu_array_copy_cells); a left call is named by its END copy */
+  const int64_t* row;         /* GenomicsDBColumnarCell::get_coordinates()[0] */
+  const int64_t* begin;       /* ... [1]: the call's begin column (coordinates and END swapped back for an END copy) */
+  const int64_t* end;
+} gdbgpu_cell_list;
+int gdbgpu_scan_cells(gdbgpu_scan* scan, gdbgpu_cell_list* out);
+
+/* ColumnHistogramOperator(begin, end, bin_size) over the listed cells (variant_operations.cc:732-765): counts[n_bins],
+ * n_bins = (end - begin) / bin_size + 1, host memory of the caller.  Nothing but the counts leaves the device. */
+int gdbgpu_scan_cells_histogram(gdbgpu_scan* scan, uint64_t begin, uint64_t end, uint64_t bin_size, uint64_t* counts, uint64_t n_bins);
+
+/* AlleleCountOperator over the listed cells (variant_operations.cc:900-1089): one record per (begin column, normalised
+ * REF, normalised ALT) with the number of GT elements naming that ALT, ordered as print_allele_counts prints them
+ * (column, REF, ALT).  Strings: bytes + ref_pos / alt_pos[2k] offset, [2k + 1] length. */
+typedef struct gdbgpu_allele_counts {
+  uint64_t n;
+  const int64_t* column; const uint64_t* count;
+  const uint32_t* ref_pos; const uint32_t* alt_pos; const uint8_t* bytes;
+} gdbgpu_allele_counts;
+int gdbgpu_scan_cells_allele_counts(gdbgpu_scan* scan, gdbgpu_allele_counts* out);
+
+/* The bytes of one column for every listed cell (what GenomicsDBColumnarCell::get_field_ptr_for_query_idx / get_field_length
+ * give the print operators): offsets[n_cells + 1] into bytes.  kind REF / ALT / GT, or the index-th allele-dependent
+ * field (gdbgpu_field_desc order) or plain field (gdbgpu_plain_field_desc order) the array was opened with. */
+#define GDBGPU_CELL_FIELD_REF      0
+#define GDBGPU_CELL_FIELD_ALT      1
+#define GDBGPU_CELL_FIELD_GT       2
+#define GDBGPU_CELL_FIELD_REMAPPED 3
+#define GDBGPU_CELL_FIELD_PLAIN    4
+int gdbgpu_scan_cells_fetch(gdbgpu_scan* scan, int32_t kind, int32_t index, const uint64_t** offsets, const uint8_t** bytes);
 
 /* library identity (for the test that checks every declared symbol is exported) */
 const char* gdbgpu_version(void);
