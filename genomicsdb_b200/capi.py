@@ -435,8 +435,8 @@ class Scan:
         n = self.cells()["row"].size
         off, by = C.c_void_p(), C.c_void_p()
         self.ctx.check(lib().gdbgpu_scan_cells_fetch(self.h, kind, index, C.byref(off), C.byref(by)))
-        o = _view(off, np.uint64, n + 1).copy()
-        return o, (bytes(_view(by, np.uint8, int(o[-1]))) if n and o[-1] else b"")
+        o = _view(off.value, np.uint64, n + 1).copy()
+        return o, (bytes(_view(by.value, np.uint8, int(o[-1]))) if n and o[-1] else b"")
 
     def close(self):
         if self.h:

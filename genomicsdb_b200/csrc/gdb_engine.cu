@@ -506,6 +506,7 @@ void scan_prepare(gdbgpu_scan* s) {
   s->produce_gt = (p.flags & GDBGPU_SCAN_PRODUCE_GT) ? 1 : 0;
   s->java = (p.flags & GDBGPU_SCAN_HTSJDK_CONVENTIONS) ? 1 : 0;
   s->prefetch = !(p.flags & GDBGPU_SCAN_NO_PREFETCH);
+  s->cells_only = (p.flags & GDBGPU_SCAN_CELLS_ONLY) != 0;
   s->info.n = 0;
   s->esum.n = 0;
   for (size_t f = 0; f < a->fields.size(); ++f) if (p.esum_remapped_mask & (1u << f)) { s->esum.remapped[s->esum.n] = 1; s->esum.index[s->esum.n] = (int32_t)f; ++s->esum.n; }
@@ -564,7 +565,6 @@ void scan_prepare(gdbgpu_scan* s) {
     CK(cudaStreamSynchronize(ctx->stream));
   }
   S.iL = hb[0]; S.i0 = hb[1]; S.i1 = hb[2];
-  s->cells_only = (p.flags & GDBGPU_SCAN_CELLS_ONLY) != 0;
   if (s->cells_only) {   // the columnar iterator neither merges calls nor minds overlaps: the left sweep is all it needs
     s->bitmap.alloc(S.n_words);
     CK(cudaMemsetAsync(s->bitmap.p, 0, S.n_words * 8, ctx->stream));
