@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <cerrno>
+#include <climits>
+#include <cstdio>
 #include <cstring>
 
 #include "gdb_json.h"
@@ -391,13 +393,46 @@ void VariantQueryProcessor::check(int rc) const {
   throw GenomicsDBGPUException(rc, m);
 }
 
-void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool, bool stage_broad_gvcf_fields) {
+void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool alleles_required, bool stage_broad_gvcf_fields, bool stage_columnar_fields) {
   const VidMapper& vid = qc.get_vid_mapper().is_initialized() ? qc.get_vid_mapper() : vid_;
   std::vector<gdbgpu_field_desc> fd;
   unsigned esum_mask = 0;
   qc.remapped_names_.clear();
   qc.remapped_names_.push_back("GT");
-  for (auto& name : qc.get_query_attributes()) {
+  // the order of the queried attributes as the reference's bookkeeping leaves it (query_variants.cc:578-637: END appended,
+  // ALT / REF / GT pulled in by allele- and genotype-dependent fields; variant_query_config.cc:161-185: END, REF, ALT swapped
+  // to the front) -- what the columnar iterator's print operators go by
+  std::vector<std::string> ordered = qc.get_query_attributes();
+  // VidMapper::add_mandatory_fields (vid_mapper.cc:611-668): QUAL and FILTER exist even when the vid mapping does not list them
+  static const FieldInfo builtin_QUAL = [] { FieldInfo f; f.name = "QUAL"; f.type = "float"; f.length = "1"; return f; }();
+  static const FieldInfo builtin_FILTER = [] { FieldInfo f; f.name = "FILTER"; f.type = "int"; f.length = "VAR"; return f; }();
+  auto columnar_field_info = [&](const std::string& name) -> const FieldInfo* {
+    const FieldInfo* fi = vid.get_field_info(name);
+    if (fi) return fi;
+    return name == "QUAL" ? &builtin_QUAL : (name == "FILTER" ? &builtin_FILTER : nullptr);
+  };
+  if (stage_columnar_fields) {
+    auto add = [&](const char* n) { if (std::find(ordered.begin(), ordered.end(), n) == ordered.end()) ordered.push_back(n); };
+    add("END");
+    if (alleles_required) { add("ALT"); add("REF"); }
+    for (size_t i = 0; i < ordered.size(); ++i) {
+      const FieldInfo* fi = columnar_field_info(ordered[i]);
+      if (!fi) {
+        if (ordered[i] == "END" || ordered[i] == "REF" || ordered[i] == "ALT") continue;
+        throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Field " + ordered[i] + " not found in vid mapping");
+      }
+      if (fi->is_allele_dependent()) { add("ALT"); add("REF"); }
+      if (fi->length == "G") add("GT");
+    }
+    size_t first_normal = 0;
+    for (const char* special : {"END", "REF", "ALT"}) {
+      auto it = std::find(ordered.begin(), ordered.end(), special);
+      if (it == ordered.end()) continue;
+      std::swap(*it, ordered[first_normal]);
+      ++first_normal;
+    }
+  }
+  for (auto& name : (stage_columnar_fields ? ordered : qc.get_query_attributes())) {
     const FieldInfo* fi = vid.get_field_info(name);
     if (!fi || !fi->is_allele_dependent()) continue;
     gdbgpu_field_desc d;
@@ -459,6 +494,34 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool, b
       if (name == "DP_FORMAT") qc.dp_fields_[2] = (unsigned)qc.plain_.size();
     }
     for (auto& pf : qc.plain_) pd.push_back(gdbgpu_plain_field_desc{pf.attribute.c_str(), pf.elem, pf.fixed_len, pf.format ? 0 : 1, pf.info_op});
+  }
+  qc.query_attrs_.clear();
+  if (stage_columnar_fields) {
+    if (stage_broad_gvcf_fields) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "do_query_bookkeeping: stage for the Broad operator or for the columnar iterator, not both");
+    int n_remapped = 0;
+    for (auto& name : ordered) {
+      const FieldInfo* fi = columnar_field_info(name);
+      const bool special = name == "END" || name == "REF" || name == "ALT" || name == "GT";
+      VariantQueryConfig::QueryAttribute qa; qa.name = name;
+      if (fi) qa.elem = fi->type == "char" ? 'c' : (fi->type == "float" ? 'f' : 'i');
+      if (!special && fi->type != "char" && fi->type != "float" && fi->type != "int") throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "columnar iterator on the GPU: type " + fi->type + " of field " + name + " is not supported");
+      if (name == "END") { qa.kind = -1; qa.fixed_len = 1; }
+      else if (name == "REF") { qa.kind = GDBGPU_CELL_FIELD_REF; qa.elem = 'c'; }
+      else if (name == "ALT") { qa.kind = GDBGPU_CELL_FIELD_ALT; qa.elem = 'c'; }
+      else if (name == "GT") { qa.kind = GDBGPU_CELL_FIELD_GT; qa.elem = 'i'; }
+      else if (fi->is_allele_dependent()) { qa.kind = GDBGPU_CELL_FIELD_REMAPPED; qa.index = n_remapped++; }
+      else {
+        if (fi->length == "2D") { qa.kind = -2; qc.query_attrs_.push_back(qa); continue; }   // not staged: only the print operators would read it
+        const bool numeric_len = !fi->length.empty() && fi->length.find_first_not_of("0123456789") == std::string::npos;
+        qa.kind = GDBGPU_CELL_FIELD_PLAIN; qa.index = (int)qc.plain_.size(); qa.fixed_len = numeric_len ? std::stoi(fi->length) : 0;
+        VariantQueryConfig::PlainField pf;
+        pf.attribute = pf.vcf_name = name; pf.fixed_len = qa.fixed_len;
+        pf.elem = qa.elem == 'c' ? GDBGPU_ELEM_CHAR : (qa.elem == 'f' ? GDBGPU_ELEM_FLOAT32 : GDBGPU_ELEM_INT32);
+        qc.plain_.push_back(pf);
+      }
+      qc.query_attrs_.push_back(qa);
+    }
+    for (auto& pf : qc.plain_) pd.push_back(gdbgpu_plain_field_desc{pf.attribute.c_str(), pf.elem, pf.fixed_len, 1, 0});
   }
   if (arr_) { gdbgpu_array_close(arr_); arr_ = nullptr; }
   check(gdbgpu_array_open_ex(sm_->ctx(), sm_->get_workspace().c_str(), array_name_.c_str(), fd.data(), (int32_t)fd.size(), pd.data(), (int32_t)pd.size(), phased, &arr_));
@@ -542,6 +605,239 @@ void VariantQueryProcessor::scan_and_operate(const int, const VariantQueryConfig
       ++st.pos_in_batch_; ++st.sites_done_;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------ columnar iterator surface
+namespace {
+const std::string g_json_indent_unit = "    ";
+inline size_t elem_size(char e) { return e == 'c' ? 1u : 4u; }
+template <class T> void print_list(std::ostream& f, const uint8_t* p, size_t n) {
+  const T* d = reinterpret_cast<const T*>(p);
+  f << "[ " << d[0];
+  for (size_t i = 1; i < n; ++i) f << ", " << d[i];
+  f << " ]";
+}
+template <class T> void print_csv_list(std::ostream& f, const uint8_t* p, size_t n, bool variable, bool valid) {
+  if (variable) f << n;
+  if (valid) {
+    if (variable) f << ",";
+    const T* d = reinterpret_cast<const T*>(p);
+    f << d[0];
+    for (size_t i = 1; i < n; ++i) f << "," << d[i];
+  } else if (!variable)
+    for (size_t i = 1; i < n; ++i) f.put(',');
+}
+}  // namespace
+
+const uint8_t* GenomicsDBColumnarCell::get_field_ptr_for_query_idx(unsigned i) const {
+  const auto& qa = qc_->get_query_attribute(i);
+  if (qa.kind < 0) return reinterpret_cast<const uint8_t*>(&end_);
+  const Column& c = (*columns_)[i];
+  return c.bytes + c.off[idx_];
+}
+size_t GenomicsDBColumnarCell::get_field_length(unsigned i) const {
+  const auto& qa = qc_->get_query_attribute(i);
+  if (qa.kind < 0) return 1;
+  const Column& c = (*columns_)[i];
+  return (size_t)(c.off[idx_ + 1] - c.off[idx_]) / elem_size(qa.elem);
+}
+// genomicsdb_columnar_field.cc:358-377: variable-length fields are valid when non-empty, fixed-length ones when any element
+// is not TileDB's empty value
+bool GenomicsDBColumnarCell::is_valid(unsigned i) const {
+  const auto& qa = qc_->get_query_attribute(i);
+  if (qa.kind < 0) return true;
+  const size_t n = get_field_length(i);
+  if (qa.fixed_len == 0) return n > 0;
+  const uint8_t* p = get_field_ptr_for_query_idx(i);
+  for (size_t k = 0; k < n; ++k) {
+    if (qa.elem == 'c') { if (p[k] != 127) return true; }
+    else { uint32_t w; memcpy(&w, p + 4 * k, 4); if (w != (qa.elem == 'f' ? 0x7F7FFFFFu : 0x7FFFFFFFu)) return true; }
+  }
+  return false;
+}
+
+// variant_cell.cc:119-165 + genomicsdb_columnar_field.cc:102-196,386-420
+void GenomicsDBColumnarCell::print(std::ostream& fptr, const VariantQueryConfig* query_config, const std::string& indent_prefix, const VidMapper* vid_mapper) const {
+  std::string indent_string = indent_prefix + g_json_indent_unit;
+  fptr << indent_prefix << "{\n";
+  fptr << indent_string << "\"row\": " << coords_[0] << ",\n";
+  fptr << indent_string << "\"interval\": [ " << coords_[1] << ", " << end_ << " ],\n";
+  if (vid_mapper) {
+    const ContigInfo* contig = vid_mapper->get_contig_location(coords_[1]);
+    if (contig) {
+      const int64_t contig_position = coords_[1] - contig->tiledb_column_offset;
+      fptr << indent_string << "\"genomic_interval\": { \"" << contig->name << "\" : [ " << contig_position + 1 << ", " << (contig_position + 1 + (end_ - coords_[1])) << " ] },\n";
+    }
+  }
+  fptr << indent_string << "\"fields\": {\n";
+  indent_string += g_json_indent_unit;
+  bool first_valid_field = true;
+  for (unsigned i = 1; i < query_config->get_num_queried_attributes(); ++i) {   // the first field is always END
+    if (!is_valid(i)) continue;
+    if (!first_valid_field) fptr << ",\n";
+    const auto& qa = query_config->get_query_attribute(i);
+    fptr << indent_string << "\"" << qa.name << "\": ";
+    const uint8_t* p = get_field_ptr_for_query_idx(i);
+    const size_t n = get_field_length(i);
+    if (qa.kind == GDBGPU_CELL_FIELD_ALT) {   // '|'-separated, '&' stands for <NON_REF>
+      fptr << "[ ";
+      size_t t0 = 0; bool first = true;
+      for (;;) {
+        size_t t1 = t0;
+        while (t1 < n && p[t1] != '|') ++t1;
+        if (!first) fptr << ", ";
+        fptr << "\"";
+        if (t1 - t0 == 1 && p[t0] == '&') fptr << "<NON_REF>"; else fptr.write(reinterpret_cast<const char*>(p + t0), t1 - t0);
+        fptr << "\"";
+        first = false;
+        if (t1 >= n) break;
+        t0 = t1 + 1;
+      }
+      fptr << " ]";
+    } else if (qa.elem == 'c') {
+      if (qa.fixed_len == 1) fptr << (char)p[0];
+      else { fptr << "\""; fptr.write(reinterpret_cast<const char*>(p), n); fptr << "\""; }
+    } else if (qa.fixed_len == 1) {
+      if (qa.elem == 'f') fptr << *reinterpret_cast<const float*>(p); else fptr << *reinterpret_cast<const int32_t*>(p);
+    } else if (qa.elem == 'f') print_list<float>(fptr, p, n);
+    else print_list<int32_t>(fptr, p, n);
+    first_valid_field = false;
+  }
+  indent_string = indent_prefix + g_json_indent_unit;
+  fptr << "\n" << indent_string << "}\n" << indent_prefix << "}";
+}
+
+// variant_cell.cc:167-185
+void GenomicsDBColumnarCell::print_csv(std::ostream& fptr, const VariantQueryConfig* query_config) const {
+  fptr << coords_[0] << "," << coords_[1] << "," << end_;
+  for (unsigned i = 1; i < query_config->get_num_queried_attributes(); ++i) {
+    fptr << ",";
+    const auto& qa = query_config->get_query_attribute(i);
+    const uint8_t* p = get_field_ptr_for_query_idx(i);
+    const size_t n = get_field_length(i);
+    const bool valid = is_valid(i), variable = qa.fixed_len == 0;
+    if (qa.elem == 'c') {
+      if (qa.fixed_len == 1) { if (valid) fptr << (char)p[0]; }
+      else if (valid) fptr.write(reinterpret_cast<const char*>(p), n);
+    } else if (qa.fixed_len == 1) {
+      if (valid) { if (qa.elem == 'f') fptr << *reinterpret_cast<const float*>(p); else fptr << *reinterpret_cast<const int32_t*>(p); }
+    } else if (qa.elem == 'f') print_csv_list<float>(fptr, p, n, variable, valid);
+    else print_csv_list<int32_t>(fptr, p, n, variable, valid);
+  }
+  fptr << "\n";
+}
+
+// variant_operations.cc:732-790
+ColumnHistogramOperator::ColumnHistogramOperator(uint64_t begin, uint64_t end, uint64_t bin_size) : m_begin_column(begin), m_end_column(end), m_bin_size(bin_size) {
+  if (end < begin || !bin_size) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "ColumnHistogramOperator: bad range");
+  m_bin_counts_vector.assign((end - begin) / bin_size + 1, 0);
+}
+void ColumnHistogramOperator::operate_on_columnar_cell(const GenomicsDBColumnarCell& cell, const VariantQueryConfig&, const VariantArraySchema&) {
+  const uint64_t b = (uint64_t)cell.get_coordinates()[1];
+  ++m_bin_counts_vector[b <= m_begin_column ? 0 : (b >= m_end_column ? m_bin_counts_vector.size() - 1 : (b - m_begin_column) / m_bin_size)];
+}
+void ColumnHistogramOperator::operate_on_device_interval(gdbgpu_scan* scan, unsigned, const VariantQueryConfig&) {
+  m_scratch.resize(m_bin_counts_vector.size());
+  if (gdbgpu_scan_cells_histogram(scan, m_begin_column, m_end_column, m_bin_size, m_scratch.data(), m_scratch.size()) != GDBGPU_OK)
+    throw GenomicsDBGPUException(GDBGPU_ERR_CUDA, "ColumnHistogramOperator: the histogram kernel failed");
+  for (size_t i = 0; i < m_scratch.size(); ++i) m_bin_counts_vector[i] += m_scratch[i];
+}
+bool ColumnHistogramOperator::equi_partition_and_print_bins(uint64_t num_bins, std::ostream& fptr) const {
+  const size_t n = m_bin_counts_vector.size();
+  if (num_bins >= n) { std::cerr << "Requested #equi bins is smaller than allocated bin counts vector, returning\n"; return false; }
+  uint64_t total = 0;
+  for (auto v : m_bin_counts_vector) total += v;
+  const double per_bin = (double)total / num_bins;
+  char line[128];
+  snprintf(line, sizeof(line), "Total %llu #bins %llu count/bins %.1f\n", (unsigned long long)total, (unsigned long long)num_bins, per_bin);
+  fptr << line;
+  for (size_t i = 0; i < n;) {   // merge bins left to right until a group holds its share
+    size_t j = i; uint64_t group = 0;
+    while ((double)group < per_bin && j < n) group += m_bin_counts_vector[j++];
+    fptr << m_begin_column + i * m_bin_size << "," << m_begin_column + j * m_bin_size - 1 << "," << group << "\n";
+    if (j == i) break;
+    i = j;
+  }
+  fptr << "\n";
+  return true;
+}
+
+// variant_operations.cc:808-846
+VariantCallPrintOperator::VariantCallPrintOperator(std::ostream& fptr, const std::string& indent_prefix, const VidMapper* vid_mapper)
+    : m_indent_prefix(indent_prefix), m_indent_prefix_plus_one(indent_prefix + g_json_indent_unit), m_indent_prefix_plus_two(indent_prefix + g_json_indent_unit + g_json_indent_unit),
+      m_fptr(&fptr), m_vid_mapper(vid_mapper && vid_mapper->is_initialized() ? vid_mapper : nullptr) {}
+void VariantCallPrintOperator::operate_on_columnar_cell(const GenomicsDBColumnarCell& cell, const VariantQueryConfig& query_config, const VariantArraySchema&) {
+  std::ostream& f = *m_fptr;
+  if (cell.at_new_query_column_interval()) {
+    if (m_num_query_intervals_printed > 0) { f << "\n" << m_indent_prefix_plus_one << "]\n" << m_indent_prefix << "},\n"; }
+    m_num_calls_printed = 0;
+    f << m_indent_prefix << "{\n";
+    const auto idx = cell.get_current_query_column_interval_idx();
+    const long long begin = query_config.get_num_column_intervals() > 0 ? query_config.get_column_begin(idx) : 0ll;
+    const long long end = query_config.get_num_column_intervals() > 0 ? query_config.get_column_end(idx) : INT64_MAX - 1ll;
+    f << m_indent_prefix_plus_one << "\"query_interval\": [ " << begin << ", " << end << " ],\n";
+    f << m_indent_prefix_plus_one << "\"variant_calls\": [\n";
+  }
+  if (m_num_calls_printed > 0) f << ",\n";
+  cell.print(f, &query_config, m_indent_prefix_plus_two, m_vid_mapper);
+  ++m_num_calls_printed;
+  ++m_num_query_intervals_printed;
+}
+void VariantCallPrintOperator::finalize() {
+  if (m_num_query_intervals_printed > 0) (*m_fptr) << "\n" << m_indent_prefix_plus_one << "]\n" << m_indent_prefix << "}";
+}
+
+// variant_operations.cc:900-1089; the counting is gdbgpu_scan_cells_allele_counts (kernels + one sort)
+AlleleCountOperator::AlleleCountOperator(const VidMapper&, const VariantQueryConfig& query_config) {
+  unsigned idx;
+  for (const char* need : {"GT", "REF", "ALT"})
+    if (!query_config.get_query_idx_for_name(need, idx)) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, std::string(need) + " field must be queried for AlleleCountOperator");
+}
+void AlleleCountOperator::operate_on_device_interval(gdbgpu_scan* scan, unsigned, const VariantQueryConfig&) {
+  gdbgpu_allele_counts ac;
+  if (gdbgpu_scan_cells_allele_counts(scan, &ac) != GDBGPU_OK) throw GenomicsDBGPUException(GDBGPU_ERR_CUDA, "AlleleCountOperator: the counting kernels failed");
+  for (uint64_t k = 0; k < ac.n; ++k)
+    m_records.push_back(Record{ac.column[k], std::string((const char*)ac.bytes + ac.ref_pos[2 * k], ac.ref_pos[2 * k + 1]),
+                               std::string((const char*)ac.bytes + ac.alt_pos[2 * k], ac.alt_pos[2 * k + 1]), ac.count[k]});
+}
+void AlleleCountOperator::print_allele_counts(std::ostream& fptr) const {
+  for (auto& r : m_records) fptr << r.column << " " << r.REF << " " << r.ALT << " " << r.count << "\n";
+}
+
+void VariantQueryProcessor::iterate_over_cells(const int, const VariantQueryConfig& qc, SingleCellOperatorBase& op, const bool) const {
+  if (!qc.is_bookkeeping_done() || qc.get_num_queried_attributes() == 0)
+    throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "iterate_over_cells: do_query_bookkeeping(config, alleles_required, false, true) must be called first");
+  const unsigned n_intervals = std::max(1u, qc.get_num_column_intervals());
+  for (unsigned i = 0; i < n_intervals; ++i) {
+    gdbgpu_scan_params p; memset(&p, 0, sizeof(p));
+    p.flags = GDBGPU_SCAN_CELLS_ONLY;
+    if (qc.get_num_column_intervals() == 0) p.flags |= GDBGPU_SCAN_FULL;
+    else { p.col_lo = qc.get_column_begin(i); p.col_hi = qc.get_column_end(i); }
+    if (!qc.query_all_rows()) { p.query_rows = qc.get_rows_to_query().data(); p.n_query_rows = qc.get_rows_to_query().size(); }
+    gdbgpu_scan* scan = nullptr;
+    check(gdbgpu_scan_begin(arr_, &p, &scan));
+    struct Guard { gdbgpu_scan* s; ~Guard() { gdbgpu_scan_end(s); } } guard{scan};
+    if (op.runs_on_device()) { op.operate_on_device_interval(scan, i, qc); continue; }
+    for (unsigned a = 0; a < qc.get_num_queried_attributes(); ++a)
+      if (qc.get_query_attribute(a).kind == -2)
+        throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "columnar iterator on the GPU: multi-dimensional field " + qc.get_query_attribute_name(a) + " is not supported");
+    gdbgpu_cell_list list;
+    check(gdbgpu_scan_cells(scan, &list));
+    std::vector<GenomicsDBColumnarCell::Column> columns(qc.get_num_queried_attributes());
+    for (unsigned a = 0; a < qc.get_num_queried_attributes(); ++a) {
+      const auto& qa = qc.get_query_attribute(a);
+      if (qa.kind < 0) continue;   // END comes with the list
+      check(gdbgpu_scan_cells_fetch(scan, qa.kind, qa.index, &columns[a].off, &columns[a].bytes));
+    }
+    GenomicsDBColumnarCell cell;
+    cell.qc_ = &qc; cell.columns_ = &columns; cell.interval_idx_ = i;
+    for (uint64_t k = 0; k < list.n_cells; ++k) {
+      cell.idx_ = k; cell.coords_[0] = list.row[k]; cell.coords_[1] = list.begin[k]; cell.end_ = list.end[k];
+      cell.at_new_interval_ = k == 0;
+      op.operate_on_columnar_cell(cell, qc, schema_);
+    }
+  }
+  op.finalize();
 }
 
 }  // namespace genomicsdb_b200

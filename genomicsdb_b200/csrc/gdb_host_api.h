@@ -25,6 +25,7 @@
 #include <map>
 #include <memory>
 #include <stdexcept>
+#include <iostream>
 #include <string>
 #include <utility>
 #include <vector>
@@ -123,6 +124,18 @@ class VariantQueryConfig {
   const std::vector<PlainField>& get_plain_fields() const { return plain_; }
   const unsigned* get_dp_rule_fields() const { return dp_fields_; }
   unsigned get_element_wise_sum_mask() const { return esum_remapped_mask_; }
+  // the queried attributes in the order the reference's bookkeeping leaves them (END, REF, ALT first:
+  // variant_query_config.cc:161-185); filled by do_query_bookkeeping(..., stage_columnar_fields = true)
+  struct QueryAttribute { std::string name; int kind = -1; int index = 0; char elem = 'i'; int fixed_len = 0; };   // kind: -1 END, -2 multi-dimensional (not staged), else GDBGPU_CELL_FIELD_*
+  unsigned get_num_queried_attributes() const { return (unsigned)query_attrs_.size(); }
+  const std::string& get_query_attribute_name(unsigned i) const { return query_attrs_[i].name; }
+  const QueryAttribute& get_query_attribute(unsigned i) const { return query_attrs_[i]; }
+  bool get_query_idx_for_name(const std::string& name, unsigned& idx) const {
+    for (unsigned i = 0; i < query_attrs_.size(); ++i) if (query_attrs_[i].name == name) { idx = i; return true; }
+    return false;
+  }
+ private:
+  std::vector<QueryAttribute> query_attrs_;
 };
 
 // ---- data model (include/genomicsdb/variant.h).  Views into the current batch: valid until the next operate() call.
@@ -276,6 +289,88 @@ class BroadCombinedGVCFOperator : public GA4GHOperator {
 };
 
 // ---- storage + engine
+// ---- the columnar iterator surface (include/genomicsdb/variant_cell.h GenomicsDBColumnarCell, genomicsdb_iterators.h,
+// include/query_operations/variant_operations.h:675-768).  The cells come from gdbgpu_scan_cells* (the device builds the
+// list in the reference iterator's order and gathers the queried columns); histogram and allele counts run as kernels.
+struct VariantArraySchema {};   // the operators' third argument; nothing on this path reads it
+class GenomicsDBColumnarCell {
+ public:
+  const int64_t* get_coordinates() const { return coords_; }   // row, begin column
+  bool at_new_query_column_interval() const { return at_new_interval_; }
+  uint64_t get_current_query_column_interval_idx() const { return interval_idx_; }
+  bool is_valid(unsigned query_idx) const;
+  size_t get_field_length(unsigned query_idx) const;            // elements
+  const uint8_t* get_field_ptr_for_query_idx(unsigned query_idx) const;
+  template <class T> const T* get_field_ptr_for_query_idx(unsigned query_idx) const { return reinterpret_cast<const T*>(get_field_ptr_for_query_idx(query_idx)); }
+  void print(std::ostream& fptr, const VariantQueryConfig* query_config, const std::string& indent_prefix, const VidMapper* vid_mapper = nullptr) const;
+  void print_csv(std::ostream& fptr, const VariantQueryConfig* query_config) const;
+ private:
+  friend class VariantQueryProcessor;
+  struct Column { const uint64_t* off = nullptr; const uint8_t* bytes = nullptr; };
+  const VariantQueryConfig* qc_ = nullptr;
+  const std::vector<Column>* columns_ = nullptr;   // one per query attribute
+  uint64_t idx_ = 0;                               // position in the cell list
+  int64_t coords_[2] = {0, 0}, end_ = 0;
+  bool at_new_interval_ = false; uint64_t interval_idx_ = 0;
+};
+
+class SingleCellOperatorBase {
+ public:
+  virtual ~SingleCellOperatorBase() = default;
+  virtual void operate_on_columnar_cell(const GenomicsDBColumnarCell&, const VariantQueryConfig&, const VariantArraySchema&) {
+    throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Sub-classes should override operate_on_columnar_cell()");
+  }
+  virtual void finalize() {}
+  // operators whose whole work is a kernel over the device's cell list take the interval's scan instead of its cells
+  virtual bool runs_on_device() const { return false; }
+  virtual void operate_on_device_interval(gdbgpu_scan*, unsigned /*column_interval_idx*/, const VariantQueryConfig&) {}
+};
+
+class ColumnHistogramOperator : public SingleCellOperatorBase {
+ public:
+  ColumnHistogramOperator(uint64_t begin, uint64_t end, uint64_t bin_size);
+  void operate_on_columnar_cell(const GenomicsDBColumnarCell& cell, const VariantQueryConfig&, const VariantArraySchema&) override;
+  bool runs_on_device() const override { return true; }
+  void operate_on_device_interval(gdbgpu_scan* scan, unsigned, const VariantQueryConfig&) override;
+  bool equi_partition_and_print_bins(uint64_t num_bins, std::ostream& fptr = std::cout) const;
+  const std::vector<uint64_t>& get_bin_counts() const { return m_bin_counts_vector; }
+ private:
+  std::vector<uint64_t> m_bin_counts_vector, m_scratch;
+  uint64_t m_begin_column, m_end_column, m_bin_size;
+};
+
+class VariantCallPrintOperator : public SingleCellOperatorBase {
+ public:
+  VariantCallPrintOperator(std::ostream& fptr = std::cout, const std::string& indent_prefix = "", const VidMapper* vid_mapper = nullptr);
+  void operate_on_columnar_cell(const GenomicsDBColumnarCell& cell, const VariantQueryConfig& query_config, const VariantArraySchema&) override;
+  void finalize() override;
+ private:
+  uint64_t m_num_calls_printed = 0, m_num_query_intervals_printed = 0;
+  std::string m_indent_prefix, m_indent_prefix_plus_one, m_indent_prefix_plus_two;
+  std::ostream* m_fptr;
+  const VidMapper* m_vid_mapper;
+};
+
+class VariantCallPrintCSVOperator : public SingleCellOperatorBase {
+ public:
+  explicit VariantCallPrintCSVOperator(std::ostream& fptr = std::cout) : m_fptr(&fptr) {}
+  void operate_on_columnar_cell(const GenomicsDBColumnarCell& cell, const VariantQueryConfig& query_config, const VariantArraySchema&) override { cell.print_csv(*m_fptr, &query_config); }
+ private:
+  std::ostream* m_fptr;
+};
+
+class AlleleCountOperator : public SingleCellOperatorBase {
+ public:
+  AlleleCountOperator(const VidMapper& vid_mapper, const VariantQueryConfig& query_config);
+  bool runs_on_device() const override { return true; }
+  void operate_on_device_interval(gdbgpu_scan* scan, unsigned, const VariantQueryConfig&) override;
+  void print_allele_counts(std::ostream& fptr = std::cout) const;
+  struct Record { int64_t column; std::string REF, ALT; uint64_t count; };
+  const std::vector<Record>& get_records() const { return m_records; }   // per query interval, then (column, REF, ALT)
+ private:
+  std::vector<Record> m_records;
+};
+
 class VariantStorageManager {
  public:
   VariantStorageManager(const std::string& workspace, unsigned segment_size = 10u * 1024u * 1024u, int cuda_device = 0);
@@ -313,7 +408,14 @@ class VariantQueryProcessor {
   // Adds END/REF/ALT/GT, resolves the allele-dependent fields among the queried attributes, stages the array in HBM.
   // stage_broad_gvcf_fields: also stage what BroadCombinedGVCFOperator combines besides the remapped fields (plain FORMAT
   // fields, scalar INFO fields, the DP rule's inputs)
-  void do_query_bookkeeping(VariantQueryConfig& query_config, bool alleles_required = true, bool stage_broad_gvcf_fields = false);
+  // stage_columnar_fields: stage EVERY queried attribute (what the columnar iterator's operators may print) and fix the
+  // query attribute order as the reference does (END, REF, ALT first)
+  void do_query_bookkeeping(VariantQueryConfig& query_config, bool alleles_required = true, bool stage_broad_gvcf_fields = false,
+                            bool stage_columnar_fields = false);
+  // query_variants.cc:557-576: every cell of every query interval (or of the array) goes to the operator, then finalize()
+  void iterate_over_cells(const int ad, const VariantQueryConfig& query_config, SingleCellOperatorBase& variant_operator,
+                          const bool use_common_array_object = true) const;
+  const VariantArraySchema& get_array_schema() const { return schema_; }
   int get_array_descriptor() const { return 0; }
   void scan_and_operate(const int ad, const VariantQueryConfig& query_config, SingleVariantOperatorBase& variant_operator,
                         unsigned column_interval_idx = 0, bool handle_spanning_deletions = false,
@@ -328,6 +430,7 @@ class VariantQueryProcessor {
   gdbgpu_array* arr_ = nullptr;
   std::vector<int64_t> coords_, end_;   // merged cell coordinates (row, col) and END, host copy
   int n_out_ = 0;
+  VariantArraySchema schema_;
 };
 
 }  // namespace genomicsdb_b200
