@@ -27,7 +27,8 @@ EXPORTS = ["gdbgpu_version", "gdbgpu_ctx_create", "gdbgpu_ctx_destroy", "gdbgpu_
            "gdbgpu_ctx_launch_count", "gdbgpu_ctx_synchronize", "gdbgpu_ctx_release_cached_memory", "gdbgpu_ctx_set_profiling",
            "gdbgpu_ctx_reset_kernel_stats", "gdbgpu_ctx_kernel_stats", "gdbgpu_array_open", "gdbgpu_array_open_ex", "gdbgpu_array_from_columns", "gdbgpu_array_get_info",
            "gdbgpu_array_copy_cells", "gdbgpu_array_close", "gdbgpu_scan_begin", "gdbgpu_scan_get_info",
-           "gdbgpu_scan_next_batch", "gdbgpu_scan_seek", "gdbgpu_scan_end"]
+           "gdbgpu_scan_next_batch", "gdbgpu_scan_seek", "gdbgpu_scan_end", "gdbgpu_scan_cells", "gdbgpu_scan_cells_histogram",
+           "gdbgpu_scan_cells_allele_counts", "gdbgpu_scan_cells_fetch"]
 
 
 class FieldDesc(C.Structure):
