@@ -54,18 +54,40 @@ __global__ void k_cells_fill(ArrayDev A, const uint32_t* __restrict__ list, uint
   begin[i] = col > e ? e : col; end[i] = col > e ? col : e;
 }
 
-// ColumnHistogramOperator::operate_on_columnar_cell; thousands of cells share a column, so a warp adds once per bin
+// ColumnHistogramOperator::operate_on_columnar_cell (variant_operations.cc:754-765)
+__device__ inline uint64_t hist_bin(const ArrayDev& A, uint64_t c, uint64_t h_begin, uint64_t h_end, uint64_t bin_size, uint64_t n_bins) {
+  const int64_t col = A.coords[2 * c + 1], e = A.end[c];
+  const uint64_t b = (uint64_t)(col > e ? e : col);
+  return b <= h_begin ? 0ull : (b >= h_end ? n_bins - 1 : (b - h_begin) / bin_size);
+}
+// the bins the listed cells touch: range[0] = lowest, range[1] = highest (the reference's tool spans 40 M bins, a query a few)
+__global__ void k_cells_bin_range(ArrayDev A, const uint32_t* __restrict__ list, uint64_t n, uint64_t h_begin, uint64_t h_end, uint64_t bin_size, uint64_t n_bins,
+                                  unsigned long long* __restrict__ range) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long lo = ~0ull, hi = 0ull;
+  if (i < n) lo = hi = hist_bin(A, list[i], h_begin, h_end, bin_size, n_bins);
+  for (int d = 16; d; d >>= 1) {
+    const unsigned long long lo2 = __shfl_xor_sync(0xffffffffu, lo, d), hi2 = __shfl_xor_sync(0xffffffffu, hi, d);
+    lo = lo2 < lo ? lo2 : lo; hi = hi2 > hi ? hi2 : hi;
+  }
+  // one atomic per block, and only when it would change the answer (every warp hitting two words serialises)
+  __shared__ unsigned long long s_lo, s_hi;
+  if (threadIdx.x == 0) { s_lo = ~0ull; s_hi = 0ull; }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && lo != ~0ull) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_lo != ~0ull) {
+    if (s_lo < *(volatile unsigned long long*)&range[0]) atomicMin(&range[0], s_lo);
+    if (s_hi > *(volatile unsigned long long*)&range[1]) atomicMax(&range[1], s_hi);
+  }
+}
+// thousands of cells share a column, so a warp adds once per bin; counts[] starts at bin `first`
 __global__ void k_cells_hist(ArrayDev A, const uint32_t* __restrict__ list, uint64_t n, uint64_t h_begin, uint64_t h_end, uint64_t bin_size, uint64_t n_bins,
-                             unsigned long long* __restrict__ counts) {
+                             uint64_t first, unsigned long long* __restrict__ counts) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool on = i < n;
   uint64_t bin = 0;
-  if (on) {
-    const uint64_t c = list[i];
-    const int64_t col = A.coords[2 * c + 1], e = A.end[c];
-    const uint64_t b = (uint64_t)(col > e ? e : col);
-    bin = b <= h_begin ? 0ull : (b >= h_end ? n_bins - 1 : (b - h_begin) / bin_size);
-  }
+  if (on) bin = hist_bin(A, list[i], h_begin, h_end, bin_size, n_bins) - first;
   const unsigned act = __ballot_sync(0xffffffffu, on);
   if (!on) return;
   const unsigned same = __match_any_sync(act, bin);
