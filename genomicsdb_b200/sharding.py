@@ -38,6 +38,46 @@ def equal_cell_cuts(cols, world):
     return out
 
 
+def equal_load_cuts_from_histogram(counts, begin, bin_size, world, col_hi=None):
+    """Column cuts from a histogram of cell begin columns (ColumnHistogramOperator bins): bins are handed to shards left to
+    right, a shard closes once it holds its share of what is left (equi_partition_and_print_bins, variant_operations.cc:767-790,
+    with the share re-computed per shard so the last one is not starved).  Cuts fall on bin boundaries.  Returns `world`
+    contiguous (lo, hi) intervals tiling [begin, col_hi]."""
+    counts = [int(c) for c in counts]
+    n_bins = len(counts)
+    col_hi = begin + n_bins * bin_size - 1 if col_hi is None else col_hi
+    out, b, left = [], 0, sum(counts)
+    for r in range(world):
+        if r == world - 1:
+            e = n_bins
+        else:
+            share, cur, e = left / (world - r), 0, b
+            while e < n_bins - (world - 1 - r) and (cur < share or e == b):
+                cur += counts[e]
+                e += 1
+            left -= cur
+        lo = begin + b * bin_size
+        hi = col_hi if r == world - 1 else begin + e * bin_size - 1
+        out.append((lo, max(hi, lo - 1)))
+        b = e
+    return out
+
+
+def device_equal_load_cuts(arr, world, bin_size, col_lo=None, col_hi=None, query_rows=None):
+    """Shard boundaries for `world` GPUs from the DEVICE histogram of the staged array's cells (gdbgpu_scan_cells_histogram:
+    only the bins cross PCIe): SURVEY 8e's "shards with ~equal cell counts".  arr: genomicsdb_b200.capi.Array."""
+    from genomicsdb_b200 import capi
+    info = arr.info()
+    lo = info.min_col if col_lo is None else col_lo
+    hi = max(info.max_col, info.max_end) if col_hi is None else col_hi
+    sc = capi.Scan(arr, lo, hi, query_rows=query_rows, flags=capi.SCAN_CELLS_ONLY)
+    try:
+        counts = sc.cells_histogram(lo, hi, bin_size)
+    finally:
+        sc.close()
+    return equal_load_cuts_from_histogram(counts.tolist(), lo, bin_size, world, col_hi=hi)
+
+
 def gather_concat(local_bytes, device=None, group=None, dst=0):
     """Rank-ordered concatenation of per-rank byte strings on rank `dst` (MPI_Gatherv in gt_mpi_gather.cc:165-263):
     all-gather of sizes, then one padded all-gather of the payloads.  Returns bytes on dst, None elsewhere."""

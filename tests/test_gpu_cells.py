@@ -109,3 +109,32 @@ def test_cells_on_a_synthetic_cohort(ctx):
                 sc.close()
     finally:
         arr.close()
+
+
+def test_equal_load_shards_from_the_device_histogram(ctx):
+    """shard boundaries with ~equal cell counts, taken from the device histogram of a cohort whose call density
+    varies along the genome; the shards' cell lists tile the whole interval's list"""
+    from genomicsdb_b200 import capi
+    from genomicsdb_b200.sharding import device_equal_load_cuts
+    from tools import gdbsyn
+    d = gdbsyn.generate(n_samples=2000, n_sites=200, spacing=100, p_var=0.15, a_pool=6, seed=11)
+    arr = gdbsyn.to_gpu_array(ctx, d)
+    lo, hi = d["col_range"]
+    try:
+        rows = np.arange(0, 2000, 3)          # uneven load: a third of the samples
+        cuts = device_equal_load_cuts(arr, 4, 100, lo, hi, query_rows=rows)
+        assert len(cuts) == 4 and cuts[0][0] == lo and cuts[-1][1] == hi
+        whole = capi.Scan(arr, lo, hi, query_rows=rows, flags=capi.SCAN_CELLS_ONLY)
+        all_cells = whole.cells()
+        whole.close()
+        loads, begun = [], []
+        for a, b in cuts:
+            sc = capi.Scan(arr, a, b, query_rows=rows, flags=capi.SCAN_CELLS_ONLY)
+            c = sc.cells()
+            sc.close()
+            loads.append(len(c["cell"]) - c["n_left"])
+            begun += c["cell"][c["n_left"]:].tolist()         # cells that begin inside the shard
+        assert begun == all_cells["cell"][all_cells["n_left"]:].tolist()
+        assert max(loads) - min(loads) <= 0.2 * (sum(loads) / 4), loads
+    finally:
+        arr.close()

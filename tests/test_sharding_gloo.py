@@ -83,3 +83,21 @@ def test_split_interval_tiles():
         assert parts[0][0] == 1000 and parts[-1][1] == 10_001_001
         for a, b in zip(parts, parts[1:]):
             assert b[0] == a[1] + 1
+
+
+def test_equal_load_cuts_from_histogram():
+    """cuts on bin boundaries, contiguous, tiling the range, each shard near its share (the device histogram of
+    tests/test_gpu_cells.py feeds this on a GPU box)"""
+    from genomicsdb_b200.sharding import equal_load_cuts_from_histogram
+    import random
+    rng = random.Random(3)
+    for world in (1, 2, 3, 8):
+        counts = [rng.choice((0, 0, 1, 5, 40, 300)) for _ in range(257)]
+        cuts = equal_load_cuts_from_histogram(counts, 1000, 50, world, col_hi=1000 + 257 * 50 - 7)
+        assert len(cuts) == world and cuts[0][0] == 1000 and cuts[-1][1] == 1000 + 257 * 50 - 7
+        for (a, b), (c, d) in zip(cuts, cuts[1:]):
+            assert c == b + 1 and (c - 1000) % 50 == 0
+        loads = [sum(counts[(a - 1000) // 50:(b - 1000) // 50 + 1]) for a, b in cuts]
+        assert sum(loads) == sum(counts)
+        assert max(loads) <= sum(counts) / world + max(counts)      # never more than one bin over the share
+    assert equal_load_cuts_from_histogram([0, 0, 0], 0, 10, 2) == [(0, 9), (10, 29)]
