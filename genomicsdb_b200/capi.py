@@ -28,7 +28,7 @@ EXPORTS = ["gdbgpu_version", "gdbgpu_ctx_create", "gdbgpu_ctx_destroy", "gdbgpu_
            "gdbgpu_ctx_reset_kernel_stats", "gdbgpu_ctx_kernel_stats", "gdbgpu_array_open", "gdbgpu_array_open_ex", "gdbgpu_array_from_columns", "gdbgpu_array_get_info",
            "gdbgpu_array_copy_cells", "gdbgpu_array_close", "gdbgpu_scan_begin", "gdbgpu_scan_get_info",
            "gdbgpu_scan_next_batch", "gdbgpu_scan_seek", "gdbgpu_scan_end", "gdbgpu_scan_cells", "gdbgpu_scan_cells_histogram",
-           "gdbgpu_scan_cells_allele_counts", "gdbgpu_scan_cells_fetch"]
+           "gdbgpu_scan_cells_allele_counts", "gdbgpu_scan_cells_fetch", "gdbgpu_scan_cells_window"]
 
 
 class FieldDesc(C.Structure):
@@ -76,7 +76,7 @@ class FieldOut(C.Structure):
 
 
 class CellList(C.Structure):
-    _fields_ = [("n_cells", C.c_uint64), ("n_left", C.c_uint64), ("cell", C.c_void_p), ("row", C.c_void_p), ("begin", C.c_void_p), ("end", C.c_void_p)]
+    _fields_ = [("n_cells", C.c_uint64), ("n_left", C.c_uint64), ("n_total", C.c_uint64), ("first", C.c_uint64), ("cell", C.c_void_p), ("row", C.c_void_p), ("begin", C.c_void_p), ("end", C.c_void_p)]
 
 
 class AlleleCounts(C.Structure):
@@ -133,6 +133,7 @@ def lib():
         L.gdbgpu_scan_next_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(Batch)]
         L.gdbgpu_scan_seek.argtypes = [C.c_void_p, C.c_uint64]
         L.gdbgpu_scan_cells.argtypes = [C.c_void_p, C.POINTER(CellList)]
+        L.gdbgpu_scan_cells_window.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.gdbgpu_scan_cells_histogram.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
         L.gdbgpu_scan_cells_allele_counts.argtypes = [C.c_void_p, C.POINTER(AlleleCounts)]
         L.gdbgpu_scan_cells_fetch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
@@ -411,8 +412,12 @@ class Scan:
         cl = CellList()
         self.ctx.check(lib().gdbgpu_scan_cells(self.h, C.byref(cl)))
         n = cl.n_cells
-        return dict(n_left=int(cl.n_left), cell=_view(cl.cell, np.uint64, n).copy(), row=_view(cl.row, np.int64, n).copy(),
+        return dict(n_left=int(cl.n_left), n_total=int(cl.n_total), first=int(cl.first), cell=_view(cl.cell, np.uint64, n).copy(), row=_view(cl.row, np.int64, n).copy(),
                     begin=_view(cl.begin, np.int64, n).copy(), end=_view(cl.end, np.int64, n).copy())
+
+    def cells_window(self, first, count=0):
+        """page through the list: cells() / cells_fetch() hand out entries [first, first + count) from now on"""
+        self.ctx.check(lib().gdbgpu_scan_cells_window(self.h, first, count))
 
     def cells_histogram(self, begin, end, bin_size):
         n_bins = (end - begin) // bin_size + 1

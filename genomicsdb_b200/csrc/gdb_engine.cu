@@ -472,6 +472,7 @@ struct gdbgpu_scan {
   int n_out = 0;
   // columnar-iterator view of the query (gdbgpu_scan_cells*): the device list and what was copied out for the caller
   bool cells_only = false, cells_built = false; uint64_t n_cells = 0, n_left = 0;
+  uint64_t win_first = 0, win_count = UINT64_MAX;   // the part of the list gdbgpu_scan_cells / _cells_fetch hand out
   DevBuf<uint32_t> cell_list;
   std::vector<uint64_t> h_cell; std::vector<int64_t> h_row, h_begin, h_end;
   std::map<std::pair<int, int>, std::pair<std::vector<uint64_t>, std::vector<uint8_t>>> fetched;
@@ -1067,21 +1068,21 @@ void cells_build(gdbgpu_scan* s) {
 
 void cells_to_host(gdbgpu_scan* s, gdbgpu_cell_list* out) {
   cells_build(s);
-  gdbgpu_ctx* ctx = s->ctx; const uint64_t n = s->n_cells;
-  if (s->h_cell.size() != n || !n) {
-    s->h_cell.resize(n); s->h_row.resize(n); s->h_begin.resize(n); s->h_end.resize(n);
-    if (n) {
-      DevBuf<uint64_t> cell; DevBuf<int64_t> row, begin, end;
-      cell.alloc(n); row.alloc(n); begin.alloc(n); end.alloc(n);
-      LAUNCH(ctx, k_cells_fill, blocks_for(n, 256), 256, s->arr->dev, s->cell_list.p, n, cell.p, row.p, begin.p, end.p);
-      CK(cudaMemcpyAsync(s->h_cell.data(), cell.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaMemcpyAsync(s->h_row.data(), row.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaMemcpyAsync(s->h_begin.data(), begin.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaMemcpyAsync(s->h_end.data(), end.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
-    }
+  gdbgpu_ctx* ctx = s->ctx;
+  const uint64_t first = std::min(s->win_first, s->n_cells), n = std::min(s->win_count, s->n_cells - first);
+  s->h_cell.resize(n); s->h_row.resize(n); s->h_begin.resize(n); s->h_end.resize(n);
+  if (n) {
+    DevBuf<uint64_t> cell; DevBuf<int64_t> row, begin, end;
+    cell.alloc(n); row.alloc(n); begin.alloc(n); end.alloc(n);
+    LAUNCH(ctx, k_cells_fill, blocks_for(n, 256), 256, s->arr->dev, s->cell_list.p + first, n, cell.p, row.p, begin.p, end.p);
+    CK(cudaMemcpyAsync(s->h_cell.data(), cell.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(s->h_row.data(), row.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(s->h_begin.data(), begin.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(s->h_end.data(), end.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
   }
-  out->n_cells = n; out->n_left = s->n_left;
+  out->n_cells = n; out->n_left = first < s->n_left ? std::min(s->n_left - first, n) : 0;
+  out->n_total = s->n_cells; out->first = first;
   out->cell = s->h_cell.data(); out->row = s->h_row.data(); out->begin = s->h_begin.data(); out->end = s->h_end.data();
 }
 
@@ -1144,7 +1145,8 @@ void cells_fetch(gdbgpu_scan* s, int32_t kind, int32_t index, const uint64_t** o
     default: throw ArgError("unknown cell field kind");
   }
   auto& slot = s->fetched[std::make_pair((int)kind, (int)index)];
-  if (slot.first.size() != s->n_cells + 1) fetch_column(s, *col, fixed_bytes, s->cell_list.p, s->n_cells, slot.first, slot.second);
+  const uint64_t first = std::min(s->win_first, s->n_cells), n = std::min(s->win_count, s->n_cells - first);
+  fetch_column(s, *col, fixed_bytes, s->cell_list.p + first, n, slot.first, slot.second);
   *offsets = slot.first.data(); *bytes = slot.second.data();
 }
 
@@ -1520,6 +1522,11 @@ int gdbgpu_scan_next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_byte
 int gdbgpu_scan_cells(gdbgpu_scan* s, gdbgpu_cell_list* out) {
   if (!s || !out) return GDBGPU_ERR_ARG;
   return guarded(s->ctx, [&] { CK(cudaSetDevice(s->ctx->device)); cells_to_host(s, out); });
+}
+int gdbgpu_scan_cells_window(gdbgpu_scan* s, uint64_t first, uint64_t count) {
+  if (!s) return GDBGPU_ERR_ARG;
+  s->win_first = first; s->win_count = count ? count : UINT64_MAX;
+  return GDBGPU_OK;
 }
 int gdbgpu_scan_cells_histogram(gdbgpu_scan* s, uint64_t begin, uint64_t end, uint64_t bin_size, uint64_t* counts, uint64_t n_bins) {
   if (!s || !counts) return GDBGPU_ERR_ARG;

@@ -7,6 +7,7 @@
 #include <cerrno>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "gdb_json.h"
@@ -821,20 +822,27 @@ void VariantQueryProcessor::iterate_over_cells(const int, const VariantQueryConf
     for (unsigned a = 0; a < qc.get_num_queried_attributes(); ++a)
       if (qc.get_query_attribute(a).kind == -2)
         throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "columnar iterator on the GPU: multi-dimensional field " + qc.get_query_attribute_name(a) + " is not supported");
-    gdbgpu_cell_list list;
-    check(gdbgpu_scan_cells(scan, &list));
+    // the list is paged through (cells and their columns cross PCIe a window at a time, as scan_and_operate's batches do)
+    static const uint64_t window = [] { const char* e = getenv("GDBGPU_CELLS_WINDOW"); uint64_t w = e ? strtoull(e, nullptr, 10) : 0; return w ? w : (1ull << 20); }();
     std::vector<GenomicsDBColumnarCell::Column> columns(qc.get_num_queried_attributes());
-    for (unsigned a = 0; a < qc.get_num_queried_attributes(); ++a) {
-      const auto& qa = qc.get_query_attribute(a);
-      if (qa.kind < 0) continue;   // END comes with the list
-      check(gdbgpu_scan_cells_fetch(scan, qa.kind, qa.index, &columns[a].off, &columns[a].bytes));
-    }
     GenomicsDBColumnarCell cell;
     cell.qc_ = &qc; cell.columns_ = &columns; cell.interval_idx_ = i;
-    for (uint64_t k = 0; k < list.n_cells; ++k) {
-      cell.idx_ = k; cell.coords_[0] = list.row[k]; cell.coords_[1] = list.begin[k]; cell.end_ = list.end[k];
-      cell.at_new_interval_ = k == 0;
-      op.operate_on_columnar_cell(cell, qc, schema_);
+    for (uint64_t first = 0;; first += window) {
+      gdbgpu_cell_list list;
+      check(gdbgpu_scan_cells_window(scan, first, window));
+      check(gdbgpu_scan_cells(scan, &list));
+      if (!list.n_cells) break;
+      for (unsigned a = 0; a < qc.get_num_queried_attributes(); ++a) {
+        const auto& qa = qc.get_query_attribute(a);
+        if (qa.kind < 0) continue;   // END comes with the list
+        check(gdbgpu_scan_cells_fetch(scan, qa.kind, qa.index, &columns[a].off, &columns[a].bytes));
+      }
+      for (uint64_t k = 0; k < list.n_cells; ++k) {
+        cell.idx_ = k; cell.coords_[0] = list.row[k]; cell.coords_[1] = list.begin[k]; cell.end_ = list.end[k];
+        cell.at_new_interval_ = first == 0 && k == 0;
+        op.operate_on_columnar_cell(cell, qc, schema_);
+      }
+      if (first + list.n_cells >= list.n_total) break;
     }
   }
   op.finalize();

@@ -266,13 +266,18 @@ void gdbgpu_scan_end(gdbgpu_scan* scan);
  * storage order.  The list is built on the device; everything below works on any scan, GDBGPU_SCAN_CELLS_ONLY makes
  * gdbgpu_scan_begin skip what only the combine needs.  Host pointers stay valid until gdbgpu_scan_end. */
 typedef struct gdbgpu_cell_list {
-  uint64_t n_cells, n_left;   /* the first n_left entries are the calls reaching in from the left */
+  uint64_t n_cells, n_left;   /* entries handed out (the window); the first n_left of them are calls reaching in from the left */
+  uint64_t n_total, first;    /* length of the interval's whole list; position of the window's first entry in it */
   const uint64_t* cell;       /* index in the array's merged cell order (gdbgpu_array_copy_cells); a left call is named by its END copy */
   const int64_t* row;         /* GenomicsDBColumnarCell::get_coordinates()[0] */
   const int64_t* begin;       /* ... [1]: the call's begin column (coordinates and END swapped back for an END copy) */
   const int64_t* end;
 } gdbgpu_cell_list;
 int gdbgpu_scan_cells(gdbgpu_scan* scan, gdbgpu_cell_list* out);
+/* Page through a long list: the following gdbgpu_scan_cells / gdbgpu_scan_cells_fetch calls hand out entries
+ * [first, first + count) only (count 0 = to the end; the default window is the whole list).  Pointers handed out for an
+ * earlier window are invalidated.  Histogram and allele counts always cover the whole list. */
+int gdbgpu_scan_cells_window(gdbgpu_scan* scan, uint64_t first, uint64_t count);
 
 /* ColumnHistogramOperator(begin, end, bin_size) over the listed cells (variant_operations.cc:732-765): counts[n_bins],
  * n_bins = (end - begin) / bin_size + 1, host memory of the caller.  Nothing but the counts leaves the device. */

@@ -105,6 +105,14 @@ def test_cells_on_a_synthetic_cohort(ctx):
                 w = np.frombuffer(by, dtype=np.int32)
                 for i, (c, _, _, _) in enumerate(want[:200]):
                     assert w[off[i] // 4:off[i + 1] // 4].tolist() == list(view.field_words(0, c))
+                # paging: a window in the middle of the list (straddling the left part when there is one)
+                first = max(0, n_left - 3) if n_left else len(want) // 3
+                sc.cells_window(first, 1000)
+                page = sc.cells()
+                assert page["n_total"] == len(want) and page["first"] == first and page["n_left"] == min(max(n_left - first, 0), 1000)
+                assert list(zip(page["cell"].tolist(), page["row"].tolist(), page["begin"].tolist(), page["end"].tolist())) == want[first:first + 1000]
+                off, by = sc.cells_fetch(capi.CELL_FIELD_REF)
+                assert [by[off[i]:off[i + 1]].decode() for i in range(len(page["cell"]))] == [view.ref_str(c) for c, _, _, _ in want[first:first + 1000]]
             finally:
                 sc.close()
     finally:

@@ -25,7 +25,7 @@ def exe():
     return g.build_tools()
 
 
-def run_tool(exe, case, tmp_path, flag, attributes=None):
+def run_tool(exe, case, tmp_path, flag, attributes=None, window=None):
     q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
          "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": attributes or case["attributes"],
          "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_column_ranges"]]}],
@@ -33,7 +33,8 @@ def run_tool(exe, case, tmp_path, flag, attributes=None):
     qf = tmp_path / "query.json"
     qf.write_text(json.dumps(q))
     out = tmp_path / "out.txt"
-    return subprocess.run([exe, "-j", str(qf), "-o", str(out), flag], capture_output=True, text=True), out
+    env = dict(os.environ, GDBGPU_CELLS_WINDOW=str(window)) if window else None
+    return subprocess.run([exe, "-j", str(qf), "-o", str(out), flag], capture_output=True, text=True, env=env), out
 
 
 # the two print commands on every array; the two device-side operators through the tool on a few (tests/test_gpu_cells.py
@@ -60,3 +61,13 @@ def test_print_calls_equals_the_reference_ci_golden_queries(exe, cid, tmp_path):
     p, out = run_tool(exe, case, tmp_path, "--print-calls", attributes=CI[cid]["attributes"])
     assert p.returncode == 0, p.stderr
     assert out.read_bytes() == open(os.path.join(CELLS, cid + ".ci.calls"), "rb").read()
+
+
+@pytest.mark.parametrize("cid", ["t0_1_2_multiple_positions", "t0_1_2_combined_at_0"])
+def test_paging_through_the_cell_list_is_transparent(exe, cid, tmp_path):
+    """iterate_over_cells with a two-cell window (gdbgpu_scan_cells_window): same bytes"""
+    case = [c for c in ALL if c["id"] == cid][0]
+    for ext, flag in MODES[:2]:
+        p, out = run_tool(exe, case, tmp_path, flag, window=2)
+        assert p.returncode == 0, p.stderr
+        assert out.read_bytes() == open(os.path.join(CELLS, cid + "." + ext), "rb").read()
