@@ -4,6 +4,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <unordered_set>
 #include <cerrno>
 #include <climits>
 #include <cstdio>
@@ -255,7 +256,7 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
   // FORMAT fields: GT first (htslib moves it to the front, vcf.c:3670-3676), then query order, DP (from DP_FORMAT) last
   if (remapped_index("GT") >= 0) m_FORMAT_fields_vec.push_back({"GT", key_of("GT"), remapped_index("GT")});
   int dp_format_plain = -1;
-  for (auto& name : qc.get_query_attributes()) {
+  for (auto& name : qc.get_ordered_query_attributes()) {   // the order the reference's bookkeeping leaves (END, REF, ALT swapped to the front)
     if (name == "GT") continue;
     const FieldInfo* fi = id_mapper.get_field_info(name);
     if (!fi) continue;
@@ -269,6 +270,7 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
     }
     for (size_t p = 0; p < plain.size(); ++p) if (plain[p].attribute == name) {
       if (plain[p].is_qual) m_QUAL_plain = (int)p;
+      else if (plain[p].is_id) m_ID_fmt_index = (int)(n_remapped + p);
       else if (plain[p].format) {
         if (name == "DP_FORMAT") dp_format_plain = (int)p;
         else m_FORMAT_fields_vec.push_back({plain[p].vcf_name, key_of(plain[p].vcf_name), (int)(n_remapped + p)});
@@ -305,7 +307,28 @@ void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint3
   struct FormatPiece { std::vector<uint8_t> head; const uint8_t* block = nullptr; size_t block_bytes = 0; };
   std::vector<FormatPiece> pieces;
   size_t indiv_bytes = 0;
-  enc_vchar(shared, "");   // ID
+  // ID: ';'-separated tokens of every live call's ID, each once (broad_combined_gvcf.cc:729-763,801-807).  The reference
+  // collects them in a std::unordered_set and emits its iteration order; the same container filled in the same (row)
+  // order reproduces it.
+  m_ID_value.clear();
+  if (m_ID_fmt_index >= 0 && b.fmt_type[(uint64_t)m_ID_fmt_index * ns + s]) {
+    const uint64_t slot = (uint64_t)m_ID_fmt_index * ns + s;
+    const uint32_t nps = b.fmt_nps[slot];
+    const uint8_t* blk = b.fmt_bytes + b.fmt_offset[slot];
+    std::unordered_set<std::string> id_set;
+    for (uint64_t q = 0; q < nq; ++q) {
+      const char* e = reinterpret_cast<const char*>(blk + q * nps);
+      if (e[0] == 0x07 || e[0] == 0x00) continue;   // no call, or a call without ID
+      size_t len = 0;
+      while (len < nps && e[len] != 0x00) ++len;
+      size_t last = 0;
+      for (size_t i = 0; i < len; ++i) if (e[i] == ';') { id_set.insert(std::string(e + last, i - last)); last = i + 1; }
+      if (len > last) id_set.insert(std::string(e + last, len - last));
+    }
+    for (const auto& str : id_set) m_ID_value += str + ';';
+    if (!m_ID_value.empty()) m_ID_value.pop_back();
+  }
+  enc_vchar(shared, m_ID_value);
   enc_vchar(shared, ref);
   for (uint32_t m = 1; m < n_allele; ++m) enc_vchar(shared, allele(m));
   shared.push_back(0x00);   // FILTER: empty typed vector
@@ -412,14 +435,14 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
     if (fi) return fi;
     return name == "QUAL" ? &builtin_QUAL : (name == "FILTER" ? &builtin_FILTER : nullptr);
   };
-  if (stage_columnar_fields) {
+  {
     auto add = [&](const char* n) { if (std::find(ordered.begin(), ordered.end(), n) == ordered.end()) ordered.push_back(n); };
     add("END");
     if (alleles_required) { add("ALT"); add("REF"); }
     for (size_t i = 0; i < ordered.size(); ++i) {
       const FieldInfo* fi = columnar_field_info(ordered[i]);
       if (!fi) {
-        if (ordered[i] == "END" || ordered[i] == "REF" || ordered[i] == "ALT") continue;
+        if (ordered[i] == "END" || ordered[i] == "REF" || ordered[i] == "ALT" || !stage_columnar_fields) continue;
         throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Field " + ordered[i] + " not found in vid mapping");
       }
       if (fi->is_allele_dependent()) { add("ALT"); add("REF"); }
@@ -433,7 +456,8 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
       ++first_normal;
     }
   }
-  for (auto& name : (stage_columnar_fields ? ordered : qc.get_query_attributes())) {
+  qc.ordered_attributes_ = ordered;
+  for (auto& name : ordered) {
     const FieldInfo* fi = vid.get_field_info(name);
     if (!fi || !fi->is_allele_dependent()) continue;
     gdbgpu_field_desc d;
@@ -454,8 +478,8 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
   qc.plain_.clear(); qc.dp_fields_[0] = qc.dp_fields_[1] = qc.dp_fields_[2] = 0;
   std::vector<gdbgpu_plain_field_desc> pd;
   if (stage_broad_gvcf_fields) {
-    static const char* skip[] = {"END", "REF", "ALT", "GT", "FILTER", "ID"};
-    for (auto& name : qc.get_query_attributes()) {
+    static const char* skip[] = {"END", "REF", "ALT", "GT", "FILTER"};
+    for (auto& name : ordered) {
       const FieldInfo* fi = vid.get_field_info(name);
       if (!fi || fi->is_allele_dependent()) continue;
       bool skipped = false;
@@ -470,6 +494,11 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
       pf.fixed_len = numeric_len ? std::stoi(fi->length) : 0;
       const bool as_format = (fi->is_format && (twin || !fi->is_info)) || (fi->is_info && fi->combine_op == "move_to_FORMAT");
       const bool scalar_op = fi->combine_op == "median" || fi->combine_op == "sum" || fi->combine_op == "mean";
+      if (name == "ID") {     // bcf1_t.id: the union of the live calls' IDs (merge_ID_field, broad_combined_gvcf.cc:729-763); collated like a string FORMAT field
+        pf.elem = GDBGPU_ELEM_CHAR; pf.fixed_len = 0; pf.format = true; pf.is_id = true;
+        qc.plain_.push_back(pf);
+        continue;
+      }
       if (name == "QUAL") {   // bcf1_t.qual through the field's combine operation, else missing (broad_combined_gvcf.cc:796-808)
         if (!scalar_op) continue;
         pf.is_qual = true; pf.fixed_len = 1; pf.elem = GDBGPU_ELEM_FLOAT32;
@@ -504,8 +533,8 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
       const FieldInfo* fi = columnar_field_info(name);
       const bool special = name == "END" || name == "REF" || name == "ALT" || name == "GT";
       VariantQueryConfig::QueryAttribute qa; qa.name = name;
-      if (fi) qa.elem = fi->type == "char" ? 'c' : (fi->type == "float" ? 'f' : 'i');
-      if (!special && fi->type != "char" && fi->type != "float" && fi->type != "int") throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "columnar iterator on the GPU: type " + fi->type + " of field " + name + " is not supported");
+      if (fi) qa.elem = fi->type == "char" ? 'c' : (fi->type == "float" ? 'f' : (fi->type == "flag" ? 'b' : 'i'));   // 'b': one byte, printed as bool
+      if (!special && fi->type != "char" && fi->type != "float" && fi->type != "int" && fi->type != "flag") throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "columnar iterator on the GPU: type " + fi->type + " of field " + name + " is not supported");
       if (name == "END") { qa.kind = -1; qa.fixed_len = 1; }
       else if (name == "REF") { qa.kind = GDBGPU_CELL_FIELD_REF; qa.elem = 'c'; }
       else if (name == "ALT") { qa.kind = GDBGPU_CELL_FIELD_ALT; qa.elem = 'c'; }
@@ -517,7 +546,7 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
         qa.kind = GDBGPU_CELL_FIELD_PLAIN; qa.index = (int)qc.plain_.size(); qa.fixed_len = numeric_len ? std::stoi(fi->length) : 0;
         VariantQueryConfig::PlainField pf;
         pf.attribute = pf.vcf_name = name; pf.fixed_len = qa.fixed_len;
-        pf.elem = qa.elem == 'c' ? GDBGPU_ELEM_CHAR : (qa.elem == 'f' ? GDBGPU_ELEM_FLOAT32 : GDBGPU_ELEM_INT32);
+        pf.elem = (qa.elem == 'c' || qa.elem == 'b') ? GDBGPU_ELEM_CHAR : (qa.elem == 'f' ? GDBGPU_ELEM_FLOAT32 : GDBGPU_ELEM_INT32);
         qc.plain_.push_back(pf);
       }
       qc.query_attrs_.push_back(qa);
@@ -611,7 +640,7 @@ void VariantQueryProcessor::scan_and_operate(const int, const VariantQueryConfig
 // ------------------------------------------------------------------------------------------------ columnar iterator surface
 namespace {
 const std::string g_json_indent_unit = "    ";
-inline size_t elem_size(char e) { return e == 'c' ? 1u : 4u; }
+inline size_t elem_size(char e) { return (e == 'c' || e == 'b') ? 1u : 4u; }
 template <class T> void print_list(std::ostream& f, const uint8_t* p, size_t n) {
   const T* d = reinterpret_cast<const T*>(p);
   f << "[ " << d[0];
@@ -651,7 +680,7 @@ bool GenomicsDBColumnarCell::is_valid(unsigned i) const {
   if (qa.fixed_len == 0) return n > 0;
   const uint8_t* p = get_field_ptr_for_query_idx(i);
   for (size_t k = 0; k < n; ++k) {
-    if (qa.elem == 'c') { if (p[k] != 127) return true; }
+    if (qa.elem == 'c' || qa.elem == 'b') { if (p[k] != 127) return true; }
     else { uint32_t w; memcpy(&w, p + 4 * k, 4); if (w != (qa.elem == 'f' ? 0x7F7FFFFFu : 0x7FFFFFFFu)) return true; }
   }
   return false;
@@ -695,7 +724,8 @@ void GenomicsDBColumnarCell::print(std::ostream& fptr, const VariantQueryConfig*
         t0 = t1 + 1;
       }
       fptr << " ]";
-    } else if (qa.elem == 'c') {
+    } else if (qa.elem == 'b') fptr << (p[0] != 0);   // BCF_HT_FLAG: GenomicsDBColumnarFieldPrintOperator<bool, false>
+    else if (qa.elem == 'c') {
       if (qa.fixed_len == 1) fptr << (char)p[0];
       else { fptr << "\""; fptr.write(reinterpret_cast<const char*>(p), n); fptr << "\""; }
     } else if (qa.fixed_len == 1) {
@@ -717,7 +747,8 @@ void GenomicsDBColumnarCell::print_csv(std::ostream& fptr, const VariantQueryCon
     const uint8_t* p = get_field_ptr_for_query_idx(i);
     const size_t n = get_field_length(i);
     const bool valid = is_valid(i), variable = qa.fixed_len == 0;
-    if (qa.elem == 'c') {
+    if (qa.elem == 'b') { if (valid) fptr << (p[0] != 0); }
+    else if (qa.elem == 'c') {
       if (qa.fixed_len == 1) { if (valid) fptr << (char)p[0]; }
       else if (valid) fptr.write(reinterpret_cast<const char*>(p), n);
     } else if (qa.fixed_len == 1) {

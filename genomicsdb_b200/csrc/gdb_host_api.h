@@ -95,6 +95,9 @@ class VariantQueryConfig {
   bool query_all_rows() const { return rows_.empty(); }
   const std::vector<int64_t>& get_rows_to_query() const { return rows_; }
   const std::vector<std::string>& get_query_attributes() const { return attributes_; }
+  // after do_query_bookkeeping: END / ALT / REF / GT added as the reference adds them, END, REF, ALT swapped to the front
+  // (query_variants.cc:578-637, variant_query_config.cc:161-185) -- the order operators see the fields in
+  const std::vector<std::string>& get_ordered_query_attributes() const { return ordered_attributes_; }
   const VidMapper& get_vid_mapper() const { return vid_; }
   unsigned get_max_diploid_alt_alleles_that_can_be_genotyped() const { return max_alt_; }
   bool produce_GT_with_min_PL_value_for_spanning_deletions() const { return min_pl_gt_; }
@@ -108,7 +111,7 @@ class VariantQueryConfig {
   std::string workspace_, array_name_;
   std::vector<std::pair<int64_t, int64_t>> intervals_;
   std::vector<int64_t> rows_;
-  std::vector<std::string> attributes_;
+  std::vector<std::string> attributes_, ordered_attributes_;
   VidMapper vid_;
   unsigned max_alt_ = 50;
   bool min_pl_gt_ = false, produce_gt_ = false, sites_only_ = false;
@@ -116,7 +119,7 @@ class VariantQueryConfig {
   std::vector<std::string> remapped_names_;
   // plain fields staged for the Broad operator (do_query_bookkeeping): FORMAT fields that are not allele-dependent, scalar
   // INFO fields with a median / sum / mean combine operation, the inputs of the DP rule
-  struct PlainField { std::string attribute, vcf_name; int elem = 0, fixed_len = 0; bool format = false; int info_op = 0; bool is_qual = false; };
+  struct PlainField { std::string attribute, vcf_name; int elem = 0, fixed_len = 0; bool format = false; int info_op = 0; bool is_qual = false, is_id = false; };
   std::vector<PlainField> plain_;
   unsigned dp_fields_[3] = {0, 0, 0};   // 1-based plain indices of INFO DP, MIN_DP, DP_FORMAT
   unsigned esum_remapped_mask_ = 0;     // remapped fields (GT not counted) combined with an element-wise sum
@@ -283,6 +286,8 @@ class BroadCombinedGVCFOperator : public GA4GHOperator {
   struct InfoField { std::string vcf_name; int key = -1; int plain_index = -1; bool is_float = false; int vector_slot = -1; };   // vector_slot >= 0: element-wise sum
   std::vector<InfoField> m_INFO_fields_vec;
   int m_END_key = -1, m_DP_key = -1, m_QUAL_plain = -1;
+  int m_ID_fmt_index = -1;        // the ID strings of the live calls, collated like a FORMAT field; merged per site (merge_ID_field)
+  std::string m_ID_value;
   unsigned m_num_vector_slots = 0;
   bool m_dp_rule = false, m_use_missing_values_not_vector_end = false;
   uint64_t m_num_records = 0;

@@ -100,6 +100,18 @@ SCENARIOS = [
     dict(name="t6_7_8_three_fragments_gz", callsets="t6_7_8.json", compress=True, batches=[(1, 1), (0, 0), (2, 2)], queries=[
         dict(id="t6_7_8_three_fragments_at_0", ranges=FULL, vcf="t6_7_8_vcf_at_0"),
     ]),
+    # the same gVCFs imported with GT stored phased (tests/run.py:493-520) and with the DS flag / ID string fields (:687-704)
+    dict(name="t0_1_2_phased_GT", callsets="t0_1_2.json", vid="vid_phased_GT.json", queries=[
+        dict(id="t0_1_2_phased_GT_at_0", ranges=FULL, vcf="t0_1_2_vcf_at_0", extra={"vid_mapping_file": "inputs/vid_phased_GT.json"}),
+        dict(id="t0_1_2_phased_GT_at_12150", ranges=[[12150, 1000000000]], vcf="t0_1_2_vcf_at_12150",
+             extra={"vid_mapping_file": "inputs/vid_phased_GT.json"}),
+    ]),
+    dict(name="t0_1_2_DS_ID", callsets="t0_1_2.json", vid="vid_DS_ID.json", queries=[
+        dict(id="t0_1_2_DS_ID_at_0", ranges=FULL, vcf=None,
+             attributes=["REF", "ALT", "BaseQRankSum", "MQ", "RAW_MQ", "MQ0", "ClippingRankSum", "MQRankSum", "ReadPosRankSum", "DP", "GT", "GQ",
+                         "SB", "AD", "PL", "DP_FORMAT", "MIN_DP", "PID", "PGT", "DS", "ID"],
+             extra={"vid_mapping_file": "inputs/vid_DS_ID.json"}),
+    ]),
     # INFO combine operations (tests/run.py:598-601, vid_info_ops0.json): QUAL median, mean, element-wise sums of A-length and
     # variable-length fields
     dict(name="info_ops0", callsets="info_ops.json", vid="vid_info_ops0.json", queries=[

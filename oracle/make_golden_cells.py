@@ -34,6 +34,8 @@ CI_CALLS = {
     "t0_1_2_at_12100_12141_to_12150_12300_17384": "t0_1_2_calls_at_12100_12141_to_12150_12300_17384",
     "t6_7_8_at_0": "t6_7_8_calls_at_0", "t6_7_8_at_8029500": "t6_7_8_calls_at_8029500",
     "test_new_fields_at_0": "test_new_fields_MLEAC_only.json", "t0_with_missing_PL_SB_fields_at_0": "t0_with_missing_PL_SB_fields_t1_calls.json",
+    "t0_1_2_phased_GT_at_0": "t0_1_2_calls_at_0_phased_GT", "t0_1_2_phased_GT_at_12150": "t0_1_2_calls_at_12150_phased_GT",
+    "t0_1_2_DS_ID_at_0": "t0_1_2_DS_ID_calls_at_0",
     "t0_1_2_uncompressed_at_0": "t0_1_2_calls_at_0", "t0_1_2_two_fragments_at_0": "t0_1_2_calls_at_0", "t0_1_2_two_fragments_at_12150": "t0_1_2_calls_at_12150",
 }
 
@@ -73,7 +75,7 @@ def main():
             open(os.path.join(out_dir, c["id"] + "." + ext), "wb").write(p.stdout)
             sizes.append("%s %d" % (ext, len(p.stdout)))
         if c["id"] in CI_CALLS:   # the CI's query for this array: its attribute list, its golden
-            attrs = ["MLEAC"] if c["id"] == "test_new_fields_at_0" else CI_ATTRIBUTES
+            attrs = ["MLEAC"] if c["id"] == "test_new_fields_at_0" else (CI_ATTRIBUTES + ["DS", "ID"] if "DS_ID" in c["id"] else CI_ATTRIBUTES)
             qc = os.path.join(tmp, c["id"] + "_ci.json")
             json.dump(dict(q, attributes=attrs), open(qc, "w"))
             p = subprocess.run(["stdbuf", "-o0", BIN + "/gt_mpi_gather", "-j", qc, "--print-calls"], capture_output=True, cwd=REF_TESTS)
