@@ -21,6 +21,7 @@ using gdb::JsonValue;
 VidMapper::VidMapper(const std::string& file) {
   JsonValue d = gdb::json_parse_file(file);
   const JsonValue& fl = d.at("fields");
+  int n_json_fields = 0;
   auto add = [&](const std::string& name, const JsonValue& v) {
     FieldInfo f; f.name = name;
     if (const JsonValue* t = v.find("type")) f.type = t->type == JsonValue::STR ? t->str : (t->type == JsonValue::ARR && !t->arr.empty() ? t->arr[0].str : "int");
@@ -39,8 +40,9 @@ VidMapper::VidMapper(const std::string& file) {
       if (name == "RAW_MQ") f.combine_op = "sum";
       if (name == "DP") f.combine_op = "DP";
     }
+    f.global_idx = n_json_fields++;
     fields_.push_back(f);
-    if (f.is_format && f.is_info) { FieldInfo g = f; g.name = name + "_FORMAT"; fields_.push_back(g); }   // vid_mapper.cc: FORMAT twin
+    if (f.is_format && f.is_info) { FieldInfo g = f; g.name = name + "_FORMAT"; g.global_idx = -1; fields_.push_back(g); }   // vid_mapper.cc: FORMAT twin
   };
   if (fl.type == JsonValue::OBJ) for (auto& kv : fl.obj) add(kv.first, kv.second);
   else for (auto& v : fl.arr) add(v.at("name").str, v);
@@ -115,6 +117,7 @@ void VariantQueryConfig::read_from_file(const std::string& filename, int rank) {
   if (const JsonValue* v = d.find("produce_GT_with_min_PL_value_for_spanning_deletions")) min_pl_gt_ = v->as_bool();
   if (const JsonValue* v = d.find("produce_GT_field")) produce_gt_ = v->as_bool();
   if (const JsonValue* v = d.find("sites_only_query")) sites_only_ = v->as_bool();
+  if (const JsonValue* v = d.find("produce_FILTER_field")) produce_filter_ = v->as_bool();
 }
 
 // ------------------------------------------------------------------------------------------------ operators
@@ -271,6 +274,7 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
     for (size_t p = 0; p < plain.size(); ++p) if (plain[p].attribute == name) {
       if (plain[p].is_qual) m_QUAL_plain = (int)p;
       else if (plain[p].is_id) m_ID_fmt_index = (int)(n_remapped + p);
+      else if (plain[p].is_filter) { /* not a query-order field: below */ }
       else if (plain[p].format) {
         if (name == "DP_FORMAT") dp_format_plain = (int)p;
         else m_FORMAT_fields_vec.push_back({plain[p].vcf_name, key_of(plain[p].vcf_name), (int)(n_remapped + p)});
@@ -281,6 +285,12 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
     }
   }
   if (dp_format_plain >= 0) m_FORMAT_fields_vec.push_back({"DP", key_of("DP"), (int)(n_remapped + dp_format_plain)});
+  for (size_t p = 0; p < plain.size(); ++p) if (plain[p].is_filter) m_FILTER_fmt_index = (int)(n_remapped + p);
+  for (auto& f : id_mapper.fields()) {   // broad_combined_gvcf.cc:306-313: vid field index -> header dictionary id (could be -1)
+    if (f.global_idx < 0) continue;
+    if ((size_t)f.global_idx >= m_global_field_idx_to_hdr_idx.size()) m_global_field_idx_to_hdr_idx.resize(f.global_idx + 1, -1);
+    m_global_field_idx_to_hdr_idx[f.global_idx] = vcf_adapter.get_dictionary_id(f.name);
+  }
   m_dp_rule = qc.get_dp_rule_fields()[0] != 0 || qc.get_dp_rule_fields()[2] != 0;
   if (m_dp_rule) m_DP_key = key_of("DP");
   m_END_key = key_of("END");
@@ -331,7 +341,35 @@ void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint3
   enc_vchar(shared, m_ID_value);
   enc_vchar(shared, ref);
   for (uint32_t m = 1; m < n_allele; ++m) enc_vchar(shared, allele(m));
-  shared.push_back(0x00);   // FILTER: empty typed vector
+  // FILTER: union of the live calls' filter indices, duplicates removed (broad_combined_gvcf.cc:845-873; the reference
+  // walks a std::unordered_set<int> filled in row order and keeps the slots of ids the header does not know)
+  bool have_filter = false;
+  if (m_FILTER_fmt_index >= 0 && b.fmt_type[(uint64_t)m_FILTER_fmt_index * ns + s]) {
+    const uint64_t slot = (uint64_t)m_FILTER_fmt_index * ns + s;
+    const uint32_t nps = b.fmt_nps[slot]; const uint8_t type = b.fmt_type[slot];
+    const uint8_t* blk = b.fmt_bytes + b.fmt_offset[slot];
+    std::unordered_set<int> filter_idx_set;
+    for (uint64_t q = 0; q < nq; ++q)
+      for (uint32_t k = 0; k < nps; ++k) {
+        int v; bool stop;
+        if (type == BT_INT8) { int8_t x = (int8_t)blk[q * nps + k]; v = x; stop = x == INT8_MIN || x == INT8_MIN + 1; }
+        else if (type == BT_INT16) { int16_t x; memcpy(&x, blk + 2 * (q * nps + k), 2); v = x; stop = x == INT16_MIN || x == INT16_MIN + 1; }
+        else { int32_t x; memcpy(&x, blk + 4 * (q * nps + k), 4); v = x; stop = x == INT32_MIN || x == INT32_MIN + 1; }
+        if (stop) break;
+        filter_idx_set.insert(v);
+      }
+    if (!filter_idx_set.empty()) {
+      m_FILTER_idx_vec.resize(filter_idx_set.size());
+      size_t idx = 0;
+      for (int g : filter_idx_set) {
+        const int h = (g >= 0 && (size_t)g < m_global_field_idx_to_hdr_idx.size()) ? m_global_field_idx_to_hdr_idx[g] : -1;
+        if (h >= 0) m_FILTER_idx_vec[idx++] = h;
+      }
+      enc_vint(shared, m_FILTER_idx_vec.data(), (uint32_t)m_FILTER_idx_vec.size());
+      have_filter = true;
+    }
+  }
+  if (!have_filter) shared.push_back(0x00);   // empty typed vector
   uint32_t n_info = 0;
   int32_t rlen = (int32_t)ref.size();
   if (end > begin) {   // handle_INFO_fields: interval -> END (1-based); bcf_update_info sets rlen from END
@@ -478,7 +516,14 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
   qc.plain_.clear(); qc.dp_fields_[0] = qc.dp_fields_[1] = qc.dp_fields_[2] = 0;
   std::vector<gdbgpu_plain_field_desc> pd;
   if (stage_broad_gvcf_fields) {
-    static const char* skip[] = {"END", "REF", "ALT", "GT", "FILTER"};
+    static const char* skip[] = {"END", "REF", "ALT", "GT"};
+    // FILTER (vid_mapper.cc:611-668 makes it an int vector even when the vid mapping does not list it): the union over the
+    // live calls goes into bcf1_t.d.flt when the query asks for it (broad_combined_gvcf.cc:845-873)
+    if (qc.produce_FILTER_field() && std::find(ordered.begin(), ordered.end(), "FILTER") != ordered.end()) {
+      VariantQueryConfig::PlainField pf;
+      pf.attribute = pf.vcf_name = "FILTER"; pf.elem = GDBGPU_ELEM_INT32; pf.fixed_len = 0; pf.format = true; pf.is_filter = true;
+      qc.plain_.push_back(pf);
+    }
     for (auto& name : ordered) {
       const FieldInfo* fi = vid.get_field_info(name);
       if (!fi || fi->is_allele_dependent()) continue;
@@ -494,6 +539,7 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
       pf.fixed_len = numeric_len ? std::stoi(fi->length) : 0;
       const bool as_format = (fi->is_format && (twin || !fi->is_info)) || (fi->is_info && fi->combine_op == "move_to_FORMAT");
       const bool scalar_op = fi->combine_op == "median" || fi->combine_op == "sum" || fi->combine_op == "mean";
+      if (name == "FILTER") continue;
       if (name == "ID") {     // bcf1_t.id: the union of the live calls' IDs (merge_ID_field, broad_combined_gvcf.cc:729-763); collated like a string FORMAT field
         pf.elem = GDBGPU_ELEM_CHAR; pf.fixed_len = 0; pf.format = true; pf.is_id = true;
         qc.plain_.push_back(pf);

@@ -50,6 +50,7 @@ struct FieldInfo {
   std::string type;        // "int", "float", "char", ...
   std::string length;      // "1", "R", "A", "G", "P", "PP", "VAR", "<n>"; 2-D descriptors are kept as "2D"
   bool is_format = false, is_info = false;
+  int global_idx = -1;     // position among the vid mapping's fields (what FILTER cells store); -1 for a FORMAT twin
   std::string combine_op;  // "VCF_field_combine_operation" of the vid mapping, else the known field's default (known_field_info.cc:284-308)
   bool is_allele_dependent() const { return length == "R" || length == "A" || length == "G"; }
 };
@@ -84,6 +85,8 @@ class VariantQueryConfig {
   void set_produce_GT_with_min_PL_value_for_spanning_deletions(bool v) { min_pl_gt_ = v; }
   void set_produce_GT_field(bool v) { produce_gt_ = v; }
   bool produce_GT_field() const { return produce_gt_; }
+  void set_produce_FILTER_field(bool v) { produce_filter_ = v; }
+  bool produce_FILTER_field() const { return produce_filter_; }
   void set_sites_only_query(bool v) { sites_only_ = v; }
   bool sites_only_query() const { return sites_only_; }
 
@@ -114,12 +117,12 @@ class VariantQueryConfig {
   std::vector<std::string> attributes_, ordered_attributes_;
   VidMapper vid_;
   unsigned max_alt_ = 50;
-  bool min_pl_gt_ = false, produce_gt_ = false, sites_only_ = false;
+  bool min_pl_gt_ = false, produce_gt_ = false, sites_only_ = false, produce_filter_ = false;
   bool bookkeeping_done_ = false;
   std::vector<std::string> remapped_names_;
   // plain fields staged for the Broad operator (do_query_bookkeeping): FORMAT fields that are not allele-dependent, scalar
   // INFO fields with a median / sum / mean combine operation, the inputs of the DP rule
-  struct PlainField { std::string attribute, vcf_name; int elem = 0, fixed_len = 0; bool format = false; int info_op = 0; bool is_qual = false, is_id = false; };
+  struct PlainField { std::string attribute, vcf_name; int elem = 0, fixed_len = 0; bool format = false; int info_op = 0; bool is_qual = false, is_id = false, is_filter = false; };
   std::vector<PlainField> plain_;
   unsigned dp_fields_[3] = {0, 0, 0};   // 1-based plain indices of INFO DP, MIN_DP, DP_FORMAT
   unsigned esum_remapped_mask_ = 0;     // remapped fields (GT not counted) combined with an element-wise sum
@@ -288,6 +291,8 @@ class BroadCombinedGVCFOperator : public GA4GHOperator {
   int m_END_key = -1, m_DP_key = -1, m_QUAL_plain = -1;
   int m_ID_fmt_index = -1;        // the ID strings of the live calls, collated like a FORMAT field; merged per site (merge_ID_field)
   std::string m_ID_value;
+  int m_FILTER_fmt_index = -1;    // the FILTER vectors of the live calls, collated like an int FORMAT field; united per site
+  std::vector<int> m_global_field_idx_to_hdr_idx, m_FILTER_idx_vec;
   unsigned m_num_vector_slots = 0;
   bool m_dp_rule = false, m_use_missing_values_not_vector_end = false;
   uint64_t m_num_records = 0;

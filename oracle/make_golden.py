@@ -234,6 +234,7 @@ def main():
                 "query_column_ranges": ([[p, p] for p in q["positions"]] if "positions" in q else q["ranges"]),
                 "query_row_ranges": [[0, 3]],
                 "produce_GT_field": bool(qj.get("produce_GT_field", False)),
+                "produce_FILTER_field": bool(qj.get("produce_FILTER_field", False)),
                 "produce_GT_with_min_PL_value_for_spanning_deletions":
                     bool(qj.get("produce_GT_with_min_PL_value_for_spanning_deletions", False)),
                 "dump": "dumps/" + q["id"] + ".bin", "dump_md5": md5(open(dump, "rb").read()),

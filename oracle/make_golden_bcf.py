@@ -46,7 +46,7 @@ def main():
             "vid_mapping_file": os.path.join(GOLD, c["vid_mapping_file"]),
             "callset_mapping_file": os.path.join(GOLD, c["callset_mapping_file"]),
             "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in c["query_column_ranges"]]}],
-            "produce_GT_field": c["produce_GT_field"],
+            "produce_GT_field": c["produce_GT_field"], "produce_FILTER_field": c.get("produce_FILTER_field", False),
             "produce_GT_with_min_PL_value_for_spanning_deletions": c["produce_GT_with_min_PL_value_for_spanning_deletions"],
         }
         qf = os.path.join(tmp, c["id"] + ".json")

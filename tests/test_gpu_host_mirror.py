@@ -62,7 +62,7 @@ def run_broad(exe, case, tmp_path, page=0, java=False, sites_only=False):
          "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": case["attributes"],
          "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_column_ranges"]]}],
          "query_row_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_row_ranges"]]}],
-         "produce_GT_field": case["produce_GT_field"], "sites_only_query": sites_only,
+         "produce_GT_field": case["produce_GT_field"], "sites_only_query": sites_only, "produce_FILTER_field": case.get("produce_FILTER_field", False),
          "produce_GT_with_min_PL_value_for_spanning_deletions": case["produce_GT_with_min_PL_value_for_spanning_deletions"]}
     qf = tmp_path / "query.json"
     qf.write_text(json.dumps(q))
