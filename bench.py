@@ -282,6 +282,25 @@ def main():
     sites_per_step = sites // args.steps
     total_sites = sum_over_ranks(float(sites))
     value = total_sites / (ms * 1e-3)
+    # ---------------- the other consumer of the staged shard: the columnar iterator's cell list + the two
+    # operators that run as kernels, over this rank's whole shard; only bins / distinct allele records cross PCIe
+    columnar = None
+    if rank == 0:
+        def cells_pass(op):
+            sc = capi.Scan(arr, q_lo, q_hi, flags=capi.SCAN_CELLS_ONLY)
+            r = op(sc)
+            sc.close()
+            ctx.synchronize()
+            return r
+        hist = lambda sc: int(sc.cells_histogram(q_lo, q_hi, 1000).sum())
+        ac = lambda sc: len(sc.cells_allele_counts())
+        cells_pass(hist), cells_pass(ac)      # warm-up (buffers)
+        t0 = time.perf_counter(); listed = cells_pass(hist); t_hist = time.perf_counter() - t0
+        t0 = time.perf_counter(); n_rec = cells_pass(ac); t_ac = time.perf_counter() - t0
+        columnar = dict(listed_cells=listed, list_plus_histogram_ms=t_hist * 1e3, listed_cells_per_s=listed / t_hist,
+                        allele_count_ms=t_ac * 1e3, allele_count_cells_per_s=listed / t_ac, allele_count_records=n_rec,
+                        note="gdbgpu_scan_begin(GDBGPU_SCAN_CELLS_ONLY) + gdbgpu_scan_cells_histogram / _cells_allele_counts over the resident shard, "
+                             "wall clock incl. the call's host side; reference tool: tools/cells_bench.py")
     arr.close()
 
     # ---------------- roofline of the dominant kernel (remap): algorithmic bytes per launch / its event-timed duration
@@ -380,6 +399,7 @@ def main():
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
                     data="synthetic", config=workload_config(args, world), clocks=sampler.summary(), e2e=e2e, e2e_int32=e2e_int32,
                     gpu_launches=int(launches), roofline=roofline, cpu_baseline=base, cpu_baseline_broad_gvcf_operator=base_bcf,
+                    columnar_iterator=columnar,
                     sites_per_step_per_gpu=int(sites_per_step), cells_per_gpu=int(info.n_cells),
                     staged_bytes_per_gpu=int(info.staged_bytes), hbm_bytes_per_gpu=int(info.hbm_bytes))
         print(json.dumps(line))
