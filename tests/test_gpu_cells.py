@@ -146,3 +146,74 @@ def test_equal_load_shards_from_the_device_histogram(ctx):
         assert max(loads) - min(loads) <= 0.2 * (sum(loads) / 4), loads
     finally:
         arr.close()
+
+
+def _random_array(rng, n_rows, span):
+    """a small gVCF-shaped array: per row, non-overlapping calls [b, e] (some single-position, some overlapping the next
+    call on purpose), each with its END copy at e when e > b; cells in column-major order; ALT pools with deletions"""
+    cells = []   # (col, row, END, ref, alt, gt)
+    for r in range(n_rows):
+        pos = int(rng.integers(0, 6))
+        while pos < span:
+            length = int(rng.choice([1, 1, 2, 5, 17]))
+            e = min(pos + length - 1, span + 5)
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                ref, alt, gt = "N", "&", [0, 0]
+            elif kind == 1:
+                ref, alt, gt = "A", "T|&", [0, 1]
+            elif kind == 2:
+                ref, alt, gt = "ATG", "A|ACG|&", [int(rng.integers(0, 3)), int(rng.integers(1, 4))]
+            else:
+                ref, alt, gt = "C", "CAA|G|&", [1, 2]
+            cells.append((pos, r, e, ref, alt, gt))
+            if e > pos:
+                cells.append((e, r, pos, ref, alt, gt))      # END copy: coordinates hold the end, END the begin
+            nxt = e + 1 + int(rng.choice([0, 0, 0, 3, 9]))
+            if rng.random() < 0.1 and e > pos + 1:
+                nxt = e - 1                                  # the next call starts inside this one
+            pos = max(nxt, pos + 1)
+    # one cell per coordinate (TileDB keeps the newest): drop collisions, column-major order
+    seen, uniq = set(), []
+    for c in sorted(cells, key=lambda c: (c[0], c[1])):
+        if (c[0], c[1]) not in seen:
+            seen.add((c[0], c[1]))
+            uniq.append(c)
+    coords = np.array([[c[1], c[0]] for c in uniq], dtype=np.int64)
+    end = np.array([c[2] for c in uniq], dtype=np.int64)
+
+    def var(strings, dtype=np.uint8):
+        vals = [np.frombuffer(s.encode(), dtype=np.uint8) if dtype == np.uint8 else np.asarray(s, dtype=np.int32) for s in strings]
+        off = np.cumsum([0] + [v.nbytes for v in vals])[:-1].astype(np.uint64)
+        return off, (np.concatenate(vals) if vals else np.zeros(0, dtype=dtype))
+    return coords, end, var([c[3] for c in uniq]), var([c[4] for c in uniq]), var([c[5] for c in uniq], np.int32), uniq
+
+
+def test_cells_on_random_small_arrays(ctx):
+    """300 random arrays x 4 queries: the device's list (left part from END copies, rows subset, empty intervals, calls that
+    overlap the next one) and allele counts against the restatement"""
+    from genomicsdb_b200 import capi
+    rng = np.random.default_rng(20240611)
+    for it in range(300):
+        n_rows, span = int(rng.integers(1, 9)), int(rng.integers(8, 70))
+        coords, end, ref, alt, gt, uniq = _random_array(rng, n_rows, span)
+        arr = capi.Array.from_columns(ctx, coords, end, ref, alt, gt, [], 0, n_rows)
+        try:
+            for _ in range(4):
+                lo = int(rng.integers(0, span + 8))
+                hi = lo + int(rng.choice([0, 0, 3, 40]))
+                rows = None if rng.random() < 0.5 else np.sort(rng.choice(n_rows, int(rng.integers(1, n_rows + 1)), replace=False))
+                full = rng.random() < 0.15
+                sc = capi.Scan(arr, None if full else lo, None if full else hi, query_rows=rows, flags=capi.SCAN_CELLS_ONLY)
+                try:
+                    got = sc.cells()
+                    want, n_left = cells_oracle.iterate(coords[:, 0], coords[:, 1], end, range(n_rows) if rows is None else rows.tolist(),
+                                                        None if full else lo, None if full else hi)
+                    key = (it, lo, hi, None if rows is None else rows.tolist(), full)
+                    assert got["n_left"] == n_left, key
+                    assert list(zip(got["cell"].tolist(), got["row"].tolist(), got["begin"].tolist(), got["end"].tolist())) == want, key
+                    assert sc.cells_allele_counts() == cells_oracle.allele_counts(want, lambda i: uniq[i][3], lambda i: uniq[i][4], lambda i: uniq[i][5], 1), key
+                finally:
+                    sc.close()
+        finally:
+            arr.close()
