@@ -16,7 +16,7 @@ LEN_R, LEN_A, LEN_G = 0, 1, 2
 ELEM_INT32, ELEM_FLOAT32, ELEM_CHAR = 0, 1, 2
 SCAN_FULL, SCAN_NO_DELETIONS, SCAN_MIN_PL_GT, SCAN_WANT_LUT, SCAN_DEVICE_OUTPUT = 1, 2, 4, 8, 16
 SCAN_BCF_FORMAT, SCAN_PRODUCE_GT, SCAN_NO_PREFETCH, SCAN_HTSJDK_CONVENTIONS = 32, 64, 128, 256
-SCAN_CELLS_ONLY = 512
+SCAN_CELLS_ONLY, SCAN_SITE_STATS, SCAN_SUMMARY_ONLY = 512, 1024, 2048
 CELL_FIELD_REF, CELL_FIELD_ALT, CELL_FIELD_GT, CELL_FIELD_REMAPPED, CELL_FIELD_PLAIN = 0, 1, 2, 3, 4
 BT_SIZE = {1: 1, 2: 2, 3: 4, 5: 4, 7: 1}
 SITE_NONREF, SITE_REMAPPED, SITE_G_SUPPRESSED = 1, 2, 4
@@ -92,7 +92,8 @@ class Batch(C.Structure):
                 ("lut_first", C.c_void_p), ("lut_len", C.c_void_p), ("lut_in2m", C.c_void_p), ("out_bytes", C.c_uint64),
                 ("n_fmt_fields", C.c_int32), ("fmt_type", C.c_void_p), ("fmt_nps", C.c_void_p), ("fmt_offset", C.c_void_p), ("fmt_bytes", C.c_void_p),
                 ("fmt_total_bytes", C.c_uint64), ("info_valid", C.c_void_p), ("info_value", C.c_void_p),
-                ("info_dp_sum", C.c_void_p), ("vec_len", C.c_void_p), ("vec_offset", C.c_void_p), ("vec_values", C.c_void_p)]
+                ("info_dp_sum", C.c_void_p), ("vec_len", C.c_void_p), ("vec_offset", C.c_void_p), ("vec_values", C.c_void_p),
+                ("site_stats", C.c_void_p)]
 
 
 _lib = None
@@ -309,6 +310,7 @@ class BatchView:
         self.site_flags = _view(b.site_flags, np.uint8, ns)
         self.n_alleles = _view(b.n_alleles, np.uint32, ns)
         self.n_live = _view(b.n_live, np.uint32, ns)
+        self.site_stats = _view(b.site_stats, np.uint32, 2 * ns).reshape(-1, 2) if b.site_stats else None
         self.allele_first = _view(b.allele_first, np.uint32, ns)
         tot = int((self.allele_first + self.n_alleles).max()) if ns else 0
         self.allele_pos = _view(b.allele_pos, np.uint32, 2 * tot).reshape(-1, 2)

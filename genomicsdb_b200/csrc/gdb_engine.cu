@@ -449,6 +449,7 @@ struct BatchBuffers {
   // state of the batch these buffers hold
   bool valid = false; uint64_t first = 0; uint32_t keep = 0, arg_sites = 0; uint64_t arg_bytes = 0, alg_bytes = 0, fmt_total = 0;
   uint32_t hc[4] = {0, 0, 0, 0};
+  DevBuf<uint32_t> site_stats; PinBuf<uint32_t> p_site_stats;   // GDBGPU_SCAN_SITE_STATS: per site, reference-block calls and calls beginning there
   PinBuf<uint32_t> p_tail;            // err[4] + cursors[4] as they stood when the batch's last kernel had run
   cudaEvent_t ev_compute = nullptr, ev_done = nullptr;
   ~BatchBuffers() { if (ev_compute) cudaEventDestroy(ev_compute); if (ev_done) cudaEventDestroy(ev_done); }
@@ -471,6 +472,7 @@ struct gdbgpu_scan {
   uint64_t avg_site_bytes = 0;
   int n_out = 0;
   // columnar-iterator view of the query (gdbgpu_scan_cells*): the device list and what was copied out for the caller
+  bool site_stats = false, summary_only = false;
   bool cells_only = false, cells_built = false; uint64_t n_cells = 0, n_left = 0;
   uint64_t win_first = 0, win_count = UINT64_MAX;   // the part of the list gdbgpu_scan_cells / _cells_fetch hand out
   DevBuf<uint32_t> cell_list;
@@ -508,6 +510,10 @@ void scan_prepare(gdbgpu_scan* s) {
   s->java = (p.flags & GDBGPU_SCAN_HTSJDK_CONVENTIONS) ? 1 : 0;
   s->prefetch = !(p.flags & GDBGPU_SCAN_NO_PREFETCH);
   s->cells_only = (p.flags & GDBGPU_SCAN_CELLS_ONLY) != 0;
+  s->site_stats = (p.flags & GDBGPU_SCAN_SITE_STATS) != 0;
+  s->summary_only = (p.flags & GDBGPU_SCAN_SUMMARY_ONLY) != 0;
+  if (s->summary_only && ((p.flags & GDBGPU_SCAN_DEVICE_OUTPUT) || (p.flags & GDBGPU_SCAN_BCF_FORMAT) || (p.flags & GDBGPU_SCAN_WANT_LUT)))
+    throw ArgError("GDBGPU_SCAN_SUMMARY_ONLY goes with host output of the per-site tables only");
   s->info.n = 0;
   s->esum.n = 0;
   for (size_t f = 0; f < a->fields.size(); ++f) if (p.esum_remapped_mask & (1u << f)) { s->esum.remapped[s->esum.n] = 1; s->esum.index[s->esum.n] = (int32_t)f; ++s->esum.n; }
@@ -747,6 +753,11 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       bb.d_n_live = bb.ctl.push(bb.h_n_live.data(), keep); bb.d_allele_first = bb.ctl.push(bb.h_allele_first.data(), keep);
     }
     bb.ctl.flush(ctx->stream);
+    if (s->site_stats) {   // the copy rides the compute stream: it is done before ev_done is
+      bb.site_stats.ensure((size_t)keep * 2); bb.p_site_stats.ensure((size_t)keep * 2);
+      LAUNCH(ctx, k_site_stats, keep, 256, a->dev, S, bb.live.p, first_site, keep, bb.site_stats.p);
+      CK(cudaMemcpyAsync(bb.p_site_stats.p, bb.site_stats.p, (size_t)keep * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (S.want_lut) {
       if (lut_words >= (1ull << 32)) throw LimitError("LUT output of one batch above 2^32 entries: lower max_sites");
       s->cap_lut = (uint32_t)std::max<uint64_t>(lut_words, 1);
@@ -933,7 +944,9 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       CK(cudaMemcpyAsync(bb.p_site_end.p, s->site_end.p + first_site, (size_t)keep * 8, cudaMemcpyDeviceToHost, cs));
       CK(cudaMemcpyAsync(bb.p_allele_pos.p, bb.allele_pos.p, (size_t)bb.hc[0] * 8, cudaMemcpyDeviceToHost, cs));
       CK(cudaMemcpyAsync(bb.p_allele_bytes.p, bb.allele_bytes.p, bb.hc[1], cudaMemcpyDeviceToHost, cs));
-      if (s->bcf_format) {
+      if (s->summary_only) {
+        // per-site tables only: nothing per call crosses PCIe
+      } else if (s->bcf_format) {
         bb.p_fmt_bytes.ensure(std::max<uint64_t>(bb.fmt_total, 16));
         if (bb.fmt_total) CK(cudaMemcpyAsync(bb.p_fmt_bytes.p, bb.fmt_bytes.p, bb.fmt_total, cudaMemcpyDeviceToHost, cs));
       } else {
@@ -981,7 +994,10 @@ void publish_batch(gdbgpu_scan* s, BatchBuffers& bb, gdbgpu_batch* out) {
   } else {
     out->site_begin = bb.p_site_begin.p; out->site_end = bb.p_site_end.p;
     out->allele_pos = bb.p_allele_pos.p; out->allele_bytes = bb.p_allele_bytes.p;
-    if (s->bcf_format) {
+    if (s->summary_only) {
+      out->live = nullptr;
+      for (int o = 0; o < n_out; ++o) out->fields[o] = gdbgpu_field_out{nullptr, bb.h_base[o].data(), bb.h_stride[o].data(), nullptr};
+    } else if (s->bcf_format) {
       out->fmt_bytes = bb.p_fmt_bytes.p; out->fmt_type = bb.h_fmt_type.data(); out->fmt_nps = bb.h_fmt_nps.data(); out->fmt_offset = bb.h_fmt_off.data();
       for (int o = 0; o < n_out; ++o) out->fields[o] = gdbgpu_field_out{nullptr, bb.h_base[o].data(), bb.h_stride[o].data(), nullptr};
     } else {
@@ -990,6 +1006,7 @@ void publish_batch(gdbgpu_scan* s, BatchBuffers& bb, gdbgpu_batch* out) {
       if (S.want_lut) { out->lut_first = bb.p_lut_first.p; out->lut_len = bb.p_lut_len.p; out->lut_in2m = bb.p_lut_in2m.p; }
     }
   }
+  out->site_stats = s->site_stats ? bb.p_site_stats.p : nullptr;
   out->fmt_total_bytes = bb.fmt_total;
   out->n_fmt_fields = s->bcf_format ? n_out + (int)a->plain.size() : 0;
   if (s->bcf_format) {

@@ -654,6 +654,7 @@ void VariantQueryProcessor::scan_and_operate(const int, const VariantQueryConfig
     if (!handle_spanning_deletions) p.flags |= GDBGPU_SCAN_NO_DELETIONS;
     if (qc.produce_GT_with_min_PL_value_for_spanning_deletions()) p.flags |= GDBGPU_SCAN_MIN_PL_GT;
     if (want_lut) p.flags |= GDBGPU_SCAN_WANT_LUT;
+    if (op.wants_site_summaries()) p.flags |= GDBGPU_SCAN_SITE_STATS | GDBGPU_SCAN_SUMMARY_ONLY;
     if (op.wants_bcf_blocks()) {
       p.flags |= GDBGPU_SCAN_BCF_FORMAT;
       if (qc.produce_GT_field()) p.flags |= GDBGPU_SCAN_PRODUCE_GT;
@@ -677,9 +678,47 @@ void VariantQueryProcessor::scan_and_operate(const int, const VariantQueryConfig
     while (st.pos_in_batch_ < st.batch_.n_sites) {
       if (op.overflow()) { if (!scan_state) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "operator overflow without a scan state"); return; }   // caller drains, then re-enters
       if (op.wants_bcf_blocks()) op.operate_on_bcf_site(st.batch_, st.pos_in_batch_, qc);
+      else if (op.wants_site_summaries()) op.operate_on_site_summary(st.batch_, st.pos_in_batch_, qc);
       else { fill_variant(st.batch_, st.pos_in_batch_, variant); op.operate(variant, qc); }
       ++st.pos_in_batch_; ++st.sites_done_;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ per-site summary operators
+void InterestingLocationsPrinter::operate(Variant& variant, const VariantQueryConfig&) {   // the materialised-Variant path (not used by scan_and_operate)
+  uint64_t num_valid_calls = 0, num_begin_at_position = 0;
+  for (auto it = variant.begin(); it != variant.end(); ++it) { ++num_valid_calls; if ((*it).get_column_begin() == variant.get_column_begin()) ++num_begin_at_position; }
+  (*m_fptr) << variant.get_column_begin() << " " << num_valid_calls << " ? " << num_begin_at_position << "\n";
+}
+void InterestingLocationsPrinter::operate_on_site_summary(const gdbgpu_batch& b, uint32_t s, const VariantQueryConfig&) {
+  (*m_fptr) << b.site_begin[s] << " " << b.n_live[s] << " " << b.site_stats[2 * s] << " " << b.site_stats[2 * s + 1] << "\n";
+}
+void MaxAllelesCountOperator::operate_on_site_summary(const gdbgpu_batch& b, uint32_t s, const VariantQueryConfig&) {
+  ++m_total_lines;
+  const uint32_t n_alt = b.n_alleles[s] - 1;
+  auto more = [](const AlleleTracker& l, const AlleleTracker& r) { return l.alt.size() > r.alt.size(); };
+  if (m_heap.size() < m_top_count || n_alt > m_heap.front().alt.size()) {
+    if (m_heap.size() >= m_top_count) { std::pop_heap(m_heap.begin(), m_heap.end(), more); m_heap.pop_back(); }
+    const uint32_t first = b.allele_first[s];
+    auto allele = [&](uint32_t m) { return std::string((const char*)b.allele_bytes + b.allele_pos[2 * (first + m)], b.allele_pos[2 * (first + m) + 1]); };
+    AlleleTracker t; t.ref = allele(0); t.column = b.site_begin[s];
+    for (uint32_t m = 1; m <= n_alt; ++m) t.alt.push_back(allele(m));
+    m_heap.push_back(std::move(t));
+    std::push_heap(m_heap.begin(), m_heap.end(), more);
+  }
+}
+void MaxAllelesCountOperator::print(std::ostream& fptr) const {
+  fptr << "TOTAL " << m_total_lines << "\n";
+  auto heap = m_heap;
+  auto more = [](const AlleleTracker& l, const AlleleTracker& r) { return l.alt.size() > r.alt.size(); };
+  while (!heap.empty()) {
+    std::pop_heap(heap.begin(), heap.end(), more);
+    const AlleleTracker& t = heap.back();
+    fptr << t.column << "," << t.ref << "," << t.alt.size();
+    for (auto& a : t.alt) fptr << "," << a;
+    fptr << "\n";
+    heap.pop_back();
   }
 }
 

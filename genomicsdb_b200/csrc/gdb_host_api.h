@@ -213,10 +213,38 @@ class SingleVariantOperatorBase {
   virtual void operate_on_bcf_site(const gdbgpu_batch&, uint32_t /*site*/, const VariantQueryConfig&) {}
   // called before the memory of the current batch is reused: anything that still points into it must be consumed now
   virtual void release_batch() {}
+  // Opt-in for operators that need per-site summaries only (merged alleles, counts over the live calls: n_live and
+  // GDBGPU_SCAN_SITE_STATS): no per-call data crosses PCIe, operate_on_site_summary replaces operate
+  virtual bool wants_site_summaries() const { return false; }
+  virtual void operate_on_site_summary(const gdbgpu_batch&, uint32_t /*site*/, const VariantQueryConfig&) {}
  protected:
   bool m_NON_REF_exists = false, m_remapping_needed = false, m_is_reference_block_only = false;
   std::string m_merged_reference_allele;
   std::vector<std::string> m_merged_alt_alleles;
+};
+// variant_operations.h:391-408, variant_operations.cc:380-400: "position valid-calls reference-block-calls calls-beginning-here"
+class InterestingLocationsPrinter : public SingleVariantOperatorBase {
+ public:
+  explicit InterestingLocationsPrinter(std::ostream& fptr) : m_fptr(&fptr) {}
+  void operate(Variant& variant, const VariantQueryConfig& query_config) override;
+  bool wants_site_summaries() const override { return true; }
+  void operate_on_site_summary(const gdbgpu_batch& b, uint32_t s, const VariantQueryConfig&) override;
+ protected:
+  std::ostream* m_fptr;
+};
+// variant_operations.h:410-475: the top_count sites with the most merged ALT alleles
+class MaxAllelesCountOperator : public SingleVariantOperatorBase {
+ public:
+  explicit MaxAllelesCountOperator(unsigned top_count = 25u) : m_top_count(top_count) {}
+  bool wants_site_summaries() const override { return true; }
+  void operate_on_site_summary(const gdbgpu_batch& b, uint32_t s, const VariantQueryConfig&) override;
+  void print(std::ostream& fptr) const;   // what the reference's destructor writes to std::cerr
+  uint64_t get_total_lines() const { return m_total_lines; }
+ private:
+  struct AlleleTracker { std::string ref; std::vector<std::string> alt; int64_t column; };
+  unsigned m_top_count;
+  std::vector<AlleleTracker> m_heap;   // min-heap on the ALT count (std::priority_queue with AlleleTrackerCompare)
+  uint64_t m_total_lines = 0;
 };
 class GA4GHOperator : public SingleVariantOperatorBase {
  public:

@@ -94,6 +94,33 @@ __global__ void k_cells_hist(ArrayDev A, const uint32_t* __restrict__ list, uint
   if ((int)(threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&counts[bin], (unsigned long long)__popc(same));
 }
 
+// InterestingLocationsPrinter::operate (variant_operations.cc:380-400) over one batch of the combine's sites: per site, the
+// live calls that are reference blocks (REF of one base, ALT = <NON_REF> alone) and the live calls that begin at the site.
+// One block per site walks its row of the live matrix; stats[2 s] = reference blocks, stats[2 s + 1] = begin here.
+__global__ void __launch_bounds__(256) k_site_stats(ArrayDev A, ScanDev S, const int32_t* __restrict__ live, uint64_t first_site, uint32_t n_sites,
+                                                    uint32_t* __restrict__ stats) {
+  const uint32_t s = blockIdx.x;
+  if (s >= n_sites) return;
+  const int64_t begin = S.site_begin[first_site + s];
+  uint32_t n_ref = 0, n_beg = 0;
+  for (uint64_t q = threadIdx.x; q < S.nq; q += blockDim.x) {
+    const int32_t e = live[(uint64_t)s * S.nq + q];
+    if (e < 0) continue;
+    const uint64_t c = (uint32_t)e & 0x3FFFFFFFu;
+    const CellDesc d = A.desc[c];
+    n_ref += (d.ref_len == 1 && d.n_alt == 1 && d.nr_idx == 1) ? 1u : 0u;
+    const int64_t col = A.coords[2 * c + 1], en = A.end[c];
+    n_beg += ((col > en ? en : col) == begin) ? 1u : 0u;
+  }
+  __shared__ uint32_t s_ref, s_beg;
+  if (threadIdx.x == 0) { s_ref = 0; s_beg = 0; }
+  __syncthreads();
+  for (int d = 16; d; d >>= 1) { n_ref += __shfl_xor_sync(0xffffffffu, n_ref, d); n_beg += __shfl_xor_sync(0xffffffffu, n_beg, d); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&s_ref, n_ref); atomicAdd(&s_beg, n_beg); }
+  __syncthreads();
+  if (threadIdx.x == 0) { stats[2 * s] = s_ref; stats[2 * s + 1] = s_beg; }
+}
+
 // --- AlleleCountOperator --------------------------------------------------------------------------------------------
 __device__ inline bool ac_symbolic(const uint8_t* a, uint32_t n) {   // VariantUtils::is_symbolic_allele (known_field_info.h:221-232)
   if (n == 0) return false;

@@ -156,6 +156,9 @@ void gdbgpu_array_close(gdbgpu_array* arr);
                                              * use_missing_values_only_not_vector_end, genomicsdb_bcf_generator.cc:60-83; variant_field_handler.cc:
                                              * 845-866): rows padded with missing instead of vector_end, a row without GT is a no-call, strings
                                              * vector_end only */
+#define GDBGPU_SCAN_SITE_STATS      1024u   /* batches carry site_stats (what InterestingLocationsPrinter prints, variant_operations.cc:380-400) */
+#define GDBGPU_SCAN_SUMMARY_ONLY    2048u   /* host output limited to the per-site tables (sites, merged alleles, n_live, site_stats): live and
+                                             * fields[].data / .len are NULL, nothing per call is copied */
 #define GDBGPU_SCAN_CELLS_ONLY       512u   /* the scan serves gdbgpu_scan_cells* only (the columnar iterator neither merges calls nor minds
                                              * overlapping ones): no sweep state is built, gdbgpu_scan_next_batch is refused */
 
@@ -245,6 +248,8 @@ typedef struct gdbgpu_batch {
   const uint32_t* vec_len;
   const uint64_t* vec_offset;
   const uint32_t* vec_values;
+  const uint32_t* site_stats; /* GDBGPU_SCAN_SITE_STATS (host memory, else NULL): [2s] live calls that are reference blocks (REF of one
+                               * base, ALT = <NON_REF> alone), [2s + 1] live calls that begin at the site */
 } gdbgpu_batch;
 
 int gdbgpu_scan_begin(gdbgpu_array* arr, const gdbgpu_scan_params* params, gdbgpu_scan** out);

@@ -66,7 +66,8 @@ def main():
         qf = os.path.join(tmp, c["id"] + ".json")
         json.dump(q, open(qf, "w"))
         sizes = []
-        for ext, args in (("calls", ["--print-calls"]), ("csv", ["--print-csv"]), ("ac", ["--print-AC"]), ("hist", ["--produce-histogram"])):
+        for ext, args in (("calls", ["--print-calls"]), ("csv", ["--print-csv"]), ("ac", ["--print-AC"]), ("hist", ["--produce-histogram"]),
+                          ("ipos", ["--produce-interesting-positions"])):   # InterestingLocationsPrinter through scan_and_operate (hot-path seam)
             # stdbuf: this build of the tool leaves without flushing a block-buffered stdout
             p = subprocess.run(["stdbuf", "-o0", BIN + "/gt_mpi_gather", "-j", qf] + args, capture_output=True, cwd=REF_TESTS)
             if p.returncode != 0:

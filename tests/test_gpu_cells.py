@@ -217,3 +217,29 @@ def test_cells_on_random_small_arrays(ctx):
                     sc.close()
         finally:
             arr.close()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_site_summaries_match_the_reference_interesting_positions(ctx, case):
+    """GDBGPU_SCAN_SITE_STATS | GDBGPU_SCAN_SUMMARY_ONLY: per site "begin, valid calls, reference-block calls, calls beginning
+    here" -- what the unmodified reference's InterestingLocationsPrinter printed through scan_and_operate
+    (gt_mpi_gather --produce-interesting-positions); no per-call data is handed out"""
+    from genomicsdb_b200 import capi
+    arr, _ = open_case(ctx, case)
+    try:
+        text = ""
+        for lo, hi in case["query_column_ranges"]:
+            sc = capi.Scan(arr, lo, hi, query_rows=case_query_rows(case), flags=capi.SCAN_SITE_STATS | capi.SCAN_SUMMARY_ONLY)
+            try:
+                while True:
+                    b = sc.next_batch(max_sites=2)
+                    if b is None:
+                        break
+                    assert b.live is None and b.site_stats is not None
+                    for s in range(b.n_sites):
+                        text += "%d %d %d %d\n" % (b.site_begin[s], b.n_live[s], b.site_stats[s, 0], b.site_stats[s, 1])
+            finally:
+                sc.close()
+        assert text == open(os.path.join(CELLS, case["id"] + ".ipos")).read()
+    finally:
+        arr.close()

@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 ALL = golden_cases()
 CELLS = os.path.join(GOLDEN, "cells")
 CI = json.load(open(os.path.join(CELLS, "ci_manifest.json")))
-MODES = (("calls", "--print-calls"), ("csv", "--print-csv"), ("ac", "--print-AC"), ("hist", "--produce-histogram"))
+MODES = (("calls", "--print-calls"), ("csv", "--print-csv"), ("ac", "--print-AC"), ("hist", "--produce-histogram"),
+         ("ipos", "--produce-interesting-positions"))     # the last one sits on scan_and_operate (InterestingLocationsPrinter), not on the iterator
 
 
 @pytest.fixture(scope="module")

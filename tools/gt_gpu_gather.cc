@@ -135,6 +135,27 @@ static int produce_broad_gvcf(const std::string& query_json, int rank, int devic
   return 0;
 }
 
+// gt_mpi_gather.cc:322-366 with PRODUCE_BROAD_GVCF_PRODUCE_INTERESTING_POSITIONS: the Broad scan loop with an operator that
+// needs per-site counts only
+static int interesting_positions(const std::string& query_json, int rank, int device, const std::string& out_file) {
+  VariantQueryConfig query_config;
+  query_config.read_from_file(query_json, rank);
+  VariantStorageManager sm(query_config.get_workspace(rank), 10u * 1024u * 1024u, device);
+  VariantQueryProcessor qp(&sm, query_config.get_array_name(rank), query_config.get_vid_mapper());
+  qp.do_query_bookkeeping(query_config, true);
+  std::ofstream file;
+  if (out_file != "-") { file.open(out_file, std::ios::binary); if (!file) { std::cerr << "cannot open " << out_file << "\n"; return -1; } }
+  std::ostream& out = out_file == "-" ? std::cout : file;
+  InterestingLocationsPrinter op(out);
+  VariantQueryProcessorScanState scan_state;
+  for (auto i = 0u; i < std::max(1u, query_config.get_num_column_intervals()); ++i) {
+    while (!scan_state.end()) qp.scan_and_operate(qp.get_array_descriptor(), query_config, op, i, true, &scan_state);
+    scan_state.reset();
+  }
+  out.flush();
+  return 0;
+}
+
 // gt_mpi_gather.cc:369-411: the four commands that sit on the columnar iterator
 static int columnar_command(const std::string& query_json, int rank, int device, const std::string& out_file, int command) {
   VariantQueryConfig query_config;
@@ -180,7 +201,7 @@ int main(int argc, char** argv) {
   std::string query_json, out_file, header_file, ref_bases_file; int rank = 0, device = 0; size_t page = 0; bool broad = false, htsjdk = false; int columnar = 0;
   static struct option long_options[] = {{"query", 1, 0, 'j'}, {"rank", 1, 0, 'r'}, {"output", 1, 0, 'o'}, {"device", 1, 0, 'd'}, {"page-size", 1, 0, 'p'},
                                          {"produce-Broad-GVCF", 0, 0, 'B'}, {"bcf-header", 1, 0, 'H'}, {"reference-bases", 1, 0, 'R'}, {"htsjdk-conventions", 0, 0, 'J'},
-                                         {"print-calls", 0, 0, 'C'}, {"print-csv", 0, 0, 'V'}, {"print-AC", 0, 0, 'A'}, {"produce-histogram", 0, 0, 'G'}, {0, 0, 0, 0}};
+                                         {"produce-interesting-positions", 0, 0, 'I'}, {"print-calls", 0, 0, 'C'}, {"print-csv", 0, 0, 'V'}, {"print-AC", 0, 0, 'A'}, {"produce-histogram", 0, 0, 'G'}, {0, 0, 0, 0}};
   int c;
   while ((c = getopt_long(argc, argv, "j:r:o:d:p:BH:R:J", long_options, NULL)) >= 0) {
     switch (c) {
@@ -193,12 +214,13 @@ int main(int argc, char** argv) {
       case 'H': header_file = optarg; break;
       case 'R': ref_bases_file = optarg; break;
       case 'J': htsjdk = true; break;
-      case 'C': case 'V': case 'A': case 'G': columnar = c; break;   // records as GenomicsDBBCFGenerator (JNI) makes them for the Java reader
+      case 'C': case 'V': case 'A': case 'G': case 'I': columnar = c; break;   // records as GenomicsDBBCFGenerator (JNI) makes them for the Java reader
       default: return -1;
     }
   }
   if (query_json.empty() || out_file.empty()) { std::cerr << "usage: gt_gpu_gather -j query.json -o dump.bin [-r rank] [-d cuda_device] [-p sites_per_page]\n"; return -1; }
   try {
+    if (columnar == 'I') return interesting_positions(query_json, rank, device, out_file);
     if (columnar) return columnar_command(query_json, rank, device, out_file, columnar);
     if (broad) {
       if (header_file.empty()) { std::cerr << "--produce-Broad-GVCF needs --bcf-header\n"; return -1; }
