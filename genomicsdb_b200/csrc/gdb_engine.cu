@@ -741,7 +741,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
     RemapOut O{};
     O.n_out = n_out;
     for (int o = 0; o < n_out; ++o) {
-      bb.out_data[o].ensure(std::max<uint64_t>(bb.h_base[o][keep], 1)); bb.out_len[o].ensure((uint64_t)keep * S.nq);
+      bb.out_data[o].ensure(s->summary_only ? 1 : std::max<uint64_t>(bb.h_base[o][keep], 1)); bb.out_len[o].ensure(s->summary_only ? 1 : (uint64_t)keep * S.nq);
       bb.out_base[o] = bb.ctl.push(bb.h_base[o].data(), (size_t)keep + 1);
       bb.out_stride[o] = bb.ctl.push(bb.h_stride[o].data(), keep);
       O.f[o] = FieldOutDev{bb.out_data[o].p, bb.out_base[o], bb.out_stride[o], bb.out_len[o].p};
@@ -765,7 +765,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       O.lut_first = bb.lut_first.p; O.lut_len = bb.lut_len.p; O.lut_in2m = bb.lut_in2m.p; O.cap_lut = s->cap_lut;
     }
     B.n_sites = keep;
-    if (!fast.empty()) {
+    if (!fast.empty() && !s->summary_only) {   // per-site summaries need no remapped fields
       const int nf = (int)a->fields.size();
       const TileTabs tabs{ctx->d_cls_tab, ctx->d_jk_tab};
       const uint32_t tiles = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
@@ -828,7 +828,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
         ++ctx->launches; CK(cudaGetLastError());
       }
     }
-    if (!slow.empty()) {
+    if (!slow.empty() && !s->summary_only) {
       uint32_t tiles = (uint32_t)((S.nq + REMAP_ROWS - 1) / REMAP_ROWS);
       LAUNCH(ctx, k_remap_generic, (unsigned)(slow.size() * tiles), REMAP_THREADS, a->dev, S, B, O, bb.slow_sites);
     }

@@ -68,7 +68,8 @@ def main():
         q = tiledb_writer.write_query_json(os.path.join(ws, "q.json"), info, lo, hi, attributes=("REF", "ALT", "GT"))
         ref_bin = os.path.join(REPO, "oracle", "_ref", "bin", "gt_mpi_gather")
         ours_bin = os.path.join(REPO, "genomicsdb_b200", "bin", "gt_gpu_gather")
-        for mode, flag in (("histogram", "--produce-histogram"), ("allele_counts", "--print-AC")):
+        for mode, flag in (("histogram", "--produce-histogram"), ("allele_counts", "--print-AC"),
+                           ("interesting_positions", "--produce-interesting-positions")):   # the last one: scan_and_operate + a per-site summary operator
             t0 = time.time()
             p = subprocess.run(["stdbuf", "-o0", ref_bin, "-j", q, flag], capture_output=True)
             t_ref = time.time() - t0
