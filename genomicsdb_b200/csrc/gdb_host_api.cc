@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 
 #include "gdb_json.h"
 
@@ -172,6 +173,10 @@ void VCFAdapter::set_vcf_header_text(const std::string& header) {
       next_ctg = std::max(next_ctg, v + 1);
     }
   }
+}
+const ContigInfo* VidMapper::get_contig_info(const std::string& name) const {
+  for (auto& c : contigs_) if (c.name == name) return &c;
+  return nullptr;
 }
 int VCFAdapter::get_dictionary_id(const std::string& name) const { for (auto& kv : ids_) if (kv.first == name) return kv.second; return -1; }
 int VCFAdapter::get_contig_id(const std::string& name) const { for (auto& kv : contigs_) if (kv.first == name) return kv.second; return -1; }
@@ -962,6 +967,82 @@ void VariantQueryProcessor::iterate_over_cells(const int, const VariantQueryConf
     }
   }
   op.finalize();
+}
+
+// ------------------------------------------------------------------------------------------------ GenomicsDBBCFGenerator
+GenomicsDBBCFGenerator::GenomicsDBBCFGenerator(const std::string&, const std::string& query_config_file, const std::string& serialized_bcf_header,
+                                               const char* chr, const int start, const int end, int my_rank, size_t buffer_capacity, size_t,
+                                               const char* output_format, const bool produce_header_only,
+                                               const bool use_missing_values_only_not_vector_end, const bool, int cuda_device,
+                                               const std::string& reference_bases_tsv)
+    : m_produce_header_only(produce_header_only), m_buffer_capacity(buffer_capacity) {
+  if (output_format && std::string(output_format) != "bu" && std::string(output_format) != "")
+    throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "GenomicsDBBCFGenerator: only uncompressed BCF (\"bu\") is produced");
+  m_query_config.read_from_file(query_config_file, my_rank);   // vid / callset mapping come from the query JSON
+  if (serialized_bcf_header.size() < 9 || serialized_bcf_header.compare(0, 5, "BCF\2\2") != 0)
+    throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "GenomicsDBBCFGenerator: the header must be a serialised BCF2 header");
+  uint32_t l_text; memcpy(&l_text, serialized_bcf_header.data() + 5, 4);
+  m_vcf_adapter.set_vcf_header_text(std::string(serialized_bcf_header.data() + 9, strnlen(serialized_bcf_header.data() + 9, l_text)));
+  m_vcf_adapter.set_buffer_capacity(buffer_capacity);
+  if (!reference_bases_tsv.empty()) {
+    std::ifstream rb(reference_bases_tsv);
+    if (!rb) throw GenomicsDBGPUException(GDBGPU_ERR_IO, "cannot open " + reference_bases_tsv);
+    std::string contig, base; long long pos;
+    while (rb >> contig >> pos >> base) m_vcf_adapter.set_reference_base(contig, pos, base[0]);
+  }
+  const VidMapper& vid_mapper = m_query_config.get_vid_mapper();
+  if (chr && strlen(chr) > 0u) {   // genomicsdb_bcf_generator.cc:57-66: VCF positions are 1-based
+    const ContigInfo* contig = vid_mapper.get_contig_info(chr);
+    if (!contig) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, std::string("Could not find TileDB column interval for contig: ") + chr);
+    m_query_config.set_column_interval_to_query(contig->tiledb_column_offset + (int64_t)start - 1, contig->tiledb_column_offset + (int64_t)end - 1);
+  }
+  m_storage_manager.reset(new VariantStorageManager(m_query_config.get_workspace(my_rank), 10u * 1024u * 1024u, cuda_device));
+  m_query_processor.reset(new VariantQueryProcessor(m_storage_manager.get(), m_query_config.get_array_name(my_rank), vid_mapper));
+  m_query_processor->do_query_bookkeeping(m_query_config, true, /*stage_broad_gvcf_fields=*/true);
+  m_vcf_adapter.append(serialized_bcf_header.data(), 9 + (size_t)l_text, false);   // print_header(): the stream starts with the header
+  m_combined_bcf_operator.reset(new BroadCombinedGVCFOperator(m_vcf_adapter, vid_mapper, m_query_config, use_missing_values_only_not_vector_end));
+  if (!produce_header_only)
+    m_query_processor->scan_and_operate(m_query_processor->get_array_descriptor(), m_query_config, *m_combined_bcf_operator, m_query_column_interval_idx, true, &m_scan_state);
+  m_read_buffer.swap(m_vcf_adapter.get_buffer());
+  m_vcf_adapter.get_buffer().clear();
+}
+GenomicsDBBCFGenerator::~GenomicsDBBCFGenerator() {
+  m_scan_state.reset();               // the scan before the array, the array before the context
+  m_combined_bcf_operator.reset();
+  m_query_processor.reset();
+  m_storage_manager.reset();
+}
+// genomicsdb_bcf_generator.cc:112-140
+void GenomicsDBBCFGenerator::produce_next_batch() {
+  if (m_done) return;
+  m_read_buffer.clear(); m_next_read_idx = 0;
+  while (m_read_buffer.empty()) {
+    if (m_produce_header_only || m_scan_state.end()) {
+      ++m_query_column_interval_idx;
+      if (m_produce_header_only || m_query_column_interval_idx >= m_query_config.get_num_column_intervals()) { m_done = true; return; }
+      m_scan_state.reset();
+    }
+    m_query_processor->scan_and_operate(m_query_processor->get_array_descriptor(), m_query_config, *m_combined_bcf_operator, m_query_column_interval_idx, true, &m_scan_state);
+    m_read_buffer.swap(m_vcf_adapter.get_buffer());
+    m_vcf_adapter.get_buffer().clear();
+  }
+}
+// genomicsdb_bcf_generator.cc:142-177
+size_t GenomicsDBBCFGenerator::read_and_advance(uint8_t* dst, size_t offset, size_t n) {
+  size_t total = 0;
+  if (n == SIZE_MAX) { produce_next_batch(); return 0; }
+  while (total < n && !m_done) {
+    if (m_next_read_idx >= m_read_buffer.size()) { produce_next_batch(); continue; }
+    const size_t k = std::min(n - total, m_read_buffer.size() - m_next_read_idx);
+    if (dst) memcpy(dst + offset + total, m_read_buffer.data() + m_next_read_idx, k);
+    m_next_read_idx += k; total += k;
+    if (m_next_read_idx >= m_read_buffer.size()) produce_next_batch();
+  }
+  return total;
+}
+uint8_t GenomicsDBBCFGenerator::read_next_byte() {
+  uint8_t tmp;
+  return read_and_advance(&tmp, 0u, 1u) > 0u ? tmp : (uint8_t)-1;
 }
 
 }  // namespace genomicsdb_b200

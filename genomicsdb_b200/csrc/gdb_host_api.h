@@ -64,6 +64,7 @@ class VidMapper {
   const std::vector<FieldInfo>& fields() const { return fields_; }
   // vid_mapper.cc get_contig_location: the contig a TileDB column falls into (nullptr: unknown position)
   const ContigInfo* get_contig_location(int64_t column) const;
+  const ContigInfo* get_contig_info(const std::string& name) const;   // nullptr: no such contig
  private:
   std::vector<FieldInfo> fields_;
   std::vector<ContigInfo> contigs_;   // sorted by tiledb_column_offset
@@ -297,7 +298,7 @@ class VCFAdapter {
 // broad_combined_gvcf.h: one BCF2 record per operate() call, appended to the adapter's buffer in serialised form
 // (u32 l_shared, u32 l_indiv, shared, indiv -- what bcf_write emits for an uncompressed BCF).  FORMAT blocks, INFO scalars
 // and the DP sum come from the kernels (GDBGPU_SCAN_BCF_FORMAT); this class adds the typed keys / size descriptors and the
-// fixed part of the record.  Not supported: 2-D / histogram / concatenate INFO operations (throws); ID merge and FILTER union are not produced.
+// fixed part of the record.  Not supported: 2-D fields and the histogram / concatenate INFO operations on them (throws).
 class BroadCombinedGVCFOperator : public GA4GHOperator {
  public:
   // use_missing_values_only_not_vector_end: what GenomicsDBBCFGenerator passes for the Java reader (genomicsdb_bcf_generator.cc:60-83)
@@ -469,6 +470,42 @@ class VariantQueryProcessor {
   std::vector<int64_t> coords_, end_;   // merged cell coordinates (row, col) and END, host copy
   int n_out_ = 0;
   VariantArraySchema schema_;
+};
+
+// ---- the JNI path's pump (include/vcf/genomicsdb_bcf_generator.h, src/vcf/genomicsdb_bcf_generator.cc:26-185): what
+// GenomicsDBQueryStream's six native methods sit on.  It owns storage manager, query processor, adapter and the Broad
+// operator, runs scan_and_operate until the adapter's buffer reports overflow, and hands the serialised BCF stream
+// (header first) out through read_and_advance / read_next_byte.  The BCF header is htslib's product on the unchanged host
+// side; it comes in serialised ("BCF\2\2", l_text, text) -- the one argument the reference's constructor does not have.
+class GenomicsDBBCFGenerator {
+ public:
+  GenomicsDBBCFGenerator(const std::string& loader_config_file, const std::string& query_config_file, const std::string& serialized_bcf_header,
+                         const char* chr, const int start, const int end, int my_rank = 0, size_t buffer_capacity = 1048576u,
+                         size_t tiledb_segment_size = 1048576u, const char* output_format = "bu", const bool produce_header_only = false,
+                         const bool use_missing_values_only_not_vector_end = false, const bool keep_idx_fields_in_bcf_header = true,
+                         int cuda_device = 0, const std::string& reference_bases_tsv = "");   // contig, 0-based position, base per line: the bases
+                                                                                               // VCFAdapter::get_reference_base_at_position serves
+  ~GenomicsDBBCFGenerator();
+  GenomicsDBBCFGenerator(const GenomicsDBBCFGenerator&) = delete;
+  GenomicsDBBCFGenerator& operator=(const GenomicsDBBCFGenerator&) = delete;
+  size_t get_buffer_capacity() const { return m_buffer_capacity; }
+  // n == SIZE_MAX: produce the next batch without advancing; dst may be NULL (skip)
+  size_t read_and_advance(uint8_t* dst, size_t offset, size_t n);
+  uint8_t read_next_byte();
+  size_t get_num_bytes_available() const { return m_read_buffer.size() - m_next_read_idx; }   // in the batch being read
+  bool end() const { return m_done; }
+ private:
+  void produce_next_batch();
+  bool m_done = false, m_produce_header_only;
+  size_t m_buffer_capacity;
+  std::unique_ptr<VariantStorageManager> m_storage_manager;
+  std::unique_ptr<VariantQueryProcessor> m_query_processor;
+  VariantQueryConfig m_query_config;
+  VCFAdapter m_vcf_adapter;
+  unsigned m_query_column_interval_idx = 0;
+  VariantQueryProcessorScanState m_scan_state;
+  std::unique_ptr<BroadCombinedGVCFOperator> m_combined_bcf_operator;
+  std::vector<uint8_t> m_read_buffer; size_t m_next_read_idx = 0;   // the batch being read (the adapter's buffer is the one being written)
 };
 
 }  // namespace genomicsdb_b200

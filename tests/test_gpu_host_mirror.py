@@ -111,3 +111,36 @@ def test_broad_gvcf_sites_only(exe, case, tmp_path):
     p, out = run_broad(exe, case, tmp_path, sites_only=True)
     assert p.returncode == 0, p.stderr
     assert out.read_bytes() == gold
+
+
+# ---------------------------------------------------------------------------------------------- the JNI path's pump
+STREAM_CASES = ["t0_1_2_at_0", "t0_1_2_multiple_positions", "haploid_triploid_deletion_produce_GT", "t0_1_2_DS_ID_at_0", "t0_1_2_at_12150"]
+
+
+@pytest.mark.parametrize("chunk,capacity", [(7, 64), (100000, 0), (4096, 3000)], ids=["7B-reads-64B-buffer", "100kB-reads", "4kB-reads-3kB-buffer"])
+@pytest.mark.parametrize("cid", STREAM_CASES)
+def test_bcf_generator_stream_equals_the_reference(exe, cid, tmp_path, chunk, capacity):
+    """GenomicsDBBCFGenerator of the mirror (what GenomicsDBQueryStream's JNI methods sit on) pulled with read_and_advance /
+    read_next_byte in small and large reads, with buffers that overflow after every record: the stream is the reference's
+    BCF (JNI conventions), header first"""
+    case = [c for c in ALL if c["id"] == cid][0]
+    gold = open(os.path.join(GOLDEN, "bcf_java", cid + ".bcf"), "rb").read()
+    q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
+         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": case["attributes"],
+         "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_column_ranges"]]}],
+         "query_row_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_row_ranges"]]}],
+         "produce_GT_field": case["produce_GT_field"], "produce_FILTER_field": case.get("produce_FILTER_field", False),
+         "produce_GT_with_min_PL_value_for_spanning_deletions": case["produce_GT_with_min_PL_value_for_spanning_deletions"]}
+    qf = tmp_path / "query.json"
+    qf.write_text(json.dumps(q))
+    out = tmp_path / "stream.bcf"
+    cmd = [exe, "-j", str(qf), "-o", str(out), "--bcf-generator", str(chunk), "--htsjdk-conventions", "--bcf-header",
+           os.path.join(GOLDEN, "bcf_java", cid + ".bcf"), "--reference-bases", os.path.join(GOLDEN, "inputs", "ref_bases.tsv")]
+    if capacity:
+        cmd += ["-p", str(capacity)]
+    if cid == "t0_1_2_at_12150":       # the interval given the way the Java reader gives it: contig, 1-based begin and end
+        cmd += ["--chromosome", "1", "--begin", "12151", "--end", "1000000001"]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert json.loads(p.stdout.strip().splitlines()[-1])["bytes"] == len(gold)
+    assert out.read_bytes() == gold

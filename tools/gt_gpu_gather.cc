@@ -18,6 +18,7 @@
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <vector>
 
 #include "../genomicsdb_b200/csrc/gdb_host_api.h"
 
@@ -135,6 +136,28 @@ static int produce_broad_gvcf(const std::string& query_json, int rank, int devic
   return 0;
 }
 
+// What the Java reader does through JNI (GenomicsDBQueryStream: jniGenomicsDBInit / Read / ReadNextByte / Skip / Close over a
+// GenomicsDBBCFGenerator): pull the serialised BCF stream in `chunk`-byte reads, every 5th read a single byte.
+static int bcf_generator_stream(const std::string& query_json, int rank, int device, const std::string& header_file, const std::string& ref_bases_file,
+                                const std::string& out_file, size_t buffer_capacity, size_t chunk, bool htsjdk_conventions,
+                                const std::string& chr, int start, int end) {
+  std::string raw_prefix;
+  read_header_text(header_file, raw_prefix);
+  GenomicsDBBCFGenerator gen("", query_json, raw_prefix, chr.c_str(), start, end, rank, buffer_capacity ? buffer_capacity : 1048576u, 1048576u, "bu", false,
+                             htsjdk_conventions, true, device, ref_bases_file);
+  std::ofstream out(out_file, std::ios::binary);
+  if (!out) { std::cerr << "cannot open " << out_file << "\n"; return -1; }
+  std::vector<uint8_t> buf(chunk);
+  uint64_t reads = 0, bytes = 0;
+  while (!gen.end()) {
+    if (++reads % 5 == 0) { if (gen.get_num_bytes_available() == 0) { gen.read_and_advance(nullptr, 0, SIZE_MAX); continue; } uint8_t b = gen.read_next_byte(); out.put((char)b); ++bytes; continue; }
+    const size_t n = gen.read_and_advance(buf.data(), 0, chunk);
+    out.write((const char*)buf.data(), n); bytes += n;
+  }
+  printf("{\"bytes\": %llu, \"reads\": %llu}\n", (unsigned long long)bytes, (unsigned long long)reads);
+  return 0;
+}
+
 // gt_mpi_gather.cc:322-366 with PRODUCE_BROAD_GVCF_PRODUCE_INTERESTING_POSITIONS: the Broad scan loop with an operator that
 // needs per-site counts only
 static int interesting_positions(const std::string& query_json, int rank, int device, const std::string& out_file) {
@@ -198,10 +221,10 @@ static int columnar_command(const std::string& query_json, int rank, int device,
 }
 
 int main(int argc, char** argv) {
-  std::string query_json, out_file, header_file, ref_bases_file; int rank = 0, device = 0; size_t page = 0; bool broad = false, htsjdk = false; int columnar = 0;
+  std::string query_json, out_file, header_file, ref_bases_file; int rank = 0, device = 0; size_t page = 0; bool broad = false, htsjdk = false; int columnar = 0; size_t stream_chunk = 0; std::string chr; int chr_start = 0, chr_end = 0;
   static struct option long_options[] = {{"query", 1, 0, 'j'}, {"rank", 1, 0, 'r'}, {"output", 1, 0, 'o'}, {"device", 1, 0, 'd'}, {"page-size", 1, 0, 'p'},
                                          {"produce-Broad-GVCF", 0, 0, 'B'}, {"bcf-header", 1, 0, 'H'}, {"reference-bases", 1, 0, 'R'}, {"htsjdk-conventions", 0, 0, 'J'},
-                                         {"produce-interesting-positions", 0, 0, 'I'}, {"print-calls", 0, 0, 'C'}, {"print-csv", 0, 0, 'V'}, {"print-AC", 0, 0, 'A'}, {"produce-histogram", 0, 0, 'G'}, {0, 0, 0, 0}};
+                                         {"produce-interesting-positions", 0, 0, 'I'}, {"bcf-generator", 1, 0, 'S'}, {"chromosome", 1, 0, 'c'}, {"begin", 1, 0, 'b'}, {"end", 1, 0, 'e'}, {"print-calls", 0, 0, 'C'}, {"print-csv", 0, 0, 'V'}, {"print-AC", 0, 0, 'A'}, {"produce-histogram", 0, 0, 'G'}, {0, 0, 0, 0}};
   int c;
   while ((c = getopt_long(argc, argv, "j:r:o:d:p:BH:R:J", long_options, NULL)) >= 0) {
     switch (c) {
@@ -214,12 +237,20 @@ int main(int argc, char** argv) {
       case 'H': header_file = optarg; break;
       case 'R': ref_bases_file = optarg; break;
       case 'J': htsjdk = true; break;
+      case 'S': stream_chunk = strtoull(optarg, 0, 10); break;   // pull the stream through GenomicsDBBCFGenerator in reads of this many bytes
+      case 'c': chr = optarg; break;
+      case 'b': chr_start = atoi(optarg); break;
+      case 'e': chr_end = atoi(optarg); break;
       case 'C': case 'V': case 'A': case 'G': case 'I': columnar = c; break;   // records as GenomicsDBBCFGenerator (JNI) makes them for the Java reader
       default: return -1;
     }
   }
   if (query_json.empty() || out_file.empty()) { std::cerr << "usage: gt_gpu_gather -j query.json -o dump.bin [-r rank] [-d cuda_device] [-p sites_per_page]\n"; return -1; }
   try {
+    if (stream_chunk) {
+      if (header_file.empty()) { std::cerr << "--bcf-generator needs --bcf-header\n"; return -1; }
+      return bcf_generator_stream(query_json, rank, device, header_file, ref_bases_file, out_file, page, stream_chunk, htsjdk, chr, chr_start, chr_end);
+    }
     if (columnar == 'I') return interesting_positions(query_json, rank, device, out_file);
     if (columnar) return columnar_command(query_json, rank, device, out_file, columnar);
     if (broad) {
