@@ -104,7 +104,8 @@ def test_broad_gvcf_overflow_resume(exe, case, tmp_path):
 
 
 @pytest.mark.parametrize("case", [c for c in ALL if c["id"] in ("t0_1_2_at_0", "t6_7_8_at_0", "haploid_triploid_deletion", "info_ops0_at_0",
-                                                                 "min_PL_spanning_deletion_min_PL", "t0_overlapping_at_0")], ids=lambda c: c["id"])
+                                                                 "min_PL_spanning_deletion_min_PL", "t0_overlapping_at_0", "t0_1_2_DS_ID_at_0",
+                                                                 "t0_1_2_at_0_FILTER", "t0_1_2_phased_GT_at_12150")], ids=lambda c: c["id"])
 def test_broad_gvcf_sites_only(exe, case, tmp_path):
     """"sites_only_query": true -- records without samples and FORMAT fields, INFO (incl. the DP rule over DP_FORMAT / MIN_DP) as before"""
     gold = open(os.path.join(GOLDEN, "bcf_sites_only", case["id"] + ".bcf"), "rb").read()
