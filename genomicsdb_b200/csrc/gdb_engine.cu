@@ -225,7 +225,7 @@ void fill_dev_view(gdbgpu_array* a) {
   D.lb_row = a->lb_row; D.num_rows = a->num_rows;
   D.desc = a->desc.p; D.hot = a->hot.p; D.warm = a->warm.p; D.cls = a->cls.p; D.effend = a->effend.p;
   a->plain_dev.n = (int32_t)a->plain.size();
-  for (size_t f = 0; f < a->plain.size(); ++f) a->plain_dev.f[f] = PlainDev{a->pm[f].fixed_len ? nullptr : a->plain[f]->off.p, a->plain[f]->val.p, a->pm[f].elem, a->pm[f].fixed_len};
+  for (size_t f = 0; f < a->plain.size(); ++f) a->plain_dev.f[f] = PlainDev{a->pm[f].fixed_len ? nullptr : a->plain[f]->off.p, a->plain[f]->val.p, a->pm[f].elem, a->pm[f].fixed_len, a->pm[f].no_format == 2 ? 1 : 0};
   D.n_rs = a->n_rs; D.rs_cell = a->rs_cell.p; D.rs_col = a->rs_col.p; D.rs_effend = a->rs_effend.p; D.row_start = a->row_start.p;
 }
 
@@ -908,7 +908,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
         } else {
           const int f = o - n_out;
           const int32_t* st = h_ps + ((uint64_t)f * keep + i) * PS_WORDS;
-          if (!st[PS_ANY] || a->pm[f].no_format) continue;
+          if (!st[PS_ANY] || a->pm[f].no_format == 1) continue;
           nps = (uint32_t)st[PS_MAXLEN];
           if (nps == 0) continue;
           type = a->pm[f].elem == ELEM_CHAR ? BT_CHAR : (a->pm[f].elem == ELEM_FLOAT32 ? BT_FLOAT : int_type(st[PS_MIN], st[PS_MAX], (uint64_t)nps * S.nq));

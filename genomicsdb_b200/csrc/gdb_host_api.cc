@@ -280,6 +280,11 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
       if (plain[p].is_qual) m_QUAL_plain = (int)p;
       else if (plain[p].is_id) m_ID_fmt_index = (int)(n_remapped + p);
       else if (plain[p].is_filter) { /* not a query-order field: below */ }
+      else if (plain[p].is_concat) {
+        InfoField f; f.vcf_name = plain[p].vcf_name; f.key = key_of(plain[p].vcf_name); f.is_float = plain[p].elem == GDBGPU_ELEM_FLOAT32;
+        f.concat_fmt_index = (int)(n_remapped + p);
+        m_INFO_fields_vec.push_back(f);
+      }
       else if (plain[p].format) {
         if (name == "DP_FORMAT") dp_format_plain = (int)p;
         else m_FORMAT_fields_vec.push_back({plain[p].vcf_name, key_of(plain[p].vcf_name), (int)(n_remapped + p)});
@@ -383,6 +388,42 @@ void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint3
     rlen = vcf_end - pos;
   }
   for (auto& f : m_INFO_fields_vec) {
+    if (f.concat_fmt_index >= 0) {   // concatenate: the rows of the collated block, row order, padding dropped
+      const uint64_t slot = (uint64_t)f.concat_fmt_index * ns + s;
+      const uint8_t type = b.fmt_type[slot];
+      if (!type) continue;
+      const uint32_t nps = b.fmt_nps[slot];
+      const uint8_t* blk = b.fmt_bytes + b.fmt_offset[slot];
+      if (type == BT_CHAR) {
+        std::string cat;
+        for (uint64_t q = 0; q < nq; ++q) {
+          const char* e = reinterpret_cast<const char*>(blk + q * nps);
+          if (e[0] == 0x07 || e[0] == 0x00) continue;
+          size_t len = 0; while (len < nps && e[len] != 0x00) ++len;
+          cat.append(e, len);
+        }
+        if (cat.empty()) continue;
+        enc_int1(shared, f.key); enc_vchar(shared, cat);
+      } else {
+        std::vector<int32_t> cat;   // floats travel as their bit patterns
+        for (uint64_t q = 0; q < nq; ++q)
+          for (uint32_t k = 0; k < nps; ++k) {
+            int32_t v; bool miss, vend;
+            if (type == BT_INT8) { int8_t x = (int8_t)blk[q * nps + k]; miss = x == INT8_MIN; vend = x == INT8_MIN + 1; v = miss ? INT32_MIN : x; }
+            else if (type == BT_INT16) { int16_t x; memcpy(&x, blk + 2 * (q * nps + k), 2); miss = x == INT16_MIN; vend = x == INT16_MIN + 1; v = miss ? INT32_MIN : x; }
+            else if (type == BT_FLOAT) { uint32_t x; memcpy(&x, blk + 4 * (q * nps + k), 4); miss = x == 0x7F800001u; vend = x == 0x7F800002u; v = (int32_t)x; }
+            else { int32_t x; memcpy(&x, blk + 4 * (q * nps + k), 4); miss = x == INT32_MIN; vend = x == INT32_MIN + 1; v = x; }
+            if (vend || (k == 0 && miss)) break;   // end of this row's vector / a row without the field
+            cat.push_back(v);
+          }
+        if (cat.empty()) continue;
+        enc_int1(shared, f.key);
+        if (f.is_float) { enc_size(shared, (int)cat.size(), BT_FLOAT); put_bytes(shared, cat.data(), cat.size() * 4); }
+        else enc_vint(shared, cat.data(), (uint32_t)cat.size());
+      }
+      ++n_info;
+      continue;
+    }
     if (f.vector_slot >= 0) {   // element-wise sum: typed vector (bcf_update_info -> bcf_enc_vint / bcf_enc_vfloat)
       const uint64_t vs = (uint64_t)f.vector_slot * ns + s;
       const uint32_t n = b.vec_len[vs];
@@ -566,6 +607,10 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
       else if (fi->is_info && scalar_op) {
         if (pf.fixed_len != 1 || pf.elem == GDBGPU_ELEM_CHAR) throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "INFO combine operation on a non-scalar field: " + name);
         pf.info_op = fi->combine_op == "median" ? GDBGPU_INFO_MEDIAN : (fi->combine_op == "sum" ? GDBGPU_INFO_SUM : GDBGPU_INFO_MEAN);
+      } else if (fi->is_info && fi->combine_op == "concatenate") {
+        // the calls' vectors appended in row order (VariantFieldHandler::concatenate_field, variant_field_handler.cc:743-800): the
+        // device collates them like a FORMAT field, the operator strings the rows of the block together
+        pf.format = true; pf.is_concat = true;
       } else if (fi->is_info && !fi->combine_op.empty())
         throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "INFO combine operation " + fi->combine_op + " of field " + name + " is not supported on the GPU");
       else continue;   // INFO field without a combine operation: the reference drops it with a warning (broad_combined_gvcf.cc:175-178)
@@ -574,7 +619,8 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
       if (name == "MIN_DP") qc.dp_fields_[1] = (unsigned)qc.plain_.size();
       if (name == "DP_FORMAT") qc.dp_fields_[2] = (unsigned)qc.plain_.size();
     }
-    for (auto& pf : qc.plain_) pd.push_back(gdbgpu_plain_field_desc{pf.attribute.c_str(), pf.elem, pf.fixed_len, pf.format ? 0 : 1, pf.info_op});
+    for (auto& pf : qc.plain_)
+      pd.push_back(gdbgpu_plain_field_desc{pf.attribute.c_str(), pf.elem, pf.fixed_len, (pf.is_id || pf.is_filter || pf.is_concat) ? 2 : (pf.format ? 0 : 1), pf.info_op});
   }
   qc.query_attrs_.clear();
   if (stage_columnar_fields) {

@@ -123,7 +123,7 @@ class VariantQueryConfig {
   std::vector<std::string> remapped_names_;
   // plain fields staged for the Broad operator (do_query_bookkeeping): FORMAT fields that are not allele-dependent, scalar
   // INFO fields with a median / sum / mean combine operation, the inputs of the DP rule
-  struct PlainField { std::string attribute, vcf_name; int elem = 0, fixed_len = 0; bool format = false; int info_op = 0; bool is_qual = false, is_id = false, is_filter = false; };
+  struct PlainField { std::string attribute, vcf_name; int elem = 0, fixed_len = 0; bool format = false; int info_op = 0; bool is_qual = false, is_id = false, is_filter = false, is_concat = false; };
   std::vector<PlainField> plain_;
   unsigned dp_fields_[3] = {0, 0, 0};   // 1-based plain indices of INFO DP, MIN_DP, DP_FORMAT
   unsigned esum_remapped_mask_ = 0;     // remapped fields (GT not counted) combined with an element-wise sum
@@ -315,7 +315,7 @@ class BroadCombinedGVCFOperator : public GA4GHOperator {
   const VidMapper* m_vid_mapper;
   struct FormatField { std::string vcf_name; int key = -1; int fmt_index = -1; };   // fmt_index: index into the batch's fmt_* tables
   std::vector<FormatField> m_FORMAT_fields_vec;   // emission order: GT first, query order, DP last (broad_combined_gvcf.cc:168-240)
-  struct InfoField { std::string vcf_name; int key = -1; int plain_index = -1; bool is_float = false; int vector_slot = -1; };   // vector_slot >= 0: element-wise sum
+  struct InfoField { std::string vcf_name; int key = -1; int plain_index = -1; bool is_float = false; int vector_slot = -1; int concat_fmt_index = -1; };   // vector_slot >= 0: element-wise sum; concat_fmt_index >= 0: concatenate
   std::vector<InfoField> m_INFO_fields_vec;
   int m_END_key = -1, m_DP_key = -1, m_QUAL_plain = -1;
   int m_ID_fmt_index = -1;        // the ID strings of the live calls, collated like a FORMAT field; merged per site (merge_ID_field)

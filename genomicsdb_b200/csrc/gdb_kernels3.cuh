@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(FMT_THREADS) k_fmt_pack(const __grid_constant_
 constexpr int MAX_PLAIN = 16;
 enum { ELEM_INT32 = 0, ELEM_FLOAT32 = 1, ELEM_CHAR = 2 };
 constexpr uint8_t TDB_NULL_CHAR = 127, BCF_STR_MISSING = 0x07, BCF_STR_VEND = 0x00;
-struct PlainDev { const uint64_t* off; const uint8_t* val; int32_t elem, fixed_len; };
+struct PlainDev { const uint64_t* off; const uint8_t* val; int32_t elem, fixed_len; int32_t host_combine; };   // host_combine: the block feeds a host-side combine (ID, FILTER, concatenate), always padded the htslib way
 struct PlainSet { int32_t n; PlainDev f[MAX_PLAIN]; };
 enum { PS_MIN = 0, PS_MAX, PS_MAXLEN, PS_ANY, PS_WORDS };   // per (plain field, site) statistics, int32 each
 
@@ -335,15 +335,16 @@ __global__ void __launch_bounds__(FMT_THREADS) k_plain_pack(const __grid_constan
     const bool valid = e >= 0 && plain_fetch(P.f[f], cell, p, n);
     if (!valid) n = 0;
     uint8_t* dst = plan.bytes + plan.off[pi];
+    const bool jv = java && !P.f[f].host_combine;
     if (type == BT_CHAR) {
       uint8_t* d = dst + (uint64_t)q * nps;
-      for (uint32_t i = 0; i < nps; ++i) d[i] = i < n ? p[i] : ((i == 0 && n == 0 && !java) ? BCF_STR_MISSING : BCF_STR_VEND);   // JNI: vector_end only
+      for (uint32_t i = 0; i < nps; ++i) d[i] = i < n ? p[i] : ((i == 0 && n == 0 && !jv) ? BCF_STR_MISSING : BCF_STR_VEND);   // JNI: vector_end only
       continue;
     }
     const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
     const uint32_t miss = missing_word(P.f[f].elem == ELEM_FLOAT32), vend = vend_word(P.f[f].elem == ELEM_FLOAT32);
     for (uint32_t i = 0; i < nps; ++i) {
-      const uint32_t v = i < n ? w[i] : (((i == 0 && n == 0) || java) ? miss : vend);
+      const uint32_t v = i < n ? w[i] : (((i == 0 && n == 0) || jv) ? miss : vend);
       const uint64_t k = (uint64_t)q * nps + i;
       if (type == BT_INT8) dst[k] = v == BCF_INT_VEND ? 0x81u : (v == BCF_INT_MISSING ? 0x80u : (uint8_t)v);
       else if (type == BT_INT16) reinterpret_cast<uint16_t*>(dst)[k] = v == BCF_INT_VEND ? 0x8001u : (v == BCF_INT_MISSING ? 0x8000u : (uint16_t)v);

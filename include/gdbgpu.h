@@ -57,7 +57,8 @@ typedef struct gdbgpu_plain_field_desc {
   const char* name;      /* TileDB attribute name, e.g. "MIN_DP" */
   int32_t elem_type;     /* GDBGPU_ELEM_* (CHAR: a string per cell) */
   int32_t fixed_len;     /* values per cell; 0 = variable length */
-  int32_t no_format;     /* 1: the field is not a FORMAT field (no block is produced for it) */
+  int32_t no_format;     /* 1: the field is not a FORMAT field (no block is produced for it); 2: a block is produced for a host-side
+                          * combine (ID / FILTER union, concatenate) and always padded with vector_end, whatever the scan's conventions */
   int32_t info_op;       /* GDBGPU_INFO_*: combine the field over the valid calls of every site (4-byte fixed-length fields) */
 } gdbgpu_plain_field_desc;
 #define GDBGPU_MAX_PLAIN_FIELDS 16

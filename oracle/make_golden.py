@@ -100,6 +100,12 @@ SCENARIOS = [
     dict(name="t6_7_8_three_fragments_gz", callsets="t6_7_8.json", compress=True, batches=[(1, 1), (0, 0), (2, 2)], queries=[
         dict(id="t6_7_8_three_fragments_at_0", ranges=FULL, vcf="t6_7_8_vcf_at_0"),
     ]),
+    # INFO concatenate (tests/run.py:602-605, vid_info_ops1.json)
+    dict(name="info_ops1", callsets="info_ops.json", vid="vid_info_ops1.json", queries=[
+        dict(id="info_ops1_at_0", ranges=FULL, vcf=None,
+             attributes=["REF", "ALT", "QUAL", "BaseQRankSum", "ClippingRankSum", "GT", "MLEAC", "MLEAF", "var_field"],
+             extra={"vid_mapping_file": "inputs/vid_info_ops1.json"}),
+    ]),
     # the same gVCFs imported with GT stored phased (tests/run.py:493-520) and with the DS flag / ID string fields (:687-704)
     dict(name="t0_1_2_phased_GT", callsets="t0_1_2.json", vid="vid_phased_GT.json", queries=[
         dict(id="t0_1_2_phased_GT_at_0", ranges=FULL, vcf="t0_1_2_vcf_at_0", extra={"vid_mapping_file": "inputs/vid_phased_GT.json"}),
