@@ -145,3 +145,45 @@ def test_bcf_generator_stream_equals_the_reference(exe, cid, tmp_path, chunk, ca
     assert p.returncode == 0, p.stderr
     assert json.loads(p.stdout.strip().splitlines()[-1])["bytes"] == len(gold)
     assert out.read_bytes() == gold
+
+
+def test_bcf_generator_header_only(exe, tmp_path):
+    """produce_header_only (GenomicsDBQueryStream's way to fetch the header): the stream is the header, then end()"""
+    case = [c for c in ALL if c["id"] == "t0_1_2_at_0"][0]
+    gold = open(os.path.join(GOLDEN, "bcf_java", "t0_1_2_at_0.bcf"), "rb").read()
+    import struct
+    l_text = struct.unpack_from("<I", gold, 5)[0]
+    q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
+         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": case["attributes"],
+         "query_column_ranges": [{"range_list": [{"low": 0, "high": 1000000000}]}]}
+    qf = tmp_path / "query.json"
+    qf.write_text(json.dumps(q))
+    out = tmp_path / "header.bcf"
+    p = subprocess.run([exe, "-j", str(qf), "-o", str(out), "--bcf-generator", "1000", "--header-only", "--bcf-header",
+                        os.path.join(GOLDEN, "bcf_java", "t0_1_2_at_0.bcf")], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert out.read_bytes() == gold[:9 + l_text]
+
+
+@pytest.mark.parametrize("cid", ["t0_1_2_multiple_positions", "t6_7_8_at_0", "haploid_triploid_deletion"])
+def test_max_alleles_count_operator(exe, cid, tmp_path):
+    """MaxAllelesCountOperator over scan_and_operate's per-site summaries: with top_count above the number of sites every site is
+    reported -- column, merged REF, number of merged ALT alleles, the ALT alleles -- as the reference's dump has them"""
+    from oracle import oracle
+    case = [c for c in ALL if c["id"] == cid][0]
+    q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
+         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": case["attributes"],
+         "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_column_ranges"]]}],
+         "query_row_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_row_ranges"]]}]}
+    qf = tmp_path / "query.json"
+    qf.write_text(json.dumps(q))
+    out = tmp_path / "top.txt"
+    p = subprocess.run([exe, "-j", str(qf), "-o", str(out), "--max-alleles", "1000"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    lines = out.read_text().splitlines()
+    _, sites = oracle.parse_dump(open(os.path.join(GOLDEN, case["dump"]), "rb").read())
+    assert lines[0] == "TOTAL %d" % len(sites)
+    want = sorted(",".join([str(s["begin"]), s["alleles"][0], str(len(s["alleles"]) - 1)] + list(s["alleles"][1:])) for s in sites)
+    assert sorted(lines[1:]) == want
+    counts = [int(l.split(",")[2]) for l in lines[1:]]
+    assert counts == sorted(counts)          # the reference pops its min-heap: fewest ALT alleles first

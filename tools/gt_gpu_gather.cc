@@ -140,10 +140,10 @@ static int produce_broad_gvcf(const std::string& query_json, int rank, int devic
 // GenomicsDBBCFGenerator): pull the serialised BCF stream in `chunk`-byte reads, every 5th read a single byte.
 static int bcf_generator_stream(const std::string& query_json, int rank, int device, const std::string& header_file, const std::string& ref_bases_file,
                                 const std::string& out_file, size_t buffer_capacity, size_t chunk, bool htsjdk_conventions,
-                                const std::string& chr, int start, int end) {
+                                const std::string& chr, int start, int end, bool header_only) {
   std::string raw_prefix;
   read_header_text(header_file, raw_prefix);
-  GenomicsDBBCFGenerator gen("", query_json, raw_prefix, chr.c_str(), start, end, rank, buffer_capacity ? buffer_capacity : 1048576u, 1048576u, "bu", false,
+  GenomicsDBBCFGenerator gen("", query_json, raw_prefix, chr.c_str(), start, end, rank, buffer_capacity ? buffer_capacity : 1048576u, 1048576u, "bu", header_only,
                              htsjdk_conventions, true, device, ref_bases_file);
   std::ofstream out(out_file, std::ios::binary);
   if (!out) { std::cerr << "cannot open " << out_file << "\n"; return -1; }
@@ -176,6 +176,25 @@ static int interesting_positions(const std::string& query_json, int rank, int de
     scan_state.reset();
   }
   out.flush();
+  return 0;
+}
+
+// MaxAllelesCountOperator (variant_operations.h:410-475) plugged into the same loop: the top_count sites by number of merged ALT alleles
+static int max_alleles(const std::string& query_json, int rank, int device, const std::string& out_file, unsigned top_count) {
+  VariantQueryConfig query_config;
+  query_config.read_from_file(query_json, rank);
+  VariantStorageManager sm(query_config.get_workspace(rank), 10u * 1024u * 1024u, device);
+  VariantQueryProcessor qp(&sm, query_config.get_array_name(rank), query_config.get_vid_mapper());
+  qp.do_query_bookkeeping(query_config, true);
+  MaxAllelesCountOperator op(top_count);
+  VariantQueryProcessorScanState scan_state;
+  for (auto i = 0u; i < std::max(1u, query_config.get_num_column_intervals()); ++i) {
+    while (!scan_state.end()) qp.scan_and_operate(qp.get_array_descriptor(), query_config, op, i, true, &scan_state);
+    scan_state.reset();
+  }
+  std::ofstream out(out_file, std::ios::binary);
+  if (!out) { std::cerr << "cannot open " << out_file << "\n"; return -1; }
+  op.print(out);
   return 0;
 }
 
@@ -221,10 +240,10 @@ static int columnar_command(const std::string& query_json, int rank, int device,
 }
 
 int main(int argc, char** argv) {
-  std::string query_json, out_file, header_file, ref_bases_file; int rank = 0, device = 0; size_t page = 0; bool broad = false, htsjdk = false; int columnar = 0; size_t stream_chunk = 0; std::string chr; int chr_start = 0, chr_end = 0;
+  std::string query_json, out_file, header_file, ref_bases_file; int rank = 0, device = 0; size_t page = 0; bool broad = false, htsjdk = false; int columnar = 0; size_t stream_chunk = 0; bool header_only = false; unsigned max_alleles_top = 0; std::string chr; int chr_start = 0, chr_end = 0;
   static struct option long_options[] = {{"query", 1, 0, 'j'}, {"rank", 1, 0, 'r'}, {"output", 1, 0, 'o'}, {"device", 1, 0, 'd'}, {"page-size", 1, 0, 'p'},
                                          {"produce-Broad-GVCF", 0, 0, 'B'}, {"bcf-header", 1, 0, 'H'}, {"reference-bases", 1, 0, 'R'}, {"htsjdk-conventions", 0, 0, 'J'},
-                                         {"produce-interesting-positions", 0, 0, 'I'}, {"bcf-generator", 1, 0, 'S'}, {"chromosome", 1, 0, 'c'}, {"begin", 1, 0, 'b'}, {"end", 1, 0, 'e'}, {"print-calls", 0, 0, 'C'}, {"print-csv", 0, 0, 'V'}, {"print-AC", 0, 0, 'A'}, {"produce-histogram", 0, 0, 'G'}, {0, 0, 0, 0}};
+                                         {"produce-interesting-positions", 0, 0, 'I'}, {"bcf-generator", 1, 0, 'S'}, {"header-only", 0, 0, 'h'}, {"max-alleles", 1, 0, 'M'}, {"chromosome", 1, 0, 'c'}, {"begin", 1, 0, 'b'}, {"end", 1, 0, 'e'}, {"print-calls", 0, 0, 'C'}, {"print-csv", 0, 0, 'V'}, {"print-AC", 0, 0, 'A'}, {"produce-histogram", 0, 0, 'G'}, {0, 0, 0, 0}};
   int c;
   while ((c = getopt_long(argc, argv, "j:r:o:d:p:BH:R:J", long_options, NULL)) >= 0) {
     switch (c) {
@@ -238,6 +257,8 @@ int main(int argc, char** argv) {
       case 'R': ref_bases_file = optarg; break;
       case 'J': htsjdk = true; break;
       case 'S': stream_chunk = strtoull(optarg, 0, 10); break;   // pull the stream through GenomicsDBBCFGenerator in reads of this many bytes
+      case 'h': header_only = true; break;
+      case 'M': max_alleles_top = (unsigned)atoi(optarg); break;   // MaxAllelesCountOperator(top_count) over the query, its report to the output file
       case 'c': chr = optarg; break;
       case 'b': chr_start = atoi(optarg); break;
       case 'e': chr_end = atoi(optarg); break;
@@ -249,8 +270,9 @@ int main(int argc, char** argv) {
   try {
     if (stream_chunk) {
       if (header_file.empty()) { std::cerr << "--bcf-generator needs --bcf-header\n"; return -1; }
-      return bcf_generator_stream(query_json, rank, device, header_file, ref_bases_file, out_file, page, stream_chunk, htsjdk, chr, chr_start, chr_end);
+      return bcf_generator_stream(query_json, rank, device, header_file, ref_bases_file, out_file, page, stream_chunk, htsjdk, chr, chr_start, chr_end, header_only);
     }
+    if (max_alleles_top) return max_alleles(query_json, rank, device, out_file, max_alleles_top);
     if (columnar == 'I') return interesting_positions(query_json, rank, device, out_file);
     if (columnar) return columnar_command(query_json, rank, device, out_file, columnar);
     if (broad) {
