@@ -191,6 +191,11 @@ def main():
     if not torch.cuda.is_available():
         sys.exit("bench.py needs a CUDA device: the combine path has no CPU fallback")
     torch.cuda.set_device(local)
+    # stdout carries ONE JSON line: whatever libraries write to file descriptor 1 on the way (NCCL prints its version banner
+    # there) goes to stderr; the descriptor is handed back right before the line is printed
+    sys.stdout.flush()
+    saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -402,7 +407,10 @@ def main():
                     columnar_iterator=columnar,
                     sites_per_step_per_gpu=int(sites_per_step), cells_per_gpu=int(info.n_cells),
                     staged_bytes_per_gpu=int(info.staged_bytes), hbm_bytes_per_gpu=int(info.hbm_bytes))
+        sys.stdout.flush()
+        os.dup2(saved_stdout_fd, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
