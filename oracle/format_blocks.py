@@ -303,6 +303,21 @@ def info_vector_sums(site, plain, remapped_fields=(), plain_fields=()):
     return out
 
 
+def info_vector_concat(site, plain, plain_fields=()):
+    """VariantFieldHandler::concatenate_field (variant_field_handler.cc:743-800) at one parsed dump site: the vectors of the
+    valid calls appended in row order, nothing dropped (a missing value inside a vector stays).  plain_fields = [(attribute,
+    elem)].  -> {name: list of uint32 words} (fields no valid call has are absent)"""
+    calls = sorted(site["calls"], key=lambda c: c["row"])
+    out = {}
+    for name, elem in plain_fields:
+        res = []
+        for c in calls:
+            res += plain.values(name, elem, plain.cell_of[(c["row"], c["begin"])])
+        if res:
+            out[name] = res
+    return out
+
+
 def enc_info_vector(words, elem):
     """typed vector of an INFO field as bcf_update_info writes it (bcf_enc_vint with wsize = -1 / bcf_enc_vfloat)"""
     if elem == "float":

@@ -132,3 +132,24 @@ def test_enc_int1_and_size_known_answers():
     assert bt == 2
     bt, desc, data = format_blocks.enc_vint([0, 32768, 1, 2], 2)
     assert bt == 3
+
+
+def test_info_concatenate_matches_reference_bcf():
+    """the reference CI's info_ops1 scenario (vid_info_ops1.json: var_field combined with "concatenate")"""
+    case = [c for c in CASES if c["id"] == "info_ops1_at_0"][0]
+    _, samples, recs = bcf_reader.read_bcf(os.path.join(GOLDEN, "bcf", case["id"] + ".bcf"))
+    names, sites = oracle.parse_dump(open(os.path.join(GOLDEN, case["dump"]), "rb").read())
+    _, cat_plain = info_vector_fields(case, names, op="concatenate")
+    assert [n for n, _, _ in cat_plain] == ["var_field"]
+    arr = tf.Array(os.path.join(GOLDEN, case["workspace"]), case["array"])
+    plain = format_blocks.PlainColumns(arr, arr.fixed("END")[:, 0], list(cat_plain))
+    n_checked = 0
+    for rec, site in zip(recs, sites):
+        vecs = format_blocks.info_vector_concat(site, plain, [(n, e) for n, e, _ in cat_plain])
+        for name, elem, _ in cat_plain:
+            assert (name in rec["info"]) == (name in vecs)
+            if name in vecs:
+                bt, n, raw = rec["info"][name]
+                assert format_blocks.enc_info_vector(vecs[name], elem) == format_blocks.enc_size(n, bt) + raw
+                n_checked += 1
+    assert n_checked == 1

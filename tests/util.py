@@ -97,13 +97,14 @@ def info_scalar_fields(case):
     return out
 
 
-def info_vector_fields(case, dump_names):
-    """(remapped [(name, elem)], plain [(attribute, elem, fixed_len)]) of the queried INFO fields combined with an element-wise sum"""
+def info_vector_fields(case, dump_names, op="element_wise_sum"):
+    """(remapped [(name, elem)], plain [(attribute, elem, fixed_len)]) of the queried INFO fields combined with an element-wise sum
+    (or, op="concatenate", strung together)"""
     vid = oracle.load_vid_fields(os.path.join(GOLDEN, case["vid_mapping_file"]))
     remapped, plain = [], []
     for name in case["attributes"]:
         ent = vid.get(name)
-        if ent is None or ent.get("combine") != "element_wise_sum" or "INFO" not in (ent.get("classes") or []) or isinstance(ent["length"], list):
+        if ent is None or ent.get("combine") != op or "INFO" not in (ent.get("classes") or []) or isinstance(ent["length"], list):
             continue   # (2-D fields such as the allele-specific annotations are not covered)
         elem = "float" if ent["type"] == "float" else "int"
         if name in dump_names:
