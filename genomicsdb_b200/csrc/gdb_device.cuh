@@ -59,9 +59,14 @@ static_assert(sizeof(HotRec) == 32, "HotRec must be one 32-byte sector");
 //   (pad to an even index) then n_alt x u64 : FNV-1a state over the token's bytes (not finished, so a REF-tail suffix can
 //   still be appended at a site whose merged REF is longer; 0 for the <NON_REF> token)
 //   then n_alt x u32 : token length | symbolic << 31 | non_ref << 30
+//   then the tokens' bytes, one after the other, padded to a word (k_union compares them with the merged allele's bytes:
+//   equal hashes alone never decide that two alleles are the same)
 //   then GT words (gt_len), then the valid words of every field in field order
 constexpr uint32_t WARM_TOK_SYMBOLIC = 0x80000000u, WARM_TOK_NONREF = 0x40000000u;
 __host__ __device__ inline uint32_t warm_hash_word(uint32_t n_fields) { return (4u + n_fields + 1u) & ~1u; }
+// word [3] of a blob: gt_len | (words taken by the token bytes) << 16
+__host__ __device__ inline uint32_t warm_gt_len(uint32_t w3) { return w3 & 0xFFFFu; }
+__host__ __device__ inline uint32_t warm_tok_words(uint32_t w3) { return w3 >> 16; }
 
 // Class word of a cell (4 bytes, built when the array is staged): the per-site scan (k_site_scan) gathers this word -- from
 // an array small enough to live in L2 -- instead of the 32-byte hot record of every live call:
@@ -74,6 +79,16 @@ __host__ __device__ inline uint32_t cls_pack(uint32_t nr, uint32_t n_alt, uint32
   return (nr ? 1u : 0u) | ((n_alt & 1u) << 1) | ((gt_len & 7u) << 2) | ((ploidy & 7u) << 5) |
          ((uint32_t)(flen[0] & 7u) << 8) | ((uint32_t)(flen[1] & 7u) << 11) | ((uint32_t)(flen[2] & 7u) << 14) | ((uint32_t)(flen[3] & 7u) << 17);
 }
+
+// one entry of a sample's cell list: everything the live-matrix walk needs from a cell in one sector
+struct __align__(16) RsRec {
+  int64_t col;        // column of the cell
+  int64_t effend;     // effective end of the call that begins there; I64_MIN for an END copy
+  uint32_t cell;      // cell index | 0x80000000 when the call contains a deletion
+  uint32_t cls;       // class word of the cell (see above)
+  uint32_t pad[2];
+};
+static_assert(sizeof(RsRec) == 32, "RsRec must be one 32-byte sector");
 
 struct VarCol {
   const uint64_t* off;   // n_cells + 1 absolute byte offsets
@@ -99,6 +114,7 @@ struct ArrayDev {
   const int64_t* effend;   // cell order; I64_MIN for END copies / rows outside the array
   // row-major index (per-sample cell lists, column ascending)
   uint64_t n_rs;
+  const struct RsRec* rs_rec;  // the same index as one 32-byte record per entry (k_live_walk reads nothing else)
   const uint32_t* rs_cell;
   const int64_t* rs_col;
   const int64_t* rs_effend;

@@ -17,7 +17,7 @@
 #include <vector>
 
 #include "gdb_inflate.cuh"
-#include "gdb_kernels4.cuh"
+#include "gdb_kernels5.cuh"
 #include "gdb_tiledb.h"
 
 using namespace gdb;
@@ -38,6 +38,7 @@ struct gdbgpu_ctx {
   std::map<std::string, std::pair<double, uint64_t>> stats;
   std::vector<BatchBuffers*> bb_pool;
   std::multimap<size_t, void*> free_blocks; size_t cached_bytes = 0;   // device blocks waiting for reuse (see dev_alloc)
+  uint32_t tma_attr_set = 0;   // k_remap_tma instantiations whose dynamic shared-memory limit has been raised
   uint32_t* d_cls_tab = nullptr; uint16_t* d_jk_tab = nullptr; int n_sms = 148;   // universal genotype tables (gdb_kernels2.cuh: TileTabs)
   cudaEvent_t get_event() { if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
   void resolve() {
@@ -189,12 +190,12 @@ struct gdbgpu_array {
   DevVar ref, alt, gt; std::vector<std::unique_ptr<DevVar>> fields;
   std::vector<std::unique_ptr<DevVar>> plain; std::vector<PlainMeta> pm; PlainSet plain_dev{};   // plain FORMAT fields (K6)
   DevBuf<CellDesc> desc; DevBuf<HotRec> hot; DevBuf<uint32_t> warm, cls; DevBuf<int64_t> effend;
-  DevBuf<uint32_t> rs_cell, rs_keys; DevBuf<int64_t> rs_col, rs_effend; DevBuf<uint64_t> row_start; uint64_t n_rs = 0;
+  DevBuf<uint32_t> rs_cell, rs_keys; DevBuf<int64_t> rs_col, rs_effend; DevBuf<uint64_t> row_start; uint64_t n_rs = 0; DevBuf<RsRec> rs_rec;
   DevBuf<uint32_t> bad_cell; DevBuf<int64_t> bad_pred_col;
   ArrayDev dev{};
   uint64_t hbm_bytes() const {
     uint64_t b = coords.bytes() + end.bytes() + ref.off.bytes() + ref.val.bytes() + alt.off.bytes() + alt.val.bytes() + gt.off.bytes() + gt.val.bytes() +
-                 desc.bytes() + hot.bytes() + warm.bytes() + cls.bytes() + effend.bytes() + rs_cell.bytes() + rs_keys.bytes() + rs_col.bytes() + rs_effend.bytes() + row_start.bytes();
+                 desc.bytes() + hot.bytes() + warm.bytes() + cls.bytes() + effend.bytes() + rs_rec.bytes() + rs_cell.bytes() + rs_keys.bytes() + rs_col.bytes() + rs_effend.bytes() + row_start.bytes();
     for (auto& f : fields) b += f->off.bytes() + f->val.bytes();
     for (auto& f : plain) b += f->off.bytes() + f->val.bytes();
     return b;
@@ -226,6 +227,7 @@ void fill_dev_view(gdbgpu_array* a) {
   D.desc = a->desc.p; D.hot = a->hot.p; D.warm = a->warm.p; D.cls = a->cls.p; D.effend = a->effend.p;
   a->plain_dev.n = (int32_t)a->plain.size();
   for (size_t f = 0; f < a->plain.size(); ++f) a->plain_dev.f[f] = PlainDev{a->pm[f].fixed_len ? nullptr : a->plain[f]->off.p, a->plain[f]->val.p, a->pm[f].elem, a->pm[f].fixed_len, a->pm[f].no_format == 2 ? 1 : 0};
+  D.rs_rec = a->rs_rec.p;
   D.n_rs = a->n_rs; D.rs_cell = a->rs_cell.p; D.rs_col = a->rs_col.p; D.rs_effend = a->rs_effend.p; D.row_start = a->row_start.p;
 }
 
@@ -360,10 +362,16 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
       a->warm.alloc(std::max<uint64_t>(h_units * 4, 4));
       a->dev.warm = a->warm.p;
       LAUNCH(ctx, k_narrow_u64, g, 256, offs64.p, n, offs.p);
-      LAUNCH(ctx, k_warm_fill, g, 256, a->dev, a->desc.p, a->hot.p, units.p, offs.p, a->warm.p);
+      DevBuf<uint32_t> werr; werr.alloc(1);
+      CK(cudaMemsetAsync(werr.p, 0, 4, ctx->stream));
+      LAUNCH(ctx, k_warm_fill, g, 256, a->dev, a->desc.p, a->hot.p, units.p, offs.p, a->warm.p, werr.p);
+      uint32_t h_werr = 0;
+      CK(cudaMemcpyAsync(&h_werr, werr.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
       a->cls.alloc(n);
+      a->dev.cls = a->cls.p;
       LAUNCH(ctx, k_cls_fill, g, 256, a->hot.p, n, a->cls.p);
       CK(cudaStreamSynchronize(ctx->stream));
+      if (h_werr) throw LimitError("a cell's ALT string or GT vector is longer than 2^16 words");
     }
     lap("classify");
     DevBuf<uint32_t> keys, vals; DevBuf<uint8_t> tmp;
@@ -385,6 +393,8 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
       LAUNCH(ctx, k_effend, blocks_for(n_rs, 256), 256, a->dev, a->desc.p, a->rs_cell.p, a->rs_col.p, a->rs_keys.p, n_rs, a->rs_effend.p, a->effend.p, stats.p,
              a->bad_cell.p, a->bad_pred_col.p, BAD_CAP);
       LAUNCH(ctx, k_rs_flag_del, blocks_for(n_rs, 256), 256, a->desc.p, a->rs_cell.p, n_rs);
+      a->rs_rec.alloc(n_rs);
+      LAUNCH(ctx, k_rs_pack, blocks_for(n_rs, 256), 256, a->dev, n_rs, a->rs_rec.p);
     }
     long long hs[4];
     CK(cudaMemcpyAsync(hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
@@ -426,7 +436,7 @@ struct CtlArena {
 // context keeps finished scans' buffers and hands them to the next scan.
 struct BatchBuffers {
   // per batch (device)
-  DevBuf<int32_t> live; DevBuf<SiteRec> sites; DevBuf<uint32_t> agg; DevBuf<uint2> nt, blk_map; DevBuf<uint32_t> cursors, allele_pos, lut_first; DevBuf<uint16_t> lut_len; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes; DevBuf<int16_t> lut_in2m;
+  DevBuf<int32_t> live; DevBuf<uint32_t> lcls; DevBuf<SiteRec> sites; DevBuf<uint32_t> agg; DevBuf<uint2> nt, blk_map; DevBuf<uint32_t> cursors, allele_pos, lut_first; DevBuf<uint16_t> lut_len; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes; DevBuf<int16_t> lut_in2m;
   DevBuf<uint32_t> out_data[MAX_FIELDS + 1]; DevBuf<uint16_t> out_len[MAX_FIELDS + 1];
   CtlArena ctl;   // everything below points into ctl.d
   uint32_t* out_stride[MAX_FIELDS + 1] = {}; uint64_t* out_base[MAX_FIELDS + 1] = {};
@@ -463,7 +473,7 @@ struct gdbgpu_scan {
   uint64_t cursor = 0;
   std::vector<int64_t> h_rows;
   DevBuf<int32_t> qrow_of_row, init_cell, dlive, ddel, live_excl, del_excl; DevBuf<int64_t> row_of_qrow, init_effend, bp, site_begin, site_end;
-  DevBuf<unsigned long long> bitmap; DevBuf<uint32_t> word_rank, bp_cell0, err, del_cells, del_words; DevBuf<uint64_t> site_start; DevBuf<DelRec> del_recs;
+  DevBuf<unsigned long long> bitmap; DevBuf<uint32_t> word_rank, bp_cell0, err, del_cells, del_words, site_c0, site_c1; DevBuf<uint64_t> site_start; DevBuf<DelRec> del_recs;
   std::unique_ptr<BatchBuffers> slot[2];   // borrowed from the context's pool for the lifetime of the scan; [cur] = batch being handed out, the other = prefetched
   int cur = 0; bool bcf_format = false, prefetch = true; int produce_gt = 0, java = 0;
   InfoSet info{};   // INFO scalars to combine + the DP rule's fields (GDBGPU_SCAN_BCF_FORMAT)
@@ -492,6 +502,7 @@ void check_scan_errors(gdbgpu_scan* s, bool& pool_overflow) {
   if (e[1] == 2) throw LimitError("more than 512 distinct ALT alleles at one site");
   if (e[1] == 3) throw LimitError("ploidy above 8 needs the general-ploidy genotype enumeration, which keeps at most 8 slots");
   if (e[1] == 4) throw LimitError("merged REF assembled from more than 32 pieces");
+  if (e[1] == 6) throw LimitError("two different ALT alleles of one site share a 64-bit hash (detected by the byte comparison; never merged silently)");
   pool_overflow = e[2] != 0;
   if (pool_overflow) CK(cudaMemsetAsync(s->err.p + 2, 0, 4, s->ctx->stream));
 }
@@ -499,6 +510,7 @@ void check_scan_errors(gdbgpu_scan* s, bool& pool_overflow) {
 void scan_prepare(gdbgpu_scan* s) {
   gdbgpu_array* a = s->arr; gdbgpu_ctx* ctx = s->ctx; ScanDev& S = s->S;
   const gdbgpu_scan_params& p = s->params;
+  S.coords = a->coords.p;
   S.scan_full = (p.flags & GDBGPU_SCAN_FULL) ? 1 : 0;
   S.handle_del = (p.flags & GDBGPU_SCAN_NO_DELETIONS) ? 0 : 1;
   S.min_pl_gt = (p.flags & GDBGPU_SCAN_MIN_PL_GT) ? 1 : 0;
@@ -636,8 +648,8 @@ void scan_prepare(gdbgpu_scan* s) {
   CK(cudaMemcpyAsync(s->site_start.p + m, &T, 8, cudaMemcpyHostToDevice, ctx->stream));
   S.n_sites = T;
   if (T) {
-    s->site_begin.alloc(T); s->site_end.alloc(T);
-    S.site_begin = s->site_begin.p; S.site_end = s->site_end.p;
+    s->site_begin.alloc(T); s->site_end.alloc(T); s->site_c0.alloc(T); s->site_c1.alloc(T);
+    S.site_begin = s->site_begin.p; S.site_end = s->site_end.p; S.site_c0 = s->site_c0.p; S.site_c1 = s->site_c1.p;
     LAUNCH(ctx, k_fill_sites, blocks_for(T, 256), 256, S, s->del_excl.p);
   }
   bool ovf = false;
@@ -677,16 +689,20 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
   uint32_t nb = (uint32_t)std::min<uint64_t>({remaining, max_sites ? max_sites : 0xFFFFFFFFull, by_live, guess + guess / 2 + 1, 1u << 20});
   const int n_out = s->n_out;
   for (;;) {
-    bb.live.ensure((uint64_t)nb * S.nq); bb.sites.ensure(nb); bb.cursors.ensure(4);
+    bb.live.ensure((uint64_t)nb * S.nq); bb.lcls.ensure((uint64_t)nb * S.nq); bb.sites.ensure(nb); bb.cursors.ensure(4);
     bb.agg.ensure((uint64_t)nb * AGG_WORDS); bb.nt.ensure((uint64_t)nb * S.nq);
     CK(cudaMemsetAsync(bb.agg.p, 0, (size_t)nb * AGG_WORDS * 4, ctx->stream));
     if (!s->cap_allele_recs) { s->cap_allele_recs = 1u << 16; s->cap_allele_bytes = 1u << 20; }
     bb.allele_pos.ensure(2ull * s->cap_allele_recs); bb.allele_hash.ensure(s->cap_allele_recs); bb.allele_bytes.ensure(s->cap_allele_bytes);
     CK(cudaMemsetAsync(bb.cursors.p, 0, 16, ctx->stream));
     BatchDev B{};
-    B.first_site = first_site; B.n_sites = nb; B.live = bb.live.p; B.sites = bb.sites.p; B.agg = bb.agg.p; B.nt = bb.nt.p; B.cursors = bb.cursors.p;
+    B.first_site = first_site; B.n_sites = nb; B.live = bb.live.p; B.lcls = bb.lcls.p; B.sites = bb.sites.p; B.agg = bb.agg.p; B.nt = bb.nt.p; B.cursors = bb.cursors.p;
     B.allele_pos = bb.allele_pos.p; B.allele_hash = bb.allele_hash.p; B.cap_allele_recs = s->cap_allele_recs; B.allele_bytes = bb.allele_bytes.p; B.cap_allele_bytes = s->cap_allele_bytes;
-    LAUNCH(ctx, k_live_walk, dim3(blocks_for(S.nq, 256), (nb + WALK_CHUNK - 1) / WALK_CHUNK), 256, a->dev, S, first_site, nb, bb.live.p);
+    {   // sites walked by one thread after one binary search: long chunks amortise the search, short ones keep the device full
+      const uint64_t want_threads = 400000;
+      uint32_t chunk = (uint32_t)std::min<uint64_t>(nb, std::max<uint64_t>(32, (uint64_t)nb * S.nq / want_threads));
+      LAUNCH(ctx, k_live_walk, dim3(blocks_for(S.nq, 256), (nb + chunk - 1) / chunk), 256, a->dev, S, first_site, nb, chunk, bb.live.p, bb.lcls.p);
+    }
     LAUNCH(ctx, k_site_scan, dim3(nb, blocks_for(S.nq, SSCAN_ROWS)), SSCAN_THREADS, a->dev, S, B);
     LAUNCH(ctx, k_union, nb, UNION_THREADS, a->dev, S, B);
     bb.h_sites.resize(nb);
@@ -695,6 +711,11 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
     bool ovf = false;
     check_scan_errors(s, ovf);
     if (ovf) { s->cap_allele_recs *= 4; s->cap_allele_bytes *= 4; continue; }
+    {   // byte comparison behind every hash match (a throughput pass over the batch's nt lists; its verdict travels with the batch's tail)
+      uint32_t max_nt = 0;
+      for (uint32_t i = 0; i < nb; ++i) if (bb.h_sites[i].n_alleles >= 2u) max_nt = std::max(max_nt, bb.h_sites[i].n_nt);
+      if (max_nt) LAUNCH(ctx, k_verify_alleles, dim3(blocks_for(max_nt, VERIFY_THREADS), nb), VERIFY_THREADS, a->dev, S, B);
+    }
     // strides / bases; keep the prefix of sites that fits
     for (int o = 0; o < n_out; ++o) { bb.h_base[o].assign(nb + 1, 0); bb.h_stride[o].assign(nb, 0); }
     uint64_t bytes = 0, alg_bytes = 0; uint32_t keep = 0; uint64_t lut_words = 0;
@@ -725,12 +746,25 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
         jk_n = std::max(jk_n, r.n_alleles * (r.n_alleles + 1u) / 2u);
       } else slow.push_back(i);
     }
-    size_t n_remap = 0;
+    size_t n_remap = 0, n_tma = 0; uint32_t tma_smem_words = 0;
     if (!fast.empty()) {
       nt_prefix.push_back(nt_prefix.back() + nt_blocks(bb.h_sites[fast.back()]));   // blocks of k_remap_nt, per site
-      // remapped sites -> k_remap_tile, copy-through sites -> k_copy_tile; both lists live in tile_sites (remapped ones first)
+      // remapped sites -> k_remap_tma when every tile of the block fits shared memory (the tiles leave through the bulk-copy
+      // engine), else k_remap_tile; copy-through sites -> k_copy_tile.  All three lists live in tile_sites, in that order
+      // GDBGPU_K5=tma: tiles built in shared memory and stored by the bulk-copy engine (k_remap_tma).  Measured slower than
+      // k_remap_tile's direct STG.128 stream on this workload (profiles/r02_k5_tma_experiments.json), so it is opt-in
+      const char* k5_env = getenv("GDBGPU_K5");
+      const bool no_tma = !(k5_env && !strcmp(k5_env, "tma"));
+      auto tma_words = [&](uint32_t i) -> uint32_t {   // words per sample over the remapped fields, 0 = not eligible
+        if (no_tma || !(bb.h_sites[i].flags & 2u)) return 0;
+        uint32_t words = 0;
+        for (int o = a->has_gt ? 1 : 0; o < n_out; ++o) { if (bb.h_stride[o][i] > 4u * TMA_MAXQ) return 0; words += bb.h_stride[o][i]; }
+        return words <= (uint32_t)TMA_SMEM_WORDS ? words : 0;
+      };
       order.reserve(fast.size());
-      for (uint32_t i : fast) if (bb.h_sites[i].flags & 2u) order.push_back(i);
+      for (uint32_t i : fast) { const uint32_t w = tma_words(i); if (w) { order.push_back(i); tma_smem_words = std::max(tma_smem_words, w); } }
+      n_tma = order.size();
+      for (uint32_t i : fast) if ((bb.h_sites[i].flags & 2u) && !tma_words(i)) order.push_back(i);
       n_remap = order.size();
       for (uint32_t i : fast) if (!(bb.h_sites[i].flags & 2u)) order.push_back(i);
     }
@@ -771,7 +805,31 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       const uint32_t tiles = (uint32_t)((S.nq + TILE_ROWS - 1) / TILE_ROWS);
       if (tiles > 65535u) throw LimitError("more than 16.7 M query rows");
       const int key = nf * 2 + (a->has_gt ? 1 : 0);
-      for (size_t first = 0; first < n_remap; first += 65535) {
+      const uint32_t tma_tiles = (uint32_t)((S.nq + TMA_ROWS - 1) / TMA_ROWS);
+      const size_t tma_smem = (size_t)TMA_ROWS * tma_smem_words * 4;
+      for (size_t first = 0; first < n_tma; first += 65535) {
+        const unsigned ny = (unsigned)std::min<size_t>(65535, n_tma - first);
+        auto launch_tma = [&](auto kern) {
+          if (!(ctx->tma_attr_set & (1u << key))) {   // tiles + static scratch exceed the default 48 KB per block
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_ROWS * TMA_SMEM_WORDS * 4));
+            ctx->tma_attr_set |= 1u << key;
+          }
+          ProfScope ps__(ctx, "k_remap_tma");
+          kern<<<dim3(tma_tiles, ny), TMA_THREADS, tma_smem, ctx->stream>>>(a->dev, S, B, O, bb.tile_sites + first, tabs);
+        };
+        switch (key) {
+          case 2: launch_tma(k_remap_tma<1, false>); break;
+          case 3: launch_tma(k_remap_tma<1, true>); break;
+          case 4: launch_tma(k_remap_tma<2, false>); break;
+          case 5: launch_tma(k_remap_tma<2, true>); break;
+          case 6: launch_tma(k_remap_tma<3, false>); break;
+          case 7: launch_tma(k_remap_tma<3, true>); break;
+          case 8: launch_tma(k_remap_tma<4, false>); break;
+          default: launch_tma(k_remap_tma<4, true>); break;
+        }
+        ++ctx->launches; CK(cudaGetLastError());
+      }
+      for (size_t first = n_tma; first < n_remap; first += 65535) {
         const unsigned ny = (unsigned)std::min<size_t>(65535, n_remap - first);
         auto launch_tile = [&](auto kern) {
           ProfScope ps__(ctx, "k_remap_tile");
@@ -979,6 +1037,7 @@ void publish_batch(gdbgpu_scan* s, BatchBuffers& bb, gdbgpu_batch* out) {
   if (e[0]) throw OverlapError("Unhandled overlapping variants (a call that is neither a deletion nor a reference block is overlapped by a later call of the same sample)");
   if (e[1] == 3) throw LimitError("ploidy above 8 needs the general-ploidy genotype enumeration, which keeps at most 8 slots");
   if (e[1] == 5) throw LimitError("element-wise INFO sum over a vector longer than 1024 values");
+  if (e[1] == 6) throw LimitError("two different ALT alleles of one site share a 64-bit hash (detected by the byte comparison; never merged silently)");
   if (e[1]) throw LimitError("engine limit exceeded in the remap kernels");
   if (e[2]) throw CudaError("internal: LUT pool overflow");
   const uint32_t keep = bb.keep; const int n_out = s->n_out;

@@ -86,9 +86,10 @@ __global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restri
   const uint8_t* alt = A.alt.val + A.alt.off[i];
   int an = alt_effective_len(alt, (int)(A.alt.off[i + 1] - A.alt.off[i]));
   int pos = 0, ts, tl, n_alt = 0, nr = 0;
+  uint32_t tok_bytes = 0;
   bool deletion = false, first_is_nr = false;
   while (next_token(alt, an, pos, ts, tl)) {
-    ++n_alt;
+    ++n_alt; tok_bytes += (uint32_t)tl;
     if (is_non_ref(alt + ts, tl)) { nr = n_alt; if (n_alt == 1) first_is_nr = true; }
     else if (d.ref_len > 1 && !is_symbolic(alt + ts, tl) && (uint32_t)tl < d.ref_len) deletion = true;
   }
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restri
   // every other cell gets a warm blob (filled by k_warm_fill once the pool offsets are known); 16-byte units
   uint32_t units = 0;
   if (!(h.inl && (d.flags & F_TRIVIAL))) {
-    uint64_t words = (uint64_t)warm_hash_word((uint32_t)A.n_fields) + 3ull * (uint64_t)n_alt + d.gt_len + field_words;
+    uint64_t words = (uint64_t)warm_hash_word((uint32_t)A.n_fields) + 3ull * (uint64_t)n_alt + ((tok_bytes + 3u) >> 2) + d.gt_len + field_words;
     units = (uint32_t)((words + 3) >> 2);
     h.w[1] = (uint32_t)words;
   }
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restri
 
 // fills the warm blobs (layout: gdb_device.cuh); warm_off = exclusive scan of warm_units
 __global__ void __launch_bounds__(256) k_warm_fill(ArrayDev A, const CellDesc* __restrict__ desc, HotRec* __restrict__ hot, const uint32_t* __restrict__ warm_units,
-                                                    const uint32_t* __restrict__ warm_off, uint32_t* __restrict__ pool) {
+                                                    const uint32_t* __restrict__ warm_off, uint32_t* __restrict__ pool, uint32_t* __restrict__ err) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n || warm_units[i] == 0) return;
   const CellDesc d = desc[i];
@@ -162,7 +163,6 @@ __global__ void __launch_bounds__(256) k_warm_fill(ArrayDev A, const CellDesc* _
   uint32_t n_alt = 0;
   { int pos = 0, ts, tl; while (next_token(alt, an, pos, ts, tl)) ++n_alt; }
   b[0] = n_alt; b[1] = d.nr_idx; b[2] = d.ref_len;
-  b[3] = d.gt_len;
   const uint32_t H0 = warm_hash_word((uint32_t)A.n_fields);
   if ((4u + (uint32_t)A.n_fields) < H0) b[H0 - 1] = 0;
   uint32_t* tok = b + H0 + 2u * n_alt;
@@ -177,6 +177,16 @@ __global__ void __launch_bounds__(256) k_warm_fill(ArrayDev A, const CellDesc* _
     }
   }
   uint32_t* w = tok + n_alt;
+  {   // token bytes, packed
+    uint8_t* tb = reinterpret_cast<uint8_t*>(w);
+    int pos = 0, ts, tl; uint32_t nb = 0;
+    while (next_token(alt, an, pos, ts, tl)) { for (int x = 0; x < tl; ++x) tb[nb + x] = alt[ts + x]; nb += (uint32_t)tl; }
+    const uint32_t tw = (nb + 3u) >> 2;
+    for (uint32_t x = nb; x < 4u * tw; ++x) tb[x] = 0;
+    if (d.gt_len > 0xFFFFu || tw > 0xFFFFu) atomicMax(err, 1u);   // engine limit: GT vector / ALT string of one cell below 2^16 words
+    b[3] = (d.gt_len & 0xFFFFu) | (tw << 16);
+    w += tw;
+  }
   if (d.gt_len) { const uint32_t* g = reinterpret_cast<const uint32_t*>(A.gt.val + A.gt.off[i]); for (uint32_t x = 0; x < d.gt_len; ++x) *w++ = g[x]; }
   for (int f = 0; f < A.n_fields; ++f) {
     uint64_t o0 = A.f[f].off[i], o1 = A.f[f].off[i + 1];
@@ -343,8 +353,10 @@ struct ScanDev {
   uint64_t* site_start;          // m + 1
   uint64_t n_sites;
   int64_t* site_begin; int64_t* site_end;
+  uint32_t* site_c0; uint32_t* site_c1;   // cells of the forward range whose column is the site's begin: [c0, c1) (empty: c0 == c1)
   // deletion pre-pass
   uint64_t n_del; const uint32_t* del_cells; const DelRec* del_recs; const uint32_t* del_words;
+  const int64_t* coords;         // the staged array's (row, col) pairs
   // error flags: [0] bad eviction hit, [1] limit exceeded (code), [2] pool overflow
   uint32_t* err;
 };
@@ -508,19 +520,35 @@ __global__ void __launch_bounds__(256) k_fill_sites(ScanDev S, const int32_t* __
   int64_t b = S.bp[i] + (stepping ? (int64_t)k : 0);
   S.site_begin[j] = b;
   S.site_end[j] = stepping ? b : S.bp[i + 1] - 1;
+  // the begin cells of column b (merge_reference_allele folds over exactly these, k_union)
+  uint32_t c0 = 0, c1 = 0;
+  if (k == 0 && S.bp_cell0[i] != 0xFFFFFFFFu) {
+    c0 = S.bp_cell0[i];
+    uint64_t l2 = c0 + 1ull, h2 = S.i1;
+    while (l2 < h2) { uint64_t mid = (l2 + h2) >> 1; if (S.coords[2 * mid + 1] == b) l2 = mid + 1; else h2 = mid; }
+    c1 = (uint32_t)l2;
+  }
+  S.site_c0[j] = c0; S.site_c1[j] = c1;
 }
 
 // ------------------------------------------------------------------------------------------------ K3 live matrix
-// One thread per queried sample walks that sample's cell list against the batch's sites ("k-way merge" of the sample
-// lists with the site list); adjacent threads write adjacent entries of each site's row -> coalesced.
-#ifndef GDB_WALK_CHUNK
-#define GDB_WALK_CHUNK 32
-#endif
-constexpr uint32_t WALK_CHUNK = GDB_WALK_CHUNK;   // sites walked by one thread after one binary search
-__global__ void __launch_bounds__(256) k_live_walk(ArrayDev A, ScanDev S, uint64_t first_site, uint32_t n_sites, int32_t* __restrict__ live) {
+__global__ void __launch_bounds__(256) k_rs_pack(ArrayDev A, uint64_t n_rs, RsRec* __restrict__ rec) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_rs) return;
+  const uint32_t rc = A.rs_cell[k];
+  RsRec r; r.col = A.rs_col[k]; r.effend = A.rs_effend[k]; r.cell = rc; r.cls = A.cls[rc & RS_CELL_MASK]; r.pad[0] = r.pad[1] = 0;
+  rec[k] = r;
+}
+// One thread per queried sample walks that sample's cell list against `chunk` consecutive sites of the batch ("k-way merge"
+// of the sample lists with the site list); adjacent threads write adjacent entries of each site's row -> coalesced.  Per
+// (site, sample) it leaves the live entry and the class word of the live call (gdb_device.cuh), so the per-site scan that
+// follows (k_site_scan) streams instead of gathering.  The list is read as 32-byte records, the next one kept in registers.
+// (A scatter formulation -- every begin cell fills its range of sites in a shared-memory tile -- was measured at 3.9 ms per
+// step against 1.8 ms for this walk: the fill loops diverge as much as the walk does, profiles/r02_k34_experiments.json.)
+__global__ void __launch_bounds__(256) k_live_walk(ArrayDev A, ScanDev S, uint64_t first_site, uint32_t n_sites, uint32_t chunk, int32_t* __restrict__ live, uint32_t* __restrict__ lcls) {
   uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= S.nq) return;
-  const uint32_t s0 = blockIdx.y * WALK_CHUNK, s1 = min(n_sites, s0 + WALK_CHUNK);
+  const uint32_t s0 = blockIdx.y * chunk, s1 = min(n_sites, s0 + chunk);
   int64_t r = S.row_of_qrow[q] - A.lb_row;
   uint64_t lo = A.row_start[r], e = A.row_start[r + 1];
   int64_t b0 = S.site_begin[first_site + s0];
@@ -528,29 +556,37 @@ __global__ void __launch_bounds__(256) k_live_walk(ArrayDev A, ScanDev S, uint64
   uint64_t k = lo, hi = e;
   while (k < hi) { uint64_t mid = (k + hi) >> 1; if (A.rs_col[mid] <= b0) k = mid + 1; else hi = mid; }
   // current call: last begin cell with q_lo < col <= b0 (or any col for a full scan), else the left-sweep call
-  int32_t cur = S.init_cell[q]; int64_t cur_eff = S.init_effend[q]; int64_t cur_begin = 0; bool cur_del = false;
-  if (cur >= 0) { uint8_t fl = A.desc[cur].flags; cur_del = fl & F_DELETION; cur_begin = (fl & F_ENDCOPY) ? A.end[cur] : A.coords[2 * (uint64_t)cur + 1]; }
+  int32_t cur = S.init_cell[q]; int64_t cur_eff = S.init_effend[q]; int64_t cur_begin = 0; bool cur_del = false; uint32_t cur_cls = CLS_DEAD;
+  if (cur >= 0) { uint8_t fl = A.desc[cur].flags; cur_del = fl & F_DELETION; cur_begin = (fl & F_ENDCOPY) ? A.end[cur] : A.coords[2 * (uint64_t)cur + 1]; cur_cls = A.cls[cur]; }
   for (uint64_t kk = k; kk > lo;) {
     --kk;
-    int64_t c = A.rs_col[kk];
+    const uint4 ra = reinterpret_cast<const uint4*>(A.rs_rec + kk)[0];
+    const int64_t c = (int64_t)(((uint64_t)ra.y << 32) | ra.x), ef = (int64_t)(((uint64_t)ra.w << 32) | ra.z);
     if (!S.scan_full && c <= S.q_lo) break;
-    int64_t ef = A.rs_effend[kk];
-    if (ef != I64_MIN) { const uint32_t rc = A.rs_cell[kk]; cur = (int32_t)(rc & RS_CELL_MASK); cur_eff = ef; cur_begin = c; cur_del = rc >> 31; break; }
+    if (ef != I64_MIN) { const uint2 rb = reinterpret_cast<const uint2*>(A.rs_rec + kk)[2]; cur = (int32_t)(rb.x & RS_CELL_MASK); cur_eff = ef; cur_begin = c; cur_del = rb.x >> 31; cur_cls = rb.y; break; }
   }
-  // the sample's next cell (column, effective end, cell) stays in registers: most sites of the chunk do not advance the
-  // list, and an advance issues the three loads of the following cell together instead of one after the other
-  int64_t next_col = INT64_MAX, next_ef = I64_MIN; uint32_t next_rc = 0;
-  if (k < e) { next_col = A.rs_col[k]; next_ef = A.rs_effend[k]; next_rc = A.rs_cell[k]; }
+  // the sample's next cell stays in registers: most sites of the chunk do not advance the list
+  int64_t next_col = INT64_MAX, next_ef = I64_MIN; uint32_t next_rc = 0, next_cls = 0;
+  auto fetch = [&](uint64_t kk) {
+    const uint4 ra = reinterpret_cast<const uint4*>(A.rs_rec + kk)[0];
+    const uint2 rb = reinterpret_cast<const uint2*>(A.rs_rec + kk)[2];
+    next_col = (int64_t)(((uint64_t)ra.y << 32) | ra.x); next_ef = (int64_t)(((uint64_t)ra.w << 32) | ra.z); next_rc = rb.x; next_cls = rb.y;
+  };
+  if (k < e) fetch(k);
   for (uint32_t s = s0; s < s1; ++s) {
     const int64_t b = S.site_begin[first_site + s];
     while (next_col <= b) {
-      if (next_ef != I64_MIN) { cur = (int32_t)(next_rc & RS_CELL_MASK); cur_eff = next_ef; cur_begin = next_col; cur_del = next_rc >> 31; }
+      if (next_ef != I64_MIN) { cur = (int32_t)(next_rc & RS_CELL_MASK); cur_eff = next_ef; cur_begin = next_col; cur_del = next_rc >> 31; cur_cls = next_cls; }
       ++k;
-      if (k < e) { next_col = A.rs_col[k]; next_ef = A.rs_effend[k]; next_rc = A.rs_cell[k]; } else next_col = INT64_MAX;
+      if (k < e) fetch(k); else next_col = INT64_MAX;
     }
-    int32_t v = -1;
-    if (cur >= 0 && cur_eff >= b) { v = cur; if (S.handle_del && cur_del && b > cur_begin) v |= LIVE_REDUCED; }
+    int32_t v = -1; uint32_t c = CLS_DEAD;
+    if (cur >= 0 && cur_eff >= b) {
+      v = cur; c = cur_cls;
+      if (S.handle_del && cur_del && b > cur_begin) { v |= LIVE_REDUCED; c = CLS_REDUCED | (uint32_t)cur; }
+    }
     live[(uint64_t)s * S.nq + q] = v;
+    lcls[(uint64_t)s * S.nq + q] = c;
   }
 }
 

@@ -242,7 +242,7 @@ __device__ inline uint64_t allele_hash(const uint8_t* t, int tl, const uint8_t* 
 }
 
 // ------------------------------------------------------------------------------------------------ K4 allele union
-constexpr int UNION_THREADS = 512;
+constexpr int UNION_THREADS = 256;
 constexpr int UNION_SLOTS = 1024;        // open-addressing table in shared memory
 constexpr int UNION_MAX_DISTINCT = 512;  // documented engine limit on distinct ALT alleles per site (excluding NON_REF)
 constexpr int REF_MAX_PIECES = 32;
@@ -265,6 +265,7 @@ enum { AGG_NLIVE = 0, AGG_NONREF, AGG_MAXGT, AGG_MAXAIN, AGG_MAXPLOIDY, AGG_NNT,
 struct BatchDev {
   uint64_t first_site; uint32_t n_sites;
   const int32_t* live;        // n_sites x nq
+  const uint32_t* lcls;       // n_sites x nq : class word of the live call (k_live_walk)
   SiteRec* sites;
   uint32_t* agg;              // n_sites x AGG_WORDS
   uint2* nt;                  // n_sites x nq : per site, its non-trivial live calls (first agg[AGG_NNT] entries, any order):
@@ -277,13 +278,14 @@ struct BatchDev {
 
 constexpr uint32_t NT_REDUCED = 0x80000000u;
 // a non-reduced, non-(trivial and inline) call through its warm blob
-struct WarmView { const uint32_t* b; uint32_t n_alt, nr_idx, ref_len, gt_len, ploidy; };
-__device__ inline WarmView warm_view(const ArrayDev& A, uint32_t blob_off) {
+struct WarmView { const uint32_t* b; uint32_t n_alt, nr_idx, ref_len, gt_len, ploidy, tok_words; };
+// `at`: the blob's bytes where the caller has staged them (shared memory), nullptr = read the pool in HBM
+__device__ inline WarmView warm_view(const ArrayDev& A, uint32_t blob_off, const uint32_t* at = nullptr) {
   WarmView v;
-  v.b = A.warm + (uint64_t)blob_off * 4u;
+  v.b = at ? at : A.warm + (uint64_t)blob_off * 4u;
   const uint4 hd = *reinterpret_cast<const uint4*>(v.b);
-  v.n_alt = hd.x; v.nr_idx = hd.y; v.ref_len = hd.z; v.gt_len = hd.w;
-  v.ploidy = hd.w ? ploidy_of(A.gt_phased, hd.w) : 0u;
+  v.n_alt = hd.x; v.nr_idx = hd.y; v.ref_len = hd.z; v.gt_len = warm_gt_len(hd.w); v.tok_words = warm_tok_words(hd.w);
+  v.ploidy = v.gt_len ? ploidy_of(A.gt_phased, v.gt_len) : 0u;
   return v;
 }
 // hash of ALT token t (0-based) as it enters the merged list at a site with merged REF `mref`; 0 for <NON_REF>
@@ -297,10 +299,11 @@ __device__ inline uint64_t warm_token_hash(const WarmView& v, uint32_t H0, uint3
 }
 __device__ inline uint64_t star_hash() { const uint8_t s = '*'; return hash_finish(fnv1a(FNV_BASIS, &s, 1) ^ (1ull << 40)); }
 
-// K4a: one pass over the live matrix; every live call contributes its 4-byte class word (layout: gdb_device.cuh).  Per
-// site: number of live calls, the maxima the output layout needs (packed into the class word of every trivial inline call)
-// and the list of all other live calls.  Grid = (sites, row chunks), so the whole GPU works on a batch whatever its number
-// of sites.
+// K4a: one streaming pass over the class words k_live_walk left per (site, sample) (layout: gdb_device.cuh).  Per site:
+// number of live calls, the maxima the output layout needs (packed into the class word of every trivial inline call) and
+// the list of all other live calls.  Grid = (sites, row chunks), so the whole GPU works on a batch whatever its number of
+// sites.  Most calls live at a site are reference blocks with one and the same class word: a word equal to the thread's
+// previous one only counts.
 constexpr int SSCAN_THREADS = 256, SSCAN_PER_THREAD = 16, SSCAN_ROWS = SSCAN_THREADS * SSCAN_PER_THREAD;
 __global__ void __launch_bounds__(SSCAN_THREADS) k_site_scan(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B) {
   __shared__ uint2 s_list[SSCAN_ROWS];
@@ -309,27 +312,24 @@ __global__ void __launch_bounds__(SSCAN_THREADS) k_site_scan(const __grid_consta
   const uint32_t js = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
   const uint64_t q0 = (uint64_t)blockIdx.y * SSCAN_ROWS;
-  const int32_t* live = B.live + (uint64_t)js * S.nq;
+  const uint32_t* lcls = B.lcls + (uint64_t)js * S.nq;
   if (tid == 0) s_cnt = 0;
   if (tid < AGG_WORDS) s_red[tid] = 0;
   __syncthreads();
   uint32_t c[SSCAN_PER_THREAD];
 #pragma unroll
-  for (int i = 0; i < SSCAN_PER_THREAD; ++i) { const uint64_t q = q0 + (uint64_t)i * SSCAN_THREADS + tid; c[i] = q < S.nq ? (uint32_t)live[q] : CLS_DEAD; }
-#pragma unroll
-  for (int i = 0; i < SSCAN_PER_THREAD; ++i) {   // live entry -> class word (all gathers of the thread in flight together)
-    const int32_t e = (int32_t)c[i];
-    c[i] = e < 0 ? CLS_DEAD : ((e & LIVE_REDUCED) ? (CLS_REDUCED | (uint32_t)(e & (LIVE_REDUCED - 1))) : A.cls[e]);
-  }
+  for (int i = 0; i < SSCAN_PER_THREAD; ++i) { const uint64_t q = q0 + (uint64_t)i * SSCAN_THREADS + tid; c[i] = q < S.nq ? lcls[q] : CLS_DEAD; }
   uint32_t n_live = 0, nonref = 0, mgt = 0, main_ = 0, mpl = 0;
   uint32_t fpl[HOT_FIELDS] = {0, 0, 0, 0}, fin[HOT_FIELDS] = {0, 0, 0, 0};
+  uint32_t last = CLS_DEAD;
 #pragma unroll
   for (int i = 0; i < SSCAN_PER_THREAD; ++i) {
     const bool live = c[i] != CLS_DEAD;
     const bool general = live && (c[i] & (CLS_GENERAL | CLS_REDUCED));
     if (live) {
       ++n_live;
-      if (!general) {
+      if (!general && c[i] != last) {
+        last = c[i];
         const uint32_t nr = c[i] & 1u, n_alt = (c[i] >> 1) & 1u, gt_len = (c[i] >> 2) & 7u, ploidy = (c[i] >> 5) & 7u;
         mgt = max(mgt, gt_len); main_ = max(main_, n_alt + 1u); mpl = max(mpl, ploidy);
         if (nr) nonref = 1;
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(SSCAN_THREADS) k_site_scan(const __grid_consta
 }
 
 // K4b: one block per site.  Merged REF from the begin cells of the site's column, merged ALT list from the site's nt list.
-__global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B) {
+__global__ void __launch_bounds__(UNION_THREADS, 4) k_union(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B) {
   __shared__ unsigned long long s_hash[UNION_SLOTS];
   __shared__ unsigned long long s_order[UNION_SLOTS];
   __shared__ uint16_t s_list[UNION_MAX_DISTINCT];
@@ -395,22 +395,8 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__
   __syncthreads();
 
   // ---- merged REF (variant_operations.cc:73-122): fold over the calls that BEGIN at this site, in row order.
-  // Those are exactly the begin cells of column b (contiguous in the merged cell order).
-  uint64_t c0 = 0, c1 = 0;
-  {
-    // breakpoint index of b -> first cell of that column
-    uint64_t lo = 0, hi = S.m;
-    while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (S.bp[mid] < b) lo = mid + 1; else hi = mid; }
-    if (lo < S.m && S.bp[lo] == b && S.bp_cell0[lo] != 0xFFFFFFFFu) {
-      c0 = S.bp_cell0[lo];
-      // column extent: gallop then bisect on the col coordinate
-      uint64_t step = 1, e = c0 + 1;
-      while (e < A.n && A.coords[2 * e + 1] == b) { e += step; step <<= 1; }
-      uint64_t l2 = (e - (step >> 1) > c0) ? e - (step >> 1) : c0 + 1, h2 = e < A.n ? e : A.n;
-      while (l2 < h2) { uint64_t mid = (l2 + h2) >> 1; if (A.coords[2 * mid + 1] == b) l2 = mid + 1; else h2 = mid; }
-      c1 = l2;
-    }
-  }
+  // Those are exactly the begin cells of column b (contiguous in the merged cell order; range found once per scan, k_fill_sites).
+  const uint64_t c0 = S.site_c0[j], c1 = S.site_c1[j];
   // a begin cell of column b whose row is queried IS the live call of that row at this site (k_live_walk), so the 16-byte
   // header of its hot record answers everything the fold asks: flags, REF length, first REF byte
   auto candidate = [&](uint64_t c, uint32_t& rl, uint8_t& first) -> bool {
@@ -421,12 +407,18 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__
     if (rl == 255u) rl = A.desc[c].ref_len;
     return true;
   };
-  for (uint64_t c = c0 + tid; c < c1; c += UNION_THREADS) {
-    uint32_t rl; uint8_t first;
-    if (!candidate(c, rl, first)) continue;
-    atomicMax(&s_maxlen, rl);
-    if (first != 'N') atomicMin(&s_k, (unsigned int)(c - c0));
-    else atomicMax(&s_maxN, rl);
+  {   // per-thread partial results first (the loads of successive trips do not wait for the shared-memory atomics)
+    uint32_t t_maxlen = 0, t_maxN = 0, t_k = 0xFFFFFFFFu;
+    for (uint64_t c = c0 + tid; c < c1; c += UNION_THREADS) {
+      uint32_t rl; uint8_t first;
+      if (!candidate(c, rl, first)) continue;
+      t_maxlen = max(t_maxlen, rl);
+      if (first != 'N') t_k = min(t_k, (uint32_t)(c - c0));
+      else t_maxN = max(t_maxN, rl);
+    }
+    if (t_maxlen) atomicMax(&s_maxlen, t_maxlen);
+    if (t_maxN) atomicMax(&s_maxN, t_maxN);
+    if (t_k != 0xFFFFFFFFu) atomicMin(&s_k, t_k);
   }
   __syncthreads();
   if (s_k == 0xFFFFFFFFu) {
@@ -503,31 +495,58 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__
   const uint32_t n_nt = agg[AGG_NNT];
   const uint2* nt = B.nt + (uint64_t)js * S.nq;
   const uint32_t H0 = warm_hash_word((uint32_t)A.n_fields);
-  if (!s_overflow) for (uint32_t i = tid; i < n_nt; i += UNION_THREADS) {
-    const uint2 ent = nt[i];
-    const uint32_t q = ent.x;
-    any = true;
-    if (ent.y & NT_REDUCED) {
-      CallView v = make_view(A, S, (int32_t)((ent.y & ~NT_REDUCED) | (uint32_t)LIVE_REDUCED));
-      loc_maxgt = max(loc_maxgt, v.gt_len); loc_maxain = max(loc_maxain, (uint32_t)v.n_alt + 1u); loc_maxploidy = max(loc_maxploidy, v.ploidy);
+  // UNION_ILP entries per thread and trip: their list entries, then the first 32 bytes of their blobs (header + field
+  // lengths) are loaded together, and the blobs' second sector (token hashes / lengths of a call with up to 3 ALT alleles)
+  // is on its way while the headers are decoded -- one memory round trip per step of the dependency chain and trip
+  // instead of one per entry
+  constexpr int UNION_ILP = 2;
+  if (!s_overflow) for (uint32_t i0 = tid; i0 < n_nt; i0 += UNION_ILP * UNION_THREADS) {
+    uint2 ent[UNION_ILP]; uint4 hd[UNION_ILP], fl[UNION_ILP];
+#pragma unroll
+    for (int u = 0; u < UNION_ILP; ++u) { const uint32_t i = i0 + u * UNION_THREADS; ent[u] = i < n_nt ? nt[i] : make_uint2(0xFFFFFFFFu, NT_REDUCED); }
+#pragma unroll
+    for (int u = 0; u < UNION_ILP; ++u) {
+      hd[u] = make_uint4(0, 0, 0, 0); fl[u] = hd[u];
+      if (!(ent[u].y & NT_REDUCED)) {
+        const uint4* p = reinterpret_cast<const uint4*>(A.warm + (uint64_t)ent[u].y * 4u);
+        hd[u] = p[0]; fl[u] = p[1];
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 2));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNION_ILP; ++u) {
+      if (ent[u].x == 0xFFFFFFFFu) continue;
+      const uint32_t q = ent[u].x;
+      any = true;
+      if (ent[u].y & NT_REDUCED) {
+        CallView v = make_view(A, S, (int32_t)((ent[u].y & ~NT_REDUCED) | (uint32_t)LIVE_REDUCED));
+        loc_maxgt = max(loc_maxgt, v.gt_len); loc_maxain = max(loc_maxain, (uint32_t)v.n_alt + 1u); loc_maxploidy = max(loc_maxploidy, v.ploidy);
+#pragma unroll
+        for (int f = 0; f < MAX_FIELDS; ++f) if (f < A.n_fields) {
+          const uint32_t* p; uint32_t n;
+          if (field_of(A, S, v, f, p, n)) { loc_maxpl[f] = max(loc_maxpl[f], v.ploidy); loc_maxin[f] = max(loc_maxin[f], n); }
+        }
+        if (v.nr_idx) loc_nonref = true;
+        insert(star_hash(), q, 1);
+        continue;
+      }
+      WarmView v;
+      v.b = A.warm + (uint64_t)ent[u].y * 4u;
+      v.n_alt = hd[u].x; v.nr_idx = hd[u].y; v.ref_len = hd[u].z; v.gt_len = warm_gt_len(hd[u].w); v.tok_words = warm_tok_words(hd[u].w);
+      v.ploidy = v.gt_len ? ploidy_of(A.gt_phased, v.gt_len) : 0u;
+      loc_maxgt = max(loc_maxgt, v.gt_len); loc_maxain = max(loc_maxain, v.n_alt + 1u); loc_maxploidy = max(loc_maxploidy, v.ploidy);
+      const uint32_t fl4[4] = {fl[u].x, fl[u].y, fl[u].z, fl[u].w};
 #pragma unroll
       for (int f = 0; f < MAX_FIELDS; ++f) if (f < A.n_fields) {
-        const uint32_t* p; uint32_t n;
-        if (field_of(A, S, v, f, p, n)) { loc_maxpl[f] = max(loc_maxpl[f], v.ploidy); loc_maxin[f] = max(loc_maxin[f], n); }
+        const uint32_t n = f < 4 ? fl4[f] : v.b[4 + f];
+        if (n) { loc_maxpl[f] = max(loc_maxpl[f], v.ploidy); loc_maxin[f] = max(loc_maxin[f], n); }
       }
       if (v.nr_idx) loc_nonref = true;
-      insert(star_hash(), q, 1);
-      continue;
-    }
-    const WarmView v = warm_view(A, ent.y);
-    loc_maxgt = max(loc_maxgt, v.gt_len); loc_maxain = max(loc_maxain, v.n_alt + 1u); loc_maxploidy = max(loc_maxploidy, v.ploidy);
-#pragma unroll
-    for (int f = 0; f < MAX_FIELDS; ++f) if (f < A.n_fields) { const uint32_t n = v.b[4 + f]; if (n) { loc_maxpl[f] = max(loc_maxpl[f], v.ploidy); loc_maxin[f] = max(loc_maxin[f], n); } }
-    if (v.nr_idx) loc_nonref = true;
-    if (v.n_alt > (uint32_t)MAX_CALL_ALLELES - 1u) { atomicMax(&S.err[1], 1u); continue; }
-    for (uint32_t t = 0; t < v.n_alt; ++t) {
-      const uint64_t h = warm_token_hash(v, H0, t, mref, mref_len);
-      if (h) insert(h, q, t + 1u);
+      if (v.n_alt > (uint32_t)MAX_CALL_ALLELES - 1u) { atomicMax(&S.err[1], 1u); continue; }
+      for (uint32_t t = 0; t < v.n_alt; ++t) {
+        const uint64_t h = warm_token_hash(v, H0, t, mref, mref_len);
+        if (h) insert(h, q, t + 1u);
+      }
     }
   }
   if (any) {
@@ -588,6 +607,7 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__
     }
   }
   __syncthreads();
+  __syncthreads();
   if (tid == 0) {
     if (s_overflow) atomicOr(&S.err[2], 1u);
     SiteRec r;
@@ -598,6 +618,49 @@ __global__ void __launch_bounds__(UNION_THREADS) k_union(const __grid_constant__
     r.max_gt_len = s_maxgt; r.max_ain = s_maxain; r.max_ploidy_all = s_maxploidy;
     for (int f = 0; f < MAX_FIELDS; ++f) { r.max_ploidy[f] = s_maxpl[f]; r.max_in_len[f] = s_maxin[f]; }
     B.sites[js] = r;
+  }
+}
+
+// K4c: equal hashes never decide alone.  k_union keys its table by a 64-bit hash of the allele string and the remap kernels
+// find a call's alleles in the merged list by that hash; this pass compares, for every ALT token of every non-trivial call
+// of the batch, the token's bytes (+ the tail of the merged REF it was extended by) with the bytes of the merged allele its
+// hash leads to -- what the reference's unordered_map<string> does implicitly (variant_operations.cc:163-190).  A mismatch
+// is a 64-bit collision between two different alleles of one site: reported (GDBGPU_ERR_LIMIT), never merged silently.
+// One thread per nt-list entry, grid = (row chunks, sites): a throughput pass, off the remap kernels' dependency chains.
+constexpr int VERIFY_THREADS = 256;
+__global__ void __launch_bounds__(VERIFY_THREADS) k_verify_alleles(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B) {
+  const uint32_t js = blockIdx.y;
+  const SiteRec* __restrict__ site = &B.sites[js];
+  const uint32_t i = blockIdx.x * VERIFY_THREADS + threadIdx.x;
+  if (i >= site->n_nt || site->n_alleles < 2u) return;
+  const uint32_t A_m = site->n_alleles, afirst = site->allele_first, mref_len = site->ref_len;
+  const uint8_t* mref = B.allele_bytes + site->ref_off;
+  const uint2 ent = B.nt[(uint64_t)js * S.nq + i];
+  auto merged_of = [&](uint64_t h) -> uint32_t { for (uint32_t m = 1; m < A_m; ++m) if (B.allele_hash[afirst + m] == h) return afirst + m; return 0xFFFFFFFFu; };
+  if (ent.y & NT_REDUCED) {   // a spanning deletion contributes "*"
+    const uint32_t m = merged_of(star_hash());
+    if (m == 0xFFFFFFFFu || B.allele_pos[2 * m + 1] != 1u || B.allele_bytes[B.allele_pos[2 * m]] != (uint8_t)'*') atomicMax(&S.err[1], 6u);
+    return;
+  }
+  const WarmView v = warm_view(A, ent.y);
+  const uint32_t H0 = warm_hash_word((uint32_t)A.n_fields);
+  const uint32_t* tokw = v.b + H0 + 2u * v.n_alt;
+  const uint8_t* tb = reinterpret_cast<const uint8_t*>(tokw + v.n_alt);
+  for (uint32_t t = 0; t < v.n_alt && t < (uint32_t)MAX_CALL_ALLELES; ++t) {
+    const uint32_t w = tokw[t], tl = w & 0x3FFFFFFFu;
+    if (!(w & WARM_TOK_NONREF)) {
+      const uint32_t m = merged_of(warm_token_hash(v, H0, t, mref, mref_len));
+      bool same = m != 0xFFFFFFFFu;
+      if (same) {
+        const uint8_t* as = B.allele_bytes + B.allele_pos[2 * m]; const uint32_t al = B.allele_pos[2 * m + 1];
+        const uint32_t sfx = (v.ref_len < mref_len && !(w & WARM_TOK_SYMBOLIC)) ? mref_len - v.ref_len : 0u;
+        same = al == tl + sfx;
+        for (uint32_t x = 0; same && x < tl; ++x) same = as[x] == tb[x];
+        for (uint32_t x = 0; same && x < sfx; ++x) same = as[tl + x] == mref[v.ref_len + x];
+      }
+      if (!same) atomicMax(&S.err[1], 6u);
+    }
+    tb += tl;
   }
 }
 
@@ -844,6 +907,11 @@ __global__ void __launch_bounds__(256) k_nt_blocks(const __grid_constant__ Batch
 }
 // everything an nt-list entry needs to know about its site
 struct NtSite { uint32_t js, A_m, sflags, mref_len; const uint8_t* mref; };
+// where nt_entry puts a row's field vectors: the site's block of the global output (tile[] unused), or the block's tile
+// in shared memory (k_remap_tma: tile[f] = row q0's vector of field f; the tile leaves the SM as one bulk copy)
+// blob_win / win_lo: a window of the warm-blob pool staged in shared memory, starting at 16-byte unit win_lo (blobs that begin
+// at or after it lie entirely inside it; nullptr = none)
+struct NtDst { bool smem; uint32_t q0; uint32_t* tile[4]; const uint32_t* blob_win; uint32_t win_lo; };
 
 // One nt-list entry (non-trivial, non-inline or spanning-deletion call) handled by NT_GL consecutive lanes of a warp: gather of
 // the warm blob (pre-hashed ALT tokens, GT / field words), allele LUT against the site's hashes, GT / field vectors written
@@ -853,7 +921,7 @@ struct NtSite { uint32_t js, A_m, sflags, mref_len; const uint8_t* mref; };
 template <int NF, bool GT>
 __device__ __forceinline__ void nt_entry(const ArrayDev& A, const ScanDev& S, const BatchDev& B, const RemapOut& O, const NtSite& st,
                                          const uint16_t* __restrict__ s_jk, const unsigned long long* __restrict__ s_ah, int* m2in_row, int8_t* in2m_row,
-                                         const bool active, const uint2 ent, const int gl) {
+                                         const bool active, const uint2 ent, const int gl, const NtDst nd = NtDst{false, 0u, {nullptr, nullptr, nullptr, nullptr}, nullptr, 0u}) {
   const uint32_t js = st.js, A_m = st.A_m, mref_len = st.mref_len;
   const uint8_t* mref = st.mref;
   const bool nonref = st.sflags & 1u, remap = st.sflags & 2u, g_suppressed = st.sflags & 4u;
@@ -881,9 +949,9 @@ __device__ __forceinline__ void nt_entry(const ArrayDev& A, const ScanDev& S, co
 #pragma unroll
       for (int f = 0; f < NF; ++f) { const uint32_t n = dr->f_len[f]; fn[f] = n == 0xFFFFFFFFu ? 0u : n; fin[f] = S.del_words + dr->f_off[f]; }
     } else {
-      wv = warm_view(A, ent.y);
+      wv = warm_view(A, ent.y, (nd.blob_win && ent.y >= nd.win_lo) ? nd.blob_win + (size_t)(ent.y - nd.win_lo) * 4u : nullptr);
       n_alt = wv.n_alt; nr_idx = wv.nr_idx; gt_len = wv.gt_len; ploidy = wv.ploidy;
-      gt = wv.b + H0 + 3u * n_alt;
+      gt = wv.b + H0 + 3u * n_alt + wv.tok_words;
       const uint32_t* p = gt + gt_len;
 #pragma unroll
       for (int f = 0; f < NF; ++f) { fn[f] = wv.b[4 + f]; fin[f] = p; p += fn[f]; }
@@ -953,7 +1021,8 @@ __device__ __forceinline__ void nt_entry(const ArrayDev& A, const ScanDev& S, co
     const uint32_t n = fn[f]; const uint32_t* in = fin[f];
     uint32_t n_out = 0;
     if (n && !(kind == KIND_G && g_suppressed)) n_out = remap ? num_elements(kind, A_m - 1u, ploidy) : n;
-    const uint32_t stride = fo.stride[js]; uint32_t* dst = fo.data + fo.base[js] + (uint64_t)q * stride;
+    const uint32_t stride = fo.stride[js];
+    uint32_t* dst = nd.smem ? nd.tile[f] + (size_t)(q - nd.q0) * stride : fo.data + fo.base[js] + (uint64_t)q * stride;
     if (gl == 0) fo.len[sq] = (uint16_t)n_out;
     // s_m2in[m] = input allele of merged allele m (NON_REF fallback folded in), or -1; the diploid loop wants it packed
     // with its triangular number: a | a(a+1)/2 << 8 (still negative when there is no input allele)
@@ -1071,8 +1140,11 @@ __global__ void __launch_bounds__(TILE_ROWS) k_copy_tile(const __grid_constant__
 }
 
 // Remapped sites.  One block = 256 samples of one site; grid = (tiles, sites).
+#ifndef GDB_TILE_BLOCKS
+#define GDB_TILE_BLOCKS 5
+#endif
 template <int NF, bool GT>
-__global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
+__global__ void __launch_bounds__(TILE_ROWS, GDB_TILE_BLOCKS) k_remap_tile(const __grid_constant__ ArrayDev A, const __grid_constant__ ScanDev S, const __grid_constant__ BatchDev B,
                                                             const __grid_constant__ RemapOut O, const uint32_t* __restrict__ site_list, const TileTabs tabs) {
   __shared__ __align__(16) uint4 s_tri[TILE_ROWS * NF];     // per (sample, field): v0, v1, v2, pad
   __shared__ uint32_t s_info[TILE_ROWS * NF];               // per (sample, field): INFO_FAST or 0
@@ -1252,6 +1324,7 @@ __global__ void __launch_bounds__(TILE_ROWS, 5) k_remap_tile(const __grid_consta
     const NtSite st{js, A_m, sflags, site_g->ref_len, B.allele_bytes + site_g->ref_off};
     const int grp = (int)tid / NT_GL, gl = (int)tid % NT_GL;
     for (uint32_t base = 0; base < n_ntl; base += NT_GROUPS) {
+      if (base + (tid & ~31u) / NT_GL >= n_ntl) break;   // none of this warp's groups has an entry (warp-uniform)
       const bool active = base + grp < n_ntl;
       const uint2 ent = active ? s_ntl[base + grp] : make_uint2(0u, 0u);
       nt_entry<NF, GT>(A, S, B, O, st, s_jk, s_ah, s_m2in[grp], s_in2m[grp], active, ent, gl);
@@ -1271,6 +1344,7 @@ __global__ void __launch_bounds__(NT_THREADS) k_remap_nt(const __grid_constant__
   const uint2 bm = blk_map[blockIdx.x];
   const SiteRec* __restrict__ site_g = &B.sites[bm.x];
   const NtSite st{bm.x, site_g->n_alleles, site_g->flags, site_g->ref_len, B.allele_bytes + site_g->ref_off};
+
   const uint32_t ei = bm.y + grp;
   const bool active = ei < site_g->n_nt;
   uint2 ent = make_uint2(0, 0);
