@@ -25,7 +25,7 @@ KIND = {"R": LEN_R, "A": LEN_A, "G": LEN_G}
 
 EXPORTS = ["gdbgpu_version", "gdbgpu_ctx_create", "gdbgpu_ctx_destroy", "gdbgpu_last_error", "gdbgpu_ctx_stream",
            "gdbgpu_ctx_launch_count", "gdbgpu_ctx_synchronize", "gdbgpu_ctx_release_cached_memory", "gdbgpu_ctx_set_profiling",
-           "gdbgpu_ctx_reset_kernel_stats", "gdbgpu_ctx_kernel_stats", "gdbgpu_array_open", "gdbgpu_array_open_ex", "gdbgpu_array_from_columns", "gdbgpu_array_get_info",
+           "gdbgpu_ctx_reset_kernel_stats", "gdbgpu_ctx_kernel_stats", "gdbgpu_array_open", "gdbgpu_array_open_ex", "gdbgpu_array_open_range", "gdbgpu_array_from_columns", "gdbgpu_array_get_info",
            "gdbgpu_array_copy_cells", "gdbgpu_array_close", "gdbgpu_scan_begin", "gdbgpu_scan_get_info",
            "gdbgpu_scan_next_batch", "gdbgpu_scan_seek", "gdbgpu_scan_end", "gdbgpu_scan_cells", "gdbgpu_scan_cells_histogram",
            "gdbgpu_scan_cells_allele_counts", "gdbgpu_scan_cells_fetch", "gdbgpu_scan_cells_window"]
@@ -125,6 +125,8 @@ def lib():
                                         C.POINTER(C.c_void_p)]
         L.gdbgpu_array_open_ex.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(FieldDesc), C.c_int32,
                                            C.POINTER(PlainFieldDesc), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.gdbgpu_array_open_range.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(FieldDesc), C.c_int32,
+                                              C.POINTER(PlainFieldDesc), C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
         L.gdbgpu_array_from_columns.argtypes = [C.c_void_p, C.POINTER(Columns), C.POINTER(C.c_void_p)]
         L.gdbgpu_array_get_info.argtypes = [C.c_void_p, C.POINTER(ArrayInfo)]
         L.gdbgpu_array_copy_cells.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -226,12 +228,17 @@ class Array:
         self.ctx, self.h, self._keep = ctx, handle, keep
 
     @classmethod
-    def open(cls, ctx, workspace, array_name, fields, gt_phased=False, plain=()):
+    def open(cls, ctx, workspace, array_name, fields, gt_phased=False, plain=(), col_range=None):
+        """col_range=(lo, hi): stage only the tiles that can hold cells of those columns (gdbgpu_array_open_range)"""
         h = C.c_void_p()
         fd = _field_descs(fields)
         pd = _plain_descs(list(plain))
-        ctx.check(lib().gdbgpu_array_open_ex(ctx.h, workspace.encode(), array_name.encode(), fd, len(fields), pd, len(plain),
-                                             int(gt_phased), C.byref(h)))
+        if col_range is None:
+            ctx.check(lib().gdbgpu_array_open_ex(ctx.h, workspace.encode(), array_name.encode(), fd, len(fields), pd, len(plain),
+                                                 int(gt_phased), C.byref(h)))
+        else:
+            ctx.check(lib().gdbgpu_array_open_range(ctx.h, workspace.encode(), array_name.encode(), fd, len(fields), pd, len(plain),
+                                                    int(gt_phased), int(col_range[0]), int(col_range[1]), C.byref(h)))
         return cls(ctx, h)
 
     @classmethod

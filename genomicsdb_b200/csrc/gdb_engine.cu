@@ -109,6 +109,13 @@ struct DevBuf {
   }
   void ensure(size_t count) { if (count > n) alloc(count + count / 4 + 16); }
   size_t bytes() const { return n * sizeof(T); }
+  // takes over the block of another buffer (any element type) as `count` elements: no copy, the source is left empty
+  template <class U> void adopt(DevBuf<U>& src, size_t count) {
+    release();
+    if (count * sizeof(T) > src.cap) throw std::runtime_error("internal: adopted block is too small");
+    p = reinterpret_cast<T*>(src.p); n = count; cap = src.cap; owner = src.owner;
+    src.p = nullptr; src.n = 0; src.cap = 0;
+  }
 };
 template <class T>
 struct PinBuf {
@@ -158,6 +165,13 @@ __global__ void k_bounds(const int64_t* coords, uint64_t n, int64_t q_lo, int64_
   while (lo < hi) { uint64_t mid = (lo + hi) >> 1; int64_t c = coords[2 * mid + 1]; if (strict ? (c <= key) : (c < key)) lo = mid + 1; else hi = mid; }
   out[t] = lo;
 }
+// rows of the staged array without any cell at or after column `col` (tile-range staging, gdbgpu_array_open_range)
+__global__ void k_rows_without_cells(ArrayDev A, int64_t col_lo, uint32_t* __restrict__ count) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= A.num_rows) return;
+  const uint64_t lo = A.row_start[r], hi = A.row_start[r + 1];
+  if (lo == hi || A.rs_col[hi - 1] < col_lo) atomicAdd(count, 1u);
+}
 __global__ void k_add_u64(uint64_t* p, uint64_t n, uint64_t add) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] += add; }
 __global__ void k_gather_bytes(const uint8_t* in, const uint32_t* perm, uint64_t n, uint32_t cell_bytes, uint8_t* out) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,6 +189,9 @@ struct HostCols {
 struct PlainMeta { std::string name; int32_t elem, fixed_len; int32_t no_format = 0, info_op = 0; };
 
 struct DevVar { DevBuf<uint64_t> off; DevBuf<uint8_t> val; uint64_t bytes = 0; };
+// a column that gdbgpu_array_open* has already placed (and inflated) in HBM: the fixed part (values, or the n + 1 value
+// offsets of a variable attribute) and the value stream.  build_array takes the blocks over instead of copying them.
+struct DevColumn { DevBuf<uint8_t> fixed, var; uint64_t var_bytes = 0; };
 
 }  // namespace
 
@@ -280,8 +297,10 @@ void gather_var(gdbgpu_ctx* ctx, const DevVar& in, const uint32_t* src, uint64_t
 
 // stage columns (already concatenated over fragments; host memory, or HBM when the tiles were inflated on the device) and
 // build the per-array indexes
+// `owned` (gdbgpu_array_open*): the same columns, already in HBM, in the order coords, END, REF, ALT, [GT], fields, plain fields
 gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<uint64_t>& frag_cells, int64_t lb_row, int64_t num_rows, int gt_phased,
-                          const std::vector<FieldMeta>& fm, const std::vector<std::string>& names, const std::vector<PlainMeta>& pm = {}) {
+                          const std::vector<FieldMeta>& fm, const std::vector<std::string>& names, const std::vector<PlainMeta>& pm = {},
+                          std::vector<DevColumn>* owned = nullptr) {
   static const bool trace = getenv("GDBGPU_TRACE") != nullptr;   // phase times of the staging on stderr
   auto t_prev = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -300,24 +319,48 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
   a->ctx = ctx; a->n = h.n; a->lb_row = lb_row; a->num_rows = num_rows; a->gt_phased = gt_phased; a->has_gt = h.has_gt; a->fm = fm; a->field_names = names;
   a->n_fragments = (uint32_t)std::max<size_t>(1, frag_cells.size());
   uint64_t n = h.n;
-  a->coords.alloc(std::max<uint64_t>(2 * n, 2)); a->end.alloc(std::max<uint64_t>(n, 1));
-  if (n) { CK(cudaMemcpyAsync(a->coords.p, h.coords, n * 16, cudaMemcpyDefault, ctx->stream)); CK(cudaMemcpyAsync(a->end.p, h.end, n * 8, cudaMemcpyDefault, ctx->stream)); }
-  a->staged_bytes = n * 24;
-  upload_var(ctx, h.ref, n, a->ref, a->staged_bytes);
-  upload_var(ctx, h.alt, n, a->alt, a->staged_bytes);
-  if (h.has_gt) upload_var(ctx, h.gt, n, a->gt, a->staged_bytes);
-  for (auto& f : h.fields) { a->fields.emplace_back(new DevVar()); upload_var(ctx, f, n, *a->fields.back(), a->staged_bytes); }
-  for (size_t f = 0; f < h.plain.size(); ++f) {
-    a->plain.emplace_back(new DevVar());
-    if (!pm[f].fixed_len) { upload_var(ctx, h.plain[f], n, *a->plain.back(), a->staged_bytes); continue; }
-    DevVar& d = *a->plain.back();
-    d.bytes = h.plain[f].bytes;
-    if (d.bytes != n * (uint64_t)pm[f].fixed_len * (pm[f].elem == ELEM_CHAR ? 1u : 4u)) throw ArgError("plain field " + pm[f].name + ": value bytes do not match n_cells x fixed_len");
-    d.val.alloc(std::max<uint64_t>(d.bytes, 1));
-    if (d.bytes) CK(cudaMemcpyAsync(d.val.p, h.plain[f].val, d.bytes, cudaMemcpyDefault, ctx->stream));
-    a->staged_bytes += d.bytes;
+  if (owned) {
+    // the columns lie in HBM already: take the blocks over (a variable attribute's fixed block has room for the sentinel offset)
+    size_t k = 0;
+    auto take_var = [&](DevVar& d) {
+      DevColumn& c = (*owned)[k++];
+      d.bytes = c.var_bytes;
+      d.off.adopt(c.fixed, n + 1); d.val.adopt(c.var, std::max<uint64_t>(c.var_bytes, 1));
+      CK(cudaMemcpyAsync(d.off.p + n, &d.bytes, 8, cudaMemcpyHostToDevice, ctx->stream));
+    };
+    a->coords.adopt((*owned)[k++].fixed, std::max<uint64_t>(2 * n, 2));
+    a->end.adopt((*owned)[k++].fixed, std::max<uint64_t>(n, 1));
+    take_var(a->ref); take_var(a->alt);
+    if (h.has_gt) take_var(a->gt);
+    for (size_t f = 0; f < h.fields.size(); ++f) { a->fields.emplace_back(new DevVar()); take_var(*a->fields.back()); }
+    for (size_t f = 0; f < h.plain.size(); ++f) {
+      a->plain.emplace_back(new DevVar());
+      if (!pm[f].fixed_len) { take_var(*a->plain.back()); continue; }
+      DevVar& d = *a->plain.back();
+      d.bytes = n * (uint64_t)pm[f].fixed_len * (pm[f].elem == ELEM_CHAR ? 1u : 4u);
+      d.val.adopt((*owned)[k++].fixed, std::max<uint64_t>(d.bytes, 1));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));   // (the sentinels came from stack variables)
+  } else {
+    a->coords.alloc(std::max<uint64_t>(2 * n, 2)); a->end.alloc(std::max<uint64_t>(n, 1));
+    if (n) { CK(cudaMemcpyAsync(a->coords.p, h.coords, n * 16, cudaMemcpyDefault, ctx->stream)); CK(cudaMemcpyAsync(a->end.p, h.end, n * 8, cudaMemcpyDefault, ctx->stream)); }
+    a->staged_bytes = n * 24;
+    upload_var(ctx, h.ref, n, a->ref, a->staged_bytes);
+    upload_var(ctx, h.alt, n, a->alt, a->staged_bytes);
+    if (h.has_gt) upload_var(ctx, h.gt, n, a->gt, a->staged_bytes);
+    for (auto& f : h.fields) { a->fields.emplace_back(new DevVar()); upload_var(ctx, f, n, *a->fields.back(), a->staged_bytes); }
+    for (size_t f = 0; f < h.plain.size(); ++f) {
+      a->plain.emplace_back(new DevVar());
+      if (!pm[f].fixed_len) { upload_var(ctx, h.plain[f], n, *a->plain.back(), a->staged_bytes); continue; }
+      DevVar& d = *a->plain.back();
+      d.bytes = h.plain[f].bytes;
+      if (d.bytes != n * (uint64_t)pm[f].fixed_len * (pm[f].elem == ELEM_CHAR ? 1u : 4u)) throw ArgError("plain field " + pm[f].name + ": value bytes do not match n_cells x fixed_len");
+      d.val.alloc(std::max<uint64_t>(d.bytes, 1));
+      if (d.bytes) CK(cudaMemcpyAsync(d.val.p, h.plain[f].val, d.bytes, cudaMemcpyDefault, ctx->stream));
+      a->staged_bytes += d.bytes;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
   }
-  CK(cudaStreamSynchronize(ctx->stream));
   lap("upload");
 
   if (frag_cells.size() > 1 && n) {   // K1
@@ -571,8 +614,10 @@ void scan_prepare(gdbgpu_scan* s) {
   if (S.scan_full) { S.q_lo = a->min_col; S.q_hi = hi_data; }
   else { S.q_lo = p.col_lo; S.q_hi = std::min(p.col_hi, hi_data); if (p.col_lo > p.col_hi) throw ArgError("col_lo > col_hi"); }
   if (S.q_lo > S.q_hi) return;
-  S.base = S.q_lo;
-  S.span_bits = (uint64_t)(S.q_hi - S.base) + 2ull;
+  // bit 0 of the breakpoint bitmap stands for q_lo itself (gdb_kernels.cuh: bp_bit); every other breakpoint is a begin column
+  // of a staged cell, or one past a (clipped) end, hence at or after min(first staged column, q_hi + 1)
+  S.base = std::max(S.q_lo, std::min(a->min_col - 1, S.q_hi));
+  S.span_bits = (uint64_t)(S.q_hi - S.base) + 3ull;
   if (S.span_bits > (1ull << 37)) throw LimitError("query column span above 2^37 positions: split the interval");
   S.n_words = (S.span_bits + 63) / 64;
   // forward range
@@ -1436,7 +1481,11 @@ int gdbgpu_array_open(gdbgpu_ctx* ctx, const char* workspace, const char* array_
 }
 int gdbgpu_array_open_ex(gdbgpu_ctx* ctx, const char* workspace, const char* array_name, const gdbgpu_field_desc* fields, int32_t n_fields,
                          const gdbgpu_plain_field_desc* plain, int32_t n_plain, int32_t gt_phased, gdbgpu_array** out) {
-  if (!ctx || !workspace || !array_name || !out || n_fields < 0 || n_plain < 0 || n_plain > MAX_PLAIN || (n_plain && !plain)) return GDBGPU_ERR_ARG;
+  return gdbgpu_array_open_range(ctx, workspace, array_name, fields, n_fields, plain, n_plain, gt_phased, INT64_MIN, INT64_MAX, out);
+}
+int gdbgpu_array_open_range(gdbgpu_ctx* ctx, const char* workspace, const char* array_name, const gdbgpu_field_desc* fields, int32_t n_fields,
+                            const gdbgpu_plain_field_desc* plain, int32_t n_plain, int32_t gt_phased, int64_t col_lo, int64_t col_hi, gdbgpu_array** out) {
+  if (!ctx || !workspace || !array_name || !out || n_fields < 0 || n_plain < 0 || n_plain > MAX_PLAIN || (n_plain && !plain) || col_lo > col_hi) return GDBGPU_ERR_ARG;
   *out = nullptr;
   return guarded(ctx, [&] {
     CK(cudaSetDevice(ctx->device));
@@ -1466,94 +1515,126 @@ int gdbgpu_array_open_ex(gdbgpu_ctx* ctx, const char* workspace, const char* arr
       if (plain[f].info_op && ((plain[f].info_op != GDBGPU_INFO_ELEMENT_WISE_SUM && fixed < 1) || plain[f].elem_type == GDBGPU_ELEM_CHAR)) throw std::runtime_error(std::string("an INFO combine operation needs a 4-byte field (fixed-length unless element-wise): ") + plain[f].name);
       pm.push_back(PlainMeta{plain[f].name, plain[f].elem_type, fixed, plain[f].no_format, plain[f].info_op});
     }
-    // Every needed column of every fragment goes to HBM as it lies on disk; compressed tiles are inflated there (k_inflate,
-    // one thread per zlib stream), straight into the column's place in the concatenation over fragments.  Var offsets of
-    // later fragments are rebased onto the concatenated value stream.
-    const size_t nfrag = ta.num_fragments();
-    std::vector<uint64_t> frag_cells;
-    uint64_t n_total = 0;
-    for (size_t fi = 0; fi < nfrag; ++fi) { frag_cells.push_back((uint64_t)ta.fragment(fi).bk.cell_num); n_total += frag_cells.back(); }
-    uint64_t file_bytes_staged = 0;   // bytes that crossed PCIe: the files as they lie on disk
-    struct DevColumn { DevBuf<uint8_t> fixed, var; uint64_t var_bytes = 0; };
-    std::vector<DevColumn> cols(ids.size());
-    // compressed files of all attributes are collected first: ONE copy of their bytes, ONE k_inflate launch over every tile
-    struct Pending { size_t arena_off; const std::vector<TdbTileSpan>* tiles; uint8_t* dst; };
-    std::vector<std::vector<TdbRawColumn>> raw(ids.size(), std::vector<TdbRawColumn>(nfrag));
-    std::vector<Pending> pending;
-    size_t arena_bytes = 0, n_jobs = 0;
-    struct Rebase { uint64_t* p; uint64_t n, add; };
-    std::vector<Rebase> rebases;
-    for (size_t k = 0; k < ids.size(); ++k) {
-      uint64_t fixed_total = 0, var_total = 0;
-      for (size_t fi = 0; fi < nfrag; ++fi) { ta.read_column_raw(fi, ids[k], raw[k][fi]); fixed_total += raw[k][fi].fixed_bytes; var_total += raw[k][fi].var_bytes; }
-      DevColumn& dc = cols[k];
-      dc.fixed.alloc(std::max<uint64_t>(fixed_total, 1)); dc.var.alloc(std::max<uint64_t>(var_total, 1)); dc.var_bytes = var_total;
-      uint64_t fixed_at = 0, var_at = 0, cells_at = 0;
-      for (size_t fi = 0; fi < nfrag; ++fi) {
-        const TdbRawColumn& r = raw[k][fi];
-        auto place = [&](const std::vector<uint8_t>& file, const std::vector<TdbTileSpan>& tiles, uint64_t bytes, uint8_t* dst) {
-          if (!bytes) return;
-          file_bytes_staged += r.compressed ? file.size() : bytes;
-          if (!r.compressed) { CK(cudaMemcpyAsync(dst, file.data(), bytes, cudaMemcpyHostToDevice, ctx->stream)); return; }
-          pending.push_back(Pending{arena_bytes, &tiles, dst});
-          arena_bytes += (file.size() + 15) & ~(size_t)15; n_jobs += tiles.size();
-          (void)file;
-        };
-        place(r.fixed_file, r.fixed_tiles, r.fixed_bytes, dc.fixed.p + fixed_at);
-        if (r.is_var) {
-          place(r.var_file, r.var_tiles, r.var_bytes, dc.var.p + var_at);
-          if (var_at) rebases.push_back(Rebase{reinterpret_cast<uint64_t*>(dc.fixed.p) + cells_at, frag_cells[fi], var_at});
-        }
-        fixed_at += r.fixed_bytes; var_at += r.var_bytes; cells_at += frag_cells[fi];
-      }
-    }
-    if (n_jobs) {
-      DevBuf<uint8_t> arena; DevBuf<InflateJob> d_jobs; DevBuf<uint32_t> inf_err;
-      arena.alloc(arena_bytes); d_jobs.alloc(n_jobs); inf_err.alloc(2);
-      CK(cudaMemsetAsync(inf_err.p, 0, 8, ctx->stream));
-      std::vector<InflateJob> jobs; jobs.reserve(n_jobs);
-      size_t pi = 0;
-      for (size_t k = 0; k < ids.size(); ++k) for (size_t fi = 0; fi < nfrag; ++fi) {
-        const TdbRawColumn& r = raw[k][fi];
-        if (!r.compressed) continue;
-        for (int part = 0; part < 2; ++part) {
-          const std::vector<uint8_t>& file = part ? r.var_file : r.fixed_file;
-          const uint64_t bytes = part ? r.var_bytes : r.fixed_bytes;
-          if ((part && !r.is_var) || !bytes) continue;
-          const Pending& pd = pending[pi++];
-          CK(cudaMemcpyAsync(arena.p + pd.arena_off, file.data(), file.size(), cudaMemcpyHostToDevice, ctx->stream));
-          for (const TdbTileSpan& t : *pd.tiles) jobs.push_back(InflateJob{arena.p + pd.arena_off + t.in_off, t.in_len, pd.dst + t.out_off, t.out_len});
-        }
-      }
-      CK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(InflateJob), cudaMemcpyHostToDevice, ctx->stream));
-      LAUNCH(ctx, k_inflate, blocks_for(jobs.size(), 64), 64, d_jobs.p, (uint64_t)jobs.size(), inf_err.p);
-      uint32_t e[2] = {0, 0};
-      CK(cudaMemcpyAsync(e, inf_err.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
-      if (e[0]) throw std::runtime_error("zlib stream of tile " + std::to_string(e[1]) + " does not inflate (" +
-                                         (e[0] == INF_ERR_HEADER ? "bad header" : e[0] == INF_ERR_SIZE ? "size mismatch" : e[0] == INF_ERR_ADLER ? "Adler-32 mismatch" : "corrupt data") + ")");
-    }
-    for (const Rebase& rb : rebases) LAUNCH(ctx, k_add_u64, blocks_for(rb.n, 256), 256, rb.p, rb.n, rb.add);
-    CK(cudaStreamSynchronize(ctx->stream));   // the host file buffers (pageable) may go once every copy has run
-    raw.clear();
-    HostCols h; h.n = n_total;
-    h.coords = reinterpret_cast<const int64_t*>(cols[0].fixed.p); h.end = reinterpret_cast<const int64_t*>(cols[1].fixed.p);
-    auto hv = [&](size_t k) { return HostVar{reinterpret_cast<const uint64_t*>(cols[k].fixed.p), cols[k].var.p, cols[k].var_bytes}; };
-    h.ref = hv(2); h.alt = hv(3);
-    size_t k = 4;
-    h.has_gt = id_gt >= 0;
-    if (h.has_gt) h.gt = hv(k++);
-    for (int f = 0; f < n_fields; ++f) h.fields.push_back(hv(k++));
-    for (int f = 0; f < n_plain; ++f, ++k) h.plain.push_back(pm[f].fixed_len ? HostVar{nullptr, cols[k].fixed.p, (uint64_t)n_total * pm[f].fixed_len * (pm[f].elem == ELEM_CHAR ? 1u : 4u)} : hv(k));
     int64_t lb = 0, ub = 0;
-    if (!ta.row_bounds(lb, ub)) {   // no GenomicsDB metadata: bound by the data
-      std::vector<int64_t> hc(2 * n_total);
-      if (n_total) CK(cudaMemcpy(hc.data(), h.coords, n_total * 16, cudaMemcpyDeviceToHost));
-      ub = -1;
-      for (uint64_t i = 0; i < n_total; ++i) ub = std::max(ub, hc[2 * i]);
+    const bool have_rows = ta.row_bounds(lb, ub);
+    const size_t nfrag = ta.num_fragments();
+    const bool whole = col_lo == INT64_MIN && col_hi == INT64_MAX;
+    // Tiles to stage, per fragment: those whose bounding coordinates overlap the column range -- the
+    // book-keeping's first / last cell of every tile, bisected.  A call that spans the range's left edge is found through its
+    // END copy (gt_get_column scans forward from col_lo until every row has shown a cell); when a row shows no cell inside
+    // the staged tiles the range grows to the right, tiles doubling, until every row has or the fragments end.
+    std::vector<int64_t> t0(nfrag, 0), t1(nfrag, 0);
+    for (size_t fi = 0; fi < nfrag; ++fi) {
+      if (whole) { t0[fi] = 0; t1[fi] = ta.fragment(fi).bk.tile_num; }
+      else ta.tile_range(fi, col_lo, col_hi, t0[fi], t1[fi]);
     }
-    *out = build_array(ctx, h, frag_cells, lb, ub - lb + 1, gt_phased, fm, names, pm);
-    (*out)->staged_bytes = file_bytes_staged;
+    for (;;) {
+      std::vector<uint64_t> frag_cells;
+      uint64_t n_total = 0;
+      bool more_to_the_right = false;
+      for (size_t fi = 0; fi < nfrag; ++fi) {
+        frag_cells.push_back((uint64_t)ta.tile_cells(fi, t0[fi], t1[fi])); n_total += frag_cells.back();
+        if (t1[fi] < ta.fragment(fi).bk.tile_num) more_to_the_right = true;
+      }
+      // Every needed column of every fragment goes to HBM as it lies on disk; compressed tiles are inflated there (k_inflate,
+      // one thread per zlib stream), straight into the column's place in the concatenation over fragments.  Var offsets are
+      // rebased onto the concatenated value stream.
+      uint64_t file_bytes_staged = 0;   // bytes that crossed PCIe: the files' tiles as they lie on disk
+      std::vector<DevColumn> cols(ids.size());
+      // compressed files of all attributes are collected first: ONE copy of their bytes, ONE k_inflate launch over every tile
+      struct Pending { size_t arena_off; const std::vector<TdbTileSpan>* tiles; uint8_t* dst; };
+      std::vector<std::vector<TdbRawColumn>> raw(ids.size(), std::vector<TdbRawColumn>(nfrag));
+      std::vector<Pending> pending;
+      size_t arena_bytes = 0, n_jobs = 0;
+      struct Rebase { uint64_t* p; uint64_t n, add; };
+      std::vector<Rebase> rebases;
+      for (size_t k = 0; k < ids.size(); ++k) {
+        uint64_t fixed_total = 0, var_total = 0;
+        for (size_t fi = 0; fi < nfrag; ++fi) { ta.read_column_raw(fi, ids[k], raw[k][fi], t0[fi], t1[fi]); fixed_total += raw[k][fi].fixed_bytes; var_total += raw[k][fi].var_bytes; }
+        DevColumn& dc = cols[k];
+        dc.fixed.alloc(std::max<uint64_t>(fixed_total, 1) + 16); dc.var.alloc(std::max<uint64_t>(var_total, 1)); dc.var_bytes = var_total;
+        uint64_t fixed_at = 0, var_at = 0, cells_at = 0;
+        for (size_t fi = 0; fi < nfrag; ++fi) {
+          const TdbRawColumn& r = raw[k][fi];
+          auto place = [&](const std::vector<uint8_t>& file, const std::vector<TdbTileSpan>& tiles, uint64_t bytes, uint8_t* dst) {
+            if (!bytes) return;
+            file_bytes_staged += r.compressed ? file.size() : bytes;
+            if (!r.compressed) { CK(cudaMemcpyAsync(dst, file.data(), bytes, cudaMemcpyHostToDevice, ctx->stream)); return; }
+            pending.push_back(Pending{arena_bytes, &tiles, dst});
+            arena_bytes += (file.size() + 15) & ~(size_t)15; n_jobs += tiles.size();
+          };
+          place(r.fixed_file, r.fixed_tiles, r.fixed_bytes, dc.fixed.p + fixed_at);
+          if (r.is_var) {
+            place(r.var_file, r.var_tiles, r.var_bytes, dc.var.p + var_at);
+            if (var_at != r.var_base && frag_cells[fi]) rebases.push_back(Rebase{reinterpret_cast<uint64_t*>(dc.fixed.p) + cells_at, frag_cells[fi], var_at - r.var_base});
+          }
+          fixed_at += r.fixed_bytes; var_at += r.var_bytes; cells_at += frag_cells[fi];
+        }
+      }
+      if (n_jobs) {
+        DevBuf<uint8_t> arena; DevBuf<InflateJob> d_jobs; DevBuf<uint32_t> inf_err;
+        arena.alloc(arena_bytes); d_jobs.alloc(n_jobs); inf_err.alloc(2);
+        CK(cudaMemsetAsync(inf_err.p, 0, 8, ctx->stream));
+        std::vector<InflateJob> jobs; jobs.reserve(n_jobs);
+        size_t pi = 0;
+        for (size_t k = 0; k < ids.size(); ++k) for (size_t fi = 0; fi < nfrag; ++fi) {
+          const TdbRawColumn& r = raw[k][fi];
+          if (!r.compressed) continue;
+          for (int part = 0; part < 2; ++part) {
+            const std::vector<uint8_t>& file = part ? r.var_file : r.fixed_file;
+            const uint64_t bytes = part ? r.var_bytes : r.fixed_bytes;
+            if ((part && !r.is_var) || !bytes) continue;
+            const Pending& pd = pending[pi++];
+            CK(cudaMemcpyAsync(arena.p + pd.arena_off, file.data(), file.size(), cudaMemcpyHostToDevice, ctx->stream));
+            for (const TdbTileSpan& t : *pd.tiles) jobs.push_back(InflateJob{arena.p + pd.arena_off + t.in_off, t.in_len, pd.dst + t.out_off, t.out_len});
+          }
+        }
+        CK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(InflateJob), cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(ctx, k_inflate, blocks_for(jobs.size(), 64), 64, d_jobs.p, (uint64_t)jobs.size(), inf_err.p);
+        uint32_t e[2] = {0, 0};
+        CK(cudaMemcpyAsync(e, inf_err.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (e[0]) throw std::runtime_error("zlib stream of tile " + std::to_string(e[1]) + " does not inflate (" +
+                                           (e[0] == INF_ERR_HEADER ? "bad header" : e[0] == INF_ERR_SIZE ? "size mismatch" : e[0] == INF_ERR_ADLER ? "Adler-32 mismatch" : "corrupt data") + ")");
+      }
+      for (const Rebase& rb : rebases) LAUNCH(ctx, k_add_u64, blocks_for(rb.n, 256), 256, rb.p, rb.n, rb.add);
+      CK(cudaStreamSynchronize(ctx->stream));   // the host file buffers (pageable) may go once every copy has run
+      raw.clear();
+      HostCols h; h.n = n_total;
+      h.coords = reinterpret_cast<const int64_t*>(cols[0].fixed.p); h.end = reinterpret_cast<const int64_t*>(cols[1].fixed.p);
+      auto hv = [&](size_t k) { return HostVar{reinterpret_cast<const uint64_t*>(cols[k].fixed.p), cols[k].var.p, cols[k].var_bytes}; };
+      h.ref = hv(2); h.alt = hv(3);
+      size_t k = 4;
+      h.has_gt = id_gt >= 0;
+      if (h.has_gt) h.gt = hv(k++);
+      for (int f = 0; f < n_fields; ++f) h.fields.push_back(hv(k++));
+      for (int f = 0; f < n_plain; ++f, ++k) h.plain.push_back(pm[f].fixed_len ? HostVar{nullptr, cols[k].fixed.p, (uint64_t)n_total * pm[f].fixed_len * (pm[f].elem == ELEM_CHAR ? 1u : 4u)} : hv(k));
+      if (!have_rows) {   // no GenomicsDB metadata: bound by the data
+        std::vector<int64_t> hc(2 * n_total);
+        if (n_total) CK(cudaMemcpy(hc.data(), h.coords, n_total * 16, cudaMemcpyDeviceToHost));
+        ub = -1;
+        for (uint64_t i = 0; i < n_total; ++i) ub = std::max(ub, hc[2 * i]);
+      }
+      std::unique_ptr<gdbgpu_array> arr(build_array(ctx, h, frag_cells, lb, ub - lb + 1, gt_phased, fm, names, pm, &cols));
+      arr->staged_bytes = file_bytes_staged;
+      if (!whole && more_to_the_right && arr->num_rows > 0) {
+        // a query may begin anywhere inside the range: the call live at its left edge is found through the row's first cell
+        // at or after that edge (gt_get_column, query_variants.cc:845-941), so every row has to show a cell at or after col_hi
+        DevBuf<uint32_t> unseen; unseen.alloc(1);
+        CK(cudaMemsetAsync(unseen.p, 0, 4, ctx->stream));
+        LAUNCH(ctx, k_rows_without_cells, blocks_for((uint64_t)arr->num_rows, 256), 256, arr->dev, col_hi, unseen.p);
+        uint32_t h_unseen = 0;
+        CK(cudaMemcpyAsync(&h_unseen, unseen.p, 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+        if (h_unseen) {
+          tl_ctx = ctx;
+          arr.reset();
+          for (size_t fi = 0; fi < nfrag; ++fi) t1[fi] = std::min<int64_t>(ta.fragment(fi).bk.tile_num, t1[fi] + std::max<int64_t>(16, t1[fi] - t0[fi]));
+          continue;
+        }
+      }
+      *out = arr.release();
+      return;
+    }
   });
 }
 

@@ -135,6 +135,22 @@ void GA4GHOperator::operate(Variant& variant, const VariantQueryConfig& query_co
   SingleVariantOperatorBase::operate(variant, query_config);
   m_max_diploid_alt_alleles_that_can_be_genotyped = query_config.get_max_diploid_alt_alleles_that_can_be_genotyped();
   m_remapped_variant = &variant;
+  if (variant.g_suppressed_) warn_too_many_alleles(query_config, variant.get_column_begin(), (unsigned)m_merged_alt_alleles.size());
+}
+// variant_operations.cc:613-629: one line on stderr per genotype-length field that is dropped at a site with more ALT
+// alleles than can be genotyped (the kernels dropped it: GDBGPU_SITE_G_SUPPRESSED)
+void GA4GHOperator::warn_too_many_alleles(const VariantQueryConfig& query_config, int64_t column, unsigned num_alt) const {
+  const VidMapper& vid = query_config.get_vid_mapper();
+  for (unsigned i = 0; i < query_config.get_num_remapped_fields(); ++i) {
+    const FieldInfo* fi = vid.get_field_info(query_config.get_remapped_field_name(i));
+    if (!fi || fi->length != "G") continue;
+    const ContigInfo* contig = vid.get_contig_location(column);
+    if (contig) std::cerr << "Chromosome " << contig->name << " position " << column - contig->tiledb_column_offset + 1 << " (";
+    std::cerr << "TileDB column " << column;
+    if (contig) std::cerr << ")";
+    std::cerr << " has too many alleles in the combined VCF record : " << num_alt << " : current limit : " << m_max_diploid_alt_alleles_that_can_be_genotyped
+              << ". Fields, such as  PL, with length equal to the number of genotypes will NOT be added for this location.\n";
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ VCFAdapter
@@ -312,6 +328,10 @@ void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint3
   const uint64_t nq = b.n_query_rows, ns = b.n_sites;
   const bool sites_only = qc.sites_only_query();   // no samples in the header, no FORMAT fields (broad_combined_gvcf.cc:178-182,302-318)
   const int64_t begin = b.site_begin[s], end = b.site_end[s];
+  if (b.site_flags[s] & GDBGPU_SITE_G_SUPPRESSED) {
+    m_max_diploid_alt_alleles_that_can_be_genotyped = qc.get_max_diploid_alt_alleles_that_can_be_genotyped();
+    warn_too_many_alleles(qc, begin, b.n_alleles[s] - 1u);
+  }
   const ContigInfo* contig = m_vid_mapper->get_contig_location(begin);
   if (!contig) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Unknown contig for position " + std::to_string(begin));
   const int rid = m_vcf_adapter->get_contig_id(contig->name);

@@ -193,6 +193,7 @@ class Variant {
  private:
   friend class VariantQueryProcessor;
   friend class SingleVariantOperatorBase;
+  friend class GA4GHOperator;
   int64_t begin_ = 0, end_ = 0;
   std::vector<VariantCall> calls_;
   // merged-site results of the kernels, picked up by SingleVariantOperatorBase::operate
@@ -253,6 +254,7 @@ class GA4GHOperator : public SingleVariantOperatorBase {
   const Variant& get_remapped_variant() const { return *m_remapped_variant; }
   bool too_many_alt_alleles_for_genotype_length_fields(unsigned num_alt_alleles) const { return num_alt_alleles > m_max_diploid_alt_alleles_that_can_be_genotyped; }
  protected:
+  void warn_too_many_alleles(const VariantQueryConfig& query_config, int64_t column, unsigned num_alt) const;
   const Variant* m_remapped_variant = nullptr;
   unsigned m_max_diploid_alt_alleles_that_can_be_genotyped = 50;
 };

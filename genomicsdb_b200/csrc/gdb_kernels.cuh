@@ -366,15 +366,20 @@ __device__ inline int32_t qrow_of(const ArrayDev& A, const ScanDev& S, int64_t r
   if (r < 0 || r >= A.num_rows) return -1;
   return S.qrow_of_row ? S.qrow_of_row[r] : (int32_t)r;
 }
+// Bitmap of breakpoints: bit 0 stands for q_lo, bit 1 + (p - base) for position p >= base, where base = q_lo clamped to just
+// below the first column of the staged data -- a query that begins far to the left of the data ([0, 1e9] over one contig)
+// does not pay for the empty stretch.  (When q_lo >= that column, base = q_lo and bit 0 is never set.)
+__device__ inline uint64_t bp_bit(const ScanDev& S, int64_t pos) { return pos >= S.base ? (uint64_t)(pos - S.base) + 1ull : 0ull; }
+__device__ inline int64_t bp_pos(const ScanDev& S, uint64_t bit) { return bit == 0 ? S.q_lo : S.base + (int64_t)(bit - 1ull); }
 __device__ inline uint64_t bp_rank(const ScanDev& S, int64_t pos) {
-  uint64_t bit = (uint64_t)(pos - S.base);
+  uint64_t bit = bp_bit(S, pos);
   uint64_t w = bit >> 6;
   unsigned long long word = S.bitmap[w];
   unsigned long long below = word & ((1ull << (bit & 63)) - 1ull);
   return (uint64_t)S.word_rank[w] + (uint64_t)__popcll(below);
 }
 __device__ inline void set_bit(const ScanDev& S, int64_t pos) {
-  uint64_t bit = (uint64_t)(pos - S.base);
+  uint64_t bit = bp_bit(S, pos);
   unsigned long long m = 1ull << (bit & 63);
   if (!(S.bitmap[bit >> 6] & m)) atomicOr(&S.bitmap[bit >> 6], m);   // thousands of cells share a column: test first
 }
@@ -442,7 +447,7 @@ __global__ void __launch_bounds__(256) k_extract_bp(ScanDev S) {
   if (w >= S.n_words) return;
   unsigned long long word = S.bitmap[w];
   uint64_t r = S.word_rank[w];
-  while (word) { int b = __ffsll((long long)word) - 1; S.bp[r] = S.base + (int64_t)(w * 64 + b); S.bp_cell0[r] = 0xFFFFFFFFu; ++r; word &= word - 1; }
+  while (word) { int b = __ffsll((long long)word) - 1; S.bp[r] = bp_pos(S, w * 64 + b); S.bp_cell0[r] = 0xFFFFFFFFu; ++r; word &= word - 1; }
 }
 // +1/-1 live-call deltas per breakpoint (and the same for calls containing a deletion); first cell of each column.
 // Cells are sorted by column, so the breakpoint ranks a block touches start at the rank of its first cell's column and
@@ -474,8 +479,8 @@ __global__ void __launch_bounds__(256) k_deltas(ArrayDev A, ScanDev S) {
     bool forward = i >= S.i0;
     if (first_of_col) {
       // record where column `col` starts if `col` is a breakpoint (it is whenever a call begins there)
-      uint64_t bit = (uint64_t)(col - S.base);
-      if (col >= S.base && bit < S.span_bits && ((S.bitmap[bit >> 6] >> (bit & 63)) & 1ull)) S.bp_cell0[bp_rank(S, col)] = (uint32_t)i;
+      uint64_t bit = bp_bit(S, col);
+      if (col >= S.q_lo && bit < S.span_bits && ((S.bitmap[bit >> 6] >> (bit & 63)) & 1ull)) S.bp_cell0[bp_rank(S, col)] = (uint32_t)i;
     }
     if (!(fl & (F_ROWOUT | F_ENDCOPY)) && forward && qrow_of(A, S, A.coords[2 * i]) >= 0) {
       uint64_t rs = bp_rank(S, col), re = bp_rank(S, clip_end(S, A.effend[i]) + 1);

@@ -2,6 +2,8 @@
 
 #include <dirent.h>
 #include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -27,6 +29,27 @@ std::vector<uint8_t> read_file(const std::string& path) {
   std::vector<uint8_t> b((size_t)n);
   if (n && fread(b.data(), 1, (size_t)n, f) != (size_t)n) { fclose(f); fail("short read on " + path); }
   fclose(f);
+  return b;
+}
+
+uint64_t file_size(const std::string& path) {
+  struct stat st;
+  if (stat(path.c_str(), &st) != 0) fail("cannot stat " + path);
+  return (uint64_t)st.st_size;
+}
+// bytes [off, off + len) of a file
+std::vector<uint8_t> read_file_range(const std::string& path, uint64_t off, uint64_t len) {
+  std::vector<uint8_t> b((size_t)len);
+  if (!len) return b;
+  int fd = open(path.c_str(), O_RDONLY);
+  if (fd < 0) fail("cannot open " + path);
+  uint64_t done = 0;
+  while (done < len) {
+    ssize_t r = pread(fd, b.data() + done, (size_t)std::min<uint64_t>(len - done, 1ull << 30), (off_t)(off + done));
+    if (r <= 0) { close(fd); fail("short read on " + path); }
+    done += (uint64_t)r;
+  }
+  close(fd);
   return b;
 }
 
@@ -184,45 +207,90 @@ bool TdbArray::row_bounds(int64_t& lb, int64_t& max_valid) const {
   return has_ub_;
 }
 
-void TdbArray::read_column_raw(size_t fi, int attr_id, TdbRawColumn& out) const {
+void TdbArray::tile_range(size_t fi, int64_t col_lo, int64_t col_hi, int64_t& tile_lo, int64_t& tile_hi) const {
+  const TdbBookKeeping& bk = fragments_[fi].bk;
+  const int64_t n = bk.tile_num;
+  if ((int64_t)bk.bounding_coords.size() != 4 * n) fail("book-keeping: bounding coordinates do not match the tile count");
+  // first tile whose last cell's column is >= col_lo
+  int64_t lo = 0, hi = n;
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (bk.bounding_coords[4 * mid + 3] < col_lo) lo = mid + 1; else hi = mid; }
+  tile_lo = lo;
+  // first tile whose first cell's column is > col_hi
+  hi = n;
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (bk.bounding_coords[4 * mid + 1] <= col_hi) lo = mid + 1; else hi = mid; }
+  tile_hi = std::max(lo, tile_lo);
+}
+int64_t TdbArray::tile_cells(size_t fi, int64_t tile_lo, int64_t tile_hi) const {
+  const TdbBookKeeping& bk = fragments_[fi].bk;
+  if (tile_hi <= tile_lo) return 0;
+  return (tile_hi - tile_lo) * schema_.capacity - (tile_hi == bk.tile_num ? schema_.capacity - bk.last_tile_cell_num : 0);
+}
+
+void TdbArray::read_column_raw(size_t fi, int attr_id, TdbRawColumn& out) const { read_column_raw(fi, attr_id, out, 0, fragments_[fi].bk.tile_num); }
+
+void TdbArray::read_column_raw(size_t fi, int attr_id, TdbRawColumn& out, int64_t t0, int64_t t1) const {
   const TdbFragment& fr = fragments_[fi];
   const int nattr = (int)schema_.attributes.size();
   const std::string name = (attr_id == nattr) ? "__coords" : schema_.attributes[attr_id];
+  if (t0 < 0 || t1 > fr.bk.tile_num || t0 > t1) fail("tile range out of bounds for " + name);
   out = TdbRawColumn();
   out.compressed = schema_.compression[attr_id] != CMP_NONE;
   if (out.compressed && schema_.compression[attr_id] != CMP_GZIP) fail("unsupported TileDB compression for " + name);
   out.is_var = attr_id < nattr && schema_.is_var(attr_id);
-  out.fixed_file = read_file(fr.dir + "/" + name + ".tdb");
   const uint64_t cell = out.is_var ? 8 : ((attr_id == nattr) ? 16 : schema_.type_size(attr_id) * (uint64_t)schema_.cell_val_num[attr_id]);
-  out.fixed_bytes = (uint64_t)fr.bk.cell_num * cell;
-  if (out.is_var) out.var_file = read_file(fr.dir + "/" + name + "_var.tdb");
+  const uint64_t cap = (uint64_t)schema_.capacity;
+  const bool to_end = t1 == fr.bk.tile_num;
+  out.cells = (uint64_t)tile_cells(fi, t0, t1);
+  out.fixed_bytes = out.cells * cell;
+  const std::string fixed_path = fr.dir + "/" + name + ".tdb", var_path = fr.dir + "/" + name + "_var.tdb";
+  if (t0 == t1) return;
   if (!out.compressed) {
-    if (out.fixed_file.size() != out.fixed_bytes) fail("column size mismatch for " + name);
-    out.var_bytes = out.var_file.size();
+    // tile i of an uncompressed attribute starts at i x capacity x cell size (read_state.cc:2581)
+    if (file_size(fixed_path) != (uint64_t)fr.bk.cell_num * cell) fail("column size mismatch for " + name);
+    out.fixed_file = read_file_range(fixed_path, (uint64_t)t0 * cap * cell, out.fixed_bytes);
+    if (out.is_var) {
+      uint64_t v0, v1;
+      memcpy(&v0, out.fixed_file.data(), 8);
+      if (to_end) v1 = file_size(var_path);
+      else { std::vector<uint8_t> nx = read_file_range(fixed_path, (uint64_t)t1 * cap * 8, 8); memcpy(&v1, nx.data(), 8); }
+      if (v1 < v0) fail("value offsets out of order for " + name);
+      out.var_base = v0; out.var_bytes = v1 - v0;
+      out.var_file = read_file_range(var_path, v0, v1 - v0);
+    }
     return;
   }
-  // tile i of the fixed file holds capacity cells (the last one last_tile_cell_num), read_state.cc:2581-2620
+  // compressed: tile i of the fixed file is one zlib stream at tile_offsets[i] holding capacity cells (the last tile
+  // last_tile_cell_num), read_state.cc:2581-2620
   const std::vector<int64_t>& offs = fr.bk.tile_offsets[attr_id];
   if ((int64_t)offs.size() != fr.bk.tile_num) fail("tile offset count mismatch for " + name);
+  const uint64_t fsize = file_size(fixed_path);
+  const uint64_t f_lo = (uint64_t)offs[t0], f_hi = to_end ? fsize : (uint64_t)offs[t1];
+  if (f_hi < f_lo || f_hi > fsize) fail("tile offsets out of range for " + name);
+  out.fixed_file = read_file_range(fixed_path, f_lo, f_hi - f_lo);
   uint64_t o = 0;
-  for (size_t i = 0; i < offs.size(); ++i) {
-    const uint64_t lo = (uint64_t)offs[i], hi = (i + 1 < offs.size()) ? (uint64_t)offs[i + 1] : out.fixed_file.size();
-    if (hi < lo || hi > out.fixed_file.size()) fail("tile offsets out of range for " + name);
-    const uint64_t cells = (i + 1 < offs.size()) ? (uint64_t)schema_.capacity : (uint64_t)fr.bk.last_tile_cell_num;
-    out.fixed_tiles.push_back(TdbTileSpan{lo, hi - lo, o, cells * cell});
+  for (int64_t i = t0; i < t1; ++i) {
+    const uint64_t lo = (uint64_t)offs[i], hi = (i + 1 < fr.bk.tile_num) ? (uint64_t)offs[i + 1] : fsize;
+    if (hi < lo || hi > fsize) fail("tile offsets out of range for " + name);
+    const uint64_t cells = (i + 1 < fr.bk.tile_num) ? cap : (uint64_t)fr.bk.last_tile_cell_num;
+    out.fixed_tiles.push_back(TdbTileSpan{lo - f_lo, hi - lo, o, cells * cell});
     o += cells * cell;
   }
   if (o != out.fixed_bytes) fail("tile sizes do not add up for " + name);
   if (out.is_var) {
     const std::vector<int64_t>& voffs = fr.bk.tile_var_offsets[attr_id];
     const std::vector<uint64_t>& vsz = fr.bk.tile_var_sizes[attr_id];
-    if (voffs.size() != vsz.size()) fail("var tile table mismatch for " + name);
+    if (voffs.size() != vsz.size() || (int64_t)voffs.size() != fr.bk.tile_num) fail("var tile table mismatch for " + name);
+    const uint64_t vsize = file_size(var_path);
+    for (int64_t i = 0; i < t0; ++i) out.var_base += vsz[i];
+    const uint64_t v_lo = (uint64_t)voffs[t0], v_hi = to_end ? vsize : (uint64_t)voffs[t1];
+    if (v_hi < v_lo || v_hi > vsize) fail("var tile offsets out of range for " + name);
+    out.var_file = read_file_range(var_path, v_lo, v_hi - v_lo);
     uint64_t vo = 0;
-    for (size_t i = 0; i < voffs.size(); ++i) {
-      const uint64_t lo = (uint64_t)voffs[i], hi = (i + 1 < voffs.size()) ? (uint64_t)voffs[i + 1] : out.var_file.size();
-      if (hi < lo || hi > out.var_file.size()) fail("var tile offsets out of range for " + name);
-      if (vsz[i] == 0) { out.var_tiles.push_back(TdbTileSpan{lo, 0, vo, 0}); continue; }   // empty var tile: nothing was written
-      out.var_tiles.push_back(TdbTileSpan{lo, hi - lo, vo, vsz[i]});
+    for (int64_t i = t0; i < t1; ++i) {
+      const uint64_t lo = (uint64_t)voffs[i], hi = (i + 1 < fr.bk.tile_num) ? (uint64_t)voffs[i + 1] : vsize;
+      if (hi < lo || hi > vsize) fail("var tile offsets out of range for " + name);
+      if (vsz[i] == 0) { out.var_tiles.push_back(TdbTileSpan{lo - v_lo, 0, vo, 0}); continue; }   // empty var tile: nothing was written
+      out.var_tiles.push_back(TdbTileSpan{lo - v_lo, hi - lo, vo, vsz[i]});
       vo += vsz[i];
     }
     out.var_bytes = vo;

@@ -45,6 +45,9 @@ struct TdbRawColumn {
   std::vector<TdbTileSpan> fixed_tiles, var_tiles;   // compressed only: one zlib stream per tile
   uint64_t fixed_bytes = 0, var_bytes = 0;       // decompressed sizes
   bool is_var = false;
+  uint64_t cells = 0;        // cells of the tiles that were read
+  uint64_t var_base = 0;     // byte offset, in the fragment's whole value stream, of the first value byte that was read: the
+                             // offsets in the fixed file are absolute (read_state.cc:2991-3001 rebases them the same way)
 };
 
 struct TdbFragment {
@@ -65,6 +68,13 @@ class TdbArray {
   // (read_state.cc:2442-2889); attr_id == schema().attributes.size() reads __coords.  Compressed tiles are inflated on
   // the device (gdb_inflate.cuh), never here; zlib is only used for the small gzip'ed book-keeping file.
   void read_column_raw(size_t fragment_idx, int attr_id, TdbRawColumn& out) const;
+  // The same for tiles [tile_lo, tile_hi) only: the files are read with pread at the tiles' offsets, nothing else is touched.
+  void read_column_raw(size_t fragment_idx, int attr_id, TdbRawColumn& out, int64_t tile_lo, int64_t tile_hi) const;
+  // Tiles of a fragment that can hold cells of columns [col_lo, col_hi]: binary search of the book-keeping's bounding
+  // coordinates (first / last cell of every tile, global order = column, then row), what
+  // ReadState::compute_tile_search_range_col_or_row does (read_state.cc:1427-1527).  tile_lo == tile_hi: none.
+  void tile_range(size_t fragment_idx, int64_t col_lo, int64_t col_hi, int64_t& tile_lo, int64_t& tile_hi) const;
+  int64_t tile_cells(size_t fragment_idx, int64_t tile_lo, int64_t tile_hi) const;
 
  private:
   std::string dir_;

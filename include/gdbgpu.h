@@ -125,7 +125,8 @@ int gdbgpu_ctx_kernel_stats(gdbgpu_ctx* ctx, const char* kernel_name, double* to
  * gdbgpu_array_open replaces VariantStorageManager::open_array + TileDB array/fragment/book-keeping load
  * (variant_storage_manager.cc:434-520; storage_manager.cc array_open; book_keeping.cc:368-422; read_state.cc:2442-2889):
  * it reads <workspace>/<array>/__array_schema.tdb and, per fragment dir, __book_keeping.tdb.gz, <ATTR>.tdb, <ATTR>_var.tdb,
- * inflates GZIP tiles on the host, copies the columns to the device and runs the fragment merge there. */
+ * copies the files' bytes to the device as they lie on disk, inflates GZIP tiles there (one zlib stream per tile and
+ * attribute file) and runs the fragment merge there. */
 int gdbgpu_array_open(gdbgpu_ctx* ctx, const char* workspace, const char* array_name,
                       const gdbgpu_field_desc* fields, int32_t n_fields, int32_t gt_phased, gdbgpu_array** out);
 /* Same, also staging plain FORMAT fields for the FORMAT collation of GDBGPU_SCAN_BCF_FORMAT. */
@@ -133,6 +134,17 @@ int gdbgpu_array_open_ex(gdbgpu_ctx* ctx, const char* workspace, const char* arr
                          const gdbgpu_field_desc* fields, int32_t n_fields,
                          const gdbgpu_plain_field_desc* plain_fields, int32_t n_plain_fields,
                          int32_t gt_phased, gdbgpu_array** out);
+/* Same, staging only the tiles that can hold cells of columns [col_lo, col_hi] (one rank's column partition):
+ * the tile range comes from a binary search of the book-keeping's bounding coordinates, as
+ * ReadState::compute_tile_search_range_col_or_row / get_next_overlapping_tile_sparse find it
+ * (dependencies/TileDB/core/src/fragment/read_state.cc:1427-1527,1006-1042); only those tiles are read (pread), copied and
+ * inflated.  The call live at a query's left edge is found through the row's first cell at or after that edge (its END
+ * copy; gt_get_column's forward scan, query_variants.cc:845-941): the staged range grows to the right until every row shows a
+ * cell at or after col_hi (or the fragments end), so every query inside [col_lo, col_hi] gives what it gives on the whole array.  INT64_MIN / INT64_MAX: the whole array. */
+int gdbgpu_array_open_range(gdbgpu_ctx* ctx, const char* workspace, const char* array_name,
+                            const gdbgpu_field_desc* fields, int32_t n_fields,
+                            const gdbgpu_plain_field_desc* plain_fields, int32_t n_plain_fields,
+                            int32_t gt_phased, int64_t col_lo, int64_t col_hi, gdbgpu_array** out);
 /* Same, from columns already decoded in host memory (loader hand-off, JNI buffers, synthetic generators). */
 int gdbgpu_array_from_columns(gdbgpu_ctx* ctx, const gdbgpu_columns* cols, gdbgpu_array** out);
 int gdbgpu_array_get_info(const gdbgpu_array* arr, gdbgpu_array_info* info);

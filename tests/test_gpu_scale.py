@@ -1,0 +1,104 @@
+"""GPU: the CUDA path against the UNMODIFIED reference at BASELINE sizes.
+
+Both sides are native programs reading the same on-disk TileDB fragment (written by tools/tiledb_writer.py from the
+GDBSYN-1 generator) and writing the canonical hot-path dump (layout: oracle/ref_harness/gdb_ref_dump.cc):
+    oracle/_ref/bin/gdb_ref_dump --mode dump     the reference's scan_and_operate + handle_deletions + GA4GHOperator::operate
+    genomicsdb_b200/bin/gt_gpu_gather            the host mirror's scan_and_operate over libgdbgpu (kernels), same operator seam
+The dumps run to gigabytes, so each program writes to a pipe and only the md5 of the stream is kept; the column range is
+cut into intervals so that the reference's single-threaded processes use the box's cores side by side.  Every queried
+row and every site of every interval is compared -- nothing is sampled.
+"""
+import hashlib
+import json
+import os
+import subprocess
+import threading
+
+import pytest
+
+from conftest import REPO
+from tools import gdbsyn, tiledb_writer
+
+pytestmark = pytest.mark.gpu
+
+REF = os.path.join(REPO, "oracle", "_ref", "bin", "gdb_ref_dump")
+OURS = os.path.join(REPO, "genomicsdb_b200", "bin", "gt_gpu_gather")
+
+
+def _md5_of(cmd, out):
+    """runs cmd + ["-o", <a pipe>] (both tools also print a JSON summary on stdout, so the dump gets a descriptor of its own),
+    leaves (md5, bytes, returncode, stderr tail) in out"""
+    r, w = os.pipe()
+    p = subprocess.Popen(cmd + ["-o", "/dev/fd/%d" % w], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, pass_fds=(w,))
+    os.close(w)
+    err = []
+    t = threading.Thread(target=lambda: err.append(p.stderr.read()))
+    t.start()
+    h, n = hashlib.md5(), 0
+    with os.fdopen(r, "rb") as f:
+        while True:
+            b = f.read(1 << 22)
+            if not b:
+                break
+            h.update(b)
+            n += len(b)
+    t.join()
+    out.extend([h.hexdigest(), n, p.wait(), err[0].decode(errors="replace")[-600:]])
+
+
+def _intervals(lo, hi, k):
+    step = (hi - lo + k) // k
+    return [(a, min(hi, a + step - 1)) for a in range(lo, hi + 1, step)]
+
+
+def compare_with_reference(tmp_path, d, n_intervals, max_parallel=None):
+    ws = str(tmp_path / "ws")
+    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+    lo, hi = d["col_range"]
+    queries = []
+    for i, (a, b) in enumerate(_intervals(lo, hi, n_intervals)):
+        queries.append((a, b, tiledb_writer.write_query_json(os.path.join(ws, "q%d.json" % i), info, a, b)))
+    # the reference: one process per interval, as many at a time as there are cores
+    ref = [[] for _ in queries]
+    par = max_parallel or max(1, min(len(queries), os.cpu_count() or 1))
+    for first in range(0, len(queries), par):
+        ts = [threading.Thread(target=_md5_of, args=([REF, "-j", q, "--mode", "dump"], ref[i]))
+              for i, (_, _, q) in enumerate(queries) if first <= i < first + par]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    # ours: one process per interval, one after the other (one GPU)
+    total = 0
+    for i, (a, b, q) in enumerate(queries):
+        got = []
+        _md5_of([OURS, "-j", q], got)
+        assert ref[i][2] == 0, "reference failed on [%d, %d]: %s" % (a, b, ref[i][3])
+        assert got[2] == 0, "gt_gpu_gather failed on [%d, %d]: %s" % (a, b, got[3])
+        assert got[1] == ref[i][1] and got[0] == ref[i][0], "dump of columns [%d, %d] differs from the reference's (%d vs %d bytes)" % (a, b, got[1], ref[i][1])
+        total += got[1]
+    return total
+
+
+@pytest.fixture(scope="module", autouse=True)
+def tools_present():
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref is not built (it is built where /root/reference exists and travels with the repo)")
+    assert os.path.exists(OURS), "gt_gpu_gather is not built: run __graft_entry__.build()"
+
+
+def test_config2_all_rows_all_sites(tmp_path):
+    """BASELINE config #2 whole: 1 k samples x 1 M positions (10 k candidate sites, ~20 k records), every row, every site"""
+    d = gdbsyn.generate(**gdbsyn.CONFIGS["config2"])
+    n = compare_with_reference(tmp_path, d, n_intervals=16)
+    assert n > 1 << 30   # gigabytes of dump went through the comparison
+
+
+def test_config3_column_slice(tmp_path):
+    """BASELINE config #3, a 6 % column slice: 10 k samples x 600 candidate sites, every row"""
+    d = gdbsyn.generate(**gdbsyn.CONFIGS["config3"], site_lo=4000, site_hi=4600)
+    compare_with_reference(tmp_path, d, n_intervals=16)
+
+
+def test_config4_width_all_rows(tmp_path):
+    """BASELINE config #4's width: 100 k samples x 12 candidate sites (max 8 ALT alleles, 10 merged alleles), all 100 k rows"""
+    d = gdbsyn.generate(**gdbsyn.CONFIGS["config4"], site_lo=700, site_hi=712)
+    compare_with_reference(tmp_path, d, n_intervals=6)

@@ -122,3 +122,27 @@ def qual_field(case):
     if ent and "QUAL" in case["attributes"] and ent.get("combine") in ("median", "sum", "mean"):
         return ("QUAL", "float", ent["combine"])
     return None
+
+
+def cells_to_columns(cells, num_rows):
+    """Hand-made cohort in the generator's dict layout (tools/gdbsyn.generate) from a list of cells
+    dict(row, col, end, ref, alt, gt=[..], pl=[..], ad=[..]); cells are put into TileDB's global order (column, then row)."""
+    import numpy as np
+    cells = sorted(cells, key=lambda c: (c["col"], c["row"]))
+    n = len(cells)
+    d = dict(coords=np.array([[c["row"], c["col"]] for c in cells], dtype=np.int64).reshape(n, 2),
+             end=np.array([c["end"] for c in cells], dtype=np.int64), num_rows=num_rows)
+    for key, dt, enc in (("ref", np.uint8, lambda c: np.frombuffer(c["ref"].encode(), dtype=np.uint8)),
+                         ("alt", np.uint8, lambda c: np.frombuffer(c["alt"].encode(), dtype=np.uint8)),
+                         ("gt", np.int32, lambda c: np.array(c.get("gt", []), dtype=np.int32)),
+                         ("pl", np.int32, lambda c: np.array(c.get("pl", []), dtype=np.int32)),
+                         ("ad", np.int32, lambda c: np.array(c.get("ad", []), dtype=np.int32))):
+        vals = [enc(c) for c in cells]
+        off = np.zeros(n, dtype=np.uint64)
+        if n:
+            off[1:] = np.cumsum([v.nbytes for v in vals])[:-1]
+        d[key] = (off, np.concatenate(vals).astype(dt) if n and sum(v.size for v in vals) else np.zeros(0, dtype=dt))
+    lo = min(c["col"] for c in cells)
+    hi = max(max(c["col"], c["end"]) for c in cells)
+    d["col_range"] = (lo, hi)
+    return d

@@ -22,7 +22,7 @@ typedef struct {
   uint64_t seed;
   int64_t n_samples, n_sites, spacing, first_col;
   double p_var;
-  int32_t a_pool;          /* 1..8 */
+  int32_t a_pool;          /* 1..64: 3 SNP bases, 5 short insertions, then insertions REF + a 3-letter code */
   int64_t site_lo, site_hi; /* shard */
 } gdbsyn_params;
 
@@ -49,17 +49,19 @@ static const char BASES[4] = {'A', 'C', 'G', 'T'};
 static const char* INS[5] = {"A", "C", "G", "T", "AA"};
 
 /* variant call of sample s at site i: returns k, fills pick strings */
-typedef struct { int k; char alt[8][4]; int alt_len[8]; char ref; int gt[2]; } var_t;
+#define SYN_MAX_POOL 64
+typedef struct { int k; char alt[8][8]; int alt_len[8]; char ref; int gt[2]; } var_t;
 static void make_variant(const gdbsyn_params* p, int64_t s, int64_t i, var_t* v) {
   uint64_t S = (uint64_t)s, I = (uint64_t)i;
   int r = (int)(mix(p->seed ^ (I * 0xD6E8FEB86659FD93ull)) & 3);
   v->ref = BASES[r];
-  char pool[8][4]; int plen[8];
+  char pool[SYN_MAX_POOL][8]; int plen[SYN_MAX_POOL];
   for (int a = 0; a < 3; ++a) { pool[a][0] = BASES[(r + 1 + a) & 3]; plen[a] = 1; }
   for (int a = 0; a < 5; ++a) { pool[3 + a][0] = BASES[r]; int l = (int)strlen(INS[a]); memcpy(pool[3 + a] + 1, INS[a], l); plen[3 + a] = 1 + l; }
-  int np = p->a_pool, kmax = np < 3 ? np : 3;
+  for (int a = 8; a < SYN_MAX_POOL; ++a) { int c = a - 8; pool[a][0] = BASES[r]; pool[a][1] = BASES[(c >> 4) & 3]; pool[a][2] = BASES[(c >> 2) & 3]; pool[a][3] = BASES[c & 3]; plen[a] = 4; }
+  int np = p->a_pool > SYN_MAX_POOL ? SYN_MAX_POOL : p->a_pool, kmax = np < 3 ? np : 3;
   v->k = 1 + (int)(h3(p->seed, S, I, 1) % (uint64_t)kmax);
-  int idx[8]; for (int a = 0; a < np; ++a) idx[a] = a;
+  int idx[SYN_MAX_POOL]; for (int a = 0; a < np; ++a) idx[a] = a;
   for (int t = 0; t < v->k; ++t) { int j = t + (int)(h3(p->seed, S, I, 2 + t) % (uint64_t)(np - t)); int tmp = idx[t]; idx[t] = idx[j]; idx[j] = tmp; }
   for (int t = 0; t < v->k; ++t) { memcpy(v->alt[t], pool[idx[t]], plen[idx[t]]); v->alt_len[t] = plen[idx[t]]; }
   int a = (int)(h3(p->seed, S, I, 10) % (uint64_t)(v->k + 1)), b = (int)(h3(p->seed, S, I, 11) % (uint64_t)(v->k + 1));
