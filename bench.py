@@ -31,6 +31,14 @@ import numpy as np  # noqa: E402
 
 COHORT = dict(n_samples=100000, n_sites=10000, spacing=1000, p_var=0.1, a_pool=8)
 SITES_PER_GPU = 1250
+# --config: which BASELINE.json configuration the main measurement runs on.  "4shard" (default) is config #4 the way
+# it is quoted: one 1/8 column shard of the 100 k-sample cohort per GPU, 8 ranks = the whole cohort (weak scaling).
+WORKLOADS = {
+    "4shard": dict(cohort=COHORT, sites_per_gpu=SITES_PER_GPU, scaling="weak"),
+    "2": dict(cohort=dict(n_samples=1000, n_sites=10000, spacing=100, p_var=0.1, a_pool=3), sites_per_gpu=None, scaling="weak"),       # whole, replicated
+    "3": dict(cohort=dict(n_samples=10000, n_sites=10000, spacing=100, p_var=0.1, a_pool=3), sites_per_gpu=None, scaling="strong"),   # whole, split over the ranks
+    "4full": dict(cohort=COHORT, sites_per_gpu=None, scaling="strong"),                                                                # whole, split over the ranks
+}
 METRIC = "combined_variant_sites_per_sec"
 REF_BIN = os.path.join(REPO, "oracle", "_ref", "bin", "gdb_ref_dump")
 
@@ -38,6 +46,16 @@ REF_BIN = os.path.join(REPO, "oracle", "_ref", "bin", "gdb_ref_dump")
 def workload_config(args, n_gpus):
     c = dict(COHORT)
     c["n_samples"] = args.samples
+    which = getattr(args, "config", "4shard")
+    if which != "4shard":
+        w = WORKLOADS[which]
+        c = dict(w["cohort"])
+        return dict(workload="GDBSYN-1 config#%s whole: %d samples x %d candidate sites (%d positions), a_pool=%d, p_var=%.2f; %s over %d GPU(s)"
+                    % (which.replace("full", ""), c["n_samples"], c["n_sites"], c["n_sites"] * c["spacing"], c["a_pool"], c["p_var"],
+                       "replicated" if w["scaling"] == "weak" else "column range split", n_gpus),
+                    samples=c["n_samples"], shards=n_gpus,
+                    l2="inputs and outputs are far larger than the 126 MB L2; no explicit flush",
+                    sharding="contig-interval (column) shards, one per GPU, no data-path collective")
     return dict(workload="GDBSYN-1 config#4 column shard: %d samples x %d candidate sites (%d positions) per GPU, a_pool=%d, p_var=%.2f; %d shard(s)"
                 % (c["n_samples"], args.sites_per_gpu, args.sites_per_gpu * c["spacing"], c["a_pool"], c["p_var"], n_gpus),
                 samples=c["n_samples"], sites_per_gpu=args.sites_per_gpu, shards=n_gpus,
@@ -163,27 +181,34 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+FIELDS = [("AD", "R", "int"), ("PL", "G", "int")]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", default="4shard", choices=sorted(WORKLOADS))
     ap.add_argument("--samples", type=int, default=COHORT["n_samples"])
     ap.add_argument("--sites-per-gpu", type=int, default=SITES_PER_GPU)
     ap.add_argument("--batch-bytes", type=int, default=8 << 30)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-batch-bytes", type=int, default=2 << 30)
+    ap.add_argument("--latency-intervals", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e from fragment files, config-#3 strong scaling, gather, latency sweep")
+    ap.add_argument("--scratch", default=os.environ.get("GDBBENCH_SCRATCH", "/tmp"))
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
 
     import torch
     import torch.distributed as dist
-    from genomicsdb_b200 import capi
-    from tools import gdbsyn
+    from genomicsdb_b200 import capi, sharding
+    from tools import gdbsyn, tiledb_writer
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,6 +216,8 @@ def main():
     if not torch.cuda.is_available():
         sys.exit("bench.py needs a CUDA device: the combine path has no CPU fallback")
     torch.cuda.set_device(local)
+    # pinned host buffers are first-touched by this process: keep it (and them) on the GPU's own NUMA node
+    numa = sharding.bind_to_gpu_numa_node(local)
     # stdout carries ONE JSON line: whatever libraries write to file descriptor 1 on the way (NCCL prints its version banner
     # there) goes to stderr; the descriptor is handed back right before the line is printed
     sys.stdout.flush()
@@ -198,6 +225,7 @@ def main():
     os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
 
     def barrier():
         if world > 1:
@@ -217,18 +245,25 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    cohort = dict(COHORT)
-    cohort["n_samples"] = args.samples
-    lo = (rank * args.sites_per_gpu) % cohort["n_sites"]
-    d = gdbsyn.generate(**cohort, site_lo=lo, site_hi=min(cohort["n_sites"], lo + args.sites_per_gpu))
+    w = WORKLOADS[args.config]
+    cohort = dict(w["cohort"])
+    if args.config == "4shard":
+        cohort["n_samples"] = args.samples
+        lo = (rank * args.sites_per_gpu) % cohort["n_sites"]
+        site_lo, site_hi = lo, min(cohort["n_sites"], lo + args.sites_per_gpu)
+    elif w["scaling"] == "weak":
+        site_lo, site_hi = 0, cohort["n_sites"]
+    else:
+        site_lo, site_hi = cohort["n_sites"] * rank // world, cohort["n_sites"] * (rank + 1) // world
+    d = gdbsyn.generate(**cohort, site_lo=site_lo, site_hi=site_hi)
     q_lo, q_hi = d["col_range"]
     manifest = gdbsyn.algorithmic_bytes(d)
 
     ctx = capi.Context(local)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
-    def one_pass(arr, flags, batch_bytes=None):
-        sc = capi.Scan(arr, q_lo, q_hi, flags=flags)
+    def one_pass(arr, flags, batch_bytes=None, lo=None, hi=None):
+        sc = capi.Scan(arr, q_lo if lo is None else lo, q_hi if hi is None else hi, flags=flags)
         sites = out_bytes = live_words = fmt_bytes = 0
         while True:
             b = sc.next_batch(0, batch_bytes or args.batch_bytes, raw=True)
@@ -273,24 +308,37 @@ def main():
     while len(sampler.rows) < 4 and time.time() - t_extra < 3.0:
         one_pass(arr, capi.SCAN_DEVICE_OUTPUT)
     sampler.stop_flag = True
-    remap_ms, remap_n = ctx.kernel_stats("k_remap")
-    copy0_ms, _ = ctx.kernel_stats("k_copy_tile")
-    remap_ms += copy0_ms   # K5 = k_remap_tile + k_copy_tile + k_remap_nt; remap_n stays the number of tile+nt launches
-    union_ms, _ = ctx.kernel_stats("k_union")
-    walk_ms, _ = ctx.kernel_stats("k_live_walk")
-    sscan_ms, _ = ctx.kernel_stats("k_site_scan")
-    tile_ms, _ = ctx.kernel_stats("k_remap_tile")
-    nt_ms, _ = ctx.kernel_stats("k_remap_nt")
-    copy_ms, _ = ctx.kernel_stats("k_copy_tile")
+    kms = {k: ctx.kernel_stats(k)[0] / args.steps for k in ("k_remap_tile", "k_remap_tma", "k_remap_nt", "k_remap_generic", "k_copy_tile", "k_site_scan",
+                                                           "k_union", "k_verify_alleles", "k_live_walk")}
+    remap_n = sum(ctx.kernel_stats(k)[1] for k in ("k_remap_tile", "k_remap_tma", "k_remap_nt", "k_remap_generic"))
+    remap_ms = (kms["k_remap_tile"] + kms["k_remap_tma"] + kms["k_remap_nt"] + kms["k_remap_generic"] + kms["k_copy_tile"]) * args.steps
     all_ms, _ = ctx.kernel_stats("k_")
-    ctx.set_profiling(False)
     sites_per_step = sites // args.steps
     total_sites = sum_over_ranks(float(sites))
     value = total_sites / (ms * 1e-3)
+
+    # ---------------- BASELINE config #5: latency of scan_and_operate over random 1 Mb intervals of the resident shard (rank 0)
+    latency = None
+    if rank == 0 and not args.no_extras and args.latency_intervals > 0 and q_hi - q_lo > 1000000:
+        rng = np.random.RandomState(4321)
+        starts = q_lo + rng.randint(0, q_hi - q_lo + 1 - 1000000, size=args.latency_intervals)
+        lat, nsite = [], []
+        for k, a0 in enumerate(list(starts[:5]) + list(starts)):
+            t0 = time.perf_counter()
+            n, _, _, _ = one_pass(arr, capi.SCAN_DEVICE_OUTPUT, lo=int(a0), hi=int(a0) + 999999)
+            ctx.synchronize()
+            if k >= 5:
+                lat.append((time.perf_counter() - t0) * 1e3)
+                nsite.append(n)
+        lat = np.array(lat)
+        latency = dict(intervals=int(args.latency_intervals), interval_positions=1000000, sites_per_interval=float(np.mean(nsite)),
+                       p50_ms=float(np.percentile(lat, 50)), p95_ms=float(np.percentile(lat, 95)), p99_ms=float(np.percentile(lat, 99)), max_ms=float(lat.max()),
+                       note="gdbgpu_scan_begin (left sweep, breakpoints) -> next_batch until empty -> scan_end per interval, host clock, output left in HBM")
+
     # ---------------- the other consumer of the staged shard: the columnar iterator's cell list + the two
     # operators that run as kernels, over this rank's whole shard; only bins / distinct allele records cross PCIe
     columnar = None
-    if rank == 0:
+    if rank == 0 and not args.no_extras:
         def cells_pass(op):
             sc = capi.Scan(arr, q_lo, q_hi, flags=capi.SCAN_CELLS_ONLY)
             r = op(sc)
@@ -306,6 +354,34 @@ def main():
                         allele_count_ms=t_ac * 1e3, allele_count_cells_per_s=listed / t_ac, allele_count_records=n_rec,
                         note="gdbgpu_scan_begin(GDBGPU_SCAN_CELLS_ONLY) + gdbgpu_scan_cells_histogram / _cells_allele_counts over the resident shard, "
                              "wall clock incl. the call's host side; reference tool: tools/cells_bench.py")
+
+    # ---------------- NCCL: the one collective of the design -- rank-ordered concatenation of a per-site summary stream
+    gather = None
+    if world > 1 and not args.no_extras:
+        sc = capi.Scan(arr, q_lo, q_hi, flags=capi.SCAN_SUMMARY_ONLY)
+        parts = []
+        while True:
+            b = sc.next_batch(0, 1 << 30)
+            if b is None:
+                break
+            rec = np.zeros((b.n_sites, 3), dtype=np.int64)
+            rec[:, 0], rec[:, 1], rec[:, 2] = b.site_begin, b.site_end, b.n_alleles
+            parts.append(rec)
+        sc.close()
+        mine = torch.from_numpy(np.concatenate(parts).view(np.uint8).reshape(-1)).to(dev)
+        sharding.gather_concat(mine, device=dev)      # warm-up (communicator, buffers)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cat = sharding.gather_concat(mine, device=dev)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        gather = dict(bytes_per_rank=int(mine.numel()), ms=dt * 1e3, bytes_on_rank0=len(cat) if rank == 0 else None, backend="nccl",
+                      what="per-site summary (begin, end, merged allele count) of every rank's shard, concatenated in rank order on rank 0: all-gather of "
+                           "the sizes + grouped ncclSend / ncclRecv of exactly those sizes (genomicsdb_b200/sharding.py: gather_concat; MPI_Gatherv in gt_mpi_gather.cc:165-263)")
+        if rank == 0:
+            allrec = np.frombuffer(cat, dtype=np.int64).reshape(-1, 3)
+            gather["records"] = int(len(allrec))
     arr.close()
 
     # ---------------- roofline of the dominant kernel (remap): algorithmic bytes per launch / its event-timed duration
@@ -317,25 +393,26 @@ def main():
     b_in_step = manifest["b_in"]
     b_out_step = out_bytes / args.steps
     achieved = ((b_in_step + b_out_step) * args.steps / 1e9) / (remap_ms * 1e-3) if remap_ms > 0 else 0.0
-    # DRAM traffic of the same kernels from the committed ncu capture (dram__bytes_read.sum + dram__bytes_write.sum), per launch
+    # DRAM traffic of the same kernels from the committed ncu capture of this round (tools/ncu_traffic.sh), per launch
     traffic, traffic_src = None, None
-    tpath = os.path.join(REPO, "profiles", "r01_k5_traffic.json")
-    if os.path.exists(tpath) and args.samples == COHORT["n_samples"] and remap_n:
+    tpath = os.path.join(REPO, "profiles", "r02_k5_traffic.json")
+    if os.path.exists(tpath) and args.config == "4shard" and args.samples == COHORT["n_samples"] and remap_n:
         tj = json.load(open(tpath))
         traffic = tj["k5_dram_bytes_per_site"] * sites / remap_n
-        traffic_src = "profiles/r01_k5_traffic.json (ncu, bytes per site of the same shard) x sites per launch"
+        traffic_src = "profiles/r02_k5_traffic.json (ncu --set full of the remap kernels at this round's HEAD, dram bytes per site of the same shard) x sites per launch"
     roofline = dict(bound="hbm", kernel="gdb::k_remap_tile (+ gdb::k_copy_tile for sites that need no remap, gdb::k_remap_nt for their rare non-trivial calls): K5 remap", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                     traffic_source=traffic_src, algorithmic_bytes_per_launch=(b_in_step + b_out_step) * args.steps / max(1, remap_n),
                     peak_source=peak_src, algorithmic_bytes_per_step=dict(b_in=b_in_step, b_out=b_out_step),
                     launches=int(remap_n), avg_launch_ms=remap_ms / max(1, remap_n),
-                    kernel_ms_per_step=dict(k_remap=remap_ms / args.steps, k_remap_tile=tile_ms / args.steps, k_remap_nt=nt_ms / args.steps, k_copy_tile=copy_ms / args.steps,
-                                            k_site_scan=sscan_ms / args.steps, k_union=union_ms / args.steps, k_live_walk=walk_ms / args.steps,
-                                            all_kernels=all_ms / args.steps),
-                    step_gbs=((b_in_step + b_out_step) * args.steps / 1e9) / (ms * 1e-3))
+                    kernel_ms_per_step=dict(kms, k_remap=remap_ms / args.steps, all_kernels=all_ms / args.steps),
+                    step_gbs=((b_in_step + b_out_step) * args.steps / 1e9) / (ms * 1e-3),
+                    step_frac=((b_in_step + b_out_step) * args.steps / 1e9) / (ms * 1e-3) / peak)
 
     # ---------------- end to end through the C ABI with host buffers
-    e2e = e2e_int32 = None
+    e2e = e2e_int32 = e2e_files = e2e_files_gzip = None
+    ctx2 = capi.Context(local) if not args.no_e2e else None
     if not args.no_e2e:
+        from concurrent.futures import ThreadPoolExecutor
         pinned = {}
 
         def pin(a):
@@ -347,64 +424,146 @@ def main():
         dp["coords"], dp["end"] = pin(d["coords"]), pin(d["end"])
         for k in ("ref", "alt", "gt", "pl", "ad"):
             dp[k] = (pin(d[k][0]), pin(d[k][1]))
+        ctxs = [ctx, ctx2]
 
-        phase_s = dict(stage=0.0, scan=0.0, close=0.0)
+        def e2e_run(flags, path, stage, steps):
+            """`stage(k)` puts step k's inputs into HBM through the C ABI (on context k % 2) and returns the array; the scan of
+            step k copies every batch back to pinned host memory.  Step k + 1 is staged (host -> device) by a second host thread
+            while step k's results travel device -> host: PCIe is full duplex.  Every step pays both copies."""
+            def scan(a):
+                i = a.info()
+                s, ob, lw, fb = one_pass(a, flags, args.e2e_batch_bytes)
+                a.close()
+                d2h_bytes = fb + s * 24 if flags & capi.SCAN_BCF_FORMAT else ob + lw * 4 + lw * 2 * 3 + s * 24
+                return s, i.staged_bytes, d2h_bytes
 
-        def e2e_step(flags):
-            t0 = time.perf_counter()
-            a = gdbsyn.to_gpu_array(ctx, dp)
-            i = a.info()
-            t1 = time.perf_counter()
-            s, ob, lw, fb = one_pass(a, flags, args.e2e_batch_bytes)
-            t2 = time.perf_counter()
-            a.close()
-            t3 = time.perf_counter()
-            phase_s["stage"] += t1 - t0
-            phase_s["scan"] += t2 - t1
-            phase_s["close"] += t3 - t2
-            # host output: BCF mode copies the typed blocks + the site table; int32 mode the vectors, their lengths and the live matrix
-            d2h_bytes = fb + s * 24 if flags & capi.SCAN_BCF_FORMAT else ob + lw * 4 + lw * 2 * 3 + s * 24
-            return s, i.staged_bytes, d2h_bytes
-
-        def e2e_run(flags, path):
-            for _ in range(2):
-                e2e_step(flags)
+            for k in range(2):
+                scan(stage(k))
             barrier()
-            for k in phase_s:
-                phase_s[k] = 0.0
             t0 = time.perf_counter()
             es = h2d = d2h = 0
-            for _ in range(args.e2e_steps):
-                s, hb, db = e2e_step(flags)
-                es += s
-                h2d += hb
-                d2h += db
+            with ThreadPoolExecutor(1) as ex:
+                fut = ex.submit(stage, 0)
+                for k in range(steps):
+                    a = fut.result()
+                    if k + 1 < steps:
+                        fut = ex.submit(stage, k + 1)
+                    s, hb, db = scan(a)
+                    es += s
+                    h2d += hb
+                    d2h += db
             ctx.synchronize()
+            ctx2.synchronize()
             dt = max_over_ranks(time.perf_counter() - t0)
-            return dict(value=sum_over_ranks(float(es)) / dt, unit="sites/s", h2d_bytes_per_step=int(h2d // args.e2e_steps),
-                        d2h_bytes_per_step=int(d2h // args.e2e_steps), steps=args.e2e_steps, ms_per_step=dt * 1e3 / args.e2e_steps,
-                        batch_bytes=args.e2e_batch_bytes, path=path,
-                        phase_ms_per_step={k: v * 1e3 / args.e2e_steps for k, v in phase_s.items()})
+            return dict(value=sum_over_ranks(float(es)) / dt, unit="sites/s", h2d_bytes_per_step=int(h2d // steps),
+                        d2h_bytes_per_step=int(d2h // steps), steps=steps, ms_per_step=dt * 1e3 / steps,
+                        batch_bytes=args.e2e_batch_bytes, path=path)
 
+        stage_cols = lambda k: gdbsyn.to_gpu_array(ctxs[k % 2], dp)
         e2e = e2e_run(capi.SCAN_BCF_FORMAT | capi.SCAN_PRODUCE_GT,
                       "gdbgpu_array_from_columns(pinned host columns) -> gdbgpu_scan_next_batch(GDBGPU_SCAN_BCF_FORMAT, host output: "
-                      "remapped GT/AD/PL collated and BCF-typed on the device, blocks copied to pinned host memory) -> close")
+                      "remapped GT/AD/PL collated and BCF-typed on the device, blocks copied to pinned host memory) -> close; "
+                      "step k+1 staged by a second host thread / context while step k's blocks are copied back", stage_cols, args.e2e_steps)
         e2e_int32 = e2e_run(0, "gdbgpu_array_from_columns(pinned host columns) -> gdbgpu_scan_next_batch(host output: 32-bit remapped "
-                               "vectors + lengths + live matrix copied to pinned host memory) -> close")
+                               "vectors + lengths + live matrix copied to pinned host memory) -> close", stage_cols, max(2, args.e2e_steps - 1))
+        if not args.no_extras:
+            # the same metric from the fragment FILES: TileDB reader (book-keeping, pread of the attribute files: page cache),
+            # H2D of the file bytes, K0 inflate when GZIP, index build, scan, D2H
+            ws = os.path.join(args.scratch, "gdbbench_%d_r%d" % (os.getpid(), rank))
+            try:
+                tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+                stage_files = lambda k: capi.Array.open(ctxs[k % 2], ws, "syn", FIELDS)
+                e2e_files = e2e_run(capi.SCAN_BCF_FORMAT | capi.SCAN_PRODUCE_GT,
+                                    "fragment files on disk (uncompressed, page cache) -> gdbgpu_array_open_ex -> gdbgpu_scan_next_batch(GDBGPU_SCAN_BCF_FORMAT, "
+                                    "host output) -> close", stage_files, args.e2e_steps)
+                shutil.rmtree(ws, ignore_errors=True)
+                if args.config == "4shard":
+                    # GZIP fragment (the reference's default): a 1/8 slice of the shard, so that writing it with zlib stays short
+                    n8 = max(8, (site_hi - site_lo) // 8)
+                    d8 = gdbsyn.generate(**cohort, site_lo=site_lo, site_hi=site_lo + n8)
+                    tiledb_writer.write_array(ws, "syn", d8, capacity=1000, compress=True)
+                    lo8, hi8 = d8["col_range"]
+                    saved = (q_lo, q_hi)
+                    q_lo, q_hi = lo8, hi8
+                    e2e_files_gzip = e2e_run(capi.SCAN_BCF_FORMAT | capi.SCAN_PRODUCE_GT,
+                                             "GZIP-compressed fragment files of a 1/8 slice of the shard (%d candidate sites) -> gdbgpu_array_open_ex (tiles "
+                                             "inflated on the device, K0) -> scan (BCF blocks to the host) -> close" % n8, stage_files, args.e2e_steps)
+                    q_lo, q_hi = saved
+                    del d8
+            finally:
+                shutil.rmtree(ws, ignore_errors=True)
+    del d
+
+    # ---------------- strong scaling on ONE on-disk array: BASELINE config #3 (10 k samples x 1 M positions), every rank opens
+    # its own tile range (cuts from the book-keeping) of the same fragment
+    strong = None
+    if not args.no_extras and args.config == "4shard":
+        c3 = WORKLOADS["3"]["cohort"]
+        ws3 = os.path.join(args.scratch, "gdbbench_c3_%s" % os.environ.get("MASTER_PORT", str(os.getpid())))
+        try:
+            if rank == 0:
+                d3 = gdbsyn.generate(**c3)
+                tiledb_writer.write_array(ws3, "syn", d3, capacity=1000)
+                del d3
+            barrier()
+            cuts = sharding.tile_balanced_cuts(ws3, "syn", world)
+            lo3, hi3 = cuts[rank]
+            t0 = time.perf_counter()
+            a3 = capi.Array.open(ctx, ws3, "syn", FIELDS, col_range=(lo3, hi3))
+            ctx.synchronize()
+            open_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            i3 = a3.info()
+            for _ in range(3):
+                one_pass(a3, capi.SCAN_DEVICE_OUTPUT, lo=lo3, hi=hi3)
+            barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            n3 = 0
+            for _ in range(args.steps):
+                n3 += one_pass(a3, capi.SCAN_DEVICE_OUTPUT, lo=lo3, hi=hi3)[0]
+            e1.record(stream)
+            ctx.synchronize()
+            torch.cuda.synchronize()
+            ms3 = max_over_ranks(e0.elapsed_time(e1))
+            a3.close()
+            tot3 = sum_over_ranks(float(n3))
+            # end to end from the files, every rank its range: open (read + H2D + index) + scan with BCF blocks to the host + close
+            barrier()
+            t0 = time.perf_counter()
+            a3 = capi.Array.open(ctx, ws3, "syn", FIELDS, col_range=(lo3, hi3))
+            n3e = one_pass(a3, capi.SCAN_BCF_FORMAT | capi.SCAN_PRODUCE_GT, args.e2e_batch_bytes, lo=lo3, hi=hi3)[0]
+            a3.close()
+            ctx.synchronize()
+            dt3 = max_over_ranks(time.perf_counter() - t0)
+            strong = dict(workload="GDBSYN-1 config#3 whole: %d samples x %d candidate sites, ONE on-disk fragment; rank r opens the tiles of its column "
+                                   "range (gdbgpu_array_column_cuts -> gdbgpu_array_open_range)" % (c3["n_samples"], c3["n_sites"]),
+                          scaling="strong", n_gpus=world, sites_per_pass=tot3 / args.steps, ms_per_pass=ms3 / args.steps,
+                          value=tot3 / (ms3 * 1e-3), unit="sites/s", open_ms=open_ms, cells_this_rank=int(i3.n_cells),
+                          cells_max_over_ranks=int(max_over_ranks(float(i3.n_cells))), staged_bytes_this_rank=int(i3.staged_bytes),
+                          e2e_from_files=dict(value=sum_over_ranks(float(n3e)) / dt3, unit="sites/s", ms=dt3 * 1e3))
+            barrier()
+        finally:
+            if rank == 0:
+                shutil.rmtree(ws3, ignore_errors=True)
     ctx.close()
+    if ctx2:
+        ctx2.close()
 
     base = base_bcf = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "4shard":
         base = cpu_baseline(args)
         if os.path.exists(REF_BIN):   # like-for-like for `e2e` (which also collates + BCF-encodes): the reference's whole Broad operator
             base_bcf = cpu_baseline(args, budget_s=8.0, mode="null")
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="sites/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
-                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling=w["scaling"], vs_baseline=None, dtype="int32",
                     data="synthetic", config=workload_config(args, world), clocks=sampler.summary(), e2e=e2e, e2e_int32=e2e_int32,
+                    e2e_from_fragment_files=e2e_files, e2e_from_gzip_fragment_files=e2e_files_gzip,
                     gpu_launches=int(launches), roofline=roofline, cpu_baseline=base, cpu_baseline_broad_gvcf_operator=base_bcf,
-                    columnar_iterator=columnar,
+                    strong_scaling_config3=strong, concatenation=gather, latency_config5=latency, columnar_iterator=columnar,
+                    numa_binding=dict(node=numa[0], cores=numa[1]) if numa else None,
                     sites_per_step_per_gpu=int(sites_per_step), cells_per_gpu=int(info.n_cells),
                     staged_bytes_per_gpu=int(info.staged_bytes), hbm_bytes_per_gpu=int(info.hbm_bytes))
         sys.stdout.flush()

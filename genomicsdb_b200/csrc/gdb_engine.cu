@@ -5,13 +5,19 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -38,6 +44,8 @@ struct gdbgpu_ctx {
   std::map<std::string, std::pair<double, uint64_t>> stats;
   std::vector<BatchBuffers*> bb_pool;
   std::multimap<size_t, void*> free_blocks; size_t cached_bytes = 0;   // device blocks waiting for reuse (see dev_alloc)
+  // file staging (gdbgpu_array_open*): worker threads pread the fragment files into pinned chunks and copy them on their own streams
+  uint8_t* stage_pin = nullptr; std::vector<cudaStream_t> stage_streams; std::vector<cudaEvent_t> stage_events;
   uint32_t tma_attr_set = 0;   // k_remap_tma instantiations whose dynamic shared-memory limit has been raised
   uint32_t* d_cls_tab = nullptr; uint16_t* d_jk_tab = nullptr; int n_sms = 148;   // universal genotype tables (gdb_kernels2.cuh: TileTabs)
   cudaEvent_t get_event() { if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
@@ -176,6 +184,60 @@ __global__ void k_add_u64(uint64_t* p, uint64_t n, uint64_t add) { uint64_t i = 
 __global__ void k_gather_bytes(const uint8_t* in, const uint32_t* perm, uint64_t n, uint32_t cell_bytes, uint8_t* out) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) for (uint32_t b = 0; b < cell_bytes; ++b) out[i * cell_bytes + b] = in[(uint64_t)perm[i] * cell_bytes + b];
+}
+
+// Fragment bytes travel disk (page cache) -> pinned chunk -> HBM: STAGE_WORKERS host threads take chunks of the jobs off one
+// counter, each with two pinned buffers and its own stream, so reads, copies of different files and PCIe overlap.  (Reading
+// whole files into pageable vectors first cost 2 s for a 3.9 GB shard; this path is bound by the page-cache copy.)
+struct FileJob { std::string path; uint64_t off, len; uint8_t* dst; };
+constexpr int STAGE_WORKERS = 8;
+constexpr size_t STAGE_CHUNK = 8u << 20;
+void stage_files(gdbgpu_ctx* ctx, const std::vector<FileJob>& jobs) {
+  if (jobs.empty()) return;
+  if (!ctx->stage_pin) {
+    CK(cudaMallocHost((void**)&ctx->stage_pin, (size_t)STAGE_WORKERS * 2 * STAGE_CHUNK));
+    for (int w = 0; w < STAGE_WORKERS; ++w) { cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); ctx->stage_streams.push_back(st); }
+    for (int w = 0; w < 2 * STAGE_WORKERS; ++w) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->stage_events.push_back(e); }
+  }
+  struct Chunk { uint32_t job; uint64_t off, len; };
+  std::vector<Chunk> chunks;
+  for (uint32_t j = 0; j < jobs.size(); ++j) for (uint64_t o = 0; o < jobs[j].len; o += STAGE_CHUNK) chunks.push_back(Chunk{j, o, std::min<uint64_t>(STAGE_CHUNK, jobs[j].len - o)});
+  std::atomic<size_t> next{0};
+  std::atomic<bool> failed{false};
+  std::string first_error;
+  std::mutex err_mu;
+  auto fail = [&](const std::string& m) { std::lock_guard<std::mutex> g(err_mu); if (!failed.exchange(true)) first_error = m; };
+  const int device = ctx->device;
+  auto worker = [&](int w) {
+    if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice failed in a staging thread"); return; }
+    int fd = -1; uint32_t fd_job = 0xFFFFFFFFu;
+    bool used[2] = {false, false};
+    for (int b = 0;; b ^= 1) {
+      const size_t c = next.fetch_add(1);
+      if (c >= chunks.size() || failed.load()) break;
+      const Chunk& ch = chunks[c]; const FileJob& jb = jobs[ch.job];
+      if (fd_job != ch.job) { if (fd >= 0) close(fd); fd = open(jb.path.c_str(), O_RDONLY); fd_job = ch.job; if (fd < 0) { fail("cannot open " + jb.path); break; } }
+      uint8_t* pin = ctx->stage_pin + ((size_t)w * 2 + b) * STAGE_CHUNK;
+      cudaEvent_t ev = ctx->stage_events[(size_t)w * 2 + b];
+      if (used[b] && cudaEventSynchronize(ev) != cudaSuccess) { fail("cudaEventSynchronize failed in a staging thread"); break; }
+      uint64_t done = 0;
+      while (done < ch.len) {
+        ssize_t r = pread(fd, pin + done, (size_t)(ch.len - done), (off_t)(jb.off + ch.off + done));
+        if (r <= 0) { fail("short read on " + jb.path); break; }
+        done += (uint64_t)r;
+      }
+      if (done < ch.len) break;
+      if (cudaMemcpyAsync(jb.dst + ch.off, pin, ch.len, cudaMemcpyHostToDevice, ctx->stage_streams[w]) != cudaSuccess || cudaEventRecord(ev, ctx->stage_streams[w]) != cudaSuccess) { fail("cudaMemcpyAsync failed in a staging thread"); break; }
+      used[b] = true;
+    }
+    if (fd >= 0) close(fd);
+    if (cudaStreamSynchronize(ctx->stage_streams[w]) != cudaSuccess) fail("a staging copy failed");
+  };
+  std::vector<std::thread> ts;
+  const int nw = (int)std::min<size_t>(STAGE_WORKERS, chunks.size());
+  for (int w = 0; w < nw; ++w) ts.emplace_back(worker, w);
+  for (auto& t : ts) t.join();
+  if (failed.load()) throw std::runtime_error(first_error);
 }
 
 struct HostVar { const uint64_t* off = nullptr; const void* val = nullptr; uint64_t bytes = 0; };
@@ -1407,6 +1469,9 @@ void gdbgpu_ctx_destroy(gdbgpu_ctx* ctx) {
   tl_ctx = nullptr;
   for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
   ctx->free_blocks.clear();
+  if (ctx->stage_pin) cudaFreeHost(ctx->stage_pin);
+  for (auto st : ctx->stage_streams) cudaStreamDestroy(st);
+  for (auto e : ctx->stage_events) cudaEventDestroy(e);
   if (ctx->d_cls_tab) cudaFree(ctx->d_cls_tab);
   if (ctx->d_jk_tab) cudaFree(ctx->d_jk_tab);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1542,7 +1607,8 @@ int gdbgpu_array_open_range(gdbgpu_ctx* ctx, const char* workspace, const char* 
       uint64_t file_bytes_staged = 0;   // bytes that crossed PCIe: the files' tiles as they lie on disk
       std::vector<DevColumn> cols(ids.size());
       // compressed files of all attributes are collected first: ONE copy of their bytes, ONE k_inflate launch over every tile
-      struct Pending { size_t arena_off; const std::vector<TdbTileSpan>* tiles; uint8_t* dst; };
+      struct Pending { size_t arena_off; const std::vector<TdbTileSpan>* tiles; uint8_t* dst; std::string path; uint64_t f_off, f_len; };
+      std::vector<FileJob> file_jobs;
       std::vector<std::vector<TdbRawColumn>> raw(ids.size(), std::vector<TdbRawColumn>(nfrag));
       std::vector<Pending> pending;
       size_t arena_bytes = 0, n_jobs = 0;
@@ -1550,45 +1616,38 @@ int gdbgpu_array_open_range(gdbgpu_ctx* ctx, const char* workspace, const char* 
       std::vector<Rebase> rebases;
       for (size_t k = 0; k < ids.size(); ++k) {
         uint64_t fixed_total = 0, var_total = 0;
-        for (size_t fi = 0; fi < nfrag; ++fi) { ta.read_column_raw(fi, ids[k], raw[k][fi], t0[fi], t1[fi]); fixed_total += raw[k][fi].fixed_bytes; var_total += raw[k][fi].var_bytes; }
+        for (size_t fi = 0; fi < nfrag; ++fi) { ta.read_column_raw(fi, ids[k], raw[k][fi], t0[fi], t1[fi], /*lazy=*/true); fixed_total += raw[k][fi].fixed_bytes; var_total += raw[k][fi].var_bytes; }
         DevColumn& dc = cols[k];
         dc.fixed.alloc(std::max<uint64_t>(fixed_total, 1) + 16); dc.var.alloc(std::max<uint64_t>(var_total, 1)); dc.var_bytes = var_total;
         uint64_t fixed_at = 0, var_at = 0, cells_at = 0;
         for (size_t fi = 0; fi < nfrag; ++fi) {
           const TdbRawColumn& r = raw[k][fi];
-          auto place = [&](const std::vector<uint8_t>& file, const std::vector<TdbTileSpan>& tiles, uint64_t bytes, uint8_t* dst) {
+          auto place = [&](const std::string& path, uint64_t f_off, uint64_t f_len, const std::vector<TdbTileSpan>& tiles, uint64_t bytes, uint8_t* dst) {
             if (!bytes) return;
-            file_bytes_staged += r.compressed ? file.size() : bytes;
-            if (!r.compressed) { CK(cudaMemcpyAsync(dst, file.data(), bytes, cudaMemcpyHostToDevice, ctx->stream)); return; }
-            pending.push_back(Pending{arena_bytes, &tiles, dst});
-            arena_bytes += (file.size() + 15) & ~(size_t)15; n_jobs += tiles.size();
+            file_bytes_staged += r.compressed ? f_len : bytes;
+            if (!r.compressed) { file_jobs.push_back(FileJob{path, f_off, bytes, dst}); return; }
+            pending.push_back(Pending{arena_bytes, &tiles, dst, path, f_off, f_len});
+            arena_bytes += (f_len + 15) & ~(size_t)15; n_jobs += tiles.size();
           };
-          place(r.fixed_file, r.fixed_tiles, r.fixed_bytes, dc.fixed.p + fixed_at);
+          place(r.fixed_path, r.fixed_off, r.fixed_len, r.fixed_tiles, r.fixed_bytes, dc.fixed.p + fixed_at);
           if (r.is_var) {
-            place(r.var_file, r.var_tiles, r.var_bytes, dc.var.p + var_at);
+            place(r.var_path, r.var_off, r.var_len, r.var_tiles, r.var_bytes, dc.var.p + var_at);
             if (var_at != r.var_base && frag_cells[fi]) rebases.push_back(Rebase{reinterpret_cast<uint64_t*>(dc.fixed.p) + cells_at, frag_cells[fi], var_at - r.var_base});
           }
           fixed_at += r.fixed_bytes; var_at += r.var_bytes; cells_at += frag_cells[fi];
         }
       }
+      DevBuf<uint8_t> arena;
+      if (n_jobs) arena.alloc(arena_bytes);
+      for (const Pending& pd : pending) file_jobs.push_back(FileJob{pd.path, pd.f_off, pd.f_len, arena.p + pd.arena_off});
+      stage_files(ctx, file_jobs);   // every byte of the range's tiles is in HBM when this returns
       if (n_jobs) {
-        DevBuf<uint8_t> arena; DevBuf<InflateJob> d_jobs; DevBuf<uint32_t> inf_err;
-        arena.alloc(arena_bytes); d_jobs.alloc(n_jobs); inf_err.alloc(2);
+        DevBuf<InflateJob> d_jobs; DevBuf<uint32_t> inf_err;
+        d_jobs.alloc(n_jobs); inf_err.alloc(2);
         CK(cudaMemsetAsync(inf_err.p, 0, 8, ctx->stream));
         std::vector<InflateJob> jobs; jobs.reserve(n_jobs);
-        size_t pi = 0;
-        for (size_t k = 0; k < ids.size(); ++k) for (size_t fi = 0; fi < nfrag; ++fi) {
-          const TdbRawColumn& r = raw[k][fi];
-          if (!r.compressed) continue;
-          for (int part = 0; part < 2; ++part) {
-            const std::vector<uint8_t>& file = part ? r.var_file : r.fixed_file;
-            const uint64_t bytes = part ? r.var_bytes : r.fixed_bytes;
-            if ((part && !r.is_var) || !bytes) continue;
-            const Pending& pd = pending[pi++];
-            CK(cudaMemcpyAsync(arena.p + pd.arena_off, file.data(), file.size(), cudaMemcpyHostToDevice, ctx->stream));
-            for (const TdbTileSpan& t : *pd.tiles) jobs.push_back(InflateJob{arena.p + pd.arena_off + t.in_off, t.in_len, pd.dst + t.out_off, t.out_len});
-          }
-        }
+        for (const Pending& pd : pending)
+          for (const TdbTileSpan& t : *pd.tiles) jobs.push_back(InflateJob{arena.p + pd.arena_off + t.in_off, t.in_len, pd.dst + t.out_off, t.out_len});
         CK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(InflateJob), cudaMemcpyHostToDevice, ctx->stream));
         LAUNCH(ctx, k_inflate, blocks_for(jobs.size(), 64), 64, d_jobs.p, (uint64_t)jobs.size(), inf_err.p);
         uint32_t e[2] = {0, 0};
@@ -1636,6 +1695,35 @@ int gdbgpu_array_open_range(gdbgpu_ctx* ctx, const char* workspace, const char* 
       return;
     }
   });
+}
+
+int gdbgpu_array_column_cuts(const char* workspace, const char* array_name, int32_t n_parts, int64_t* cuts) {
+  if (!workspace || !array_name || n_parts < 1 || !cuts) return GDBGPU_ERR_ARG;
+  try {
+    TdbArray ta(workspace, array_name);
+    // tiles of all fragments by the column of their first cell; a part closes at a tile boundary once it holds its share
+    struct Tile { int64_t first_col, last_col; int64_t cells; };
+    std::vector<Tile> tiles;
+    for (size_t fi = 0; fi < ta.num_fragments(); ++fi) {
+      const TdbBookKeeping& bk = ta.fragment(fi).bk;
+      for (int64_t t = 0; t < bk.tile_num; ++t)
+        tiles.push_back(Tile{bk.bounding_coords[4 * t + 1], bk.bounding_coords[4 * t + 3], ta.tile_cells(fi, t, t + 1)});
+    }
+    if (tiles.empty()) { for (int32_t r = 0; r <= n_parts; ++r) cuts[r] = 0; return GDBGPU_OK; }
+    std::sort(tiles.begin(), tiles.end(), [](const Tile& a, const Tile& b) { return a.first_col < b.first_col; });
+    int64_t total = 0, hi = tiles[0].last_col;
+    for (const Tile& t : tiles) { total += t.cells; hi = std::max(hi, t.last_col); }
+    cuts[0] = tiles[0].first_col; cuts[n_parts] = hi + 1;
+    int64_t acc = 0; size_t i = 0;
+    for (int32_t r = 1; r < n_parts; ++r) {
+      const int64_t want = total * r / n_parts;
+      while (i < tiles.size() && acc + tiles[i].cells <= want) acc += tiles[i++].cells;
+      // the cut sits at the first column of the next tile, never before the previous cut
+      int64_t c = i < tiles.size() ? tiles[i].first_col : hi + 1;
+      cuts[r] = std::max(c, cuts[r - 1]);
+    }
+    return GDBGPU_OK;
+  } catch (const std::exception&) { return GDBGPU_ERR_IO; }
 }
 
 int gdbgpu_array_get_info(const gdbgpu_array* a, gdbgpu_array_info* info) {

@@ -228,7 +228,7 @@ int64_t TdbArray::tile_cells(size_t fi, int64_t tile_lo, int64_t tile_hi) const 
 
 void TdbArray::read_column_raw(size_t fi, int attr_id, TdbRawColumn& out) const { read_column_raw(fi, attr_id, out, 0, fragments_[fi].bk.tile_num); }
 
-void TdbArray::read_column_raw(size_t fi, int attr_id, TdbRawColumn& out, int64_t t0, int64_t t1) const {
+void TdbArray::read_column_raw(size_t fi, int attr_id, TdbRawColumn& out, int64_t t0, int64_t t1, bool lazy) const {
   const TdbFragment& fr = fragments_[fi];
   const int nattr = (int)schema_.attributes.size();
   const std::string name = (attr_id == nattr) ? "__coords" : schema_.attributes[attr_id];
@@ -243,19 +243,24 @@ void TdbArray::read_column_raw(size_t fi, int attr_id, TdbRawColumn& out, int64_
   out.cells = (uint64_t)tile_cells(fi, t0, t1);
   out.fixed_bytes = out.cells * cell;
   const std::string fixed_path = fr.dir + "/" + name + ".tdb", var_path = fr.dir + "/" + name + "_var.tdb";
+  out.fixed_path = fixed_path; out.var_path = var_path;
   if (t0 == t1) return;
+  auto fetch = [&](const std::string& path, uint64_t off, uint64_t len, std::vector<uint8_t>& bytes, uint64_t& o_off, uint64_t& o_len) {
+    o_off = off; o_len = len;
+    if (!lazy) bytes = read_file_range(path, off, len);
+  };
   if (!out.compressed) {
     // tile i of an uncompressed attribute starts at i x capacity x cell size (read_state.cc:2581)
     if (file_size(fixed_path) != (uint64_t)fr.bk.cell_num * cell) fail("column size mismatch for " + name);
-    out.fixed_file = read_file_range(fixed_path, (uint64_t)t0 * cap * cell, out.fixed_bytes);
+    fetch(fixed_path, (uint64_t)t0 * cap * cell, out.fixed_bytes, out.fixed_file, out.fixed_off, out.fixed_len);
     if (out.is_var) {
       uint64_t v0, v1;
-      memcpy(&v0, out.fixed_file.data(), 8);
+      { std::vector<uint8_t> first = read_file_range(fixed_path, (uint64_t)t0 * cap * 8, 8); memcpy(&v0, first.data(), 8); }
       if (to_end) v1 = file_size(var_path);
       else { std::vector<uint8_t> nx = read_file_range(fixed_path, (uint64_t)t1 * cap * 8, 8); memcpy(&v1, nx.data(), 8); }
       if (v1 < v0) fail("value offsets out of order for " + name);
       out.var_base = v0; out.var_bytes = v1 - v0;
-      out.var_file = read_file_range(var_path, v0, v1 - v0);
+      fetch(var_path, v0, v1 - v0, out.var_file, out.var_off, out.var_len);
     }
     return;
   }
@@ -266,7 +271,7 @@ void TdbArray::read_column_raw(size_t fi, int attr_id, TdbRawColumn& out, int64_
   const uint64_t fsize = file_size(fixed_path);
   const uint64_t f_lo = (uint64_t)offs[t0], f_hi = to_end ? fsize : (uint64_t)offs[t1];
   if (f_hi < f_lo || f_hi > fsize) fail("tile offsets out of range for " + name);
-  out.fixed_file = read_file_range(fixed_path, f_lo, f_hi - f_lo);
+  fetch(fixed_path, f_lo, f_hi - f_lo, out.fixed_file, out.fixed_off, out.fixed_len);
   uint64_t o = 0;
   for (int64_t i = t0; i < t1; ++i) {
     const uint64_t lo = (uint64_t)offs[i], hi = (i + 1 < fr.bk.tile_num) ? (uint64_t)offs[i + 1] : fsize;
@@ -284,7 +289,7 @@ void TdbArray::read_column_raw(size_t fi, int attr_id, TdbRawColumn& out, int64_
     for (int64_t i = 0; i < t0; ++i) out.var_base += vsz[i];
     const uint64_t v_lo = (uint64_t)voffs[t0], v_hi = to_end ? vsize : (uint64_t)voffs[t1];
     if (v_hi < v_lo || v_hi > vsize) fail("var tile offsets out of range for " + name);
-    out.var_file = read_file_range(var_path, v_lo, v_hi - v_lo);
+    fetch(var_path, v_lo, v_hi - v_lo, out.var_file, out.var_off, out.var_len);
     uint64_t vo = 0;
     for (int64_t i = t0; i < t1; ++i) {
       const uint64_t lo = (uint64_t)voffs[i], hi = (i + 1 < fr.bk.tile_num) ? (uint64_t)voffs[i + 1] : vsize;

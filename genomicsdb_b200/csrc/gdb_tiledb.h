@@ -45,6 +45,10 @@ struct TdbRawColumn {
   std::vector<TdbTileSpan> fixed_tiles, var_tiles;   // compressed only: one zlib stream per tile
   uint64_t fixed_bytes = 0, var_bytes = 0;       // decompressed sizes
   bool is_var = false;
+  // lazy reads: where the bytes are instead of the bytes (fixed_file / var_file stay empty); in_off of the tile spans is
+  // relative to fixed_off / var_off as it is relative to the start of fixed_file / var_file otherwise
+  std::string fixed_path, var_path;
+  uint64_t fixed_off = 0, fixed_len = 0, var_off = 0, var_len = 0;
   uint64_t cells = 0;        // cells of the tiles that were read
   uint64_t var_base = 0;     // byte offset, in the fragment's whole value stream, of the first value byte that was read: the
                              // offsets in the fixed file are absolute (read_state.cc:2991-3001 rebases them the same way)
@@ -69,7 +73,8 @@ class TdbArray {
   // the device (gdb_inflate.cuh), never here; zlib is only used for the small gzip'ed book-keeping file.
   void read_column_raw(size_t fragment_idx, int attr_id, TdbRawColumn& out) const;
   // The same for tiles [tile_lo, tile_hi) only: the files are read with pread at the tiles' offsets, nothing else is touched.
-  void read_column_raw(size_t fragment_idx, int attr_id, TdbRawColumn& out, int64_t tile_lo, int64_t tile_hi) const;
+  // lazy: only say where the bytes are (TdbRawColumn::*_path, *_off, *_len); the caller streams them (gdb_engine.cu: stage_files)
+  void read_column_raw(size_t fragment_idx, int attr_id, TdbRawColumn& out, int64_t tile_lo, int64_t tile_hi, bool lazy = false) const;
   // Tiles of a fragment that can hold cells of columns [col_lo, col_hi]: binary search of the book-keeping's bounding
   // coordinates (first / last cell of every tile, global order = column, then row), what
   // ReadState::compute_tile_search_range_col_or_row does (read_state.cc:1427-1527).  tile_lo == tile_hi: none.

@@ -79,21 +79,70 @@ def device_equal_load_cuts(arr, world, bin_size, col_lo=None, col_hi=None, query
 
 
 def gather_concat(local_bytes, device=None, group=None, dst=0):
-    """Rank-ordered concatenation of per-rank byte strings on rank `dst` (MPI_Gatherv in gt_mpi_gather.cc:165-263):
-    all-gather of sizes, then one padded all-gather of the payloads.  Returns bytes on dst, None elsewhere."""
+    """Rank-ordered concatenation of per-rank byte strings on rank `dst`: MPI_Gather of the sizes + MPI_Gatherv of the
+    payloads in gt_mpi_gather.cc:165-263.  Here: an all-gather of the sizes (8 bytes per rank), then every other rank sends
+    exactly its bytes to `dst`, which posts one receive of exactly that size per sender (grouped isend / irecv: ncclSend /
+    ncclRecv inside one group on NCCL).  Nothing is padded and nobody but `dst` holds more than its own payload.
+    local_bytes: bytes-like, or a uint8 tensor (a tensor already on `device` is sent as it is).  Returns bytes on dst, None elsewhere."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = device or torch.device("cpu")
-    size = torch.tensor([len(local_bytes)], dtype=torch.int64, device=dev)
+    if torch.is_tensor(local_bytes):
+        mine = local_bytes.to(dev).contiguous().view(torch.uint8).reshape(-1)
+    else:
+        mine = torch.frombuffer(bytearray(local_bytes), dtype=torch.uint8).to(dev) if len(local_bytes) else torch.zeros(0, dtype=torch.uint8, device=dev)
+    size = torch.tensor([mine.numel()], dtype=torch.int64, device=dev)
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(sizes, size, group=group)
     sizes = [int(s.item()) for s in sizes]
-    m = max(sizes + [1])
-    buf = torch.zeros(m, dtype=torch.uint8, device=dev)
-    if local_bytes:
-        buf[:len(local_bytes)] = torch.frombuffer(bytearray(local_bytes), dtype=torch.uint8).to(dev)
-    parts = [torch.zeros(m, dtype=torch.uint8, device=dev) for _ in range(world)]
-    dist.all_gather(parts, buf, group=group)
+    ops, parts = [], {}
+    if rank == dst:
+        for r in range(world):
+            if r != dst and sizes[r]:
+                parts[r] = torch.empty(sizes[r], dtype=torch.uint8, device=dev)
+                ops.append(dist.P2POp(dist.irecv, parts[r], r, group=group))
+    elif mine.numel():
+        ops.append(dist.P2POp(dist.isend, mine, dst, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
     if rank != dst:
         return None
-    return b"".join(bytes(parts[r][:sizes[r]].cpu().numpy().tobytes()) for r in range(world))
+    parts[dst] = mine
+    return b"".join(parts[r].cpu().numpy().tobytes() for r in range(world) if sizes[r])
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pins this process (and the pinned host buffers it is about to allocate: first touch) to the CPU cores of the NUMA node
+    the rank's GPU hangs off -- with 8 ranks on a two-socket box, staging and result copies that cross the socket
+    interconnect share one link.  Returns (numa node, number of cores) or None when the topology cannot be read."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node, len(allowed)
+    except Exception:
+        return None
+
+
+def tile_balanced_cuts(workspace, array_name, world):
+    """Column cuts for `world` ranks with ~equal cell counts, taken from the fragments' book-keeping alone (tile bounding
+    coordinates): no cell is read.  Returns `world` (lo, hi) intervals tiling the array's columns."""
+    import ctypes as C
+    from genomicsdb_b200 import capi
+    cuts = (C.c_int64 * (world + 1))()
+    rc = capi.lib().gdbgpu_array_column_cuts(workspace.encode(), array_name.encode(), world, cuts)
+    if rc != capi.OK:
+        raise capi.GdbGpuError(rc, "cannot read the book-keeping of %s/%s" % (workspace, array_name))
+    return [(int(cuts[r]), int(cuts[r + 1]) - 1) for r in range(world)]

@@ -145,6 +145,11 @@ int gdbgpu_array_open_range(gdbgpu_ctx* ctx, const char* workspace, const char* 
                             const gdbgpu_field_desc* fields, int32_t n_fields,
                             const gdbgpu_plain_field_desc* plain_fields, int32_t n_plain_fields,
                             int32_t gt_phased, int64_t col_lo, int64_t col_hi, gdbgpu_array** out);
+/* Column cuts for n_parts ranks with about equal cell counts, from the fragments' book-keeping alone (tile bounding
+ * coordinates and tile sizes; no attribute file is read): cuts[0] = first column, cuts[n_parts] = one past the last, rank r
+ * owns [cuts[r], cuts[r + 1] - 1] -- SURVEY 8e; the reference leaves this to the loader's column_partitions
+ * (genomicsdb_config_base.cc:205-223) or to ColumnHistogramOperator::equi_partition_and_print_bins.  Host only. */
+int gdbgpu_array_column_cuts(const char* workspace, const char* array_name, int32_t n_parts, int64_t* cuts);
 /* Same, from columns already decoded in host memory (loader hand-off, JNI buffers, synthetic generators). */
 int gdbgpu_array_from_columns(gdbgpu_ctx* ctx, const gdbgpu_columns* cols, gdbgpu_array** out);
 int gdbgpu_array_get_info(const gdbgpu_array* arr, gdbgpu_array_info* info);
