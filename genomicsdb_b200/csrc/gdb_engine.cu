@@ -1589,10 +1589,15 @@ int gdbgpu_array_open_range(gdbgpu_ctx* ctx, const char* workspace, const char* 
     // END copy (gt_get_column scans forward from col_lo until every row has shown a cell); when a row shows no cell inside
     // the staged tiles the range grows to the right, tiles doubling, until every row has or the fragments end.
     std::vector<int64_t> t0(nfrag, 0), t1(nfrag, 0);
+    // ... starting with a margin of about 16 cells per row past col_hi: in a cohort where every sample has calls all along the
+    // genome that already holds every row's next cell, and the first attempt is the last
+    int64_t margin_tiles = 0;
+    if (!whole && have_rows && sc.capacity > 0) margin_tiles = (16 * (ub - lb + 1) + sc.capacity - 1) / sc.capacity;
     for (size_t fi = 0; fi < nfrag; ++fi) {
       if (whole) { t0[fi] = 0; t1[fi] = ta.fragment(fi).bk.tile_num; }
-      else ta.tile_range(fi, col_lo, col_hi, t0[fi], t1[fi]);
+      else { ta.tile_range(fi, col_lo, col_hi, t0[fi], t1[fi]); t1[fi] = std::min<int64_t>(ta.fragment(fi).bk.tile_num, t1[fi] + margin_tiles); }
     }
+    margin_tiles = std::max<int64_t>(margin_tiles, 16);
     for (;;) {
       std::vector<uint64_t> frag_cells;
       uint64_t n_total = 0;
@@ -1687,7 +1692,8 @@ int gdbgpu_array_open_range(gdbgpu_ctx* ctx, const char* workspace, const char* 
         if (h_unseen) {
           tl_ctx = ctx;
           arr.reset();
-          for (size_t fi = 0; fi < nfrag; ++fi) t1[fi] = std::min<int64_t>(ta.fragment(fi).bk.tile_num, t1[fi] + std::max<int64_t>(16, t1[fi] - t0[fi]));
+          for (size_t fi = 0; fi < nfrag; ++fi) t1[fi] = std::min<int64_t>(ta.fragment(fi).bk.tile_num, t1[fi] + margin_tiles);
+          margin_tiles *= 2;
           continue;
         }
       }
