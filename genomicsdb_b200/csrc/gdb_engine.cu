@@ -23,7 +23,7 @@
 #include <vector>
 
 #include "gdb_inflate.cuh"
-#include "gdb_kernels5.cuh"
+#include "gdb_kernels6.cuh"
 #include "gdb_tiledb.h"
 
 using namespace gdb;
@@ -46,6 +46,7 @@ struct gdbgpu_ctx {
   std::multimap<size_t, void*> free_blocks; size_t cached_bytes = 0;   // device blocks waiting for reuse (see dev_alloc)
   // file staging (gdbgpu_array_open*): worker threads pread the fragment files into pinned chunks and copy them on their own streams
   uint8_t* stage_pin = nullptr; std::vector<cudaStream_t> stage_streams; std::vector<cudaEvent_t> stage_events;
+  uint32_t mix_attr_set = 0;   // k_remap_mix instantiations whose dynamic shared-memory limit has been raised
   uint32_t tma_attr_set = 0;   // k_remap_tma instantiations whose dynamic shared-memory limit has been raised
   uint32_t* d_cls_tab = nullptr; uint16_t* d_jk_tab = nullptr; int n_sms = 148;   // universal genotype tables (gdb_kernels2.cuh: TileTabs)
   cudaEvent_t get_event() { if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
@@ -541,7 +542,7 @@ struct CtlArena {
 // context keeps finished scans' buffers and hands them to the next scan.
 struct BatchBuffers {
   // per batch (device)
-  DevBuf<int32_t> live; DevBuf<uint32_t> lcls; DevBuf<SiteRec> sites; DevBuf<uint32_t> agg; DevBuf<uint2> nt, blk_map; DevBuf<uint32_t> cursors, allele_pos, lut_first; DevBuf<uint16_t> lut_len; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes; DevBuf<int16_t> lut_in2m;
+  DevBuf<int32_t> live; DevBuf<uint32_t> lcls; DevBuf<SiteRec> sites; DevBuf<uint32_t> agg; DevBuf<uint2> nt, nt_lut, blk_map; DevBuf<unsigned long long> sig_keys; DevBuf<uint32_t> sig_perm; uint32_t* sig_off_d = nullptr; DevBuf<uint32_t> cursors, allele_pos, lut_first; DevBuf<uint16_t> lut_len; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes; DevBuf<int16_t> lut_in2m;
   DevBuf<uint32_t> out_data[MAX_FIELDS + 1]; DevBuf<uint16_t> out_len[MAX_FIELDS + 1];
   CtlArena ctl;   // everything below points into ctl.d
   uint32_t* out_stride[MAX_FIELDS + 1] = {}; uint64_t* out_base[MAX_FIELDS + 1] = {};
@@ -797,13 +798,16 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
   const int n_out = s->n_out;
   for (;;) {
     bb.live.ensure((uint64_t)nb * S.nq); bb.lcls.ensure((uint64_t)nb * S.nq); bb.sites.ensure(nb); bb.cursors.ensure(4);
-    bb.agg.ensure((uint64_t)nb * AGG_WORDS); bb.nt.ensure((uint64_t)nb * S.nq);
+    bb.agg.ensure((uint64_t)nb * AGG_WORDS); bb.nt.ensure((uint64_t)nb * S.nq); bb.nt_lut.ensure((uint64_t)nb * S.nq);
     CK(cudaMemsetAsync(bb.agg.p, 0, (size_t)nb * AGG_WORDS * 4, ctx->stream));
     if (!s->cap_allele_recs) { s->cap_allele_recs = 1u << 16; s->cap_allele_bytes = 1u << 20; }
     bb.allele_pos.ensure(2ull * s->cap_allele_recs); bb.allele_hash.ensure(s->cap_allele_recs); bb.allele_bytes.ensure(s->cap_allele_bytes);
     CK(cudaMemsetAsync(bb.cursors.p, 0, 16, ctx->stream));
     BatchDev B{};
-    B.first_site = first_site; B.n_sites = nb; B.live = bb.live.p; B.lcls = bb.lcls.p; B.sites = bb.sites.p; B.agg = bb.agg.p; B.nt = bb.nt.p; B.cursors = bb.cursors.p;
+    B.first_site = first_site; B.n_sites = nb; B.live = bb.live.p; B.lcls = bb.lcls.p; B.sites = bb.sites.p; B.agg = bb.agg.p; B.nt = bb.nt.p; B.nt_lut = bb.nt_lut.p; B.cursors = bb.cursors.p;
+    // signature tables (gdb_kernels2.cuh: nt_lut): one slot per 64 samples, only for scans wide enough to repeat signatures
+    B.sig_slots = 0; B.sig_keys = nullptr;
+    if (S.nq >= SIG_MIN_ROWS) { uint32_t sl = 64; while (sl < SIG_MAX_SLOTS && (uint64_t)sl * 64 < S.nq) sl *= 2; B.sig_slots = sl; bb.sig_keys.ensure((uint64_t)nb * sl); B.sig_keys = bb.sig_keys.p; }
     B.allele_pos = bb.allele_pos.p; B.allele_hash = bb.allele_hash.p; B.cap_allele_recs = s->cap_allele_recs; B.allele_bytes = bb.allele_bytes.p; B.cap_allele_bytes = s->cap_allele_bytes;
     {   // sites walked by one thread after one binary search: long chunks amortise the search, short ones keep the device full
       const uint64_t want_threads = 400000;
@@ -821,6 +825,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
     {   // byte comparison behind every hash match (a throughput pass over the batch's nt lists; its verdict travels with the batch's tail)
       uint32_t max_nt = 0;
       for (uint32_t i = 0; i < nb; ++i) if (bb.h_sites[i].n_alleles >= 2u) max_nt = std::max(max_nt, bb.h_sites[i].n_nt);
+      if (max_nt && B.sig_keys) CK(cudaMemsetAsync(bb.sig_keys.p, 0xFF, (size_t)nb * B.sig_slots * 8, ctx->stream));
       if (max_nt) LAUNCH(ctx, k_verify_alleles, dim3(blocks_for(max_nt, VERIFY_THREADS), nb), VERIFY_THREADS, a->dev, S, B);
     }
     // strides / bases; keep the prefix of sites that fits
@@ -840,7 +845,11 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
     s->avg_site_bytes = std::max<uint64_t>(1, bytes / keep);
     // split the batch: the tile kernels take every ordinary site, the generic kernel the pathological ones.  k_remap_tile
     // remaps the non-trivial calls of its sites itself (phase C); k_remap_nt only serves the copy-through sites
-    auto nt_blocks = [](const SiteRec& r) -> uint32_t { return (r.flags & 2u) ? 0u : (r.n_nt + NT_GROUPS - 1) / NT_GROUPS; };
+    // GDBGPU_K5 selects the remap kernel of the remapped sites: "mix" (default: k_remap_mix, tile blocks and nt blocks in one
+    // grid), "tile" (k_remap_tile, the tile's non-trivial calls as a third phase of the block), "tma" (k_remap_tma)
+    const char* k5_env = getenv("GDBGPU_K5");
+    const bool k5_mix = !k5_env || !strcmp(k5_env, "mix");
+    auto nt_blocks = [k5_mix](const SiteRec& r) -> uint32_t { return ((r.flags & 2u) && !k5_mix) ? 0u : (r.n_nt + NT_GROUPS - 1) / NT_GROUPS; };
     std::vector<uint32_t> fast, slow, nt_prefix, order;
     uint32_t jk_n = 4;
     for (uint32_t i = 0; i < keep; ++i) {
@@ -860,7 +869,6 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       // engine), else k_remap_tile; copy-through sites -> k_copy_tile.  All three lists live in tile_sites, in that order
       // GDBGPU_K5=tma: tiles built in shared memory and stored by the bulk-copy engine (k_remap_tma).  Measured slower than
       // k_remap_tile's direct STG.128 stream on this workload (profiles/r02_k5_tma_experiments.json), so it is opt-in
-      const char* k5_env = getenv("GDBGPU_K5");
       const bool no_tma = !(k5_env && !strcmp(k5_env, "tma"));
       auto tma_words = [&](uint32_t i) -> uint32_t {   // words per sample over the remapped fields, 0 = not eligible
         if (no_tma || !(bb.h_sites[i].flags & 2u)) return 0;
@@ -878,7 +886,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
     bb.h_site_flags.resize(keep); bb.h_n_alleles.resize(keep); bb.h_n_live.resize(keep); bb.h_allele_first.resize(keep);
     for (uint32_t i = 0; i < keep; ++i) { const SiteRec& r = bb.h_sites[i]; bb.h_site_flags[i] = (uint8_t)r.flags; bb.h_n_alleles[i] = r.n_alleles; bb.h_n_live[i] = r.n_live; bb.h_allele_first[i] = r.allele_first; }
     // one pinned block, one copy: bases, strides, site lists, site table (+ the FORMAT plan later)
-    bb.ctl.begin((size_t)n_out * ((size_t)keep * 12 + 64) + (size_t)keep * 48 + (size_t)(n_out + MAX_PLAIN) * keep * 13 + 4096);
+    bb.ctl.begin((size_t)n_out * ((size_t)keep * 12 + 64) + (size_t)keep * 56 + (size_t)(n_out + MAX_PLAIN) * keep * 13 + 4096);
     RemapOut O{};
     O.n_out = n_out;
     for (int o = 0; o < n_out; ++o) {
@@ -887,6 +895,18 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       bb.out_stride[o] = bb.ctl.push(bb.h_stride[o].data(), keep);
       O.f[o] = FieldOutDev{bb.out_data[o].p, bb.out_base[o], bb.out_stride[o], bb.out_len[o].p};
     }
+    // permutation rows of the sites' call signatures (k_sig_perm): sig_slots rows of 8 + sum of strides bytes per eligible site
+    std::vector<uint32_t> sig_off(keep, 0xFFFFFFFFu);
+    uint64_t sig_words = 0;
+    if (k5_mix && !s->summary_only && B.sig_keys) for (uint32_t i : fast) {
+      const SiteRec& r = bb.h_sites[i];
+      if (!(r.flags & 2u) || !r.n_nt || r.n_alleles > 0xFDu) continue;
+      uint32_t row_words = SIG_HDR_BYTES / 4; bool ok = true;
+      for (int o = a->has_gt ? 1 : 0; o < n_out; ++o) { row_words += bb.h_stride[o][i] >> 2; ok = ok && r.max_in_len[o - (a->has_gt ? 1 : 0)] <= PERM_MAX_IN; }
+      if (!ok || sig_words + (uint64_t)B.sig_slots * row_words >= 0xFFFFFFFFull) continue;
+      sig_off[i] = (uint32_t)sig_words; sig_words += (uint64_t)B.sig_slots * row_words;
+    }
+    bb.sig_off_d = bb.ctl.push(sig_off.data(), sig_off.size());
     bb.fast_sites = bb.ctl.push(fast.data(), fast.size()); bb.nt_prefix_d = bb.ctl.push(nt_prefix.data(), nt_prefix.size());
     bb.tile_sites = bb.ctl.push(order.data(), order.size()); bb.slow_sites = bb.ctl.push(slow.data(), slow.size());
     if (s->device_output) {
@@ -936,7 +956,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
         }
         ++ctx->launches; CK(cudaGetLastError());
       }
-      for (size_t first = n_tma; first < n_remap; first += 65535) {
+      for (size_t first = n_tma; first < n_remap && !k5_mix; first += 65535) {
         const unsigned ny = (unsigned)std::min<size_t>(65535, n_remap - first);
         auto launch_tile = [&](auto kern) {
           ProfScope ps__(ctx, "k_remap_tile");
@@ -954,7 +974,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
         }
         ++ctx->launches; CK(cudaGetLastError());
       }
-      for (size_t first = n_remap; first < order.size(); first += 65535) {
+      for (size_t first = n_remap; first < order.size() && !k5_mix; first += 65535) {
         const unsigned ny = (unsigned)std::min<size_t>(65535, order.size() - first);
         auto launch_copy = [&](auto kern) {
           ProfScope ps__(ctx, "k_copy_tile");
@@ -972,10 +992,45 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
         }
         ++ctx->launches; CK(cudaGetLastError());
       }
-      const uint32_t n_blk = nt_prefix.back();
+      const uint32_t n_blk_all = nt_prefix.back();
+      const uint32_t n_blk = n_blk_all;
       if (n_blk) {
         bb.blk_map.ensure(n_blk);
         LAUNCH(ctx, k_nt_blocks, (unsigned)fast.size(), 256, B, bb.fast_sites, bb.nt_prefix_d, bb.blk_map.p);
+      }
+      if (k5_mix) {
+        if (sig_words) { bb.sig_perm.ensure(sig_words); LAUNCH(ctx, k_sig_perm, keep, SIGPERM_THREADS, a->dev, B, O, bb.sig_off_d, bb.sig_perm.p); }
+        // remapped sites' tile blocks and every site's nt blocks, one grid (gdb_kernels6.cuh)
+        const uint32_t n_bands = (uint32_t)((fast.size() + MIX_SPB - 1) / MIX_SPB);
+        uint64_t n_tb = (uint64_t)n_bands * tiles;
+        uint32_t n_blk = n_blk_all;
+        if (const char* dbg = getenv("GDBGPU_MIX_ONLY")) { if (!strcmp(dbg, "tile")) n_blk = 0; else if (!strcmp(dbg, "nt")) n_tb = 0; }   // timing experiments only: wrong results
+        if (n_tb + n_blk >= (1ull << 31)) throw LimitError("more than 2^31 blocks in one batch: lower max_sites");
+        if (n_tb + n_blk) {
+          // ceil(2^32 N / G), below 2^32 (a grid of nt blocks only is flagged by tile_groups = 0 and f(b) = b)
+          const uint64_t G = n_tb + n_blk;
+          const uint32_t nt_ratio = n_tb ? (uint32_t)((((uint64_t)n_blk << 32) + G - 1) / G) : 0xFFFFFFFFu;
+          auto launch_mix = [&](auto kern, size_t smem_bytes) {
+            if (!(ctx->mix_attr_set & (1u << key))) {   // live entries + hot-record ring + tile buffers exceed the default 48 KB per block
+              CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+              ctx->mix_attr_set |= 1u << key;
+            }
+            ProfScope ps__(ctx, "k_remap_mix");
+            kern<<<(unsigned)(n_tb + n_blk), TILE_ROWS, smem_bytes, ctx->stream>>>(a->dev, S, B, O, fast.size() == keep ? nullptr : bb.fast_sites, (uint32_t)fast.size(), tiles, n_tb ? 1u : 0u, bb.blk_map.p, n_blk, nt_ratio, tabs, sig_words ? bb.sig_off_d : nullptr, bb.sig_perm.p);
+          };
+          switch (key) {
+            case 2: launch_mix(k_remap_mix<1, false>, MixSmem<1>::BYTES); break;
+            case 3: launch_mix(k_remap_mix<1, true>, MixSmem<1>::BYTES); break;
+            case 4: launch_mix(k_remap_mix<2, false>, MixSmem<2>::BYTES); break;
+            case 5: launch_mix(k_remap_mix<2, true>, MixSmem<2>::BYTES); break;
+            case 6: launch_mix(k_remap_mix<3, false>, MixSmem<3>::BYTES); break;
+            case 7: launch_mix(k_remap_mix<3, true>, MixSmem<3>::BYTES); break;
+            case 8: launch_mix(k_remap_mix<4, false>, MixSmem<4>::BYTES); break;
+            default: launch_mix(k_remap_mix<4, true>, MixSmem<4>::BYTES); break;
+          }
+          ++ctx->launches; CK(cudaGetLastError());
+        }
+      } else if (n_blk) {
         auto launch_nt = [&](auto kern) {
           ProfScope ps__(ctx, "k_remap_nt");
           kern<<<n_blk, NT_THREADS, 0, ctx->stream>>>(a->dev, S, B, O, bb.blk_map.p, jk_n, tabs);

@@ -270,6 +270,13 @@ struct BatchDev {
   uint32_t* agg;              // n_sites x AGG_WORDS
   uint2* nt;                  // n_sites x nq : per site, its non-trivial live calls (first agg[AGG_NNT] entries, any order):
                               //   .x = query row, .y = warm-blob offset (16-byte units), or NT_REDUCED | cell for a spanning deletion
+  // allele LUT of every nt-list entry, as k_verify_alleles found it, indexed by (site, SAMPLE): bytes 0..5 = merged allele of input
+  // ALT 1..6 (0xFF: none), the upper 16 bits = slot of the call's signature in the site's table (SIG_NONE: no slot -- the remap
+  // kernels then rebuild the LUT from the hashes).  Calls with one and the same (LUT, #ALT, NON_REF index, ploidy) share one
+  // permutation row per site (k_sig_perm), so remapping such a call is a gather through that row (k_remap_mix).
+  uint2* nt_lut;
+  unsigned long long* sig_keys;   // n_sites x sig_slots, SIG_EMPTY = free (nullptr: no signature tables in this scan)
+  uint32_t sig_slots;             // a power of two
   // pools (atomic bump allocation; overflow -> err[2])
   uint32_t* cursors;          // [0] allele records, [1] allele bytes, [2] lut words
   uint32_t* allele_pos; uint64_t* allele_hash; uint32_t cap_allele_recs;
@@ -277,6 +284,11 @@ struct BatchDev {
 };
 
 constexpr uint32_t NT_REDUCED = 0x80000000u;
+constexpr uint32_t SIG_MAX_SLOTS = 1024, SIG_NONE = 0xFFFFu, SIG_MAX_ALT = 6, SIG_MIN_ROWS = 4096;   // tables only for scans of >= SIG_MIN_ROWS samples
+constexpr unsigned long long SIG_EMPTY = ~0ull;
+constexpr uint32_t SIG_HDR_BYTES = 8;                   // a permutation row starts with the output length of every field (4 x u16)
+constexpr uint32_t PERM_MISSING = 0xFFu, PERM_PAD = 0xFEu, PERM_MAX_IN = 0xFDu;   // a row's bytes: input index, or one of the two
+__device__ inline uint32_t sig_slot_of(unsigned long long key) { key ^= key >> 29; key *= 0x9E3779B97F4A7C15ull; return (uint32_t)(key >> 40); }
 // a non-reduced, non-(trivial and inline) call through its warm blob
 struct WarmView { const uint32_t* b; uint32_t n_alt, nr_idx, ref_len, gt_len, ploidy, tok_words; };
 // `at`: the blob's bytes where the caller has staged them (shared memory), nullptr = read the pool in HBM
@@ -635,33 +647,60 @@ __global__ void __launch_bounds__(VERIFY_THREADS) k_verify_alleles(const __grid_
   if (i >= site->n_nt || site->n_alleles < 2u) return;
   const uint32_t A_m = site->n_alleles, afirst = site->allele_first, mref_len = site->ref_len;
   const uint8_t* mref = B.allele_bytes + site->ref_off;
-  const uint2 ent = B.nt[(uint64_t)js * S.nq + i];
+  const uint64_t at = (uint64_t)js * S.nq + i;
+  const uint2 ent = B.nt[at];
   auto merged_of = [&](uint64_t h) -> uint32_t { for (uint32_t m = 1; m < A_m; ++m) if (B.allele_hash[afirst + m] == h) return afirst + m; return 0xFFFFFFFFu; };
+  unsigned long long lut = 0x0000FFFFFFFFFFFFull;   // bytes 0..5: merged allele of input ALT 1..6
+  uint32_t n_alt = 0, nr_idx = 0, ploidy = 0;
+  auto set_lut = [&](uint32_t t, uint32_t m) { if (t < SIG_MAX_ALT) lut = (lut & ~(0xFFull << (8 * t))) | ((unsigned long long)(m & 0xFFu) << (8 * t)); };
   if (ent.y & NT_REDUCED) {   // a spanning deletion contributes "*"
     const uint32_t m = merged_of(star_hash());
     if (m == 0xFFFFFFFFu || B.allele_pos[2 * m + 1] != 1u || B.allele_bytes[B.allele_pos[2 * m]] != (uint8_t)'*') atomicMax(&S.err[1], 6u);
-    return;
-  }
-  const WarmView v = warm_view(A, ent.y);
-  const uint32_t H0 = warm_hash_word((uint32_t)A.n_fields);
-  const uint32_t* tokw = v.b + H0 + 2u * v.n_alt;
-  const uint8_t* tb = reinterpret_cast<const uint8_t*>(tokw + v.n_alt);
-  for (uint32_t t = 0; t < v.n_alt && t < (uint32_t)MAX_CALL_ALLELES; ++t) {
-    const uint32_t w = tokw[t], tl = w & 0x3FFFFFFFu;
-    if (!(w & WARM_TOK_NONREF)) {
-      const uint32_t m = merged_of(warm_token_hash(v, H0, t, mref, mref_len));
-      bool same = m != 0xFFFFFFFFu;
-      if (same) {
-        const uint8_t* as = B.allele_bytes + B.allele_pos[2 * m]; const uint32_t al = B.allele_pos[2 * m + 1];
-        const uint32_t sfx = (v.ref_len < mref_len && !(w & WARM_TOK_SYMBOLIC)) ? mref_len - v.ref_len : 0u;
-        same = al == tl + sfx;
-        for (uint32_t x = 0; same && x < tl; ++x) same = as[x] == tb[x];
-        for (uint32_t x = 0; same && x < sfx; ++x) same = as[tl + x] == mref[v.ref_len + x];
+    const uint32_t cell = ent.y & ~NT_REDUCED;
+    const DelRec* dr = find_delrec(S, cell);
+    const CellDesc d = A.desc[cell];
+    n_alt = dr->n_alt; nr_idx = dr->has_nr ? 2u : 0u;
+    const uint32_t gt_len = (d.flags & F_GTVALID) ? d.gt_len : 0u; ploidy = gt_len ? ploidy_of(A.gt_phased, gt_len) : 0u;
+    if (m != 0xFFFFFFFFu) set_lut(0, m - afirst);
+    if (nr_idx) set_lut(nr_idx - 1u, A_m - 1u);
+  } else {
+    const WarmView v = warm_view(A, ent.y);
+    const uint32_t H0 = warm_hash_word((uint32_t)A.n_fields);
+    const uint32_t* tokw = v.b + H0 + 2u * v.n_alt;
+    const uint8_t* tb = reinterpret_cast<const uint8_t*>(tokw + v.n_alt);
+    n_alt = v.n_alt; nr_idx = v.nr_idx; ploidy = v.ploidy;
+    for (uint32_t t = 0; t < v.n_alt && t < (uint32_t)MAX_CALL_ALLELES; ++t) {
+      const uint32_t w = tokw[t], tl = w & 0x3FFFFFFFu;
+      if (!(w & WARM_TOK_NONREF)) {
+        const uint32_t m = merged_of(warm_token_hash(v, H0, t, mref, mref_len));
+        bool same = m != 0xFFFFFFFFu;
+        if (same) {
+          const uint8_t* as = B.allele_bytes + B.allele_pos[2 * m]; const uint32_t al = B.allele_pos[2 * m + 1];
+          const uint32_t sfx = (v.ref_len < mref_len && !(w & WARM_TOK_SYMBOLIC)) ? mref_len - v.ref_len : 0u;
+          same = al == tl + sfx;
+          for (uint32_t x = 0; same && x < tl; ++x) same = as[x] == tb[x];
+          for (uint32_t x = 0; same && x < sfx; ++x) same = as[tl + x] == mref[v.ref_len + x];
+        }
+        if (!same) atomicMax(&S.err[1], 6u);
+        else set_lut(t, m - afirst);
       }
-      if (!same) atomicMax(&S.err[1], 6u);
+      tb += tl;
     }
-    tb += tl;
+    if (nr_idx) set_lut(nr_idx - 1u, A_m - 1u);   // after the tokens: the remap kernels give <NON_REF> the last merged index whatever its hash
   }
+  // ---- the call's signature -> its slot in the site's table (open addressing, first come first served)
+  uint32_t slot = SIG_NONE;
+  if (B.sig_keys && n_alt <= SIG_MAX_ALT && ploidy <= 2u && A_m <= 0xFDu && (site->flags & 2u)) {
+    const unsigned long long key = lut | ((unsigned long long)(n_alt | (nr_idx << 3) | (ploidy << 6)) << 48);
+    unsigned long long* tab = B.sig_keys + (uint64_t)js * B.sig_slots;
+    uint32_t p = sig_slot_of(key) & (B.sig_slots - 1u);
+    for (uint32_t probe = 0; probe < 32u; ++probe, p = (p + 1u) & (B.sig_slots - 1u)) {   // a full neighbourhood: the call keeps its own LUT
+      unsigned long long cur = tab[p];
+      if (cur == SIG_EMPTY) cur = atomicCAS(&tab[p], SIG_EMPTY, key);
+      if (cur == SIG_EMPTY || cur == key) { slot = p; break; }
+    }
+  }
+  B.nt_lut[(uint64_t)js * S.nq + ent.x] = make_uint2((uint32_t)lut, (uint32_t)(lut >> 32) | (slot << 16));   // by sample
 }
 
 // ------------------------------------------------------------------------------------------------ K5 remap

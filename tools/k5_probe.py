@@ -16,13 +16,20 @@ import numpy as np  # noqa: E402
 from genomicsdb_b200 import capi  # noqa: E402
 from tools import gdbsyn  # noqa: E402
 
-KERNELS = ["k_verify_alleles", "k_remap_tma", "k_remap_tile", "k_copy_tile", "k_remap_nt", "k_remap_generic", "k_live_walk", "k_site_scan", "k_union", "k_"]
+KERNELS = ["k_verify_alleles", "k_sig_perm", "k_nt_blocks", "k_remap_mix", "k_remap_tma", "k_remap_tile", "k_copy_tile", "k_remap_nt", "k_remap_generic", "k_live_walk", "k_site_scan", "k_union", "k_"]
+
+
+_SET = set()
 
 
 def set_variant(v):
+    for k in _SET:
+        os.environ.pop(k, None)
+    _SET.clear()
     for kv in v.split("+"):
         k, _, val = kv.partition("=")
         os.environ[k] = val
+        _SET.add(k)
 
 
 def digest_pass(arr, q_lo, q_hi, flags, batch_bytes):
@@ -51,7 +58,7 @@ def main():
     ap.add_argument("--sites", type=int, default=1250)
     ap.add_argument("--ab-samples", type=int, default=20000)
     ap.add_argument("--ab-sites", type=int, default=60)
-    ap.add_argument("--variants", default="GDBGPU_K5=tile,GDBGPU_K5=tma")
+    ap.add_argument("--variants", default="GDBGPU_K5=tile,GDBGPU_K5=mix")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--batch-bytes", type=int, default=8 << 30)
     ap.add_argument("--no-ab", action="store_true")
