@@ -28,7 +28,9 @@ EXPORTS = ["gdbgpu_version", "gdbgpu_ctx_create", "gdbgpu_ctx_destroy", "gdbgpu_
            "gdbgpu_ctx_reset_kernel_stats", "gdbgpu_ctx_kernel_stats", "gdbgpu_array_open", "gdbgpu_array_open_ex", "gdbgpu_array_open_range", "gdbgpu_array_column_cuts", "gdbgpu_array_from_columns", "gdbgpu_array_get_info",
            "gdbgpu_array_copy_cells", "gdbgpu_array_close", "gdbgpu_scan_begin", "gdbgpu_scan_get_info",
            "gdbgpu_scan_next_batch", "gdbgpu_scan_seek", "gdbgpu_scan_end", "gdbgpu_scan_cells", "gdbgpu_scan_cells_histogram",
-           "gdbgpu_scan_cells_allele_counts", "gdbgpu_scan_cells_fetch", "gdbgpu_scan_cells_window"]
+           "gdbgpu_scan_cells_allele_counts", "gdbgpu_scan_cells_fetch", "gdbgpu_scan_cells_window",
+           "gdbgpu_stream_open", "gdbgpu_stream_close", "gdbgpu_stream_num_bytes_available", "gdbgpu_stream_read_next_byte",
+           "gdbgpu_stream_read", "gdbgpu_stream_skip", "gdbgpu_stream_last_error"]
 
 
 class FieldDesc(C.Structure):
@@ -142,6 +144,17 @@ def lib():
         L.gdbgpu_scan_cells_allele_counts.argtypes = [C.c_void_p, C.POINTER(AlleleCounts)]
         L.gdbgpu_scan_cells_fetch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.gdbgpu_scan_end.argtypes = [C.c_void_p]
+        L.gdbgpu_stream_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.gdbgpu_stream_close.argtypes = [C.c_void_p]
+        L.gdbgpu_stream_num_bytes_available.restype = C.c_uint64
+        L.gdbgpu_stream_num_bytes_available.argtypes = [C.c_void_p]
+        L.gdbgpu_stream_read_next_byte.argtypes = [C.c_void_p]
+        L.gdbgpu_stream_read.restype = C.c_int64
+        L.gdbgpu_stream_read.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
+        L.gdbgpu_stream_skip.restype = C.c_int64
+        L.gdbgpu_stream_skip.argtypes = [C.c_void_p, C.c_uint64]
+        L.gdbgpu_stream_last_error.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -458,3 +471,40 @@ class Scan:
         if self.h:
             lib().gdbgpu_scan_end(self.h)
             self.h = C.c_void_p()
+
+
+class QueryStream:
+    """The Java reader's query stream through the C ABI (gdbgpu_stream_*: one call per native method of
+    GenomicsDBQueryStream, jni/src/genomicsdb_GenomicsDBQueryStream.cc:29-111): an uncompressed BCF2 stream."""
+
+    def __init__(self, loader_json, query_json, chr="", start=0, end=0, rank=0, buffer_capacity=1 << 20, segment_size=1 << 20,
+                 is_bcf=True, produce_header_only=False, use_missing_values_only_not_vector_end=False, keep_idx_fields_in_bcf_header=True):
+        L = lib()
+        h = C.c_void_p()
+        rc = L.gdbgpu_stream_open((loader_json or "").encode(), query_json.encode(), (chr or "").encode(), start, end, rank, buffer_capacity,
+                                  segment_size, int(is_bcf), int(produce_header_only), int(use_missing_values_only_not_vector_end),
+                                  int(keep_idx_fields_in_bcf_header), C.byref(h))
+        if rc != 0:
+            raise GdbGpuError(rc, L.gdbgpu_stream_last_error().decode())
+        self._h = h
+
+    def num_bytes_available(self):
+        return lib().gdbgpu_stream_num_bytes_available(self._h)
+
+    def read(self, n):
+        buf = (C.c_uint8 * n)()
+        k = lib().gdbgpu_stream_read(self._h, buf, 0, n)
+        if k < 0:
+            raise GdbGpuError(ERR_IO, lib().gdbgpu_stream_last_error().decode())
+        return bytes(buf[:k])
+
+    def read_next_byte(self):
+        return lib().gdbgpu_stream_read_next_byte(self._h)
+
+    def skip(self, n):
+        return lib().gdbgpu_stream_skip(self._h, n)
+
+    def close(self):
+        if self._h:
+            lib().gdbgpu_stream_close(self._h)
+            self._h = None

@@ -13,6 +13,7 @@
 #include <fstream>
 
 #include "gdb_json.h"
+#include "gdb_vcf_header.h"
 
 namespace genomicsdb_b200 {
 
@@ -33,7 +34,7 @@ VidMapper::VidMapper(const std::string& file) {
       else if (l->type == JsonValue::NUM) f.length = std::to_string(l->as_int());
       else if (l->type == JsonValue::ARR) f.length = "2D";
     }
-    if (const JsonValue* c = v.find("vcf_field_class")) for (auto& x : c->arr) { if (x.str == "FORMAT") f.is_format = true; if (x.str == "INFO") f.is_info = true; }
+    if (const JsonValue* c = v.find("vcf_field_class")) for (auto& x : c->arr) { if (x.str == "FORMAT") f.is_format = true; if (x.str == "INFO") f.is_info = true; if (x.str == "FILTER") f.is_filter = true; }
     if (const JsonValue* c = v.find("VCF_field_combine_operation")) f.combine_op = c->str;
     else {   // defaults of the known fields (known_field_info.cc:284-308)
       static const char* medians[] = {"BaseQRankSum", "ClippingRankSum", "MQRankSum", "ReadPosRankSum", "MQ", "MQ0", "ExcessHet"};
@@ -56,6 +57,7 @@ VidMapper::VidMapper(const std::string& file) {
     };
     if (cl->type == JsonValue::OBJ) for (auto& kv : cl->obj) addc(kv.first, kv.second);
     else for (auto& v : cl->arr) addc(v.at("name").str, v);
+    contigs_file_order_ = contigs_;
     std::sort(contigs_.begin(), contigs_.end(), [](const ContigInfo& a, const ContigInfo& b) { return a.tiledb_column_offset < b.tiledb_column_offset; });
   }
 }
@@ -113,7 +115,13 @@ void VariantQueryConfig::read_from_file(const std::string& filename, int rank) {
     else if (mine.type == JsonValue::ARR) for (auto& it : mine.arr) add_item(it);
     set_rows_to_query(rows);
   }
-  if (const JsonValue* v = d.find("vid_mapping_file")) vid_ = VidMapper(v->str);
+  if (const JsonValue* v = d.find("vid_mapping_file")) vid_ = VidMapper(per_rank(*v).str);
+  if (const JsonValue* v = d.find("callset_mapping_file")) callset_mapping_file_ = per_rank(*v).str;
+  if (vid_.is_initialized() && !callset_mapping_file_.empty() && !vid_.is_callset_mapping_initialized()) vid_.read_callsets_file(callset_mapping_file_);
+  if (const JsonValue* v = d.find("vcf_header_filename")) vcf_header_filename_ = per_rank(*v).str;
+  if (const JsonValue* v = d.find("reference_genome")) reference_genome_ = per_rank(*v).str;
+  if (const JsonValue* v = d.find("vcf_output_format")) vcf_output_format_ = v->str;
+  if (const JsonValue* v = d.find("segment_size")) segment_size_ = (size_t)v->as_int();
   if (const JsonValue* v = d.find("max_diploid_alt_alleles_that_can_be_genotyped")) max_alt_ = (unsigned)v->as_int();
   if (const JsonValue* v = d.find("produce_GT_with_min_PL_value_for_spanning_deletions")) min_pl_gt_ = v->as_bool();
   if (const JsonValue* v = d.find("produce_GT_field")) produce_gt_ = v->as_bool();
@@ -227,11 +235,6 @@ void VCFAdapter::flush() {
   pending_.clear(); pending_bytes_ = 0;
   chunks_.clear(); chunk_used_ = chunk_cap_ = 0;
 }
-char VCFAdapter::get_reference_base_at_position(const std::string& contig, int64_t pos) const {
-  auto it = ref_bases_.find(contig + ":" + std::to_string(pos));
-  return it == ref_bases_.end() ? 'N' : it->second;
-}
-
 // ------------------------------------------------------------------------------------------------ BroadCombinedGVCFOperator
 namespace {
 // htslib typed values (vcf.h bcf_enc_int1 / bcf_enc_size, vcf.c bcf_enc_vchar / bcf_enc_vfloat)
@@ -269,6 +272,7 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
                                                      bool use_missing_values_only_not_vector_end)
     : m_vcf_adapter(&vcf_adapter), m_vid_mapper(&id_mapper), m_use_missing_values_not_vector_end(use_missing_values_only_not_vector_end) {
   if (!qc.is_bookkeeping_done()) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "BroadCombinedGVCFOperator: do_query_bookkeeping(config, true, true) must be called first");
+  if (vcf_adapter.is_initialized_from_config()) build_header(vcf_adapter, id_mapper, qc);
   auto key_of = [&](const std::string& vcf_name) {
     int k = vcf_adapter.get_dictionary_id(vcf_name);
     if (k < 0) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "field " + vcf_name + " is not in the VCF header");
@@ -321,6 +325,54 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
   if (m_dp_rule) m_DP_key = key_of("DP");
   m_END_key = key_of("END");
   m_num_vector_slots = n_remapped - (remapped_index("GT") >= 0 ? 1u : 0u) + (unsigned)plain.size();
+}
+
+// broad_combined_gvcf.cc:168-330: the template header gets the queried INFO / FORMAT fields it lacks, the FILTER lines when
+// FILTER is queried, the contigs of the vid mapping and -- unless the query is sites-only -- the samples of the queried rows;
+// then it is "cleaned up completely" (written without IDX fields, read back) and goes to the head of the output.
+bool add_field_to_hdr_if_missing(VCFHeaderLines& hdr, const VidMapper& id_mapper, const std::string& field_name, const std::string& vcf_name, int field_type_idx);   // gdb_host_config.cc
+void BroadCombinedGVCFOperator::build_header(VCFAdapter& vcf_adapter, const VidMapper& id_mapper, const VariantQueryConfig& qc) {
+  if (!id_mapper.is_callset_mapping_initialized() && !qc.sites_only_query())
+    throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Callset mapping in id mapper is not initialized");
+  VCFHeaderLines& hdr = *vcf_adapter.header_lines();
+  const bool sites_only = qc.sites_only_query();
+  bool filter_queried = false;
+  for (auto& name : qc.get_ordered_query_attributes()) {
+    if (name == "FILTER") { filter_queried = true; continue; }
+    const FieldInfo* fi = id_mapper.get_field_info(name);
+    if (!fi) continue;
+    const bool twin = name.size() > 7 && name.compare(name.size() - 7, 7, "_FORMAT") == 0;
+    const std::string vcf_name = twin ? name.substr(0, name.size() - 7) : name;
+    const bool is_info = fi->is_info && !twin, is_format = fi->is_format && (twin || !fi->is_info);
+    const std::string& op = fi->combine_op;
+    const bool dp_rule = vcf_name == "DP" && !twin && op == "DP";
+    const bool add_to_INFO = is_info && name != "END" && !dp_rule && op != "move_to_FORMAT";
+    const bool add_to_FORMAT = (is_format && (!sites_only || name == "DP_FORMAT" || name == "MIN_DP")) || (is_info && (dp_rule || (op == "move_to_FORMAT" && !sites_only)));
+    if (add_to_INFO) {
+      if (op.empty()) std::cerr << "WARNING: No valid combination operation found for INFO field " << vcf_name << " - the field will NOT be part of INFO fields in the generated VCF records\n";
+      else add_field_to_hdr_if_missing(hdr, id_mapper, name, vcf_name, HL_INFO);
+    }
+    if (add_to_FORMAT) {
+      if (is_format || op == "move_to_FORMAT") add_field_to_hdr_if_missing(hdr, id_mapper, name, vcf_name, HL_FMT);
+      else add_field_to_hdr_if_missing(hdr, id_mapper, name, "DP", HL_INFO);
+    }
+  }
+  if (filter_queried) for (auto& f : id_mapper.fields()) if (f.is_filter) add_field_to_hdr_if_missing(hdr, id_mapper, f.name, f.name, HL_FLT);
+  for (unsigned i = 0; i < id_mapper.get_num_contigs(); ++i) {
+    const ContigInfo& c = id_mapper.get_contig_info(i);
+    if (hdr.name2id(c.name) < 0) hdr.append("##contig=<ID=" + c.name + ",length=" + std::to_string(c.length) + ">");
+  }
+  if (!sites_only) {
+    std::string callset_name;
+    for (uint64_t i = 0; i < qc.get_num_rows_to_query(); ++i) {
+      const int64_t row_idx = qc.get_array_row_idx_for_query_row_idx(i);
+      if (!id_mapper.get_callset_name(row_idx, callset_name) || callset_name.empty())
+        throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "No sample/CallSet name specified in JSON file/Protobuf object for TileDB row " + std::to_string(row_idx));
+      if (!hdr.add_sample(callset_name)) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Could not add sample " + callset_name + " to the combined VCF/gVCF header");
+    }
+  }
+  vcf_adapter.finalize_header(!sites_only);
+  vcf_adapter.print_header();
 }
 
 // BroadCombinedGVCFOperator::operate (broad_combined_gvcf.cc:765-901) + bcf_write (htslib vcf.c) for one site
@@ -1036,20 +1088,27 @@ void VariantQueryProcessor::iterate_over_cells(const int, const VariantQueryConf
 }
 
 // ------------------------------------------------------------------------------------------------ GenomicsDBBCFGenerator
-GenomicsDBBCFGenerator::GenomicsDBBCFGenerator(const std::string&, const std::string& query_config_file, const std::string& serialized_bcf_header,
-                                               const char* chr, const int start, const int end, int my_rank, size_t buffer_capacity, size_t,
-                                               const char* output_format, const bool produce_header_only,
-                                               const bool use_missing_values_only_not_vector_end, const bool, int cuda_device,
-                                               const std::string& reference_bases_tsv)
-    : m_produce_header_only(produce_header_only), m_buffer_capacity(buffer_capacity) {
+// genomicsdb_bcf_generator.cc:27-93.  serialized_bcf_header == nullptr: the header is generated here, from the configuration
+void GenomicsDBBCFGenerator::construct(const std::string& loader_config_file, const std::string& query_config_file, const std::string* serialized_bcf_header,
+                                       const char* chr, int start, int end, int my_rank, const char* output_format,
+                                       bool use_missing_values_only_not_vector_end, int cuda_device, const std::string& reference_bases_tsv) {
   if (output_format && std::string(output_format) != "bu" && std::string(output_format) != "")
     throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "GenomicsDBBCFGenerator: only uncompressed BCF (\"bu\") is produced");
-  m_query_config.read_from_file(query_config_file, my_rank);   // vid / callset mapping come from the query JSON
-  if (serialized_bcf_header.size() < 9 || serialized_bcf_header.compare(0, 5, "BCF\2\2") != 0)
-    throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "GenomicsDBBCFGenerator: the header must be a serialised BCF2 header");
-  uint32_t l_text; memcpy(&l_text, serialized_bcf_header.data() + 5, 4);
-  m_vcf_adapter.set_vcf_header_text(std::string(serialized_bcf_header.data() + 9, strnlen(serialized_bcf_header.data() + 9, l_text)));
-  m_vcf_adapter.set_buffer_capacity(buffer_capacity);
+  GenomicsDBImportConfig loader_config;
+  if (!loader_config_file.empty()) {   // vid / callset mapping, workspace and array may come from the loader's file
+    loader_config.read_from_file(loader_config_file, my_rank);
+    m_query_config.update_from_loader(loader_config, my_rank);
+  }
+  m_query_config.read_from_file(query_config_file, my_rank);
+  if (!loader_config_file.empty()) m_query_config.subset_query_column_ranges_based_on_partition(loader_config, my_rank);
+  m_query_config.set_vcf_output_format("bu");
+  if (serialized_bcf_header) {
+    if (serialized_bcf_header->size() < 9 || serialized_bcf_header->compare(0, 5, "BCF\2\2") != 0)
+      throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "GenomicsDBBCFGenerator: the header must be a serialised BCF2 header");
+    uint32_t l_text; memcpy(&l_text, serialized_bcf_header->data() + 5, 4);
+    m_vcf_adapter.set_vcf_header_text(std::string(serialized_bcf_header->data() + 9, strnlen(serialized_bcf_header->data() + 9, l_text)));
+  } else m_vcf_adapter.initialize(m_query_config);
+  m_vcf_adapter.set_buffer_capacity(m_buffer_capacity);
   if (!reference_bases_tsv.empty()) {
     std::ifstream rb(reference_bases_tsv);
     if (!rb) throw GenomicsDBGPUException(GDBGPU_ERR_IO, "cannot open " + reference_bases_tsv);
@@ -1065,12 +1124,27 @@ GenomicsDBBCFGenerator::GenomicsDBBCFGenerator(const std::string&, const std::st
   m_storage_manager.reset(new VariantStorageManager(m_query_config.get_workspace(my_rank), 10u * 1024u * 1024u, cuda_device));
   m_query_processor.reset(new VariantQueryProcessor(m_storage_manager.get(), m_query_config.get_array_name(my_rank), vid_mapper));
   m_query_processor->do_query_bookkeeping(m_query_config, true, /*stage_broad_gvcf_fields=*/true);
-  m_vcf_adapter.append(serialized_bcf_header.data(), 9 + (size_t)l_text, false);   // print_header(): the stream starts with the header
-  m_combined_bcf_operator.reset(new BroadCombinedGVCFOperator(m_vcf_adapter, vid_mapper, m_query_config, use_missing_values_only_not_vector_end));
-  if (!produce_header_only)
+  if (serialized_bcf_header) { uint32_t l_text; memcpy(&l_text, serialized_bcf_header->data() + 5, 4); m_vcf_adapter.append(serialized_bcf_header->data(), 9 + (size_t)l_text, false); }   // print_header()
+  m_combined_bcf_operator.reset(new BroadCombinedGVCFOperator(m_vcf_adapter, vid_mapper, m_query_config, use_missing_values_only_not_vector_end));   // generated headers are printed here
+  if (!m_produce_header_only)
     m_query_processor->scan_and_operate(m_query_processor->get_array_descriptor(), m_query_config, *m_combined_bcf_operator, m_query_column_interval_idx, true, &m_scan_state);
   m_read_buffer.swap(m_vcf_adapter.get_buffer());
   m_vcf_adapter.get_buffer().clear();
+}
+GenomicsDBBCFGenerator::GenomicsDBBCFGenerator(const std::string& loader_config_file, const std::string& query_config_file, const std::string& serialized_bcf_header,
+                                               const char* chr, const int start, const int end, int my_rank, size_t buffer_capacity, size_t,
+                                               const char* output_format, const bool produce_header_only,
+                                               const bool use_missing_values_only_not_vector_end, const bool keep_idx_fields_in_bcf_header, int cuda_device,
+                                               const std::string& reference_bases_tsv)
+    : m_produce_header_only(produce_header_only), m_buffer_capacity(buffer_capacity), m_vcf_adapter(keep_idx_fields_in_bcf_header) {
+  construct(loader_config_file, query_config_file, &serialized_bcf_header, chr, start, end, my_rank, output_format, use_missing_values_only_not_vector_end, cuda_device, reference_bases_tsv);
+}
+GenomicsDBBCFGenerator::GenomicsDBBCFGenerator(const std::string& loader_config_file, const std::string& query_config_file,
+                                               const char* chr, const int start, const int end, int my_rank, size_t buffer_capacity, size_t,
+                                               const char* output_format, const bool produce_header_only,
+                                               const bool use_missing_values_only_not_vector_end, const bool keep_idx_fields_in_bcf_header)
+    : m_produce_header_only(produce_header_only), m_buffer_capacity(buffer_capacity), m_vcf_adapter(keep_idx_fields_in_bcf_header) {
+  construct(loader_config_file, query_config_file, nullptr, chr, start, end, my_rank, output_format, use_missing_values_only_not_vector_end, 0, "");
 }
 GenomicsDBBCFGenerator::~GenomicsDBBCFGenerator() {
   m_scan_state.reset();               // the scan before the array, the array before the context

@@ -41,6 +41,7 @@ class GenomicsDBGPUException : public std::runtime_error {
  private:
   int code_;
 };
+class VariantOperationException : public GenomicsDBGPUException { public: explicit VariantOperationException(const std::string& m) : GenomicsDBGPUException(GDBGPU_ERR_ARG, m) {} };
 // query_variants.cc:533-535
 class VariantQueryProcessorException : public GenomicsDBGPUException { using GenomicsDBGPUException::GenomicsDBGPUException; };
 
@@ -49,7 +50,7 @@ struct FieldInfo {
   std::string name;
   std::string type;        // "int", "float", "char", ...
   std::string length;      // "1", "R", "A", "G", "P", "PP", "VAR", "<n>"; 2-D descriptors are kept as "2D"
-  bool is_format = false, is_info = false;
+  bool is_format = false, is_info = false, is_filter = false;
   int global_idx = -1;     // position among the vid mapping's fields (what FILTER cells store); -1 for a FORMAT twin
   std::string combine_op;  // "VCF_field_combine_operation" of the vid mapping, else the known field's default (known_field_info.cc:284-308)
   bool is_allele_dependent() const { return length == "R" || length == "A" || length == "G"; }
@@ -65,9 +66,44 @@ class VidMapper {
   // vid_mapper.cc get_contig_location: the contig a TileDB column falls into (nullptr: unknown position)
   const ContigInfo* get_contig_location(int64_t column) const;
   const ContigInfo* get_contig_info(const std::string& name) const;   // nullptr: no such contig
+  bool get_contig_info(const std::string& name, ContigInfo& info) const { const ContigInfo* c = get_contig_info(name); if (c) info = *c; return c != nullptr; }
+  // contigs in the order of the vid mapping file (VidMapper::get_contig_info(idx): the order contig lines are added to a header in)
+  unsigned get_num_contigs() const { return (unsigned)contigs_file_order_.size(); }
+  const ContigInfo& get_contig_info(unsigned idx) const { return contigs_file_order_[idx]; }
+  // callset mapping (vid_mapper.cc:686-711,319-325): sample name of every TileDB row
+  void read_callsets_file(const std::string& callset_mapping_file);
+  bool is_callset_mapping_initialized() const { return !callset_names_.empty(); }
+  bool get_callset_name(int64_t row_idx, std::string& callset_name) const;
+  int64_t get_max_callset_row_idx() const { return (int64_t)callset_names_.size() - 1; }
  private:
   std::vector<FieldInfo> fields_;
   std::vector<ContigInfo> contigs_;   // sorted by tiledb_column_offset
+  std::vector<ContigInfo> contigs_file_order_;
+  std::vector<std::string> callset_names_;   // by row
+};
+
+// ---- loader configuration (include/config/genomicsdb_config_base.h GenomicsDBImportConfig, src/config/json_config.cc:340-440,
+// 718-790): what the query side takes from it -- workspace / array / mapping files of the rank's column partition and the
+// partition's column range
+class GenomicsDBImportConfig {
+ public:
+  void read_from_file(const std::string& filename, const int rank = 0);
+  bool is_partitioned_by_column() const { return !row_based_; }
+  std::pair<int64_t, int64_t> get_column_partition(const int rank, const unsigned idx = 0u) const;
+  const std::string& get_workspace(const int rank) const;
+  const std::string& get_array_name(const int rank) const;
+  const VidMapper& get_vid_mapper() const { return vid_; }
+  const std::string& get_callset_mapping_file() const { return callset_mapping_file_; }
+  const std::string& get_vcf_header_filename() const { return vcf_header_filename_; }
+  const std::string& get_reference_genome() const { return reference_genome_; }
+  size_t get_segment_size() const { return segment_size_; }
+ private:
+  bool row_based_ = false, partitions_specified_ = false;
+  std::vector<std::pair<int64_t, int64_t>> partitions_;   // in file order, ends fixed against the sorted order
+  std::vector<std::string> workspaces_, array_names_;
+  VidMapper vid_;
+  std::string callset_mapping_file_, vcf_header_filename_, reference_genome_;
+  size_t segment_size_ = 10u * 1024u * 1024u;
 };
 
 // ---- query configuration (include/config/variant_query_config.h)
@@ -90,6 +126,19 @@ class VariantQueryConfig {
   bool produce_FILTER_field() const { return produce_filter_; }
   void set_sites_only_query(bool v) { sites_only_ = v; }
   bool sites_only_query() const { return sites_only_; }
+  // genomicsdb_config_base.cc:179-223: what a query takes from the loader's configuration (gt_mpi_gather -l, the JNI path)
+  void update_from_loader(const GenomicsDBImportConfig& loader_config, const int rank = 0);
+  void subset_query_column_ranges_based_on_partition(const GenomicsDBImportConfig& loader_config, const int rank = 0);
+  void set_vcf_output_format(const std::string& f) { vcf_output_format_ = f; }
+  const std::string& get_vcf_output_format() const { return vcf_output_format_; }
+  const std::string& get_vcf_header_filename() const { return vcf_header_filename_; }
+  void set_vcf_header_filename(const std::string& f) { vcf_header_filename_ = f; }
+  const std::string& get_reference_genome() const { return reference_genome_; }
+  void set_reference_genome(const std::string& f) { reference_genome_ = f; }
+  size_t get_segment_size() const { return segment_size_; }
+  // rows of the query in query order (all rows of the callset mapping when none are given)
+  uint64_t get_num_rows_to_query() const { return rows_.empty() ? (uint64_t)(vid_.get_max_callset_row_idx() + 1) : rows_.size(); }
+  int64_t get_array_row_idx_for_query_row_idx(uint64_t i) const { return rows_.empty() ? (int64_t)i : rows_[i]; }
 
   const std::string& get_workspace(int = 0) const { return workspace_; }
   const std::string& get_array_name(int = 0) const { return array_name_; }
@@ -120,6 +169,8 @@ class VariantQueryConfig {
   unsigned max_alt_ = 50;
   bool min_pl_gt_ = false, produce_gt_ = false, sites_only_ = false, produce_filter_ = false;
   bool bookkeeping_done_ = false;
+  std::string vcf_header_filename_, reference_genome_, vcf_output_format_ = "bu", callset_mapping_file_;
+  size_t segment_size_ = 10u * 1024u * 1024u;
   std::vector<std::string> remapped_names_;
   // plain fields staged for the Broad operator (do_query_bookkeeping): FORMAT fields that are not allele-dependent, scalar
   // INFO fields with a median / sum / mean combine operation, the inputs of the DP rule
@@ -263,8 +314,24 @@ class GA4GHOperator : public SingleVariantOperatorBase {
 // dictionary (bcf_hdr_id2int), the reference genome (get_reference_base_at_position) and the output buffer whose fill level
 // drives overflow() (VCFSerializedBufferAdapter, vcf_adapter.h:190-260).  The header itself is produced by the unchanged
 // host code (htslib); here it is read back from its serialised form.
+class VCFHeaderLines;   // gdb_vcf_header.h
+class IndexedFasta;
 class VCFAdapter {
  public:
+  explicit VCFAdapter(bool keep_idx_fields_in_bcf_header = true);
+  virtual ~VCFAdapter();
+  VCFAdapter(const VCFAdapter&) = delete;
+  VCFAdapter& operator=(const VCFAdapter&) = delete;
+  // vcf_adapter.cc:309-380: the template VCF header (vcf_header_filename of the configuration; none: the default header) and
+  // the reference genome (an indexed FASTA: <file>.fai).  BroadCombinedGVCFOperator's constructor then adds the queried
+  // fields, the contigs of the vid mapping and the samples of the query, and print_header() puts the serialised BCF header
+  // at the head of the output -- header generation needs nothing from outside this library.
+  void initialize(const VariantQueryConfig& config);
+  bool is_initialized_from_config() const { return lines_ != nullptr; }
+  VCFHeaderLines* header_lines() { return lines_.get(); }
+  // takes the header as the lines stand, sets the dictionary used by the records
+  void finalize_header(bool with_samples);
+  virtual void print_header();   // "BCF\2\2", l_text, text
   // `header` = the BCF header text (bcf_hdr_t as htslib writes it: ##FILTER / ##INFO / ##FORMAT / ##contig lines, #CHROM line)
   void set_vcf_header_text(const std::string& header);
   const std::string& get_vcf_header_text() const { return header_; }
@@ -293,9 +360,40 @@ class VCFAdapter {
   std::string header_;
   std::vector<std::pair<std::string, int>> ids_, contigs_;
   std::map<std::string, char> ref_bases_;
+  std::unique_ptr<VCFHeaderLines> lines_;
+  bool keep_idx_ = true;
+  mutable std::unique_ptr<IndexedFasta> fasta_;   // the reference genome (ReferenceGenomeInfo, vcf_adapter.cc:31-58)
+  bool header_printed_ = false;
   std::vector<uint8_t> buffer_;
   size_t capacity_ = 0;
 };
+
+// vcf_adapter.h:190-260: the adapter the command line tool uses -- records accumulate in an RWBuffer the caller owns and
+// do_output() writes them to the output file
+struct RWBuffer {
+  std::vector<uint8_t> m_buffer;
+  size_t m_num_valid_bytes = 0, m_next_read_idx = 0;
+};
+class VCFSerializedBufferAdapter : public VCFAdapter {
+ public:
+  explicit VCFSerializedBufferAdapter(bool keep_idx_fields_in_bcf_header = true, bool do_output = true) : VCFAdapter(keep_idx_fields_in_bcf_header), m_do_output(do_output) {}
+  void set_buffer(RWBuffer& buffer) { m_rw_buffer = &buffer; }
+  void set_output_file(FILE* f) { m_output_fptr = f; }
+  void do_output();    // writes what scan_and_operate left behind (and forgets it); the caller resets m_num_valid_bytes
+ private:
+  RWBuffer* m_rw_buffer = nullptr; FILE* m_output_fptr = stdout; bool m_do_output;
+};
+// include/utils/timer.h: wall + cpu seconds, printed as the reference prints them (GENOMICSDB_TIMER lines)
+class Timer {
+ public:
+  Timer() { start(); }
+  void start();
+  void stop();
+  void print(const std::string& prefix = "", std::ostream& fptr = std::cerr) const;
+ private:
+  double wall0_ = 0, cpu0_ = 0, wall_ = 0, cpu_ = 0, cum_wall_ = 0, cum_cpu_ = 0;
+};
+enum ProduceBroadGVCFSubOperation { PRODUCE_BROAD_GVCF_UNKNOWN = 0, PRODUCE_BROAD_GVCF_PRODUCE_GVCF, PRODUCE_BROAD_GVCF_PRODUCE_INTERESTING_POSITIONS };
 
 // broad_combined_gvcf.h: one BCF2 record per operate() call, appended to the adapter's buffer in serialised form
 // (u32 l_shared, u32 l_indiv, shared, indiv -- what bcf_write emits for an uncompressed BCF).  FORMAT blocks, INFO scalars
@@ -306,12 +404,20 @@ class BroadCombinedGVCFOperator : public GA4GHOperator {
   // use_missing_values_only_not_vector_end: what GenomicsDBBCFGenerator passes for the Java reader (genomicsdb_bcf_generator.cc:60-83)
   BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, const VidMapper& id_mapper, const VariantQueryConfig& query_config,
                             bool use_missing_values_only_not_vector_end = false);
+  // the reference's own signature (broad_combined_gvcf.h:80-83)
+  BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, const VidMapper& id_mapper, const VariantQueryConfig& query_config,
+                            const unsigned max_diploid_alt_alleles_that_can_be_genotyped, const bool use_missing_values_only_not_vector_end = false)
+      : BroadCombinedGVCFOperator(vcf_adapter, id_mapper, query_config, use_missing_values_only_not_vector_end) {
+    m_max_diploid_alt_alleles_that_can_be_genotyped = max_diploid_alt_alleles_that_can_be_genotyped;
+  }
   bool wants_bcf_blocks() const override { return true; }
   bool wants_htsjdk_conventions() const override { return m_use_missing_values_not_vector_end; }
   void operate_on_bcf_site(const gdbgpu_batch& batch, uint32_t site, const VariantQueryConfig& query_config) override;
   bool overflow() const override { return m_vcf_adapter->overflow(); }
   void release_batch() override { m_vcf_adapter->flush(); }
   uint64_t get_num_records() const { return m_num_records; }
+  // broad_combined_gvcf.cc:168-330: queried fields, contigs and samples into the adapter's template header; header printed
+  static void build_header(VCFAdapter& vcf_adapter, const VidMapper& id_mapper, const VariantQueryConfig& query_config);
  private:
   VCFAdapter* m_vcf_adapter;
   const VidMapper* m_vid_mapper;
@@ -453,6 +559,10 @@ class VariantQueryProcessor {
   // query attribute order as the reference does (END, REF, ALT first)
   void do_query_bookkeeping(VariantQueryConfig& query_config, bool alleles_required = true, bool stage_broad_gvcf_fields = false,
                             bool stage_columnar_fields = false);
+  // the reference's own signature (query_variants.h:216-217): everything an operator of the combine path may want is staged
+  void do_query_bookkeeping(const VariantArraySchema&, VariantQueryConfig& query_config, const VidMapper&, const bool alleles_required) {
+    do_query_bookkeeping(query_config, alleles_required, /*stage_broad_gvcf_fields=*/true);
+  }
   // query_variants.cc:557-576: every cell of every query interval (or of the array) goes to the operator, then finalize()
   void iterate_over_cells(const int ad, const VariantQueryConfig& query_config, SingleCellOperatorBase& variant_operator,
                           const bool use_common_array_object = true) const;
@@ -481,6 +591,12 @@ class VariantQueryProcessor {
 // side; it comes in serialised ("BCF\2\2", l_text, text) -- the one argument the reference's constructor does not have.
 class GenomicsDBBCFGenerator {
  public:
+  // the reference's own signature (genomicsdb_bcf_generator.h:58-64): the header is generated here (template header of the
+  // configuration + queried fields + contigs + samples), the reference bases come from the configuration's indexed FASTA
+  GenomicsDBBCFGenerator(const std::string& loader_config_file, const std::string& query_config_file,
+                         const char* chr, const int start, const int end, int my_rank = 0, size_t buffer_capacity = 1048576u,
+                         size_t tiledb_segment_size = 1048576u, const char* output_format = "bu", const bool produce_header_only = false,
+                         const bool use_missing_values_only_not_vector_end = false, const bool keep_idx_fields_in_bcf_header = true);
   GenomicsDBBCFGenerator(const std::string& loader_config_file, const std::string& query_config_file, const std::string& serialized_bcf_header,
                          const char* chr, const int start, const int end, int my_rank = 0, size_t buffer_capacity = 1048576u,
                          size_t tiledb_segment_size = 1048576u, const char* output_format = "bu", const bool produce_header_only = false,
@@ -498,6 +614,8 @@ class GenomicsDBBCFGenerator {
   bool end() const { return m_done; }
  private:
   void produce_next_batch();
+  void construct(const std::string& loader_config_file, const std::string& query_config_file, const std::string* serialized_bcf_header, const char* chr, int start, int end,
+                 int my_rank, const char* output_format, bool use_missing_values_only_not_vector_end, int cuda_device, const std::string& reference_bases_tsv);
   bool m_done = false, m_produce_header_only;
   size_t m_buffer_capacity;
   std::unique_ptr<VariantStorageManager> m_storage_manager;

@@ -47,9 +47,13 @@ __global__ void __launch_bounds__(SIGPERM_THREADS) k_sig_perm(const __grid_const
   int* m2in = s_m2in[warp];
   // one warp per occupied slot: merged -> input allele (the last input allele naming a merged allele wins, <NON_REF> stands in
   // for the rest), then one lane per output word
-  for (uint32_t slot = warp; slot < B.sig_slots; slot += SIGPERM_THREADS / 32) {
-    const unsigned long long key = B.sig_keys[(uint64_t)js * B.sig_slots + slot];
-    if (key == SIG_EMPTY) continue;   // warp-uniform
+  for (uint32_t slot0 = warp * 32u; slot0 < B.sig_slots; slot0 += SIGPERM_THREADS) {   // 32 slots per load, then the occupied ones in turn
+    const unsigned long long my_key = slot0 + lane < B.sig_slots ? B.sig_keys[(uint64_t)js * B.sig_slots + slot0 + lane] : SIG_EMPTY;
+    uint32_t occ = __ballot_sync(0xFFFFFFFFu, my_key != SIG_EMPTY);
+    while (occ) {
+    const uint32_t src = __ffs(occ) - 1u; occ &= occ - 1u;
+    const unsigned long long key = __shfl_sync(0xFFFFFFFFu, my_key, src);
+    const uint32_t slot = slot0 + src;
     const uint32_t meta = (uint32_t)(key >> 48), n_alt = meta & 7u, nr_idx = (meta >> 3) & 7u, ploidy = meta >> 6;
     uint8_t* row = reinterpret_cast<uint8_t*>(sig_perm + off + (uint64_t)slot * row_words);
     __syncwarp();
@@ -83,9 +87,14 @@ __global__ void __launch_bounds__(SIGPERM_THREADS) k_sig_perm(const __grid_const
       }
       pb += stride;
     }
+    }
   }
 }
 
+#ifndef GDB_MIX_BAND_PHASE_C
+#define GDB_MIX_BAND_PHASE_C 0   // 1: band blocks write their samples' signature-row calls themselves (phase C).  Measured: the calls' gather
+                                 // chain then sits between two block barriers of every site -- 18.1 ms against 9.5 ms with the calls in nt blocks
+#endif
 #ifndef GDB_MIX_TRI_BUFS
 #define GDB_MIX_TRI_BUFS 1   // value-quad buffers of a band block: 2 saves one barrier per site, 1 saves 4 KB x fields of shared memory (occupancy)
 #endif
@@ -235,14 +244,16 @@ __global__ void __launch_bounds__(TILE_ROWS, GDB_MIX_BLOCKS) k_remap_mix(const _
     if (tid < st.A_m) s_ah[tid] = B.allele_hash[site_g->allele_first + tid];
     const uint32_t jk_n = (st.A_m * (st.A_m + 1u)) >> 1;
     for (uint32_t g = tid; g < ((jk_n + 3u) & ~3u) && g < (uint32_t)TILE_MAX_G + 6u; g += TILE_ROWS) s_jk[g] = tabs.jk[g];   // whole quads: the tail is read, then discarded
-    // ---- calls whose signature has a permutation row (k_sig_perm) are written by the band block that holds their sample
-    // (phase C there); what is left for the nt blocks: copy-through sites, long ALT lists, sites without a signature table
+    // ---- calls whose signature has a permutation row (k_sig_perm): a gather through the row instead of a LUT of their own
+    // (nt_apply); the others -- copy-through sites, long ALT lists, sites without a signature table -- rebuild theirs (nt_entry)
     const uint32_t soff = sig_off ? sig_off[st.js] : 0xFFFFFFFFu;
     uint2 rec = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
     if (active && soff != 0xFFFFFFFFu && !O.lut_first) rec = B.nt_lut[(uint64_t)st.js * S.nq + ent.x];
-    const bool by_band = active && soff != 0xFFFFFFFFu && !O.lut_first && (rec.y >> 16) != SIG_NONE;
+    const bool fast = active && soff != 0xFFFFFFFFu && !O.lut_first && (rec.y >> 16) != SIG_NONE;
+    const bool by_band = GDB_MIX_BAND_PHASE_C && fast;   // written by the band block that holds the sample
     if (!__syncthreads_or(active && !by_band)) return;
-    nt_entry<NF, GT>(A, S, B, O, st, s_jk, s_ah, s_m2in[grp], s_in2m[grp], active && !by_band, ent, gl);
+    if (__any_sync(0xFFFFFFFFu, active && !fast)) nt_entry<NF, GT>(A, S, B, O, st, s_jk, s_ah, s_m2in[grp], s_in2m[grp], active && !fast, ent, gl);
+    if (fast && !by_band) { const SigSite ss{st.js, st.A_m, st.sflags, sig_perm + soff}; nt_apply<NF, GT>(A, S, O, ss, ent.x, ent.y, rec, gl); }
     return;
   }
 
@@ -431,7 +442,7 @@ __global__ void __launch_bounds__(TILE_ROWS, GDB_MIX_BLOCKS) k_remap_mix(const _
       } else if (on_nt_list) {
 #pragma unroll
         for (int f = 0; f < NF; ++f) tri4[f] = make_uint4(0u, 0u, 0u, 0u);
-        if (soff != 0xFFFFFFFFu) {   // phase C of this block writes the row when its signature has a permutation row
+        if (GDB_MIX_BAND_PHASE_C && soff != 0xFFFFFFFFu) {   // phase C of this block writes the row when its signature has a permutation row
           s_ntl[atomicAdd(&s_cnt[par], 1u)] = make_uint2(tid, (e & LIVE_REDUCED) ? (NT_REDUCED | (uint32_t)(e & (LIVE_REDUCED - 1))) : h0.w);
           asm volatile("prefetch.global.L2 [%0];" ::"l"(&B.nt_lut[sq]));
           if (!(e & LIVE_REDUCED)) {   // the call's warm blob (h1.x words at 16-byte unit h0.w) travels to L2 while phases A / B run

@@ -326,6 +326,32 @@ int gdbgpu_scan_cells_allele_counts(gdbgpu_scan* scan, gdbgpu_allele_counts* out
 #define GDBGPU_CELL_FIELD_PLAIN    4
 int gdbgpu_scan_cells_fetch(gdbgpu_scan* scan, int32_t kind, int32_t index, const uint64_t** offsets, const uint8_t** bytes);
 
+/* ---- The query stream of the Java reader (com.intel.genomicsdb.reader.GenomicsDBQueryStream).  One entry point per native
+ * method of src/main/jni/src/genomicsdb_GenomicsDBQueryStream.cc:29-111, same arguments in the same order; the handle is
+ * what the JNI layer keeps in its jlong (there a GenomicsDBBCFGenerator*, src/main/cpp/src/vcf/genomicsdb_bcf_generator.cc).
+ * The stream is an uncompressed BCF2 file: header (generated from the configuration: template header + queried fields +
+ * contigs of the vid mapping + samples of the queried rows), then one record per combined site of the interval
+ * chr:start-end (1-based; chr empty: the query file's own column ranges).  loader_configuration_file may be NULL or empty
+ * when the query file names workspace, array, vid and callset mapping itself; with it, the rank's column partition bounds
+ * the query (update_from_loader / subset_query_column_ranges_based_on_partition). */
+typedef struct gdbgpu_stream gdbgpu_stream;
+/* jniGenomicsDBInit */
+int gdbgpu_stream_open(const char* loader_configuration_file, const char* query_configuration_file, const char* chr, int start, int end, int rank,
+                       uint64_t buffer_capacity, uint64_t segment_size, int is_bcf, int produce_header_only, int use_missing_values_only_not_vector_end,
+                       int keep_idx_fields_in_bcf_header, gdbgpu_stream** out);
+/* jniGenomicsDBClose */
+int gdbgpu_stream_close(gdbgpu_stream* stream);
+/* jniGenomicsDBGetNumBytesAvailable: the capacity of the stream's buffer (what the reference answers) */
+uint64_t gdbgpu_stream_num_bytes_available(gdbgpu_stream* stream);
+/* jniGenomicsDBReadNextByte: the next byte as a signed char, -1 at the end of the stream */
+int gdbgpu_stream_read_next_byte(gdbgpu_stream* stream);
+/* jniGenomicsDBRead: up to n bytes into dst + offset; returns the number of bytes copied (0 at the end), -1 on error */
+int64_t gdbgpu_stream_read(gdbgpu_stream* stream, uint8_t* dst, uint64_t offset, uint64_t n);
+/* jniGenomicsDBSkip */
+int64_t gdbgpu_stream_skip(gdbgpu_stream* stream, uint64_t n);
+/* message of the last failed gdbgpu_stream_* call of this thread */
+const char* gdbgpu_stream_last_error(void);
+
 /* library identity (for the test that checks every declared symbol is exported) */
 const char* gdbgpu_version(void);
 

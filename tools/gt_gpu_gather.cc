@@ -91,13 +91,16 @@ static std::string read_header_text(const std::string& path, std::string& raw_pr
   return all;
 }
 
-static int produce_broad_gvcf(const std::string& query_json, int rank, int device, const std::string& header_file, const std::string& ref_bases_file,
+static int produce_broad_gvcf(const std::string& query_json, const std::string& loader_json, int rank, int device, const std::string& header_file, const std::string& ref_bases_file,
                               const std::string& out_file, size_t buffer_capacity, bool htsjdk_conventions) {
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
   const auto t0 = now();
   VariantQueryConfig query_config;
+  GenomicsDBImportConfig loader_config;   // tools/src/gt_mpi_gather.cc:560-575
+  if (!loader_json.empty()) { loader_config.read_from_file(loader_json, rank); query_config.update_from_loader(loader_config, rank); }
   query_config.read_from_file(query_json, rank);
+  if (!loader_json.empty()) query_config.subset_query_column_ranges_based_on_partition(loader_config, rank);
   VariantStorageManager sm(query_config.get_workspace(rank), 10u * 1024u * 1024u, device);
   const auto t1 = now();   // CUDA context is up
   VariantQueryProcessor qp(&sm, query_config.get_array_name(rank), query_config.get_vid_mapper());
@@ -105,7 +108,10 @@ static int produce_broad_gvcf(const std::string& query_json, int rank, int devic
   const auto t2 = now();   // fragment files are staged in HBM
   VCFAdapter vcf_adapter;
   std::string raw_prefix;
-  vcf_adapter.set_vcf_header_text(read_header_text(header_file, raw_prefix));
+  // the header: generated from the configuration (template header + queried fields + contigs + samples), as the reference does
+  // (VCFAdapter::initialize); or, with --bcf-header, taken verbatim from a BCF / VCF file
+  if (header_file.empty()) vcf_adapter.initialize(query_config);
+  else vcf_adapter.set_vcf_header_text(read_header_text(header_file, raw_prefix));
   vcf_adapter.set_buffer_capacity(buffer_capacity);
   if (!ref_bases_file.empty()) {
     std::ifstream rb(ref_bases_file);
@@ -140,11 +146,17 @@ static int produce_broad_gvcf(const std::string& query_json, int rank, int devic
 // GenomicsDBBCFGenerator): pull the serialised BCF stream in `chunk`-byte reads, every 5th read a single byte.
 static int bcf_generator_stream(const std::string& query_json, int rank, int device, const std::string& header_file, const std::string& ref_bases_file,
                                 const std::string& out_file, size_t buffer_capacity, size_t chunk, bool htsjdk_conventions,
-                                const std::string& chr, int start, int end, bool header_only) {
+                                const std::string& chr, int start, int end, bool header_only, const std::string& loader_json) {
   std::string raw_prefix;
-  read_header_text(header_file, raw_prefix);
-  GenomicsDBBCFGenerator gen("", query_json, raw_prefix, chr.c_str(), start, end, rank, buffer_capacity ? buffer_capacity : 1048576u, 1048576u, "bu", header_only,
-                             htsjdk_conventions, true, device, ref_bases_file);
+  if (!header_file.empty()) read_header_text(header_file, raw_prefix);
+  std::unique_ptr<GenomicsDBBCFGenerator> gen_ptr;
+  if (header_file.empty())   // the reference's own constructor: everything from the loader / query configuration
+    gen_ptr.reset(new GenomicsDBBCFGenerator(loader_json, query_json, chr.c_str(), start, end, rank, buffer_capacity ? buffer_capacity : 1048576u, 1048576u, "bu", header_only,
+                                             htsjdk_conventions, true));
+  else
+    gen_ptr.reset(new GenomicsDBBCFGenerator(loader_json, query_json, raw_prefix, chr.c_str(), start, end, rank, buffer_capacity ? buffer_capacity : 1048576u, 1048576u, "bu", header_only,
+                                             htsjdk_conventions, true, device, ref_bases_file));
+  GenomicsDBBCFGenerator& gen = *gen_ptr;
   std::ofstream out(out_file, std::ios::binary);
   if (!out) { std::cerr << "cannot open " << out_file << "\n"; return -1; }
   std::vector<uint8_t> buf(chunk);
@@ -240,14 +252,15 @@ static int columnar_command(const std::string& query_json, int rank, int device,
 }
 
 int main(int argc, char** argv) {
-  std::string query_json, out_file, header_file, ref_bases_file; int rank = 0, device = 0; size_t page = 0; bool broad = false, htsjdk = false; int columnar = 0; size_t stream_chunk = 0; bool header_only = false; unsigned max_alleles_top = 0; std::string chr; int chr_start = 0, chr_end = 0;
+  std::string query_json, loader_json, out_file, header_file, ref_bases_file; int rank = 0, device = 0; size_t page = 0; bool broad = false, htsjdk = false; int columnar = 0; size_t stream_chunk = 0; bool header_only = false; unsigned max_alleles_top = 0; std::string chr; int chr_start = 0, chr_end = 0;
   static struct option long_options[] = {{"query", 1, 0, 'j'}, {"rank", 1, 0, 'r'}, {"output", 1, 0, 'o'}, {"device", 1, 0, 'd'}, {"page-size", 1, 0, 'p'},
-                                         {"produce-Broad-GVCF", 0, 0, 'B'}, {"bcf-header", 1, 0, 'H'}, {"reference-bases", 1, 0, 'R'}, {"htsjdk-conventions", 0, 0, 'J'},
+                                         {"produce-Broad-GVCF", 0, 0, 'B'}, {"loader-json-config", 1, 0, 'l'}, {"bcf-header", 1, 0, 'H'}, {"reference-bases", 1, 0, 'R'}, {"htsjdk-conventions", 0, 0, 'J'},
                                          {"produce-interesting-positions", 0, 0, 'I'}, {"bcf-generator", 1, 0, 'S'}, {"header-only", 0, 0, 'h'}, {"max-alleles", 1, 0, 'M'}, {"chromosome", 1, 0, 'c'}, {"begin", 1, 0, 'b'}, {"end", 1, 0, 'e'}, {"print-calls", 0, 0, 'C'}, {"print-csv", 0, 0, 'V'}, {"print-AC", 0, 0, 'A'}, {"produce-histogram", 0, 0, 'G'}, {0, 0, 0, 0}};
   int c;
-  while ((c = getopt_long(argc, argv, "j:r:o:d:p:BH:R:J", long_options, NULL)) >= 0) {
+  while ((c = getopt_long(argc, argv, "j:l:r:o:d:p:BH:R:J", long_options, NULL)) >= 0) {
     switch (c) {
       case 'j': query_json = optarg; break;
+      case 'l': loader_json = optarg; break;   // gt_mpi_gather -l: workspace / array / mappings / column partition of the rank from the loader's file
       case 'r': rank = atoi(optarg); break;
       case 'o': out_file = optarg; break;
       case 'd': device = atoi(optarg); break;
@@ -269,15 +282,13 @@ int main(int argc, char** argv) {
   if (query_json.empty() || out_file.empty()) { std::cerr << "usage: gt_gpu_gather -j query.json -o dump.bin [-r rank] [-d cuda_device] [-p sites_per_page]\n"; return -1; }
   try {
     if (stream_chunk) {
-      if (header_file.empty()) { std::cerr << "--bcf-generator needs --bcf-header\n"; return -1; }
-      return bcf_generator_stream(query_json, rank, device, header_file, ref_bases_file, out_file, page, stream_chunk, htsjdk, chr, chr_start, chr_end, header_only);
+      return bcf_generator_stream(query_json, rank, device, header_file, ref_bases_file, out_file, page, stream_chunk, htsjdk, chr, chr_start, chr_end, header_only, loader_json);
     }
     if (max_alleles_top) return max_alleles(query_json, rank, device, out_file, max_alleles_top);
     if (columnar == 'I') return interesting_positions(query_json, rank, device, out_file);
     if (columnar) return columnar_command(query_json, rank, device, out_file, columnar);
     if (broad) {
-      if (header_file.empty()) { std::cerr << "--produce-Broad-GVCF needs --bcf-header\n"; return -1; }
-      return produce_broad_gvcf(query_json, rank, device, header_file, ref_bases_file, out_file, page, htsjdk);
+      return produce_broad_gvcf(query_json, loader_json, rank, device, header_file, ref_bases_file, out_file, page, htsjdk);
     }
     VariantQueryConfig query_config;
     query_config.read_from_file(query_json, rank);
