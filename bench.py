@@ -308,10 +308,10 @@ def main():
     while len(sampler.rows) < 4 and time.time() - t_extra < 3.0:
         one_pass(arr, capi.SCAN_DEVICE_OUTPUT)
     sampler.stop_flag = True
-    kms = {k: ctx.kernel_stats(k)[0] / args.steps for k in ("k_remap_tile", "k_remap_tma", "k_remap_nt", "k_remap_generic", "k_copy_tile", "k_site_scan",
-                                                           "k_union", "k_verify_alleles", "k_live_walk")}
-    remap_n = sum(ctx.kernel_stats(k)[1] for k in ("k_remap_tile", "k_remap_tma", "k_remap_nt", "k_remap_generic"))
-    remap_ms = (kms["k_remap_tile"] + kms["k_remap_tma"] + kms["k_remap_nt"] + kms["k_remap_generic"] + kms["k_copy_tile"]) * args.steps
+    kms = {k: ctx.kernel_stats(k)[0] / args.steps for k in ("k_remap_mix", "k_remap_tile", "k_remap_tma", "k_remap_nt", "k_remap_generic", "k_copy_tile", "k_site_scan",
+                                                           "k_union", "k_verify_alleles", "k_sig_perm", "k_live_walk")}
+    remap_n = sum(ctx.kernel_stats(k)[1] for k in ("k_remap_mix", "k_remap_tile", "k_remap_tma", "k_remap_nt", "k_remap_generic"))
+    remap_ms = (kms["k_remap_mix"] + kms["k_remap_tile"] + kms["k_remap_tma"] + kms["k_remap_nt"] + kms["k_remap_generic"] + kms["k_copy_tile"]) * args.steps
     all_ms, _ = ctx.kernel_stats("k_")
     sites_per_step = sites // args.steps
     total_sites = sum_over_ranks(float(sites))
@@ -400,7 +400,7 @@ def main():
         tj = json.load(open(tpath))
         traffic = tj["k5_dram_bytes_per_site"] * sites / remap_n
         traffic_src = "profiles/r02_k5_traffic.json (ncu --set full of the remap kernels at this round's HEAD, dram bytes per site of the same shard) x sites per launch"
-    roofline = dict(bound="hbm", kernel="gdb::k_remap_tile (+ gdb::k_copy_tile for sites that need no remap, gdb::k_remap_nt for their rare non-trivial calls): K5 remap", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+    roofline = dict(bound="hbm", kernel="gdb::k_remap_mix: K5 remap (band blocks: 256 samples x 8 sites, remapped and copy-through; nt blocks: the non-trivial calls) -- with GDBGPU_K5=tile: gdb::k_remap_tile + k_copy_tile + k_remap_nt", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                     traffic_source=traffic_src, algorithmic_bytes_per_launch=(b_in_step + b_out_step) * args.steps / max(1, remap_n),
                     peak_source=peak_src, algorithmic_bytes_per_step=dict(b_in=b_in_step, b_out=b_out_step),
                     launches=int(remap_n), avg_launch_ms=remap_ms / max(1, remap_n),

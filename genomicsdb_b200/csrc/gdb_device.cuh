@@ -44,7 +44,7 @@ struct __align__(16) HotRec {
   uint8_t nr_idx;
   uint8_t gt_len;             // words; 0 when GT is invalid
   uint8_t inl;                // 1: w[] holds GT then the valid fields' words, flen[] their lengths
-  uint8_t flen[HOT_FIELDS];   // input length (words) of field f, 0 = absent / every element NULL
+  uint8_t flen[HOT_FIELDS];   // input length (words) of field f (saturates at 255), 0 = absent / every element NULL; set for every cell
   uint8_t ref_len8;           // REF length, saturates at 255 (then CellDesc has it)
   uint8_t ref0;               // first byte of REF (merge_reference_allele only asks whether it is 'N')
   uint32_t w[HOT_WORDS];

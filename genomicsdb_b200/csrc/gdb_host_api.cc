@@ -366,6 +366,7 @@ void BroadCombinedGVCFOperator::build_header(VCFAdapter& vcf_adapter, const VidM
     std::string callset_name;
     for (uint64_t i = 0; i < qc.get_num_rows_to_query(); ++i) {
       const int64_t row_idx = qc.get_array_row_idx_for_query_row_idx(i);
+      if (row_idx > id_mapper.get_max_callset_row_idx()) continue;   // rows past the array's last one are not part of the query (the reference clamps them away)
       if (!id_mapper.get_callset_name(row_idx, callset_name) || callset_name.empty())
         throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "No sample/CallSet name specified in JSON file/Protobuf object for TileDB row " + std::to_string(row_idx));
       if (!hdr.add_sample(callset_name)) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Could not add sample " + callset_name + " to the combined VCF/gVCF header");

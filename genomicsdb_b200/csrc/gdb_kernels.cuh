@@ -129,6 +129,9 @@ __global__ void __launch_bounds__(256) k_classify(ArrayDev A, CellDesc* __restri
     if (f < HOT_FIELDS) flen[f] = n;
     used += n; field_words += n;
   }
+  // which fields the call carries is recorded for every cell (saturating; the words themselves only when they fit): the remap
+  // kernels know the output lengths of a call from this record alone
+  for (int f = 0; f < A.n_fields && f < HOT_FIELDS; ++f) h.flen[f] = (uint8_t)(flen[f] > 255u ? 255u : flen[f]);
   if (fits && used <= HOT_WORDS) {
     h.inl = 1;
     uint32_t k = 0;

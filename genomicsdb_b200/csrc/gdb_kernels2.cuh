@@ -270,7 +270,7 @@ struct BatchDev {
   uint32_t* agg;              // n_sites x AGG_WORDS
   uint2* nt;                  // n_sites x nq : per site, its non-trivial live calls (first agg[AGG_NNT] entries, any order):
                               //   .x = query row, .y = warm-blob offset (16-byte units), or NT_REDUCED | cell for a spanning deletion
-  // allele LUT of every nt-list entry, as k_verify_alleles found it, indexed by (site, SAMPLE): bytes 0..5 = merged allele of input
+  // allele LUT of every nt-list entry, as k_verify_alleles found it (same indexing as nt): bytes 0..5 = merged allele of input
   // ALT 1..6 (0xFF: none), the upper 16 bits = slot of the call's signature in the site's table (SIG_NONE: no slot -- the remap
   // kernels then rebuild the LUT from the hashes).  Calls with one and the same (LUT, #ALT, NON_REF index, ploidy) share one
   // permutation row per site (k_sig_perm), so remapping such a call is a gather through that row (k_remap_mix).
@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(VERIFY_THREADS) k_verify_alleles(const __grid_
       if (cur == SIG_EMPTY || cur == key) { slot = p; break; }
     }
   }
-  B.nt_lut[(uint64_t)js * S.nq + ent.x] = make_uint2((uint32_t)lut, (uint32_t)(lut >> 32) | (slot << 16));   // by sample
+  B.nt_lut[at] = make_uint2((uint32_t)lut, (uint32_t)(lut >> 32) | (slot << 16));
 }
 
 // ------------------------------------------------------------------------------------------------ K5 remap

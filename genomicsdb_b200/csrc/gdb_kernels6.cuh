@@ -91,10 +91,8 @@ __global__ void __launch_bounds__(SIGPERM_THREADS) k_sig_perm(const __grid_const
   }
 }
 
-#ifndef GDB_MIX_BAND_PHASE_C
-#define GDB_MIX_BAND_PHASE_C 0   // 1: band blocks write their samples' signature-row calls themselves (phase C).  Measured: the calls' gather
-                                 // chain then sits between two block barriers of every site -- 18.1 ms against 9.5 ms with the calls in nt blocks
-#endif
+// (Tried and dropped: band blocks writing their samples' signature-row calls themselves, as a third phase per site -- the calls'
+// gather chain then sits between two block barriers of every site: 18.1 ms per step against 9.5 ms with the calls in nt blocks.)
 #ifndef GDB_MIX_TRI_BUFS
 #define GDB_MIX_TRI_BUFS 1   // value-quad buffers of a band block: 2 saves one barrier per site, 1 saves 4 KB x fields of shared memory (occupancy)
 #endif
@@ -116,10 +114,9 @@ struct MixSmem {
   static constexpr int CFG_WORDS = TILE_ROWS * NF;
   static constexpr int FC_WORDS = 16 * NF;                    // two buffers; per field: lpr, rpi, pad word of the site's plan
   static constexpr int SITE_WORDS = 8 + 4 * NF;               // per site of the band: js, A_m, flags, GT stride / dst, sig_off, -, per field stride / ploidy / dst
-  static constexpr int NTL_WORDS = 2 * TILE_ROWS + 4;         // the site's calls for phase C: (sample of the tile, warm-blob offset or NT_REDUCED | cell), two counters
   static constexpr int LIVE_WORDS = MIX_SPB * TILE_ROWS;      // the band's live entries, one bulk copy per site
   static constexpr int RING_WORDS = MIX_DEPTH * 2 * 4 * TILE_ROWS;   // hot records: [stage][half][sample] x 16 bytes
-  static constexpr int TILE_BYTES = (RING_WORDS + LIVE_WORDS + GDB_MIX_TRI_BUFS * TRI_WORDS + HW_WORDS + CFG_WORDS + FC_WORDS + SITE_WORDS * MIX_SPB + NTL_WORDS) * 4 + 16;   // + the mbarrier
+  static constexpr int TILE_BYTES = (RING_WORDS + LIVE_WORDS + GDB_MIX_TRI_BUFS * TRI_WORDS + HW_WORDS + CFG_WORDS + FC_WORDS + SITE_WORDS * MIX_SPB) * 4 + 16;   // + the mbarrier
   // nt role
   static constexpr int JK_BYTES = ((TILE_MAX_G + 6) * 2 + 15) & ~15;
   static constexpr int AH_BYTES = TILE_MAX_A * 8;
@@ -179,7 +176,7 @@ __device__ __forceinline__ void nt_apply(const ArrayDev& A, const ScanDev& S, co
       }
       dst[i] = val;
     }
-    if (gl == 0) fo.len[sq] = (uint16_t)gt_len;
+    if (gl == 0 && (ent_y & NT_REDUCED)) fo.len[sq] = (uint16_t)gt_len;   // other calls: the band block wrote the lengths with the neighbours'
   }
   uint32_t row_words = SIG_HDR_BYTES / 4;
 #pragma unroll
@@ -194,7 +191,7 @@ __device__ __forceinline__ void nt_apply(const ArrayDev& A, const ScanDev& S, co
     const uint32_t n = fn[f]; const uint32_t* in = fin[f];
     const uint32_t stride = fo.stride[js], lpr = stride >> 2;
     const uint32_t n_out = n ? (((f < 2 ? hdr.x : hdr.y) >> (16 * (f & 1))) & 0xFFFFu) : 0u;
-    if (gl == 0) fo.len[sq] = (uint16_t)n_out;
+    if (gl == 0 && (ent_y & NT_REDUCED)) fo.len[sq] = (uint16_t)n_out;
     uint4* dst4 = reinterpret_cast<uint4*>(fo.data + fo.base[js] + (uint64_t)q * stride);
     for (uint32_t qd = gl; qd < lpr; qd += NT_GL) {
       const uint32_t p4 = n ? prm[qd] : 0xFEFEFEFEu;
@@ -248,12 +245,11 @@ __global__ void __launch_bounds__(TILE_ROWS, GDB_MIX_BLOCKS) k_remap_mix(const _
     // (nt_apply); the others -- copy-through sites, long ALT lists, sites without a signature table -- rebuild theirs (nt_entry)
     const uint32_t soff = sig_off ? sig_off[st.js] : 0xFFFFFFFFu;
     uint2 rec = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-    if (active && soff != 0xFFFFFFFFu && !O.lut_first) rec = B.nt_lut[(uint64_t)st.js * S.nq + ent.x];
+    if (active && soff != 0xFFFFFFFFu && !O.lut_first) rec = B.nt_lut[(uint64_t)st.js * S.nq + ei];
     const bool fast = active && soff != 0xFFFFFFFFu && !O.lut_first && (rec.y >> 16) != SIG_NONE;
-    const bool by_band = GDB_MIX_BAND_PHASE_C && fast;   // written by the band block that holds the sample
-    if (!__syncthreads_or(active && !by_band)) return;
+    __syncthreads();
     if (__any_sync(0xFFFFFFFFu, active && !fast)) nt_entry<NF, GT>(A, S, B, O, st, s_jk, s_ah, s_m2in[grp], s_in2m[grp], active && !fast, ent, gl);
-    if (fast && !by_band) { const SigSite ss{st.js, st.A_m, st.sflags, sig_perm + soff}; nt_apply<NF, GT>(A, S, O, ss, ent.x, ent.y, rec, gl); }
+    if (fast) { const SigSite ss{st.js, st.A_m, st.sflags, sig_perm + soff}; nt_apply<NF, GT>(A, S, O, ss, ent.x, ent.y, rec, gl); }
     return;
   }
 
@@ -268,9 +264,7 @@ __global__ void __launch_bounds__(TILE_ROWS, GDB_MIX_BLOCKS) k_remap_mix(const _
   uint32_t* const s_cfg = s_hw + MixSmem<NF>::HW_WORDS;                      // [f * TILE_ROWS + t]
   uint32_t* const s_fc = s_cfg + MixSmem<NF>::CFG_WORDS;                     // [8 * NF * buf + 8 * f + {lpr, rpi, pad}] of the site's plan
   uint32_t* const s_site = s_fc + MixSmem<NF>::FC_WORDS;                     // [SITE_WORDS * k + ...] parameters of the band's sites
-  uint2* const s_ntl = reinterpret_cast<uint2*>(s_site + MixSmem<NF>::SITE_WORDS * MIX_SPB);
-  uint32_t* const s_cnt = reinterpret_cast<uint32_t*>(s_ntl + TILE_ROWS);   // [parity of the remapped site]
-  unsigned long long* const s_bar = reinterpret_cast<unsigned long long*>(s_cnt + 4);
+  unsigned long long* const s_bar = reinterpret_cast<unsigned long long*>(s_site + MixSmem<NF>::SITE_WORDS * MIX_SPB);
   constexpr int SW = MixSmem<NF>::SITE_WORDS;   // js, A_m, flags, gt stride, gt dst (2), sig_off, -, then per field: stride, site ploidy, dst (2)
   const uint32_t tb = blockIdx.x - nt_before;
   const uint32_t band = tb / tiles, tile = tb - band * tiles;
@@ -286,7 +280,6 @@ __global__ void __launch_bounds__(TILE_ROWS, GDB_MIX_BLOCKS) k_remap_mix(const _
   const bool bulk_ok = (((uintptr_t)B.live & 15u) == 0) && ((nq & 3u) == 0);
   const uint32_t bulk_words = bulk_ok ? (rows & ~3u) : 0u;
   if (tid == 0) {
-    s_cnt[0] = 0; s_cnt[1] = 0;
     mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (bulk_words) {
       mbar_expect_tx(s_bar, bulk_words * 4u * n_k);
@@ -333,7 +326,6 @@ __global__ void __launch_bounds__(TILE_ROWS, GDB_MIX_BLOCKS) k_remap_mix(const _
   int32_t e_prev = -1;
   uint32_t buf = 0, plan_key[NF];
   bool any_remapped = false;
-  uint32_t par = 0;   // parity of the remapped site (phase C counters)
 #pragma unroll
   for (int f = 0; f < NF; ++f) plan_key[f] = 0xFFFFFFFFu;
 
@@ -395,9 +387,8 @@ __global__ void __launch_bounds__(TILE_ROWS, GDB_MIX_BLOCKS) k_remap_mix(const _
     }
 
     // ------------------------------------------------------------------ remapped site
-    if (any_remapped) __syncthreads();   // every thread is done with the remapped site before: its value quads (one buffer) and its phase-C list
+    if (GDB_MIX_TRI_BUFS == 1 && any_remapped) __syncthreads();   // every thread is done streaming the remapped site before out of the one buffer
     any_remapped = true;
-    const uint32_t soff = sw[6];
     // ---- per-field plan of phase B; kept while the sites' layouts stay the same
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
@@ -442,12 +433,16 @@ __global__ void __launch_bounds__(TILE_ROWS, GDB_MIX_BLOCKS) k_remap_mix(const _
       } else if (on_nt_list) {
 #pragma unroll
         for (int f = 0; f < NF; ++f) tri4[f] = make_uint4(0u, 0u, 0u, 0u);
-        if (GDB_MIX_BAND_PHASE_C && soff != 0xFFFFFFFFu) {   // phase C of this block writes the row when its signature has a permutation row
-          s_ntl[atomicAdd(&s_cnt[par], 1u)] = make_uint2(tid, (e & LIVE_REDUCED) ? (NT_REDUCED | (uint32_t)(e & (LIVE_REDUCED - 1))) : h0.w);
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(&B.nt_lut[sq]));
-          if (!(e & LIVE_REDUCED)) {   // the call's warm blob (h1.x words at 16-byte unit h0.w) travels to L2 while phases A / B run
-            const char* blob = reinterpret_cast<const char*>(A.warm) + (uint64_t)h0.w * 16u;
-            for (uint32_t off = 0; off < h1.x * 4u; off += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(blob + off));
+        if (!(e & LIVE_REDUCED)) {
+          // the row's vectors come from an nt block, but its lengths are known here (the hot record has the call's ploidy and which
+          // fields it carries): written with the neighbours' they leave L2 as whole sectors, where 2-byte stores from an nt block
+          // would make every one of them a read-modify-write in DRAM
+          if (GT) O.f[0].len[sq] = (uint16_t)gt_len;
+#pragma unroll
+          for (int f = 0; f < NF; ++f) {
+            const uint32_t n = (fl4 >> (8 * f)) & 0xFF;
+            const int kind = A.fm[f].kind;
+            O.f[o_f0 + f].len[sq] = (uint16_t)((n && !(kind == KIND_G && g_suppressed)) ? num_elements_le2(kind, A_m - 1u, ploidy) : 0u);
           }
         }
       } else {
@@ -515,9 +510,7 @@ __global__ void __launch_bounds__(TILE_ROWS, GDB_MIX_BLOCKS) k_remap_mix(const _
         }
       }
     }
-    __syncthreads();   // the site's value quads, s_fc and phase-C list are complete
-    const uint32_t n_c = s_cnt[par];
-    if (tid == 0) s_cnt[par ^ 1u] = 0;   // last read after the barrier of the remapped site before
+    __syncthreads();   // the site's value quads and s_fc are complete
 
     // ---------------------------------------------------------------- phase B: the block streams the tile out
     // Field f of the tile is rows x lpr quads, contiguous.  Thread t keeps ONE quad column (t % lpr) and walks the rows
@@ -554,20 +547,6 @@ __global__ void __launch_bounds__(TILE_ROWS, GDB_MIX_BLOCKS) k_remap_mix(const _
       }
     }
     if (GDB_MIX_TRI_BUFS == 2) buf ^= 1u;
-    par ^= 1u;
-    // ---------------------------------------------------------------- phase C: the tile's calls with a permutation row
-    // ~10 % of the rows.  Written here, next to their neighbours in time, so that the lines they share with trivial rows leave
-    // L2 whole; their blobs were asked for during phase A.
-    if (n_c) {
-      const SigSite ss{js, A_m, sflags, sig_perm + soff};
-      const uint32_t grp = tid / NT_GL; const int gl = (int)(tid % NT_GL);
-      for (uint32_t i = grp; i < n_c; i += NT_GROUPS) {
-        const uint2 it = s_ntl[i];
-        const uint32_t qq = tile * TILE_ROWS + it.x;
-        const uint2 rec = B.nt_lut[(uint64_t)js * nq + qq];
-        if ((rec.y >> 16) != SIG_NONE) nt_apply<NF, GT>(A, S, O, ss, qq, it.y, rec, gl);   // else: an nt block writes the row
-      }
-    }
   }
 }
 

@@ -46,7 +46,7 @@ def test_shards_of_an_on_disk_cohort(ctx, tmp_path, compress):
                 si = shard.info()
                 assert si.n_cells <= whole.info().n_cells
                 if a == lo:
-                    assert si.n_cells < whole.info().n_cells * 0.75
+                    assert si.n_cells < whole.info().n_cells * 0.85   # a seventh of the columns + border tiles + the margin that holds the END copies
                 total_staged += si.staged_bytes
                 for q in ([a, b], [a + 100, a + 100], [a + 57, min(b, a + 2000)], [b - 10, b]):
                     want = dumps(whole, [q], ["GT", "AD", "PL"])
