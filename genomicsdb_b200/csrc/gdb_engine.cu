@@ -306,7 +306,7 @@ void fill_dev_view(gdbgpu_array* a) {
   D.lb_row = a->lb_row; D.num_rows = a->num_rows;
   D.desc = a->desc.p; D.hot = a->hot.p; D.warm = a->warm.p; D.cls = a->cls.p; D.effend = a->effend.p;
   a->plain_dev.n = (int32_t)a->plain.size();
-  for (size_t f = 0; f < a->plain.size(); ++f) a->plain_dev.f[f] = PlainDev{a->pm[f].fixed_len ? nullptr : a->plain[f]->off.p, a->plain[f]->val.p, a->pm[f].elem, a->pm[f].fixed_len, a->pm[f].no_format == 2 ? 1 : 0};
+  for (size_t f = 0; f < a->plain.size(); ++f) a->plain_dev.f[f] = PlainDev{a->pm[f].fixed_len ? nullptr : a->plain[f]->off.p, a->plain[f]->val.p, a->pm[f].elem, a->pm[f].fixed_len, a->pm[f].no_format == 2 ? HC_BLOCK : (a->pm[f].no_format == 3 ? (HC_BLOCK | HC_RAW | HC_SKIP_REDUCED) : (a->pm[f].no_format == 4 ? (HC_BLOCK | HC_SKIP_REDUCED) : 0))};
   D.rs_rec = a->rs_rec.p;
   D.n_rs = a->n_rs; D.rs_cell = a->rs_cell.p; D.rs_col = a->rs_col.p; D.rs_effend = a->rs_effend.p; D.row_start = a->row_start.p;
 }
@@ -376,7 +376,7 @@ gdbgpu_array* build_array(gdbgpu_ctx* ctx, const HostCols& h, const std::vector<
   if (h.n >= (1ull << 30)) throw LimitError("more than 2^30 cells in one staged array: shard the column range across GPUs");
   if (h.fields.size() > (size_t)MAX_FIELDS) throw LimitError("more than 15 allele-dependent fields queried");
   if (num_rows < 0 || num_rows >= (1ll << 31)) throw LimitError("row count out of range");
-  if (pm.size() > (size_t)MAX_PLAIN || pm.size() != h.plain.size()) throw LimitError("more than 16 plain FORMAT fields");
+  if (pm.size() > (size_t)MAX_PLAIN || pm.size() != h.plain.size()) throw LimitError("more than 24 plain FORMAT fields");
   std::unique_ptr<gdbgpu_array> a(new gdbgpu_array());
   a->pm = pm;
   a->ctx = ctx; a->n = h.n; a->lb_row = lb_row; a->num_rows = num_rows; a->gt_phased = gt_phased; a->has_gt = h.has_gt; a->fm = fm; a->field_names = names;
@@ -1581,7 +1581,7 @@ int gdbgpu_array_from_columns(gdbgpu_ctx* ctx, const gdbgpu_columns* c, gdbgpu_a
       names.push_back(nm);
     }
     std::vector<PlainMeta> pm;
-    if (c->n_plain_fields < 0 || c->n_plain_fields > MAX_PLAIN) throw LimitError("more than 16 plain FORMAT fields");
+    if (c->n_plain_fields < 0 || c->n_plain_fields > MAX_PLAIN) throw LimitError("more than 24 plain FORMAT fields");
     for (int f = 0; f < c->n_plain_fields; ++f) {
       const gdbgpu_plain_field_desc& d = c->plain_descs[f];
       if (d.elem_type < 0 || d.elem_type > GDBGPU_ELEM_CHAR || d.fixed_len < 0) throw ArgError("bad plain field descriptor");

@@ -11,6 +11,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iomanip>
+#include <map>
+#include <sstream>
 
 #include "gdb_json.h"
 #include "gdb_vcf_header.h"
@@ -32,8 +35,18 @@ VidMapper::VidMapper(const std::string& file) {
     if (const JsonValue* l = v.find("length")) {
       if (l->type == JsonValue::STR) f.length = l->str;
       else if (l->type == JsonValue::NUM) f.length = std::to_string(l->as_int());
-      else if (l->type == JsonValue::ARR) f.length = "2D";
+      else if (l->type == JsonValue::ARR) {
+        if (l->arr.size() == 1) f.length = l->arr[0].type == JsonValue::NUM ? std::to_string(l->arr[0].as_int()) : l->arr[0].str;
+        else { f.length = "2D"; for (auto& x : l->arr) f.dim_lengths.push_back(x.type == JsonValue::NUM ? std::to_string(x.as_int()) : x.str); }
+      }
     }
+    if (const JsonValue* t = v.find("type")) { if (t->type == JsonValue::ARR) for (auto& x : t->arr) f.tuple_types.push_back(x.str); }
+    if (const JsonValue* dl = v.find("vcf_delimiter")) {
+      if (dl->type == JsonValue::ARR) { for (auto& x : dl->arr) f.vcf_delimiters.push_back(x.str.empty() ? ',' : x.str[0]); }
+      else if (dl->type == JsonValue::STR && !dl->str.empty()) f.vcf_delimiters.push_back(dl->str[0]);
+    }
+    if (f.tuple_types.size() > 1) f.length = "2D";   // a vector of tuples is handled like a multi-dimensional field (raw bytes, Type=String)
+    while (f.length == "2D" && f.vcf_delimiters.size() < 2) f.vcf_delimiters.push_back(f.vcf_delimiters.empty() ? '|' : ',');
     if (const JsonValue* c = v.find("vcf_field_class")) for (auto& x : c->arr) { if (x.str == "FORMAT") f.is_format = true; if (x.str == "INFO") f.is_info = true; if (x.str == "FILTER") f.is_filter = true; }
     if (const JsonValue* c = v.find("VCF_field_combine_operation")) f.combine_op = c->str;
     else {   // defaults of the known fields (known_field_info.cc:284-308)
@@ -45,6 +58,11 @@ VidMapper::VidMapper(const std::string& file) {
     f.global_idx = n_json_fields++;
     fields_.push_back(f);
     if (f.is_format && f.is_info) { FieldInfo g = f; g.name = name + "_FORMAT"; g.global_idx = -1; fields_.push_back(g); }   // vid_mapper.cc: FORMAT twin
+    if (f.is_composite())   // vid_mapper.cc flatten_field: one attribute per tuple element
+      for (size_t j = 0; j < f.tuple_types.size(); ++j) {
+        FieldInfo g = f; g.name = name + "_tuple_element_" + std::to_string(j); g.parent = name; g.tuple_index = (int)j; g.type = f.tuple_types[j]; g.global_idx = -1;
+        fields_.push_back(g);
+      }
   };
   if (fl.type == JsonValue::OBJ) for (auto& kv : fl.obj) add(kv.first, kv.second);
   else for (auto& v : fl.arr) add(v.at("name").str, v);
@@ -300,6 +318,22 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
       if (plain[p].is_qual) m_QUAL_plain = (int)p;
       else if (plain[p].is_id) m_ID_fmt_index = (int)(n_remapped + p);
       else if (plain[p].is_filter) { /* not a query-order field: below */ }
+      else if (plain[p].is_raw) {
+        if (name == "REF") { m_raw_REF_fmt_index = (int)(n_remapped + p); continue; }
+        if (name == "ALT") { m_raw_ALT_fmt_index = (int)(n_remapped + p); continue; }
+        if (fi->combine_op == "histogram_sum") {
+          const FieldInfo* parent = id_mapper.get_field_info(fi->parent);
+          const int parent_idx = parent ? parent->global_idx : 0;
+          auto it = std::find_if(m_INFO_histogram_fields.begin(), m_INFO_histogram_fields.end(), [&](const HistogramField& h) { return h.parent_idx == parent_idx; });
+          if (it == m_INFO_histogram_fields.end()) { HistogramField h; h.parent_idx = parent_idx; h.key = key_of(fi->vcf_name()); m_INFO_histogram_fields.push_back(h); it = m_INFO_histogram_fields.end() - 1; }
+          const int e = fi->tuple_index == 0 ? 0 : 1;
+          it->raw_fmt_index[e] = (int)(n_remapped + p); it->fi[e] = fi;
+        } else {
+          InfoField f; f.vcf_name = plain[p].vcf_name; f.key = key_of(plain[p].vcf_name); f.is_float = fi->type == "float";
+          f.raw_fmt_index = (int)(n_remapped + p); f.fi = fi;
+          m_INFO_fields_vec.push_back(f);
+        }
+      }
       else if (plain[p].is_concat) {
         InfoField f; f.vcf_name = plain[p].vcf_name; f.key = key_of(plain[p].vcf_name); f.is_float = plain[p].elem == GDBGPU_ELEM_FLOAT32;
         f.concat_fmt_index = (int)(n_remapped + p);
@@ -316,6 +350,9 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
   }
   if (dp_format_plain >= 0) m_FORMAT_fields_vec.push_back({"DP", key_of("DP"), (int)(n_remapped + dp_format_plain)});
   for (size_t p = 0; p < plain.size(); ++p) if (plain[p].is_filter) m_FILTER_fmt_index = (int)(n_remapped + p);
+  for (size_t p = 0; p < plain.size(); ++p) if (plain[p].is_raw && plain[p].attribute == "REF") m_raw_REF_fmt_index = (int)(n_remapped + p); else if (plain[p].is_raw && plain[p].attribute == "ALT") m_raw_ALT_fmt_index = (int)(n_remapped + p);
+  std::sort(m_INFO_histogram_fields.begin(), m_INFO_histogram_fields.end(), [](const HistogramField& a, const HistogramField& b) { return a.parent_idx < b.parent_idx; });
+  for (auto& h : m_INFO_histogram_fields) if (h.raw_fmt_index[0] < 0 || h.raw_fmt_index[1] < 0) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "histogram_sum: both tuple elements of the field must be queried");
   for (auto& f : id_mapper.fields()) {   // broad_combined_gvcf.cc:306-313: vid field index -> header dictionary id (could be -1)
     if (f.global_idx < 0) continue;
     if ((size_t)f.global_idx >= m_global_field_idx_to_hdr_idx.size()) m_global_field_idx_to_hdr_idx.resize(f.global_idx + 1, -1);
@@ -342,7 +379,7 @@ void BroadCombinedGVCFOperator::build_header(VCFAdapter& vcf_adapter, const VidM
     const FieldInfo* fi = id_mapper.get_field_info(name);
     if (!fi) continue;
     const bool twin = name.size() > 7 && name.compare(name.size() - 7, 7, "_FORMAT") == 0;
-    const std::string vcf_name = twin ? name.substr(0, name.size() - 7) : name;
+    const std::string vcf_name = twin ? name.substr(0, name.size() - 7) : fi->vcf_name();   // a flattened tuple element goes by its parent's name
     const bool is_info = fi->is_info && !twin, is_format = fi->is_format && (twin || !fi->is_info);
     const std::string& op = fi->combine_op;
     const bool dp_rule = vcf_name == "DP" && !twin && op == "DP";
@@ -350,7 +387,7 @@ void BroadCombinedGVCFOperator::build_header(VCFAdapter& vcf_adapter, const VidM
     const bool add_to_FORMAT = (is_format && (!sites_only || name == "DP_FORMAT" || name == "MIN_DP")) || (is_info && (dp_rule || (op == "move_to_FORMAT" && !sites_only)));
     if (add_to_INFO) {
       if (op.empty()) std::cerr << "WARNING: No valid combination operation found for INFO field " << vcf_name << " - the field will NOT be part of INFO fields in the generated VCF records\n";
-      else add_field_to_hdr_if_missing(hdr, id_mapper, name, vcf_name, HL_INFO);
+      else add_field_to_hdr_if_missing(hdr, id_mapper, fi->parent.empty() ? name : fi->parent, vcf_name, HL_INFO);
     }
     if (add_to_FORMAT) {
       if (is_format || op == "move_to_FORMAT") add_field_to_hdr_if_missing(hdr, id_mapper, name, vcf_name, HL_FMT);
@@ -374,6 +411,91 @@ void BroadCombinedGVCFOperator::build_header(VCFAdapter& vcf_adapter, const VidM
   }
   vcf_adapter.finalize_header(!sites_only);
   vcf_adapter.print_header();
+}
+
+// One call's value of a 2-D field, cut into its dimension-0 entries.  The stored value (genomicsdb_multid_vector_field.h:66-83) is
+// <u64 bytes of data><entry 0 data><entry 1 data>...<u64 #entries><u64 offset of entry 0, entry 1, ..., end>.  Where the reference
+// hands the combine the REMAPPED variant (a site that needs remapping, a field whose first dimension follows the alleles:
+// broad_combined_gvcf.cc:386-388,573-574), the entries are those of remap_allele_specific_annotations (variant_operations.cc:
+// 482-555): one per merged allele (R) or merged ALT allele (A), taken from the input allele that names it, else from the
+// call's <NON_REF>, else empty.  The call's input -> merged allele mapping is rebuilt from its own REF / ALT strings with the
+// rules of merge_alt_alleles (variant_operations.cc:133-228): a shorter REF extends non-symbolic ALT alleles by the merged REF's tail.
+bool BroadCombinedGVCFOperator::multid_entries(const gdbgpu_batch& b, uint32_t s, uint64_t q, int raw_fmt_index, const FieldInfo& fi,
+                                               std::vector<std::pair<const uint8_t*, uint64_t>>& entries) const {
+  entries.clear();
+  const uint64_t ns = b.n_sites;
+  auto raw_row = [&](int fmt_index, const uint8_t*& p, uint32_t& len) -> bool {
+    const uint64_t slot = (uint64_t)fmt_index * ns + s;
+    if (!b.fmt_type[slot]) return false;
+    const uint32_t nps = b.fmt_nps[slot];
+    const uint8_t* row = b.fmt_bytes + b.fmt_offset[slot] + q * nps;
+    memcpy(&len, row, 4);
+    if (len == 0xFFFFFFFFu) return false;
+    if (len + 4u > nps) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "raw field row longer than its block's row");
+    p = row + 4;
+    return true;
+  };
+  const uint8_t* v = nullptr; uint32_t vlen = 0;
+  if (!raw_row(raw_fmt_index, v, vlen)) return false;
+  auto rd64 = [](const uint8_t* p) { uint64_t x; memcpy(&x, p, 8); return x; };
+  const std::string bad = "malformed multi-dimensional value of field " + fi.name;
+  if (vlen < 24) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, bad);
+  const uint64_t data_bytes = rd64(v);
+  if (data_bytes > vlen - 24u) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, bad);
+  const uint64_t n_in = rd64(v + 8 + data_bytes);
+  if (n_in > (vlen - 24u - data_bytes) / 8u) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, bad);
+  const uint8_t* offs = v + 8 + data_bytes + 8;
+  auto input_entry = [&](uint64_t j) {
+    const uint64_t o0 = rd64(offs + 8 * j), o1 = rd64(offs + 8 * (j + 1));
+    if (o0 > o1 || o1 > data_bytes) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, bad);
+    return std::make_pair(v + 8 + o0, o1 - o0);
+  };
+  const bool site_remapped = b.site_flags[s] & GDBGPU_SITE_REMAPPED;
+  if (!site_remapped || !fi.dim0_allele_dependent()) {
+    for (uint64_t j = 0; j < n_in; ++j) entries.push_back(input_entry(j));
+    return true;
+  }
+  // merged -> input allele of this call
+  const uint8_t *rp = nullptr, *ap = nullptr; uint32_t rlen = 0, alen = 0;
+  if (m_raw_REF_fmt_index < 0 || m_raw_ALT_fmt_index < 0 || !raw_row(m_raw_REF_fmt_index, rp, rlen) || !raw_row(m_raw_ALT_fmt_index, ap, alen))
+    throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "a call with a multi-dimensional field has no REF / ALT");
+  const uint32_t first = b.allele_first[s], n_merged = b.n_alleles[s];
+  auto merged = [&](uint32_t m) { return std::string((const char*)b.allele_bytes + b.allele_pos[2 * (first + m)], b.allele_pos[2 * (first + m) + 1]); };
+  const std::string merged_ref = merged(0);
+  const bool nonref_exists = n_merged > 1 && merged(n_merged - 1) == "<NON_REF>";
+  std::vector<int64_t> m2in(n_merged, -1);
+  m2in[0] = 0;
+  int64_t input_nonref = -1;
+  {
+    const std::string alt((const char*)ap, alen);
+    size_t pos = 0; int64_t input_idx = 1;
+    while (pos <= alt.size() && !alt.empty()) {
+      size_t e = alt.find('|', pos); if (e == std::string::npos) e = alt.size();
+      std::string tok = alt.substr(pos, e - pos);
+      if (tok == "&") input_nonref = input_idx;
+      else {
+        const bool symbolic = tok == "*" || (!tok.empty() && tok.front() == '<' && tok.back() == '>') || tok.find('[') != std::string::npos || tok.find(']') != std::string::npos;
+        if (rlen < merged_ref.size() && !symbolic) tok.append(merged_ref, rlen, merged_ref.size() - rlen);
+        for (uint32_t m = 1; m < n_merged; ++m) if (merged(m) == tok) { m2in[m] = input_idx; break; }
+      }
+      ++input_idx;
+      if (e == alt.size()) break;
+      pos = e + 1;
+    }
+  }
+  if (nonref_exists && input_nonref >= 0) m2in[n_merged - 1] = input_nonref;
+  const bool alt_only = fi.dim_lengths[0] == "A";
+  const uint32_t length = alt_only ? n_merged - 1u : n_merged;
+  const int64_t input_nr = nonref_exists ? m2in[n_merged - 1] : -1;
+  for (uint32_t j = 0; j < length; ++j) {
+    int64_t in = m2in[alt_only ? j + 1u : j];
+    if (in < 0) in = input_nr;
+    if (in < 0) { entries.emplace_back(v, 0); continue; }
+    const int64_t input_j = alt_only ? in - 1 : in;
+    if (input_j >= 0 && (uint64_t)input_j < n_in) entries.push_back(input_entry((uint64_t)input_j));
+    else entries.emplace_back(v, 0);
+  }
+  return true;
 }
 
 // BroadCombinedGVCFOperator::operate (broad_combined_gvcf.cc:765-901) + bcf_write (htslib vcf.c) for one site
@@ -460,7 +582,47 @@ void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint3
     enc_int1(shared, m_END_key); enc_int1(shared, vcf_end); ++n_info;
     rlen = vcf_end - pos;
   }
+  std::vector<std::pair<const uint8_t*, uint64_t>> entries, entries2;
   for (auto& f : m_INFO_fields_vec) {
+    if (f.raw_fmt_index >= 0) {   // element-wise sum of a 2-D field, stringified (variant_field_handler.cc:667-741)
+      uint64_t num_valid = 0;
+      std::vector<std::vector<uint32_t>> result;   // float sums are kept as floats below; the words carry either type
+      for (uint64_t q = 0; q < nq; ++q) {
+        if (!multid_entries(b, s, q, f.raw_fmt_index, *f.fi, entries)) continue;
+        if (entries.size() > result.size()) result.resize(entries.size());
+        for (size_t d = 0; d < entries.size(); ++d) {
+          const uint64_t n = entries[d].second / 4;
+          if (n > result[d].size()) result[d].resize(n, f.is_float ? 0x7F800001u : 0x80000000u);
+          for (uint64_t i = 0; i < n; ++i) {
+            uint32_t w; memcpy(&w, entries[d].first + 4 * i, 4);
+            const bool w_ok = f.is_float ? (w != 0x7F800001u && w != 0x7F800002u) : (w != 0x80000000u && w != 0x80000001u);
+            if (!w_ok) continue;
+            uint32_t& r = result[d][i];
+            const bool r_ok = f.is_float ? (r != 0x7F800001u && r != 0x7F800002u) : (r != 0x80000000u && r != 0x80000001u);
+            if (!r_ok) r = w;
+            else if (f.is_float) { float a, c; memcpy(&a, &r, 4); memcpy(&c, &w, 4); a += c; memcpy(&r, &a, 4); }
+            else r = (uint32_t)((int32_t)r + (int32_t)w);
+            ++num_valid;
+          }
+        }
+      }
+      if (!num_valid) continue;
+      std::stringstream str;
+      for (size_t d = 0; d < result.size(); ++d) {
+        if (d) str << f.fi->vcf_delimiters[0];
+        for (size_t i = 0; i < result[d].size(); ++i) {
+          if (i) str << f.fi->vcf_delimiters[1];
+          const uint32_t r = result[d][i];
+          if (f.is_float) { if (r != 0x7F800001u && r != 0x7F800002u) { float a; memcpy(&a, &r, 4); str << std::fixed << std::setprecision(3) << a; } }
+          else if (r != 0x80000000u && r != 0x80000001u) str << std::fixed << std::setprecision(3) << (int32_t)r;
+        }
+      }
+      const std::string out_str = str.str();
+      if (out_str.empty()) continue;   // bcf_update_info with n == 0 removes the tag
+      enc_int1(shared, f.key); enc_vchar(shared, out_str);
+      ++n_info;
+      continue;
+    }
     if (f.concat_fmt_index >= 0) {   // concatenate: the rows of the collated block, row order, padding dropped
       const uint64_t slot = (uint64_t)f.concat_fmt_index * ns + s;
       const uint8_t type = b.fmt_type[slot];
@@ -513,6 +675,54 @@ void BroadCombinedGVCFOperator::operate_on_bcf_site(const gdbgpu_batch& b, uint3
     enc_int1(shared, f.key);
     if (f.is_float) { enc_size(shared, 1, BT_FLOAT); put<uint32_t>(shared, b.info_value[slot]); }
     else enc_int1(shared, (int32_t)b.info_value[slot]);
+    ++n_info;
+  }
+  for (auto& h : m_INFO_histogram_fields) {   // compute_valid_histogram_sum_2D_vector_and_stringify (broad_combined_gvcf.cc:432-520)
+    const bool bin_float = h.fi[0]->type == "float", count_float = h.fi[1]->type == "float";
+    uint64_t num_calls_with_field = 0;
+    // bins ordered as std::map<T1, T2> orders them; counts summed in T2
+    struct Count { int32_t i = 0; float f = 0.f; };
+    std::vector<std::map<float, Count>> hf; std::vector<std::map<int32_t, Count>> hi;
+    for (uint64_t q = 0; q < nq; ++q) {
+      const bool v0 = multid_entries(b, s, q, h.raw_fmt_index[0], *h.fi[0], entries);
+      const bool v1 = multid_entries(b, s, q, h.raw_fmt_index[1], *h.fi[1], entries2);
+      if (!v0 || !v1) continue;
+      const size_t nd = std::min(entries.size(), entries2.size());
+      if (bin_float) { if (entries.size() > hf.size()) hf.resize(entries.size()); } else if (entries.size() > hi.size()) hi.resize(entries.size());
+      for (size_t d = 0; d < nd; ++d) {
+        const uint64_t n = std::min(entries[d].second, entries2[d].second) / 4;
+        for (uint64_t i = 0; i < n; ++i) {
+          uint32_t wb, wc; memcpy(&wb, entries[d].first + 4 * i, 4); memcpy(&wc, entries2[d].first + 4 * i, 4);
+          const bool b_ok = bin_float ? (wb != 0x7F800001u && wb != 0x7F800002u) : (wb != 0x80000000u && wb != 0x80000001u);
+          const bool c_ok = count_float ? (wc != 0x7F800001u && wc != 0x7F800002u) : (wc != 0x80000000u && wc != 0x80000001u);
+          if (!b_ok || !c_ok) continue;
+          Count add; if (count_float) memcpy(&add.f, &wc, 4); else add.i = (int32_t)wc;
+          Count* slot; bool fresh;
+          if (bin_float) { float key; memcpy(&key, &wb, 4); auto r = hf[d].insert(std::make_pair(key, add)); slot = &r.first->second; fresh = r.second; }
+          else { auto r = hi[d].insert(std::make_pair((int32_t)wb, add)); slot = &r.first->second; fresh = r.second; }
+          if (!fresh) { if (count_float) slot->f += add.f; else slot->i += add.i; }
+        }
+      }
+      ++num_calls_with_field;
+    }
+    if (!num_calls_with_field) continue;
+    std::stringstream str;
+    const char d0 = h.fi[0]->vcf_delimiters[0], d1 = h.fi[0]->vcf_delimiters[1];
+    const size_t n_outer = bin_float ? hf.size() : hi.size();
+    for (size_t d = 0; d < n_outer; ++d) {
+      if (d) str << d0;
+      bool first = true;
+      auto put_pair = [&](auto key, const Count& c) {
+        if (!first) str << d1;
+        str << std::fixed << std::setprecision(3) << key << d1;
+        if (count_float) str << c.f; else str << c.i;
+        first = false;
+      };
+      if (bin_float) for (auto& kv : hf[d]) put_pair(kv.first, kv.second); else for (auto& kv : hi[d]) put_pair(kv.first, kv.second);
+    }
+    const std::string out_str = str.str();
+    if (out_str.empty()) continue;   // bcf_update_info with n == 0 removes the tag
+    enc_int1(shared, h.key); enc_vchar(shared, out_str);
     ++n_info;
   }
   const bool remapped = b.site_flags[s] & GDBGPU_SITE_REMAPPED;
@@ -592,6 +802,17 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
     if (fi) return fi;
     return name == "QUAL" ? &builtin_QUAL : (name == "FILTER" ? &builtin_FILTER : nullptr);
   };
+  {   // VariantQueryConfig::flatten_composite_fields (variant_query_config.cc:187-231): the elements of a composite field join the
+      // query at its end, the composite field leaves it
+    std::vector<std::string> flat, kept;
+    for (auto& name : ordered) {
+      const FieldInfo* fi = vid.get_field_info(name);
+      if (fi && fi->is_composite()) { for (size_t j = 0; j < fi->tuple_types.size(); ++j) flat.push_back(name + "_tuple_element_" + std::to_string(j)); }
+      else kept.push_back(name);
+    }
+    for (auto& n : flat) if (std::find(kept.begin(), kept.end(), n) == kept.end()) kept.push_back(n);
+    ordered.swap(kept);
+  }
   {
     auto add = [&](const char* n) { if (std::find(ordered.begin(), ordered.end(), n) == ordered.end()) ordered.push_back(n); };
     add("END");
@@ -636,6 +857,7 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
   std::vector<gdbgpu_plain_field_desc> pd;
   if (stage_broad_gvcf_fields) {
     static const char* skip[] = {"END", "REF", "ALT", "GT"};
+    bool need_raw_alleles = false;
     // FILTER (vid_mapper.cc:611-668 makes it an int vector even when the vid mapping does not list it): the union over the
     // live calls goes into bcf1_t.d.flt when the query asks for it (broad_combined_gvcf.cc:845-873)
     if (qc.produce_FILTER_field() && std::find(ordered.begin(), ordered.end(), "FILTER") != ordered.end()) {
@@ -649,7 +871,27 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
       bool skipped = false;
       for (const char* k : skip) if (name == k) skipped = true;
       if (skipped) continue;
-      if (fi->length == "2D") throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "BroadCombinedGVCFOperator on the GPU: multi-dimensional field " + name + " is not supported");
+      if (fi->is_multid()) {
+        // multi-dimensional INFO fields (allele-specific annotations): element-wise sum (variant_field_handler.cc:667-715) and
+        // histogram sum over the two elements of a tuple (broad_combined_gvcf.cc:432-520).  The calls' raw values travel as rows
+        // of a block (no_format = 3) and are combined by the operator: one short vector per call that has the field at all.
+        if (!fi->is_info || (fi->combine_op != "element_wise_sum" && fi->combine_op != "histogram_sum")) {
+          if (fi->is_info && fi->combine_op.empty()) continue;   // dropped with a warning, like any INFO field without an operation
+          throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "BroadCombinedGVCFOperator on the GPU: multi-dimensional field " + name + " with operation '" + fi->combine_op + "' is not supported");
+        }
+        if (fi->dim_lengths.size() != 2) throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "multi-dimensional field " + name + ": only 2 dimensions are supported");
+        if (fi->combine_op == "histogram_sum") {
+          if (fi->parent.empty() || fi->tuple_types.size() != 2)
+            throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Operation histogram_sum is only supported for fields whose elements are tuple with 2 constituent elements; field " + fi->vcf_name() + " does not satisfy this requirement");
+          if (fi->type != "int" && fi->type != "float")
+            throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Operation histogram_sum is only supported for fields whose elements are tuple with 2 constituent elements that are int or float; field " + fi->vcf_name() + " does not satisfy this requirement");
+        } else if (!fi->parent.empty()) throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "element-wise sum of tuple field " + fi->vcf_name() + " is not supported");
+        VariantQueryConfig::PlainField pf;
+        pf.attribute = name; pf.vcf_name = fi->vcf_name(); pf.elem = GDBGPU_ELEM_CHAR; pf.fixed_len = 0; pf.format = true; pf.is_raw = true;
+        qc.plain_.push_back(pf);
+        if (fi->dim0_allele_dependent()) need_raw_alleles = true;
+        continue;
+      }
       const bool twin = name.size() > 7 && name.compare(name.size() - 7, 7, "_FORMAT") == 0;
       VariantQueryConfig::PlainField pf;
       pf.attribute = name; pf.vcf_name = twin ? name.substr(0, name.size() - 7) : name;
@@ -692,8 +934,14 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
       if (name == "MIN_DP") qc.dp_fields_[1] = (unsigned)qc.plain_.size();
       if (name == "DP_FORMAT") qc.dp_fields_[2] = (unsigned)qc.plain_.size();
     }
+    if (need_raw_alleles)   // the allele remap of those fields (remap_allele_specific_annotations, variant_operations.cc:482-555) is redone by the
+      for (const char* n : {"REF", "ALT"}) {   // operator for the few calls that carry them: their REF / ALT strings come along the same way
+        VariantQueryConfig::PlainField pf;
+        pf.attribute = pf.vcf_name = n; pf.elem = GDBGPU_ELEM_CHAR; pf.fixed_len = 0; pf.format = true; pf.is_raw = true;
+        qc.plain_.push_back(pf);
+      }
     for (auto& pf : qc.plain_)
-      pd.push_back(gdbgpu_plain_field_desc{pf.attribute.c_str(), pf.elem, pf.fixed_len, (pf.is_id || pf.is_filter || pf.is_concat) ? 2 : (pf.format ? 0 : 1), pf.info_op});
+      pd.push_back(gdbgpu_plain_field_desc{pf.attribute.c_str(), pf.elem, pf.fixed_len, pf.is_raw ? 3 : (pf.is_concat ? 4 : ((pf.is_id || pf.is_filter) ? 2 : (pf.format ? 0 : 1))), pf.info_op});
   }
   qc.query_attrs_.clear();
   if (stage_columnar_fields) {
@@ -711,7 +959,7 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
       else if (name == "GT") { qa.kind = GDBGPU_CELL_FIELD_GT; qa.elem = 'i'; }
       else if (fi->is_allele_dependent()) { qa.kind = GDBGPU_CELL_FIELD_REMAPPED; qa.index = n_remapped++; }
       else {
-        if (fi->length == "2D") { qa.kind = -2; qc.query_attrs_.push_back(qa); continue; }   // not staged: only the print operators would read it
+        if (fi->is_multid()) qa.elem = 'c';   // a multi-dimensional value is a byte string to the print operators (they print it raw)
         const bool numeric_len = !fi->length.empty() && fi->length.find_first_not_of("0123456789") == std::string::npos;
         qa.kind = GDBGPU_CELL_FIELD_PLAIN; qa.index = (int)qc.plain_.size(); qa.fixed_len = numeric_len ? std::stoi(fi->length) : 0;
         VariantQueryConfig::PlainField pf;

@@ -54,6 +54,19 @@ struct FieldInfo {
   int global_idx = -1;     // position among the vid mapping's fields (what FILTER cells store); -1 for a FORMAT twin
   std::string combine_op;  // "VCF_field_combine_operation" of the vid mapping, else the known field's default (known_field_info.cc:284-308)
   bool is_allele_dependent() const { return length == "R" || length == "A" || length == "G"; }
+  // multi-dimensional fields and fields whose elements are tuples (vid_mapper.cc, genomicsdb_multid_vector_field.h:66-83): length
+  // stays "2D", the per-dimension descriptors, VCF delimiters and tuple element types are kept here.  A composite field (tuple
+  // of n > 1 elements) is stored as n flattened attributes <name>_tuple_element_<j> (VidMapper::get_flattened_field_info); each
+  // gets its own FieldInfo naming its parent.
+  std::vector<std::string> dim_lengths;    // {"R", "var"}
+  std::vector<char> vcf_delimiters;        // {'|', ','}
+  std::vector<std::string> tuple_types;    // {"float", "int"}
+  std::string parent;                      // flattened element: the composite field's name (== its VCF name)
+  int tuple_index = 0;
+  bool is_multid() const { return length == "2D"; }
+  bool is_composite() const { return tuple_types.size() > 1 && parent.empty(); }
+  bool dim0_allele_dependent() const { return !dim_lengths.empty() && (dim_lengths[0] == "R" || dim_lengths[0] == "A"); }
+  const std::string& vcf_name() const { return parent.empty() ? name : parent; }
 };
 struct ContigInfo { std::string name; int64_t tiledb_column_offset = 0, length = 0; };
 class VidMapper {
@@ -174,7 +187,7 @@ class VariantQueryConfig {
   std::vector<std::string> remapped_names_;
   // plain fields staged for the Broad operator (do_query_bookkeeping): FORMAT fields that are not allele-dependent, scalar
   // INFO fields with a median / sum / mean combine operation, the inputs of the DP rule
-  struct PlainField { std::string attribute, vcf_name; int elem = 0, fixed_len = 0; bool format = false; int info_op = 0; bool is_qual = false, is_id = false, is_filter = false, is_concat = false; };
+  struct PlainField { std::string attribute, vcf_name; int elem = 0, fixed_len = 0; bool format = false; int info_op = 0; bool is_qual = false, is_id = false, is_filter = false, is_concat = false, is_raw = false; };   // is_raw: multi-dimensional field (or the REF / ALT its remap needs), combined by the operator
   std::vector<PlainField> plain_;
   unsigned dp_fields_[3] = {0, 0, 0};   // 1-based plain indices of INFO DP, MIN_DP, DP_FORMAT
   unsigned esum_remapped_mask_ = 0;     // remapped fields (GT not counted) combined with an element-wise sum
@@ -423,8 +436,16 @@ class BroadCombinedGVCFOperator : public GA4GHOperator {
   const VidMapper* m_vid_mapper;
   struct FormatField { std::string vcf_name; int key = -1; int fmt_index = -1; };   // fmt_index: index into the batch's fmt_* tables
   std::vector<FormatField> m_FORMAT_fields_vec;   // emission order: GT first, query order, DP last (broad_combined_gvcf.cc:168-240)
-  struct InfoField { std::string vcf_name; int key = -1; int plain_index = -1; bool is_float = false; int vector_slot = -1; int concat_fmt_index = -1; };   // vector_slot >= 0: element-wise sum; concat_fmt_index >= 0: concatenate
+  struct InfoField { std::string vcf_name; int key = -1; int plain_index = -1; bool is_float = false; int vector_slot = -1; int concat_fmt_index = -1;
+                     int raw_fmt_index = -1; const FieldInfo* fi = nullptr; };   // vector_slot >= 0: element-wise sum; concat_fmt_index >= 0: concatenate; raw_fmt_index >= 0: element-wise sum of a 2-D field
   std::vector<InfoField> m_INFO_fields_vec;
+  // histogram_sum fields (broad_combined_gvcf.cc:194-217,544-585): the two flattened elements of a tuple field, in the order of the
+  // parents' vid mapping indices (the reference walks a std::map keyed by them) -- after every other INFO field
+  struct HistogramField { int parent_idx = 0; int key = -1; int raw_fmt_index[2] = {-1, -1}; const FieldInfo* fi[2] = {nullptr, nullptr}; };
+  std::vector<HistogramField> m_INFO_histogram_fields;
+  int m_raw_REF_fmt_index = -1, m_raw_ALT_fmt_index = -1;   // the live calls' own REF / ALT strings (rows of a block), for the allele remap of 2-D fields
+  // one call's 2-D value cut into its entries (remapped onto the merged alleles where the reference remaps it); false: the call has no value
+  bool multid_entries(const gdbgpu_batch& b, uint32_t s, uint64_t q, int raw_fmt_index, const FieldInfo& fi, std::vector<std::pair<const uint8_t*, uint64_t>>& entries) const;
   int m_END_key = -1, m_DP_key = -1, m_QUAL_plain = -1;
   int m_ID_fmt_index = -1;        // the ID strings of the live calls, collated like a FORMAT field; merged per site (merge_ID_field)
   std::string m_ID_value;

@@ -261,10 +261,16 @@ __global__ void __launch_bounds__(FMT_THREADS) k_fmt_pack(const __grid_constant_
 // values), with the same row rules as above (collect_and_extend_fields, variant_field_handler.cc:804-871) and, for
 // strings, bcf_str_missing / bcf_str_vector_end (htslib vcf.h) and BCF_BT_CHAR blocks (vcf.c:3653-3657).  A field of a
 // call is valid unless every element is the TileDB null of its type (variant_field_data.h:236-251,365-384).
-constexpr int MAX_PLAIN = 16;
+constexpr int MAX_PLAIN = 24;
 enum { ELEM_INT32 = 0, ELEM_FLOAT32 = 1, ELEM_CHAR = 2 };
 constexpr uint8_t TDB_NULL_CHAR = 127, BCF_STR_MISSING = 0x07, BCF_STR_VEND = 0x00;
-struct PlainDev { const uint64_t* off; const uint8_t* val; int32_t elem, fixed_len; int32_t host_combine; };   // host_combine: the block feeds a host-side combine (ID, FILTER, concatenate), always padded the htslib way
+// host_combine: the block feeds a host-side combine, always padded the htslib way -- HC_BLOCK (ID, FILTER union, concatenate);
+// | HC_SKIP_REDUCED: calls in spanning-deletion form have no value (handle_deletions invalidates their INFO fields,
+// broad_combined_gvcf.cc:1067-1075); | HC_RAW: every row is [u32 byte length, 0xFFFFFFFF = no value][the cell's bytes][zero pad] --
+// multi-dimensional fields (genomicsdb_multid_vector_field.h:66-83: sizes and offsets inside the value) and the REF / ALT
+// strings their allele remap needs, binary-safe
+enum { HC_BLOCK = 1, HC_RAW = 2, HC_SKIP_REDUCED = 4 };
+struct PlainDev { const uint64_t* off; const uint8_t* val; int32_t elem, fixed_len; int32_t host_combine; };
 struct PlainSet { int32_t n; PlainDev f[MAX_PLAIN]; };
 enum { PS_MIN = 0, PS_MAX, PS_MAXLEN, PS_ANY, PS_WORDS };   // per (plain field, site) statistics, int32 each
 
@@ -293,7 +299,8 @@ __global__ void __launch_bounds__(FMT_THREADS) k_plain_scan(const __grid_constan
   const uint32_t lane = tid & 31;
   for (int f = 0; f < P.n; ++f) {   // every lane takes part: the statistics are reduced over the warp before they touch shared memory
     const uint8_t* p = nullptr; uint32_t n = 0;
-    const bool valid = e >= 0 && plain_fetch(P.f[f], cell, p, n);
+    bool valid = e >= 0 && !((P.f[f].host_combine & HC_SKIP_REDUCED) && (e & LIVE_REDUCED)) && plain_fetch(P.f[f], cell, p, n);
+    if (valid && (P.f[f].host_combine & HC_RAW)) n += 4u;   // the length word in front of the bytes
     int32_t lo = INT32_MAX, hi = INT32_MIN + 1;
     if (valid && P.f[f].elem == ELEM_INT32) {
       const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
@@ -332,12 +339,18 @@ __global__ void __launch_bounds__(FMT_THREADS) k_plain_pack(const __grid_constan
     if (type == BT_NONE) continue;
     const uint32_t nps = plan.nps[pi];
     const uint8_t* p = nullptr; uint32_t n = 0;
-    const bool valid = e >= 0 && plain_fetch(P.f[f], cell, p, n);
+    const bool valid = e >= 0 && !((P.f[f].host_combine & HC_SKIP_REDUCED) && (e & LIVE_REDUCED)) && plain_fetch(P.f[f], cell, p, n);
     if (!valid) n = 0;
     uint8_t* dst = plan.bytes + plan.off[pi];
     const bool jv = java && !P.f[f].host_combine;
     if (type == BT_CHAR) {
       uint8_t* d = dst + (uint64_t)q * nps;
+      if (P.f[f].host_combine & HC_RAW) {
+        const uint32_t len = valid ? n : 0xFFFFFFFFu;
+        for (uint32_t i = 0; i < 4u; ++i) d[i] = (uint8_t)(len >> (8u * i));
+        for (uint32_t i = 4u; i < nps; ++i) d[i] = i - 4u < n ? p[i - 4u] : 0u;
+        continue;
+      }
       for (uint32_t i = 0; i < nps; ++i) d[i] = i < n ? p[i] : ((i == 0 && n == 0 && !jv) ? BCF_STR_MISSING : BCF_STR_VEND);   // JNI: vector_end only
       continue;
     }

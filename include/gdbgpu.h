@@ -58,10 +58,15 @@ typedef struct gdbgpu_plain_field_desc {
   int32_t elem_type;     /* GDBGPU_ELEM_* (CHAR: a string per cell) */
   int32_t fixed_len;     /* values per cell; 0 = variable length */
   int32_t no_format;     /* 1: the field is not a FORMAT field (no block is produced for it); 2: a block is produced for a host-side
-                          * combine (ID / FILTER union, concatenate) and always padded with vector_end, whatever the scan's conventions */
+                          * combine (ID / FILTER union) and always padded with vector_end, whatever the scan's conventions; 4: as 2, and
+                          * calls in spanning-deletion form have no value (INFO fields: concatenate; broad_combined_gvcf.cc:1067-1075);
+                          * 3: raw rows for a host-side combine of a multi-dimensional field (variant_operations.cc:482-555,
+                          * broad_combined_gvcf.cc:432-520; CHAR, variable length): a BCF_BT_CHAR block whose row is
+                          * [u32 byte length, 0xFFFFFFFF = no value][the cell's bytes][zero padding], calls in spanning-deletion form
+                          * have no value */
   int32_t info_op;       /* GDBGPU_INFO_*: combine the field over the valid calls of every site (4-byte fixed-length fields) */
 } gdbgpu_plain_field_desc;
-#define GDBGPU_MAX_PLAIN_FIELDS 16
+#define GDBGPU_MAX_PLAIN_FIELDS 24
 
 /* Host-resident columns in TileDB's own in-file layout (global cell order = column-major (col,row)); what
  * ArrayReadState::read_sparse hands to GenomicsDB one segment at a time (array_read_state.cc:1529-1598), here whole.

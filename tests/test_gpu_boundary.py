@@ -51,7 +51,7 @@ def loader_json(case, tmp_path, partitions=None):
     return str(lf)
 
 
-@pytest.mark.parametrize("case", [c for c in ALL if c["id"] != "t0_1_2_all_asa_at_0"], ids=lambda c: c["id"])
+@pytest.mark.parametrize("case", ALL, ids=lambda c: c["id"])
 def test_whole_bcf_with_generated_header(exe, case, tmp_path):
     """no --bcf-header, no --reference-bases: header lines, dictionary indices, contigs, samples and the N -> reference base
     substitutions all come from this library; the file equals the reference's byte for byte"""

@@ -48,9 +48,6 @@ RUNS = [(c, m) for c in ALL for m in MODES if m[0] in ("calls", "csv") or c["id"
 def test_columnar_command_output_equals_the_reference(exe, case, tmp_path, mode):
     ext, flag = mode
     p, out = run_tool(exe, case, tmp_path, flag)
-    if case["id"] == "t0_1_2_all_asa_at_0" and ext in ("calls", "csv"):   # 2-D fields: a documented limit, reported, not guessed
-        assert p.returncode != 0 and "multi-dimensional" in p.stderr
-        return
     assert p.returncode == 0, p.stderr
     assert out.read_bytes() == open(os.path.join(CELLS, case["id"] + "." + ext), "rb").read()
 

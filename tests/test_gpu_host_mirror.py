@@ -83,9 +83,6 @@ def test_broad_gvcf_bcf_file_equals_the_reference(exe, case, tmp_path, java):
     operator writes when constructed the way the JNI path (Java GenomicsDBFeatureReader) constructs it"""
     gold = open(os.path.join(GOLDEN, "bcf_java" if java else "bcf", case["id"] + ".bcf"), "rb").read()
     p, out = run_broad(exe, case, tmp_path, java=java)
-    if case["id"] == "t0_1_2_all_asa_at_0":       # allele-specific annotations are 2-D fields: a documented limit, reported, not guessed
-        assert p.returncode != 0 and "not supported" in p.stderr
-        return
     assert p.returncode == 0, p.stderr
     assert json.loads(p.stdout.strip().splitlines()[-1])["records"] == case["sites"]
     got = out.read_bytes()
