@@ -538,11 +538,27 @@ struct CtlArena {
   }
 };
 
+// K3/K4 state of a WINDOW of consecutive sites of a scan: live matrix, class words, site table, nt lists + per-call allele
+// LUTs, signature tables, the merged-allele pools.  None of it depends on how the sites are cut into batches, so it is
+// computed once for as many sites as a memory budget allows (GDBGPU_FRONT_BYTES, default 6 GiB: 24 bytes per (site, query
+// row)) -- k_live_walk / k_site_scan / k_union / k_verify_alleles run with grids of thousands of blocks instead of one
+// under-filled wave per batch, no site is scanned twice because a batch kept fewer sites than were guessed, and the one
+// host round trip K4 needs (site table -> output layout) happens once per window, not once per batch: the batches that
+// follow only plan (host, from the mirrored site table) and launch K5 / K6 back to back.
+struct FrontWindow {
+  DevBuf<int32_t> live; DevBuf<uint32_t> lcls; DevBuf<SiteRec> sites; DevBuf<uint32_t> agg; DevBuf<uint2> nt, nt_lut; DevBuf<unsigned long long> sig_keys;
+  DevBuf<uint32_t> cursors, allele_pos; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes;
+  std::vector<SiteRec> h_sites; uint32_t hc[4] = {0, 0, 0, 0};
+  uint64_t first = 0; uint32_t n = 0, sig_slots = 0; bool valid = false;
+};
+
 // Per-batch device / pinned-host buffers.  They are large (GBs) and expensive to create (cudaMalloc, cudaMallocHost), so a
 // context keeps finished scans' buffers and hands them to the next scan.
 struct BatchBuffers {
   // per batch (device)
-  DevBuf<int32_t> live; DevBuf<uint32_t> lcls; DevBuf<SiteRec> sites; DevBuf<uint32_t> agg; DevBuf<uint2> nt, nt_lut, blk_map; DevBuf<unsigned long long> sig_keys; DevBuf<uint32_t> sig_perm; uint32_t* sig_off_d = nullptr; DevBuf<uint32_t> cursors, allele_pos, lut_first; DevBuf<uint16_t> lut_len; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes; DevBuf<int16_t> lut_in2m;
+  DevBuf<uint2> blk_map; DevBuf<uint32_t> sig_perm; uint32_t* sig_off_d = nullptr; DevBuf<uint32_t> cursors, lut_first; DevBuf<uint16_t> lut_len; DevBuf<int16_t> lut_in2m;
+  const int32_t* live = nullptr;   // the batch's rows of the window's live matrix
+  const uint32_t* allele_pos = nullptr; const uint8_t* allele_bytes = nullptr;   // the window's allele pools (SiteRec::allele_first indexes them)
   DevBuf<uint32_t> out_data[MAX_FIELDS + 1]; DevBuf<uint16_t> out_len[MAX_FIELDS + 1];
   CtlArena ctl;   // everything below points into ctl.d
   uint32_t* out_stride[MAX_FIELDS + 1] = {}; uint64_t* out_base[MAX_FIELDS + 1] = {};
@@ -550,7 +566,7 @@ struct BatchBuffers {
   uint32_t *fast_sites = nullptr, *slow_sites = nullptr, *tile_sites = nullptr, *nt_prefix_d = nullptr;
   uint8_t* fmt_type_d = nullptr; uint32_t* fmt_nps_d = nullptr; uint64_t* fmt_off_d = nullptr;
   // per batch (host mirrors)
-  std::vector<SiteRec> h_sites;
+  const SiteRec* h_sites = nullptr;   // the batch's part of the window's mirrored site table
   std::vector<uint8_t> h_site_flags; std::vector<uint32_t> h_n_alleles, h_n_live, h_allele_first;
   std::vector<uint64_t> h_base[MAX_FIELDS + 1]; std::vector<uint32_t> h_stride[MAX_FIELDS + 1];
   PinBuf<int64_t> p_site_begin, p_site_end; PinBuf<int32_t> p_live; PinBuf<uint32_t> p_allele_pos, p_lut_first, p_out_data[MAX_FIELDS + 1]; PinBuf<uint8_t> p_allele_bytes;
@@ -580,6 +596,7 @@ struct gdbgpu_scan {
   std::vector<int64_t> h_rows;
   DevBuf<int32_t> qrow_of_row, init_cell, dlive, ddel, live_excl, del_excl; DevBuf<int64_t> row_of_qrow, init_effend, bp, site_begin, site_end;
   DevBuf<unsigned long long> bitmap; DevBuf<uint32_t> word_rank, bp_cell0, err, del_cells, del_words, site_c0, site_c1; DevBuf<uint64_t> site_start; DevBuf<DelRec> del_recs;
+  FrontWindow front;
   std::unique_ptr<BatchBuffers> slot[2];   // borrowed from the context's pool for the lifetime of the scan; [cur] = batch being handed out, the other = prefetched
   int cur = 0; bool bcf_format = false, prefetch = true; int produce_gt = 0, java = 0;
   InfoSet info{};   // INFO scalars to combine + the DP rule's fields (GDBGPU_SCAN_BCF_FORMAT)
@@ -785,61 +802,92 @@ uint32_t stride_of(const gdbgpu_array* a, const SiteRec& r, int o) {
 
 // Runs every kernel of the batch starting at site `first` into `bb` and queues the device -> host copies of its results
 // on the copy stream.  Nothing here waits for those copies: publish_batch does.
+// K3/K4 for the window of sites starting at first_site (see FrontWindow)
+void compute_front(gdbgpu_scan* s, uint64_t first_site, uint32_t max_sites) {
+  gdbgpu_array* a = s->arr; gdbgpu_ctx* ctx = s->ctx; ScanDev& S = s->S; FrontWindow& w = s->front;
+  w.valid = false;
+  // batches still in flight read the window they were cut from (their device -> host copies run on the copy stream)
+  for (auto& sl : s->slot) if (sl && sl->ev_done) CK(cudaStreamWaitEvent(ctx->stream, sl->ev_done, 0));
+  static const uint64_t budget = [] { const char* e = getenv("GDBGPU_FRONT_BYTES"); const uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v ? v : (6ull << 30); }();
+  const uint64_t remaining = S.n_sites - first_site;
+  // a caller paging in small batches gets small windows (every batch copies the window's allele pool)
+  const uint32_t nb = (uint32_t)std::min<uint64_t>({remaining, std::max<uint64_t>(1, budget / std::max<uint64_t>(1, S.nq * 24)), 1u << 20, max_sites ? std::max<uint64_t>(64, 16ull * max_sites) : ~0ull});
+  for (;;) {
+    w.live.ensure((uint64_t)nb * S.nq); w.lcls.ensure((uint64_t)nb * S.nq); w.sites.ensure(nb); w.cursors.ensure(4);
+    w.agg.ensure((uint64_t)nb * AGG_WORDS); w.nt.ensure((uint64_t)nb * S.nq); w.nt_lut.ensure((uint64_t)nb * S.nq);
+    CK(cudaMemsetAsync(w.agg.p, 0, (size_t)nb * AGG_WORDS * 4, ctx->stream));
+    if (!s->cap_allele_recs) { s->cap_allele_recs = 1u << 16; s->cap_allele_bytes = 1u << 20; }
+    while (s->cap_allele_recs < 16ull * nb && s->cap_allele_recs < (1u << 28)) { s->cap_allele_recs *= 2; s->cap_allele_bytes *= 2; }
+    w.allele_pos.ensure(2ull * s->cap_allele_recs); w.allele_hash.ensure(s->cap_allele_recs); w.allele_bytes.ensure(s->cap_allele_bytes);
+    CK(cudaMemsetAsync(w.cursors.p, 0, 16, ctx->stream));
+    BatchDev B{};
+    B.first_site = first_site; B.n_sites = nb; B.live = w.live.p; B.lcls = w.lcls.p; B.sites = w.sites.p; B.agg = w.agg.p; B.nt = w.nt.p; B.nt_lut = w.nt_lut.p; B.cursors = w.cursors.p;
+    // signature tables (gdb_kernels2.cuh: nt_lut): one slot per 64 samples, only for scans wide enough to repeat signatures
+    B.sig_slots = 0; B.sig_keys = nullptr;
+    if (S.nq >= SIG_MIN_ROWS) { uint32_t sl = 64; while (sl < SIG_MAX_SLOTS && (uint64_t)sl * 64 < S.nq) sl *= 2; B.sig_slots = sl; w.sig_keys.ensure((uint64_t)nb * sl); B.sig_keys = w.sig_keys.p; }
+    w.sig_slots = B.sig_slots;
+    B.allele_pos = w.allele_pos.p; B.allele_hash = w.allele_hash.p; B.cap_allele_recs = s->cap_allele_recs; B.allele_bytes = w.allele_bytes.p; B.cap_allele_bytes = s->cap_allele_bytes;
+    {   // sites walked by one thread after one binary search: long chunks amortise the search, short ones keep the device full
+      const uint64_t want_threads = 400000;
+      uint32_t chunk = (uint32_t)std::min<uint64_t>(nb, std::max<uint64_t>(32, (uint64_t)nb * S.nq / want_threads));
+      LAUNCH(ctx, k_live_walk, dim3(blocks_for(S.nq, 256), (nb + chunk - 1) / chunk), 256, a->dev, S, first_site, nb, chunk, w.live.p, w.lcls.p);
+    }
+    LAUNCH(ctx, k_site_scan, dim3(nb, blocks_for(S.nq, SSCAN_ROWS)), SSCAN_THREADS, a->dev, S, B);
+    LAUNCH(ctx, k_union, nb, UNION_THREADS, a->dev, S, B);
+    w.h_sites.resize(nb);
+    CK(cudaMemcpyAsync(w.h_sites.data(), w.sites.p, (size_t)nb * sizeof(SiteRec), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(w.hc, w.cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream));   // allele pools are final after k_union
+    bool ovf = false;
+    check_scan_errors(s, ovf);
+    if (ovf) { s->cap_allele_recs *= 4; s->cap_allele_bytes *= 4; continue; }
+    {   // byte comparison behind every hash match (a throughput pass over the window's nt lists; its verdict travels with the batches' tails)
+      uint32_t max_nt = 0;
+      for (uint32_t i = 0; i < nb; ++i) if (w.h_sites[i].n_alleles >= 2u) max_nt = std::max(max_nt, w.h_sites[i].n_nt);
+      if (max_nt && B.sig_keys) CK(cudaMemsetAsync(w.sig_keys.p, 0xFF, (size_t)nb * B.sig_slots * 8, ctx->stream));
+      for (uint32_t s0 = 0; s0 < nb && max_nt; s0 += 65535u) {   // grid.y is the site
+        BatchDev Bp = B; const uint32_t ns = std::min<uint32_t>(65535u, nb - s0);
+        Bp.first_site = first_site + s0; Bp.n_sites = ns; Bp.live = B.live + (uint64_t)s0 * S.nq; Bp.lcls = B.lcls + (uint64_t)s0 * S.nq; Bp.sites = B.sites + s0; Bp.agg = B.agg + (uint64_t)s0 * AGG_WORDS;
+        Bp.nt = B.nt + (uint64_t)s0 * S.nq; Bp.nt_lut = B.nt_lut + (uint64_t)s0 * S.nq; if (B.sig_keys) Bp.sig_keys = B.sig_keys + (uint64_t)s0 * B.sig_slots;
+        LAUNCH(ctx, k_verify_alleles, dim3(blocks_for(max_nt, VERIFY_THREADS), ns), VERIFY_THREADS, a->dev, S, Bp);
+      }
+    }
+    w.first = first_site; w.n = nb; w.valid = true;
+    return;
+  }
+}
+
 void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32_t max_sites, uint64_t max_bytes) {
   gdbgpu_array* a = s->arr; gdbgpu_ctx* ctx = s->ctx; ScanDev& S = s->S;
   bb.valid = false; bb.first = first_site; bb.arg_sites = max_sites; bb.arg_bytes = max_bytes; bb.keep = 0; bb.fmt_total = 0;
   if (!bb.ev_compute) { CK(cudaEventCreateWithFlags(&bb.ev_compute, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&bb.ev_done, cudaEventDisableTiming)); }
   if (max_bytes == 0) max_bytes = 1ull << 30;
-  uint64_t remaining = S.n_sites - first_site;
-  // sites whose live matrix fits a fixed budget, and (by the running average) whose output fits max_bytes
-  uint64_t by_live = std::max<uint64_t>(1, (256ull << 20) / std::max<uint64_t>(1, S.nq * 4));
-  uint64_t guess = s->avg_site_bytes ? std::max<uint64_t>(1, max_bytes / s->avg_site_bytes) : 64;
-  uint32_t nb = (uint32_t)std::min<uint64_t>({remaining, max_sites ? max_sites : 0xFFFFFFFFull, by_live, guess + guess / 2 + 1, 1u << 20});
+  FrontWindow& w = s->front;
+  if (!w.valid || first_site < w.first || first_site >= w.first + w.n) compute_front(s, first_site, max_sites);
+  const uint32_t woff = (uint32_t)(first_site - w.first);
+  const uint32_t nb = (uint32_t)std::min<uint64_t>({(uint64_t)w.n - woff, max_sites ? max_sites : 0xFFFFFFFFull, 1u << 20});
   const int n_out = s->n_out;
-  for (;;) {
-    bb.live.ensure((uint64_t)nb * S.nq); bb.lcls.ensure((uint64_t)nb * S.nq); bb.sites.ensure(nb); bb.cursors.ensure(4);
-    bb.agg.ensure((uint64_t)nb * AGG_WORDS); bb.nt.ensure((uint64_t)nb * S.nq); bb.nt_lut.ensure((uint64_t)nb * S.nq);
-    CK(cudaMemsetAsync(bb.agg.p, 0, (size_t)nb * AGG_WORDS * 4, ctx->stream));
-    if (!s->cap_allele_recs) { s->cap_allele_recs = 1u << 16; s->cap_allele_bytes = 1u << 20; }
-    bb.allele_pos.ensure(2ull * s->cap_allele_recs); bb.allele_hash.ensure(s->cap_allele_recs); bb.allele_bytes.ensure(s->cap_allele_bytes);
-    CK(cudaMemsetAsync(bb.cursors.p, 0, 16, ctx->stream));
+  {
+    bb.cursors.ensure(4);
+    CK(cudaMemsetAsync(bb.cursors.p, 0, 16, ctx->stream));   // [2]: the batch's LUT cursor (the remap kernels advance it)
+    bb.h_sites = w.h_sites.data() + woff; bb.live = w.live.p + (uint64_t)woff * S.nq; bb.allele_pos = w.allele_pos.p; bb.allele_bytes = w.allele_bytes.p;
+    bb.hc[0] = w.hc[0]; bb.hc[1] = w.hc[1]; bb.hc[2] = bb.hc[3] = 0;
     BatchDev B{};
-    B.first_site = first_site; B.n_sites = nb; B.live = bb.live.p; B.lcls = bb.lcls.p; B.sites = bb.sites.p; B.agg = bb.agg.p; B.nt = bb.nt.p; B.nt_lut = bb.nt_lut.p; B.cursors = bb.cursors.p;
-    // signature tables (gdb_kernels2.cuh: nt_lut): one slot per 64 samples, only for scans wide enough to repeat signatures
-    B.sig_slots = 0; B.sig_keys = nullptr;
-    if (S.nq >= SIG_MIN_ROWS) { uint32_t sl = 64; while (sl < SIG_MAX_SLOTS && (uint64_t)sl * 64 < S.nq) sl *= 2; B.sig_slots = sl; bb.sig_keys.ensure((uint64_t)nb * sl); B.sig_keys = bb.sig_keys.p; }
-    B.allele_pos = bb.allele_pos.p; B.allele_hash = bb.allele_hash.p; B.cap_allele_recs = s->cap_allele_recs; B.allele_bytes = bb.allele_bytes.p; B.cap_allele_bytes = s->cap_allele_bytes;
-    {   // sites walked by one thread after one binary search: long chunks amortise the search, short ones keep the device full
-      const uint64_t want_threads = 400000;
-      uint32_t chunk = (uint32_t)std::min<uint64_t>(nb, std::max<uint64_t>(32, (uint64_t)nb * S.nq / want_threads));
-      LAUNCH(ctx, k_live_walk, dim3(blocks_for(S.nq, 256), (nb + chunk - 1) / chunk), 256, a->dev, S, first_site, nb, chunk, bb.live.p, bb.lcls.p);
-    }
-    LAUNCH(ctx, k_site_scan, dim3(nb, blocks_for(S.nq, SSCAN_ROWS)), SSCAN_THREADS, a->dev, S, B);
-    LAUNCH(ctx, k_union, nb, UNION_THREADS, a->dev, S, B);
-    bb.h_sites.resize(nb);
-    CK(cudaMemcpyAsync(bb.h_sites.data(), bb.sites.p, (size_t)nb * sizeof(SiteRec), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(bb.hc, bb.cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream));   // allele pools are final after k_union
-    bool ovf = false;
-    check_scan_errors(s, ovf);
-    if (ovf) { s->cap_allele_recs *= 4; s->cap_allele_bytes *= 4; continue; }
-    {   // byte comparison behind every hash match (a throughput pass over the batch's nt lists; its verdict travels with the batch's tail)
-      uint32_t max_nt = 0;
-      for (uint32_t i = 0; i < nb; ++i) if (bb.h_sites[i].n_alleles >= 2u) max_nt = std::max(max_nt, bb.h_sites[i].n_nt);
-      if (max_nt && B.sig_keys) CK(cudaMemsetAsync(bb.sig_keys.p, 0xFF, (size_t)nb * B.sig_slots * 8, ctx->stream));
-      if (max_nt) LAUNCH(ctx, k_verify_alleles, dim3(blocks_for(max_nt, VERIFY_THREADS), nb), VERIFY_THREADS, a->dev, S, B);
-    }
+    B.first_site = first_site; B.n_sites = nb; B.live = w.live.p + (uint64_t)woff * S.nq; B.lcls = w.lcls.p + (uint64_t)woff * S.nq; B.sites = w.sites.p + woff; B.agg = w.agg.p + (uint64_t)woff * AGG_WORDS;
+    B.nt = w.nt.p + (uint64_t)woff * S.nq; B.nt_lut = w.nt_lut.p + (uint64_t)woff * S.nq; B.cursors = bb.cursors.p;
+    B.sig_slots = w.sig_slots; B.sig_keys = w.sig_slots ? w.sig_keys.p + (uint64_t)woff * w.sig_slots : nullptr;
+    B.allele_pos = w.allele_pos.p; B.allele_hash = w.allele_hash.p; B.cap_allele_recs = s->cap_allele_recs; B.allele_bytes = w.allele_bytes.p; B.cap_allele_bytes = s->cap_allele_bytes;
     // strides / bases; keep the prefix of sites that fits
-    for (int o = 0; o < n_out; ++o) { bb.h_base[o].assign(nb + 1, 0); bb.h_stride[o].assign(nb, 0); }
+    for (int o = 0; o < n_out; ++o) { bb.h_base[o].assign(1, 0); bb.h_stride[o].clear(); }
     uint64_t bytes = 0, alg_bytes = 0; uint32_t keep = 0; uint64_t lut_words = 0;
     for (uint32_t i = 0; i < nb; ++i) {
-      uint64_t site_bytes = 0, site_alg = 0;
+      uint64_t site_bytes = 0, site_alg = 0; uint32_t st[MAX_FIELDS + 1];
       for (int o = 0; o < n_out; ++o) {
-        uint32_t st = stride_of(a, bb.h_sites[i], o); bb.h_stride[o][i] = st;
-        site_bytes += (((uint64_t)st * S.nq + 3) & ~3ull) * 4 + S.nq * 2;
+        st[o] = stride_of(a, bb.h_sites[i], o);
+        site_bytes += (((uint64_t)st[o] * S.nq + 3) & ~3ull) * 4 + S.nq * 2;
         site_alg += (uint64_t)stride_needed(a, bb.h_sites[i], o) * S.nq * 4;
       }
       if (i > 0 && bytes + site_bytes > max_bytes) break;
-      for (int o = 0; o < n_out; ++o) bb.h_base[o][i + 1] = (bb.h_base[o][i] + (uint64_t)bb.h_stride[o][i] * S.nq + 3) & ~3ull;   // 16-byte aligned sites
+      for (int o = 0; o < n_out; ++o) { bb.h_stride[o].push_back(st[o]); bb.h_base[o].push_back((bb.h_base[o][i] + (uint64_t)st[o] * S.nq + 3) & ~3ull); }   // 16-byte aligned sites
       bytes += site_bytes; alg_bytes += site_alg; lut_words += (uint64_t)bb.h_sites[i].max_ain * S.nq; keep = i + 1;
     }
     s->avg_site_bytes = std::max<uint64_t>(1, bytes / keep);
@@ -916,7 +964,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
     bb.ctl.flush(ctx->stream);
     if (s->site_stats) {   // the copy rides the compute stream: it is done before ev_done is
       bb.site_stats.ensure((size_t)keep * 2); bb.p_site_stats.ensure((size_t)keep * 2);
-      LAUNCH(ctx, k_site_stats, keep, 256, a->dev, S, bb.live.p, first_site, keep, bb.site_stats.p);
+      LAUNCH(ctx, k_site_stats, keep, 256, a->dev, S, bb.live, first_site, keep, bb.site_stats.p);
       CK(cudaMemcpyAsync(bb.p_site_stats.p, bb.site_stats.p, (size_t)keep * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (S.want_lut) {
@@ -1067,14 +1115,14 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       const unsigned chunks = (unsigned)std::min<uint64_t>(64, std::max<uint64_t>(1, max_words / (FMT_THREADS * 16)));
       const unsigned row_blocks = blocks_for(S.nq, FMT_THREADS);
       LAUNCH(ctx, k_fmt_range, dim3(chunks, keep), FMT_THREADS, a->dev, O, keep, (uint32_t)S.nq, s->produce_gt, s->java, bb.fmt_mm.p);
-      if (n_plain) LAUNCH(ctx, k_plain_scan, dim3(row_blocks, keep), FMT_THREADS, a->plain_dev, bb.live.p, keep, (uint32_t)S.nq, bb.fmt_mm.p + 2 * n_rp);
+      if (n_plain) LAUNCH(ctx, k_plain_scan, dim3(row_blocks, keep), FMT_THREADS, a->plain_dev, bb.live, keep, (uint32_t)S.nq, bb.fmt_mm.p + 2 * n_rp);
       const bool dp_rule = s->info.dp_info >= 0 || s->info.dp_format >= 0;
       bb.h_info_value.assign((size_t)n_plain * keep, 0); bb.h_info_valid.assign((size_t)n_plain * keep, 0); bb.h_dp_sum.assign(keep, 0);
       const int n_info = s->info.n;
       if (n_info || dp_rule) {   // INFO scalars: ordered compaction of the valid values, then median / sum / mean; DP sum
         bb.info_vals.ensure(std::max<uint64_t>((uint64_t)n_info * keep * S.nq, 1)); bb.info_cnt.ensure(std::max<uint64_t>((uint64_t)n_info * keep, 1));
         bb.info_value_d.ensure(std::max<uint64_t>((uint64_t)n_info * keep, 1)); bb.info_valid_d.ensure(std::max<uint64_t>((uint64_t)n_info * keep, 1)); bb.dp_sum_d.ensure(keep);
-        LAUNCH(ctx, k_info_collect, keep, FMT_THREADS, a->plain_dev, s->info, bb.live.p, keep, (uint32_t)S.nq, bb.info_vals.p, bb.info_cnt.p, bb.dp_sum_d.p);
+        LAUNCH(ctx, k_info_collect, keep, FMT_THREADS, a->plain_dev, s->info, bb.live, keep, (uint32_t)S.nq, bb.info_vals.p, bb.info_cnt.p, bb.dp_sum_d.p);
         if (n_info) LAUNCH(ctx, k_info_reduce, dim3(keep, n_info), FMT_THREADS, a->plain_dev, s->info, keep, (uint32_t)S.nq, bb.info_vals.p, bb.info_cnt.p, bb.info_value_d.p, bb.info_valid_d.p);
         // results land at the plain-field index of every INFO field
         for (int k = 0; k < n_info; ++k) {
@@ -1089,7 +1137,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       std::vector<uint32_t> h_esum_len;
       if (n_esum) {   // element-wise sums: fixed-capacity slots on the device, compacted on the host below
         bb.esum_values.ensure((uint64_t)n_esum * keep * ESUM_CAP); bb.esum_lens.ensure((uint64_t)n_esum * keep);
-        LAUNCH(ctx, k_info_esum, dim3(keep, n_esum), ESUM_THREADS, a->dev, a->plain_dev, O, s->esum, bb.live.p, reinterpret_cast<const int32_t*>(bb.fmt_mm.p + 2 * n_rp), keep,
+        LAUNCH(ctx, k_info_esum, dim3(keep, n_esum), ESUM_THREADS, a->dev, a->plain_dev, O, s->esum, bb.live, reinterpret_cast<const int32_t*>(bb.fmt_mm.p + 2 * n_rp), keep,
                (uint32_t)S.nq, bb.esum_values.p, bb.esum_lens.p, s->err.p);
         h_esum_len.resize((size_t)n_esum * keep); bb.h_esum_raw.resize((size_t)n_esum * keep * ESUM_CAP);
         CK(cudaMemcpyAsync(h_esum_len.data(), bb.esum_lens.p, h_esum_len.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1144,13 +1192,13 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       const FmtPlanDev P{bb.fmt_type_d, bb.fmt_nps_d, bb.fmt_off_d, bb.fmt_bytes.p};
       LAUNCH(ctx, k_fmt_pack, dim3(chunks, keep), FMT_THREADS, a->dev, O, P, keep, (uint32_t)S.nq, s->produce_gt, s->java);
       LAUNCH(ctx, k_fmt_pack_tile, dim3(blocks_for(S.nq, PACK_ROWS), keep), FMT_THREADS, a->dev, O, P, keep, (uint32_t)S.nq, s->java);
-      if (n_plain) LAUNCH(ctx, k_plain_pack, dim3(row_blocks, keep), FMT_THREADS, a->plain_dev, P, n_out, bb.live.p, keep, (uint32_t)S.nq, s->java);
+      if (n_plain) LAUNCH(ctx, k_plain_pack, dim3(row_blocks, keep), FMT_THREADS, a->plain_dev, P, n_out, bb.live, keep, (uint32_t)S.nq, s->java);
     }
     // ---- results: site metadata (host mirrors), then the copies of everything the caller asked for
     bb.keep = keep; bb.alg_bytes = alg_bytes;
     bb.p_tail.ensure(8);
     if (S.want_lut) {   // the LUT copy is sized by a cursor only the remap kernels advance
-      CK(cudaMemcpyAsync(bb.hc, bb.cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+      CK(cudaMemcpyAsync(bb.hc + 2, bb.cursors.p + 2, 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
     }
     CK(cudaMemcpyAsync(bb.p_tail.p, s->err.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(bb.p_tail.p + 4, bb.cursors.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1162,8 +1210,8 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       bb.p_allele_pos.ensure(2ull * std::max<uint32_t>(bb.hc[0], 1)); bb.p_allele_bytes.ensure(std::max<uint32_t>(bb.hc[1], 1));
       CK(cudaMemcpyAsync(bb.p_site_begin.p, s->site_begin.p + first_site, (size_t)keep * 8, cudaMemcpyDeviceToHost, cs));
       CK(cudaMemcpyAsync(bb.p_site_end.p, s->site_end.p + first_site, (size_t)keep * 8, cudaMemcpyDeviceToHost, cs));
-      CK(cudaMemcpyAsync(bb.p_allele_pos.p, bb.allele_pos.p, (size_t)bb.hc[0] * 8, cudaMemcpyDeviceToHost, cs));
-      CK(cudaMemcpyAsync(bb.p_allele_bytes.p, bb.allele_bytes.p, bb.hc[1], cudaMemcpyDeviceToHost, cs));
+      CK(cudaMemcpyAsync(bb.p_allele_pos.p, bb.allele_pos, (size_t)bb.hc[0] * 8, cudaMemcpyDeviceToHost, cs));
+      CK(cudaMemcpyAsync(bb.p_allele_bytes.p, bb.allele_bytes, bb.hc[1], cudaMemcpyDeviceToHost, cs));
       if (s->summary_only) {
         // per-site tables only: nothing per call crosses PCIe
       } else if (s->bcf_format) {
@@ -1171,7 +1219,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
         if (bb.fmt_total) CK(cudaMemcpyAsync(bb.p_fmt_bytes.p, bb.fmt_bytes.p, bb.fmt_total, cudaMemcpyDeviceToHost, cs));
       } else {
         bb.p_live.ensure((uint64_t)keep * S.nq);
-        CK(cudaMemcpyAsync(bb.p_live.p, bb.live.p, (size_t)keep * S.nq * 4, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(bb.p_live.p, bb.live, (size_t)keep * S.nq * 4, cudaMemcpyDeviceToHost, cs));
         for (int o = 0; o < n_out; ++o) {
           bb.p_out_data[o].ensure(std::max<uint64_t>(bb.h_base[o][keep], 1)); bb.p_out_len[o].ensure((uint64_t)keep * S.nq);
           if (bb.h_base[o][keep]) CK(cudaMemcpyAsync(bb.p_out_data[o].p, bb.out_data[o].p, bb.h_base[o][keep] * 4, cudaMemcpyDeviceToHost, cs));
@@ -1208,7 +1256,7 @@ void publish_batch(gdbgpu_scan* s, BatchBuffers& bb, gdbgpu_batch* out) {
   if (s->device_output) {
     out->site_begin = s->site_begin.p + bb.first; out->site_end = s->site_end.p + bb.first;
     out->site_flags = bb.d_site_flags; out->n_alleles = bb.d_n_alleles; out->n_live = bb.d_n_live; out->allele_first = bb.d_allele_first;
-    out->allele_pos = bb.allele_pos.p; out->allele_bytes = bb.allele_bytes.p; out->live = bb.live.p;
+    out->allele_pos = bb.allele_pos; out->allele_bytes = bb.allele_bytes; out->live = bb.live;
     for (int o = 0; o < n_out; ++o) out->fields[o] = gdbgpu_field_out{bb.out_data[o].p, bb.out_base[o], bb.out_stride[o], bb.out_len[o].p};
     if (S.want_lut) { out->lut_first = bb.lut_first.p; out->lut_len = bb.lut_len.p; out->lut_in2m = bb.lut_in2m.p; }
     if (s->bcf_format) { out->fmt_bytes = bb.fmt_bytes.p; out->fmt_type = bb.fmt_type_d; out->fmt_nps = bb.fmt_nps_d; out->fmt_offset = bb.fmt_off_d; }
@@ -1257,7 +1305,8 @@ int next_batch(gdbgpu_scan* s, uint32_t max_sites, uint64_t max_bytes, gdbgpu_ba
   BatchBuffers& c = scan_slot(s, s->cur);
   if (!holds(c, s->cursor)) compute_batch(s, c, s->cursor, max_sites, max_bytes);
   const uint64_t next_first = c.first + c.keep;
-  if (s->prefetch && next_first < S.n_sites) {
+  // (device output: the caller still reads this batch's rows of the window's live matrix and allele pools, so the next window waits for the next call)
+  if (s->prefetch && next_first < S.n_sites && !(s->device_output && next_first >= s->front.first + s->front.n)) {
     BatchBuffers& n = scan_slot(s, s->cur ^ 1);
     if (!holds(n, next_first)) compute_batch(s, n, next_first, max_sites, max_bytes);
   }
