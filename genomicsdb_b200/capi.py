@@ -25,7 +25,7 @@ KIND = {"R": LEN_R, "A": LEN_A, "G": LEN_G}
 
 EXPORTS = ["gdbgpu_version", "gdbgpu_ctx_create", "gdbgpu_ctx_destroy", "gdbgpu_last_error", "gdbgpu_ctx_stream",
            "gdbgpu_ctx_launch_count", "gdbgpu_ctx_synchronize", "gdbgpu_ctx_release_cached_memory", "gdbgpu_ctx_set_profiling",
-           "gdbgpu_ctx_reset_kernel_stats", "gdbgpu_ctx_kernel_stats", "gdbgpu_array_open", "gdbgpu_array_open_ex", "gdbgpu_array_open_range", "gdbgpu_array_column_cuts", "gdbgpu_array_from_columns", "gdbgpu_array_get_info",
+           "gdbgpu_ctx_reset_kernel_stats", "gdbgpu_ctx_kernel_stats", "gdbgpu_array_open", "gdbgpu_array_open_ex", "gdbgpu_array_open_range", "gdbgpu_array_column_cuts", "gdbgpu_inflate_streams", "gdbgpu_array_from_columns", "gdbgpu_array_get_info",
            "gdbgpu_array_copy_cells", "gdbgpu_array_close", "gdbgpu_scan_begin", "gdbgpu_scan_get_info",
            "gdbgpu_scan_next_batch", "gdbgpu_scan_seek", "gdbgpu_scan_end", "gdbgpu_scan_cells", "gdbgpu_scan_cells_histogram",
            "gdbgpu_scan_cells_allele_counts", "gdbgpu_scan_cells_fetch", "gdbgpu_scan_cells_window",
@@ -130,6 +130,7 @@ def lib():
         L.gdbgpu_array_open_range.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(FieldDesc), C.c_int32,
                                               C.POINTER(PlainFieldDesc), C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
         L.gdbgpu_array_column_cuts.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_int64)]
+        L.gdbgpu_inflate_streams.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_double)]
         L.gdbgpu_array_from_columns.argtypes = [C.c_void_p, C.POINTER(Columns), C.POINTER(C.c_void_p)]
         L.gdbgpu_array_get_info.argtypes = [C.c_void_p, C.POINTER(ArrayInfo)]
         L.gdbgpu_array_copy_cells.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -207,6 +208,21 @@ class Context:
         ms, n = C.c_double(), C.c_uint64()
         self.check(lib().gdbgpu_ctx_kernel_stats(self.h, name.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def inflate_streams(self, streams, out_sizes):
+        """K0 on its own: `streams` (list of bytes, one zlib stream each) -> (list of inflated bytes, kernel ms)"""
+        import numpy as np
+        n = len(streams)
+        in_off = np.zeros(n + 1, dtype=np.uint64)
+        out_off = np.zeros(n + 1, dtype=np.uint64)
+        in_off[1:] = np.cumsum([len(x) for x in streams], dtype=np.uint64)
+        out_off[1:] = np.cumsum(list(out_sizes), dtype=np.uint64)
+        blob = b"".join(streams)
+        out = np.zeros(max(int(out_off[-1]), 1), dtype=np.uint8)
+        ms = C.c_double(0.0)
+        self.check(lib().gdbgpu_inflate_streams(self.h, blob, in_off.ctypes.data_as(C.POINTER(C.c_uint64)), out.ctypes.data_as(C.c_void_p),
+                                                out_off.ctypes.data_as(C.POINTER(C.c_uint64)), n, C.byref(ms)))
+        return [out[int(out_off[i]):int(out_off[i + 1])].tobytes() for i in range(n)], ms.value
 
     def close(self):
         if self.h:

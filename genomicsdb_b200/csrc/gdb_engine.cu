@@ -358,6 +358,30 @@ void gather_var(gdbgpu_ctx* ctx, const DevVar& in, const uint32_t* src, uint64_t
   CK(cudaStreamSynchronize(ctx->stream));
 }
 
+// K0 launch: one warp per stream, the longest streams first (a launch lasts as long as its last stream); throws on a corrupt stream
+void inflate_jobs(gdbgpu_ctx* ctx, const std::vector<InflateJob>& jobs) {
+  if (jobs.empty()) return;
+  DevBuf<InflateJob> d_jobs; DevBuf<uint32_t> inf_err, d_order;
+  d_jobs.alloc(jobs.size()); inf_err.alloc(2); d_order.alloc(jobs.size());
+  CK(cudaMemsetAsync(inf_err.p, 0, 8, ctx->stream));
+  CK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(InflateJob), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<uint32_t> order(jobs.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return jobs[x].out_len > jobs[y].out_len; });
+  CK(cudaMemcpyAsync(d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INFLATE_SMEM));
+  {
+    ProfScope ps__(ctx, "k_inflate");
+    k_inflate<<<blocks_for(jobs.size(), inflate_detail::WARPS_PER_BLOCK), INFLATE_THREADS, INFLATE_SMEM, ctx->stream>>>(d_jobs.p, d_order.p, (uint64_t)jobs.size(), inf_err.p);
+  }
+  ++ctx->launches; CK(cudaGetLastError());
+  uint32_t e[2] = {0, 0};
+  CK(cudaMemcpyAsync(e, inf_err.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (e[0]) throw std::runtime_error("zlib stream of tile " + std::to_string(e[1]) + " does not inflate (" +
+                                     (e[0] == INF_ERR_HEADER ? "bad header" : e[0] == INF_ERR_SIZE ? "size mismatch" : e[0] == INF_ERR_ADLER ? "Adler-32 mismatch" : "corrupt data") + ")");
+}
+
 // stage columns (already concatenated over fragments; host memory, or HBM when the tiles were inflated on the device) and
 // build the per-array indexes
 // `owned` (gdbgpu_array_open*): the same columns, already in HBM, in the order coords, END, REF, ALT, [GT], fields, plain fields
@@ -1751,19 +1775,10 @@ int gdbgpu_array_open_range(gdbgpu_ctx* ctx, const char* workspace, const char* 
       for (const Pending& pd : pending) file_jobs.push_back(FileJob{pd.path, pd.f_off, pd.f_len, arena.p + pd.arena_off});
       stage_files(ctx, file_jobs);   // every byte of the range's tiles is in HBM when this returns
       if (n_jobs) {
-        DevBuf<InflateJob> d_jobs; DevBuf<uint32_t> inf_err;
-        d_jobs.alloc(n_jobs); inf_err.alloc(2);
-        CK(cudaMemsetAsync(inf_err.p, 0, 8, ctx->stream));
         std::vector<InflateJob> jobs; jobs.reserve(n_jobs);
         for (const Pending& pd : pending)
           for (const TdbTileSpan& t : *pd.tiles) jobs.push_back(InflateJob{arena.p + pd.arena_off + t.in_off, t.in_len, pd.dst + t.out_off, t.out_len});
-        CK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(InflateJob), cudaMemcpyHostToDevice, ctx->stream));
-        LAUNCH(ctx, k_inflate, blocks_for(jobs.size(), 64), 64, d_jobs.p, (uint64_t)jobs.size(), inf_err.p);
-        uint32_t e[2] = {0, 0};
-        CK(cudaMemcpyAsync(e, inf_err.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (e[0]) throw std::runtime_error("zlib stream of tile " + std::to_string(e[1]) + " does not inflate (" +
-                                           (e[0] == INF_ERR_HEADER ? "bad header" : e[0] == INF_ERR_SIZE ? "size mismatch" : e[0] == INF_ERR_ADLER ? "Adler-32 mismatch" : "corrupt data") + ")");
+        inflate_jobs(ctx, jobs);
       }
       for (const Rebase& rb : rebases) LAUNCH(ctx, k_add_u64, blocks_for(rb.n, 256), 256, rb.p, rb.n, rb.add);
       CK(cudaStreamSynchronize(ctx->stream));   // the host file buffers (pageable) may go once every copy has run
@@ -1804,6 +1819,31 @@ int gdbgpu_array_open_range(gdbgpu_ctx* ctx, const char* workspace, const char* 
       *out = arr.release();
       return;
     }
+  });
+}
+
+int gdbgpu_inflate_streams(gdbgpu_ctx* ctx, const void* in, const uint64_t* in_offsets, void* out, const uint64_t* out_offsets, uint64_t n, double* kernel_ms) {
+  if (!ctx || !in_offsets || !out_offsets || (n && (!in || !out))) return GDBGPU_ERR_ARG;
+  return guarded(ctx, [&] {
+    CK(cudaSetDevice(ctx->device));
+    if (kernel_ms) *kernel_ms = 0.0;
+    if (!n) return;
+    for (uint64_t i = 0; i < n; ++i) if (in_offsets[i + 1] < in_offsets[i] || out_offsets[i + 1] < out_offsets[i]) throw ArgError("offsets must not decrease");
+    DevBuf<uint8_t> d_in, d_out;
+    d_in.alloc(std::max<uint64_t>(in_offsets[n], 16)); d_out.alloc(std::max<uint64_t>(out_offsets[n], 16));
+    CK(cudaMemcpyAsync(d_in.p, in, in_offsets[n], cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<InflateJob> jobs(n);
+    for (uint64_t i = 0; i < n; ++i) jobs[i] = InflateJob{d_in.p + in_offsets[i], in_offsets[i + 1] - in_offsets[i], d_out.p + out_offsets[i], out_offsets[i + 1] - out_offsets[i]};
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, ctx->stream));
+    try { inflate_jobs(ctx, jobs); } catch (...) { cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaMemcpyAsync(out, d_out.p, out_offsets[n], cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    if (kernel_ms) *kernel_ms = ms;   // the launch + its error word read back
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
   });
 }
 

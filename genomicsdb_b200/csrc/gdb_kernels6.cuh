@@ -99,12 +99,18 @@ __global__ void __launch_bounds__(SIGPERM_THREADS) k_sig_perm(const __grid_const
 #ifndef GDB_MIX_BLOCKS
 #define GDB_MIX_BLOCKS 5
 #endif
-constexpr int MIX_SPB = 8;   // consecutive sites a band block walks
+#ifndef GDB_MIX_SPB
+#define GDB_MIX_SPB 8
+#endif
+constexpr int MIX_SPB = GDB_MIX_SPB;   // consecutive sites a band block walks
 
 // per-thread, per-field column plan of phase B (computed once per block, the same for every tile of the site)
 constexpr uint32_t CFG_VALID = 1u << 16;   // r_off(8) | class of word 0..3 (2 bits each, 3 = padding) << 8 | valid << 16 | iterations of a full tile << 17
 
-constexpr int MIX_DEPTH = 2;   // hot records in flight: tiles t .. t + MIX_DEPTH - 1
+#ifndef GDB_MIX_DEPTH
+#define GDB_MIX_DEPTH 2
+#endif
+constexpr int MIX_DEPTH = GDB_MIX_DEPTH;   // hot records in flight: tiles t .. t + MIX_DEPTH - 1
 
 template <int NF>
 struct MixSmem {

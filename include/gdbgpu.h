@@ -155,6 +155,14 @@ int gdbgpu_array_open_range(gdbgpu_ctx* ctx, const char* workspace, const char* 
  * owns [cuts[r], cuts[r + 1] - 1] -- SURVEY 8e; the reference leaves this to the loader's column_partitions
  * (genomicsdb_config_base.cc:205-223) or to ColumnHistogramOperator::equi_partition_and_print_bins.  Host only. */
 int gdbgpu_array_column_cuts(const char* workspace, const char* array_name, int32_t n_parts, int64_t* cuts);
+
+/* K0 on its own: inflates n zlib streams (RFC 1950; what TileDB's gunzip does per tile, dependencies/TileDB/core/src/misc/
+ * utils.cc:466-512 via ReadState::decompress_tile_gzip, fragment/read_state.cc:1595-1702) on the device, one warp per
+ * stream.  Stream i is in[in_offsets[i] .. in_offsets[i+1]) and must inflate to exactly out_offsets[i+1] - out_offsets[i]
+ * bytes at out + out_offsets[i] (host buffers; n + 1 offsets each).  GDBGPU_ERR_IO when a stream is corrupt (header, data,
+ * size or Adler-32); kernel_ms (optional) receives the kernel's CUDA-event time. */
+int gdbgpu_inflate_streams(gdbgpu_ctx* ctx, const void* in, const uint64_t* in_offsets, void* out, const uint64_t* out_offsets,
+                           uint64_t n, double* kernel_ms);
 /* Same, from columns already decoded in host memory (loader hand-off, JNI buffers, synthetic generators). */
 int gdbgpu_array_from_columns(gdbgpu_ctx* ctx, const gdbgpu_columns* cols, gdbgpu_array** out);
 int gdbgpu_array_get_info(const gdbgpu_array* arr, gdbgpu_array_info* info);
