@@ -161,7 +161,6 @@ void radix_sort_pairs(gdbgpu_ctx* ctx, const K* kin, K* kout, const V* vin, V* v
 
 __global__ void k_narrow_u64(const uint64_t* in, uint64_t n, uint32_t* out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = (uint32_t)in[i]; }
 __global__ void k_iota(uint32_t* p, uint64_t n) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = (uint32_t)i; }
-__global__ void k_gather_u64(const uint64_t* in, const uint32_t* perm, uint64_t n, uint64_t* out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = in[perm[i]]; }
 __global__ void k_flag_del(ArrayDev A, uint32_t* flag) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < A.n) flag[i] = (A.desc[i].flags & F_DELETION) && !(A.desc[i].flags & F_ROWOUT) ? 1u : 0u; }
 __global__ void k_compact_idx(const uint32_t* flag, const uint32_t* pos, uint64_t n, uint32_t* out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n && flag[i]) out[pos[i]] = (uint32_t)i; }
 __global__ void k_bounds(const int64_t* coords, uint64_t n, int64_t q_lo, int64_t q_hi, uint64_t* out) {
@@ -314,21 +313,30 @@ void fill_dev_view(gdbgpu_array* a) {
 // K1: merge the concatenated cells of several fragments into global (col,row) order, newest fragment wins.
 // Returns src[] (device) = for each surviving merged cell, its index in the concatenation.
 void fragment_merge(gdbgpu_ctx* ctx, const int64_t* d_coords, uint64_t n_all, const std::vector<uint64_t>& frag_cells, DevBuf<uint32_t>& src, uint64_t& n_out) {
-  std::vector<uint32_t> frag_of(n_all);
-  { uint64_t p = 0; for (uint32_t f = 0; f < frag_cells.size(); ++f) for (uint64_t k = 0; k < frag_cells[f]; ++k) frag_of[p++] = f; }
-  DevBuf<uint32_t> d_frag, kfrag, perm_a, perm_b, k32; DevBuf<uint64_t> kcol, krow, k64a, k64b; DevBuf<uint8_t> tmp;
-  d_frag.alloc(n_all); kfrag.alloc(n_all); perm_a.alloc(n_all); perm_b.alloc(n_all); k32.alloc(n_all);
-  kcol.alloc(n_all); krow.alloc(n_all); k64a.alloc(n_all); k64b.alloc(n_all);
-  CK(cudaMemcpyAsync(d_frag.p, frag_of.data(), n_all * 4, cudaMemcpyHostToDevice, ctx->stream));
+  // runs = the fragments, oldest first; each round merges neighbours (gdb_kernels.cuh: k_merge_path)
+  DevBuf<int64_t> col[2], row[2]; DevBuf<uint32_t> cell[2]; DevBuf<uint64_t> d_runs; DevBuf<uint2> d_tiles;
+  for (int b = 0; b < 2; ++b) { col[b].alloc(n_all); row[b].alloc(n_all); cell[b].alloc(n_all); }
   unsigned g = blocks_for(n_all, 256);
-  LAUNCH(ctx, k_merge_keys, g, 256, d_coords, d_frag.p, (uint32_t)frag_cells.size(), n_all, kcol.p, krow.p, kfrag.p);
-  LAUNCH(ctx, k_iota, g, 256, perm_a.p, n_all);
-  // LSD: fragment (newest first), then row, then column -- each pass stable
-  radix_sort_pairs(ctx, kfrag.p, k32.p, perm_a.p, perm_b.p, n_all, 32, tmp);
-  LAUNCH(ctx, k_gather_u64, g, 256, krow.p, perm_b.p, n_all, k64a.p);
-  radix_sort_pairs(ctx, k64a.p, k64b.p, perm_b.p, perm_a.p, n_all, 64, tmp);
-  LAUNCH(ctx, k_gather_u64, g, 256, kcol.p, perm_a.p, n_all, k64a.p);
-  radix_sort_pairs(ctx, k64a.p, k64b.p, perm_a.p, perm_b.p, n_all, 64, tmp);
+  LAUNCH(ctx, k_merge_init, g, 256, d_coords, n_all, col[0].p, row[0].p, cell[0].p);
+  std::vector<uint64_t> runs(1, 0);
+  for (uint64_t c : frag_cells) runs.push_back(runs.back() + c);
+  int cur = 0;
+  while (runs.size() > 2) {
+    const uint32_t n_runs = (uint32_t)runs.size() - 1, n_pairs = (n_runs + 1) / 2;
+    std::vector<uint2> tiles; std::vector<uint64_t> next(1, 0);
+    for (uint32_t p = 0; p < n_pairs; ++p) {
+      const uint64_t lo = runs[2 * p], hi = runs[std::min<uint32_t>(2 * p + 2, n_runs)];
+      for (uint64_t t = 0; t * MERGE_TILE < hi - lo; ++t) tiles.push_back(make_uint2(p, (uint32_t)t));
+      next.push_back(hi);
+    }
+    d_runs.alloc(runs.size()); d_tiles.alloc(std::max<size_t>(tiles.size(), 1));
+    CK(cudaMemcpyAsync(d_runs.p, runs.data(), runs.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+    if (!tiles.empty()) LAUNCH(ctx, k_merge_path, (unsigned)tiles.size(), MERGE_THREADS, col[cur].p, row[cur].p, cell[cur].p, col[cur ^ 1].p, row[cur ^ 1].p, cell[cur ^ 1].p, d_runs.p, n_runs, d_tiles.p);
+    CK(cudaStreamSynchronize(ctx->stream));   // the host vectors of this round may go
+    runs.swap(next); cur ^= 1;
+  }
+  DevBuf<uint32_t>& perm_b = cell[cur];
   // perm_b = merged order incl. shadowed duplicates
   DevBuf<uint32_t> keep, pos, total; DevBuf<uint32_t> sums;
   keep.alloc(n_all); pos.alloc(n_all); total.alloc(1);

@@ -289,15 +289,68 @@ __global__ void __launch_bounds__(256) k_effend_rowout(ArrayDev A, const CellDes
 }
 
 // ------------------------------------------------------------------------------------------------ K1 fragment merge
-// Cells of all fragments concatenated; key = (col, row, newest fragment first).  The sort itself is a radix sort on
-// three 64-bit passes (host side, gdb_engine.cu); these kernels build keys, drop shadowed duplicates and gather.
-__global__ void __launch_bounds__(256) k_merge_keys(const int64_t* __restrict__ coords, const uint32_t* __restrict__ frag_of, uint32_t n_frag, uint64_t n,
-                                                     uint64_t* __restrict__ kcol, uint64_t* __restrict__ krow, uint32_t* __restrict__ kfrag) {
+// Every fragment is a run of cells already in global (col, row) order; the array is their k-way merge, and of two cells with
+// the same coordinates the one of the NEWER fragment wins (ArrayReadState::read / sort_fragment_cell_pos_ranges + PQ order,
+// array_read_state.cc:1836-2132, comparator :2369-2402).  Here: log2(k) rounds of pairwise merges of neighbouring runs (run
+// 2i = the older fragments, run 2i + 1 = the newer ones; on equal keys the newer run's cell goes first), each round one
+// streaming pass: a block produces MERGE_TILE consecutive outputs of one pair -- two binary searches along the merge path
+// find which pieces of the two runs they come from, the pieces are loaded into shared memory, every element finds its rank
+// among the other run's piece by a binary search there.  Keys travel with the cell index as three streams (col, row, cell).
+constexpr int MERGE_THREADS = 256, MERGE_VT = 8, MERGE_TILE = MERGE_THREADS * MERGE_VT;
+struct MergeKey { int64_t col, row; };
+__device__ inline bool key_less(int64_t ac, int64_t ar, int64_t bc, int64_t br) { return ac < bc || (ac == bc && ar < br); }
+
+__global__ void __launch_bounds__(256) k_merge_init(const int64_t* __restrict__ coords, uint64_t n, int64_t* __restrict__ col, int64_t* __restrict__ row, uint32_t* __restrict__ cell) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  kcol[i] = (uint64_t)coords[2 * i + 1] ^ 0x8000000000000000ull;   // order-preserving for signed values
-  krow[i] = (uint64_t)coords[2 * i] ^ 0x8000000000000000ull;
-  kfrag[i] = n_frag - 1 - frag_of[i];
+  row[i] = coords[2 * i]; col[i] = coords[2 * i + 1]; cell[i] = (uint32_t)i;
+}
+// tile_pair[t] = (pair index, tile index within the pair); run_start[0 .. n_runs] = where the runs of this round begin;
+// pair p merges runs 2p (A, older) and 2p + 1 (B, newer; empty when 2p + 1 == n_runs) into [run_start[2p], run_start[2p + 2])
+__global__ void __launch_bounds__(MERGE_THREADS) k_merge_path(const int64_t* __restrict__ col_in, const int64_t* __restrict__ row_in, const uint32_t* __restrict__ cell_in,
+                                                              int64_t* __restrict__ col_out, int64_t* __restrict__ row_out, uint32_t* __restrict__ cell_out,
+                                                              const uint64_t* __restrict__ run_start, const uint32_t n_runs, const uint2* __restrict__ tile_pair) {
+  __shared__ int64_t s_col[MERGE_TILE], s_row[MERGE_TILE];
+  __shared__ uint32_t s_cell[MERGE_TILE];
+  __shared__ uint64_t s_split[2];
+  const uint32_t tid = threadIdx.x;
+  const uint2 tp = tile_pair[blockIdx.x];
+  const uint64_t a_lo = run_start[2 * tp.x], b_lo = run_start[min(2 * tp.x + 1, n_runs)], b_hi = run_start[min(2 * tp.x + 2, n_runs)];
+  const uint64_t nA = b_lo - a_lo, nB = b_hi - b_lo;
+  const uint64_t d0 = (uint64_t)tp.y * MERGE_TILE, d1 = min(d0 + (uint64_t)MERGE_TILE, nA + nB);
+  // merge path: how many of the first d outputs come from A -- the first i with !(A[i] < B[d - 1 - i]) (B goes first on equal keys)
+  if (tid < 2) {
+    const uint64_t d = tid == 0 ? d0 : d1;
+    uint64_t lo = d > nB ? d - nB : 0, hi = min(d, nA);
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi) >> 1, ia = a_lo + mid, ib = b_lo + (d - 1 - mid);
+      if (key_less(col_in[ia], row_in[ia], col_in[ib], row_in[ib])) lo = mid + 1; else hi = mid;
+    }
+    s_split[tid] = lo;
+  }
+  __syncthreads();
+  const uint64_t a0 = s_split[0], a1 = s_split[1], b0 = d0 - a0, b1 = d1 - a1;
+  const uint32_t na = (uint32_t)(a1 - a0), nb = (uint32_t)(b1 - b0);   // na + nb <= MERGE_TILE; A's piece at [0, na), B's at [na, na + nb)
+  for (uint32_t i = tid; i < na + nb; i += MERGE_THREADS) {
+    const uint64_t g = i < na ? a_lo + a0 + i : b_lo + b0 + (i - na);
+    s_col[i] = col_in[g]; s_row[i] = row_in[g]; s_cell[i] = cell_in[g];
+  }
+  __syncthreads();
+  const uint64_t out0 = a_lo + d0;
+  for (uint32_t i = tid; i < na + nb; i += MERGE_THREADS) {
+    const int64_t c = s_col[i], r = s_row[i];
+    uint32_t lo, hi, rank;
+    if (i < na) {   // an A element: after the B elements with key <= its own
+      lo = na; hi = na + nb;
+      while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (!key_less(c, r, s_col[mid], s_row[mid])) lo = mid + 1; else hi = mid; }
+      rank = i + (lo - na);
+    } else {        // a B element: after the A elements with key < its own
+      lo = 0; hi = na;
+      while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (key_less(s_col[mid], s_row[mid], c, r)) lo = mid + 1; else hi = mid; }
+      rank = (i - na) + lo;
+    }
+    col_out[out0 + rank] = c; row_out[out0 + rank] = r; cell_out[out0 + rank] = s_cell[i];
+  }
 }
 __global__ void __launch_bounds__(256) k_merge_keep(const int64_t* __restrict__ coords, const uint32_t* __restrict__ perm, uint64_t n, uint32_t* __restrict__ keep) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

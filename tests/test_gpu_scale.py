@@ -51,9 +51,9 @@ def _intervals(lo, hi, k):
     return [(a, min(hi, a + step - 1)) for a in range(lo, hi + 1, step)]
 
 
-def compare_with_reference(tmp_path, d, n_intervals, max_parallel=None):
+def compare_with_reference(tmp_path, d, n_intervals, max_parallel=None, **writer_args):
     ws = str(tmp_path / "ws")
-    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000, **writer_args)
     lo, hi = d["col_range"]
     queries = []
     for i, (a, b) in enumerate(_intervals(lo, hi, n_intervals)):
@@ -102,3 +102,13 @@ def test_config4_width_all_rows(tmp_path):
     """BASELINE config #4's width: 100 k samples x 12 candidate sites (max 8 ALT alleles, 10 merged alleles), all 100 k rows"""
     d = gdbsyn.generate(**gdbsyn.CONFIGS["config4"], site_lo=700, site_hi=712)
     compare_with_reference(tmp_path, d, n_intervals=6)
+
+
+@pytest.mark.parametrize("n_fragments,compress", [(8, False), (64, False), (5, True)], ids=["8-fragments", "64-fragments", "5-gzip-fragments"])
+def test_many_fragments_newest_wins(tmp_path, n_fragments, compress):
+    """an array imported in many batches (the production default): every fragment spans all columns and holds its batch's samples,
+    and re-imports every 7th call of the batch before it with a changed PL -- the k-way merge (K1: merge path over the
+    fragments' sorted runs) must interleave the runs in (column, row) order and let the newest copy win, as the reference's
+    ArrayReadState does (array_read_state.cc:1836-2132, :2369-2402)"""
+    d = gdbsyn.generate(n_samples=2000, n_sites=10000, spacing=100, p_var=0.1, a_pool=4, site_lo=100, site_hi=700, with_fixed=True)
+    compare_with_reference(tmp_path, d, n_intervals=4, n_fragments=n_fragments, dup_every=7, compress=compress)

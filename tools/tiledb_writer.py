@@ -115,18 +115,39 @@ def _write_tiles(path, data, tile_bytes, level=6):
     return offs
 
 
-def write_array(workspace, array_name, d, capacity=1000, compress=False):
-    """d: tools.gdbsyn.generate(..., with_fixed=True).  Returns dict(workspace, array, vid, callsets, vcf_header, fasta)."""
-    os.makedirs(workspace, exist_ok=True)
-    open(os.path.join(workspace, "__tiledb_workspace.tdb"), "wb").close()
-    adir = os.path.join(workspace, array_name)
-    fdir = os.path.join(adir, "__00000000-0000-4000-8000-0000000000001_1700000000000")
+def subset_cells(d, idx, bump_pl=None):
+    """the cells `idx` (ascending) of a GDBSYN-1 column set as a column set of its own; bump_pl: positions in idx whose first PL value
+    is raised by one (a re-imported call that differs from the one it shadows)"""
+    idx = np.asarray(idx, dtype=np.int64)
+    out = dict(d)
+    out["coords"] = d["coords"][idx]
+    out["end"] = d["end"][idx]
+    for key in ("dp", "gq", "min_dp"):
+        if d.get(key) is not None:
+            out[key] = d[key][idx]
+    for key in ("ref", "alt", "gt", "ad", "pl"):
+        off, val = d[key]
+        vb = val.view(np.uint8)
+        ends = np.concatenate([off[1:], [vb.nbytes]]).astype(np.int64)
+        lens = ends[idx] - off[idx].astype(np.int64)
+        noff = np.zeros(len(idx), dtype=np.uint64)
+        if len(idx):
+            noff[1:] = np.cumsum(lens)[:-1]
+        total = int(lens.sum())
+        # gather the byte ranges: index of every output byte
+        src = np.repeat(off[idx].astype(np.int64) - noff.astype(np.int64), lens) + np.arange(total, dtype=np.int64)
+        nval = vb[src].copy()
+        if key == "pl" and bump_pl is not None and len(bump_pl):
+            w = nval.view("<i4")
+            at = (noff[bump_pl] // 4).astype(np.int64)
+            at = at[lens[bump_pl] >= 4]
+            w[at] += 1
+        out[key] = (noff, nval.view(val.dtype) if total % val.dtype.itemsize == 0 else nval)
+    return out
+
+
+def _write_fragment(fdir, d, capacity, compress):
     os.makedirs(fdir, exist_ok=True)
-    os.makedirs(os.path.join(adir, "genomicsdb_meta_dir"), exist_ok=True)
-    open(os.path.join(adir, ".__consolidation_lock"), "wb").close()
-    open(os.path.join(adir, "__array_schema.tdb"), "wb").write(_schema_bytes(os.path.abspath(adir), capacity, compress))
-    json.dump({"lb_row_idx": 0, "max_valid_row_idx_in_array": int(d["num_rows"]) - 1},
-              open(os.path.join(adir, "genomicsdb_meta_dir", "genomicsdb_meta_00000000-0000-4000-8000-000000000000.json"), "w"))
     open(os.path.join(fdir, "__tiledb_fragment.tdb"), "wb").close()
     n = len(d["end"])
     qual = np.full(n, np.float32(3.4028234663852886e38), dtype="<f4")    # TileDB NULL
@@ -171,6 +192,37 @@ def write_array(workspace, array_name, d, capacity=1000, compress=False):
         tables["tile_offsets"].append(_write_tiles(os.path.join(fdir, "__coords.tdb"), d["coords"].astype("<i8").tobytes(), capacity * 16))
     with gzip.open(os.path.join(fdir, "__book_keeping.tdb.gz"), "wb", compresslevel=1) as f:
         f.write(_book_keeping_bytes(d["coords"], capacity, tables))
+    return tables
+
+
+def write_array(workspace, array_name, d, capacity=1000, compress=False, n_fragments=1, dup_every=0):
+    """d: tools.gdbsyn.generate(..., with_fixed=True).  Returns dict(workspace, array, vid, callsets, vcf_header, fasta).
+    n_fragments > 1: the cells go to that many fragments as batches of samples would (fragment f holds the rows r with r % n == f, each
+    spans every column), named so that a higher f is newer; dup_every > 0: fragment f also holds every dup_every-th cell of fragment
+    f - 1 again with a changed PL (a re-import), so that the older copy is shadowed (array_read_state.cc:2369-2402)."""
+    os.makedirs(workspace, exist_ok=True)
+    open(os.path.join(workspace, "__tiledb_workspace.tdb"), "wb").close()
+    adir = os.path.join(workspace, array_name)
+    os.makedirs(os.path.join(adir, "genomicsdb_meta_dir"), exist_ok=True)
+    open(os.path.join(adir, ".__consolidation_lock"), "wb").close()
+    open(os.path.join(adir, "__array_schema.tdb"), "wb").write(_schema_bytes(os.path.abspath(adir), capacity, compress))
+    json.dump({"lb_row_idx": 0, "max_valid_row_idx_in_array": int(d["num_rows"]) - 1},
+              open(os.path.join(adir, "genomicsdb_meta_dir", "genomicsdb_meta_00000000-0000-4000-8000-000000000000.json"), "w"))
+    if n_fragments <= 1:
+        fdir = os.path.join(adir, "__00000000-0000-4000-8000-0000000000001_1700000000000")
+        tables = _write_fragment(fdir, d, capacity, compress)
+    else:
+        rows = d["coords"][:, 0]
+        begin = d["coords"][:, 1] <= d["end"]          # not an END copy
+        for f in range(n_fragments):
+            own = np.nonzero(rows % n_fragments == f)[0]
+            extra = np.zeros(0, dtype=np.int64)
+            if dup_every and f > 0:
+                extra = np.nonzero((rows % n_fragments == f - 1) & begin)[0][::dup_every]
+            idx = np.sort(np.concatenate([own, extra]))
+            bump = np.nonzero(np.isin(idx, extra))[0]
+            fdir = os.path.join(adir, "__00000000-0000-4000-8000-%013d_%d" % (f + 1, 1700000000000 + f))
+            tables = _write_fragment(fdir, subset_cells(d, idx, bump), capacity, compress)
     # mapping files + template header + a reference FASTA long enough for the columns used
     vid_path = os.path.join(workspace, "vid.json")
     json.dump(VID, open(vid_path, "w"))
