@@ -550,6 +550,42 @@ def main():
     if ctx2:
         ctx2.close()
 
+    # ---------------- the box's host path: pinned D2H / H2D of this rank alone and of all ranks at once (what caps e2e at N > 1)
+    host_path = None
+    if not args.no_extras:
+        nbytes = 1 << 30
+        hbuf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        dbuf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+        def copy_gbs(d2h, reps=4):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                if d2h:
+                    hbuf.copy_(dbuf, non_blocking=True)
+                else:
+                    dbuf.copy_(hbuf, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            return nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        copy_gbs(True, 1)
+        alone = {}
+        for r in range(world):          # one rank at a time
+            barrier()
+            if r == rank:
+                alone = dict(d2h=copy_gbs(True), h2d=copy_gbs(False))
+        barrier()
+        conc_d2h = copy_gbs(True)       # every rank at once
+        barrier()
+        conc_h2d = copy_gbs(False)
+        barrier()
+        host_path = dict(bytes=nbytes, d2h_alone_gbs_min_over_ranks=-max_over_ranks(-alone["d2h"]), h2d_alone_gbs_min_over_ranks=-max_over_ranks(-alone["h2d"]),
+                         d2h_all_ranks_at_once_gbs_sum=sum_over_ranks(conc_d2h), d2h_all_ranks_at_once_gbs_min=-max_over_ranks(-conc_d2h),
+                         h2d_all_ranks_at_once_gbs_sum=sum_over_ranks(conc_h2d), h2d_all_ranks_at_once_gbs_min=-max_over_ranks(-conc_h2d),
+                         note="1 GiB pinned copies, CUDA events; e2e moves h2d_bytes_per_step + d2h_bytes_per_step per rank and step over this path")
+        del hbuf, dbuf
+
     base = base_bcf = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "4shard":
         base = cpu_baseline(args)
@@ -563,7 +599,7 @@ def main():
                     e2e_from_fragment_files=e2e_files, e2e_from_gzip_fragment_files=e2e_files_gzip,
                     gpu_launches=int(launches), roofline=roofline, cpu_baseline=base, cpu_baseline_broad_gvcf_operator=base_bcf,
                     strong_scaling_config3=strong, concatenation=gather, latency_config5=latency, columnar_iterator=columnar,
-                    numa_binding=dict(node=numa[0], cores=numa[1]) if numa else None,
+                    numa_binding=dict(node=numa[0], cores=numa[1]) if numa else None, host_path=host_path,
                     sites_per_step_per_gpu=int(sites_per_step), cells_per_gpu=int(info.n_cells),
                     staged_bytes_per_gpu=int(info.staged_bytes), hbm_bytes_per_gpu=int(info.hbm_bytes))
         sys.stdout.flush()

@@ -13,6 +13,8 @@
 #include <fstream>
 #include <iomanip>
 #include <map>
+#include <set>
+#include <tuple>
 #include <sstream>
 
 #include "gdb_json.h"
@@ -959,7 +961,7 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
       else if (name == "GT") { qa.kind = GDBGPU_CELL_FIELD_GT; qa.elem = 'i'; }
       else if (fi->is_allele_dependent()) { qa.kind = GDBGPU_CELL_FIELD_REMAPPED; qa.index = n_remapped++; }
       else {
-        if (fi->is_multid()) qa.elem = 'c';   // a multi-dimensional value is a byte string to the print operators (they print it raw)
+        if (fi->is_multid()) { qa.elem = 'c'; qa.multid = true; }   // a multi-dimensional value is a byte string to the print operators (they print it raw)
         const bool numeric_len = !fi->length.empty() && fi->length.find_first_not_of("0123456789") == std::string::npos;
         qa.kind = GDBGPU_CELL_FIELD_PLAIN; qa.index = (int)qc.plain_.size(); qa.fixed_len = numeric_len ? std::stoi(fi->length) : 0;
         VariantQueryConfig::PlainField pf;
@@ -1297,43 +1299,239 @@ void VariantQueryProcessor::iterate_over_cells(const int, const VariantQueryConf
   if (!qc.is_bookkeeping_done() || qc.get_num_queried_attributes() == 0)
     throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "iterate_over_cells: do_query_bookkeeping(config, alleles_required, false, true) must be called first");
   const unsigned n_intervals = std::max(1u, qc.get_num_column_intervals());
-  for (unsigned i = 0; i < n_intervals; ++i) {
-    gdbgpu_scan_params p; memset(&p, 0, sizeof(p));
-    p.flags = GDBGPU_SCAN_CELLS_ONLY;
-    if (qc.get_num_column_intervals() == 0) p.flags |= GDBGPU_SCAN_FULL;
-    else { p.col_lo = qc.get_column_begin(i); p.col_hi = qc.get_column_end(i); }
-    if (!qc.query_all_rows()) { p.query_rows = qc.get_rows_to_query().data(); p.n_query_rows = qc.get_rows_to_query().size(); }
-    gdbgpu_scan* scan = nullptr;
-    check(gdbgpu_scan_begin(arr_, &p, &scan));
-    struct Guard { gdbgpu_scan* s; ~Guard() { gdbgpu_scan_end(s); } } guard{scan};
-    if (op.runs_on_device()) { op.operate_on_device_interval(scan, i, qc); continue; }
-    for (unsigned a = 0; a < qc.get_num_queried_attributes(); ++a)
-      if (qc.get_query_attribute(a).kind == -2)
-        throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "columnar iterator on the GPU: multi-dimensional field " + qc.get_query_attribute_name(a) + " is not supported");
-    // the list is paged through (cells and their columns cross PCIe a window at a time, as scan_and_operate's batches do)
-    static const uint64_t window = [] { const char* e = getenv("GDBGPU_CELLS_WINDOW"); uint64_t w = e ? strtoull(e, nullptr, 10) : 0; return w ? w : (1ull << 20); }();
-    std::vector<GenomicsDBColumnarCell::Column> columns(qc.get_num_queried_attributes());
-    GenomicsDBColumnarCell cell;
-    cell.qc_ = &qc; cell.columns_ = &columns; cell.interval_idx_ = i;
-    for (uint64_t first = 0;; first += window) {
-      gdbgpu_cell_list list;
-      check(gdbgpu_scan_cells_window(scan, first, window));
-      check(gdbgpu_scan_cells(scan, &list));
-      if (!list.n_cells) break;
-      for (unsigned a = 0; a < qc.get_num_queried_attributes(); ++a) {
-        const auto& qa = qc.get_query_attribute(a);
-        if (qa.kind < 0) continue;   // END comes with the list
-        check(gdbgpu_scan_cells_fetch(scan, qa.kind, qa.index, &columns[a].off, &columns[a].bytes));
-      }
-      for (uint64_t k = 0; k < list.n_cells; ++k) {
-        cell.idx_ = k; cell.coords_[0] = list.row[k]; cell.coords_[1] = list.begin[k]; cell.end_ = list.end[k];
-        cell.at_new_interval_ = first == 0 && k == 0;
-        op.operate_on_columnar_cell(cell, qc, schema_);
-      }
-      if (first + list.n_cells >= list.n_total) break;
+  for (unsigned i = 0; i < n_intervals; ++i) iterate_over_cells_of_interval(qc, op, i);
+  op.finalize();
+}
+void VariantQueryProcessor::iterate_over_cells_of_interval(const VariantQueryConfig& qc, SingleCellOperatorBase& op, unsigned i) const {
+  gdbgpu_scan_params p; memset(&p, 0, sizeof(p));
+  p.flags = GDBGPU_SCAN_CELLS_ONLY;
+  if (qc.get_num_column_intervals() == 0) p.flags |= GDBGPU_SCAN_FULL;
+  else { p.col_lo = qc.get_column_begin(i); p.col_hi = qc.get_column_end(i); }
+  if (!qc.query_all_rows()) { p.query_rows = qc.get_rows_to_query().data(); p.n_query_rows = qc.get_rows_to_query().size(); }
+  gdbgpu_scan* scan = nullptr;
+  check(gdbgpu_scan_begin(arr_, &p, &scan));
+  struct Guard { gdbgpu_scan* s; ~Guard() { gdbgpu_scan_end(s); } } guard{scan};
+  if (op.runs_on_device()) { op.operate_on_device_interval(scan, i, qc); return; }
+  // the list is paged through (cells and their columns cross PCIe a window at a time, as scan_and_operate's batches do)
+  static const uint64_t window = [] { const char* e = getenv("GDBGPU_CELLS_WINDOW"); uint64_t w = e ? strtoull(e, nullptr, 10) : 0; return w ? w : (1ull << 20); }();
+  std::vector<GenomicsDBColumnarCell::Column> columns(qc.get_num_queried_attributes());
+  GenomicsDBColumnarCell cell;
+  cell.qc_ = &qc; cell.columns_ = &columns; cell.interval_idx_ = i;
+  for (uint64_t first = 0;; first += window) {
+    gdbgpu_cell_list list;
+    check(gdbgpu_scan_cells_window(scan, first, window));
+    check(gdbgpu_scan_cells(scan, &list));
+    if (!list.n_cells) break;
+    for (unsigned a = 0; a < qc.get_num_queried_attributes(); ++a) {
+      const auto& qa = qc.get_query_attribute(a);
+      if (qa.kind < 0) continue;   // END comes with the list
+      check(gdbgpu_scan_cells_fetch(scan, qa.kind, qa.index, &columns[a].off, &columns[a].bytes));
+    }
+    for (uint64_t k = 0; k < list.n_cells; ++k) {
+      cell.idx_ = k; cell.coords_[0] = list.row[k]; cell.coords_[1] = list.begin[k]; cell.end_ = list.end[k];
+      cell.at_new_interval_ = first == 0 && k == 0;
+      op.operate_on_columnar_cell(cell, qc, schema_);
+    }
+    if (first + list.n_cells >= list.n_total) break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GA4GH range query
+namespace {
+// a field of a call as VariantFieldBase::print gives it (variant_field_data.h:211,257,540-556 and the vector printers): strings
+// quoted, ALT as [ "A","<NON_REF>" ], numbers as [ a,b ] with floats in the stream's fixed notation
+std::string ga4gh_number_list(const uint8_t* p, size_t n, char elem) {
+  std::ostringstream o;
+  o << std::fixed << std::setprecision(6);
+  o << "[ ";
+  for (size_t i = 0; i < n; ++i) {
+    if (i) o << ",";
+    if (elem == 'f') { float v; memcpy(&v, p + 4 * i, 4); o << v; }
+    else if (elem == 'b') o << (int)(p[i] != 0);
+    else { int32_t v; memcpy(&v, p + 4 * i, 4); o << v; }
+  }
+  o << " ]";
+  return o.str();
+}
+std::string ga4gh_alt_list(const std::vector<std::string>& alt) {
+  std::string o = "[ ";
+  for (size_t i = 0; i < alt.size(); ++i) { if (i) o += ","; o += "\"" + (alt[i] == "&" ? std::string("<NON_REF>") : alt[i]) + "\""; }
+  return o + " ]";
+}
+class GA4GHCallCollector : public SingleCellOperatorBase {
+ public:
+  GA4GHCallCollector(std::vector<GA4GHVariant>& variants) : m_variants(&variants) {}
+  void operate_on_columnar_cell(const GenomicsDBColumnarCell& cell, const VariantQueryConfig& qc, const VariantArraySchema&) override {
+    GA4GHVariantCall call;
+    call.row = (uint64_t)cell.get_coordinates()[0]; call.begin = cell.get_coordinates()[1]; call.end = cell.get_end_position();
+    const unsigned n = qc.get_num_queried_attributes();
+    call.fields.assign(n, std::string());
+    bool have_ref = false, have_alt = false;
+    for (unsigned i = 0; i < n; ++i) {
+      const auto& qa = qc.get_query_attribute(i);
+      if (qa.kind == -1 || !cell.is_valid(i)) continue;   // END is the call's interval, not a field
+      const uint8_t* p = cell.get_field_ptr_for_query_idx(i);
+      const size_t len = cell.get_field_length(i);
+      if (qa.kind == GDBGPU_CELL_FIELD_REF) { call.REF.assign((const char*)p, len); call.fields[i] = "\"" + call.REF + "\""; have_ref = true; }
+      else if (qa.kind == GDBGPU_CELL_FIELD_ALT) {
+        const std::string alt((const char*)p, len);
+        for (size_t t0 = 0;;) { const size_t t1 = alt.find('|', t0); call.ALT.push_back(alt.substr(t0, t1 == std::string::npos ? std::string::npos : t1 - t0)); if (t1 == std::string::npos) break; t0 = t1 + 1; }
+        call.fields[i] = ga4gh_alt_list(call.ALT); have_alt = true;
+      } else if (qa.multid) {   // a vector of bytes to the reference's printer: [ 24,0,0, ... ]
+        std::string o = "[ ";
+        for (size_t k = 0; k < len; ++k) { if (k) o += ","; o += std::to_string((unsigned)p[k]); }
+        call.fields[i] = o + " ]";
+      } else if (qa.elem == 'c') call.fields[i] = "\"" + std::string((const char*)p, len) + "\"";
+      else call.fields[i] = ga4gh_number_list(p, len, qa.elem);
+    }
+    // GA4GHCallInfoToVariantIdx::find_or_insert (variant.cc:26-70): begin, end, REF, the set of ALT alleles; a call without REF / ALT
+    // in the query always opens a variant of its own
+    uint64_t idx = m_variants->size();
+    bool fresh = true;
+    if (have_ref && have_alt) {
+      Key key{call.begin, call.end, call.REF, std::set<std::string>(call.ALT.begin(), call.ALT.end())};
+      auto it = m_index.find(key);
+      if (it == m_index.end()) m_index.emplace(std::move(key), idx); else { fresh = false; idx = it->second; }
+    }
+    if (fresh) m_variants->emplace_back();
+    GA4GHVariant& v = (*m_variants)[idx];
+    v.begin = call.begin; v.end = call.end;
+    v.calls.push_back(std::move(call));
+  }
+ private:
+  typedef std::tuple<int64_t, int64_t, std::string, std::set<std::string>> Key;
+  std::vector<GA4GHVariant>* m_variants;
+  std::map<Key, uint64_t> m_index;
+};
+}  // namespace
+
+void VariantQueryProcessor::gt_get_column_interval(const int, const VariantQueryConfig& qc, unsigned column_interval_idx, std::vector<GA4GHVariant>& variants) const {
+  if (!qc.is_bookkeeping_done() || qc.get_num_queried_attributes() == 0)
+    throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "gt_get_column_interval: do_query_bookkeeping(config, true, false, true) must be called first");
+  const size_t start_variant_idx = variants.size();
+  GA4GHCallCollector collector(variants);   // the grouping is per interval (call_info_2_variant is local to the reference's function)
+  iterate_over_cells_of_interval(qc, collector, column_interval_idx);
+  for (size_t i = start_variant_idx; i < variants.size(); ++i)
+    if (variants[i].get_num_calls() > 1u) remap_ga4gh_variant(qc, variants[i]);   // possible re-arrangement of PL / AD / GT (query_variants.cc:823-834)
+}
+
+// GA4GHOperator::operate + copy_back_remapped_fields (variant_operations.cc:572-731) for one variant of several calls: its calls
+// are the live calls of their rows at the variant's begin column, so the combine kernels over that one column and those rows
+// give the merged REF / ALT and every call's re-indexed GT / allele-dependent fields (no handle_deletions on this path)
+void VariantQueryProcessor::remap_ga4gh_variant(const VariantQueryConfig& qc, GA4GHVariant& v) const {
+  std::vector<int64_t> rows;
+  for (auto& c : v.calls) rows.push_back((int64_t)c.row);
+  std::sort(rows.begin(), rows.end());
+  rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+  gdbgpu_scan_params p; memset(&p, 0, sizeof(p));
+  p.flags = GDBGPU_SCAN_NO_DELETIONS | GDBGPU_SCAN_NO_PREFETCH;
+  p.col_lo = p.col_hi = v.begin;
+  p.query_rows = rows.data(); p.n_query_rows = rows.size();
+  p.max_diploid_alt_alleles = qc.get_max_diploid_alt_alleles_that_can_be_genotyped();
+  gdbgpu_scan* scan = nullptr;
+  check(gdbgpu_scan_begin(arr_, &p, &scan));
+  struct Guard { gdbgpu_scan* s; ~Guard() { gdbgpu_scan_end(s); } } guard{scan};
+  gdbgpu_batch b;
+  check(gdbgpu_scan_next_batch(scan, 0, 0, &b));
+  uint32_t s = 0;
+  while (s < b.n_sites && b.site_begin[s] != v.begin) ++s;
+  if (s >= b.n_sites) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "GA4GH range query: no site at column " + std::to_string(v.begin));
+  const uint32_t first = b.allele_first[s], n_allele = b.n_alleles[s];
+  auto allele = [&](uint32_t m) { return std::string((const char*)b.allele_bytes + b.allele_pos[2 * (first + m)], b.allele_pos[2 * (first + m) + 1]); };
+  v.has_common_fields = true;
+  v.common_REF = allele(0);
+  v.common_ALT.clear();
+  for (uint32_t m = 1; m < n_allele; ++m) v.common_ALT.push_back(allele(m));
+  if (!(b.site_flags[s] & GDBGPU_SITE_REMAPPED)) return;   // reference blocks only: m_remapping_needed is false, nothing is copied back
+  const uint64_t nq = b.n_query_rows;
+  gdbgpu_array_info info;
+  check(gdbgpu_array_get_info(arr_, &info));
+  for (auto& c : v.calls) {
+    const uint64_t q = (uint64_t)(std::lower_bound(rows.begin(), rows.end(), (int64_t)c.row) - rows.begin());
+    if (b.live[(uint64_t)s * nq + q] < 0) continue;
+    for (unsigned i = 0; i < qc.get_num_queried_attributes(); ++i) {
+      const auto& qa = qc.get_query_attribute(i);
+      int o;
+      if (qa.kind == GDBGPU_CELL_FIELD_GT) { if (!info.has_gt) continue; o = 0; }
+      else if (qa.kind == GDBGPU_CELL_FIELD_REMAPPED) o = (info.has_gt ? 1 : 0) + qa.index;
+      else continue;
+      if (c.fields[i].empty()) continue;   // not valid in the call: stays so
+      const gdbgpu_field_out& f = b.fields[o];
+      const uint32_t len = f.len[(uint64_t)s * nq + q];
+      const uint32_t* w = f.data + f.base[s] + q * (uint64_t)f.stride[s];
+      c.fields[i] = ga4gh_number_list(reinterpret_cast<const uint8_t*>(w), len, qa.elem == 'f' ? 'f' : 'i');
     }
   }
-  op.finalize();
+}
+
+void GA4GHVariantCall::print(std::ostream& fptr, const VariantQueryConfig* qc, const std::string& indent_prefix, const VidMapper* vid_mapper) const {   // variant.cc:225-265
+  auto indent_string = indent_prefix + g_json_indent_unit;
+  fptr << indent_prefix << "{\n";
+  fptr << indent_string << "\"row\": " << row << ",\n";
+  fptr << indent_string << "\"interval\": [ " << begin << ", " << end << " ],\n";
+  if (vid_mapper) {
+    const ContigInfo* contig = vid_mapper->get_contig_location(begin);
+    if (contig) {
+      const int64_t pos = begin - contig->tiledb_column_offset;
+      fptr << indent_string << "\"genomic_interval\": { \"" << contig->name << "\" : [ " << pos + 1 << ", " << (pos + 1 + (end - begin)) << " ] },\n";
+    }
+  }
+  fptr << indent_string << "\"fields\": {\n";
+  indent_string += g_json_indent_unit;
+  bool first_valid_field = true;
+  for (unsigned idx = 0; idx < fields.size(); ++idx) {
+    if (fields[idx].empty()) continue;
+    if (!first_valid_field) fptr << ",\n";
+    if (qc) fptr << indent_string << "\"" << qc->get_query_attribute_name(idx) << "\": ";
+    else fptr << indent_string << "\"field_" << idx << "\": ";
+    fptr << fields[idx];
+    first_valid_field = false;
+  }
+  indent_string = indent_prefix + g_json_indent_unit;
+  fptr << "\n" << indent_string << "}\n" << indent_prefix << "}";
+}
+void GA4GHVariant::print(std::ostream& fptr, const VariantQueryConfig* qc, const std::string& indent_prefix, const VidMapper* vid_mapper) const {   // variant.cc:427-478
+  fptr << indent_prefix << "{\n";
+  std::string indent_string = indent_prefix + g_json_indent_unit;
+  fptr << indent_string << "\"interval\": [ " << begin << ", " << end << " ],\n";
+  if (vid_mapper) {
+    const ContigInfo* contig = vid_mapper->get_contig_location(begin);
+    if (contig) {
+      const int64_t pos = begin - contig->tiledb_column_offset;
+      fptr << indent_string << "\"genomic_interval\": { \"" << contig->name << "\" : [ " << pos + 1 << ", " << (pos + 1 + (end - begin)) << " ] },\n";
+    }
+  }
+  fptr << indent_string << " \"common_fields\" : {\n";
+  indent_string += g_json_indent_unit;
+  if (has_common_fields) {   // the merged REF and ALT, under the names of the query's REF / ALT attributes
+    unsigned ref_idx = 0, alt_idx = 0;
+    const bool named = qc && qc->get_query_idx_for_name("REF", ref_idx) && qc->get_query_idx_for_name("ALT", alt_idx);
+    fptr << indent_string << "\"" << (named ? qc->get_query_attribute_name(ref_idx) : std::string("field_0")) << "\": \"" << common_REF << "\",\n";
+    fptr << indent_string << "\"" << (named ? qc->get_query_attribute_name(alt_idx) : std::string("field_1")) << "\": " << ga4gh_alt_list(common_ALT);
+  }
+  indent_string = indent_prefix + g_json_indent_unit;
+  fptr << "\n" << indent_string << "},\n";
+  fptr << indent_string << "\"variant_calls\": [\n";
+  indent_string += g_json_indent_unit;
+  for (size_t i = 0; i < calls.size(); ++i) {
+    if (i) fptr << ",\n";
+    calls[i].print(fptr, qc, indent_string, vid_mapper);
+  }
+  indent_string = indent_prefix + g_json_indent_unit;
+  fptr << "\n" << indent_string << "]\n";
+  fptr << indent_prefix << "}";
+}
+void print_variants(const std::vector<GA4GHVariant>& variants, const std::string& output_format, const VariantQueryConfig& qc, std::ostream& fptr, const VidMapper* id_mapper) {
+  if (!output_format.empty() && output_format != "default")
+    throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "print_variants: output format " + output_format + " is not supported (only the default JSON)");
+  fptr << "{\n" << g_json_indent_unit << "\"variants\": [\n";
+  const std::string indent_prefix = std::string(g_json_indent_unit) + g_json_indent_unit;
+  for (size_t i = 0; i < variants.size(); ++i) {
+    if (i) fptr << ",\n";
+    variants[i].print(fptr, &qc, indent_prefix, id_mapper);
+  }
+  fptr << "\n" << g_json_indent_unit << "]\n";
+  fptr << "}\n";
 }
 
 // ------------------------------------------------------------------------------------------------ GenomicsDBBCFGenerator

@@ -197,7 +197,7 @@ class VariantQueryConfig {
   unsigned get_element_wise_sum_mask() const { return esum_remapped_mask_; }
   // the queried attributes in the order the reference's bookkeeping leaves them (END, REF, ALT first:
   // variant_query_config.cc:161-185); filled by do_query_bookkeeping(..., stage_columnar_fields = true)
-  struct QueryAttribute { std::string name; int kind = -1; int index = 0; char elem = 'i'; int fixed_len = 0; };   // kind: -1 END, -2 multi-dimensional (not staged), else GDBGPU_CELL_FIELD_*
+  struct QueryAttribute { std::string name; int kind = -1; int index = 0; char elem = 'i'; int fixed_len = 0; bool multid = false; };   // kind: -1 END, -2 multi-dimensional (not staged), else GDBGPU_CELL_FIELD_*
   unsigned get_num_queried_attributes() const { return (unsigned)query_attrs_.size(); }
   const std::string& get_query_attribute_name(unsigned i) const { return query_attrs_[i].name; }
   const QueryAttribute& get_query_attribute(unsigned i) const { return query_attrs_[i]; }
@@ -464,6 +464,7 @@ struct VariantArraySchema {};   // the operators' third argument; nothing on thi
 class GenomicsDBColumnarCell {
  public:
   const int64_t* get_coordinates() const { return coords_; }   // row, begin column
+  int64_t get_end_position() const { return end_; }   // the cell's END
   bool at_new_query_column_interval() const { return at_new_interval_; }
   uint64_t get_current_query_column_interval_idx() const { return interval_idx_; }
   bool is_valid(unsigned query_idx) const;
@@ -553,6 +554,27 @@ class VariantStorageManager {
 };
 
 // query_variants.h:126-191
+// ---- GA4GH range query results (include/genomicsdb/variant.h Variant / VariantCall as gt_get_column_interval fills them).  Owning
+// objects: the calls come from the columnar iterator's cell list, a field is kept as the text Variant::print gives it.
+struct GA4GHVariantCall {
+  uint64_t row = 0; int64_t begin = 0, end = 0;
+  std::string REF; std::vector<std::string> ALT;     // as stored (<NON_REF> is "&")
+  std::vector<std::string> fields;                   // by query attribute index; empty: the field is not valid for this call
+  void print(std::ostream& fptr, const VariantQueryConfig* query_config, const std::string& indent_prefix, const VidMapper* vid_mapper = nullptr) const;
+};
+struct GA4GHVariant {
+  int64_t begin = 0, end = 0;
+  std::vector<GA4GHVariantCall> calls;
+  bool has_common_fields = false; std::string common_REF; std::vector<std::string> common_ALT;   // set by GA4GHOperator for variants of several calls
+  uint64_t get_num_calls() const { return calls.size(); }
+  uint64_t get_column_begin() const { return (uint64_t)begin; }
+  uint64_t get_column_end() const { return (uint64_t)end; }
+  void print(std::ostream& fptr, const VariantQueryConfig* query_config, const std::string& indent_prefix, const VidMapper* vid_mapper = nullptr) const;   // variant.cc:427-478
+};
+// variant.cc:942-1020, the default output format: { "variants": [ ... ] }
+void print_variants(const std::vector<GA4GHVariant>& variants, const std::string& output_format, const VariantQueryConfig& query_config, std::ostream& fptr,
+                    const VidMapper* id_mapper = nullptr);
+
 class VariantQueryProcessorScanState {
  public:
   ~VariantQueryProcessorScanState() { reset(); }
@@ -593,8 +615,16 @@ class VariantQueryProcessor {
                         unsigned column_interval_idx = 0, bool handle_spanning_deletions = false,
                         VariantQueryProcessorScanState* scan_state = nullptr, bool want_alleles_LUT = false) const;
   gdbgpu_array* array() const { return arr_; }
+  // query_variants.cc:687-843 (the GA4GH range query): the calls of one query interval -- those reaching into it
+  // from the left, then those beginning inside it -- grouped into variants of calls that share begin, end, REF and the SET of
+  // ALT alleles (GA4GHCallInfoToVariantIdx, variant.cc:26-70); a variant of several calls goes through GA4GHOperator (merged
+  // REF / ALT as its common fields, GT and the allele-dependent fields re-indexed onto the merged alleles).  Appends to `variants`.
+  // Needs do_query_bookkeeping(config, true, false, /*stage_columnar_fields=*/true).
+  void gt_get_column_interval(const int ad, const VariantQueryConfig& query_config, unsigned column_interval_idx, std::vector<GA4GHVariant>& variants) const;
  private:
   void check(int rc) const;
+  void iterate_over_cells_of_interval(const VariantQueryConfig& query_config, SingleCellOperatorBase& variant_operator, unsigned column_interval_idx) const;
+  void remap_ga4gh_variant(const VariantQueryConfig& query_config, GA4GHVariant& variant) const;
   void fill_variant(const gdbgpu_batch& b, uint32_t s, Variant& v) const;
   VariantStorageManager* sm_;
   std::string array_name_;

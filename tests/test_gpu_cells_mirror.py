@@ -69,3 +69,28 @@ def test_paging_through_the_cell_list_is_transparent(exe, cid, tmp_path):
         p, out = run_tool(exe, case, tmp_path, flag, window=2)
         assert p.returncode == 0, p.stderr
         assert out.read_bytes() == open(os.path.join(CELLS, cid + "." + ext), "rb").read()
+
+
+# ---------------------------------------------------------------------------------------------- the GA4GH range query
+VARIANTS = os.path.join(GOLDEN, "variants")
+
+
+@pytest.mark.parametrize("case", ALL, ids=[c["id"] for c in ALL])
+def test_range_query_equals_the_reference(exe, case, tmp_path):
+    """gt_gpu_gather --range-query (VariantQueryProcessor::gt_get_column_interval of the mirror: the columnar iterator's cell list
+    grouped into GA4GH variants, variants of several calls re-indexed by the combine kernels, print_variants) against the stdout
+    of the unmodified reference's `gt_mpi_gather -j <query>` (run_range_query, its default command) on the same array"""
+    p, out = run_tool(exe, case, tmp_path, "--range-query")
+    assert p.returncode == 0, p.stderr
+    assert out.read_bytes() == open(os.path.join(VARIANTS, case["id"] + ".variants"), "rb").read()
+
+
+@pytest.mark.parametrize("cid", sorted(json.load(open(os.path.join(GOLDEN, "variants", "ci.json")))["ci_cases"]))
+def test_range_query_equals_the_reference_ci_goldens(exe, cid, tmp_path):
+    """the reference CI's own range queries (tests/run.py attribute lists; our copies are md5-identical to its *_variants_* goldens)"""
+    ci = json.load(open(os.path.join(VARIANTS, "ci.json")))
+    case = [c for c in ALL if c["id"] == cid][0]
+    attrs = ci["ci_attributes"] + (["DS", "ID"] if "DS_ID" in cid else [])
+    p, out = run_tool(exe, case, tmp_path, "--range-query", attributes=attrs)
+    assert p.returncode == 0, p.stderr
+    assert out.read_bytes() == open(os.path.join(VARIANTS, cid + ".ci.variants"), "rb").read()

@@ -216,7 +216,7 @@ static int columnar_command(const std::string& query_json, int rank, int device,
   query_config.read_from_file(query_json, rank);
   VariantStorageManager sm(query_config.get_workspace(rank), 10u * 1024u * 1024u, device);
   VariantQueryProcessor qp(&sm, query_config.get_array_name(rank), query_config.get_vid_mapper());
-  qp.do_query_bookkeeping(query_config, /*alleles_required=*/false, false, /*stage_columnar_fields=*/true);
+  qp.do_query_bookkeeping(query_config, /*alleles_required=*/command == 'Q', false, /*stage_columnar_fields=*/true);   // gt_mpi_gather.cc:583-585
   std::ofstream file;
   if (out_file != "-") { file.open(out_file, std::ios::binary); if (!file) { std::cerr << "cannot open " << out_file << "\n"; return -1; } }
   std::ostream& out = out_file == "-" ? std::cout : file;
@@ -240,6 +240,12 @@ static int columnar_command(const std::string& query_json, int rank, int device,
       AC_counter.print_allele_counts(out);
       break;
     }
+    case 'Q': {   // run_range_query (gt_mpi_gather.cc:102-319), the reference tool's default command: the GA4GH range query
+      std::vector<GA4GHVariant> variants;
+      for (auto i = 0u; i < query_config.get_num_column_intervals(); ++i) qp.gt_get_column_interval(qp.get_array_descriptor(), query_config, i, variants);
+      print_variants(variants, "default", query_config, out, &query_config.get_vid_mapper());
+      break;
+    }
     case 'G': {
       ColumnHistogramOperator histogram_op(0, 4000000000ull, 100);
       qp.iterate_over_cells(qp.get_array_descriptor(), query_config, histogram_op, true);
@@ -255,7 +261,7 @@ int main(int argc, char** argv) {
   std::string query_json, loader_json, out_file, header_file, ref_bases_file; int rank = 0, device = 0; size_t page = 0; bool broad = false, htsjdk = false; int columnar = 0; size_t stream_chunk = 0; bool header_only = false; unsigned max_alleles_top = 0; std::string chr; int chr_start = 0, chr_end = 0;
   static struct option long_options[] = {{"query", 1, 0, 'j'}, {"rank", 1, 0, 'r'}, {"output", 1, 0, 'o'}, {"device", 1, 0, 'd'}, {"page-size", 1, 0, 'p'},
                                          {"produce-Broad-GVCF", 0, 0, 'B'}, {"loader-json-config", 1, 0, 'l'}, {"bcf-header", 1, 0, 'H'}, {"reference-bases", 1, 0, 'R'}, {"htsjdk-conventions", 0, 0, 'J'},
-                                         {"produce-interesting-positions", 0, 0, 'I'}, {"bcf-generator", 1, 0, 'S'}, {"header-only", 0, 0, 'h'}, {"max-alleles", 1, 0, 'M'}, {"chromosome", 1, 0, 'c'}, {"begin", 1, 0, 'b'}, {"end", 1, 0, 'e'}, {"print-calls", 0, 0, 'C'}, {"print-csv", 0, 0, 'V'}, {"print-AC", 0, 0, 'A'}, {"produce-histogram", 0, 0, 'G'}, {0, 0, 0, 0}};
+                                         {"produce-interesting-positions", 0, 0, 'I'}, {"bcf-generator", 1, 0, 'S'}, {"header-only", 0, 0, 'h'}, {"max-alleles", 1, 0, 'M'}, {"chromosome", 1, 0, 'c'}, {"begin", 1, 0, 'b'}, {"end", 1, 0, 'e'}, {"print-calls", 0, 0, 'C'}, {"print-csv", 0, 0, 'V'}, {"print-AC", 0, 0, 'A'}, {"produce-histogram", 0, 0, 'G'}, {"range-query", 0, 0, 'Q'}, {0, 0, 0, 0}};
   int c;
   while ((c = getopt_long(argc, argv, "j:l:r:o:d:p:BH:R:J", long_options, NULL)) >= 0) {
     switch (c) {
@@ -275,7 +281,7 @@ int main(int argc, char** argv) {
       case 'c': chr = optarg; break;
       case 'b': chr_start = atoi(optarg); break;
       case 'e': chr_end = atoi(optarg); break;
-      case 'C': case 'V': case 'A': case 'G': case 'I': columnar = c; break;   // records as GenomicsDBBCFGenerator (JNI) makes them for the Java reader
+      case 'C': case 'V': case 'A': case 'G': case 'I': case 'Q': columnar = c; break;   // records as GenomicsDBBCFGenerator (JNI) makes them for the Java reader
       default: return -1;
     }
   }
