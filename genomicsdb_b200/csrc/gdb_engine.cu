@@ -582,13 +582,18 @@ struct FrontWindow {
   DevBuf<uint32_t> cursors, allele_pos; DevBuf<uint64_t> allele_hash; DevBuf<uint8_t> allele_bytes;
   std::vector<SiteRec> h_sites; uint32_t hc[4] = {0, 0, 0, 0};
   uint64_t first = 0; uint32_t n = 0, sig_slots = 0; bool valid = false;
+  // K4d: the permutation rows of the sites' call signatures (k_sig_perm), for the whole window
+  DevBuf<uint32_t> sig_perm; CtlArena* ctl = nullptr; uint32_t* sig_off_d = nullptr; uint64_t sig_words = 0;
+  ~FrontWindow();
 };
+
+FrontWindow::~FrontWindow() { delete ctl; }
 
 // Per-batch device / pinned-host buffers.  They are large (GBs) and expensive to create (cudaMalloc, cudaMallocHost), so a
 // context keeps finished scans' buffers and hands them to the next scan.
 struct BatchBuffers {
   // per batch (device)
-  DevBuf<uint2> blk_map; DevBuf<uint32_t> sig_perm; uint32_t* sig_off_d = nullptr; DevBuf<uint32_t> cursors, lut_first; DevBuf<uint16_t> lut_len; DevBuf<int16_t> lut_in2m;
+  DevBuf<uint2> blk_map; DevBuf<uint32_t> cursors, lut_first; DevBuf<uint16_t> lut_len; DevBuf<int16_t> lut_in2m;
   const int32_t* live = nullptr;   // the batch's rows of the window's live matrix
   const uint32_t* allele_pos = nullptr; const uint8_t* allele_bytes = nullptr;   // the window's allele pools (SiteRec::allele_first indexes them)
   DevBuf<uint32_t> out_data[MAX_FIELDS + 1]; DevBuf<uint16_t> out_len[MAX_FIELDS + 1];
@@ -883,6 +888,40 @@ void compute_front(gdbgpu_scan* s, uint64_t first_site, uint32_t max_sites) {
         LAUNCH(ctx, k_verify_alleles, dim3(blocks_for(max_nt, VERIFY_THREADS), ns), VERIFY_THREADS, a->dev, S, Bp);
       }
     }
+    // K4d, once per window: one permutation row per occupied signature slot of every site the band kernel serves (it needs the
+    // output strides, which are a function of the site alone)
+    w.sig_words = 0; w.sig_off_d = nullptr;
+    {
+      const char* k5_env = getenv("GDBGPU_K5");
+      const bool k5_mix = !k5_env || !strcmp(k5_env, "mix");
+      const int n_out = s->n_out, o_f0 = a->has_gt ? 1 : 0;
+      if (k5_mix && !s->summary_only && B.sig_keys && a->fields.size() >= 1 && a->fields.size() <= (size_t)TILE_MAX_FIELDS) {
+        std::vector<uint32_t> sig_off(nb, 0xFFFFFFFFu);
+        std::vector<std::vector<uint32_t>> stride(n_out, std::vector<uint32_t>(nb, 0));
+        uint64_t words = 0;
+        for (uint32_t i = 0; i < nb; ++i) {
+          const SiteRec& r = w.h_sites[i];
+          for (int o = 0; o < n_out; ++o) stride[o][i] = stride_of(a, r, o);
+          const bool tile_path = r.n_alleles <= (uint32_t)TILE_MAX_A && r.max_ain <= (uint32_t)TILE_MAX_A && r.max_gt_len <= (uint32_t)TILE_MAX_GT && r.max_ploidy_all <= 2u;
+          if (!tile_path || !(r.flags & 2u) || !r.n_nt || r.n_alleles > 0xFDu) continue;
+          uint32_t row_words = SIG_HDR_BYTES / 4; bool ok = true;
+          for (int o = o_f0; o < n_out; ++o) { row_words += stride[o][i] >> 2; ok = ok && r.max_in_len[o - o_f0] <= PERM_MAX_IN; }
+          if (!ok || words + (uint64_t)B.sig_slots * row_words >= (1ull << 29)) continue;   // (2 GiB of rows at most; the sites beyond rebuild their LUTs per call)
+          sig_off[i] = (uint32_t)words; words += (uint64_t)B.sig_slots * row_words;
+        }
+        if (words) {
+          if (!w.ctl) w.ctl = new CtlArena();
+          w.ctl->begin((size_t)(n_out + 1) * nb * 4 + 256);
+          RemapOut Ow{}; Ow.n_out = n_out;
+          for (int o = 0; o < n_out; ++o) Ow.f[o].stride = w.ctl->push(stride[o].data(), nb);
+          w.sig_off_d = w.ctl->push(sig_off.data(), nb);
+          w.ctl->flush(ctx->stream);
+          w.sig_perm.ensure(words);
+          LAUNCH(ctx, k_sig_perm, nb, SIGPERM_THREADS, a->dev, B, Ow, w.sig_off_d, w.sig_perm.p);
+          w.sig_words = words;
+        }
+      }
+    }
     w.first = first_site; w.n = nb; w.valid = true;
     return;
   }
@@ -975,18 +1014,6 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       bb.out_stride[o] = bb.ctl.push(bb.h_stride[o].data(), keep);
       O.f[o] = FieldOutDev{bb.out_data[o].p, bb.out_base[o], bb.out_stride[o], bb.out_len[o].p};
     }
-    // permutation rows of the sites' call signatures (k_sig_perm): sig_slots rows of 8 + sum of strides bytes per eligible site
-    std::vector<uint32_t> sig_off(keep, 0xFFFFFFFFu);
-    uint64_t sig_words = 0;
-    if (k5_mix && !s->summary_only && B.sig_keys) for (uint32_t i : fast) {
-      const SiteRec& r = bb.h_sites[i];
-      if (!(r.flags & 2u) || !r.n_nt || r.n_alleles > 0xFDu) continue;
-      uint32_t row_words = SIG_HDR_BYTES / 4; bool ok = true;
-      for (int o = a->has_gt ? 1 : 0; o < n_out; ++o) { row_words += bb.h_stride[o][i] >> 2; ok = ok && r.max_in_len[o - (a->has_gt ? 1 : 0)] <= PERM_MAX_IN; }
-      if (!ok || sig_words + (uint64_t)B.sig_slots * row_words >= 0xFFFFFFFFull) continue;
-      sig_off[i] = (uint32_t)sig_words; sig_words += (uint64_t)B.sig_slots * row_words;
-    }
-    bb.sig_off_d = bb.ctl.push(sig_off.data(), sig_off.size());
     bb.fast_sites = bb.ctl.push(fast.data(), fast.size()); bb.nt_prefix_d = bb.ctl.push(nt_prefix.data(), nt_prefix.size());
     bb.tile_sites = bb.ctl.push(order.data(), order.size()); bb.slow_sites = bb.ctl.push(slow.data(), slow.size());
     if (s->device_output) {
@@ -1079,7 +1106,6 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
         LAUNCH(ctx, k_nt_blocks, (unsigned)fast.size(), 256, B, bb.fast_sites, bb.nt_prefix_d, bb.blk_map.p);
       }
       if (k5_mix) {
-        if (sig_words) { bb.sig_perm.ensure(sig_words); LAUNCH(ctx, k_sig_perm, keep, SIGPERM_THREADS, a->dev, B, O, bb.sig_off_d, bb.sig_perm.p); }
         // remapped sites' tile blocks and every site's nt blocks, one grid (gdb_kernels6.cuh)
         const uint32_t n_bands = (uint32_t)((fast.size() + MIX_SPB - 1) / MIX_SPB);
         uint64_t n_tb = (uint64_t)n_bands * tiles;
@@ -1096,7 +1122,7 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
               ctx->mix_attr_set |= 1u << key;
             }
             ProfScope ps__(ctx, "k_remap_mix");
-            kern<<<(unsigned)(n_tb + n_blk), TILE_ROWS, smem_bytes, ctx->stream>>>(a->dev, S, B, O, fast.size() == keep ? nullptr : bb.fast_sites, (uint32_t)fast.size(), tiles, n_tb ? 1u : 0u, bb.blk_map.p, n_blk, nt_ratio, tabs, sig_words ? bb.sig_off_d : nullptr, bb.sig_perm.p);
+            kern<<<(unsigned)(n_tb + n_blk), TILE_ROWS, smem_bytes, ctx->stream>>>(a->dev, S, B, O, fast.size() == keep ? nullptr : bb.fast_sites, (uint32_t)fast.size(), tiles, n_tb ? 1u : 0u, bb.blk_map.p, n_blk, nt_ratio, tabs, (w.sig_words && !S.want_lut) ? w.sig_off_d + woff : nullptr, w.sig_perm.p);
           };
           switch (key) {
             case 2: launch_mix(k_remap_mix<1, false>, MixSmem<1>::BYTES); break;

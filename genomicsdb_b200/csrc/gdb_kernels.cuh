@@ -626,20 +626,24 @@ __global__ void __launch_bounds__(256) k_live_walk(ArrayDev A, ScanDev S, uint64
     if (!S.scan_full && c <= S.q_lo) break;
     if (ef != I64_MIN) { const uint2 rb = reinterpret_cast<const uint2*>(A.rs_rec + kk)[2]; cur = (int32_t)(rb.x & RS_CELL_MASK); cur_eff = ef; cur_begin = c; cur_del = rb.x >> 31; cur_cls = rb.y; break; }
   }
-  // the sample's next cell stays in registers: most sites of the chunk do not advance the list
+  // the sample's next TWO cells stay in registers (most sites of the chunk do not advance the list; when one does, the record
+  // after it is already on its way: the walk is a dependent chain of L2 / HBM latencies otherwise)
   int64_t next_col = INT64_MAX, next_ef = I64_MIN; uint32_t next_rc = 0, next_cls = 0;
-  auto fetch = [&](uint64_t kk) {
-    const uint4 ra = reinterpret_cast<const uint4*>(A.rs_rec + kk)[0];
-    const uint2 rb = reinterpret_cast<const uint2*>(A.rs_rec + kk)[2];
-    next_col = (int64_t)(((uint64_t)ra.y << 32) | ra.x); next_ef = (int64_t)(((uint64_t)ra.w << 32) | ra.z); next_rc = rb.x; next_cls = rb.y;
+  uint4 pa = make_uint4(0xFFFFFFFFu, 0x7FFFFFFFu, 0, 0x80000000u); uint2 pb = make_uint2(0, 0);   // the record after `next` (col = INT64_MAX past the end)
+  auto load2 = [&](uint64_t kk) {
+    if (kk < e) { pa = reinterpret_cast<const uint4*>(A.rs_rec + kk)[0]; pb = reinterpret_cast<const uint2*>(A.rs_rec + kk)[2]; }
+    else pa = make_uint4(0xFFFFFFFFu, 0x7FFFFFFFu, 0, 0x80000000u);
   };
-  if (k < e) fetch(k);
+  auto shift = [&]() {
+    next_col = (int64_t)(((uint64_t)pa.y << 32) | pa.x); next_ef = (int64_t)(((uint64_t)pa.w << 32) | pa.z); next_rc = pb.x; next_cls = pb.y;
+  };
+  load2(k); shift(); load2(k + 1);
   for (uint32_t s = s0; s < s1; ++s) {
     const int64_t b = S.site_begin[first_site + s];
     while (next_col <= b) {
       if (next_ef != I64_MIN) { cur = (int32_t)(next_rc & RS_CELL_MASK); cur_eff = next_ef; cur_begin = next_col; cur_del = next_rc >> 31; cur_cls = next_cls; }
       ++k;
-      if (k < e) fetch(k); else next_col = INT64_MAX;
+      shift(); load2(k + 1);
     }
     int32_t v = -1; uint32_t c = CLS_DEAD;
     if (cur >= 0 && cur_eff >= b) {
