@@ -66,7 +66,7 @@ struct Stream {
   // input: 32-bit words from the 4-byte aligned address at or below the first deflate byte
   const uint32_t* gwords; uint32_t n_words, next; uint64_t buf; int cnt; bool bad;
   // output
-  uint8_t* out; uint64_t out_len, pos, flushed; uint32_t skew; uint32_t adler_a, adler_b;
+  uint8_t* out; uint32_t out_len, pos, flushed, check; uint32_t skew; uint32_t adler_a, adler_b;   // (a tile is far below 4 GB)
 
   __device__ void stage_block(uint32_t b) {   // words [64 b, 64 b + 64) -> their half of the staging buffer
     __syncwarp();   // every lane is done reading the block this one replaces
@@ -75,14 +75,15 @@ struct Stream {
     m->stage[(w0 + 1u) & (STAGE_WORDS - 1)] = w0 + 1u < n_words ? gwords[w0 + 1u] : 0u;
   }
   __device__ void refill() {   // at least 33 valid bits afterwards (zero bits past the end of the stream: `bad` is set two words later)
-    while (cnt <= 32) {
+    if (cnt <= 32) {
       if ((next & 63u) == 0u) { stage_block(next / 64u + 1u); __syncwarp(); }
       if (next >= n_words + 2u) bad = true;
       buf |= (uint64_t)m->stage[next & (STAGE_WORDS - 1)] << cnt;
       cnt += 32; ++next;
     }
   }
-  __device__ uint32_t bits(int need) {   // need <= 16
+  __device__ uint32_t bits(int need) {   // need <= 24
+    if (need == 0) return 0u;
     refill();
     const uint32_t v = (uint32_t)buf & ((1u << need) - 1u);
     buf >>= need; cnt -= need;
@@ -122,7 +123,7 @@ struct Stream {
   __device__ void flush_bytes(uint32_t n) {   // n <= 512 bytes, byte stores
     uint32_t s1 = 0, s2 = 0;
     for (uint32_t i = lane; i < n; i += 32u) {
-      const uint32_t d = m->win[((uint32_t)flushed + i + skew) & WIN_MASK];
+      const uint32_t d = m->win[(flushed + i + skew) & WIN_MASK];
       out[flushed + i] = (uint8_t)d;
       s1 += d; s2 += (n - i) * d;
     }
@@ -133,13 +134,13 @@ struct Stream {
     __syncwarp();
     const uint32_t a = (uint32_t)((uintptr_t)(out + flushed) & 511u);
     if (a) {   // up to the next 512-byte boundary of the output
-      const uint64_t h = 512u - a;
-      if (pos - flushed >= h) flush_bytes((uint32_t)h);
-      else if (final) flush_bytes((uint32_t)(pos - flushed));
-      else return;
+      const uint32_t h = 512u - a;
+      if (pos - flushed >= h) flush_bytes(h);
+      else if (final) flush_bytes(pos - flushed);
+      else { check = min(out_len, flushed + FLUSH_AT); return; }
     }
     while (pos - flushed >= 512u) {
-      const uint4 v = *reinterpret_cast<const uint4*>(&m->win[((uint32_t)flushed + 16u * lane + skew) & WIN_MASK]);
+      const uint4 v = *reinterpret_cast<const uint4*>(&m->win[(flushed + 16u * lane + skew) & WIN_MASK]);
       *reinterpret_cast<uint4*>(out + flushed + 16u * lane) = v;
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
       uint32_t s1 = 0, s2 = 0;
@@ -148,28 +149,28 @@ struct Stream {
       adler_fold(s1, s2, 512u);
       flushed += 512u;
     }
-    if (final) while (pos > flushed) flush_bytes((uint32_t)(pos - flushed < 512u ? pos - flushed : 512u));
+    if (final) while (pos > flushed) flush_bytes(pos - flushed < 512u ? pos - flushed : 512u);
+    check = min(out_len, flushed + FLUSH_AT);   // the next position at which the decoder has to look up from its loop
   }
-  __device__ bool literal(uint32_t sym) {
-    if (pos >= out_len) return false;
-    if (lane == 0) m->win[((uint32_t)pos + skew) & WIN_MASK] = (uint8_t)sym;
+  __device__ bool literal(uint32_t sym) {   // one compare covers "output full" and "time to flush"
+    if (pos >= check) { if (pos >= out_len) return false; flush(false); }
+    if (lane == 0) m->win[(pos + skew) & WIN_MASK] = (uint8_t)sym;
     ++pos;
     return true;
   }
-  __device__ bool match(uint32_t len, uint64_t dist) {
-    if (dist > pos || pos + len > out_len) return false;
+  __device__ bool match(uint32_t len, uint32_t dist) {
+    if (dist > pos || len > out_len - pos) return false;
     __syncwarp();   // the literals and matches before this one are in the ring for every lane
+    const uint32_t from = pos - dist + skew, to = pos + skew;
     if (dist <= RING_REACH) {
-      for (uint32_t i = lane; i < len; i += 32u) {
-        const uint32_t src = (uint32_t)(pos - dist) + (dist >= len ? i : i % (uint32_t)dist);
-        m->win[((uint32_t)pos + i + skew) & WIN_MASK] = m->win[(src + skew) & WIN_MASK];
-      }
+      if (dist >= len) { for (uint32_t i = lane; i < len; i += 32u) m->win[(to + i) & WIN_MASK] = m->win[(from + i) & WIN_MASK]; }
+      else for (uint32_t i = lane; i < len; i += 32u) m->win[(to + i) & WIN_MASK] = m->win[(from + i % dist) & WIN_MASK];   // overlapping: the pattern repeats
     } else {   // the source left the ring long ago: it is in HBM (dist > len here, no overlap)
       if (pos - dist + len > flushed) flush(true);   // (only a small ring can hold unflushed bytes that far back)
-      for (uint32_t i = lane; i < len; i += 32u) m->win[((uint32_t)pos + i + skew) & WIN_MASK] = __ldcg(out + (pos - dist) + i);
+      for (uint32_t i = lane; i < len; i += 32u) m->win[(to + i) & WIN_MASK] = __ldcg(out + (pos - dist) + i);
     }
     pos += len;
-    if (pos - flushed >= FLUSH_AT) flush(false);
+    if (pos >= check && pos < out_len) flush(false);
     return true;
   }
 };
@@ -224,14 +225,14 @@ __device__ inline bool codes(Stream& s) {
   for (;;) {
     int sym = s.decode_len();
     if (sym < 0 || s.bad) return false;
-    if (sym < 256) { if (!s.literal((uint32_t)sym)) return false; if (s.pos - s.flushed >= FLUSH_AT) s.flush(false); continue; }
+    if (sym < 256) { if (!s.literal((uint32_t)sym)) return false; continue; }
     if (sym == 256) return true;
     sym -= 257;
     if (sym >= 29) return false;
     const uint32_t len = c_lens[sym] + s.bits(c_lext[sym]);
     const int ds = s.decode_dist();
     if (ds < 0 || ds >= 30) return false;
-    const uint64_t dist = c_dists[ds] + s.bits(c_dext[ds]);
+    const uint32_t dist = c_dists[ds] + s.bits(c_dext[ds]);
     if (s.bad || !s.match(len, dist)) return false;
   }
 }
@@ -248,7 +249,8 @@ __device__ inline uint32_t inflate_stream(WarpMem* m, uint32_t lane, const uint8
   s.gwords = reinterpret_cast<const uint32_t*>(d0 - lead);
   s.n_words = (uint32_t)((lead + (in_len - 6) + 3u) / 4u);
   s.next = 0; s.buf = 0; s.cnt = 0; s.bad = false;
-  s.out = out; s.out_len = out_len; s.pos = 0; s.flushed = 0; s.skew = (uint32_t)((uintptr_t)out & 15u); s.adler_a = 1; s.adler_b = 0;
+  if (out_len >= (1ull << 32)) return INF_ERR_SIZE;
+  s.out = out; s.out_len = (uint32_t)out_len; s.pos = 0; s.flushed = 0; s.check = min((uint32_t)out_len, FLUSH_AT); s.skew = (uint32_t)((uintptr_t)out & 15u); s.adler_a = 1; s.adler_b = 0;
   __syncwarp();
   s.stage_block(0);
   __syncwarp();
@@ -261,8 +263,8 @@ __device__ inline uint32_t inflate_stream(WarpMem* m, uint32_t lane, const uint8
     if (type == 0) {   // stored: back to the byte boundary, LEN / NLEN, then LEN bytes
       s.bits(s.cnt & 7);
       const uint32_t n = s.bits(16), nn = s.bits(16);
-      if (s.bad || n != (~nn & 0xFFFFu) || s.pos + n > out_len) return INF_ERR_DATA;
-      for (uint32_t i = 0; i < n; ++i) { s.literal(s.bits(8)); if (s.pos - s.flushed >= FLUSH_AT) s.flush(false); }
+      if (s.bad || n != (~nn & 0xFFFFu) || n > s.out_len - s.pos) return INF_ERR_DATA;
+      for (uint32_t i = 0; i < n; ++i) s.literal(s.bits(8));
       if (s.bad) return INF_ERR_DATA;
     } else if (type == 1 || type == 2) {
       int nlen = FIXLCODES, ndist = MAXDCODES;
@@ -317,7 +319,7 @@ __device__ inline uint32_t inflate_stream(WarpMem* m, uint32_t lane, const uint8
   } while (!last);
   // the decoder may have buffered whole words past the last block, but it must not have used bits the stream does not have
   if ((uint64_t)s.next * 32u - (uint64_t)s.cnt > 8ull * (lead + (in_len - 6))) return INF_ERR_DATA;
-  if (s.pos != out_len) return INF_ERR_SIZE;
+  if (s.pos != s.out_len) return INF_ERR_SIZE;
   s.flush(true);
   const uint8_t* t = in + in_len - 4;
   const uint32_t want = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
