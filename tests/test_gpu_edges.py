@@ -65,7 +65,8 @@ def five_fields(d):
 
 def test_five_remapped_fields(ctx):
     """more remapped fields than the tile kernels take (4): every site goes through k_remap_generic; against the restatement"""
-    from genomicsdb_b200 import capi, dump
+    from genomicsdb_b200 import capi
+    from tools import dump
     d = gdbsyn.generate(n_samples=150, n_sites=40, spacing=100, p_var=0.2, a_pool=8)
     fields = five_fields(d)
 
@@ -176,7 +177,7 @@ def test_limit_column_span(ctx):
 
 def test_query_far_left_of_the_data_costs_nothing(ctx):
     """the breakpoint bitmap is based at the data, not at the query's begin: [0, 2^40] over a small cohort works and equals the full scan"""
-    from genomicsdb_b200 import dump
+    from tools import dump
     d = gdbsyn.generate(n_samples=30, n_sites=20, spacing=100, p_var=0.2, a_pool=4, first_col=5_000_000_000)
     arr = gdbsyn.to_gpu_array(ctx, d)
     try:

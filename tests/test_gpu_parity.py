@@ -20,7 +20,8 @@ def ctx():
 
 
 def gpu_dump(ctx, case, **kw):
-    from genomicsdb_b200 import capi, dump
+    from genomicsdb_b200 import capi
+    from tools import dump
     fields, phased = case_fields(case)
     arr = capi.Array.open(ctx, os.path.join(GOLDEN, case["workspace"]), case["array"], fields, gt_phased=phased)
     try:

@@ -22,7 +22,7 @@ def ctx():
 
 
 def dumps(arr, ranges, names, **kw):
-    from genomicsdb_b200 import dump
+    from tools import dump
     return dump.combine_dump(arr, ranges, names, **kw)
 
 

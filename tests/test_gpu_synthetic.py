@@ -19,7 +19,7 @@ def ctx():
 
 
 def both(ctx, d, ranges, rows=None, **kw):
-    from genomicsdb_b200 import dump
+    from tools import dump
     cols = gdbsyn.to_oracle_columns(d)
     want, n = oracle.combine_query(cols, ranges, query_rows=rows)
     arr = gdbsyn.to_gpu_array(ctx, d)
@@ -187,7 +187,8 @@ def test_compressed_fragment_is_inflated_on_the_device(ctx, tmp_path, capacity):
     """a GZIP-compressed fragment (one zlib stream per tile, dynamic Huffman blocks at 1000 cells per tile) written in the
     reference's on-disk format: gdbgpu_array_open inflates the tiles on the device (k_inflate); the combine over it equals
     the oracle over the generated columns, and equals the open of the uncompressed twin"""
-    from genomicsdb_b200 import capi, dump
+    from genomicsdb_b200 import capi
+    from tools import dump
     from tools import tiledb_writer
     d = gdbsyn.generate(n_samples=300, n_sites=200, spacing=100, p_var=0.1, a_pool=8, with_fixed=True)
     want, n = oracle.combine_query(gdbsyn.to_oracle_columns(d), [])

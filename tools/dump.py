@@ -6,7 +6,7 @@ import struct
 
 import numpy as np
 
-from . import capi
+from genomicsdb_b200 import capi
 
 MAGIC = 0x31444247
 
