@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(UNION_THREADS, 4) k_union(const __grid_constan
   __shared__ unsigned long long s_order[UNION_SLOTS];
   __shared__ uint16_t s_list[UNION_MAX_DISTINCT];
   __shared__ uint16_t s_rank[UNION_MAX_DISTINCT];
-  __shared__ uint32_t s_piece_cell[REF_MAX_PIECES], s_piece_from[REF_MAX_PIECES], s_piece_to[REF_MAX_PIECES];
+  __shared__ uint32_t s_piece_cell[REF_MAX_PIECES], s_piece_from[REF_MAX_PIECES], s_piece_to[REF_MAX_PIECES], s_piece_dst[REF_MAX_PIECES];   // bytes [from, to) of the cell's REF land at dst of the merged REF
   __shared__ unsigned int s_k, s_next, s_maxN, s_maxlen, s_ndist, s_nonref, s_maxgt, s_maxain, s_maxploidy, s_npieces, s_reflen, s_refoff, s_afirst, s_overflow;
   __shared__ unsigned int s_maxpl[MAX_FIELDS], s_maxin[MAX_FIELDS];
 
@@ -440,12 +440,27 @@ __global__ void __launch_bounds__(UNION_THREADS, 4) k_union(const __grid_constan
         if (candidate(c, rl, first) && first == 'N' && rl == s_maxN) atomicMin(&s_next, (unsigned int)(c - c0));
       }
       __syncthreads();
-      if (tid == 0) { s_piece_cell[0] = (uint32_t)(c0 + s_next); s_piece_from[0] = 0; s_piece_to[0] = s_maxN; s_npieces = 1; s_reflen = s_maxN; }
+      if (tid == 0) { s_piece_cell[0] = (uint32_t)(c0 + s_next); s_piece_from[0] = 0; s_piece_to[0] = s_maxN; s_piece_dst[0] = 0; s_npieces = 1; s_reflen = s_maxN; }
     } else if (tid == 0) { s_npieces = 0; s_reflen = 1; }
     __syncthreads();
   } else {
-    uint32_t last = s_k, cur_len = A.desc[c0 + s_k].ref_len;
-    if (tid == 0) { s_piece_cell[0] = (uint32_t)(c0 + last); s_piece_from[0] = 0; s_piece_to[0] = cur_len; s_npieces = 1; }
+    uint32_t last = s_k, cur_len = A.desc[c0 + s_k].ref_len, str_len = cur_len;
+    if (tid == 0) { s_piece_cell[0] = (uint32_t)(c0 + last); s_piece_from[0] = 0; s_piece_to[0] = cur_len; s_piece_dst[0] = 0; s_npieces = 1; }
+    // The reference's fold compares every REF with a LENGTH REGISTER, not with the string it holds: an N-leading REF of several
+    // bases seen before the first real REF raises the register, the real REF then replaces the string but not the register
+    // (variant_operations.cc:108-121).  A later REF is appended only when it is longer than the register, and from the
+    // register's offset.  (N-leading REFs longer than one base do not occur in gVCFs; s_maxN > 1 is never true there.)
+    if (s_maxN > 1) {
+      __syncthreads();
+      if (tid == 0) s_next = 0;
+      __syncthreads();
+      for (uint64_t c = c0 + tid; c < c0 + s_k; c += UNION_THREADS) {
+        uint32_t rl; uint8_t first;
+        if (candidate(c, rl, first) && first == 'N') atomicMax(&s_next, rl);
+      }
+      __syncthreads();
+      cur_len = max(cur_len, s_next);
+    }
     while (s_maxlen > cur_len) {   // later, longer REFs append their tail ("record breakers"); none when nothing is longer
       __syncthreads();
       if (tid == 0) s_next = 0xFFFFFFFFu;
@@ -459,13 +474,13 @@ __global__ void __launch_bounds__(UNION_THREADS, 4) k_union(const __grid_constan
       if (nx == 0xFFFFFFFFu) break;
       uint32_t nl = A.desc[c0 + nx].ref_len;
       if (tid == 0) {
-        if (s_npieces < REF_MAX_PIECES) { s_piece_cell[s_npieces] = (uint32_t)(c0 + nx); s_piece_from[s_npieces] = cur_len; s_piece_to[s_npieces] = nl; ++s_npieces; }
+        if (s_npieces < REF_MAX_PIECES) { s_piece_cell[s_npieces] = (uint32_t)(c0 + nx); s_piece_from[s_npieces] = cur_len; s_piece_to[s_npieces] = nl; s_piece_dst[s_npieces] = str_len; ++s_npieces; }
         else atomicMax(&S.err[1], 4u);
       }
-      last = nx; cur_len = nl;
+      last = nx; str_len += nl - cur_len; cur_len = nl;
     }
     __syncthreads();
-    if (tid == 0) s_reflen = cur_len;
+    if (tid == 0) s_reflen = str_len;
     __syncthreads();
   }
   if (tid == 0) {
@@ -480,7 +495,7 @@ __global__ void __launch_bounds__(UNION_THREADS, 4) k_union(const __grid_constan
     if (s_npieces == 0) { if (tid == 0) mref[0] = 'N'; }
     else for (uint32_t p = 0; p < s_npieces; ++p) {
       const uint8_t* src = A.ref.val + A.ref.off[s_piece_cell[p]];
-      for (uint32_t i = s_piece_from[p] + tid; i < s_piece_to[p]; i += UNION_THREADS) mref[i] = src[i];
+      for (uint32_t i = s_piece_from[p] + tid; i < s_piece_to[p]; i += UNION_THREADS) mref[s_piece_dst[p] + (i - s_piece_from[p])] = src[i];
     }
   }
   __syncthreads();   // mref is read below by other threads of this block (global memory, same block: needs the barrier only)

@@ -439,13 +439,15 @@ static void malt_push(op_t* o, const char* s, int32_t n, const char* suffix, int
 static void merge_alleles(op_t* o) {
   /* merge_reference_allele */
   str_assign(&o->mref, "N", 1);
+  int32_t ml = 1;   /* merged_ref_length: a register of its own -- it is NOT refreshed when a shorter real REF replaces an N-leading one
+                       (variant_operations.cc:108-121), so later REFs are compared with, and appended from, the stale length */
   for (int64_t q = 0; q < o->nq; ++q) {
     call_t* c = &o->calls[q];
     if (!c->valid || c->begin < o->site_begin) continue;
-    int32_t ml = o->mref.n;
     if (c->ref.n > ml) {
       if (ml > 0 && o->mref.s[0] == 'N') str_assign(&o->mref, c->ref.s, c->ref.n);
-      else { o->mref.s = (char*)realloc(o->mref.s, c->ref.n + 1); memcpy(o->mref.s + ml, c->ref.s + ml, c->ref.n - ml); o->mref.n = c->ref.n; o->mref.s[c->ref.n] = 0; }
+      else { int32_t have = o->mref.n, add = c->ref.n - ml; o->mref.s = (char*)realloc(o->mref.s, have + add + 1); memcpy(o->mref.s + have, c->ref.s + ml, add); o->mref.n = have + add; o->mref.s[have + add] = 0; }
+      ml = c->ref.n;
     } else if (o->mref.s[0] == 'N' && !(c->ref.n > 0 && c->ref.s[0] == 'N')) str_assign(&o->mref, c->ref.s, c->ref.n);
   }
   /* merge_alt_alleles: first-seen order over valid calls in row order, NON_REF last */
