@@ -845,7 +845,7 @@ void compute_front(gdbgpu_scan* s, uint64_t first_site, uint32_t max_sites) {
   w.valid = false;
   // batches still in flight read the window they were cut from (their device -> host copies run on the copy stream)
   for (auto& sl : s->slot) if (sl && sl->ev_done) CK(cudaStreamWaitEvent(ctx->stream, sl->ev_done, 0));
-  static const uint64_t budget = [] { const char* e = getenv("GDBGPU_FRONT_BYTES"); const uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v ? v : (6ull << 30); }();
+  const uint64_t budget = [] { const char* e = getenv("GDBGPU_FRONT_BYTES"); const uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v ? v : (6ull << 30); }();
   const uint64_t remaining = S.n_sites - first_site;
   // a caller paging in small batches gets small windows (every batch copies the window's allele pool)
   const uint32_t nb = (uint32_t)std::min<uint64_t>({remaining, std::max<uint64_t>(1, budget / std::max<uint64_t>(1, S.nq * 24)), 1u << 20, max_sites ? std::max<uint64_t>(64, 16ull * max_sites) : ~0ull});

@@ -251,3 +251,69 @@ def test_cached_device_memory_is_reused_and_can_be_released(ctx):
     assert torch.cuda.mem_get_info()[0] == free0          # steady state: nothing new from the driver
     ctx.release_cached_memory()
     assert torch.cuda.mem_get_info()[0] > free0
+
+
+def _scan_arrays(arr, flags, max_sites=0, max_bytes=0):
+    """one record per SITE (whatever the batches were): tables, alleles, live row, every field's stride / lengths / vectors"""
+    from genomicsdb_b200 import capi
+    sc = capi.Scan(arr, flags=flags)
+    out = []
+    try:
+        while True:
+            b = sc.next_batch(max_sites, max_bytes)
+            if b is None:
+                break
+            for s in range(b.n_sites):
+                rec = [int(b.site_begin[s]), int(b.site_end[s]), int(b.n_alleles[s]), np.array(b.live[s]), b"|".join(b.alleles(s))]
+                for f in b.fields:
+                    base, stride = int(f["base"][s]), int(f["stride"][s])
+                    rec += [stride, np.array(f["len"][s]), np.array(f["data"][base:base + b.nq * stride])]
+                out.append(rec)
+    finally:
+        sc.close()
+    return out
+
+
+def _same(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert len(x) == len(y)
+        for u, v in zip(x, y):
+            assert np.array_equal(u, v) if isinstance(u, np.ndarray) else u == v
+
+
+def test_signature_rows_equal_per_call_luts(ctx):
+    """scans of >= 4096 samples remap the non-trivial calls through one permutation row per call signature (k_verify_alleles,
+    k_sig_perm, nt_apply); a scan that also asks for the per-call LUTs rebuilds every call's LUT instead (nt_entry) -- the
+    remapped vectors must not differ, and the LUT scan is the one the oracle comparison runs on"""
+    from genomicsdb_b200 import capi
+    d = gdbsyn.generate(n_samples=6000, n_sites=48, spacing=1000, p_var=0.15, a_pool=8)
+    both(ctx, d, [])                                   # per-call LUT path against the oracle
+    arr = gdbsyn.to_gpu_array(ctx, d)
+    try:
+        _same(_scan_arrays(arr, 0, max_sites=7), _scan_arrays(arr, capi.SCAN_WANT_LUT, max_sites=7))
+    finally:
+        arr.close()
+
+
+def test_many_front_windows(ctx, monkeypatch):
+    """K3/K4 run once per window of sites (6 GiB of front state by default: one window in every other test); with a budget of a
+    few sites per window the batches stop at window borders, with and without prefetch, in tiny and in large batches -- the sites
+    and every vector are the same"""
+    from genomicsdb_b200 import capi
+    d = gdbsyn.generate(n_samples=5000, n_sites=60, spacing=1000, p_var=0.15, a_pool=8)
+    arr = gdbsyn.to_gpu_array(ctx, d)
+    try:
+        want = _scan_arrays(arr, 0)
+        monkeypatch.setenv("GDBGPU_FRONT_BYTES", str(24 * 5000 * 7))          # 7 sites per window
+        _same(_scan_arrays(arr, 0, max_sites=5), want)
+        _same(_scan_arrays(arr, capi.SCAN_NO_PREFETCH, max_sites=5), want)
+        _same(_scan_arrays(arr, 0), want)
+        _same(_scan_arrays(arr, 0, max_bytes=3 << 20), want)
+    finally:
+        monkeypatch.delenv("GDBGPU_FRONT_BYTES", raising=False)
+        arr.close()
+    monkeypatch.setenv("GDBGPU_FRONT_BYTES", str(24 * 300 * 3))               # and against the oracle: 3 sites per window
+    d2 = gdbsyn.generate(n_samples=300, n_sites=100, spacing=100, p_var=0.1, a_pool=3)
+    both(ctx, d2, [])
+    both(ctx, d2, [], max_sites=2)
