@@ -57,7 +57,7 @@ def test_overflow_resume_protocol(exe, case, tmp_path):
 ALL = golden_cases()
 
 
-def run_broad(exe, case, tmp_path, page=0, java=False, sites_only=False):
+def run_broad(exe, case, tmp_path, page=0, java=False, sites_only=False, env=None):
     q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
          "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": case["attributes"],
          "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_column_ranges"]]}],
@@ -71,7 +71,7 @@ def run_broad(exe, case, tmp_path, page=0, java=False, sites_only=False):
            os.path.join(GOLDEN, "bcf_sites_only" if sites_only else ("bcf_java" if java else "bcf"), case["id"] + ".bcf"),
            "--reference-bases", os.path.join(GOLDEN, "inputs", "ref_bases.tsv")] + (["-p", str(page)] if page else []) + \
           (["--htsjdk-conventions"] if java else [])
-    return subprocess.run(cmd, capture_output=True, text=True), out
+    return subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, **env) if env else None), out
 
 
 @pytest.mark.parametrize("java", [False, True], ids=["htslib", "java"])
@@ -184,3 +184,16 @@ def test_max_alleles_count_operator(exe, cid, tmp_path):
     assert sorted(lines[1:]) == want
     counts = [int(l.split(",")[2]) for l in lines[1:]]
     assert counts == sorted(counts)          # the reference pops its min-heap: fewest ALT alleles first
+
+
+@pytest.mark.parametrize("cid", ["t0_1_2_combined_at_0", "haploid_triploid_deletion_produce_GT", "t0_1_2_all_asa_at_0", "info_ops1_at_0"])
+def test_broad_gvcf_across_front_windows(exe, cid, tmp_path):
+    """one site per front window (GDBGPU_FRONT_BYTES = 1): K6's collation, the INFO combines and the records read every batch's
+    rows of a window that is recomputed for the next site -- the file is the reference's all the same"""
+    case = [c for c in ALL if c["id"] == cid][0]
+    gold = open(os.path.join(GOLDEN, "bcf", cid + ".bcf"), "rb").read()
+    p, out = run_broad(exe, case, tmp_path, env={"GDBGPU_FRONT_BYTES": "1"})
+    assert p.returncode == 0, p.stderr
+    assert out.read_bytes() == gold
+
+
