@@ -193,7 +193,7 @@ def main():
     ap.add_argument("--config", default="4shard", choices=sorted(WORKLOADS))
     ap.add_argument("--samples", type=int, default=COHORT["n_samples"])
     ap.add_argument("--sites-per-gpu", type=int, default=SITES_PER_GPU)
-    ap.add_argument("--batch-bytes", type=int, default=8 << 30)
+    ap.add_argument("--batch-bytes", type=int, default=16 << 30)
     ap.add_argument("--e2e-steps", type=int, default=8)   # the first step's staging is not hidden behind a scan: enough steps to show the steady state
     ap.add_argument("--e2e-batch-bytes", type=int, default=2 << 30)
     ap.add_argument("--latency-intervals", type=int, default=200)
