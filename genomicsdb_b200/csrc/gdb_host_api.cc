@@ -185,7 +185,7 @@ void GA4GHOperator::warn_too_many_alleles(const VariantQueryConfig& query_config
 // BCF dictionary of strings: FILTER / INFO / FORMAT IDs share one index space (IDX= when htslib wrote it, else order of first
 // appearance, PASS = 0); contigs have their own (htslib vcf.c bcf_hdr_sync)
 void VCFAdapter::set_vcf_header_text(const std::string& header) {
-  header_ = header; ids_.clear(); contigs_.clear();
+  header_ = header; ids_.clear(); contigs_.clear(); info_ids_.clear();
   int next_id = 0, next_ctg = 0;
   size_t pos = 0;
   while (pos < header.size()) {
@@ -203,6 +203,7 @@ void VCFAdapter::set_vcf_header_text(const std::string& header) {
     const bool dict = line.compare(0, 10, "##FILTER=<") == 0 || line.compare(0, 8, "##INFO=<") == 0 || line.compare(0, 10, "##FORMAT=<") == 0;
     if (dict) {
       const std::string id = attr("ID=");
+      if (line.compare(0, 8, "##INFO=<") == 0) info_ids_.insert(id);
       bool known = false;
       for (auto& kv : ids_) if (kv.first == id) known = true;
       if (known) continue;
@@ -361,7 +362,7 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
     m_global_field_idx_to_hdr_idx[f.global_idx] = vcf_adapter.get_dictionary_id(f.name);
   }
   m_dp_rule = qc.get_dp_rule_fields()[0] != 0 || qc.get_dp_rule_fields()[2] != 0;
-  if (m_dp_rule) m_DP_key = key_of("DP");
+  if (m_dp_rule) { m_DP_key = key_of("DP"); m_dp_rule = vcf_adapter.has_info_line("DP"); }   // bcf_update_info_int32 fails without an ##INFO line: no INFO/DP then
   m_END_key = key_of("END");
   m_num_vector_slots = n_remapped - (remapped_index("GT") >= 0 ? 1u : 0u) + (unsigned)plain.size();
 }
@@ -915,12 +916,14 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
         qc.plain_.push_back(pf);
         continue;
       }
-      if (as_format) pf.format = true;
+      // the known field DP in the FORMAT vector (FORMAT-only in the vid mapping, or INFO combined with the DP rule) is not inserted: its
+      // values are the per-call inputs of INFO/DP (handle_FORMAT_fields, broad_combined_gvcf.cc:669-673,685-727)
+      if (name == "DP" && (as_format || (fi->is_info && fi->combine_op == "DP"))) { /* DP rule input only */ }
+      else if (as_format) pf.format = true;
       else if (fi->is_info && fi->combine_op == "element_wise_sum") {
         if (pf.elem == GDBGPU_ELEM_CHAR) throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "element-wise sum of a string field: " + name);
         pf.info_op = GDBGPU_INFO_ELEMENT_WISE_SUM;
       }
-      else if (fi->is_info && name == "DP" && fi->combine_op == "DP") { /* DP rule input only */ }
       else if (fi->is_info && scalar_op) {
         if (pf.fixed_len != 1 || pf.elem == GDBGPU_ELEM_CHAR) throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "INFO combine operation on a non-scalar field: " + name);
         pf.info_op = fi->combine_op == "median" ? GDBGPU_INFO_MEDIAN : (fi->combine_op == "sum" ? GDBGPU_INFO_SUM : GDBGPU_INFO_MEAN);
@@ -932,7 +935,7 @@ void VariantQueryProcessor::do_query_bookkeeping(VariantQueryConfig& qc, bool al
         throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "INFO combine operation " + fi->combine_op + " of field " + name + " is not supported on the GPU");
       else continue;   // INFO field without a combine operation: the reference drops it with a warning (broad_combined_gvcf.cc:175-178)
       qc.plain_.push_back(pf);
-      if (name == "DP" && !as_format) qc.dp_fields_[0] = (unsigned)qc.plain_.size();
+      if (name == "DP") qc.dp_fields_[0] = (unsigned)qc.plain_.size();
       if (name == "MIN_DP") qc.dp_fields_[1] = (unsigned)qc.plain_.size();
       if (name == "DP_FORMAT") qc.dp_fields_[2] = (unsigned)qc.plain_.size();
     }

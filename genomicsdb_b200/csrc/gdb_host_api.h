@@ -26,6 +26,7 @@
 #include <memory>
 #include <stdexcept>
 #include <iostream>
+#include <set>
 #include <string>
 #include <utility>
 #include <vector>
@@ -349,6 +350,7 @@ class VCFAdapter {
   void set_vcf_header_text(const std::string& header);
   const std::string& get_vcf_header_text() const { return header_; }
   int get_dictionary_id(const std::string& name) const;   // -1: not in the header
+  bool has_info_line(const std::string& name) const { return info_ids_.count(name) != 0; }   // the header declares ##INFO=<ID=name,...>
   int get_contig_id(const std::string& name) const;
   void set_reference_base(const std::string& contig, int64_t pos, char base) { ref_bases_[contig + ":" + std::to_string(pos)] = base; }
   char get_reference_base_at_position(const std::string& contig, int64_t pos) const;   // 'N' when unknown
@@ -372,6 +374,8 @@ class VCFAdapter {
   size_t pending_bytes_ = 0; uint64_t bytes_written_ = 0; int fd_ = -1;
   std::string header_;
   std::vector<std::pair<std::string, int>> ids_, contigs_;
+  std::set<std::string> info_ids_;   // IDs with an ##INFO line
+  void collect_info_ids();
   std::map<std::string, char> ref_bases_;
   std::unique_ptr<VCFHeaderLines> lines_;
   bool keep_idx_ = true;

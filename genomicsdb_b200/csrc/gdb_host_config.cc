@@ -173,6 +173,15 @@ void VCFAdapter::finalize_header(bool) {
   header_ = lines_->format(true);
   ids_ = lines_->ids();
   contigs_ = lines_->contigs();
+  collect_info_ids();
+}
+void VCFAdapter::collect_info_ids() {
+  info_ids_.clear();
+  for (size_t pos = 0; (pos = header_.find("##INFO=<ID=", pos)) != std::string::npos;) {
+    pos += 11;
+    const size_t e = header_.find_first_of(",>", pos);
+    info_ids_.insert(header_.substr(pos, e == std::string::npos ? std::string::npos : e - pos));
+  }
 }
 
 // bcf_hdr_write / bcf_hdr_serialize (vcf.c:986-1051): magic, l_text counting the closing NUL, text

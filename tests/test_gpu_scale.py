@@ -112,3 +112,42 @@ def test_many_fragments_newest_wins(tmp_path, n_fragments, compress):
     ArrayReadState does (array_read_state.cc:1836-2132, :2369-2402)"""
     d = gdbsyn.generate(n_samples=2000, n_sites=10000, spacing=100, p_var=0.1, a_pool=4, site_lo=100, site_hi=700, with_fixed=True)
     compare_with_reference(tmp_path, d, n_intervals=4, n_fragments=n_fragments, dup_every=7, compress=compress)
+
+
+def test_spanning_deletions_at_cohort_scale(tmp_path):
+    """2 000 samples, 300 candidate sites, a third of the variant calls turned into 2-4 base deletions (tools/gdbsyn_deletions.py):
+    handle_deletions, the `*` allele, 1-bp stepping while a deletion is live and the reduced PL / AD / GT of every spanning call,
+    every row and every site against the unmodified reference"""
+    from tools import gdbsyn_deletions
+    d = gdbsyn.generate(n_samples=2000, n_sites=10000, spacing=100, p_var=0.1, a_pool=6, site_lo=200, site_hi=500, with_fixed=True)
+    dd = gdbsyn_deletions.with_deletions(d, share=0.3)
+    assert dd["n_deletion_calls"] > 10000
+    compare_with_reference(tmp_path, dd, n_intervals=8)
+
+
+@pytest.mark.parametrize("deletions", [False, True], ids=["plain", "deletions"])
+def test_broad_gvcf_file_of_a_synthetic_cohort(tmp_path, deletions):
+    """tool against tool on the same on-disk array: the unmodified `gt_mpi_gather --produce-Broad-GVCF -O bu` and
+    `gt_gpu_gather --produce-Broad-GVCF` (header generated in-library, reference bases from the indexed FASTA) write the same
+    BCF file, byte for byte -- 600 samples, 150 candidate sites, with GQ / MIN_DP / DP; once with a third of the variant calls
+    turned into deletions (spanning `*` alleles, min-PL GT off)"""
+    from tools import gdbsyn_deletions
+    ref_tool = os.path.join(REPO, "oracle", "_ref", "bin", "gt_mpi_gather")
+    if not os.path.exists(ref_tool):
+        pytest.skip("oracle/_ref is not built")
+    d = gdbsyn.generate(n_samples=600, n_sites=10000, spacing=100, p_var=0.12, a_pool=6, site_lo=50, site_hi=200, with_fixed=True)
+    if deletions:
+        d = gdbsyn_deletions.with_deletions(d, share=0.3)
+    ws = str(tmp_path / "ws")
+    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+    lo, hi = d["col_range"]
+    q = tiledb_writer.write_query_json(os.path.join(ws, "q.json"), info, lo, hi, attributes=("REF", "ALT", "GT", "AD", "PL", "GQ", "MIN_DP", "DP"))
+    ref_out, our_out = str(tmp_path / "ref.bcf"), str(tmp_path / "ours.bcf")
+    with open(ref_out, "wb") as f:
+        p = subprocess.run([ref_tool, "-j", q, "--produce-Broad-GVCF", "-O", "bu"], stdout=f, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr[-800:]
+    p2 = subprocess.run([OURS, "-j", q, "--produce-Broad-GVCF", "-o", our_out], capture_output=True, text=True)
+    assert p2.returncode == 0, p2.stderr[-800:]
+    want, got = open(ref_out, "rb").read(), open(our_out, "rb").read()
+    assert len(want) > 1 << 20
+    assert len(got) == len(want) and got == want

@@ -87,3 +87,16 @@ def test_kernels_equal_the_reference(ref_present, tmp_path, plan):
     want = _dump([REF, "-j", q, "--mode", "dump"], str(tmp_path / "ref.bin"))
     got = _dump([OURS, "-j", q], str(tmp_path / "ours.bin"))
     assert hashlib.md5(got).hexdigest() == hashlib.md5(want).hexdigest() and got == want
+
+
+def test_restatement_equals_the_reference_on_a_cohort_with_deletions(ref_present, tmp_path):
+    """the C restatement against the unmodified reference on a synthetic cohort whose variant calls are deletions to a third
+    (tools/gdbsyn_deletions.py): spanning-deletion form, 1-bp stepping, reduced vectors"""
+    from oracle import oracle
+    from tools import gdbsyn_deletions
+    d = gdbsyn_deletions.with_deletions(gdbsyn.generate(n_samples=60, n_sites=80, spacing=100, p_var=0.2, a_pool=5, with_fixed=True))
+    info = tiledb_writer.write_array(str(tmp_path / "ws"), "syn", d)
+    q = tiledb_writer.write_query_json(str(tmp_path / "q.json"), info)
+    want = _dump([REF, "-j", q, "--mode", "dump"], str(tmp_path / "ref.bin"))
+    got, n = oracle.combine_query(oracle.load_columns(info["workspace"], "syn", info["vid"], ["END", "REF", "ALT", "GT", "AD", "PL"]), [])
+    assert n > 200 and got == want
