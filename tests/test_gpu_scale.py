@@ -151,3 +151,47 @@ def test_broad_gvcf_file_of_a_synthetic_cohort(tmp_path, deletions):
     want, got = open(ref_out, "rb").read(), open(our_out, "rb").read()
     assert len(want) > 1 << 20
     assert len(got) == len(want) and got == want
+
+
+QUERY_VARIANTS = {
+    "produce_GT": {"produce_GT_field": True},
+    "min_PL_GT": {"produce_GT_field": True, "produce_GT_with_min_PL_value_for_spanning_deletions": True},
+    "sites_only": {"sites_only_query": True},
+    "row_subset": {"query_row_ranges": [{"range_list": [{"low": 7, "high": 211}, {"low": 400, "high": 590}]}]},
+    "two_intervals": "two_intervals",
+    "max_alt_2": {"max_diploid_alt_alleles_that_can_be_genotyped": 2, "produce_GT_field": True},
+}
+
+
+@pytest.mark.parametrize("variant", sorted(QUERY_VARIANTS))
+def test_broad_gvcf_file_query_options_on_a_cohort_with_deletions(tmp_path, variant):
+    """the options of the query JSON that change the records (GT with alleles, the min-PL genotype of spanning deletions, sites-only
+    records, a row subset, several column intervals, PL dropped above 2 ALT alleles), each tool against tool on the 600-sample cohort
+    with deletions: same BCF file"""
+    import json
+    from tools import gdbsyn_deletions
+    ref_tool = os.path.join(REPO, "oracle", "_ref", "bin", "gt_mpi_gather")
+    if not os.path.exists(ref_tool):
+        pytest.skip("oracle/_ref is not built")
+    d = gdbsyn_deletions.with_deletions(gdbsyn.generate(n_samples=600, n_sites=10000, spacing=100, p_var=0.12, a_pool=6, site_lo=50, site_hi=170, with_fixed=True), share=0.3)
+    ws = str(tmp_path / "ws")
+    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+    lo, hi = d["col_range"]
+    qf = tiledb_writer.write_query_json(os.path.join(ws, "q.json"), info, lo, hi, attributes=("REF", "ALT", "GT", "AD", "PL", "GQ", "MIN_DP"))
+    q = json.load(open(qf))
+    opt = QUERY_VARIANTS[variant]
+    if opt == "two_intervals":
+        mid = (lo + hi) // 2
+        q["query_column_ranges"] = [{"range_list": [{"low": lo + 950, "high": mid - 333}, {"low": mid + 1, "high": hi - 1200}]}]
+    else:
+        q.update(opt)
+    json.dump(q, open(qf, "w"))
+    ref_out, our_out = str(tmp_path / "ref.bcf"), str(tmp_path / "ours.bcf")
+    with open(ref_out, "wb") as f:
+        p = subprocess.run([ref_tool, "-j", qf, "--produce-Broad-GVCF", "-O", "bu"], stdout=f, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr[-800:]
+    p2 = subprocess.run([OURS, "-j", qf, "--produce-Broad-GVCF", "-o", our_out], capture_output=True, text=True)
+    assert p2.returncode == 0, p2.stderr[-800:]
+    want, got = open(ref_out, "rb").read(), open(our_out, "rb").read()
+    assert len(want) > 10000
+    assert len(got) == len(want) and got == want
