@@ -195,3 +195,30 @@ def test_broad_gvcf_file_query_options_on_a_cohort_with_deletions(tmp_path, vari
     want, got = open(ref_out, "rb").read(), open(our_out, "rb").read()
     assert len(want) > 10000
     assert len(got) == len(want) and got == want
+
+
+@pytest.mark.parametrize("produce_gt", [False, True], ids=["no-GT", "GT"])
+def test_jni_conventions_on_a_cohort_with_deletions(tmp_path, produce_gt):
+    """the records the JNI path hands to the Java reader (BroadCombinedGVCFOperator constructed with
+    use_missing_values_only_not_vector_end: missing instead of vector_end padding, no-call GT for rows without a call): the
+    unmodified reference classes driven by oracle/ref_harness (gdb_ref_dump --mode bcf-java) against
+    gt_gpu_gather --produce-Broad-GVCF --htsjdk-conventions on the 600-sample cohort with deletions"""
+    import json
+    from tools import gdbsyn_deletions
+    d = gdbsyn_deletions.with_deletions(gdbsyn.generate(n_samples=600, n_sites=10000, spacing=100, p_var=0.12, a_pool=6, site_lo=50, site_hi=170, with_fixed=True), share=0.3)
+    ws = str(tmp_path / "ws")
+    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+    lo, hi = d["col_range"]
+    qf = tiledb_writer.write_query_json(os.path.join(ws, "q.json"), info, lo, hi, attributes=("REF", "ALT", "GT", "AD", "PL", "GQ", "MIN_DP"))
+    if produce_gt:
+        q = json.load(open(qf))
+        q["produce_GT_field"] = True
+        json.dump(q, open(qf, "w"))
+    p = subprocess.run([REF, "-j", qf, "--mode", "bcf-java"], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode(errors="replace")[-800:]
+    our_out = str(tmp_path / "ours.bcf")
+    p2 = subprocess.run([OURS, "-j", qf, "--produce-Broad-GVCF", "--htsjdk-conventions", "-o", our_out], capture_output=True, text=True)
+    assert p2.returncode == 0, p2.stderr[-800:]
+    want, got = p.stdout, open(our_out, "rb").read()
+    assert len(want) > 100000
+    assert len(got) == len(want) and got == want
