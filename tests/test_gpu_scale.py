@@ -222,3 +222,28 @@ def test_jni_conventions_on_a_cohort_with_deletions(tmp_path, produce_gt):
     want, got = p.stdout, open(our_out, "rb").read()
     assert len(want) > 100000
     assert len(got) == len(want) and got == want
+
+
+@pytest.mark.parametrize("flag", ["--range-query", "--print-calls", "--print-csv", "--print-AC", "--produce-histogram", "--produce-interesting-positions"])
+def test_tool_commands_on_a_cohort_with_deletions(tmp_path, flag):
+    """the reference tool's other commands on a 250-sample cohort with deletions, stdout against stdout: the GA4GH range query (its
+    default command; here hundreds of variants hold several calls whose ALT lists name the same alleles in different orders, so
+    the re-indexing of merged variants is not the identity), the four columnar-iterator commands, the interesting positions"""
+    from tools import gdbsyn_deletions
+    ref_tool = os.path.join(REPO, "oracle", "_ref", "bin", "gt_mpi_gather")
+    if not os.path.exists(ref_tool):
+        pytest.skip("oracle/_ref is not built")
+    d = gdbsyn_deletions.with_deletions(gdbsyn.generate(n_samples=250, n_sites=10000, spacing=100, p_var=0.15, a_pool=4, site_lo=20, site_hi=60, with_fixed=True), share=0.3)
+    ws = str(tmp_path / "ws")
+    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+    lo, hi = d["col_range"]
+    qf = tiledb_writer.write_query_json(os.path.join(ws, "q.json"), info, lo + 700, hi - 900, attributes=("REF", "ALT", "GT", "AD", "PL", "GQ", "MIN_DP", "DP"))
+    ref_cmd = ["stdbuf", "-o0", ref_tool, "-j", qf] + ([] if flag == "--range-query" else [flag])   # (this build of the tool leaves without flushing a block-buffered stdout)
+    p = subprocess.run(ref_cmd, capture_output=True)
+    assert p.returncode == 0, p.stderr.decode(errors="replace")[-800:]
+    out = str(tmp_path / "ours.txt")
+    p2 = subprocess.run([OURS, "-j", qf, "-o", out, flag], capture_output=True, text=True)
+    assert p2.returncode == 0, p2.stderr[-800:]
+    want, got = p.stdout, open(out, "rb").read()
+    assert len(want) > 1000
+    assert got == want
