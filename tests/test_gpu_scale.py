@@ -125,12 +125,13 @@ def test_spanning_deletions_at_cohort_scale(tmp_path):
     compare_with_reference(tmp_path, dd, n_intervals=8)
 
 
-@pytest.mark.parametrize("deletions", [False, True], ids=["plain", "deletions"])
-def test_broad_gvcf_file_of_a_synthetic_cohort(tmp_path, deletions):
+@pytest.mark.parametrize("deletions,writer_args", [(False, {}), (True, {}), (True, dict(compress=True, n_fragments=5, dup_every=9))],
+                         ids=["plain", "deletions", "deletions-5-gzip-fragments"])
+def test_broad_gvcf_file_of_a_synthetic_cohort(tmp_path, deletions, writer_args):
     """tool against tool on the same on-disk array: the unmodified `gt_mpi_gather --produce-Broad-GVCF -O bu` and
     `gt_gpu_gather --produce-Broad-GVCF` (header generated in-library, reference bases from the indexed FASTA) write the same
     BCF file, byte for byte -- 600 samples, 150 candidate sites, with GQ / MIN_DP / DP; once with a third of the variant calls
-    turned into deletions (spanning `*` alleles, min-PL GT off)"""
+    turned into deletions (spanning `*` alleles, min-PL GT off), once more from five GZIP fragments with re-imported calls"""
     from tools import gdbsyn_deletions
     ref_tool = os.path.join(REPO, "oracle", "_ref", "bin", "gt_mpi_gather")
     if not os.path.exists(ref_tool):
@@ -139,7 +140,7 @@ def test_broad_gvcf_file_of_a_synthetic_cohort(tmp_path, deletions):
     if deletions:
         d = gdbsyn_deletions.with_deletions(d, share=0.3)
     ws = str(tmp_path / "ws")
-    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000, **writer_args)
     lo, hi = d["col_range"]
     q = tiledb_writer.write_query_json(os.path.join(ws, "q.json"), info, lo, hi, attributes=("REF", "ALT", "GT", "AD", "PL", "GQ", "MIN_DP", "DP"))
     ref_out, our_out = str(tmp_path / "ref.bcf"), str(tmp_path / "ours.bcf")
