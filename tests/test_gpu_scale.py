@@ -248,3 +248,30 @@ def test_tool_commands_on_a_cohort_with_deletions(tmp_path, flag):
     want, got = p.stdout, open(out, "rb").read()
     assert len(want) > 1000
     assert got == want
+
+
+@pytest.mark.parametrize("shape", [dict(n_samples=300, a_pool=64, sites=(100, 160)), dict(n_samples=5000, a_pool=8, sites=(300, 318))],
+                         ids=["64-allele-pool", "5000-samples"])
+def test_broad_gvcf_file_wide_sites_and_wide_cohorts(tmp_path, shape):
+    """whole BCF files tool against tool where (i) sites carry 45-60 merged alleles (PL dropped above 50 ALT alleles, the generic
+    remap kernel) and (ii) the cohort is wide enough (>= 4096 samples) for the signature-row remap path, both with deletions"""
+    from tools import gdbsyn_deletions
+    ref_tool = os.path.join(REPO, "oracle", "_ref", "bin", "gt_mpi_gather")
+    if not os.path.exists(ref_tool):
+        pytest.skip("oracle/_ref is not built")
+    d = gdbsyn.generate(n_samples=shape["n_samples"], n_sites=10000, spacing=100, p_var=0.15, a_pool=shape["a_pool"],
+                        site_lo=shape["sites"][0], site_hi=shape["sites"][1], with_fixed=True)
+    d = gdbsyn_deletions.with_deletions(d, share=0.25)
+    ws = str(tmp_path / "ws")
+    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+    lo, hi = d["col_range"]
+    q = tiledb_writer.write_query_json(os.path.join(ws, "q.json"), info, lo, hi, attributes=("REF", "ALT", "GT", "AD", "PL", "GQ", "MIN_DP"))
+    ref_out, our_out = str(tmp_path / "ref.bcf"), str(tmp_path / "ours.bcf")
+    with open(ref_out, "wb") as f:
+        p = subprocess.run([ref_tool, "-j", q, "--produce-Broad-GVCF", "-O", "bu"], stdout=f, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr[-800:]
+    p2 = subprocess.run([OURS, "-j", q, "--produce-Broad-GVCF", "-o", our_out], capture_output=True, text=True)
+    assert p2.returncode == 0, p2.stderr[-800:]
+    want, got = open(ref_out, "rb").read(), open(our_out, "rb").read()
+    assert len(want) > 100000
+    assert len(got) == len(want) and got == want
