@@ -303,7 +303,11 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
   const auto& plain = qc.get_plain_fields();
   auto remapped_index = [&](const std::string& name) -> int { for (unsigned i = 0; i < n_remapped; ++i) if (qc.get_remapped_field_name(i) == name) return (int)i; return -1; };
   // FORMAT fields: GT first (htslib moves it to the front, vcf.c:3670-3676), then query order, DP (from DP_FORMAT) last
-  if (remapped_index("GT") >= 0) m_FORMAT_fields_vec.push_back({"GT", key_of("GT"), remapped_index("GT")});
+  // (the kernels remap GT whenever the array has it; the record only carries it when the query does -- listed, or pulled in by a
+  // genotype-dependent field, query_variants.cc:617-623)
+  const auto& ordered_attrs = qc.get_ordered_query_attributes();
+  const bool gt_queried = std::find(ordered_attrs.begin(), ordered_attrs.end(), "GT") != ordered_attrs.end();
+  if (remapped_index("GT") >= 0 && gt_queried) m_FORMAT_fields_vec.push_back({"GT", key_of("GT"), remapped_index("GT")});
   int dp_format_plain = -1;
   for (auto& name : qc.get_ordered_query_attributes()) {   // the order the reference's bookkeeping leaves (END, REF, ALT swapped to the front)
     if (name == "GT") continue;

@@ -275,3 +275,38 @@ def test_broad_gvcf_file_wide_sites_and_wide_cohorts(tmp_path, shape):
     want, got = open(ref_out, "rb").read(), open(our_out, "rb").read()
     assert len(want) > 100000
     assert len(got) == len(want) and got == want
+
+
+ATTRIBUTE_SETS = {
+    "PL_only": ("REF", "ALT", "PL"),
+    "AD_GQ": ("REF", "ALT", "AD", "GQ"),
+    "GT_only": ("GT",),
+    "no_alleles_listed": ("GT", "AD", "PL", "MIN_DP"),
+    "MIN_DP_GQ_only": ("GQ", "MIN_DP"),
+    "PL_before_GT": ("PL", "AD", "GT", "REF", "ALT"),
+}
+
+
+@pytest.mark.parametrize("which", sorted(ATTRIBUTE_SETS))
+def test_broad_gvcf_file_attribute_sets(tmp_path, which):
+    """what the query lists decides which kernels are instantiated (with / without GT, one / two remapped fields) and which
+    attributes the bookkeeping adds on its own (END, REF / ALT for allele-dependent fields, GT for genotype-dependent ones) and in
+    which order the record's fields come: a few attribute lists, tool against tool on the cohort with deletions"""
+    from tools import gdbsyn_deletions
+    ref_tool = os.path.join(REPO, "oracle", "_ref", "bin", "gt_mpi_gather")
+    if not os.path.exists(ref_tool):
+        pytest.skip("oracle/_ref is not built")
+    d = gdbsyn_deletions.with_deletions(gdbsyn.generate(n_samples=400, n_sites=10000, spacing=100, p_var=0.12, a_pool=6, site_lo=50, site_hi=130, with_fixed=True), share=0.3)
+    ws = str(tmp_path / "ws")
+    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+    lo, hi = d["col_range"]
+    q = tiledb_writer.write_query_json(os.path.join(ws, "q.json"), info, lo, hi, attributes=ATTRIBUTE_SETS[which])
+    ref_out, our_out = str(tmp_path / "ref.bcf"), str(tmp_path / "ours.bcf")
+    with open(ref_out, "wb") as f:
+        p = subprocess.run([ref_tool, "-j", q, "--produce-Broad-GVCF", "-O", "bu"], stdout=f, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr[-800:]
+    p2 = subprocess.run([OURS, "-j", q, "--produce-Broad-GVCF", "-o", our_out], capture_output=True, text=True)
+    assert p2.returncode == 0, p2.stderr[-800:]
+    want, got = open(ref_out, "rb").read(), open(our_out, "rb").read()
+    assert len(want) > 10000
+    assert len(got) == len(want) and got == want
