@@ -161,6 +161,8 @@ QUERY_VARIANTS = {
     "row_subset": {"query_row_ranges": [{"range_list": [{"low": 7, "high": 211}, {"low": 400, "high": 590}]}]},
     "two_intervals": "two_intervals",
     "max_alt_2": {"max_diploid_alt_alleles_that_can_be_genotyped": 2, "produce_GT_field": True},
+    "inside_deletions": "inside_deletions",      # intervals that begin one and three bases into the deletions of a site
+    "paged_small_windows": "paged",              # a 150 KB output buffer (overflow / resume all the way) over 3-site front windows
 }
 
 
@@ -181,9 +183,16 @@ def test_broad_gvcf_file_query_options_on_a_cohort_with_deletions(tmp_path, vari
     qf = tiledb_writer.write_query_json(os.path.join(ws, "q.json"), info, lo, hi, attributes=("REF", "ALT", "GT", "AD", "PL", "GQ", "MIN_DP"))
     q = json.load(open(qf))
     opt = QUERY_VARIANTS[variant]
+    extra, env = [], None
     if opt == "two_intervals":
         mid = (lo + hi) // 2
         q["query_column_ranges"] = [{"range_list": [{"low": lo + 950, "high": mid - 333}, {"low": mid + 1, "high": hi - 1200}]}]
+    elif opt == "inside_deletions":
+        c = 1000 + 100 * 90           # the column of candidate site 90 (first_col + site * spacing)
+        q["query_column_ranges"] = [{"range_list": [{"low": c + 1, "high": c + 2}, {"low": c + 3, "high": c + 450}, {"low": c + 501, "high": c + 501}]}]
+        q["produce_GT_field"] = True
+    elif opt == "paged":
+        extra, env = ["-p", "150000"], dict(os.environ, GDBGPU_FRONT_BYTES=str(24 * 600 * 3))
     else:
         q.update(opt)
     json.dump(q, open(qf, "w"))
@@ -191,7 +200,7 @@ def test_broad_gvcf_file_query_options_on_a_cohort_with_deletions(tmp_path, vari
     with open(ref_out, "wb") as f:
         p = subprocess.run([ref_tool, "-j", qf, "--produce-Broad-GVCF", "-O", "bu"], stdout=f, stderr=subprocess.PIPE, text=True)
     assert p.returncode == 0, p.stderr[-800:]
-    p2 = subprocess.run([OURS, "-j", qf, "--produce-Broad-GVCF", "-o", our_out], capture_output=True, text=True)
+    p2 = subprocess.run([OURS, "-j", qf, "--produce-Broad-GVCF", "-o", our_out] + extra, capture_output=True, text=True, env=env)
     assert p2.returncode == 0, p2.stderr[-800:]
     want, got = open(ref_out, "rb").read(), open(our_out, "rb").read()
     assert len(want) > 10000
