@@ -319,3 +319,47 @@ def test_broad_gvcf_file_attribute_sets(tmp_path, which):
     want, got = open(ref_out, "rb").read(), open(our_out, "rb").read()
     assert len(want) > 10000
     assert len(got) == len(want) and got == want
+
+
+@pytest.mark.parametrize("flag", ["--range-query", "--print-calls", "--print-AC", "--produce-interesting-positions"])
+def test_tool_commands_row_subset_and_intervals(tmp_path, flag):
+    """the same commands with a row subset and three query intervals (one of them a single position inside a deletion)"""
+    import json
+    from tools import gdbsyn_deletions
+    ref_tool = os.path.join(REPO, "oracle", "_ref", "bin", "gt_mpi_gather")
+    if not os.path.exists(ref_tool):
+        pytest.skip("oracle/_ref is not built")
+    d = gdbsyn_deletions.with_deletions(gdbsyn.generate(n_samples=250, n_sites=10000, spacing=100, p_var=0.15, a_pool=4, site_lo=20, site_hi=60, with_fixed=True), share=0.3)
+    ws = str(tmp_path / "ws")
+    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+    lo, hi = d["col_range"]
+    qf = tiledb_writer.write_query_json(os.path.join(ws, "q.json"), info, lo, hi, attributes=("REF", "ALT", "GT", "AD", "PL", "GQ"))
+    q = json.load(open(qf))
+    c = 1000 + 100 * 40
+    q["query_column_ranges"] = [{"range_list": [{"low": lo + 333, "high": c - 77}, {"low": c + 1, "high": c + 1}, {"low": c + 2, "high": hi - 500}]}]
+    q["query_row_ranges"] = [{"range_list": [{"low": 3, "high": 101}, {"low": 200, "high": 249}]}]
+    json.dump(q, open(qf, "w"))
+    p = subprocess.run(["stdbuf", "-o0", ref_tool, "-j", qf] + ([] if flag == "--range-query" else [flag]), capture_output=True)
+    assert p.returncode == 0, p.stderr.decode(errors="replace")[-800:]
+    out = str(tmp_path / "ours.txt")
+    p2 = subprocess.run([OURS, "-j", qf, "-o", out, flag], capture_output=True, text=True)
+    assert p2.returncode == 0, p2.stderr[-800:]
+    assert len(p.stdout) > 1000 and open(out, "rb").read() == p.stdout
+
+
+def test_jni_stream_of_a_cohort_with_deletions(tmp_path):
+    """GenomicsDBBCFGenerator of the mirror pulled in 64 KB reads with a 1 MB buffer (what the JNI methods sit on) over the
+    600-sample cohort with deletions: the stream is the reference's BCF under the JNI conventions, header first"""
+    from tools import gdbsyn_deletions
+    d = gdbsyn_deletions.with_deletions(gdbsyn.generate(n_samples=600, n_sites=10000, spacing=100, p_var=0.12, a_pool=6, site_lo=50, site_hi=170, with_fixed=True), share=0.3)
+    ws = str(tmp_path / "ws")
+    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+    lo, hi = d["col_range"]
+    qf = tiledb_writer.write_query_json(os.path.join(ws, "q.json"), info, lo, hi, attributes=("REF", "ALT", "GT", "AD", "PL", "GQ", "MIN_DP"))
+    p = subprocess.run([REF, "-j", qf, "--mode", "bcf-java"], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode(errors="replace")[-800:]
+    out = str(tmp_path / "ours.bcf")
+    p2 = subprocess.run([OURS, "-j", qf, "--bcf-generator", "65536", "-p", "1000000", "--htsjdk-conventions", "-o", out], capture_output=True, text=True)
+    assert p2.returncode == 0, p2.stderr[-800:]
+    got = open(out, "rb").read()
+    assert len(got) == len(p.stdout) and got == p.stdout
