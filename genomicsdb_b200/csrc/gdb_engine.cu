@@ -639,7 +639,6 @@ struct gdbgpu_scan {
   InfoSet info{};   // INFO scalars to combine + the DP rule's fields (GDBGPU_SCAN_BCF_FORMAT)
   EsumSet esum{};   // vector fields combined with an element-wise sum
   uint32_t cap_allele_recs = 0, cap_allele_bytes = 0, cap_lut = 0;
-  uint64_t avg_site_bytes = 0;
   int n_out = 0;
   // columnar-iterator view of the query (gdbgpu_scan_cells*): the device list and what was copied out for the caller
   bool site_stats = false, summary_only = false;
@@ -961,7 +960,6 @@ void compute_batch(gdbgpu_scan* s, BatchBuffers& bb, uint64_t first_site, uint32
       for (int o = 0; o < n_out; ++o) { bb.h_stride[o].push_back(st[o]); bb.h_base[o].push_back((bb.h_base[o][i] + (uint64_t)st[o] * S.nq + 3) & ~3ull); }   // 16-byte aligned sites
       bytes += site_bytes; alg_bytes += site_alg; lut_words += (uint64_t)bb.h_sites[i].max_ain * S.nq; keep = i + 1;
     }
-    s->avg_site_bytes = std::max<uint64_t>(1, bytes / keep);
     // split the batch: the tile kernels take every ordinary site, the generic kernel the pathological ones.  k_remap_tile
     // remaps the non-trivial calls of its sites itself (phase C); k_remap_nt only serves the copy-through sites
     // GDBGPU_K5 selects the remap kernel of the remapped sites: "mix" (default: k_remap_mix, tile blocks and nt blocks in one

@@ -393,7 +393,6 @@ __global__ void __launch_bounds__(UNION_THREADS, 4) k_union(const __grid_constan
 
   const uint32_t js = blockIdx.x;
   const uint64_t j = B.first_site + js;
-  const int64_t b = S.site_begin[j];
   const int32_t* live = B.live + (uint64_t)js * S.nq;
   const uint32_t* agg = B.agg + (uint64_t)js * AGG_WORDS;
   const int tid = threadIdx.x;
