@@ -11,7 +11,8 @@
 //     (RFC 1951 3.2.2; the structure of zlib's contrib/puff/puff.c, a public-domain reference decoder that is not part of
 //     /root/reference) for the rare longer codes.
 //   * The compressed bytes are staged through shared memory 256 bytes at a time by coalesced loads, one block ahead.
-//   * The most recent 8 KB of output live in a shared-memory ring.  An LZ77 match is copied by the whole warp (258 bytes = 9
+//   * The most recent 2 KB of output (GDB_INFLATE_WIN; 8 KB and 4 KB rings were slower: 20.0 / 16.4 / 14.2 ms on the open benchmark,
+//     occupancy 16 / 24 / 32 warps per SM) live in a shared-memory ring.  An LZ77 match is copied by the whole warp (258 bytes = 9
 //     strided trips, overlapping matches by index arithmetic), from the ring when its source is still there, from the bytes
 //     already flushed to HBM otherwise; the ring leaves for HBM in 512-byte pieces, 16 bytes per lane, aligned to the output
 //     address (the ring index is skewed by the output pointer's misalignment so that both sides are 16-byte aligned).
