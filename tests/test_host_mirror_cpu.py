@@ -40,3 +40,27 @@ def test_header_dictionary_vid_mapping_and_query_json(tmp_path):
     assert (got["PL_length"], got["MQ_op"], got["DP_FORMAT_is_format"]) == ("G", "median", 1)
     assert got["intervals"] == sorted(case["query_column_ranges"])          # sorted like the reference (variant_query_config.cc:69-73)
     assert got["n_rows"] == 4 and got["produce_GT"] == 1 and got["n_attributes"] == len(case["attributes"])
+
+
+def test_vid_mapping_of_multidimensional_and_tuple_fields(tmp_path):
+    """length / type / vcf_delimiter given as lists (vid_mapper.cc, genomicsdb_multid_vector_field.h): a 2-D field keeps its
+    per-dimension descriptors and delimiters; a field of tuples is composite and comes with one flattened attribute per tuple
+    element (<name>_tuple_element_<j>, as the array's schema names them) that goes by its parent's VCF name"""
+    import __graft_entry__ as g
+    lib = g.build_gpu_lib()
+    exe = str(tmp_path / "vid_2d_probe")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(REPO, "tests", "cpp", "vid_2d_probe.cc"), "-o", exe,
+                           "-I" + os.path.join(REPO, "include"), "-L" + os.path.dirname(lib), "-lgdbgpu", "-Wl,-rpath," + os.path.dirname(lib)])
+    names = ["AS_RAW_MQ", "AS_RAW_MQRankSum", "AS_RAW_MQRankSum_tuple_element_0", "AS_RAW_MQRankSum_tuple_element_1", "PL", "no_such"]
+    out = subprocess.run([exe, os.path.join(GOLDEN, "inputs", "vid_all_asa.json")] + names, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got = json.loads(out.stdout)
+    mq = got["AS_RAW_MQ"]
+    assert (mq["multid"], mq["composite"], mq["type"], mq["dims"], mq["delims"], mq["op"], mq["dim0_allele"], mq["allele_dependent"]) == \
+           (1, 0, "float", ["R", "var"], "|,", "element_wise_sum", 1, 0)
+    rs = got["AS_RAW_MQRankSum"]
+    assert (rs["multid"], rs["composite"], rs["op"], rs["vcf_name"]) == (1, 1, "histogram_sum", "AS_RAW_MQRankSum")
+    e0, e1 = got["AS_RAW_MQRankSum_tuple_element_0"], got["AS_RAW_MQRankSum_tuple_element_1"]
+    assert (e0["type"], e0["parent"], e0["tuple_index"], e0["vcf_name"], e0["composite"], e0["multid"]) == ("float", "AS_RAW_MQRankSum", 0, "AS_RAW_MQRankSum", 0, 1)
+    assert (e1["type"], e1["parent"], e1["tuple_index"], e1["dims"], e1["delims"]) == ("int", "AS_RAW_MQRankSum", 1, ["R", "var"], "|,")
+    assert got["PL"]["multid"] == 0 and got["PL"]["allele_dependent"] == 1 and got["no_such"] is None
