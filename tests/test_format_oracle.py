@@ -153,3 +153,40 @@ def test_info_concatenate_matches_reference_bcf():
                 assert format_blocks.enc_info_vector(vecs[name], elem) == format_blocks.enc_size(n, bt) + raw
                 n_checked += 1
     assert n_checked == 1
+
+
+@pytest.mark.parametrize("produce_gt", [False, True], ids=["no-GT", "GT"])
+def test_format_blocks_match_reference_bcf_on_a_cohort_with_deletions(tmp_path, produce_gt):
+    """the two restatements chained (combine_oracle.c -> format_blocks.py) against the unmodified reference's BCF on a synthetic
+    cohort whose variant calls are deletions to a third (tools/gdbsyn_deletions.py): GT / AD / PL blocks of every record"""
+    import json
+    import subprocess
+    from conftest import REPO
+    from tools import gdbsyn, gdbsyn_deletions, tiledb_writer
+    ref_tool = os.path.join(REPO, "oracle", "_ref", "bin", "gt_mpi_gather")
+    if not os.path.exists(ref_tool):
+        pytest.skip("oracle/_ref is not built")
+    d = gdbsyn_deletions.with_deletions(gdbsyn.generate(n_samples=70, n_sites=90, spacing=100, p_var=0.2, a_pool=5, with_fixed=True), share=0.35)
+    info = tiledb_writer.write_array(str(tmp_path / "ws"), "syn", d)
+    lo, hi = d["col_range"]
+    qf = tiledb_writer.write_query_json(str(tmp_path / "q.json"), info, lo, hi, attributes=("REF", "ALT", "GT", "AD", "PL"))
+    if produce_gt:
+        q = json.load(open(qf))
+        q["produce_GT_field"] = True
+        json.dump(q, open(qf, "w"))
+    bcf = str(tmp_path / "ref.bcf")
+    with open(bcf, "wb") as f:
+        p = subprocess.run([ref_tool, "-j", qf, "--produce-Broad-GVCF", "-O", "bu"], stdout=f, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr[-600:]
+    _, samples, recs = bcf_reader.read_bcf(bcf)
+    cols = oracle.load_columns(info["workspace"], "syn", info["vid"], ["END", "REF", "ALT", "GT", "AD", "PL"])
+    dump, n = oracle.combine_query(cols, [[lo, hi]])
+    names, sites = oracle.parse_dump(dump)
+    assert len(recs) == len(sites) == n and n > 200
+    rows = list(range(len(samples)))
+    for rec, site in zip(recs, sites):
+        want = {k: v for k, v in rec["fmt"].items() if k in ("GT", "AD", "PL")}
+        got = format_blocks.site_blocks(site, ["GT", "AD", "PL"], rows, {"AD": "int", "PL": "int"}, False, produce_gt)
+        assert sorted(got) == sorted(want), (site["begin"], sorted(got), sorted(want))
+        for k, (bt, nps, data, hdr) in want.items():
+            assert (got[k][0], got[k][1]) == (bt, nps) and got[k][2] == data, (site["begin"], k)
