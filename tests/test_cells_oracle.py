@@ -89,3 +89,33 @@ def test_left_cells_come_first_ordered_by_begin_then_row():
     assert cells == [(3, 0, 5, 20), (2, 2, 10, 10)]
     cells, n_left = cells_oracle.iterate(row, col, end, [0, 1, 2])
     assert n_left == 0 and [c[0] for c in cells] == [0, 1, 2]
+
+
+def test_restatement_matches_the_reference_tool_on_a_cohort_with_deletions(tmp_path):
+    """the iterator's order, the histogram and the allele counts of a mid-array interval of a synthetic cohort whose variant calls
+    are deletions to a third (tools/gdbsyn_deletions.py: calls that reach into the interval from the left, END duplicates,
+    normalised deletion alleles) against the unmodified reference tool run here"""
+    import subprocess
+    from conftest import REPO
+    from tools import gdbsyn, gdbsyn_deletions, tiledb_writer
+    ref_tool = os.path.join(REPO, "oracle", "_ref", "bin", "gt_mpi_gather")
+    if not os.path.exists(ref_tool):
+        pytest.skip("oracle/_ref is not built")
+    d = gdbsyn_deletions.with_deletions(gdbsyn.generate(n_samples=120, n_sites=80, spacing=100, p_var=0.2, a_pool=5, with_fixed=True), share=0.35)
+    info = tiledb_writer.write_array(str(tmp_path / "ws"), "syn", d)
+    lo, hi = d["col_range"]
+    q_lo, q_hi = 1000 + 100 * 20 + 1, hi - 1500      # begins one base into the deletions of site 20
+    qf = tiledb_writer.write_query_json(str(tmp_path / "q.json"), info, q_lo, q_hi, attributes=("REF", "ALT", "GT"))
+    run = lambda flag: subprocess.run(["stdbuf", "-o0", ref_tool, "-j", qf, flag], capture_output=True, check=True).stdout.decode()
+    arr = tiledb_fragment.Array(info["workspace"], "syn")
+    end = arr.fixed("END").reshape(-1).astype(np.int64)
+    cells, n_left = cells_oracle.iterate(arr.row, arr.col, end, list(range(120)), q_lo, q_hi)
+    assert n_left > 100 and len(cells) > 1000
+    ref, alt = var_strings(arr, "REF"), var_strings(arr, "ALT")
+    got = ["%d,%d,%d,%s,%s" % (r, b, e, ref(i), alt(i)) for i, r, b, e in cells]
+    want = [",".join(l.split(",")[:5]) for l in run("--print-csv").splitlines()]
+    assert got == want
+    h, n_bins = cells_oracle.histogram(cells, 0, 4000000000, 100)
+    assert cells_oracle.histogram_text(h, n_bins, 0, 100) == run("--produce-histogram")
+    goff, gval = arr.var("GT")
+    assert cells_oracle.allele_counts_text(cells_oracle.allele_counts(cells, ref, alt, lambda i: gval[goff[i]:goff[i + 1]], 1)) == run("--print-AC")
