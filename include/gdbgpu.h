@@ -288,7 +288,10 @@ int gdbgpu_scan_get_info(const gdbgpu_scan* scan, gdbgpu_scan_info* info);
 /* Produces the next <= max_sites sites whose remapped output fits max_bytes (0 = engine default); n_sites==0 at the end.
  * The batch stays valid until the next call on the same scan.  Unless GDBGPU_SCAN_NO_PREFETCH is set the engine starts
  * computing the following batch (same limits) before it returns, so its kernels overlap this batch's copy to the host.  Re-entrant like the reference's overflow/resume
- * protocol (query_variants.cc:305,415,460-475): the caller drains a batch, then asks for the next. */
+ * protocol (query_variants.cc:305,415,460-475): the caller drains a batch, then asks for the next.
+ * The interval sweep, the per-site allele union and the allele verification run once per WINDOW of consecutive sites (as many as
+ * GDBGPU_FRONT_BYTES of device memory hold at 24 bytes per (site, query row); default 6 GiB), the batches are cut from it: a batch
+ * never spans two windows, so it may hold fewer sites than the limits allow; allele_first indexes the window's allele pool. */
 int gdbgpu_scan_next_batch(gdbgpu_scan* scan, uint32_t max_sites, uint64_t max_bytes, gdbgpu_batch* batch);
 /* Rewind to site idx (resume after a consumer-side overflow in the middle of a batch). */
 int gdbgpu_scan_seek(gdbgpu_scan* scan, uint64_t site_idx);
