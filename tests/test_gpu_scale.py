@@ -163,6 +163,8 @@ QUERY_VARIANTS = {
     "max_alt_2": {"max_diploid_alt_alleles_that_can_be_genotyped": 2, "produce_GT_field": True},
     "inside_deletions": "inside_deletions",      # intervals that begin one and three bases into the deletions of a site
     "paged_small_windows": "paged",              # a 150 KB output buffer (overflow / resume all the way) over 3-site front windows
+    "scan_full": "scan_full",                    # no query_column_ranges: the whole array
+    "left_and_right_of_the_data": "outside",     # intervals that hold no call: header-only file
 }
 
 
@@ -191,6 +193,11 @@ def test_broad_gvcf_file_query_options_on_a_cohort_with_deletions(tmp_path, vari
         c = 1000 + 100 * 90           # the column of candidate site 90 (first_col + site * spacing)
         q["query_column_ranges"] = [{"range_list": [{"low": c + 1, "high": c + 2}, {"low": c + 3, "high": c + 450}, {"low": c + 501, "high": c + 501}]}]
         q["produce_GT_field"] = True
+    elif opt == "scan_full":
+        del q["query_column_ranges"]
+        q["scan_full"] = True
+    elif opt == "outside":
+        q["query_column_ranges"] = [{"range_list": [{"low": 10, "high": 500}, {"low": hi + 5000, "high": hi + 9000}]}]
     elif opt == "paged":
         extra, env = ["-p", "150000"], dict(os.environ, GDBGPU_FRONT_BYTES=str(24 * 600 * 3))
     else:
@@ -203,7 +210,7 @@ def test_broad_gvcf_file_query_options_on_a_cohort_with_deletions(tmp_path, vari
     p2 = subprocess.run([OURS, "-j", qf, "--produce-Broad-GVCF", "-o", our_out] + extra, capture_output=True, text=True, env=env)
     assert p2.returncode == 0, p2.stderr[-800:]
     want, got = open(ref_out, "rb").read(), open(our_out, "rb").read()
-    assert len(want) > 10000
+    assert len(want) > (1000 if opt == "outside" else 10000)
     assert len(got) == len(want) and got == want
 
 
