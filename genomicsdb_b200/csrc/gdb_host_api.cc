@@ -111,7 +111,9 @@ void VariantQueryConfig::read_from_file(const std::string& filename, int rank) {
   if (!attrs) attrs = d.find("query_attributes");
   if (attrs) { attributes_.clear(); for (auto& x : attrs->arr) attributes_.push_back(x.str); }
   intervals_.clear();
-  bool scan_full = d.has("scan_full") && d.at("scan_full").as_bool();
+  // json_config.cc:253-260: the PRESENCE of "scan_full" (whatever its value) makes the query the whole array -- every column and
+  // every row; "query_column_ranges" and "query_row_ranges" beside it are not read
+  const bool scan_full = d.has("scan_full");
   if (!scan_full) if (const JsonValue* q = d.find("query_column_ranges")) {
     const JsonValue& mine = per_rank(*q);
     auto add_item = [&](const JsonValue& it) {
@@ -123,7 +125,7 @@ void VariantQueryConfig::read_from_file(const std::string& filename, int rank) {
     else if (mine.type == JsonValue::ARR) for (auto& it : mine.arr) add_item(it);
   }
   rows_.clear();
-  if (const JsonValue* q = d.find("query_row_ranges")) {
+  if (!scan_full) if (const JsonValue* q = d.find("query_row_ranges")) {
     const JsonValue& mine = per_rank(*q);
     std::vector<int64_t> rows;
     auto add_item = [&](const JsonValue& it) {
