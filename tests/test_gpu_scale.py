@@ -165,6 +165,7 @@ QUERY_VARIANTS = {
     "paged_small_windows": "paged",              # a 150 KB output buffer (overflow / resume all the way) over 3-site front windows
     "scan_full": "scan_full",                    # no query_column_ranges: the whole array
     "left_and_right_of_the_data": "outside",     # intervals that hold no call: header-only file
+    "list_syntax_unsorted_overlapping": "lists",  # [[ [lo, hi], pos, ... ]] per-rank list syntax, unsorted, overlapping intervals
 }
 
 
@@ -196,6 +197,10 @@ def test_broad_gvcf_file_query_options_on_a_cohort_with_deletions(tmp_path, vari
     elif opt == "scan_full":
         del q["query_column_ranges"]
         q["scan_full"] = True
+    elif opt == "lists":
+        c = 1000 + 100 * 100
+        q["query_column_ranges"] = [[[c + 700, c + 1500], c - 350, [c - 900, c + 900], [c + 100, c + 100]]]
+        q["query_row_ranges"] = [[[100, 300], 7, [450, 599]]]
     elif opt == "outside":
         q["query_column_ranges"] = [{"range_list": [{"low": 10, "high": 500}, {"low": hi + 5000, "high": hi + 9000}]}]
     elif opt == "paged":
@@ -392,3 +397,23 @@ def test_hot_path_dump_row_subset_on_a_cohort_with_deletions(tmp_path, scan_full
     _md5_of([OURS, "-j", qf], got)
     assert ref[2] == 0 and got[2] == 0, (ref[3], got[3])
     assert ref[1] > 100000 and (got[0], got[1]) == (ref[0], ref[1])
+
+
+@pytest.mark.parametrize("flag", ["--print-calls", "--print-AC", "--range-query"])
+def test_tool_commands_scan_full(tmp_path, flag):
+    """the columnar commands over the whole array ("scan_full" in the query JSON)"""
+    from tools import gdbsyn_deletions
+    ref_tool = os.path.join(REPO, "oracle", "_ref", "bin", "gt_mpi_gather")
+    if not os.path.exists(ref_tool):
+        pytest.skip("oracle/_ref is not built")
+    d = gdbsyn_deletions.with_deletions(gdbsyn.generate(n_samples=120, n_sites=10000, spacing=100, p_var=0.15, a_pool=4, site_lo=20, site_hi=50, with_fixed=True), share=0.3)
+    ws = str(tmp_path / "ws")
+    info = tiledb_writer.write_array(ws, "syn", d, capacity=1000)
+    qf = tiledb_writer.write_query_json(os.path.join(ws, "q.json"), info, None, None, attributes=("REF", "ALT", "GT", "AD", "PL", "GQ"))
+    p = subprocess.run(["stdbuf", "-o0", ref_tool, "-j", qf] + ([] if flag == "--range-query" else [flag]), capture_output=True)
+    assert p.returncode == 0, p.stderr.decode(errors="replace")[-800:]
+    out = str(tmp_path / "ours.txt")
+    p2 = subprocess.run([OURS, "-j", qf, "-o", out, flag], capture_output=True, text=True)
+    assert p2.returncode == 0, p2.stderr[-800:]
+    # the range query walks the query's column intervals, and "scan_full" leaves none: an empty variant list
+    assert len(p.stdout) > (0 if flag == "--range-query" else 1000) and open(out, "rb").read() == p.stdout
