@@ -333,7 +333,8 @@ static void heap_down(op_t* o, int64_t i) {
   for (;;) { int64_t l = 2 * i + 1, r = l + 1, m = i;
     if (l < o->heap_n && o->calls[o->heap[l]].end < o->calls[o->heap[m]].end) m = l;
     if (r < o->heap_n && o->calls[o->heap[r]].end < o->calls[o->heap[m]].end) m = r;
-    if (m == i) break; heap_swap(o, m, i); i = m; }
+    if (m == i) break;
+    heap_swap(o, m, i); i = m; }
 }
 static void heap_push(op_t* o, int64_t q) { o->heap[o->heap_n] = q; o->calls[q].heap_pos = o->heap_n; heap_up(o, o->heap_n++); }
 static void heap_remove(op_t* o, int64_t pos) {
