@@ -94,62 +94,15 @@ const FieldInfo* VidMapper::get_field_info(const std::string& name) const {
 // ------------------------------------------------------------------------------------------------ VariantQueryConfig
 void VariantQueryConfig::add_column_interval_to_query(int64_t b, int64_t e) {
   intervals_.push_back({b, e});
-  std::sort(intervals_.begin(), intervals_.end());   // variant_query_config.cc:69-73
+  // variant_query_config.cc:32-35,69-73: ordered by begin alone, re-sorted after every addition (intervals that share a begin
+  // keep the order that leaves them in)
+  std::sort(intervals_.begin(), intervals_.end(), [](const std::pair<int64_t, int64_t>& x, const std::pair<int64_t, int64_t>& y) { return x.first < y.first; });
 }
 void VariantQueryConfig::set_rows_to_query(const std::vector<int64_t>& rows) {
   rows_ = rows;
   std::sort(rows_.begin(), rows_.end());             // variant_query_config.cc:60-67
 }
-// keys as parsed by the reference: src/main/cpp/src/config/json_config.cc:207-656
-void VariantQueryConfig::read_from_file(const std::string& filename, int rank) {
-  JsonValue d = gdb::json_parse_file(filename);
-  auto per_rank = [&](const JsonValue& v) -> const JsonValue& { return (v.type == JsonValue::ARR && !v.arr.empty()) ? v.arr[std::min<size_t>((size_t)rank, v.arr.size() - 1)] : v; };
-  if (const JsonValue* w = d.find("workspace")) workspace_ = per_rank(*w).str;
-  if (const JsonValue* a = d.find("array_name")) array_name_ = per_rank(*a).str;
-  else if (const JsonValue* a2 = d.find("array")) array_name_ = per_rank(*a2).str;
-  const JsonValue* attrs = d.find("attributes");
-  if (!attrs) attrs = d.find("query_attributes");
-  if (attrs) { attributes_.clear(); for (auto& x : attrs->arr) attributes_.push_back(x.str); }
-  intervals_.clear();
-  // json_config.cc:253-260: the PRESENCE of "scan_full" (whatever its value) makes the query the whole array -- every column and
-  // every row; "query_column_ranges" and "query_row_ranges" beside it are not read
-  const bool scan_full = d.has("scan_full");
-  if (!scan_full) if (const JsonValue* q = d.find("query_column_ranges")) {
-    const JsonValue& mine = per_rank(*q);
-    auto add_item = [&](const JsonValue& it) {
-      if (it.type == JsonValue::NUM) add_column_interval_to_query(it.as_int(), it.as_int());
-      else if (it.type == JsonValue::ARR && it.arr.size() == 2) add_column_interval_to_query(it.arr[0].as_int(), it.arr[1].as_int());
-      else if (it.type == JsonValue::OBJ && it.has("low")) add_column_interval_to_query(it.at("low").as_int(), it.at("high").as_int());
-    };
-    if (mine.type == JsonValue::OBJ && mine.has("range_list")) for (auto& it : mine.at("range_list").arr) add_item(it);
-    else if (mine.type == JsonValue::ARR) for (auto& it : mine.arr) add_item(it);
-  }
-  rows_.clear();
-  if (!scan_full) if (const JsonValue* q = d.find("query_row_ranges")) {
-    const JsonValue& mine = per_rank(*q);
-    std::vector<int64_t> rows;
-    auto add_item = [&](const JsonValue& it) {
-      if (it.type == JsonValue::NUM) rows.push_back(it.as_int());
-      else if (it.type == JsonValue::ARR && it.arr.size() == 2) for (int64_t r = it.arr[0].as_int(); r <= it.arr[1].as_int(); ++r) rows.push_back(r);
-      else if (it.type == JsonValue::OBJ && it.has("low")) for (int64_t r = it.at("low").as_int(); r <= it.at("high").as_int(); ++r) rows.push_back(r);
-    };
-    if (mine.type == JsonValue::OBJ && mine.has("range_list")) for (auto& it : mine.at("range_list").arr) add_item(it);
-    else if (mine.type == JsonValue::ARR) for (auto& it : mine.arr) add_item(it);
-    set_rows_to_query(rows);
-  }
-  if (const JsonValue* v = d.find("vid_mapping_file")) vid_ = VidMapper(per_rank(*v).str);
-  if (const JsonValue* v = d.find("callset_mapping_file")) callset_mapping_file_ = per_rank(*v).str;
-  if (vid_.is_initialized() && !callset_mapping_file_.empty() && !vid_.is_callset_mapping_initialized()) vid_.read_callsets_file(callset_mapping_file_);
-  if (const JsonValue* v = d.find("vcf_header_filename")) vcf_header_filename_ = per_rank(*v).str;
-  if (const JsonValue* v = d.find("reference_genome")) reference_genome_ = per_rank(*v).str;
-  if (const JsonValue* v = d.find("vcf_output_format")) vcf_output_format_ = v->str;
-  if (const JsonValue* v = d.find("segment_size")) segment_size_ = (size_t)v->as_int();
-  if (const JsonValue* v = d.find("max_diploid_alt_alleles_that_can_be_genotyped")) max_alt_ = (unsigned)v->as_int();
-  if (const JsonValue* v = d.find("produce_GT_with_min_PL_value_for_spanning_deletions")) min_pl_gt_ = v->as_bool();
-  if (const JsonValue* v = d.find("produce_GT_field")) produce_gt_ = v->as_bool();
-  if (const JsonValue* v = d.find("sites_only_query")) sites_only_ = v->as_bool();
-  if (const JsonValue* v = d.find("produce_FILTER_field")) produce_filter_ = v->as_bool();
-}
+// VariantQueryConfig::read_from_file: gdb_host_config.cc (with the loader's configuration)
 
 // ------------------------------------------------------------------------------------------------ operators
 // variant_operations.cc:362-378 -- the merge itself ran on the GPU (k_union); pick the results up

@@ -156,6 +156,8 @@ class VariantQueryConfig {
 
   const std::string& get_workspace(int = 0) const { return workspace_; }
   const std::string& get_array_name(int = 0) const { return array_name_; }
+  // the rank's ranges as the file lists them (GenomicsDBConfigBase::get_query_column_ranges): what the partition subset edits
+  const std::vector<std::pair<int64_t, int64_t>>& get_query_column_ranges(int = 0) const { return base_column_ranges_; }
   unsigned get_num_column_intervals() const { return (unsigned)intervals_.size(); }
   int64_t get_column_begin(unsigned i) const { return intervals_[i].first; }
   int64_t get_column_end(unsigned i) const { return intervals_[i].second; }
@@ -176,7 +178,7 @@ class VariantQueryConfig {
  private:
   friend class VariantQueryProcessor;
   std::string workspace_, array_name_;
-  std::vector<std::pair<int64_t, int64_t>> intervals_;
+  std::vector<std::pair<int64_t, int64_t>> intervals_, base_column_ranges_;
   std::vector<int64_t> rows_;
   std::vector<std::string> attributes_, ordered_attributes_;
   VidMapper vid_;

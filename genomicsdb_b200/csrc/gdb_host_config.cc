@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstring>
 #include <fstream>
+#include <iostream>
 #include <sstream>
 
 #include "gdb_host_api.h"
@@ -51,15 +52,116 @@ std::string per_rank_string(const JsonValue& v, int rank) {
   if (v.type == JsonValue::ARR) return v.arr.empty() ? std::string() : v.arr[std::min<size_t>((size_t)rank, v.arr.size() - 1)].str;
   return v.str;
 }
-// { "chr" : pos } / { "chr" : [ b, e ] } (json_config.cc extract_contig_interval_from_object)
+[[noreturn]] void bad_config(const std::string& what) { throw GenomicsDBGPUException(GDBGPU_ERR_ARG, what); }
+// genomicsdb_config_base.cc:36-57: 1-based contig positions -> 0-based columns; a begin past the contig is an error, an end
+// past it is cut to the contig's length
+std::pair<int64_t, int64_t> contig_positions_to_columns(const ContigInfo& c, int64_t begin, int64_t end) {
+  std::pair<int64_t, int64_t> r(std::min(begin, end), std::max(begin, end));
+  if (r.first > c.length) bad_config("Position " + std::to_string(r.first) + " queried for contig " + c.name + " which is of length " + std::to_string(c.length) + "; queried position is past end of contig");
+  if (r.second > c.length) {
+    std::cerr << "WARNING: position " << r.second << " queried for contig " << c.name << " which is of length " << c.length << "; queried interval is past end of contig, truncating to contig length";
+    r.second = c.length;
+  }
+  r.first += c.tiledb_column_offset - 1;
+  r.second += c.tiledb_column_offset - 1;
+  return r;
+}
+const ContigInfo& contig_named(const VidMapper& vid, const std::string& name) {
+  const ContigInfo* c = vid.get_contig_info(name);
+  if (!c) bad_config("JSONConfigBase::read_from_file: Invalid contig name : " + name);
+  return *c;
+}
+// { "chr" : pos } / { "chr" : [ b, e ] } / { "contig_position" : { "contig" : .., "position" : .. } }
+// (json_config.cc:55-98 extract_contig_interval_from_object)
 std::pair<int64_t, int64_t> contig_interval(const JsonValue& o, const VidMapper& vid) {
-  if (o.type != JsonValue::OBJ || o.obj.size() != 1) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "a contig position must be { \"<contig>\" : <position> }");
-  const ContigInfo* c = vid.get_contig_info(o.obj[0].first);
-  if (!c) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "unknown contig " + o.obj[0].first);
-  const JsonValue& v = o.obj[0].second;
-  if (v.type == JsonValue::ARR && v.arr.size() == 2) return {c->tiledb_column_offset + v.arr[0].as_int() - 1, c->tiledb_column_offset + v.arr[1].as_int() - 1};
-  if (v.type == JsonValue::NUM) return {c->tiledb_column_offset + v.as_int() - 1, c->tiledb_column_offset + v.as_int() - 1};
-  return {c->tiledb_column_offset, c->tiledb_column_offset + c->length - 1};
+  if (o.type != JsonValue::OBJ || o.obj.size() != 1) bad_config("a contig position must be { \"<contig>\" : <position> } or { \"<contig>\" : [ <begin>, <end> ] }");
+  std::string name = o.obj[0].first;
+  const JsonValue* pos = &o.obj[0].second;
+  if (name == "contig_position") {
+    const JsonValue& d = *pos;
+    if (d.type != JsonValue::OBJ || d.obj.size() != 2 || !d.has("contig") || d.at("contig").type != JsonValue::STR || !d.has("position") || !d.at("position").is_int)
+      bad_config("\"contig_position\" must be { \"contig\" : <name>, \"position\" : <int> }");
+    name = d.at("contig").str;
+    pos = &d.at("position");
+  }
+  const ContigInfo& c = contig_named(vid, name);
+  if (pos->type == JsonValue::ARR) {
+    if (pos->arr.size() != 2 || !pos->arr[0].is_int || !pos->arr[1].is_int) bad_config("a contig interval must be [ <begin>, <end> ]");
+    return contig_positions_to_columns(c, pos->arr[0].as_int(), pos->arr[1].as_int());
+  }
+  if (!pos->is_int) bad_config("a contig position must be an integer");
+  return contig_positions_to_columns(c, pos->as_int(), pos->as_int());
+}
+// the protobuf-generated forms (json_config.cc:101-193 extract_interval_from_PB_struct_or_return_false)
+bool pb_interval(const JsonValue& o, const VidMapper& vid, std::pair<int64_t, int64_t>& r) {
+  if (o.type != JsonValue::OBJ) return false;
+  if (o.obj.size() == 2 && o.has("low") && o.has("high")) { r = {o.at("low").as_int(), o.at("high").as_int()}; return true; }
+  if (o.obj.size() != 1) return false;
+  if (const JsonValue* ci = o.find("column_interval")) {
+    if (ci->type != JsonValue::OBJ) return false;
+    const JsonValue* t = ci->find("column_interval");
+    if (t && t->type == JsonValue::OBJ && t->has("begin") && t->has("end")) { r = {t->at("begin").as_int(), t->at("end").as_int()}; return true; }
+    const JsonValue* g = ci->find("contig_interval");
+    if (g && g->type == JsonValue::OBJ && g->has("contig") && g->has("begin") && g->has("end")) {
+      r = contig_positions_to_columns(contig_named(vid, g->at("contig").str), g->at("begin").as_int(), g->at("end").as_int());
+      return true;
+    }
+    return false;
+  }
+  if (const JsonValue* co = o.find("column")) {
+    if (co->type != JsonValue::OBJ) return false;
+    const JsonValue* t = co->find("tiledb_column");
+    if (t && t->is_int) { r = {t->as_int(), t->as_int()}; return true; }
+    const JsonValue* g = co->find("contig_position");
+    if (g && g->type == JsonValue::OBJ && g->has("contig") && g->has("position")) {
+      const int64_t p = g->at("position").as_int();
+      r = contig_positions_to_columns(contig_named(vid, g->at("contig").str), p, p);
+      return true;
+    }
+  }
+  return false;
+}
+// "column_partitions" / "row_partitions": [ { "begin" : b [, "end" : e] [, "workspace" : .., "array" : ..] }, ... ]
+// (json_config.cc:341-418,472-531); a partition without a usable end stops where the next one, in begin order, starts
+void read_partitions(const JsonValue& list, bool columns, const VidMapper& vid, std::vector<std::pair<int64_t, int64_t>>& parts,
+                     std::vector<std::string>& workspaces, std::vector<std::string>& array_names) {
+  if (list.type != JsonValue::ARR) bad_config(columns ? "\"column_partitions\" must be a list" : "\"row_partitions\" must be a list");
+  const std::string ws0 = workspaces.size() == 1 ? workspaces[0] : "", an0 = array_names.size() == 1 ? array_names[0] : "";
+  const size_t n = list.arr.size();
+  parts.assign(n, {0, INT64_MAX - 1});
+  for (size_t i = 0; i < n; ++i) {
+    const JsonValue& p = list.arr[i];
+    if (p.type != JsonValue::OBJ || !p.has("begin")) bad_config("a partition needs \"begin\"");
+    const JsonValue& b = p.at("begin");
+    if (!(b.is_int || (columns && b.type == JsonValue::OBJ))) bad_config("a partition's \"begin\" must be an integer or a contig position");
+    parts[i].first = b.is_int ? b.as_int() : contig_interval(b, vid).first;
+    if (const JsonValue* e = p.find("end")) {
+      if (!(e->is_int || (columns && e->type == JsonValue::OBJ))) bad_config("a partition's \"end\" must be an integer or a contig position");
+      parts[i].second = e->is_int ? e->as_int() : contig_interval(*e, vid).first;
+    }
+    if (parts[i].first > parts[i].second) std::swap(parts[i].first, parts[i].second);
+    if (const JsonValue* w = p.find("workspace")) { if (workspaces.size() < n) workspaces.resize(n, ws0); workspaces[i] = w->str; }
+    if (p.has("array") && p.has("array_name")) bad_config("a partition names both \"array\" and \"array_name\"");
+    const JsonValue* a = p.find("array"); if (!a) a = p.find("array_name");
+    if (a) { if (array_names.size() <= n) array_names.resize(n, an0); array_names[i] = a->str; }
+  }
+  std::vector<size_t> order(n);
+  for (size_t i = 0; i < n; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](size_t x, size_t y) { return parts[x].first < parts[y].first; });
+  for (size_t k = 0; k + 1 < n; ++k) {
+    auto& cur = parts[order[k]]; const auto& nxt = parts[order[k + 1]];
+    if (cur.first == nxt.first) bad_config(columns ? "Cannot have two column partitions with the same begin value" : "Cannot have two row partitions with the same begin value");
+    if (cur.second >= nxt.first) cur.second = nxt.first - 1;
+  }
+}
+// one name for all ranks, or a list with one per rank (json_config.cc:207-250,560-575)
+std::string string_of_rank(const JsonValue& v, int rank, const char* key) {
+  if (v.type == JsonValue::ARR) {
+    if (rank < 0 || (size_t)rank >= v.arr.size() || v.arr[rank].type != JsonValue::STR) bad_config(std::string("\"") + key + "\" holds no string for rank " + std::to_string(rank));
+    return v.arr[rank].str;
+  }
+  if (v.type != JsonValue::STR) bad_config(std::string("\"") + key + "\" must be a string or a list of strings");
+  return v.str;
 }
 }  // namespace
 
@@ -76,34 +178,12 @@ void GenomicsDBImportConfig::read_from_file(const std::string& filename, const i
   const JsonValue* an = d.find("array"); if (!an) an = d.find("array_name");
   if (an) { if (an->type == JsonValue::ARR) for (auto& x : an->arr) array_names_.push_back(x.str); else array_names_.push_back(an->str); }
   partitions_.clear(); partitions_specified_ = false;
+  if (!d.has("size_per_column_partition")) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "the loader configuration has no \"size_per_column_partition\"");   // json_config.cc:718-721
   if (row_based_) { if (!d.has("row_partitions")) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "row based partitioning without \"row_partitions\""); return; }
   const JsonValue* cp = d.find("column_partitions");
   if (!cp || cp->type != JsonValue::ARR) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "the loader configuration has no \"column_partitions\"");
   partitions_specified_ = true;
-  const std::string ws0 = workspaces_.size() == 1 ? workspaces_[0] : "", an0 = array_names_.size() == 1 ? array_names_[0] : "";
-  const size_t n = cp->arr.size();
-  partitions_.resize(n);
-  for (size_t i = 0; i < n; ++i) {
-    const JsonValue& p = cp->arr[i];
-    if (!p.has("begin")) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "a column partition needs \"begin\"");
-    const JsonValue& b = p.at("begin");
-    partitions_[i].first = b.type == JsonValue::NUM ? b.as_int() : contig_interval(b, vid_).first;
-    partitions_[i].second = INT64_MAX - 1;
-    if (const JsonValue* e = p.find("end")) partitions_[i].second = e->type == JsonValue::NUM ? e->as_int() : contig_interval(*e, vid_).first;
-    if (partitions_[i].first > partitions_[i].second) std::swap(partitions_[i].first, partitions_[i].second);
-    if (const JsonValue* w = p.find("workspace")) { if (workspaces_.size() < n) workspaces_.resize(n, ws0); workspaces_[i] = w->str; }
-    const JsonValue* a = p.find("array"); if (!a) a = p.find("array_name");
-    if (a) { if (array_names_.size() < n) array_names_.resize(n, an0); array_names_[i] = a->str; }
-  }
-  // a partition ends where the next one (in column order) begins
-  std::vector<size_t> order(n);
-  for (size_t i = 0; i < n; ++i) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](size_t x, size_t y) { return partitions_[x].first < partitions_[y].first; });
-  for (size_t k = 0; k + 1 < n; ++k) {
-    auto& cur = partitions_[order[k]]; const auto& nxt = partitions_[order[k + 1]];
-    if (cur.first == nxt.first) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Cannot have two column partitions with the same begin value");
-    if (cur.second >= nxt.first) cur.second = nxt.first - 1;
-  }
+  read_partitions(*cp, true, vid_, partitions_, workspaces_, array_names_);
 }
 std::pair<int64_t, int64_t> GenomicsDBImportConfig::get_column_partition(const int rank, const unsigned idx) const {
   (void)idx;
@@ -121,6 +201,172 @@ const std::string& GenomicsDBImportConfig::get_array_name(const int rank) const 
   return array_names_.size() == 1 ? array_names_[0] : array_names_[std::min<size_t>((size_t)rank, array_names_.size() - 1)];
 }
 
+// ------------------------------------------------------------------------------------------------ query configuration
+// JSONConfigBase::read_from_file + VariantQueryConfig::read_from_file (json_config.cc:195-656, variant_query_config.cc:234-278):
+// the same keys, forms and refusals.  Intervals: [ [ [b, e], p, "contig", { "contig" : [b, e] }, { "contig" : p }, <protobuf
+// forms> ], ... ] -- one inner list for all ranks or one per rank; rows likewise.
+void VariantQueryConfig::read_from_file(const std::string& filename, int rank) {
+  JsonValue d;
+  try { d = gdb::json_parse_file(filename); } catch (const std::exception& e) { bad_config("Syntax error in JSON file " + filename + " (" + e.what() + ")"); }
+  // the mappings come first: contig names in the intervals need them (json_config.cc:204,660-706)
+  std::string vid_file;
+  if (const JsonValue* v = d.find("vid_mapping_file")) vid_file = string_of_rank(*v, rank, "vid_mapping_file");
+  if (const JsonValue* v = d.find("callset_mapping_file")) callset_mapping_file_ = string_of_rank(*v, rank, "callset_mapping_file");
+  if (!vid_file.empty()) vid_ = VidMapper(vid_file);
+  if (vid_.is_initialized() && !callset_mapping_file_.empty() && !vid_.is_callset_mapping_initialized()) vid_.read_callsets_file(callset_mapping_file_);
+  std::vector<std::string> workspaces, array_names;
+  if (!workspace_.empty()) workspaces.push_back(workspace_);   // from the loader's configuration
+  if (!array_name_.empty()) array_names.push_back(array_name_);
+  if (const JsonValue* w = d.find("workspace")) {
+    workspaces.clear();
+    if (w->type == JsonValue::ARR) for (auto& x : w->arr) { if (x.type != JsonValue::STR) bad_config("\"workspace\" must hold strings"); workspaces.push_back(x.str); }
+    else if (w->type == JsonValue::STR) workspaces.push_back(w->str);
+    else bad_config("\"workspace\" must be a string or a list of strings");
+  }
+  if (d.has("array") && d.has("array_name")) bad_config("the configuration names both \"array\" and \"array_name\"");
+  const JsonValue* an = d.find("array"); if (!an) an = d.find("array_name");
+  if (an) {
+    array_names.clear();
+    if (an->type == JsonValue::ARR) for (auto& x : an->arr) { if (x.type != JsonValue::STR) bad_config("\"array\" must hold strings"); array_names.push_back(x.str); }
+    else if (an->type == JsonValue::STR) array_names.push_back(an->str);
+    else bad_config("\"array\" must be a string or a list of strings");
+  }
+  bool single_workspace = workspaces.size() <= 1 && !(d.has("workspace") && d.at("workspace").type == JsonValue::ARR);
+  bool single_array = array_names.size() <= 1 && !(an && an->type == JsonValue::ARR);
+
+  typedef std::pair<int64_t, int64_t> Range;
+  std::vector<std::vector<Range>> column_ranges, row_ranges;
+  // json_config.cc:253-260: the PRESENCE of "scan_full" (whatever its value) makes the query the whole array -- every column and
+  // every row; "query_column_ranges" and "query_row_ranges" beside it are not read
+  const bool scan_full = d.has("scan_full");
+  if (scan_full) {
+    column_ranges.assign(1, std::vector<Range>(1, Range(0, INT64_MAX - 1)));
+  } else {
+    if (d.has("row_partitions") && d.has("column_partitions")) bad_config("Cannot have both \"row_partitions\" and \"column_partitions\" simultaneously in the JSON file");
+    if (!(d.has("query_column_ranges") || d.has("column_partitions") || d.has("query_row_ranges") || d.has("row_partitions")))
+      bad_config("Must have one of \"query_column_ranges\" or \"column_partitions\" or \"query_row_ranges\" or \"row_partitions\"");
+    if (d.has("query_column_ranges") && d.has("column_partitions")) bad_config("Cannot use both \"query_column_ranges\" and \"column_partitions\" simultaneously");
+    if (d.has("query_row_ranges") && d.has("row_partitions")) bad_config("Cannot use both \"query_row_ranges\" and \"row_partitions\" simultaneously");
+    // the list of one rank: a plain list, or the protobuf wrapper { "range_list" : [..] } / { "column_or_interval_list" : [..] }
+    auto list_of = [&](const JsonValue& e, bool columns, bool& skip) -> const JsonValue& {
+      skip = false;
+      if (e.type == JsonValue::ARR) return e;
+      if (e.type != JsonValue::OBJ) bad_config("a rank's ranges must be a list or { \"range_list\" : [ .. ] }");
+      if (columns && e.obj.empty()) { skip = true; return e; }
+      const JsonValue* l = e.obj.size() == 1 ? e.find("range_list") : nullptr;
+      if (!l && columns && e.obj.size() == 1) l = e.find("column_or_interval_list");
+      if (!l || l->type != JsonValue::ARR) bad_config("a rank's ranges must be a list or { \"range_list\" : [ .. ] }");
+      return *l;
+    };
+    if (const JsonValue* q = d.find("query_column_ranges")) {
+      if (q->type != JsonValue::ARR) bad_config("\"query_column_ranges\" must be a list");
+      column_ranges.resize(q->arr.size());
+      for (size_t i = 0; i < q->arr.size(); ++i) {
+        bool skip;
+        const JsonValue& l = list_of(q->arr[i], true, skip);
+        if (skip) continue;
+        for (const JsonValue& it : l.arr) {
+          Range r;
+          if (it.type == JsonValue::ARR) {
+            if (it.arr.size() != 2 || !it.arr[0].is_int || !it.arr[1].is_int) bad_config("a column interval must be [ <begin>, <end> ]");
+            r = Range(it.arr[0].as_int(), it.arr[1].as_int());
+          } else if (it.is_int) r = Range(it.as_int(), it.as_int());
+          else if (it.type == JsonValue::STR) {   // a whole contig
+            const ContigInfo& c = contig_named(vid_, it.str);
+            r = Range(c.tiledb_column_offset, c.tiledb_column_offset + c.length - 1);
+          } else if (!pb_interval(it, vid_, r)) r = contig_interval(it, vid_);
+          if (r.first > r.second) std::swap(r.first, r.second);
+          column_ranges[i].push_back(r);
+        }
+      }
+    } else if (const JsonValue* cp = d.find("column_partitions")) {
+      std::vector<Range> parts;
+      const bool had_ws_list = workspaces.size() > 1, had_an_list = array_names.size() > 1;
+      const size_t nw = workspaces.size(), na = array_names.size();
+      read_partitions(*cp, true, vid_, parts, workspaces, array_names);
+      if (workspaces.size() != nw || had_ws_list) single_workspace = false;
+      else for (auto& p : cp->arr) if (p.has("workspace")) single_workspace = false;
+      if (array_names.size() != na || had_an_list) single_array = false;
+      else for (auto& p : cp->arr) if (p.has("array") || p.has("array_name")) single_array = false;
+      for (auto& p : parts) column_ranges.push_back(std::vector<Range>(1, p));
+    }
+    if (const JsonValue* q = d.find("query_row_ranges")) {
+      if (q->type != JsonValue::ARR) bad_config("\"query_row_ranges\" must be a list");
+      row_ranges.resize(q->arr.size());
+      for (size_t i = 0; i < q->arr.size(); ++i) {
+        bool skip;
+        const JsonValue& l = list_of(q->arr[i], false, skip);
+        for (const JsonValue& it : l.arr) {
+          Range r(0, 0);
+          if (it.type == JsonValue::ARR) {
+            if (it.arr.size() != 2 || !it.arr[0].is_int || !it.arr[1].is_int) bad_config("a row interval must be [ <first>, <last> ]");
+            r = Range(it.arr[0].as_int(), it.arr[1].as_int());
+          } else if (it.is_int) r = Range(it.as_int(), it.as_int());
+          else if (it.type == JsonValue::OBJ) { if (!pb_interval(it, vid_, r)) bad_config("a row interval must be [ <first>, <last> ], a row or { \"low\" : .., \"high\" : .. }"); }
+          if (r.first > r.second) std::swap(r.first, r.second);
+          row_ranges[i].push_back(r);
+        }
+      }
+    } else if (const JsonValue* rp = d.find("row_partitions")) {
+      std::vector<Range> parts;
+      read_partitions(*rp, false, vid_, parts, workspaces, array_names);
+      for (auto& p : rp->arr) { if (p.has("workspace")) single_workspace = false; if (p.has("array") || p.has("array_name")) single_array = false; }
+      for (auto& p : parts) row_ranges.push_back(std::vector<Range>(1, p));
+    }
+  }
+  if (d.has("query_attributes") && d.has("attributes")) bad_config("Query configuration cannot have both \"query_attributes\" and \"attributes\"");
+  const JsonValue* attrs = d.find("query_attributes");
+  if (!attrs) attrs = d.find("attributes");
+  attributes_.clear();
+  if (attrs) {
+    if (attrs->type != JsonValue::ARR) bad_config("\"attributes\" must be a list of strings");
+    for (auto& x : attrs->arr) {
+      if (x.type != JsonValue::STR) bad_config("\"attributes\" must be a list of strings");
+      if (std::find(attributes_.begin(), attributes_.end(), x.str) == attributes_.end()) attributes_.push_back(x.str);   // variant_query_config.cc:37-45: a name once
+    }
+  }
+  if (const JsonValue* v = d.find("segment_size")) { if (!v->is_int) bad_config("\"segment_size\" must be an integer"); segment_size_ = (size_t)v->as_int(); }
+  if (const JsonValue* v = d.find("vcf_header_filename")) vcf_header_filename_ = string_of_rank(*v, rank, "vcf_header_filename");
+  if (const JsonValue* v = d.find("reference_genome")) reference_genome_ = string_of_rank(*v, rank, "reference_genome");
+  if (const JsonValue* v = d.find("vcf_output_format")) vcf_output_format_ = v->str;
+  max_alt_ = d.has("max_diploid_alt_alleles_that_can_be_genotyped") ? (unsigned)d.at("max_diploid_alt_alleles_that_can_be_genotyped").as_int() : 50u;
+  min_pl_gt_ = d.has("produce_GT_with_min_PL_value_for_spanning_deletions") && d.at("produce_GT_with_min_PL_value_for_spanning_deletions").as_bool();
+  produce_gt_ = d.has("produce_GT_field") && d.at("produce_GT_field").as_bool();
+  sites_only_ = d.has("sites_only_query") && d.at("sites_only_query").as_bool();
+  produce_filter_ = d.has("produce_FILTER_field") && d.at("produce_FILTER_field").as_bool();
+
+  // variant_query_config.cc:240-277: this rank's workspace, array, intervals and rows
+  if (!(vid_.is_initialized() && vid_.is_callset_mapping_initialized())) bad_config("the query needs a vid mapping and a callset mapping (its own, or the loader's)");
+  if (workspaces.empty()) bad_config("No workspace specified");
+  if (!single_workspace && (size_t)rank >= workspaces.size()) bad_config("Could not find workspace for rank " + std::to_string(rank));
+  workspace_ = single_workspace ? workspaces[0] : workspaces[rank];
+  if (workspace_.empty()) bad_config("Empty workspace string");
+  if (array_names.empty()) bad_config("No array specified");
+  if (!single_array && (size_t)rank >= array_names.size()) bad_config("Could not find array for rank " + std::to_string(rank));
+  array_name_ = single_array ? array_names[0] : array_names[rank];
+  if (array_name_.empty()) bad_config("Empty array name");
+  if (column_ranges.empty() && !scan_full) bad_config("Query column ranges not specified");
+  if (column_ranges.size() != 1 && (size_t)rank >= column_ranges.size()) bad_config("Rank >= query column ranges vector size");
+  base_column_ranges_ = column_ranges[column_ranges.size() == 1 ? 0 : rank];
+  intervals_.clear();
+  if (!scan_full) for (auto& r : base_column_ranges_) add_column_interval_to_query(r.first, r.second);
+  rows_.clear();
+  if (!scan_full && !row_ranges.empty()) {
+    if (row_ranges.size() != 1 && (size_t)rank >= row_ranges.size()) bad_config("Rank >= query row ranges vector size");
+    std::vector<int64_t> rows;
+    // every row of every range is listed (variant_query_config.cc:266-274); an open-ended row partition cannot be (the reference
+    // dies in its vector's resize there)
+    uint64_t total = 0;
+    for (auto& r : row_ranges[row_ranges.size() == 1 ? 0 : rank]) {
+      total += (uint64_t)r.second - (uint64_t)r.first + 1u;
+      if (total > (1ull << 31)) bad_config("the queried row ranges list more than 2^31 rows");
+    }
+    rows.reserve(total);
+    for (auto& r : row_ranges[row_ranges.size() == 1 ? 0 : rank]) for (int64_t i = r.first; i <= r.second; ++i) rows.push_back(i);
+    set_rows_to_query(rows);
+  }
+}
+
 // genomicsdb_config_base.cc:179-201: called BEFORE the query's own file is read, which then overrides what it names itself
 void VariantQueryConfig::update_from_loader(const GenomicsDBImportConfig& loader_config, const int rank) {
   if (workspace_.empty()) workspace_ = loader_config.get_workspace(rank);
@@ -130,13 +376,16 @@ void VariantQueryConfig::update_from_loader(const GenomicsDBImportConfig& loader
   if (reference_genome_.empty()) reference_genome_ = loader_config.get_reference_genome();
   if (callset_mapping_file_.empty()) callset_mapping_file_ = loader_config.get_callset_mapping_file();
 }
-// genomicsdb_config_base.cc:203-223: of the query's intervals a rank keeps those that touch its column partition
+// genomicsdb_config_base.cc:203-223: of the rank's ranges AS READ FROM THE FILE the base configuration keeps those that touch
+// its column partition.  Both callers (gt_mpi_gather.cc:554-557, genomicsdb_bcf_generator.cc:51-53) call it after
+// read_from_file, which has already handed every range to add_column_interval_to_query -- the intervals the scan walks are
+// not touched, in the reference and here: with a loader JSON every rank still produces the whole query.
 void VariantQueryConfig::subset_query_column_ranges_based_on_partition(const GenomicsDBImportConfig& loader_config, const int rank) {
   if (!loader_config.is_partitioned_by_column()) return;
   const auto mine = loader_config.get_column_partition(rank);
   std::vector<std::pair<int64_t, int64_t>> kept;
-  for (auto& q : intervals_) if (q.second >= mine.first && q.first <= mine.second) kept.push_back(q);
-  intervals_.swap(kept);
+  for (auto& q : base_column_ranges_) if (q.second >= mine.first && q.first <= mine.second) kept.push_back(q);
+  base_column_ranges_.swap(kept);
 }
 
 // ------------------------------------------------------------------------------------------------ VCFAdapter: header + genome

@@ -348,8 +348,10 @@ int gdbgpu_scan_cells_fetch(gdbgpu_scan* scan, int32_t kind, int32_t index, cons
  * The stream is an uncompressed BCF2 file: header (generated from the configuration: template header + queried fields +
  * contigs of the vid mapping + samples of the queried rows), then one record per combined site of the interval
  * chr:start-end (1-based; chr empty: the query file's own column ranges).  loader_configuration_file may be NULL or empty
- * when the query file names workspace, array, vid and callset mapping itself; with it, the rank's column partition bounds
- * the query (update_from_loader / subset_query_column_ranges_based_on_partition). */
+ * when the query file names workspace, array, vid and callset mapping itself; with it, the rank's partition supplies what
+ * the query file leaves out (update_from_loader).  As in the reference the scanned intervals stay the query file's own
+ * (subset_query_column_ranges_based_on_partition runs after they were handed to the query and edits the base list only);
+ * a rank's share of a query is the query file's per-rank list of ranges. */
 typedef struct gdbgpu_stream gdbgpu_stream;
 /* jniGenomicsDBInit */
 int gdbgpu_stream_open(const char* loader_configuration_file, const char* query_configuration_file, const char* chr, int start, int end, int rank,

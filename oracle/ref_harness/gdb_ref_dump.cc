@@ -9,6 +9,7 @@
  *   --mode hot   : same work without the dump (CPU timing of the hot path alone)
  *   --mode null  : the full BroadCombinedGVCFOperator::operate with a VCFAdapter whose hand-off is a no-op
  *                  (INFO/FORMAT collation + bcf1_t build, no serialisation)
+ *   --mode config : print the query configuration as the reference's classes hold it after parsing (no storage opened)
  *   --mode bcf-java : the reference's own BroadCombinedGVCFOperator + VCFAdapter writing uncompressed BCF to stdout, constructed
  *                  as the JNI path constructs it (genomicsdb_bcf_generator.cc:60-83: use_missing_values_only_not_vector_end =
  *                  true, the conventions htsjdk's BCF2 codec needs); gt_mpi_gather has no switch for it
@@ -186,6 +187,44 @@ int main(int argc, char** argv)
       }
     }
     sm.close_array(qp.get_array_descriptor());
+    GenomicsDBProtoBufInitAndCleanup::shutdown_protobuf_library();
+    return 0;
+  }
+  if(mode_str == "config")
+  {
+    // the query configuration as the reference's own classes hold it after the calls gt_mpi_gather.cc:547-557 makes
+    // (loader first, the query file, then the partition subset): one JSON line, no storage is opened
+    VariantQueryConfig query_config;
+    GenomicsDBImportConfig loader_config;
+    if(!loader_json.empty())
+    {
+      loader_config.read_from_file(loader_json, rank);
+      query_config.update_from_loader(loader_config, rank);
+    }
+    query_config.read_from_file(query_json, rank);
+    if(!loader_json.empty())
+      query_config.subset_query_column_ranges_based_on_partition(loader_config, rank);
+    std::cout << "{\"workspace\": \"" << query_config.get_workspace(rank) << "\", \"array\": \"" << query_config.get_array_name(rank) << "\", \"intervals\": [";
+    for(auto i=0u;i<query_config.get_num_column_intervals();++i)
+      std::cout << (i ? ", " : "") << "[" << (long long)query_config.get_column_begin(i) << ", " << (long long)query_config.get_column_end(i) << "]";
+    std::cout << "], \"base_ranges\": [";
+    auto& base = query_config.get_query_column_ranges(rank);
+    for(auto i=0u;i<base.size();++i)
+      std::cout << (i ? ", " : "") << "[" << (long long)base[i].first << ", " << (long long)base[i].second << "]";
+    std::cout << "], \"all_rows\": " << (query_config.query_all_rows() ? "true" : "false") << ", \"rows\": [";
+    auto& rows = query_config.get_rows_to_query();
+    for(auto i=0u;i<rows.size();++i)
+      std::cout << (i ? ", " : "") << (long long)rows[i];
+    std::cout << "], \"attributes\": [";
+    for(auto i=0u;i<query_config.get_num_queried_attributes();++i)
+      std::cout << (i ? ", " : "") << "\"" << query_config.get_query_attribute_name(i) << "\"";
+    std::cout << "], \"segment_size\": " << query_config.get_segment_size()
+      << ", \"max_diploid_alt_alleles_that_can_be_genotyped\": " << query_config.get_max_diploid_alt_alleles_that_can_be_genotyped()
+      << ", \"produce_GT_field\": " << query_config.produce_GT_field() << ", \"produce_FILTER_field\": " << query_config.produce_FILTER_field()
+      << ", \"sites_only_query\": " << query_config.sites_only_query()
+      << ", \"produce_GT_with_min_PL_value_for_spanning_deletions\": " << query_config.produce_GT_with_min_PL_value_for_spanning_deletions()
+      << ", \"vcf_header_filename\": \"" << query_config.get_vcf_header_filename() << "\", \"reference_genome\": \"" << query_config.get_reference_genome()
+      << "\", \"vcf_output_format\": \"" << query_config.get_vcf_output_format() << "\"}" << std::endl;
     GenomicsDBProtoBufInitAndCleanup::shutdown_protobuf_library();
     return 0;
   }

@@ -28,7 +28,7 @@ def exe():
 
 def run_tool(exe, case, tmp_path, flag, attributes=None, window=None):
     q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
-         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": attributes or case["attributes"],
+         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "callset_mapping_file": os.path.join(GOLDEN, case["callset_mapping_file"]), "attributes": attributes or case["attributes"],
          "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_column_ranges"]]}],
          "query_row_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_row_ranges"]]}]}
     qf = tmp_path / "query.json"

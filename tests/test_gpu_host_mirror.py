@@ -24,7 +24,7 @@ def exe():
 
 def run_case(exe, case, tmp_path, page):
     q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
-         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": case["attributes"],
+         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "callset_mapping_file": os.path.join(GOLDEN, case["callset_mapping_file"]), "attributes": case["attributes"],
          "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_column_ranges"]]}],
          "query_row_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_row_ranges"]]}],
          "produce_GT_with_min_PL_value_for_spanning_deletions": case["produce_GT_with_min_PL_value_for_spanning_deletions"]}
@@ -59,7 +59,7 @@ ALL = golden_cases()
 
 def run_broad(exe, case, tmp_path, page=0, java=False, sites_only=False, env=None):
     q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
-         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": case["attributes"],
+         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "callset_mapping_file": os.path.join(GOLDEN, case["callset_mapping_file"]), "attributes": case["attributes"],
          "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_column_ranges"]]}],
          "query_row_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_row_ranges"]]}],
          "produce_GT_field": case["produce_GT_field"], "sites_only_query": sites_only, "produce_FILTER_field": case.get("produce_FILTER_field", False),
@@ -124,7 +124,7 @@ def test_bcf_generator_stream_equals_the_reference(exe, cid, tmp_path, chunk, ca
     case = [c for c in ALL if c["id"] == cid][0]
     gold = open(os.path.join(GOLDEN, "bcf_java", cid + ".bcf"), "rb").read()
     q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
-         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": case["attributes"],
+         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "callset_mapping_file": os.path.join(GOLDEN, case["callset_mapping_file"]), "attributes": case["attributes"],
          "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_column_ranges"]]}],
          "query_row_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_row_ranges"]]}],
          "produce_GT_field": case["produce_GT_field"], "produce_FILTER_field": case.get("produce_FILTER_field", False),
@@ -151,7 +151,7 @@ def test_bcf_generator_header_only(exe, tmp_path):
     import struct
     l_text = struct.unpack_from("<I", gold, 5)[0]
     q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
-         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": case["attributes"],
+         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "callset_mapping_file": os.path.join(GOLDEN, case["callset_mapping_file"]), "attributes": case["attributes"],
          "query_column_ranges": [{"range_list": [{"low": 0, "high": 1000000000}]}]}
     qf = tmp_path / "query.json"
     qf.write_text(json.dumps(q))
@@ -169,7 +169,7 @@ def test_max_alleles_count_operator(exe, cid, tmp_path):
     from oracle import oracle
     case = [c for c in ALL if c["id"] == cid][0]
     q = {"workspace": os.path.join(GOLDEN, case["workspace"]), "array_name": case["array"],
-         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "attributes": case["attributes"],
+         "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "callset_mapping_file": os.path.join(GOLDEN, case["callset_mapping_file"]), "attributes": case["attributes"],
          "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_column_ranges"]]}],
          "query_row_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in case["query_row_ranges"]]}]}
     qf = tmp_path / "query.json"

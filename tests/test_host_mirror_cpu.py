@@ -21,7 +21,7 @@ def test_header_dictionary_vid_mapping_and_query_json(tmp_path):
     exe = build_probe(tmp_path)
     case = [c for c in golden_cases() if c["id"] == "t0_1_2_at_12100_12141_to_12150_12300_17384"][0]
     bcf = os.path.join(GOLDEN, "bcf", case["id"] + ".bcf")
-    q = {"workspace": "/nowhere", "array_name": "x", "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]),
+    q = {"workspace": "/nowhere", "array_name": "x", "vid_mapping_file": os.path.join(GOLDEN, case["vid_mapping_file"]), "callset_mapping_file": os.path.join(GOLDEN, case["callset_mapping_file"]),
          "attributes": case["attributes"], "produce_GT_field": True,
          "query_column_ranges": [{"range_list": [{"low": lo, "high": hi} for lo, hi in reversed(case["query_column_ranges"])]}],
          "query_row_ranges": [{"range_list": [{"low": 0, "high": 2}, 7]}]}
