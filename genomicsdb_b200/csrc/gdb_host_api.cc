@@ -25,61 +25,180 @@ namespace genomicsdb_b200 {
 using gdb::JsonValue;
 
 // ------------------------------------------------------------------------------------------------ VidMapper
+// FileBasedVidMapper (vid_mapper.cc:1209-1443): "contigs" and "fields" as a dictionary name -> info or a list of info
+// dictionaries; type and length in every spelling the reference reads, reduced to one ("int" / "float" / "char" / "flag";
+// "<n>" / "A" / "R" / "G" / "P" / "PP" / "VAR"); fields indexed as the reference indexes them -- a field that is both INFO and
+// FORMAT is followed by its <name>_FORMAT twin, a field of tuples by one <name>_tuple_element_<j> per tuple element, and all of
+// them count (FILTER cells hold these indices).  What the reference refuses is refused.
+namespace {
+[[noreturn]] void bad_vid(const std::string& what) { throw GenomicsDBGPUException(GDBGPU_ERR_ARG, what); }
+std::string canonical_type(const std::string& t, const std::string& field) {   // vid_mapper.cc:51-89
+  static const char* const ints[] = {"int", "Int", "integer", "Integer"}, * const floats[] = {"float", "Float"},
+                   * const flags[] = {"bool", "Bool", "boolean", "Boolean", "flag", "Flag"}, * const chars[] = {"string", "String", "char", "Char"};
+  for (const char* x : ints) if (t == x) return "int";
+  for (const char* x : floats) if (t == x) return "float";
+  for (const char* x : flags) if (t == x) return "flag";
+  for (const char* x : chars) if (t == x) return "char";
+  bad_vid("Unhandled field type " + t + " of field " + field);
+}
+std::string canonical_length_string(const std::string& s, const std::string& field) {   // vid_mapper.cc:33-49,802-830
+  std::string u = s;
+  for (char& c : u) c = (char)toupper((unsigned char)c);
+  if (u == "A" || u == "BCF_VL_A") return "A";
+  if (u == "R" || u == "BCF_VL_R") return "R";
+  if (u == "G" || u == "BCF_VL_G") return "G";
+  if (u == "P" || u == "BCF_VL_P") return "P";
+  if (u == "VAR" || u == "BCF_VL_VAR") return "VAR";
+  if (u == "PP" || u == "PHASED_PLOIDY") return "PP";
+  if (u == "BCF_VL_FIXED") return "1";
+  char* end = nullptr;
+  const unsigned long long n = strtoull(s.c_str(), &end, 0);
+  if (!s.empty() && (size_t)(end - s.c_str()) == s.size()) return std::to_string(n);
+  std::cerr << "WARNING: unknown length descriptor " << s << " for field " << field << " ; setting to 'VAR'\n";
+  return "VAR";
+}
+std::string canonical_length(const JsonValue& l, const std::string& field) {   // one dimension (vid_mapper.cc:1491-1528)
+  if (l.is_int) return std::to_string(l.as_int());
+  if (l.type == JsonValue::STR) return canonical_length_string(l.str, field);
+  if (l.type == JsonValue::OBJ) {   // protobuf: { "variable_length_descriptor" : "R" } / { "fixed_length" : 2 }
+    if (const JsonValue* v = l.find("variable_length_descriptor")) { if (v->type != JsonValue::STR) bad_vid("\"variable_length_descriptor\" of field " + field + " must be a string"); return canonical_length_string(v->str, field); }
+    const JsonValue* f = l.find("fixed_length");
+    if (!f || !f->is_int) bad_vid("the length of field " + field + " needs \"variable_length_descriptor\" or an integer \"fixed_length\"");
+    return std::to_string(f->as_int());
+  }
+  bad_vid("the length of field " + field + " must be an integer, a string, a dictionary or a list of those");
+}
+// a known field the vid mapping gives no length for (known_field_info.cc:239-283)
+std::string known_field_length(const std::string& name) {
+  if (name == "REF" || name == "ALT" || name == "FILTER" || name == "PGT" || name == "PID") return "VAR";
+  if (name == "AF" || name == "AC") return "A";
+  if (name == "AD") return "R";
+  if (name == "PL") return "G";
+  if (name == "GT") return "PP";
+  if (name == "SB") return "4";
+  return "1";
+}
+std::string entry_name(const JsonValue& v, std::initializer_list<const char*> keys, const char* what, size_t idx) {
+  std::string name; unsigned found = 0;
+  for (const char* k : keys) if (const JsonValue* n = v.find(k)) { name = n->str; ++found; }
+  if (found != 1) bad_vid(std::string(what) + " info dict with index " + std::to_string(idx) + (found ? " has two or more of its name keys" : " has no name key"));
+  return name;
+}
+}  // namespace
+
 VidMapper::VidMapper(const std::string& file) {
-  JsonValue d = gdb::json_parse_file(file);
-  const JsonValue& fl = d.at("fields");
-  int n_json_fields = 0;
+  JsonValue d;
+  try { d = gdb::json_parse_file(file); } catch (const std::exception& e) { bad_vid("Syntax error in JSON file " + file + " (" + e.what() + ")"); }
+  // callsets may sit in the vid mapping itself (vid_mapper.cc:686-711: a file name, "callsets", or protobuf's "callset_mapping")
+  if (const JsonValue* c = d.find("callset_mapping_file")) { if (c->type != JsonValue::STR && c->type != JsonValue::ARR) bad_vid("\"callset_mapping_file\" must be a string or a list of strings"); read_callsets_file(c->type == JsonValue::STR ? c->str : (c->arr.empty() ? std::string() : c->arr[0].str)); }
+  if (const JsonValue* c = d.find("callsets")) read_callsets(*c);
+  if (const JsonValue* c = d.find("callset_mapping")) { if (c->type != JsonValue::OBJ || !c->has("callsets")) bad_vid("\"callset_mapping\" must hold \"callsets\""); read_callsets(c->at("callsets")); }
+  const JsonValue* cl = d.find("contigs");
+  if (!cl || (cl->type != JsonValue::OBJ && cl->type != JsonValue::ARR)) bad_vid("the vid mapping " + file + " has no \"contigs\"");
+  {
+    bool duplicate = false;
+    auto addc = [&](const std::string& name, const JsonValue& v) {
+      if (v.type != JsonValue::OBJ) bad_vid("contig " + name + ": the info must be a dictionary");
+      if (get_contig_info(name)) { std::cerr << "Duplicate contig/chromosome name " << name << " found in vid file " << file << "\n"; duplicate = true; return; }
+      const JsonValue* o = v.find("tiledb_column_offset"); const JsonValue* l = v.find("length");
+      if (!o || !o->is_int || o->as_int() < 0) bad_vid("contig " + name + " needs an integer \"tiledb_column_offset\" >= 0");
+      if (!l || !l->is_int || l->as_int() < 0) bad_vid("contig " + name + " needs an integer \"length\" >= 0");
+      ContigInfo c; c.name = name; c.tiledb_column_offset = o->as_int(); c.length = l->as_int();
+      contigs_.push_back(c);
+    };
+    if (cl->type == JsonValue::OBJ) for (auto& kv : cl->obj) addc(kv.first, kv.second);
+    else for (size_t i = 0; i < cl->arr.size(); ++i) { if (cl->arr[i].type != JsonValue::OBJ) bad_vid("a contig's info must be a dictionary"); addc(entry_name(cl->arr[i], {"name", "contig_name", "chromosome_name"}, "Contig", i), cl->arr[i]); }
+    if (duplicate) bad_vid("Duplicate contigs exist in vid file " + file);
+    contigs_file_order_ = contigs_;
+    std::stable_sort(contigs_.begin(), contigs_.end(), [](const ContigInfo& a, const ContigInfo& b) { return a.tiledb_column_offset < b.tiledb_column_offset; });
+    for (size_t i = 1; i < contigs_.size(); ++i)
+      if (contigs_[i].tiledb_column_offset <= contigs_[i - 1].tiledb_column_offset + contigs_[i - 1].length - 1) {
+        std::cerr << "Contig/chromosome " << contigs_[i].name << " begins at TileDB column " << contigs_[i].tiledb_column_offset << " and intersects with contig/chromosome " << contigs_[i - 1].name << "\n";
+        bad_vid("Overlapping contigs exist in vid file " + file);
+      }
+  }
+  const JsonValue* fl = d.find("fields");
+  if (!fl || (fl->type != JsonValue::OBJ && fl->type != JsonValue::ARR)) bad_vid("the vid mapping " + file + " has no \"fields\"");
+  int field_idx = 0;
+  bool duplicate_fields = false;
   auto add = [&](const std::string& name, const JsonValue& v) {
+    if (v.type != JsonValue::OBJ) bad_vid("field " + name + ": the info must be a dictionary");
+    if (get_field_info(name)) { std::cerr << "Duplicate field name " << name << " found in vid attribute \"fields\"\n"; duplicate_fields = true; return; }
     FieldInfo f; f.name = name;
-    if (const JsonValue* t = v.find("type")) f.type = t->type == JsonValue::STR ? t->str : (t->type == JsonValue::ARR && !t->arr.empty() ? t->arr[0].str : "int");
-    else f.type = "int";
+    if (const JsonValue* c = v.find("vcf_field_class")) {
+      if (c->type != JsonValue::ARR) bad_vid("\"vcf_field_class\" of field " + name + " must be a list");
+      for (auto& x : c->arr) { if (x.str == "FORMAT") f.is_format = true; if (x.str == "INFO") f.is_info = true; if (x.str == "FILTER") f.is_filter = true; }
+    }
     f.length = "1";
     if (const JsonValue* l = v.find("length")) {
-      if (l->type == JsonValue::STR) f.length = l->str;
-      else if (l->type == JsonValue::NUM) f.length = std::to_string(l->as_int());
-      else if (l->type == JsonValue::ARR) {
-        if (l->arr.size() == 1) f.length = l->arr[0].type == JsonValue::NUM ? std::to_string(l->arr[0].as_int()) : l->arr[0].str;
-        else { f.length = "2D"; for (auto& x : l->arr) f.dim_lengths.push_back(x.type == JsonValue::NUM ? std::to_string(x.as_int()) : x.str); }
-      }
+      if (l->type == JsonValue::ARR) {
+        if (l->arr.size() == 1) f.length = canonical_length(l->arr[0], name);
+        else { f.length = "2D"; for (auto& x : l->arr) f.dim_lengths.push_back(canonical_length(x, name)); }
+      } else f.length = canonical_length(*l, name);
+    } else f.length = known_field_length(name);
+    const JsonValue* t = v.find("type");
+    if (!t) bad_vid("field " + name + " has no \"type\"");
+    if (t->type == JsonValue::STR) f.type = canonical_type(t->str, name);
+    else if (t->type == JsonValue::ARR) {
+      for (auto& x : t->arr) { if (x.type != JsonValue::STR) bad_vid("\"type\" of field " + name + " must hold strings"); f.tuple_types.push_back(canonical_type(x.str, name)); }
+      f.type = f.tuple_types.empty() ? "int" : f.tuple_types[0];
+    } else bad_vid("Attribute 'type' of field " + name + " must be a string or an array");
+    if (const JsonValue* vt = v.find("vcf_type")) {   // read for its refusals only: the VCF side of a multi-dimensional field is always a string
+      if (vt->type == JsonValue::STR) canonical_type(vt->str, name);
+      else if (vt->type == JsonValue::ARR) { for (auto& x : vt->arr) canonical_type(x.str, name); }
+      else bad_vid("Attribute 'vcf_type' of field " + name + " must be a string or an array");
     }
-    if (const JsonValue* t = v.find("type")) { if (t->type == JsonValue::ARR) for (auto& x : t->arr) f.tuple_types.push_back(x.str); }
-    if (const JsonValue* dl = v.find("vcf_delimiter")) {
-      if (dl->type == JsonValue::ARR) { for (auto& x : dl->arr) f.vcf_delimiters.push_back(x.str.empty() ? ',' : x.str[0]); }
-      else if (dl->type == JsonValue::STR && !dl->str.empty()) f.vcf_delimiters.push_back(dl->str[0]);
-    }
-    if (f.tuple_types.size() > 1) f.length = "2D";   // a vector of tuples is handled like a multi-dimensional field (raw bytes, Type=String)
-    while (f.length == "2D" && f.vcf_delimiters.size() < 2) f.vcf_delimiters.push_back(f.vcf_delimiters.empty() ? '|' : ',');
-    if (const JsonValue* c = v.find("vcf_field_class")) for (auto& x : c->arr) { if (x.str == "FORMAT") f.is_format = true; if (x.str == "INFO") f.is_info = true; if (x.str == "FILTER") f.is_filter = true; }
-    if (const JsonValue* c = v.find("VCF_field_combine_operation")) f.combine_op = c->str;
-    else {   // defaults of the known fields (known_field_info.cc:284-308)
+    if (f.length == "2D")   // vid_mapper.cc:200-215
+      for (auto& e : (f.tuple_types.empty() ? std::vector<std::string>(1, f.type) : f.tuple_types))
+        if (e != "int" && e != "float") bad_vid("Unhandled element type for multi-D field " + name + "; only float and int multi-d fields supported");
+    if (const JsonValue* c = v.find("VCF_field_combine_operation")) {
+      static const char* const ops[] = {"sum", "mean", "median", "move_to_FORMAT", "element_wise_sum", "elementwise_sum", "concatenate", "histogram_sum"};
+      bool known = false;
+      for (const char* o : ops) if (c->type == JsonValue::STR && c->str == o) known = true;
+      if (!known) bad_vid("Unknown VCF field combine operation " + c->str + " specified for field " + name);
+      f.combine_op = c->str == "elementwise_sum" ? "element_wise_sum" : c->str;
+      if (f.combine_op == "concatenate" && (f.length == "2D" ? f.dim_lengths[0] : f.length) != "VAR")
+        bad_vid("VCF field combined operation 'concatenate' can only be used with fields whose length descriptors are 'VAR';  field " + name + " does not have 'VAR' as its length descriptor");
+    } else {   // defaults of the known fields (known_field_info.cc:284-308)
       static const char* medians[] = {"BaseQRankSum", "ClippingRankSum", "MQRankSum", "ReadPosRankSum", "MQ", "MQ0", "ExcessHet"};
       for (const char* m : medians) if (name == m) f.combine_op = "median";
       if (name == "RAW_MQ") f.combine_op = "sum";
       if (name == "DP") f.combine_op = "DP";
     }
-    f.global_idx = n_json_fields++;
+    if (const JsonValue* dl = v.find("vcf_delimiter")) {
+      if (dl->type == JsonValue::ARR) { for (auto& x : dl->arr) { if (x.type != JsonValue::STR) bad_vid("\"vcf_delimiter\" of field " + name + " must hold strings"); f.vcf_delimiters.push_back(x.str.empty() ? ',' : x.str[0]); } }
+      else if (dl->type == JsonValue::STR) { if (!dl->str.empty()) f.vcf_delimiters.push_back(dl->str[0]); }
+      else bad_vid("\"vcf_delimiter\" of field " + name + " must be a string or a list of strings");
+    }
+    if (f.tuple_types.size() > 1) { if (f.length != "2D") { f.dim_lengths.assign(1, f.length); f.length = "2D"; } }   // a vector of tuples is handled like a multi-dimensional field (raw bytes, Type=String)
+    while (f.length == "2D" && f.vcf_delimiters.size() < 2) f.vcf_delimiters.push_back(f.vcf_delimiters.empty() ? '|' : ',');
+    f.global_idx = field_idx++;
     fields_.push_back(f);
-    if (f.is_format && f.is_info) { FieldInfo g = f; g.name = name + "_FORMAT"; g.global_idx = -1; fields_.push_back(g); }   // vid_mapper.cc: FORMAT twin
-    if (f.is_composite())   // vid_mapper.cc flatten_field: one attribute per tuple element
-      for (size_t j = 0; j < f.tuple_types.size(); ++j) {
-        FieldInfo g = f; g.name = name + "_tuple_element_" + std::to_string(j); g.parent = name; g.tuple_index = (int)j; g.type = f.tuple_types[j]; g.global_idx = -1;
-        fields_.push_back(g);
-      }
+    // vid_mapper.cc:727-788 flatten_field: the FORMAT twin, then one attribute per tuple element (of the field, then of its twin)
+    const bool both = f.is_format && f.is_info;
+    if (both) { FieldInfo g = f; g.name = name + "_FORMAT"; g.is_format_twin = true; g.global_idx = field_idx++; fields_.push_back(g); }
+    if (f.is_composite())
+      for (int j = 0; j < (both ? 2 : 1); ++j)
+        for (size_t e = 0; e < f.tuple_types.size(); ++e) {
+          FieldInfo g = f; g.name = name + (j ? "_FORMAT" : "") + "_tuple_element_" + std::to_string(e); g.parent = name + (j ? "_FORMAT" : ""); g.tuple_index = (int)e; g.type = f.tuple_types[e];
+          g.is_format_twin = j == 1; g.global_idx = field_idx++;
+          fields_.push_back(g);
+        }
   };
-  if (fl.type == JsonValue::OBJ) for (auto& kv : fl.obj) add(kv.first, kv.second);
-  else for (auto& v : fl.arr) add(v.at("name").str, v);
-  if (const JsonValue* cl = d.find("contigs")) {
-    auto addc = [&](const std::string& name, const JsonValue& v) {
-      ContigInfo c; c.name = name;
-      if (const JsonValue* o = v.find("tiledb_column_offset")) c.tiledb_column_offset = o->as_int();
-      if (const JsonValue* l = v.find("length")) c.length = l->as_int();
-      contigs_.push_back(c);
-    };
-    if (cl->type == JsonValue::OBJ) for (auto& kv : cl->obj) addc(kv.first, kv.second);
-    else for (auto& v : cl->arr) addc(v.at("name").str, v);
-    contigs_file_order_ = contigs_;
-    std::sort(contigs_.begin(), contigs_.end(), [](const ContigInfo& a, const ContigInfo& b) { return a.tiledb_column_offset < b.tiledb_column_offset; });
+  if (fl->type == JsonValue::OBJ) for (auto& kv : fl->obj) add(kv.first, kv.second);
+  else for (size_t i = 0; i < fl->arr.size(); ++i) {
+    const JsonValue& v = fl->arr[i];
+    if (v.type != JsonValue::OBJ) bad_vid("a field's info must be a dictionary");
+    if (v.has("name") && v.has("field_name")) bad_vid("Field information dictionary with index " + std::to_string(i) + " has both \"field_name\" or \"name\" keys - only one should be specified");
+    if (!v.has("name") && !v.has("field_name")) bad_vid("Field information dictionary with index " + std::to_string(i) + " does not have a \"field_name\" or \"name\" key");
+    add(v.has("name") ? v.at("name").str : v.at("field_name").str, v);
   }
+  if (duplicate_fields) bad_vid("Duplicate fields exist in vid attribute \"fields\"");
+  // END, REF, ALT, QUAL and FILTER follow when the file does not list them (vid_mapper.cc:611-684); the mirror answers for
+  // them where they are asked about (do_query_bookkeeping) and keeps fields_ to what the file names
+  num_fields_ = field_idx;
+  for (const char* m : {"END", "REF", "ALT", "QUAL", "FILTER"}) if (!get_field_info(m)) ++num_fields_;
+  initialized_ = true;
 }
 const ContigInfo* VidMapper::get_contig_location(int64_t column) const {
   const ContigInfo* best = nullptr;
@@ -318,7 +437,9 @@ BroadCombinedGVCFOperator::BroadCombinedGVCFOperator(VCFAdapter& vcf_adapter, co
   for (auto& f : id_mapper.fields()) {   // broad_combined_gvcf.cc:306-313: vid field index -> header dictionary id (could be -1)
     if (f.global_idx < 0) continue;
     if ((size_t)f.global_idx >= m_global_field_idx_to_hdr_idx.size()) m_global_field_idx_to_hdr_idx.resize(f.global_idx + 1, -1);
-    m_global_field_idx_to_hdr_idx[f.global_idx] = vcf_adapter.get_dictionary_id(f.name);
+    std::string vcf_name = f.vcf_name();   // a twin and a flattened element go by the VCF name of the field they come from
+    if (f.is_format_twin && vcf_name.size() > 7 && vcf_name.compare(vcf_name.size() - 7, 7, "_FORMAT") == 0) vcf_name.resize(vcf_name.size() - 7);
+    m_global_field_idx_to_hdr_idx[f.global_idx] = vcf_adapter.get_dictionary_id(vcf_name);
   }
   m_dp_rule = qc.get_dp_rule_fields()[0] != 0 || qc.get_dp_rule_fields()[2] != 0;
   if (m_dp_rule) { m_DP_key = key_of("DP"); m_dp_rule = vcf_adapter.has_info_line("DP"); }   // bcf_update_info_int32 fails without an ##INFO line: no INFO/DP then

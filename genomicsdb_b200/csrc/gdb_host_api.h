@@ -33,6 +33,7 @@
 
 #include "../../include/gdbgpu.h"
 
+namespace gdb { struct JsonValue; }
 namespace genomicsdb_b200 {
 
 class GenomicsDBGPUException : public std::runtime_error {
@@ -52,7 +53,8 @@ struct FieldInfo {
   std::string type;        // "int", "float", "char", ...
   std::string length;      // "1", "R", "A", "G", "P", "PP", "VAR", "<n>"; 2-D descriptors are kept as "2D"
   bool is_format = false, is_info = false, is_filter = false;
-  int global_idx = -1;     // position among the vid mapping's fields (what FILTER cells store); -1 for a FORMAT twin
+  int global_idx = -1;     // the reference's field index (what FILTER cells store): file order, FORMAT twins and flattened tuple elements counted
+  bool is_format_twin = false;   // <name>_FORMAT of a field that is both INFO and FORMAT (or a tuple element of that twin)
   std::string combine_op;  // "VCF_field_combine_operation" of the vid mapping, else the known field's default (known_field_info.cc:284-308)
   bool is_allele_dependent() const { return length == "R" || length == "A" || length == "G"; }
   // multi-dimensional fields and fields whose elements are tuples (vid_mapper.cc, genomicsdb_multid_vector_field.h:66-83): length
@@ -74,7 +76,8 @@ class VidMapper {
  public:
   VidMapper() = default;
   explicit VidMapper(const std::string& vid_json_file);
-  bool is_initialized() const { return !fields_.empty(); }
+  bool is_initialized() const { return initialized_; }
+  unsigned get_num_fields() const { return (unsigned)num_fields_; }   // with the mandatory fields the file does not list
   const FieldInfo* get_field_info(const std::string& name) const;
   const std::vector<FieldInfo>& fields() const { return fields_; }
   // vid_mapper.cc get_contig_location: the contig a TileDB column falls into (nullptr: unknown position)
@@ -86,7 +89,8 @@ class VidMapper {
   const ContigInfo& get_contig_info(unsigned idx) const { return contigs_file_order_[idx]; }
   // callset mapping (vid_mapper.cc:686-711,319-325): sample name of every TileDB row
   void read_callsets_file(const std::string& callset_mapping_file);
-  bool is_callset_mapping_initialized() const { return !callset_names_.empty(); }
+  void read_callsets(const gdb::JsonValue& callsets);   // a dictionary name -> info or a list of info dictionaries
+  bool is_callset_mapping_initialized() const { return callsets_initialized_; }
   bool get_callset_name(int64_t row_idx, std::string& callset_name) const;
   int64_t get_max_callset_row_idx() const { return (int64_t)callset_names_.size() - 1; }
  private:
@@ -94,6 +98,9 @@ class VidMapper {
   std::vector<ContigInfo> contigs_;   // sorted by tiledb_column_offset
   std::vector<ContigInfo> contigs_file_order_;
   std::vector<std::string> callset_names_;   // by row
+  std::vector<bool> callset_rows_named_;
+  int num_fields_ = 0;
+  bool initialized_ = false, callsets_initialized_ = false;
 };
 
 // ---- loader configuration (include/config/genomicsdb_config_base.h GenomicsDBImportConfig, src/config/json_config.cc:340-440,

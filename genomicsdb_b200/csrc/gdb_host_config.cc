@@ -24,21 +24,47 @@ namespace genomicsdb_b200 {
 using gdb::JsonValue;
 
 // ------------------------------------------------------------------------------------------------ callsets
+// vid_mapper.cc:841-858,946-1055: "callsets" as a dictionary name -> info or a list of info dictionaries ("name" /
+// "callset_name" / "sample_name"); "row_idx" is required; one name per row and one row per name; every row up to the largest
+// must be named
 void VidMapper::read_callsets_file(const std::string& file) {
-  JsonValue d = gdb::json_parse_file(file);
+  JsonValue d;
+  try { d = gdb::json_parse_file(file); } catch (const std::exception& e) { throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Syntax error in JSON file " + file + " (" + e.what() + ")"); }
   const JsonValue* cs = d.find("callsets");
   if (!cs) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "no \"callsets\" in " + file);
-  callset_names_.clear();
-  auto add = [&](const std::string& name, const JsonValue& v, int64_t dflt) {
+  read_callsets(*cs);
+}
+void VidMapper::read_callsets(const JsonValue& cs) {
+  auto bad = [](const std::string& what) { throw GenomicsDBGPUException(GDBGPU_ERR_ARG, what); };
+  if (cs.type != JsonValue::OBJ && cs.type != JsonValue::ARR) bad("\"callsets\" must be a dictionary or a list");
+  auto add = [&](const std::string& name, const JsonValue& v) {
+    if (v.type != JsonValue::OBJ) bad("callset " + name + ": the info must be a dictionary");
     const JsonValue* r = v.find("row_idx");
-    const int64_t row = r ? r->as_int() : dflt;
-    if (row < 0) return;
-    if ((size_t)row >= callset_names_.size()) callset_names_.resize(row + 1);
+    if (!r || !r->is_int || r->as_int() < 0) bad("callset " + name + " needs an integer \"row_idx\" >= 0");
+    const int64_t row = r->as_int();
+    if (v.has("filename") && v.has("stream_name")) bad("Cannot have both \"filename\" and \"stream_name\" as the data source for sample/CallSet " + name);
+    for (size_t i = 0; i < callset_names_.size(); ++i)
+      if (callset_rows_named_[i] && callset_names_[i] == name && (int64_t)i != row)
+        bad("Duplicate with conflicting row index for sample/callset name " + name + " found in callsets mapping " + std::to_string(i) + ", " + std::to_string(row));
+    if ((size_t)row >= callset_names_.size()) { callset_names_.resize(row + 1); callset_rows_named_.resize(row + 1, false); }
+    if (callset_rows_named_[row] && callset_names_[row] != name) bad("Sample/callset " + name + " has the same row idx as " + callset_names_[row]);
     callset_names_[row] = name;
+    callset_rows_named_[row] = true;
   };
-  int64_t i = 0;
-  if (cs->type == JsonValue::OBJ) for (auto& kv : cs->obj) add(kv.first, kv.second, i++);
-  else for (auto& v : cs->arr) add(v.has("sample_name") ? v.at("sample_name").str : v.at("name").str, v, i++);
+  if (cs.type == JsonValue::OBJ) for (auto& kv : cs.obj) add(kv.first, kv.second);
+  else for (size_t i = 0; i < cs.arr.size(); ++i) {
+    const JsonValue& v = cs.arr[i];
+    if (v.type != JsonValue::OBJ) bad("a callset's info must be a dictionary");
+    std::string name; unsigned found = 0;
+    for (const char* k : {"name", "callset_name", "sample_name"}) if (const JsonValue* n = v.find(k)) { name = n->str; ++found; }
+    if (found == 0) bad("Callset info dict with index " + std::to_string(i) + " does not have any one of the keys \"name\", \"callset_name\" or \"sample_name\"");
+    if (found > 1) bad("Callset info dict with index " + std::to_string(i) + " has two or more of the keys \"name\", \"callset_name\" or \"sample_name\" - at most one is allowed");
+    add(name, v);
+  }
+  bool missing = false;
+  for (size_t i = 0; i < callset_names_.size(); ++i) if (!callset_rows_named_[i]) { std::cerr << "Sample/callset information missing for row " << i << "\n"; missing = true; }
+  if (missing) bad("Row indexes with missing sample/callset information found in callsets mapping");
+  callsets_initialized_ = true;
 }
 bool VidMapper::get_callset_name(int64_t row_idx, std::string& callset_name) const {
   if (row_idx < 0 || (size_t)row_idx >= callset_names_.size()) return false;

@@ -9,6 +9,7 @@
  *   --mode hot   : same work without the dump (CPU timing of the hot path alone)
  *   --mode null  : the full BroadCombinedGVCFOperator::operate with a VCFAdapter whose hand-off is a no-op
  *                  (INFO/FORMAT collation + bcf1_t build, no serialisation)
+ *   --mode vid    : print the vid mapping (-j vid.json [-l callsets.json]) as FileBasedVidMapper holds it
  *   --mode config : print the query configuration as the reference's classes hold it after parsing (no storage opened)
  *   --mode bcf-java : the reference's own BroadCombinedGVCFOperator + VCFAdapter writing uncompressed BCF to stdout, constructed
  *                  as the JNI path constructs it (genomicsdb_bcf_generator.cc:60-83: use_missing_values_only_not_vector_end =
@@ -188,6 +189,80 @@ int main(int argc, char** argv)
     }
     sm.close_array(qp.get_array_descriptor());
     GenomicsDBProtoBufInitAndCleanup::shutdown_protobuf_library();
+    return 0;
+  }
+  if(mode_str == "vid")
+  {
+    // the vid mapping (-j names the file; -l, optional, a callset mapping file) as the reference's FileBasedVidMapper holds it:
+    // every field in index order (FORMAT twins, flattened tuple elements and the mandatory fields included), contigs, callsets
+    FileBasedVidMapper vid(query_json);
+    if(!loader_json.empty())
+      vid.parse_callsets_json(loader_json, true);
+    auto ht_name = [](const int ht) { return ht == BCF_HT_FLAG ? "flag" : ht == BCF_HT_INT ? "int" : ht == BCF_HT_REAL ? "float" : (ht == BCF_HT_STR || ht == BCF_HT_CHAR) ? "char" : "?"; };
+    std::cout << "{\"fields\": [";
+    for(auto i=0u;i<vid.get_num_fields();++i)
+    {
+      auto& f = vid.get_field_info(i);
+      std::cout << (i ? ", " : "") << "{\"name\": \"" << f.m_name << "\", \"idx\": " << f.m_field_idx << ", \"vcf_name\": \"" << f.m_vcf_name
+        << "\", \"class\": \"" << (f.m_is_vcf_INFO_field ? "I" : "") << (f.m_is_vcf_FORMAT_field ? "F" : "") << (f.m_is_vcf_FILTER_field ? "T" : "")
+        << "\", \"type\": [";
+      auto& t = f.get_genomicsdb_type();
+      for(auto j=0u;j<t.get_num_elements_in_tuple();++j)
+      {
+        auto ht = t.get_tuple_element_bcf_ht_type(j);
+        std::cout << (j ? ", " : "") << "\"" << ht_name(ht) << "\"";
+      }
+      std::cout << "], \"length\": [";
+      auto& l = f.m_length_descriptor;
+      for(auto d=0u;d<l.get_num_dimensions();++d)
+      {
+        std::cout << (d ? ", " : "") << "\"";
+        if(l.is_fixed_size_dimension(d))
+          std::cout << l.get_num_elements_in_dimension(d);
+        else
+          std::cout << g_length_descriptor_int_to_string[l.get_length_descriptor(d)];
+        std::cout << "\"";
+      }
+      std::cout << "], \"op\": " << f.m_VCF_field_combine_operation << ", \"flattened\": " << f.is_flattened_field();
+      if(l.get_num_dimensions() > 1u)
+      {
+        std::cout << ", \"delims\": \"";
+        for(auto d=0u;d<l.get_num_dimensions();++d)
+          std::cout << l.get_vcf_delimiter(d);
+        std::cout << "\"";
+      }
+      std::cout << "}";
+    }
+    std::cout << "], \"contigs\": [";
+    for(auto i=0u;i<vid.get_num_contigs();++i)
+    {
+      auto& c = vid.get_contig_info(i);
+      std::cout << (i ? ", " : "") << "[\"" << c.m_name << "\", " << c.m_tiledb_column_offset << ", " << c.m_length << "]";
+    }
+    std::cout << "], \"callsets\": [";
+    if(vid.is_callset_mapping_initialized())
+      for(auto r=0ll;r<=vid.get_max_callset_row_idx();++r)
+      {
+        std::string name;
+        vid.get_callset_name(r, name);
+        std::cout << (r ? ", " : "") << "\"" << name << "\"";
+      }
+    std::cout << "], \"locate\": [";
+    // a few columns -> (contig, 0-based position), -1: none
+    auto first = true;
+    for(auto i=0u;i<vid.get_num_contigs();++i)
+    {
+      auto& c = vid.get_contig_info(i);
+      for(auto col : { c.m_tiledb_column_offset - 1, c.m_tiledb_column_offset, c.m_tiledb_column_offset + c.m_length - 1, c.m_tiledb_column_offset + c.m_length })
+      {
+        std::string name;
+        int64_t pos = -1;
+        auto found = (col >= 0) && vid.get_contig_location(col, name, pos);
+        std::cout << (first ? "" : ", ") << "[" << col << ", \"" << (found ? name : "") << "\", " << (found ? pos : -1) << "]";
+        first = false;
+      }
+    }
+    std::cout << "]}" << std::endl;
     return 0;
   }
   if(mode_str == "config")

@@ -57,10 +57,10 @@ def test_vid_mapping_of_multidimensional_and_tuple_fields(tmp_path):
     got = json.loads(out.stdout)
     mq = got["AS_RAW_MQ"]
     assert (mq["multid"], mq["composite"], mq["type"], mq["dims"], mq["delims"], mq["op"], mq["dim0_allele"], mq["allele_dependent"]) == \
-           (1, 0, "float", ["R", "var"], "|,", "element_wise_sum", 1, 0)
+           (1, 0, "float", ["R", "VAR"], "|,", "element_wise_sum", 1, 0)
     rs = got["AS_RAW_MQRankSum"]
     assert (rs["multid"], rs["composite"], rs["op"], rs["vcf_name"]) == (1, 1, "histogram_sum", "AS_RAW_MQRankSum")
     e0, e1 = got["AS_RAW_MQRankSum_tuple_element_0"], got["AS_RAW_MQRankSum_tuple_element_1"]
     assert (e0["type"], e0["parent"], e0["tuple_index"], e0["vcf_name"], e0["composite"], e0["multid"]) == ("float", "AS_RAW_MQRankSum", 0, "AS_RAW_MQRankSum", 0, 1)
-    assert (e1["type"], e1["parent"], e1["tuple_index"], e1["dims"], e1["delims"]) == ("int", "AS_RAW_MQRankSum", 1, ["R", "var"], "|,")
+    assert (e1["type"], e1["parent"], e1["tuple_index"], e1["dims"], e1["delims"]) == ("int", "AS_RAW_MQRankSum", 1, ["R", "VAR"], "|,")
     assert got["PL"]["multid"] == 0 and got["PL"]["allele_dependent"] == 1 and got["no_such"] is None
