@@ -153,6 +153,8 @@ class VariantQueryConfig {
   void set_vcf_output_format(const std::string& f) { vcf_output_format_ = f; }
   const std::string& get_vcf_output_format() const { return vcf_output_format_; }
   const std::string& get_vcf_header_filename() const { return vcf_header_filename_; }
+  // where the Broad GVCF goes ("-": stdout, the default; json_config.cc:577-617: one name, one per rank, or the rank's column partition's)
+  const std::string& get_vcf_output_filename() const { return vcf_output_filename_; }
   void set_vcf_header_filename(const std::string& f) { vcf_header_filename_ = f; }
   const std::string& get_reference_genome() const { return reference_genome_; }
   void set_reference_genome(const std::string& f) { reference_genome_ = f; }
@@ -192,7 +194,7 @@ class VariantQueryConfig {
   unsigned max_alt_ = 50;
   bool min_pl_gt_ = false, produce_gt_ = false, sites_only_ = false, produce_filter_ = false;
   bool bookkeeping_done_ = false;
-  std::string vcf_header_filename_, reference_genome_, vcf_output_format_ = "bu", callset_mapping_file_;
+  std::string vcf_header_filename_, reference_genome_, vcf_output_format_ = "bu", callset_mapping_file_, vcf_output_filename_ = "-";
   size_t segment_size_ = 10u * 1024u * 1024u;
   std::vector<std::string> remapped_names_;
   // plain fields staged for the Broad operator (do_query_bookkeeping): FORMAT fields that are not allele-dependent, scalar

@@ -354,6 +354,11 @@ void VariantQueryConfig::read_from_file(const std::string& filename, int rank) {
   if (const JsonValue* v = d.find("segment_size")) { if (!v->is_int) bad_config("\"segment_size\" must be an integer"); segment_size_ = (size_t)v->as_int(); }
   if (const JsonValue* v = d.find("vcf_header_filename")) vcf_header_filename_ = string_of_rank(*v, rank, "vcf_header_filename");
   if (const JsonValue* v = d.find("reference_genome")) reference_genome_ = string_of_rank(*v, rank, "reference_genome");
+  vcf_output_filename_ = "-";   // stdout
+  if (const JsonValue* v = d.find("vcf_output_filename")) vcf_output_filename_ = string_of_rank(*v, rank, "vcf_output_filename");
+  if (const JsonValue* cp = d.find("column_partitions"))   // json_config.cc:600-617: the rank's partition may name its own
+    if (cp->type == JsonValue::ARR && rank >= 0 && (size_t)rank < cp->arr.size())
+      if (const JsonValue* v = cp->arr[rank].find("vcf_output_filename")) { if (v->type != JsonValue::STR) bad_config("a partition's \"vcf_output_filename\" must be a string"); vcf_output_filename_ = v->str; }
   if (const JsonValue* v = d.find("vcf_output_format")) vcf_output_format_ = v->str;
   max_alt_ = d.has("max_diploid_alt_alleles_that_can_be_genotyped") ? (unsigned)d.at("max_diploid_alt_alleles_that_can_be_genotyped").as_int() : 50u;
   min_pl_gt_ = d.has("produce_GT_with_min_PL_value_for_spanning_deletions") && d.at("produce_GT_with_min_PL_value_for_spanning_deletions").as_bool();

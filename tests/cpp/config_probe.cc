@@ -37,7 +37,8 @@ int main(int argc, char** argv) {
               << ", \"produce_GT_field\": " << qc.produce_GT_field() << ", \"produce_FILTER_field\": " << qc.produce_FILTER_field()
               << ", \"sites_only_query\": " << qc.sites_only_query()
               << ", \"produce_GT_with_min_PL_value_for_spanning_deletions\": " << qc.produce_GT_with_min_PL_value_for_spanning_deletions()
-              << ", \"vcf_header_filename\": \"" << qc.get_vcf_header_filename() << "\", \"reference_genome\": \"" << qc.get_reference_genome() << "\"}" << std::endl;
+              << ", \"vcf_header_filename\": \"" << qc.get_vcf_header_filename() << "\", \"reference_genome\": \"" << qc.get_reference_genome()
+              << "\", \"vcf_output_filename\": \"" << qc.get_vcf_output_filename() << "\"}" << std::endl;
   } catch (const std::exception& e) {
     std::cerr << e.what() << "\n";
     return 1;

@@ -118,6 +118,25 @@ def test_rank_partitions_leave_the_query_whole(exe, tmp_path):
         assert out.read_bytes() == gold
 
 
+def test_reference_command_line_and_output_destination(exe, tmp_path):
+    """the reference tool's own spellings (--json-config, -O bu) and its destinations: the Broad GVCF goes to stdout, or to the
+    configuration's "vcf_output_filename" (json_config.cc:577-617), when no -o is given"""
+    case = [c for c in ALL if c["id"] == "t0_1_2_at_12150"][0]
+    gold = open(os.path.join(GOLDEN, "bcf", case["id"] + ".bcf"), "rb").read()
+    qf = query_json(case, tmp_path)
+    p = subprocess.run([exe, "--json-config", qf, "--produce-Broad-GVCF", "-O", "bu", "-s", "1048576"], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode(errors="replace")
+    assert p.stdout == gold
+    q = json.load(open(qf))
+    q["vcf_output_filename"] = str(tmp_path / "named_in_the_query.bcf")
+    json.dump(q, open(qf, "w"))
+    p = subprocess.run([exe, "--json-config", qf, "--produce-Broad-GVCF"], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode(errors="replace")
+    assert open(q["vcf_output_filename"], "rb").read() == gold   # (stdout then carries the tool's own one-line run summary)
+    p = subprocess.run([exe, "--json-config", qf, "--print-calls"], capture_output=True)
+    assert p.returncode == 0 and p.stdout.startswith(b"{")
+
+
 # ---------------------------------------------------------------------------------------------- the C ABI of the query stream
 @pytest.mark.parametrize("cid", ["t0_1_2_at_0", "t0_1_2_multiple_positions", "haploid_triploid_deletion_produce_GT"])
 @pytest.mark.parametrize("read_size,capacity", [(7, 64), (1 << 16, 1 << 20)], ids=["7B-reads", "64kB-reads"])

@@ -72,7 +72,9 @@ ACCEPTED = {
     "row_partitions_in_the_query": (q(row_partitions=[{"begin": 2}, {"begin": 0}]), None, ()),   # refused (no column ranges)
     "row_partitions_with_columns": (q(query_column_ranges=[[[0, 100]]], row_partitions=[{"begin": 2, "end": 3}, {"begin": 0, "end": 5}, {"begin": 9, "end": 7}]), None, (0, 1, 2)),
     "per_rank_workspace_and_array": (q(workspace=["/w0", "/w1"], array=None, array_name=["a0", "a1"], query_column_ranges=[[1]]), None, (0, 1)),
-    "per_rank_files": (q(query_column_ranges=[[1]], vcf_header_filename=["h0.vcf", "h1.vcf"], reference_genome=["r0.fa", "r1.fa"]), None, (0, 1)),
+    "per_rank_files": (q(query_column_ranges=[[1]], vcf_header_filename=["h0.vcf", "h1.vcf"], reference_genome=["r0.fa", "r1.fa"], vcf_output_filename=["o0.bcf", "o1.bcf"]), None, (0, 1)),
+    "output_file": (q(query_column_ranges=[[1]], vcf_output_filename="out.bcf"), None, (0,)),
+    "output_file_of_the_rank_s_partition": (q(vcf_output_filename="all.bcf", column_partitions=[{"begin": 0, "vcf_output_filename": "p0.bcf"}, {"begin": 100}]), None, (0, 1)),
     "options": (q(query_column_ranges=[[1]], segment_size=4096, max_diploid_alt_alleles_that_can_be_genotyped=3, produce_GT_field=True, produce_FILTER_field=True,
                   sites_only_query=True, produce_GT_with_min_PL_value_for_spanning_deletions=True, vcf_header_filename="h.vcf", reference_genome="r.fa"), None, (0,)),
     "query_attributes_spelling_and_a_repeated_name": (q(attributes=None, query_attributes=["PL", "REF", "PL", "GT", "REF"], query_column_ranges=[[1]]), None, (0,)),

@@ -261,10 +261,20 @@ int main(int argc, char** argv) {
   std::string query_json, loader_json, out_file, header_file, ref_bases_file; int rank = 0, device = 0; size_t page = 0; bool broad = false, htsjdk = false; int columnar = 0; size_t stream_chunk = 0; bool header_only = false; unsigned max_alleles_top = 0; std::string chr; int chr_start = 0, chr_end = 0;
   static struct option long_options[] = {{"query", 1, 0, 'j'}, {"rank", 1, 0, 'r'}, {"output", 1, 0, 'o'}, {"device", 1, 0, 'd'}, {"page-size", 1, 0, 'p'},
                                          {"produce-Broad-GVCF", 0, 0, 'B'}, {"loader-json-config", 1, 0, 'l'}, {"bcf-header", 1, 0, 'H'}, {"reference-bases", 1, 0, 'R'}, {"htsjdk-conventions", 0, 0, 'J'},
-                                         {"produce-interesting-positions", 0, 0, 'I'}, {"bcf-generator", 1, 0, 'S'}, {"header-only", 0, 0, 'h'}, {"max-alleles", 1, 0, 'M'}, {"chromosome", 1, 0, 'c'}, {"begin", 1, 0, 'b'}, {"end", 1, 0, 'e'}, {"print-calls", 0, 0, 'C'}, {"print-csv", 0, 0, 'V'}, {"print-AC", 0, 0, 'A'}, {"produce-histogram", 0, 0, 'G'}, {"range-query", 0, 0, 'Q'}, {0, 0, 0, 0}};
+                                         {"produce-interesting-positions", 0, 0, 'I'}, {"bcf-generator", 1, 0, 'S'}, {"header-only", 0, 0, 'h'}, {"max-alleles", 1, 0, 'M'}, {"chromosome", 1, 0, 'c'}, {"begin", 1, 0, 'b'}, {"end", 1, 0, 'e'}, {"print-calls", 0, 0, 'C'}, {"print-csv", 0, 0, 'V'}, {"print-AC", 0, 0, 'a'}, {"produce-histogram", 0, 0, 'G'}, {"range-query", 0, 0, 'Q'},
+                                         // the reference tool's own spellings (tools/src/gt_mpi_gather.cc:438-455)
+                                         {"json-config", 1, 0, 'j'}, {"output-format", 1, 0, 'O'}, {"workspace", 1, 0, 'w'}, {"array", 1, 0, 'A'}, {"segment-size", 1, 0, 's'},
+                                         {"skip-query-on-root", 0, 0, 'k'}, {"version", 0, 0, 'v'}, {0, 0, 0, 0}};
   int c;
-  while ((c = getopt_long(argc, argv, "j:l:r:o:d:p:BH:R:J", long_options, NULL)) >= 0) {
+  std::string output_format;
+  while ((c = getopt_long(argc, argv, "j:l:r:o:d:p:BH:R:JO:w:A:s:", long_options, NULL)) >= 0) {
     switch (c) {
+      case 'O': output_format = optarg; break;   // gt_mpi_gather -O: only uncompressed BCF ("bu") is produced here
+      case 'w': case 'A': break;                 // read and, as in the reference (gt_mpi_gather.cc:564-565), overridden by the configuration's workspace / array
+      case 's': break;                           // TileDB segment size: fragment files are staged whole, there is no segment
+      case 'k': break;                           // MPI gather detail of the reference tool: one process per GPU here, every rank queries
+      case 'v': std::cout << gdbgpu_version() << "\n"; return 0;
+      case 'a': columnar = 'A'; break;
       case 'j': query_json = optarg; break;
       case 'l': loader_json = optarg; break;   // gt_mpi_gather -l: workspace / array / mappings / column partition of the rank from the loader's file
       case 'r': rank = atoi(optarg); break;
@@ -281,12 +291,19 @@ int main(int argc, char** argv) {
       case 'c': chr = optarg; break;
       case 'b': chr_start = atoi(optarg); break;
       case 'e': chr_end = atoi(optarg); break;
-      case 'C': case 'V': case 'A': case 'G': case 'I': case 'Q': columnar = c; break;   // records as GenomicsDBBCFGenerator (JNI) makes them for the Java reader
+      case 'C': case 'V': case 'G': case 'I': case 'Q': columnar = c; break;   // records as GenomicsDBBCFGenerator (JNI) makes them for the Java reader
       default: return -1;
     }
   }
-  if (query_json.empty() || out_file.empty()) { std::cerr << "usage: gt_gpu_gather -j query.json -o dump.bin [-r rank] [-d cuda_device] [-p sites_per_page]\n"; return -1; }
+  if (query_json.empty()) { std::cerr << "Query JSON file (-j) is a mandatory argument - unspecified\n"; return -1; }
+  if (!output_format.empty() && output_format != "bu") { std::cerr << "gt_gpu_gather: output format '" << output_format << "' is not produced on this path (uncompressed BCF, \"bu\", only)\n"; return -1; }
   try {
+    if (out_file.empty()) {
+      // the reference tool writes to stdout, the Broad GVCF to the configuration's "vcf_output_filename" (default "-": stdout)
+      if (broad && !stream_chunk) { VariantQueryConfig qc; if (!loader_json.empty()) { GenomicsDBImportConfig lc; lc.read_from_file(loader_json, rank); qc.update_from_loader(lc, rank); } qc.read_from_file(query_json, rank); out_file = qc.get_vcf_output_filename(); }
+      else if (columnar) out_file = "-";
+      else { std::cerr << "usage: gt_gpu_gather -j query.json -o dump.bin [-r rank] [-d cuda_device] [-p sites_per_page]\n"; return -1; }
+    }
     if (stream_chunk) {
       return bcf_generator_stream(query_json, rank, device, header_file, ref_bases_file, out_file, page, stream_chunk, htsjdk, chr, chr_start, chr_end, header_only, loader_json);
     }
