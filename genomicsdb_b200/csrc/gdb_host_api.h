@@ -119,7 +119,7 @@ class GenomicsDBImportConfig {
   const std::string& get_reference_genome() const { return reference_genome_; }
   size_t get_segment_size() const { return segment_size_; }
  private:
-  bool row_based_ = false, partitions_specified_ = false;
+  bool row_based_ = false, partitions_specified_ = false, single_workspace_ = false, single_array_ = false;
   std::vector<std::pair<int64_t, int64_t>> partitions_;   // in file order, ends fixed against the sorted order
   std::vector<std::string> workspaces_, array_names_;
   VidMapper vid_;

@@ -210,21 +210,31 @@ void GenomicsDBImportConfig::read_from_file(const std::string& filename, const i
   if (!cp || cp->type != JsonValue::ARR) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "the loader configuration has no \"column_partitions\"");
   partitions_specified_ = true;
   read_partitions(*cp, true, vid_, partitions_, workspaces_, array_names_);
+  // json_config.cc:207-250,384-402: one name serves every rank only when it is given once, as a string, outside the partitions
+  single_workspace_ = d.has("workspace") && d.at("workspace").type != JsonValue::ARR;
+  single_array_ = an && an->type != JsonValue::ARR;
+  for (auto& p : cp->arr) { if (p.has("workspace")) single_workspace_ = false; if (p.has("array") || p.has("array_name")) single_array_ = false; }
 }
 std::pair<int64_t, int64_t> GenomicsDBImportConfig::get_column_partition(const int rank, const unsigned idx) const {
   (void)idx;
   if (!partitions_specified_ || partitions_.empty()) return {0, INT64_MAX - 1};
-  return partitions_[std::min<size_t>((size_t)rank, partitions_.size() - 1)];
+  // genomicsdb_config_base.cc:89-100: every rank must have its own partition (only a single list of query_column_ranges serves all)
+  if (rank < 0 || (size_t)rank >= partitions_.size()) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "No column partition/query interval available for process with rank " + std::to_string(rank));
+  return partitions_[rank];
 }
 const std::string& GenomicsDBImportConfig::get_workspace(const int rank) const {
   static const std::string none;
   if (workspaces_.empty()) return none;
-  return workspaces_.size() == 1 ? workspaces_[0] : workspaces_[std::min<size_t>((size_t)rank, workspaces_.size() - 1)];
+  if (single_workspace_) return workspaces_[0];   // genomicsdb_config_base.cc:59-66
+  if (rank < 0 || (size_t)rank >= workspaces_.size()) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Workspace not defined for rank " + std::to_string(rank));
+  return workspaces_[rank];
 }
 const std::string& GenomicsDBImportConfig::get_array_name(const int rank) const {
   static const std::string none;
   if (array_names_.empty()) return none;
-  return array_names_.size() == 1 ? array_names_[0] : array_names_[std::min<size_t>((size_t)rank, array_names_.size() - 1)];
+  if (single_array_) return array_names_[0];   // genomicsdb_config_base.cc:68-75
+  if (rank < 0 || (size_t)rank >= array_names_.size()) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Could not find array for rank " + std::to_string(rank));
+  return array_names_[rank];
 }
 
 // ------------------------------------------------------------------------------------------------ query configuration
@@ -377,23 +387,26 @@ void VariantQueryConfig::read_from_file(const std::string& filename, int rank) {
   array_name_ = single_array ? array_names[0] : array_names[rank];
   if (array_name_.empty()) bad_config("Empty array name");
   if (column_ranges.empty() && !scan_full) bad_config("Query column ranges not specified");
-  if (column_ranges.size() != 1 && (size_t)rank >= column_ranges.size()) bad_config("Rank >= query column ranges vector size");
-  base_column_ranges_ = column_ranges[column_ranges.size() == 1 ? 0 : rank];
+  // json_config.cc:275-276,428-429: ONE list of query_column_ranges / query_row_ranges serves every rank; partitions do not
+  const bool single_columns = scan_full || (d.has("query_column_ranges") && column_ranges.size() == 1);
+  const bool single_rows = d.has("query_row_ranges") && row_ranges.size() == 1;
+  if (!single_columns && (size_t)rank >= column_ranges.size()) bad_config("Rank >= query column ranges vector size");
+  base_column_ranges_ = column_ranges[single_columns ? 0 : rank];
   intervals_.clear();
   if (!scan_full) for (auto& r : base_column_ranges_) add_column_interval_to_query(r.first, r.second);
   rows_.clear();
   if (!scan_full && !row_ranges.empty()) {
-    if (row_ranges.size() != 1 && (size_t)rank >= row_ranges.size()) bad_config("Rank >= query row ranges vector size");
+    if (!single_rows && (size_t)rank >= row_ranges.size()) bad_config("Rank >= query row ranges vector size");
     std::vector<int64_t> rows;
     // every row of every range is listed (variant_query_config.cc:266-274); an open-ended row partition cannot be (the reference
     // dies in its vector's resize there)
     uint64_t total = 0;
-    for (auto& r : row_ranges[row_ranges.size() == 1 ? 0 : rank]) {
+    for (auto& r : row_ranges[single_rows ? 0 : rank]) {
       total += (uint64_t)r.second - (uint64_t)r.first + 1u;
       if (total > (1ull << 31)) bad_config("the queried row ranges list more than 2^31 rows");
     }
     rows.reserve(total);
-    for (auto& r : row_ranges[row_ranges.size() == 1 ? 0 : rank]) for (int64_t i = r.first; i <= r.second; ++i) rows.push_back(i);
+    for (auto& r : row_ranges[single_rows ? 0 : rank]) for (int64_t i = r.first; i <= r.second; ++i) rows.push_back(i);
     set_rows_to_query(rows);
   }
 }

@@ -82,6 +82,12 @@ ACCEPTED = {
     "loader_supplies_storage_and_mappings": (q(workspace=None, array=None, vid_mapping_file=None, callset_mapping_file=None, query_column_ranges=[[[0, 50], [4000, 4100], 7000]]),
                                              {"row_based_partitioning": False, "column_partitions": [{"begin": 0, "workspace": "/lw0", "array": "la0"}, {"begin": 4050, "workspace": "/lw1", "array": "la1"}],
                                               "vid_mapping_file": VID, "callset_mapping_file": CALLSETS, "size_per_column_partition": 1000}, (0, 1)),
+    "one_loader_partition_serves_every_rank": (q(workspace=None, array=None, query_column_ranges=[[[0, 50], 9000]]),
+                                               {"row_based_partitioning": False, "column_partitions": [{"begin": 100, "workspace": "/lw0", "array": "la0"}],
+                                                "vid_mapping_file": VID, "callset_mapping_file": CALLSETS, "size_per_column_partition": 1000}, (0,)),
+    "one_loader_partition_and_storage_named_outside_it": (q(workspace=None, array=None, query_column_ranges=[[[0, 50], 9000]]),
+                                               {"row_based_partitioning": False, "column_partitions": [{"begin": 100}], "workspace": "/lw", "array": "la",
+                                                "vid_mapping_file": VID, "callset_mapping_file": CALLSETS, "size_per_column_partition": 1000}, (0,)),
     "query_overrides_the_loader": (q(query_column_ranges=[[[0, 50], 9000]]),
                                    {"row_based_partitioning": False, "column_partitions": [{"begin": 0, "workspace": "/lw0", "array": "la0"}, {"begin": 4050, "workspace": "/lw1", "array": "la1"}],
                                     "vid_mapping_file": VID, "callset_mapping_file": CALLSETS, "size_per_column_partition": 1000}, (0, 1)),
@@ -109,11 +115,25 @@ REFUSED = {
     "no_callset_mapping": q(callset_mapping_file=None, query_column_ranges=[[1]]),
     "syntax_error": "{ \"workspace\": ",
 }
+LOADER2 = {"row_based_partitioning": False, "column_partitions": [{"begin": 0, "workspace": "/lw0", "array": "la0"}, {"begin": 4050, "workspace": "/lw1", "array": "la1"}],
+           "vid_mapping_file": VID, "callset_mapping_file": CALLSETS, "size_per_column_partition": 1000}
+LOADER_REFUSED = {   # (query, loader, rank)
+    "rank_past_the_loader_s_partitions": (q(query_column_ranges=[[[0, 50]]]), LOADER2, 2),
+    "rank_past_the_loader_s_storage": (q(workspace=None, array=None, query_column_ranges=[[[0, 50]]]), LOADER2, 2),
+    "storage_named_inside_the_only_partition_serves_rank_0_alone": (q(workspace=None, array=None, query_column_ranges=[[[0, 50]]]),
+        {"row_based_partitioning": False, "column_partitions": [{"begin": 100, "workspace": "/lw0", "array": "la0"}], "vid_mapping_file": VID, "callset_mapping_file": CALLSETS, "size_per_column_partition": 1000}, 5),
+    "one_loader_partition_serves_rank_0_alone": (q(query_column_ranges=[[[0, 50]]]),
+        {"row_based_partitioning": False, "column_partitions": [{"begin": 100}], "workspace": "/lw", "array": "la", "vid_mapping_file": VID, "callset_mapping_file": CALLSETS, "size_per_column_partition": 1000}, 1),
+    "loader_without_partitions": (q(query_column_ranges=[[[0, 50]]]), {"row_based_partitioning": False, "vid_mapping_file": VID, "callset_mapping_file": CALLSETS, "size_per_column_partition": 1000}, 0),
+    "loader_without_size_per_column_partition": (q(query_column_ranges=[[[0, 50]]]), {k: v for k, v in LOADER2.items() if k != "size_per_column_partition"}, 0),
+}
 RANK_REFUSED = {   # accepted for the ranks the lists cover, refused past them
     "a_list_per_rank": (ACCEPTED["a_list_per_rank"][0], 3),
     "per_rank_workspace_and_array": (ACCEPTED["per_rank_workspace_and_array"][0], 2),
     "per_rank_files": (ACCEPTED["per_rank_files"][0], 2),
     "column_partitions_in_the_query": (ACCEPTED["column_partitions_in_the_query"][0], 3),
+    "one_column_partition_in_the_query": (q(column_partitions=[{"begin": 5}]), 1),
+    "one_row_partition_in_the_query": (q(query_column_ranges=[[1]], row_partitions=[{"begin": 0, "end": 2}]), 1),
 }
 
 
@@ -154,5 +174,13 @@ def test_configurations_the_reference_refuses(probe, tmp_path, name):
 def test_rank_past_the_per_rank_lists(probe, tmp_path, name):
     query, rank = RANK_REFUSED[name]
     ref, ours = run_both(probe, tmp_path, query, None, rank)
+    assert ref.returncode != 0, ref.stdout
+    assert ours.returncode == 1 and ours.stderr.strip(), (ours.returncode, ours.stdout, ours.stderr)
+
+
+@pytest.mark.parametrize("name", list(LOADER_REFUSED))
+def test_loader_configurations_the_reference_refuses(probe, tmp_path, name):
+    query, loader, rank = LOADER_REFUSED[name]
+    ref, ours = run_both(probe, tmp_path, query, loader, rank)
     assert ref.returncode != 0, ref.stdout
     assert ours.returncode == 1 and ours.stderr.strip(), (ours.returncode, ours.stdout, ours.stderr)
