@@ -446,7 +446,7 @@ void VCFAdapter::initialize(const VariantQueryConfig& config) {
     if (!f) throw GenomicsDBGPUException(GDBGPU_ERR_IO, "Could not open template VCF header file " + config.get_vcf_header_filename());
     std::stringstream ss; ss << f.rdbuf();
     lines_.reset(new VCFHeaderLines(false));
-    lines_->parse(ss.str(), /*sample_line_required=*/false);
+    if (!lines_->parse(ss.str(), /*sample_line_required=*/false)) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Could not parse template VCF header file " + config.get_vcf_header_filename());
   }
   const std::string& fmt = config.get_vcf_output_format();
   if (!(fmt.empty() || fmt == "bu")) throw GenomicsDBGPUException(GDBGPU_ERR_LIMIT, "only uncompressed BCF (\"bu\") is produced on this path");

@@ -9,6 +9,7 @@
 #include <cctype>
 #include <climits>
 #include <cstring>
+#include <strings.h>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
@@ -197,7 +198,14 @@ bool VCFHeaderLines::append(const std::string& line) {
 bool VCFHeaderLines::parse(const std::string& text, bool sample_line_required) {
   const char* p = text.c_str();
   int len = 0;
-  add_rec(parse_line(p, &len));   // "fileformat" is expected first
+  // "fileformat" must come first: the reference's htslib still reads the rest but reports failure (vcf.c:652-658,714-720), and
+  // the reader above it then has no header
+  bool ok = true;
+  {
+    auto first = parse_line(p, &len);
+    if (!first || strcasecmp(first->key.c_str(), "fileformat") != 0) ok = false;
+    add_rec(std::move(first));
+  }
   add_rec(parse_line("##FILTER=<ID=PASS,Description=\"All filters passed\">", &len));   // PASS first in the dictionary
   int done = 0;
   do {
@@ -216,7 +224,8 @@ bool VCFHeaderLines::parse(const std::string& text, bool sample_line_required) {
       if (eol) p = eol + 1; else done = -1;
     } else done = 1;
   } while (!done);
-  if (done < 0) return !sample_line_required;
+  if (done < 0) return ok && !sample_line_required;
+  if (!ok) return false;
   // sample line: columns past the ninth
   int i = 0;
   const char* q;

@@ -9,6 +9,7 @@
  *   --mode hot   : same work without the dump (CPU timing of the hot path alone)
  *   --mode null  : the full BroadCombinedGVCFOperator::operate with a VCFAdapter whose hand-off is a no-op
  *                  (INFO/FORMAT collation + bcf1_t build, no serialisation)
+ *   --mode header : htslib's header bookkeeping on a header text (-j) plus lines to append (-l)
  *   --mode vid    : print the vid mapping (-j vid.json [-l callsets.json]) as FileBasedVidMapper holds it
  *   --mode config : print the query configuration as the reference's classes hold it after parsing (no storage opened)
  *   --mode bcf-java : the reference's own BroadCombinedGVCFOperator + VCFAdapter writing uncompressed BCF to stdout, constructed
@@ -27,6 +28,8 @@
  *              nfields x { u32 n, u32 word[n] }      n==0 : field invalid / suppressed
  */
 #include <iostream>
+#include <fstream>
+#include <sstream>
 #include <string>
 #include <vector>
 #include <cstdio>
@@ -189,6 +192,41 @@ int main(int argc, char** argv)
     }
     sm.close_array(qp.get_array_descriptor());
     GenomicsDBProtoBufInitAndCleanup::shutdown_protobuf_library();
+    return 0;
+  }
+  if(mode_str == "header")
+  {
+    // htslib's header bookkeeping (the reference's own copy): -j names a header text ("" lines: bcf_hdr_init("w")), -l, optional,
+    // a file of lines to append one by one (a line "SAMPLE <name>" adds a sample); then what the Broad operator does before it
+    // writes the header (broad_combined_gvcf.cc:314-325): format without IDX, parse again, format as BCF.  Printed: the final
+    // text, then "ID <name> <idx>" per dictionary entry.
+    std::ifstream f(query_json); std::stringstream ss; ss << f.rdbuf();
+    auto text = ss.str();
+    size_t hdr_len = 0;
+    bcf_hdr_t* h = bcf_hdr_init(text.empty() ? "w" : "r");
+    if(!text.empty() && bcf_hdr_parse_required_sample_line(h, &(text[0]), &hdr_len, 0) != 0) { std::cerr << "parse failed\n"; return 1; }
+    if(!loader_json.empty())
+    {
+      std::ifstream l(loader_json); std::string line;
+      while(std::getline(l, line))
+      {
+        if(line.compare(0, 7, "SAMPLE ") == 0) std::cout << "add_sample " << bcf_hdr_add_sample(h, line.c_str()+7) << "\n";
+        else std::cout << "append " << bcf_hdr_append(h, line.c_str()) << "\n";
+      }
+      bcf_hdr_add_sample(h, 0);
+      bcf_hdr_sync(h);
+    }
+    kstring_t a = {0, 0, 0};
+    bcf_hdr_format(h, 0, &a);
+    bcf_hdr_t* h2 = bcf_hdr_init("r");
+    if(bcf_hdr_parse_required_sample_line(h2, a.s, &hdr_len, 0) != 0) { std::cerr << "second parse failed\n"; return 1; }
+    kstring_t b = {0, 0, 0};
+    bcf_hdr_format(h2, 1, &b);
+    std::cout << b.s;
+    for(int t : { BCF_DT_ID, BCF_DT_CTG })
+      for(int i=0;i<h2->n[t];++i)
+        if(h2->id[t][i].key) std::cout << (t == BCF_DT_ID ? "ID " : "CTG ") << h2->id[t][i].key << " " << i << "\n";
+    std::cout << "nsamples " << bcf_hdr_nsamples(h2) << "\n";
     return 0;
   }
   if(mode_str == "vid")

@@ -1,0 +1,79 @@
+"""CPU: VCFHeaderLines -- htslib's header bookkeeping restated in the library (bcf_hdr_parse / append / add_sample / sync / format,
+the dictionaries of IDs and contigs) -- against the reference's own htslib (oracle/_ref/bin/gdb_ref_dump --mode header) on header
+texts a template may hold: IDX fields, repeated IDs, one ID as FILTER, INFO and FORMAT, lines in any order, generic and
+structured lines, quoted commas, a missing fileformat line, samples; and on the lines the Broad operator appends."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, REPO
+
+REF = os.path.join(REPO, "oracle", "_ref", "bin", "gdb_ref_dump")
+CHROM = "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n"
+
+
+@pytest.fixture(scope="module")
+def probe(tmp_path_factory):
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref is not built")
+    import __graft_entry__ as g
+    lib = g.build_gpu_lib()
+    exe = str(tmp_path_factory.mktemp("probe") / "header_probe")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(REPO, "tests", "cpp", "header_probe.cc"), "-o", exe,
+                           "-I" + os.path.join(REPO, "include"), "-L" + os.path.dirname(lib), "-lgdbgpu", "-Wl,-rpath," + os.path.dirname(lib)])
+    return exe
+
+
+TEMPLATE = open(os.path.join(GOLDEN, "inputs", "template_vcf_header.vcf")).read()
+APPENDED = ["##INFO=<ID=NEW_INFO,Number=1,Type=Integer,Description=\"added\">",
+            "##FORMAT=<ID=NEW_FMT,Number=R,Type=Float,Description=\"added, with a comma\">",
+            "##FORMAT=<ID=DP,Number=1,Type=Integer,Description=\"already there\">",
+            "##FILTER=<ID=q10,Description=\"Quality below 10\">",
+            "##contig=<ID=chrNew,length=12345>",
+            "##contig=<ID=1,length=5>",
+            "##source=a generic line",
+            "SAMPLE HG00141", "SAMPLE HG01958", "SAMPLE HG00141", "SAMPLE with space"]
+CASES = {
+    "template": (TEMPLATE, None),
+    "template_plus_appended_lines_and_samples": (TEMPLATE, APPENDED),
+    "write_mode_start": ("", APPENDED),
+    "no_fileformat_line": ("##INFO=<ID=DP,Number=1,Type=Integer,Description=\"d\">\n" + CHROM, None),
+    "idx_fields_out_of_order": ("##fileformat=VCFv4.2\n##FILTER=<ID=PASS,Description=\"All filters passed\",IDX=0>\n##INFO=<ID=B,Number=1,Type=Integer,Description=\"b\",IDX=5>\n"
+                                "##INFO=<ID=A,Number=1,Type=Integer,Description=\"a\",IDX=2>\n##FORMAT=<ID=C,Number=1,Type=Integer,Description=\"c\">\n"
+                                "##contig=<ID=z,length=10,IDX=1>\n##contig=<ID=y,length=20,IDX=0>\n" + CHROM, ["##INFO=<ID=D,Number=1,Type=Integer,Description=\"d\">"]),
+    "one_id_in_three_dictionaries": ("##fileformat=VCFv4.2\n##FILTER=<ID=DP,Description=\"f\">\n##INFO=<ID=DP,Number=1,Type=Integer,Description=\"i\">\n"
+                                     "##FORMAT=<ID=DP,Number=1,Type=Integer,Description=\"g\">\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"gt\">\n" + CHROM, None),
+    "the_same_line_twice": ("##fileformat=VCFv4.2\n##INFO=<ID=DP,Number=1,Type=Integer,Description=\"first\">\n##INFO=<ID=DP,Number=1,Type=Integer,Description=\"second\">\n"
+                            "##contig=<ID=1,length=10>\n##contig=<ID=1,length=20>\n" + CHROM, None),
+    "no_pass_filter_and_other_filters_first": ("##fileformat=VCFv4.1\n##FILTER=<ID=LowQual,Description=\"Low quality\">\n##INFO=<ID=END,Number=1,Type=Integer,Description=\"e\">\n" + CHROM, None),
+    "number_and_type_spellings": ("##fileformat=VCFv4.2\n##INFO=<ID=A,Number=A,Type=Float,Description=\"a\">\n##INFO=<ID=G,Number=G,Type=Integer,Description=\"g\">\n"
+                                  "##INFO=<ID=R,Number=R,Type=Character,Description=\"r\">\n##INFO=<ID=V,Number=.,Type=String,Description=\"v\">\n"
+                                  "##INFO=<ID=F,Number=0,Type=Flag,Description=\"f\">\n##FORMAT=<ID=N,Number=12,Type=Integer,Description=\"n\">\n" + CHROM, None),
+    "extra_keys_quotes_and_commas": ("##fileformat=VCFv4.2\n##INFO=<ID=X,Number=1,Type=Integer,Description=\"has, commas = and \\\"quotes\\\"\",Source=\"s\",Version=\"3\">\n"
+                                     "##ALT=<ID=NON_REF,Description=\"Represents any possible alternative allele at this location\">\n"
+                                     "##GATKCommandLine=<ID=HaplotypeCaller,Version=3.4,Date=\"Mon\",CommandLineOptions=\"a=b c=d\">\n"
+                                     "##contig=<ID=1,length=249250621,assembly=b37>\n##reference=file:///ref.fasta\n##source=SelectVariants\n" + CHROM, None),
+    "samples_in_the_template": ("##fileformat=VCFv4.2\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"gt\">\n" + CHROM[:-1] + "\tFORMAT\tS1\tS2\n", ["SAMPLE S3", "SAMPLE S1"]),
+    "lines_after_the_contigs": ("##fileformat=VCFv4.2\n##contig=<ID=2,length=10>\n##INFO=<ID=DP,Number=1,Type=Integer,Description=\"d\">\n##contig=<ID=1,length=10>\n"
+                                "##FILTER=<ID=q,Description=\"q\">\n" + CHROM, ["##contig=<ID=3,length=3>", "##INFO=<ID=AF,Number=A,Type=Float,Description=\"af\">"]),
+    "windows_line_ends_are_not_special": ("##fileformat=VCFv4.2\n##INFO=<ID=DP,Number=1,Type=Integer,Description=\"d\">\n\n" + CHROM, None),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_header_as_htslib_keeps_it(probe, tmp_path, name):
+    text, lines = CASES[name]
+    hf = tmp_path / "h.vcf"
+    hf.write_text(text)
+    ref_args, our_args = [REF, "--mode", "header", "-j", str(hf)], [probe, str(hf)]
+    if lines is not None:
+        lf = tmp_path / "lines.txt"
+        lf.write_text("\n".join(lines) + "\n")
+        ref_args += ["-l", str(lf)]
+        our_args.append(str(lf))
+    ref = subprocess.run(ref_args, capture_output=True, text=True)
+    ours = subprocess.run(our_args, capture_output=True, text=True)
+    assert (ref.returncode == 0) == (ours.returncode == 0), (ref.stderr[-400:], ours.stderr[-400:])
+    if ref.returncode == 0:
+        assert ours.stdout == ref.stdout
