@@ -103,15 +103,19 @@ bool VCFHeaderLines::register_rec(VCFHeaderRec* r) {
     idx = (int)x;
     return true;
   };
-  auto take_idx = [](std::vector<bool>& used, int& n, int& id) {   // bcf_hdr_set_idx
+  auto take_idx = [](std::vector<bool>& used, int& n, int& id, const std::string& tag) {   // bcf_hdr_set_idx
     if (id == -1) id = n++;
+    else if (id < n && id < (int)used.size() && used[id])   // the reference's htslib ends the process here (vcf.c:389-394)
+      throw std::runtime_error("Conflicting IDX=" + std::to_string(id) + " lines in the header dictionary, the new tag is " + tag);
     if (id >= n) n = id + 1;
     if ((int)used.size() < n) used.resize(n, false);
     used[id] = true;
   };
   if (r->key == "contig") {
     r->type = HL_CTG;
-    int i = r->find_key("ID");
+    int i = r->find_key("length");
+    if (i >= 0) { int len; if (sscanf(r->kv[i].second.c_str(), "%d", &len) != 1) return false; }   // a length that is no number: the line is dropped
+    i = r->find_key("ID");
     if (i < 0) return false;
     const std::string id = r->kv[i].second;
     if (ctgs_.count(id)) return false;   // already present
@@ -120,7 +124,7 @@ bool VCFHeaderLines::register_rec(VCFHeaderRec* r) {
     if (k >= 0 && !parse_idx(r->kv[k].second, idx)) return false;
     CtgInfo& c = ctgs_[id];
     c.id = idx; c.rec = r;
-    take_idx(ctg_used_, n_ctgs_, c.id);
+    take_idx(ctg_used_, n_ctgs_, c.id, id);
     if (idx == -1) r->kv.emplace_back("IDX", std::to_string(c.id));
     return true;
   }
@@ -165,7 +169,7 @@ bool VCFHeaderLines::register_rec(VCFHeaderRec* r) {
   }
   IdInfo& e = ids_[*id];
   e.info[r->type] = info; e.rec[r->type] = r; e.id = idx;
-  take_idx(id_used_, n_ids_, e.id);
+  take_idx(id_used_, n_ids_, e.id, *id);
   if (idx == -1) r->kv.emplace_back("IDX", std::to_string(e.id));
   return true;
 }
@@ -231,11 +235,11 @@ bool VCFHeaderLines::parse(const std::string& text, bool sample_line_required) {
   const char* q;
   for (p = q = p;; ++q) {
     if (*q != '\t' && *q != 0 && *q != '\n') continue;
-    if (++i > 9) add_sample(std::string(p, q - p));
+    if (++i > 9 && !add_sample(std::string(p, q - p))) ok = false;   // a sample named twice: every name is still read, the parse fails (vcf.c:122-140)
     if (*q == 0 || *q == '\n') break;
     p = q + 1;
   }
-  return true;
+  return ok;
 }
 
 // vcf.c:736-795 (the branch with a key)

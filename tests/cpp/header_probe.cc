@@ -9,6 +9,7 @@
 using namespace genomicsdb_b200;
 int main(int argc, char** argv) {
   if (argc < 2) return 2;
+  try {
   std::ifstream f(argv[1]); std::stringstream ss; ss << f.rdbuf();
   const std::string text = ss.str();
   VCFHeaderLines h(text.empty());
@@ -26,5 +27,6 @@ int main(int argc, char** argv) {
   for (auto& kv : h2.ids()) std::cout << "ID " << kv.first << " " << kv.second << "\n";
   for (auto& kv : h2.contigs()) std::cout << "CTG " << kv.first << " " << kv.second << "\n";
   std::cout << "nsamples " << h2.nsamples() << "\n";
+  } catch (const std::exception& e) { std::cerr << e.what() << "\n"; return 1; }
   return 0;
 }

@@ -57,6 +57,15 @@ CASES = {
     "samples_in_the_template": ("##fileformat=VCFv4.2\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"gt\">\n" + CHROM[:-1] + "\tFORMAT\tS1\tS2\n", ["SAMPLE S3", "SAMPLE S1"]),
     "lines_after_the_contigs": ("##fileformat=VCFv4.2\n##contig=<ID=2,length=10>\n##INFO=<ID=DP,Number=1,Type=Integer,Description=\"d\">\n##contig=<ID=1,length=10>\n"
                                 "##FILTER=<ID=q,Description=\"q\">\n" + CHROM, ["##contig=<ID=3,length=3>", "##INFO=<ID=AF,Number=A,Type=Float,Description=\"af\">"]),
+    # lines htslib drops, and headers it fails on
+    "contig_lengths_that_are_no_numbers": ("##fileformat=VCFv4.2\n##contig=<ID=1>\n##contig=<ID=2,length=abc>\n##contig=<ID=3,length=12x>\n" + CHROM, None),
+    "two_ids_with_one_idx": ("##fileformat=VCFv4.2\n##INFO=<ID=A,Number=1,Type=Integer,Description=\"a\",IDX=3>\n##INFO=<ID=B,Number=1,Type=Integer,Description=\"b\",IDX=3>\n" + CHROM, None),
+    "two_contigs_with_one_idx": ("##fileformat=VCFv4.2\n##contig=<ID=a,length=1,IDX=2>\n##contig=<ID=b,length=1,IDX=2>\n" + CHROM, None),
+    "a_sample_named_twice_in_the_template": ("##fileformat=VCFv4.2\n" + CHROM[:-1] + "\tFORMAT\tS1\tS2\tS1\n", None),
+    "malformed_lines": ("##fileformat=VCFv4.2\n##INFO=<ID=X,Number=1,Type=Integer,Description=\"x\"\n##INFO=<Number=1,Type=Integer,Description=\"no id\">\nnot a header line\n"
+                        "##INFO=<ID=Y, Number=1, Type=Double, Description=unquoted text>\n##FILTER=<ID=PASS,Description=\"mine\">\n##FILTER=<ID=q,Description=\"q\",IDX=9>\n" + CHROM, None),
+    "no_sample_line_at_all": ("##fileformat=VCFv4.2\n##INFO=<ID=X,Number=1,Type=Integer,Description=\"x\">\n", None),
+    "other_structured_lines": ("##fileformat=VCFv4.2\n##ALT=<ID=DEL,Description=\"d\">\n##PEDIGREE=<Name_0=a,Name_1=b>\n##SAMPLE=<ID=S,Genomes=g>\n##META=<ID=m,Type=String,Number=.,Values=[a, b]>\n" + CHROM, None),
     "windows_line_ends_are_not_special": ("##fileformat=VCFv4.2\n##INFO=<ID=DP,Number=1,Type=Integer,Description=\"d\">\n\n" + CHROM, None),
 }
 
