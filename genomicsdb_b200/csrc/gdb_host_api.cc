@@ -143,9 +143,10 @@ VidMapper::VidMapper(const std::string& file) {
       for (auto& x : t->arr) { if (x.type != JsonValue::STR) bad_vid("\"type\" of field " + name + " must hold strings"); f.tuple_types.push_back(canonical_type(x.str, name)); }
       f.type = f.tuple_types.empty() ? "int" : f.tuple_types[0];
     } else bad_vid("Attribute 'type' of field " + name + " must be a string or an array");
-    if (const JsonValue* vt = v.find("vcf_type")) {   // read for its refusals only: the VCF side of a multi-dimensional field is always a string
-      if (vt->type == JsonValue::STR) canonical_type(vt->str, name);
-      else if (vt->type == JsonValue::ARR) { for (auto& x : vt->arr) canonical_type(x.str, name); }
+    f.vcf_type = f.type;
+    if (const JsonValue* vt = v.find("vcf_type")) {   // what the header line declares (vcf_adapter.cc:128,167); a multi-dimensional field is always a string there
+      if (vt->type == JsonValue::STR) f.vcf_type = canonical_type(vt->str, name);
+      else if (vt->type == JsonValue::ARR) { for (size_t i = 0; i < vt->arr.size(); ++i) { const std::string t = canonical_type(vt->arr[i].str, name); if (i == 0) f.vcf_type = t; } }
       else bad_vid("Attribute 'vcf_type' of field " + name + " must be a string or an array");
     }
     if (f.length == "2D")   // vid_mapper.cc:200-215

@@ -50,7 +50,8 @@ class VariantQueryProcessorException : public GenomicsDBGPUException { using Gen
 // ---- field / contig / callset mapping (src/main/cpp/src/utils/vid_mapper.cc, file-based mapper)
 struct FieldInfo {
   std::string name;
-  std::string type;        // "int", "float", "char", ...
+  std::string type;        // "int", "float", "char", "flag"
+  std::string vcf_type;    // the type the VCF header declares ("vcf_type" of the vid mapping; the field's own type when absent)
   std::string length;      // "1", "R", "A", "G", "P", "PP", "VAR", "<n>"; 2-D descriptors are kept as "2D"
   bool is_format = false, is_info = false, is_filter = false;
   int global_idx = -1;     // the reference's field index (what FILTER cells store): file order, FORMAT twins and flattened tuple elements counted

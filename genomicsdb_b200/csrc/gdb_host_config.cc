@@ -507,34 +507,49 @@ bool add_field_to_hdr_if_missing(VCFHeaderLines& hdr, const VidMapper& id_mapper
     hdr.remove(field_type_idx, vcf_name);
     exists = false; removed = true;
   }
-  if (exists) return false;
+  if (exists) {
+    // vcf_adapter.cc:207-259: the template's line and the vid mapping must agree on length and type (GT, strings and FILTERs are
+    // not looked at)
+    const int ht = hdr.id2type(field_type_idx, vcf_name);
+    if (vcf_name != "GT" && ht != HT_STR && field_type_idx != HL_FLT) {
+      if (!fi) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "field " + field_name + " is not in the vid mapping");
+      const bool fixed = !multid && !fi->length.empty() && isdigit((unsigned char)fi->length[0]);
+      const long n = fixed ? atol(fi->length.c_str()) : 0;
+      const int hl = hdr.id2length(field_type_idx, vcf_name), hn = hdr.id2number(field_type_idx, vcf_name);
+      const bool agree = (fixed && hl == VL_FIXED && n == hn) || (!fixed && hl != VL_FIXED) || (ht == HT_FLAG && fixed && n == 1 && hl == VL_FIXED && hn == 0);
+      if (!agree) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Conflicting field length descriptors and/or field lengths in the vid JSON and VCF header for field " + field_name);
+      const std::string& vt = fi->vcf_type.empty() ? fi->type : fi->vcf_type;
+      const int vid_ht = vt == "flag" ? HT_FLAG : vt == "int" ? HT_INT : vt == "float" ? HT_REAL : HT_STR;
+      if ((ht == HT_FLAG || ht == HT_INT || ht == HT_REAL) && vid_ht != ht)
+        throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Conflicting data types in the vid JSON and VCF header for field " + field_name);
+    }
+    return false;
+  }
   std::string line = "##";
   line += field_type_idx == HL_FLT ? "FILTER" : (field_type_idx == HL_INFO ? "INFO" : "FORMAT");
   line += "=<ID=" + vcf_name;
   if (field_type_idx != HL_FLT) {
-    if (field_type_idx == HL_FMT && vcf_name == "GT") line += ",Number=1,Type=String";   // GT is weird
+    if (field_type_idx == HL_FMT && vcf_name == "GT") line += ",Number=1,Type=String,Description=\"Genotype\"";   // GT is weird -- and gets the general Description below as well
     else {
       if (!fi) throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "field " + field_name + " is not in the vid mapping");
-      std::string type = fi->type;
-      for (auto& c : type) c = (char)tolower((unsigned char)c);
-      const bool is_flag = type == "flag" || type == "bool" || type == "boolean";
+      const std::string& type = fi->vcf_type.empty() ? fi->type : fi->vcf_type;
+      const bool is_flag = type == "flag";
       line += ",Number=";
       if (is_flag) line += "0";
       else if (multid) line += "1";
       else if (fi->length == "R" || fi->length == "A" || fi->length == "G") line += fi->length;
       else if (!fi->length.empty() && isdigit((unsigned char)fi->length[0])) line += fi->length;
-      else if (fi->length == "VAR" || fi->length == "var" || fi->length == "." ) line += ".";
+      else if (fi->length == "VAR") line += ".";
       else throw GenomicsDBGPUException(GDBGPU_ERR_ARG, "Unhandled field length descriptor " + fi->length + " of field " + field_name);
       line += ",Type=";
       if (multid) line += "String";
       else if (is_flag) line += "Flag";
-      else if (type == "int" || type == "integer" || type == "int32" || type == "int64") line += "Integer";
-      else if (type == "float" || type == "double") line += "Float";
+      else if (type == "int") line += "Integer";
+      else if (type == "float") line += "Float";
       else line += "String";
     }
   }
-  if (field_type_idx == HL_FMT && vcf_name == "GT") line += ",Description=\"Genotype\"";
-  else if (removed && !description_value.empty()) line += ",Description=" + description_value;   // the value carries its quotes
+  if (removed && !description_value.empty()) line += ",Description=" + description_value;   // the value carries its quotes
   else line += ",Description=\"" + vcf_name + "\"";
   line += ">";
   hdr.append(line);

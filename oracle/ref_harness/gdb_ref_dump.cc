@@ -210,7 +210,15 @@ int main(int argc, char** argv)
       std::ifstream l(loader_json); std::string line;
       while(std::getline(l, line))
       {
-        if(line.compare(0, 7, "SAMPLE ") == 0) std::cout << "add_sample " << bcf_hdr_add_sample(h, line.c_str()+7) << "\n";
+        if(line.compare(0, 6, "FIELD ") == 0 && line.size() > 8)   // "FIELD I|F|T <name>": VCFAdapter::add_field_to_hdr_if_missing with the vid mapping named by -o
+        {
+          static FileBasedVidMapper* vid = 0;
+          if(!vid) vid = new FileBasedVidMapper(out_file);
+          const int type = line[6] == 'I' ? BCF_HL_INFO : line[6] == 'F' ? BCF_HL_FMT : BCF_HL_FLT;
+          try { std::cout << "field " << VCFAdapter::add_field_to_hdr_if_missing(h, vid, line.substr(8), type) << "\n"; }
+          catch(const std::exception& e) { std::cout << "field refused\n"; }
+        }
+        else if(line.compare(0, 7, "SAMPLE ") == 0) std::cout << "add_sample " << bcf_hdr_add_sample(h, line.c_str()+7) << "\n";
         else std::cout << "append " << bcf_hdr_append(h, line.c_str()) << "\n";
       }
       bcf_hdr_add_sample(h, 0);

@@ -5,8 +5,10 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include "../../genomicsdb_b200/csrc/gdb_host_api.h"
 #include "../../genomicsdb_b200/csrc/gdb_vcf_header.h"
 using namespace genomicsdb_b200;
+namespace genomicsdb_b200 { bool add_field_to_hdr_if_missing(VCFHeaderLines& hdr, const VidMapper& id_mapper, const std::string& field_name, const std::string& vcf_name, int field_type_idx); }
 int main(int argc, char** argv) {
   if (argc < 2) return 2;
   try {
@@ -17,7 +19,14 @@ int main(int argc, char** argv) {
   if (argc > 2) {
     std::ifstream l(argv[2]); std::string line;
     while (std::getline(l, line)) {
-      if (line.compare(0, 7, "SAMPLE ") == 0) std::cout << "add_sample " << (h.add_sample(line.substr(7)) ? 0 : -1) << "\n";
+      if (line.compare(0, 6, "FIELD ") == 0 && line.size() > 8) {   // add_field_to_hdr_if_missing with the vid mapping argv[3]
+        static VidMapper* vid = nullptr;
+        if (!vid) vid = new VidMapper(argv[3]);
+        const int type = line[6] == 'I' ? HL_INFO : line[6] == 'F' ? HL_FMT : HL_FLT;
+        const std::string name = line.substr(8);
+        try { std::cout << "field " << (add_field_to_hdr_if_missing(h, *vid, name, name, type) ? 1 : 0) << "\n"; }
+        catch (const std::exception&) { std::cout << "field refused\n"; }
+      } else if (line.compare(0, 7, "SAMPLE ") == 0) std::cout << "add_sample " << (h.add_sample(line.substr(7)) ? 0 : -1) << "\n";
       else std::cout << "append " << (h.append(line) ? 0 : -1) << "\n";
     }
   }

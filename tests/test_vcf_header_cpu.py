@@ -2,6 +2,8 @@
 the dictionaries of IDs and contigs) -- against the reference's own htslib (oracle/_ref/bin/gdb_ref_dump --mode header) on header
 texts a template may hold: IDX fields, repeated IDs, one ID as FILTER, INFO and FORMAT, lines in any order, generic and
 structured lines, quoted commas, a missing fileformat line, samples; and on the lines the Broad operator appends."""
+import glob
+import json
 import os
 import subprocess
 
@@ -86,3 +88,66 @@ def test_header_as_htslib_keeps_it(probe, tmp_path, name):
     assert (ref.returncode == 0) == (ours.returncode == 0), (ref.stderr[-400:], ours.stderr[-400:])
     if ref.returncode == 0:
         assert ours.stdout == ref.stdout
+
+
+# ---- VCFAdapter::add_field_to_hdr_if_missing (vcf_adapter.cc:59-260): the line a queried field gets when the template lacks it
+# (Number / Type from the vid mapping, "vcf_type" when given, multi-dimensional fields as Number=1 String keeping the template's
+# Description, GT's two Descriptions), and the refusal when template and vid mapping disagree on a field's length or type
+FIELD_VID = {"contigs": {"1": {"length": 1000, "tiledb_column_offset": 0}}, "fields": {
+    "GT": {"type": "int", "length": "PP", "vcf_field_class": ["FORMAT"]},
+    "PL": {"type": "int", "length": "G", "vcf_field_class": ["FORMAT"]},
+    "AD": {"type": "int", "length": "R", "vcf_field_class": ["FORMAT"]},
+    "AF": {"type": "float", "length": "A", "vcf_field_class": ["INFO"]},
+    "SB": {"type": "int", "length": 4, "vcf_field_class": ["FORMAT"]},
+    "PID": {"type": "char", "length": "VAR", "vcf_field_class": ["FORMAT"]},
+    "DB": {"type": "flag", "vcf_field_class": ["INFO"]},
+    "C1": {"type": "char", "length": 1, "vcf_field_class": ["INFO"]},
+    "PLOIDY": {"type": "int", "length": "P", "vcf_field_class": ["FORMAT"]},
+    "DP": {"type": "int", "vcf_field_class": ["INFO", "FORMAT"]},
+    "MQ": {"type": "float", "vcf_field_class": ["INFO"]},
+    "MQ0": {"type": "int", "vcf_field_class": ["INFO"]},
+    "LowQual": {"type": "int", "vcf_field_class": ["FILTER"]},
+    "AS": {"type": "float", "length": ["R", "var"], "vcf_field_class": ["INFO"], "vcf_delimiter": ["|", ","], "VCF_field_combine_operation": "element_wise_sum"},
+    "HS": {"type": ["float", "int"], "length": ["R", "var"], "vcf_field_class": ["INFO"], "vcf_delimiter": ["|", ","], "VCF_field_combine_operation": "histogram_sum"},
+    "VT": {"type": "int", "vcf_type": "String", "length": "VAR", "vcf_field_class": ["INFO"]},
+    "VAR_IN_VID": {"type": "int", "length": "VAR", "vcf_field_class": ["INFO"]},
+    "FLAG1": {"type": "flag", "length": 1, "vcf_field_class": ["INFO"]}}}
+FIELD_TEMPLATE = ("##fileformat=VCFv4.2\n##INFO=<ID=MQ,Number=1,Type=Float,Description=\"template MQ\">\n##INFO=<ID=AS,Number=.,Type=Float,Description=\"template AS, wrong type\">\n"
+                  "##FORMAT=<ID=SB,Number=2,Type=Integer,Description=\"wrong length\">\n##FORMAT=<ID=AD,Number=R,Type=Float,Description=\"wrong type\">\n"
+                  "##INFO=<ID=DB,Number=0,Type=Flag,Description=\"flag ok\">\n##FORMAT=<ID=PID,Number=1,Type=String,Description=\"string number 1 ok\">\n"
+                  "##INFO=<ID=MQ0,Number=1,Type=Float,Description=\"int in the vid mapping\">\n##INFO=<ID=VAR_IN_VID,Number=3,Type=Integer,Description=\"fixed here\">\n"
+                  "##INFO=<ID=FLAG1,Number=0,Type=Flag,Description=\"length 1 in the vid mapping\">\n##INFO=<ID=AF,Number=.,Type=Float,Description=\"any variable length will do\">\n" + CHROM)
+FIELD_LINES = ["FIELD F GT", "FIELD F PL", "FIELD F AD", "FIELD I AF", "FIELD F SB", "FIELD F PID", "FIELD I DB", "FIELD I C1", "FIELD F PLOIDY", "FIELD I DP", "FIELD F DP", "FIELD I MQ",
+               "FIELD I MQ0", "FIELD T LowQual", "FIELD I AS", "FIELD I HS", "FIELD I VT", "FIELD I VAR_IN_VID", "FIELD I FLAG1", "FIELD T not_in_the_vid_mapping"]
+
+
+def run_fields(probe, tmp_path, template, lines, vid_path):
+    hf, lf = tmp_path / "h.vcf", tmp_path / "lines.txt"
+    hf.write_text(template)
+    lf.write_text("\n".join(lines) + "\n")
+    ref = subprocess.run([REF, "--mode", "header", "-j", str(hf), "-l", str(lf), "-o", vid_path], capture_output=True, text=True)
+    ours = subprocess.run([probe, str(hf), str(lf), vid_path], capture_output=True, text=True)
+    assert ref.returncode == 0 and ours.returncode == 0, (ref.stderr[-400:], ours.stderr[-400:])
+    assert ours.stdout == ref.stdout
+    return ours.stdout
+
+
+def test_field_lines_and_refusals(probe, tmp_path):
+    vf = tmp_path / "vid.json"
+    vf.write_text(json.dumps(FIELD_VID))
+    out = run_fields(probe, tmp_path, FIELD_TEMPLATE, FIELD_LINES, str(vf))
+    verdicts = dict(zip([l.split()[2] + "/" + l.split()[1] for l in FIELD_LINES], out.splitlines()))
+    assert verdicts["GT/F"] == "field 1" and verdicts["MQ/I"] == "field 0" and verdicts["AS/I"] == "field 1"
+    for name in ("AD/F", "SB/F", "MQ0/I", "VAR_IN_VID/I"):
+        assert verdicts[name].endswith("refused"), name
+    assert "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\",Description=\"GT\"" in out
+    assert "##INFO=<ID=AS,Number=1,Type=String,Description=\"template AS, wrong type\"" in out
+
+
+@pytest.mark.parametrize("vid", sorted(os.path.basename(f) for f in glob.glob(os.path.join(GOLDEN, "inputs", "vid*.json"))))
+def test_every_field_of_the_golden_vid_mappings_against_the_template(probe, tmp_path, vid):
+    path = os.path.join(GOLDEN, "inputs", vid)
+    fields = json.load(open(path))["fields"]
+    lines = ["FIELD %s %s" % ({"INFO": "I", "FORMAT": "F", "FILTER": "T"}[c], n) for n, d in fields.items() for c in d.get("vcf_field_class", [])]
+    out = run_fields(probe, tmp_path, TEMPLATE, lines, path)
+    assert "refused" not in out
