@@ -345,7 +345,9 @@ int main(int argc, char** argv)
       << ", \"sites_only_query\": " << query_config.sites_only_query()
       << ", \"produce_GT_with_min_PL_value_for_spanning_deletions\": " << query_config.produce_GT_with_min_PL_value_for_spanning_deletions()
       << ", \"vcf_header_filename\": \"" << query_config.get_vcf_header_filename() << "\", \"reference_genome\": \"" << query_config.get_reference_genome()
-      << "\", \"vcf_output_filename\": \"" << query_config.get_vcf_output_filename()
+      << "\", \"loader_partition\": [" << (loader_json.empty() ? 0ll : (long long)loader_config.get_column_partition(rank).first) << ", "
+      << (loader_json.empty() ? 0ll : (long long)loader_config.get_column_partition(rank).second) << "]"
+      << ", \"vcf_output_filename\": \"" << query_config.get_vcf_output_filename()
       << "\", \"vcf_output_format\": \"" << query_config.get_vcf_output_format() << "\"}" << std::endl;
     GenomicsDBProtoBufInitAndCleanup::shutdown_protobuf_library();
     return 0;

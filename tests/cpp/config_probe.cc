@@ -38,7 +38,8 @@ int main(int argc, char** argv) {
               << ", \"sites_only_query\": " << qc.sites_only_query()
               << ", \"produce_GT_with_min_PL_value_for_spanning_deletions\": " << qc.produce_GT_with_min_PL_value_for_spanning_deletions()
               << ", \"vcf_header_filename\": \"" << qc.get_vcf_header_filename() << "\", \"reference_genome\": \"" << qc.get_reference_genome()
-              << "\", \"vcf_output_filename\": \"" << qc.get_vcf_output_filename() << "\"}" << std::endl;
+              << "\", \"loader_partition\": [" << (loader.empty() ? 0ll : (long long)lc.get_column_partition(rank).first) << ", " << (loader.empty() ? 0ll : (long long)lc.get_column_partition(rank).second) << "]"
+              << ", \"vcf_output_filename\": \"" << qc.get_vcf_output_filename() << "\"}" << std::endl;
   } catch (const std::exception& e) {
     std::cerr << e.what() << "\n";
     return 1;

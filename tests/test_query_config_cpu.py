@@ -88,6 +88,9 @@ ACCEPTED = {
     "one_loader_partition_and_storage_named_outside_it": (q(workspace=None, array=None, query_column_ranges=[[[0, 50], 9000]]),
                                                {"row_based_partitioning": False, "column_partitions": [{"begin": 100}], "workspace": "/lw", "array": "la",
                                                 "vid_mapping_file": VID, "callset_mapping_file": CALLSETS, "size_per_column_partition": 1000}, (0,)),
+    "loader_partitions_unsorted_with_ends_and_contig_bounds": (q(query_column_ranges=[[[0, 50]]]),
+        {"row_based_partitioning": False, "size_per_column_partition": 1000, "vid_mapping_file": VID, "callset_mapping_file": CALLSETS, "workspace": "/lw", "array": "la",
+         "column_partitions": [{"begin": 5000, "end": 100000}, {"begin": 0}, {"begin": {"2": 100}, "end": {"2": [500, 600]}}, {"begin": 700, "end": 650}, {"begin": 100000, "end": 99999999999}]}, (0, 1, 2, 3, 4)),
     "query_overrides_the_loader": (q(query_column_ranges=[[[0, 50], 9000]]),
                                    {"row_based_partitioning": False, "column_partitions": [{"begin": 0, "workspace": "/lw0", "array": "la0"}, {"begin": 4050, "workspace": "/lw1", "array": "la1"}],
                                     "vid_mapping_file": VID, "callset_mapping_file": CALLSETS, "size_per_column_partition": 1000}, (0, 1)),
