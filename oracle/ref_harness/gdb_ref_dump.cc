@@ -9,6 +9,7 @@
  *   --mode hot   : same work without the dump (CPU timing of the hot path alone)
  *   --mode null  : the full BroadCombinedGVCFOperator::operate with a VCFAdapter whose hand-off is a no-op
  *                  (INFO/FORMAT collation + bcf1_t build, no serialisation)
+ *   --mode fasta  : bases of an indexed FASTA (-j) at the "contig pos" lines of -l, through ReferenceGenomeInfo
  *   --mode header : htslib's header bookkeeping on a header text (-j) plus lines to append (-l)
  *   --mode vid    : print the vid mapping (-j vid.json [-l callsets.json]) as FileBasedVidMapper holds it
  *   --mode config : print the query configuration as the reference's classes hold it after parsing (no storage opened)
@@ -192,6 +193,17 @@ int main(int argc, char** argv)
     }
     sm.close_array(qp.get_array_descriptor());
     GenomicsDBProtoBufInitAndCleanup::shutdown_protobuf_library();
+    return 0;
+  }
+  if(mode_str == "fasta")
+  {
+    // ReferenceGenomeInfo (vcf_adapter.cc:31-58) on an indexed FASTA (-j; the .fai is built when missing): one line "contig pos"
+    // of -l per query, in the file's order (the reader keeps a 32 KB window), the base printed per line
+    ReferenceGenomeInfo info;
+    info.initialize(query_json);
+    std::ifstream l(loader_json); std::string contig; int pos;
+    while(l >> contig >> pos)
+      std::cout << contig << " " << pos << " " << info.get_reference_base_at_position(contig.c_str(), pos) << "\n";
     return 0;
   }
   if(mode_str == "header")
